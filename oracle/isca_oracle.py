@@ -1,0 +1,1284 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for the Isca spectral dynamical core hot path.
+
+This file is a NumPy fp64 restatement of the reference algorithm. It is the checker the
+CUDA path is compared against; it is never imported by the product package
+(`isca_b200/`). Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+cpu_baseline / `--impl reference` legs may import it.
+
+PARITY UNPINNED BY THE REFERENCE: the reference ships no golden vectors or known-answer
+tests for this path and no Fortran compiler exists in this image, so the
+reference itself cannot be run.  The oracle is instead pinned by mathematical identities
+(tests/test_oracle_identities.py): Gauss quadrature exactness, Legendre orthonormality,
+transform round trips, analytic harmonics, operator inverses, implicit-matrix inverse,
+mass-fixer invariance, closed-form Held-Suarez T_eq.
+
+Array conventions (identical to the reference's Fortran memory order, so arrays can be
+handed to the C ABI unchanged):
+  grid 3-D   : shape (K, J, I)      == Fortran (lon, lat, lev)
+  grid 2-D   : shape (J, I)
+  spectral 3D: shape (K, N+1, M+1)  == Fortran (m, n, lev), complex128
+  spectral 2D: shape (N+1, M+1)
+with I=lon_max, J=lat_max, K=num_levels, M=num_fourier, N=num_spherical.
+
+Every function cites the reference file:line (relative to /root/reference/src) it follows.
+"""
+from __future__ import annotations
+
+import dataclasses
+from dataclasses import dataclass, field
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# constants  (shared/constants/constants.F90:83-86,120-126,238-266)
+# --------------------------------------------------------------------------------------
+PI = 3.14159265358979323846
+RADIUS = 6376.0e3
+GRAV = 9.80
+RDGAS = 287.04
+KAPPA = 2.0 / 7.0
+CP_AIR = RDGAS / KAPPA
+RVGAS = 461.50
+OMEGA = 7.2921150e-5
+
+
+@dataclass
+class Config:
+    """Union of the namelist variables the hot path reads.
+
+    spectral_dynamics_nml: atmos_spectral/model/spectral_dynamics.F90:152-224
+    hs_forcing_nml       : atmos_param/hs_forcing/hs_forcing.F90:74-122
+    spectral_init_cond_nml: atmos_spectral/init/spectral_init_cond.F90:68-74
+    main_nml dt_atmos    : atmos_solo/atmos_model.F90:111
+    """
+    lon_max: int = 128
+    lat_max: int = 64
+    num_fourier: int = 42
+    num_spherical: int = 43
+    num_levels: int = 18
+    dt_atmos: float = 600.0
+    # spectral_dynamics_nml
+    damping_option: str = "resolution_dependent"
+    damping_order: int = 2
+    damping_coeff: float = 1.15740741e-4
+    damping_order_vor: int = -1
+    damping_coeff_vor: float = -1.0
+    damping_order_div: int = -1
+    damping_coeff_div: float = -1.0
+    eddy_sponge_coeff: float = 0.0
+    zmu_sponge_coeff: float = 0.0
+    zmv_sponge_coeff: float = 0.0
+    do_mass_correction: bool = True
+    do_energy_correction: bool = True
+    do_water_correction: bool = True
+    use_virtual_temperature: bool = False
+    use_implicit: bool = True
+    robert_coeff: float = 0.04
+    raw_filter_coeff: float = 1.0
+    alpha_implicit: float = 0.5
+    vert_coord_option: str = "even_sigma"
+    scale_heights: float = 4.0
+    surf_res: float = 0.1
+    exponent: float = 2.5
+    p_press: float = 0.1
+    p_sigma: float = 0.3
+    vert_advect_uv: str = "second_centered"
+    vert_advect_t: str = "second_centered"
+    vert_difference_option: str = "simmons_and_burridge"
+    reference_sea_level_press: float = 101325.0
+    initial_sphum: float = 0.0
+    water_correction_limit: float = 0.0
+    valid_range_t: tuple = (100.0, 500.0)
+    initial_temperature: float = 264.0
+    # tracers (field_table): 0 tracers, or 1 grid tracer 'sphum' advected with
+    # finite_volume_parabolic (src/extra/model/dry/field_table)
+    num_tracers: int = 0
+    tracer_robert_coeff: float = -1.0   # <0: use robert_coeff
+    # hs_forcing_nml
+    no_forcing: bool = False
+    t_zero: float = 315.0
+    t_strat: float = 200.0
+    delh: float = 60.0
+    delv: float = 10.0
+    eps: float = 0.0
+    sigma_b: float = 0.7
+    P00: float = 1.0e5
+    ka: float = -40.0
+    ks: float = -4.0
+    kf: float = -1.0
+    do_conserve_energy: bool = True
+    trflux: float = 1.0e-5
+    trsink: float = -4.0
+    # constants_nml
+    radius: float = RADIUS
+    omega: float = OMEGA
+    grav: float = GRAV
+    rdgas: float = RDGAS
+    kappa: float = KAPPA
+
+    @property
+    def cp_air(self):
+        return self.rdgas / self.kappa
+
+
+RESOLUTIONS = {  # extra/python/isca/experiment.py:29-58 plus T341
+    "T21": dict(lon_max=64, lat_max=32, num_fourier=21, num_spherical=22),
+    "T42": dict(lon_max=128, lat_max=64, num_fourier=42, num_spherical=43),
+    "T85": dict(lon_max=256, lat_max=128, num_fourier=85, num_spherical=86),
+    "T170": dict(lon_max=512, lat_max=256, num_fourier=170, num_spherical=171),
+    "T341": dict(lon_max=1024, lat_max=512, num_fourier=341, num_spherical=342),
+}
+
+
+def held_suarez_config(res: str, num_levels: int, dt_atmos: float, num_tracers: int = 0) -> Config:
+    """exp/test_cases/held_suarez/held_suarez_test_case.py:45-95 namelist at a given resolution."""
+    c = Config(**RESOLUTIONS[res], num_levels=num_levels, dt_atmos=dt_atmos)
+    c.damping_order = 4
+    c.water_correction_limit = 200.0e2
+    c.reference_sea_level_press = 1.0e5
+    c.valid_range_t = (100.0, 800.0)
+    c.initial_sphum = 0.0
+    c.vert_coord_option = "uneven_sigma"
+    c.scale_heights = 6.0
+    c.exponent = 7.5
+    c.surf_res = 0.5
+    c.num_tracers = num_tracers
+    if num_tracers == 0:
+        c.do_water_correction = False   # dry_model => must be off (spectral_dynamics.F90:1264)
+    return c
+
+
+# --------------------------------------------------------------------------------------
+# Gaussian grid and Legendre tables
+# --------------------------------------------------------------------------------------
+def compute_gaussian(n_hem: int):
+    """atmos_spectral/tools/gauss_and_legendre.F90:111-183 (Newton iteration on P_n)."""
+    converg = 0.1 ** 15          # precision(real*8) = 15
+    itermax = 10
+    n = 2 * n_hem
+    sin_hem = np.zeros(n_hem)
+    wts_hem = np.zeros(n_hem)
+    for i in range(1, n_hem + 1):
+        z = np.cos(PI * (i - 0.25) / (n + 0.5))
+        ok = False
+        for _ in range(itermax):
+            p1 = 1.0
+            p2 = 0.0
+            for j in range(1, n + 1):
+                p3 = p2
+                p2 = p1
+                p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j
+            pp = n * (z * p1 - p2) / (z * z - 1.0)
+            z1 = z
+            z = z1 - p1 / pp
+            if abs(z - z1) < converg:
+                ok = True
+                break
+        if not ok:
+            raise RuntimeError("compute_gaussian: abscissas failed to converge")
+        sin_hem[i - 1] = z
+        wts_hem[i - 1] = 2.0 / ((1.0 - z * z) * pp * pp)
+    return sin_hem, wts_hem
+
+
+def compute_legendre(num_fourier: int, num_spherical: int, sin_lat: np.ndarray):
+    """atmos_spectral/tools/gauss_and_legendre.F90:47-108 (fourier_inc = 1).
+
+    Returns legendre[j, n, m] (Fortran (m,n,j))."""
+    M, N = num_fourier, num_spherical
+    nlat = sin_lat.shape[0]
+    m = np.arange(M + 1, dtype=np.float64)[None, :]
+    n = np.arange(N + 1, dtype=np.float64)[:, None]
+    m2 = m * m + 0 * n
+    l2 = (m + n) ** 2
+    eps = np.sqrt((l2 - m2) / (4.0 * l2 - 1.0))          # eps[n, m]
+    b = np.zeros(M + 1)
+    mm = np.arange(1, M + 1, dtype=np.float64)
+    b[1:] = np.sqrt(0.5 * (2.0 * mm + 1.0) / mm)
+    leg = np.zeros((nlat, N + 1, M + 1))
+    for j in range(nlat):
+        s = sin_lat[j]
+        cos_lat = np.sqrt(1 - s * s)
+        poly = np.zeros((N + 1, M + 1))
+        poly[0, 0] = np.sqrt(0.5)
+        for mi in range(1, M + 1):
+            poly[0, mi] = b[mi] * cos_lat * poly[0, mi - 1]
+        poly[1, :] = s * poly[0, :] / eps[1, :]
+        for ni in range(2, N + 1):
+            poly[ni, :] = (s * poly[ni - 1, :] - eps[ni - 1, :] * poly[ni - 2, :]) / eps[ni, :]
+        leg[j] = poly
+    return leg
+
+
+class Tables:
+    """spherical_init (atmos_spectral/tools/spherical.F90:137-216), define_gaussian /
+    define_legendre (spherical_fourier.F90:376-431), grid_fourier_init (grid_fourier.F90:105-118)."""
+
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        I, J, M, N = cfg.lon_max, cfg.lat_max, cfg.num_fourier, cfg.num_spherical
+        a = cfg.radius
+        self.sin_hem, self.wts_hem = compute_gaussian(J // 2)
+        sin_lat = np.zeros(J)
+        wts_lat = np.zeros(J)
+        sin_lat[: J // 2] = -self.sin_hem            # south_to_north
+        for j in range(J // 2):
+            sin_lat[J - 1 - j] = -sin_lat[j]
+            wts_lat[j] = self.wts_hem[j]
+            wts_lat[J - 1 - j] = self.wts_hem[j]
+        self.sin_lat = sin_lat
+        self.wts_lat = wts_lat
+        self.cos_lat = np.sqrt(1 - sin_lat * sin_lat)
+        self.cosm_lat = 1.0 / self.cos_lat
+        self.cosm2_lat = 1.0 / (self.cos_lat * self.cos_lat)
+        self.deg_lat = np.arcsin(sin_lat) * 180.0 / PI
+        self.rad_lat = self.deg_lat * PI / 180.0       # atmosphere.F90:250-253
+        self.deg_lon = np.arange(I) * 360.0 / I
+        self.global_sum_of_wts = float(np.sum(wts_lat))
+        self.legendre = compute_legendre(M, N, self.sin_hem)            # [j, n, m]
+        self.legendre_wts = self.legendre * self.wts_hem[:, None, None]
+        # coefficient tables, all [n, m]
+        m = np.arange(M + 1, dtype=np.float64)[None, :] + np.zeros((N + 1, 1))
+        n = np.arange(N + 1, dtype=np.float64)[:, None] + np.zeros((1, M + 1))
+        L = m + n
+        self.fourier_wave = m
+        self.spherical_wave = L
+        self.triangle_mask = np.where(L > N - 1, 0.0, 1.0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            eps = np.sqrt((L ** 2 - m ** 2) / (4.0 * L ** 2 - 1.0))
+        self.epsilon = eps
+        self.eigen_laplacian = L * (L + 1.0) / (a * a)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            self.coef_uvm = np.where(L > 0, -a * eps / np.where(L > 0, L, 1.0), 0.0)
+            self.coef_uvc = np.where(L > 0, -a * m / np.where(L > 0, L * (L + 1.0), 1.0), 0.0)
+        self.coef_uvp = np.zeros_like(L)
+        self.coef_uvp[:N, :] = -a * eps[1:, :] / (L[:N, :] + 1.0)
+        self.coef_alpm = (L + 1.0) * eps / a
+        self.coef_alpp = np.zeros_like(L)
+        self.coef_alpp[:N, :] = L[:N, :] * eps[1:, :] / a
+        self.coef_dym = (L - 1.0) * eps / a
+        self.coef_dx = m / a
+        self.coef_dyp = np.zeros_like(L)
+        self.coef_dyp[:N, :] = (L[:N, :] + 2.0) * eps[1:, :] / a
+        self.coriolis = 2 * cfg.omega * sin_lat
+
+
+# --------------------------------------------------------------------------------------
+# Transforms
+# --------------------------------------------------------------------------------------
+class Transforms:
+    def __init__(self, tb: Tables):
+        self.tb = tb
+        self.cfg = tb.cfg
+
+    # ---- FFT: fft_grid_to_fourier / fft_fourier_to_grid (shared/fft/fft.F90:483-718;
+    #      convention shared/fft/fft99.F90:195-209: forward 1/N-normalised, inverse unscaled)
+    def grid_to_fourier(self, grid):
+        I, M = self.cfg.lon_max, self.cfg.num_fourier
+        f = np.fft.rfft(grid, axis=-1) / I
+        return f[..., : M + 1]                  # transforms.F90:509 (trunc_fourier)
+
+    def fourier_to_grid(self, four):
+        I, M = self.cfg.lon_max, self.cfg.num_fourier
+        full = np.zeros(four.shape[:-1] + (I // 2 + 1,), dtype=np.complex128)
+        full[..., : M + 1] = four               # transforms.F90:424 zero m>M
+        return np.fft.irfft(full, n=I, axis=-1) * I
+
+    # ---- Legendre: trans_spherical_to_fourier / trans_fourier_to_spherical
+    #      (spherical_fourier.F90:177-261, 264-339)
+    def spherical_to_fourier(self, spec):
+        """spec [..., n, m] -> fourier [..., j, m] (south to north)."""
+        P = self.tb.legendre                    # [jh, n, m]
+        J = self.cfg.lat_max
+        ev = np.einsum("jnm,...nm->...jm", P[:, 0::2, :], spec[..., 0::2, :])
+        od = np.einsum("jnm,...nm->...jm", P[:, 1::2, :], spec[..., 1::2, :])
+        out = np.zeros(spec.shape[:-2] + (J, spec.shape[-1]), dtype=np.complex128)
+        out[..., : J // 2, :] = ev - od                       # south  (:233)
+        out[..., J // 2:, :] = (ev + od)[..., ::-1, :]        # north mirror (:232)
+        return out
+
+    def fourier_to_spherical(self, four):
+        Pw = self.tb.legendre_wts
+        J = self.cfg.lat_max
+        south = four[..., : J // 2, :]
+        north = four[..., J // 2:, :][..., ::-1, :]
+        x_even = north + south                  # :311
+        x_odd = north - south                   # :312
+        N = self.cfg.num_spherical
+        out = np.zeros(four.shape[:-2] + (N + 1, four.shape[-1]), dtype=np.complex128)
+        out[..., 0::2, :] = np.einsum("jnm,...jm->...nm", Pw[:, 0::2, :], x_even)
+        out[..., 1::2, :] = np.einsum("jnm,...jm->...nm", Pw[:, 1::2, :], x_odd)
+        return out
+
+    # ---- transforms.F90:379-442 / 462-533
+    def spherical_to_grid(self, spec):
+        return self.fourier_to_grid(self.spherical_to_fourier(spec))
+
+    def grid_to_spherical(self, grid, do_truncation=True):
+        s = self.fourier_to_spherical(self.grid_to_fourier(grid))
+        if do_truncation:
+            s = s * self.tb.triangle_mask       # spherical.F90:564-600
+        return s
+
+    def divide_by_cos(self, g):                 # transforms.F90:599-622
+        return g * self.tb.cosm_lat[:, None]
+
+    # ---- spherical operators (spherical.F90)
+    @staticmethod
+    def _times_i(s):
+        return 1j * s                           # cmplx(-aimag, real)
+
+    def lon_deriv_cos(self, s):                 # spherical.F90:270-297
+        return self.tb.coef_dx * self._times_i(s)
+
+    def lat_deriv_cos(self, s):                 # spherical.F90:300-337
+        N = self.cfg.num_spherical
+        d = np.zeros_like(s)
+        d[..., 1:, :] = -s[..., : N, :] * self.tb.coef_dym[1:, :]
+        d[..., : N, :] = d[..., : N, :] + s[..., 1:, :] * self.tb.coef_dyp[: N, :]
+        return d
+
+    def gradient_cos(self, s):                  # spherical.F90:340-351
+        return self.lon_deriv_cos(s), self.lat_deriv_cos(s)
+
+    def laplacian(self, s):                     # spherical.F90:354-406
+        return s * (-self.tb.eigen_laplacian)
+
+    def ucos_vcos(self, vor, div):              # spherical.F90:409-469
+        tb, N = self.tb, self.cfg.num_spherical
+        u = tb.coef_uvc * self._times_i(div)
+        v = tb.coef_uvc * self._times_i(vor)
+        u[..., 1:, :] = u[..., 1:, :] + tb.coef_uvm[1:, :] * vor[..., : N, :]
+        v[..., 1:, :] = v[..., 1:, :] - tb.coef_uvm[1:, :] * div[..., : N, :]
+        u[..., : N, :] = u[..., : N, :] - tb.coef_uvp[: N, :] * vor[..., 1:, :]
+        v[..., : N, :] = v[..., : N, :] + tb.coef_uvp[: N, :] * div[..., 1:, :]
+        return u, v
+
+    def alpha_operator(self, a, b, isign):      # spherical.F90:512-561
+        tb, N = self.tb, self.cfg.num_spherical
+        al = tb.coef_dx * self._times_i(a)
+        al[..., 1:, :] = al[..., 1:, :] - isign * tb.coef_alpm[1:, :] * b[..., : N, :]
+        al[..., : N, :] = al[..., : N, :] + isign * tb.coef_alpp[: N, :] * b[..., 1:, :]
+        return al
+
+    def vor_div(self, ucos, vcos):              # spherical.F90:472-509
+        return self.alpha_operator(vcos, ucos, -1), self.alpha_operator(ucos, vcos, +1)
+
+    # ---- compositions (transforms.F90:700-831)
+    def uv_grid_from_vor_div(self, vor, div):
+        us, vs = self.ucos_vcos(vor, div)
+        return self.divide_by_cos(self.spherical_to_grid(us)), self.divide_by_cos(self.spherical_to_grid(vs))
+
+    def vor_div_from_uv_grid(self, ug, vg):
+        dx = self.grid_to_spherical(self.divide_by_cos(ug), do_truncation=False)
+        dy = self.grid_to_spherical(self.divide_by_cos(vg), do_truncation=False)
+        vor, div = self.vor_div(dx, dy)
+        return vor * self.tb.triangle_mask, div * self.tb.triangle_mask
+
+    def horizontal_advection(self, field_spec, ug, vg, tendency):
+        dxs, dys = self.gradient_cos(field_spec)
+        dxg = self.divide_by_cos(self.spherical_to_grid(dxs))
+        dyg = self.divide_by_cos(self.spherical_to_grid(dys))
+        return tendency - ug * dxg - vg * dyg
+
+    def area_weighted_global_mean(self, f):     # transforms.F90:1059-1077
+        w = self.tb.wts_lat[:, None] * f
+        return float(np.sum(w) / (self.tb.global_sum_of_wts * self.cfg.lon_max))
+
+
+# --------------------------------------------------------------------------------------
+# vertical coordinate  (atmos_spectral/init/vert_coordinate.F90:89-310)
+# --------------------------------------------------------------------------------------
+def compute_vert_coord(cfg: Config):
+    K = cfg.num_levels
+    a = np.zeros(K + 1)
+    b = np.zeros(K + 1)
+    if cfg.vert_coord_option == "even_sigma":
+        for k in range(1, K + 1):
+            b[k - 1] = float(k - 1) / float(K)
+        b[K] = 1.0
+    elif cfg.vert_coord_option == "uneven_sigma":
+        s2 = 1.0 - cfg.surf_res
+        for k in range(1, K + 1):
+            zeta = 1.0 - (float(k - 1) / float(K))
+            z = cfg.surf_res * zeta + s2 * (zeta ** cfg.exponent)
+            b[k - 1] = np.exp(-z * cfg.scale_heights)
+        b[K] = 1.0
+        b[0] = 0.0
+    else:
+        raise ValueError(f'"{cfg.vert_coord_option}" is not a supported vert_coord_option')
+    return a, b
+
+
+# --------------------------------------------------------------------------------------
+# pressure / geopotential   (atmos_spectral/model/press_and_geopot.F90)
+# --------------------------------------------------------------------------------------
+class PressGeopot:
+    def __init__(self, cfg, pk, bk):
+        self.cfg, self.pk, self.bk = cfg, pk, bk
+        if cfg.vert_difference_option != "simmons_and_burridge":
+            raise ValueError("only simmons_and_burridge is supported")
+
+    def half_level_pressures(self, ps):         # :116-132
+        return self.pk[:, None, None] + self.bk[:, None, None] * ps[None]
+
+    def pressure_variables(self, ps):           # :152-221 (ps may be scalar-shaped (1,1))
+        pk, bk = self.pk, self.bk
+        ps = np.atleast_2d(ps)
+        p_half = self.half_level_pressures(ps)
+        K = p_half.shape[0] - 1
+        ln_p_half = np.zeros_like(p_half)
+        ln_p_full = np.zeros((K,) + ps.shape)
+        if pk[0] == 0.0 and bk[0] == 0.0:
+            ln_p_half[1:] = np.log(p_half[1:])
+            for k in range(1, K):
+                alpha = 1.0 - p_half[k] * (ln_p_half[k + 1] - ln_p_half[k]) / (p_half[k + 1] - p_half[k])
+                ln_p_full[k] = ln_p_half[k + 1] - alpha
+            ln_p_full[0] = ln_p_half[1] + (-1.0)       # ln_top_level_factor
+            ln_p_half[0] = 0.0
+        else:
+            ln_p_half[:] = np.log(p_half)
+            for k in range(K):
+                alpha = 1.0 - p_half[k] * (ln_p_half[k + 1] - ln_p_half[k]) / (p_half[k + 1] - p_half[k])
+                ln_p_full[k] = ln_p_half[k + 1] - alpha
+        p_full = np.exp(ln_p_full)
+        return p_half, ln_p_half, p_full, ln_p_full
+
+    def compute_geopotential(self, t, ln_p_half, ln_p_full, surf_geopotential, q=None):   # :314-359
+        K = t.shape[0]
+        gh = np.zeros((K + 1,) + t.shape[1:])
+        gh[K] = surf_geopotential
+        ktop = 1 if self.pk[0] == 0.0 else 0
+        if self.cfg.use_virtual_temperature:
+            vt = t * (1.0 + (RVGAS / self.cfg.rdgas - 1.0) * q)
+        else:
+            vt = t
+        for k in range(K - 1, ktop - 1, -1):
+            gh[k] = gh[k + 1] + self.cfg.rdgas * vt[k] * (ln_p_half[k + 1] - ln_p_half[k])
+        gf = gh[1:] + self.cfg.rdgas * vt * (ln_p_half[1:] - ln_p_full)
+        return gf, gh
+
+    def compute_pressures_and_heights(self, t, ps, surf_geopotential, q=None):   # :363-387
+        p_half, ln_p_half, p_full, ln_p_full = self.pressure_variables(ps)
+        zf, zh = self.compute_geopotential(t, ln_p_half, ln_p_full, surf_geopotential, q)
+        return zf / self.cfg.grav, zh / self.cfg.grav, p_full, p_half
+
+
+# --------------------------------------------------------------------------------------
+# matrix inverse   (atmos_spectral/model/matrix_invert.F90:38-148)
+# --------------------------------------------------------------------------------------
+def invert(matrix):
+    n = matrix.shape[0]
+    ac = np.zeros((2 * n, n))
+    ac[:n, :] = matrix
+    for j in range(n):
+        ac[n + j, j] = 1.0
+    for k in range(n):
+        h = ac[k, k:n]
+        # max_mag: first index of strictly larger magnitude than h(1)
+        mx = 0
+        rmax = abs(h[0])
+        for i in range(h.shape[0]):
+            if abs(h[i]) > rmax:
+                rmax = abs(h[i])
+                mx = i
+        L = mx + k
+        if k - L < 0:
+            tmp = ac[k:, k].copy()
+            ac[k:, k] = ac[k:, L]
+            ac[k:, L] = tmp
+        hh = ac[k:, k] / ac[k, k]
+        temp = hh[:, None] * ac[k, :][None, :]
+        ac[k:, :] = ac[k:, :] - temp
+        ac[k:, k] = hh
+    return ac[n:, :].copy()
+
+
+# --------------------------------------------------------------------------------------
+# semi-implicit   (atmos_spectral/model/implicit.F90)
+# --------------------------------------------------------------------------------------
+class Implicit:
+    def __init__(self, cfg, tb, pk, bk, pg: PressGeopot):
+        self.cfg, self.tb, self.pk, self.bk, self.pg = cfg, tb, pk, bk, pg
+        K = cfg.num_levels
+        self.K = K
+        self.alpha = cfg.alpha_implicit
+        self.ref_t = np.full(K, 300.0)                       # spectral_dynamics.F90:473
+        self.ref_ps = cfg.reference_sea_level_press
+        self.dpk = pk[1:] - pk[:-1]
+        self.dbk = bk[1:] - bk[:-1]
+        self.num_total_wavenumbers = cfg.num_spherical - 1   # triangular
+        _, lnh, _, lnf = pg.pressure_variables(np.array([[self.ref_ps]]))
+        self.ref_ln_p_half = lnh[:, 0, 0]
+        self.ref_ln_p_full = lnf[:, 0, 0]
+        del_ln_p_half = np.zeros(K + 1)                      # implicit.F90:141-149
+        for k in range(1, K + 1):
+            del_ln_p_half[k] = bk[k] / (pk[k] + bk[k] * self.ref_ps)
+        if pk[0] == 0.0:
+            del_ln_p_half[0] = 1.0 / self.ref_ps
+        else:
+            del_ln_p_half[0] = bk[0] / (pk[0] + bk[0] * self.ref_ps)
+        eps = 1.0e-5
+        _, _, _, l1 = pg.pressure_variables(np.array([[self.ref_ps * (1.0 - 0.5 * eps)]]))
+        _, _, _, l2 = pg.pressure_variables(np.array([[self.ref_ps * (1.0 + 0.5 * eps)]]))
+        del_ln_p_full = (l2[:, 0, 0] - l1[:, 0, 0]) / (eps * self.ref_ps)
+        self.del_ln_p_half, self.del_ln_p_full = del_ln_p_half, del_ln_p_full
+        self._build_matrix()
+        self.dt = 0.0
+        self.xi = 0.0
+        self.wave_matrix = None
+
+    def linear_geopotential(self, del_t, del_ln_p_half, del_ln_p_full):
+        """implicit.F90:329-359; arrays indexed [k, ...]."""
+        K, rd = self.K, self.cfg.rdgas
+        t, lh, lf = self.ref_t, self.ref_ln_p_half, self.ref_ln_p_full
+        gh = np.zeros((K + 1,) + del_t.shape[1:], dtype=del_t.dtype)
+        for k in range(K - 1, 0, -1):
+            gh[k] = gh[k + 1] + rd * (del_t[k] * (lh[k + 1] - lh[k]) + t[k] * (del_ln_p_half[k + 1] - del_ln_p_half[k]))
+        g = np.zeros_like(del_t)
+        for k in range(K):
+            g[k] = gh[k + 1] + rd * (del_t[k] * (lh[k + 1] - lf[k]) + t[k] * (del_ln_p_half[k + 1] - del_ln_p_full[k]))
+        return g
+
+    def linear_tp_tendency(self, div):
+        """implicit.F90:414-480; div [k, ...] -> (dt_p_surf [...], dt_t [k, ...])."""
+        K, kappa = self.K, self.cfg.kappa
+        t, lh, lf = self.ref_t, self.ref_ln_p_half, self.ref_ln_p_full
+        dmean_tot = np.zeros(div.shape[1:], dtype=div.dtype)
+        dt_t = np.zeros_like(div)
+        vert_vel = np.zeros((K + 1,) + div.shape[1:], dtype=div.dtype)
+        for k in range(K):
+            dp = self.dpk[k] + self.dbk[k] * self.ref_ps
+            dp_inv = 1 / dp
+            dlog_1 = lh[k + 1] - lf[k]
+            dlog_3 = lh[k + 1] - lh[k]
+            dmean = div[k] * dp
+            dt_t[k] = -kappa * t[k] * (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv
+            dmean_tot = dmean_tot + dmean
+            vert_vel[k + 1] = -dmean_tot
+        dt_p = -dmean_tot
+        for k in range(1, K):
+            vert_vel[k] = vert_vel[k] + dmean_tot * self.bk[k]
+        temp = np.zeros_like(vert_vel)
+        for k in range(1, K):
+            temp[k] = -vert_vel[k] * (t[k] - t[k - 1])
+        for k in range(K):
+            dp = self.dpk[k] + self.dbk[k] * self.ref_ps
+            dp_inv = 1 / dp
+            dt_t[k] = dt_t[k] + 0.5 * dp_inv * (temp[k + 1] + temp[k])
+        return dt_p, dt_t
+
+    def pres_grad_funct(self):                  # implicit.F90:389-410
+        K = self.K
+        x = np.zeros(K)
+        for k in range(K):
+            dlog_1 = self.ref_ln_p_half[k + 1] - self.ref_ln_p_full[k]
+            dlog_2 = self.ref_ln_p_full[k] - self.ref_ln_p_half[k]
+            x[k] = self.cfg.rdgas * self.ref_t[k] * (self.bk[k + 1] * dlog_1 + self.bk[k] * dlog_2) / (
+                self.dpk[k] + self.dbk[k] * self.ref_ps)
+        return x
+
+    def _build_matrix(self):                    # implicit.F90:168-214
+        K = self.K
+        tau = np.zeros((K, K))
+        nu = np.zeros(K)
+        gamma = np.zeros((K, K))
+        zero = np.zeros(K)
+        zero1 = np.zeros(K + 1)
+        for k in range(K):
+            inp = np.zeros(K)
+            inp[k] = 1.0
+            dt_p, dt_t = self.linear_tp_tendency(inp)
+            nu[k] = -dt_p
+            tau[:, k] = -dt_t
+            gamma[:, k] = self.linear_geopotential(inp, zero1, zero)
+        h1 = self.pres_grad_funct()
+        h2 = self.linear_geopotential(zero, self.del_ln_p_half, self.del_ln_p_full)
+        self.h = h1 + h2
+        div_mat = np.zeros((K, K))
+        for k in range(K):
+            for kk in range(K):
+                s = self.h[k] * nu[kk]
+                for kkk in range(K):
+                    s = s + gamma[k, kkk] * tau[kkk, kk]
+                div_mat[k, kk] = s
+        self.div_mat = div_mat
+
+    def build_wave_matrices(self):              # implicit.F90:218-237
+        K = self.K
+        nw = self.num_total_wavenumbers
+        wm = np.zeros((nw + 1, K, K))
+        for L in range(nw + 1):
+            factor = self.xi * self.xi * L * (L + 1) / self.cfg.radius ** 2
+            wm[L] = invert(np.eye(K) + factor * self.div_mat)
+        self.wave_matrix = wm
+
+    def implicit_correction(self, dt_divs, dt_ts, dt_ln_ps, divs, ts, ln_ps, dt_in, previous, current):
+        """implicit.F90:241-325. divs/ts: [level, k, n, m]; ln_ps: [level, n, m]."""
+        if dt_in != self.dt:
+            self.dt = dt_in
+            self.xi = dt_in * self.alpha
+            self.build_wave_matrices()
+        xi = self.xi
+        # adjust_dt_divs
+        divs_temp = divs[previous] - divs[current]
+        dt_ps_temp, dt_ts_temp = self.linear_tp_tendency(divs_temp)
+        dt_ts = dt_ts + dt_ts_temp
+        dt_ln_ps = dt_ln_ps + dt_ps_temp / self.ref_ps
+        ts_temp = ts[previous] - ts[current] + xi * dt_ts
+        ps_temp = ln_ps[previous] - ln_ps[current] + xi * dt_ln_ps
+        zf = np.zeros_like(ts_temp)
+        zh = np.zeros((self.K + 1,) + ts_temp.shape[1:], dtype=ts_temp.dtype)
+        geopot = self.linear_geopotential(ts_temp, zh, zf)
+        eigen = self.tb.eigen_laplacian
+        dt_divs = dt_divs + eigen * (geopot + self.h[:, None, None] * ps_temp * self.ref_ps)
+        # per-(m,n) matvec with wave_matrix(L)
+        Lw = self.tb.spherical_wave.astype(int)
+        ok = Lw <= self.num_total_wavenumbers
+        Lc = np.where(ok, Lw, 0)
+        W = self.wave_matrix[Lc]                               # [n, m, k, kk]
+        work = np.einsum("nmkq,qnm->knm", W, dt_divs)
+        dt_divs = np.where(ok[None], work, dt_divs)
+        dt_ps_temp, dt_ts_temp = self.linear_tp_tendency(dt_divs)
+        dt_ts = dt_ts + xi * dt_ts_temp
+        dt_ln_ps = dt_ln_ps + xi * dt_ps_temp / self.ref_ps
+        return dt_divs, dt_ts, dt_ln_ps
+
+
+# --------------------------------------------------------------------------------------
+# spectral damping  (atmos_spectral/model/spectral_damping.F90:56-291)
+# --------------------------------------------------------------------------------------
+class SpectralDamping:
+    def __init__(self, cfg, tb):
+        self.cfg = cfg
+        if cfg.damping_option != "resolution_dependent":
+            raise ValueError("only damping_option='resolution_dependent' is supported")
+        eigen = tb.eigen_laplacian                           # [n, m]
+        N = cfg.num_spherical
+        o_v = cfg.damping_order if cfg.damping_order_vor == -1 else cfg.damping_order_vor
+        o_d = cfg.damping_order if cfg.damping_order_div == -1 else cfg.damping_order_div
+        c_v = cfg.damping_coeff if cfg.damping_coeff_vor == -1.0 else cfg.damping_coeff_vor
+        c_d = cfg.damping_coeff if cfg.damping_coeff_div == -1.0 else cfg.damping_coeff_div
+        ref = eigen[N - 1, 0]
+        self.damping = cfg.damping_coeff * ((eigen / ref) ** cfg.damping_order)
+        self.damping_vor = c_v * ((eigen / ref) ** o_v)
+        self.damping_div = c_d * ((eigen / ref) ** o_d)
+        self.zmu = cfg.zmu_sponge_coeff * eigen[:, 0]
+        self.zmv = cfg.zmv_sponge_coeff * eigen[:, 0]
+        self.eddy = cfg.eddy_sponge_coeff * eigen
+
+    @staticmethod
+    def _damp(spec, dt_spec, damping, dt):
+        coeff = 1.0 / (1.0 + damping * dt)
+        return coeff * (dt_spec - damping * spec)
+
+    def _sponge(self, spec, dt_spec, zm, dt):
+        out = dt_spec.copy()
+        # level 1 only: eddies m != 0 (:220-226), zonal mean m = 0 (:228-232)
+        out[0, :, 1:] = (dt_spec[0, :, 1:] - self.eddy[:, 1:] * spec[0, :, 1:]) / (1.0 + self.eddy[:, 1:] * dt)
+        out[0, :, 0] = (dt_spec[0, :, 0] - zm * spec[0, :, 0]) / (1.0 + zm * dt)
+        return out
+
+    def damp(self, spec, dt_spec, dt):
+        return self._damp(spec, dt_spec, self.damping, dt)
+
+    def damp_vor(self, spec, dt_spec, dt):
+        return self._sponge(spec, self._damp(spec, dt_spec, self.damping_vor, dt), self.zmu, dt)
+
+    def damp_div(self, spec, dt_spec, dt):
+        return self._sponge(spec, self._damp(spec, dt_spec, self.damping_div, dt), self.zmv, dt)
+
+
+# --------------------------------------------------------------------------------------
+# vertical advection  (atmos_shared/vert_advection/vert_advection.F90:70-478)
+# --------------------------------------------------------------------------------------
+SECOND_CENTERED = "second_centered"
+FINITE_VOLUME_PARABOLIC = "finite_volume_parabolic"
+
+
+def _slope_z(r, dz, limit=True, linear=True):
+    """vert_advection.F90:504-563. r, dz: [k, ...]."""
+    K = r.shape[0]
+    slope = np.zeros_like(r)
+    grad = np.zeros_like(r)                                   # grad[k] == Fortran grad(k+1), k>=1
+    grad[1:] = (r[1:] - r[:-1]) / (dz[1:] + dz[:-1])
+    if linear:
+        slope[1:K - 1] = (grad[2:K] + grad[1:K - 1]) * dz[1:K - 1]
+    else:
+        for k in range(1, K - 1):
+            slope[k] = (grad[k + 1] * (2.0 * dz[k - 1] + dz[k]) + grad[k] * (2.0 * dz[k + 1] + dz[k])) \
+                * dz[k] / (dz[k - 1] + dz[k] + dz[k + 1])
+    slope[0] = 2.0 * grad[1] * dz[0]
+    slope[K - 1] = 2.0 * grad[K - 1] * dz[K - 1]
+    if limit:
+        for k in range(K):
+            if 1 <= k <= K - 2:
+                rmin = np.minimum(np.minimum(r[k - 1], r[k]), r[k + 1])
+                rmax = np.maximum(np.maximum(r[k - 1], r[k]), r[k + 1])
+                sgn = np.where(slope[k] >= 0.0, 1.0, -1.0)
+                slope[k] = sgn * np.minimum(np.minimum(np.abs(slope[k]), 2.0 * (r[k] - rmin)), 2.0 * (rmax - r[k]))
+            else:
+                slope[k] = 0.0
+    return slope
+
+
+def _compute_weights(dz):
+    """vert_advection.F90:567-629. returns zwt[0..3][k, ...] (only k = 2..K-2 (0-based) are defined)."""
+    K = dz.shape[0]
+    zwt = np.zeros((4,) + dz.shape)
+    for k in range(2, K - 1):               # Fortran k = 3 .. n-1
+        denom1 = 1.0 / (dz[k - 1] + dz[k])
+        denom2 = 1.0 / (dz[k - 2] + dz[k - 1] + dz[k] + dz[k + 1])
+        denom3 = 1.0 / (2 * dz[k - 1] + dz[k])
+        denom4 = 1.0 / (dz[k - 1] + 2 * dz[k])
+        num3 = dz[k - 2] + dz[k - 1]
+        num4 = dz[k] + dz[k + 1]
+        x = num3 * denom3 - num4 * denom4
+        y = 2.0 * dz[k - 1] * dz[k]
+        zwt[0, k] = dz[k - 1] * denom1
+        zwt[1, k] = zwt[0, k] + x * y * denom1 * denom2
+        zwt[2, k] = dz[k - 1] * num3 * denom3 * denom2
+        zwt[3, k] = dz[k] * num4 * denom4 * denom2
+    return zwt
+
+
+def vert_advection(dt, w, dz, r, scheme):
+    """ADVECTIVE_FORM tendency, r/dz: [K, ...], w: [K+1, ...]."""
+    K = r.shape[0]
+    flux = np.zeros_like(w)
+    flux[0] = w[0] * r[0]
+    flux[K] = w[K] * r[K - 1]
+    if scheme == SECOND_CENTERED:
+        flux[1:K] = w[1:K] * (0.5 * (r[1:K] + r[0:K - 1]))
+    elif scheme == FINITE_VOLUME_PARABOLIC:
+        zwt = _compute_weights(dz)
+        slp = _slope_z(r, dz, linear=False)
+        r_left = np.zeros_like(r)
+        r_right = np.zeros_like(r)
+        for k in range(2, K - 1):
+            r_left[k] = r[k - 1] + zwt[1, k] * (r[k] - r[k - 1]) - zwt[2, k] * slp[k] + zwt[3, k] * slp[k - 1]
+            r_right[k - 1] = r_left[k]
+        r_left[1] = r[1] - 0.5 * slp[1]
+        r_right[K - 2] = r[K - 2] + 0.5 * slp[K - 2]
+        r_left[0] = r[0] - 0.5 * slp[0]
+        r_right[0] = r[0] + 0.5 * slp[0]
+        r_left[K - 1] = r[K - 1] - 0.5 * slp[K - 1]
+        r_right[K - 1] = r[K - 1] + 0.5 * slp[K - 1]
+        # Colella-Woodward limiter (:340-356)
+        for k in range(K):
+            test_1 = (r_right[k] - r[k]) * (r[k] - r_left[k]) <= 0.0
+            r_left[k] = np.where(test_1, r[k], r_left[k])
+            r_right[k] = np.where(test_1, r[k], r_right[k])
+            if k == 0 or k == K - 1:
+                continue
+            rm = r_right[k] - r_left[k]
+            a = rm * (r[k] - 0.5 * (r_right[k] + r_left[k]))
+            b = rm * rm / 6.0
+            new_left = np.where(a > b, 3.0 * r[k] - 2.0 * r_right[k], r_left[k])
+            r_left[k] = new_left
+            r_right[k] = np.where(a < -b, 3.0 * r[k] - 2.0 * r_left[k], r_right[k])
+        tt = 2.0 / 3.0
+        shape = r.shape[1:]
+        rf = r.reshape(K, -1)
+        dzf = dz.reshape(K, -1)
+        wf = w.reshape(K + 1, -1)
+        rl = r_left.reshape(K, -1)
+        rr = r_right.reshape(K, -1)
+        fl = flux.reshape(K + 1, -1)
+        ncol = rf.shape[1]
+        cols = np.arange(ncol)
+        for k in range(1, K):                   # Fortran k = ks+1 .. ke
+            wk = wf[k]
+            pos = wk >= 0.0
+            # ---- w >= 0 branch: upstream cell kk = k-1 (0-based)
+            cn_p = dt * wk / dzf[k - 1]
+            cn_n = -dt * wk / dzf[k]
+            cn = np.where(pos, cn_p, cn_n)
+            kk = np.where(pos, k - 1, k).astype(np.int64)
+            rsum = np.zeros(ncol)
+            dzsum = np.zeros(ncol)
+            dtw = np.where(pos, dt * wk, -dt * wk)
+            big = cn > 1.0
+            if np.any(big):
+                idx = np.nonzero(big)[0]
+                for c in idx:
+                    kc = int(kk[c])
+                    step = -1 if pos[c] else 1
+                    lim = 0                      # Fortran: kk==1 (pos) / kk==ks (neg) both -> index 0
+                    while dzsum[c] + dzf[kc, c] < dtw[c]:
+                        if kc == lim:
+                            break
+                        dzsum[c] += dzf[kc, c]
+                        rsum[c] += rf[kc, c]
+                        kc += step
+                    kk[c] = kc
+            xx = np.where(big, (dtw - dzsum) / dzf[kk, cols], cn)
+            rm = rr[kk, cols] - rl[kk, cols]
+            r6 = 6.0 * (rf[kk, cols] - 0.5 * (rr[kk, cols] + rl[kk, cols]))
+            r6 = np.where(pos & (kk == 0), 0.0, r6)
+            r6 = np.where((~pos) & (kk == K - 1), 0.0, r6)
+            rst_p = rr[kk, cols] - 0.5 * xx * (rm - (1.0 - tt * xx) * r6)
+            rst_n = rl[kk, cols] + 0.5 * xx * (rm + (1.0 - tt * xx) * r6)
+            rst = np.where(pos, rst_p, rst_n)
+            rst = np.where(big, (xx * rst + rsum) / np.where(big, cn, 1.0), rst)
+            fl[k] = wk * rst
+        flux = fl.reshape((K + 1,) + shape)
+    else:
+        raise ValueError(f"unsupported vertical advection scheme {scheme}")
+    return -(flux[1:] - flux[:-1] - r * (w[1:] - w[:-1])) / dz
+
+
+# --------------------------------------------------------------------------------------
+# Held-Suarez forcing  (atmos_param/hs_forcing/hs_forcing.F90:148-272,508-724)
+# --------------------------------------------------------------------------------------
+class HSForcing:
+    def __init__(self, cfg: Config, tb: Tables):
+        self.cfg, self.tb = cfg, tb
+        self.tka = -1.0 / (86400 * cfg.ka) if cfg.ka < 0 else cfg.ka
+        self.tks = -1.0 / (86400 * cfg.ks) if cfg.ks < 0 else cfg.ks
+        self.vkf = -1.0 / (86400 * cfg.kf) if cfg.kf < 0 else cfg.kf
+        self.trsink = -86400.0 * cfg.trsink if cfg.trsink < 0 else cfg.trsink
+
+    def rayleigh_damping(self, ps, p_full, u, v):
+        c = self.cfg
+        vcoeff = -self.vkf / (1.0 - c.sigma_b)
+        rps = 1.0 / ps
+        sigma = p_full * rps[None]
+        act = (sigma <= 1.0) & (sigma > c.sigma_b)
+        vfactr = vcoeff * (sigma - c.sigma_b)
+        return np.where(act, vfactr * u, 0.0), np.where(act, vfactr * v, 0.0)
+
+    def teq(self, p_full):
+        c = self.cfg
+        lat = self.tb.rad_lat[:, None]
+        sin_lat = np.sin(lat)
+        sin_lat_2 = sin_lat * sin_lat
+        cos_lat_2 = 1.0 - sin_lat_2
+        t_star = c.t_zero - c.delh * sin_lat_2 - c.eps * sin_lat
+        tstr = c.t_strat - c.eps * sin_lat
+        p_norm = p_full / c.P00
+        the = t_star[None] - c.delv * cos_lat_2[None] * np.log(p_norm)
+        teq = the * p_norm ** c.kappa
+        return np.maximum(teq, tstr[None] + 0 * teq)
+
+    def newtonian_damping(self, ps, p_full, t):
+        c = self.cfg
+        lat = self.tb.rad_lat[:, None]
+        sin_lat = np.sin(lat)
+        cos_lat_2 = 1.0 - sin_lat * sin_lat
+        cos_lat_4 = cos_lat_2 * cos_lat_2
+        teq = self.teq(p_full)
+        tcoeff = (self.tks - self.tka) / (1.0 - c.sigma_b)
+        rps = 1.0 / ps
+        sigma = p_full * rps[None]
+        act = (sigma <= 1.0) & (sigma > c.sigma_b)
+        tfactr = tcoeff * (sigma - c.sigma_b)
+        tdamp = np.where(act, self.tka + cos_lat_4[None] * tfactr, self.tka)
+        return -tdamp * (t - teq), teq
+
+    def tracer_source_sink(self, flux, damp, p_half, r):
+        rdamp = damp
+        if rdamp < 0.0:
+            rdamp = -86400.0 * rdamp
+        if rdamp > 0.0:
+            rdamp = 1.0 / rdamp
+        source = np.zeros_like(r)
+        K = r.shape[0]
+        pmass = p_half[K] - p_half[K - 1]
+        source[K - 1] = flux / pmass
+        return source - rdamp * r
+
+    def __call__(self, dt, p_half, p_full, u, v, t, r, udt, vdt, tdt, rdt):
+        """hs_forcing(...) with um=u, vm=v, tm=t, rm=r as called from atmosphere.F90:304-311."""
+        c = self.cfg
+        if c.no_forcing:
+            return udt, vdt, tdt, rdt
+        ps = p_half[-1]
+        utnd, vtnd = self.rayleigh_damping(ps, p_full, u, v)
+        if c.do_conserve_energy:
+            ttnd = -((u + 0.5 * utnd * dt) * utnd + (v + 0.5 * vtnd * dt) * vtnd) / c.cp_air
+            tdt = tdt + ttnd
+        udt = udt + utnd
+        vdt = vdt + vtnd
+        ttnd, _ = self.newtonian_damping(ps, p_full, t)
+        tdt = tdt + ttnd
+        if r is not None and len(r) > 0:
+            new = []
+            for n in range(len(r)):
+                rst = r[n] + dt * rdt[n]
+                rtnd = self.tracer_source_sink(c.trflux, self.trsink, p_half, rst)
+                new.append(rdt[n] + rtnd)
+            rdt = new
+        return udt, vdt, tdt, rdt
+
+
+# --------------------------------------------------------------------------------------
+# Lin-Rood A-grid horizontal tracer advection (atmos_spectral/model/fv_advection.F90)
+# --------------------------------------------------------------------------------------
+class FVAdvection:
+    def __init__(self, cfg: Config, tb: Tables):
+        """fv_advection_init :59-121 with yy = latitude boundaries from get_grid_boundaries
+        (spherical_fourier.F90 / transforms.F90: sin of boundaries = cumulative Gaussian weights)."""
+        self.cfg = cfg
+        nx, ny = cfg.lon_max, cfg.lat_max
+        self.nx, self.ny = nx, ny
+        # transforms.F90 get_grid_boundaries: lat_boundaries from cumulative weights
+        sin_b = np.zeros(ny + 1)
+        sin_b[0] = -1.0
+        ssum = sin_b[0]
+        for j in range(ny - 1):
+            ssum = ssum + tb.wts_lat[j]
+            sin_b[j + 1] = ssum
+        sin_b[ny] = 1.0
+        yy = np.arcsin(sin_b)
+        self.yy_rad = yy.copy()
+        y = 0.5 * (yy[1:] + yy[:-1])
+        self.c = np.cos(y)
+        self.s = np.sin(y)
+        self.cc = np.cos(yy)
+        dy = np.zeros(ny + 4)                   # index j -> dy[j+1] for j=-1..ny+2
+        dy[2:ny + 2] = yy[1:] - yy[:-1]
+        dy[0] = dy[3]                           # dy(-1) = dy(2)
+        dy[1] = dy[2]                           # dy(0)  = dy(1)
+        dy[ny + 2] = dy[ny + 1]                 # dy(ny+1) = dy(ny)
+        dy[ny + 3] = dy[ny]                     # dy(ny+2) = dy(ny-1)
+        self.dy = dy * cfg.radius
+        self.dx = 2.0 * PI * cfg.radius / float(nx)
+
+    def DY(self, j):                            # Fortran dy(j), j in -1..ny+2
+        return self.dy[j + 1]
+
+
+# --------------------------------------------------------------------------------------
+# The dynamical core step
+# --------------------------------------------------------------------------------------
+class SpectralCore:
+    """atmosphere_mod + spectral_dynamics_mod state and step
+    (atmos_spectral/driver/solo/atmosphere.F90:120-352, model/spectral_dynamics.F90:230-1338)."""
+
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        self.tb = Tables(cfg)
+        self.tr = Transforms(self.tb)
+        self.pk, self.bk = compute_vert_coord(cfg)
+        self.dpk = self.pk[1:] - self.pk[:-1]
+        self.dbk = self.bk[1:] - self.bk[:-1]
+        self.pg = PressGeopot(cfg, self.pk, self.bk)
+        self.damp = SpectralDamping(cfg, self.tb)
+        self.impl = Implicit(cfg, self.tb, self.pk, self.bk, self.pg) if cfg.use_implicit else None
+        self.hs = HSForcing(cfg, self.tb)
+        self.dry_model = cfg.num_tracers == 0
+        if cfg.do_water_correction and self.dry_model:
+            raise ValueError("do_water_correction must be .false. in a dry model")
+        K, J, I, M, N = cfg.num_levels, cfg.lat_max, cfg.lon_max, cfg.num_fourier, cfg.num_spherical
+        z3 = lambda: np.zeros((2, K, N + 1, M + 1), dtype=np.complex128)
+        self.vors, self.divs, self.ts = z3(), z3(), z3()
+        self.ln_ps = np.zeros((2, N + 1, M + 1), dtype=np.complex128)
+        g3 = lambda: np.zeros((2, K, J, I))
+        self.ug, self.vg, self.tg = g3(), g3(), g3()
+        self.psg = np.zeros((2, J, I))
+        self.vorg = np.zeros((K, J, I))
+        self.divg = np.zeros((K, J, I))
+        self.surf_geopotential = np.zeros((J, I))
+        self.grid_tracers = np.zeros((2, cfg.num_tracers, K, J, I))
+        self.previous = 0
+        self.current = 0
+        self.wg_full = np.zeros((K, J, I))
+        self.p_half = np.zeros((2, K + 1, J, I))
+        self.p_full = np.zeros((2, K, J, I))
+        self.z_half = np.zeros((2, K + 1, J, I))
+        self.z_full = np.zeros((2, K, J, I))
+        self.mean_surf_press_previous = 0.0
+        self.mean_energy_previous = 0.0
+        self.mean_water_previous = 0.0
+        self.step_count = 0
+        self.last = {}
+
+    # ---- cold start: spectral_initialize_fields.F90:45-135 + spectral_dynamics.F90:583-630
+    def cold_start(self):
+        cfg, tr = self.cfg, self.tr
+        K = cfg.num_levels
+        vors = np.zeros_like(self.vors[0])
+        divs = np.zeros_like(vors)
+        pert = 1.0e-7
+        for (m, n) in ((1, 3), (5, 3), (1, 2), (5, 2)):
+            if m <= cfg.num_fourier and n <= cfg.num_spherical:
+                vors[K - 3:K, n, m] = pert
+        ug, vg = tr.uv_grid_from_vor_div(vors, divs)
+        tg = np.full_like(ug, cfg.initial_temperature)
+        ln_psg = np.log(cfg.reference_sea_level_press) - self.surf_geopotential / (cfg.rdgas * cfg.initial_temperature)
+        ts = tr.grid_to_spherical(tg)
+        tg = tr.spherical_to_grid(ts)
+        ln_ps = tr.grid_to_spherical(ln_psg)
+        ln_psg = tr.spherical_to_grid(ln_ps)
+        psg = np.exp(ln_psg)
+        vors, divs = tr.vor_div_from_uv_grid(ug, vg)
+        ug, vg = tr.uv_grid_from_vor_div(vors, divs)
+        self.vorg = tr.spherical_to_grid(vors)
+        self.divg = tr.spherical_to_grid(divs)
+        for lev in (0, 1):
+            self.vors[lev], self.divs[lev], self.ts[lev], self.ln_ps[lev] = vors, divs, ts, ln_ps
+            self.ug[lev], self.vg[lev], self.tg[lev], self.psg[lev] = ug, vg, tg, psg
+        if cfg.num_tracers:
+            self.grid_tracers[:] = cfg.initial_sphum
+        self.previous = self.current = 0
+        self.finish_init()
+
+    def set_state(self, **kw):
+        """Restart-style initialisation from explicit arrays (both time levels given)."""
+        for k, v in kw.items():
+            getattr(self, k)[...] = v
+        self.finish_init()
+
+    def finish_init(self):
+        """atmosphere_init: compute_pressures_and_heights on both levels (atmosphere.F90:228-247)."""
+        for lev in {self.current, self.previous}:
+            q = self.grid_tracers[lev, 0] if not self.dry_model else None
+            zf, zh, pf, ph = self.pg.compute_pressures_and_heights(self.tg[lev], self.psg[lev], self.surf_geopotential, q)
+            self.z_full[lev], self.z_half[lev], self.p_full[lev], self.p_half[lev] = zf, zh, pf, ph
+
+    # ---- global integrals
+    def mass_weighted_global_integral(self, field, ps):   # global_integral.F90:49-81
+        p_half = self.pg.half_level_pressures(ps)
+        dp = p_half[1:] - p_half[:-1]
+        vi = np.zeros_like(ps)
+        for k in range(field.shape[0]):
+            vi = vi + field[k] * dp[k]
+        return self.tr.area_weighted_global_mean(vi) / self.cfg.grav
+
+    # ---- four_in_one (spectral_dynamics.F90:1038-1112)
+    def four_in_one(self, divg, u, v, t, ps, ln_p_half, ln_p_full, p_full, dx_psg, dy_psg, dt_psg, dt_tg, dt_ug, dt_vg):
+        cfg = self.cfg
+        K = cfg.num_levels
+        kappa = cfg.rdgas / cfg.cp_air
+        dmean_tot = np.zeros_like(ps)
+        wg = np.zeros((K + 1,) + ps.shape)
+        wg_full = np.zeros((K,) + ps.shape)
+        dt_ug, dt_vg, dt_tg = dt_ug.copy(), dt_vg.copy(), dt_tg.copy()
+        bk = self.bk
+        for k in range(K):
+            dp = self.dpk[k] + self.dbk[k] * ps
+            dp_inv = 1 / dp
+            dlog_1 = ln_p_half[k + 1] - ln_p_full[k]
+            dlog_2 = ln_p_full[k] - ln_p_half[k]
+            dlog_3 = ln_p_half[k + 1] - ln_p_half[k]
+            x1 = (bk[k + 1] * dlog_1 + bk[k] * dlog_2) * dp_inv
+            x2 = x1 * dx_psg
+            x3 = x1 * dy_psg
+            dt_ug[k] = dt_ug[k] - cfg.rdgas * t[k] * x2
+            dt_vg[k] = dt_vg[k] - cfg.rdgas * t[k] * x3
+            dmean = divg[k] * dp + self.dbk[k] * (u[k] * dx_psg + v[k] * dy_psg)
+            x4 = (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv
+            x5 = x4 - u[k] * x2 - v[k] * x3
+            dt_tg[k] = dt_tg[k] - kappa * t[k] * x5
+            wg_full[k] = -x5 * p_full[k]
+            dmean_tot = dmean_tot + dmean
+            wg[k + 1] = -dmean_tot
+        dt_psg = dt_psg - dmean_tot
+        for k in range(1, K):
+            wg[k] = wg[k] + dmean_tot * bk[k]
+        wg[0] = 0.0
+        wg[K] = 0.0
+        return dt_psg, wg, wg_full, dt_tg, dt_ug, dt_vg
+
+    # ---- one call of atmosphere(Time) (atmosphere.F90:276-352)
+    def step(self, physics=True, keep=False):
+        cfg, tr = self.cfg, self.tr
+        K = cfg.num_levels
+        prev, cur = self.previous, self.current
+        delta_t = cfg.dt_atmos if prev == cur else 2 * cfg.dt_atmos
+        dt_ug = np.zeros_like(self.ug[0])
+        dt_vg = np.zeros_like(dt_ug)
+        dt_tg = np.zeros_like(dt_ug)
+        dt_psg = np.zeros_like(self.psg[0])
+        dt_tracers = [np.zeros_like(dt_ug) for _ in range(cfg.num_tracers)]
+        if physics:
+            r = [self.grid_tracers[prev, n] for n in range(cfg.num_tracers)]
+            dt_ug, dt_vg, dt_tg, dt_tracers = self.hs(delta_t, self.p_half[cur], self.p_full[cur],
+                                                      self.ug[prev], self.vg[prev], self.tg[prev], r,
+                                                      dt_ug, dt_vg, dt_tg, dt_tracers)
+        fut = 1 - cur
+        self.spectral_dynamics(fut, dt_psg, dt_ug, dt_vg, dt_tg, dt_tracers, delta_t, keep)
+        q = self.grid_tracers[fut, 0] if not self.dry_model else None
+        zf, zh, pf, ph = self.pg.compute_pressures_and_heights(self.tg[fut], self.psg[fut], self.surf_geopotential, q)
+        self.z_full[fut], self.z_half[fut], self.p_full[fut], self.p_half[fut] = zf, zh, pf, ph
+        self.step_count += 1
+
+    # ---- spectral_dynamics (spectral_dynamics.F90:780-1034), num_steps = 1
+    def spectral_dynamics(self, future, dt_psg, dt_ug, dt_vg, dt_tg, dt_tracers, delta_t, keep=False):
+        cfg, tr, pg = self.cfg, self.tr, self.pg
+        prev, cur = self.previous, self.current
+        assert future == 1 - cur
+        K = cfg.num_levels
+        rc, raw = cfg.robert_coeff, cfg.raw_filter_coeff
+
+        # initialize_corrections (:1306-1338)
+        if cfg.do_mass_correction:
+            self.mean_surf_press_previous = tr.area_weighted_global_mean(self.psg[prev])
+        if cfg.do_energy_correction:
+            energy = 0.5 * ((self.ug[prev] + dt_ug * delta_t) ** 2 + (self.vg[prev] + dt_vg * delta_t) ** 2) \
+                + cfg.cp_air * (self.tg[prev] + dt_tg * delta_t)
+            self.mean_energy_previous = self.mass_weighted_global_integral(energy, self.psg[prev])
+        if cfg.do_water_correction:
+            self.mean_water_previous = self.mass_weighted_global_integral(
+                self.grid_tracers[prev, 0] + delta_t * dt_tracers[0], self.psg[prev])
+
+        p_half, ln_p_half, p_full, ln_p_full = pg.pressure_variables(self.psg[cur])
+        self.p_half[cur], self.p_full[cur] = p_half, p_full
+
+        # compute_pressure_gradient (:1192-1209)
+        dxs, dys = tr.gradient_cos(self.ln_ps[cur])
+        dx_psg = tr.divide_by_cos(self.psg[cur] * tr.spherical_to_grid(dxs))
+        dy_psg = tr.divide_by_cos(self.psg[cur] * tr.spherical_to_grid(dys))
+
+        if cfg.use_virtual_temperature and not self.dry_model:
+            virtual_t = self.tg[cur] * (1.0 + (RVGAS / cfg.rdgas - 1.0) * self.grid_tracers[cur, 0])
+        else:
+            virtual_t = self.tg[cur]
+
+        dt_psg_tmp, wg, wg_full, dt_tg_tmp, dt_ug_tmp, dt_vg_tmp = self.four_in_one(
+            self.divg, self.ug[cur], self.vg[cur], virtual_t, self.psg[cur], ln_p_half, ln_p_full, p_full,
+            dx_psg, dy_psg, dt_psg, dt_tg, dt_ug, dt_vg)
+        self.wg_full = wg_full
+
+        qcur = None if self.dry_model else self.grid_tracers[cur, 0]
+        phig_full, _ = pg.compute_geopotential(self.tg[cur], ln_p_half, ln_p_full, self.surf_geopotential, qcur)
+
+        dt_ln_psg = dt_psg_tmp / self.psg[cur]
+        dt_ln_ps = tr.grid_to_spherical(dt_ln_psg)
+
+        dp = p_half[1:] - p_half[:-1]
+        lev_uv = cur if cfg.vert_advect_uv == SECOND_CENTERED else prev
+        dt_ug_tmp = dt_ug_tmp + vert_advection(delta_t, wg, dp, self.ug[lev_uv], cfg.vert_advect_uv)
+        dt_vg_tmp = dt_vg_tmp + vert_advection(delta_t, wg, dp, self.vg[lev_uv], cfg.vert_advect_uv)
+        lev_t = cur if cfg.vert_advect_t == SECOND_CENTERED else prev
+        dt_tg_tmp = dt_tg_tmp + vert_advection(delta_t, wg, dp, self.tg[lev_t], cfg.vert_advect_t)
+
+        dt_tg_tmp = tr.horizontal_advection(self.ts[cur], self.ug[cur], self.vg[cur], dt_tg_tmp)
+        dt_ts = tr.grid_to_spherical(dt_tg_tmp)
+
+        absv = self.vorg + self.tb.coriolis[None, :, None]
+        dt_ug_tmp = dt_ug_tmp + absv * self.vg[cur]
+        dt_vg_tmp = dt_vg_tmp - absv * self.ug[cur]
+
+        dt_vors, dt_divs = tr.vor_div_from_uv_grid(dt_ug_tmp, dt_vg_tmp)
+
+        phig_full_plus_ke = phig_full + 0.5 * (self.ug[cur] ** 2 + self.vg[cur] ** 2)
+        phis_plus_ke = tr.grid_to_spherical(phig_full_plus_ke)
+        dt_divs = dt_divs - tr.laplacian(phis_plus_ke)
+        if keep:
+            self.last = dict(dt_vors_explicit=dt_vors.copy(), dt_divs_explicit=dt_divs.copy(),
+                             dt_ts_explicit=dt_ts.copy(), dt_ln_ps_explicit=dt_ln_ps.copy(),
+                             wg=wg, dx_psg=dx_psg, dy_psg=dy_psg)
+
+        if cfg.use_implicit:
+            dt_divs, dt_ts, dt_ln_ps = self.impl.implicit_correction(
+                dt_divs, dt_ts, dt_ln_ps, self.divs, self.ts, self.ln_ps, delta_t, prev, cur)
+
+        dt_vors = self.damp.damp_vor(self.vors[prev], dt_vors, delta_t)
+        dt_divs = self.damp.damp_div(self.divs[prev], dt_divs, delta_t)
+        dt_ts = self.damp.damp(self.ts[prev], dt_ts, delta_t)
+        if keep:
+            self.last.update(dt_vors=dt_vors.copy(), dt_divs=dt_divs.copy(), dt_ts=dt_ts.copy(), dt_ln_ps=dt_ln_ps.copy())
+
+        # leapfrog_2level_A (leapfrog.F90:58-83) for ln_ps, vors, divs, ts
+        part = {}
+        for name, a, dta in (("ln_ps", self.ln_ps, dt_ln_ps), ("vors", self.vors, dt_vors),
+                             ("divs", self.divs, dt_divs), ("ts", self.ts, dt_ts)):
+            pf = a[prev] - 2.0 * a[cur]
+            part[name] = pf
+            if prev == cur:
+                a[future] = a[prev] + delta_t * dta
+                a[cur] = a[cur] + rc * pf * raw
+            else:
+                a[cur] = a[cur] + rc * pf * raw
+                a[future] = a[prev] + delta_t * dta
+
+        self.divg = tr.spherical_to_grid(self.divs[future])
+        self.vorg = tr.spherical_to_grid(self.vors[future])
+        self.ug[future], self.vg[future] = tr.uv_grid_from_vor_div(self.vors[future], self.divs[future])
+        self.tg[future] = tr.spherical_to_grid(self.ts[future])
+        ln_psg = tr.spherical_to_grid(self.ln_ps[future])
+        self.psg[future] = np.exp(ln_psg)
+
+        tmin, tmax = self.tg[future].min(), self.tg[future].max()
+        if tmin < cfg.valid_range_t[0] or tmax > cfg.valid_range_t[1]:
+            raise FloatingPointError("temperatures out of valid range")
+
+        part_tr = self.update_tracers(dt_tracers, wg, p_half, delta_t, future)
+        self.compute_corrections(delta_t, future, p_full)
+
+        self.previous = cur
+        self.current = future
+        # complete_robert_filter -> leapfrog_2level_B (leapfrog.F90:87-105) with (previous, current) swapped in
+        p, c = self.previous, self.current
+        for name, a in (("ln_ps", self.ln_ps), ("vors", self.vors), ("divs", self.divs), ("ts", self.ts)):
+            a[p] = a[p] + rc * a[c] * raw
+            a[c] = a[c] + rc * (part[name] + a[c]) * (raw - 1.0)
+        rct = cfg.robert_coeff if cfg.tracer_robert_coeff < 0 else cfg.tracer_robert_coeff
+        for n in range(cfg.num_tracers):
+            a = self.grid_tracers
+            a[p, n] = a[p, n] + rct * a[c, n] * raw
+            a[c, n] = a[c, n] + rct * (part_tr[n] + a[c, n]) * (raw - 1.0)
+
+    # ---- update_tracers, grid tracers only (spectral_dynamics.F90:1116-1188)
+    def update_tracers(self, dt_tr, wg, p_half, delta_t, future):
+        cfg = self.cfg
+        prev, cur = self.previous, self.current
+        rct = cfg.robert_coeff if cfg.tracer_robert_coeff < 0 else cfg.tracer_robert_coeff
+        parts = []
+        if cfg.num_tracers == 0:
+            return parts
+        from .fv_advection import a_grid_horiz_advection     # noqa: local import keeps core importable
+        dp = p_half[1:] - p_half[:-1]
+        for n in range(cfg.num_tracers):
+            tr_future = self.grid_tracers[prev, n] + delta_t * dt_tr[n]
+            dq = a_grid_horiz_advection(self.fv, self.ug[cur], self.vg[cur], tr_future, delta_t, np.zeros_like(tr_future))
+            tr_future = tr_future + delta_t * dq
+            dt_tmp = vert_advection(delta_t, wg, dp, tr_future, FINITE_VOLUME_PARABOLIC)
+            tr_future = tr_future + delta_t * dt_tmp
+            pf = self.grid_tracers[prev, n] - 2.0 * self.grid_tracers[cur, n]
+            parts.append(pf)
+            self.grid_tracers[cur, n] = self.grid_tracers[cur, n] + rct * pf * cfg.raw_filter_coeff
+            self.grid_tracers[future, n] = tr_future
+        return parts
+
+    # ---- compute_corrections (spectral_dynamics.F90:1213-1302)
+    def compute_corrections(self, delta_t, future, p_full):
+        cfg, tr = self.cfg, self.tr
+        if cfg.do_mass_correction:
+            mean_ps = tr.area_weighted_global_mean(self.psg[future])
+            f = self.mean_surf_press_previous / mean_ps
+            self.psg[future] = f * self.psg[future]
+            self.ln_ps[future, 0, 0] = self.ln_ps[future, 0, 0] + np.sqrt(2.0) * np.log(f)
+        if cfg.do_energy_correction:
+            mean_e = self.mass_weighted_global_integral(
+                0.5 * (self.ug[future] ** 2 + self.vg[future] ** 2) + cfg.cp_air * self.tg[future], self.psg[future])
+            tc = cfg.grav * (self.mean_energy_previous - mean_e) / (cfg.cp_air * self.mean_surf_press_previous)
+            self.tg[future] = self.tg[future] + tc
+            self.ts[future, :, 0, 0] = self.ts[future, :, 0, 0] + np.sqrt(2.0) * tc
+        if cfg.do_water_correction:
+            q = self.grid_tracers[future, 0]
+            mean_w = self.mass_weighted_global_integral(q, self.psg[future])
+            mask = (p_full >= cfg.water_correction_limit)
+            corr = self.mass_weighted_global_integral(q * mask, self.psg[future])
+            ncorr = self.mass_weighted_global_integral(q * (p_full < cfg.water_correction_limit), self.psg[future])
+            if mean_w > 0.0:
+                wf = self.mean_water_previous / mean_w
+                wf = wf * (1.0 + ncorr / corr) - ncorr / corr
+                self.grid_tracers[future, 0] = np.where(mask, wf * q, q)
+
+    @property
+    def fv(self):
+        if not hasattr(self, "_fv"):
+            self._fv = FVAdvection(self.cfg, self.tb)
+        return self._fv
+
+    # ---- convenience for tests / bench
+    def state(self):
+        c, p = self.current, self.previous
+        return dict(vors=self.vors[c].copy(), divs=self.divs[c].copy(), ts=self.ts[c].copy(), ln_ps=self.ln_ps[c].copy(),
+                    vors_prev=self.vors[p].copy(), divs_prev=self.divs[p].copy(), ts_prev=self.ts[p].copy(),
+                    ln_ps_prev=self.ln_ps[p].copy(),
+                    ug=self.ug[c].copy(), vg=self.vg[c].copy(), tg=self.tg[c].copy(), psg=self.psg[c].copy(),
+                    vorg=self.vorg.copy(), divg=self.divg.copy(), wg_full=self.wg_full.copy(),
+                    p_full=self.p_full[c].copy(), z_full=self.z_full[c].copy())
