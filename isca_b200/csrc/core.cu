@@ -1,0 +1,804 @@
+// core.cu -- handle, device-resident model state, step orchestration and the C ABI.
+//
+// Host-side mirror of atmosphere_mod / spectral_dynamics_mod
+// (atmos_spectral/driver/solo/atmosphere.F90:120-399, model/spectral_dynamics.F90:230-1034).
+#include "device.h"
+#include "spectral.h"
+#include "grid.h"
+#include <cstring>
+#include <map>
+#include <algorithm>
+
+using namespace isca;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " +   \
+                               __FILE__ + ":" + std::to_string(__LINE__));                       \
+  } while (0)
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+template <class T>
+struct DBuf {                       // owning device buffer
+  T* p = nullptr; size_t n = 0;
+  void alloc(size_t count, bool zero = true) {
+    release(); n = count;
+    if (count) { CK(cudaMalloc(&p, count * sizeof(T))); if (zero) CK(cudaMemset(p, 0, count * sizeof(T))); }
+  }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  void upload(const std::vector<T>& h) { alloc(h.size(), false); if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DBuf() { release(); }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct IscaHandle_t {
+  IscaConfig cfg;
+  Geometry g;
+  HostTables ht;
+  DevTables dt;
+  Params pr;
+  cudaStream_t st = nullptr;
+  std::string err;
+  long long launches = 0;
+  long long steps = 0;
+  double last_step_ms = 0.0;
+  int previous = 0, current = 0;
+
+  // ---- device tables
+  DBuf<int> d_m_of, d_off, d_pos, d_row_m, d_row_n;
+  DBuf<double> d_sin_lat, d_cos_lat, d_cosm_lat, d_wts_lat, d_coriolis, d_rad_lat, d_pk, d_bk, d_dpk, d_dbk;
+  DBuf<double> d_leg, d_legw;
+  DBuf<double> d_eigen, d_uvm, d_uvc, d_uvp, d_alpm, d_alpp, d_dym, d_dx, d_dyp, d_mask, d_damp, d_dampv, d_dampd, d_eddy, d_zmu, d_zmv;
+  DBuf<double> d_rlh, d_rlf, d_rt, d_h;
+  DBuf<double> d_twiddle;
+  std::map<double, DBuf<double>*> wave_cache;          // xi -> wave matrices
+
+  // ---- state
+  DBuf<double2> vors[2], divs[2], ts[2], lnps[2];
+  DBuf<double> u[2], v[2], T[2], ps[2];
+  DBuf<double> vorg, divg, phis, wg_full;
+  // ---- work
+  DBuf<double2> dt_vors, w_div, w_T, w_lnps, k_dt_vors, k_dt_divs, k_dt_ts, k_dt_lnps;
+  DBuf<double2> specA, specB, specC;
+  DBuf<double> four;
+  DBuf<double> gradA;        // [2K+2] planes: dxT, dyT, dxlnps, dylnps
+  DBuf<double> gridB;        // [4K+1] planes: dt_T, A, B, Phi, dt_lnps
+  DBuf<double> ext_tend;     // [3K+1] planes for externally supplied tendencies
+  DBuf<LevDesc> levsA, levsB, levsC[2];
+  DBuf<unsigned char> truncB;
+  DBuf<double> part, scal;
+  DBuf<int> ops_sum2, ops_sum1, ops_en;
+  int LpA = 0, LpB = 0, LpC = 0;
+  int keep_tend = 0;
+  // ---- scratch for the transforms_mod-level API
+  DBuf<double2> x_rect, x_spec;
+  DBuf<double> x_grid, x_four;
+  DBuf<LevDesc> x_levs;
+  DBuf<unsigned char> x_trunc;
+
+  size_t nplane() const { return (size_t)g.Jloc * g.I; }
+  size_t n3() const { return (size_t)g.K * g.Jloc * g.I; }
+  size_t nspec3() const { return (size_t)g.T * g.K; }
+  double denom() const { return ht.global_sum_of_wts * g.I; }
+  int owns_m0() const { return g.owner[0] == g.rank ? 1 : 0; }
+};
+typedef IscaHandle_t H;
+
+// ---------------------------------------------------------------------------------------------
+static void upload_tables(H& h) {
+  const Geometry& g = h.g; const HostTables& t = h.ht;
+  h.d_m_of.upload(g.m_of); h.d_off.upload(g.off); h.d_pos.upload(g.pos);
+  h.d_row_m.upload(t.row_m); h.d_row_n.upload(t.row_n);
+  h.d_sin_lat.upload(t.sin_lat); h.d_cos_lat.upload(t.cos_lat); h.d_cosm_lat.upload(t.cosm_lat);
+  h.d_wts_lat.upload(t.wts_lat); h.d_coriolis.upload(t.coriolis); h.d_rad_lat.upload(t.rad_lat);
+  h.d_pk.upload(t.pk); h.d_bk.upload(t.bk); h.d_dpk.upload(t.dpk); h.d_dbk.upload(t.dbk);
+  h.d_leg.upload(t.leg); h.d_legw.upload(t.legw);
+  h.d_eigen.upload(t.eigen); h.d_uvm.upload(t.coef_uvm); h.d_uvc.upload(t.coef_uvc); h.d_uvp.upload(t.coef_uvp);
+  h.d_alpm.upload(t.coef_alpm); h.d_alpp.upload(t.coef_alpp); h.d_dym.upload(t.coef_dym); h.d_dx.upload(t.coef_dx);
+  h.d_dyp.upload(t.coef_dyp); h.d_mask.upload(t.trunc_mask);
+  h.d_damp.upload(t.damping); h.d_dampv.upload(t.damping_vor); h.d_dampd.upload(t.damping_div);
+  h.d_eddy.upload(t.eddy_sponge); h.d_zmu.upload(t.zmu_sponge); h.d_zmv.upload(t.zmv_sponge);
+  h.d_rlh.upload(t.ref_ln_p_half); h.d_rlf.upload(t.ref_ln_p_full); h.d_rt.upload(t.ref_t); h.d_h.upload(t.h);
+  h.d_twiddle.upload(t.twiddle);
+  DevTables& d = h.dt;
+  d.g.I = g.I; d.g.J = g.J; d.g.K = g.K; d.g.M = g.M; d.g.N = g.N; d.g.Jh = g.Jh; d.g.P = g.P; d.g.rank = g.rank;
+  d.g.Jloc = g.Jloc; d.g.j0 = g.j0; d.g.nm = g.nm; d.g.T = g.T;
+  d.g.m_of = h.d_m_of.p; d.g.off = h.d_off.p; d.g.pos = h.d_pos.p; d.g.row_m = h.d_row_m.p;
+  d.row_n = h.d_row_n.p;
+  d.sin_lat = h.d_sin_lat.p; d.cos_lat = h.d_cos_lat.p; d.cosm_lat = h.d_cosm_lat.p; d.wts_lat = h.d_wts_lat.p;
+  d.coriolis = h.d_coriolis.p; d.rad_lat = h.d_rad_lat.p;
+  d.pk = h.d_pk.p; d.bk = h.d_bk.p; d.dpk = h.d_dpk.p; d.dbk = h.d_dbk.p;
+  d.leg = h.d_leg.p; d.legw = h.d_legw.p;
+  d.eigen = h.d_eigen.p; d.coef_uvm = h.d_uvm.p; d.coef_uvc = h.d_uvc.p; d.coef_uvp = h.d_uvp.p;
+  d.coef_alpm = h.d_alpm.p; d.coef_alpp = h.d_alpp.p; d.coef_dym = h.d_dym.p; d.coef_dx = h.d_dx.p; d.coef_dyp = h.d_dyp.p;
+  d.trunc_mask = h.d_mask.p; d.damping = h.d_damp.p; d.damping_vor = h.d_dampv.p; d.damping_div = h.d_dampd.p;
+  d.eddy_sponge = h.d_eddy.p; d.zmu_sponge = h.d_zmu.p; d.zmv_sponge = h.d_zmv.p;
+  d.ref_ln_p_half = h.d_rlh.p; d.ref_ln_p_full = h.d_rlf.p; d.ref_t = h.d_rt.p; d.h_impl = h.d_h.p;
+  d.wave_matrix = nullptr;
+  d.twiddle = reinterpret_cast<const double2*>(h.d_twiddle.p);
+}
+
+static void set_params(H& h) {
+  const IscaConfig& c = h.cfg; Params& p = h.pr;
+  p.rdgas = c.rdgas; p.kappa = c.rdgas / (c.rdgas / c.kappa); p.cp_air = c.rdgas / c.kappa; p.grav = c.grav;
+  p.radius = c.radius; p.omega = c.omega; p.ref_ps = c.reference_sea_level_press; p.dt_atmos = c.dt_atmos;
+  p.robert_coeff = c.robert_coeff; p.raw_filter_coeff = c.raw_filter_coeff; p.virtual_factor = 0.0;
+  p.tka = c.ka < 0. ? -1. / (86400 * c.ka) : c.ka;          // hs_forcing.F90:392-404
+  p.tks = c.ks < 0. ? -1. / (86400 * c.ks) : c.ks;
+  p.vkf = c.kf < 0. ? -1. / (86400 * c.kf) : c.kf;
+  p.sigma_b = c.sigma_b; p.t_zero = c.t_zero; p.t_strat = c.t_strat; p.delh = c.delh; p.delv = c.delv; p.eps = c.eps;
+  p.P00 = c.P00; p.do_conserve_energy = c.do_conserve_energy; p.no_forcing = c.no_forcing; p.physics_on = 1;
+  p.pk0_zero = (h.ht.pk[0] == 0.0); p.pkbk0_zero = (h.ht.pk[0] == 0.0 && h.ht.bk[0] == 0.0);
+  p.vr_tmin = c.valid_range_t[0]; p.vr_tmax = c.valid_range_t[1];
+  p.xi = 0; p.delta_t = 0; p.first_step = 1;
+}
+
+static void alloc_state(H& h) {
+  const Geometry& g = h.g; const int K = g.K;
+  for (int s = 0; s < 2; ++s) {
+    h.vors[s].alloc(h.nspec3()); h.divs[s].alloc(h.nspec3()); h.ts[s].alloc(h.nspec3()); h.lnps[s].alloc(g.T);
+    h.u[s].alloc(h.n3()); h.v[s].alloc(h.n3()); h.T[s].alloc(h.n3()); h.ps[s].alloc(h.nplane());
+  }
+  h.vorg.alloc(h.n3()); h.divg.alloc(h.n3()); h.phis.alloc(h.nplane()); h.wg_full.alloc(h.n3());
+  h.dt_vors.alloc(h.nspec3()); h.w_div.alloc(h.nspec3()); h.w_T.alloc(h.nspec3()); h.w_lnps.alloc(g.T);
+  h.k_dt_vors.alloc(h.nspec3()); h.k_dt_divs.alloc(h.nspec3()); h.k_dt_ts.alloc(h.nspec3()); h.k_dt_lnps.alloc(g.T);
+  h.LpA = round_up(2 * K + 2, 16); h.LpB = round_up(4 * K + 1, 16); h.LpC = round_up(5 * K + 1, 16);
+  h.specA.alloc((size_t)g.T * h.LpA); h.specB.alloc((size_t)g.T * h.LpB); h.specC.alloc((size_t)g.T * h.LpC);
+  const int Lmax = std::max(h.LpA, std::max(h.LpB, h.LpC));
+  h.four.alloc((size_t)(g.M + 1) * g.J / g.P * 2 * Lmax * (g.P > 1 ? 1 : 1));
+  h.gradA.alloc((size_t)(2 * K + 2) * h.nplane());
+  h.gridB.alloc((size_t)(4 * K + 1) * h.nplane());
+  h.part.alloc(3 * h.nplane()); h.scal.alloc(SC_COUNT);
+  h.ops_sum2.upload({0, 0}); h.ops_sum1.upload({0}); h.ops_en.upload({0, 1, 2});
+  const size_t pl = h.nplane();
+  // level descriptors
+  std::vector<LevDesc> la(2 * K + 2), lb(4 * K + 1);
+  for (int k = 0; k < K; ++k) {
+    la[k] = {h.gradA.p + (size_t)k * pl, 1, 0};                 // dx T  -> divide_by_cos
+    la[K + k] = {h.gradA.p + (size_t)(K + k) * pl, 1, 0};       // dy T
+  }
+  la[2 * K] = {h.gradA.p + (size_t)(2 * K) * pl, 0, 0};         // dx ln ps (cos division after *psg, in grid_step)
+  la[2 * K + 1] = {h.gradA.p + (size_t)(2 * K + 1) * pl, 0, 0};
+  h.levsA.upload(la);
+  for (int i = 0; i < 4 * K + 1; ++i) lb[i] = {h.gridB.p + (size_t)i * pl, 0, 0};
+  h.levsB.upload(lb);
+  for (int f = 0; f < 2; ++f) {
+    std::vector<LevDesc> lc(5 * K + 1);
+    for (int k = 0; k < K; ++k) {
+      lc[k] = {h.vorg.p + (size_t)k * pl, 0, 0};
+      lc[K + k] = {h.divg.p + (size_t)k * pl, 0, 0};
+      lc[2 * K + k] = {h.u[f].p + (size_t)k * pl, 1, 0};
+      lc[3 * K + k] = {h.v[f].p + (size_t)k * pl, 1, 0};
+      lc[4 * K + k] = {h.T[f].p + (size_t)k * pl, 0, 0};
+    }
+    lc[5 * K] = {h.ps[f].p, 2, 0};                               // psg = exp(ln_psg)
+    h.levsC[f].upload(lc);
+  }
+  std::vector<unsigned char> tb(h.LpB, 0);
+  for (int k = 0; k < K; ++k) { tb[k] = 1; tb[3 * K + k] = 1; }  // dt_T, Phi+KE truncated; A,B not (transforms.F90:766-770)
+  tb[4 * K] = 1;
+  h.truncB.upload(tb);
+}
+
+static void ensure_wave_matrix(H& h, double xi) {
+  auto it = h.wave_cache.find(xi);
+  if (it == h.wave_cache.end()) {
+    std::vector<double> wm;
+    build_wave_matrices(h.cfg, h.g, h.ht, xi, wm);
+    DBuf<double>* b = new DBuf<double>();
+    b->upload(wm);
+    it = h.wave_cache.emplace(xi, b).first;
+  }
+  h.dt.wave_matrix = it->second->p;
+}
+
+// exchange of the Fourier buffer between the lat-owner and m-owner layouts (transpose_fourier /
+// reverse_transpose_fourier, tools/transforms.F90:970-1056).  One rank: the two layouts coincide.
+static void exchange_fourier(H& h, int /*direction*/, int /*Lp*/) {
+  if (h.g.P == 1) return;
+  throw std::runtime_error("multi-rank Fourier exchange is not available in this build");
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic batched transforms on device data
+// ---------------------------------------------------------------------------------------------
+static void dev_inverse(H& h, const double2* spec, int Lp, const LevDesc* levs, int nlev) {
+  launch_legendre_inv(h.dt, spec, h.four.p, Lp, h.st); h.launches++;
+  exchange_fourier(h, 0, Lp);
+  launch_fft_inv(h.dt, h.four.p, levs, nlev, Lp, h.st); h.launches++;
+}
+static void dev_forward(H& h, const LevDesc* levs, int nlev, double2* spec, int Lp, const unsigned char* trunc) {
+  launch_fft_fwd(h.dt, h.four.p, levs, nlev, Lp, h.st); h.launches++;
+  exchange_fourier(h, 1, Lp);
+  launch_legendre_fwd(h.dt, h.four.p, spec, Lp, trunc, h.st); h.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one time step: atmosphere(Time) (atmosphere.F90:276-352)
+// ---------------------------------------------------------------------------------------------
+static void step_once(H& h, int physics_on, const double* dtu_in, const double* dtv_in, const double* dtt_in) {
+  const Geometry& g = h.g; const int K = g.K;
+  const int prev = h.previous, cur = h.current, fut = 1 - cur;
+  const double delta_t = (prev == cur) ? h.cfg.dt_atmos : 2 * h.cfg.dt_atmos;     // atmosphere.F90:292-296
+  Params& pr = h.pr;
+  pr.delta_t = delta_t; pr.first_step = (prev == cur); pr.physics_on = physics_on;
+  pr.xi = delta_t * h.cfg.alpha_implicit;
+  if (h.cfg.use_implicit) ensure_wave_matrix(h, pr.xi);                          // implicit.F90:260-264
+  const size_t pl = h.nplane();
+  cudaStream_t st = h.st;
+
+  // gradients of T(current), ln ps(current)  (horizontal_advection, compute_pressure_gradient)
+  launch_spec_gradient(h.dt, h.ts[cur].p, K, K, h.specA.p, h.LpA, 0, K, st);
+  launch_spec_gradient(h.dt, h.lnps[cur].p, 1, 1, h.specA.p, h.LpA, 2 * K, 2 * K + 1, st);
+  h.launches += 2;
+  dev_inverse(h, h.specA.p, h.LpA, h.levsA.p, 2 * K + 2);
+
+  GridStepArgs ga;
+  ga.u_cur = h.u[cur].p; ga.v_cur = h.v[cur].p; ga.t_cur = h.T[cur].p;
+  ga.u_prev = h.u[prev].p; ga.v_prev = h.v[prev].p; ga.t_prev = h.T[prev].p;
+  ga.vor_cur = h.vorg.p; ga.div_cur = h.divg.p; ga.ps_cur = h.ps[cur].p; ga.ps_prev = h.ps[prev].p; ga.phis = h.phis.p;
+  ga.dx_t = h.gradA.p; ga.dy_t = h.gradA.p + (size_t)K * pl;
+  ga.dx_lnps = h.gradA.p + (size_t)(2 * K) * pl; ga.dy_lnps = h.gradA.p + (size_t)(2 * K + 1) * pl;
+  ga.dt_u_in = dtu_in; ga.dt_v_in = dtv_in; ga.dt_t_in = dtt_in;
+  ga.out_T = h.gridB.p; ga.out_A = h.gridB.p + (size_t)K * pl; ga.out_B = h.gridB.p + (size_t)(2 * K) * pl;
+  ga.out_phi = h.gridB.p + (size_t)(3 * K) * pl; ga.dt_lnps = h.gridB.p + (size_t)(4 * K) * pl;
+  ga.wg_full = h.wg_full.p; ga.part = h.part.p;
+  launch_grid_step(h.dt, pr, ga, st); h.launches++;
+  launch_reduce(h.part.p, pl, 2, h.ops_sum2.p, h.scal.p + SC_SUM_PS_PREV, st); h.launches++;
+
+  dev_forward(h, h.levsB.p, 4 * K + 1, h.specB.p, h.LpB, h.truncB.p);
+
+  SpecStepArgs sa;
+  sa.specB = h.specB.p; sa.LpB = h.LpB; sa.oT = 0; sa.oA = K; sa.oB = 2 * K; sa.oPhi = 3 * K; sa.oLnps = 4 * K;
+  sa.vors_prev = h.vors[prev].p; sa.divs_prev = h.divs[prev].p; sa.ts_prev = h.ts[prev].p; sa.lnps_prev = h.lnps[prev].p;
+  sa.vors_cur = h.vors[cur].p; sa.divs_cur = h.divs[cur].p; sa.ts_cur = h.ts[cur].p; sa.lnps_cur = h.lnps[cur].p;
+  sa.vors_cur_w = h.vors[cur].p; sa.divs_cur_w = h.divs[cur].p; sa.ts_cur_w = h.ts[cur].p; sa.lnps_cur_w = h.lnps[cur].p;
+  sa.vors_fut = h.vors[fut].p; sa.divs_fut = h.divs[fut].p; sa.ts_fut = h.ts[fut].p; sa.lnps_fut = h.lnps[fut].p;
+  sa.dt_vors = h.dt_vors.p; sa.w_div = h.w_div.p; sa.w_T = h.w_T.p; sa.w_lnps = h.w_lnps.p;
+  sa.specC = h.specC.p; sa.LpC = h.LpC; sa.cVor = 0; sa.cDiv = K; sa.cU = 2 * K; sa.cV = 3 * K; sa.cT = 4 * K; sa.cLnps = 5 * K;
+  sa.use_implicit = h.cfg.use_implicit;
+  sa.keep_tend = h.keep_tend; sa.k_dt_vors = h.k_dt_vors.p; sa.k_dt_divs = h.k_dt_divs.p; sa.k_dt_ts = h.k_dt_ts.p;
+  sa.k_dt_lnps = h.k_dt_lnps.p;
+  launch_spec_step(h.dt, pr, sa, st); h.launches += (h.cfg.use_implicit ? 4 : 3);
+
+  dev_inverse(h, h.specC.p, h.LpC, h.levsC[fut].p, 5 * K + 1);
+
+  // compute_corrections (spectral_dynamics.F90:1213-1302)
+  launch_colsum_ps(h.dt, h.ps[fut].p, h.part.p, st);
+  launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_SUM_PS_FUT, st);
+  launch_apply_mass(h.dt, h.ps[fut].p, h.lnps[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_mass_correction, st);
+  launch_colsum_energy(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.part.p, st);
+  launch_reduce(h.part.p, pl, 3, h.ops_en.p, h.scal.p + SC_SUM_EN_FUT, st);
+  launch_apply_energy(h.dt, pr, h.T[fut].p, h.ts[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_energy_correction, st);
+  h.launches += 6;
+
+  // time-level swap, then complete_robert_filter -> leapfrog_2level_B: a(previous) += rc*a(current)*raw
+  h.previous = cur; h.current = fut;
+  const double rc = h.cfg.robert_coeff, raw = h.cfg.raw_filter_coeff;
+  launch_spec_robert_b(h.vors[cur].p, h.vors[fut].p, h.nspec3(), rc, raw, st);
+  launch_spec_robert_b(h.divs[cur].p, h.divs[fut].p, h.nspec3(), rc, raw, st);
+  launch_spec_robert_b(h.ts[cur].p, h.ts[fut].p, h.nspec3(), rc, raw, st);
+  launch_spec_robert_b(h.lnps[cur].p, h.lnps[fut].p, (size_t)g.T, rc, raw, st);
+  h.launches += 4;
+  h.steps++;
+}
+
+static void check_t_flag(H& h) {
+  double flag[1];
+  CK(cudaMemcpyAsync(flag, h.scal.p + SC_T_FLAG, sizeof(double), cudaMemcpyDeviceToHost, h.st));
+  CK(cudaStreamSynchronize(h.st));
+  if (flag[0] != 0.0) throw std::runtime_error("spectral_dynamics: temperatures out of valid range");
+}
+
+// ---------------------------------------------------------------------------------------------
+// transforms_mod-level helpers on host arrays (reference rectangular layout)
+// ---------------------------------------------------------------------------------------------
+static void x_prepare(H& h, int nlev, int nfields) {
+  const Geometry& g = h.g;
+  const int Lp = round_up(nlev * nfields, 16);
+  h.x_rect.ensure((size_t)nlev * nfields * (g.N + 1) * (g.M + 1));
+  h.x_spec.ensure((size_t)g.T * Lp);
+  h.x_grid.ensure((size_t)nlev * nfields * h.nplane());
+  if ((size_t)(g.M + 1) * g.Jloc * 2 * Lp > h.four.n) h.four.alloc((size_t)(g.M + 1) * g.Jloc * 2 * Lp);
+  h.x_levs.ensure(nlev * nfields);
+  h.x_trunc.ensure(Lp);
+}
+static void x_set_levs(H& h, int ntot, int op_from, int op) {
+  std::vector<LevDesc> l(ntot);
+  for (int i = 0; i < ntot; ++i) l[i] = {h.x_grid.p + (size_t)i * h.nplane(), (i >= op_from) ? op : 0, 0};
+  CK(cudaMemcpyAsync(h.x_levs.p, l.data(), sizeof(LevDesc) * ntot, cudaMemcpyHostToDevice, h.st));
+  CK(cudaStreamSynchronize(h.st));
+}
+
+// ---------------------------------------------------------------------------------------------
+// cold start (spectral_initialize_fields.F90:45-135)
+// ---------------------------------------------------------------------------------------------
+static void cold_start(H& h) {
+  const Geometry& g = h.g; const int K = g.K; const IscaConfig& c = h.cfg;
+  const size_t pl = h.nplane();
+  cudaStream_t st = h.st;
+  x_prepare(h, K, 2);
+  const int Lp = round_up(2 * K, 16);
+  // initial vorticity perturbation (:87-107)
+  std::vector<double2> sp((size_t)g.T * Lp, make_double2(0, 0));
+  const int pert_m[4] = {1, 5, 1, 5}, pert_n[4] = {3, 3, 2, 2};
+  for (int q = 0; q < 4; ++q) {
+    int m = pert_m[q], n = pert_n[q];
+    if (m > g.M || n > g.N || g.owner[m] != g.rank) continue;
+    int mi = (int)(std::find(g.m_of.begin(), g.m_of.end(), m) - g.m_of.begin());
+    if (n >= g.M - m + 2) continue;
+    for (int k = K - 3; k < K; ++k) if (k >= 0) sp[(size_t)(g.off[mi] + n) * Lp + k].x = 1.e-7;
+  }
+  CK(cudaMemcpy(h.x_spec.p, sp.data(), sp.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  // uv_grid_from_vor_div(vors, 0): levels [vor | div | ucos | vcos] needs 4K levels -> reuse specC
+  CK(cudaMemsetAsync(h.specC.p, 0, h.specC.n * sizeof(double2), st));
+  // copy vor into specC[.., 0..K)
+  {
+    std::vector<double2> sc((size_t)g.T * h.LpC, make_double2(0, 0));
+    for (int p = 0; p < g.T; ++p) for (int k = 0; k < K; ++k) sc[(size_t)p * h.LpC + k] = sp[(size_t)p * Lp + k];
+    CK(cudaMemcpy(h.specC.p, sc.data(), sc.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  // T = initial_temperature, ln ps = log(p0) - phis/(rd*T0)  -> spectral and back (:113-119)
+  {
+    std::vector<double> tg(h.n3(), c.initial_temperature), phis(pl), lnps(pl);
+    CK(cudaMemcpy(phis.data(), h.phis.p, pl * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < pl; ++i) lnps[i] = std::log(c.reference_sea_level_press) - phis[i] / (c.rdgas * c.initial_temperature);
+    CK(cudaMemcpy(h.T[0].p, tg.data(), tg.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.ps[0].p, lnps.data(), pl * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  // forward: [T(K) | lnps(1)] with truncation
+  {
+    std::vector<LevDesc> l(K + 1);
+    for (int k = 0; k < K; ++k) l[k] = {h.T[0].p + (size_t)k * pl, 0, 0};
+    l[K] = {h.ps[0].p, 0, 0};
+    DBuf<LevDesc> dl; dl.upload(l);
+    const int LpT = round_up(K + 1, 16);
+    DBuf<double2> tmp; tmp.alloc((size_t)g.T * LpT);
+    DBuf<unsigned char> tr; tr.upload(std::vector<unsigned char>(LpT, 1));
+    dev_forward(h, dl.p, K + 1, tmp.p, LpT, tr.p);
+    // back to grid: T plain, lnps -> exp
+    l[K].op = 2; dl.upload(l);
+    dev_inverse(h, tmp.p, LpT, dl.p, K + 1);
+    // store spectral ts, ln_ps (slot 0)
+    std::vector<double2> ht_((size_t)g.T * LpT);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(ht_.data(), tmp.p, ht_.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    std::vector<double2> ts((size_t)g.T * K), ln((size_t)g.T);
+    for (int p = 0; p < g.T; ++p) { for (int k = 0; k < K; ++k) ts[(size_t)p * K + k] = ht_[(size_t)p * LpT + k]; ln[p] = ht_[(size_t)p * LpT + K]; }
+    CK(cudaMemcpy(h.ts[0].p, ts.data(), ts.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.lnps[0].p, ln.data(), ln.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  // u, v from the perturbation vorticity; then vor/div from (u,v); then u,v,vorg,divg from those (:108-123)
+  {
+    launch_spec_ucos_vcos(h.dt, h.specC.p, h.LpC, K, 0, K, 2 * K, 3 * K, st);
+    dev_inverse(h, h.specC.p, h.LpC, h.levsC[0].p, 4 * K);      // vorg, divg, u[0], v[0] (op 1 = /cos)
+    // vor_div_from_uv_grid: divide_by_cos, forward without truncation, alpha operators, truncate
+    launch_divide_by_cos(h.dt, h.u[0].p, K, st);
+    launch_divide_by_cos(h.dt, h.v[0].p, K, st);
+    std::vector<LevDesc> l(2 * K);
+    for (int k = 0; k < K; ++k) { l[k] = {h.u[0].p + (size_t)k * pl, 0, 0}; l[K + k] = {h.v[0].p + (size_t)k * pl, 0, 0}; }
+    DBuf<LevDesc> dl; dl.upload(l);
+    DBuf<unsigned char> tr; tr.upload(std::vector<unsigned char>(Lp, 0));
+    dev_forward(h, dl.p, 2 * K, h.x_spec.p, Lp, tr.p);
+    launch_spec_vor_div(h.dt, h.x_spec.p, Lp, K, 0, K, h.specC.p, h.LpC, 0, K, st);
+    launch_spec_ucos_vcos(h.dt, h.specC.p, h.LpC, K, 0, K, 2 * K, 3 * K, st);
+    dev_inverse(h, h.specC.p, h.LpC, h.levsC[0].p, 4 * K);
+    CK(cudaStreamSynchronize(st));
+    std::vector<double2> sc((size_t)g.T * h.LpC);
+    CK(cudaMemcpy(sc.data(), h.specC.p, sc.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    std::vector<double2> vo((size_t)g.T * K), di((size_t)g.T * K);
+    for (int p = 0; p < g.T; ++p) for (int k = 0; k < K; ++k) { vo[(size_t)p * K + k] = sc[(size_t)p * h.LpC + k]; di[(size_t)p * K + k] = sc[(size_t)p * h.LpC + K + k]; }
+    CK(cudaMemcpy(h.vors[0].p, vo.data(), vo.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.divs[0].p, di.data(), di.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  // both time levels identical (spectral_dynamics.F90:616-624)
+  CK(cudaMemcpy(h.vors[1].p, h.vors[0].p, h.nspec3() * sizeof(double2), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h.divs[1].p, h.divs[0].p, h.nspec3() * sizeof(double2), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h.ts[1].p, h.ts[0].p, h.nspec3() * sizeof(double2), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h.lnps[1].p, h.lnps[0].p, (size_t)g.T * sizeof(double2), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h.u[1].p, h.u[0].p, h.n3() * sizeof(double), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h.v[1].p, h.v[0].p, h.n3() * sizeof(double), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h.T[1].p, h.T[0].p, h.n3() * sizeof(double), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h.ps[1].p, h.ps[0].p, pl * sizeof(double), cudaMemcpyDeviceToDevice));
+  h.previous = 0; h.current = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+#define API_BEGIN(h) if (!(h)) return 1; try {
+#define API_END(h) } catch (const std::exception& e) { (h)->err = e.what(); return 2; } return 0;
+
+extern "C" {
+
+void isca_b200_default_config(IscaConfig* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->abi_version = ISCA_B200_ABI_VERSION;
+  c->lon_max = 128; c->lat_max = 64; c->num_fourier = 42; c->num_spherical = 43; c->num_levels = 18; c->dt_atmos = 600.;
+  c->damping_order = 2; c->damping_order_vor = -1; c->damping_order_div = -1;
+  c->damping_coeff = 1.15740741e-4; c->damping_coeff_vor = -1.; c->damping_coeff_div = -1.;
+  c->do_mass_correction = 1; c->do_energy_correction = 1; c->do_water_correction = 1;
+  c->use_virtual_temperature = 0; c->use_implicit = 1;
+  c->robert_coeff = .04; c->raw_filter_coeff = 1.0; c->alpha_implicit = .5;
+  c->vert_coord_option = 0; c->scale_heights = 4.; c->surf_res = .1; c->exponent = 2.5; c->p_press = .1; c->p_sigma = .3;
+  c->reference_sea_level_press = 101325.; c->initial_sphum = 0.; c->water_correction_limit = 0.;
+  c->valid_range_t[0] = 100.; c->valid_range_t[1] = 500.; c->initial_temperature = 264.;
+  c->num_tracers = 0; c->tracer_robert_coeff = -1.;
+  c->no_forcing = 0; c->do_conserve_energy = 1;
+  c->t_zero = 315.; c->t_strat = 200.; c->delh = 60.; c->delv = 10.; c->eps = 0.; c->sigma_b = 0.7; c->P00 = 1.e5;
+  c->ka = -40.; c->ks = -4.; c->kf = -1.; c->trflux = 1.e-5; c->trsink = -4.;
+  c->radius = 6376.0e3; c->omega = 7.2921150e-5; c->grav = 9.80; c->rdgas = 287.04; c->kappa = 2. / 7.;
+}
+
+const char* isca_b200_last_error(IscaHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int isca_b200_nccl_unique_id(void* /*out128*/) { g_create_error = "NCCL support is not available in this build"; return 3; }
+
+int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* /*nccl_unique_id*/, IscaHandle* out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return 1; }
+  *out = nullptr;
+  H* h = nullptr;
+  try {
+    if (cfg->abi_version != ISCA_B200_ABI_VERSION) throw std::runtime_error("IscaConfig.abi_version mismatch");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw std::runtime_error("no CUDA device: isca_b200 has no CPU fallback");
+    if (nranks != 1) throw std::runtime_error("multi-rank runs are not available in this build");
+    // unsupported namelist values fail loudly
+    if (cfg->raw_filter_coeff != 1.0) throw std::runtime_error("raw_filter_coeff /= 1 is not supported");
+    if (cfg->vert_advect_uv != 0 || cfg->vert_advect_t != 0) throw std::runtime_error("only second_centered vertical advection of u,v,T is supported");
+    if (cfg->use_virtual_temperature) throw std::runtime_error("use_virtual_temperature is not supported");
+    if (cfg->num_tracers != 0) throw std::runtime_error("tracers are not supported in this build");
+    if (cfg->do_water_correction && cfg->num_tracers == 0) throw std::runtime_error("do_water_correction must be .false. in a dry model (spectral_dynamics.F90:1264)");
+    if ((cfg->do_energy_correction || cfg->do_water_correction) && !cfg->do_mass_correction) throw std::runtime_error("energy/water correction requires mass correction (spectral_dynamics.F90:409-415)");
+    h = new H();
+    h->cfg = *cfg;
+    CK(cudaSetDevice(rank % ndev));
+    build_geometry(*cfg, rank, nranks, h->g);
+    build_tables(*cfg, h->g, h->ht);
+    h->cfg.pk = nullptr; h->cfg.bk = nullptr;
+    CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    upload_tables(*h);
+    set_params(*h);
+    alloc_state(*h);
+    CK(cudaStreamSynchronize(h->st));
+    *out = h;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete h;
+    return 2;
+  }
+  return 0;
+}
+
+int isca_b200_destroy(IscaHandle h) {
+  if (!h) return 1;
+  cudaStreamSynchronize(h->st);
+  for (auto& kv : h->wave_cache) delete kv.second;
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+int isca_b200_cold_start(IscaHandle h) { API_BEGIN(h) cold_start(*h); CK(cudaStreamSynchronize(h->st)); API_END(h) }
+
+int isca_b200_set_surf_geopotential(IscaHandle h, const double* sg) {
+  API_BEGIN(h) CK(cudaMemcpy(h->phis.p, sg, h->nplane() * sizeof(double), cudaMemcpyHostToDevice)); API_END(h)
+}
+
+int isca_b200_set_grid_state(IscaHandle h, int slot, const double* ug, const double* vg, const double* tg,
+                             const double* psg, const double* /*tracers*/) {
+  API_BEGIN(h)
+  if (slot < 0 || slot > 1) throw std::runtime_error("slot must be 0 or 1");
+  if (ug) CK(cudaMemcpy(h->u[slot].p, ug, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
+  if (vg) CK(cudaMemcpy(h->v[slot].p, vg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
+  if (tg) CK(cudaMemcpy(h->T[slot].p, tg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
+  if (psg) CK(cudaMemcpy(h->ps[slot].p, psg, h->nplane() * sizeof(double), cudaMemcpyHostToDevice));
+  API_END(h)
+}
+
+static void set_spec(H& h, DBuf<double2>& dst, const double* src, int nlev) {
+  const Geometry& g = h.g;
+  h.x_rect.ensure((size_t)nlev * (g.N + 1) * (g.M + 1));
+  CK(cudaMemcpy(h.x_rect.p, src, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), cudaMemcpyHostToDevice));
+  launch_pack_spec(h.dt, h.x_rect.p, dst.p, nlev, nlev, 0, h.st);
+  CK(cudaStreamSynchronize(h.st));
+}
+static void get_spec(H& h, const double2* src, int Ls, int lev0, double* dst, int nlev) {
+  const Geometry& g = h.g;
+  h.x_rect.ensure((size_t)nlev * (g.N + 1) * (g.M + 1));
+  CK(cudaMemsetAsync(h.x_rect.p, 0, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), h.st));
+  launch_unpack_spec(h.dt, src, h.x_rect.p, nlev, Ls, lev0, h.st);
+  CK(cudaStreamSynchronize(h.st));
+  CK(cudaMemcpy(dst, h.x_rect.p, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), cudaMemcpyDeviceToHost));
+}
+
+int isca_b200_set_spectral_state(IscaHandle h, int slot, const double* vors, const double* divs, const double* ts,
+                                 const double* ln_ps) {
+  API_BEGIN(h)
+  if (slot < 0 || slot > 1) throw std::runtime_error("slot must be 0 or 1");
+  if (vors) set_spec(*h, h->vors[slot], vors, h->g.K);
+  if (divs) set_spec(*h, h->divs[slot], divs, h->g.K);
+  if (ts) set_spec(*h, h->ts[slot], ts, h->g.K);
+  if (ln_ps) set_spec(*h, h->lnps[slot], ln_ps, 1);
+  API_END(h)
+}
+
+int isca_b200_set_vor_div_grid(IscaHandle h, const double* vorg, const double* divg) {
+  API_BEGIN(h)
+  if (vorg) CK(cudaMemcpy(h->vorg.p, vorg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
+  if (divg) CK(cudaMemcpy(h->divg.p, divg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
+  API_END(h)
+}
+
+int isca_b200_set_time_pointers(IscaHandle h, int previous_slot, int current_slot) {
+  API_BEGIN(h)
+  if (previous_slot < 0 || previous_slot > 1 || current_slot < 0 || current_slot > 1) throw std::runtime_error("slots must be 0 or 1");
+  h->previous = previous_slot; h->current = current_slot;
+  API_END(h)
+}
+int isca_b200_get_time_pointers(IscaHandle h, int* p, int* c) { API_BEGIN(h) *p = h->previous; *c = h->current; API_END(h) }
+
+static int run_steps(IscaHandle h, int n, int physics) {
+  API_BEGIN(h)
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, h->st));
+  for (int i = 0; i < n; ++i) step_once(*h, physics, nullptr, nullptr, nullptr);
+  CK(cudaEventRecord(e1, h->st));
+  check_t_flag(*h);
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->last_step_ms = n > 0 ? ms / n : 0.0;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  API_END(h)
+}
+int isca_b200_step(IscaHandle h, int n_steps) { return run_steps(h, n_steps, 1); }
+int isca_b200_step_dynamics_only(IscaHandle h, int n_steps) { return run_steps(h, n_steps, 0); }
+
+int isca_b200_spectral_dynamics(IscaHandle h, const double* dt_psg, const double* dt_ug, const double* dt_vg,
+                                const double* dt_tg, double* psg_final, double* ug_final, double* vg_final,
+                                double* tg_final, double* wg_full, double* p_full) {
+  API_BEGIN(h)
+  if (dt_psg) throw std::runtime_error("non-zero dt_psg is not supported (the solo driver always passes zero, atmosphere.F90:289)");
+  const size_t n3 = h->n3();
+  h->ext_tend.ensure(3 * n3);
+  const double* src[3] = {dt_ug, dt_vg, dt_tg};
+  for (int f = 0; f < 3; ++f) {
+    if (src[f]) CK(cudaMemcpyAsync(h->ext_tend.p + f * n3, src[f], n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    else CK(cudaMemsetAsync(h->ext_tend.p + f * n3, 0, n3 * sizeof(double), h->st));
+  }
+  step_once(*h, 0, h->ext_tend.p, h->ext_tend.p + n3, h->ext_tend.p + 2 * n3);
+  const int c = h->current;
+  if (psg_final) CK(cudaMemcpyAsync(psg_final, h->ps[c].p, h->nplane() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (ug_final) CK(cudaMemcpyAsync(ug_final, h->u[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (vg_final) CK(cudaMemcpyAsync(vg_final, h->v[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (tg_final) CK(cudaMemcpyAsync(tg_final, h->T[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (wg_full) CK(cudaMemcpyAsync(wg_full, h->wg_full.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (p_full) {
+    h->x_grid.ensure(n3);
+    launch_press_heights(h->dt, h->pr, h->T[h->previous].p, h->ps[h->previous].p, h->phis.p, h->x_grid.p, nullptr, nullptr, nullptr, h->st);
+    CK(cudaMemcpyAsync(p_full, h->x_grid.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  }
+  check_t_flag(*h);
+  API_END(h)
+}
+
+static int slot_of(H& h, int level) {
+  if (level == ISCA_LEVEL_CURRENT) return h.current;
+  if (level == ISCA_LEVEL_PREVIOUS) return h.previous;
+  if (level == 0 || level == 1) return level;
+  throw std::runtime_error("invalid time level selector");
+}
+
+int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
+  API_BEGIN(h)
+  const int s = slot_of(*h, level);
+  const size_t n3 = h->n3(), pl = h->nplane();
+  CK(cudaStreamSynchronize(h->st));
+  switch (id) {
+    case ISCA_F_PS: CK(cudaMemcpy(host, h->ps[s].p, pl * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_U: CK(cudaMemcpy(host, h->u[s].p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_V: CK(cudaMemcpy(host, h->v[s].p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_T: CK(cudaMemcpy(host, h->T[s].p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_VOR: CK(cudaMemcpy(host, h->vorg.p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_DIV: CK(cudaMemcpy(host, h->divg.p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_WG_FULL: CK(cudaMemcpy(host, h->wg_full.p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_P_FULL: case ISCA_F_P_HALF: case ISCA_F_Z_FULL: case ISCA_F_Z_HALF: {
+      const size_t nh = n3 + pl;
+      h->x_grid.ensure(nh);
+      double* pf = (id == ISCA_F_P_FULL) ? h->x_grid.p : nullptr;
+      double* ph = (id == ISCA_F_P_HALF) ? h->x_grid.p : nullptr;
+      double* zf = (id == ISCA_F_Z_FULL) ? h->x_grid.p : nullptr;
+      double* zh = (id == ISCA_F_Z_HALF) ? h->x_grid.p : nullptr;
+      launch_press_heights(h->dt, h->pr, h->T[s].p, h->ps[s].p, h->phis.p, pf, ph, zf, zh, h->st);
+      CK(cudaStreamSynchronize(h->st));
+      const size_t cnt = (id == ISCA_F_P_HALF || id == ISCA_F_Z_HALF) ? nh : n3;
+      CK(cudaMemcpy(host, h->x_grid.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+      break;
+    }
+    default: throw std::runtime_error("unknown field id");
+  }
+  API_END(h)
+}
+
+int isca_b200_get_spectral(IscaHandle h, int id, int level, double* host) {
+  API_BEGIN(h)
+  const int K = h->g.K;
+  if (id >= 8 && id <= 11) {       // final spectral tendencies of the last step (keep_tend)
+    const double2* src[4] = {h->k_dt_vors.p, h->k_dt_divs.p, h->k_dt_ts.p, h->k_dt_lnps.p};
+    get_spec(*h, src[id - 8], id == 11 ? 1 : K, 0, host, id == 11 ? 1 : K);
+  } else {
+    const int s = slot_of(*h, level);
+    switch (id) {
+      case ISCA_S_VOR: get_spec(*h, h->vors[s].p, K, 0, host, K); break;
+      case ISCA_S_DIV: get_spec(*h, h->divs[s].p, K, 0, host, K); break;
+      case ISCA_S_T: get_spec(*h, h->ts[s].p, K, 0, host, K); break;
+      case ISCA_S_LNPS: get_spec(*h, h->lnps[s].p, 1, 0, host, 1); break;
+      default: throw std::runtime_error("unknown spectral field id");
+    }
+  }
+  API_END(h)
+}
+
+int isca_b200_get_scalar(IscaHandle h, int id, double* value) {
+  API_BEGIN(h)
+  double sc[SC_COUNT];
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaMemcpy(sc, h->scal.p, sizeof(sc), cudaMemcpyDeviceToHost));
+  switch (id) {
+    case ISCA_SC_MEAN_PS: *value = sc[SC_MEAN_PS_PREV]; break;
+    case ISCA_SC_MEAN_ENERGY: *value = sc[SC_MEAN_EN_PREV]; break;
+    case ISCA_SC_T_MIN: *value = sc[SC_TMIN]; break;
+    case ISCA_SC_T_MAX: *value = sc[SC_TMAX]; break;
+    case ISCA_SC_STEP_COUNT: *value = (double)h->steps; break;
+    case ISCA_SC_KERNEL_LAUNCHES: *value = (double)h->launches; break;
+    case ISCA_SC_LAST_STEP_MS: *value = h->last_step_ms; break;
+    case 100: h->keep_tend = 1; *value = 1; break;      // enable tendency capture (tests)
+    default: throw std::runtime_error("unknown scalar id");
+  }
+  API_END(h)
+}
+
+int isca_b200_get_table(IscaHandle h, int id, double* host, int count) {
+  API_BEGIN(h)
+  const std::vector<double>* v = nullptr;
+  switch (id) {
+    case ISCA_TB_SIN_LAT: v = &h->ht.sin_lat; break;
+    case ISCA_TB_WTS_LAT: v = &h->ht.wts_lat; break;
+    case ISCA_TB_DEG_LAT: v = &h->ht.deg_lat; break;
+    case ISCA_TB_DEG_LON: v = &h->ht.deg_lon; break;
+    case ISCA_TB_PK: v = &h->ht.pk; break;
+    case ISCA_TB_BK: v = &h->ht.bk; break;
+    default: throw std::runtime_error("unknown table id");
+  }
+  if ((size_t)count != v->size()) throw std::runtime_error("table size mismatch");
+  std::memcpy(host, v->data(), v->size() * sizeof(double));
+  API_END(h)
+}
+
+// ---- transforms_mod level ---------------------------------------------------------------------
+int isca_b200_spherical_to_grid(IscaHandle h, const double* spec, double* grid, int nlev) {
+  API_BEGIN(h)
+  const Geometry& g = h->g;
+  x_prepare(*h, nlev, 1);
+  const int Lp = round_up(nlev, 16);
+  CK(cudaMemcpy(h->x_rect.p, spec, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), cudaMemcpyHostToDevice));
+  CK(cudaMemsetAsync(h->x_spec.p, 0, (size_t)g.T * Lp * sizeof(double2), h->st));
+  launch_pack_spec(h->dt, h->x_rect.p, h->x_spec.p, nlev, Lp, 0, h->st);
+  x_set_levs(*h, nlev, 0, 0);
+  dev_inverse(*h, h->x_spec.p, Lp, h->x_levs.p, nlev);
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaMemcpy(grid, h->x_grid.p, (size_t)nlev * h->nplane() * sizeof(double), cudaMemcpyDeviceToHost));
+  API_END(h)
+}
+
+int isca_b200_grid_to_spherical(IscaHandle h, const double* grid, double* spec, int nlev, int do_truncation) {
+  API_BEGIN(h)
+  x_prepare(*h, nlev, 1);
+  const int Lp = round_up(nlev, 16);
+  CK(cudaMemcpy(h->x_grid.p, grid, (size_t)nlev * h->nplane() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemsetAsync(h->x_trunc.p, do_truncation ? 1 : 0, Lp, h->st));
+  x_set_levs(*h, nlev, 0, 0);
+  dev_forward(*h, h->x_levs.p, nlev, h->x_spec.p, Lp, h->x_trunc.p);
+  get_spec(*h, h->x_spec.p, Lp, 0, spec, nlev);
+  API_END(h)
+}
+
+int isca_b200_uv_grid_from_vor_div(IscaHandle h, const double* vors, const double* divs, double* ug, double* vg, int nlev) {
+  API_BEGIN(h)
+  const Geometry& g = h->g;
+  x_prepare(*h, nlev, 4);
+  const int Lp = round_up(4 * nlev, 16);
+  const size_t nr = (size_t)nlev * (g.N + 1) * (g.M + 1);
+  CK(cudaMemsetAsync(h->x_spec.p, 0, (size_t)g.T * Lp * sizeof(double2), h->st));
+  CK(cudaMemcpy(h->x_rect.p, vors, nr * sizeof(double2), cudaMemcpyHostToDevice));
+  launch_pack_spec(h->dt, h->x_rect.p, h->x_spec.p, nlev, Lp, 0, h->st);
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaMemcpy(h->x_rect.p, divs, nr * sizeof(double2), cudaMemcpyHostToDevice));
+  launch_pack_spec(h->dt, h->x_rect.p, h->x_spec.p, nlev, Lp, nlev, h->st);
+  launch_spec_ucos_vcos(h->dt, h->x_spec.p, Lp, nlev, 0, nlev, 2 * nlev, 3 * nlev, h->st);
+  x_set_levs(*h, 4 * nlev, 2 * nlev, 1);
+  dev_inverse(*h, h->x_spec.p, Lp, h->x_levs.p, 4 * nlev);
+  CK(cudaStreamSynchronize(h->st));
+  const size_t n = (size_t)nlev * h->nplane();
+  CK(cudaMemcpy(ug, h->x_grid.p + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(vg, h->x_grid.p + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+  API_END(h)
+}
+
+int isca_b200_vor_div_from_uv_grid(IscaHandle h, const double* ug, const double* vg, double* vors, double* divs, int nlev) {
+  API_BEGIN(h)
+  const Geometry& g = h->g;
+  x_prepare(*h, nlev, 2);
+  const int Lp = round_up(2 * nlev, 16);
+  const size_t n = (size_t)nlev * h->nplane();
+  CK(cudaMemcpy(h->x_grid.p, ug, n * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->x_grid.p + n, vg, n * sizeof(double), cudaMemcpyHostToDevice));
+  launch_divide_by_cos(h->dt, h->x_grid.p, 2 * nlev, h->st);
+  CK(cudaMemsetAsync(h->x_trunc.p, 0, Lp, h->st));
+  x_set_levs(*h, 2 * nlev, 0, 0);
+  dev_forward(*h, h->x_levs.p, 2 * nlev, h->x_spec.p, Lp, h->x_trunc.p);
+  DBuf<double2> out; out.alloc((size_t)g.T * Lp);
+  launch_spec_vor_div(h->dt, h->x_spec.p, Lp, nlev, 0, nlev, out.p, Lp, 0, nlev, h->st);
+  get_spec(*h, out.p, Lp, 0, vors, nlev);
+  get_spec(*h, out.p, Lp, nlev, divs, nlev);
+  API_END(h)
+}
+
+int isca_b200_time_transforms(IscaHandle h, int nlev, int reps, double ms_out[4]) {
+  API_BEGIN(h)
+  const Geometry& g = h->g;
+  x_prepare(*h, nlev, 1);
+  const int Lp = round_up(nlev, 16);
+  // synthetic spectrum: deterministic, triangular, decaying with total wavenumber
+  std::vector<double2> sp((size_t)g.T * Lp, make_double2(0, 0));
+  unsigned long long s = 1234;
+  for (int p = 0; p < g.T; ++p) {
+    int m = g.m_of[h->ht.row_m[p]], n = h->ht.row_n[p];
+    if (m + n > g.M) continue;
+    double sc = 1.0 / ((1.0 + m + n) * (1.0 + m + n));
+    for (int k = 0; k < nlev; ++k) {
+      s = s * 6364136223846793005ULL + 1442695040888963407ULL; double a = ((s >> 11) * (1.0 / 9007199254740992.0)) - 0.5;
+      s = s * 6364136223846793005ULL + 1442695040888963407ULL; double b = ((s >> 11) * (1.0 / 9007199254740992.0)) - 0.5;
+      sp[(size_t)p * Lp + k] = make_double2(a * sc, m == 0 ? 0.0 : b * sc);
+    }
+  }
+  CK(cudaMemcpy(h->x_spec.p, sp.data(), sp.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  CK(cudaMemsetAsync(h->x_trunc.p, 1, Lp, h->st));
+  x_set_levs(*h, nlev, 0, 0);
+  cudaEvent_t ev[5]; for (auto& e : ev) CK(cudaEventCreate(&e));
+  double acc[4] = {0, 0, 0, 0};
+  for (int r = -2; r < reps; ++r) {
+    CK(cudaEventRecord(ev[0], h->st));
+    launch_legendre_inv(h->dt, h->x_spec.p, h->four.p, Lp, h->st);
+    CK(cudaEventRecord(ev[1], h->st));
+    launch_fft_inv(h->dt, h->four.p, h->x_levs.p, nlev, Lp, h->st);
+    CK(cudaEventRecord(ev[2], h->st));
+    launch_fft_fwd(h->dt, h->four.p, h->x_levs.p, nlev, Lp, h->st);
+    CK(cudaEventRecord(ev[3], h->st));
+    launch_legendre_fwd(h->dt, h->four.p, h->x_spec.p, Lp, h->x_trunc.p, h->st);
+    CK(cudaEventRecord(ev[4], h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->launches += 4;
+    if (r >= 0) for (int i = 0; i < 4; ++i) { float ms; CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); acc[i] += ms; }
+  }
+  for (int i = 0; i < 4; ++i) ms_out[i] = acc[i] / (reps > 0 ? reps : 1);
+  for (auto& e : ev) cudaEventDestroy(e);
+  API_END(h)
+}
+
+int isca_b200_profile_step(IscaHandle h, int /*n_steps*/, double* /*ms_out*/, int /*max_groups*/, char* /*names*/, int /*capacity*/) {
+  if (!h) return -1;
+  h->err = "profile_step is not implemented yet";
+  return -1;
+}
+
+}  // extern "C"

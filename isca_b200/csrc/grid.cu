@@ -1,0 +1,369 @@
+// grid.cu -- grid-space column kernels (one thread per (lon, lat) column, k-recurrences in registers).
+//
+//   grid_step_kernel   hs_forcing (atmos_param/hs_forcing/hs_forcing.F90:148-272, 508-679) +
+//                      initialize_corrections (model/spectral_dynamics.F90:1306-1338) +
+//                      pressure_variables (model/press_and_geopot.F90:152-221) +
+//                      compute_pressure_gradient (:1192-1209), four_in_one (:1038-1112),
+//                      compute_geopotential (press_and_geopot.F90:314-359),
+//                      vert_advection second_centered (atmos_shared/vert_advection/vert_advection.F90:163-173,440-476),
+//                      horizontal_advection tail (tools/transforms.F90:826), Coriolis/KE block (:893-902)
+//   colsum / reduce    area_weighted_global_mean (tools/transforms.F90:1059-1077),
+//                      mass_weighted_global_integral (model/global_integral.F90:49-81)
+//   apply_* kernels    compute_corrections (model/spectral_dynamics.F90:1213-1302)
+//   press_heights      compute_pressures_and_heights (press_and_geopot.F90:363-387)
+#include "device.h"
+#include "grid.h"
+
+namespace isca {
+
+// pressure_variables for one column, one level at a time, bottom-up.
+struct PressLevel { double p_half_k, p_half_k1, ln_half_k, ln_half_k1, ln_full, p_full; };
+
+__device__ __forceinline__ void press_level(const DevTables& t, const Params& pr, int k, double ps, double ln_half_k1,
+                                            PressLevel& o) {
+  o.p_half_k = t.pk[k] + t.bk[k] * ps;
+  o.p_half_k1 = t.pk[k + 1] + t.bk[k + 1] * ps;
+  o.ln_half_k1 = ln_half_k1;
+  if (k == 0 && pr.pkbk0_zero) {
+    o.ln_half_k = 0.0;
+    o.ln_full = ln_half_k1 + (-1.0);                 // ln_top_level_factor (press_and_geopot.F90:103,186)
+  } else {
+    o.ln_half_k = log(o.p_half_k);
+    const double alpha = 1.0 - o.p_half_k * (o.ln_half_k1 - o.ln_half_k) / (o.p_half_k1 - o.p_half_k);
+    o.ln_full = o.ln_half_k1 - alpha;
+  }
+  o.p_full = exp(o.ln_full);
+}
+
+__global__ void __launch_bounds__(128)
+grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
+  const GeomDev& g = t.g;
+  const int I = g.I, K = g.K;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jl = blockIdx.y;
+  if (i >= I) return;
+  const int j = g.j0 + jl;
+  const size_t col = (size_t)jl * I + i;
+  const size_t plane = (size_t)g.Jloc * I;
+
+  const double ps_c = a.ps_cur[col], ps_p = a.ps_prev[col];
+  const double cosm = t.cosm_lat[j];
+  // compute_pressure_gradient: dx_psg = psg * S2G(dx ln ps), then divide_by_cos
+  const double dx_psg = (ps_c * a.dx_lnps[col]) * cosm;
+  const double dy_psg = (ps_c * a.dy_lnps[col]) * cosm;
+
+  // ---- pass 1 (top-down): cumulative mass divergence  (four_in_one :1073-1083)
+  double cum[ISCA_KMAX + 1];
+  cum[0] = 0.0;
+  {
+    double dmean_tot = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const size_t e = (size_t)k * plane + col;
+      const double dp = t.dpk[k] + t.dbk[k] * ps_c;
+      const double dmean = a.div_cur[e] * dp + t.dbk[k] * (a.u_cur[e] * dx_psg + a.v_cur[e] * dy_psg);
+      dmean_tot = dmean_tot + dmean;
+      cum[k + 1] = dmean_tot;
+    }
+  }
+  const double dmean_total = cum[K];
+  a.dt_lnps[col] = (0.0 - dmean_total) / ps_c;       // dt_psg = dt_psg - dmean_tot ; dt_ln_psg = dt_psg/psg
+
+  // Held-Suarez latitude constants (newtonian_damping :527-545)
+  const double lat = t.rad_lat[j];
+  const double sin_lat = sin(lat);
+  const double sin_lat_2 = sin_lat * sin_lat;
+  const double cos_lat_2 = 1.0 - sin_lat_2;
+  const double cos_lat_4 = cos_lat_2 * cos_lat_2;
+  const double t_star = pr.t_zero - pr.delh * sin_lat_2 - pr.eps * sin_lat;
+  const double tstr = pr.t_strat - pr.eps * sin_lat;
+  const double tcoeff = (pr.tks - pr.tka) / (1.0 - pr.sigma_b);
+  const double vcoeff = -pr.vkf / (1.0 - pr.sigma_b);
+  const double ps_hs = t.pk[K] + t.bk[K] * ps_c;     // ps = p_half(:,:,size(p_half,3))
+  const double rps = 1. / ps_hs;
+  const double fcor = t.coriolis[j];
+  const double delta_t = pr.delta_t;
+
+  // ---- pass 2 (bottom-up)
+  double gh_below = a.phis[col];                     // geopot_half(K+1) = surf_geopotential
+  double ln_half_below = log(t.pk[K] + t.bk[K] * ps_c);
+  double energy_int = 0.0;
+  // rolling values for the centred vertical advection (need k-1, k, k+1 of u, v, T at `cur`)
+  double u_dn = 0.0, v_dn = 0.0, T_dn = 0.0;         // level k+1
+  double u_k = a.u_cur[(size_t)(K - 1) * plane + col], v_k = a.v_cur[(size_t)(K - 1) * plane + col],
+         T_k = a.t_cur[(size_t)(K - 1) * plane + col];
+  for (int k = K - 1; k >= 0; --k) {
+    const size_t e = (size_t)k * plane + col;
+    double u_up = 0.0, v_up = 0.0, T_up = 0.0;       // level k-1
+    if (k > 0) { u_up = a.u_cur[e - plane]; v_up = a.v_cur[e - plane]; T_up = a.t_cur[e - plane]; }
+    PressLevel pl;
+    press_level(t, pr, k, ps_c, ln_half_below, pl);
+
+    // ---------------- physics: hs_forcing on (u,v,T)(previous), pressures of `current`
+    double dt_u = 0.0, dt_v = 0.0, dt_T = 0.0;
+    const double u_p = a.u_prev[e], v_p = a.v_prev[e], T_p = a.t_prev[e];
+    if (pr.physics_on && !pr.no_forcing) {
+      const double sigma = pl.p_full * rps;
+      double utnd = 0.0, vtnd = 0.0;
+      const bool in_bl = (sigma <= 1.0 && sigma > pr.sigma_b);
+      if (in_bl) { const double vfactr = vcoeff * (sigma - pr.sigma_b); utnd = vfactr * u_p; vtnd = vfactr * v_p; }
+      if (pr.do_conserve_energy) {
+        const double ttnd = -((u_p + .5 * utnd * delta_t) * utnd + (v_p + .5 * vtnd * delta_t) * vtnd) / pr.cp_air;
+        dt_T = dt_T + ttnd;
+      }
+      dt_u = dt_u + utnd; dt_v = dt_v + vtnd;
+      const double p_norm = pl.p_full / pr.P00;
+      const double the = t_star - pr.delv * cos_lat_2 * log(p_norm);
+      double teq = the * pow(p_norm, pr.kappa);
+      teq = fmax(teq, tstr);
+      double tdamp = pr.tka;
+      if (in_bl) { const double tfactr = tcoeff * (sigma - pr.sigma_b); tdamp = pr.tka + cos_lat_4 * tfactr; }
+      dt_T = dt_T + (-tdamp * (T_p - teq));
+    } else if (a.dt_u_in) {                          // tendencies supplied by the caller (spectral_dynamics API)
+      dt_u = a.dt_u_in[e]; dt_v = a.dt_v_in[e]; dt_T = a.dt_t_in[e];
+    }
+    // initialize_corrections: energy of (previous + dt*delta_t), mass-weighted with psg(previous)
+    {
+      const double up = u_p + dt_u * delta_t, vp = v_p + dt_v * delta_t;
+      const double en = 0.5 * (up * up + vp * vp) + pr.cp_air * (T_p + dt_T * delta_t);
+      const double dpp = (t.pk[k + 1] + t.bk[k + 1] * ps_p) - (t.pk[k] + t.bk[k] * ps_p);
+      energy_int = energy_int + en * dpp;
+    }
+
+    // ---------------- four_in_one, level k
+    const double Tv = T_k;                            // use_virtual_temperature = .false. (dry) -> virtual_t = tg
+    const double dp = t.dpk[k] + t.dbk[k] * ps_c;
+    const double dp_inv = 1 / dp;
+    const double dlog_1 = pl.ln_half_k1 - pl.ln_full;
+    const double dlog_2 = pl.ln_full - pl.ln_half_k;
+    const double dlog_3 = pl.ln_half_k1 - pl.ln_half_k;
+    const double x1 = (t.bk[k + 1] * dlog_1 + t.bk[k] * dlog_2) * dp_inv;
+    const double x2 = x1 * dx_psg;
+    const double x3 = x1 * dy_psg;
+    dt_u = dt_u - pr.rdgas * Tv * x2;
+    dt_v = dt_v - pr.rdgas * Tv * x3;
+    const double dmean_tot = cum[k];
+    const double dmean = a.div_cur[e] * dp + t.dbk[k] * (u_k * dx_psg + v_k * dy_psg);
+    const double x4 = (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv;
+    const double x5 = x4 - u_k * x2 - v_k * x3;
+    dt_T = dt_T - pr.kappa * Tv * x5;
+    if (a.wg_full) a.wg_full[e] = -x5 * pl.p_full;
+    // wg at the two interfaces of level k (:1102-1108)
+    double w_top = (k == 0) ? 0.0 : (-cum[k] + dmean_total * t.bk[k]);
+    double w_bot = (k == K - 1) ? 0.0 : (-cum[k + 1] + dmean_total * t.bk[k + 1]);
+
+    // ---------------- compute_geopotential
+    const double gfull = gh_below + pr.rdgas * T_k * (pl.ln_half_k1 - pl.ln_full);
+    if (!(k == 0 && pr.pk0_zero)) gh_below = gh_below + pr.rdgas * T_k * (pl.ln_half_k1 - pl.ln_half_k);
+
+    // ---------------- vert_advection, second_centered, advective form, time_level = current
+    {
+      const double dz = pl.p_half_k1 - pl.p_half_k;  // dp = p_half(k+1) - p_half(k)
+      // flux(k) = w(k)*0.5*(r(k)+r(k-1)) (interfaces ks+1..ke); flux(ks) = w(ks)*r(ks); flux(ke+1) = w(ke+1)*r(ke)
+      const double fu_t = (k == 0) ? w_top * u_k : w_top * (0.5 * (u_k + u_up));
+      const double fu_b = (k == K - 1) ? w_bot * u_k : w_bot * (0.5 * (u_dn + u_k));
+      dt_u = dt_u + (-(fu_b - fu_t - u_k * (w_bot - w_top)) / dz);
+      const double fv_t = (k == 0) ? w_top * v_k : w_top * (0.5 * (v_k + v_up));
+      const double fv_b = (k == K - 1) ? w_bot * v_k : w_bot * (0.5 * (v_dn + v_k));
+      dt_v = dt_v + (-(fv_b - fv_t - v_k * (w_bot - w_top)) / dz);
+      const double ft_t = (k == 0) ? w_top * T_k : w_top * (0.5 * (T_k + T_up));
+      const double ft_b = (k == K - 1) ? w_bot * T_k : w_bot * (0.5 * (T_dn + T_k));
+      dt_T = dt_T + (-(ft_b - ft_t - T_k * (w_bot - w_top)) / dz);
+    }
+    // ---------------- horizontal_advection of T (dx, dy already divided by cos in the FFT epilogue)
+    dt_T = dt_T - u_k * a.dx_t[e] - v_k * a.dy_t[e];
+    // ---------------- Coriolis / vorticity
+    const double absv = a.vor_cur[e] + fcor;
+    dt_u = dt_u + absv * v_k;
+    dt_v = dt_v - absv * u_k;
+
+    // ---------------- outputs for the forward transforms
+    a.out_A[e] = dt_u * cosm;                          // vor_div_from_uv_grid: divide_by_cos(u_grid)
+    a.out_B[e] = dt_v * cosm;
+    a.out_T[e] = dt_T;
+    a.out_phi[e] = gfull + .5 * (u_k * u_k + v_k * v_k);
+
+    ln_half_below = pl.ln_half_k;
+    u_dn = u_k; v_dn = v_k; T_dn = T_k;
+    u_k = u_up; v_k = v_up; T_k = T_up;
+  }
+  const double w = t.wts_lat[j];
+  a.part[0 * plane + col] = w * ps_p;                  // area_weighted_global_mean(psg(previous))
+  a.part[1 * plane + col] = w * energy_int;            // mass_weighted_global_integral(energy, psg(previous))
+}
+
+void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& a, cudaStream_t st) {
+  dim3 block(128), grid((t.g.I + 127) / 128, t.g.Jloc);
+  grid_step_kernel<<<grid, block, 0, st>>>(t, pr, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic reduction of nq per-column arrays: out[q] = sum / min / max of part[q][0..n)
+// One CTA, fixed summation tree -> bitwise reproducible run to run.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+reduce_kernel(const double* __restrict__ part, size_t n, int nq, const int* __restrict__ ops, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  for (int q = 0; q < nq; ++q) {
+    const int op = ops[q];
+    double acc = (op == 0) ? 0.0 : ((op == 1) ? 1.0e300 : -1.0e300);
+    for (size_t i = threadIdx.x; i < n; i += 1024) {
+      const double v = part[(size_t)q * n + i];
+      acc = (op == 0) ? acc + v : ((op == 1) ? fmin(acc, v) : fmax(acc, v));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        const double x = sh[threadIdx.x], y = sh[threadIdx.x + s];
+        sh[threadIdx.x] = (op == 0) ? x + y : ((op == 1) ? fmin(x, y) : fmax(x, y));
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[q] = sh[0];
+    __syncthreads();
+  }
+}
+void launch_reduce(const double* part, size_t n, int nq, const int* ops, double* out, cudaStream_t st) {
+  reduce_kernel<<<1, 1024, 0, st>>>(part, n, nq, ops, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// post-transform: mass fixer
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_ps_kernel(DevTables t, const double* __restrict__ ps, double* __restrict__ part) {
+  const GeomDev& g = t.g;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
+  if (i >= g.I) return;
+  part[(size_t)jl * g.I + i] = t.wts_lat[g.j0 + jl] * ps[(size_t)jl * g.I + i];
+}
+void launch_colsum_ps(const DevTables& t, const double* ps, double* part, cudaStream_t st) {
+  dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
+  colsum_ps_kernel<<<grid, 128, 0, st>>>(t, ps, part);
+}
+
+// scal[SC_*]: see grid.h.  mass_correction_factor = mean_ps_prev / mean_ps_tmp
+__global__ void apply_mass_kernel(DevTables t, double* __restrict__ ps, double2* __restrict__ lnps_fut,
+                                  double* __restrict__ scal, double denom, int owns_m0, int do_mass) {
+  const GeomDev& g = t.g;
+  const size_t n = (size_t)g.Jloc * g.I;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const double mean_prev = scal[SC_SUM_PS_PREV] / denom;
+  const double mean_tmp = scal[SC_SUM_PS_FUT] / denom;
+  const double f = do_mass ? (mean_prev / mean_tmp) : 1.0;
+  if (idx < n && do_mass) ps[idx] = f * ps[idx];
+  if (idx == 0) {
+    scal[SC_MEAN_PS_PREV] = mean_prev;
+    scal[SC_MASS_FACTOR] = f;
+    if (owns_m0 && do_mass) lnps_fut[0].x = lnps_fut[0].x + sqrt(2.) * log(f);   // ln_ps(0,0,future) (:1231)
+  }
+}
+void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double* scal, double denom, int owns_m0,
+                       int do_mass, cudaStream_t st) {
+  size_t n = (size_t)t.g.Jloc * t.g.I;
+  apply_mass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, ps, lnps_fut, scal, denom, owns_m0, do_mass);
+}
+
+// ---------------------------------------------------------------------------------------------
+// post-transform: energy fixer.  part[0] = w * sum_k (0.5(u^2+v^2)+cp T) dp ; part[1] = min T ; part[2] = max T
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_energy_kernel(DevTables t, Params pr, const double* __restrict__ u, const double* __restrict__ v,
+                                     const double* __restrict__ T, const double* __restrict__ ps, double* __restrict__ part) {
+  const GeomDev& g = t.g;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
+  if (i >= g.I) return;
+  const size_t col = (size_t)jl * g.I + i, plane = (size_t)g.Jloc * g.I;
+  const double p_s = ps[col];
+  double vi = 0.0, tmin = 1.0e300, tmax = -1.0e300;
+  for (int k = 0; k < g.K; ++k) {
+    const size_t e = (size_t)k * plane + col;
+    const double uu = u[e], vv = v[e], tt = T[e];
+    const double dp = (t.pk[k + 1] + t.bk[k + 1] * p_s) - (t.pk[k] + t.bk[k] * p_s);
+    vi = vi + (0.5 * (uu * uu + vv * vv) + pr.cp_air * tt) * dp;
+    tmin = fmin(tmin, tt); tmax = fmax(tmax, tt);
+  }
+  part[col] = t.wts_lat[g.j0 + jl] * vi;
+  part[plane + col] = tmin;
+  part[2 * plane + col] = tmax;
+}
+void launch_colsum_energy(const DevTables& t, const Params& pr, const double* u, const double* v, const double* T,
+                          const double* ps, double* part, cudaStream_t st) {
+  dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
+  colsum_energy_kernel<<<grid, 128, 0, st>>>(t, pr, u, v, T, ps, part);
+}
+
+__global__ void apply_energy_kernel(DevTables t, Params pr, double* __restrict__ T, double2* __restrict__ ts_fut,
+                                    double* __restrict__ scal, double denom, int owns_m0, int do_energy) {
+  const GeomDev& g = t.g;
+  const size_t n = (size_t)g.K * g.Jloc * g.I;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const double mean_e_prev = scal[SC_SUM_EN_PREV] / denom / pr.grav;
+  const double mean_e_tmp = scal[SC_SUM_EN_FUT] / denom / pr.grav;
+  const double tc = do_energy ? pr.grav * (mean_e_prev - mean_e_tmp) / (pr.cp_air * scal[SC_MEAN_PS_PREV]) : 0.0;
+  if (do_energy) {
+    if (idx < n) T[idx] = T[idx] + tc;
+    if (owns_m0 && idx < (size_t)g.K) ts_fut[idx].x = ts_fut[idx].x + sqrt(2.) * tc;   // ts(0,0,:,future) (:1241)
+  }
+  if (idx == 0) {
+    scal[SC_MEAN_EN_PREV] = mean_e_prev;
+    scal[SC_T_CORR] = tc;
+    if (scal[SC_TMIN] < pr.vr_tmin || scal[SC_TMAX] > pr.vr_tmax) scal[SC_T_FLAG] = 1.0;   // valid_range_t (:940)
+  }
+}
+void launch_apply_energy(const DevTables& t, const Params& pr, double* T, double2* ts_fut, double* scal, double denom,
+                         int owns_m0, int do_energy, cudaStream_t st) {
+  size_t n = (size_t)t.g.K * t.g.Jloc * t.g.I;
+  apply_energy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, pr, T, ts_fut, scal, denom, owns_m0, do_energy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compute_pressures_and_heights (dry): p_half, p_full, z_half, z_full for diagnostics / physics API
+// ---------------------------------------------------------------------------------------------
+__global__ void press_heights_kernel(DevTables t, Params pr, const double* __restrict__ T, const double* __restrict__ ps,
+                                     const double* __restrict__ phis, double* p_full, double* p_half, double* z_full,
+                                     double* z_half) {
+  const GeomDev& g = t.g;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
+  if (i >= g.I) return;
+  const int K = g.K;
+  const size_t col = (size_t)jl * g.I + i, plane = (size_t)g.Jloc * g.I;
+  const double p_s = ps[col];
+  double gh_below = phis[col];
+  double ln_half_below = log(t.pk[K] + t.bk[K] * p_s);
+  if (p_half) p_half[(size_t)K * plane + col] = t.pk[K] + t.bk[K] * p_s;
+  if (z_half) z_half[(size_t)K * plane + col] = gh_below / pr.grav;
+  for (int k = K - 1; k >= 0; --k) {
+    const size_t e = (size_t)k * plane + col;
+    PressLevel pl;
+    press_level(t, pr, k, p_s, ln_half_below, pl);
+    const double tt = T[e];
+    const double gfull = gh_below + pr.rdgas * tt * (pl.ln_half_k1 - pl.ln_full);
+    double gh = 0.0;
+    if (!(k == 0 && pr.pk0_zero)) gh = gh_below + pr.rdgas * tt * (pl.ln_half_k1 - pl.ln_half_k);
+    if (p_full) p_full[e] = pl.p_full;
+    if (p_half) p_half[e] = pl.p_half_k;
+    if (z_full) z_full[e] = gfull / pr.grav;
+    if (z_half) z_half[e] = gh / pr.grav;
+    gh_below = gh; ln_half_below = pl.ln_half_k;
+  }
+}
+void launch_press_heights(const DevTables& t, const Params& pr, const double* T, const double* ps, const double* phis,
+                          double* p_full, double* p_half, double* z_full, double* z_half, cudaStream_t st) {
+  dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
+  press_heights_kernel<<<grid, 128, 0, st>>>(t, pr, T, ps, phis, p_full, p_half, z_full, z_half);
+}
+
+// small helpers
+__global__ void scale_rows_kernel(DevTables t, double* __restrict__ f, int nlev, int which) {
+  const GeomDev& g = t.g;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
+  if (i >= g.I) return;
+  const double s = (which == 0) ? t.cosm_lat[g.j0 + jl] : t.cos_lat[g.j0 + jl];
+  const size_t plane = (size_t)g.Jloc * g.I;
+  for (int k = 0; k < nlev; ++k) f[(size_t)k * plane + (size_t)jl * g.I + i] *= s;
+}
+void launch_divide_by_cos(const DevTables& t, double* f, int nlev, cudaStream_t st) {
+  dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
+  scale_rows_kernel<<<grid, 128, 0, st>>>(t, f, nlev, 0);
+}
+
+}  // namespace isca

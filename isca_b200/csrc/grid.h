@@ -1,0 +1,43 @@
+// grid.h -- argument bundle of the grid-space column kernels.
+#pragma once
+#include "device.h"
+
+namespace isca {
+
+// device scalar slots
+enum {
+  SC_SUM_PS_PREV = 0, SC_SUM_EN_PREV = 1,           // reductions of grid_step partials
+  SC_SUM_PS_FUT = 2,                                // reduction for the mass fixer
+  SC_SUM_EN_FUT = 3, SC_TMIN = 4, SC_TMAX = 5,      // reductions for the energy fixer / range check
+  SC_MEAN_PS_PREV = 6, SC_MASS_FACTOR = 7, SC_MEAN_EN_PREV = 8, SC_T_CORR = 9, SC_T_FLAG = 10,
+  SC_COUNT = 16
+};
+
+struct GridStepArgs {
+  // state (planes [K][Jloc][I] / [Jloc][I])
+  const double *u_cur, *v_cur, *t_cur, *u_prev, *v_prev, *t_prev, *vor_cur, *div_cur;
+  const double *ps_cur, *ps_prev, *phis;
+  // gradients from the inverse batch
+  const double *dx_t, *dy_t, *dx_lnps, *dy_lnps;
+  // optional externally supplied tendencies (spectral_dynamics API), NULL otherwise
+  const double *dt_u_in, *dt_v_in, *dt_t_in;
+  // outputs (forward batch planes)
+  double *out_A, *out_B, *out_T, *out_phi, *dt_lnps;
+  double *wg_full;          // may be NULL
+  double *part;             // [2][Jloc*I] per-column partials for the global means
+};
+
+void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& a, cudaStream_t st);
+void launch_reduce(const double* part, size_t n, int nq, const int* ops, double* out, cudaStream_t st);
+void launch_colsum_ps(const DevTables& t, const double* ps, double* part, cudaStream_t st);
+void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double* scal, double denom, int owns_m0,
+                       int do_mass, cudaStream_t st);
+void launch_colsum_energy(const DevTables& t, const Params& pr, const double* u, const double* v, const double* T,
+                          const double* ps, double* part, cudaStream_t st);
+void launch_apply_energy(const DevTables& t, const Params& pr, double* T, double2* ts_fut, double* scal, double denom,
+                         int owns_m0, int do_energy, cudaStream_t st);
+void launch_press_heights(const DevTables& t, const Params& pr, const double* T, const double* ps, const double* phis,
+                          double* p_full, double* p_half, double* z_full, double* z_half, cudaStream_t st);
+void launch_divide_by_cos(const DevTables& t, double* f, int nlev, cudaStream_t st);
+
+}  // namespace isca
