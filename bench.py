@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- model-days/sec of the Isca spectral-dynamical-core hot path on B200.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the NumPy oracle (port of the reference algorithm)
+
+A "step" is one model time step (one `atmosphere(Time)` call: Held-Suarez forcing + spectral dynamics)
+on a synthetic Held-Suarez state (cold start + on-device spin-up).  Workload: Held-Suarez dry core
+T170 L40 (lon 512 x lat 256, dt = 150 s), the configuration BASELINE.json's metric is quoted on
+(MiMA physics of configs[3] is not built yet).  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES = {  # lon, lat, M, dt (s) -- SURVEY.md section 8d (dt by CFL scaling from T42's 600 s)
+    "T21": (64, 32, 21, 1200.0), "T42": (128, 64, 42, 600.0), "T85": (256, 128, 85, 300.0),
+    "T170": (512, 256, 170, 150.0), "T341": (1024, 512, 341, 75.0),
+}
+
+
+def hs_namelist(res: str, levels: int):
+    """exp/test_cases/held_suarez/held_suarez_test_case.py namelist (dry: no tracer, water fixer off)."""
+    lon, lat, M, dt = RES[res]
+    return dict(lon_max=lon, lat_max=lat, num_fourier=M, num_spherical=M + 1, num_levels=levels, dt_atmos=dt,
+                damping_order=4, water_correction_limit=200.e2, reference_sea_level_press=1.0e5,
+                valid_range_t=(100., 800.), initial_sphum=0.0, vert_coord_option="uneven_sigma",
+                scale_heights=6.0, exponent=7.5, surf_res=0.5, do_water_correction=False, num_tracers=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work per step (DESIGN.md section "Kernels and rooflines")
+# ---------------------------------------------------------------------------------------------
+def work_model(res: str, K: int):
+    I, J, M, _ = RES[res]
+    T = (M + 1) * (M + 4) // 2                      # retained (m,n) pairs incl. the extra row
+    lev_inv = (2 * K + 2) + (5 * K + 1)             # gradient batch + future-state batch
+    lev_fwd = 4 * K + 1
+    leg_flops = 2.0 * T * J                         # per level, either direction (complex x real MAC = 4 flop, hemispheric fold)
+    four_bytes = 16.0 * (M + 1) * J                 # Fourier intermediate per level
+    grid_bytes = 8.0 * I * J
+    spec_bytes = 16.0 * T
+    w = {
+        "legendre_inv": dict(flops=leg_flops * lev_inv, bytes=(spec_bytes + four_bytes) * lev_inv),
+        "legendre_fwd": dict(flops=leg_flops * lev_fwd, bytes=(spec_bytes + four_bytes) * lev_fwd),
+        "fft_inv": dict(bytes=(four_bytes + grid_bytes) * lev_inv),
+        "fft_fwd": dict(bytes=(four_bytes + grid_bytes) * lev_fwd),
+        # grid column kernel: reads u,v,T (cur, prev), vor, div, dxT, dyT (10 x 3-D), writes A,B,dT,Phi,wg_full (5 x 3-D)
+        "grid_step": dict(bytes=grid_bytes * K * 15),
+        # spectral step: specB (4K+1 levels) in, 3x2 state levels in, 3 state out x2, work arrays, specC out (5K+1)
+        "spectral": dict(bytes=spec_bytes * K * (4 + 6 + 6 + 8 + 5)),
+        # corrections: colsum_energy reads 3 x 3-D, apply_energy r/w 1 x 3-D
+        "corrections": dict(bytes=grid_bytes * K * 5),
+    }
+    return w, dict(T=T, lev_inv=lev_inv, lev_fwd=lev_fwd)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+FP64_TENSOR_PEAK_TFLOPS = 37.2   # measured on this pool: tools/probe_fp64.cu, profiles/r01_probe_fp64.txt (DMMA m8n8k4)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference algorithm), bounded sample
+# ---------------------------------------------------------------------------------------------
+def run_cpu(res, K, steps, warmup, spin=2):
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    cfg = held_suarez_config(res, K, RES[res][3])
+    t0 = time.time()
+    core = SpectralCore(cfg)
+    core.cold_start()
+    t_init = time.time() - t0
+    for _ in range(max(warmup, spin)):
+        core.step()
+    t0 = time.time()
+    for _ in range(steps):
+        core.step()
+    sec = time.time() - t0
+    try:
+        import threadpoolctl
+        nthreads = max([p["num_threads"] for p in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        nthreads = 1
+    return dict(sec_per_step=sec / steps, steps=steps, init_s=t_init, threads=nthreads,
+                value=steps * cfg.dt_atmos / 86400.0 / sec)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--res", default="T170")
+    ap.add_argument("--levels", type=int, default=40)
+    ap.add_argument("--spinup", type=int, default=200, help="on-device spin-up steps before warm-up (non-trivial fields)")
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    res, K = args.res, args.levels
+    I, J, M, dt = RES[res]
+    workload = f"Held-Suarez dry core {res} L{K} (lon {I} x lat {J}, dt={dt:g}s), fp64, synthetic cold start + {args.spinup}-step spin-up"
+    metric, unit = "model_days_per_sec", "model-days/s"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, args.cpu_steps if args.steps > 20 else args.steps))
+        r = run_cpu(res, K, steps, min(args.warmup, 1))
+        line = {
+            "impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "note": "CPU arm = NumPy restatement (oracle port) of the reference algorithm; "
+                       "the Fortran/MPI reference cannot be built here (no Fortran compiler)"},
+            "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port",
+                             "sample": f"{steps} model steps of {res} L{K} after cold start + 2 steps"},
+            "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repo's CUDA arm
+    import torch
+    from isca_b200 import api
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if world > 1:
+        raise SystemExit("multi-GPU sharding of the Fourier transpose is not built yet in this round (DESIGN.md section e)")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+
+    cfg = api.make_config(**hs_namelist(res, K))
+    atm = api.Atmosphere.atmosphere_init(cfg)
+    atm.atmosphere(args.spinup)                      # spin-up (untimed)
+    atm.atmosphere(max(args.warmup, 3))              # warm-up (untimed; also captures the CUDA graphs)
+
+    # ---- device-resident timed region: EXACTLY `steps` steps, CUDA events on the launching stream
+    l0 = atm.get_scalar(api.SC_KERNEL_LAUNCHES)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    atm.atmosphere(args.steps)
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    clocks = sampler.stop()
+    ms_per_step = atm.get_scalar(api.SC_LAST_STEP_MS)
+    launches = int(atm.get_scalar(api.SC_KERNEL_LAUNCHES) - l0)
+    value = dt / 86400.0 / (ms_per_step * 1e-3)
+
+    # ---- per-kernel-group timings (CUDA events inside the library, eager launches)
+    groups = atm.profile_step(20)
+    wm, sizes = work_model(res, K)
+    peaks = measured_peaks()
+
+    def gsum(prefix):
+        return sum(v for k, v in groups.items() if k.startswith(prefix))
+    g_ms = {"legendre_inv": gsum("legendre_inv"), "legendre_fwd": gsum("legendre_fwd"), "fft_inv": gsum("fft_inv"),
+            "fft_fwd": gsum("fft_fwd"), "grid_step": gsum("grid_step"), "spectral": gsum("spec"),
+            "corrections": gsum("corr")}
+    tot = sum(groups.values())
+    dom = max(g_ms, key=g_ms.get)
+    dom_bytes = wm[dom]["bytes"]
+    achieved = dom_bytes / (g_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "share_of_step": g_ms[dom] / tot, "algorithmic_bytes_per_step": dom_bytes, "ms_per_step": g_ms[dom]}
+    leg_ms = g_ms["legendre_inv"] + g_ms["legendre_fwd"]
+    leg_fl = wm["legendre_inv"]["flops"] + wm["legendre_fwd"]["flops"]
+    legendre = {"tflops": leg_fl / (leg_ms * 1e-3) / 1e12, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s (fp64 DMMA)",
+                "frac": leg_fl / (leg_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS, "ms_per_step": leg_ms,
+                "algorithmic_flops_per_step": leg_fl,
+                "peak_source": "measured mma.sync m8n8k4 f64 peak on this pool (profiles/r01_probe_fp64.txt)"}
+    groups_out = {k: round(v, 5) for k, v in groups.items()}
+
+    # ---- end to end through the reference's operator API with HOST buffers:
+    # spectral_dynamics(dt_ug, dt_vg, dt_tg -> psg, ug, vg, tg) every step, pinned host memory,
+    # H2D of the tendencies and D2H of the new state inside the timed region.
+    n3 = (K, J, I)
+    pin = lambda shape: torch.zeros(shape, dtype=torch.float64).pin_memory().numpy()
+    tend = [pin(n3) for _ in range(3)]
+    outs = {"psg": pin((J, I)), "ug": pin(n3), "vg": pin(n3), "tg": pin(n3)}
+    for _ in range(3):
+        atm.spectral_dynamics_into(tend, outs)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(args.e2e_steps):
+        atm.spectral_dynamics_into(tend, outs)
+    torch.cuda.synchronize()
+    e2e_sec = (time.time() - t0) / args.e2e_steps
+    h2d = 3 * 8 * K * J * I
+    d2h = (3 * K + 1) * 8 * J * I
+    e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
+           "api": "isca_b200_spectral_dynamics: host tendencies in, host state out, every step (reference spectral_dynamics argument list)"}
+    # informational: the atmosphere_mod boundary (state resident) with a per-step D2H of the ps diagnostic
+    ps_host = pin((J, I))
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(args.e2e_steps):
+        atm.atmosphere(1)
+        atm.get_field(api.F_PS, out=ps_host)
+    torch.cuda.synchronize()
+    res_sec = (time.time() - t0) / args.e2e_steps
+    e2e_atm = {"value": dt / 86400.0 / res_sec, "unit": unit, "ms_per_step": res_sec * 1e3,
+               "api": "isca_b200_step(1) + isca_b200_get_field(ps) every step (atmosphere_mod boundary, state resident)",
+               "d2h_bytes_per_step": 8 * J * I, "h2d_bytes_per_step": 0}
+
+    tmin, tmax = atm.get_scalar(api.SC_T_MIN), atm.get_scalar(api.SC_T_MAX)
+    atm.atmosphere_end()
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        r = run_cpu(res, K, args.cpu_steps, 1)
+        cpu_baseline = {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port",
+                        "ms_per_step": r["sec_per_step"] * 1e3,
+                        "sample": f"{args.cpu_steps} model steps of {res} L{K} (NumPy oracle, cold start + 2 steps)"}
+
+    working_set_mb = (8.0 * I * J * K * 25 + 16.0 * (M + 1) * J * (5 * K + 1)) / 1e6
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "parallelism": f"dp{world} (latitudes x zonal wavenumbers)",
+                   "steps_per_sec": 1e3 / ms_per_step, "wall_ms_per_step": wall / args.steps * 1e3,
+                   "l2": f"per-step working set ~{working_set_mb:.0f} MB > 126 MB L2: inputs larger than L2, no flush",
+                   "cuda_graph": True, "T_range_K": [tmin, tmax]},
+        "clocks": clocks,
+        "e2e": e2e, "e2e_atmosphere_mod": e2e_atm,
+        "gpu_launches": launches,
+        "roofline": roofline, "legendre_gemm": legendre, "kernel_groups_ms": groups_out,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

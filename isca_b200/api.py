@@ -323,7 +323,7 @@ class Atmosphere:
         return out
 
     def state(self):
-        """Snapshot of the prognostic state in the oracle's naming."""
+        """Snapshot of the prognostic state under the reference variable names."""
         return dict(
             vors=self.get_spectral(S_VOR), divs=self.get_spectral(S_DIV), ts=self.get_spectral(S_T),
             ln_ps=self.get_spectral(S_LNPS),
@@ -374,6 +374,23 @@ class Atmosphere:
         self._ck(self.lib.isca_b200_vor_div_from_uv_grid(self.h, _ptr(ug), _ptr(vg), _ptr(vors), _ptr(divs), nlev),
                  "vor_div_from_uv_grid")
         return vors, divs
+
+    def spectral_dynamics_into(self, tend, outs):
+        """spectral_dynamics with caller-owned (e.g. pinned) host arrays: tend = [dt_ug, dt_vg, dt_tg],
+        outs = dict(psg=, ug=, vg=, tg=); no allocation."""
+        self._ck(self.lib.isca_b200_spectral_dynamics(self.h, None, _ptr(tend[0]), _ptr(tend[1]), _ptr(tend[2]),
+                                                      _ptr(outs.get("psg")), _ptr(outs.get("ug")), _ptr(outs.get("vg")),
+                                                      _ptr(outs.get("tg")), _ptr(outs.get("wg_full")), _ptr(outs.get("p_full"))),
+                 "spectral_dynamics")
+
+    def profile_step(self, n_steps=10):
+        """Average milliseconds per kernel group over n eager steps (CUDA events on the library's stream)."""
+        ms = (C.c_double * 64)()
+        names = C.create_string_buffer(4096)
+        n = self.lib.isca_b200_profile_step(self.h, n_steps, ms, 64, names, 4096)
+        if n < 0:
+            self._ck(1, "profile_step")
+        return dict(zip(names.value.decode().split(";"), [ms[i] for i in range(n)]))
 
     def time_transforms(self, nlev, reps=5):
         ms = (C.c_double * 4)()

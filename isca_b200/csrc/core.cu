@@ -21,6 +21,21 @@ using namespace isca;
 
 static thread_local std::string g_create_error;
 
+// Stream-ordered host<->device copies.  A plain cudaMemcpy from pageable memory may return before
+// the DMA has landed and is not ordered against work on a non-blocking stream, so every copy goes
+// through the library's stream and is followed by a stream synchronize.
+static void h2d_on(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+}
+static void d2h_on(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+}
+static void d2d_on(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+}
+
 namespace {
 
 template <class T>
@@ -31,7 +46,7 @@ struct DBuf {                       // owning device buffer
     if (count) { CK(cudaMalloc(&p, count * sizeof(T))); if (zero) CK(cudaMemset(p, 0, count * sizeof(T))); }
   }
   void ensure(size_t count) { if (count > n) alloc(count); }
-  void upload(const std::vector<T>& h) { alloc(h.size(), false); if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+  void upload(const std::vector<T>& h) { alloc(h.size(), false); if (!h.empty()) { CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); CK(cudaDeviceSynchronize()); } }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DBuf() { release(); }
 };
@@ -79,6 +94,18 @@ struct IscaHandle_t {
   DBuf<int> ops_sum2, ops_sum1, ops_en;
   int LpA = 0, LpB = 0, LpC = 0;
   int keep_tend = 0;
+  // ---- CUDA graphs of the step, one per (current slot, physics) variant of the leapfrog step
+  struct StepGraph { int uses = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  StepGraph graphs[4];
+  bool use_graph = true;
+  // ---- per-kernel-group profiling with CUDA events (isca_b200_profile_step)
+  bool profiling = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  void mark(const char* name) {
+    if (!profiling) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+    marks.emplace_back(name, e);
+  }
   // ---- scratch for the transforms_mod-level API
   DBuf<double2> x_rect, x_spec;
   DBuf<double> x_grid, x_four;
@@ -211,15 +238,20 @@ static void exchange_fourier(H& h, int /*direction*/, int /*Lp*/) {
 // ---------------------------------------------------------------------------------------------
 // generic batched transforms on device data
 // ---------------------------------------------------------------------------------------------
-static void dev_inverse(H& h, const double2* spec, int Lp, const LevDesc* levs, int nlev) {
+static void dev_inverse(H& h, const double2* spec, int Lp, const LevDesc* levs, int nlev, const char* tag = "") {
   launch_legendre_inv(h.dt, spec, h.four.p, Lp, h.st); h.launches++;
+  if (h.profiling) h.mark((std::string("legendre_inv") + tag).c_str());
   exchange_fourier(h, 0, Lp);
   launch_fft_inv(h.dt, h.four.p, levs, nlev, Lp, h.st); h.launches++;
+  if (h.profiling) h.mark((std::string("fft_inv") + tag).c_str());
 }
-static void dev_forward(H& h, const LevDesc* levs, int nlev, double2* spec, int Lp, const unsigned char* trunc) {
+static void dev_forward(H& h, const LevDesc* levs, int nlev, double2* spec, int Lp, const unsigned char* trunc,
+                        const char* tag = "") {
   launch_fft_fwd(h.dt, h.four.p, levs, nlev, Lp, h.st); h.launches++;
+  if (h.profiling) h.mark((std::string("fft_fwd") + tag).c_str());
   exchange_fourier(h, 1, Lp);
   launch_legendre_fwd(h.dt, h.four.p, spec, Lp, trunc, h.st); h.launches++;
+  if (h.profiling) h.mark((std::string("legendre_fwd") + tag).c_str());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,7 +272,8 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   launch_spec_gradient(h.dt, h.ts[cur].p, K, K, h.specA.p, h.LpA, 0, K, st);
   launch_spec_gradient(h.dt, h.lnps[cur].p, 1, 1, h.specA.p, h.LpA, 2 * K, 2 * K + 1, st);
   h.launches += 2;
-  dev_inverse(h, h.specA.p, h.LpA, h.levsA.p, 2 * K + 2);
+  h.mark("spec_gradient");
+  dev_inverse(h, h.specA.p, h.LpA, h.levsA.p, 2 * K + 2, "_grad");
 
   GridStepArgs ga;
   ga.u_cur = h.u[cur].p; ga.v_cur = h.v[cur].p; ga.t_cur = h.T[cur].p;
@@ -253,9 +286,11 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   ga.out_phi = h.gridB.p + (size_t)(3 * K) * pl; ga.dt_lnps = h.gridB.p + (size_t)(4 * K) * pl;
   ga.wg_full = h.wg_full.p; ga.part = h.part.p;
   launch_grid_step(h.dt, pr, ga, st); h.launches++;
+  h.mark("grid_step");
   launch_reduce(h.part.p, pl, 2, h.ops_sum2.p, h.scal.p + SC_SUM_PS_PREV, st); h.launches++;
+  h.mark("corr_reduce_prev");
 
-  dev_forward(h, h.levsB.p, 4 * K + 1, h.specB.p, h.LpB, h.truncB.p);
+  dev_forward(h, h.levsB.p, 4 * K + 1, h.specB.p, h.LpB, h.truncB.p, "_tend");
 
   SpecStepArgs sa;
   sa.specB = h.specB.p; sa.LpB = h.LpB; sa.oT = 0; sa.oA = K; sa.oB = 2 * K; sa.oPhi = 3 * K; sa.oLnps = 4 * K;
@@ -269,8 +304,9 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   sa.keep_tend = h.keep_tend; sa.k_dt_vors = h.k_dt_vors.p; sa.k_dt_divs = h.k_dt_divs.p; sa.k_dt_ts = h.k_dt_ts.p;
   sa.k_dt_lnps = h.k_dt_lnps.p;
   launch_spec_step(h.dt, pr, sa, st); h.launches += (h.cfg.use_implicit ? 4 : 3);
+  h.mark("spec_step");
 
-  dev_inverse(h, h.specC.p, h.LpC, h.levsC[fut].p, 5 * K + 1);
+  dev_inverse(h, h.specC.p, h.LpC, h.levsC[fut].p, 5 * K + 1, "_state");
 
   // compute_corrections (spectral_dynamics.F90:1213-1302)
   launch_colsum_ps(h.dt, h.ps[fut].p, h.part.p, st);
@@ -280,6 +316,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   launch_reduce(h.part.p, pl, 3, h.ops_en.p, h.scal.p + SC_SUM_EN_FUT, st);
   launch_apply_energy(h.dt, pr, h.T[fut].p, h.ts[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_energy_correction, st);
   h.launches += 6;
+  h.mark("corr_mass_energy");
 
   // time-level swap, then complete_robert_filter -> leapfrog_2level_B: a(previous) += rc*a(current)*raw
   h.previous = cur; h.current = fut;
@@ -289,6 +326,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   launch_spec_robert_b(h.ts[cur].p, h.ts[fut].p, h.nspec3(), rc, raw, st);
   launch_spec_robert_b(h.lnps[cur].p, h.lnps[fut].p, (size_t)g.T, rc, raw, st);
   h.launches += 4;
+  h.mark("spec_robert_b");
   h.steps++;
 }
 
@@ -338,22 +376,22 @@ static void cold_start(H& h) {
     if (n >= g.M - m + 2) continue;
     for (int k = K - 3; k < K; ++k) if (k >= 0) sp[(size_t)(g.off[mi] + n) * Lp + k].x = 1.e-7;
   }
-  CK(cudaMemcpy(h.x_spec.p, sp.data(), sp.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  h2d_on(h.st, h.x_spec.p, sp.data(), sp.size() * sizeof(double2));
   // uv_grid_from_vor_div(vors, 0): levels [vor | div | ucos | vcos] needs 4K levels -> reuse specC
   CK(cudaMemsetAsync(h.specC.p, 0, h.specC.n * sizeof(double2), st));
   // copy vor into specC[.., 0..K)
   {
     std::vector<double2> sc((size_t)g.T * h.LpC, make_double2(0, 0));
     for (int p = 0; p < g.T; ++p) for (int k = 0; k < K; ++k) sc[(size_t)p * h.LpC + k] = sp[(size_t)p * Lp + k];
-    CK(cudaMemcpy(h.specC.p, sc.data(), sc.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    h2d_on(h.st, h.specC.p, sc.data(), sc.size() * sizeof(double2));
   }
   // T = initial_temperature, ln ps = log(p0) - phis/(rd*T0)  -> spectral and back (:113-119)
   {
     std::vector<double> tg(h.n3(), c.initial_temperature), phis(pl), lnps(pl);
-    CK(cudaMemcpy(phis.data(), h.phis.p, pl * sizeof(double), cudaMemcpyDeviceToHost));
+    d2h_on(h.st, phis.data(), h.phis.p, pl * sizeof(double));
     for (size_t i = 0; i < pl; ++i) lnps[i] = std::log(c.reference_sea_level_press) - phis[i] / (c.rdgas * c.initial_temperature);
-    CK(cudaMemcpy(h.T[0].p, tg.data(), tg.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h.ps[0].p, lnps.data(), pl * sizeof(double), cudaMemcpyHostToDevice));
+    h2d_on(h.st, h.T[0].p, tg.data(), tg.size() * sizeof(double));
+    h2d_on(h.st, h.ps[0].p, lnps.data(), pl * sizeof(double));
   }
   // forward: [T(K) | lnps(1)] with truncation
   {
@@ -371,11 +409,11 @@ static void cold_start(H& h) {
     // store spectral ts, ln_ps (slot 0)
     std::vector<double2> ht_((size_t)g.T * LpT);
     CK(cudaStreamSynchronize(st));
-    CK(cudaMemcpy(ht_.data(), tmp.p, ht_.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    d2h_on(h.st, ht_.data(), tmp.p, ht_.size() * sizeof(double2));
     std::vector<double2> ts((size_t)g.T * K), ln((size_t)g.T);
     for (int p = 0; p < g.T; ++p) { for (int k = 0; k < K; ++k) ts[(size_t)p * K + k] = ht_[(size_t)p * LpT + k]; ln[p] = ht_[(size_t)p * LpT + K]; }
-    CK(cudaMemcpy(h.ts[0].p, ts.data(), ts.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h.lnps[0].p, ln.data(), ln.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    h2d_on(h.st, h.ts[0].p, ts.data(), ts.size() * sizeof(double2));
+    h2d_on(h.st, h.lnps[0].p, ln.data(), ln.size() * sizeof(double2));
   }
   // u, v from the perturbation vorticity; then vor/div from (u,v); then u,v,vorg,divg from those (:108-123)
   {
@@ -394,21 +432,21 @@ static void cold_start(H& h) {
     dev_inverse(h, h.specC.p, h.LpC, h.levsC[0].p, 4 * K);
     CK(cudaStreamSynchronize(st));
     std::vector<double2> sc((size_t)g.T * h.LpC);
-    CK(cudaMemcpy(sc.data(), h.specC.p, sc.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    d2h_on(h.st, sc.data(), h.specC.p, sc.size() * sizeof(double2));
     std::vector<double2> vo((size_t)g.T * K), di((size_t)g.T * K);
     for (int p = 0; p < g.T; ++p) for (int k = 0; k < K; ++k) { vo[(size_t)p * K + k] = sc[(size_t)p * h.LpC + k]; di[(size_t)p * K + k] = sc[(size_t)p * h.LpC + K + k]; }
-    CK(cudaMemcpy(h.vors[0].p, vo.data(), vo.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h.divs[0].p, di.data(), di.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    h2d_on(h.st, h.vors[0].p, vo.data(), vo.size() * sizeof(double2));
+    h2d_on(h.st, h.divs[0].p, di.data(), di.size() * sizeof(double2));
   }
   // both time levels identical (spectral_dynamics.F90:616-624)
-  CK(cudaMemcpy(h.vors[1].p, h.vors[0].p, h.nspec3() * sizeof(double2), cudaMemcpyDeviceToDevice));
-  CK(cudaMemcpy(h.divs[1].p, h.divs[0].p, h.nspec3() * sizeof(double2), cudaMemcpyDeviceToDevice));
-  CK(cudaMemcpy(h.ts[1].p, h.ts[0].p, h.nspec3() * sizeof(double2), cudaMemcpyDeviceToDevice));
-  CK(cudaMemcpy(h.lnps[1].p, h.lnps[0].p, (size_t)g.T * sizeof(double2), cudaMemcpyDeviceToDevice));
-  CK(cudaMemcpy(h.u[1].p, h.u[0].p, h.n3() * sizeof(double), cudaMemcpyDeviceToDevice));
-  CK(cudaMemcpy(h.v[1].p, h.v[0].p, h.n3() * sizeof(double), cudaMemcpyDeviceToDevice));
-  CK(cudaMemcpy(h.T[1].p, h.T[0].p, h.n3() * sizeof(double), cudaMemcpyDeviceToDevice));
-  CK(cudaMemcpy(h.ps[1].p, h.ps[0].p, pl * sizeof(double), cudaMemcpyDeviceToDevice));
+  d2d_on(h.st, h.vors[1].p, h.vors[0].p, h.nspec3() * sizeof(double2));
+  d2d_on(h.st, h.divs[1].p, h.divs[0].p, h.nspec3() * sizeof(double2));
+  d2d_on(h.st, h.ts[1].p, h.ts[0].p, h.nspec3() * sizeof(double2));
+  d2d_on(h.st, h.lnps[1].p, h.lnps[0].p, (size_t)g.T * sizeof(double2));
+  d2d_on(h.st, h.u[1].p, h.u[0].p, h.n3() * sizeof(double));
+  d2d_on(h.st, h.v[1].p, h.v[0].p, h.n3() * sizeof(double));
+  d2d_on(h.st, h.T[1].p, h.T[0].p, h.n3() * sizeof(double));
+  d2d_on(h.st, h.ps[1].p, h.ps[0].p, pl * sizeof(double));
   h.previous = 0; h.current = 0;
 }
 
@@ -467,6 +505,7 @@ int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* /*
     build_tables(*cfg, h->g, h->ht);
     h->cfg.pk = nullptr; h->cfg.bk = nullptr;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    h->use_graph = (std::getenv("ISCA_B200_NO_GRAPH") == nullptr);
     upload_tables(*h);
     set_params(*h);
     alloc_state(*h);
@@ -484,6 +523,7 @@ int isca_b200_destroy(IscaHandle h) {
   if (!h) return 1;
   cudaStreamSynchronize(h->st);
   for (auto& kv : h->wave_cache) delete kv.second;
+  for (auto& sg : h->graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;
@@ -492,24 +532,24 @@ int isca_b200_destroy(IscaHandle h) {
 int isca_b200_cold_start(IscaHandle h) { API_BEGIN(h) cold_start(*h); CK(cudaStreamSynchronize(h->st)); API_END(h) }
 
 int isca_b200_set_surf_geopotential(IscaHandle h, const double* sg) {
-  API_BEGIN(h) CK(cudaMemcpy(h->phis.p, sg, h->nplane() * sizeof(double), cudaMemcpyHostToDevice)); API_END(h)
+  API_BEGIN(h) h2d_on(h->st, h->phis.p, sg, h->nplane() * sizeof(double)); API_END(h)
 }
 
 int isca_b200_set_grid_state(IscaHandle h, int slot, const double* ug, const double* vg, const double* tg,
                              const double* psg, const double* /*tracers*/) {
   API_BEGIN(h)
   if (slot < 0 || slot > 1) throw std::runtime_error("slot must be 0 or 1");
-  if (ug) CK(cudaMemcpy(h->u[slot].p, ug, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
-  if (vg) CK(cudaMemcpy(h->v[slot].p, vg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
-  if (tg) CK(cudaMemcpy(h->T[slot].p, tg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
-  if (psg) CK(cudaMemcpy(h->ps[slot].p, psg, h->nplane() * sizeof(double), cudaMemcpyHostToDevice));
+  if (ug) h2d_on(h->st, h->u[slot].p, ug, h->n3() * sizeof(double));
+  if (vg) h2d_on(h->st, h->v[slot].p, vg, h->n3() * sizeof(double));
+  if (tg) h2d_on(h->st, h->T[slot].p, tg, h->n3() * sizeof(double));
+  if (psg) h2d_on(h->st, h->ps[slot].p, psg, h->nplane() * sizeof(double));
   API_END(h)
 }
 
 static void set_spec(H& h, DBuf<double2>& dst, const double* src, int nlev) {
   const Geometry& g = h.g;
   h.x_rect.ensure((size_t)nlev * (g.N + 1) * (g.M + 1));
-  CK(cudaMemcpy(h.x_rect.p, src, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), cudaMemcpyHostToDevice));
+  h2d_on(h.st, h.x_rect.p, src, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2));
   launch_pack_spec(h.dt, h.x_rect.p, dst.p, nlev, nlev, 0, h.st);
   CK(cudaStreamSynchronize(h.st));
 }
@@ -519,7 +559,7 @@ static void get_spec(H& h, const double2* src, int Ls, int lev0, double* dst, in
   CK(cudaMemsetAsync(h.x_rect.p, 0, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), h.st));
   launch_unpack_spec(h.dt, src, h.x_rect.p, nlev, Ls, lev0, h.st);
   CK(cudaStreamSynchronize(h.st));
-  CK(cudaMemcpy(dst, h.x_rect.p, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), cudaMemcpyDeviceToHost));
+  d2h_on(h.st, dst, h.x_rect.p, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2));
 }
 
 int isca_b200_set_spectral_state(IscaHandle h, int slot, const double* vors, const double* divs, const double* ts,
@@ -535,8 +575,8 @@ int isca_b200_set_spectral_state(IscaHandle h, int slot, const double* vors, con
 
 int isca_b200_set_vor_div_grid(IscaHandle h, const double* vorg, const double* divg) {
   API_BEGIN(h)
-  if (vorg) CK(cudaMemcpy(h->vorg.p, vorg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
-  if (divg) CK(cudaMemcpy(h->divg.p, divg, h->n3() * sizeof(double), cudaMemcpyHostToDevice));
+  if (vorg) h2d_on(h->st, h->vorg.p, vorg, h->n3() * sizeof(double));
+  if (divg) h2d_on(h->st, h->divg.p, divg, h->n3() * sizeof(double));
   API_END(h)
 }
 
@@ -548,11 +588,39 @@ int isca_b200_set_time_pointers(IscaHandle h, int previous_slot, int current_slo
 }
 int isca_b200_get_time_pointers(IscaHandle h, int* p, int* c) { API_BEGIN(h) *p = h->previous; *c = h->current; API_END(h) }
 
+// One model step, replayed from a captured CUDA graph when possible.  The first (forward) step and
+// the first occurrence of every variant run eagerly (they also perform lazy one-time setup).
+static void step_graphed(H& h, int physics) {
+  const bool first = (h.previous == h.current);
+  if (!h.use_graph || first || h.keep_tend) { step_once(h, physics, nullptr, nullptr, nullptr); return; }
+  H::StepGraph& sg = h.graphs[h.current + 2 * (physics ? 1 : 0)];
+  sg.uses++;
+  if (sg.uses == 1) { step_once(h, physics, nullptr, nullptr, nullptr); return; }
+  if (!sg.exec) {
+    if (h.cfg.use_implicit) ensure_wave_matrix(h, 2 * h.cfg.dt_atmos * h.cfg.alpha_implicit);   // no uploads inside capture
+    const int prev = h.previous, cur = h.current;
+    const long long l0 = h.launches, s0 = h.steps;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(h.st, cudaStreamCaptureModeThreadLocal));
+    try { step_once(h, physics, nullptr, nullptr, nullptr); }
+    catch (...) { cudaStreamEndCapture(h.st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+    CK(cudaStreamEndCapture(h.st, &graph));
+    CK(cudaGraphInstantiate(&sg.exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    sg.launches = h.launches - l0;
+    h.launches = l0; h.steps = s0; h.previous = prev; h.current = cur;   // capture did not execute anything
+  }
+  CK(cudaGraphLaunch(sg.exec, h.st));
+  const int cur = h.current;
+  h.previous = cur; h.current = 1 - cur;
+  h.launches += sg.launches; h.steps++;
+}
+
 static int run_steps(IscaHandle h, int n, int physics) {
   API_BEGIN(h)
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, h->st));
-  for (int i = 0; i < n; ++i) step_once(*h, physics, nullptr, nullptr, nullptr);
+  for (int i = 0; i < n; ++i) step_graphed(*h, physics);
   CK(cudaEventRecord(e1, h->st));
   check_t_flag(*h);
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -604,13 +672,13 @@ int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
   const size_t n3 = h->n3(), pl = h->nplane();
   CK(cudaStreamSynchronize(h->st));
   switch (id) {
-    case ISCA_F_PS: CK(cudaMemcpy(host, h->ps[s].p, pl * sizeof(double), cudaMemcpyDeviceToHost)); break;
-    case ISCA_F_U: CK(cudaMemcpy(host, h->u[s].p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
-    case ISCA_F_V: CK(cudaMemcpy(host, h->v[s].p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
-    case ISCA_F_T: CK(cudaMemcpy(host, h->T[s].p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
-    case ISCA_F_VOR: CK(cudaMemcpy(host, h->vorg.p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
-    case ISCA_F_DIV: CK(cudaMemcpy(host, h->divg.p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
-    case ISCA_F_WG_FULL: CK(cudaMemcpy(host, h->wg_full.p, n3 * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case ISCA_F_PS: d2h_on(h->st, host, h->ps[s].p, pl * sizeof(double)); break;
+    case ISCA_F_U: d2h_on(h->st, host, h->u[s].p, n3 * sizeof(double)); break;
+    case ISCA_F_V: d2h_on(h->st, host, h->v[s].p, n3 * sizeof(double)); break;
+    case ISCA_F_T: d2h_on(h->st, host, h->T[s].p, n3 * sizeof(double)); break;
+    case ISCA_F_VOR: d2h_on(h->st, host, h->vorg.p, n3 * sizeof(double)); break;
+    case ISCA_F_DIV: d2h_on(h->st, host, h->divg.p, n3 * sizeof(double)); break;
+    case ISCA_F_WG_FULL: d2h_on(h->st, host, h->wg_full.p, n3 * sizeof(double)); break;
     case ISCA_F_P_FULL: case ISCA_F_P_HALF: case ISCA_F_Z_FULL: case ISCA_F_Z_HALF: {
       const size_t nh = n3 + pl;
       h->x_grid.ensure(nh);
@@ -621,7 +689,7 @@ int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
       launch_press_heights(h->dt, h->pr, h->T[s].p, h->ps[s].p, h->phis.p, pf, ph, zf, zh, h->st);
       CK(cudaStreamSynchronize(h->st));
       const size_t cnt = (id == ISCA_F_P_HALF || id == ISCA_F_Z_HALF) ? nh : n3;
-      CK(cudaMemcpy(host, h->x_grid.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+      d2h_on(h->st, host, h->x_grid.p, cnt * sizeof(double));
       break;
     }
     default: throw std::runtime_error("unknown field id");
@@ -652,7 +720,7 @@ int isca_b200_get_scalar(IscaHandle h, int id, double* value) {
   API_BEGIN(h)
   double sc[SC_COUNT];
   CK(cudaStreamSynchronize(h->st));
-  CK(cudaMemcpy(sc, h->scal.p, sizeof(sc), cudaMemcpyDeviceToHost));
+  d2h_on(h->st, sc, h->scal.p, sizeof(sc));
   switch (id) {
     case ISCA_SC_MEAN_PS: *value = sc[SC_MEAN_PS_PREV]; break;
     case ISCA_SC_MEAN_ENERGY: *value = sc[SC_MEAN_EN_PREV]; break;
@@ -690,13 +758,13 @@ int isca_b200_spherical_to_grid(IscaHandle h, const double* spec, double* grid, 
   const Geometry& g = h->g;
   x_prepare(*h, nlev, 1);
   const int Lp = round_up(nlev, 16);
-  CK(cudaMemcpy(h->x_rect.p, spec, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2), cudaMemcpyHostToDevice));
+  h2d_on(h->st, h->x_rect.p, spec, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2));
   CK(cudaMemsetAsync(h->x_spec.p, 0, (size_t)g.T * Lp * sizeof(double2), h->st));
   launch_pack_spec(h->dt, h->x_rect.p, h->x_spec.p, nlev, Lp, 0, h->st);
   x_set_levs(*h, nlev, 0, 0);
   dev_inverse(*h, h->x_spec.p, Lp, h->x_levs.p, nlev);
   CK(cudaStreamSynchronize(h->st));
-  CK(cudaMemcpy(grid, h->x_grid.p, (size_t)nlev * h->nplane() * sizeof(double), cudaMemcpyDeviceToHost));
+  d2h_on(h->st, grid, h->x_grid.p, (size_t)nlev * h->nplane() * sizeof(double));
   API_END(h)
 }
 
@@ -704,7 +772,7 @@ int isca_b200_grid_to_spherical(IscaHandle h, const double* grid, double* spec, 
   API_BEGIN(h)
   x_prepare(*h, nlev, 1);
   const int Lp = round_up(nlev, 16);
-  CK(cudaMemcpy(h->x_grid.p, grid, (size_t)nlev * h->nplane() * sizeof(double), cudaMemcpyHostToDevice));
+  h2d_on(h->st, h->x_grid.p, grid, (size_t)nlev * h->nplane() * sizeof(double));
   CK(cudaMemsetAsync(h->x_trunc.p, do_truncation ? 1 : 0, Lp, h->st));
   x_set_levs(*h, nlev, 0, 0);
   dev_forward(*h, h->x_levs.p, nlev, h->x_spec.p, Lp, h->x_trunc.p);
@@ -719,18 +787,18 @@ int isca_b200_uv_grid_from_vor_div(IscaHandle h, const double* vors, const doubl
   const int Lp = round_up(4 * nlev, 16);
   const size_t nr = (size_t)nlev * (g.N + 1) * (g.M + 1);
   CK(cudaMemsetAsync(h->x_spec.p, 0, (size_t)g.T * Lp * sizeof(double2), h->st));
-  CK(cudaMemcpy(h->x_rect.p, vors, nr * sizeof(double2), cudaMemcpyHostToDevice));
+  h2d_on(h->st, h->x_rect.p, vors, nr * sizeof(double2));
   launch_pack_spec(h->dt, h->x_rect.p, h->x_spec.p, nlev, Lp, 0, h->st);
   CK(cudaStreamSynchronize(h->st));
-  CK(cudaMemcpy(h->x_rect.p, divs, nr * sizeof(double2), cudaMemcpyHostToDevice));
+  h2d_on(h->st, h->x_rect.p, divs, nr * sizeof(double2));
   launch_pack_spec(h->dt, h->x_rect.p, h->x_spec.p, nlev, Lp, nlev, h->st);
   launch_spec_ucos_vcos(h->dt, h->x_spec.p, Lp, nlev, 0, nlev, 2 * nlev, 3 * nlev, h->st);
   x_set_levs(*h, 4 * nlev, 2 * nlev, 1);
   dev_inverse(*h, h->x_spec.p, Lp, h->x_levs.p, 4 * nlev);
   CK(cudaStreamSynchronize(h->st));
   const size_t n = (size_t)nlev * h->nplane();
-  CK(cudaMemcpy(ug, h->x_grid.p + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(vg, h->x_grid.p + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+  d2h_on(h->st, ug, h->x_grid.p + 2 * n, n * sizeof(double));
+  d2h_on(h->st, vg, h->x_grid.p + 3 * n, n * sizeof(double));
   API_END(h)
 }
 
@@ -740,8 +808,8 @@ int isca_b200_vor_div_from_uv_grid(IscaHandle h, const double* ug, const double*
   x_prepare(*h, nlev, 2);
   const int Lp = round_up(2 * nlev, 16);
   const size_t n = (size_t)nlev * h->nplane();
-  CK(cudaMemcpy(h->x_grid.p, ug, n * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->x_grid.p + n, vg, n * sizeof(double), cudaMemcpyHostToDevice));
+  h2d_on(h->st, h->x_grid.p, ug, n * sizeof(double));
+  h2d_on(h->st, h->x_grid.p + n, vg, n * sizeof(double));
   launch_divide_by_cos(h->dt, h->x_grid.p, 2 * nlev, h->st);
   CK(cudaMemsetAsync(h->x_trunc.p, 0, Lp, h->st));
   x_set_levs(*h, 2 * nlev, 0, 0);
@@ -771,7 +839,7 @@ int isca_b200_time_transforms(IscaHandle h, int nlev, int reps, double ms_out[4]
       sp[(size_t)p * Lp + k] = make_double2(a * sc, m == 0 ? 0.0 : b * sc);
     }
   }
-  CK(cudaMemcpy(h->x_spec.p, sp.data(), sp.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  h2d_on(h->st, h->x_spec.p, sp.data(), sp.size() * sizeof(double2));
   CK(cudaMemsetAsync(h->x_trunc.p, 1, Lp, h->st));
   x_set_levs(*h, nlev, 0, 0);
   cudaEvent_t ev[5]; for (auto& e : ev) CK(cudaEventCreate(&e));
@@ -795,10 +863,37 @@ int isca_b200_time_transforms(IscaHandle h, int nlev, int reps, double ms_out[4]
   API_END(h)
 }
 
-int isca_b200_profile_step(IscaHandle h, int /*n_steps*/, double* /*ms_out*/, int /*max_groups*/, char* /*names*/, int /*capacity*/) {
+int isca_b200_profile_step(IscaHandle h, int n_steps, double* ms_out, int max_groups, char* names, int capacity) {
   if (!h) return -1;
-  h->err = "profile_step is not implemented yet";
-  return -1;
+  try {
+    std::vector<std::string> order;
+    std::map<std::string, double> acc;
+    for (int i = 0; i < n_steps; ++i) {
+      h->profiling = true; h->marks.clear();
+      h->mark("start");
+      step_once(*h, 1, nullptr, nullptr, nullptr);
+      CK(cudaStreamSynchronize(h->st));
+      h->profiling = false;
+      for (size_t q = 1; q < h->marks.size(); ++q) {
+        float ms = 0; CK(cudaEventElapsedTime(&ms, h->marks[q - 1].second, h->marks[q].second));
+        if (!acc.count(h->marks[q].first)) order.push_back(h->marks[q].first);
+        acc[h->marks[q].first] += ms;
+      }
+      for (auto& m : h->marks) cudaEventDestroy(m.second);
+      h->marks.clear();
+    }
+    check_t_flag(*h);
+    std::string joined;
+    int n = 0;
+    for (auto& nm : order) {
+      if (n >= max_groups) break;
+      ms_out[n++] = acc[nm] / (n_steps > 0 ? n_steps : 1);
+      joined += (joined.empty() ? "" : ";") + nm;
+    }
+    if ((int)joined.size() + 1 > capacity) throw std::runtime_error("names buffer too small");
+    std::memcpy(names, joined.c_str(), joined.size() + 1);
+    return n;
+  } catch (const std::exception& e) { h->profiling = false; h->err = e.what(); return -1; }
 }
 
 }  // extern "C"

@@ -285,29 +285,47 @@ class Transforms:
 
     # ---- Legendre: trans_spherical_to_fourier / trans_fourier_to_spherical
     #      (spherical_fourier.F90:177-261, 264-339)
+    def _tables_m_major(self):
+        if not hasattr(self, "_Pe"):
+            P, Pw = self.tb.legendre, self.tb.legendre_wts           # [jh, n, m]
+            self._Pe = np.ascontiguousarray(P[:, 0::2, :].transpose(2, 0, 1))     # [m, jh, ne]
+            self._Po = np.ascontiguousarray(P[:, 1::2, :].transpose(2, 0, 1))
+            self._Pwe = np.ascontiguousarray(Pw[:, 0::2, :].transpose(2, 1, 0))   # [m, ne, jh]
+            self._Pwo = np.ascontiguousarray(Pw[:, 1::2, :].transpose(2, 1, 0))
+        return self._Pe, self._Po, self._Pwe, self._Pwo
+
     def spherical_to_fourier(self, spec):
-        """spec [..., n, m] -> fourier [..., j, m] (south to north)."""
-        P = self.tb.legendre                    # [jh, n, m]
+        """spec [..., n, m] -> fourier [..., j, m] (south to north).  Per-m matrix products
+        E = P_even S_even, O = P_odd S_odd (spherical_fourier.F90:228-236)."""
+        Pe, Po, _, _ = self._tables_m_major()
         J = self.cfg.lat_max
-        ev = np.einsum("jnm,...nm->...jm", P[:, 0::2, :], spec[..., 0::2, :])
-        od = np.einsum("jnm,...nm->...jm", P[:, 1::2, :], spec[..., 1::2, :])
-        out = np.zeros(spec.shape[:-2] + (J, spec.shape[-1]), dtype=np.complex128)
-        out[..., : J // 2, :] = ev - od                       # south  (:233)
-        out[..., J // 2:, :] = (ev + od)[..., ::-1, :]        # north mirror (:232)
-        return out
+        lead = spec.shape[:-2]
+        Mp1 = spec.shape[-1]
+        X = np.moveaxis(spec, -1, 0).reshape(Mp1, -1, spec.shape[-2])          # [m, L, n]
+        ev = np.matmul(Pe, X[:, :, 0::2].transpose(0, 2, 1))                    # [m, jh, L]
+        od = np.matmul(Po, X[:, :, 1::2].transpose(0, 2, 1))
+        out = np.zeros((Mp1, J, X.shape[1]), dtype=np.complex128)
+        out[:, : J // 2, :] = ev - od                        # south  (:233)
+        out[:, J // 2:, :] = (ev + od)[:, ::-1, :]           # north mirror (:232)
+        return np.moveaxis(out.reshape((Mp1, J) + lead), 0, -1).transpose(
+            tuple(range(1, 1 + len(lead))) + (0, len(lead) + 1)) if lead else out[:, :, 0].T
 
     def fourier_to_spherical(self, four):
-        Pw = self.tb.legendre_wts
+        _, _, Pwe, Pwo = self._tables_m_major()
         J = self.cfg.lat_max
-        south = four[..., : J // 2, :]
-        north = four[..., J // 2:, :][..., ::-1, :]
-        x_even = north + south                  # :311
-        x_odd = north - south                   # :312
         N = self.cfg.num_spherical
-        out = np.zeros(four.shape[:-2] + (N + 1, four.shape[-1]), dtype=np.complex128)
-        out[..., 0::2, :] = np.einsum("jnm,...jm->...nm", Pw[:, 0::2, :], x_even)
-        out[..., 1::2, :] = np.einsum("jnm,...jm->...nm", Pw[:, 1::2, :], x_odd)
-        return out
+        lead = four.shape[:-2]
+        Mp1 = four.shape[-1]
+        F = np.moveaxis(four, -1, 0).reshape(Mp1, -1, J)                        # [m, L, j]
+        south = F[:, :, : J // 2]
+        north = F[:, :, J // 2:][:, :, ::-1]
+        x_even = (north + south).transpose(0, 2, 1)          # :311   [m, jh, L]
+        x_odd = (north - south).transpose(0, 2, 1)           # :312
+        out = np.zeros((Mp1, N + 1, F.shape[1]), dtype=np.complex128)
+        out[:, 0::2, :] = np.matmul(Pwe, x_even)
+        out[:, 1::2, :] = np.matmul(Pwo, x_odd)
+        return np.moveaxis(out.reshape((Mp1, N + 1) + lead), 0, -1).transpose(
+            tuple(range(1, 1 + len(lead))) + (0, len(lead) + 1)) if lead else out[:, :, 0].T
 
     # ---- transforms.F90:379-442 / 462-533
     def spherical_to_grid(self, spec):

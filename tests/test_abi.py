@@ -1,0 +1,85 @@
+"""C-ABI checks that need no GPU: the library builds, loads, exports every symbol declared in
+include/isca_b200.h, the ctypes struct matches the C struct, and the product path fails loudly
+(no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "isca_b200.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(isca_b200_\w+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(lib_built):
+    from isca_b200 import api
+    lib = api.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/isca_b200.h but not exported"
+    assert set(api.EXPORTS) == set(syms)
+
+
+def test_config_struct_layout_matches_c(lib_built, tmp_path):
+    """sizeof/offsets of IscaConfig as seen by a C compiler == the ctypes mirror."""
+    from isca_b200 import api
+    src = tmp_path / "sz.c"
+    fields = [f[0] for f in api.IscaConfigStruct._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(IscaConfig, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "isca_b200.h"\nint main(){printf("%zu\\n", sizeof(IscaConfig));' + body + "return 0;}")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == C.sizeof(api.IscaConfigStruct)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(api.IscaConfigStruct, f).offset == int(off), f
+
+
+def test_default_config_is_reference_namelist(lib_built):
+    from isca_b200 import api
+    c = api.make_config()
+    # spectral_dynamics.F90:152-206 defaults
+    assert (c.lon_max, c.lat_max, c.num_fourier, c.num_spherical, c.num_levels) == (128, 64, 42, 43, 18)
+    assert c.damping_order == 2 and abs(c.damping_coeff - 1.15740741e-4) < 1e-20
+    assert c.robert_coeff == 0.04 and c.alpha_implicit == 0.5 and c.raw_filter_coeff == 1.0
+    assert c.reference_sea_level_press == 101325.0
+    # hs_forcing.F90:78-83
+    assert (c.t_zero, c.t_strat, c.delh, c.delv, c.sigma_b, c.ka, c.ks, c.kf) == (315., 200., 60., 10., 0.7, -40., -4., -1.)
+    with pytest.raises(api.IscaError):
+        api.make_config(not_a_namelist_variable=1)
+    with pytest.raises(api.IscaError):
+        api.make_config(vert_coord_option="nonsense")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback(lib_built):
+    from isca_b200 import api
+    with pytest.raises(api.IscaError) as e:
+        api.Atmosphere(api.make_config())
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The shipped package must never route through the oracle."""
+    pkg = os.path.join(ROOT, "isca_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt, f"{f} mentions the oracle"

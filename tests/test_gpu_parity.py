@@ -1,0 +1,248 @@
+"""GPU parity tests (run on the B200 box): every stage of the CUDA path, called through the C ABI,
+against the CPU oracle on the same seeded inputs, plus size-independent properties at the
+BASELINE.json full sizes (T170 L40) where the oracle is too slow to be the checker.
+
+Tolerances: the north-star asks for per-step spectral tendencies within 1e-10 relative of the fp64
+reference path; transforms are held to 1e-12, developed-state steps to 1e-10 (relative to the field
+maximum: max|a-b| / max|b|)."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_TRANSFORM = 1e-12
+TOL_STEP = 1e-10
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def api(lib_built):
+    from isca_b200 import api as _api
+    return _api
+
+
+def make(api, res, K, dt):
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    cfg = held_suarez_config(res, K, dt)
+    core = SpectralCore(cfg)
+    atm = api.Atmosphere(api.config_from_namelist_object(cfg))
+    return cfg, core, atm
+
+
+def rand_spec(tb, nlev, seed):
+    rng = np.random.default_rng(seed)
+    shape = (nlev,) + tb.triangle_mask.shape
+    s = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * tb.triangle_mask
+    s[:, :, 0] = s[:, :, 0].real
+    return s
+
+
+@pytest.mark.parametrize("res,nlev", [("T21", 1), ("T21", 7), ("T42", 5), ("T85", 40)])
+def test_transforms_match_oracle(api, res, nlev):
+    cfg, core, atm = make(api, res, 5, 600.0)
+    tb, tr = core.tb, core.tr
+    assert rel(atm.get_table(api.TB_SIN_LAT), tb.sin_lat) < 1e-15
+    assert rel(atm.get_table(api.TB_WTS_LAT), tb.wts_lat) < 1e-14
+    s = rand_spec(tb, nlev, 11)
+    g = atm.trans_spherical_to_grid(s)
+    assert rel(g, tr.spherical_to_grid(s)) < TOL_TRANSFORM
+    s2 = atm.trans_grid_to_spherical(g)
+    assert rel(s2, tr.grid_to_spherical(g)) < TOL_TRANSFORM
+    assert rel(s2, s) < TOL_TRANSFORM                                  # round trip (identity 3)
+    tri1 = tb.spherical_wave <= cfg.num_fourier + 1                    # rows the packed layout carries
+    s3 = atm.trans_grid_to_spherical(g, do_truncation=False)
+    assert rel(s3 * tri1, tr.grid_to_spherical(g, do_truncation=False) * tri1) < TOL_TRANSFORM
+    # 2-D overloads
+    g2 = atm.trans_spherical_to_grid(s[0])
+    assert rel(g2, g[0]) < 1e-15
+    v, d = s.copy(), s[::-1].copy()
+    v[:, 0, 0] = 0; d[:, 0, 0] = 0
+    ug, vg = atm.uv_grid_from_vor_div(v, d)
+    uo, vo = tr.uv_grid_from_vor_div(v, d)
+    assert rel(ug, uo) < TOL_TRANSFORM and rel(vg, vo) < TOL_TRANSFORM
+    v2, d2 = atm.vor_div_from_uv_grid(uo, vo)
+    assert rel(v2, v) < 1e-11 and rel(d2, d) < 1e-11                   # operator inverse (identity 5)
+    atm.atmosphere_end()
+
+
+def test_analytic_harmonics_on_gpu(api):
+    cfg, core, atm = make(api, "T42", 3, 600.0)
+    tb = core.tb
+    c = atm.trans_grid_to_spherical(np.full((cfg.lat_max, cfg.lon_max), 2.5))
+    assert abs(c[0, 0] - np.sqrt(2.0) * 2.5) < 1e-13
+    c[0, 0] = 0
+    assert np.abs(c).max() < 1e-13
+    lon = np.arange(cfg.lon_max) * 2 * np.pi / cfg.lon_max
+    g = np.cos(3 * lon)[None, :] * tb.cos_lat[:, None] ** 3
+    s = atm.trans_grid_to_spherical(g)
+    big = np.abs(s) > 1e-12
+    assert big.sum() == 1 and big[0, 3]
+    # solid-body rotation: vorticity 2 U sin(lat)/a, no divergence
+    U = 30.0
+    ug = U * tb.cos_lat[:, None] * np.ones((1, cfg.lon_max))
+    vor, div = atm.vor_div_from_uv_grid(ug[None], 0 * ug[None])
+    vg = atm.trans_spherical_to_grid(vor)[0]
+    assert np.abs(vg - 2 * U * tb.sin_lat[:, None] / cfg.radius).max() < 1e-12 * U / cfg.radius * 10
+    assert np.abs(div).max() < 1e-17
+    atm.atmosphere_end()
+
+
+@pytest.mark.parametrize("res,K,dt", [("T21", 25, 1200.0), ("T42", 18, 600.0)])
+def test_cold_start_matches_oracle(api, res, K, dt):
+    cfg, core, atm = make(api, res, K, dt)
+    core.cold_start()
+    atm.cold_start()
+    got, ref = atm.state(), core.state()
+    for k in ("vors", "divs", "ts", "ln_ps", "ug", "vg", "tg", "psg", "vorg", "p_full", "z_full"):
+        assert rel(got[k], ref[k]) < 1e-12, k
+    atm.atmosphere_end()
+
+
+def upload(atm, core):
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+
+
+@pytest.mark.parametrize("res,K,dt,spin", [("T21", 25, 1200.0, 300), ("T42", 18, 900.0, 60)])
+def test_steps_from_developed_state_match_oracle(api, res, K, dt, spin):
+    """Per-step parity from identical, well-conditioned states (restart path): first a leapfrog step,
+    then two more; spectral tendencies and the full state are compared after every step."""
+    cfg, core, atm = make(api, res, K, dt)
+    core.cold_start()
+    for _ in range(spin):
+        core.step()
+    upload(atm, core)
+    atm.enable_tendency_capture()
+    for i in range(3):
+        core.step(keep=True)
+        atm.atmosphere(1)
+        got, ref = atm.state(), core.state()
+        for k, sid in (("dt_vors", api.S_DT_VOR), ("dt_divs", api.S_DT_DIV), ("dt_ts", api.S_DT_T), ("dt_ln_ps", api.S_DT_LNPS)):
+            assert rel(atm.get_spectral(sid), core.last[k]) < TOL_STEP, (i, k)
+        for k in ("vors", "divs", "ts", "ln_ps", "vors_prev", "divs_prev", "ts_prev", "ln_ps_prev",
+                  "ug", "vg", "tg", "psg", "vorg", "divg", "wg_full", "p_full", "z_full"):
+            assert rel(got[k], ref[k]) < TOL_STEP, (i, k)
+    assert atm.get_time_pointers() == (core.previous, core.current)
+    atm.atmosphere_end()
+
+
+def test_first_step_is_forward_euler_and_graph_replay_is_exact(api):
+    """previous == current on the first step (delta_t = dt, atmosphere.F90:292); later steps replay a
+    CUDA graph: eager and graphed runs must agree bit for bit."""
+    cfg, core, atm = make(api, "T21", 10, 1200.0)
+    core.cold_start(); atm.cold_start()
+    core.step(); atm.atmosphere(1)
+    assert rel(atm.get_spectral(api.S_VOR), core.state()["vors"]) < 1e-9     # near-rest state: ill-conditioned, loose
+    atm.atmosphere(9)
+    a = atm.state()
+    os.environ["ISCA_B200_NO_GRAPH"] = "1"
+    try:
+        atm2 = api.Atmosphere(api.config_from_namelist_object(cfg))
+        atm2.cold_start(); atm2.atmosphere(10)
+        b = atm2.state()
+    finally:
+        del os.environ["ISCA_B200_NO_GRAPH"]
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    atm.atmosphere_end(); atm2.atmosphere_end()
+
+
+def test_spectral_dynamics_host_api_matches_dynamics_only_step(api):
+    """isca_b200_spectral_dynamics(host tendencies -> host state) == oracle spectral_dynamics with the same tendencies."""
+    cfg, core, atm = make(api, "T21", 12, 1200.0)
+    core.cold_start()
+    for _ in range(50):
+        core.step()
+    upload(atm, core)
+    rng = np.random.default_rng(3)
+    K, J, I = cfg.num_levels, cfg.lat_max, cfg.lon_max
+    dtu, dtv, dtt = (1e-5 * rng.standard_normal((K, J, I)) for _ in range(3))
+    out = atm.spectral_dynamics(dtu, dtv, dtt, want=("psg", "ug", "vg", "tg", "wg_full"))
+    fut = 1 - core.current
+    delta_t = 2 * cfg.dt_atmos
+    core.spectral_dynamics(fut, np.zeros((J, I)), dtu, dtv, dtt, [], delta_t)
+    ref = core.state()
+    for k in ("psg", "ug", "vg", "tg", "wg_full"):
+        assert rel(out[k], ref[k]) < TOL_STEP, k
+    atm.atmosphere_end()
+
+
+def test_golden_fixture_t21(api):
+    """Committed fixture (tests/golden/make_golden.py): Held-Suarez T21 L10 after 40 steps from cold start."""
+    g = np.load(os.path.join(GOLDEN, "hs_t21l10_40steps.npz"))
+    from oracle.isca_oracle import held_suarez_config
+    cfg = held_suarez_config("T21", 10, 1200.0)
+    atm = api.Atmosphere.atmosphere_init(api.config_from_namelist_object(cfg))
+    atm.atmosphere(40)
+    st = atm.state()
+    # 40 steps from a near-rest state: round-off differences grow slowly; 1e-8 is the trajectory tolerance here
+    assert rel(st["ln_ps"], g["ln_ps"]) < 1e-8
+    assert rel(st["ts"], g["ts"]) < 1e-8
+    assert rel(st["psg"], g["psg"]) < 1e-10
+    assert rel(st["tg"], g["tg"]) < 1e-10
+    atm.atmosphere_end()
+
+
+def test_full_size_properties_t170(api):
+    """BASELINE size (T170 L40): size-independent properties instead of the (slow) oracle."""
+    cfg, core_unused, atm = None, None, None
+    from oracle.isca_oracle import held_suarez_config, Tables
+    cfg = held_suarez_config("T170", 40, 150.0)
+    atm = api.Atmosphere.atmosphere_init(api.config_from_namelist_object(cfg))
+    w = atm.get_table(api.TB_WTS_LAT)
+    assert abs(w.sum() - 2.0) < 1e-13
+    # transform round trip on a random band-limited field
+    rng = np.random.default_rng(5)
+    M, N = cfg.num_fourier, cfg.num_spherical
+    m = np.arange(M + 1)[None, :]; n = np.arange(N + 1)[:, None]
+    mask = (m + n <= M).astype(float)
+    s = (rng.standard_normal((4, N + 1, M + 1)) + 1j * rng.standard_normal((4, N + 1, M + 1))) * mask / (1.0 + m + n) ** 2
+    s[:, :, 0] = s[:, :, 0].real
+    g = atm.trans_spherical_to_grid(s)
+    assert rel(atm.trans_grid_to_spherical(g), s) < 1e-12
+    # linearity
+    g2 = atm.trans_spherical_to_grid(2.0 * s + s[::-1])
+    assert rel(g2, 2.0 * g + g[::-1]) < 1e-13
+    # mass conservation and boundedness over 50 steps; spectral/grid temperature stay consistent
+    ps0 = atm.get_field(api.F_PS)
+    m0 = float((w[:, None] * ps0).sum() / (2.0 * cfg.lon_max))
+    atm.atmosphere(50)
+    ps1 = atm.get_field(api.F_PS)
+    m1 = float((w[:, None] * ps1).sum() / (2.0 * cfg.lon_max))
+    assert abs(m1 - m0) / m0 < 1e-13
+    T = atm.get_field(api.F_T)
+    assert np.isfinite(T).all() and 200.0 < T.min() and T.max() < 330.0
+    Tg = atm.trans_spherical_to_grid(atm.get_spectral(api.S_T))
+    assert rel(Tg, T) < 1e-12
+    u, v = atm.uv_grid_from_vor_div(atm.get_spectral(api.S_VOR), atm.get_spectral(api.S_DIV))
+    assert rel(u, atm.get_field(api.F_U)) < 1e-10
+    atm.atmosphere_end()
+
+
+def test_unsupported_namelist_values_fail_loudly(api):
+    with pytest.raises(api.IscaError):
+        api.Atmosphere(api.make_config(raw_filter_coeff=0.5))
+    with pytest.raises(api.IscaError):
+        api.Atmosphere(api.make_config(num_tracers=1))
+    with pytest.raises(api.IscaError):
+        api.Atmosphere(api.make_config(lon_max=96))          # not a power of two
+    with pytest.raises(api.IscaError):
+        api.Atmosphere(api.make_config(do_water_correction=True))   # dry model (spectral_dynamics.F90:1264)
+
+
+def test_temperature_range_check_is_fatal(api):
+    cfg = api.make_config(lon_max=64, lat_max=32, num_fourier=21, num_spherical=22, num_levels=8, dt_atmos=1200.0,
+                          do_water_correction=False, valid_range_t=(270.0, 500.0))
+    atm = api.Atmosphere.atmosphere_init(cfg)              # initial T = 264 K < 270 K
+    with pytest.raises(api.IscaError) as e:
+        atm.atmosphere(1)
+    assert "temperatures out of valid range" in str(e.value)
+    atm.atmosphere_end()
