@@ -90,7 +90,7 @@ struct IscaHandle_t {
   DBuf<double> ext_tend;     // [3K+1] planes for externally supplied tendencies
   DBuf<LevDesc> levsA, levsB, levsC[2];
   DBuf<unsigned char> truncB;
-  DBuf<double> part, scal;
+  DBuf<double> part, scal, red_tmp;
   DBuf<int> ops_sum2, ops_sum1, ops_en;
   int LpA = 0, LpB = 0, LpC = 0;
   int keep_tend = 0;
@@ -184,7 +184,7 @@ static void alloc_state(H& h) {
   h.four.alloc((size_t)(g.M + 1) * g.J / g.P * 2 * Lmax * (g.P > 1 ? 1 : 1));
   h.gradA.alloc((size_t)(2 * K + 2) * h.nplane());
   h.gridB.alloc((size_t)(4 * K + 1) * h.nplane());
-  h.part.alloc(3 * h.nplane()); h.scal.alloc(SC_COUNT);
+  h.part.alloc(3 * h.nplane()); h.scal.alloc(SC_COUNT); h.red_tmp.alloc(4 * 128);
   h.ops_sum2.upload({0, 0}); h.ops_sum1.upload({0}); h.ops_en.upload({0, 1, 2});
   const size_t pl = h.nplane();
   // level descriptors
@@ -287,7 +287,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   ga.wg_full = h.wg_full.p; ga.part = h.part.p;
   launch_grid_step(h.dt, pr, ga, st); h.launches++;
   h.mark("grid_step");
-  launch_reduce(h.part.p, pl, 2, h.ops_sum2.p, h.scal.p + SC_SUM_PS_PREV, st); h.launches++;
+  launch_reduce(h.part.p, pl, 2, h.ops_sum2.p, h.scal.p + SC_SUM_PS_PREV, h.red_tmp.p, st); h.launches += 2;
   h.mark("corr_reduce_prev");
 
   dev_forward(h, h.levsB.p, 4 * K + 1, h.specB.p, h.LpB, h.truncB.p, "_tend");
@@ -310,12 +310,12 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
 
   // compute_corrections (spectral_dynamics.F90:1213-1302)
   launch_colsum_ps(h.dt, h.ps[fut].p, h.part.p, st);
-  launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_SUM_PS_FUT, st);
+  launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_SUM_PS_FUT, h.red_tmp.p, st);
   launch_apply_mass(h.dt, h.ps[fut].p, h.lnps[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_mass_correction, st);
   launch_colsum_energy(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.part.p, st);
-  launch_reduce(h.part.p, pl, 3, h.ops_en.p, h.scal.p + SC_SUM_EN_FUT, st);
+  launch_reduce(h.part.p, pl, 3, h.ops_en.p, h.scal.p + SC_SUM_EN_FUT, h.red_tmp.p, st);
   launch_apply_energy(h.dt, pr, h.T[fut].p, h.ts[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_energy_correction, st);
-  h.launches += 6;
+  h.launches += 8;
   h.mark("corr_mass_energy");
 
   // time-level swap, then complete_robert_filter -> leapfrog_2level_B: a(previous) += rc*a(current)*raw

@@ -4,10 +4,14 @@
 // Temperton FFT99 passes behind them (shared/fft/fft99.F90).  Convention (fft99.F90:195-209):
 //   forward  c_k = (1/N) sum_j x_j exp(-2 pi i j k / N)      (only k <= num_fourier kept, transforms.F90:509)
 //   inverse  x_j = sum_{k=0}^{N-1} c_k exp(+2 pi i j k / N)  with Hermitian completion, c_k = 0 for k > num_fourier
-// N = lon_max is a power of two.  A real transform of length N is done as a complex transform of
-// length H = N/2 (radix-4 Stockham autosort passes + one radix-2 pass when log2(H) is odd) plus the
-// split/merge step.  One CTA handles LT lines = LT consecutive batch levels at one latitude, so the
-// Fourier-side accesses ([m][lat][level] complex) are contiguous runs of LT*16 bytes.
+// N = lon_max is a power of two.  A real transform of length N is a complex transform of length H = N/2
+// plus a split/merge step.  The complex transform is a Stockham autosort FFT with two or three
+// high-radix passes (radix 16/8/4 butterflies held entirely in registers):
+//     pass 1 reads its inputs straight from global memory (forward) or from the staged Fourier tile
+//     (inverse), the last pass writes straight to global memory (inverse) -- the data crosses shared
+//     memory once per extra pass instead of once per radix-2/4 stage.
+// One CTA handles LT = 8 lines = 8 consecutive batch levels at one latitude, so that the Fourier-side
+// accesses ([m][lat][level] complex) are contiguous 128-byte runs.
 #include "device.h"
 
 namespace isca {
@@ -24,117 +28,176 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 
-// twiddle exp(sign * 2 pi i q / I): table holds exp(-2 pi i q / I), q < I
+// twiddle exp(SIGN * 2 pi i q / I): table holds exp(-2 pi i q / I), q < I
 template <int SIGN>
 __device__ __forceinline__ double2 tw(const double2* __restrict__ table, int q) {
-  double2 w = table[q];
+  double2 w = __ldg(table + q);
   if (SIGN > 0) w.y = -w.y;
   return w;
 }
 
-// Complex FFT of length H on one line held in shared memory, executed by H/4 threads (lt = thread
-// index within the line).  Stockham autosort: ping-pong between a and b.  Returns pointer to result.
-// All threads of the CTA must call this (it contains __syncthreads()).
-template <int SIGN>
-__device__ double2* cfft_line(double2* a, double2* b, int H, int I, int lt, const double2* __restrict__ table) {
-  const int Q = H >> 2;                      // threads per line
-  int Ns = 1;
-  // radix-4 passes while 4*Ns <= H
-  while (Ns * 4 <= H) {
-    __syncthreads();
-    {
-      const int j = lt;                      // j < H/4
-      const int k = j & (Ns - 1);            // j % Ns
-      const int stride_tw = I / (Ns * 4);    // twiddle step: exp(-+2 pi i k t / (4 Ns))
-      double2 v0 = a[j], v1 = a[j + Q], v2 = a[j + 2 * Q], v3 = a[j + 3 * Q];
-      if (Ns > 1) {
-        v1 = cmul(v1, tw<SIGN>(table, k * stride_tw));
-        v2 = cmul(v2, tw<SIGN>(table, 2 * k * stride_tw));
-        v3 = cmul(v3, tw<SIGN>(table, 3 * k * stride_tw));
-      }
-      // radix-4 butterfly
-      double2 s0 = cadd(v0, v2), d0 = csub(v0, v2), s1 = cadd(v1, v3), d1 = csub(v1, v3);
-      // multiply d1 by -i (forward) or +i (inverse)
-      double2 d1r = (SIGN < 0) ? make_double2(d1.y, -d1.x) : make_double2(-d1.y, d1.x);
-      const int j0 = ((j - k) << 2) + k;     // (j / Ns) * Ns * 4 + k
-      b[j0] = cadd(s0, s1);
-      b[j0 + Ns] = cadd(d0, d1r);
-      b[j0 + 2 * Ns] = csub(s0, s1);
-      b[j0 + 3 * Ns] = csub(d0, d1r);
-    }
-    double2* tswap = a; a = b; b = tswap;
-    Ns <<= 2;
-  }
-  if (Ns < H) {                              // one radix-2 pass: Ns * 2 == H
-    __syncthreads();
-    const int half = H >> 1;
-    for (int j = lt; j < half; j += Q) {
-      const int k = j & (Ns - 1);
-      const int stride_tw = I / (Ns * 2);
-      double2 v0 = a[j], v1 = a[j + half];
-      v1 = cmul(v1, tw<SIGN>(table, k * stride_tw));
-      const int j0 = ((j - k) << 1) + k;
-      b[j0] = cadd(v0, v1);
-      b[j0 + Ns] = csub(v0, v1);
-    }
-    double2* tswap = a; a = b; b = tswap;
-  }
-  __syncthreads();
-  return a;
+// ---- in-register DFT of length N in {2,4,8,16}, natural order in and out ----------------------
+// exp(-2 pi i k / 16), k < 8
+__device__ __forceinline__ double2 w16(int k) {
+  constexpr double c[8] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173,
+                           0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128675613};
+  constexpr double s[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128675613,
+                           1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
+  return make_double2(c[k], -s[k]);
 }
+
+template <int N, int SIGN>
+struct Dft {
+  static __device__ __forceinline__ void run(double2 (&v)[N]) {
+    double2 e[N / 2], o[N / 2];
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+    Dft<N / 2, SIGN>::run(e);
+    Dft<N / 2, SIGN>::run(o);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      double2 w = w16(k * (16 / N));
+      if (SIGN > 0) w.y = -w.y;
+      double2 t;
+      if (k == 0) t = o[0];
+      else if (4 * k == N) t = (SIGN < 0) ? make_double2(o[k].y, -o[k].x) : make_double2(-o[k].y, o[k].x);
+      else t = cmul(o[k], w);
+      v[k] = cadd(e[k], t);
+      v[k + N / 2] = csub(e[k], t);
+    }
+  }
+};
+template <int SIGN>
+struct Dft<2, SIGN> {
+  static __device__ __forceinline__ void run(double2 (&v)[2]) {
+    double2 a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+  }
+};
+template <int SIGN>
+struct Dft<1, SIGN> {
+  static __device__ __forceinline__ void run(double2 (&)[1]) {}
+};
 
 constexpr int FFT_LT = 8;     // lines (levels) per CTA
 
+template <int H, int R1>
+struct FftShape {
+  static constexpr int PADP = R1;                                   // one pad element every R1 (first-pass write stride)
+  static constexpr int LS = ((H + H / R1 + 1) | 1);                 // odd line stride (in double2): conflict-free across lines
+  __device__ static __forceinline__ int pad(int i) { return i + i / PADP; }
+};
+
+// One Stockham pass of radix R on a line in shared memory: src (padded) -> dst (padded).
+//   Ns = product of the radices of the earlier passes.
+template <int H, int R, int R1, int SIGN, int Q>
+__device__ __forceinline__ void pass_smem(const double2* __restrict__ src, double2* __restrict__ dst, int Ns, int I, int lt,
+                                          const double2* __restrict__ table) {
+  typedef FftShape<H, R1> S;
+  const int stride_tw = I / (Ns * R);
+#pragma unroll 1
+  for (int j = lt; j < H / R; j += Q) {
+    const int k = j & (Ns - 1);
+    double2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = src[S::pad(j + r * (H / R))];
+#pragma unroll
+    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw<SIGN>(table, k * r * stride_tw));
+    Dft<R, SIGN>::run(v);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[S::pad(j0 + r * Ns)] = v[r];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// inverse: Fourier (layout B) -> grid planes.   grid = (ceil(nlev/LT), Jloc), block = LT * H/4
+// inverse: Fourier (layout B) -> grid planes.   grid = (ceil(nlev/LT), Jloc), block = LT * Q
 // ---------------------------------------------------------------------------------------------
-__global__ void fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __restrict__ levs,
-                               int nlev, int Lp) {
+template <int H, int R1, int R2, int R3, int Q>
+__global__ void __launch_bounds__(FFT_LT * Q)
+fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp) {
+  typedef FftShape<H, R1> S;
+  constexpr int I = 2 * H;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   const GeomDev& g = t.g;
-  const int I = g.I, H = I >> 1, Q = H >> 2, C = 2 * Lp;
-  double2* bufA = reinterpret_cast<double2*>(fft_smem);             // [LT][H + 1]  (X[0..H])
-  double2* bufB = bufA + FFT_LT * (H + 1);                          // [LT][H]
+  const int C = 2 * Lp;
+  double2* bufX = reinterpret_cast<double2*>(fft_smem);             // [LT][LS]  staged X[0..H]
+  double2* bufA = bufX + FFT_LT * S::LS;                            // [LT][LS]
   const int lev0 = blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
-  const int nthreads = blockDim.x;
+  constexpr int NT = FFT_LT * Q;
 
-  // 1. load X[m][lev] (m <= M) -- zero elsewhere (transforms.F90:424)
-  for (int idx = tid; idx < FFT_LT * (H + 1); idx += nthreads) {
-    int k = idx / FFT_LT, l = idx - k * FFT_LT;
+  // 1. stage X[m][lev] (m <= M), zero elsewhere (transforms.F90:424); unpadded index k <= H
+  for (int idx = tid; idx < FFT_LT * (H + 1); idx += NT) {
+    const int k = idx / FFT_LT, l = idx - k * FFT_LT;
     double2 v = make_double2(0.0, 0.0);
     if (k <= g.M && lev0 + l < nlev)
       v = *reinterpret_cast<const double2*>(four + fourB_index(g, k, jl, C) + 2 * (lev0 + l));
-    bufA[l * (H + 1) + k] = v;
+    bufX[l * S::LS + k] = v;
   }
   __syncthreads();
-  // 2. merge: Z[k] = (X[k] + conj X[H-k]) + i w^{-k} (X[k] - conj X[H-k]),  k < H
   const int line = tid / Q, lt = tid - line * Q;
-  {
-    double2* X = bufA + line * (H + 1);
-    double2* Z = bufB + line * H;
-    for (int k = lt; k < H; k += Q) {
-      double2 xk = X[k], xc = cconj(X[H - k]);
-      if (k == 0) { xk.y = 0.0; xc = make_double2(0.0, 0.0); xc = cconj(X[H]); }
-      double2 e = cadd(xk, xc), o = csub(xk, xc);
-      double2 wo = cmul(o, tw<+1>(t.twiddle, k));
-      Z[k] = make_double2(e.x - wo.y, e.y + wo.x);       // e + i*wo
-    }
-  }
-  // 3. complex inverse FFT of length H
-  double2* res = cfft_line<+1>(bufB + line * H, bufA + line * (H + 1), H, I, lt, t.twiddle);
-  // 4. store: x[2n] = Re z[n], x[2n+1] = Im z[n]
+  const double2* X = bufX + line * S::LS;
+  double2* A = bufA + line * S::LS;
+  double2* B = bufX + line * S::LS;
   const int lev = lev0 + line;
-  if (lev < nlev) {
-    const LevDesc d = levs[lev];
+
+  // 2. pass 1 (radix R1, Ns = 1): inputs are the merged spectrum
+  //    Z[k] = (X[k] + conj X[H-k]) + i w^{-k} (X[k] - conj X[H-k]),  k < H
+#pragma unroll 1
+  for (int j = lt; j < H / R1; j += Q) {
+    double2 v[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      const int k = j + r * (H / R1);
+      double2 xk = X[k];
+      const double2 xc = cconj(X[H - k]);
+      if (k == 0) xk.y = 0.0;
+      const double2 e = cadd(xk, xc), o = csub(xk, xc);
+      const double2 wo = cmul(o, tw<+1>(t.twiddle, k));
+      v[r] = make_double2(e.x - wo.y, e.y + wo.x);                   // e + i*wo
+    }
+    Dft<R1, +1>::run(v);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) A[S::pad(j * R1 + r)] = v[r];
+  }
+  __syncthreads();                       // also: every thread is done reading X before B (= bufX) is overwritten
+  const double2* last_src = A;
+  int Ns = R1;
+  if (R3 > 1) {
+    pass_smem<H, R2, R1, +1, Q>(A, B, Ns, I, lt, t.twiddle);
+    __syncthreads();
+    last_src = B;
+    Ns *= R2;
+  }
+  // 3. last pass: smem -> registers -> global (x[2n] = Re z[n], x[2n+1] = Im z[n])
+  constexpr int RL = (R3 > 1) ? R3 : R2;
+  {
+    const int stride_tw = I / (Ns * RL);
+    LevDesc d; d.ptr = nullptr; d.op = 0;
+    if (lev < nlev) d = levs[lev];
     double2* out = reinterpret_cast<double2*>(d.ptr + (size_t)jl * I);
     const double sc = (d.op == 1) ? t.cosm_lat[g.j0 + jl] : 1.0;
-    for (int n = lt; n < H; n += Q) {
-      double2 z = res[n];
-      if (d.op == 2) { z.x = exp(z.x); z.y = exp(z.y); }
-      else if (d.op == 1) { z.x *= sc; z.y *= sc; }
-      out[n] = z;
+#pragma unroll 1
+    for (int j = lt; j < H / RL; j += Q) {
+      const int k = j & (Ns - 1);
+      double2 v[RL];
+#pragma unroll
+      for (int r = 0; r < RL; ++r) v[r] = last_src[S::pad(j + r * (H / RL))];
+#pragma unroll
+      for (int r = 1; r < RL; ++r) v[r] = cmul(v[r], tw<+1>(t.twiddle, k * r * stride_tw));
+      Dft<RL, +1>::run(v);
+      if (lev < nlev) {
+        // Ns * RL == H  ->  j0 = j, outputs at j + r * Ns
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          double2 z = v[r];
+          if (d.op == 2) { z.x = exp(z.x); z.y = exp(z.y); }
+          else if (d.op == 1) { z.x *= sc; z.y *= sc; }
+          out[j + r * Ns] = z;
+        }
+      }
     }
   }
 }
@@ -142,79 +205,107 @@ __global__ void fft_inv_kernel(DevTables t, const double* __restrict__ four, con
 // ---------------------------------------------------------------------------------------------
 // forward: grid planes -> Fourier (layout B)
 // ---------------------------------------------------------------------------------------------
-__global__ void fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict__ levs,
-                               int nlev, int Lp) {
+template <int H, int R1, int R2, int R3, int Q>
+__global__ void __launch_bounds__(FFT_LT * Q)
+fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp) {
+  typedef FftShape<H, R1> S;
+  constexpr int I = 2 * H;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   const GeomDev& g = t.g;
-  const int I = g.I, H = I >> 1, Q = H >> 2, C = 2 * Lp;
-  double2* bufA = reinterpret_cast<double2*>(fft_smem);             // [LT][H + 1]
-  double2* bufB = bufA + FFT_LT * (H + 1);                          // [LT][H]
+  const int C = 2 * Lp;
+  double2* buf0 = reinterpret_cast<double2*>(fft_smem);             // [LT][LS]
+  double2* buf1 = buf0 + FFT_LT * S::LS;                            // [LT][LS]
   const int lev0 = blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
-  const int nthreads = blockDim.x;
+  constexpr int NT = FFT_LT * Q;
   const int line = tid / Q, lt = tid - line * Q;
   const int lev = lev0 + line;
+  double2* A = buf0 + line * S::LS;
+  double2* B = buf1 + line * S::LS;
 
-  // 1. load z[n] = x[2n] + i x[2n+1]
+  // 1. pass 1 (radix R1, Ns = 1) straight from global: z[n] = x[2n] + i x[2n+1]
   {
-    double2* Z = bufB + line * H;
-    if (lev < nlev) {
-      const LevDesc d = levs[lev];
-      const double2* in = reinterpret_cast<const double2*>(d.ptr + (size_t)jl * I);
-      for (int n = lt; n < H; n += Q) Z[n] = in[n];
-    } else {
-      for (int n = lt; n < H; n += Q) Z[n] = make_double2(0.0, 0.0);
-    }
-  }
-  // 2. complex forward FFT
-  double2* res = cfft_line<-1>(bufB + line * H, bufA + line * (H + 1), H, I, lt, t.twiddle);
-  // res is either bufA-line or bufB-line; split needs Z[k] and Z[H-k] -> write X into the other buffer
-  double2* other = (res == bufB + line * H) ? (bufA + line * (H + 1)) : (bufB + line * H);
-  {
-    const double inv = 1.0 / (double)I;
-    for (int k = lt; k <= g.M; k += Q) {
-      double2 zk = res[k];
-      double2 zc = cconj(res[(k == 0) ? 0 : (H - k)]);
-      double2 e = cadd(zk, zc), o = csub(zk, zc);
-      double2 wo = cmul(o, tw<-1>(t.twiddle, k));
-      // X[k] = 0.5*(e) - 0.5*i*wo
-      other[k] = make_double2(0.5 * (e.x + wo.y) * inv, 0.5 * (e.y - wo.x) * inv);
+    const double2* in = nullptr;
+    if (lev < nlev) in = reinterpret_cast<const double2*>(levs[lev].ptr + (size_t)jl * I);
+#pragma unroll 1
+    for (int j = lt; j < H / R1; j += Q) {
+      double2 v[R1];
+#pragma unroll
+      for (int r = 0; r < R1; ++r) v[r] = in ? in[j + r * (H / R1)] : make_double2(0.0, 0.0);
+      Dft<R1, -1>::run(v);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) A[S::pad(j * R1 + r)] = v[r];
     }
   }
   __syncthreads();
-  // 3. store X[m][lev], m <= M: LT complex contiguous per m
-  for (int idx = tid; idx < FFT_LT * (g.M + 1); idx += nthreads) {
-    int k = idx / FFT_LT, l = idx - k * FFT_LT;
-    if (lev0 + l < nlev) {
-      double2* src_line = ((res == bufB + line * H) ? bufA : bufB);
-      // all lines use the same ping-pong parity, so `other` of line l is:
-      double2* ol = (res == bufB + line * H) ? (bufA + l * (H + 1)) : (bufB + l * H);
-      (void)src_line;
-      *reinterpret_cast<double2*>(four + fourB_index(g, k, jl, C) + 2 * (lev0 + l)) = ol[k];
-    }
+  int Ns = R1;
+  pass_smem<H, R2, R1, -1, Q>(A, B, Ns, I, lt, t.twiddle);
+  __syncthreads();
+  const double2* Zbase = buf1;
+  if (R3 > 1) {
+    Ns *= R2;
+    pass_smem<H, (R3 > 1 ? R3 : 2), R1, -1, Q>(B, A, Ns, I, lt, t.twiddle);
+    __syncthreads();
+    Zbase = buf0;
+  }
+  // 2. split + store: X[k] = 0.5 (Z[k] + conj Z[H-k]) - 0.5 i w^k (Z[k] - conj Z[H-k]), scaled by 1/I, k <= M;
+  //    threads ordered (level fastest) so that every m writes LT complex = 128 contiguous bytes
+  const double inv = 1.0 / (double)I;
+  for (int idx = tid; idx < FFT_LT * (g.M + 1); idx += NT) {
+    const int k = idx / FFT_LT, l = idx - k * FFT_LT;
+    if (lev0 + l >= nlev) continue;
+    const double2* Z = Zbase + l * S::LS;
+    const double2 zk = Z[S::pad(k)];
+    const double2 zc = cconj(Z[S::pad((k == 0) ? 0 : (H - k))]);
+    const double2 e = cadd(zk, zc), o = csub(zk, zc);
+    const double2 wo = cmul(o, tw<-1>(t.twiddle, k));
+    const double2 x = make_double2(0.5 * (e.x + wo.y) * inv, 0.5 * (e.y - wo.x) * inv);
+    *reinterpret_cast<double2*>(four + fourB_index(g, k, jl, C) + 2 * (lev0 + l)) = x;
   }
 }
 
-static size_t fft_smem_bytes(int I) { int H = I / 2; return sizeof(double2) * FFT_LT * (2 * H + 1); }
+template <int H, int R1, int R2, int R3, int Q>
+static void launch_inv_shape(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
+  typedef FftShape<H, R1> S;
+  const size_t smem = sizeof(double2) * 2 * FFT_LT * S::LS;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(fft_inv_kernel<H, R1, R2, R3, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  dim3 grid((nlev + FFT_LT - 1) / FFT_LT, t.g.Jloc);
+  fft_inv_kernel<H, R1, R2, R3, Q><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+}
+template <int H, int R1, int R2, int R3, int Q>
+static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
+  typedef FftShape<H, R1> S;
+  const size_t smem = sizeof(double2) * 2 * FFT_LT * S::LS;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  dim3 grid((nlev + FFT_LT - 1) / FFT_LT, t.g.Jloc);
+  fft_fwd_kernel<H, R1, R2, R3, Q><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+}
 
+// radix plans: H = I/2 = R1*R2*R3, Q = H / max radix threads per line
 void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
-  const GeomDev& g = t.g;
-  const int H = g.I / 2, Q = H / 4;
-  size_t smem = fft_smem_bytes(g.I);
-  static size_t attr = 0;
-  if (smem > attr) { cudaFuncSetAttribute(fft_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-  dim3 grid((nlev + FFT_LT - 1) / FFT_LT, g.Jloc);
-  fft_inv_kernel<<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+  switch (t.g.I) {
+    case 1024: launch_inv_shape<512, 8, 8, 8, 64>(t, four, levs, nlev, Lp, st); break;
+    case 512:  launch_inv_shape<256, 16, 16, 1, 16>(t, four, levs, nlev, Lp, st); break;
+    case 256:  launch_inv_shape<128, 8, 16, 1, 8>(t, four, levs, nlev, Lp, st); break;
+    case 128:  launch_inv_shape<64, 8, 8, 1, 8>(t, four, levs, nlev, Lp, st); break;
+    case 64:   launch_inv_shape<32, 4, 8, 1, 4>(t, four, levs, nlev, Lp, st); break;
+    case 32:   launch_inv_shape<16, 4, 4, 1, 4>(t, four, levs, nlev, Lp, st); break;
+    default: break;   // rejected in build_geometry
+  }
 }
 void launch_fft_fwd(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
-  const GeomDev& g = t.g;
-  const int H = g.I / 2, Q = H / 4;
-  size_t smem = fft_smem_bytes(g.I);
-  static size_t attr = 0;
-  if (smem > attr) { cudaFuncSetAttribute(fft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-  dim3 grid((nlev + FFT_LT - 1) / FFT_LT, g.Jloc);
-  fft_fwd_kernel<<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+  switch (t.g.I) {
+    case 1024: launch_fwd_shape<512, 8, 8, 8, 64>(t, four, levs, nlev, Lp, st); break;
+    case 512:  launch_fwd_shape<256, 16, 16, 1, 16>(t, four, levs, nlev, Lp, st); break;
+    case 256:  launch_fwd_shape<128, 8, 16, 1, 8>(t, four, levs, nlev, Lp, st); break;
+    case 128:  launch_fwd_shape<64, 8, 8, 1, 8>(t, four, levs, nlev, Lp, st); break;
+    case 64:   launch_fwd_shape<32, 4, 8, 1, 4>(t, four, levs, nlev, Lp, st); break;
+    case 32:   launch_fwd_shape<16, 4, 4, 1, 4>(t, four, levs, nlev, Lp, st); break;
+    default: break;
+  }
 }
 
 }  // namespace isca

@@ -35,16 +35,29 @@ __device__ __forceinline__ void press_level(const DevTables& t, const Params& pr
   o.p_full = exp(o.ln_full);
 }
 
-__global__ void __launch_bounds__(128)
+// Column kernel, k-split: one warp = 32 consecutive longitudes x one chunk of CH levels; KW = 4 warps
+// (chunks) per column group.  The vertical recurrences (cumulative mass divergence top-down,
+// hydrostatic integral bottom-up, energy integral) are done per chunk in registers and stitched
+// through shared memory, which quadruples the available parallelism of a 131 072-column grid and
+// shortens every dependent chain by 4.
+constexpr int GS_KW = 4;
+
+template <int CH>
+__global__ void __launch_bounds__(32 * GS_KW)
 grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const GeomDev& g = t.g;
   const int I = g.I, K = g.K;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   const int jl = blockIdx.y;
-  if (i >= I) return;
   const int j = g.j0 + jl;
-  const size_t col = (size_t)jl * I + i;
+  const bool live = (i < I);
+  const size_t col = (size_t)jl * I + (live ? i : 0);
   const size_t plane = (size_t)g.Jloc * I;
+  __shared__ double s_tot[GS_KW][32], s_gh[GS_KW][32], s_en[GS_KW][32];
+
+  const int k_lo = w * CH;
+  const int k_hi = (k_lo + CH < K) ? (k_lo + CH) : K;          // chunk = [k_lo, k_hi), may be empty
 
   const double ps_c = a.ps_cur[col], ps_p = a.ps_prev[col];
   const double cosm = t.cosm_lat[j];
@@ -52,21 +65,29 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const double dx_psg = (ps_c * a.dx_lnps[col]) * cosm;
   const double dy_psg = (ps_c * a.dy_lnps[col]) * cosm;
 
-  // ---- pass 1 (top-down): cumulative mass divergence  (four_in_one :1073-1083)
-  double cum[ISCA_KMAX + 1];
+  // ---- pass 1 (top-down within the chunk): cumulative mass divergence (four_in_one :1073-1083)
+  double cum[CH + 1];
   cum[0] = 0.0;
-  {
-    double dmean_tot = 0.0;
-    for (int k = 0; k < K; ++k) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int k = k_lo + c;
+    double dmean = 0.0;
+    if (k < k_hi) {
       const size_t e = (size_t)k * plane + col;
       const double dp = t.dpk[k] + t.dbk[k] * ps_c;
-      const double dmean = a.div_cur[e] * dp + t.dbk[k] * (a.u_cur[e] * dx_psg + a.v_cur[e] * dy_psg);
-      dmean_tot = dmean_tot + dmean;
-      cum[k + 1] = dmean_tot;
+      dmean = a.div_cur[e] * dp + t.dbk[k] * (a.u_cur[e] * dx_psg + a.v_cur[e] * dy_psg);
     }
+    cum[c + 1] = cum[c] + dmean;
   }
-  const double dmean_total = cum[K];
-  a.dt_lnps[col] = (0.0 - dmean_total) / ps_c;       // dt_psg = dt_psg - dmean_tot ; dt_ln_psg = dt_psg/psg
+  s_tot[w][lane] = cum[CH];
+  __syncthreads();
+  double cum_off = 0.0, dmean_total = 0.0;
+#pragma unroll
+  for (int q = 0; q < GS_KW; ++q) {
+    if (q == w) cum_off = dmean_total;
+    dmean_total = dmean_total + s_tot[q][lane];
+  }
+  if (w == 0 && live) a.dt_lnps[col] = (0.0 - dmean_total) / ps_c;   // dt_psg = dt_psg - dmean_tot ; dt_ln_psg = dt_psg/psg
 
   // Held-Suarez latitude constants (newtonian_damping :527-545)
   const double lat = t.rad_lat[j];
@@ -82,16 +103,25 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const double rps = 1. / ps_hs;
   const double fcor = t.coriolis[j];
   const double delta_t = pr.delta_t;
+  const double ln_p00 = log(pr.P00);
 
-  // ---- pass 2 (bottom-up)
-  double gh_below = a.phis[col];                     // geopot_half(K+1) = surf_geopotential
-  double ln_half_below = log(t.pk[K] + t.bk[K] * ps_c);
+  // ---- pass 2 (bottom-up within the chunk)
+  double phi[CH];
+  double gh_local = 0.0;                              // geopot_half relative to the chunk's bottom interface
   double energy_int = 0.0;
-  // rolling values for the centred vertical advection (need k-1, k, k+1 of u, v, T at `cur`)
-  double u_dn = 0.0, v_dn = 0.0, T_dn = 0.0;         // level k+1
-  double u_k = a.u_cur[(size_t)(K - 1) * plane + col], v_k = a.v_cur[(size_t)(K - 1) * plane + col],
-         T_k = a.t_cur[(size_t)(K - 1) * plane + col];
-  for (int k = K - 1; k >= 0; --k) {
+  double ln_half_below = 0.0;
+  double u_dn = 0.0, v_dn = 0.0, T_dn = 0.0, u_k = 0.0, v_k = 0.0, T_k = 0.0;
+  if (k_hi > k_lo) {
+    ln_half_below = log(t.pk[k_hi] + t.bk[k_hi] * ps_c);
+    const size_t e = (size_t)(k_hi - 1) * plane + col;
+    u_k = a.u_cur[e]; v_k = a.v_cur[e]; T_k = a.t_cur[e];
+    if (k_hi < K) { u_dn = a.u_cur[e + plane]; v_dn = a.v_cur[e + plane]; T_dn = a.t_cur[e + plane]; }
+  }
+#pragma unroll
+  for (int c = CH - 1; c >= 0; --c) {
+    const int k = k_lo + c;
+    phi[c] = 0.0;
+    if (k >= k_hi) continue;
     const size_t e = (size_t)k * plane + col;
     double u_up = 0.0, v_up = 0.0, T_up = 0.0;       // level k-1
     if (k > 0) { u_up = a.u_cur[e - plane]; v_up = a.v_cur[e - plane]; T_up = a.t_cur[e - plane]; }
@@ -111,9 +141,10 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
         dt_T = dt_T + ttnd;
       }
       dt_u = dt_u + utnd; dt_v = dt_v + vtnd;
-      const double p_norm = pl.p_full / pr.P00;
-      const double the = t_star - pr.delv * cos_lat_2 * log(p_norm);
-      double teq = the * pow(p_norm, pr.kappa);
+      // p_norm = p_full/P00; log(p_norm) = ln_p_full - log(P00); p_norm**kappa = exp(kappa*log(p_norm))
+      const double ln_pn = pl.ln_full - ln_p00;
+      const double the = t_star - pr.delv * cos_lat_2 * ln_pn;
+      double teq = the * exp(pr.kappa * ln_pn);
       teq = fmax(teq, tstr);
       double tdamp = pr.tka;
       if (in_bl) { const double tfactr = tcoeff * (sigma - pr.sigma_b); tdamp = pr.tka + cos_lat_4 * tfactr; }
@@ -141,24 +172,23 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
     const double x3 = x1 * dy_psg;
     dt_u = dt_u - pr.rdgas * Tv * x2;
     dt_v = dt_v - pr.rdgas * Tv * x3;
-    const double dmean_tot = cum[k];
+    const double cum_k = cum_off + cum[c], cum_k1 = cum_off + cum[c + 1];
     const double dmean = a.div_cur[e] * dp + t.dbk[k] * (u_k * dx_psg + v_k * dy_psg);
-    const double x4 = (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv;
+    const double x4 = (cum_k * dlog_3 + dmean * dlog_1) * dp_inv;
     const double x5 = x4 - u_k * x2 - v_k * x3;
     dt_T = dt_T - pr.kappa * Tv * x5;
-    if (a.wg_full) a.wg_full[e] = -x5 * pl.p_full;
+    if (a.wg_full && live) a.wg_full[e] = -x5 * pl.p_full;
     // wg at the two interfaces of level k (:1102-1108)
-    double w_top = (k == 0) ? 0.0 : (-cum[k] + dmean_total * t.bk[k]);
-    double w_bot = (k == K - 1) ? 0.0 : (-cum[k + 1] + dmean_total * t.bk[k + 1]);
+    const double w_top = (k == 0) ? 0.0 : (-cum_k + dmean_total * t.bk[k]);
+    const double w_bot = (k == K - 1) ? 0.0 : (-cum_k1 + dmean_total * t.bk[k + 1]);
 
-    // ---------------- compute_geopotential
-    const double gfull = gh_below + pr.rdgas * T_k * (pl.ln_half_k1 - pl.ln_full);
-    if (!(k == 0 && pr.pk0_zero)) gh_below = gh_below + pr.rdgas * T_k * (pl.ln_half_k1 - pl.ln_half_k);
+    // ---------------- compute_geopotential (relative to the chunk's bottom interface)
+    const double gfull = gh_local + pr.rdgas * T_k * (pl.ln_half_k1 - pl.ln_full);
+    if (!(k == 0 && pr.pk0_zero)) gh_local = gh_local + pr.rdgas * T_k * (pl.ln_half_k1 - pl.ln_half_k);
 
     // ---------------- vert_advection, second_centered, advective form, time_level = current
     {
       const double dz = pl.p_half_k1 - pl.p_half_k;  // dp = p_half(k+1) - p_half(k)
-      // flux(k) = w(k)*0.5*(r(k)+r(k-1)) (interfaces ks+1..ke); flux(ks) = w(ks)*r(ks); flux(ke+1) = w(ke+1)*r(ke)
       const double fu_t = (k == 0) ? w_top * u_k : w_top * (0.5 * (u_k + u_up));
       const double fu_b = (k == K - 1) ? w_bot * u_k : w_bot * (0.5 * (u_dn + u_k));
       dt_u = dt_u + (-(fu_b - fu_t - u_k * (w_bot - w_top)) / dz);
@@ -177,54 +207,94 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
     dt_v = dt_v - absv * u_k;
 
     // ---------------- outputs for the forward transforms
-    a.out_A[e] = dt_u * cosm;                          // vor_div_from_uv_grid: divide_by_cos(u_grid)
-    a.out_B[e] = dt_v * cosm;
-    a.out_T[e] = dt_T;
-    a.out_phi[e] = gfull + .5 * (u_k * u_k + v_k * v_k);
+    if (live) {
+      a.out_A[e] = dt_u * cosm;                        // vor_div_from_uv_grid: divide_by_cos(u_grid)
+      a.out_B[e] = dt_v * cosm;
+      a.out_T[e] = dt_T;
+    }
+    phi[c] = gfull + .5 * (u_k * u_k + v_k * v_k);
 
     ln_half_below = pl.ln_half_k;
     u_dn = u_k; v_dn = v_k; T_dn = T_k;
     u_k = u_up; v_k = v_up; T_k = T_up;
   }
-  const double w = t.wts_lat[j];
-  a.part[0 * plane + col] = w * ps_p;                  // area_weighted_global_mean(psg(previous))
-  a.part[1 * plane + col] = w * energy_int;            // mass_weighted_global_integral(energy, psg(previous))
+  s_gh[w][lane] = gh_local;
+  s_en[w][lane] = energy_int;
+  __syncthreads();
+  // geopotential at the chunk's bottom interface: surf_geopotential + contributions of the chunks below
+  double gh_off = a.phis[col];
+#pragma unroll
+  for (int q = GS_KW - 1; q >= 0; --q) if (q > w) gh_off = gh_off + s_gh[q][lane];
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = k_lo + c;
+      if (k < k_hi) a.out_phi[(size_t)k * plane + col] = gh_off + phi[c];
+    }
+    if (w == 0) {
+      double en = 0.0;
+#pragma unroll
+      for (int q = GS_KW - 1; q >= 0; --q) en = en + s_en[q][lane];
+      const double wt = t.wts_lat[j];
+      a.part[0 * plane + col] = wt * ps_p;             // area_weighted_global_mean(psg(previous))
+      a.part[1 * plane + col] = wt * en;               // mass_weighted_global_integral(energy, psg(previous))
+    }
+  }
 }
 
 void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& a, cudaStream_t st) {
-  dim3 block(128), grid((t.g.I + 127) / 128, t.g.Jloc);
-  grid_step_kernel<<<grid, block, 0, st>>>(t, pr, a);
+  dim3 block(32 * GS_KW), grid((t.g.I + 31) / 32, t.g.Jloc);
+  const int ch = (t.g.K + GS_KW - 1) / GS_KW;
+  if (ch <= 4) grid_step_kernel<4><<<grid, block, 0, st>>>(t, pr, a);
+  else if (ch <= 7) grid_step_kernel<7><<<grid, block, 0, st>>>(t, pr, a);
+  else if (ch <= 10) grid_step_kernel<10><<<grid, block, 0, st>>>(t, pr, a);
+  else if (ch <= 15) grid_step_kernel<15><<<grid, block, 0, st>>>(t, pr, a);
+  else grid_step_kernel<24><<<grid, block, 0, st>>>(t, pr, a);
 }
 
 // ---------------------------------------------------------------------------------------------
 // deterministic reduction of nq per-column arrays: out[q] = sum / min / max of part[q][0..n)
 // One CTA, fixed summation tree -> bitwise reproducible run to run.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-reduce_kernel(const double* __restrict__ part, size_t n, int nq, const int* __restrict__ ops, double* __restrict__ out) {
-  __shared__ double sh[1024];
-  for (int q = 0; q < nq; ++q) {
-    const int op = ops[q];
-    double acc = (op == 0) ? 0.0 : ((op == 1) ? 1.0e300 : -1.0e300);
-    for (size_t i = threadIdx.x; i < n; i += 1024) {
-      const double v = part[(size_t)q * n + i];
-      acc = (op == 0) ? acc + v : ((op == 1) ? fmin(acc, v) : fmax(acc, v));
-    }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
-      if (threadIdx.x < s) {
-        const double x = sh[threadIdx.x], y = sh[threadIdx.x + s];
-        sh[threadIdx.x] = (op == 0) ? x + y : ((op == 1) ? fmin(x, y) : fmax(x, y));
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[q] = sh[0];
+// Stage 1: RED_NB CTAs, each reduces a fixed contiguous slice in a fixed order; stage 2: one CTA
+// combines the RED_NB partials.  Fixed slices + fixed trees -> bitwise reproducible run to run.
+constexpr int RED_NB = 128;
+__device__ __forceinline__ double red_op(int op, double x, double y) {
+  return (op == 0) ? x + y : ((op == 1) ? fmin(x, y) : fmax(x, y));
+}
+__device__ __forceinline__ double red_init(int op) { return (op == 0) ? 0.0 : ((op == 1) ? 1.0e300 : -1.0e300); }
+
+__global__ void __launch_bounds__(256)
+reduce_stage1_kernel(const double* __restrict__ part, size_t n, const int* __restrict__ ops, double* __restrict__ tmp) {
+  __shared__ double sh[256];
+  const int q = blockIdx.y, op = ops[q];
+  const size_t per = (n + RED_NB - 1) / RED_NB;
+  const size_t lo = (size_t)blockIdx.x * per, hi = (lo + per < n) ? lo + per : n;
+  double acc = red_init(op);
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) acc = red_op(op, acc, part[(size_t)q * n + i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = red_op(op, sh[threadIdx.x], sh[threadIdx.x + s]);
     __syncthreads();
   }
+  if (threadIdx.x == 0) tmp[q * RED_NB + blockIdx.x] = sh[0];
 }
-void launch_reduce(const double* part, size_t n, int nq, const int* ops, double* out, cudaStream_t st) {
-  reduce_kernel<<<1, 1024, 0, st>>>(part, n, nq, ops, out);
+__global__ void __launch_bounds__(RED_NB)
+reduce_stage2_kernel(const double* __restrict__ tmp, const int* __restrict__ ops, double* __restrict__ out) {
+  __shared__ double sh[RED_NB];
+  const int q = blockIdx.x, op = ops[q];
+  sh[threadIdx.x] = tmp[q * RED_NB + threadIdx.x];
+  __syncthreads();
+  for (int s = RED_NB / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = red_op(op, sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[q] = sh[0];
+}
+void launch_reduce(const double* part, size_t n, int nq, const int* ops, double* out, double* tmp, cudaStream_t st) {
+  reduce_stage1_kernel<<<dim3(RED_NB, nq), 256, 0, st>>>(part, n, ops, tmp);
+  reduce_stage2_kernel<<<nq, RED_NB, 0, st>>>(tmp, ops, out);
 }
 
 // ---------------------------------------------------------------------------------------------

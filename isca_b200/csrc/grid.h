@@ -28,7 +28,7 @@ struct GridStepArgs {
 };
 
 void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& a, cudaStream_t st);
-void launch_reduce(const double* part, size_t n, int nq, const int* ops, double* out, cudaStream_t st);
+void launch_reduce(const double* part, size_t n, int nq, const int* ops, double* out, double* tmp, cudaStream_t st);  // tmp: [nq*128]
 void launch_colsum_ps(const DevTables& t, const double* ps, double* part, cudaStream_t st);
 void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double* scal, double denom, int owns_m0,
                        int do_mass, cudaStream_t st);

@@ -21,7 +21,7 @@ void build_geometry(const IscaConfig& c, int rank, int nranks, Geometry& g) {
   if (g.J % 2) throw std::runtime_error("lat_max must be even");
   if (g.J % nranks) throw std::runtime_error("lat_max must be divisible by the number of ranks (spec_mpp.F90:69-75)");
   if (g.I < 2 * g.M + 1 && g.I / 2 < g.M) throw std::runtime_error("lon_max too small for num_fourier");
-  if ((g.I & (g.I - 1)) != 0 || g.I < 16 || g.I > 1024) throw std::runtime_error("lon_max must be a power of two in [16, 1024]");
+  if ((g.I & (g.I - 1)) != 0 || g.I < 32 || g.I > 1024) throw std::runtime_error("lon_max must be a power of two in [32, 1024]");
   if (g.K > ISCA_KMAX) throw std::runtime_error("num_levels exceeds ISCA_KMAX");
   g.Jloc = g.J / nranks; g.j0 = rank * g.Jloc;
   g.owner.assign(g.M + 1, 0);

@@ -98,8 +98,11 @@ def test_cold_start_matches_oracle(api, res, K, dt):
     core.cold_start()
     atm.cold_start()
     got, ref = atm.state(), core.state()
-    for k in ("vors", "divs", "ts", "ln_ps", "ug", "vg", "tg", "psg", "vorg", "p_full", "z_full"):
+    for k in ("vors", "ts", "ln_ps", "ug", "vg", "tg", "psg", "vorg", "p_full", "z_full"):
         assert rel(got[k], ref[k]) < 1e-12, k
+    # the initial divergence is round-off of a non-divergent flow: compare on the scale of the vorticity
+    assert np.abs(got["divs"] - ref["divs"]).max() < 1e-12 * np.abs(ref["vors"]).max()
+    assert np.abs(got["divg"] - ref["divg"]).max() < 1e-12 * np.abs(ref["vorg"]).max()
     atm.atmosphere_end()
 
 
