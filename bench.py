@@ -194,16 +194,37 @@ def main():
     # ------------------------------------------------------------------ this repo's CUDA arm
     import torch
     from isca_b200 import api
-    if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
-    if world > 1:
-        raise SystemExit("multi-GPU sharding of the Fourier transpose is not built yet in this round (DESIGN.md section e)")
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [api.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    J_glob = J
+    J = J // world                                   # this rank's latitude block
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     cfg = api.make_config(**hs_namelist(res, K))
-    atm = api.Atmosphere.atmosphere_init(cfg)
+    atm = api.Atmosphere(cfg, rank=rank, nranks=world, nccl_unique_id=uid)
+    atm.cold_start()
     atm.atmosphere(args.spinup)                      # spin-up (untimed)
     atm.atmosphere(max(args.warmup, 3))              # warm-up (untimed; also captures the CUDA graphs)
 
@@ -211,19 +232,23 @@ def main():
     l0 = atm.get_scalar(api.SC_KERNEL_LAUNCHES)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.time()
     atm.atmosphere(args.steps)
-    torch.cuda.synchronize()
-    wall = time.time() - t0
+    barrier()
+    wall = max_over_ranks(time.time() - t0)
     clocks = sampler.stop()
-    ms_per_step = atm.get_scalar(api.SC_LAST_STEP_MS)
-    launches = int(atm.get_scalar(api.SC_KERNEL_LAUNCHES) - l0)
+    ms_per_step = max_over_ranks(atm.get_scalar(api.SC_LAST_STEP_MS))      # CUDA events on the launching stream, max over ranks
+    launches = int(atm.get_scalar(api.SC_KERNEL_LAUNCHES) - l0) * world
     value = dt / 86400.0 / (ms_per_step * 1e-3)
 
     # ---- per-kernel-group timings (CUDA events inside the library, eager launches)
     groups = atm.profile_step(20)
     wm, sizes = work_model(res, K)
+    if world > 1:                                    # per-rank share of the algorithmic work
+        for v in wm.values():
+            for kk in v:
+                v[kk] = v[kk] / world
     peaks = measured_peaks()
 
     def gsum(prefix):
@@ -231,6 +256,7 @@ def main():
     g_ms = {"legendre_inv": gsum("legendre_inv"), "legendre_fwd": gsum("legendre_fwd"), "fft_inv": gsum("fft_inv"),
             "fft_fwd": gsum("fft_fwd"), "grid_step": gsum("grid_step"), "spectral": gsum("spec"),
             "corrections": gsum("corr")}
+    exch_ms = gsum("exchange")
     tot = sum(groups.values())
     dom = max(g_ms, key=g_ms.get)
     dom_bytes = wm[dom]["bytes"]
@@ -255,35 +281,41 @@ def main():
     outs = {"psg": pin((J, I)), "ug": pin(n3), "vg": pin(n3), "tg": pin(n3)}
     for _ in range(3):
         atm.spectral_dynamics_into(tend, outs)
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.time()
     for _ in range(args.e2e_steps):
         atm.spectral_dynamics_into(tend, outs)
-    torch.cuda.synchronize()
-    e2e_sec = (time.time() - t0) / args.e2e_steps
-    h2d = 3 * 8 * K * J * I
-    d2h = (3 * K + 1) * 8 * J * I
+    barrier()
+    e2e_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
+    h2d = 3 * 8 * K * J_glob * I                     # whole job, all ranks
+    d2h = (3 * K + 1) * 8 * J_glob * I
     e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
            "api": "isca_b200_spectral_dynamics: host tendencies in, host state out, every step (reference spectral_dynamics argument list)"}
     # informational: the atmosphere_mod boundary (state resident) with a per-step D2H of the ps diagnostic
     ps_host = pin((J, I))
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.time()
     for _ in range(args.e2e_steps):
         atm.atmosphere(1)
         atm.get_field(api.F_PS, out=ps_host)
-    torch.cuda.synchronize()
-    res_sec = (time.time() - t0) / args.e2e_steps
+    barrier()
+    res_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
     e2e_atm = {"value": dt / 86400.0 / res_sec, "unit": unit, "ms_per_step": res_sec * 1e3,
                "api": "isca_b200_step(1) + isca_b200_get_field(ps) every step (atmosphere_mod boundary, state resident)",
-               "d2h_bytes_per_step": 8 * J * I, "h2d_bytes_per_step": 0}
+               "d2h_bytes_per_step": 8 * J_glob * I, "h2d_bytes_per_step": 0}
 
     tmin, tmax = atm.get_scalar(api.SC_T_MIN), atm.get_scalar(api.SC_T_MAX)
     atm.atmosphere_end()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    J = J_glob
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         r = run_cpu(res, K, args.cpu_steps, 1)
         cpu_baseline = {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port",
                         "ms_per_step": r["sec_per_step"] * 1e3,
@@ -301,7 +333,7 @@ def main():
         "clocks": clocks,
         "e2e": e2e, "e2e_atmosphere_mod": e2e_atm,
         "gpu_launches": launches,
-        "roofline": roofline, "legendre_gemm": legendre, "kernel_groups_ms": groups_out,
+        "roofline": roofline, "legendre_gemm": legendre, "kernel_groups_ms": groups_out, "exchange_ms_per_step": exch_ms,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

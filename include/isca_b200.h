@@ -107,6 +107,14 @@ const char* isca_b200_last_error(IscaHandle h);   /* h may be NULL (create error
 /* bytes of an ncclUniqueId written to out (rank 0 calls this, the host runtime broadcasts) */
 int isca_b200_nccl_unique_id(void* out128);
 
+/* The decomposition the library uses for (rank, nranks): the rank's contiguous latitude block
+ * (grid domain of tools/spec_mpp.F90:61-65) and its zonal wavenumbers (spectral domain; dealt in snake
+ * order instead of spec_mpp.F90:77-80's contiguous blocks, to balance the triangle).  m_list has room for
+ * num_fourier+1 entries; owner/pos have num_fourier+1 entries (pos = row of m in the lat-owner-side
+ * Fourier buffer).  Needs no GPU. */
+int isca_b200_decomposition(const IscaConfig* cfg, int rank, int nranks, int* lat_start, int* lat_count,
+                            int* num_m, int* m_list, int* owner, int* pos);
+
 /* cold start: spectral_init_cond 'quiescent' -> spectral_initialize_fields
  * (atmos_spectral/init/spectral_initialize_fields.F90:45-135), previous = current. */
 int isca_b200_cold_start(IscaHandle h);

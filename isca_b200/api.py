@@ -65,7 +65,7 @@ EXPORTS = [
     "isca_b200_spectral_dynamics", "isca_b200_get_field", "isca_b200_get_spectral", "isca_b200_get_scalar",
     "isca_b200_get_table", "isca_b200_get_time_pointers", "isca_b200_spherical_to_grid",
     "isca_b200_grid_to_spherical", "isca_b200_uv_grid_from_vor_div", "isca_b200_vor_div_from_uv_grid",
-    "isca_b200_time_transforms", "isca_b200_profile_step",
+    "isca_b200_time_transforms", "isca_b200_profile_step", "isca_b200_decomposition",
 ]
 
 # field / scalar ids (include/isca_b200.h)
@@ -120,6 +120,8 @@ def load_library() -> C.CDLL:
     lib.isca_b200_vor_div_from_uv_grid.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     lib.isca_b200_time_transforms.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.isca_b200_profile_step.argtypes = [vp, C.c_int, dp, C.c_int, C.c_char_p, C.c_int]
+    ip = C.POINTER(C.c_int)
+    lib.isca_b200_decomposition.argtypes = [C.POINTER(IscaConfigStruct), C.c_int, C.c_int, ip, ip, ip, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("isca_b200_default_config", "isca_b200_last_error"):
@@ -130,6 +132,31 @@ def load_library() -> C.CDLL:
 
 class IscaError(RuntimeError):
     """error_mesg(..., FATAL) analogue."""
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId (rank 0 creates it, the host runtime broadcasts it to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.isca_b200_nccl_unique_id(buf) != 0:
+        raise IscaError("nccl_unique_id: " + lib.isca_b200_last_error(None).decode())
+    return buf.raw
+
+
+def decomposition(config, rank, nranks):
+    """The library's (rank, nranks) decomposition: dict(lat_start, lat_count, m_list, owner, pos). CPU only."""
+    lib = load_library()
+    M = config.num_fourier
+    j0, jc, nm = C.c_int(), C.c_int(), C.c_int()
+    m_list = np.zeros(M + 1, dtype=np.int32)
+    owner = np.zeros(M + 1, dtype=np.int32)
+    pos = np.zeros(M + 1, dtype=np.int32)
+    rc = lib.isca_b200_decomposition(C.byref(config), rank, nranks, C.byref(j0), C.byref(jc), C.byref(nm),
+                                     m_list.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p),
+                                     pos.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise IscaError("decomposition: " + lib.isca_b200_last_error(None).decode())
+    return dict(lat_start=j0.value, lat_count=jc.value, m_list=m_list[: nm.value].copy(), owner=owner, pos=pos)
 
 
 def make_config(**kw) -> IscaConfigStruct:
@@ -199,7 +226,8 @@ class Atmosphere:
         self.h = C.c_void_p()
         uid = None
         if nccl_unique_id is not None:
-            uid = C.cast(C.create_string_buffer(nccl_unique_id, 128), C.c_void_p)
+            self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            uid = C.cast(self._uid_buf, C.c_void_p)
         rc = self.lib.isca_b200_create(C.byref(config), rank, nranks, uid, C.byref(self.h))
         if rc != 0:
             msg = self.lib.isca_b200_last_error(None)

@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"])
     return LIB
 
 

@@ -5,6 +5,7 @@
 #include "device.h"
 #include "spectral.h"
 #include "grid.h"
+#include "nccl_dyn.h"
 #include <cstring>
 #include <map>
 #include <algorithm>
@@ -84,7 +85,15 @@ struct IscaHandle_t {
   // ---- work
   DBuf<double2> dt_vors, w_div, w_T, w_lnps, k_dt_vors, k_dt_divs, k_dt_ts, k_dt_lnps;
   DBuf<double2> specA, specB, specC;
-  DBuf<double> four;
+  DBuf<double> four;         // Fourier buffer, m-owner layout (A)
+  DBuf<double> fourB;        // Fourier buffer, lat-owner layout (B); only allocated when P > 1
+  NcclApi nccl; NcclComm comm = nullptr;
+  double* four_lat() { return g.P > 1 ? fourB.p : four.p; }
+  void ensure_four(int Lp) {
+    const size_t needA = (size_t)g.nm * g.J * 2 * Lp, needB = (size_t)(g.M + 1) * g.Jloc * 2 * Lp;
+    if (needA > four.n) four.alloc(needA);
+    if (g.P > 1 && needB > fourB.n) fourB.alloc(needB);
+  }
   DBuf<double> gradA;        // [2K+2] planes: dxT, dyT, dxlnps, dylnps
   DBuf<double> gridB;        // [4K+1] planes: dt_T, A, B, Phi, dt_lnps
   DBuf<double> ext_tend;     // [3K+1] planes for externally supplied tendencies
@@ -181,7 +190,7 @@ static void alloc_state(H& h) {
   h.LpA = round_up(2 * K + 2, 16); h.LpB = round_up(4 * K + 1, 16); h.LpC = round_up(5 * K + 1, 16);
   h.specA.alloc((size_t)g.T * h.LpA); h.specB.alloc((size_t)g.T * h.LpB); h.specC.alloc((size_t)g.T * h.LpC);
   const int Lmax = std::max(h.LpA, std::max(h.LpB, h.LpC));
-  h.four.alloc((size_t)(g.M + 1) * g.J / g.P * 2 * Lmax * (g.P > 1 ? 1 : 1));
+  h.ensure_four(Lmax);
   h.gradA.alloc((size_t)(2 * K + 2) * h.nplane());
   h.gridB.alloc((size_t)(4 * K + 1) * h.nplane());
   h.part.alloc(3 * h.nplane()); h.scal.alloc(SC_COUNT); h.red_tmp.alloc(4 * 128);
@@ -230,9 +239,36 @@ static void ensure_wave_matrix(H& h, double xi) {
 
 // exchange of the Fourier buffer between the lat-owner and m-owner layouts (transpose_fourier /
 // reverse_transpose_fourier, tools/transforms.F90:970-1056).  One rank: the two layouts coincide.
-static void exchange_fourier(H& h, int /*direction*/, int /*Lp*/) {
+//   direction 0 (spectral -> grid): layout A (mine: [dest s][mi][jl][C]) -> layout B ([pos[m]][jl][C])
+//   direction 1 (grid -> spectral): layout B -> layout A
+// Every per-peer block is contiguous on both sides (the kernels index straight into the per-peer slabs),
+// so the whole transpose is one grouped NCCL send/recv per batch -- no pack/unpack kernels, no barrier.
+static void exchange_fourier(H& h, int direction, int Lp) {
+  const Geometry& g = h.g;
+  if (g.P == 1) return;
+  const size_t C = 2 * (size_t)Lp;
+  const NcclApi& n = h.nccl;
+  n.ck(n.GroupStart(), "ncclGroupStart");
+  for (int r = 0; r < g.P; ++r) {
+    double* a_blk = h.four.p + (size_t)r * g.nm * g.Jloc * C;                 // my m's, rank r's latitudes
+    double* b_blk = h.fourB.p + (size_t)g.roff[r] * g.Jloc * C;               // rank r's m's, my latitudes
+    const size_t na = (size_t)g.nm * g.Jloc * C, nb = (size_t)g.nm_rank[r] * g.Jloc * C;
+    if (direction == 0) {
+      n.ck(n.Send(a_blk, na, NCCL_FLOAT64, r, h.comm, h.st), "ncclSend");
+      n.ck(n.Recv(b_blk, nb, NCCL_FLOAT64, r, h.comm, h.st), "ncclRecv");
+    } else {
+      n.ck(n.Send(b_blk, nb, NCCL_FLOAT64, r, h.comm, h.st), "ncclSend");
+      n.ck(n.Recv(a_blk, na, NCCL_FLOAT64, r, h.comm, h.st), "ncclRecv");
+    }
+  }
+  n.ck(n.GroupEnd(), "ncclGroupEnd");
+  h.mark(direction == 0 ? "exchange_inv" : "exchange_fwd");
+}
+// global reductions across ranks of `count` device scalars (area_weighted_global_mean's mpp_global_field +
+// sum, tools/transforms.F90:1059-1077, becomes a local fixed-order reduction + one small all-reduce)
+static void allreduce_scalars(H& h, double* dev, int count, int op) {
   if (h.g.P == 1) return;
-  throw std::runtime_error("multi-rank Fourier exchange is not available in this build");
+  h.nccl.ck(h.nccl.AllReduce(dev, dev, (size_t)count, NCCL_FLOAT64, op, h.comm, h.st), "ncclAllReduce");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,12 +278,12 @@ static void dev_inverse(H& h, const double2* spec, int Lp, const LevDesc* levs, 
   launch_legendre_inv(h.dt, spec, h.four.p, Lp, h.st); h.launches++;
   if (h.profiling) h.mark((std::string("legendre_inv") + tag).c_str());
   exchange_fourier(h, 0, Lp);
-  launch_fft_inv(h.dt, h.four.p, levs, nlev, Lp, h.st); h.launches++;
+  launch_fft_inv(h.dt, h.four_lat(), levs, nlev, Lp, h.st); h.launches++;
   if (h.profiling) h.mark((std::string("fft_inv") + tag).c_str());
 }
 static void dev_forward(H& h, const LevDesc* levs, int nlev, double2* spec, int Lp, const unsigned char* trunc,
                         const char* tag = "") {
-  launch_fft_fwd(h.dt, h.four.p, levs, nlev, Lp, h.st); h.launches++;
+  launch_fft_fwd(h.dt, h.four_lat(), levs, nlev, Lp, h.st); h.launches++;
   if (h.profiling) h.mark((std::string("fft_fwd") + tag).c_str());
   exchange_fourier(h, 1, Lp);
   launch_legendre_fwd(h.dt, h.four.p, spec, Lp, trunc, h.st); h.launches++;
@@ -288,6 +324,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   launch_grid_step(h.dt, pr, ga, st); h.launches++;
   h.mark("grid_step");
   launch_reduce(h.part.p, pl, 2, h.ops_sum2.p, h.scal.p + SC_SUM_PS_PREV, h.red_tmp.p, st); h.launches += 2;
+  allreduce_scalars(h, h.scal.p + SC_SUM_PS_PREV, 2, NCCL_SUM);
   h.mark("corr_reduce_prev");
 
   dev_forward(h, h.levsB.p, 4 * K + 1, h.specB.p, h.LpB, h.truncB.p, "_tend");
@@ -311,9 +348,13 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   // compute_corrections (spectral_dynamics.F90:1213-1302)
   launch_colsum_ps(h.dt, h.ps[fut].p, h.part.p, st);
   launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_SUM_PS_FUT, h.red_tmp.p, st);
+  allreduce_scalars(h, h.scal.p + SC_SUM_PS_FUT, 1, NCCL_SUM);
   launch_apply_mass(h.dt, h.ps[fut].p, h.lnps[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_mass_correction, st);
   launch_colsum_energy(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.part.p, st);
   launch_reduce(h.part.p, pl, 3, h.ops_en.p, h.scal.p + SC_SUM_EN_FUT, h.red_tmp.p, st);
+  allreduce_scalars(h, h.scal.p + SC_SUM_EN_FUT, 1, NCCL_SUM);
+  allreduce_scalars(h, h.scal.p + SC_TMIN, 1, NCCL_MIN);
+  allreduce_scalars(h, h.scal.p + SC_TMAX, 1, NCCL_MAX);
   launch_apply_energy(h.dt, pr, h.T[fut].p, h.ts[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_energy_correction, st);
   h.launches += 8;
   h.mark("corr_mass_energy");
@@ -346,7 +387,7 @@ static void x_prepare(H& h, int nlev, int nfields) {
   h.x_rect.ensure((size_t)nlev * nfields * (g.N + 1) * (g.M + 1));
   h.x_spec.ensure((size_t)g.T * Lp);
   h.x_grid.ensure((size_t)nlev * nfields * h.nplane());
-  if ((size_t)(g.M + 1) * g.Jloc * 2 * Lp > h.four.n) h.four.alloc((size_t)(g.M + 1) * g.Jloc * 2 * Lp);
+  h.ensure_four(Lp);
   h.x_levs.ensure(nlev * nfields);
   h.x_trunc.ensure(Lp);
 }
@@ -479,9 +520,30 @@ void isca_b200_default_config(IscaConfig* c) {
 
 const char* isca_b200_last_error(IscaHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int isca_b200_nccl_unique_id(void* /*out128*/) { g_create_error = "NCCL support is not available in this build"; return 3; }
+int isca_b200_nccl_unique_id(void* out128) {
+  try {
+    static NcclApi api;
+    api.load();
+    NcclUniqueId id;
+    api.ck(api.GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(out128, id.internal, 128);
+  } catch (const std::exception& e) { g_create_error = e.what(); return 3; }
+  return 0;
+}
 
-int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* /*nccl_unique_id*/, IscaHandle* out) {
+int isca_b200_decomposition(const IscaConfig* cfg, int rank, int nranks, int* lat_start, int* lat_count, int* num_m,
+                            int* m_list, int* owner, int* pos) {
+  try {
+    Geometry g;
+    build_geometry(*cfg, rank, nranks, g);
+    *lat_start = g.j0; *lat_count = g.Jloc; *num_m = g.nm;
+    for (int i = 0; i < g.nm; ++i) m_list[i] = g.m_of[i];
+    for (int m = 0; m <= g.M; ++m) { owner[m] = g.owner[m]; pos[m] = g.pos[m]; }
+  } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
+  return 0;
+}
+
+int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* nccl_unique_id, IscaHandle* out) {
   if (!cfg || !out) { g_create_error = "null argument"; return 1; }
   *out = nullptr;
   H* h = nullptr;
@@ -490,7 +552,8 @@ int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* /*
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
       throw std::runtime_error("no CUDA device: isca_b200 has no CPU fallback");
-    if (nranks != 1) throw std::runtime_error("multi-rank runs are not available in this build");
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("invalid rank / nranks");
+    if (nranks > 1 && !nccl_unique_id) throw std::runtime_error("nranks > 1 needs the shared ncclUniqueId");
     // unsupported namelist values fail loudly
     if (cfg->raw_filter_coeff != 1.0) throw std::runtime_error("raw_filter_coeff /= 1 is not supported");
     if (cfg->vert_advect_uv != 0 || cfg->vert_advect_t != 0) throw std::runtime_error("only second_centered vertical advection of u,v,T is supported");
@@ -506,6 +569,12 @@ int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* /*
     h->cfg.pk = nullptr; h->cfg.bk = nullptr;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     h->use_graph = (std::getenv("ISCA_B200_NO_GRAPH") == nullptr);
+    if (nranks > 1) {
+      h->nccl.load();
+      NcclUniqueId id; std::memcpy(id.internal, nccl_unique_id, 128);
+      h->nccl.ck(h->nccl.CommInitRank(&h->comm, nranks, id, rank), "ncclCommInitRank");
+      if (std::getenv("ISCA_B200_GRAPH_MULTI") == nullptr) h->use_graph = false;   // NCCL calls are issued eagerly by default
+    }
     upload_tables(*h);
     set_params(*h);
     alloc_state(*h);
@@ -524,6 +593,7 @@ int isca_b200_destroy(IscaHandle h) {
   cudaStreamSynchronize(h->st);
   for (auto& kv : h->wave_cache) delete kv.second;
   for (auto& sg : h->graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
+  if (h->comm) h->nccl.CommDestroy(h->comm);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;
@@ -848,9 +918,9 @@ int isca_b200_time_transforms(IscaHandle h, int nlev, int reps, double ms_out[4]
     CK(cudaEventRecord(ev[0], h->st));
     launch_legendre_inv(h->dt, h->x_spec.p, h->four.p, Lp, h->st);
     CK(cudaEventRecord(ev[1], h->st));
-    launch_fft_inv(h->dt, h->four.p, h->x_levs.p, nlev, Lp, h->st);
+    launch_fft_inv(h->dt, h->four_lat(), h->x_levs.p, nlev, Lp, h->st);
     CK(cudaEventRecord(ev[2], h->st));
-    launch_fft_fwd(h->dt, h->four.p, h->x_levs.p, nlev, Lp, h->st);
+    launch_fft_fwd(h->dt, h->four_lat(), h->x_levs.p, nlev, Lp, h->st);
     CK(cudaEventRecord(ev[3], h->st));
     launch_legendre_fwd(h->dt, h->four.p, h->x_spec.p, Lp, h->x_trunc.p, h->st);
     CK(cudaEventRecord(ev[4], h->st));
