@@ -9,7 +9,7 @@
 #include <stdexcept>
 #include "../../include/isca_b200.h"
 
-#define ISCA_KMAX 96          // max num_levels supported by the column kernels (registers/local arrays)
+#define ISCA_KMAX 80          // max num_levels supported by the column kernels (registers/local arrays)
 
 namespace isca {
 

@@ -88,114 +88,138 @@ struct FftShape {
   __device__ static __forceinline__ int pad(int i) { return i + i / PADP; }
 };
 
-// One Stockham pass of radix R on a line in shared memory: src (padded) -> dst (padded).
-//   Ns = product of the radices of the earlier passes.
+// One Stockham pass of radix R (Ns = product of the earlier radices) split in two halves so that a
+// single shared-memory buffer per line suffices: every thread first pulls all its butterflies into
+// registers (read half), the CTA synchronises, then the results are scattered back (write half).
 template <int H, int R, int R1, int SIGN, int Q>
-__device__ __forceinline__ void pass_smem(const double2* __restrict__ src, double2* __restrict__ dst, int Ns, int I, int lt,
-                                          const double2* __restrict__ table) {
+__device__ __forceinline__ void pass_read(const double2* __restrict__ src, double2 (&v)[(H / R + Q - 1) / Q][R], int Ns, int I,
+                                          int lt, const double2* __restrict__ table) {
   typedef FftShape<H, R1> S;
+  constexpr int NB = (H / R + Q - 1) / Q;
   const int stride_tw = I / (Ns * R);
-#pragma unroll 1
-  for (int j = lt; j < H / R; j += Q) {
-    const int k = j & (Ns - 1);
-    double2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = src[S::pad(j + r * (H / R))];
+  for (int b = 0; b < NB; ++b) {
+    const int j = lt + b * Q;
+    if (j < H / R) {
+      const int k = j & (Ns - 1);
 #pragma unroll
-    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw<SIGN>(table, k * r * stride_tw));
-    Dft<R, SIGN>::run(v);
-    const int j0 = (j - k) * R + k;
+      for (int r = 0; r < R; ++r) v[b][r] = src[S::pad(j + r * (H / R))];
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[S::pad(j0 + r * Ns)] = v[r];
+      for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], tw<SIGN>(table, k * r * stride_tw));
+      Dft<R, SIGN>::run(v[b]);
+    }
+  }
+}
+template <int H, int R, int R1, int Q>
+__device__ __forceinline__ void pass_write(double2* __restrict__ dst, const double2 (&v)[(H / R + Q - 1) / Q][R], int Ns, int lt) {
+  typedef FftShape<H, R1> S;
+  constexpr int NB = (H / R + Q - 1) / Q;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int j = lt + b * Q;
+    if (j < H / R) {
+      const int k = j & (Ns - 1);
+      const int j0 = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) dst[S::pad(j0 + r * Ns)] = v[b][r];
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // inverse: Fourier (layout B) -> grid planes.   grid = (ceil(nlev/LT), Jloc), block = LT * Q
 // ---------------------------------------------------------------------------------------------
-template <int H, int R1, int R2, int R3, int Q>
-__global__ void __launch_bounds__(FFT_LT * Q)
+template <int H, int R1, int R2, int R3, int Q, int MINB>
+__global__ void __launch_bounds__(FFT_LT * Q, MINB)
 fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp) {
   typedef FftShape<H, R1> S;
   constexpr int I = 2 * H;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  double2* bufX = reinterpret_cast<double2*>(fft_smem);             // [LT][LS]  staged X[0..H]
-  double2* bufA = bufX + FFT_LT * S::LS;                            // [LT][LS]
+  double2* buf = reinterpret_cast<double2*>(fft_smem);              // [LT][LS]
   const int lev0 = blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
   constexpr int NT = FFT_LT * Q;
 
   // 1. stage X[m][lev] (m <= M), zero elsewhere (transforms.F90:424); unpadded index k <= H
-  for (int idx = tid; idx < FFT_LT * (H + 1); idx += NT) {
-    const int k = idx / FFT_LT, l = idx - k * FFT_LT;
-    double2 v = make_double2(0.0, 0.0);
-    if (k <= g.M && lev0 + l < nlev)
-      v = *reinterpret_cast<const double2*>(four + fourB_index(g, k, jl, C) + 2 * (lev0 + l));
-    bufX[l * S::LS + k] = v;
+  {
+    constexpr int NIT = (FFT_LT * (H + 1) + NT - 1) / NT;
+#pragma unroll 4
+    for (int q = 0; q < NIT; ++q) {
+      const int idx = tid + q * NT;
+      const int k = idx / FFT_LT, l = idx - k * FFT_LT;
+      if (k <= H) {
+        double2 v = make_double2(0.0, 0.0);
+        if (k <= g.M && lev0 + l < nlev)
+          v = *reinterpret_cast<const double2*>(four + fourB_index(g, k, jl, C) + 2 * (lev0 + l));
+        buf[l * S::LS + k] = v;
+      }
+    }
   }
   __syncthreads();
   const int line = tid / Q, lt = tid - line * Q;
-  const double2* X = bufX + line * S::LS;
-  double2* A = bufA + line * S::LS;
-  double2* B = bufX + line * S::LS;
+  double2* A = buf + line * S::LS;
   const int lev = lev0 + line;
 
   // 2. pass 1 (radix R1, Ns = 1): inputs are the merged spectrum
   //    Z[k] = (X[k] + conj X[H-k]) + i w^{-k} (X[k] - conj X[H-k]),  k < H
-#pragma unroll 1
-  for (int j = lt; j < H / R1; j += Q) {
-    double2 v[R1];
+  {
+    constexpr int NB1 = (H / R1 + Q - 1) / Q;
+    double2 v[NB1][R1];
 #pragma unroll
-    for (int r = 0; r < R1; ++r) {
-      const int k = j + r * (H / R1);
-      double2 xk = X[k];
-      const double2 xc = cconj(X[H - k]);
-      if (k == 0) xk.y = 0.0;
-      const double2 e = cadd(xk, xc), o = csub(xk, xc);
-      const double2 wo = cmul(o, tw<+1>(t.twiddle, k));
-      v[r] = make_double2(e.x - wo.y, e.y + wo.x);                   // e + i*wo
+    for (int b = 0; b < NB1; ++b) {
+      const int j = lt + b * Q;
+      if (j < H / R1) {
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          const int k = j + r * (H / R1);
+          double2 xk = A[k];
+          const double2 xc = cconj(A[H - k]);
+          if (k == 0) xk.y = 0.0;
+          const double2 e = cadd(xk, xc), o = csub(xk, xc);
+          const double2 wo = cmul(o, tw<+1>(t.twiddle, k));
+          v[b][r] = make_double2(e.x - wo.y, e.y + wo.x);            // e + i*wo
+        }
+        Dft<R1, +1>::run(v[b]);
+      }
     }
-    Dft<R1, +1>::run(v);
-#pragma unroll
-    for (int r = 0; r < R1; ++r) A[S::pad(j * R1 + r)] = v[r];
+    __syncthreads();                     // every thread is done reading X before the buffer is overwritten
+    pass_write<H, R1, R1, Q>(A, v, 1, lt);
   }
-  __syncthreads();                       // also: every thread is done reading X before B (= bufX) is overwritten
-  const double2* last_src = A;
+  __syncthreads();
   int Ns = R1;
   if (R3 > 1) {
-    pass_smem<H, R2, R1, +1, Q>(A, B, Ns, I, lt, t.twiddle);
+    constexpr int NB2 = (H / R2 + Q - 1) / Q;
+    double2 v[NB2][R2];
+    pass_read<H, R2, R1, +1, Q>(A, v, Ns, I, lt, t.twiddle);
     __syncthreads();
-    last_src = B;
+    pass_write<H, R2, R1, Q>(A, v, Ns, lt);
+    __syncthreads();
     Ns *= R2;
   }
   // 3. last pass: smem -> registers -> global (x[2n] = Re z[n], x[2n+1] = Im z[n])
   constexpr int RL = (R3 > 1) ? R3 : R2;
   {
-    const int stride_tw = I / (Ns * RL);
-    LevDesc d; d.ptr = nullptr; d.op = 0;
-    if (lev < nlev) d = levs[lev];
-    double2* out = reinterpret_cast<double2*>(d.ptr + (size_t)jl * I);
-    const double sc = (d.op == 1) ? t.cosm_lat[g.j0 + jl] : 1.0;
-#pragma unroll 1
-    for (int j = lt; j < H / RL; j += Q) {
-      const int k = j & (Ns - 1);
-      double2 v[RL];
+    constexpr int NBL = (H / RL + Q - 1) / Q;
+    double2 v[NBL][RL];
+    pass_read<H, RL, R1, +1, Q>(A, v, Ns, I, lt, t.twiddle);
+    if (lev < nlev) {
+      const LevDesc d = levs[lev];
+      double2* out = reinterpret_cast<double2*>(d.ptr + (size_t)jl * I);
+      const double sc = (d.op == 1) ? t.cosm_lat[g.j0 + jl] : 1.0;
 #pragma unroll
-      for (int r = 0; r < RL; ++r) v[r] = last_src[S::pad(j + r * (H / RL))];
+      for (int b = 0; b < NBL; ++b) {
+        const int j = lt + b * Q;                    // Ns * RL == H  ->  j0 = j, outputs at j + r * Ns
+        if (j < H / RL) {
 #pragma unroll
-      for (int r = 1; r < RL; ++r) v[r] = cmul(v[r], tw<+1>(t.twiddle, k * r * stride_tw));
-      Dft<RL, +1>::run(v);
-      if (lev < nlev) {
-        // Ns * RL == H  ->  j0 = j, outputs at j + r * Ns
-#pragma unroll
-        for (int r = 0; r < RL; ++r) {
-          double2 z = v[r];
-          if (d.op == 2) { z.x = exp(z.x); z.y = exp(z.y); }
-          else if (d.op == 1) { z.x *= sc; z.y *= sc; }
-          out[j + r * Ns] = z;
+          for (int r = 0; r < RL; ++r) {
+            double2 z = v[b][r];
+            if (d.op == 2) { z.x = exp(z.x); z.y = exp(z.y); }
+            else if (d.op == 1) { z.x *= sc; z.y *= sc; }
+            out[j + r * Ns] = z;
+          }
         }
       }
     }
@@ -205,57 +229,68 @@ fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __re
 // ---------------------------------------------------------------------------------------------
 // forward: grid planes -> Fourier (layout B)
 // ---------------------------------------------------------------------------------------------
-template <int H, int R1, int R2, int R3, int Q>
-__global__ void __launch_bounds__(FFT_LT * Q)
+template <int H, int R1, int R2, int R3, int Q, int MINB>
+__global__ void __launch_bounds__(FFT_LT * Q, MINB)
 fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp) {
   typedef FftShape<H, R1> S;
   constexpr int I = 2 * H;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  double2* buf0 = reinterpret_cast<double2*>(fft_smem);             // [LT][LS]
-  double2* buf1 = buf0 + FFT_LT * S::LS;                            // [LT][LS]
+  double2* buf = reinterpret_cast<double2*>(fft_smem);              // [LT][LS]
   const int lev0 = blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
   constexpr int NT = FFT_LT * Q;
   const int line = tid / Q, lt = tid - line * Q;
   const int lev = lev0 + line;
-  double2* A = buf0 + line * S::LS;
-  double2* B = buf1 + line * S::LS;
+  double2* A = buf + line * S::LS;
 
   // 1. pass 1 (radix R1, Ns = 1) straight from global: z[n] = x[2n] + i x[2n+1]
   {
+    constexpr int NB1 = (H / R1 + Q - 1) / Q;
+    double2 v[NB1][R1];
     const double2* in = nullptr;
     if (lev < nlev) in = reinterpret_cast<const double2*>(levs[lev].ptr + (size_t)jl * I);
-#pragma unroll 1
-    for (int j = lt; j < H / R1; j += Q) {
-      double2 v[R1];
 #pragma unroll
-      for (int r = 0; r < R1; ++r) v[r] = in ? in[j + r * (H / R1)] : make_double2(0.0, 0.0);
-      Dft<R1, -1>::run(v);
+    for (int b = 0; b < NB1; ++b) {
+      const int j = lt + b * Q;
+      if (j < H / R1) {
 #pragma unroll
-      for (int r = 0; r < R1; ++r) A[S::pad(j * R1 + r)] = v[r];
+        for (int r = 0; r < R1; ++r) v[b][r] = in ? in[j + r * (H / R1)] : make_double2(0.0, 0.0);
+        Dft<R1, -1>::run(v[b]);
+      }
     }
+    pass_write<H, R1, R1, Q>(A, v, 1, lt);
   }
   __syncthreads();
   int Ns = R1;
-  pass_smem<H, R2, R1, -1, Q>(A, B, Ns, I, lt, t.twiddle);
-  __syncthreads();
-  const double2* Zbase = buf1;
-  if (R3 > 1) {
-    Ns *= R2;
-    pass_smem<H, (R3 > 1 ? R3 : 2), R1, -1, Q>(B, A, Ns, I, lt, t.twiddle);
+  {
+    constexpr int NB2 = (H / R2 + Q - 1) / Q;
+    double2 v[NB2][R2];
+    pass_read<H, R2, R1, -1, Q>(A, v, Ns, I, lt, t.twiddle);
     __syncthreads();
-    Zbase = buf0;
+    pass_write<H, R2, R1, Q>(A, v, Ns, lt);
+    __syncthreads();
+    Ns *= R2;
+  }
+  if (R3 > 1) {
+    constexpr int R3E = (R3 > 1) ? R3 : 2;
+    constexpr int NB3 = (H / R3E + Q - 1) / Q;
+    double2 v[NB3][R3E];
+    pass_read<H, R3E, R1, -1, Q>(A, v, Ns, I, lt, t.twiddle);
+    __syncthreads();
+    pass_write<H, R3E, R1, Q>(A, v, Ns, lt);
+    __syncthreads();
   }
   // 2. split + store: X[k] = 0.5 (Z[k] + conj Z[H-k]) - 0.5 i w^k (Z[k] - conj Z[H-k]), scaled by 1/I, k <= M;
   //    threads ordered (level fastest) so that every m writes LT complex = 128 contiguous bytes
   const double inv = 1.0 / (double)I;
+#pragma unroll 4
   for (int idx = tid; idx < FFT_LT * (g.M + 1); idx += NT) {
     const int k = idx / FFT_LT, l = idx - k * FFT_LT;
     if (lev0 + l >= nlev) continue;
-    const double2* Z = Zbase + l * S::LS;
+    const double2* Z = buf + l * S::LS;
     const double2 zk = Z[S::pad(k)];
     const double2 zc = cconj(Z[S::pad((k == 0) ? 0 : (H - k))]);
     const double2 e = cadd(zk, zc), o = csub(zk, zc);
@@ -265,45 +300,45 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
   }
 }
 
-template <int H, int R1, int R2, int R3, int Q>
+template <int H, int R1, int R2, int R3, int Q, int MINB>
 static void launch_inv_shape(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
   typedef FftShape<H, R1> S;
-  const size_t smem = sizeof(double2) * 2 * FFT_LT * S::LS;
+  const size_t smem = sizeof(double2) * FFT_LT * S::LS;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(fft_inv_kernel<H, R1, R2, R3, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(fft_inv_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   dim3 grid((nlev + FFT_LT - 1) / FFT_LT, t.g.Jloc);
-  fft_inv_kernel<H, R1, R2, R3, Q><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+  fft_inv_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
 }
-template <int H, int R1, int R2, int R3, int Q>
+template <int H, int R1, int R2, int R3, int Q, int MINB>
 static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
   typedef FftShape<H, R1> S;
-  const size_t smem = sizeof(double2) * 2 * FFT_LT * S::LS;
+  const size_t smem = sizeof(double2) * FFT_LT * S::LS;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   dim3 grid((nlev + FFT_LT - 1) / FFT_LT, t.g.Jloc);
-  fft_fwd_kernel<H, R1, R2, R3, Q><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+  fft_fwd_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
 }
 
 // radix plans: H = I/2 = R1*R2*R3, Q = H / max radix threads per line
 void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
   switch (t.g.I) {
-    case 1024: launch_inv_shape<512, 8, 8, 8, 64>(t, four, levs, nlev, Lp, st); break;
-    case 512:  launch_inv_shape<256, 16, 16, 1, 16>(t, four, levs, nlev, Lp, st); break;
-    case 256:  launch_inv_shape<128, 8, 16, 1, 8>(t, four, levs, nlev, Lp, st); break;
-    case 128:  launch_inv_shape<64, 8, 8, 1, 8>(t, four, levs, nlev, Lp, st); break;
-    case 64:   launch_inv_shape<32, 4, 8, 1, 4>(t, four, levs, nlev, Lp, st); break;
-    case 32:   launch_inv_shape<16, 4, 4, 1, 4>(t, four, levs, nlev, Lp, st); break;
+    case 1024: launch_inv_shape<512, 8, 8, 8, 64, 2>(t, four, levs, nlev, Lp, st); break;
+    case 512:  launch_inv_shape<256, 16, 16, 1, 16, 5>(t, four, levs, nlev, Lp, st); break;
+    case 256:  launch_inv_shape<128, 8, 16, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
+    case 128:  launch_inv_shape<64, 8, 8, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
+    case 64:   launch_inv_shape<32, 4, 8, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
+    case 32:   launch_inv_shape<16, 4, 4, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
     default: break;   // rejected in build_geometry
   }
 }
 void launch_fft_fwd(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
   switch (t.g.I) {
-    case 1024: launch_fwd_shape<512, 8, 8, 8, 64>(t, four, levs, nlev, Lp, st); break;
-    case 512:  launch_fwd_shape<256, 16, 16, 1, 16>(t, four, levs, nlev, Lp, st); break;
-    case 256:  launch_fwd_shape<128, 8, 16, 1, 8>(t, four, levs, nlev, Lp, st); break;
-    case 128:  launch_fwd_shape<64, 8, 8, 1, 8>(t, four, levs, nlev, Lp, st); break;
-    case 64:   launch_fwd_shape<32, 4, 8, 1, 4>(t, four, levs, nlev, Lp, st); break;
-    case 32:   launch_fwd_shape<16, 4, 4, 1, 4>(t, four, levs, nlev, Lp, st); break;
+    case 1024: launch_fwd_shape<512, 8, 8, 8, 64, 2>(t, four, levs, nlev, Lp, st); break;
+    case 512:  launch_fwd_shape<256, 16, 16, 1, 16, 5>(t, four, levs, nlev, Lp, st); break;
+    case 256:  launch_fwd_shape<128, 8, 16, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
+    case 128:  launch_fwd_shape<64, 8, 8, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
+    case 64:   launch_fwd_shape<32, 4, 8, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
+    case 32:   launch_fwd_shape<16, 4, 4, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
     default: break;
   }
 }

@@ -43,7 +43,7 @@ __device__ __forceinline__ void press_level(const DevTables& t, const Params& pr
 constexpr int GS_KW = 4;
 
 template <int CH>
-__global__ void __launch_bounds__(32 * GS_KW)
+__global__ void __launch_bounds__(32 * GS_KW, (CH <= 10) ? 6 : 4)
 grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const GeomDev& g = t.g;
   const int I = g.I, K = g.K;
@@ -55,6 +55,9 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const size_t col = (size_t)jl * I + (live ? i : 0);
   const size_t plane = (size_t)g.Jloc * I;
   __shared__ double s_tot[GS_KW][32], s_gh[GS_KW][32], s_en[GS_KW][32];
+  // per-thread chunk arrays live in shared memory ([c][thread], conflict-free) to keep registers for occupancy
+  __shared__ double s_cum[CH + 1][32 * GS_KW], s_phi[CH][32 * GS_KW];
+  const int tx = threadIdx.x;
 
   const int k_lo = w * CH;
   const int k_hi = (k_lo + CH < K) ? (k_lo + CH) : K;          // chunk = [k_lo, k_hi), may be empty
@@ -66,20 +69,23 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const double dy_psg = (ps_c * a.dy_lnps[col]) * cosm;
 
   // ---- pass 1 (top-down within the chunk): cumulative mass divergence (four_in_one :1073-1083)
-  double cum[CH + 1];
-  cum[0] = 0.0;
+  {
+    double run = 0.0;
+    s_cum[0][tx] = 0.0;
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int k = k_lo + c;
-    double dmean = 0.0;
-    if (k < k_hi) {
-      const size_t e = (size_t)k * plane + col;
-      const double dp = t.dpk[k] + t.dbk[k] * ps_c;
-      dmean = a.div_cur[e] * dp + t.dbk[k] * (a.u_cur[e] * dx_psg + a.v_cur[e] * dy_psg);
+    for (int c = 0; c < CH; ++c) {
+      const int k = k_lo + c;
+      double dmean = 0.0;
+      if (k < k_hi) {
+        const size_t e = (size_t)k * plane + col;
+        const double dp = t.dpk[k] + t.dbk[k] * ps_c;
+        dmean = a.div_cur[e] * dp + t.dbk[k] * (a.u_cur[e] * dx_psg + a.v_cur[e] * dy_psg);
+      }
+      run = run + dmean;
+      s_cum[c + 1][tx] = run;
     }
-    cum[c + 1] = cum[c] + dmean;
+    s_tot[w][lane] = run;
   }
-  s_tot[w][lane] = cum[CH];
   __syncthreads();
   double cum_off = 0.0, dmean_total = 0.0;
 #pragma unroll
@@ -106,7 +112,6 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const double ln_p00 = log(pr.P00);
 
   // ---- pass 2 (bottom-up within the chunk)
-  double phi[CH];
   double gh_local = 0.0;                              // geopot_half relative to the chunk's bottom interface
   double energy_int = 0.0;
   double ln_half_below = 0.0;
@@ -120,7 +125,6 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
 #pragma unroll
   for (int c = CH - 1; c >= 0; --c) {
     const int k = k_lo + c;
-    phi[c] = 0.0;
     if (k >= k_hi) continue;
     const size_t e = (size_t)k * plane + col;
     double u_up = 0.0, v_up = 0.0, T_up = 0.0;       // level k-1
@@ -172,7 +176,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
     const double x3 = x1 * dy_psg;
     dt_u = dt_u - pr.rdgas * Tv * x2;
     dt_v = dt_v - pr.rdgas * Tv * x3;
-    const double cum_k = cum_off + cum[c], cum_k1 = cum_off + cum[c + 1];
+    const double cum_k = cum_off + s_cum[c][tx], cum_k1 = cum_off + s_cum[c + 1][tx];
     const double dmean = a.div_cur[e] * dp + t.dbk[k] * (u_k * dx_psg + v_k * dy_psg);
     const double x4 = (cum_k * dlog_3 + dmean * dlog_1) * dp_inv;
     const double x5 = x4 - u_k * x2 - v_k * x3;
@@ -212,7 +216,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
       a.out_B[e] = dt_v * cosm;
       a.out_T[e] = dt_T;
     }
-    phi[c] = gfull + .5 * (u_k * u_k + v_k * v_k);
+    s_phi[c][tx] = gfull + .5 * (u_k * u_k + v_k * v_k);
 
     ln_half_below = pl.ln_half_k;
     u_dn = u_k; v_dn = v_k; T_dn = T_k;
@@ -229,7 +233,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int k = k_lo + c;
-      if (k < k_hi) a.out_phi[(size_t)k * plane + col] = gh_off + phi[c];
+      if (k < k_hi) a.out_phi[(size_t)k * plane + col] = gh_off + s_phi[c][tx];
     }
     if (w == 0) {
       double en = 0.0;
@@ -249,7 +253,7 @@ void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& 
   else if (ch <= 7) grid_step_kernel<7><<<grid, block, 0, st>>>(t, pr, a);
   else if (ch <= 10) grid_step_kernel<10><<<grid, block, 0, st>>>(t, pr, a);
   else if (ch <= 15) grid_step_kernel<15><<<grid, block, 0, st>>>(t, pr, a);
-  else grid_step_kernel<24><<<grid, block, 0, st>>>(t, pr, a);
+  else grid_step_kernel<20><<<grid, block, 0, st>>>(t, pr, a);
 }
 
 // ---------------------------------------------------------------------------------------------

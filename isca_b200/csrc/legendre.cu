@@ -104,8 +104,11 @@ legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __res
     __syncthreads();
     if (ch + 1 < nchunks) load_chunk((ch + 1) & 1, ch + 1);
     const int st = ch & 1;
-#pragma unroll
-    for (int kk = 0; kk < LEG_KC / 4; ++kk) {
+    // rows of this chunk that exist: n < Nm  ->  per parity ceil((Nm - nbase)/2), in k-steps of 4
+    const int rem = Nm - ch * 2 * LEG_KC;
+    const int ksteps = (rem >= 2 * LEG_KC) ? (LEG_KC / 4) : ((rem + 7) >> 3);
+#pragma unroll 1
+    for (int kk = 0; kk < ksteps; ++kk) {
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         double a[MT], b[NT];
@@ -172,8 +175,8 @@ legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __res
                     const unsigned char* __restrict__ lev_trunc) {
   constexpr int XS = LEG_CT + 4;            // 36 == 4 mod 16
   constexpr int WS = FWD_KC + 4;            // 20 == 4 mod 16
-  __shared__ __align__(16) double Xs[2][FWD_KC][XS];          // [plus/minus][jh][c]
-  __shared__ __align__(16) double Ws[2][FWD_NT / 2][WS];      // [parity][n][jh]
+  __shared__ __align__(16) double Xs[2][2][FWD_KC][XS];       // [stage][plus/minus][jh][c]
+  __shared__ __align__(16) double Ws[2][2][FWD_NT / 2][WS];   // [stage][parity][n][jh]
 
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
@@ -193,38 +196,56 @@ legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __res
 #pragma unroll
     for (int b = 0; b < 2; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
-  for (int jh0 = 0; jh0 < g.Jh; jh0 += FWD_KC) {
-    __syncthreads();
-    // X tiles: 16 jh x 32 c, plus and minus
-    for (int idx = tid; idx < FWD_KC * (LEG_CT / 2); idx += 128) {
-      int r = idx / (LEG_CT / 2), v = idx - r * (LEG_CT / 2);
-      int jh = jh0 + r;
-      const double2 fs = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, jh, C) + c0 + 2 * v);
-      const double2 fn = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, g.J - 1 - jh, C) + c0 + 2 * v);
-      Xs[0][r][2 * v] = fn.x + fs.x; Xs[0][r][2 * v + 1] = fn.y + fs.y;
-      Xs[1][r][2 * v] = fn.x - fs.x; Xs[1][r][2 * v + 1] = fn.y - fs.y;
+  // register-staged software pipeline: the global loads of chunk ch+1 are in flight while chunk ch is
+  // multiplied; X tile = 16 jh x 16 double2 (2 per thread), W tile = 32 n x 8 double2 (2 per thread)
+  double2 xs_[2], xn_[2], w_[2];
+  auto prefetch = [&](int jh0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + q * 128;
+      const int r = idx / (LEG_CT / 2), v = idx - r * (LEG_CT / 2);
+      const int jh = jh0 + r;
+      xs_[q] = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, jh, C) + c0 + 2 * v);
+      xn_[q] = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, g.J - 1 - jh, C) + c0 + 2 * v);
+      const int rw = idx / (FWD_KC / 2), vw = idx - rw * (FWD_KC / 2);
+      const int n = nt0 + rw;
+      w_[q] = make_double2(0.0, 0.0);
+      if (n < Nm) w_[q] = *reinterpret_cast<const double2*>(t.legw + (size_t)(row0 + n) * g.Jh + jh0 + 2 * vw);
     }
-    // weighted Legendre rows: 32 n x 16 jh
-    for (int idx = tid; idx < FWD_NT * (FWD_KC / 2); idx += 128) {
-      int r = idx / (FWD_KC / 2), v = idx - r * (FWD_KC / 2);
-      int n = nt0 + r;
-      double2 w = make_double2(0.0, 0.0);
-      if (n < Nm) w = *reinterpret_cast<const double2*>(t.legw + (size_t)(row0 + n) * g.Jh + jh0 + 2 * v);
-      Ws[r & 1][r >> 1][2 * v] = w.x; Ws[r & 1][r >> 1][2 * v + 1] = w.y;
+  };
+  auto stage = [&](int st) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + q * 128;
+      const int r = idx / (LEG_CT / 2), v = idx - r * (LEG_CT / 2);
+      Xs[st][0][r][2 * v] = xn_[q].x + xs_[q].x; Xs[st][0][r][2 * v + 1] = xn_[q].y + xs_[q].y;   // x_even (:311)
+      Xs[st][1][r][2 * v] = xn_[q].x - xs_[q].x; Xs[st][1][r][2 * v + 1] = xn_[q].y - xs_[q].y;   // x_odd  (:312)
+      const int rw = idx / (FWD_KC / 2), vw = idx - rw * (FWD_KC / 2);
+      Ws[st][rw & 1][rw >> 1][2 * vw] = w_[q].x; Ws[st][rw & 1][rw >> 1][2 * vw + 1] = w_[q].y;
     }
-    __syncthreads();
+  };
+
+  const int nch = g.Jh / FWD_KC;
+  prefetch(0);
+  stage(0);
+  __syncthreads();
+  for (int ch = 0; ch < nch; ++ch) {
+    const int st = ch & 1;
+    if (ch + 1 < nch) prefetch((ch + 1) * FWD_KC);
 #pragma unroll
     for (int kk = 0; kk < FWD_KC / 4; ++kk) {
       double a[2], b[2];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = Ws[par][mt * 8 + (lane >> 2)][kk * 4 + (lane & 3)];
+      for (int mt = 0; mt < 2; ++mt) a[mt] = Ws[st][par][mt * 8 + (lane >> 2)][kk * 4 + (lane & 3)];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) b[nt] = Xs[par][kk * 4 + (lane & 3)][wc * 16 + nt * 8 + (lane >> 2)];
+      for (int nt = 0; nt < 2; ++nt) b[nt] = Xs[st][par][kk * 4 + (lane & 3)][wc * 16 + nt * 8 + (lane >> 2)];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
+    if (ch + 1 < nch) stage(st ^ 1);
+    __syncthreads();
   }
 
   double* specd = reinterpret_cast<double*>(spec);
