@@ -72,7 +72,7 @@ struct IscaHandle_t {
   // ---- device tables
   DBuf<int> d_m_of, d_off, d_pos, d_row_m, d_row_n;
   DBuf<double> d_sin_lat, d_cos_lat, d_cosm_lat, d_wts_lat, d_coriolis, d_rad_lat, d_pk, d_bk, d_dpk, d_dbk;
-  DBuf<double> d_leg, d_legw;
+  DBuf<double> d_leg, d_legw, d_ln_bk;
   DBuf<double> d_eigen, d_uvm, d_uvc, d_uvp, d_alpm, d_alpp, d_dym, d_dx, d_dyp, d_mask, d_damp, d_dampv, d_dampd, d_eddy, d_zmu, d_zmv;
   DBuf<double> d_rlh, d_rlf, d_rt, d_h;
   DBuf<double> d_twiddle;
@@ -103,6 +103,7 @@ struct IscaHandle_t {
   DBuf<int> ops_sum2, ops_sum1, ops_en;
   int LpA = 0, LpB = 0, LpC = 0;
   int keep_tend = 0;
+  bool grad_valid = false;   // gradA planes hold the gradients of the current level (computed by the previous step)
   // ---- CUDA graphs of the step, one per (current slot, physics) variant of the leapfrog step
   struct StepGraph { int uses = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
   StepGraph graphs[4];
@@ -138,6 +139,11 @@ static void upload_tables(H& h) {
   h.d_wts_lat.upload(t.wts_lat); h.d_coriolis.upload(t.coriolis); h.d_rad_lat.upload(t.rad_lat);
   h.d_pk.upload(t.pk); h.d_bk.upload(t.bk); h.d_dpk.upload(t.dpk); h.d_dbk.upload(t.dbk);
   h.d_leg.upload(t.leg); h.d_legw.upload(t.legw);
+  {
+    std::vector<double> lb(t.bk.size(), 0.0);
+    for (size_t k = 0; k < lb.size(); ++k) if (t.bk[k] > 0.0) lb[k] = std::log(t.bk[k]);
+    h.d_ln_bk.upload(lb);
+  }
   h.d_eigen.upload(t.eigen); h.d_uvm.upload(t.coef_uvm); h.d_uvc.upload(t.coef_uvc); h.d_uvp.upload(t.coef_uvp);
   h.d_alpm.upload(t.coef_alpm); h.d_alpp.upload(t.coef_alpp); h.d_dym.upload(t.coef_dym); h.d_dx.upload(t.coef_dx);
   h.d_dyp.upload(t.coef_dyp); h.d_mask.upload(t.trunc_mask);
@@ -152,7 +158,7 @@ static void upload_tables(H& h) {
   d.row_n = h.d_row_n.p;
   d.sin_lat = h.d_sin_lat.p; d.cos_lat = h.d_cos_lat.p; d.cosm_lat = h.d_cosm_lat.p; d.wts_lat = h.d_wts_lat.p;
   d.coriolis = h.d_coriolis.p; d.rad_lat = h.d_rad_lat.p;
-  d.pk = h.d_pk.p; d.bk = h.d_bk.p; d.dpk = h.d_dpk.p; d.dbk = h.d_dbk.p;
+  d.pk = h.d_pk.p; d.bk = h.d_bk.p; d.dpk = h.d_dpk.p; d.dbk = h.d_dbk.p; d.ln_bk = h.d_ln_bk.p;
   d.leg = h.d_leg.p; d.legw = h.d_legw.p;
   d.eigen = h.d_eigen.p; d.coef_uvm = h.d_uvm.p; d.coef_uvc = h.d_uvc.p; d.coef_uvp = h.d_uvp.p;
   d.coef_alpm = h.d_alpm.p; d.coef_alpp = h.d_alpp.p; d.coef_dym = h.d_dym.p; d.coef_dx = h.d_dx.p; d.coef_dyp = h.d_dyp.p;
@@ -175,6 +181,9 @@ static void set_params(H& h) {
   p.P00 = c.P00; p.do_conserve_energy = c.do_conserve_energy; p.no_forcing = c.no_forcing; p.physics_on = 1;
   p.pk0_zero = (h.ht.pk[0] == 0.0); p.pkbk0_zero = (h.ht.pk[0] == 0.0 && h.ht.bk[0] == 0.0);
   p.vr_tmin = c.valid_range_t[0]; p.vr_tmax = c.valid_range_t[1];
+  p.pure_sigma = 1;
+  for (double v : h.ht.pk) if (v != 0.0) p.pure_sigma = 0;
+  for (size_t k = 1; k < h.ht.bk.size(); ++k) if (!(h.ht.bk[k] > 0.0)) p.pure_sigma = 0;
   p.xi = 0; p.delta_t = 0; p.first_step = 1;
 }
 
@@ -187,7 +196,7 @@ static void alloc_state(H& h) {
   h.vorg.alloc(h.n3()); h.divg.alloc(h.n3()); h.phis.alloc(h.nplane()); h.wg_full.alloc(h.n3());
   h.dt_vors.alloc(h.nspec3()); h.w_div.alloc(h.nspec3()); h.w_T.alloc(h.nspec3()); h.w_lnps.alloc(g.T);
   h.k_dt_vors.alloc(h.nspec3()); h.k_dt_divs.alloc(h.nspec3()); h.k_dt_ts.alloc(h.nspec3()); h.k_dt_lnps.alloc(g.T);
-  h.LpA = round_up(2 * K + 2, 16); h.LpB = round_up(4 * K + 1, 16); h.LpC = round_up(5 * K + 1, 16);
+  h.LpA = round_up(2 * K + 2, 16); h.LpB = round_up(4 * K + 1, 16); h.LpC = round_up(7 * K + 3, 16);
   h.specA.alloc((size_t)g.T * h.LpA); h.specB.alloc((size_t)g.T * h.LpB); h.specC.alloc((size_t)g.T * h.LpC);
   const int Lmax = std::max(h.LpA, std::max(h.LpB, h.LpC));
   h.ensure_four(Lmax);
@@ -208,7 +217,7 @@ static void alloc_state(H& h) {
   for (int i = 0; i < 4 * K + 1; ++i) lb[i] = {h.gridB.p + (size_t)i * pl, 0, 0};
   h.levsB.upload(lb);
   for (int f = 0; f < 2; ++f) {
-    std::vector<LevDesc> lc(5 * K + 1);
+    std::vector<LevDesc> lc(7 * K + 3);
     for (int k = 0; k < K; ++k) {
       lc[k] = {h.vorg.p + (size_t)k * pl, 0, 0};
       lc[K + k] = {h.divg.p + (size_t)k * pl, 0, 0};
@@ -217,6 +226,7 @@ static void alloc_state(H& h) {
       lc[4 * K + k] = {h.T[f].p + (size_t)k * pl, 0, 0};
     }
     lc[5 * K] = {h.ps[f].p, 2, 0};                               // psg = exp(ln_psg)
+    for (int i = 0; i < 2 * K + 2; ++i) lc[5 * K + 1 + i] = la[i];  // gradients for the next step (same planes/ops as batch A)
     h.levsC[f].upload(lc);
   }
   std::vector<unsigned char> tb(h.LpB, 0);
@@ -304,12 +314,15 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   const size_t pl = h.nplane();
   cudaStream_t st = h.st;
 
-  // gradients of T(current), ln ps(current)  (horizontal_advection, compute_pressure_gradient)
-  launch_spec_gradient(h.dt, h.ts[cur].p, K, K, h.specA.p, h.LpA, 0, K, st);
-  launch_spec_gradient(h.dt, h.lnps[cur].p, 1, 1, h.specA.p, h.LpA, 2 * K, 2 * K + 1, st);
-  h.launches += 2;
-  h.mark("spec_gradient");
-  dev_inverse(h, h.specA.p, h.LpA, h.levsA.p, 2 * K + 2, "_grad");
+  // gradients of T(current), ln ps(current)  (horizontal_advection, compute_pressure_gradient): normally
+  // produced by the previous step's inverse batch; computed here after a (re)start
+  if (!h.grad_valid) {
+    launch_spec_gradient(h.dt, h.ts[cur].p, K, K, h.specA.p, h.LpA, 0, K, st);
+    launch_spec_gradient(h.dt, h.lnps[cur].p, 1, 1, h.specA.p, h.LpA, 2 * K, 2 * K + 1, st);
+    h.launches += 2;
+    h.mark("spec_gradient");
+    dev_inverse(h, h.specA.p, h.LpA, h.levsA.p, 2 * K + 2, "_grad");
+  }
 
   GridStepArgs ga;
   ga.u_cur = h.u[cur].p; ga.v_cur = h.v[cur].p; ga.t_cur = h.T[cur].p;
@@ -337,37 +350,37 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   sa.vors_fut = h.vors[fut].p; sa.divs_fut = h.divs[fut].p; sa.ts_fut = h.ts[fut].p; sa.lnps_fut = h.lnps[fut].p;
   sa.dt_vors = h.dt_vors.p; sa.w_div = h.w_div.p; sa.w_T = h.w_T.p; sa.w_lnps = h.w_lnps.p;
   sa.specC = h.specC.p; sa.LpC = h.LpC; sa.cVor = 0; sa.cDiv = K; sa.cU = 2 * K; sa.cV = 3 * K; sa.cT = 4 * K; sa.cLnps = 5 * K;
+  sa.cDxT = 5 * K + 1; sa.cDyT = 6 * K + 1; sa.cDxL = 7 * K + 1; sa.cDyL = 7 * K + 2;
+  sa.fuse_robert_b = 1;
   sa.use_implicit = h.cfg.use_implicit;
   sa.keep_tend = h.keep_tend; sa.k_dt_vors = h.k_dt_vors.p; sa.k_dt_divs = h.k_dt_divs.p; sa.k_dt_ts = h.k_dt_ts.p;
   sa.k_dt_lnps = h.k_dt_lnps.p;
   launch_spec_step(h.dt, pr, sa, st); h.launches += (h.cfg.use_implicit ? 4 : 3);
   h.mark("spec_step");
 
-  dev_inverse(h, h.specC.p, h.LpC, h.levsC[fut].p, 5 * K + 1, "_state");
+  dev_inverse(h, h.specC.p, h.LpC, h.levsC[fut].p, 7 * K + 3, "_state");
+  h.grad_valid = true;
 
   // compute_corrections (spectral_dynamics.F90:1213-1302)
   launch_colsum_ps(h.dt, h.ps[fut].p, h.part.p, st);
   launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_SUM_PS_FUT, h.red_tmp.p, st);
   allreduce_scalars(h, h.scal.p + SC_SUM_PS_FUT, 1, NCCL_SUM);
-  launch_apply_mass(h.dt, h.ps[fut].p, h.lnps[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_mass_correction, st);
+  const double rc_raw = h.cfg.robert_coeff * h.cfg.raw_filter_coeff;
+  launch_apply_mass(h.dt, h.ps[fut].p, h.lnps[fut].p, h.lnps[cur].p, rc_raw, h.scal.p, h.denom(), h.owns_m0(),
+                    h.cfg.do_mass_correction, st);
   launch_colsum_energy(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.part.p, st);
   launch_reduce(h.part.p, pl, 3, h.ops_en.p, h.scal.p + SC_SUM_EN_FUT, h.red_tmp.p, st);
   allreduce_scalars(h, h.scal.p + SC_SUM_EN_FUT, 1, NCCL_SUM);
   allreduce_scalars(h, h.scal.p + SC_TMIN, 1, NCCL_MIN);
   allreduce_scalars(h, h.scal.p + SC_TMAX, 1, NCCL_MAX);
-  launch_apply_energy(h.dt, pr, h.T[fut].p, h.ts[fut].p, h.scal.p, h.denom(), h.owns_m0(), h.cfg.do_energy_correction, st);
+  launch_apply_energy(h.dt, pr, h.T[fut].p, h.ts[fut].p, h.ts[cur].p, rc_raw, h.scal.p, h.denom(), h.owns_m0(),
+                      h.cfg.do_energy_correction, st);
   h.launches += 8;
   h.mark("corr_mass_energy");
 
-  // time-level swap, then complete_robert_filter -> leapfrog_2level_B: a(previous) += rc*a(current)*raw
+  // time-level swap.  complete_robert_filter -> leapfrog_2level_B (a(previous) += rc*a(current)*raw) is fused into
+  // spec_update (all coefficients) and apply_mass / apply_energy (the fixers' (0,0) increments).
   h.previous = cur; h.current = fut;
-  const double rc = h.cfg.robert_coeff, raw = h.cfg.raw_filter_coeff;
-  launch_spec_robert_b(h.vors[cur].p, h.vors[fut].p, h.nspec3(), rc, raw, st);
-  launch_spec_robert_b(h.divs[cur].p, h.divs[fut].p, h.nspec3(), rc, raw, st);
-  launch_spec_robert_b(h.ts[cur].p, h.ts[fut].p, h.nspec3(), rc, raw, st);
-  launch_spec_robert_b(h.lnps[cur].p, h.lnps[fut].p, (size_t)g.T, rc, raw, st);
-  h.launches += 4;
-  h.mark("spec_robert_b");
   h.steps++;
 }
 
@@ -489,6 +502,7 @@ static void cold_start(H& h) {
   d2d_on(h.st, h.T[1].p, h.T[0].p, h.n3() * sizeof(double));
   d2d_on(h.st, h.ps[1].p, h.ps[0].p, pl * sizeof(double));
   h.previous = 0; h.current = 0;
+  h.grad_valid = false;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -613,6 +627,7 @@ int isca_b200_set_grid_state(IscaHandle h, int slot, const double* ug, const dou
   if (vg) h2d_on(h->st, h->v[slot].p, vg, h->n3() * sizeof(double));
   if (tg) h2d_on(h->st, h->T[slot].p, tg, h->n3() * sizeof(double));
   if (psg) h2d_on(h->st, h->ps[slot].p, psg, h->nplane() * sizeof(double));
+  h->grad_valid = false;
   API_END(h)
 }
 
@@ -640,6 +655,7 @@ int isca_b200_set_spectral_state(IscaHandle h, int slot, const double* vors, con
   if (divs) set_spec(*h, h->divs[slot], divs, h->g.K);
   if (ts) set_spec(*h, h->ts[slot], ts, h->g.K);
   if (ln_ps) set_spec(*h, h->lnps[slot], ln_ps, 1);
+  h->grad_valid = false;
   API_END(h)
 }
 
@@ -654,6 +670,7 @@ int isca_b200_set_time_pointers(IscaHandle h, int previous_slot, int current_slo
   API_BEGIN(h)
   if (previous_slot < 0 || previous_slot > 1 || current_slot < 0 || current_slot > 1) throw std::runtime_error("slots must be 0 or 1");
   h->previous = previous_slot; h->current = current_slot;
+  h->grad_valid = false;
   API_END(h)
 }
 int isca_b200_get_time_pointers(IscaHandle h, int* p, int* c) { API_BEGIN(h) *p = h->previous; *c = h->current; API_END(h) }
@@ -662,7 +679,7 @@ int isca_b200_get_time_pointers(IscaHandle h, int* p, int* c) { API_BEGIN(h) *p 
 // the first occurrence of every variant run eagerly (they also perform lazy one-time setup).
 static void step_graphed(H& h, int physics) {
   const bool first = (h.previous == h.current);
-  if (!h.use_graph || first || h.keep_tend) { step_once(h, physics, nullptr, nullptr, nullptr); return; }
+  if (!h.use_graph || first || h.keep_tend || !h.grad_valid) { step_once(h, physics, nullptr, nullptr, nullptr); return; }
   H::StepGraph& sg = h.graphs[h.current + 2 * (physics ? 1 : 0)];
   sg.uses++;
   if (sg.uses == 1) { step_once(h, physics, nullptr, nullptr, nullptr); return; }

@@ -11,6 +11,7 @@ struct DevTables {
   // Gaussian grid [J] (global index) and vertical coordinate
   const double *sin_lat, *cos_lat, *cosm_lat, *wts_lat, *coriolis, *rad_lat;
   const double *pk, *bk, *dpk, *dbk;           // [K+1],[K+1],[K],[K]
+  const double *ln_bk;                         // [K+1] log(bk) (0 where bk == 0); used when pk == 0 everywhere
   // Legendre tables, packed [T][Jh]
   const double *leg, *legw;
   // per packed row [T]
@@ -44,6 +45,7 @@ struct Params {
   int do_conserve_energy, no_forcing, physics_on;
   int first_step;                // previous == current
   int pk0_zero, pkbk0_zero;      // pk(1)==0 ; pk(1)==0 && bk(1)==0
+  int pure_sigma;                // pk == 0 at every half level
   double vr_tmin, vr_tmax;
 };
 

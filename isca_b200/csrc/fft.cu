@@ -141,51 +141,51 @@ fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __re
   const int lev0 = blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
-  constexpr int NT = FFT_LT * Q;
 
-  // 1. stage X[m][lev] (m <= M), zero elsewhere (transforms.F90:424); unpadded index k <= H
-  {
-    constexpr int NIT = (FFT_LT * (H + 1) + NT - 1) / NT;
-#pragma unroll 4
-    for (int q = 0; q < NIT; ++q) {
-      const int idx = tid + q * NT;
-      const int k = idx / FFT_LT, l = idx - k * FFT_LT;
-      if (k <= H) {
-        double2 v = make_double2(0.0, 0.0);
-        if (k <= g.M && lev0 + l < nlev)
-          v = *reinterpret_cast<const double2*>(four + fourB_index(g, k, jl, C) + 2 * (lev0 + l));
-        buf[l * S::LS + k] = v;
-      }
-    }
-  }
-  __syncthreads();
   const int line = tid / Q, lt = tid - line * Q;
   double2* A = buf + line * S::LS;
   const int lev = lev0 + line;
 
-  // 2. pass 1 (radix R1, Ns = 1): inputs are the merged spectrum
-  //    Z[k] = (X[k] + conj X[H-k]) + i w^{-k} (X[k] - conj X[H-k]),  k < H
+  // 1.+2. pass 1 (radix R1, Ns = 1) straight from global memory: the merged spectrum
+  //    Z[k] = (X[k] + conj X[H-k]) + i w^{-k} (X[k] - conj X[H-k]),  k < H,   X[k] = 0 for k > M (transforms.F90:424)
+  //    A warp covers two adjacent levels x 16 consecutive m: every 32-byte sector is fully used, and all
+  //    2*R1 loads of a thread are independent (no staging pass, no barrier before the butterflies).
   {
     constexpr int NB1 = (H / R1 + Q - 1) / Q;
     double2 v[NB1][R1];
+    const bool live = lev < nlev;
+    const double* base = four + (size_t)jl * C + 2 * lev;
+    const size_t mstride = (size_t)g.Jloc * C;
 #pragma unroll
     for (int b = 0; b < NB1; ++b) {
       const int j = lt + b * Q;
       if (j < H / R1) {
+        constexpr int RC = (R1 > 8) ? 8 : R1;          // loads are issued in chunks of RC butterflies legs (register budget)
 #pragma unroll
-        for (int r = 0; r < R1; ++r) {
-          const int k = j + r * (H / R1);
-          double2 xk = A[k];
-          const double2 xc = cconj(A[H - k]);
-          if (k == 0) xk.y = 0.0;
-          const double2 e = cadd(xk, xc), o = csub(xk, xc);
-          const double2 wo = cmul(o, tw<+1>(t.twiddle, k));
-          v[b][r] = make_double2(e.x - wo.y, e.y + wo.x);            // e + i*wo
+        for (int r0 = 0; r0 < R1; r0 += RC) {
+          double2 xk[RC], xc[RC];
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            const int k = j + (r0 + q) * (H / R1);
+            const int kc = H - k;
+            xk[q] = make_double2(0.0, 0.0); xc[q] = make_double2(0.0, 0.0);
+            if (live && k <= g.M) xk[q] = *reinterpret_cast<const double2*>(base + (size_t)g.pos[k] * mstride);
+            if (live && kc <= g.M) xc[q] = *reinterpret_cast<const double2*>(base + (size_t)g.pos[kc] * mstride);
+          }
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            const int k = j + (r0 + q) * (H / R1);
+            double2 a = xk[q];
+            const double2 c = cconj(xc[q]);
+            if (k == 0) a.y = 0.0;
+            const double2 e = cadd(a, c), o = csub(a, c);
+            const double2 wo = cmul(o, tw<+1>(t.twiddle, k));
+            v[b][r0 + q] = make_double2(e.x - wo.y, e.y + wo.x);     // e + i*wo
+          }
         }
         Dft<R1, +1>::run(v[b]);
       }
     }
-    __syncthreads();                     // every thread is done reading X before the buffer is overwritten
     pass_write<H, R1, R1, Q>(A, v, 1, lt);
   }
   __syncthreads();
@@ -322,8 +322,8 @@ static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* le
 // radix plans: H = I/2 = R1*R2*R3, Q = H / max radix threads per line
 void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
   switch (t.g.I) {
-    case 1024: launch_inv_shape<512, 8, 8, 8, 64, 2>(t, four, levs, nlev, Lp, st); break;
-    case 512:  launch_inv_shape<256, 16, 16, 1, 16, 5>(t, four, levs, nlev, Lp, st); break;
+    case 1024: launch_inv_shape<512, 8, 8, 8, 64, 1>(t, four, levs, nlev, Lp, st); break;
+    case 512:  launch_inv_shape<256, 16, 16, 1, 16, 4>(t, four, levs, nlev, Lp, st); break;
     case 256:  launch_inv_shape<128, 8, 16, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
     case 128:  launch_inv_shape<64, 8, 8, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
     case 64:   launch_inv_shape<32, 4, 8, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;

@@ -19,8 +19,15 @@ namespace isca {
 // pressure_variables for one column, one level at a time, bottom-up.
 struct PressLevel { double p_half_k, p_half_k1, ln_half_k, ln_half_k1, ln_full, p_full; };
 
-__device__ __forceinline__ void press_level(const DevTables& t, const Params& pr, int k, double ps, double ln_half_k1,
-                                            PressLevel& o) {
+// ln(p_half(k)): for a pure sigma coordinate (pk == 0 everywhere) p_half = bk*ps, so the logarithm is
+// ln(bk) (host table) + ln(ps) (one log per column) instead of one log per level; the two forms differ by
+// at most ~2 ulp of ln p (~4e-15 absolute), far inside the parity tolerance.
+__device__ __forceinline__ double ln_p_half(const DevTables& t, const Params& pr, int k, double p_half_k, double ln_ps) {
+  return pr.pure_sigma ? (t.ln_bk[k] + ln_ps) : log(p_half_k);
+}
+
+__device__ __forceinline__ void press_level(const DevTables& t, const Params& pr, int k, double ps, double ln_ps,
+                                            double ln_half_k1, PressLevel& o) {
   o.p_half_k = t.pk[k] + t.bk[k] * ps;
   o.p_half_k1 = t.pk[k + 1] + t.bk[k + 1] * ps;
   o.ln_half_k1 = ln_half_k1;
@@ -28,7 +35,7 @@ __device__ __forceinline__ void press_level(const DevTables& t, const Params& pr
     o.ln_half_k = 0.0;
     o.ln_full = ln_half_k1 + (-1.0);                 // ln_top_level_factor (press_and_geopot.F90:103,186)
   } else {
-    o.ln_half_k = log(o.p_half_k);
+    o.ln_half_k = ln_p_half(t, pr, k, o.p_half_k, ln_ps);
     const double alpha = 1.0 - o.p_half_k * (o.ln_half_k1 - o.ln_half_k) / (o.p_half_k1 - o.p_half_k);
     o.ln_full = o.ln_half_k1 - alpha;
   }
@@ -115,9 +122,11 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   double gh_local = 0.0;                              // geopot_half relative to the chunk's bottom interface
   double energy_int = 0.0;
   double ln_half_below = 0.0;
+  const double ln_ps = pr.pure_sigma ? log(ps_c) : 0.0;
+  const double inv_cp = 1.0 / pr.cp_air;
   double u_dn = 0.0, v_dn = 0.0, T_dn = 0.0, u_k = 0.0, v_k = 0.0, T_k = 0.0;
   if (k_hi > k_lo) {
-    ln_half_below = log(t.pk[k_hi] + t.bk[k_hi] * ps_c);
+    ln_half_below = ln_p_half(t, pr, k_hi, t.pk[k_hi] + t.bk[k_hi] * ps_c, ln_ps);
     const size_t e = (size_t)(k_hi - 1) * plane + col;
     u_k = a.u_cur[e]; v_k = a.v_cur[e]; T_k = a.t_cur[e];
     if (k_hi < K) { u_dn = a.u_cur[e + plane]; v_dn = a.v_cur[e + plane]; T_dn = a.t_cur[e + plane]; }
@@ -130,7 +139,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
     double u_up = 0.0, v_up = 0.0, T_up = 0.0;       // level k-1
     if (k > 0) { u_up = a.u_cur[e - plane]; v_up = a.v_cur[e - plane]; T_up = a.t_cur[e - plane]; }
     PressLevel pl;
-    press_level(t, pr, k, ps_c, ln_half_below, pl);
+    press_level(t, pr, k, ps_c, ln_ps, ln_half_below, pl);
 
     // ---------------- physics: hs_forcing on (u,v,T)(previous), pressures of `current`
     double dt_u = 0.0, dt_v = 0.0, dt_T = 0.0;
@@ -141,7 +150,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
       const bool in_bl = (sigma <= 1.0 && sigma > pr.sigma_b);
       if (in_bl) { const double vfactr = vcoeff * (sigma - pr.sigma_b); utnd = vfactr * u_p; vtnd = vfactr * v_p; }
       if (pr.do_conserve_energy) {
-        const double ttnd = -((u_p + .5 * utnd * delta_t) * utnd + (v_p + .5 * vtnd * delta_t) * vtnd) / pr.cp_air;
+        const double ttnd = -((u_p + .5 * utnd * delta_t) * utnd + (v_p + .5 * vtnd * delta_t) * vtnd) * inv_cp;
         dt_T = dt_T + ttnd;
       }
       dt_u = dt_u + utnd; dt_v = dt_v + vtnd;
@@ -192,16 +201,16 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
 
     // ---------------- vert_advection, second_centered, advective form, time_level = current
     {
-      const double dz = pl.p_half_k1 - pl.p_half_k;  // dp = p_half(k+1) - p_half(k)
+      const double rdz = 1.0 / (pl.p_half_k1 - pl.p_half_k);  // dp = p_half(k+1) - p_half(k); one reciprocal for the 3 fields
       const double fu_t = (k == 0) ? w_top * u_k : w_top * (0.5 * (u_k + u_up));
       const double fu_b = (k == K - 1) ? w_bot * u_k : w_bot * (0.5 * (u_dn + u_k));
-      dt_u = dt_u + (-(fu_b - fu_t - u_k * (w_bot - w_top)) / dz);
+      dt_u = dt_u + (-(fu_b - fu_t - u_k * (w_bot - w_top)) * rdz);
       const double fv_t = (k == 0) ? w_top * v_k : w_top * (0.5 * (v_k + v_up));
       const double fv_b = (k == K - 1) ? w_bot * v_k : w_bot * (0.5 * (v_dn + v_k));
-      dt_v = dt_v + (-(fv_b - fv_t - v_k * (w_bot - w_top)) / dz);
+      dt_v = dt_v + (-(fv_b - fv_t - v_k * (w_bot - w_top)) * rdz);
       const double ft_t = (k == 0) ? w_top * T_k : w_top * (0.5 * (T_k + T_up));
       const double ft_b = (k == K - 1) ? w_bot * T_k : w_bot * (0.5 * (T_dn + T_k));
-      dt_T = dt_T + (-(ft_b - ft_t - T_k * (w_bot - w_top)) / dz);
+      dt_T = dt_T + (-(ft_b - ft_t - T_k * (w_bot - w_top)) * rdz);
     }
     // ---------------- horizontal_advection of T (dx, dy already divided by cos in the FFT epilogue)
     dt_T = dt_T - u_k * a.dx_t[e] - v_k * a.dy_t[e];
@@ -317,6 +326,7 @@ void launch_colsum_ps(const DevTables& t, const double* ps, double* part, cudaSt
 
 // scal[SC_*]: see grid.h.  mass_correction_factor = mean_ps_prev / mean_ps_tmp
 __global__ void apply_mass_kernel(DevTables t, double* __restrict__ ps, double2* __restrict__ lnps_fut,
+                                  double2* __restrict__ lnps_cur, double rc_raw,
                                   double* __restrict__ scal, double denom, int owns_m0, int do_mass) {
   const GeomDev& g = t.g;
   const size_t n = (size_t)g.Jloc * g.I;
@@ -328,13 +338,17 @@ __global__ void apply_mass_kernel(DevTables t, double* __restrict__ ps, double2*
   if (idx == 0) {
     scal[SC_MEAN_PS_PREV] = mean_prev;
     scal[SC_MASS_FACTOR] = f;
-    if (owns_m0 && do_mass) lnps_fut[0].x = lnps_fut[0].x + sqrt(2.) * log(f);   // ln_ps(0,0,future) (:1231)
+    if (owns_m0 && do_mass) {
+      const double inc = sqrt(2.) * log(f);
+      lnps_fut[0].x = lnps_fut[0].x + inc;                                      // ln_ps(0,0,future) (:1231)
+      if (lnps_cur) lnps_cur[0].x = lnps_cur[0].x + rc_raw * inc;                // fused leapfrog_2level_B sees the fixed value
+    }
   }
 }
-void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double* scal, double denom, int owns_m0,
-                       int do_mass, cudaStream_t st) {
+void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double2* lnps_cur, double rc_raw, double* scal,
+                       double denom, int owns_m0, int do_mass, cudaStream_t st) {
   size_t n = (size_t)t.g.Jloc * t.g.I;
-  apply_mass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, ps, lnps_fut, scal, denom, owns_m0, do_mass);
+  apply_mass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, ps, lnps_fut, lnps_cur, rc_raw, scal, denom, owns_m0, do_mass);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,6 +380,7 @@ void launch_colsum_energy(const DevTables& t, const Params& pr, const double* u,
 }
 
 __global__ void apply_energy_kernel(DevTables t, Params pr, double* __restrict__ T, double2* __restrict__ ts_fut,
+                                    double2* __restrict__ ts_cur, double rc_raw,
                                     double* __restrict__ scal, double denom, int owns_m0, int do_energy) {
   const GeomDev& g = t.g;
   const size_t n = (size_t)g.K * g.Jloc * g.I;
@@ -375,7 +390,10 @@ __global__ void apply_energy_kernel(DevTables t, Params pr, double* __restrict__
   const double tc = do_energy ? pr.grav * (mean_e_prev - mean_e_tmp) / (pr.cp_air * scal[SC_MEAN_PS_PREV]) : 0.0;
   if (do_energy) {
     if (idx < n) T[idx] = T[idx] + tc;
-    if (owns_m0 && idx < (size_t)g.K) ts_fut[idx].x = ts_fut[idx].x + sqrt(2.) * tc;   // ts(0,0,:,future) (:1241)
+    if (owns_m0 && idx < (size_t)g.K) {
+      ts_fut[idx].x = ts_fut[idx].x + sqrt(2.) * tc;                            // ts(0,0,:,future) (:1241)
+      if (ts_cur) ts_cur[idx].x = ts_cur[idx].x + rc_raw * (sqrt(2.) * tc);      // fused leapfrog_2level_B
+    }
   }
   if (idx == 0) {
     scal[SC_MEAN_EN_PREV] = mean_e_prev;
@@ -383,10 +401,10 @@ __global__ void apply_energy_kernel(DevTables t, Params pr, double* __restrict__
     if (scal[SC_TMIN] < pr.vr_tmin || scal[SC_TMAX] > pr.vr_tmax) scal[SC_T_FLAG] = 1.0;   // valid_range_t (:940)
   }
 }
-void launch_apply_energy(const DevTables& t, const Params& pr, double* T, double2* ts_fut, double* scal, double denom,
-                         int owns_m0, int do_energy, cudaStream_t st) {
+void launch_apply_energy(const DevTables& t, const Params& pr, double* T, double2* ts_fut, double2* ts_cur, double rc_raw,
+                         double* scal, double denom, int owns_m0, int do_energy, cudaStream_t st) {
   size_t n = (size_t)t.g.K * t.g.Jloc * t.g.I;
-  apply_energy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, pr, T, ts_fut, scal, denom, owns_m0, do_energy);
+  apply_energy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, pr, T, ts_fut, ts_cur, rc_raw, scal, denom, owns_m0, do_energy);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -402,13 +420,14 @@ __global__ void press_heights_kernel(DevTables t, Params pr, const double* __res
   const size_t col = (size_t)jl * g.I + i, plane = (size_t)g.Jloc * g.I;
   const double p_s = ps[col];
   double gh_below = phis[col];
-  double ln_half_below = log(t.pk[K] + t.bk[K] * p_s);
+  const double ln_ps = pr.pure_sigma ? log(p_s) : 0.0;
+  double ln_half_below = ln_p_half(t, pr, K, t.pk[K] + t.bk[K] * p_s, ln_ps);
   if (p_half) p_half[(size_t)K * plane + col] = t.pk[K] + t.bk[K] * p_s;
   if (z_half) z_half[(size_t)K * plane + col] = gh_below / pr.grav;
   for (int k = K - 1; k >= 0; --k) {
     const size_t e = (size_t)k * plane + col;
     PressLevel pl;
-    press_level(t, pr, k, p_s, ln_half_below, pl);
+    press_level(t, pr, k, p_s, ln_ps, ln_half_below, pl);
     const double tt = T[e];
     const double gfull = gh_below + pr.rdgas * tt * (pl.ln_half_k1 - pl.ln_full);
     double gh = 0.0;

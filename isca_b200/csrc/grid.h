@@ -30,12 +30,12 @@ struct GridStepArgs {
 void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& a, cudaStream_t st);
 void launch_reduce(const double* part, size_t n, int nq, const int* ops, double* out, double* tmp, cudaStream_t st);  // tmp: [nq*128]
 void launch_colsum_ps(const DevTables& t, const double* ps, double* part, cudaStream_t st);
-void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double* scal, double denom, int owns_m0,
-                       int do_mass, cudaStream_t st);
+void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double2* lnps_cur, double rc_raw, double* scal,
+                       double denom, int owns_m0, int do_mass, cudaStream_t st);
 void launch_colsum_energy(const DevTables& t, const Params& pr, const double* u, const double* v, const double* T,
                           const double* ps, double* part, cudaStream_t st);
-void launch_apply_energy(const DevTables& t, const Params& pr, double* T, double2* ts_fut, double* scal, double denom,
-                         int owns_m0, int do_energy, cudaStream_t st);
+void launch_apply_energy(const DevTables& t, const Params& pr, double* T, double2* ts_fut, double2* ts_cur, double rc_raw,
+                         double* scal, double denom, int owns_m0, int do_energy, cudaStream_t st);
 void launch_press_heights(const DevTables& t, const Params& pr, const double* T, const double* ps, const double* phis,
                           double* p_full, double* p_half, double* z_full, double* z_half, cudaStream_t st);
 void launch_divide_by_cos(const DevTables& t, double* f, int nlev, cudaStream_t st);

@@ -84,6 +84,54 @@ void launch_spec_ucos_vcos(const DevTables& t, double2* buf, int Lp, int nlev, i
   spec_ucos_vcos_kernel<<<t.g.T, 64, 0, st>>>(t, buf, Lp, nlev, vor_off, div_off, u_off, v_off);
 }
 
+// Fused tail of the spectral step, all inside the next inverse batch buffer:
+//   (vor, div) -> (u cos, v cos)                                   compute_ucos_vcos   spherical.F90:409-469
+//   T, ln ps   -> (dx, dy) gradients used by the NEXT step        compute_gradient_cos spherical.F90:270-351
+// The gradients are unaffected by the mass/energy fixers (they only change the (0,0) coefficient, whose
+// gradient is identically zero) and, with raw_filter_coeff = 1, by leapfrog_2level_B.
+__global__ void spec_post_kernel(DevTables t, double2* __restrict__ buf, int Lp, int K, int vor_off, int div_off, int u_off,
+                                 int v_off, int t_off, int lnps_off, int dxt_off, int dyt_off, int dxl_off, int dyl_off) {
+  const GeomDev& g = t.g;
+  const int p = blockIdx.x;
+  const int n = t.row_n[p];
+  const int m = g.m_of[g.row_m[p]];
+  const int Nm = g.M - m + 2;
+  const double uvc = t.coef_uvc[p], uvm = t.coef_uvm[p], uvp = t.coef_uvp[p];
+  const double cdx = t.coef_dx[p], cdym = t.coef_dym[p], cdyp = t.coef_dyp[p];
+  const bool has_m = (n >= 1), has_p = (n + 1 < Nm);
+  double2* row = buf + (size_t)p * Lp;
+  const double2* rm = row - Lp;
+  const double2* rp = row + Lp;
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+    if (k < K) {
+      const double2 vor = row[vor_off + k], div = row[div_off + k];
+      double2 u = times_i(div); u.x *= uvc; u.y *= uvc;
+      double2 v = times_i(vor); v.x *= uvc; v.y *= uvc;
+      if (has_m) {
+        const double2 vm = rm[vor_off + k], dm = rm[div_off + k];
+        u.x = u.x + uvm * vm.x; u.y = u.y + uvm * vm.y;
+        v.x = v.x - uvm * dm.x; v.y = v.y - uvm * dm.y;
+      }
+      if (has_p) {
+        const double2 vp = rp[vor_off + k], dp = rp[div_off + k];
+        u.x = u.x - uvp * vp.x; u.y = u.y - uvp * vp.y;
+        v.x = v.x + uvp * dp.x; v.y = v.y + uvp * dp.y;
+      }
+      row[u_off + k] = u; row[v_off + k] = v;
+    }
+    // gradient of T (k < K) or of ln ps (k == K)
+    const int so = (k < K) ? t_off + k : lnps_off;
+    const int dxo = (k < K) ? dxt_off + k : dxl_off;
+    const int dyo = (k < K) ? dyt_off + k : dyl_off;
+    const double2 s0 = row[so];
+    double2 dx = times_i(s0); dx.x *= cdx; dx.y *= cdx;
+    double2 dy = make_double2(0.0, 0.0);
+    if (has_m) { const double2 sm = rm[so]; dy.x = -sm.x * cdym; dy.y = -sm.y * cdym; }
+    if (has_p) { const double2 sp = rp[so]; dy.x = dy.x + sp.x * cdyp; dy.y = dy.y + sp.y * cdyp; }
+    row[dxo] = dx; row[dyo] = dy;
+  }
+}
+
 // (u cos / cos^2 .. ) -> (vor, div): vor = alpha(vcos_s, ucos_s, -1), div = alpha(ucos_s, vcos_s, +1), truncated
 __global__ void spec_vor_div_kernel(DevTables t, const double2* __restrict__ buf, int Lp, int nlev, int a_off, int b_off,
                                     double2* __restrict__ out, int Lo, int vor_off, int div_off) {
@@ -121,6 +169,7 @@ void launch_spec_vor_div(const DevTables& t, const double2* buf, int Lp, int nle
 // ---------------------------------------------------------------------------------------------
 constexpr int RP = 16;            // packed rows per CTA
 constexpr int NC = 2 * RP;        // real columns per CTA
+constexpr int NCP = NC + 1;       // padded row stride of the [k][column] shared tiles (odd: conflict-free both ways)
 
 // linear_tp_tendency (implicit.F90:414-480) for one real column held in shared memory [k][NC].
 // ref_temperature_implicit is 300 K at every level (spectral_dynamics.F90:473), so the
@@ -133,8 +182,8 @@ __device__ __forceinline__ double tp_tendency_column(const DevTables& t, const P
     const double dp_inv = 1 / dp;
     const double dlog_1 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k];
     const double dlog_3 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k];
-    const double dmean = div[k * NC + col] * dp;
-    dt_t[k * NC + col] = -pr.kappa * t.ref_t[k] * (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv;
+    const double dmean = div[k * NCP + col] * dp;
+    dt_t[k * NCP + col] = -pr.kappa * t.ref_t[k] * (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv;
     dmean_tot = dmean_tot + dmean;
   }
   return -dmean_tot;      // dt_p_surf
@@ -146,10 +195,10 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
   const GeomDev& g = t.g;
   const int K = g.K;
   double* s_ddiv = sm;                    // [K][NC] dt_divs
-  double* s_dT = s_ddiv + K * NC;         // [K][NC] dt_ts
-  double* s_dD = s_dT + K * NC;           // [K][NC] divs(prev) - divs(cur); later scratch
-  double* s_dTs = s_dD + K * NC;          // [K][NC] ts(prev) - ts(cur)
-  double* s_ps = s_dTs + K * NC;          // [2][NC]  dt_ln_ps ; ln_ps(prev)-ln_ps(cur)
+  double* s_dT = s_ddiv + K * NCP;         // [K][NC] dt_ts
+  double* s_dD = s_dT + K * NCP;           // [K][NC] divs(prev) - divs(cur); later scratch
+  double* s_dTs = s_dD + K * NCP;          // [K][NC] ts(prev) - ts(cur)
+  double* s_ps = s_dTs + K * NCP;          // [2][NC]  dt_ln_ps ; ln_ps(prev)-ln_ps(cur)
   const int p0 = blockIdx.x * RP;
   const int tid = threadIdx.x;
   const int LpB = a.LpB;
@@ -190,10 +239,10 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
       dTs = make_double2(tpv.x - tcu.x, tpv.y - tcu.y);
     }
     const int c = 2 * r;
-    s_ddiv[k * NC + c] = ddiv.x; s_ddiv[k * NC + c + 1] = ddiv.y;
-    s_dT[k * NC + c] = dT.x;     s_dT[k * NC + c + 1] = dT.y;
-    s_dD[k * NC + c] = dD.x;     s_dD[k * NC + c + 1] = dD.y;
-    s_dTs[k * NC + c] = dTs.x;   s_dTs[k * NC + c + 1] = dTs.y;
+    s_ddiv[k * NCP + c] = ddiv.x; s_ddiv[k * NCP + c + 1] = ddiv.y;
+    s_dT[k * NCP + c] = dT.x;     s_dT[k * NCP + c + 1] = dT.y;
+    s_dD[k * NCP + c] = dD.x;     s_dD[k * NCP + c + 1] = dD.y;
+    s_dTs[k * NCP + c] = dTs.x;   s_dTs[k * NCP + c + 1] = dTs.y;
   }
   if (tid < RP) {
     const int p = p0 + tid;
@@ -221,10 +270,10 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
         const double dp_inv = 1 / dp;
         const double dlog_1 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k];
         const double dlog_3 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k];
-        const double dmean = s_dD[k * NC + col] * dp;
+        const double dmean = s_dD[k * NCP + col] * dp;
         const double dtt = -pr.kappa * t.ref_t[k] * (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv;
         dmean_tot = dmean_tot + dmean;
-        s_dT[k * NC + col] = s_dT[k * NC + col] + dtt;
+        s_dT[k * NCP + col] = s_dT[k * NCP + col] + dtt;
       }
       const double dt_ps_temp = -dmean_tot;
       const double dlnps = s_ps[col] + dt_ps_temp / pr.ref_ps;
@@ -234,9 +283,9 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
       const double eig = t.eigen[p];
       double gh = 0.0;                                  // geopot_half(K+1)
       for (int k = K - 1; k >= 0; --k) {
-        const double ts_temp = s_dTs[k * NC + col] + xi * s_dT[k * NC + col];
+        const double ts_temp = s_dTs[k * NCP + col] + xi * s_dT[k * NCP + col];
         const double geopot = gh + pr.rdgas * (ts_temp * (t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k]) + t.ref_t[k] * (0.0 - 0.0));
-        s_ddiv[k * NC + col] = s_ddiv[k * NC + col] + eig * (geopot + t.h_impl[k] * ps_temp * pr.ref_ps);
+        s_ddiv[k * NCP + col] = s_ddiv[k * NCP + col] + eig * (geopot + t.h_impl[k] * ps_temp * pr.ref_ps);
         if (k >= 1) gh = gh + pr.rdgas * (ts_temp * (t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k]) + t.ref_t[k] * (0.0 - 0.0));
       }
     }
@@ -248,8 +297,8 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
     const int p = p0 + r;
     if (p < g.T) {
       const int c = 2 * r;
-      a.w_div[(size_t)p * K + k] = make_double2(s_ddiv[k * NC + c], s_ddiv[k * NC + c + 1]);
-      a.w_T[(size_t)p * K + k] = make_double2(s_dT[k * NC + c], s_dT[k * NC + c + 1]);
+      a.w_div[(size_t)p * K + k] = make_double2(s_ddiv[k * NCP + c], s_ddiv[k * NCP + c + 1]);
+      a.w_T[(size_t)p * K + k] = make_double2(s_dT[k * NCP + c], s_dT[k * NCP + c + 1]);
     }
   }
   if (tid < RP && p0 + tid < g.T) a.w_lnps[p0 + tid] = make_double2(s_ps[2 * tid], s_ps[2 * tid + 1]);
@@ -308,8 +357,8 @@ spec_update_kernel(DevTables t, Params pr, SpecStepArgs a) {
   const GeomDev& g = t.g;
   const int K = g.K;
   double* s_ddiv = sm;                    // [K][NC]
-  double* s_tmp = s_ddiv + K * NC;        // [K][NC] dt_ts_temp
-  double* s_ps = s_tmp + K * NC;          // [NC] dt_ps_temp
+  double* s_tmp = s_ddiv + K * NCP;        // [K][NC] dt_ts_temp
+  double* s_ps = s_tmp + K * NCP;          // [NC] dt_ps_temp
   const int p0 = blockIdx.x * RP;
   const int tid = threadIdx.x;
 
@@ -318,13 +367,13 @@ spec_update_kernel(DevTables t, Params pr, SpecStepArgs a) {
     const int p = p0 + r;
     double2 v = make_double2(0, 0);
     if (p < g.T) v = a.w_div[(size_t)p * K + k];
-    s_ddiv[k * NC + 2 * r] = v.x; s_ddiv[k * NC + 2 * r + 1] = v.y;
+    s_ddiv[k * NCP + 2 * r] = v.x; s_ddiv[k * NCP + 2 * r + 1] = v.y;
   }
   __syncthreads();
   if (tid < NC) {
     double dps = 0.0;
     if (a.use_implicit) dps = tp_tendency_column(t, pr, s_ddiv, s_tmp, K, tid);
-    else for (int k = 0; k < K; ++k) s_tmp[k * NC + tid] = 0.0;
+    else for (int k = 0; k < K; ++k) s_tmp[k * NCP + tid] = 0.0;
     s_ps[tid] = dps;
   }
   __syncthreads();
@@ -341,8 +390,8 @@ spec_update_kernel(DevTables t, Params pr, SpecStepArgs a) {
     const int n = t.row_n[p];
     // implicit_correction tail: dt_ts = dt_ts + xi*dt_ts_temp
     double2 dT = a.w_T[e];
-    if (a.use_implicit) { dT.x = dT.x + xi * s_tmp[k * NC + 2 * r]; dT.y = dT.y + xi * s_tmp[k * NC + 2 * r + 1]; }
-    double2 dD = make_double2(s_ddiv[k * NC + 2 * r], s_ddiv[k * NC + 2 * r + 1]);
+    if (a.use_implicit) { dT.x = dT.x + xi * s_tmp[k * NCP + 2 * r]; dT.y = dT.y + xi * s_tmp[k * NCP + 2 * r + 1]; }
+    double2 dD = make_double2(s_ddiv[k * NCP + 2 * r], s_ddiv[k * NCP + 2 * r + 1]);
     double2 dV = a.dt_vors[e];
     // damping (spectral_damping.F90:172-291) against the previous time level
     const double2 vp = a.vors_prev[e], dp_ = a.divs_prev[e], tp = a.ts_prev[e];
@@ -375,6 +424,11 @@ spec_update_kernel(DevTables t, Params pr, SpecStepArgs a) {
     vcn = make_double2(vc.x + rc * (vp.x - 2.0 * vc.x) * raw, vc.y + rc * (vp.y - 2.0 * vc.y) * raw);
     dcn = make_double2(dc.x + rc * (dp_.x - 2.0 * dc.x) * raw, dc.y + rc * (dp_.y - 2.0 * dc.y) * raw);
     tcn = make_double2(tc.x + rc * (tp.x - 2.0 * tc.x) * raw, tc.y + rc * (tp.y - 2.0 * tc.y) * raw);
+    if (a.fuse_robert_b) {   // leapfrog_2level_B: a(cur) += rc*a(fut)*raw; the fixers' (0,0) increments are patched in later
+      vcn.x = vcn.x + rc * vf.x * raw; vcn.y = vcn.y + rc * vf.y * raw;
+      dcn.x = dcn.x + rc * df.x * raw; dcn.y = dcn.y + rc * df.y * raw;
+      tcn.x = tcn.x + rc * tf.x * raw; tcn.y = tcn.y + rc * tf.y * raw;
+    }
     a.vors_cur_w[e] = vcn; a.divs_cur_w[e] = dcn; a.ts_cur_w[e] = tcn;
     a.vors_fut[e] = vf; a.divs_fut[e] = df; a.ts_fut[e] = tf;
     a.specC[(size_t)p * LpC + a.cVor + k] = vf;
@@ -388,7 +442,8 @@ spec_update_kernel(DevTables t, Params pr, SpecStepArgs a) {
     if (a.use_implicit) { dl.x = dl.x + xi * s_ps[2 * tid] / pr.ref_ps; dl.y = dl.y + xi * s_ps[2 * tid + 1] / pr.ref_ps; }
     const double2 lp = a.lnps_prev[p], lc = a.lnps_cur[p];
     const double2 lf = make_double2(lp.x + dt * dl.x, lp.y + dt * dl.y);
-    const double2 lcn = make_double2(lc.x + rc * (lp.x - 2.0 * lc.x) * raw, lc.y + rc * (lp.y - 2.0 * lc.y) * raw);
+    double2 lcn = make_double2(lc.x + rc * (lp.x - 2.0 * lc.x) * raw, lc.y + rc * (lp.y - 2.0 * lc.y) * raw);
+    if (a.fuse_robert_b) { lcn.x = lcn.x + rc * lf.x * raw; lcn.y = lcn.y + rc * lf.y * raw; }
     a.lnps_cur_w[p] = lcn;
     a.lnps_fut[p] = lf;
     a.specC[(size_t)p * LpC + a.cLnps] = lf;
@@ -401,7 +456,7 @@ void launch_spec_step(const DevTables& t, const Params& pr, const SpecStepArgs& 
   const int K = g.K;
   const int nb = (g.T + RP - 1) / RP;
   {
-    size_t smem = sizeof(double) * ((size_t)4 * K * NC + 2 * NC);
+    size_t smem = sizeof(double) * ((size_t)4 * K * NCP + 2 * NC);
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(spec_tend_adjust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
     spec_tend_adjust_kernel<<<nb, 128, smem, st>>>(t, pr, a);
@@ -414,12 +469,13 @@ void launch_spec_step(const DevTables& t, const Params& pr, const SpecStepArgs& 
     spec_wave_matvec_kernel<<<grid, WM_COLS, smem, st>>>(t, a.w_div);
   }
   {
-    size_t smem = sizeof(double) * ((size_t)2 * K * NC + NC);
+    size_t smem = sizeof(double) * ((size_t)2 * K * NCP + NC);
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(spec_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
     spec_update_kernel<<<nb, 128, smem, st>>>(t, pr, a);
   }
-  launch_spec_ucos_vcos(t, a.specC, a.LpC, K, a.cVor, a.cDiv, a.cU, a.cV, st);
+  spec_post_kernel<<<g.T, 64, 0, st>>>(t, a.specC, a.LpC, K, a.cVor, a.cDiv, a.cU, a.cV, a.cT, a.cLnps,
+                                       a.cDxT, a.cDyT, a.cDxL, a.cDyL);
 }
 
 // ---------------------------------------------------------------------------------------------

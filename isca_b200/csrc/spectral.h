@@ -16,6 +16,8 @@ struct SpecStepArgs {
   double2 *dt_vors, *w_div, *w_T, *w_lnps;
   // next inverse batch [T][LpC]: offsets of vor(K), div(K), ucos(K), vcos(K), T(K), lnps(1)
   double2* specC; int LpC; int cVor, cDiv, cU, cV, cT, cLnps;
+  int cDxT, cDyT, cDxL, cDyL;   // gradient levels for the next step: dx T (K), dy T (K), dx ln ps, dy ln ps
+  int fuse_robert_b;
   int use_implicit;
   // optional copies of the final spectral tendencies (parity tests)
   int keep_tend; double2 *k_dt_vors, *k_dt_divs, *k_dt_ts, *k_dt_lnps;

@@ -930,43 +930,6 @@ class HSForcing:
 
 
 # --------------------------------------------------------------------------------------
-# Lin-Rood A-grid horizontal tracer advection (atmos_spectral/model/fv_advection.F90)
-# --------------------------------------------------------------------------------------
-class FVAdvection:
-    def __init__(self, cfg: Config, tb: Tables):
-        """fv_advection_init :59-121 with yy = latitude boundaries from get_grid_boundaries
-        (spherical_fourier.F90 / transforms.F90: sin of boundaries = cumulative Gaussian weights)."""
-        self.cfg = cfg
-        nx, ny = cfg.lon_max, cfg.lat_max
-        self.nx, self.ny = nx, ny
-        # transforms.F90 get_grid_boundaries: lat_boundaries from cumulative weights
-        sin_b = np.zeros(ny + 1)
-        sin_b[0] = -1.0
-        ssum = sin_b[0]
-        for j in range(ny - 1):
-            ssum = ssum + tb.wts_lat[j]
-            sin_b[j + 1] = ssum
-        sin_b[ny] = 1.0
-        yy = np.arcsin(sin_b)
-        self.yy_rad = yy.copy()
-        y = 0.5 * (yy[1:] + yy[:-1])
-        self.c = np.cos(y)
-        self.s = np.sin(y)
-        self.cc = np.cos(yy)
-        dy = np.zeros(ny + 4)                   # index j -> dy[j+1] for j=-1..ny+2
-        dy[2:ny + 2] = yy[1:] - yy[:-1]
-        dy[0] = dy[3]                           # dy(-1) = dy(2)
-        dy[1] = dy[2]                           # dy(0)  = dy(1)
-        dy[ny + 2] = dy[ny + 1]                 # dy(ny+1) = dy(ny)
-        dy[ny + 3] = dy[ny]                     # dy(ny+2) = dy(ny-1)
-        self.dy = dy * cfg.radius
-        self.dx = 2.0 * PI * cfg.radius / float(nx)
-
-    def DY(self, j):                            # Fortran dy(j), j in -1..ny+2
-        return self.dy[j + 1]
-
-
-# --------------------------------------------------------------------------------------
 # The dynamical core step
 # --------------------------------------------------------------------------------------
 class SpectralCore:
@@ -1246,7 +1209,7 @@ class SpectralCore:
         parts = []
         if cfg.num_tracers == 0:
             return parts
-        from .fv_advection import a_grid_horiz_advection     # noqa: local import keeps core importable
+        from .fv_advection import a_grid_horiz_advection
         dp = p_half[1:] - p_half[:-1]
         for n in range(cfg.num_tracers):
             tr_future = self.grid_tracers[prev, n] + delta_t * dt_tr[n]
@@ -1288,7 +1251,8 @@ class SpectralCore:
     @property
     def fv(self):
         if not hasattr(self, "_fv"):
-            self._fv = FVAdvection(self.cfg, self.tb)
+            from .fv_advection import FVGrid
+            self._fv = FVGrid(self.cfg, self.tb)
         return self._fv
 
     # ---- convenience for tests / bench
