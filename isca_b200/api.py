@@ -70,6 +70,7 @@ EXPORTS = [
 
 # field / scalar ids (include/isca_b200.h)
 F_PS, F_U, F_V, F_T, F_VOR, F_DIV, F_WG_FULL, F_P_FULL, F_P_HALF, F_Z_FULL, F_Z_HALF = range(11)
+F_TRACER0 = 16
 S_VOR, S_DIV, S_T, S_LNPS = range(4)
 S_DT_VOR, S_DT_DIV, S_DT_T, S_DT_LNPS = 8, 9, 10, 11
 LEVEL_CURRENT, LEVEL_PREVIOUS = -1, -2
@@ -288,10 +289,10 @@ class Atmosphere:
         return {k: v for k, v in out.items() if v is not None}
 
     # ---- state I/O (restart path / diag mirrors) ---------------------------------------------
-    def set_grid_state(self, slot, ug=None, vg=None, tg=None, psg=None):
+    def set_grid_state(self, slot, ug=None, vg=None, tg=None, psg=None, tracers=None):
         s3 = (self.K, self.Jloc, self.I)
-        a = [_in(ug, s3), _in(vg, s3), _in(tg, s3), _in(psg, (self.Jloc, self.I))]
-        self._ck(self.lib.isca_b200_set_grid_state(self.h, slot, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), None),
+        a = [_in(ug, s3), _in(vg, s3), _in(tg, s3), _in(psg, (self.Jloc, self.I)), _in(tracers, s3)]
+        self._ck(self.lib.isca_b200_set_grid_state(self.h, slot, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4])),
                  "set_grid_state")
 
     def set_spectral_state(self, slot, vors=None, divs=None, ts=None, ln_ps=None):

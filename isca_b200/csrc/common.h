@@ -61,6 +61,8 @@ struct HostTables {
   std::vector<int>    row_m, row_n;                  // [T]
   // semi-implicit reference state (implicit.F90)
   std::vector<double> ref_ln_p_half, ref_ln_p_full, ref_t, h, div_mat;  // [K+1],[K],[K],[K],[K*K]
+  // finite-volume tracer grid (fv_advection_init): see tracer.h
+  std::vector<double> fv_c, fv_cc, fv_dy, fv_dyy, fv_dy_plus, fv_dy_minus; double fv_dx;
   std::vector<double> twiddle;                       // [I/2][2]: exp(-2 pi i k / I), k < I/2
   double ref_ps;
   double global_sum_of_wts;

@@ -6,6 +6,7 @@
 #include "spectral.h"
 #include "grid.h"
 #include "nccl_dyn.h"
+#include "tracer.h"
 #include <cstring>
 #include <map>
 #include <algorithm>
@@ -82,6 +83,11 @@ struct IscaHandle_t {
   DBuf<double2> vors[2], divs[2], ts[2], lnps[2];
   DBuf<double> u[2], v[2], T[2], ps[2];
   DBuf<double> vorg, divg, phis, wg_full;
+  // ---- grid tracer (sphum)
+  DBuf<double> q[2], tr0, trq1, trq2, tr1, wg;
+  DBuf<double> d_fv_c, d_fv_cc, d_fv_dy, d_fv_dyy, d_fv_dyp, d_fv_dym;
+  FvTables fv;
+  DBuf<int> ops_sum3;
   // ---- work
   DBuf<double2> dt_vors, w_div, w_T, w_lnps, k_dt_vors, k_dt_divs, k_dt_ts, k_dt_lnps;
   DBuf<double2> specA, specB, specC;
@@ -194,6 +200,17 @@ static void alloc_state(H& h) {
     h.u[s].alloc(h.n3()); h.v[s].alloc(h.n3()); h.T[s].alloc(h.n3()); h.ps[s].alloc(h.nplane());
   }
   h.vorg.alloc(h.n3()); h.divg.alloc(h.n3()); h.phis.alloc(h.nplane()); h.wg_full.alloc(h.n3());
+  if (h.cfg.num_tracers > 0) {
+    for (int s = 0; s < 2; ++s) h.q[s].alloc(h.n3());
+    h.tr0.alloc(h.n3()); h.trq1.alloc(h.n3()); h.trq2.alloc(h.n3()); h.tr1.alloc(h.n3());
+    h.wg.alloc(h.n3() + h.nplane());
+    const HostTables& t = h.ht;
+    h.d_fv_c.upload(t.fv_c); h.d_fv_cc.upload(t.fv_cc); h.d_fv_dy.upload(t.fv_dy); h.d_fv_dyy.upload(t.fv_dyy);
+    h.d_fv_dyp.upload(t.fv_dy_plus); h.d_fv_dym.upload(t.fv_dy_minus);
+    h.fv.c = h.d_fv_c.p; h.fv.cc = h.d_fv_cc.p; h.fv.dy = h.d_fv_dy.p; h.fv.dyy = h.d_fv_dyy.p;
+    h.fv.dy_plus = h.d_fv_dyp.p; h.fv.dy_minus = h.d_fv_dym.p; h.fv.dx = t.fv_dx;
+    h.ops_sum3.upload({0, 0, 0});
+  }
   h.dt_vors.alloc(h.nspec3()); h.w_div.alloc(h.nspec3()); h.w_T.alloc(h.nspec3()); h.w_lnps.alloc(g.T);
   h.k_dt_vors.alloc(h.nspec3()); h.k_dt_divs.alloc(h.nspec3()); h.k_dt_ts.alloc(h.nspec3()); h.k_dt_lnps.alloc(g.T);
   h.LpA = round_up(2 * K + 2, 16); h.LpB = round_up(4 * K + 1, 16); h.LpC = round_up(7 * K + 3, 16);
@@ -334,11 +351,34 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   ga.out_T = h.gridB.p; ga.out_A = h.gridB.p + (size_t)K * pl; ga.out_B = h.gridB.p + (size_t)(2 * K) * pl;
   ga.out_phi = h.gridB.p + (size_t)(3 * K) * pl; ga.dt_lnps = h.gridB.p + (size_t)(4 * K) * pl;
   ga.wg_full = h.wg_full.p; ga.part = h.part.p;
+  ga.wg = (h.cfg.num_tracers > 0) ? h.wg.p : nullptr;
   launch_grid_step(h.dt, pr, ga, st); h.launches++;
   h.mark("grid_step");
   launch_reduce(h.part.p, pl, 2, h.ops_sum2.p, h.scal.p + SC_SUM_PS_PREV, h.red_tmp.p, st); h.launches += 2;
   allreduce_scalars(h, h.scal.p + SC_SUM_PS_PREV, 2, NCCL_SUM);
   h.mark("corr_reduce_prev");
+
+  // ---- grid tracer: update_tracers (spectral_dynamics.F90:1116-1188); needs only the `current` winds and wg
+  TracerArgs ta;
+  if (h.cfg.num_tracers > 0) {
+    const IscaConfig& c = h.cfg;
+    ta.q_prev = h.q[prev].p; ta.q_cur = h.q[cur].p; ta.q_cur_w = h.q[cur].p; ta.q_fut = h.q[fut].p;
+    ta.u_cur = h.u[cur].p; ta.v_cur = h.v[cur].p; ta.ps_cur = h.ps[cur].p; ta.ps_prev = h.ps[prev].p; ta.ps_fut = h.ps[fut].p;
+    ta.wg = h.wg.p; ta.tr0 = h.tr0.p; ta.q1 = h.trq1.p; ta.q2 = h.trq2.p; ta.tr1 = h.tr1.p; ta.part = h.part.p;
+    ta.delta_t = delta_t; ta.trflux = c.trflux;
+    const double sink_s = c.trsink < 0. ? -86400. * c.trsink : c.trsink;       // hs_forcing.F90:408-409, 697-699
+    ta.trdamp = sink_s > 0. ? 1. / sink_s : 0.;
+    ta.robert_coeff = c.tracer_robert_coeff < 0. ? c.robert_coeff : c.tracer_robert_coeff;
+    ta.raw_filter_coeff = c.raw_filter_coeff; ta.water_limit = c.water_correction_limit; ta.physics_on = physics_on;
+    launch_tracer_source(h.dt, pr, ta, st);
+    launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_W_PREV, h.red_tmp.p, st);
+    allreduce_scalars(h, h.scal.p + SC_W_PREV, 1, NCCL_SUM);
+    launch_tracer_semi(h.dt, h.fv, ta, st);
+    launch_tracer_flux(h.dt, h.fv, ta, st);
+    launch_tracer_ppm(h.dt, pr, ta, st);
+    h.launches += 6;
+    h.mark("tracer_advection");
+  }
 
   dev_forward(h, h.levsB.p, 4 * K + 1, h.specB.p, h.LpB, h.truncB.p, "_tend");
 
@@ -377,6 +417,14 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
                       h.cfg.do_energy_correction, st);
   h.launches += 8;
   h.mark("corr_mass_energy");
+  if (h.cfg.num_tracers > 0) {
+    launch_tracer_water_colsum(h.dt, pr, ta, st);
+    launch_reduce(h.part.p, pl, 3, h.ops_sum3.p, h.scal.p + SC_W_ALL, h.red_tmp.p, st);
+    allreduce_scalars(h, h.scal.p + SC_W_ALL, 3, NCCL_SUM);
+    launch_tracer_water_apply(h.dt, pr, ta, h.scal.p + SC_W_PREV, h.denom(), h.cfg.do_water_correction, st);
+    h.launches += 4;
+    h.mark("tracer_water_fixer");
+  }
 
   // time-level swap.  complete_robert_filter -> leapfrog_2level_B (a(previous) += rc*a(current)*raw) is fused into
   // spec_update (all coefficients) and apply_mass / apply_energy (the fixers' (0,0) increments).
@@ -501,6 +549,10 @@ static void cold_start(H& h) {
   d2d_on(h.st, h.v[1].p, h.v[0].p, h.n3() * sizeof(double));
   d2d_on(h.st, h.T[1].p, h.T[0].p, h.n3() * sizeof(double));
   d2d_on(h.st, h.ps[1].p, h.ps[0].p, pl * sizeof(double));
+  if (h.cfg.num_tracers > 0) {
+    std::vector<double> q0(h.n3(), c.initial_sphum);                // spectral_dynamics.F90:584-590
+    for (int s2 = 0; s2 < 2; ++s2) h2d_on(st, h.q[s2].p, q0.data(), q0.size() * sizeof(double));
+  }
   h.previous = 0; h.current = 0;
   h.grad_valid = false;
 }
@@ -572,7 +624,9 @@ int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* nc
     if (cfg->raw_filter_coeff != 1.0) throw std::runtime_error("raw_filter_coeff /= 1 is not supported");
     if (cfg->vert_advect_uv != 0 || cfg->vert_advect_t != 0) throw std::runtime_error("only second_centered vertical advection of u,v,T is supported");
     if (cfg->use_virtual_temperature) throw std::runtime_error("use_virtual_temperature is not supported");
-    if (cfg->num_tracers != 0) throw std::runtime_error("tracers are not supported in this build");
+    if (cfg->num_tracers < 0 || cfg->num_tracers > 1) throw std::runtime_error("only 0 or 1 (grid, finite_volume_parabolic sphum) tracers are supported");
+    if (cfg->num_tracers == 1 && nranks > 1) throw std::runtime_error("the grid tracer is single-rank only in this build (latitude halo exchange not built)");
+    if (cfg->num_tracers == 1 && cfg->num_levels < 4) throw std::runtime_error("the PPM tracer advection needs num_levels >= 4");
     if (cfg->do_water_correction && cfg->num_tracers == 0) throw std::runtime_error("do_water_correction must be .false. in a dry model (spectral_dynamics.F90:1264)");
     if ((cfg->do_energy_correction || cfg->do_water_correction) && !cfg->do_mass_correction) throw std::runtime_error("energy/water correction requires mass correction (spectral_dynamics.F90:409-415)");
     h = new H();
@@ -620,13 +674,17 @@ int isca_b200_set_surf_geopotential(IscaHandle h, const double* sg) {
 }
 
 int isca_b200_set_grid_state(IscaHandle h, int slot, const double* ug, const double* vg, const double* tg,
-                             const double* psg, const double* /*tracers*/) {
+                             const double* psg, const double* tracers) {
   API_BEGIN(h)
   if (slot < 0 || slot > 1) throw std::runtime_error("slot must be 0 or 1");
   if (ug) h2d_on(h->st, h->u[slot].p, ug, h->n3() * sizeof(double));
   if (vg) h2d_on(h->st, h->v[slot].p, vg, h->n3() * sizeof(double));
   if (tg) h2d_on(h->st, h->T[slot].p, tg, h->n3() * sizeof(double));
   if (psg) h2d_on(h->st, h->ps[slot].p, psg, h->nplane() * sizeof(double));
+  if (tracers) {
+    if (h->cfg.num_tracers < 1) throw std::runtime_error("no tracer configured");
+    h2d_on(h->st, h->q[slot].p, tracers, h->n3() * sizeof(double));
+  }
   h->grad_valid = false;
   API_END(h)
 }
@@ -766,6 +824,9 @@ int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
     case ISCA_F_VOR: d2h_on(h->st, host, h->vorg.p, n3 * sizeof(double)); break;
     case ISCA_F_DIV: d2h_on(h->st, host, h->divg.p, n3 * sizeof(double)); break;
     case ISCA_F_WG_FULL: d2h_on(h->st, host, h->wg_full.p, n3 * sizeof(double)); break;
+    case ISCA_F_TRACER0:
+      if (h->cfg.num_tracers < 1) throw std::runtime_error("no tracer configured");
+      d2h_on(h->st, host, h->q[s].p, n3 * sizeof(double)); break;
     case ISCA_F_P_FULL: case ISCA_F_P_HALF: case ISCA_F_Z_FULL: case ISCA_F_Z_HALF: {
       const size_t nh = n3 + pl;
       h->x_grid.ensure(nh);

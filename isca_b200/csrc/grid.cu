@@ -194,6 +194,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
     // wg at the two interfaces of level k (:1102-1108)
     const double w_top = (k == 0) ? 0.0 : (-cum_k + dmean_total * t.bk[k]);
     const double w_bot = (k == K - 1) ? 0.0 : (-cum_k1 + dmean_total * t.bk[k + 1]);
+    if (a.wg && live) { a.wg[e] = w_top; if (k == K - 1) a.wg[e + plane] = w_bot; }
 
     // ---------------- compute_geopotential (relative to the chunk's bottom interface)
     const double gfull = gh_local + pr.rdgas * T_k * (pl.ln_half_k1 - pl.ln_full);

@@ -10,6 +10,7 @@ enum {
   SC_SUM_PS_FUT = 2,                                // reduction for the mass fixer
   SC_SUM_EN_FUT = 3, SC_TMIN = 4, SC_TMAX = 5,      // reductions for the energy fixer / range check
   SC_MEAN_PS_PREV = 6, SC_MASS_FACTOR = 7, SC_MEAN_EN_PREV = 8, SC_T_CORR = 9, SC_T_FLAG = 10,
+  SC_W_PREV = 11, SC_W_ALL = 12, SC_W_CORR = 13, SC_W_NOT = 14,   // water fixer sums
   SC_COUNT = 16
 };
 
@@ -24,6 +25,7 @@ struct GridStepArgs {
   // outputs (forward batch planes)
   double *out_A, *out_B, *out_T, *out_phi, *dt_lnps;
   double *wg_full;          // may be NULL
+  double *wg;               // [K+1] interface mass fluxes (needed by the tracer PPM step); may be NULL
   double *part;             // [2][Jloc*I] per-column partials for the global means
 };
 

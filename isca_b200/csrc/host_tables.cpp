@@ -338,6 +338,33 @@ void build_tables(const IscaConfig& c, const Geometry& g, HostTables& t) {
     t.ref_ln_p_half = r.lh; t.ref_ln_p_full = r.lf; t.ref_t = r.t; t.ref_ps = r.ref_ps;
   }
 
+  // ---- finite-volume tracer grid: fv_advection_init (model/fv_advection.F90:59-121) with the latitude
+  //      boundaries of transforms_init (tools/transforms.F90:314-321)
+  {
+    std::vector<double> yy(J + 1), y(J);
+    yy[0] = -.5 * PI;
+    double sum_wts = 0.;
+    for (int j = 1; j <= J - 1; ++j) { sum_wts = sum_wts + t.wts_lat[j - 1]; yy[j] = std::asin(sum_wts - 1.); }
+    yy[J] = .5 * PI;
+    t.fv_c.resize(J); t.fv_cc.resize(J + 1); t.fv_dy.assign(J + 4, 0.0); t.fv_dyy.assign(J + 1, 0.0);
+    t.fv_dy_plus.resize(J + 2); t.fv_dy_minus.resize(J + 2);
+    for (int j = 0; j < J; ++j) { y[j] = 0.5 * (yy[j + 1] + yy[j]); t.fv_c[j] = std::cos(y[j]); }
+    for (int j = 0; j <= J; ++j) t.fv_cc[j] = std::cos(yy[j]);
+    std::vector<double>& dy = t.fv_dy;                      // dy[j+1] = dy(j), j = -1..J+2
+    for (int j = 1; j <= J; ++j) dy[j + 1] = yy[j] - yy[j - 1];
+    dy[0] = dy[3]; dy[1] = dy[2]; dy[J + 2] = dy[J + 1]; dy[J + 3] = dy[J];
+    for (int j = 2; j <= J; ++j) t.fv_dyy[j - 1] = y[j - 1] - y[j - 2];
+    t.fv_dyy[0] = 2 * (y[0] - yy[0]);
+    t.fv_dyy[J] = 2 * (yy[J] - y[J - 1]);
+    for (int j = 0; j <= J + 1; ++j) {
+      t.fv_dy_plus[j] = dy[j + 1] / (dy[j + 1] + dy[j + 2]);
+      t.fv_dy_minus[j] = dy[j + 1] / (dy[j] + dy[j + 1]);
+    }
+    for (auto& v : t.fv_dy) v = v * c.radius;
+    for (auto& v : t.fv_dyy) v = v * c.radius;
+    t.fv_dx = 2.0 * PI * c.radius / (double)I;
+  }
+
   // ---- FFT twiddles exp(-2 pi i k / I), k < I, from long double for full fp64 accuracy
   t.twiddle.resize((size_t)2 * I);
   for (int k = 0; k < I; ++k) {

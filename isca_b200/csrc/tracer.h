@@ -1,0 +1,37 @@
+// tracer.h -- grid tracer (sphum) path: Lin-Rood A-grid horizontal advection, PPM vertical advection,
+// Held-Suarez tracer source/sink, water fixer.
+#pragma once
+#include "device.h"
+
+namespace isca {
+
+// finite-volume grid metrics of fv_advection_init (atmos_spectral/model/fv_advection.F90:59-121); device pointers
+struct FvTables {
+  const double *c, *cc;            // cos at cell centres [J], at boundaries [J+1]
+  const double *dy;                // dy(-1:J+2) * radius, stored with offset 1: dy[j+1] = dy(j)
+  const double *dyy;               // dyy(1:J+1) * radius, dyy[j-1] = dyy(j)
+  const double *dy_plus, *dy_minus;  // (0:J+1)
+  double dx;
+};
+
+struct TracerArgs {
+  // state
+  const double *q_prev, *q_cur; double *q_cur_w, *q_fut;
+  const double *u_cur, *v_cur, *ps_cur, *ps_prev, *ps_fut;
+  const double *wg;                // [K+1] planes: downward mass flux at the interfaces (four_in_one)
+  // work planes [K]
+  double *tr0, *q1, *q2, *tr1;
+  double *part;                    // per-column partials [3][Jloc*I]
+  double delta_t, trflux, trdamp, robert_coeff, raw_filter_coeff, water_limit;
+  int physics_on;
+};
+
+void launch_tracer_source(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);
+void launch_tracer_semi(const DevTables& t, const FvTables& f, const TracerArgs& a, cudaStream_t st);
+void launch_tracer_flux(const DevTables& t, const FvTables& f, const TracerArgs& a, cudaStream_t st);
+void launch_tracer_ppm(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);
+void launch_tracer_water_colsum(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);
+void launch_tracer_water_apply(const DevTables& t, const Params& pr, const TracerArgs& a, const double* scal, double denom,
+                               int do_water, cudaStream_t st);
+
+}  // namespace isca
