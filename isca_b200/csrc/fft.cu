@@ -13,6 +13,7 @@
 // One CTA handles LT = 8 lines = 8 consecutive batch levels at one latitude, so that the Fourier-side
 // accesses ([m][lat][level] complex) are contiguous 128-byte runs.
 #include "device.h"
+#include <cstdlib>
 
 namespace isca {
 
@@ -320,7 +321,13 @@ static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* le
 }
 
 // radix plans: H = I/2 = R1*R2*R3, Q = H / max radix threads per line
+static int fft_plan_override() {
+  static int plan = -1;
+  if (plan < 0) { const char* e = std::getenv("ISCA_B200_FFT_PLAN"); plan = e ? std::atoi(e) : 0; }
+  return plan;
+}
 void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
+  if (t.g.I == 512 && fft_plan_override() == 884) { launch_inv_shape<256, 8, 8, 4, 32, 3>(t, four, levs, nlev, Lp, st); return; }
   switch (t.g.I) {
     case 1024: launch_inv_shape<512, 8, 8, 8, 64, 1>(t, four, levs, nlev, Lp, st); break;
     case 512:  launch_inv_shape<256, 16, 16, 1, 16, 4>(t, four, levs, nlev, Lp, st); break;
@@ -332,6 +339,7 @@ void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs,
   }
 }
 void launch_fft_fwd(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
+  if (t.g.I == 512 && fft_plan_override() == 884) { launch_fwd_shape<256, 8, 8, 4, 32, 4>(t, four, levs, nlev, Lp, st); return; }
   switch (t.g.I) {
     case 1024: launch_fwd_shape<512, 8, 8, 8, 64, 2>(t, four, levs, nlev, Lp, st); break;
     case 512:  launch_fwd_shape<256, 16, 16, 1, 16, 5>(t, four, levs, nlev, Lp, st); break;

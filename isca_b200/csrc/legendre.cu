@@ -170,112 +170,81 @@ void launch_legendre_inv(const DevTables& t, const double2* spec, double* four, 
 constexpr int FWD_NT = 32;      // n rows per CTA tile (both parities)
 constexpr int FWD_KC = 16;      // jh per k-chunk
 
-// One CTA = (one m, 32 columns): the folded tiles X+ = F_N + F_S and X- = F_N - F_S of ALL hemisphere
-// latitudes are built once in shared memory (the Fourier buffer is read exactly once), then the CTA
-// walks over the n tiles of this m, streaming the weighted Legendre rows through a register-staged
-// double buffer.
 __global__ void __launch_bounds__(128)
 legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __restrict__ spec, int Lp,
                     const unsigned char* __restrict__ lev_trunc) {
   constexpr int XS = LEG_CT + 4;            // 36 == 4 mod 16
   constexpr int WS = FWD_KC + 4;            // 20 == 4 mod 16
-  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
-  const GeomDev& g = t.g;
-  const int Jh = g.Jh;
-  double* Xs = reinterpret_cast<double*>(leg_smem_raw);                 // [2][Jh][XS]
-  double* Ws = Xs + (size_t)2 * Jh * XS;                                // [2 stages][2 parities][16][WS]
-  auto X = [&](int pm, int jh, int c) -> double& { return Xs[((size_t)pm * Jh + jh) * XS + c]; };
-  auto W = [&](int st, int par, int r, int c) -> double& { return Ws[(((size_t)st * 2 + par) * (FWD_NT / 2) + r) * WS + c]; };
+  __shared__ __align__(16) double Xs[2][FWD_KC][XS];          // [plus/minus][jh][c]
+  __shared__ __align__(16) double Ws[2][FWD_NT / 2][WS];      // [parity][n][jh]
 
+  const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  const int c0 = blockIdx.x * LEG_CT;
-  const int mi = blockIdx.y;
+  // grid = (n tile, column tile, m): the n tiles of one (m, column tile) share the same Fourier rows and are
+  // scheduled back to back, so the re-reads of the X tile hit L2 instead of HBM
+  const int c0 = blockIdx.y * LEG_CT;
+  const int mi = blockIdx.z;
   const int m = g.m_of[mi];
   const int Nm = g.M - m + 2;
+  const int nt0 = blockIdx.x * FWD_NT;
+  if (nt0 >= Nm) return;
   const int row0 = g.off[mi];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int par = warp & 1, wc = warp >> 1;
 
-  // fold: x_even = F_N + F_S, x_odd = F_N - F_S (spherical_fourier.F90:311-312)
-  for (int idx = tid; idx < Jh * (LEG_CT / 2); idx += 128) {
-    const int jh = idx / (LEG_CT / 2), v = idx - jh * (LEG_CT / 2);
-    const double2 fs = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, jh, C) + c0 + 2 * v);
-    const double2 fn = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, g.J - 1 - jh, C) + c0 + 2 * v);
-    X(0, jh, 2 * v) = fn.x + fs.x; X(0, jh, 2 * v + 1) = fn.y + fs.y;
-    X(1, jh, 2 * v) = fn.x - fs.x; X(1, jh, 2 * v + 1) = fn.y - fs.y;
-  }
-
-  const int nch = Jh / FWD_KC;
-  const int ntiles = (Nm + FWD_NT - 1) / FWD_NT;
-  const int total = ntiles * nch;                       // flattened (n tile, jh chunk) pipeline
-  double2 w_[2];
-  auto prefetch = [&](int it) {
-    const int nt0 = (it / nch) * FWD_NT, jh0 = (it % nch) * FWD_KC;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int idx = tid + q * 128;
-      const int rw = idx / (FWD_KC / 2), vw = idx - rw * (FWD_KC / 2);
-      const int n = nt0 + rw;
-      w_[q] = make_double2(0.0, 0.0);
-      if (n < Nm) w_[q] = *reinterpret_cast<const double2*>(t.legw + (size_t)(row0 + n) * Jh + jh0 + 2 * vw);
-    }
-  };
-  auto stage = [&](int st) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int idx = tid + q * 128;
-      const int rw = idx / (FWD_KC / 2), vw = idx - rw * (FWD_KC / 2);
-      W(st, rw & 1, rw >> 1, 2 * vw) = w_[q].x; W(st, rw & 1, rw >> 1, 2 * vw + 1) = w_[q].y;
-    }
-  };
-
   double acc[2][2][2];
-  prefetch(0);
-  stage(0);
-  __syncthreads();
-  double* specd = reinterpret_cast<double*>(spec);
-  for (int it = 0; it < total; ++it) {
-    const int st = it & 1;
-    const int ch = it % nch;
-    if (ch == 0) {
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    for (int b = 0; b < 2; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+  for (int jh0 = 0; jh0 < g.Jh; jh0 += FWD_KC) {
+    __syncthreads();
+    // X tiles: 16 jh x 32 c, plus and minus
+    for (int idx = tid; idx < FWD_KC * (LEG_CT / 2); idx += 128) {
+      int r = idx / (LEG_CT / 2), v = idx - r * (LEG_CT / 2);
+      int jh = jh0 + r;
+      const double2 fs = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, jh, C) + c0 + 2 * v);
+      const double2 fn = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, g.J - 1 - jh, C) + c0 + 2 * v);
+      Xs[0][r][2 * v] = fn.x + fs.x; Xs[0][r][2 * v + 1] = fn.y + fs.y;
+      Xs[1][r][2 * v] = fn.x - fs.x; Xs[1][r][2 * v + 1] = fn.y - fs.y;
     }
-    if (it + 1 < total) prefetch(it + 1);
-    const int jh0 = ch * FWD_KC;
+    // weighted Legendre rows: 32 n x 16 jh
+    for (int idx = tid; idx < FWD_NT * (FWD_KC / 2); idx += 128) {
+      int r = idx / (FWD_KC / 2), v = idx - r * (FWD_KC / 2);
+      int n = nt0 + r;
+      double2 w = make_double2(0.0, 0.0);
+      if (n < Nm) w = *reinterpret_cast<const double2*>(t.legw + (size_t)(row0 + n) * g.Jh + jh0 + 2 * v);
+      Ws[r & 1][r >> 1][2 * v] = w.x; Ws[r & 1][r >> 1][2 * v + 1] = w.y;
+    }
+    __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < FWD_KC / 4; ++kk) {
       double a[2], b[2];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = W(st, par, mt * 8 + (lane >> 2), kk * 4 + (lane & 3));
+      for (int mt = 0; mt < 2; ++mt) a[mt] = Ws[par][mt * 8 + (lane >> 2)][kk * 4 + (lane & 3)];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) b[nt] = X(par, jh0 + kk * 4 + (lane & 3), wc * 16 + nt * 8 + (lane >> 2));
+      for (int nt = 0; nt < 2; ++nt) b[nt] = Xs[par][kk * 4 + (lane & 3)][wc * 16 + nt * 8 + (lane >> 2)];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
-    if (ch == nch - 1) {                                 // this n tile is complete
-      const int nt0 = (it / nch) * FWD_NT;
+  }
+
+  double* specd = reinterpret_cast<double*>(spec);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int n = nt0 + 2 * (mt * 8 + (lane >> 2)) + par;
-        if (n < Nm) {
-          const bool beyond = (m + n > g.M);
+  for (int mt = 0; mt < 2; ++mt) {
+    const int n = nt0 + 2 * (mt * 8 + (lane >> 2)) + par;
+    if (n >= Nm) continue;
+    const bool beyond = (m + n > g.M);
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
-            const int c = c0 + wc * 16 + nt * 8 + (lane & 3) * 2;
-            double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-            if (beyond && lev_trunc[c >> 1]) v = make_double2(0.0, 0.0);     // triangular_truncation (spherical.F90:564-600)
-            *reinterpret_cast<double2*>(specd + (size_t)(row0 + n) * C + c) = v;
-          }
-        }
-      }
+    for (int nt = 0; nt < 2; ++nt) {
+      const int c = c0 + wc * 16 + nt * 8 + (lane & 3) * 2;
+      double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      if (beyond && lev_trunc[c >> 1]) v = make_double2(0.0, 0.0);     // triangular_truncation (spherical.F90:564-600)
+      *reinterpret_cast<double2*>(specd + (size_t)(row0 + n) * C + c) = v;
     }
-    if (it + 1 < total) stage(st ^ 1);
-    __syncthreads();
   }
 }
 
@@ -283,11 +252,8 @@ void launch_legendre_fwd(const DevTables& t, const double* four, double2* spec, 
                          const unsigned char* lev_trunc, cudaStream_t st) {
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  const size_t smem = sizeof(double) * ((size_t)2 * g.Jh * (LEG_CT + 4) + (size_t)2 * 2 * (FWD_NT / 2) * (FWD_KC + 4));
-  static size_t attr = 0;
-  if (smem > attr) { cudaFuncSetAttribute(legendre_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-  dim3 grid(C / LEG_CT, g.nm);
-  legendre_fwd_kernel<<<grid, 128, smem, st>>>(t, four, spec, Lp, lev_trunc);
+  dim3 grid((g.M + 2 + FWD_NT - 1) / FWD_NT, C / LEG_CT, g.nm);
+  legendre_fwd_kernel<<<grid, 128, 0, st>>>(t, four, spec, Lp, lev_trunc);
 }
 
 // ---------------------------------------------------------------------------------------------
