@@ -64,6 +64,9 @@ struct IscaHandle_t {
   DevTables dt;
   Params pr;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;              // second stream: Legendre of sub-batch i+1 overlaps the FFT of sub-batch i
+  cudaEvent_t ev_pipe[8] = {nullptr};
+  int pipe_parts = 3;
   std::string err;
   long long launches = 0;
   long long steps = 0;
@@ -302,19 +305,61 @@ static void allreduce_scalars(H& h, double* dev, int count, int op) {
 // generic batched transforms on device data
 // ---------------------------------------------------------------------------------------------
 static void dev_inverse(H& h, const double2* spec, int Lp, const LevDesc* levs, int nlev, const char* tag = "") {
-  launch_legendre_inv(h.dt, spec, h.four.p, Lp, h.st); h.launches++;
-  if (h.profiling) h.mark((std::string("legendre_inv") + tag).c_str());
-  exchange_fourier(h, 0, Lp);
-  launch_fft_inv(h.dt, h.four_lat(), levs, nlev, Lp, h.st); h.launches++;
-  if (h.profiling) h.mark((std::string("fft_inv") + tag).c_str());
+  const int nct = Lp / 16;                               // 32-column tiles of the batch
+  const int np = (h.g.P == 1 && !h.profiling) ? std::min(h.pipe_parts, nct) : 1;
+  if (np <= 1) {
+    launch_legendre_inv(h.dt, spec, h.four.p, Lp, h.st); h.launches++;
+    if (h.profiling) h.mark((std::string("legendre_inv") + tag).c_str());
+    exchange_fourier(h, 0, Lp);
+    launch_fft_inv(h.dt, h.four_lat(), levs, nlev, Lp, h.st); h.launches++;
+    if (h.profiling) h.mark((std::string("fft_inv") + tag).c_str());
+    return;
+  }
+  // software pipeline over np sub-batches on two streams: Legendre(i) runs beside FFT(i-1)
+  CK(cudaEventRecord(h.ev_pipe[0], h.st));
+  CK(cudaStreamWaitEvent(h.st2, h.ev_pipe[0], 0));
+  int ct = 0;
+  for (int i = 0; i < np; ++i) {
+    const int cnt = (nct - ct + (np - i) - 1) / (np - i);
+    cudaStream_t s = (i & 1) ? h.st2 : h.st;
+    if (i > 0) CK(cudaStreamWaitEvent(s, h.ev_pipe[1 + ((i - 1) & 1)], 0));      // stagger: after Legendre(i-1)
+    launch_legendre_inv(h.dt, spec, h.four.p, Lp, s, ct, cnt);
+    CK(cudaEventRecord(h.ev_pipe[1 + (i & 1)], s));
+    const int lev_begin = ct * 16, lev_end = std::min((ct + cnt) * 16, nlev);
+    if (lev_begin < lev_end) { launch_fft_inv(h.dt, h.four.p, levs, lev_end, Lp, s, lev_begin); h.launches++; }
+    h.launches++;
+    ct += cnt;
+  }
+  CK(cudaEventRecord(h.ev_pipe[3], h.st2));
+  CK(cudaStreamWaitEvent(h.st, h.ev_pipe[3], 0));
 }
 static void dev_forward(H& h, const LevDesc* levs, int nlev, double2* spec, int Lp, const unsigned char* trunc,
                         const char* tag = "") {
-  launch_fft_fwd(h.dt, h.four_lat(), levs, nlev, Lp, h.st); h.launches++;
-  if (h.profiling) h.mark((std::string("fft_fwd") + tag).c_str());
-  exchange_fourier(h, 1, Lp);
-  launch_legendre_fwd(h.dt, h.four.p, spec, Lp, trunc, h.st); h.launches++;
-  if (h.profiling) h.mark((std::string("legendre_fwd") + tag).c_str());
+  const int nct = Lp / 16;
+  const int np = (h.g.P == 1 && !h.profiling) ? std::min(h.pipe_parts, nct) : 1;
+  if (np <= 1) {
+    launch_fft_fwd(h.dt, h.four_lat(), levs, nlev, Lp, h.st); h.launches++;
+    if (h.profiling) h.mark((std::string("fft_fwd") + tag).c_str());
+    exchange_fourier(h, 1, Lp);
+    launch_legendre_fwd(h.dt, h.four.p, spec, Lp, trunc, h.st); h.launches++;
+    if (h.profiling) h.mark((std::string("legendre_fwd") + tag).c_str());
+    return;
+  }
+  CK(cudaEventRecord(h.ev_pipe[0], h.st));
+  CK(cudaStreamWaitEvent(h.st2, h.ev_pipe[0], 0));
+  int ct = 0;
+  for (int i = 0; i < np; ++i) {
+    const int cnt = (nct - ct + (np - i) - 1) / (np - i);
+    cudaStream_t s = (i & 1) ? h.st2 : h.st;
+    if (i > 0) CK(cudaStreamWaitEvent(s, h.ev_pipe[1 + ((i - 1) & 1)], 0));      // stagger: after FFT(i-1)
+    const int lev_begin = ct * 16, lev_end = std::min((ct + cnt) * 16, nlev);
+    if (lev_begin < lev_end) { launch_fft_fwd(h.dt, h.four.p, levs, lev_end, Lp, s, lev_begin); h.launches++; }
+    CK(cudaEventRecord(h.ev_pipe[1 + (i & 1)], s));
+    launch_legendre_fwd(h.dt, h.four.p, spec, Lp, trunc, s, ct, cnt); h.launches++;
+    ct += cnt;
+  }
+  CK(cudaEventRecord(h.ev_pipe[3], h.st2));
+  CK(cudaStreamWaitEvent(h.st, h.ev_pipe[3], 0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -637,6 +682,9 @@ int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* nc
     h->cfg.pk = nullptr; h->cfg.bk = nullptr;
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     h->use_graph = (std::getenv("ISCA_B200_NO_GRAPH") == nullptr);
+    CK(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+    for (auto& e : h->ev_pipe) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char* e = std::getenv("ISCA_B200_PIPE")) h->pipe_parts = std::max(1, std::atoi(e));
     if (nranks > 1) {
       h->nccl.load();
       NcclUniqueId id; std::memcpy(id.internal, nccl_unique_id, 128);
@@ -663,6 +711,8 @@ int isca_b200_destroy(IscaHandle h) {
   for (auto& sg : h->graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
   if (h->comm) h->nccl.CommDestroy(h->comm);
   if (h->st) cudaStreamDestroy(h->st);
+  if (h->st2) cudaStreamDestroy(h->st2);
+  for (auto& e : h->ev_pipe) if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }

@@ -51,12 +51,13 @@ struct Params {
 
 // ---- launches (all asynchronous on `st`) ----------------------------------------------------
 // Legendre: spec batch [T][Lp] complex  <->  Fourier buffer (m-owner layout), C = 2*Lp doubles
-void launch_legendre_inv(const DevTables& t, const double2* spec, double* four, int Lp, cudaStream_t st);
+// ct_begin/ct_count: range of 32-column (16-level) tiles; lev_begin: first level (FFT processes [lev_begin, nlev))
+void launch_legendre_inv(const DevTables& t, const double2* spec, double* four, int Lp, cudaStream_t st, int ct_begin = 0, int ct_count = -1);
 void launch_legendre_fwd(const DevTables& t, const double* four, double2* spec, int Lp,
-                         const unsigned char* lev_trunc, cudaStream_t st);
+                         const unsigned char* lev_trunc, cudaStream_t st, int ct_begin = 0, int ct_count = -1);
 // FFT: Fourier buffer (lat-owner layout) <-> grid planes described by LevDesc[nlev]
-void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st);
-void launch_fft_fwd(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st);
+void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin = 0);
+void launch_fft_fwd(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin = 0);
 
 // layout conversion between the reference's rectangular (m,n,lev) arrays and the packed layout
 void launch_pack_spec(const DevTables& t, const double2* rect, double2* packed, int nlev, int Lp, int lev0, cudaStream_t st);

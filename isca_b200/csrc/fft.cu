@@ -132,14 +132,14 @@ __device__ __forceinline__ void pass_write(double2* __restrict__ dst, const doub
 // ---------------------------------------------------------------------------------------------
 template <int H, int R1, int R2, int R3, int Q, int MINB>
 __global__ void __launch_bounds__(FFT_LT * Q, MINB)
-fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp) {
+fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp, int lev_begin) {
   typedef FftShape<H, R1> S;
   constexpr int I = 2 * H;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
   double2* buf = reinterpret_cast<double2*>(fft_smem);              // [LT][LS]
-  const int lev0 = blockIdx.x * FFT_LT;
+  const int lev0 = lev_begin + blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
 
@@ -232,14 +232,14 @@ fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __re
 // ---------------------------------------------------------------------------------------------
 template <int H, int R1, int R2, int R3, int Q, int MINB>
 __global__ void __launch_bounds__(FFT_LT * Q, MINB)
-fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp) {
+fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict__ levs, int nlev, int Lp, int lev_begin) {
   typedef FftShape<H, R1> S;
   constexpr int I = 2 * H;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
   double2* buf = reinterpret_cast<double2*>(fft_smem);              // [LT][LS]
-  const int lev0 = blockIdx.x * FFT_LT;
+  const int lev0 = lev_begin + blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
   constexpr int NT = FFT_LT * Q;
@@ -302,22 +302,22 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
 }
 
 template <int H, int R1, int R2, int R3, int Q, int MINB>
-static void launch_inv_shape(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
+static void launch_inv_shape(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin) {
   typedef FftShape<H, R1> S;
   const size_t smem = sizeof(double2) * FFT_LT * S::LS;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(fft_inv_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  dim3 grid((nlev + FFT_LT - 1) / FFT_LT, t.g.Jloc);
-  fft_inv_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+  dim3 grid((nlev - lev_begin + FFT_LT - 1) / FFT_LT, t.g.Jloc);
+  fft_inv_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp, lev_begin);
 }
 template <int H, int R1, int R2, int R3, int Q, int MINB>
-static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
+static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin) {
   typedef FftShape<H, R1> S;
   const size_t smem = sizeof(double2) * FFT_LT * S::LS;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  dim3 grid((nlev + FFT_LT - 1) / FFT_LT, t.g.Jloc);
-  fft_fwd_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp);
+  dim3 grid((nlev - lev_begin + FFT_LT - 1) / FFT_LT, t.g.Jloc);
+  fft_fwd_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp, lev_begin);
 }
 
 // radix plans: H = I/2 = R1*R2*R3, Q = H / max radix threads per line
@@ -326,27 +326,27 @@ static int fft_plan_override() {
   if (plan < 0) { const char* e = std::getenv("ISCA_B200_FFT_PLAN"); plan = e ? std::atoi(e) : 0; }
   return plan;
 }
-void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
-  if (t.g.I == 512 && fft_plan_override() == 884) { launch_inv_shape<256, 8, 8, 4, 32, 3>(t, four, levs, nlev, Lp, st); return; }
+void launch_fft_inv(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin) {
+  if (t.g.I == 512 && fft_plan_override() == 884) { launch_inv_shape<256, 8, 8, 4, 32, 3>(t, four, levs, nlev, Lp, st, lev_begin); return; }
   switch (t.g.I) {
-    case 1024: launch_inv_shape<512, 8, 8, 8, 64, 1>(t, four, levs, nlev, Lp, st); break;
-    case 512:  launch_inv_shape<256, 16, 16, 1, 16, 4>(t, four, levs, nlev, Lp, st); break;
-    case 256:  launch_inv_shape<128, 8, 16, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
-    case 128:  launch_inv_shape<64, 8, 8, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
-    case 64:   launch_inv_shape<32, 4, 8, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
-    case 32:   launch_inv_shape<16, 4, 4, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
+    case 1024: launch_inv_shape<512, 8, 8, 8, 64, 1>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 512:  launch_inv_shape<256, 16, 16, 1, 16, 4>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 256:  launch_inv_shape<128, 8, 16, 1, 8, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 128:  launch_inv_shape<64, 8, 8, 1, 8, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 64:   launch_inv_shape<32, 4, 8, 1, 4, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 32:   launch_inv_shape<16, 4, 4, 1, 4, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
     default: break;   // rejected in build_geometry
   }
 }
-void launch_fft_fwd(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st) {
-  if (t.g.I == 512 && fft_plan_override() == 884) { launch_fwd_shape<256, 8, 8, 4, 32, 4>(t, four, levs, nlev, Lp, st); return; }
+void launch_fft_fwd(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin) {
+  if (t.g.I == 512 && fft_plan_override() == 884) { launch_fwd_shape<256, 8, 8, 4, 32, 4>(t, four, levs, nlev, Lp, st, lev_begin); return; }
   switch (t.g.I) {
-    case 1024: launch_fwd_shape<512, 8, 8, 8, 64, 2>(t, four, levs, nlev, Lp, st); break;
-    case 512:  launch_fwd_shape<256, 16, 16, 1, 16, 5>(t, four, levs, nlev, Lp, st); break;
-    case 256:  launch_fwd_shape<128, 8, 16, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
-    case 128:  launch_fwd_shape<64, 8, 8, 1, 8, 8>(t, four, levs, nlev, Lp, st); break;
-    case 64:   launch_fwd_shape<32, 4, 8, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
-    case 32:   launch_fwd_shape<16, 4, 4, 1, 4, 8>(t, four, levs, nlev, Lp, st); break;
+    case 1024: launch_fwd_shape<512, 8, 8, 8, 64, 2>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 512:  launch_fwd_shape<256, 16, 16, 1, 16, 5>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 256:  launch_fwd_shape<128, 8, 16, 1, 8, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 128:  launch_fwd_shape<64, 8, 8, 1, 8, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 64:   launch_fwd_shape<32, 4, 8, 1, 4, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
+    case 32:   launch_fwd_shape<16, 4, 4, 1, 4, 8>(t, four, levs, nlev, Lp, st, lev_begin); break;
     default: break;
   }
 }

@@ -41,7 +41,7 @@ constexpr int LEG_KC = 16;      // n rows per parity per k-chunk
 
 template <int JT, int WJ>
 __global__ void __launch_bounds__(128)
-legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __restrict__ four, int Lp) {
+legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __restrict__ four, int Lp, int ct_begin) {
   constexpr int WC = 4 / WJ;
   constexpr int WTJ = JT / WJ, WTC = LEG_CT / WC;
   constexpr int MT = WTJ / 8, NT = WTC / 8;
@@ -54,7 +54,7 @@ legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __res
 
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  const int c0 = blockIdx.x * LEG_CT;
+  const int c0 = (ct_begin + blockIdx.x) * LEG_CT;
   const int mi = blockIdx.y;
   const int jt0 = blockIdx.z * JT;
   const int m = g.m_of[mi];
@@ -143,7 +143,7 @@ legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __res
 }
 
 template <int JT, int WJ>
-static void launch_inv_t(const DevTables& t, const double2* spec, double* four, int Lp, cudaStream_t st) {
+static void launch_inv_t(const DevTables& t, const double2* spec, double* four, int Lp, cudaStream_t st, int ct_begin, int ct_count) {
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
   const size_t smem = sizeof(double) * 2 * 2 * LEG_KC * ((JT + 4) + (LEG_CT + 4));
@@ -152,14 +152,14 @@ static void launch_inv_t(const DevTables& t, const double2* spec, double* four, 
     cudaFuncSetAttribute(legendre_inv_kernel<JT, WJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  dim3 grid(C / LEG_CT, g.nm, g.Jh / JT);
-  legendre_inv_kernel<JT, WJ><<<grid, 128, smem, st>>>(t, spec, four, Lp);
+  dim3 grid(ct_count < 0 ? C / LEG_CT - ct_begin : ct_count, g.nm, g.Jh / JT);
+  legendre_inv_kernel<JT, WJ><<<grid, 128, smem, st>>>(t, spec, four, Lp, ct_begin);
 }
-void launch_legendre_inv(const DevTables& t, const double2* spec, double* four, int Lp, cudaStream_t st) {
+void launch_legendre_inv(const DevTables& t, const double2* spec, double* four, int Lp, cudaStream_t st, int ct_begin, int ct_count) {
   const GeomDev& g = t.g;
-  if (g.Jh % 64 == 0) launch_inv_t<64, 4>(t, spec, four, Lp, st);
-  else if (g.Jh % 32 == 0) launch_inv_t<32, 2>(t, spec, four, Lp, st);
-  else launch_inv_t<16, 1>(t, spec, four, Lp, st);
+  if (g.Jh % 64 == 0) launch_inv_t<64, 4>(t, spec, four, Lp, st, ct_begin, ct_count);
+  else if (g.Jh % 32 == 0) launch_inv_t<32, 2>(t, spec, four, Lp, st, ct_begin, ct_count);
+  else launch_inv_t<16, 1>(t, spec, four, Lp, st, ct_begin, ct_count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -168,25 +168,27 @@ void launch_legendre_inv(const DevTables& t, const double2* spec, double* four, 
 //   Reduction over the hemisphere latitudes jh in chunks of 16; the (F_N +- F_S) fold is the prologue.
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_NT = 32;      // n rows per CTA tile (both parities)
-constexpr int FWD_KC = 16;      // jh per k-chunk
 
+template <int FWD_KC>
 __global__ void __launch_bounds__(128)
 legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __restrict__ spec, int Lp,
-                    const unsigned char* __restrict__ lev_trunc) {
+                    const unsigned char* __restrict__ lev_trunc, int ct_begin) {
   constexpr int XS = LEG_CT + 4;            // 36 == 4 mod 16
-  constexpr int WS = FWD_KC + 4;            // 20 == 4 mod 16
-  __shared__ __align__(16) double Xs[2][FWD_KC][XS];          // [plus/minus][jh][c]
-  __shared__ __align__(16) double Ws[2][FWD_NT / 2][WS];      // [parity][n][jh]
+  constexpr int WS = FWD_KC + 4;            // == 4 mod 16
+  constexpr int NQ = FWD_KC / 8;            // double2 per thread per tile (X: KC x 16, W: 32 x KC/2; 128 threads)
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  typedef double (*XsT)[2][FWD_KC][XS];
+  typedef double (*WsT)[2][FWD_NT / 2][WS];
+  XsT Xs = reinterpret_cast<XsT>(leg_smem_raw);                                             // [stage][plus/minus][jh][c]
+  WsT Ws = reinterpret_cast<WsT>(leg_smem_raw + sizeof(double) * 2 * 2 * FWD_KC * XS);     // [stage][parity][n][jh]
 
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  // grid = (n tile, column tile, m): the n tiles of one (m, column tile) share the same Fourier rows and are
-  // scheduled back to back, so the re-reads of the X tile hit L2 instead of HBM
-  const int c0 = blockIdx.y * LEG_CT;
-  const int mi = blockIdx.z;
+  const int c0 = (ct_begin + blockIdx.x) * LEG_CT;
+  const int mi = blockIdx.y;
   const int m = g.m_of[mi];
   const int Nm = g.M - m + 2;
-  const int nt0 = blockIdx.x * FWD_NT;
+  const int nt0 = blockIdx.z * FWD_NT;
   if (nt0 >= Nm) return;
   const int row0 = g.off[mi];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -198,38 +200,55 @@ legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __res
 #pragma unroll
     for (int b = 0; b < 2; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
-  for (int jh0 = 0; jh0 < g.Jh; jh0 += FWD_KC) {
-    __syncthreads();
-    // X tiles: 16 jh x 32 c, plus and minus
-    for (int idx = tid; idx < FWD_KC * (LEG_CT / 2); idx += 128) {
-      int r = idx / (LEG_CT / 2), v = idx - r * (LEG_CT / 2);
-      int jh = jh0 + r;
-      const double2 fs = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, jh, C) + c0 + 2 * v);
-      const double2 fn = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, g.J - 1 - jh, C) + c0 + 2 * v);
-      Xs[0][r][2 * v] = fn.x + fs.x; Xs[0][r][2 * v + 1] = fn.y + fs.y;
-      Xs[1][r][2 * v] = fn.x - fs.x; Xs[1][r][2 * v + 1] = fn.y - fs.y;
+  // register-staged software pipeline: the global loads of chunk ch+1 are in flight while chunk ch is multiplied
+  double2 xs_[NQ], xn_[NQ], w_[NQ];
+  auto prefetch = [&](int jh0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int idx = tid + q * 128;
+      const int r = idx / (LEG_CT / 2), v = idx - r * (LEG_CT / 2);
+      const int jh = jh0 + r;
+      xs_[q] = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, jh, C) + c0 + 2 * v);
+      xn_[q] = *reinterpret_cast<const double2*>(four + fourA_index(g, mi, g.J - 1 - jh, C) + c0 + 2 * v);
+      const int rw = idx / (FWD_KC / 2), vw = idx - rw * (FWD_KC / 2);
+      const int n = nt0 + rw;
+      w_[q] = make_double2(0.0, 0.0);
+      if (n < Nm) w_[q] = *reinterpret_cast<const double2*>(t.legw + (size_t)(row0 + n) * g.Jh + jh0 + 2 * vw);
     }
-    // weighted Legendre rows: 32 n x 16 jh
-    for (int idx = tid; idx < FWD_NT * (FWD_KC / 2); idx += 128) {
-      int r = idx / (FWD_KC / 2), v = idx - r * (FWD_KC / 2);
-      int n = nt0 + r;
-      double2 w = make_double2(0.0, 0.0);
-      if (n < Nm) w = *reinterpret_cast<const double2*>(t.legw + (size_t)(row0 + n) * g.Jh + jh0 + 2 * v);
-      Ws[r & 1][r >> 1][2 * v] = w.x; Ws[r & 1][r >> 1][2 * v + 1] = w.y;
+  };
+  auto stage = [&](int st) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int idx = tid + q * 128;
+      const int r = idx / (LEG_CT / 2), v = idx - r * (LEG_CT / 2);
+      Xs[st][0][r][2 * v] = xn_[q].x + xs_[q].x; Xs[st][0][r][2 * v + 1] = xn_[q].y + xs_[q].y;   // x_even (:311)
+      Xs[st][1][r][2 * v] = xn_[q].x - xs_[q].x; Xs[st][1][r][2 * v + 1] = xn_[q].y - xs_[q].y;   // x_odd  (:312)
+      const int rw = idx / (FWD_KC / 2), vw = idx - rw * (FWD_KC / 2);
+      Ws[st][rw & 1][rw >> 1][2 * vw] = w_[q].x; Ws[st][rw & 1][rw >> 1][2 * vw + 1] = w_[q].y;
     }
-    __syncthreads();
+  };
+
+  const int nch = g.Jh / FWD_KC;
+  prefetch(0);
+  stage(0);
+  __syncthreads();
+  for (int ch = 0; ch < nch; ++ch) {
+    const int st = ch & 1;
+    if (ch + 1 < nch) prefetch((ch + 1) * FWD_KC);
 #pragma unroll
     for (int kk = 0; kk < FWD_KC / 4; ++kk) {
       double a[2], b[2];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = Ws[par][mt * 8 + (lane >> 2)][kk * 4 + (lane & 3)];
+      for (int mt = 0; mt < 2; ++mt) a[mt] = Ws[st][par][mt * 8 + (lane >> 2)][kk * 4 + (lane & 3)];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) b[nt] = Xs[par][kk * 4 + (lane & 3)][wc * 16 + nt * 8 + (lane >> 2)];
+      for (int nt = 0; nt < 2; ++nt) b[nt] = Xs[st][par][kk * 4 + (lane & 3)][wc * 16 + nt * 8 + (lane >> 2)];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
+    if (ch + 1 < nch) stage(st ^ 1);
+    __syncthreads();
   }
 
   double* specd = reinterpret_cast<double*>(spec);
@@ -249,11 +268,21 @@ legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __res
 }
 
 void launch_legendre_fwd(const DevTables& t, const double* four, double2* spec, int Lp,
-                         const unsigned char* lev_trunc, cudaStream_t st) {
+                         const unsigned char* lev_trunc, cudaStream_t st, int ct_begin, int ct_count) {
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  dim3 grid((g.M + 2 + FWD_NT - 1) / FWD_NT, C / LEG_CT, g.nm);
-  legendre_fwd_kernel<<<grid, 128, 0, st>>>(t, four, spec, Lp, lev_trunc);
+  dim3 grid(ct_count < 0 ? C / LEG_CT - ct_begin : ct_count, g.nm, (g.M + 2 + FWD_NT - 1) / FWD_NT);
+  if (g.Jh % 32 == 0) {
+    constexpr int KC = 32;
+    const size_t smem = sizeof(double) * (2 * 2 * KC * (LEG_CT + 4) + 2 * 2 * (FWD_NT / 2) * (KC + 4));
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(legendre_fwd_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    legendre_fwd_kernel<KC><<<grid, 128, smem, st>>>(t, four, spec, Lp, lev_trunc, ct_begin);
+  } else {
+    constexpr int KC = 16;
+    const size_t smem = sizeof(double) * (2 * 2 * KC * (LEG_CT + 4) + 2 * 2 * (FWD_NT / 2) * (KC + 4));
+    legendre_fwd_kernel<KC><<<grid, 128, smem, st>>>(t, four, spec, Lp, lev_trunc, ct_begin);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -295,9 +295,10 @@ tracer_ppm_kernel(DevTables t, Params pr, TracerArgs a) {
     }
     const double rdt = -(flux_below - flux_above - r[k] * (w[k + 1] - w[k])) / dz[k];
     const size_t e = (size_t)k * plane + col;
-    a.q_fut[e] = r[k] + dt * rdt;                     // tr_future + delta_t*dt_tmp
-    // leapfrog part A for the grid tracer (:1165-1169): current += rc*(previous - 2 current)*raw
+    // leapfrog part A for the grid tracer (:1165-1169): current += rc*(previous - 2 current)*raw.
+    // `future` shares its storage slot with `previous` (two time levels): read before the future value is written.
     const double qp = a.q_prev[e], qc = a.q_cur[e];
+    a.q_fut[e] = r[k] + dt * rdt;                     // tr_future + delta_t*dt_tmp
     a.q_cur_w[e] = qc + rc * (qp - 2.0 * qc) * raw;
     flux_above = flux_below;
   }
