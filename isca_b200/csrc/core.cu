@@ -66,7 +66,7 @@ struct IscaHandle_t {
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;              // second stream: Legendre of sub-batch i+1 overlaps the FFT of sub-batch i
   cudaEvent_t ev_pipe[8] = {nullptr};
-  int pipe_parts = 3;
+  int pipe_parts = 1;                      // >1 measured slower on B200 (profiles/r01_experiments.md); ISCA_B200_PIPE overrides
   std::string err;
   long long launches = 0;
   long long steps = 0;
@@ -396,6 +396,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   ga.out_T = h.gridB.p; ga.out_A = h.gridB.p + (size_t)K * pl; ga.out_B = h.gridB.p + (size_t)(2 * K) * pl;
   ga.out_phi = h.gridB.p + (size_t)(3 * K) * pl; ga.dt_lnps = h.gridB.p + (size_t)(4 * K) * pl;
   ga.wg_full = h.wg_full.p; ga.part = h.part.p;
+  ga.scal = h.scal.p; ga.slot_cur = cur; ga.slot_prev = prev;
   ga.wg = (h.cfg.num_tracers > 0) ? h.wg.p : nullptr;
   launch_grid_step(h.dt, pr, ga, st); h.launches++;
   h.mark("grid_step");
@@ -458,7 +459,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   allreduce_scalars(h, h.scal.p + SC_SUM_EN_FUT, 1, NCCL_SUM);
   allreduce_scalars(h, h.scal.p + SC_TMIN, 1, NCCL_MIN);
   allreduce_scalars(h, h.scal.p + SC_TMAX, 1, NCCL_MAX);
-  launch_apply_energy(h.dt, pr, h.T[fut].p, h.ts[fut].p, h.ts[cur].p, rc_raw, h.scal.p, h.denom(), h.owns_m0(),
+  launch_apply_energy(h.dt, pr, fut, h.ts[fut].p, h.ts[cur].p, rc_raw, h.scal.p, h.denom(), h.owns_m0(),
                       h.cfg.do_energy_correction, st);
   h.launches += 8;
   h.mark("corr_mass_energy");
@@ -598,6 +599,8 @@ static void cold_start(H& h) {
     std::vector<double> q0(h.n3(), c.initial_sphum);                // spectral_dynamics.F90:584-590
     for (int s2 = 0; s2 < 2; ++s2) h2d_on(st, h.q[s2].p, q0.data(), q0.size() * sizeof(double));
   }
+  CK(cudaMemsetAsync(h.scal.p + SC_TSHIFT0, 0, 2 * sizeof(double), st));
+  CK(cudaStreamSynchronize(st));
   h.previous = 0; h.current = 0;
   h.grad_valid = false;
 }
@@ -729,7 +732,10 @@ int isca_b200_set_grid_state(IscaHandle h, int slot, const double* ug, const dou
   if (slot < 0 || slot > 1) throw std::runtime_error("slot must be 0 or 1");
   if (ug) h2d_on(h->st, h->u[slot].p, ug, h->n3() * sizeof(double));
   if (vg) h2d_on(h->st, h->v[slot].p, vg, h->n3() * sizeof(double));
-  if (tg) h2d_on(h->st, h->T[slot].p, tg, h->n3() * sizeof(double));
+  if (tg) {
+    h2d_on(h->st, h->T[slot].p, tg, h->n3() * sizeof(double));
+    CK(cudaMemsetAsync(h->scal.p + SC_TSHIFT0 + slot, 0, sizeof(double), h->st));
+  }
   if (psg) h2d_on(h->st, h->ps[slot].p, psg, h->nplane() * sizeof(double));
   if (tracers) {
     if (h->cfg.num_tracers < 1) throw std::runtime_error("no tracer configured");
@@ -843,10 +849,14 @@ int isca_b200_spectral_dynamics(IscaHandle h, const double* dt_psg, const double
   if (psg_final) CK(cudaMemcpyAsync(psg_final, h->ps[c].p, h->nplane() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   if (ug_final) CK(cudaMemcpyAsync(ug_final, h->u[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   if (vg_final) CK(cudaMemcpyAsync(vg_final, h->v[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  if (tg_final) CK(cudaMemcpyAsync(tg_final, h->T[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (tg_final) {
+    launch_materialize_t(h->dt, h->T[c].p, h->scal.p, c, h->st);
+    CK(cudaMemcpyAsync(tg_final, h->T[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  }
   if (wg_full) CK(cudaMemcpyAsync(wg_full, h->wg_full.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   if (p_full) {
     h->x_grid.ensure(n3);
+    launch_materialize_t(h->dt, h->T[h->previous].p, h->scal.p, h->previous, h->st);
     launch_press_heights(h->dt, h->pr, h->T[h->previous].p, h->ps[h->previous].p, h->phis.p, h->x_grid.p, nullptr, nullptr, nullptr, h->st);
     CK(cudaMemcpyAsync(p_full, h->x_grid.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   }
@@ -870,7 +880,9 @@ int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
     case ISCA_F_PS: d2h_on(h->st, host, h->ps[s].p, pl * sizeof(double)); break;
     case ISCA_F_U: d2h_on(h->st, host, h->u[s].p, n3 * sizeof(double)); break;
     case ISCA_F_V: d2h_on(h->st, host, h->v[s].p, n3 * sizeof(double)); break;
-    case ISCA_F_T: d2h_on(h->st, host, h->T[s].p, n3 * sizeof(double)); break;
+    case ISCA_F_T:
+      launch_materialize_t(h->dt, h->T[s].p, h->scal.p, s, h->st);
+      d2h_on(h->st, host, h->T[s].p, n3 * sizeof(double)); break;
     case ISCA_F_VOR: d2h_on(h->st, host, h->vorg.p, n3 * sizeof(double)); break;
     case ISCA_F_DIV: d2h_on(h->st, host, h->divg.p, n3 * sizeof(double)); break;
     case ISCA_F_WG_FULL: d2h_on(h->st, host, h->wg_full.p, n3 * sizeof(double)); break;
@@ -884,6 +896,7 @@ int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
       double* ph = (id == ISCA_F_P_HALF) ? h->x_grid.p : nullptr;
       double* zf = (id == ISCA_F_Z_FULL) ? h->x_grid.p : nullptr;
       double* zh = (id == ISCA_F_Z_HALF) ? h->x_grid.p : nullptr;
+      launch_materialize_t(h->dt, h->T[s].p, h->scal.p, s, h->st);
       launch_press_heights(h->dt, h->pr, h->T[s].p, h->ps[s].p, h->phis.p, pf, ph, zf, zh, h->st);
       CK(cudaStreamSynchronize(h->st));
       const size_t cnt = (id == ISCA_F_P_HALF || id == ISCA_F_Z_HALF) ? nh : n3;

@@ -10,8 +10,9 @@ enum {
   SC_SUM_PS_FUT = 2,                                // reduction for the mass fixer
   SC_SUM_EN_FUT = 3, SC_TMIN = 4, SC_TMAX = 5,      // reductions for the energy fixer / range check
   SC_MEAN_PS_PREV = 6, SC_MASS_FACTOR = 7, SC_MEAN_EN_PREV = 8, SC_T_CORR = 9, SC_T_FLAG = 10,
+  SC_TSHIFT0 = 16, SC_TSHIFT1 = 17,   // pending energy-fixer temperature increment of storage slot 0 / 1 (applied on read)
   SC_W_PREV = 11, SC_W_ALL = 12, SC_W_CORR = 13, SC_W_NOT = 14,   // water fixer sums
-  SC_COUNT = 16
+  SC_COUNT = 24
 };
 
 struct GridStepArgs {
@@ -27,6 +28,8 @@ struct GridStepArgs {
   double *wg_full;          // may be NULL
   double *wg;               // [K+1] interface mass fluxes (needed by the tracer PPM step); may be NULL
   double *part;             // [2][Jloc*I] per-column partials for the global means
+  const double *scal;       // device scalars (pending temperature shifts)
+  int slot_cur, slot_prev;
 };
 
 void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& a, cudaStream_t st);
@@ -36,8 +39,9 @@ void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double
                        double denom, int owns_m0, int do_mass, cudaStream_t st);
 void launch_colsum_energy(const DevTables& t, const Params& pr, const double* u, const double* v, const double* T,
                           const double* ps, double* part, cudaStream_t st);
-void launch_apply_energy(const DevTables& t, const Params& pr, double* T, double2* ts_fut, double2* ts_cur, double rc_raw,
+void launch_apply_energy(const DevTables& t, const Params& pr, int slot_fut, double2* ts_fut, double2* ts_cur, double rc_raw,
                          double* scal, double denom, int owns_m0, int do_energy, cudaStream_t st);
+void launch_materialize_t(const DevTables& t, double* T, double* scal, int slot, cudaStream_t st);
 void launch_press_heights(const DevTables& t, const Params& pr, const double* T, const double* ps, const double* phis,
                           double* p_full, double* p_half, double* z_full, double* z_half, cudaStream_t st);
 void launch_divide_by_cos(const DevTables& t, double* f, int nlev, cudaStream_t st);

@@ -272,7 +272,7 @@ void launch_legendre_fwd(const DevTables& t, const double* four, double2* spec, 
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
   dim3 grid(ct_count < 0 ? C / LEG_CT - ct_begin : ct_count, g.nm, (g.M + 2 + FWD_NT - 1) / FWD_NT);
-  if (g.Jh % 32 == 0) {
+  if (false) {                     // KC = 32 measured slower (fewer resident CTAs): profiles/r01_experiments.md
     constexpr int KC = 32;
     const size_t smem = sizeof(double) * (2 * 2 * KC * (LEG_CT + 4) + 2 * 2 * (FWD_NT / 2) * (KC + 4));
     static bool attr = false;
