@@ -64,11 +64,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   __shared__ double s_tot[GS_KW][32], s_gh[GS_KW][32], s_en[GS_KW][32];
   // per-thread chunk arrays live in shared memory ([c][thread], conflict-free) to keep registers for occupancy
   __shared__ double s_cum[CH + 1][32 * GS_KW], s_phi[CH][32 * GS_KW];
-  // vertical-coordinate tables in shared memory (warp-uniform index -> broadcast LDS instead of LDG + 64-bit address math)
-  __shared__ double s_pk[ISCA_KMAX + 1], s_bk[ISCA_KMAX + 1], s_lnbk[ISCA_KMAX + 1];
   const int tx = threadIdx.x;
-  for (int q = tx; q <= K; q += 32 * GS_KW) { s_pk[q] = t.pk[q]; s_bk[q] = t.bk[q]; s_lnbk[q] = t.ln_bk[q]; }
-  __syncthreads();
 
   const int k_lo = w * CH;
   const int k_hi = (k_lo + CH < K) ? (k_lo + CH) : K;          // chunk = [k_lo, k_hi), may be empty
@@ -91,9 +87,8 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
       double dmean = 0.0;
       if (k < k_hi) {
         const size_t e = (size_t)k * plane + col;
-        const double dpk_ = s_pk[k + 1] - s_pk[k], dbk_ = s_bk[k + 1] - s_bk[k];     // dpk, dbk (spectral_dynamics.F90:451-454)
-        const double dp = dpk_ + dbk_ * ps_c;
-        dmean = a.div_cur[e] * dp + dbk_ * (a.u_cur[e] * dx_psg + a.v_cur[e] * dy_psg);
+        const double dp = t.dpk[k] + t.dbk[k] * ps_c;
+        dmean = a.div_cur[e] * dp + t.dbk[k] * (a.u_cur[e] * dx_psg + a.v_cur[e] * dy_psg);
       }
       run = run + dmean;
       s_cum[c + 1][tx] = run;
@@ -119,7 +114,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const double tstr = pr.t_strat - pr.eps * sin_lat;
   const double tcoeff = (pr.tks - pr.tka) / (1.0 - pr.sigma_b);
   const double vcoeff = -pr.vkf / (1.0 - pr.sigma_b);
-  const double ps_hs = s_pk[K] + s_bk[K] * ps_c;     // ps = p_half(:,:,size(p_half,3))
+  const double ps_hs = t.pk[K] + t.bk[K] * ps_c;     // ps = p_half(:,:,size(p_half,3))
   const double rps = 1. / ps_hs;
   const double fcor = t.coriolis[j];
   const double delta_t = pr.delta_t;
@@ -133,7 +128,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   const double inv_cp = 1.0 / pr.cp_air;
   double u_dn = 0.0, v_dn = 0.0, T_dn = 0.0, u_k = 0.0, v_k = 0.0, T_k = 0.0;
   if (k_hi > k_lo) {
-    ln_half_below = pr.pure_sigma ? (s_lnbk[k_hi] + ln_ps) : log(s_pk[k_hi] + s_bk[k_hi] * ps_c);
+    ln_half_below = ln_p_half(t, pr, k_hi, t.pk[k_hi] + t.bk[k_hi] * ps_c, ln_ps);
     const size_t e = (size_t)(k_hi - 1) * plane + col;
     u_k = a.u_cur[e]; v_k = a.v_cur[e]; T_k = a.t_cur[e] + sh_c;
     if (k_hi < K) { u_dn = a.u_cur[e + plane]; v_dn = a.v_cur[e + plane]; T_dn = a.t_cur[e + plane] + sh_c; }
@@ -146,21 +141,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
     double u_up = 0.0, v_up = 0.0, T_up = 0.0;       // level k-1
     if (k > 0) { u_up = a.u_cur[e - plane]; v_up = a.v_cur[e - plane]; T_up = a.t_cur[e - plane] + sh_c; }
     PressLevel pl;
-    {   // pressure_variables for level k from the shared tables (same arithmetic as press_level())
-      const double pk0 = s_pk[k], bk0 = s_bk[k], pk1 = s_pk[k + 1], bk1 = s_bk[k + 1];
-      pl.p_half_k = pk0 + bk0 * ps_c;
-      pl.p_half_k1 = pk1 + bk1 * ps_c;
-      pl.ln_half_k1 = ln_half_below;
-      if (k == 0 && pr.pkbk0_zero) {
-        pl.ln_half_k = 0.0;
-        pl.ln_full = ln_half_below + (-1.0);
-      } else {
-        pl.ln_half_k = pr.pure_sigma ? (s_lnbk[k] + ln_ps) : log(pl.p_half_k);
-        const double alpha = 1.0 - pl.p_half_k * (pl.ln_half_k1 - pl.ln_half_k) / (pl.p_half_k1 - pl.p_half_k);
-        pl.ln_full = pl.ln_half_k1 - alpha;
-      }
-      pl.p_full = exp(pl.ln_full);
-    }
+    press_level(t, pr, k, ps_c, ln_ps, ln_half_below, pl);
 
     // ---------------- physics: hs_forcing on (u,v,T)(previous), pressures of `current`
     double dt_u = 0.0, dt_v = 0.0, dt_T = 0.0;
@@ -190,32 +171,31 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
     {
       const double up = u_p + dt_u * delta_t, vp = v_p + dt_v * delta_t;
       const double en = 0.5 * (up * up + vp * vp) + pr.cp_air * (T_p + dt_T * delta_t);
-      const double dpp = (s_pk[k + 1] + s_bk[k + 1] * ps_p) - (s_pk[k] + s_bk[k] * ps_p);
+      const double dpp = (t.pk[k + 1] + t.bk[k + 1] * ps_p) - (t.pk[k] + t.bk[k] * ps_p);
       energy_int = energy_int + en * dpp;
     }
 
     // ---------------- four_in_one, level k
     const double Tv = T_k;                            // use_virtual_temperature = .false. (dry) -> virtual_t = tg
-    const double dbk_ = s_bk[k + 1] - s_bk[k];
-    const double dp = (s_pk[k + 1] - s_pk[k]) + dbk_ * ps_c;
+    const double dp = t.dpk[k] + t.dbk[k] * ps_c;
     const double dp_inv = 1 / dp;
     const double dlog_1 = pl.ln_half_k1 - pl.ln_full;
     const double dlog_2 = pl.ln_full - pl.ln_half_k;
     const double dlog_3 = pl.ln_half_k1 - pl.ln_half_k;
-    const double x1 = (s_bk[k + 1] * dlog_1 + s_bk[k] * dlog_2) * dp_inv;
+    const double x1 = (t.bk[k + 1] * dlog_1 + t.bk[k] * dlog_2) * dp_inv;
     const double x2 = x1 * dx_psg;
     const double x3 = x1 * dy_psg;
     dt_u = dt_u - pr.rdgas * Tv * x2;
     dt_v = dt_v - pr.rdgas * Tv * x3;
     const double cum_k = cum_off + s_cum[c][tx], cum_k1 = cum_off + s_cum[c + 1][tx];
-    const double dmean = a.div_cur[e] * dp + dbk_ * (u_k * dx_psg + v_k * dy_psg);
+    const double dmean = a.div_cur[e] * dp + t.dbk[k] * (u_k * dx_psg + v_k * dy_psg);
     const double x4 = (cum_k * dlog_3 + dmean * dlog_1) * dp_inv;
     const double x5 = x4 - u_k * x2 - v_k * x3;
     dt_T = dt_T - pr.kappa * Tv * x5;
     if (a.wg_full && live) a.wg_full[e] = -x5 * pl.p_full;
     // wg at the two interfaces of level k (:1102-1108)
-    const double w_top = (k == 0) ? 0.0 : (-cum_k + dmean_total * s_bk[k]);
-    const double w_bot = (k == K - 1) ? 0.0 : (-cum_k1 + dmean_total * s_bk[k + 1]);
+    const double w_top = (k == 0) ? 0.0 : (-cum_k + dmean_total * t.bk[k]);
+    const double w_bot = (k == K - 1) ? 0.0 : (-cum_k1 + dmean_total * t.bk[k + 1]);
     if (a.wg && live) { a.wg[e] = w_top; if (k == K - 1) a.wg[e + plane] = w_bot; }
 
     // ---------------- compute_geopotential (relative to the chunk's bottom interface)

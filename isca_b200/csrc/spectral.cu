@@ -174,16 +174,27 @@ constexpr int NCP = NC + 1;       // padded row stride of the [k][column] shared
 // linear_tp_tendency (implicit.F90:414-480) for one real column held in shared memory [k][NC].
 // ref_temperature_implicit is 300 K at every level (spectral_dynamics.F90:473), so the
 // vert_vel*(t_ref(k)-t_ref(k-1)) term of :464-476 is identically zero and is not evaluated.
-__device__ __forceinline__ double tp_tendency_column(const DevTables& t, const Params& pr, const double* div, double* dt_t,
+// Column-independent factors of the reference-state recurrences, hoisted out of the per-column loops
+// (same operands, same operation order as implicit.F90:441-448 / :345-356, so the results are unchanged):
+//   lc[0][k] = dp = dpk(k)+dbk(k)*p_surf_ref, lc[1][k] = 1/dp, lc[2][k] = dlog_1, lc[3][k] = dlog_3,
+//   lc[4][k] = ln_p_half(k+1)-ln_p_full(k) (= dlog_1), lc[5][k] = ln_p_half(k+1)-ln_p_half(k) (= dlog_3), lc[6][k] = t_ref(k)
+constexpr int NLC = 5;
+__device__ __forceinline__ void load_level_consts(const DevTables& t, const Params& pr, double* lc, int K) {
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const double dp = t.dpk[k] + t.dbk[k] * pr.ref_ps;
+    lc[0 * K + k] = dp;
+    lc[1 * K + k] = 1 / dp;
+    lc[2 * K + k] = t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k];
+    lc[3 * K + k] = t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k];
+    lc[4 * K + k] = t.ref_t[k];
+  }
+}
+__device__ __forceinline__ double tp_tendency_column(const Params& pr, const double* lc, const double* div, double* dt_t,
                                                      int K, int col) {
   double dmean_tot = 0.0;
   for (int k = 0; k < K; ++k) {
-    const double dp = t.dpk[k] + t.dbk[k] * pr.ref_ps;
-    const double dp_inv = 1 / dp;
-    const double dlog_1 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k];
-    const double dlog_3 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k];
-    const double dmean = div[k * NCP + col] * dp;
-    dt_t[k * NCP + col] = -pr.kappa * t.ref_t[k] * (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv;
+    const double dmean = div[k * NCP + col] * lc[k];
+    dt_t[k * NCP + col] = -pr.kappa * lc[4 * K + k] * (dmean_tot * lc[3 * K + k] + dmean * lc[2 * K + k]) * lc[K + k];
     dmean_tot = dmean_tot + dmean;
   }
   return -dmean_tot;      // dt_p_surf
@@ -199,9 +210,11 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
   double* s_dD = s_dT + K * NCP;           // [K][NC] divs(prev) - divs(cur); later scratch
   double* s_dTs = s_dD + K * NCP;          // [K][NC] ts(prev) - ts(cur)
   double* s_ps = s_dTs + K * NCP;          // [2][NC]  dt_ln_ps ; ln_ps(prev)-ln_ps(cur)
+  double* s_lc = s_ps + 2 * NC;            // [NLC][K] level constants
   const int p0 = blockIdx.x * RP;
   const int tid = threadIdx.x;
   const int LpB = a.LpB;
+  load_level_consts(t, pr, s_lc, K);
 
   // phase 1: elementwise (row, level)
   for (int idx = tid; idx < RP * K; idx += blockDim.x) {
@@ -266,12 +279,8 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
       // dt_ts += tp(dD).dt_t ; dt_ln_ps += tp(dD).dt_p / ref_ps   -- reuse s_dD as output of tp (reads then writes same k)
       double dmean_tot = 0.0;
       for (int k = 0; k < K; ++k) {
-        const double dp = t.dpk[k] + t.dbk[k] * pr.ref_ps;
-        const double dp_inv = 1 / dp;
-        const double dlog_1 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k];
-        const double dlog_3 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k];
-        const double dmean = s_dD[k * NCP + col] * dp;
-        const double dtt = -pr.kappa * t.ref_t[k] * (dmean_tot * dlog_3 + dmean * dlog_1) * dp_inv;
+        const double dmean = s_dD[k * NCP + col] * s_lc[k];
+        const double dtt = -pr.kappa * s_lc[4 * K + k] * (dmean_tot * s_lc[3 * K + k] + dmean * s_lc[2 * K + k]) * s_lc[K + k];
         dmean_tot = dmean_tot + dmean;
         s_dT[k * NCP + col] = s_dT[k * NCP + col] + dtt;
       }
@@ -284,9 +293,9 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
       double gh = 0.0;                                  // geopot_half(K+1)
       for (int k = K - 1; k >= 0; --k) {
         const double ts_temp = s_dTs[k * NCP + col] + xi * s_dT[k * NCP + col];
-        const double geopot = gh + pr.rdgas * (ts_temp * (t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k]) + t.ref_t[k] * (0.0 - 0.0));
+        const double geopot = gh + pr.rdgas * (ts_temp * s_lc[2 * K + k] + s_lc[4 * K + k] * (0.0 - 0.0));
         s_ddiv[k * NCP + col] = s_ddiv[k * NCP + col] + eig * (geopot + t.h_impl[k] * ps_temp * pr.ref_ps);
-        if (k >= 1) gh = gh + pr.rdgas * (ts_temp * (t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k]) + t.ref_t[k] * (0.0 - 0.0));
+        if (k >= 1) gh = gh + pr.rdgas * (ts_temp * s_lc[3 * K + k] + s_lc[4 * K + k] * (0.0 - 0.0));
       }
     }
   }
@@ -308,7 +317,8 @@ spec_tend_adjust_kernel(DevTables t, Params pr, SpecStepArgs a) {
 // S2: per total wavenumber L, y = wave_matrix(L) x  for every column with m + n = L
 // ---------------------------------------------------------------------------------------------
 constexpr int WM_COLS = 64;      // real columns per CTA
-__global__ void __launch_bounds__(WM_COLS)
+constexpr int WM_KG = 4;         // output-level groups per column (threads = WM_COLS * WM_KG)
+__global__ void __launch_bounds__(WM_COLS * WM_KG)
 spec_wave_matvec_kernel(DevTables t, double2* __restrict__ w_div) {
   extern __shared__ __align__(16) double sm[];
   const GeomDev& g = t.g;
@@ -316,18 +326,17 @@ spec_wave_matvec_kernel(DevTables t, double2* __restrict__ w_div) {
   const int L = blockIdx.x;
   double* W = sm;                 // [K][K]
   double* X = W + K * K;          // [K][WM_COLS]
-  // columns of this L: local mi with m_of[mi] <= L; chunk by blockIdx.y
   const int tid = threadIdx.x;
-  const int col = blockIdx.y * WM_COLS + tid;     // real column index: (mi_idx, reim)
-  // count of local m <= L: m_of is ascending
-  int cnt = 0;
+  const int cl = tid % WM_COLS, kg = tid / WM_COLS;
+  const int col = blockIdx.y * WM_COLS + cl;      // real column index: (mi_idx, reim)
+  int cnt = 0;                                    // number of local m <= L (m_of is ascending)
   {
     int lo = 0, hi = g.nm;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (g.m_of[mid] <= L) lo = mid + 1; else hi = mid; }
     cnt = lo;
   }
   if (blockIdx.y * WM_COLS >= 2 * cnt) return;
-  for (int i = tid; i < K * K; i += WM_COLS) W[i] = t.wave_matrix[(size_t)L * K * K + i];
+  for (int i = tid; i < K * K; i += WM_COLS * WM_KG) W[i] = t.wave_matrix[(size_t)L * K * K + i];
   const bool active = col < 2 * cnt;
   size_t base = 0;
   if (active) {
@@ -335,14 +344,14 @@ spec_wave_matvec_kernel(DevTables t, double2* __restrict__ w_div) {
     const int p = g.off[mi] + (L - g.m_of[mi]);
     base = ((size_t)p * K) * 2 + (col & 1);
     const double* src = reinterpret_cast<const double*>(w_div);
-    for (int k = 0; k < K; ++k) X[k * WM_COLS + tid] = src[base + 2 * k];
+    for (int k = kg; k < K; k += WM_KG) X[k * WM_COLS + cl] = src[base + 2 * k];
   }
   __syncthreads();
   if (active) {
     double* dst = reinterpret_cast<double*>(w_div);
-    for (int k = 0; k < K; ++k) {
+    for (int k = kg; k < K; k += WM_KG) {
       double s = 0.0;
-      for (int q = 0; q < K; ++q) s += W[k * K + q] * X[q * WM_COLS + tid];   // matmul(wave_matrix(:,:,L), dt_divs(m,n,:))
+      for (int q = 0; q < K; ++q) s += W[k * K + q] * X[q * WM_COLS + cl];   // matmul(wave_matrix(:,:,L), dt_divs(m,n,:))
       dst[base + 2 * k] = s;
     }
   }
@@ -359,8 +368,10 @@ spec_update_kernel(DevTables t, Params pr, SpecStepArgs a) {
   double* s_ddiv = sm;                    // [K][NC]
   double* s_tmp = s_ddiv + K * NCP;        // [K][NC] dt_ts_temp
   double* s_ps = s_tmp + K * NCP;          // [NC] dt_ps_temp
+  double* s_lc = s_ps + NC;                // [NLC][K] level constants
   const int p0 = blockIdx.x * RP;
   const int tid = threadIdx.x;
+  load_level_consts(t, pr, s_lc, K);
 
   for (int idx = tid; idx < RP * K; idx += blockDim.x) {
     const int r = idx / K, k = idx - r * K;
@@ -372,7 +383,7 @@ spec_update_kernel(DevTables t, Params pr, SpecStepArgs a) {
   __syncthreads();
   if (tid < NC) {
     double dps = 0.0;
-    if (a.use_implicit) dps = tp_tendency_column(t, pr, s_ddiv, s_tmp, K, tid);
+    if (a.use_implicit) dps = tp_tendency_column(pr, s_lc, s_ddiv, s_tmp, K, tid);
     else for (int k = 0; k < K; ++k) s_tmp[k * NCP + tid] = 0.0;
     s_ps[tid] = dps;
   }
@@ -456,7 +467,7 @@ void launch_spec_step(const DevTables& t, const Params& pr, const SpecStepArgs& 
   const int K = g.K;
   const int nb = (g.T + RP - 1) / RP;
   {
-    size_t smem = sizeof(double) * ((size_t)4 * K * NCP + 2 * NC);
+    size_t smem = sizeof(double) * ((size_t)4 * K * NCP + 2 * NC + (size_t)NLC * K);
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(spec_tend_adjust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
     spec_tend_adjust_kernel<<<nb, 128, smem, st>>>(t, pr, a);
@@ -466,10 +477,10 @@ void launch_spec_step(const DevTables& t, const Params& pr, const SpecStepArgs& 
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(spec_wave_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
     dim3 grid(g.M + 1, (2 * g.nm + WM_COLS - 1) / WM_COLS);
-    spec_wave_matvec_kernel<<<grid, WM_COLS, smem, st>>>(t, a.w_div);
+    spec_wave_matvec_kernel<<<grid, WM_COLS * WM_KG, smem, st>>>(t, a.w_div);
   }
   {
-    size_t smem = sizeof(double) * ((size_t)2 * K * NCP + NC);
+    size_t smem = sizeof(double) * ((size_t)2 * K * NCP + NC + (size_t)NLC * K);
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(spec_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
     spec_update_kernel<<<nb, 128, smem, st>>>(t, pr, a);
