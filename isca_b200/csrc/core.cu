@@ -77,6 +77,7 @@ struct IscaHandle_t {
   DBuf<int> d_m_of, d_off, d_pos, d_row_m, d_row_n;
   DBuf<double> d_sin_lat, d_cos_lat, d_cosm_lat, d_wts_lat, d_coriolis, d_rad_lat, d_pk, d_bk, d_dpk, d_dbk;
   DBuf<double> d_leg, d_legw, d_ln_bk;
+  DBuf<double> d_sg[9];
   DBuf<double> d_eigen, d_uvm, d_uvc, d_uvp, d_alpm, d_alpp, d_dym, d_dx, d_dyp, d_mask, d_damp, d_dampv, d_dampd, d_eddy, d_zmu, d_zmv;
   DBuf<double> d_rlh, d_rlf, d_rt, d_h;
   DBuf<double> d_twiddle;
@@ -194,6 +195,34 @@ static void set_params(H& h) {
   for (double v : h.ht.pk) if (v != 0.0) p.pure_sigma = 0;
   for (size_t k = 1; k < h.ht.bk.size(); ++k) if (!(h.ht.bk[k] > 0.0)) p.pure_sigma = 0;
   p.xi = 0; p.delta_t = 0; p.first_step = 1;
+  // pure-sigma fast path tables (see grid.cu)
+  const std::vector<double>& bk = h.ht.bk;
+  const int K = h.g.K;
+  p.sigma_fast = (p.pure_sigma && p.pkbk0_zero && bk[K] == 1.0 && std::getenv("ISCA_B200_NO_SIGMA_FAST") == nullptr) ? 1 : 0;
+  if (p.sigma_fast) {
+    std::vector<double> db(K), rdb(K), al(K), d3(K), lf(K), pf(K), pfk(K), x1c(K), lnb(K + 1, 0.0);
+    for (int k = 1; k <= K; ++k) lnb[k] = std::log(bk[k]);
+    for (int k = 0; k < K; ++k) {
+      db[k] = bk[k + 1] - bk[k];
+      rdb[k] = 1.0 / db[k];
+      double d2;
+      if (k == 0) { al[k] = 1.0; d3[k] = 0.0; lf[k] = lnb[1] - 1.0; d2 = 0.0; }      // ln_p_full(1) = ln_p_half(2) - 1 ; bk(1) = 0
+      else {
+        d3[k] = lnb[k + 1] - lnb[k];
+        al[k] = 1.0 - bk[k] * d3[k] / db[k];
+        lf[k] = lnb[k + 1] - al[k];
+        d2 = lf[k] - lnb[k];
+      }
+      pf[k] = std::exp(lf[k]);
+      pfk[k] = std::exp(p.kappa * lf[k]);
+      x1c[k] = (bk[k + 1] * al[k] + bk[k] * d2) / db[k];
+    }
+    const std::vector<double>* src[9] = {&bk, &db, &rdb, &al, &d3, &lf, &pf, &pfk, &x1c};
+    for (int q = 0; q < 9; ++q) h.d_sg[q].upload(*src[q]);
+    SigmaTables& sg = h.dt.sig;
+    sg.b = h.d_sg[0].p; sg.db = h.d_sg[1].p; sg.rdb = h.d_sg[2].p; sg.al = h.d_sg[3].p; sg.d3 = h.d_sg[4].p;
+    sg.lf = h.d_sg[5].p; sg.pf = h.d_sg[6].p; sg.pfk = h.d_sg[7].p; sg.x1c = h.d_sg[8].p;
+  }
 }
 
 static void alloc_state(H& h) {

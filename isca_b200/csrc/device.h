@@ -5,9 +5,23 @@
 
 namespace isca {
 
+// per-level constants of the pure-sigma fast path (grid.cu: grid_step_sigma_kernel); device pointers, [K] (b: [K+1])
+struct SigmaTables {
+  const double *b;      // bk
+  const double *db;     // bk(k+1) - bk(k)
+  const double *rdb;    // 1 / db
+  const double *al;     // alpha(k) = ln_p_half(k+1) - ln_p_full(k)            (dlog_1)
+  const double *d3;     // ln bk(k+1) - ln bk(k)                                (dlog_3; 0 at the top level)
+  const double *lf;     // ln(p_full/ps)
+  const double *pf;     // p_full/ps
+  const double *pfk;    // (p_full/ps)^kappa
+  const double *x1c;    // (bk(k+1)*dlog_1 + bk(k)*dlog_2) / db                 (x1 * ps)
+};
+
 // All device-resident constant tables.  Pointers are device pointers.
 struct DevTables {
   GeomDev g;
+  SigmaTables sig;
   // Gaussian grid [J] (global index) and vertical coordinate
   const double *sin_lat, *cos_lat, *cosm_lat, *wts_lat, *coriolis, *rad_lat;
   const double *pk, *bk, *dpk, *dbk;           // [K+1],[K+1],[K],[K]
@@ -46,6 +60,7 @@ struct Params {
   int first_step;                // previous == current
   int pk0_zero, pkbk0_zero;      // pk(1)==0 ; pk(1)==0 && bk(1)==0
   int pure_sigma;                // pk == 0 at every half level
+  int sigma_fast;                // pure sigma, zero top, bk(K+1) == 1: grid_step_sigma_kernel is used
   double vr_tmin, vr_tmax;
 };
 

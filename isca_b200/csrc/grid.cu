@@ -258,9 +258,203 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pure sigma coordinate (pk == 0 at every interface, bk(K+1) == 1): p_half = bk*ps, so every logarithm,
+// exponential and quotient of pressure_variables / four_in_one / hs_forcing factors into a host-computed
+// per-level constant times a per-column scalar (ps, 1/ps, ln ps, (ps/P00)^kappa):
+//   ln p_full(k) = LF(k) + ln ps,  p_full(k) = PF(k)*ps,  dlog_1 = AL(k),  dlog_2 = D2(k),  dlog_3 = D3(k),
+//   dp = DB(k)*ps,  sigma = PF(k),  p_norm^kappa = PFK(k)*(ps/P00)^kappa.
+// The column loop then contains no transcendental and no division.  Mathematically identical to the
+// generic kernel; the arithmetic is re-associated, so results agree to a few ulp, not bit for bit
+// (tests hold both against the oracle at the same tolerance).  Mass fluxes are carried divided by ps.
+// ---------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(32 * GS_KW, (CH <= 10) ? 6 : 4)
+grid_step_sigma_kernel(DevTables t, Params pr, GridStepArgs a) {
+  const GeomDev& g = t.g;
+  const int I = g.I, K = g.K;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int jl = blockIdx.y;
+  const int j = g.j0 + jl;
+  const bool live = (i < I);
+  const size_t col = (size_t)jl * I + (live ? i : 0);
+  const size_t plane = (size_t)g.Jloc * I;
+  __shared__ double s_tot[GS_KW][32], s_gh[GS_KW][32], s_en[GS_KW][32];
+  __shared__ double s_cum[CH + 1][32 * GS_KW], s_phi[CH][32 * GS_KW];
+  const int tx = threadIdx.x;
+  const SigmaTables& sg = t.sig;
+
+  const int k_lo = w * CH;
+  const int k_hi = (k_lo + CH < K) ? (k_lo + CH) : K;
+
+  const double ps_c = a.ps_cur[col], ps_p = a.ps_prev[col];
+  const double cosm = t.cosm_lat[j];
+  const double sh_c = a.scal[SC_TSHIFT0 + a.slot_cur], sh_p = a.scal[SC_TSHIFT0 + a.slot_prev];
+  const double gx = a.dx_lnps[col] * cosm, gy = a.dy_lnps[col] * cosm;      // (1/ps) * grad(ps) / cos
+  const double ln_ps = log(ps_c);
+
+  // ---- pass 1: cumulative (mass divergence)/ps, top-down within the chunk
+  {
+    double run = 0.0;
+    s_cum[0][tx] = 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = k_lo + c;
+      double dm = 0.0;
+      if (k < k_hi) {
+        const size_t e = (size_t)k * plane + col;
+        dm = sg.db[k] * (a.div_cur[e] + (a.u_cur[e] * gx + a.v_cur[e] * gy));
+      }
+      run = run + dm;
+      s_cum[c + 1][tx] = run;
+    }
+    s_tot[w][lane] = run;
+  }
+  __syncthreads();
+  double cum_off = 0.0, tot = 0.0;
+#pragma unroll
+  for (int q = 0; q < GS_KW; ++q) {
+    if (q == w) cum_off = tot;
+    tot = tot + s_tot[q][lane];
+  }
+  if (w == 0 && live) a.dt_lnps[col] = 0.0 - tot;                           // dt_ln_psg = -dmean_tot/psg
+
+  // Held-Suarez latitude / column factors
+  const double lat = t.rad_lat[j];
+  const double sin_lat = sin(lat);
+  const double sin_lat_2 = sin_lat * sin_lat;
+  const double cos_lat_2 = 1.0 - sin_lat_2;
+  const double cos_lat_4 = cos_lat_2 * cos_lat_2;
+  const double t_star = pr.t_zero - pr.delh * sin_lat_2 - pr.eps * sin_lat;
+  const double tstr = pr.t_strat - pr.eps * sin_lat;
+  const double tcoeff = (pr.tks - pr.tka) / (1.0 - pr.sigma_b);
+  const double vcoeff = -pr.vkf / (1.0 - pr.sigma_b);
+  const double fcor = t.coriolis[j];
+  const double delta_t = pr.delta_t;
+  const double inv_cp = 1.0 / pr.cp_air;
+  const double ln_pn0 = ln_ps - log(pr.P00);                                 // ln(ps/P00)
+  const double pk_col = exp(pr.kappa * ln_pn0);                              // (ps/P00)^kappa
+  const bool hs_on = (pr.physics_on && !pr.no_forcing);
+
+  // ---- pass 2: bottom-up within the chunk
+  double gh_local = 0.0, energy_int = 0.0;
+  double u_dn = 0.0, v_dn = 0.0, T_dn = 0.0, u_k = 0.0, v_k = 0.0, T_k = 0.0;
+  if (k_hi > k_lo) {
+    const size_t e = (size_t)(k_hi - 1) * plane + col;
+    u_k = a.u_cur[e]; v_k = a.v_cur[e]; T_k = a.t_cur[e] + sh_c;
+    if (k_hi < K) { u_dn = a.u_cur[e + plane]; v_dn = a.v_cur[e + plane]; T_dn = a.t_cur[e + plane] + sh_c; }
+  }
+#pragma unroll
+  for (int c = CH - 1; c >= 0; --c) {
+    const int k = k_lo + c;
+    if (k >= k_hi) continue;
+    const size_t e = (size_t)k * plane + col;
+    double u_up = 0.0, v_up = 0.0, T_up = 0.0;
+    if (k > 0) { u_up = a.u_cur[e - plane]; v_up = a.v_cur[e - plane]; T_up = a.t_cur[e - plane] + sh_c; }
+    const double dbk = sg.db[k], rdb = sg.rdb[k], al = sg.al[k], d3 = sg.d3[k], pf = sg.pf[k];
+
+    // ---------------- hs_forcing
+    double dt_u = 0.0, dt_v = 0.0, dt_T = 0.0;
+    const double u_p = a.u_prev[e], v_p = a.v_prev[e], T_p = a.t_prev[e] + sh_p;
+    if (hs_on) {
+      const double sigma = pf;                                                // p_full/ps
+      double utnd = 0.0, vtnd = 0.0;
+      const bool in_bl = (sigma <= 1.0 && sigma > pr.sigma_b);
+      if (in_bl) { const double vfactr = vcoeff * (sigma - pr.sigma_b); utnd = vfactr * u_p; vtnd = vfactr * v_p; }
+      if (pr.do_conserve_energy) dt_T = dt_T + (-((u_p + .5 * utnd * delta_t) * utnd + (v_p + .5 * vtnd * delta_t) * vtnd) * inv_cp);
+      dt_u = dt_u + utnd; dt_v = dt_v + vtnd;
+      const double ln_pn = sg.lf[k] + ln_pn0;                                 // ln(p_full/P00)
+      double teq = (t_star - pr.delv * cos_lat_2 * ln_pn) * (sg.pfk[k] * pk_col);
+      teq = fmax(teq, tstr);
+      double tdamp = pr.tka;
+      if (in_bl) tdamp = pr.tka + cos_lat_4 * (tcoeff * (sigma - pr.sigma_b));
+      dt_T = dt_T + (-tdamp * (T_p - teq));
+    } else if (a.dt_u_in) {
+      dt_u = a.dt_u_in[e]; dt_v = a.dt_v_in[e]; dt_T = a.dt_t_in[e];
+    }
+    {   // initialize_corrections energy integral, dp(previous) = db*ps(previous)
+      const double up = u_p + dt_u * delta_t, vp = v_p + dt_v * delta_t;
+      energy_int = energy_int + (0.5 * (up * up + vp * vp) + pr.cp_air * (T_p + dt_T * delta_t)) * (dbk * ps_p);
+    }
+
+    // ---------------- four_in_one
+    const double x2 = sg.x1c[k] * gx, x3 = sg.x1c[k] * gy;                    // x1*dx_psg, x1*dy_psg
+    dt_u = dt_u - pr.rdgas * T_k * x2;
+    dt_v = dt_v - pr.rdgas * T_k * x3;
+    const double cum_k = cum_off + s_cum[c][tx], cum_k1 = cum_off + s_cum[c + 1][tx];
+    const double dm = dbk * (a.div_cur[e] + (u_k * gx + v_k * gy));
+    const double x4 = (cum_k * d3 + dm * al) * rdb;
+    const double x5 = x4 - u_k * x2 - v_k * x3;
+    dt_T = dt_T - pr.kappa * T_k * x5;
+    if (a.wg_full && live) a.wg_full[e] = -x5 * (pf * ps_c);
+    const double w_top = (k == 0) ? 0.0 : (-cum_k + tot * sg.b[k]);           // wg/ps at the interfaces
+    const double w_bot = (k == K - 1) ? 0.0 : (-cum_k1 + tot * sg.b[k + 1]);
+    if (a.wg && live) { a.wg[e] = w_top * ps_c; if (k == K - 1) a.wg[e + plane] = w_bot * ps_c; }
+
+    // ---------------- compute_geopotential
+    const double gfull = gh_local + pr.rdgas * T_k * al;
+    if (k != 0) gh_local = gh_local + pr.rdgas * T_k * d3;
+
+    // ---------------- vert_advection (second_centered, advective form): (w/ps) / db
+    {
+      const double fu_t = (k == 0) ? w_top * u_k : w_top * (0.5 * (u_k + u_up));
+      const double fu_b = (k == K - 1) ? w_bot * u_k : w_bot * (0.5 * (u_dn + u_k));
+      dt_u = dt_u + (-(fu_b - fu_t - u_k * (w_bot - w_top)) * rdb);
+      const double fv_t = (k == 0) ? w_top * v_k : w_top * (0.5 * (v_k + v_up));
+      const double fv_b = (k == K - 1) ? w_bot * v_k : w_bot * (0.5 * (v_dn + v_k));
+      dt_v = dt_v + (-(fv_b - fv_t - v_k * (w_bot - w_top)) * rdb);
+      const double ft_t = (k == 0) ? w_top * T_k : w_top * (0.5 * (T_k + T_up));
+      const double ft_b = (k == K - 1) ? w_bot * T_k : w_bot * (0.5 * (T_dn + T_k));
+      dt_T = dt_T + (-(ft_b - ft_t - T_k * (w_bot - w_top)) * rdb);
+    }
+    dt_T = dt_T - u_k * a.dx_t[e] - v_k * a.dy_t[e];
+    const double absv = a.vor_cur[e] + fcor;
+    dt_u = dt_u + absv * v_k;
+    dt_v = dt_v - absv * u_k;
+    if (live) {
+      a.out_A[e] = dt_u * cosm;
+      a.out_B[e] = dt_v * cosm;
+      a.out_T[e] = dt_T;
+    }
+    s_phi[c][tx] = gfull + .5 * (u_k * u_k + v_k * v_k);
+    u_dn = u_k; v_dn = v_k; T_dn = T_k;
+    u_k = u_up; v_k = v_up; T_k = T_up;
+  }
+  s_gh[w][lane] = gh_local;
+  s_en[w][lane] = energy_int;
+  __syncthreads();
+  double gh_off = a.phis[col];
+#pragma unroll
+  for (int q = GS_KW - 1; q >= 0; --q) if (q > w) gh_off = gh_off + s_gh[q][lane];
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = k_lo + c;
+      if (k < k_hi) a.out_phi[(size_t)k * plane + col] = gh_off + s_phi[c][tx];
+    }
+    if (w == 0) {
+      double en = 0.0;
+#pragma unroll
+      for (int q = GS_KW - 1; q >= 0; --q) en = en + s_en[q][lane];
+      const double wt = t.wts_lat[j];
+      a.part[0 * plane + col] = wt * ps_p;
+      a.part[1 * plane + col] = wt * en;
+    }
+  }
+}
+
 void launch_grid_step(const DevTables& t, const Params& pr, const GridStepArgs& a, cudaStream_t st) {
   dim3 block(32 * GS_KW), grid((t.g.I + 31) / 32, t.g.Jloc);
   const int ch = (t.g.K + GS_KW - 1) / GS_KW;
+  if (pr.sigma_fast) {
+    if (ch <= 4) grid_step_sigma_kernel<4><<<grid, block, 0, st>>>(t, pr, a);
+    else if (ch <= 7) grid_step_sigma_kernel<7><<<grid, block, 0, st>>>(t, pr, a);
+    else if (ch <= 10) grid_step_sigma_kernel<10><<<grid, block, 0, st>>>(t, pr, a);
+    else if (ch <= 15) grid_step_sigma_kernel<15><<<grid, block, 0, st>>>(t, pr, a);
+    else grid_step_sigma_kernel<20><<<grid, block, 0, st>>>(t, pr, a);
+    return;
+  }
   if (ch <= 4) grid_step_kernel<4><<<grid, block, 0, st>>>(t, pr, a);
   else if (ch <= 7) grid_step_kernel<7><<<grid, block, 0, st>>>(t, pr, a);
   else if (ch <= 10) grid_step_kernel<10><<<grid, block, 0, st>>>(t, pr, a);
