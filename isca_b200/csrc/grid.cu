@@ -266,7 +266,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
 //   dp = DB(k)*ps,  sigma = PF(k),  p_norm^kappa = PFK(k)*(ps/P00)^kappa.
 // The column loop then contains no transcendental and no division.  Mathematically identical to the
 // generic kernel; the arithmetic is re-associated, so results agree to a few ulp, not bit for bit
-// (tests hold both against the oracle at the same tolerance).  Mass fluxes are carried divided by ps.
+// (the parity tests hold both kernels to the same tolerance).  Mass fluxes are carried divided by ps.
 // ---------------------------------------------------------------------------------------------
 template <int CH>
 __global__ void __launch_bounds__(32 * GS_KW, (CH <= 10) ? 6 : 4)
