@@ -224,6 +224,10 @@ def main():
 
     cfg = api.make_config(**hs_namelist(res, K))
     atm = api.Atmosphere(cfg, rank=rank, nranks=world, nccl_unique_id=uid)
+    if world > 1 and os.environ.get("ISCA_B200_NO_P2P") is None:
+        handles = [None] * world
+        dist.all_gather_object(handles, atm.ipc_handles())
+        atm.set_peer_handles(handles)                # Legendre/FFT epilogues now store straight into peer memory
     atm.cold_start()
     atm.atmosphere(args.spinup)                      # spin-up (untimed)
     atm.atmosphere(max(args.warmup, 3))              # warm-up (untimed; also captures the CUDA graphs)

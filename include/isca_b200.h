@@ -107,6 +107,14 @@ const char* isca_b200_last_error(IscaHandle h);   /* h may be NULL (create error
 /* bytes of an ncclUniqueId written to out (rank 0 calls this, the host runtime broadcasts) */
 int isca_b200_nccl_unique_id(void* out128);
 
+/* Peer-memory transpose (nranks > 1, one process per GPU of one NVLink/NVSwitch domain): every rank exports
+ * its two Fourier buffers (2 x 64-byte cudaIpcMemHandle_t), the host runtime all-gathers the nranks x 128 bytes
+ * (rank order) and hands them back; from then on the Legendre / FFT kernels store straight into the peers'
+ * buffers and the per-transform exchange is only a one-element all-reduce used as a barrier.  Without this
+ * call the transpose (tools/transforms.F90:970-1056 transpose_fourier) is a grouped ncclSend/ncclRecv. */
+int isca_b200_ipc_handles(IscaHandle h, void* out128);
+int isca_b200_set_peer_handles(IscaHandle h, const void* all_handles);
+
 /* The decomposition the library uses for (rank, nranks): the rank's contiguous latitude block
  * (grid domain of tools/spec_mpp.F90:61-65) and its zonal wavenumbers (spectral domain; dealt in snake
  * order instead of spec_mpp.F90:77-80's contiguous blocks, to balance the triangle).  m_list has room for

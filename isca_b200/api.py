@@ -66,6 +66,7 @@ EXPORTS = [
     "isca_b200_get_table", "isca_b200_get_time_pointers", "isca_b200_spherical_to_grid",
     "isca_b200_grid_to_spherical", "isca_b200_uv_grid_from_vor_div", "isca_b200_vor_div_from_uv_grid",
     "isca_b200_time_transforms", "isca_b200_profile_step", "isca_b200_decomposition",
+    "isca_b200_ipc_handles", "isca_b200_set_peer_handles",
 ]
 
 # field / scalar ids (include/isca_b200.h)
@@ -121,6 +122,8 @@ def load_library() -> C.CDLL:
     lib.isca_b200_vor_div_from_uv_grid.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     lib.isca_b200_time_transforms.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.isca_b200_profile_step.argtypes = [vp, C.c_int, dp, C.c_int, C.c_char_p, C.c_int]
+    lib.isca_b200_ipc_handles.argtypes = [vp, vp]
+    lib.isca_b200_set_peer_handles.argtypes = [vp, vp]
     ip = C.POINTER(C.c_int)
     lib.isca_b200_decomposition.argtypes = [C.POINTER(IscaConfigStruct), C.c_int, C.c_int, ip, ip, ip, vp, vp, vp]
     for name in EXPORTS:
@@ -243,6 +246,18 @@ class Atmosphere:
         if rc != 0:
             msg = self.lib.isca_b200_last_error(self.h)
             raise IscaError(f"{where}: " + (msg.decode() if msg else f"error {rc}"))
+
+    # ---- peer-memory transpose (multi-rank) ------------------------------------------------
+    def ipc_handles(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.isca_b200_ipc_handles(self.h, buf), "ipc_handles")
+        return buf.raw
+
+    def set_peer_handles(self, all_handles):
+        """all_handles: list of the nranks 128-byte blobs returned by ipc_handles(), in rank order."""
+        blob = b"".join(bytes(x) for x in all_handles)
+        self._blob = C.create_string_buffer(blob, len(blob))
+        self._ck(self.lib.isca_b200_set_peer_handles(self.h, self._blob), "set_peer_handles")
 
     # ---- atmosphere_mod ------------------------------------------------------------------
     @classmethod

@@ -45,6 +45,16 @@ struct GeomDev {
   const int* off;             // [nm+1]
   const int* pos;             // [M+1]
   const int* row_m;           // [T] local mi of packed row
+  // peer-memory transpose (one process per GPU, buffers mapped with CUDA IPC): when p2p != 0 the Legendre
+  // epilogue stores straight into the destination rank's lat-owner buffer and the FFT epilogue straight into the
+  // destination rank's m-owner buffer, over NVLink; no send/recv, no staging copy.
+  int p2p;
+  const int* owner;           // [M+1] rank owning m
+  const int* lidx;            // [M+1] local index of m on its owner
+  const int* nm_rank;         // [P]
+  const int* roff;            // [P+1]
+  double* const* peerA;       // [P] m-owner-layout Fourier buffer of every rank
+  double* const* peerB;       // [P] lat-owner-layout Fourier buffer of every rank
 };
 
 // host-computed double tables (see host_tables.cpp)

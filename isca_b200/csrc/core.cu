@@ -74,7 +74,11 @@ struct IscaHandle_t {
   int previous = 0, current = 0;
 
   // ---- device tables
-  DBuf<int> d_m_of, d_off, d_pos, d_row_m, d_row_n;
+  DBuf<int> d_m_of, d_off, d_pos, d_row_m, d_row_n, d_owner, d_lidx, d_nm_rank, d_roff;
+  DBuf<double*> d_peerA, d_peerB;
+  std::vector<void*> ipc_opened;
+  DBuf<double> barrier_token;
+  bool p2p = false;
   DBuf<double> d_sin_lat, d_cos_lat, d_cosm_lat, d_wts_lat, d_coriolis, d_rad_lat, d_pk, d_bk, d_dpk, d_dbk;
   DBuf<double> d_leg, d_legw, d_ln_bk;
   DBuf<double> d_sg[9];
@@ -100,7 +104,9 @@ struct IscaHandle_t {
   NcclApi nccl; NcclComm comm = nullptr;
   double* four_lat() { return g.P > 1 ? fourB.p : four.p; }
   void ensure_four(int Lp) {
-    const size_t needA = (size_t)g.nm * g.J * 2 * Lp, needB = (size_t)(g.M + 1) * g.Jloc * 2 * Lp;
+    // m-owner buffer: nm*J rows (sized with nm_max so that every rank's buffer is equally large for peer writes)
+    const size_t needA = (size_t)g.nm_max * g.J * 2 * Lp, needB = (size_t)(g.M + 1) * g.Jloc * 2 * Lp;
+    if (p2p && (needA > four.n || needB > fourB.n)) throw std::runtime_error("transform batch too large for the peer-mapped Fourier buffers");
     if (needA > four.n) four.alloc(needA);
     if (g.P > 1 && needB > fourB.n) fourB.alloc(needB);
   }
@@ -145,6 +151,11 @@ static void upload_tables(H& h) {
   const Geometry& g = h.g; const HostTables& t = h.ht;
   h.d_m_of.upload(g.m_of); h.d_off.upload(g.off); h.d_pos.upload(g.pos);
   h.d_row_m.upload(t.row_m); h.d_row_n.upload(t.row_n);
+  {
+    std::vector<int> lidx(g.M + 1, 0), cnt(g.P, 0);
+    for (int m = 0; m <= g.M; ++m) lidx[m] = cnt[g.owner[m]]++;
+    h.d_owner.upload(g.owner); h.d_lidx.upload(lidx); h.d_nm_rank.upload(g.nm_rank); h.d_roff.upload(g.roff);
+  }
   h.d_sin_lat.upload(t.sin_lat); h.d_cos_lat.upload(t.cos_lat); h.d_cosm_lat.upload(t.cosm_lat);
   h.d_wts_lat.upload(t.wts_lat); h.d_coriolis.upload(t.coriolis); h.d_rad_lat.upload(t.rad_lat);
   h.d_pk.upload(t.pk); h.d_bk.upload(t.bk); h.d_dpk.upload(t.dpk); h.d_dbk.upload(t.dbk);
@@ -165,6 +176,8 @@ static void upload_tables(H& h) {
   d.g.I = g.I; d.g.J = g.J; d.g.K = g.K; d.g.M = g.M; d.g.N = g.N; d.g.Jh = g.Jh; d.g.P = g.P; d.g.rank = g.rank;
   d.g.Jloc = g.Jloc; d.g.j0 = g.j0; d.g.nm = g.nm; d.g.T = g.T;
   d.g.m_of = h.d_m_of.p; d.g.off = h.d_off.p; d.g.pos = h.d_pos.p; d.g.row_m = h.d_row_m.p;
+  d.g.p2p = 0; d.g.owner = h.d_owner.p; d.g.lidx = h.d_lidx.p; d.g.nm_rank = h.d_nm_rank.p; d.g.roff = h.d_roff.p;
+  d.g.peerA = nullptr; d.g.peerB = nullptr;
   d.row_n = h.d_row_n.p;
   d.sin_lat = h.d_sin_lat.p; d.cos_lat = h.d_cos_lat.p; d.cosm_lat = h.d_cosm_lat.p; d.wts_lat = h.d_wts_lat.p;
   d.coriolis = h.d_coriolis.p; d.rad_lat = h.d_rad_lat.p;
@@ -305,6 +318,13 @@ static void ensure_wave_matrix(H& h, double xi) {
 static void exchange_fourier(H& h, int direction, int Lp) {
   const Geometry& g = h.g;
   if (g.P == 1) return;
+  if (h.p2p) {
+    // the producing kernel already stored into the peers' buffers; a one-element all-reduce is the inter-GPU
+    // barrier: it completes on a rank only after every rank's producer kernel (earlier in its stream) finished
+    h.nccl.ck(h.nccl.AllReduce(h.barrier_token.p, h.barrier_token.p, 1, NCCL_FLOAT64, NCCL_SUM, h.comm, h.st), "ncclAllReduce(barrier)");
+    h.mark(direction == 0 ? "exchange_inv" : "exchange_fwd");
+    return;
+  }
   const size_t C = 2 * (size_t)Lp;
   const NcclApi& n = h.nccl;
   n.ck(n.GroupStart(), "ncclGroupStart");
@@ -674,6 +694,41 @@ int isca_b200_nccl_unique_id(void* out128) {
   return 0;
 }
 
+int isca_b200_ipc_handles(IscaHandle h, void* out128) {
+  API_BEGIN(h)
+  if (h->g.P < 2) throw std::runtime_error("peer access needs nranks > 1");
+  cudaIpcMemHandle_t ha, hb;
+  CK(cudaIpcGetMemHandle(&ha, h->four.p));
+  CK(cudaIpcGetMemHandle(&hb, h->fourB.p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(out128, &ha, 64); std::memcpy((char*)out128 + 64, &hb, 64);
+  API_END(h)
+}
+
+int isca_b200_set_peer_handles(IscaHandle h, const void* all_handles) {
+  API_BEGIN(h)
+  const int P = h->g.P;
+  if (P < 2) throw std::runtime_error("peer access needs nranks > 1");
+  std::vector<double*> pa(P, nullptr), pb(P, nullptr);
+  for (int r = 0; r < P; ++r) {
+    if (r == h->g.rank) { pa[r] = h->four.p; pb[r] = h->fourB.p; continue; }
+    cudaIpcMemHandle_t ha, hb;
+    std::memcpy(&ha, (const char*)all_handles + (size_t)r * 128, 64);
+    std::memcpy(&hb, (const char*)all_handles + (size_t)r * 128 + 64, 64);
+    void *qa = nullptr, *qb = nullptr;
+    CK(cudaIpcOpenMemHandle(&qa, ha, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&qb, hb, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(qa); h->ipc_opened.push_back(qb);
+    pa[r] = (double*)qa; pb[r] = (double*)qb;
+  }
+  h->d_peerA.upload(pa); h->d_peerB.upload(pb);
+  h->dt.g.peerA = h->d_peerA.p; h->dt.g.peerB = h->d_peerB.p; h->dt.g.p2p = 1;
+  h->p2p = true;
+  h->barrier_token.alloc(1);
+  for (auto& sg : h->graphs) if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; sg.uses = 0; }
+  API_END(h)
+}
+
 int isca_b200_decomposition(const IscaConfig* cfg, int rank, int nranks, int* lat_start, int* lat_count, int* num_m,
                             int* m_list, int* owner, int* pos) {
   try {
@@ -741,6 +796,7 @@ int isca_b200_destroy(IscaHandle h) {
   cudaStreamSynchronize(h->st);
   for (auto& kv : h->wave_cache) delete kv.second;
   for (auto& sg : h->graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
+  for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
   if (h->comm) h->nccl.CommDestroy(h->comm);
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st2) cudaStreamDestroy(h->st2);

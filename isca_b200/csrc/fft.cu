@@ -297,7 +297,12 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
     const double2 e = cadd(zk, zc), o = csub(zk, zc);
     const double2 wo = cmul(o, tw<-1>(t.twiddle, k));
     const double2 x = make_double2(0.5 * (e.x + wo.y) * inv, 0.5 * (e.y - wo.x) * inv);
-    *reinterpret_cast<double2*>(four + fourB_index(g, k, jl, C) + 2 * (lev0 + l)) = x;
+    double* dst;
+    if (g.p2p) {        // store into the m-owner buffer of the rank that owns wavenumber k (peer memory over NVLink)
+      const int r = g.owner[k];
+      dst = g.peerA[r] + ((size_t)(g.rank * g.nm_rank[r] + g.lidx[k]) * g.Jloc + jl) * (size_t)C;
+    } else dst = four + fourB_index(g, k, jl, C);
+    *reinterpret_cast<double2*>(dst + 2 * (lev0 + l)) = x;
   }
 }
 

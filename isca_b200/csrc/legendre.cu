@@ -129,8 +129,16 @@ legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __res
   for (int mt = 0; mt < MT; ++mt) {
     const int jh = jt0 + wj * WTJ + mt * 8 + (lane >> 2);
     const int js = jh, jn = g.J - 1 - jh;
-    double* rowS = four + fourA_index(g, mi, js, C);
-    double* rowN = four + fourA_index(g, mi, jn, C);
+    double *rowS, *rowN;
+    if (g.p2p) {        // store into the lat-owner buffer of the rank that owns the latitude (peer memory over NVLink)
+      const int ss = js / g.Jloc, sn = jn / g.Jloc;
+      const size_t prow = (size_t)(g.roff[g.rank] + mi) * g.Jloc;
+      rowS = g.peerB[ss] + (prow + (js - ss * g.Jloc)) * (size_t)C;
+      rowN = g.peerB[sn] + (prow + (jn - sn * g.Jloc)) * (size_t)C;
+    } else {
+      rowS = four + fourA_index(g, mi, js, C);
+      rowN = four + fourA_index(g, mi, jn, C);
+    }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int c = c0 + wc * WTC + nt * 8 + (lane & 3) * 2;

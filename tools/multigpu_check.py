@@ -22,6 +22,10 @@ def main():
     box = [api.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     atm = api.Atmosphere(cfg, rank=rank, nranks=world, nccl_unique_id=box[0])
+    if os.environ.get("ISCA_B200_NO_P2P") is None:
+        handles = [None] * world
+        dist.all_gather_object(handles, atm.ipc_handles())
+        atm.set_peer_handles(handles)
     atm.cold_start()
     atm.atmosphere(nsteps)
     loc = dict(u=atm.get_field(api.F_U), T=atm.get_field(api.F_T), ps=atm.get_field(api.F_PS), vor=atm.get_field(api.F_VOR),
