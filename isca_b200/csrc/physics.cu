@@ -1,0 +1,500 @@
+// physics.cu -- per-column physics kernels (one thread per column, planes [lev][lat][lon] so that a warp reads 32
+// consecutive longitudes of one level: fully coalesced) and their C ABI (include/isca_b200_physics.h).
+//
+//   sat_vapor_pres do_simple tables + lookup   shared/sat_vapor_pres/sat_vapor_pres_k.F90:161-266, 1132-1158, 457-540
+//   lscale_cond + precip_evap                  atmos_param/lscale_cond/lscale_cond.F90:79-255
+//   two_stream_gray_rad down/up (frierson)     atmos_param/two_stream_gray_rad/two_stream_gray_rad.F90:386-776
+//   rayleigh sponge                            atmos_param/damping_driver/damping_driver.f90:404-420, 594-636
+//
+// All four are streaming kernels bounded by HBM: algorithmic bytes per column are listed at each launch.
+#include "../../include/isca_b200_physics.h"
+#include "common.h"
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct SvpDev {
+  const double *tab, *dtab, *d2tab;
+  double tminl, dtinvl, tepsl, dtres;
+  int n;
+};
+
+struct PhysConst {
+  double grav, rdgas, rvgas, cp_air, hlv, stefan, pstd;
+  double hc; int do_evap;
+  double solar_constant, del_sol, del_sw, ir_tau_eq, ir_tau_pole, atm_abs, sw_diff, linear_tau, wv_exponent,
+         solar_exponent, odp, diabatic_acce;
+};
+
+__device__ __forceinline__ bool svp_lookup(const SvpDev& s, double T, double& es, double& des) {
+  double tmp = T - s.tminl;
+  double x = s.dtinvl * (tmp + s.tepsl);
+  if (!(x > -1.0 && x < (double)s.n)) { es = 0.0; des = 0.0; return false; }
+  int ind = (int)x;                                   // truncation, like the Fortran int()
+  double dl = tmp - s.dtres * (double)ind;
+  double t0 = __ldg(s.tab + ind), t1 = __ldg(s.dtab + ind), t2 = __ldg(s.d2tab + ind);
+  es = t0 + dl * (t1 + dl * t2);
+  des = t1 + 2.0 * dl * t2;
+  return true;
+}
+
+__device__ __forceinline__ void qs_from_es(double es, double des, double press, double hc, double eps, double& qs, double& dqs) {
+  des *= hc; es *= hc;
+  double denom = press - (1.0 - eps) * es;
+  qs = denom > 0.0 ? eps * es / denom : eps;
+  dqs = eps * press * des / (denom * denom);
+}
+
+__global__ void lookup_kernel(SvpDev s, int n, const double* __restrict__ T, double* __restrict__ es, double* __restrict__ des, int* err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a, b;
+  if (!svp_lookup(s, T[i], a, b)) atomicExch(err, 1);
+  es[i] = a; des[i] = b;
+}
+
+__global__ void compute_qs_kernel(SvpDev s, PhysConst c, int n, const double* __restrict__ T, const double* __restrict__ P,
+                                  double* __restrict__ qs, double* __restrict__ dqs, int* err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a, b, q, d;
+  if (!svp_lookup(s, T[i], a, b)) atomicExch(err, 1);
+  qs_from_es(a, b, P[i], c.hc, c.rdgas / c.rvgas, q, d);
+  qs[i] = q; dqs[i] = d;
+}
+
+// lscale_cond: one top-down sweep fuses compute_qs, the adjustment, precip_evap and the rain integral.
+// bytes/column: read t, q, pfull (3K) + phalf (K+1), write tdel, qdel (2K) + rain (1)  = (6K + 2) * 8
+__global__ void __launch_bounds__(128) lscale_cond_kernel(SvpDev s, PhysConst c, int ncol, int K,
+    const double* __restrict__ tin, const double* __restrict__ qin, const double* __restrict__ pfull,
+    const double* __restrict__ phalf, double* __restrict__ rain, double* __restrict__ tdel, double* __restrict__ qdel, int* err) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const double hlcp = c.hlv / c.cp_air, eps = c.rdgas / c.rvgas;
+  double exq = 0.0, precip = 0.0;
+  double ph0 = phalf[col];
+  bool bad = false;
+  for (int k = 0; k < K; ++k) {
+    size_t o = (size_t)k * ncol + col;
+    double t = tin[o], q = qin[o], p = pfull[o], ph1 = phalf[o + ncol];
+    double es, des, qsat, dqsat;
+    bad |= !svp_lookup(s, t, es, des);
+    qs_from_es(es, des, p, c.hc, eps, qsat, dqsat);
+    double qd = 0.0, td = 0.0;
+    if ((q - qsat) * qsat > 0.0) { qd = (qsat - q) / (1.0 + hlcp * dqsat); td = -hlcp * qd; }
+    double pmass = (ph1 - ph0) / c.grav;
+    if (c.do_evap) {
+      if (qd < 0.0) exq = exq - qd * pmass;
+      if (qd >= 0.0 && exq > 0.0) {
+        exq = exq / pmass;
+        double d = (qsat - q) / (1.0 + hlcp * dqsat);
+        d = fmin(fmax(d, 0.0), exq);
+        qd = qd + d;
+        td = td - d * hlcp;
+        exq = (exq - d) * pmass;
+      }
+    }
+    precip = precip - pmass * qd;
+    tdel[o] = td; qdel[o] = qd;
+    ph0 = ph1;
+  }
+  rain[col] = fmax(precip, 0.0);
+  if (bad) atomicExch(err, 1);
+}
+
+__device__ __forceinline__ double lw_tau_at(const PhysConst& c, double lw_tau_0, double p) {
+  double r = p / c.pstd;
+  return lw_tau_0 * (c.linear_tau * p / c.pstd + (1.0 - c.linear_tau) * pow(r, c.wv_exponent));
+}
+
+// two_stream_gray_rad_down: only the two surface fluxes leave the kernel.
+// bytes/column: read t (K) + p_half (K+1) + lat, albedo (2), write 2   = (2K + 5) * 8
+__global__ void __launch_bounds__(128) gray_down_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
+    const double* __restrict__ p_half, const double* __restrict__ t, const double* __restrict__ albedo,
+    double* __restrict__ net_surf_sw_down, double* __restrict__ surf_lw_down) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  double sl = sin(lat[col]);
+  double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
+  double insolation = 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * sl);
+  double sw_tau_0 = (1.0 - c.sw_diff * sl * sl) * c.atm_abs;
+  double lw_tau_0 = (c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * sl * sl) * c.odp;
+  double tau0 = lw_tau_at(c, lw_tau_0, p_half[col]);
+  double lw_down = 0.0;
+  for (int k = 0; k < K; ++k) {
+    size_t o = (size_t)k * ncol + col;
+    double tau1 = lw_tau_at(c, lw_tau_0, p_half[o + ncol]);
+    double tr = exp(-(tau1 - tau0));
+    double tk = t[o];
+    double b = c.stefan * ((tk * tk) * (tk * tk));
+    lw_down = lw_down * tr + b * (1.0 - tr);
+    tau0 = tau1;
+  }
+  double ps = p_half[(size_t)K * ncol + col];
+  double sw_down_s = insolation * exp(-(sw_tau_0 * pow(ps / c.pstd, c.solar_exponent)));
+  surf_lw_down[col] = lw_down;
+  net_surf_sw_down[col] = (1.0 - albedo[col]) * sw_down_s;
+}
+
+// two_stream_gray_rad_up: the down sweep is recomputed (its fluxes stay in thread-local storage) and the up sweep
+// accumulates the flux divergence into tdt.
+// bytes/column: read t (K) + p_half (K+1) + tdt (K) + lat, t_surf, albedo (3), write tdt (K) + olr (1)  = (4K + 5) * 8
+__global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
+    const double* __restrict__ p_half, const double* __restrict__ t, const double* __restrict__ t_surf,
+    const double* __restrict__ albedo, double* __restrict__ tdt, double* __restrict__ olr) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  double lwd[ISCA_KMAX + 1], trs[ISCA_KMAX];
+  double sl = sin(lat[col]);
+  double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
+  double insolation = 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * sl);
+  double sw_tau_0 = (1.0 - c.sw_diff * sl * sl) * c.atm_abs;
+  double lw_tau_0 = (c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * sl * sl) * c.odp;
+  double tau0 = lw_tau_at(c, lw_tau_0, p_half[col]);
+  lwd[0] = 0.0;
+  for (int k = 0; k < K; ++k) {
+    size_t o = (size_t)k * ncol + col;
+    double tau1 = lw_tau_at(c, lw_tau_0, p_half[o + ncol]);
+    double tr = exp(-(tau1 - tau0));
+    double tk = t[o];
+    double b = c.stefan * ((tk * tk) * (tk * tk));
+    lwd[k + 1] = lwd[k] * tr + b * (1.0 - tr);
+    trs[k] = tr;
+    tau0 = tau1;
+  }
+  double ph1 = p_half[(size_t)K * ncol + col];
+  double sw_down1 = insolation * exp(-(sw_tau_0 * pow(ph1 / c.pstd, c.solar_exponent)));
+  double sw_up = albedo[col] * sw_down1;
+  double ts = t_surf[col];
+  double lw_up1 = c.stefan * ((ts * ts) * (ts * ts));
+  double flux1 = (lw_up1 - lwd[K]) + (sw_up - sw_down1);
+  for (int k = K - 1; k >= 0; --k) {
+    size_t o = (size_t)k * ncol + col;
+    double tk = t[o];
+    double b = c.stefan * ((tk * tk) * (tk * tk));
+    double lw_up0 = lw_up1 * trs[k] + b * (1.0 - trs[k]);
+    double ph0 = p_half[o];
+    double sw_down0 = insolation * exp(-(sw_tau_0 * pow(ph0 / c.pstd, c.solar_exponent)));
+    double flux0 = (lw_up0 - lwd[k]) + (sw_up - sw_down0);
+    double tdt_rad = c.diabatic_acce * (flux1 - flux0) * c.grav / (c.cp_air * (ph1 - ph0));
+    tdt[o] = tdt[o] + tdt_rad;
+    lw_up1 = lw_up0; flux1 = flux0; ph1 = ph0;
+  }
+  if (olr) olr[col] = lw_up1;
+}
+
+// rayleigh sponge.  bytes/element over the damped levels: read p_full, u, v (3), write udt, vdt, tdt (3)
+__global__ void rayleigh_kernel(PhysConst c, size_t ncol, int K, int nlev, double rfactr, double pb, double delt, int conserve,
+    const double* __restrict__ p_full, const double* __restrict__ u, const double* __restrict__ v,
+    double* __restrict__ udt, double* __restrict__ vdt, double* __restrict__ tdt) {
+  size_t n = ncol * (size_t)K, lim = ncol * (size_t)nlev;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double a = 0.0, b = 0.0, h = 0.0;
+    if (i < lim) {
+      double p = p_full[i];
+      if (p < pb) {
+        double d = pb - p;
+        double fact = rfactr * (d * d) / (pb * pb);
+        double uu = u[i], vv = v[i];
+        a = -uu * fact; b = -vv * fact;
+        if (conserve) h = -((uu + 0.5 * delt * a) * a + (vv + 0.5 * delt * b) * b) / c.cp_air;
+      }
+    }
+    udt[i] = a; vdt[i] = b; tdt[i] = h;
+  }
+}
+
+struct Dev {                 // owning device array
+  double* p = nullptr; size_t n = 0;
+  bool ensure(size_t count) {
+    if (count <= n) return true;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (cudaMalloc(&p, count * sizeof(double)) != cudaSuccess) return false;
+    n = count; return true;
+  }
+  ~Dev() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+struct IscaPhysics_t {
+  IscaPhysicsConfig cfg;
+  PhysConst pc;
+  SvpDev svp;
+  Dev tab;                   // TABLE | DTABLE | D2TABLE
+  Dev buf[10];
+  int* d_err = nullptr;
+  cudaStream_t st = nullptr;
+  std::string err;
+  size_t ncol = 0; int K = 0;
+};
+
+namespace {
+
+int fail(IscaPhysics p, const std::string& m) { if (p) p->err = m; g_err = m; return 1; }
+
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(p, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+int up(IscaPhysics p, Dev& d, const double* h, size_t n) {
+  if (!h) return fail(p, "null input array");
+  if (!d.ensure(n)) return fail(p, "cudaMalloc failed");
+  PCK(cudaMemcpyAsync(d.p, h, n * sizeof(double), cudaMemcpyHostToDevice, p->st));
+  return 0;
+}
+int down(IscaPhysics p, const Dev& d, double* h, size_t n) {
+  if (!h) return fail(p, "null output array");
+  PCK(cudaMemcpyAsync(h, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+  return 0;
+}
+int finish(IscaPhysics p, const char* what) {
+  int e = 0;
+  PCK(cudaGetLastError());
+  PCK(cudaMemcpyAsync(&e, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  PCK(cudaStreamSynchronize(p->st));
+  if (e) {
+    PCK(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->st));
+    return fail(p, std::string(what) + ": lookup_es: temperature outside the saturation vapour pressure table (table overflow)");
+  }
+  return 0;
+}
+
+void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd) {
+  int nb = (int)((p->ncol + 127) / 128);
+  lscale_cond_kernel<<<nb, 128, 0, p->st>>>(p->svp, p->pc, (int)p->ncol, p->K, t, q, pf, ph, rain, td, qd, p->d_err);
+}
+void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* alb, double* sw, double* lw) {
+  int nb = (int)((p->ncol + 127) / 128);
+  gray_down_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, alb, sw, lw);
+}
+void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* ts, const double* alb, double* tdt, double* olr) {
+  int nb = (int)((p->ncol + 127) / 128);
+  gray_up_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, ts, alb, tdt, olr);
+}
+int rayleigh_nlev(const double* pref, int K, double pb) {      // minloc(abs(pref - 2*sponge_pbottom)) over the K+1 entries
+  int best = 0; double bv = fabs(pref[0] - 2.0 * pb);
+  for (int k = 1; k <= K; ++k) { double v = fabs(pref[k] - 2.0 * pb); if (v < bv) { bv = v; best = k; } }
+  int nlev = best + 1;
+  return nlev > K ? K : nlev;
+}
+double rayleigh_rfactr(double trayfric) {
+  if (trayfric > 0.0) return 1.0 / trayfric;
+  if (trayfric < 0.0) return (1.0 / fabs(trayfric)) * (1.0 / 86400.0);
+  return 0.0;
+}
+void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, const double* u, const double* v, double* udt, double* vdt, double* tdt) {
+  rayleigh_kernel<<<148 * 8, 256, 0, p->st>>>(p->pc, p->ncol, p->K, nlev, rayleigh_rfactr(p->cfg.trayfric), p->cfg.sponge_pbottom,
+                                              delt, p->cfg.do_conserve_energy, pf, u, v, udt, vdt, tdt);
+}
+
+}  // namespace
+
+extern "C" {
+
+int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
+  if (!c) return 1;
+  std::memset(c, 0, sizeof(*c));
+  c->abi_version = 1;
+  c->grav = 9.80; c->rdgas = 287.04; c->rvgas = 461.50; c->cp_air = 287.04 / (2.0 / 7.0); c->hlv = 2.500e6;
+  c->tfreeze = 273.16; c->stefan = 5.6734e-8; c->pstd_mks = 101325.0;
+  c->es0 = 1.0; c->hc = 1.0; c->do_evap = 0;
+  c->solar_constant = 1360.0; c->del_sol = 1.4; c->del_sw = 0.0; c->ir_tau_eq = 6.0; c->ir_tau_pole = 1.5;
+  c->atm_abs = 0.0; c->sw_diff = 0.0; c->linear_tau = 0.1; c->wv_exponent = 4.0; c->solar_exponent = 4.0;
+  c->odp = 1.0; c->diabatic_acce = 1.0;
+  c->trayfric = 0.0; c->sponge_pbottom = 50.0; c->do_conserve_energy = 1;
+  return 0;
+}
+
+const char* isca_b200_physics_last_error(IscaPhysics p) { return p ? p->err.c_str() : g_err.c_str(); }
+
+int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
+  IscaPhysics p = nullptr;
+  if (!cfg || !out) return fail(nullptr, "null argument");
+  if (cfg->abi_version != 1) return fail(nullptr, "IscaPhysicsConfig abi_version mismatch");
+  if (cfg->num_lon < 1 || cfg->num_lat < 1 || cfg->num_levels < 1 || cfg->num_levels > ISCA_KMAX)
+    return fail(nullptr, "bad dimensions (num_levels must be 1.." + std::to_string(ISCA_KMAX) + ")");
+  if (!(cfg->hc > 0.0 && cfg->hc <= 1.0)) return fail(nullptr, "lscale_cond: hc must be in (0, 1]");   // lscale_cond.F90:323
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, "no CUDA device: the physics kernels have no CPU path");
+  p = new IscaPhysics_t();
+  p->cfg = *cfg;
+  p->ncol = (size_t)cfg->num_lon * cfg->num_lat; p->K = cfg->num_levels;
+  PhysConst& c = p->pc;
+  c.grav = cfg->grav; c.rdgas = cfg->rdgas; c.rvgas = cfg->rvgas; c.cp_air = cfg->cp_air; c.hlv = cfg->hlv; c.stefan = cfg->stefan;
+  c.pstd = cfg->pstd_mks; c.hc = cfg->hc; c.do_evap = cfg->do_evap;
+  c.solar_constant = cfg->solar_constant; c.del_sol = cfg->del_sol; c.del_sw = cfg->del_sw; c.ir_tau_eq = cfg->ir_tau_eq;
+  c.ir_tau_pole = cfg->ir_tau_pole; c.atm_abs = cfg->atm_abs; c.sw_diff = cfg->sw_diff; c.linear_tau = cfg->linear_tau;
+  c.wv_exponent = cfg->wv_exponent; c.solar_exponent = cfg->solar_exponent; c.odp = cfg->odp; c.diabatic_acce = cfg->diabatic_acce;
+  // do_simple saturation vapour pressure tables (sat_vapor_pres_k.F90:161-266): tcmin=-173, tcmax=350, esres=10
+  const int tcmin = -173, tcmax = 350, esres = 10;
+  const int n = (tcmax - tcmin) * esres + 1;
+  std::vector<double> tb(3 * (size_t)n);
+  double dtres = (double)(tcmax - tcmin) / (double)(n - 1);
+  double tminl = (double)tcmin + cfg->tfreeze, dtinvl = 1.0 / dtres;
+  for (int i = 0; i < n; ++i) {
+    double tem = tminl + dtres * (double)i;
+    tb[i] = cfg->es0 * 610.78 * std::exp(-cfg->hlv / cfg->rvgas * (1.0 / tem - 1.0 / cfg->tfreeze));
+    tb[n + i] = cfg->hlv * tb[i] / cfg->rvgas / (tem * tem);
+  }
+  for (int i = 1; i < n - 1; ++i) tb[2 * n + i] = 0.25 * dtinvl * (tb[n + i + 1] - tb[n + i - 1]);
+  tb[2 * n] = 0.50 * dtinvl * (tb[n + 1] - tb[n]);
+  tb[2 * n + n - 1] = 0.50 * dtinvl * (tb[n + n - 1] - tb[n + n - 2]);
+  if (cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking) != cudaSuccess || !p->tab.ensure(tb.size()) ||
+      cudaMalloc(&p->d_err, sizeof(int)) != cudaSuccess) { delete p; return fail(nullptr, "CUDA allocation failed"); }
+  cudaMemcpyAsync(p->tab.p, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice, p->st);
+  cudaMemsetAsync(p->d_err, 0, sizeof(int), p->st);
+  if (cudaStreamSynchronize(p->st) != cudaSuccess) { delete p; return fail(nullptr, "table upload failed"); }
+  p->svp = SvpDev{p->tab.p, p->tab.p + n, p->tab.p + 2 * n, tminl, dtinvl, 0.5 * dtres, dtres, n};
+  *out = p;
+  return 0;
+}
+
+int isca_b200_physics_destroy(IscaPhysics p) {
+  if (!p) return 0;
+  if (p->d_err) cudaFree(p->d_err);
+  if (p->st) cudaStreamDestroy(p->st);
+  delete p;
+  return 0;
+}
+
+int isca_b200_lookup_es_des(IscaPhysics p, int n, const double* temp, double* es, double* des) {
+  if (!p) return fail(nullptr, "null handle");
+  if (n <= 0) return 0;
+  if (up(p, p->buf[0], temp, n)) return 1;
+  if (!p->buf[1].ensure(n) || !p->buf[2].ensure(n)) return fail(p, "cudaMalloc failed");
+  lookup_kernel<<<(n + 255) / 256, 256, 0, p->st>>>(p->svp, n, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->d_err);
+  if (down(p, p->buf[1], es, n) || down(p, p->buf[2], des, n)) return 1;
+  return finish(p, "lookup_es_des");
+}
+
+int isca_b200_compute_qs(IscaPhysics p, int n, const double* temp, const double* press, double* qs, double* dqsdT) {
+  if (!p) return fail(nullptr, "null handle");
+  if (n <= 0) return 0;
+  if (up(p, p->buf[0], temp, n) || up(p, p->buf[1], press, n)) return 1;
+  if (!p->buf[2].ensure(n) || !p->buf[3].ensure(n)) return fail(p, "cudaMalloc failed");
+  compute_qs_kernel<<<(n + 255) / 256, 256, 0, p->st>>>(p->svp, p->pc, n, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->d_err);
+  if (down(p, p->buf[2], qs, n) || down(p, p->buf[3], dqsdT, n)) return 1;
+  return finish(p, "compute_qs");
+}
+
+int isca_b200_lscale_cond(IscaPhysics p, const double* tin, const double* qin, const double* pfull, const double* phalf,
+                          double* rain, double* tdel, double* qdel) {
+  if (!p) return fail(nullptr, "null handle");
+  size_t nc = p->ncol, n3 = nc * p->K;
+  if (up(p, p->buf[0], tin, n3) || up(p, p->buf[1], qin, n3) || up(p, p->buf[2], pfull, n3) || up(p, p->buf[3], phalf, n3 + nc)) return 1;
+  if (!p->buf[4].ensure(nc) || !p->buf[5].ensure(n3) || !p->buf[6].ensure(n3)) return fail(p, "cudaMalloc failed");
+  launch_lscale(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p);
+  if (down(p, p->buf[4], rain, nc) || down(p, p->buf[5], tdel, n3) || down(p, p->buf[6], qdel, n3)) return 1;
+  return finish(p, "lscale_cond");
+}
+
+int isca_b200_two_stream_gray_rad_down(IscaPhysics p, const double* lat, const double* p_half, const double* t,
+                                       const double* albedo, double* net_surf_sw_down, double* surf_lw_down) {
+  if (!p) return fail(nullptr, "null handle");
+  size_t nc = p->ncol, n3 = nc * p->K;
+  if (up(p, p->buf[0], lat, nc) || up(p, p->buf[1], p_half, n3 + nc) || up(p, p->buf[2], t, n3) || up(p, p->buf[3], albedo, nc)) return 1;
+  if (!p->buf[4].ensure(nc) || !p->buf[5].ensure(nc)) return fail(p, "cudaMalloc failed");
+  launch_gray_down(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p);
+  if (down(p, p->buf[4], net_surf_sw_down, nc) || down(p, p->buf[5], surf_lw_down, nc)) return 1;
+  return finish(p, "two_stream_gray_rad_down");
+}
+
+int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const double* p_half, const double* t,
+                                     const double* t_surf, const double* albedo, double* tdt, double* olr) {
+  if (!p) return fail(nullptr, "null handle");
+  size_t nc = p->ncol, n3 = nc * p->K;
+  if (up(p, p->buf[0], lat, nc) || up(p, p->buf[1], p_half, n3 + nc) || up(p, p->buf[2], t, n3) || up(p, p->buf[3], t_surf, nc) ||
+      up(p, p->buf[4], albedo, nc) || up(p, p->buf[5], tdt, n3)) return 1;
+  if (!p->buf[6].ensure(nc)) return fail(p, "cudaMalloc failed");
+  launch_gray_up(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p);
+  if (down(p, p->buf[5], tdt, n3)) return 1;
+  if (olr && down(p, p->buf[6], olr, nc)) return 1;
+  return finish(p, "two_stream_gray_rad_up");
+}
+
+int isca_b200_rayleigh_damping(IscaPhysics p, double delt, const double* p_full, const double* u, const double* v,
+                               const double* pref, double* udt, double* vdt, double* tdt) {
+  if (!p) return fail(nullptr, "null handle");
+  if (!pref) return fail(p, "null pref");
+  size_t n3 = p->ncol * p->K;
+  if (up(p, p->buf[0], p_full, n3) || up(p, p->buf[1], u, n3) || up(p, p->buf[2], v, n3)) return 1;
+  if (!p->buf[3].ensure(n3) || !p->buf[4].ensure(n3) || !p->buf[5].ensure(n3)) return fail(p, "cudaMalloc failed");
+  int nlev = rayleigh_nlev(pref, p->K, p->cfg.sponge_pbottom);
+  launch_rayleigh(p, nlev, delt, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p);
+  if (down(p, p->buf[3], udt, n3) || down(p, p->buf[4], vdt, n3) || down(p, p->buf[5], tdt, n3)) return 1;
+  return finish(p, "rayleigh_damping");
+}
+
+int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, double* bytes) {
+  if (!p || !ms || !bytes) return fail(p, "null argument");
+  if (reps < 1) reps = 1;
+  size_t nc = p->ncol, n3 = nc * p->K; int K = p->K;
+  // synthetic resident columns: sigma levels under ps = 1e5, a lapse-rate temperature profile, 80% relative humidity aloft
+  std::vector<double> ph(n3 + nc), pf(n3), t(n3), q(n3), two(nc), u(n3);
+  for (size_t c = 0; c < nc; ++c) {
+    double ps = 1.0e5 - 50.0 * (double)(c % 97);
+    for (int k = 0; k <= K; ++k) ph[(size_t)k * nc + c] = ps * (double)k / K;
+    for (int k = 0; k < K; ++k) {
+      double p_ = 0.5 * (ph[(size_t)k * nc + c] + ph[(size_t)(k + 1) * nc + c]);
+      pf[(size_t)k * nc + c] = p_;
+      t[(size_t)k * nc + c] = 200.0 + 95.0 * p_ / 1.0e5 + 0.01 * (double)(c % 13);
+      q[(size_t)k * nc + c] = 1.0e-3 * p_ / 1.0e5 * (double)(1 + c % 20);
+      u[(size_t)k * nc + c] = 10.0 + 0.1 * k;
+    }
+    two[c] = -1.5 + 3.0 * (double)c / nc;
+  }
+  for (int i = 0; i < 4; ++i) if (!p->buf[i].ensure(n3 + nc)) return fail(p, "cudaMalloc failed");
+  for (int i = 4; i < 10; ++i) if (!p->buf[i].ensure(n3 + nc)) return fail(p, "cudaMalloc failed");
+  if (up(p, p->buf[0], t.data(), n3) || up(p, p->buf[1], q.data(), n3) || up(p, p->buf[2], pf.data(), n3) ||
+      up(p, p->buf[3], ph.data(), n3 + nc) || up(p, p->buf[7], two.data(), nc) || up(p, p->buf[8], u.data(), n3)) return 1;
+  PCK(cudaMemsetAsync(p->buf[9].p, 0, nc * sizeof(double), p->st));     // albedo = 0
+  std::vector<double> pref(K + 1);
+  for (int k = 0; k <= K; ++k) pref[k] = 1.0e5 * (k + 0.5) / K;
+  int nlev = K;                                                          // time the full-depth sponge
+  (void)pref;
+  cudaEvent_t e0, e1;
+  PCK(cudaEventCreate(&e0)); PCK(cudaEventCreate(&e1));
+  auto run = [&]() {
+    switch (which) {
+      case 0: launch_lscale(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p); break;
+      case 1: launch_gray_down(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[9].p, p->buf[4].p, p->buf[5].p); break;
+      case 2: launch_gray_up(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[9].p + 0, p->buf[9].p, p->buf[6].p, p->buf[4].p); break;
+      default: launch_rayleigh(p, nlev, 600.0, p->buf[2].p, p->buf[8].p, p->buf[8].p, p->buf[4].p, p->buf[5].p, p->buf[6].p); break;
+    }
+  };
+  if (which == 2) {   // t_surf must be a temperature
+    std::vector<double> ts(nc, 288.0);
+    if (up(p, p->buf[1], ts.data(), nc)) return 1;
+  }
+  auto run2 = [&]() {
+    if (which == 2) launch_gray_up(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[1].p, p->buf[9].p, p->buf[6].p, p->buf[4].p);
+    else run();
+  };
+  for (int i = 0; i < 3; ++i) run2();
+  PCK(cudaEventRecord(e0, p->st));
+  for (int i = 0; i < reps; ++i) run2();
+  PCK(cudaEventRecord(e1, p->st));
+  PCK(cudaEventSynchronize(e1));
+  float f = 0.f;
+  PCK(cudaEventElapsedTime(&f, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms = (double)f / reps;
+  double per_col;
+  switch (which) {
+    case 0: per_col = 6.0 * K + 2.0; break;
+    case 1: per_col = 2.0 * K + 5.0; break;
+    case 2: per_col = 4.0 * K + 5.0; break;
+    default: per_col = 6.0 * K; break;
+  }
+  *bytes = per_col * 8.0 * (double)nc;
+  return finish(p, "physics_time");
+}
+
+}  // extern "C"

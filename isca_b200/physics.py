@@ -1,0 +1,159 @@
+"""Host-side mirror of the column-physics interface (include/isca_b200_physics.h).
+
+Method names and argument meaning follow the Fortran modules they replace:
+  sat_vapor_pres_mod: lookup_es_des, compute_qs       (shared/sat_vapor_pres/sat_vapor_pres.F90)
+  lscale_cond_mod:    lscale_cond                     (atmos_param/lscale_cond/lscale_cond.F90:79)
+  two_stream_gray_rad_mod: two_stream_gray_rad_down / _up  (atmos_param/two_stream_gray_rad/two_stream_gray_rad.F90:386, 659)
+  damping_driver_mod: rayleigh                        (atmos_param/damping_driver/damping_driver.f90:594)
+Arrays are numpy float64 [lev, lat, lon] (the Fortran (lon, lat, lev) memory order).  Everything runs in the CUDA
+library; there is no CPU path."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from .api import load_library, IscaError
+
+PHYSICS_EXPORTS = [
+    "isca_b200_physics_default_config", "isca_b200_physics_create", "isca_b200_physics_destroy",
+    "isca_b200_physics_last_error", "isca_b200_lookup_es_des", "isca_b200_compute_qs", "isca_b200_lscale_cond",
+    "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_rayleigh_damping",
+    "isca_b200_physics_time",
+]
+
+
+class IscaPhysicsConfigStruct(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("abi_version", "num_lon", "num_lat", "num_levels")] + \
+               [(n, C.c_double) for n in ("grav", "rdgas", "rvgas", "cp_air", "hlv", "tfreeze", "stefan", "pstd_mks", "es0", "hc")] + \
+               [("do_evap", C.c_int)] + \
+               [(n, C.c_double) for n in ("solar_constant", "del_sol", "del_sw", "ir_tau_eq", "ir_tau_pole", "atm_abs", "sw_diff",
+                                          "linear_tau", "wv_exponent", "solar_exponent", "odp", "diabatic_acce",
+                                          "trayfric", "sponge_pbottom")] + \
+               [("do_conserve_energy", C.c_int)]
+
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = load_library()
+    if not _bound:
+        dp, vp = C.POINTER(C.c_double), C.c_void_p
+        lib.isca_b200_physics_default_config.argtypes = [C.POINTER(IscaPhysicsConfigStruct)]
+        lib.isca_b200_physics_create.argtypes = [C.POINTER(IscaPhysicsConfigStruct), C.POINTER(vp)]
+        lib.isca_b200_physics_destroy.argtypes = [vp]
+        lib.isca_b200_physics_last_error.argtypes = [vp]
+        lib.isca_b200_physics_last_error.restype = C.c_char_p
+        lib.isca_b200_lookup_es_des.argtypes = [vp, C.c_int, dp, dp, dp]
+        lib.isca_b200_compute_qs.argtypes = [vp, C.c_int, dp, dp, dp, dp]
+        lib.isca_b200_lscale_cond.argtypes = [vp] + [dp] * 7
+        lib.isca_b200_two_stream_gray_rad_down.argtypes = [vp] + [dp] * 6
+        lib.isca_b200_two_stream_gray_rad_up.argtypes = [vp] + [dp] * 7
+        lib.isca_b200_rayleigh_damping.argtypes = [vp, C.c_double] + [dp] * 7
+        lib.isca_b200_physics_time.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+        _bound = True
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _in(a, shape, name):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != tuple(shape):
+        raise IscaError(f"{name}: expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+class ColumnPhysics:
+    """One handle per (num_lon, num_lat, num_levels) window; keyword arguments are the namelist variables."""
+
+    def __init__(self, num_lon, num_lat, num_levels, **nml):
+        lib = _lib()
+        c = IscaPhysicsConfigStruct()
+        lib.isca_b200_physics_default_config(C.byref(c))
+        c.num_lon, c.num_lat, c.num_levels = num_lon, num_lat, num_levels
+        names = {f[0] for f in IscaPhysicsConfigStruct._fields_}
+        for k, v in nml.items():
+            if k not in names:
+                raise IscaError(f"unknown namelist variable {k}")
+            setattr(c, k, v)
+        self.config = c
+        self._h = C.c_void_p()
+        if lib.isca_b200_physics_create(C.byref(c), C.byref(self._h)) != 0:
+            raise IscaError("physics_create: " + lib.isca_b200_physics_last_error(None).decode())
+        self._lib = lib
+        self.s2 = (num_lat, num_lon)
+        self.s3 = (num_levels, num_lat, num_lon)
+        self.s3h = (num_levels + 1, num_lat, num_lon)
+
+    def close(self):
+        if self._h:
+            self._lib.isca_b200_physics_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise IscaError(f"{what}: " + self._lib.isca_b200_physics_last_error(self._h).decode())
+
+    def lookup_es_des(self, temp):
+        t = np.ascontiguousarray(temp, dtype=np.float64)
+        es, des = np.empty_like(t), np.empty_like(t)
+        self._ck(self._lib.isca_b200_lookup_es_des(self._h, t.size, _p(t), _p(es), _p(des)), "lookup_es_des")
+        return es, des
+
+    def compute_qs(self, temp, press):
+        t = np.ascontiguousarray(temp, dtype=np.float64)
+        pr = _in(press, t.shape, "press")
+        qs, dqs = np.empty_like(t), np.empty_like(t)
+        self._ck(self._lib.isca_b200_compute_qs(self._h, t.size, _p(t), _p(pr), _p(qs), _p(dqs)), "compute_qs")
+        return qs, dqs
+
+    def lscale_cond(self, tin, qin, pfull, phalf):
+        """-> rain [lat, lon], tdel, qdel [lev, lat, lon]"""
+        tin, qin, pfull = (_in(a, self.s3, n) for a, n in ((tin, "tin"), (qin, "qin"), (pfull, "pfull")))
+        phalf = _in(phalf, self.s3h, "phalf")
+        rain, tdel, qdel = np.empty(self.s2), np.empty(self.s3), np.empty(self.s3)
+        self._ck(self._lib.isca_b200_lscale_cond(self._h, _p(tin), _p(qin), _p(pfull), _p(phalf), _p(rain), _p(tdel), _p(qdel)),
+                 "lscale_cond")
+        return rain, tdel, qdel
+
+    def two_stream_gray_rad_down(self, lat, p_half, t, albedo):
+        """-> net_surf_sw_down, surf_lw_down [lat, lon]"""
+        lat, albedo = _in(lat, self.s2, "lat"), _in(albedo, self.s2, "albedo")
+        p_half, t = _in(p_half, self.s3h, "p_half"), _in(t, self.s3, "t")
+        sw, lw = np.empty(self.s2), np.empty(self.s2)
+        self._ck(self._lib.isca_b200_two_stream_gray_rad_down(self._h, _p(lat), _p(p_half), _p(t), _p(albedo), _p(sw), _p(lw)),
+                 "two_stream_gray_rad_down")
+        return sw, lw
+
+    def two_stream_gray_rad_up(self, lat, p_half, t, t_surf, albedo, tdt):
+        """-> tdt + radiative heating [lev, lat, lon], olr [lat, lon]"""
+        lat, albedo, t_surf = _in(lat, self.s2, "lat"), _in(albedo, self.s2, "albedo"), _in(t_surf, self.s2, "t_surf")
+        p_half, t = _in(p_half, self.s3h, "p_half"), _in(t, self.s3, "t")
+        out = np.array(_in(tdt, self.s3, "tdt"), copy=True)
+        olr = np.empty(self.s2)
+        self._ck(self._lib.isca_b200_two_stream_gray_rad_up(self._h, _p(lat), _p(p_half), _p(t), _p(t_surf), _p(albedo), _p(out), _p(olr)),
+                 "two_stream_gray_rad_up")
+        return out, olr
+
+    def rayleigh_damping(self, delt, p_full, u, v, pref):
+        """-> udt, vdt, tdt [lev, lat, lon]"""
+        p_full, u, v = (_in(a, self.s3, n) for a, n in ((p_full, "p_full"), (u, "u"), (v, "v")))
+        pref = _in(pref, (self.s3[0] + 1,), "pref")
+        udt, vdt, tdt = np.empty(self.s3), np.empty(self.s3), np.empty(self.s3)
+        self._ck(self._lib.isca_b200_rayleigh_damping(self._h, float(delt), _p(p_full), _p(u), _p(v), _p(pref), _p(udt), _p(vdt), _p(tdt)),
+                 "rayleigh_damping")
+        return udt, vdt, tdt
+
+    def time_kernel(self, which, reps=20):
+        """(ms per launch, algorithmic bytes per launch) on resident synthetic columns."""
+        ms, by = C.c_double(), C.c_double()
+        self._ck(self._lib.isca_b200_physics_time(self._h, which, reps, C.byref(ms), C.byref(by)), "physics_time")
+        return ms.value, by.value

@@ -83,3 +83,39 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt, f"{f} mentions the oracle"
+
+
+PHYS_HEADER = os.path.join(ROOT, "include", "isca_b200_physics.h")
+
+
+def test_physics_header_symbols_exported_and_struct_layout(lib_built, tmp_path):
+    from isca_b200 import api, physics
+    lib = api.load_library()
+    txt = re.sub(r"/\*.*?\*/", "", open(PHYS_HEADER).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(isca_b200_\w+)\s*\(", txt)))
+    assert set(syms) == set(physics.PHYSICS_EXPORTS)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/isca_b200_physics.h but not exported"
+    fields = [f[0] for f in physics.IscaPhysicsConfigStruct._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(IscaPhysicsConfig, {f}));' for f in fields)
+    src = tmp_path / "psz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "isca_b200_physics.h"\nint main(){printf("%zu\\n", sizeof(IscaPhysicsConfig));' + body + "return 0;}")
+    exe = tmp_path / "psz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == C.sizeof(physics.IscaPhysicsConfigStruct)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(physics.IscaPhysicsConfigStruct, f).offset == int(off), f
+    # namelist defaults: two_stream_gray_rad.F90:72-113, lscale_cond.F90:48-52, damping_driver.f90:60-78
+    c = physics.IscaPhysicsConfigStruct()
+    lib.isca_b200_physics_default_config(C.byref(c))
+    assert (c.solar_constant, c.del_sol, c.ir_tau_eq, c.ir_tau_pole, c.linear_tau, c.wv_exponent) == (1360.0, 1.4, 6.0, 1.5, 0.1, 4.0)
+    assert (c.hc, c.do_evap, c.trayfric, c.sponge_pbottom) == (1.0, 0, 0.0, 50.0)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_physics_no_cpu_fallback(lib_built):
+    from isca_b200 import api, physics
+    with pytest.raises(api.IscaError) as e:
+        physics.ColumnPhysics(8, 4, 5)
+    assert "CUDA" in str(e.value)
