@@ -27,6 +27,11 @@ typedef struct IscaPhysicsConfig {
          wv_exponent, solar_exponent, odp, diabatic_acce;
   /* damping_driver_nml: trayfric, sponge_pbottom (damping_driver.f90:60-78) */
   double trayfric, sponge_pbottom; int do_conserve_energy;
+  /* vert_diff_nml (vert_diff.F90:70-77; do_mcm_plev = .false. only) */
+  int vert_diff_do_conserve_energy, use_virtual_temp_vert_diff;
+  /* mixed_layer_nml: evaporation (mixed_layer.F90:87); heat capacity, q-flux and albedo maps are set by
+   * isca_b200_mixed_layer_init */
+  int evaporation;
 } IscaPhysicsConfig;
 
 int isca_b200_physics_default_config(IscaPhysicsConfig* cfg);
@@ -62,7 +67,37 @@ int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const dou
 int isca_b200_rayleigh_damping(IscaPhysics p, double delt, const double* p_full, const double* u, const double* v,
                                const double* pref, double* udt, double* vdt, double* tdt);
 
-/* device-resident timing of one kernel (which: 0 lscale_cond, 1 gray_rad_down, 2 gray_rad_up, 3 rayleigh) on
+/* gcm_vert_diff_down (vert_diff.F90:270-402), sphum the only diffused tracer, no kbot.  All 3-D arrays [K][J][I]
+ * (p_half [K+1][J][I]); tau_u, tau_v [J][I] are updated in place; dt_u, dt_v, dt_t are updated in place; dt_q is
+ * read only; dissipative_heat is written.  The tridiagonal factors (vert_diff_mod e_global, f_t_global, f_q_global) and
+ * the surf_diff_type fields stay on the device inside the handle until gcm_vert_diff_up. */
+int isca_b200_gcm_vert_diff_down(IscaPhysics p, double delt, const double* u, const double* v, const double* t,
+                                 const double* q, const double* diff_m, const double* diff_t, const double* p_half,
+                                 const double* p_full, const double* z_full, double* tau_u, double* tau_v,
+                                 const double* dtau_du, const double* dtau_dv, double* dt_u, double* dt_v,
+                                 double* dt_t, const double* dt_q, double* dissipative_heat);
+
+/* surf_diff_type / module-state inspection (tests): id 0 delta_t, 1 dflux_t, 2 delta_tr(sphum), 3 dflux_tr(sphum),
+ * 4 dtmass, 5 delta_u, 6 delta_v ([J][I]); 16 e_global, 17 f_t_global, 18 f_q_global ([K][J][I]). */
+int isca_b200_get_tri_surf(IscaPhysics p, int id, double* host);
+
+/* mixed_layer_init subset: per-column heat capacity (land_sea_heat_capacity, J/m2/K) and ocean_qflux [J][I]. */
+int isca_b200_mixed_layer_init(IscaPhysics p, const double* heat_capacity, const double* ocean_qflux);
+
+/* mixed_layer (mixed_layer.F90:568-745; do_calc_eff_heat_cap path, no prescribed SST / ice / flux anomalies):
+ * implicit slab update of t_surf [J][I] (in place) and of the handle's Tri_surf delta_t, delta_tr(sphum).
+ * delta_t_surf (may be NULL) receives the increment. */
+int isca_b200_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double* flux_t, const double* flux_q,
+                          const double* flux_r, const double* net_surf_sw_down, const double* surf_lw_down,
+                          const double* dhdt_surf, const double* dedt_surf, const double* dedq_surf,
+                          const double* drdt_surf, const double* dhdt_atm, const double* dedq_atm,
+                          double* delta_t_surf);
+
+/* gcm_vert_diff_up (vert_diff.F90:406-467): back-substitution -> dt_t, dt_q [K][J][I] (overwritten). */
+int isca_b200_gcm_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q);
+
+/* device-resident timing of one kernel (which: 0 lscale_cond, 1 gray_rad_down, 2 gray_rad_up, 3 rayleigh,
+ * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up) on
  * synthetic resident columns; returns average ms per launch (CUDA events) and the algorithmic bytes per launch. */
 int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, double* bytes);
 

@@ -139,14 +139,9 @@ fft_inv_kernel(DevTables t, const double* __restrict__ four, const LevDesc* __re
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
   double2* buf = reinterpret_cast<double2*>(fft_smem);              // [LT][LS]
-  int* s_pos = reinterpret_cast<int*>(buf + FFT_LT * S::LS);        // [M+1] row of wavenumber m in the Fourier buffer
   const int lev0 = lev_begin + blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
-  // the m -> buffer-row table goes to shared memory first: a global lookup in front of every data load would
-  // put a second full memory latency on the critical path (it was the top stall of the first version)
-  for (int q = tid; q <= g.M; q += FFT_LT * Q) s_pos[q] = g.pos[q];
-  __syncthreads();
 
   const int line = tid / Q, lt = tid - line * Q;
   double2* A = buf + line * S::LS;
@@ -244,16 +239,10 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
   double2* buf = reinterpret_cast<double2*>(fft_smem);              // [LT][LS]
-  int* s_row = reinterpret_cast<int*>(buf + FFT_LT * S::LS);        // [M+1] destination row of wavenumber m
-  int* s_own = s_row + (g.M + 1);                                   // [M+1] destination rank (peer-memory mode)
   const int lev0 = lev_begin + blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
   constexpr int NT = FFT_LT * Q;
-  for (int q = tid; q <= g.M; q += NT) {
-    if (g.p2p) { const int r = g.owner[q]; s_own[q] = r; s_row[q] = g.rank * g.nm_rank[r] + g.lidx[q]; }
-    else { s_own[q] = 0; s_row[q] = g.pos[q]; }
-  }
   const int line = tid / Q, lt = tid - line * Q;
   const int lev = lev0 + line;
   double2* A = buf + line * S::LS;
@@ -308,8 +297,11 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
     const double2 e = cadd(zk, zc), o = csub(zk, zc);
     const double2 wo = cmul(o, tw<-1>(t.twiddle, k));
     const double2 x = make_double2(0.5 * (e.x + wo.y) * inv, 0.5 * (e.y - wo.x) * inv);
-    // peer-memory mode: the row lives in the m-owner buffer of the rank that owns wavenumber k (store over NVLink)
-    double* dst = (g.p2p ? g.peerA[s_own[k]] : four) + ((size_t)s_row[k] * g.Jloc + jl) * (size_t)C;
+    double* dst;
+    if (g.p2p) {        // store into the m-owner buffer of the rank that owns wavenumber k (peer memory over NVLink)
+      const int r = g.owner[k];
+      dst = g.peerA[r] + ((size_t)(g.rank * g.nm_rank[r] + g.lidx[k]) * g.Jloc + jl) * (size_t)C;
+    } else dst = four + fourB_index(g, k, jl, C);
     *reinterpret_cast<double2*>(dst + 2 * (lev0 + l)) = x;
   }
 }
@@ -317,20 +309,18 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
 template <int H, int R1, int R2, int R3, int Q, int MINB>
 static void launch_inv_shape(const DevTables& t, const double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin) {
   typedef FftShape<H, R1> S;
-  const size_t smem = sizeof(double2) * FFT_LT * S::LS + sizeof(int) * (t.g.M + 1);
+  const size_t smem = sizeof(double2) * FFT_LT * S::LS;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(fft_inv_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sizeof(double2) * FFT_LT * S::LS + sizeof(int) * (H + 1))); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(fft_inv_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   dim3 grid((nlev - lev_begin + FFT_LT - 1) / FFT_LT, t.g.Jloc);
   fft_inv_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp, lev_begin);
 }
 template <int H, int R1, int R2, int R3, int Q, int MINB>
 static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin) {
   typedef FftShape<H, R1> S;
-  const size_t smem = sizeof(double2) * FFT_LT * S::LS + sizeof(int) * 2 * (t.g.M + 1);
+  const size_t smem = sizeof(double2) * FFT_LT * S::LS;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sizeof(double2) * FFT_LT * S::LS + sizeof(int) * 2 * (H + 1))); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   dim3 grid((nlev - lev_begin + FFT_LT - 1) / FFT_LT, t.g.Jloc);
   fft_fwd_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp, lev_begin);
 }

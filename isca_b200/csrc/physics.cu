@@ -7,50 +7,15 @@
 //   rayleigh sponge                            atmos_param/damping_driver/damping_driver.f90:404-420, 594-636
 //
 // All four are streaming kernels bounded by HBM: algorithmic bytes per column are listed at each launch.
-#include "../../include/isca_b200_physics.h"
-#include "common.h"
-#include <cuda_runtime.h>
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
+#include "physics_common.h"
+
+using namespace isca_phys;
+
+namespace isca_phys {
+std::string& thread_error() { static thread_local std::string e; return e; }
+}
 
 namespace {
-
-thread_local std::string g_err;
-
-struct SvpDev {
-  const double *tab, *dtab, *d2tab;
-  double tminl, dtinvl, tepsl, dtres;
-  int n;
-};
-
-struct PhysConst {
-  double grav, rdgas, rvgas, cp_air, hlv, stefan, pstd;
-  double hc; int do_evap;
-  double solar_constant, del_sol, del_sw, ir_tau_eq, ir_tau_pole, atm_abs, sw_diff, linear_tau, wv_exponent,
-         solar_exponent, odp, diabatic_acce;
-};
-
-__device__ __forceinline__ bool svp_lookup(const SvpDev& s, double T, double& es, double& des) {
-  double tmp = T - s.tminl;
-  double x = s.dtinvl * (tmp + s.tepsl);
-  if (!(x > -1.0 && x < (double)s.n)) { es = 0.0; des = 0.0; return false; }
-  int ind = (int)x;                                   // truncation, like the Fortran int()
-  double dl = tmp - s.dtres * (double)ind;
-  double t0 = __ldg(s.tab + ind), t1 = __ldg(s.dtab + ind), t2 = __ldg(s.d2tab + ind);
-  es = t0 + dl * (t1 + dl * t2);
-  des = t1 + 2.0 * dl * t2;
-  return true;
-}
-
-__device__ __forceinline__ void qs_from_es(double es, double des, double press, double hc, double eps, double& qs, double& dqs) {
-  des *= hc; es *= hc;
-  double denom = press - (1.0 - eps) * es;
-  qs = denom > 0.0 ? eps * es / denom : eps;
-  dqs = eps * press * des / (denom * denom);
-}
 
 __global__ void lookup_kernel(SvpDev s, int n, const double* __restrict__ T, double* __restrict__ es, double* __restrict__ des, int* err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,9 +74,24 @@ __global__ void __launch_bounds__(128) lscale_cond_kernel(SvpDev s, PhysConst c,
   if (bad) atomicExch(err, 1);
 }
 
+// x**e of the reference; small integer exponents (the namelist defaults are 4) avoid the generic fp64 pow, which
+// otherwise makes the radiation kernels instruction-bound instead of HBM-bound (results differ by <= 1 ulp).
+__device__ __forceinline__ double pow_nml(double x, double e) {
+  if (e == 4.0) { double x2 = x * x; return x2 * x2; }
+  if (e == 2.0) return x * x;
+  if (e == 1.0) return x;
+  return pow(x, e);
+}
+
 __device__ __forceinline__ double lw_tau_at(const PhysConst& c, double lw_tau_0, double p) {
   double r = p / c.pstd;
-  return lw_tau_0 * (c.linear_tau * p / c.pstd + (1.0 - c.linear_tau) * pow(r, c.wv_exponent));
+  return lw_tau_0 * (c.linear_tau * p / c.pstd + (1.0 - c.linear_tau) * pow_nml(r, c.wv_exponent));
+}
+
+// sw_down = insolation * exp(-sw_tau_0 (p/pstd)**solar_exponent); a transparent atmosphere (atm_abs = 0) needs no exp
+__device__ __forceinline__ double sw_down_at(const PhysConst& c, double insolation, double sw_tau_0, double p) {
+  if (sw_tau_0 == 0.0) return insolation;
+  return insolation * exp(-(sw_tau_0 * pow_nml(p / c.pstd, c.solar_exponent)));
 }
 
 // two_stream_gray_rad_down: only the two surface fluxes leave the kernel.
@@ -138,7 +118,7 @@ __global__ void __launch_bounds__(128) gray_down_kernel(PhysConst c, int ncol, i
     tau0 = tau1;
   }
   double ps = p_half[(size_t)K * ncol + col];
-  double sw_down_s = insolation * exp(-(sw_tau_0 * pow(ps / c.pstd, c.solar_exponent)));
+  double sw_down_s = sw_down_at(c, insolation, sw_tau_0, ps);
   surf_lw_down[col] = lw_down;
   net_surf_sw_down[col] = (1.0 - albedo[col]) * sw_down_s;
 }
@@ -170,7 +150,7 @@ __global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int
     tau0 = tau1;
   }
   double ph1 = p_half[(size_t)K * ncol + col];
-  double sw_down1 = insolation * exp(-(sw_tau_0 * pow(ph1 / c.pstd, c.solar_exponent)));
+  double sw_down1 = sw_down_at(c, insolation, sw_tau_0, ph1);
   double sw_up = albedo[col] * sw_down1;
   double ts = t_surf[col];
   double lw_up1 = c.stefan * ((ts * ts) * (ts * ts));
@@ -181,7 +161,7 @@ __global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int
     double b = c.stefan * ((tk * tk) * (tk * tk));
     double lw_up0 = lw_up1 * trs[k] + b * (1.0 - trs[k]);
     double ph0 = p_half[o];
-    double sw_down0 = insolation * exp(-(sw_tau_0 * pow(ph0 / c.pstd, c.solar_exponent)));
+    double sw_down0 = sw_down_at(c, insolation, sw_tau_0, ph0);
     double flux0 = (lw_up0 - lwd[k]) + (sw_up - sw_down0);
     double tdt_rad = c.diabatic_acce * (flux1 - flux0) * c.grav / (c.cp_air * (ph1 - ph0));
     tdt[o] = tdt[o] + tdt_rad;
@@ -209,61 +189,6 @@ __global__ void rayleigh_kernel(PhysConst c, size_t ncol, int K, int nlev, doubl
     }
     udt[i] = a; vdt[i] = b; tdt[i] = h;
   }
-}
-
-struct Dev {                 // owning device array
-  double* p = nullptr; size_t n = 0;
-  bool ensure(size_t count) {
-    if (count <= n) return true;
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
-    if (cudaMalloc(&p, count * sizeof(double)) != cudaSuccess) return false;
-    n = count; return true;
-  }
-  ~Dev() { if (p) cudaFree(p); }
-};
-
-}  // namespace
-
-struct IscaPhysics_t {
-  IscaPhysicsConfig cfg;
-  PhysConst pc;
-  SvpDev svp;
-  Dev tab;                   // TABLE | DTABLE | D2TABLE
-  Dev buf[10];
-  int* d_err = nullptr;
-  cudaStream_t st = nullptr;
-  std::string err;
-  size_t ncol = 0; int K = 0;
-};
-
-namespace {
-
-int fail(IscaPhysics p, const std::string& m) { if (p) p->err = m; g_err = m; return 1; }
-
-#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(p, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
-
-int up(IscaPhysics p, Dev& d, const double* h, size_t n) {
-  if (!h) return fail(p, "null input array");
-  if (!d.ensure(n)) return fail(p, "cudaMalloc failed");
-  PCK(cudaMemcpyAsync(d.p, h, n * sizeof(double), cudaMemcpyHostToDevice, p->st));
-  return 0;
-}
-int down(IscaPhysics p, const Dev& d, double* h, size_t n) {
-  if (!h) return fail(p, "null output array");
-  PCK(cudaMemcpyAsync(h, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, p->st));
-  return 0;
-}
-int finish(IscaPhysics p, const char* what) {
-  int e = 0;
-  PCK(cudaGetLastError());
-  PCK(cudaMemcpyAsync(&e, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, p->st));
-  PCK(cudaStreamSynchronize(p->st));
-  if (e) {
-    PCK(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->st));
-    return fail(p, std::string(what) + ": lookup_es: temperature outside the saturation vapour pressure table (table overflow)");
-  }
-  return 0;
 }
 
 void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd) {
@@ -309,10 +234,11 @@ int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
   c->atm_abs = 0.0; c->sw_diff = 0.0; c->linear_tau = 0.1; c->wv_exponent = 4.0; c->solar_exponent = 4.0;
   c->odp = 1.0; c->diabatic_acce = 1.0;
   c->trayfric = 0.0; c->sponge_pbottom = 50.0; c->do_conserve_energy = 1;
+  c->vert_diff_do_conserve_energy = 1; c->use_virtual_temp_vert_diff = 0; c->evaporation = 1;
   return 0;
 }
 
-const char* isca_b200_physics_last_error(IscaPhysics p) { return p ? p->err.c_str() : g_err.c_str(); }
+const char* isca_b200_physics_last_error(IscaPhysics p) { return p ? p->err.c_str() : isca_phys::thread_error().c_str(); }
 
 int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   IscaPhysics p = nullptr;
@@ -437,7 +363,7 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
   if (reps < 1) reps = 1;
   size_t nc = p->ncol, n3 = nc * p->K; int K = p->K;
   // synthetic resident columns: sigma levels under ps = 1e5, a lapse-rate temperature profile, 80% relative humidity aloft
-  std::vector<double> ph(n3 + nc), pf(n3), t(n3), q(n3), two(nc), u(n3);
+  std::vector<double> ph(n3 + nc), pf(n3), t(n3), q(n3), two(nc), u(n3), zf(n3);
   for (size_t c = 0; c < nc; ++c) {
     double ps = 1.0e5 - 50.0 * (double)(c % 97);
     for (int k = 0; k <= K; ++k) ph[(size_t)k * nc + c] = ps * (double)k / K;
@@ -447,14 +373,22 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
       t[(size_t)k * nc + c] = 200.0 + 95.0 * p_ / 1.0e5 + 0.01 * (double)(c % 13);
       q[(size_t)k * nc + c] = 1.0e-3 * p_ / 1.0e5 * (double)(1 + c % 20);
       u[(size_t)k * nc + c] = 10.0 + 0.1 * k;
+      zf[(size_t)k * nc + c] = 7.0e3 * std::log(ps / p_);
     }
     two[c] = -1.5 + 3.0 * (double)c / nc;
   }
   for (int i = 0; i < 4; ++i) if (!p->buf[i].ensure(n3 + nc)) return fail(p, "cudaMalloc failed");
-  for (int i = 4; i < 10; ++i) if (!p->buf[i].ensure(n3 + nc)) return fail(p, "cudaMalloc failed");
+  for (int i = 4; i < 14; ++i) if (!p->buf[i].ensure(n3 + nc)) return fail(p, "cudaMalloc failed");
+  if (which >= 4) {
+    if (p->K < 3 || prepare_vert_diff_state(p)) return fail(p, "vert_diff timing needs K >= 3");
+    if (up(p, p->buf[10], zf.data(), n3)) return 1;
+    PCK(cudaMemsetAsync(p->buf[11].p, 0, (n3 + nc) * sizeof(double), p->st));   // tendencies / stresses start from zero
+    PCK(cudaMemsetAsync(p->buf[12].p, 0, (n3 + nc) * sizeof(double), p->st));
+    PCK(cudaMemsetAsync(p->buf[13].p, 0, (n3 + nc) * sizeof(double), p->st));
+  }
   if (up(p, p->buf[0], t.data(), n3) || up(p, p->buf[1], q.data(), n3) || up(p, p->buf[2], pf.data(), n3) ||
       up(p, p->buf[3], ph.data(), n3 + nc) || up(p, p->buf[7], two.data(), nc) || up(p, p->buf[8], u.data(), n3)) return 1;
-  PCK(cudaMemsetAsync(p->buf[9].p, 0, nc * sizeof(double), p->st));     // albedo = 0
+  PCK(cudaMemsetAsync(p->buf[9].p, 0, (n3 + nc) * sizeof(double), p->st));     // albedo = 0 (and zero surface stresses)
   std::vector<double> pref(K + 1);
   for (int k = 0; k <= K; ++k) pref[k] = 1.0e5 * (k + 0.5) / K;
   int nlev = K;                                                          // time the full-depth sponge
@@ -466,7 +400,13 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
       case 0: launch_lscale(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p); break;
       case 1: launch_gray_down(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[9].p, p->buf[4].p, p->buf[5].p); break;
       case 2: launch_gray_up(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[9].p + 0, p->buf[9].p, p->buf[6].p, p->buf[4].p); break;
-      default: launch_rayleigh(p, nlev, 600.0, p->buf[2].p, p->buf[8].p, p->buf[8].p, p->buf[4].p, p->buf[5].p, p->buf[6].p); break;
+      case 3: launch_rayleigh(p, nlev, 600.0, p->buf[2].p, p->buf[8].p, p->buf[8].p, p->buf[4].p, p->buf[5].p, p->buf[6].p); break;
+      case 4:   // diffusivities = the wind profile (10..14 m2/s); stresses and their derivatives zero
+        launch_vert_diff_down(p, 600.0, p->buf[8].p, p->buf[8].p, p->buf[0].p, p->buf[1].p, p->buf[8].p, p->buf[8].p, p->buf[3].p,
+                              p->buf[10].p, p->buf[9].p, p->buf[9].p + nc, p->buf[9].p + 2 * nc, p->buf[9].p + 3 * nc, p->buf[11].p,
+                              p->buf[12].p, p->buf[13].p, p->buf[4].p, p->buf[5].p);
+        break;
+      default: launch_vert_diff_up(p, 600.0, p->buf[5].p, p->buf[6].p); break;
     }
   };
   if (which == 2) {   // t_surf must be a temperature
@@ -491,7 +431,9 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
     case 0: per_col = 6.0 * K + 2.0; break;
     case 1: per_col = 2.0 * K + 5.0; break;
     case 2: per_col = 4.0 * K + 5.0; break;
-    default: per_col = 6.0 * K; break;
+    case 3: per_col = 6.0 * K; break;
+    case 4: per_col = 19.0 * K + 14.0; break;
+    default: per_col = 5.0 * K; break;
   }
   *bytes = per_col * 8.0 * (double)nc;
   return finish(p, "physics_time");

@@ -1,0 +1,122 @@
+// physics_common.h -- shared definitions of the column-physics kernels (physics*.cu): the handle, device buffers,
+// saturation-vapour-pressure lookup and the host<->device staging helpers of the host-array C ABI.
+#pragma once
+#include "../../include/isca_b200_physics.h"
+#include "common.h"
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace isca_phys {
+
+struct SvpDev {
+  const double *tab, *dtab, *d2tab;
+  double tminl, dtinvl, tepsl, dtres;
+  int n;
+};
+
+struct PhysConst {
+  double grav, rdgas, rvgas, cp_air, hlv, stefan, pstd;
+  double hc; int do_evap;
+  double solar_constant, del_sol, del_sw, ir_tau_eq, ir_tau_pole, atm_abs, sw_diff, linear_tau, wv_exponent,
+         solar_exponent, odp, diabatic_acce;
+};
+
+// lookup_es_des (sat_vapor_pres_k.F90:1132-1158): table index + 2nd-order Taylor; false = outside the table
+__device__ __forceinline__ bool svp_lookup(const SvpDev& s, double T, double& es, double& des) {
+  double tmp = T - s.tminl;
+  double x = s.dtinvl * (tmp + s.tepsl);
+  if (!(x > -1.0 && x < (double)s.n)) { es = 0.0; des = 0.0; return false; }
+  int ind = (int)x;                                   // truncation, like the Fortran int()
+  double dl = tmp - s.dtres * (double)ind;
+  double t0 = __ldg(s.tab + ind), t1 = __ldg(s.dtab + ind), t2 = __ldg(s.d2tab + ind);
+  es = t0 + dl * (t1 + dl * t2);
+  des = t1 + 2.0 * dl * t2;
+  return true;
+}
+
+// compute_qs_k (sat_vapor_pres_k.F90:457-540, q absent)
+__device__ __forceinline__ void qs_from_es(double es, double des, double press, double hc, double eps, double& qs, double& dqs) {
+  des *= hc; es *= hc;
+  double denom = press - (1.0 - eps) * es;
+  qs = denom > 0.0 ? eps * es / denom : eps;
+  dqs = eps * press * des / (denom * denom);
+}
+
+struct Dev {                 // owning device array
+  double* p = nullptr; size_t n = 0;
+  bool ensure(size_t count) {
+    if (count <= n) return true;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (cudaMalloc(&p, count * sizeof(double)) != cudaSuccess) return false;
+    n = count; return true;
+  }
+  ~Dev() { if (p) cudaFree(p); }
+};
+
+// module state kept between calls, as the Fortran modules keep it (vert_diff_mod e_global/f_t_global/f_q_global and the
+// surf_diff_type Tri_surf of idealized_moist_phys; mixed_layer_mod arrays)
+enum StateId { ST_E_GLOBAL = 0, ST_F_T_GLOBAL, ST_F_Q_GLOBAL, ST_TRI_DELTA_T, ST_TRI_DFLUX_T, ST_TRI_DELTA_Q, ST_TRI_DFLUX_Q,
+               ST_TRI_DTMASS, ST_TRI_DELTA_U, ST_TRI_DELTA_V, ST_ML_HEAT_CAP, ST_ML_QFLUX, ST_COUNT };
+
+}  // namespace isca_phys
+
+struct IscaPhysics_t {
+  IscaPhysicsConfig cfg;
+  isca_phys::PhysConst pc;
+  isca_phys::SvpDev svp;
+  isca_phys::Dev tab;                   // TABLE | DTABLE | D2TABLE
+  isca_phys::Dev buf[24];               // staging of the host-array entry points
+  isca_phys::Dev state[isca_phys::ST_COUNT];
+  bool vert_diff_down_done = false;
+  int* d_err = nullptr;
+  cudaStream_t st = nullptr;
+  std::string err;
+  size_t ncol = 0; int K = 0;
+};
+
+namespace isca_phys {
+
+std::string& thread_error();
+inline int fail(IscaPhysics p, const std::string& m) { if (p) p->err = m; thread_error() = m; return 1; }
+
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return isca_phys::fail(p, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+inline int up(IscaPhysics p, Dev& d, const double* h, size_t n) {
+  if (!h) return fail(p, "null input array");
+  if (!d.ensure(n)) return fail(p, "cudaMalloc failed");
+  PCK(cudaMemcpyAsync(d.p, h, n * sizeof(double), cudaMemcpyHostToDevice, p->st));
+  return 0;
+}
+inline int down(IscaPhysics p, const Dev& d, double* h, size_t n) {
+  if (!h) return fail(p, "null output array");
+  PCK(cudaMemcpyAsync(h, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+  return 0;
+}
+// waits for the stream and turns the device error flag (saturation-table overflow) into a failure
+inline int finish(IscaPhysics p, const char* what) {
+  int e = 0;
+  PCK(cudaGetLastError());
+  PCK(cudaMemcpyAsync(&e, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  PCK(cudaStreamSynchronize(p->st));
+  if (e) {
+    PCK(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->st));
+    return fail(p, std::string(what) + ": lookup_es: temperature outside the saturation vapour pressure table (table overflow)");
+  }
+  return 0;
+}
+inline int col_blocks(IscaPhysics p, int threads) { return (int)((p->ncol + threads - 1) / threads); }
+
+// device-pointer launches shared between files (physics_diff.cu)
+int prepare_vert_diff_state(IscaPhysics p);
+void launch_vert_diff_down(IscaPhysics p, double delt, const double* u, const double* v, const double* t, const double* q,
+                           const double* diff_m, const double* diff_t, const double* p_half, const double* z_full, double* tau_u,
+                           double* tau_v, const double* dtau_du, const double* dtau_dv, double* dt_u, double* dt_v, double* dt_t,
+                           const double* dt_q, double* diss);
+void launch_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q);
+
+}  // namespace isca_phys

@@ -1,0 +1,332 @@
+// physics_diff.cu -- implicit vertical diffusion split around the surface (vert_diff_mod) and the slab mixed layer.
+//
+//   gcm_vert_diff_down / uv_vert_diff / vert_diff_down_2 / compute_e,f,mu,nu / explicit_tend / diff_surface / vert_diff_up
+//                         atmos_param/vert_diff/vert_diff.F90:270-467, 556-617, 806-1087
+//   mixed_layer           atmos_spectral/driver/solo/mixed_layer.F90:568-745
+//
+// One thread per column.  The momentum system is eliminated, closed by the surface stress and back-substituted inside the
+// kernel (its factors never leave thread-local storage); the temperature / humidity elimination stores e, f_t, f_q (the
+// reference's module state) for gcm_vert_diff_up, which runs after the surface has been updated.
+#include "physics_common.h"
+
+using namespace isca_phys;
+
+namespace {
+
+struct Surf { double mu_delt_n, nu_n, e_n1, f1_delt_n1, f2_delt_n1, delta1_n, delta2_n; };
+
+// vert_diff_down_2 (explicit_tend + compute_e + compute_f) for two fields sharing mu, nu.  xi*(k), dt*(k) load level k,
+// store(k, e, f1, f2) receives the factors of levels 0..K-2.
+template <class XI1, class XI2, class DT1, class DT2, class ST>
+__device__ __forceinline__ Surf down2(int K, double delt, const double* mu, const double* nu, XI1 xi1, XI2 xi2, DT1 dt1, DT2 dt2, ST store) {
+  Surf s;
+  double x1 = xi1(0), x2 = xi2(0);
+  double fl1 = 0.0, fl2 = 0.0;                    // fluxx(k)
+  double e_prev = 0.0, f1_prev = 0.0, f2_prev = 0.0;
+  for (int k = 0; k < K; ++k) {
+    double d1, d2, a = 0.0, x1p = 0.0, x2p = 0.0, fl1p = 0.0, fl2p = 0.0;
+    if (k < K - 1) {
+      x1p = xi1(k + 1); x2p = xi2(k + 1);
+      fl1p = nu[k + 1] * (x1p - x1); fl2p = nu[k + 1] * (x2p - x2);
+      d1 = dt1(k) + mu[k] * (fl1p - fl1);
+      d2 = dt2(k) + mu[k] * (fl2p - fl2);
+      a = -mu[k] * nu[k + 1] * delt;
+    } else {
+      d1 = dt1(k) - mu[k] * fl1;
+      d2 = dt2(k) - mu[k] * fl2;
+    }
+    double c = k > 0 ? -mu[k] * nu[k] * delt : 0.0;
+    double b = 1.0 - a - c;
+    if (k < K - 1) {
+      double e, f1, f2;
+      if (k == 0) { e = -a / b; f1 = d1 / b; f2 = d2 / b; }
+      else {
+        double g = 1.0 / (b + c * e_prev);
+        e = -a * g; f1 = (d1 - c * f1_prev) * g; f2 = (d2 - c * f2_prev) * g;
+      }
+      store(k, e, f1, f2);
+      e_prev = e; f1_prev = f1; f2_prev = f2;
+    } else {
+      s.mu_delt_n = mu[k] * delt; s.nu_n = nu[k];
+      s.e_n1 = e_prev; s.f1_delt_n1 = f1_prev * delt; s.f2_delt_n1 = f2_prev * delt;
+      s.delta1_n = d1 * delt; s.delta2_n = d2 * delt;
+    }
+    x1 = x1p; x2 = x2p; fl1 = fl1p; fl2 = fl2p;
+  }
+  return s;
+}
+
+// diff_surface (vert_diff.F90:866-888)
+__device__ __forceinline__ void diff_surface(double mu_delt, double nu, double e_n1, double f_delt_n1, double dflux_datmos,
+                                             double& flux, double factor, double& delta_xi) {
+  double fff = 1.0 / factor;
+  double dflux = -nu * (1.0 - e_n1);
+  delta_xi = delta_xi + mu_delt * nu * f_delt_n1;
+  delta_xi = (delta_xi + mu_delt * flux * fff) / (1.0 - mu_delt * (dflux + dflux_datmos * fff));
+  flux = flux + dflux_datmos * delta_xi;
+}
+
+struct DiffArgs {
+  int ncol, K; double delt, grav, rdgas, cp_air, d608; int conserve, use_virtual;
+  const double *u, *v, *t, *q, *diff_m, *diff_t, *p_half, *z_full, *dtau_du, *dtau_dv, *dt_q;
+  double *tau_u, *tau_v, *dt_u, *dt_v, *dt_t, *diss;
+  double *e_g, *ft_g, *fq_g, *tri_delta_t, *tri_dflux_t, *tri_delta_q, *tri_dflux_q, *tri_dtmass, *tri_delta_u, *tri_delta_v;
+};
+
+// bytes/column: read u,v,t,q,diff_m,diff_t,z_full,dt_u,dt_v,dt_t,dt_q (11K) + p_half (K+1) + 4; write dt_u,dt_v,dt_t,diss,
+// e,f_t,f_q (7K) + 9  =  (19K + 14) * 8
+__global__ void __launch_bounds__(128) vert_diff_down_kernel(DiffArgs a) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.ncol) return;
+  const int K = a.K; const size_t nc = a.ncol;
+  double mu[ISCA_KMAX], nu[ISCA_KMAX], e[ISCA_KMAX], f1[ISCA_KMAX], f2[ISCA_KMAX];
+  auto at = [&](const double* p, int k) { return p[(size_t)k * nc + col]; };
+  // compute_mu, compute_nu(diff_m)
+  {
+    double ph0 = at(a.p_half, 0), tv_prev = 0.0, z_prev = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double ph1 = at(a.p_half, k + 1);
+      mu[k] = a.grav / (ph1 - ph0);
+      double tv = at(a.t, k); if (a.use_virtual) tv = tv * (1.0 + a.d608 * at(a.q, k));
+      double z = at(a.z_full, k);
+      if (k > 0) { double rho_half = 2.0 * ph0 / (a.rdgas * (tv + tv_prev)); nu[k] = rho_half * at(a.diff_m, k) / (z_prev - z); }
+      else nu[k] = 0.0;
+      ph0 = ph1; tv_prev = tv; z_prev = z;
+    }
+  }
+  // uv_vert_diff
+  Surf s = down2(K, a.delt, mu, nu, [&](int k) { return at(a.u, k); }, [&](int k) { return at(a.v, k); },
+                 [&](int k) { return at(a.dt_u, k); }, [&](int k) { return at(a.dt_v, k); },
+                 [&](int k, double ee, double g1, double g2) { e[k] = ee; f1[k] = g1; f2[k] = g2; });
+  double tau_u = a.tau_u[col], tau_v = a.tau_v[col];
+  double delta_u_n = s.delta1_n, delta_v_n = s.delta2_n;
+  diff_surface(s.mu_delt_n, s.nu_n, s.e_n1, s.f1_delt_n1, a.dtau_du[col], tau_u, 1.0, delta_u_n);
+  diff_surface(s.mu_delt_n, s.nu_n, s.e_n1, s.f2_delt_n1, a.dtau_dv[col], tau_v, 1.0, delta_v_n);
+  a.tau_u[col] = tau_u; a.tau_v[col] = tau_v;
+  {
+    const double half_delt = 0.5 * a.delt, cp_inv = 1.0 / a.cp_air;
+    double nu_ = delta_u_n / a.delt, nv_ = delta_v_n / a.delt;
+    for (int k = K - 1; k >= 0; --k) {
+      size_t o = (size_t)k * nc + col;
+      if (k < K - 1) { nu_ = e[k] * nu_ + f1[k]; nv_ = e[k] * nv_ + f2[k]; }
+      double heat = 0.0;
+      if (a.conserve) {
+        double du = nu_ - a.dt_u[o], dv = nv_ - a.dt_v[o];
+        heat = -cp_inv * ((a.u[o] + half_delt * du) * du + (a.v[o] + half_delt * dv) * dv);
+        a.dt_t[o] = a.dt_t[o] + heat;
+      }
+      a.dt_u[o] = nu_; a.dt_v[o] = nv_; a.diss[o] = heat;
+    }
+  }
+  // compute_nu(diff_t), vert_diff_down_2(tt, q)
+  {
+    double tv_prev = 0.0, z_prev = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double tv = at(a.t, k); if (a.use_virtual) tv = tv * (1.0 + a.d608 * at(a.q, k));
+      double z = at(a.z_full, k);
+      if (k > 0) { double rho_half = 2.0 * at(a.p_half, k) / (a.rdgas * (tv + tv_prev)); nu[k] = rho_half * at(a.diff_t, k) / (z_prev - z); }
+      tv_prev = tv; z_prev = z;
+    }
+  }
+  const double gcp = a.grav / a.cp_air;
+  s = down2(K, a.delt, mu, nu, [&](int k) { return at(a.t, k) + at(a.z_full, k) * gcp; }, [&](int k) { return at(a.q, k); },
+            [&](int k) { return at(a.dt_t, k); }, [&](int k) { return at(a.dt_q, k); },
+            [&](int k, double ee, double g1, double g2) { size_t o = (size_t)k * nc + col; a.e_g[o] = ee; a.ft_g[o] = g1; a.fq_g[o] = g2; });
+  a.tri_delta_t[col] = s.delta1_n + s.mu_delt_n * s.nu_n * s.f1_delt_n1;
+  a.tri_dflux_t[col] = -s.nu_n * (1.0 - s.e_n1);
+  a.tri_delta_q[col] = s.delta2_n + s.mu_delt_n * s.nu_n * s.f2_delt_n1;
+  a.tri_dflux_q[col] = -s.nu_n * (1.0 - s.e_n1);
+  a.tri_dtmass[col] = s.mu_delt_n;
+  a.tri_delta_u[col] = delta_u_n;
+  a.tri_delta_v[col] = delta_v_n;
+}
+
+// bytes/column: read e, f_t, f_q (3(K-1)) + 2, write dt_t, dt_q (2K)  ~ 5K * 8
+__global__ void __launch_bounds__(128) vert_diff_up_kernel(int ncol, int K, double delt, const double* __restrict__ e,
+    const double* __restrict__ ft, const double* __restrict__ fq, const double* __restrict__ delta_t, const double* __restrict__ delta_q,
+    double* __restrict__ dt_t, double* __restrict__ dt_q) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  double xt = delta_t[col] / delt, xq = delta_q[col] / delt;
+  size_t o = (size_t)(K - 1) * ncol + col;
+  dt_t[o] = xt; dt_q[o] = xq;
+  for (int k = K - 2; k >= 0; --k) {
+    o -= ncol;
+    double ee = e[o];
+    xt = ee * xt + ft[o]; xq = ee * xq + fq[o];
+    dt_t[o] = xt; dt_q[o] = xq;
+  }
+}
+
+struct MixedArgs {
+  int ncol; double dt, cp_air, hlv; int evaporation;
+  const double *flux_t, *flux_q, *flux_r, *sw, *lw, *dhdt_surf, *dedt_surf, *dedq_surf, *drdt_surf, *dhdt_atm, *dedq_atm,
+               *heat_cap, *qflux, *dtmass, *dflux_t, *dflux_q;
+  double *t_surf, *delta_t, *delta_q, *delta_t_surf;
+};
+
+// mixed_layer.F90:629-745; returns a non-finite increment when eff_heat_capacity == 0 (the reference aborts)
+__global__ void mixed_layer_kernel(MixedArgs a, int* err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.ncol) return;
+  const double inv_cp = 1.0 / a.cp_air;
+  double dtmass = a.dtmass[i], dhdt_atm = a.dhdt_atm[i], dedq_atm = a.dedq_atm[i];
+  double gamma_t = 1.0 / (1.0 - dtmass * (a.dflux_t[i] + dhdt_atm * inv_cp));
+  double gamma_q = 1.0 / (1.0 - dtmass * (a.dflux_q[i] + dedq_atm));
+  double flux_t = a.flux_t[i], flux_q = a.flux_q[i];
+  double fn_t = gamma_t * (a.delta_t[i] + dtmass * flux_t * inv_cp);
+  double fn_q = gamma_q * (a.delta_q[i] + dtmass * flux_q);
+  double en_t = gamma_t * dtmass * a.dhdt_surf[i] * inv_cp;
+  double en_q = gamma_q * dtmass * a.dedt_surf[i];
+  double alpha_t = flux_t * inv_cp + dhdt_atm * inv_cp * fn_t;
+  double alpha_q = flux_q + dedq_atm * fn_q;
+  double alpha_lw = a.flux_r[i];
+  double beta_t = a.dhdt_surf[i] * inv_cp + dhdt_atm * inv_cp * en_t;
+  double beta_q = a.dedt_surf[i] + dedq_atm * en_q;
+  double beta_lw = a.drdt_surf[i];
+  double corrected_flux = -a.sw[i] - a.lw[i] + alpha_t * a.cp_air + alpha_lw - a.qflux[i];
+  double t_surf_dependence = beta_t * a.cp_air + beta_lw;
+  if (a.evaporation) {
+    corrected_flux = corrected_flux + alpha_q * a.hlv;
+    t_surf_dependence = t_surf_dependence + beta_q * a.hlv;
+  }
+  double eff = a.heat_cap[i] + t_surf_dependence * a.dt;
+  if (eff == 0.0) atomicExch(err, 2);
+  double d = -corrected_flux * a.dt / eff;
+  a.t_surf[i] = a.t_surf[i] + d;
+  a.delta_t[i] = fn_t + en_t * d;
+  if (a.evaporation) a.delta_q[i] = fn_q + en_q * d;
+  if (a.delta_t_surf) a.delta_t_surf[i] = d;
+}
+
+int ensure_state(IscaPhysics p) {
+  size_t nc = p->ncol, n3 = nc * p->K;
+  for (int i = ST_E_GLOBAL; i <= ST_F_Q_GLOBAL; ++i) if (!p->state[i].ensure(n3)) return fail(p, "cudaMalloc failed");
+  for (int i = ST_TRI_DELTA_T; i < ST_COUNT; ++i) if (!p->state[i].ensure(nc)) return fail(p, "cudaMalloc failed");
+  return 0;
+}
+
+}  // namespace
+
+namespace isca_phys {
+
+// device-pointer launch used by the host-array entry point and by the timing hook
+void launch_vert_diff_down(IscaPhysics p, double delt, const double* u, const double* v, const double* t, const double* q,
+                           const double* diff_m, const double* diff_t, const double* p_half, const double* z_full, double* tau_u,
+                           double* tau_v, const double* dtau_du, const double* dtau_dv, double* dt_u, double* dt_v, double* dt_t,
+                           const double* dt_q, double* diss) {
+  DiffArgs a;
+  a.ncol = (int)p->ncol; a.K = p->K; a.delt = delt; a.grav = p->cfg.grav; a.rdgas = p->cfg.rdgas; a.cp_air = p->cfg.cp_air;
+  a.d608 = (p->cfg.rvgas - p->cfg.rdgas) / p->cfg.rdgas;
+  a.conserve = p->cfg.vert_diff_do_conserve_energy; a.use_virtual = p->cfg.use_virtual_temp_vert_diff;
+  a.u = u; a.v = v; a.t = t; a.q = q; a.diff_m = diff_m; a.diff_t = diff_t; a.p_half = p_half; a.z_full = z_full;
+  a.dtau_du = dtau_du; a.dtau_dv = dtau_dv; a.dt_q = dt_q; a.tau_u = tau_u; a.tau_v = tau_v; a.dt_u = dt_u; a.dt_v = dt_v;
+  a.dt_t = dt_t; a.diss = diss;
+  a.e_g = p->state[ST_E_GLOBAL].p; a.ft_g = p->state[ST_F_T_GLOBAL].p; a.fq_g = p->state[ST_F_Q_GLOBAL].p;
+  a.tri_delta_t = p->state[ST_TRI_DELTA_T].p; a.tri_dflux_t = p->state[ST_TRI_DFLUX_T].p; a.tri_delta_q = p->state[ST_TRI_DELTA_Q].p;
+  a.tri_dflux_q = p->state[ST_TRI_DFLUX_Q].p; a.tri_dtmass = p->state[ST_TRI_DTMASS].p; a.tri_delta_u = p->state[ST_TRI_DELTA_U].p;
+  a.tri_delta_v = p->state[ST_TRI_DELTA_V].p;
+  vert_diff_down_kernel<<<col_blocks(p, 128), 128, 0, p->st>>>(a);
+}
+
+void launch_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q) {
+  vert_diff_up_kernel<<<col_blocks(p, 128), 128, 0, p->st>>>((int)p->ncol, p->K, delt, p->state[ST_E_GLOBAL].p, p->state[ST_F_T_GLOBAL].p,
+      p->state[ST_F_Q_GLOBAL].p, p->state[ST_TRI_DELTA_T].p, p->state[ST_TRI_DELTA_Q].p, dt_t, dt_q);
+}
+
+int prepare_vert_diff_state(IscaPhysics p) { return ensure_state(p); }
+
+}  // namespace isca_phys
+
+extern "C" {
+
+int isca_b200_gcm_vert_diff_down(IscaPhysics p, double delt, const double* u, const double* v, const double* t,
+                                 const double* q, const double* diff_m, const double* diff_t, const double* p_half,
+                                 const double* p_full, const double* z_full, double* tau_u, double* tau_v,
+                                 const double* dtau_du, const double* dtau_dv, double* dt_u, double* dt_v,
+                                 double* dt_t, const double* dt_q, double* dissipative_heat) {
+  if (!p) return fail(nullptr, "null handle");
+  if (p->K < 2) return fail(p, "gcm_vert_diff_down needs at least 2 levels");
+  if (!p_full) return fail(p, "null input array");                 // only used by do_mcm_plev, kept for the reference argument list
+  size_t nc = p->ncol, n3 = nc * p->K;
+  if (ensure_state(p)) return 1;
+  Dev* b = p->buf;
+  if (up(p, b[0], u, n3) || up(p, b[1], v, n3) || up(p, b[2], t, n3) || up(p, b[3], q, n3) || up(p, b[4], diff_m, n3) ||
+      up(p, b[5], diff_t, n3) || up(p, b[6], p_half, n3 + nc) || up(p, b[7], z_full, n3) || up(p, b[8], tau_u, nc) ||
+      up(p, b[9], tau_v, nc) || up(p, b[10], dtau_du, nc) || up(p, b[11], dtau_dv, nc) || up(p, b[12], dt_u, n3) ||
+      up(p, b[13], dt_v, n3) || up(p, b[14], dt_t, n3) || up(p, b[15], dt_q, n3)) return 1;
+  if (!b[16].ensure(n3)) return fail(p, "cudaMalloc failed");
+  launch_vert_diff_down(p, delt, b[0].p, b[1].p, b[2].p, b[3].p, b[4].p, b[5].p, b[6].p, b[7].p, b[8].p, b[9].p, b[10].p, b[11].p,
+                        b[12].p, b[13].p, b[14].p, b[15].p, b[16].p);
+  if (down(p, b[8], tau_u, nc) || down(p, b[9], tau_v, nc) || down(p, b[12], dt_u, n3) || down(p, b[13], dt_v, n3) ||
+      down(p, b[14], dt_t, n3) || down(p, b[16], dissipative_heat, n3)) return 1;
+  if (finish(p, "gcm_vert_diff_down")) return 1;
+  p->vert_diff_down_done = true;
+  return 0;
+}
+
+int isca_b200_get_tri_surf(IscaPhysics p, int id, double* host) {
+  if (!p) return fail(nullptr, "null handle");
+  if (!p->vert_diff_down_done) return fail(p, "get_tri_surf: gcm_vert_diff_down has not been called");
+  size_t nc = p->ncol, n3 = nc * p->K;
+  if (id >= 0 && id <= 6) { if (down(p, p->state[ST_TRI_DELTA_T + id], host, nc)) return 1; }
+  else if (id >= 16 && id <= 18) {
+    // levels 0..K-2 hold factors; the last level is never written by the reference either: report zeros
+    if (!host) return fail(p, "null output array");
+    PCK(cudaMemsetAsync(p->state[ST_E_GLOBAL + id - 16].p + (n3 - nc), 0, nc * sizeof(double), p->st));
+    if (down(p, p->state[ST_E_GLOBAL + id - 16], host, n3)) return 1;
+  } else return fail(p, "get_tri_surf: unknown id");
+  return finish(p, "get_tri_surf");
+}
+
+int isca_b200_mixed_layer_init(IscaPhysics p, const double* heat_capacity, const double* ocean_qflux) {
+  if (!p) return fail(nullptr, "null handle");
+  if (up(p, p->state[ST_ML_HEAT_CAP], heat_capacity, p->ncol) || up(p, p->state[ST_ML_QFLUX], ocean_qflux, p->ncol)) return 1;
+  return finish(p, "mixed_layer_init");
+}
+
+int isca_b200_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double* flux_t, const double* flux_q,
+                          const double* flux_r, const double* net_surf_sw_down, const double* surf_lw_down,
+                          const double* dhdt_surf, const double* dedt_surf, const double* dedq_surf,
+                          const double* drdt_surf, const double* dhdt_atm, const double* dedq_atm, double* delta_t_surf) {
+  if (!p) return fail(nullptr, "null handle");
+  if (!p->vert_diff_down_done) return fail(p, "mixed_layer: Tri_surf is not defined (gcm_vert_diff_down has not been called)");
+  if (!p->state[ST_ML_HEAT_CAP].p) return fail(p, "mixed_layer: mixed_layer module is not initialized");
+  size_t nc = p->ncol;
+  Dev* b = p->buf;
+  const double* in[12] = {t_surf, flux_t, flux_q, flux_r, net_surf_sw_down, surf_lw_down, dhdt_surf, dedt_surf, dedq_surf, drdt_surf,
+                          dhdt_atm, dedq_atm};
+  for (int i = 0; i < 12; ++i) if (up(p, b[i], in[i], nc)) return 1;
+  if (!b[12].ensure(nc)) return fail(p, "cudaMalloc failed");
+  MixedArgs a;
+  a.ncol = (int)nc; a.dt = dt; a.cp_air = p->cfg.cp_air; a.hlv = p->cfg.hlv; a.evaporation = p->cfg.evaporation;
+  a.t_surf = b[0].p; a.flux_t = b[1].p; a.flux_q = b[2].p; a.flux_r = b[3].p; a.sw = b[4].p; a.lw = b[5].p; a.dhdt_surf = b[6].p;
+  a.dedt_surf = b[7].p; a.dedq_surf = b[8].p; a.drdt_surf = b[9].p; a.dhdt_atm = b[10].p; a.dedq_atm = b[11].p;
+  a.heat_cap = p->state[ST_ML_HEAT_CAP].p; a.qflux = p->state[ST_ML_QFLUX].p; a.dtmass = p->state[ST_TRI_DTMASS].p;
+  a.dflux_t = p->state[ST_TRI_DFLUX_T].p; a.dflux_q = p->state[ST_TRI_DFLUX_Q].p; a.delta_t = p->state[ST_TRI_DELTA_T].p;
+  a.delta_q = p->state[ST_TRI_DELTA_Q].p; a.delta_t_surf = b[12].p;
+  mixed_layer_kernel<<<(int)((nc + 255) / 256), 256, 0, p->st>>>(a, p->d_err);
+  if (down(p, b[0], t_surf, nc)) return 1;
+  if (delta_t_surf && down(p, b[12], delta_t_surf, nc)) return 1;
+  int e = 0;
+  PCK(cudaGetLastError());
+  PCK(cudaMemcpyAsync(&e, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  PCK(cudaStreamSynchronize(p->st));
+  if (e) {
+    PCK(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->st));
+    return fail(p, "mixed_layer: Avoiding division by zero (eff_heat_capacity == 0)");
+  }
+  return 0;
+}
+
+int isca_b200_gcm_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q) {
+  if (!p) return fail(nullptr, "null handle");
+  if (!p->vert_diff_down_done) return fail(p, "gcm_vert_diff_up: gcm_vert_diff_down has not been called");
+  size_t n3 = p->ncol * p->K;
+  if (!p->buf[0].ensure(n3) || !p->buf[1].ensure(n3)) return fail(p, "cudaMalloc failed");
+  launch_vert_diff_up(p, delt, p->buf[0].p, p->buf[1].p);
+  if (down(p, p->buf[0], dt_t, n3) || down(p, p->buf[1], dt_q, n3)) return 1;
+  return finish(p, "gcm_vert_diff_up");
+}
+
+}  // extern "C"

@@ -16,7 +16,8 @@ PHYSICS_EXPORTS = [
     "isca_b200_physics_default_config", "isca_b200_physics_create", "isca_b200_physics_destroy",
     "isca_b200_physics_last_error", "isca_b200_lookup_es_des", "isca_b200_compute_qs", "isca_b200_lscale_cond",
     "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_rayleigh_damping",
-    "isca_b200_physics_time",
+    "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
+    "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up",
 ]
 
 
@@ -27,7 +28,7 @@ class IscaPhysicsConfigStruct(C.Structure):
                [(n, C.c_double) for n in ("solar_constant", "del_sol", "del_sw", "ir_tau_eq", "ir_tau_pole", "atm_abs", "sw_diff",
                                           "linear_tau", "wv_exponent", "solar_exponent", "odp", "diabatic_acce",
                                           "trayfric", "sponge_pbottom")] + \
-               [("do_conserve_energy", C.c_int)]
+               [(n, C.c_int) for n in ("do_conserve_energy", "vert_diff_do_conserve_energy", "use_virtual_temp_vert_diff", "evaporation")]
 
 
 _bound = False
@@ -50,6 +51,11 @@ def _lib():
         lib.isca_b200_two_stream_gray_rad_up.argtypes = [vp] + [dp] * 7
         lib.isca_b200_rayleigh_damping.argtypes = [vp, C.c_double] + [dp] * 7
         lib.isca_b200_physics_time.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+        lib.isca_b200_gcm_vert_diff_down.argtypes = [vp, C.c_double] + [dp] * 18
+        lib.isca_b200_get_tri_surf.argtypes = [vp, C.c_int, dp]
+        lib.isca_b200_mixed_layer_init.argtypes = [vp, dp, dp]
+        lib.isca_b200_mixed_layer.argtypes = [vp, C.c_double] + [dp] * 13
+        lib.isca_b200_gcm_vert_diff_up.argtypes = [vp, C.c_double, dp, dp]
         _bound = True
     return lib
 
@@ -151,6 +157,50 @@ class ColumnPhysics:
         self._ck(self._lib.isca_b200_rayleigh_damping(self._h, float(delt), _p(p_full), _p(u), _p(v), _p(pref), _p(udt), _p(vdt), _p(tdt)),
                  "rayleigh_damping")
         return udt, vdt, tdt
+
+    TRI_IDS = dict(delta_t=0, dflux_t=1, delta_q=2, dflux_q=3, dtmass=4, delta_u=5, delta_v=6, e_global=16, f_t_global=17, f_q_global=18)
+
+    def gcm_vert_diff_down(self, delt, u, v, t, q, diff_m, diff_t, p_half, p_full, z_full, tau_u, tau_v, dtau_du, dtau_dv,
+                           dt_u, dt_v, dt_t, dt_q):
+        """-> dict(dt_u, dt_v, dt_t, tau_u, tau_v, dissipative_heat); Tri_surf and e/f factors stay in the handle."""
+        a3 = [_in(x, self.s3, n) for x, n in ((u, "u"), (v, "v"), (t, "t"), (q, "q"), (diff_m, "diff_m"), (diff_t, "diff_t"))]
+        p_half = _in(p_half, self.s3h, "p_half")
+        p_full, z_full = _in(p_full, self.s3, "p_full"), _in(z_full, self.s3, "z_full")
+        tau_u, tau_v = np.array(_in(tau_u, self.s2, "tau_u"), copy=True), np.array(_in(tau_v, self.s2, "tau_v"), copy=True)
+        dtau_du, dtau_dv = _in(dtau_du, self.s2, "dtau_du"), _in(dtau_dv, self.s2, "dtau_dv")
+        dt_u, dt_v, dt_t = (np.array(_in(x, self.s3, n), copy=True) for x, n in ((dt_u, "dt_u"), (dt_v, "dt_v"), (dt_t, "dt_t")))
+        dt_q = _in(dt_q, self.s3, "dt_q")
+        heat = np.empty(self.s3)
+        self._ck(self._lib.isca_b200_gcm_vert_diff_down(self._h, float(delt), *[_p(x) for x in a3], _p(p_half), _p(p_full), _p(z_full),
+                                                        _p(tau_u), _p(tau_v), _p(dtau_du), _p(dtau_dv), _p(dt_u), _p(dt_v), _p(dt_t),
+                                                        _p(dt_q), _p(heat)), "gcm_vert_diff_down")
+        return dict(dt_u=dt_u, dt_v=dt_v, dt_t=dt_t, tau_u=tau_u, tau_v=tau_v, dissipative_heat=heat)
+
+    def tri_surf(self, name):
+        i = self.TRI_IDS[name]
+        out = np.empty(self.s2 if i < 16 else self.s3)
+        self._ck(self._lib.isca_b200_get_tri_surf(self._h, i, _p(out)), "get_tri_surf")
+        return out
+
+    def mixed_layer_init(self, heat_capacity, ocean_qflux):
+        hc, qf = _in(heat_capacity, self.s2, "heat_capacity"), _in(ocean_qflux, self.s2, "ocean_qflux")
+        self._ck(self._lib.isca_b200_mixed_layer_init(self._h, _p(hc), _p(qf)), "mixed_layer_init")
+
+    def mixed_layer(self, dt, t_surf, flux_t, flux_q, flux_r, net_surf_sw_down, surf_lw_down, dhdt_surf, dedt_surf, dedq_surf,
+                    drdt_surf, dhdt_atm, dedq_atm):
+        """-> new t_surf, delta_t_surf [lat, lon]; Tri_surf delta_t / delta_tr(sphum) are updated inside the handle."""
+        ts = np.array(_in(t_surf, self.s2, "t_surf"), copy=True)
+        rest = [_in(x, self.s2, "mixed_layer input") for x in (flux_t, flux_q, flux_r, net_surf_sw_down, surf_lw_down, dhdt_surf,
+                                                                dedt_surf, dedq_surf, drdt_surf, dhdt_atm, dedq_atm)]
+        d = np.empty(self.s2)
+        self._ck(self._lib.isca_b200_mixed_layer(self._h, float(dt), _p(ts), *[_p(x) for x in rest], _p(d)), "mixed_layer")
+        return ts, d
+
+    def gcm_vert_diff_up(self, delt):
+        """-> dt_t, dt_q [lev, lat, lon]"""
+        dt_t, dt_q = np.empty(self.s3), np.empty(self.s3)
+        self._ck(self._lib.isca_b200_gcm_vert_diff_up(self._h, float(delt), _p(dt_t), _p(dt_q)), "gcm_vert_diff_up")
+        return dt_t, dt_q
 
     def time_kernel(self, which, reps=20):
         """(ms per launch, algorithmic bytes per launch) on resident synthetic columns."""

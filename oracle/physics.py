@@ -164,3 +164,155 @@ def rayleigh_sponge(dt, p_full, u, v, pref, sponge_pbottom=5000.0, trayfric=-0.2
         for k in range(nlev):
             tdt[k] = -((u[k] + 0.5 * dt * udt[k]) * udt[k] + (v[k] + 0.5 * dt * vdt[k]) * vdt[k]) / CP_AIR
     return udt, vdt, tdt, nlev
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# vertical diffusion (atmos_param/vert_diff/vert_diff.F90) and the slab mixed layer
+# (atmos_spectral/driver/solo/mixed_layer.F90:568-745)
+D608 = (RVGAS - RDGAS) / RDGAS
+
+
+def compute_mu(p_half):
+    """vert_diff.F90:1031-1046"""
+    return GRAV / (p_half[1:] - p_half[:-1])
+
+
+def compute_nu(diff, p_half, p_full, z_full, t, q, use_virtual_temp=True):
+    """vert_diff.F90:1050-1087 (do_mcm_plev = .false.); nu(1) is never defined by the reference: 0 here."""
+    tt = t * (1.0 + D608 * q) if use_virtual_temp else t
+    nu = np.zeros_like(t)
+    rho_half = 2.0 * p_half[1:-1] / (RDGAS * (tt[1:] + tt[:-1]))
+    nu[1:] = rho_half * diff[1:] / (z_full[:-1] - z_full[1:])
+    return nu
+
+
+def explicit_tend(mu, nu, xi, dt_xi):
+    """vert_diff.F90:1005-1027; returns the updated tendency."""
+    fl = np.zeros_like(xi)
+    fl[1:] = nu[1:] * (xi[1:] - xi[:-1])
+    out = dt_xi.copy()
+    out[:-1] = out[:-1] + mu[:-1] * (fl[1:] - fl[:-1])
+    out[-1] = out[-1] - mu[-1] * fl[-1]
+    return out
+
+
+def compute_e(delt, mu, nu):
+    """vert_diff.F90:951-980"""
+    K = mu.shape[0]
+    a = np.zeros_like(mu); c = np.zeros_like(mu); g = np.zeros_like(mu); e = np.zeros_like(mu)
+    a[:-1] = -mu[:-1] * nu[1:] * delt
+    c[1:] = -mu[1:] * nu[1:] * delt
+    b = 1.0 - a - c
+    e[0] = -a[0] / b[0]
+    for k in range(1, K - 1):
+        g[k] = 1.0 / (b[k] + c[k] * e[k - 1])
+        e[k] = -a[k] * g[k]
+    return e, a, b, c, g
+
+
+def compute_f(dt_xi, b, c, g):
+    """vert_diff.F90:984-1001"""
+    f = np.zeros_like(dt_xi)
+    f[0] = dt_xi[0] / b[0]
+    for k in range(1, dt_xi.shape[0] - 1):
+        f[k] = (dt_xi[k] - c[k] * f[k - 1]) * g[k]
+    return f
+
+
+def vert_diff_down_2(delt, mu, nu, xi_1, xi_2, dt_xi_1, dt_xi_2):
+    """vert_diff.F90:806-862 (no kbot)"""
+    d1 = explicit_tend(mu, nu, xi_1, dt_xi_1)
+    d2 = explicit_tend(mu, nu, xi_2, dt_xi_2)
+    e, a, b, c, g = compute_e(delt, mu, nu)
+    f1 = compute_f(d1, b, c, g)
+    f2 = compute_f(d2, b, c, g)
+    return dict(e=e, f_1=f1, f_2=f2, mu_delt_n=mu[-1] * delt, nu_n=nu[-1], e_n1=e[-2],
+                f_1_delt_n1=f1[-2] * delt, f_2_delt_n1=f2[-2] * delt, delta_1_n=d1[-1] * delt, delta_2_n=d2[-1] * delt)
+
+
+def diff_surface(mu_delt, nu, e_n1, f_delt_n1, dflux_datmos, flux, factor, delta_xi):
+    """vert_diff.F90:866-888; returns (flux, delta_xi)."""
+    fff = 1.0 / factor
+    dflux = -nu * (1.0 - e_n1)
+    delta_xi = delta_xi + mu_delt * nu * f_delt_n1
+    delta_xi = (delta_xi + mu_delt * flux * fff) / (1.0 - mu_delt * (dflux + dflux_datmos * fff))
+    flux = flux + dflux_datmos * delta_xi
+    return flux, delta_xi
+
+
+def vert_diff_up(delt, e, f, delta_xi_n):
+    """vert_diff.F90:892-947 (no kbot)"""
+    K = e.shape[0]
+    out = np.zeros_like(e)
+    out[K - 1] = delta_xi_n / delt
+    for k in range(K - 2, -1, -1):
+        out[k] = e[k] * out[k + 1] + f[k]
+    return out
+
+
+def gcm_vert_diff_down(delt, u, v, t, q, diff_m, diff_t, p_half, p_full, z_full, tau_u, tau_v, dtau_du, dtau_dv,
+                       dt_u, dt_v, dt_t, dt_q, do_conserve_energy=True, use_virtual_temp=False):
+    """vert_diff.F90:270-402 with sphum the only tracer (diffused with temperature by vert_diff_down_2).
+    Returns the updated dt_u, dt_v, dt_t, tau_u, tau_v, dissipative_heat and the module state / Tri_surf dict."""
+    gcp = GRAV / CP_AIR
+    tt = t + z_full * gcp
+    mu = compute_mu(p_half)
+    nu = compute_nu(diff_m, p_half, p_full, z_full, t, q, use_virtual_temp)
+    # uv_vert_diff :558-617
+    r = vert_diff_down_2(delt, mu, nu, u, v, dt_u, dt_v)
+    tau_u, delta_u_n = diff_surface(r["mu_delt_n"], r["nu_n"], r["e_n1"], r["f_1_delt_n1"], dtau_du, tau_u, 1.0, r["delta_1_n"])
+    tau_v, delta_v_n = diff_surface(r["mu_delt_n"], r["nu_n"], r["e_n1"], r["f_2_delt_n1"], dtau_dv, tau_v, 1.0, r["delta_2_n"])
+    new_u = vert_diff_up(delt, r["e"], r["f_1"], delta_u_n)
+    new_v = vert_diff_up(delt, r["e"], r["f_2"], delta_v_n)
+    if do_conserve_energy:
+        du, dv = new_u - dt_u, new_v - dt_v
+        heat = -(1.0 / CP_AIR) * ((u + 0.5 * delt * du) * du + (v + 0.5 * delt * dv) * dv)
+        dt_t = dt_t + heat
+    else:
+        heat = np.zeros_like(t)
+    nu = compute_nu(diff_t, p_half, p_full, z_full, t, q, use_virtual_temp)
+    r = vert_diff_down_2(delt, mu, nu, tt, q, dt_t, dt_q)
+    tri = dict(delta_t=r["delta_1_n"] + r["mu_delt_n"] * r["nu_n"] * r["f_1_delt_n1"],
+               dflux_t=-r["nu_n"] * (1.0 - r["e_n1"]),
+               delta_q=r["delta_2_n"] + r["mu_delt_n"] * r["nu_n"] * r["f_2_delt_n1"],
+               dflux_q=-r["nu_n"] * (1.0 - r["e_n1"]),
+               dtmass=r["mu_delt_n"], delta_u=delta_u_n, delta_v=delta_v_n,
+               e_global=r["e"], f_t_global=r["f_1"], f_q_global=r["f_2"])
+    return dict(dt_u=new_u, dt_v=new_v, dt_t=dt_t, tau_u=tau_u, tau_v=tau_v, dissipative_heat=heat, tri=tri)
+
+
+def mixed_layer(tri, dt, t_surf, flux_t, flux_q, flux_r, net_surf_sw_down, surf_lw_down, dhdt_surf, dedt_surf, dedq_surf,
+                drdt_surf, dhdt_atm, dedq_atm, heat_capacity, ocean_qflux, evaporation=True):
+    """mixed_layer.F90:568-745, do_calc_eff_heat_cap path (no prescribed SST, no ice, no flux anomalies).
+    Returns the new t_surf and the updated Tri_surf delta_t / delta_q."""
+    inv_cp = 1.0 / CP_AIR
+    gamma_t = 1.0 / (1.0 - tri["dtmass"] * (tri["dflux_t"] + dhdt_atm * inv_cp))
+    gamma_q = 1.0 / (1.0 - tri["dtmass"] * (tri["dflux_q"] + dedq_atm))
+    fn_t = gamma_t * (tri["delta_t"] + tri["dtmass"] * flux_t * inv_cp)
+    fn_q = gamma_q * (tri["delta_q"] + tri["dtmass"] * flux_q)
+    en_t = gamma_t * tri["dtmass"] * dhdt_surf * inv_cp
+    en_q = gamma_q * tri["dtmass"] * dedt_surf
+    alpha_t = flux_t * inv_cp + dhdt_atm * inv_cp * fn_t
+    alpha_q = flux_q + dedq_atm * fn_q
+    alpha_lw = flux_r
+    beta_t = dhdt_surf * inv_cp + dhdt_atm * inv_cp * en_t
+    beta_q = dedt_surf + dedq_atm * en_q
+    beta_lw = drdt_surf
+    corrected_flux = -net_surf_sw_down - surf_lw_down + alpha_t * CP_AIR + alpha_lw - ocean_qflux
+    t_surf_dependence = beta_t * CP_AIR + beta_lw
+    if evaporation:
+        corrected_flux = corrected_flux + alpha_q * HLV
+        t_surf_dependence = t_surf_dependence + beta_q * HLV
+    eff = heat_capacity + t_surf_dependence * dt
+    delta_t_surf = -corrected_flux * dt / eff
+    out = dict(tri)
+    out["delta_t"] = fn_t + en_t * delta_t_surf
+    if evaporation:
+        out["delta_q"] = fn_q + en_q * delta_t_surf
+    return t_surf + delta_t_surf, out, delta_t_surf
+
+
+def gcm_vert_diff_up(delt, tri):
+    """vert_diff.F90:406-467 -> dt_t, dt_q"""
+    return (vert_diff_up(delt, tri["e_global"], tri["f_t_global"], tri["delta_t"]),
+            vert_diff_up(delt, tri["e_global"], tri["f_q_global"], tri["delta_q"]))

@@ -42,7 +42,10 @@ def test_sat_vapor_pres_tables(mods):
     pr = np.random.default_rng(1).uniform(100.0, 1.05e5, T.shape)
     qs, dqs = cp.compute_qs(T, pr)
     qo, dqo = s.compute_qs(T, pr)
-    assert np.max(np.abs(qs / qo - 1)) < 1e-12 and np.max(np.abs(dqs / dqo - 1)) < 1e-12
+    eo2, _ = s.lookup_es_des(T)
+    well = (pr - (1 - O.RDGAS / O.RVGAS) * eo2) > 0.5 * pr             # away from the es -> p cancellation in the denominator
+    assert np.max(np.abs(qs / qo - 1)[well]) < 1e-13 and np.max(np.abs(dqs / dqo - 1)[well]) < 1e-13
+    assert np.max(np.abs(qs / qo - 1)) < 1e-9 and np.max(np.abs(dqs / dqo - 1)) < 1e-9
     with pytest.raises(physics.IscaError) as e:                        # reference: table overflow is FATAL
         cp.lookup_es_des(np.array([300.0, 90.0]))
     assert "table" in str(e.value)
@@ -120,6 +123,71 @@ def test_physics_kernels_full_size_timing(mods):
     """T170 window (512 x 256 x 40): the kernels run and report a plausible streaming rate."""
     physics, _ = mods
     cp = physics.ColumnPhysics(512, 256, 40, do_evap=1)
-    for which in range(4):
+    for which in range(6):
         ms, by = cp.time_kernel(which, reps=10)
         assert ms > 0 and by / (ms * 1e-3) / 1e9 > 50.0, (which, ms, by)
+
+
+def diff_case(K, J, I, seed):
+    from oracle import physics as O
+    rng, ps, ph, pf, t, lat = columns(K, J, I, seed)
+    q = 5e-3 * (pf / 1e5) ** 2 * rng.uniform(0.5, 1.5, t.shape)
+    dlnp = np.log(ph[1:] / np.maximum(ph[:-1], 0.3 * ph[1]))
+    zh = np.concatenate([np.cumsum((O.RDGAS * t * dlnp / O.GRAV)[::-1], 0)[::-1], np.zeros((1, J, I))])
+    z = 0.5 * (zh[1:] + zh[:-1])
+    u, v = 10 * rng.standard_normal(t.shape), 5 * rng.standard_normal(t.shape)
+    dm, dh = rng.uniform(0.0, 30.0, t.shape), rng.uniform(0.0, 30.0, t.shape)
+    dm[: K // 3] = 0.0
+    return rng, ph, pf, t, q, z, u, v, dm, dh
+
+
+@pytest.mark.parametrize("K,J,I,virt,conserve", [(2, 3, 4, 0, 1), (14, 6, 10, 0, 1), (40, 32, 64, 1, 1), (25, 8, 16, 0, 0), (80, 2, 32, 1, 1)])
+def test_vert_diff_and_mixed_layer(mods, K, J, I, virt, conserve):
+    physics, O = mods
+    rng, ph, pf, t, q, z, u, v, dm, dh = diff_case(K, J, I, 11 + K)
+    f2 = lambda lo, hi: rng.uniform(lo, hi, (J, I))
+    tau_u, tau_v, dtau_du, dtau_dv = f2(-0.2, 0.2), f2(-0.2, 0.2), f2(-0.05, -0.005), f2(-0.05, -0.005)
+    dt_u, dt_v = 1e-4 * rng.standard_normal(t.shape), 1e-4 * rng.standard_normal(t.shape)
+    dt_t, dt_q = 1e-4 * rng.standard_normal(t.shape), 1e-8 * rng.standard_normal(t.shape)
+    delt = 720.0
+    cp = physics.ColumnPhysics(I, J, K, use_virtual_temp_vert_diff=virt, vert_diff_do_conserve_energy=conserve)
+    with pytest.raises(physics.IscaError):
+        cp.gcm_vert_diff_up(delt)                                     # reference: module state undefined before the down sweep
+    g = cp.gcm_vert_diff_down(delt, u, v, t, q, dm, dh, ph, pf, z, tau_u, tau_v, dtau_du, dtau_dv, dt_u, dt_v, dt_t, dt_q)
+    o = O.gcm_vert_diff_down(delt, u, v, t, q, dm, dh, ph, pf, z, tau_u, tau_v, dtau_du, dtau_dv, dt_u, dt_v, dt_t, dt_q,
+                             do_conserve_energy=bool(conserve), use_virtual_temp=bool(virt))
+    for k in ("dt_u", "dt_v", "dt_t", "tau_u", "tau_v"):
+        assert rel(g[k], o[k]) < TOL, k
+    assert rel(g["dissipative_heat"], o["dissipative_heat"]) < 1e-11 if conserve else np.all(g["dissipative_heat"] == 0)
+    for k in ("delta_t", "dflux_t", "delta_q", "dflux_q", "dtmass", "delta_u", "delta_v", "e_global", "f_t_global", "f_q_global"):
+        assert rel(cp.tri_surf(k), o["tri"][k]) < TOL, k
+    # slab mixed layer, then the upward sweep
+    ts = f2(275, 300)
+    args = dict(flux_t=f2(-20, 60), flux_q=f2(0, 1e-4), flux_r=f2(350, 450), net_surf_sw_down=f2(0, 300), surf_lw_down=f2(250, 400),
+                dhdt_surf=f2(5, 20), dedt_surf=f2(1e-6, 5e-6), dedq_surf=f2(0, 1e-2), drdt_surf=f2(4, 6), dhdt_atm=f2(-20, -5),
+                dedq_atm=f2(-1e-2, -1e-3))
+    cap = np.full((J, I), 40.0 * 1.035e3 * 3989.24495292815) * f2(0.5, 1.5)
+    qfl = f2(-30, 30)
+    with pytest.raises(physics.IscaError):
+        cp.mixed_layer(360.0, ts, **args)                              # mixed_layer_init has not been called
+    cp.mixed_layer_init(cap, qfl)
+    ts_g, d_g = cp.mixed_layer(360.0, ts, **args)
+    ts_o, tri_o, d_o = O.mixed_layer(o["tri"], 360.0, ts, heat_capacity=cap, ocean_qflux=qfl, **args)
+    assert rel(d_g, d_o) < 1e-11 and rel(ts_g, ts_o) < 1e-14
+    assert rel(cp.tri_surf("delta_t"), tri_o["delta_t"]) < 1e-11 and rel(cp.tri_surf("delta_q"), tri_o["delta_q"]) < 1e-11
+    t_g, q_g = cp.gcm_vert_diff_up(delt)
+    t_o, q_o = O.gcm_vert_diff_up(delt, tri_o)
+    assert rel(t_g, t_o) < 1e-11 and rel(q_g, q_o) < 1e-11
+
+
+def test_mixed_layer_zero_effective_heat_capacity_is_fatal(mods):
+    physics, O = mods
+    K, J, I = 5, 2, 4
+    rng, ph, pf, t, q, z, u, v, dm, dh = diff_case(K, J, I, 3)
+    z2, z3 = np.zeros((J, I)), np.zeros_like(t)
+    cp = physics.ColumnPhysics(I, J, K)
+    cp.gcm_vert_diff_down(600.0, u, v, t, q, dm, dh, ph, pf, z, z2, z2, z2, z2, z3, z3, z3, z3)
+    cp.mixed_layer_init(z2, z2)
+    with pytest.raises(physics.IscaError) as e:
+        cp.mixed_layer(300.0, z2 + 280.0, *[z2] * 11)
+    assert "division by zero" in str(e.value)

@@ -97,3 +97,77 @@ def test_rayleigh_sponge_levels_and_energy():
     ke0 = 0.5 * (u ** 2 + v ** 2)
     ke1 = 0.5 * ((u + dt * udt) ** 2 + (v + dt * vdt) ** 2)
     assert np.allclose((ke1 - ke0)[damped] / dt, -(P.CP_AIR * tdt)[damped], rtol=1e-11)
+
+
+def diff_case(K=14, J=3, I=5, seed=5):
+    rng, ps, ph, pf, t = columns(K, J, I, seed)
+    q = 5e-3 * (pf / 1e5) ** 2 * rng.uniform(0.5, 1.5, t.shape)
+    dlnp = np.log(ph[1:] / np.maximum(ph[:-1], 0.3 * ph[1]))
+    zh = np.concatenate([np.cumsum((P.RDGAS * t * dlnp / P.GRAV)[::-1], 0)[::-1], np.zeros((1, J, I))])
+    z = 0.5 * (zh[1:] + zh[:-1])
+    u, v = 10 * rng.standard_normal(t.shape), 5 * rng.standard_normal(t.shape)
+    dm, dh = rng.uniform(0.0, 30.0, t.shape), rng.uniform(0.0, 30.0, t.shape)
+    dm[: K // 3] = 0.0                                     # no mixing aloft
+    return rng, ph, pf, t, q, z, u, v, dm, dh
+
+
+def test_vert_diff_is_the_implicit_tridiagonal_solve_and_conserves():
+    rng, ph, pf, t, q, z, u, v, dm, dh = diff_case()
+    K, J, I = t.shape
+    zero2, zero3 = np.zeros((J, I)), np.zeros_like(t)
+    delt = 900.0
+    r = P.gcm_vert_diff_down(delt, u, v, t, q, dm, dh, ph, pf, z, zero2, zero2, zero2, zero2, zero3, zero3, zero3, zero3)
+    dp = ph[1:] - ph[:-1]
+    # zero surface stress: column momentum is conserved, dissipated kinetic energy reappears as heat
+    assert np.abs((r["dt_u"] * dp).sum(0)).max() < 1e-12 * np.abs(u * dp).sum(0).max()
+    ke0 = 0.5 * (u ** 2 + v ** 2)
+    ke1 = 0.5 * ((u + delt * r["dt_u"]) ** 2 + (v + delt * r["dt_v"]) ** 2)
+    assert np.allclose(((ke1 - ke0) / delt * dp).sum(0), -(P.CP_AIR * r["dissipative_heat"] * dp).sum(0), rtol=1e-10)
+    assert np.all((r["dissipative_heat"] * dp).sum(0) >= 0)
+    # dense solve of (I - delt*D) x = dt_explicit for u in one column
+    j, i = 1, 2
+    mu = P.compute_mu(ph)[:, j, i]; nu = P.compute_nu(dm, ph, pf, z, t, q, False)[:, j, i]
+    A = np.zeros((K, K))
+    for k in range(K):
+        if k > 0:
+            A[k, k - 1] += mu[k] * nu[k]; A[k, k] -= mu[k] * nu[k]
+        if k < K - 1:
+            A[k, k + 1] += mu[k] * nu[k + 1]; A[k, k] -= mu[k] * nu[k + 1]
+    x = np.linalg.solve(np.eye(K) - delt * A, A @ u[:, j, i])
+    assert np.allclose(r["dt_u"][:, j, i], x, rtol=1e-9, atol=1e-14)
+    # closing the T/q system with zero surface flux (mixed layer bypassed) conserves column dry static energy and water
+    tri = r["tri"]
+    _, dT = P.diff_surface(tri["dtmass"], 0 * zero2, 0 * zero2, 0 * zero2, zero2, zero2, 1.0, tri["delta_t"].copy())
+    dt_t, dt_q = P.gcm_vert_diff_up(delt, tri)
+    # (delta_t already contains the nu*f term; with dflux + dflux_datmos = -nu(1-e) the closure divides by 1 - mu*dflux)
+    closed = dict(tri)
+    closed["delta_t"] = tri["delta_t"] / (1.0 - tri["dtmass"] * tri["dflux_t"])
+    closed["delta_q"] = tri["delta_q"] / (1.0 - tri["dtmass"] * tri["dflux_q"])
+    dt_t, dt_q = P.gcm_vert_diff_up(delt, closed)
+    assert np.abs((dt_q * dp).sum(0)).max() < 1e-12 * np.abs(q * dp).sum(0).max()
+    assert np.abs(((dt_t - r["dissipative_heat"]) * dp).sum(0)).max() < 1e-11 * np.abs(t * dp).sum(0).max() / delt
+
+
+def test_mixed_layer_energy_balance():
+    rng, ph, pf, t, q, z, u, v, dm, dh = diff_case()
+    K, J, I = t.shape
+    zero2, zero3 = np.zeros((J, I)), np.zeros_like(t)
+    delt = 900.0
+    tri = P.gcm_vert_diff_down(delt, u, v, t, q, dm, dh, ph, pf, z, zero2, zero2, zero2, zero2, zero3, zero3, zero3, zero3)["tri"]
+    f = lambda lo, hi: rng.uniform(lo, hi, (J, I))
+    ts = f(280, 300)
+    args = dict(flux_t=f(-20, 60), flux_q=f(0, 1e-4), flux_r=f(350, 450), net_surf_sw_down=f(0, 300), surf_lw_down=f(250, 400),
+                dhdt_surf=f(5, 20), dedt_surf=f(1e-6, 5e-6), dedq_surf=f(0, 1e-2), drdt_surf=f(4, 6), dhdt_atm=f(-20, -5),
+                dedq_atm=f(-1e-2, -1e-3))
+    cap = np.full((J, I), 40.0 * 1.035e3 * 3989.24495292815)
+    ts2, tri2, d = P.mixed_layer(tri, 450.0, ts, heat_capacity=cap, ocean_qflux=zero2, **args)
+    assert np.allclose(ts2 - ts, d)
+    # implicit surface energy balance: C dTs/dt = SW + LW_down - LW_up(new) - SH(new) - LH(new), fluxes linearised about the old state
+    dT1, dq1 = tri2["delta_t"], tri2["delta_q"]               # lowest-level increments consistent with the new surface
+    sh = args["flux_t"] + args["dhdt_surf"] * d + args["dhdt_atm"] * dT1
+    lh = P.HLV * (args["flux_q"] + args["dedt_surf"] * d + args["dedq_atm"] * dq1)
+    lw = args["flux_r"] + args["drdt_surf"] * d
+    assert np.allclose(cap * d / 450.0, args["net_surf_sw_down"] + args["surf_lw_down"] - lw - sh - lh, rtol=1e-9)
+    # a huge heat capacity pins the surface
+    ts3, _, d3 = P.mixed_layer(tri, 450.0, ts, heat_capacity=cap * 1e12, ocean_qflux=zero2, **args)
+    assert np.max(np.abs(d3)) < 1e-9
