@@ -32,6 +32,11 @@ typedef struct IscaPhysicsConfig {
   /* mixed_layer_nml: evaporation (mixed_layer.F90:87); heat capacity, q-flux and albedo maps are set by
    * isca_b200_mixed_layer_init */
   int evaporation;
+  /* monin_obukhov_nml (monin_obukhov.F90:76-83) and VONKARM (constants.F90:239) */
+  double rich_crit, drag_min, zeta_trans, vonkarm; int neutral, stable_option;
+  /* surface_flux_nml (surface_flux.F90:225-253); bucket hydrology, ncar_ocean_flux and raoult_sat_vap are not built */
+  int no_neg_q, use_virtual_temp, alt_gustiness, old_dtaudv, use_mixing_ratio, surface_flux_do_simple;
+  double gust_const, gust_min, land_humidity_prefactor, land_evap_prefactor;
 } IscaPhysicsConfig;
 
 int isca_b200_physics_default_config(IscaPhysicsConfig* cfg);
@@ -96,8 +101,36 @@ int isca_b200_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double
 /* gcm_vert_diff_up (vert_diff.F90:406-467): back-substitution -> dt_t, dt_q [K][J][I] (overwritten). */
 int isca_b200_gcm_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q);
 
+/* Monin-Obukhov similarity kernels on n independent points (monin_obukhov_kernel.F90): mo_drag = monin_obukhov_drag_1d
+ * (:122-241, with the Newton iteration monin_obukhov_solve_zeta :245-411), mo_profile = monin_obukhov_profile_1d (:498-640),
+ * stable_mix = monin_obukhov_stable_mix (:810-868), mo_diff = monin_obukhov_diff (:35-118; z [nk][n], k_m, k_h [nk][n]). */
+int isca_b200_mo_drag(IscaPhysics p, int n, const double* pt, const double* pt0, const double* z, const double* z0,
+                      const double* zt, const double* zq, const double* speed, double* drag_m, double* drag_t,
+                      double* drag_q, double* u_star, double* b_star);
+int isca_b200_mo_profile(IscaPhysics p, int n, double zref, double zref_t, const double* z, const double* z0,
+                         const double* zt, const double* zq, const double* u_star, const double* b_star,
+                         double* del_m, double* del_t, double* del_q);
+int isca_b200_stable_mix(IscaPhysics p, int n, const double* rich, double* mix);
+int isca_b200_mo_diff(IscaPhysics p, int n, int nk, const double* z, const double* u_star, const double* b_star,
+                      double* k_m, double* k_h);
+
+/* surface_flux (surface_flux.F90:338-700; bucket = .false., every point available).  All arrays [J][I]. */
+typedef struct IscaSurfaceFluxArgs {
+  /* in */
+  const double *t_atm, *q_atm, *u_atm, *v_atm, *p_atm, *z_atm, *p_surf, *t_surf, *t_ca, *u_surf, *v_surf,
+               *rough_mom, *rough_heat, *rough_moist, *rough_scale, *gust;
+  const int* land;                 /* 1 = land */
+  /* inout */
+  double* q_surf;
+  /* out */
+  double *flux_t, *flux_q, *flux_r, *flux_u, *flux_v, *cd_m, *cd_t, *cd_q, *w_atm, *u_star, *b_star, *q_star,
+         *dhdt_surf, *dedt_surf, *dedq_surf, *drdt_surf, *dhdt_atm, *dedq_atm, *dtaudu_atm, *dtaudv_atm,
+         *ex_del_m, *ex_del_h, *ex_del_q, *temp_2m, *u_10m, *v_10m, *q_2m, *rh_2m;
+} IscaSurfaceFluxArgs;
+int isca_b200_surface_flux(IscaPhysics p, const IscaSurfaceFluxArgs* args);
+
 /* device-resident timing of one kernel (which: 0 lscale_cond, 1 gray_rad_down, 2 gray_rad_up, 3 rayleigh,
- * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up) on
+ * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up, 6 surface_flux) on
  * synthetic resident columns; returns average ms per launch (CUDA events) and the algorithmic bytes per launch. */
 int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, double* bytes);
 

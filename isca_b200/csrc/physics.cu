@@ -235,6 +235,9 @@ int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
   c->odp = 1.0; c->diabatic_acce = 1.0;
   c->trayfric = 0.0; c->sponge_pbottom = 50.0; c->do_conserve_energy = 1;
   c->vert_diff_do_conserve_energy = 1; c->use_virtual_temp_vert_diff = 0; c->evaporation = 1;
+  c->rich_crit = 2.0; c->drag_min = 1.0e-05; c->zeta_trans = 0.5; c->vonkarm = 0.40; c->neutral = 0; c->stable_option = 1;
+  c->no_neg_q = 0; c->use_virtual_temp = 1; c->alt_gustiness = 0; c->old_dtaudv = 0; c->use_mixing_ratio = 0;
+  c->surface_flux_do_simple = 0; c->gust_const = 1.0; c->gust_min = 0.0; c->land_humidity_prefactor = 1.0; c->land_evap_prefactor = 1.0;
   return 0;
 }
 
@@ -247,6 +250,11 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   if (cfg->num_lon < 1 || cfg->num_lat < 1 || cfg->num_levels < 1 || cfg->num_levels > ISCA_KMAX)
     return fail(nullptr, "bad dimensions (num_levels must be 1.." + std::to_string(ISCA_KMAX) + ")");
   if (!(cfg->hc > 0.0 && cfg->hc <= 1.0)) return fail(nullptr, "lscale_cond: hc must be in (0, 1]");   // lscale_cond.F90:323
+  // monin_obukhov_init checks (monin_obukhov.F90:111-126)
+  if (cfg->rich_crit <= 0.25) return fail(nullptr, "rich_crit in monin_obukhov_mod must be > 0.25");
+  if (cfg->drag_min <= 0.0) return fail(nullptr, "drag_min in monin_obukhov_mod must be >= 0.0");
+  if (cfg->stable_option < 1 || cfg->stable_option > 2) return fail(nullptr, "the only allowable values of stable_option are 1 and 2");
+  if (cfg->stable_option == 2 && cfg->zeta_trans < 0) return fail(nullptr, "zeta_trans must be positive");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, "no CUDA device: the physics kernels have no CPU path");
   p = new IscaPhysics_t();

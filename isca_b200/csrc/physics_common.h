@@ -46,6 +46,8 @@ __device__ __forceinline__ void qs_from_es(double es, double des, double press, 
   dqs = eps * press * des / (denom * denom);
 }
 
+struct MoConst { double rich_crit, drag_min, zeta_trans, vonkarm, grav; int neutral, stable_option; };
+
 struct Dev {                 // owning device array
   double* p = nullptr; size_t n = 0;
   bool ensure(size_t count) {
@@ -118,5 +120,6 @@ void launch_vert_diff_down(IscaPhysics p, double delt, const double* u, const do
                            double* tau_v, const double* dtau_du, const double* dtau_dv, double* dt_u, double* dt_v, double* dt_t,
                            const double* dt_q, double* diss);
 void launch_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q);
+void launch_surface_flux(IscaPhysics p, const IscaSurfaceFluxArgs& dev);     // physics_surface.cu; device pointers
 
 }  // namespace isca_phys

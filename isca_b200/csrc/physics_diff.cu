@@ -202,7 +202,7 @@ __global__ void mixed_layer_kernel(MixedArgs a, int* err) {
 int ensure_state(IscaPhysics p) {
   size_t nc = p->ncol, n3 = nc * p->K;
   for (int i = ST_E_GLOBAL; i <= ST_F_Q_GLOBAL; ++i) if (!p->state[i].ensure(n3)) return fail(p, "cudaMalloc failed");
-  for (int i = ST_TRI_DELTA_T; i < ST_COUNT; ++i) if (!p->state[i].ensure(nc)) return fail(p, "cudaMalloc failed");
+  for (int i = ST_TRI_DELTA_T; i <= ST_TRI_DELTA_V; ++i) if (!p->state[i].ensure(nc)) return fail(p, "cudaMalloc failed");
   return 0;
 }
 

@@ -17,8 +17,20 @@ PHYSICS_EXPORTS = [
     "isca_b200_physics_last_error", "isca_b200_lookup_es_des", "isca_b200_compute_qs", "isca_b200_lscale_cond",
     "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_rayleigh_damping",
     "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
-    "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up",
+    "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
+    "isca_b200_mo_diff", "isca_b200_surface_flux",
 ]
+
+SURFACE_FLUX_IN = ("t_atm", "q_atm", "u_atm", "v_atm", "p_atm", "z_atm", "p_surf", "t_surf", "t_ca", "u_surf", "v_surf",
+                   "rough_mom", "rough_heat", "rough_moist", "rough_scale", "gust")
+SURFACE_FLUX_OUT = ("flux_t", "flux_q", "flux_r", "flux_u", "flux_v", "cd_m", "cd_t", "cd_q", "w_atm", "u_star", "b_star", "q_star",
+                    "dhdt_surf", "dedt_surf", "dedq_surf", "drdt_surf", "dhdt_atm", "dedq_atm", "dtaudu_atm", "dtaudv_atm",
+                    "ex_del_m", "ex_del_h", "ex_del_q", "temp_2m", "u_10m", "v_10m", "q_2m", "rh_2m")
+
+
+class IscaSurfaceFluxArgsStruct(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in SURFACE_FLUX_IN] + [("land", C.POINTER(C.c_int)), ("q_surf", C.POINTER(C.c_double))] + \
+               [(n, C.POINTER(C.c_double)) for n in SURFACE_FLUX_OUT]
 
 
 class IscaPhysicsConfigStruct(C.Structure):
@@ -28,7 +40,11 @@ class IscaPhysicsConfigStruct(C.Structure):
                [(n, C.c_double) for n in ("solar_constant", "del_sol", "del_sw", "ir_tau_eq", "ir_tau_pole", "atm_abs", "sw_diff",
                                           "linear_tau", "wv_exponent", "solar_exponent", "odp", "diabatic_acce",
                                           "trayfric", "sponge_pbottom")] + \
-               [(n, C.c_int) for n in ("do_conserve_energy", "vert_diff_do_conserve_energy", "use_virtual_temp_vert_diff", "evaporation")]
+               [(n, C.c_int) for n in ("do_conserve_energy", "vert_diff_do_conserve_energy", "use_virtual_temp_vert_diff", "evaporation")] + \
+               [(n, C.c_double) for n in ("rich_crit", "drag_min", "zeta_trans", "vonkarm")] + \
+               [(n, C.c_int) for n in ("neutral", "stable_option", "no_neg_q", "use_virtual_temp", "alt_gustiness", "old_dtaudv",
+                                       "use_mixing_ratio", "surface_flux_do_simple")] + \
+               [(n, C.c_double) for n in ("gust_const", "gust_min", "land_humidity_prefactor", "land_evap_prefactor")]
 
 
 _bound = False
@@ -56,6 +72,11 @@ def _lib():
         lib.isca_b200_mixed_layer_init.argtypes = [vp, dp, dp]
         lib.isca_b200_mixed_layer.argtypes = [vp, C.c_double] + [dp] * 13
         lib.isca_b200_gcm_vert_diff_up.argtypes = [vp, C.c_double, dp, dp]
+        lib.isca_b200_mo_drag.argtypes = [vp, C.c_int] + [dp] * 12
+        lib.isca_b200_mo_profile.argtypes = [vp, C.c_int, C.c_double, C.c_double] + [dp] * 9
+        lib.isca_b200_stable_mix.argtypes = [vp, C.c_int, dp, dp]
+        lib.isca_b200_mo_diff.argtypes = [vp, C.c_int, C.c_int] + [dp] * 5
+        lib.isca_b200_surface_flux.argtypes = [vp, C.POINTER(IscaSurfaceFluxArgsStruct)]
         _bound = True
     return lib
 
@@ -201,6 +222,58 @@ class ColumnPhysics:
         dt_t, dt_q = np.empty(self.s3), np.empty(self.s3)
         self._ck(self._lib.isca_b200_gcm_vert_diff_up(self._h, float(delt), _p(dt_t), _p(dt_q)), "gcm_vert_diff_up")
         return dt_t, dt_q
+
+    def mo_drag(self, pt, pt0, z, z0, zt, zq, speed):
+        """monin_obukhov_drag_1d on flat arrays -> drag_m, drag_t, drag_q, u_star, b_star"""
+        a = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (pt, pt0, z, z0, zt, zq, speed)]
+        n = a[0].size
+        out = [np.empty(n) for _ in range(5)]
+        self._ck(self._lib.isca_b200_mo_drag(self._h, n, *[_p(x) for x in a], *[_p(x) for x in out]), "mo_drag")
+        return tuple(out)
+
+    def mo_profile(self, zref, zref_t, z, z0, zt, zq, u_star, b_star):
+        """monin_obukhov_profile_1d -> del_m, del_t, del_q"""
+        a = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (z, z0, zt, zq, u_star, b_star)]
+        n = a[0].size
+        out = [np.empty(n) for _ in range(3)]
+        self._ck(self._lib.isca_b200_mo_profile(self._h, n, float(zref), float(zref_t), *[_p(x) for x in a], *[_p(x) for x in out]), "mo_profile")
+        return tuple(out)
+
+    def stable_mix(self, rich):
+        r = np.ascontiguousarray(rich, dtype=np.float64)
+        mix = np.empty_like(r)
+        self._ck(self._lib.isca_b200_stable_mix(self._h, r.size, _p(r), _p(mix)), "stable_mix")
+        return mix
+
+    def mo_diff(self, z, u_star, b_star):
+        """monin_obukhov_diff: z [nk, n], u_star, b_star [n] -> k_m, k_h [nk, n]"""
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        nk, n = z.shape
+        us, bs = _in(u_star, (n,), "u_star"), _in(b_star, (n,), "b_star")
+        km, kh = np.empty_like(z), np.empty_like(z)
+        self._ck(self._lib.isca_b200_mo_diff(self._h, n, nk, _p(z), _p(us), _p(bs), _p(km), _p(kh)), "mo_diff")
+        return km, kh
+
+    def surface_flux(self, land, q_surf, **inputs):
+        """surface_flux (bucket off): keyword inputs named as the reference arguments (SURFACE_FLUX_IN), land a bool/int
+        [lat, lon] mask, q_surf [lat, lon] (inout) -> dict of the outputs (SURFACE_FLUX_OUT + q_surf)."""
+        a = IscaSurfaceFluxArgsStruct()
+        keep = []
+        for n in SURFACE_FLUX_IN:
+            if n not in inputs:
+                raise IscaError(f"surface_flux: missing input {n}")
+            x = _in(inputs[n], self.s2, n); keep.append(x); setattr(a, n, _p(x))
+        ld = np.ascontiguousarray(land, dtype=np.int32)
+        if ld.shape != self.s2:
+            raise IscaError("surface_flux: land has the wrong shape")
+        a.land = ld.ctypes.data_as(C.POINTER(C.c_int))
+        out = {n: np.empty(self.s2) for n in SURFACE_FLUX_OUT}
+        out["q_surf"] = np.array(_in(q_surf, self.s2, "q_surf"), copy=True)
+        a.q_surf = _p(out["q_surf"])
+        for n in SURFACE_FLUX_OUT:
+            setattr(a, n, _p(out[n]))
+        self._ck(self._lib.isca_b200_surface_flux(self._h, C.byref(a)), "surface_flux")
+        return out
 
     def time_kernel(self, which, reps=20):
         """(ms per launch, algorithmic bytes per launch) on resident synthetic columns."""

@@ -316,3 +316,294 @@ def gcm_vert_diff_up(delt, tri):
     """vert_diff.F90:406-467 -> dt_t, dt_q"""
     return (vert_diff_up(delt, tri["e_global"], tri["f_t_global"], tri["delta_t"]),
             vert_diff_up(delt, tri["e_global"], tri["f_q_global"], tri["delta_q"]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Monin-Obukhov similarity (atmos_param/monin_obukhov/monin_obukhov_kernel.F90) and the bulk surface fluxes
+# (coupler/surface_flux.F90:338-700).  PINNED against the reference's own known-answer self-test
+# (monin_obukhov_kernel.F90:905-1120, CHKSUM_DRAG / CHKSUM_STABLE_MIX / CHKSUM_DIFF / CHKSUM_PROFILE).
+VONKARM = 0.40
+
+
+@dataclass
+class MOConfig:
+    """monin_obukhov_nml defaults (monin_obukhov.F90:76-83)"""
+    rich_crit: float = 2.0
+    drag_min: float = 1.0e-05
+    neutral: bool = False
+    stable_option: int = 1
+    zeta_trans: float = 0.5
+
+
+def mo_derivative_m(c: MOConfig, zeta):
+    """monin_obukhov_derivative_m :456-494"""
+    b_stab = 1.0 / c.rich_crit
+    uns = zeta < 0.0
+    zu = np.where(uns, zeta, 0.0)
+    zs = np.where(uns, 0.0, zeta)
+    x = (1 - 16.0 * zu) ** (-0.5)
+    phi_u = np.sqrt(x)
+    if c.stable_option == 1:
+        phi_s = 1.0 + zs * (5.0 + b_stab * zs) / (1.0 + zs)
+    else:
+        lam = 1.0 + (5.0 - b_stab) * c.zeta_trans
+        phi_s = np.where(zs < c.zeta_trans, 1 + 5.0 * zs, lam + b_stab * zs)
+    return np.where(uns, phi_u, phi_s)
+
+
+def mo_derivative_t(c: MOConfig, zeta):
+    """monin_obukhov_derivative_t :415-452"""
+    b_stab = 1.0 / c.rich_crit
+    uns = zeta < 0.0
+    zu = np.where(uns, zeta, 0.0)
+    zs = np.where(uns, 0.0, zeta)
+    phi_u = (1 - 16.0 * zu) ** (-0.5)
+    if c.stable_option == 1:
+        phi_s = 1.0 + zs * (5.0 + b_stab * zs) / (1.0 + zs)
+    else:
+        lam = 1.0 + (5.0 - b_stab) * c.zeta_trans
+        phi_s = np.where(zs < c.zeta_trans, 1 + 5.0 * zs, lam + b_stab * zs)
+    return np.where(uns, phi_u, phi_s)
+
+
+def _psi_stable(c, ln, zeta, zeta_0):
+    b_stab = 1.0 / c.rich_crit
+    if c.stable_option == 1:
+        return ln + (5.0 - b_stab) * np.log((1.0 + zeta) / (1.0 + zeta_0)) + b_stab * (zeta - zeta_0)
+    lam = 1.0 + (5.0 - b_stab) * c.zeta_trans
+    weak = zeta <= c.zeta_trans
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x = (lam - 1.0) * np.log(np.where(weak, c.zeta_trans, zeta) / c.zeta_trans) + b_stab * (zeta - c.zeta_trans)
+    strong = np.where(zeta_0 <= c.zeta_trans, ln + x + 5.0 * (c.zeta_trans - zeta_0), lam * ln + b_stab * (zeta - zeta_0))
+    return np.where(weak, ln + 5.0 * (zeta - zeta_0), strong)
+
+
+def mo_integral_m(c: MOConfig, zeta, zeta_0, ln_z_z0):
+    """monin_obukhov_integral_m :644-715"""
+    uns = zeta < 0.0
+    zu, z0u = np.where(uns, zeta, 0.0), np.where(uns, zeta_0, 0.0)
+    x = np.sqrt(np.sqrt(1 - 16.0 * zu))
+    x_0 = np.sqrt(np.sqrt(1 - 16.0 * z0u))
+    x1, x1_0 = 1.0 + x, 1.0 + x_0
+    num = x1 * x1 * (1.0 + x * x)
+    denom = x1_0 * x1_0 * (1.0 + x_0 * x_0)
+    y = np.arctan(x) - np.arctan(x_0)
+    psi_u = ln_z_z0 - np.log(num / denom) + 2 * y
+    psi_s = _psi_stable(c, ln_z_z0, np.where(uns, 0.0, zeta), np.where(uns, 0.0, zeta_0))
+    return np.where(uns, psi_u, psi_s)
+
+
+def mo_integral_tq(c: MOConfig, zeta, zeta_t, zeta_q, ln_z_zt, ln_z_zq):
+    """monin_obukhov_integral_tq :719-806"""
+    uns = zeta < 0.0
+    zu = np.where(uns, zeta, 0.0)
+    x = np.sqrt(1 - 16.0 * zu)
+    x_t = np.sqrt(1 - 16.0 * np.where(uns, zeta_t, 0.0))
+    x_q = np.sqrt(1 - 16.0 * np.where(uns, zeta_q, 0.0))
+    pt_u = ln_z_zt - 2.0 * np.log((1.0 + x) / (1.0 + x_t))
+    pq_u = ln_z_zq - 2.0 * np.log((1.0 + x) / (1.0 + x_q))
+    zs = np.where(uns, 0.0, zeta)
+    pt_s = _psi_stable(c, ln_z_zt, zs, np.where(uns, 0.0, zeta_t))
+    pq_s = _psi_stable(c, ln_z_zq, zs, np.where(uns, 0.0, zeta_q))
+    return np.where(uns, pt_u, pt_s), np.where(uns, pq_u, pq_s)
+
+
+def mo_solve_zeta(c: MOConfig, rich, z, z0, zt, zq, mask, error=1e-4, zeta_min=1e-6, max_iter=20):
+    """monin_obukhov_solve_zeta :245-411 (Newton iteration on zeta, per-point freeze once converged)."""
+    z_z0, z_zt, z_zq = z / z0, z / zt, z / zq
+    ln_z_z0, ln_z_zt, ln_z_zq = np.log(z_z0), np.log(z_zt), np.log(z_zq)
+    f_m, f_t, f_q = np.zeros_like(rich), np.zeros_like(rich), np.zeros_like(rich)
+    corr = np.zeros_like(rich)
+    mask_1 = mask.copy()
+    zeta = np.where(mask_1, rich * ln_z_z0 * ln_z_z0 / ln_z_zt, 0.0)
+    zeta = np.where(mask_1 & (rich >= 0.0), zeta / (1.0 - rich / c.rich_crit), zeta)
+    for _ in range(max_iter):
+        small_z = mask_1 & (np.abs(zeta) < zeta_min)
+        zeta = np.where(small_z, 0.0, zeta)
+        f_m = np.where(small_z, ln_z_z0, f_m); f_t = np.where(small_z, ln_z_zt, f_t); f_q = np.where(small_z, ln_z_zq, f_q)
+        mask_1 = mask_1 & ~small_z
+        zs = np.where(mask_1, zeta, 1.0)
+        rzeta = 1.0 / zs
+        zeta_0 = np.where(mask_1, zeta / z_z0, 0.0)
+        zeta_t = np.where(mask_1, zeta / z_zt, 0.0)
+        zeta_q = np.where(mask_1, zeta / z_zq, 0.0)
+        zm = np.where(mask_1, zeta, 0.0)
+        phi_m, phi_m_0 = mo_derivative_m(c, zm), mo_derivative_m(c, zeta_0)
+        phi_t, phi_t_0 = mo_derivative_t(c, zm), mo_derivative_t(c, zeta_t)
+        fm_new = mo_integral_m(c, zm, zeta_0, ln_z_z0)
+        ft_new, fq_new = mo_integral_tq(c, zm, zeta_t, zeta_q, ln_z_zt, ln_z_zq)
+        f_m = np.where(mask_1, fm_new, f_m); f_t = np.where(mask_1, ft_new, f_t); f_q = np.where(mask_1, fq_new, f_q)
+        df_m = (phi_m - phi_m_0) * rzeta
+        df_t = (phi_t - phi_t_0) * rzeta
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rich_1 = zs * f_t / (f_m * f_m)
+            d_rich = rich_1 * (rzeta + df_t / f_t - 2.0 * df_m / f_m)
+            correction = (rich - rich_1) / d_rich
+            cnew = np.minimum(np.abs(correction), np.abs(correction / zs))
+        corr = np.where(mask_1, cnew, corr)
+        if corr.max(initial=0.0) > error:
+            mask_1 = mask_1 & (corr > error)
+            zeta = np.where(mask_1, zeta + correction, zeta)
+        else:
+            break
+    return f_m, f_t, f_q
+
+
+def mo_drag(c: MOConfig, pt, pt0, z, z0, zt, zq, speed, small=1e-4):
+    """monin_obukhov_drag_1d :122-241 -> drag_m, drag_t, drag_q, u_star, b_star"""
+    r_crit = 0.95 * c.rich_crit
+    sqrt_drag_min = np.sqrt(c.drag_min) if c.drag_min != 0.0 else 0.0
+    delta_b = GRAV * (pt0 - pt) / pt0
+    rich = -z * delta_b / (speed * speed + small)
+    zz = np.maximum(np.maximum(z, z0), np.maximum(zt, zq))
+    if c.neutral:
+        us, bs, qs = VONKARM / np.log(zz / z0), VONKARM / np.log(zz / zt), VONKARM / np.log(zz / zq)
+        return us * us, us * bs, us * qs, us * speed, bs * delta_b
+    m1 = rich < r_crit
+    fm, ft, fq = mo_solve_zeta(c, rich, zz, z0, zt, zq, m1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        us = np.where(m1, np.maximum(VONKARM / fm, sqrt_drag_min), sqrt_drag_min)
+        bs = np.where(m1, np.maximum(VONKARM / ft, sqrt_drag_min), sqrt_drag_min)
+        qs = np.where(m1, np.maximum(VONKARM / fq, sqrt_drag_min), sqrt_drag_min)
+    drag_m = np.where(m1, us * us, c.drag_min)
+    drag_t = np.where(m1, us * bs, c.drag_min)
+    drag_q = np.where(m1, us * qs, c.drag_min)
+    return drag_m, drag_t, drag_q, us * speed, bs * delta_b
+
+
+def mo_profile(c: MOConfig, zref, zref_t, z, z0, zt, zq, u_star, b_star):
+    """monin_obukhov_profile_1d :498-640 -> del_m, del_t, del_q"""
+    ln_z_z0, ln_z_zt, ln_z_zq = np.log(z / z0), np.log(z / zt), np.log(z / zq)
+    ln_z_zref, ln_z_zref_t = np.log(z / zref), np.log(z / zref_t)
+    if c.neutral:
+        return 1.0 - ln_z_zref / ln_z_z0, 1.0 - ln_z_zref_t / ln_z_zt, 1.0 - ln_z_zref_t / ln_z_zq
+    pos = u_star > 0.0
+    mo_length_inv = np.where(pos, -VONKARM * b_star / np.where(pos, u_star * u_star, 1.0), 0.0)
+    zeta, zeta_0, zeta_t, zeta_q = z * mo_length_inv, z0 * mo_length_inv, zt * mo_length_inv, zq * mo_length_inv
+    zeta_ref, zeta_ref_t = zref * mo_length_inv, zref_t * mo_length_inv
+    f_m = mo_integral_m(c, zeta, zeta_0, ln_z_z0)
+    f_m_ref = mo_integral_m(c, zeta, zeta_ref, ln_z_zref)
+    f_t, f_q = mo_integral_tq(c, zeta, zeta_t, zeta_q, ln_z_zt, ln_z_zq)
+    f_t_ref, f_q_ref = mo_integral_tq(c, zeta, zeta_ref_t, zeta_ref_t, ln_z_zref_t, ln_z_zref_t)
+    return 1.0 - f_m_ref / f_m, 1.0 - f_t_ref / f_t, 1.0 - f_q_ref / f_q
+
+
+def mo_stable_mix(c: MOConfig, rich):
+    """monin_obukhov_stable_mix :810-868"""
+    b_stab = 1.0 / c.rich_crit
+    mix = np.zeros_like(rich)
+    if c.stable_option == 1:
+        ok = (rich > 0.0) & (rich < c.rich_crit)
+        r = 1.0 / np.where(ok, rich, 1.0)
+        a = r - b_stab
+        b = r - (1.0 + 5.0)
+        zeta = (-b + np.sqrt(b * b - 4.0 * a * (-1.0))) / (2.0 * a)
+        phi = 1.0 + b_stab * zeta + (5.0 - b_stab) * zeta / (1.0 + zeta)
+        return np.where(ok, 1.0 / (phi * phi), 0.0)
+    rich_trans = c.zeta_trans / (1.0 + 5.0 * c.zeta_trans)
+    lam = 1.0 + (5.0 - b_stab) * c.zeta_trans
+    mix = np.where((rich > 0.0) & (rich <= rich_trans), (1.0 - 5.0 * rich) ** 2, mix)
+    mix = np.where((rich > rich_trans) & (rich < c.rich_crit), ((1.0 - b_stab * rich) / lam) ** 2, mix)
+    return mix
+
+
+def mo_diff(c: MOConfig, z, u_star, b_star, ustar_min=1e-10):
+    """monin_obukhov_diff :35-118; z [K,...], u_star/b_star [...] -> k_m, k_h"""
+    uss = np.maximum(u_star, ustar_min)
+    if c.neutral:
+        k_m = VONKARM * uss * z
+        return k_m, k_m.copy()
+    zeta = -VONKARM * b_star * z / (uss * uss)
+    return VONKARM * uss * z / mo_derivative_m(c, zeta), VONKARM * uss * z / mo_derivative_t(c, zeta)
+
+
+@dataclass
+class SurfaceFluxConfig:
+    """surface_flux_nml defaults (surface_flux.F90:225-239); bucket, ncar_ocean_flux, raoult_sat_vap not restated."""
+    no_neg_q: bool = False
+    use_virtual_temp: bool = True
+    alt_gustiness: bool = False
+    old_dtaudv: bool = False
+    use_mixing_ratio: bool = False
+    gust_const: float = 1.0
+    gust_min: float = 0.0
+    do_simple: bool = False
+    land_humidity_prefactor: float = 1.0
+    land_evap_prefactor: float = 1.0
+
+
+def surface_flux(svp: SatVaporPres, mo: MOConfig, c: SurfaceFluxConfig, t_atm, q_atm_in, u_atm, v_atm, p_atm, z_atm, p_surf,
+                 t_surf, t_ca, q_surf, u_surf, v_surf, rough_mom, rough_heat, rough_moist, rough_scale, gust, land):
+    """surface_flux_1d (surface_flux.F90:338-700), bucket = .false., every point available.  Returns a dict of the outputs."""
+    del_temp = 0.1; del_temp_inv = 1.0 / del_temp
+    d622 = RDGAS / RVGAS; d378 = 1.0 - d622
+    d608 = d378 / d622 if c.use_virtual_temp else 0.0
+    kappa = RDGAS / CP_AIR
+    t_surf0 = np.where(land, t_ca, t_surf)
+    t_surf1 = t_surf0 + del_temp
+    e_sat, _ = svp.lookup_es_des(t_surf0)
+    e_sat1, _ = svp.lookup_es_des(t_surf1)
+    if c.use_mixing_ratio:
+        q_sat, q_sat1 = d622 * e_sat / (p_surf - e_sat), d622 * e_sat1 / (p_surf - e_sat1)
+    elif c.do_simple:
+        q_sat, q_sat1 = d622 * e_sat / p_surf, d622 * e_sat1 / p_surf
+    else:
+        q_sat, q_sat1 = d622 * e_sat / (p_surf - d378 * e_sat), d622 * e_sat1 / (p_surf - d378 * e_sat1)
+    q_surf0 = q_sat
+    q_atm = np.where(q_atm_in < 0.0, 0.0, q_atm_in) if c.no_neg_q else q_atm_in
+    p_ratio = (p_surf / p_atm) ** kappa
+    tv_atm = t_atm * (1.0 + d608 * q_atm)
+    th_atm = t_atm * p_ratio
+    thv_atm = tv_atm * p_ratio
+    thv_surf = t_surf0 * (1.0 + d608 * q_surf0)
+    u_dif, v_dif = u_surf - u_atm, v_surf - v_atm
+    if c.alt_gustiness:
+        w_atm = np.maximum(np.sqrt(u_dif ** 2 + v_dif ** 2), c.gust_const)
+        big = w_atm > c.gust_const
+        dw_atmdu, dw_atmdv = np.where(big, u_dif / w_atm, 0.0), np.where(big, v_dif / w_atm, 0.0)
+    else:
+        w_gust = np.maximum(gust, c.gust_min) if c.gust_min > 0.0 else gust
+        w_atm = np.sqrt(u_dif * u_dif + v_dif * v_dif + w_gust * w_gust)
+        dw_atmdu, dw_atmdv = u_dif / w_atm, v_dif / w_atm
+    cd_m, cd_t, cd_q, u_star, b_star = mo_drag(mo, thv_atm, thv_surf, z_atm, rough_mom, rough_heat, rough_moist, w_atm)
+    ex_del_m, ex_del_h, ex_del_q = mo_profile(mo, 10.0, 2.0, z_atm, rough_mom, rough_heat, rough_moist, u_star, b_star)
+    temp_2m = t_surf + (t_atm - t_surf) * ex_del_h
+    u_10m, v_10m = u_atm * ex_del_m, v_atm * ex_del_m
+    q_2m = q_surf + (q_atm - q_surf) * ex_del_q                       # q_surf: the value on entry (intent inout)
+    e_sat_2m, _ = svp.lookup_es_des(temp_2m)
+    if c.use_mixing_ratio:
+        q_sat_2m = d622 * e_sat_2m / (p_surf - e_sat_2m)
+    elif c.do_simple:
+        q_sat_2m = d622 * e_sat_2m / p_surf
+    else:
+        q_sat_2m = d622 * e_sat_2m / (p_surf - d378 * e_sat)          # sic: e_sat, as in the reference (:550)
+    rh_2m = q_2m / q_sat_2m
+    cd_m = cd_m * (np.log(z_atm / rough_mom + 1) / np.log(z_atm / rough_scale + 1)) ** 2
+    drag_t, drag_q, drag_m = cd_t * w_atm, cd_q * w_atm, cd_m * w_atm
+    rho = p_atm / (RDGAS * tv_atm)
+    rho_drag = CP_AIR * drag_t * rho
+    flux_t = rho_drag * (t_surf0 - th_atm)
+    dhdt_surf = rho_drag
+    dhdt_atm = -rho_drag * p_ratio
+    rho_drag = drag_q * rho
+    flux_q = np.where(land, rho_drag * c.land_evap_prefactor * (c.land_humidity_prefactor * q_surf0 - q_atm), rho_drag * (q_surf0 - q_atm))
+    dedt_surf = np.where(land, rho_drag * c.land_evap_prefactor * (c.land_humidity_prefactor * q_sat1 - q_sat) * del_temp_inv,
+                         rho_drag * (q_sat1 - q_sat) * del_temp_inv)
+    dedq_surf = np.zeros_like(flux_q)
+    dedq_atm = -rho_drag
+    q_star = flux_q / (u_star * rho)
+    q_surf_out = q_atm + flux_q / (rho * cd_q * w_atm)
+    flux_r = STEFAN * t_surf ** 4
+    drdt_surf = 4 * STEFAN * t_surf ** 3
+    rho_drag = drag_m * rho
+    flux_u, flux_v = rho_drag * u_dif, rho_drag * v_dif
+    if c.old_dtaudv:
+        dtaudu_atm = dtaudv_atm = -rho_drag
+    else:
+        dtaudu_atm = -cd_m * rho * (dw_atmdu * u_dif + w_atm)
+        dtaudv_atm = -cd_m * rho * (dw_atmdv * v_dif + w_atm)
+    return dict(flux_t=flux_t, flux_q=flux_q, flux_r=flux_r, flux_u=flux_u, flux_v=flux_v, cd_m=cd_m, cd_t=cd_t, cd_q=cd_q,
+                w_atm=w_atm, u_star=u_star, b_star=b_star, q_star=q_star, dhdt_surf=dhdt_surf, dedt_surf=dedt_surf,
+                dedq_surf=dedq_surf, drdt_surf=drdt_surf, dhdt_atm=dhdt_atm, dedq_atm=dedq_atm, dtaudu_atm=dtaudu_atm,
+                dtaudv_atm=dtaudv_atm, ex_del_m=ex_del_m, ex_del_h=ex_del_h, ex_del_q=ex_del_q, temp_2m=temp_2m, u_10m=u_10m,
+                v_10m=v_10m, q_2m=q_2m, rh_2m=rh_2m, q_surf=q_surf_out)

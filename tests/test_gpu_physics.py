@@ -191,3 +191,102 @@ def test_mixed_layer_zero_effective_heat_capacity_is_fatal(mods):
     with pytest.raises(physics.IscaError) as e:
         cp.mixed_layer(300.0, z2 + 280.0, *[z2] * 11)
     assert "division by zero" in str(e.value)
+
+
+def _kat():
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "monin_obukhov_kat.py")
+    spec = importlib.util.spec_from_file_location("monin_obukhov_kat", path)
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_monin_obukhov_reference_known_answers(mods):
+    """The reference's own self-test vectors (monin_obukhov_kernel.F90:905-1120) through the CUDA kernels: every output
+    within 4 ulp of the pinned CPU restatement, checksums within a few units of the published ones."""
+    physics, O = mods
+    K = _kat()
+    nml = dict(K.NML); nml["neutral"] = int(nml["neutral"])
+    cp = physics.ColumnPhysics(5, 1, 2, **nml)
+    c = O.MOConfig(**K.NML)
+    ulps = lambda a, b: np.max(np.abs(a - b) / np.spacing(np.abs(b)))
+    g = cp.mo_drag(K.PT, K.PT0, K.Z, K.Z0, K.ZT, K.ZQ, K.SPEED)
+    o = O.mo_drag(c, K.PT, K.PT0, K.Z, K.Z0, K.ZT, K.ZQ, K.SPEED)
+    assert max(ulps(a, b) for a, b in zip(g, o)) <= 16
+    assert K.distance(K.checksum(g), K.CHKSUM_DRAG) <= 64
+    g = cp.stable_mix(K.RICH)
+    assert ulps(g[3:], O.mo_stable_mix(c, K.RICH)[3:]) <= 4 and np.all(g[:3] == 0)
+    assert K.distance(K.checksum([g]), K.CHKSUM_STABLE_MIX) <= 8
+    km, kh = cp.mo_diff(np.array([[K.DIFF_Z]]), np.array([K.DIFF_USTAR]), np.array([K.DIFF_BSTAR]))
+    assert K.distance(K.checksum([km, kh]), K.CHKSUM_DIFF) <= 8
+    g = cp.mo_profile(K.ZREF, K.ZREF_T, K.Z, K.Z0, K.ZT, K.ZQ, K.U_STAR, K.B_STAR)
+    o = O.mo_profile(c, K.ZREF, K.ZREF_T, K.Z, K.Z0, K.ZT, K.ZQ, K.U_STAR, K.B_STAR)
+    assert max(ulps(a, b) for a, b in zip(g, o)) <= 16
+    assert K.distance(K.checksum(g), K.CHKSUM_PROFILE) <= 64
+
+
+@pytest.mark.parametrize("nml", [dict(), dict(stable_option=2, zeta_trans=0.3, rich_crit=4.0), dict(neutral=1), dict(drag_min=1e-3)])
+def test_monin_obukhov_random_points(mods, nml):
+    physics, O = mods
+    rng = np.random.default_rng(9)
+    n = 20000
+    pt0 = rng.uniform(250, 310, n)
+    pt = pt0 + rng.uniform(-8, 8, n)
+    pt[:50] = pt0[:50]                                                  # neutral stratification: zeta -> 0 branch
+    z = rng.uniform(5, 80, n)
+    z0, zt, zq = (10 ** rng.uniform(-5, -0.5, n) for _ in range(3))
+    speed = rng.uniform(0.05, 25, n)
+    speed[50:100] = 1e-3                                                # very stable / very unstable limits
+    cp = physics.ColumnPhysics(8, 4, 2, **nml)
+    onml = {k: (bool(v) if k == "neutral" else v) for k, v in nml.items()}
+    c = O.MOConfig(**onml)
+    g = cp.mo_drag(pt, pt0, z, z0, zt, zq, speed)
+    o = O.mo_drag(c, pt, pt0, z, z0, zt, zq, speed)
+    for a, b, name in zip(g, o, ("drag_m", "drag_t", "drag_q", "u_star", "b_star")):
+        assert np.max(np.abs(a - b) / (np.abs(b) + 1e-300)) < 1e-10, name   # Newton stops at 1e-4: amplified rounding only
+    gp = cp.mo_profile(10.0, 2.0, z, z0, zt, zq, g[3], g[4])
+    op = O.mo_profile(c, 10.0, 2.0, z, z0, zt, zq, g[3], g[4])
+    for a, b in zip(gp, op):
+        assert rel(a, b) < 1e-11
+    rich = rng.uniform(-1, 6, n)
+    assert rel(cp.stable_mix(rich), O.mo_stable_mix(c, rich)) < 1e-13
+    zz = rng.uniform(5, 3000, (7, n))
+    km, kh = cp.mo_diff(zz, g[3], g[4])
+    ko, ho = O.mo_diff(c, zz, g[3], g[4])
+    assert np.max(np.abs(km / ko - 1)) < 1e-13 and np.max(np.abs(kh / ho - 1)) < 1e-13
+
+
+def test_monin_obukhov_init_checks(mods):
+    physics, _ = mods
+    for bad in (dict(rich_crit=0.25), dict(drag_min=0.0), dict(stable_option=3), dict(stable_option=2, zeta_trans=-1.0)):
+        with pytest.raises(physics.IscaError):
+            physics.ColumnPhysics(4, 2, 2, **bad)
+
+
+@pytest.mark.parametrize("nml", [dict(), dict(use_virtual_temp=0, old_dtaudv=1, no_neg_q=1), dict(alt_gustiness=1, gust_const=2.0),
+                                 dict(surface_flux_do_simple=1, gust_min=1.5, land_humidity_prefactor=0.7, land_evap_prefactor=0.5),
+                                 dict(use_mixing_ratio=1)])
+def test_surface_flux(mods, nml):
+    physics, O = mods
+    J, I = 24, 48
+    rng = np.random.default_rng(21)
+    f = lambda lo, hi: rng.uniform(lo, hi, (J, I))
+    t_surf = f(255, 305)
+    d = dict(t_atm=t_surf + f(-6, 4), q_atm=f(-1e-4, 1.5e-2), u_atm=f(-15, 15), v_atm=f(-10, 10), p_surf=f(9.6e4, 1.03e5),
+             z_atm=f(15, 60), t_surf=t_surf, t_ca=t_surf + f(-1, 1), u_surf=f(-0.5, 0.5), v_surf=f(-0.5, 0.5),
+             rough_mom=f(1e-4, 0.1), rough_heat=f(1e-4, 0.1), rough_moist=f(1e-4, 0.1), gust=f(0.5, 2.0))
+    d["p_atm"] = d["p_surf"] * f(0.985, 0.998)
+    d["rough_scale"] = d["rough_mom"] * f(0.5, 2.0)
+    land = rng.uniform(size=(J, I)) < 0.3
+    q_surf = f(1e-3, 2e-2)
+    cp = physics.ColumnPhysics(I, J, 2, **nml)
+    g = cp.surface_flux(land, q_surf, **d)
+    names = dict(surface_flux_do_simple="do_simple")
+    oc = O.SurfaceFluxConfig(**{names.get(k, k): (bool(v) if isinstance(v, int) else v) for k, v in nml.items()})
+    o = O.surface_flux(O.SatVaporPres(), O.MOConfig(), oc, q_atm_in=d["q_atm"], q_surf=q_surf, land=land,
+                       **{k: v for k, v in d.items() if k != "q_atm"})
+    for k in physics.SURFACE_FLUX_OUT + ("q_surf",):
+        assert rel(g[k], o[k]) < 1e-10, k
+    bad = dict(d); bad["t_surf"] = t_surf.copy(); bad["t_surf"][3, 3] = 20.0
+    with pytest.raises(physics.IscaError):
+        cp.surface_flux(land, q_surf, **bad)

@@ -171,3 +171,61 @@ def test_mixed_layer_energy_balance():
     # a huge heat capacity pins the surface
     ts3, _, d3 = P.mixed_layer(tri, 450.0, ts, heat_capacity=cap * 1e12, ocean_qflux=zero2, **args)
     assert np.max(np.abs(d3)) < 1e-9
+
+
+def _kat():
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "monin_obukhov_kat.py")
+    spec = importlib.util.spec_from_file_location("monin_obukhov_kat", path)
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_monin_obukhov_matches_reference_self_test_checksums():
+    """PIN: the reference's own known-answer test (monin_obukhov_kernel.F90:905-1120).  The restatement reproduces the
+    Intel checksums exactly (distance 0 in units of the last bit)."""
+    K = _kat()
+    c = P.MOConfig(**K.NML)
+    assert K.distance(K.checksum(P.mo_drag(c, K.PT, K.PT0, K.Z, K.Z0, K.ZT, K.ZQ, K.SPEED)), K.CHKSUM_DRAG) <= 2
+    assert K.distance(K.checksum([P.mo_stable_mix(c, K.RICH)]), K.CHKSUM_STABLE_MIX) <= 2
+    km, kh = P.mo_diff(c, np.array([[K.DIFF_Z]]), np.array([K.DIFF_USTAR]), np.array([K.DIFF_BSTAR]))
+    assert K.distance(K.checksum([km, kh]), K.CHKSUM_DIFF) <= 2
+    assert K.distance(K.checksum(P.mo_profile(c, K.ZREF, K.ZREF_T, K.Z, K.Z0, K.ZT, K.ZQ, K.U_STAR, K.B_STAR)), K.CHKSUM_PROFILE) <= 2
+
+
+def surface_case(J=6, I=9, seed=2):
+    rng = np.random.default_rng(seed)
+    f = lambda lo, hi: rng.uniform(lo, hi, (J, I))
+    t_surf = f(260, 305)
+    d = dict(t_atm=t_surf + f(-6, 4), q_atm=f(1e-4, 1.5e-2), u_atm=f(-15, 15), v_atm=f(-10, 10), p_surf=f(9.6e4, 1.03e5),
+             z_atm=f(15, 60), t_surf=t_surf, t_ca=t_surf + f(-1, 1), u_surf=np.zeros((J, I)), v_surf=np.zeros((J, I)),
+             rough_mom=f(1e-4, 0.1), rough_heat=f(1e-4, 0.1), rough_moist=f(1e-4, 0.1), gust=np.ones((J, I)))
+    d["p_atm"] = d["p_surf"] * f(0.985, 0.998)
+    d["rough_scale"] = d["rough_mom"].copy()
+    land = rng.uniform(size=(J, I)) < 0.3
+    q_surf = f(1e-3, 2e-2)
+    return d, land, q_surf
+
+
+def test_surface_flux_consistency():
+    d, land, q_surf = surface_case()
+    s, mo = P.SatVaporPres(), P.MOConfig()
+    o = P.surface_flux(s, mo, P.SurfaceFluxConfig(), q_atm_in=d["q_atm"], q_surf=q_surf, land=land,
+                       **{k: v for k, v in d.items() if k != "q_atm"})
+    # bulk formulae close: flux = rho * C * |V| * difference; derivatives are the analytic ones
+    tv = d["t_atm"] * (1 + P.D608 * d["q_atm"])
+    rho = d["p_atm"] / (P.RDGAS * tv)
+    th = d["t_atm"] * (d["p_surf"] / d["p_atm"]) ** P.KAPPA
+    t0 = np.where(land, d["t_ca"], d["t_surf"])
+    assert np.allclose(o["flux_t"], P.CP_AIR * rho * o["cd_t"] * o["w_atm"] * (t0 - th), rtol=1e-13)
+    assert np.allclose(o["flux_u"], -rho * o["cd_m"] * o["w_atm"] * d["u_atm"], rtol=1e-13)
+    assert np.allclose(o["dhdt_surf"], o["flux_t"] / (t0 - th), rtol=1e-10)
+    assert np.all(o["cd_m"] > 0) and np.all(o["cd_m"] < 0.1) and np.all(o["u_star"] > 0)
+    assert np.all((o["ex_del_h"] > 0) & (o["ex_del_h"] < 1)) and np.all((o["ex_del_m"] > 0) & (o["ex_del_m"] < 1))
+    assert np.allclose(o["flux_r"], P.STEFAN * d["t_surf"] ** 4) and np.allclose(o["drdt_surf"] * d["t_surf"], 4 * o["flux_r"])
+    # stable (surface colder) columns have smaller exchange coefficients than unstable ones with the same geometry
+    d2 = {k: np.full_like(v, v.flat[0]) for k, v in d.items()}
+    d2["t_atm"] = d2["t_surf"] + np.linspace(-5, 5, d2["t_surf"].size).reshape(d2["t_surf"].shape)
+    o2 = P.surface_flux(s, mo, P.SurfaceFluxConfig(), q_atm_in=d2["q_atm"], q_surf=q_surf, land=np.zeros_like(land),
+                        **{k: v for k, v in d2.items() if k != "q_atm"})
+    assert np.all(np.diff(o2["cd_t"].ravel()) <= 1e-15)
