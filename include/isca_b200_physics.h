@@ -37,6 +37,11 @@ typedef struct IscaPhysicsConfig {
   /* surface_flux_nml (surface_flux.F90:225-253); bucket hydrology, ncar_ocean_flux and raoult_sat_vap are not built */
   int no_neg_q, use_virtual_temp, alt_gustiness, old_dtaudv, use_mixing_ratio, surface_flux_do_simple;
   double gust_const, gust_min, land_humidity_prefactor, land_evap_prefactor;
+  /* diffusivity_nml (diffusivity.F90:97-122).  free_atm_diff, pbl_mcm and use_pog_bug_fix = .false. are rejected at create */
+  int fixed_depth, diffusivity_do_entrain, diffusivity_do_simple, free_atm_diff, pbl_mcm, use_pog_bug_fix;
+  double depth_0, frac_inner, rich_crit_pbl, entr_ratio, parcel_buoy, znom, background_m, background_t;
+  /* qe_moist_convection_nml (qe_moist_convection.F90:61-75) */
+  double tau_bm, rhbm, Tmin, Tmax, val_inc;
 } IscaPhysicsConfig;
 
 int isca_b200_physics_default_config(IscaPhysicsConfig* cfg);
@@ -129,8 +134,24 @@ typedef struct IscaSurfaceFluxArgs {
 } IscaSurfaceFluxArgs;
 int isca_b200_surface_flux(IscaPhysics p, const IscaSurfaceFluxArgs* args);
 
+/* diffusivity (diffusivity.F90:263-354: pbl_depth :358-456, diffusivity_pbl :458-526, diffusivity_entr :732-750), no kbot,
+ * no ind_lcl.  t, q, u, v, p_full, z_full [K][J][I]; p_half, z_half [K+1][J][I]; u_star, b_star [J][I];
+ * out h [J][I]; k_m, k_t [K][J][I] in/out (the incoming values are added, as the reference does). */
+int isca_b200_diffusivity(IscaPhysics p, const double* t, const double* q, const double* u, const double* v,
+                          const double* p_full, const double* p_half, const double* z_full, const double* z_half,
+                          const double* u_star, const double* b_star, double* h, double* k_m, double* k_t);
+
+/* qe_moist_convection (qe_moist_convection.F90:157-186 -> SBM_convection_scheme :189-369), argument order of the reference
+ * without coldT.  Tin, qin, p_full [K][J][I], p_half [K+1][J][I]; out rain, snow, CAPE, CIN, invtau_* [J][I] (snow = 0),
+ * deltaT, deltaq, qref, Tref [K][J][I] (increments over dt, not rates), int convflag, kLZBs, kLCLs [J][I] (levels 1-based,
+ * 0 = none).  As in the reference only the last column of invtau_q_relaxation / invtau_t_relaxation is non-zero. */
+int isca_b200_qe_moist_convection(IscaPhysics p, double dt, const double* Tin, const double* qin, const double* p_full,
+                                  const double* p_half, double* rain, double* snow, double* deltaT, double* deltaq,
+                                  double* qref, int* convflag, int* kLZBs, double* cape, double* cin,
+                                  double* invtau_q_relaxation, double* invtau_t_relaxation, double* Tref, int* kLCLs);
+
 /* device-resident timing of one kernel (which: 0 lscale_cond, 1 gray_rad_down, 2 gray_rad_up, 3 rayleigh,
- * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up, 6 surface_flux) on
+ * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up, 6 surface_flux, 7 diffusivity, 8 qe_moist_convection) on
  * synthetic resident columns; returns average ms per launch (CUDA events) and the algorithmic bytes per launch. */
 int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, double* bytes);
 

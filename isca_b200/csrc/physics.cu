@@ -238,6 +238,10 @@ int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
   c->rich_crit = 2.0; c->drag_min = 1.0e-05; c->zeta_trans = 0.5; c->vonkarm = 0.40; c->neutral = 0; c->stable_option = 1;
   c->no_neg_q = 0; c->use_virtual_temp = 1; c->alt_gustiness = 0; c->old_dtaudv = 0; c->use_mixing_ratio = 0;
   c->surface_flux_do_simple = 0; c->gust_const = 1.0; c->gust_min = 0.0; c->land_humidity_prefactor = 1.0; c->land_evap_prefactor = 1.0;
+  c->fixed_depth = 0; c->diffusivity_do_entrain = 1; c->diffusivity_do_simple = 0; c->free_atm_diff = 0; c->pbl_mcm = 0; c->use_pog_bug_fix = 1;
+  c->depth_0 = 5000.0; c->frac_inner = 0.1; c->rich_crit_pbl = 1.0; c->entr_ratio = 0.2; c->parcel_buoy = 2.0; c->znom = 1000.0;
+  c->background_m = 0.0; c->background_t = 0.0;
+  c->tau_bm = 7200.0; c->rhbm = 0.8; c->Tmin = 173.0; c->Tmax = 335.0; c->val_inc = 0.01;
   return 0;
 }
 
@@ -255,6 +259,14 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   if (cfg->drag_min <= 0.0) return fail(nullptr, "drag_min in monin_obukhov_mod must be >= 0.0");
   if (cfg->stable_option < 1 || cfg->stable_option > 2) return fail(nullptr, "the only allowable values of stable_option are 1 and 2");
   if (cfg->stable_option == 2 && cfg->zeta_trans < 0) return fail(nullptr, "zeta_trans must be positive");
+  // diffusivity_init checks (diffusivity.F90:178-215) and the options that are not built
+  if (cfg->frac_inner <= 0.0 || cfg->frac_inner >= 1.0) return fail(nullptr, "diffusivity_init: frac_inner must be between 0 and 1");
+  if (cfg->rich_crit_pbl < 0.0) return fail(nullptr, "diffusivity_init: rich_crit_pbl must be greater than or equal to zero");
+  if (cfg->entr_ratio < 0.0) return fail(nullptr, "diffusivity_init: entr_ratio must be greater than or equal to zero");
+  if (cfg->znom <= 0.0) return fail(nullptr, "diffusivity_init: znom must be greater than zero");
+  if (cfg->background_m < 0.0 || cfg->background_t < 0.0) return fail(nullptr, "diffusivity_init: background diffusivities must be >= 0");
+  if (cfg->free_atm_diff || cfg->pbl_mcm || !cfg->use_pog_bug_fix)
+    return fail(nullptr, "diffusivity: free_atm_diff, pbl_mcm and use_pog_bug_fix = .false. are not supported by isca_b200");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, "no CUDA device: the physics kernels have no CPU path");
   p = new IscaPhysics_t();
@@ -286,6 +298,8 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   cudaMemsetAsync(p->d_err, 0, sizeof(int), p->st);
   if (cudaStreamSynchronize(p->st) != cudaSuccess) { delete p; return fail(nullptr, "table upload failed"); }
   p->svp = SvpDev{p->tab.p, p->tab.p + n, p->tab.p + 2 * n, tminl, dtinvl, 0.5 * dtres, dtres, n};
+  p->svp_host = tb;
+  if (build_lcl_table(p)) { std::string m = p->err; isca_b200_physics_destroy(p); return fail(nullptr, m); }
   *out = p;
   return 0;
 }

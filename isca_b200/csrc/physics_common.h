@@ -72,6 +72,9 @@ struct IscaPhysics_t {
   isca_phys::PhysConst pc;
   isca_phys::SvpDev svp;
   isca_phys::Dev tab;                   // TABLE | DTABLE | D2TABLE
+  std::vector<double> svp_host;         // host copy of the same tables (LCL table construction)
+  isca_phys::Dev lcl_tab;               // qe_moist_convection lcl_temp_table
+  int lcl_n = 0; double lcl_val_min = 0.0, lcl_val_max = 0.0;
   isca_phys::Dev buf[24];               // staging of the host-array entry points
   isca_phys::Dev state[isca_phys::ST_COUNT];
   bool vert_diff_down_done = false;
@@ -121,5 +124,11 @@ void launch_vert_diff_down(IscaPhysics p, double delt, const double* u, const do
                            const double* dt_q, double* diss);
 void launch_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q);
 void launch_surface_flux(IscaPhysics p, const IscaSurfaceFluxArgs& dev);     // physics_surface.cu; device pointers
+int build_lcl_table(IscaPhysics p);                                             // physics_conv.cu
+void launch_sbm_convection(IscaPhysics p, double dt, const double* Tin, const double* qin, const double* p_full, const double* p_half,
+                           double* rain, double* deltaT, double* deltaq, double* qref, double* Tref, int* convflag, int* kLZBs, int* kLCLs,
+                           double* cape, double* cin, double* itq, double* itt);
+void launch_diffusivity(IscaPhysics p, const double* t, const double* q, const double* u, const double* v, const double* z_full,
+                        const double* z_half, const double* u_star, const double* b_star, double* h, double* k_m, double* k_t);
 
 }  // namespace isca_phys

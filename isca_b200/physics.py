@@ -18,7 +18,7 @@ PHYSICS_EXPORTS = [
     "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_rayleigh_damping",
     "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
     "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
-    "isca_b200_mo_diff", "isca_b200_surface_flux",
+    "isca_b200_mo_diff", "isca_b200_surface_flux", "isca_b200_diffusivity", "isca_b200_qe_moist_convection",
 ]
 
 SURFACE_FLUX_IN = ("t_atm", "q_atm", "u_atm", "v_atm", "p_atm", "z_atm", "p_surf", "t_surf", "t_ca", "u_surf", "v_surf",
@@ -44,7 +44,11 @@ class IscaPhysicsConfigStruct(C.Structure):
                [(n, C.c_double) for n in ("rich_crit", "drag_min", "zeta_trans", "vonkarm")] + \
                [(n, C.c_int) for n in ("neutral", "stable_option", "no_neg_q", "use_virtual_temp", "alt_gustiness", "old_dtaudv",
                                        "use_mixing_ratio", "surface_flux_do_simple")] + \
-               [(n, C.c_double) for n in ("gust_const", "gust_min", "land_humidity_prefactor", "land_evap_prefactor")]
+               [(n, C.c_double) for n in ("gust_const", "gust_min", "land_humidity_prefactor", "land_evap_prefactor")] + \
+               [(n, C.c_int) for n in ("fixed_depth", "diffusivity_do_entrain", "diffusivity_do_simple", "free_atm_diff", "pbl_mcm",
+                                       "use_pog_bug_fix")] + \
+               [(n, C.c_double) for n in ("depth_0", "frac_inner", "rich_crit_pbl", "entr_ratio", "parcel_buoy", "znom", "background_m",
+                                          "background_t", "tau_bm", "rhbm", "Tmin", "Tmax", "val_inc")]
 
 
 _bound = False
@@ -77,6 +81,9 @@ def _lib():
         lib.isca_b200_stable_mix.argtypes = [vp, C.c_int, dp, dp]
         lib.isca_b200_mo_diff.argtypes = [vp, C.c_int, C.c_int] + [dp] * 5
         lib.isca_b200_surface_flux.argtypes = [vp, C.POINTER(IscaSurfaceFluxArgsStruct)]
+        lib.isca_b200_diffusivity.argtypes = [vp] + [dp] * 13
+        ip = C.POINTER(C.c_int)
+        lib.isca_b200_qe_moist_convection.argtypes = [vp, C.c_double] + [dp] * 9 + [ip, ip] + [dp] * 5 + [ip]
         _bound = True
     return lib
 
@@ -274,6 +281,33 @@ class ColumnPhysics:
             setattr(a, n, _p(out[n]))
         self._ck(self._lib.isca_b200_surface_flux(self._h, C.byref(a)), "surface_flux")
         return out
+
+    def diffusivity(self, t, q, u, v, p_full, p_half, z_full, z_half, u_star, b_star, k_m=None, k_t=None):
+        """-> h [lat, lon], k_m, k_t [lev, lat, lon] (k_m, k_t in are added; default zeros as in vert_turb_driver)"""
+        a = [_in(x, self.s3, n) for x, n in ((t, "t"), (q, "q"), (u, "u"), (v, "v"), (p_full, "p_full"))]
+        p_half, z_half = _in(p_half, self.s3h, "p_half"), _in(z_half, self.s3h, "z_half")
+        z_full = _in(z_full, self.s3, "z_full")
+        us, bs = _in(u_star, self.s2, "u_star"), _in(b_star, self.s2, "b_star")
+        km = np.zeros(self.s3) if k_m is None else np.array(_in(k_m, self.s3, "k_m"), copy=True)
+        kt = np.zeros(self.s3) if k_t is None else np.array(_in(k_t, self.s3, "k_t"), copy=True)
+        h = np.empty(self.s2)
+        self._ck(self._lib.isca_b200_diffusivity(self._h, *[_p(x) for x in a], _p(p_half), _p(z_full), _p(z_half), _p(us), _p(bs),
+                                                 _p(h), _p(km), _p(kt)), "diffusivity")
+        return h, km, kt
+
+    def qe_moist_convection(self, dt, Tin, qin, p_full, p_half):
+        """-> dict(rain, snow, deltaT, deltaq, qref, convflag, kLZBs, CAPE, CIN, invtau_q_relaxation, invtau_t_relaxation, Tref, kLCLs)"""
+        Tin, qin, p_full = (_in(x, self.s3, n) for x, n in ((Tin, "Tin"), (qin, "qin"), (p_full, "p_full")))
+        p_half = _in(p_half, self.s3h, "p_half")
+        o = {n: np.empty(self.s2) for n in ("rain", "snow", "CAPE", "CIN", "invtau_q_relaxation", "invtau_t_relaxation")}
+        o.update({n: np.empty(self.s3) for n in ("deltaT", "deltaq", "qref", "Tref")})
+        o.update({n: np.empty(self.s2, dtype=np.int32) for n in ("convflag", "kLZBs", "kLCLs")})
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self._ck(self._lib.isca_b200_qe_moist_convection(self._h, float(dt), _p(Tin), _p(qin), _p(p_full), _p(p_half), _p(o["rain"]), _p(o["snow"]),
+                                                         _p(o["deltaT"]), _p(o["deltaq"]), _p(o["qref"]), ip(o["convflag"]), ip(o["kLZBs"]),
+                                                         _p(o["CAPE"]), _p(o["CIN"]), _p(o["invtau_q_relaxation"]),
+                                                         _p(o["invtau_t_relaxation"]), _p(o["Tref"]), ip(o["kLCLs"])), "qe_moist_convection")
+        return o
 
     def time_kernel(self, which, reps=20):
         """(ms per launch, algorithmic bytes per launch) on resident synthetic columns."""

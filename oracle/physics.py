@@ -607,3 +607,368 @@ def surface_flux(svp: SatVaporPres, mo: MOConfig, c: SurfaceFluxConfig, t_atm, q
                 dedq_surf=dedq_surf, drdt_surf=drdt_surf, dhdt_atm=dhdt_atm, dedq_atm=dedq_atm, dtaudu_atm=dtaudu_atm,
                 dtaudv_atm=dtaudv_atm, ex_del_m=ex_del_m, ex_del_h=ex_del_h, ex_del_q=ex_del_q, temp_2m=temp_2m, u_10m=u_10m,
                 v_10m=v_10m, q_2m=q_2m, rh_2m=rh_2m, q_surf=q_surf_out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K-profile boundary layer diffusivities (atmos_param/diffusivity/diffusivity.F90:263-530, 732-750), as called by
+# vert_turb_driver with do_diffusivity = .true. (vert_turb_driver.F90:277-292)
+@dataclass
+class DiffusivityConfig:
+    """diffusivity_nml defaults (diffusivity.F90:97-118); free_atm_diff, pbl_mcm, use_pog_bug_fix=.false. not restated."""
+    fixed_depth: bool = False
+    depth_0: float = 5000.0
+    frac_inner: float = 0.1
+    rich_crit_pbl: float = 1.0
+    entr_ratio: float = 0.2
+    parcel_buoy: float = 2.0
+    znom: float = 1000.0
+    background_m: float = 0.0
+    background_t: float = 0.0
+    do_entrain: bool = True
+    do_simple: bool = False
+
+
+def pbl_depth(c: DiffusivityConfig, mo: MOConfig, t, u, v, z, u_star, b_star, small=1e-4):
+    """diffusivity.F90:358-456 (no kbot); t is the (virtual) dry static energy / cp."""
+    K = t.shape[0]
+    tbot = t[K - 1]
+    rich = z * GRAV * (t - tbot[None]) / tbot[None] / (u * u + v * v + small)
+    h_inner = np.full_like(tbot, c.frac_inner * c.znom)
+    ws, _ = mo_diff(mo, h_inner[None], u_star, b_star)
+    ws = np.maximum(small, ws[0] / VONKARM / h_inner)
+    h = z[K - 1].copy()
+    done = np.zeros(tbot.shape, bool)
+    rich_branch = (b_star <= 0.0) | c.do_simple
+    # Richardson-number search
+    h1, r1 = z[K - 1].copy(), rich[K - 1].copy()
+    for k in range(K - 2, -1, -1):
+        r2, h2 = rich[k], z[k]
+        hit = rich_branch & ~done & (r2 > c.rich_crit_pbl)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            h = np.where(hit, h2 + (h1 - h2) * (r2 - c.rich_crit_pbl) / (r2 - r1), h)
+        done |= hit
+        r1, h1 = r2, h2
+    # parcel search
+    with np.errstate(divide="ignore", invalid="ignore"):
+        svp = tbot * (1.0 + (c.parcel_buoy * u_star * b_star / GRAV / ws))
+    h1, t1 = z[K - 1].copy(), tbot.copy()
+    for k in range(K - 2, -1, -1):
+        h2, t2 = z[k], t[k]
+        hit = ~rich_branch & ~done & (t2 > svp)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            h = np.where(hit, h2 + (h1 - h2) * (t2 - svp) / (t2 - t1), h)
+        done |= hit
+        h1, t1 = h2, t2
+    return h
+
+
+def diffusivity(c: DiffusivityConfig, mo: MOConfig, t, q, u, v, p_full, p_half, z_full, z_half, u_star, b_star, k_m, k_t, small=1e-4):
+    """diffusivity.F90:263-354 -> h, k_m, k_t (k_m, k_t in: values to be added, as vert_turb_driver passes zeros)."""
+    K = t.shape[0]
+    gcp = GRAV / CP_AIR
+    z_surf = z_half[K]
+    z_full_ag = z_full - z_surf[None]
+    z_half_ag = z_half - z_surf[None]
+    svcp = (t + gcp * z_full_ag) if c.do_simple else (t * (1.0 + D608 * q) + gcp * z_full_ag)
+    if c.fixed_depth:
+        h = np.full_like(u_star, c.depth_0)
+    else:
+        h = pbl_depth(c, mo, svcp, u, v, z_full_ag, u_star, b_star)
+    # diffusivity_pbl :458-526 (use_pog_bug_fix = .true.: the result is a per-column function)
+    zm = z_half_ag
+    h_inner = c.frac_inner * h
+    km_ref, kt_ref = mo_diff(mo, h_inner[None], u_star, b_star)
+    km_ref, kt_ref = km_ref[0], kt_ref[0]
+    km_sl, kt_sl = mo_diff(mo, np.maximum(zm[:K], 0.0), u_star, b_star)
+    new_m, new_t = np.zeros_like(t), np.zeros_like(t)
+    for k in range(1, K):
+        inner = zm[k] < h_inner
+        mid = (zm[k] >= h_inner) & (zm[k] < h)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            factor = (zm[k] / h_inner) * (1.0 - (zm[k] - h_inner) / (h - h_inner)) ** 2
+        new_m[k] = np.where(mid, km_ref * factor, np.where(inner, km_sl[k], 0.0))
+        new_t[k] = np.where(mid, kt_ref * factor, np.where(inner, kt_sl[k], 0.0))
+    k_m, k_t = new_m + k_m, new_t + k_t
+    if c.entr_ratio > 0.0 and not c.fixed_depth and c.do_entrain:                      # diffusivity_entr :732-750
+        for k in range(1, K):
+            m = (b_star > 0.0) & (z_full_ag[k - 1] > h) & (z_full_ag[k] <= h)
+            val = (z_full_ag[k - 1] - z_full_ag[k]) * c.entr_ratio * svcp[k] * u_star * b_star / GRAV / np.maximum(small, svcp[k - 1] - svcp[k])
+            k_t[k] = np.where(m, val, k_t[k]); k_m[k] = np.where(m, val, k_m[k])
+    if c.background_m > 0.0:
+        k_m = np.maximum(k_m, c.background_m)
+    if c.background_t > 0.0:
+        k_t = np.maximum(k_t, c.background_t)
+    return h, k_m, k_t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Simplified Betts-Miller convection (atmos_param/qe_moist_convection/qe_moist_convection.F90:77-1179).
+# Written column by column with scalar loops exactly as the reference (small test sizes only).
+import math
+
+
+class SBMConvection:
+    """qe_moist_convection_mod: namelist tau_bm, rhbm, Tmin, Tmax, val_inc (:61-75) + the LCL temperature table (:113-154)."""
+    SMALL = 1.0e-10
+    PREF = 1.0e5
+
+    def __init__(self, svp: SatVaporPres, tau_bm=7200.0, rhbm=0.8, Tmin=173.0, Tmax=335.0, val_inc=0.01):
+        self.svp, self.tau_bm, self.rhbm, self.Tmin, self.Tmax, self.val_inc = svp, tau_bm, rhbm, Tmin, Tmax, val_inc
+        self.val_min = math.log(self.es(Tmin) / (Tmin ** (1.0 / KAPPA)))
+        self.val_max = math.log(self.es(Tmax) / (Tmax ** (1.0 / KAPPA)))
+        n = int(math.ceil((self.val_max - self.val_min) / val_inc))
+        tab, guess = np.zeros(n), Tmin
+        for k in range(n):
+            tab[k] = self._lcl_temp(self.val_min + k * val_inc, guess)
+            guess = tab[k]
+        self.lcl_temp_table = tab
+
+    def es(self, T):
+        s = self.svp
+        tmp = T - s.tminl
+        ind = int(s.dtinvl * (tmp + s.tepsl))
+        if ind < 0 or ind >= s.table_siz or not (s.dtinvl * (tmp + s.tepsl) > -1.0):
+            raise FloatingPointError("escomp: temperature out of the table range")
+        dl = tmp - s.dtres * ind
+        return s.TABLE[ind] + dl * (s.DTABLE[ind] + dl * s.D2TABLE[ind])
+
+    def _lcl_temp(self, value, guess):
+        """lcl_temp :1090-1117 (Newton)"""
+        T, dT, it = guess, 1.0e-7 + 1.0, 0
+        while abs(dT) > 1.0e-7 and it < 100:
+            f = value - math.log(self.es(T) * T ** (-1 / KAPPA))
+            df = 1 / KAPPA * T ** (-1) - HLV / RVGAS * T ** (-2)
+            dT = f / df
+            T = T - dT
+            it += 1
+        if not dT < 1.0e-7:
+            raise FloatingPointError("qe_moist_convection: LCL calculation did not converge")
+        return T
+
+    def get_lcl_temp(self, value):
+        """:1053-1082"""
+        if value < self.val_min:
+            raise FloatingPointError("get_lcl_temp: value to low.")
+        if value > self.val_max:
+            raise FloatingPointError("get_lcl_temp: value too high.")
+        iv = int(math.floor((value - self.val_min) / self.val_inc)) + 1
+        if iv + 1 > self.lcl_temp_table.size:
+            raise FloatingPointError("get_lcl_temp: value too high.")     # the reference reads past the table here
+        w_floor = self.val_min + (iv - 1) * self.val_inc
+        w_ceil = (value - w_floor) / self.val_inc
+        return self.lcl_temp_table[iv] * w_ceil - self.lcl_temp_table[iv - 1] * (w_ceil - 1)
+
+    @staticmethod
+    def mixing_ratio(e, p):
+        return RDGAS * e / RVGAS / (p - e)
+
+    @staticmethod
+    def virtual_temp(T, r):
+        q = r / (1.0 + r)
+        return T * (1.0 + q * (RVGAS / RDGAS - 1.0))
+
+    def cape_calculation(self, pf, ph, Tin, rin):
+        """CAPE_calculation / CAPE_below_LCL / CAPE_above_LCL :373-690.  Levels are 0-based here; kLZB, kLCL are returned
+        1-based (0 = not found) as the reference reports them."""
+        K = Tin.size
+        ks = K - 1
+        small = self.SMALL
+        Tp, rp = Tin.copy(), rin.copy()
+        st = dict(nocape=True, CAPE=0.0, CIN=0.0, kLFC=0, kLZB=0)
+        Tv = np.array([self.virtual_temp(Tin[k], rin[k]) for k in range(K)])
+        T0, r0 = Tin[ks], rin[ks]
+        rs = self.mixing_ratio(self.es(T0), pf[ks])
+        saturated = r0 >= rs
+
+        def nocape_reset():
+            st["kLZB"] = 0; st["kLFC"] = 0; st["CIN"] = 0.0
+            Tp[:] = Tin; rp[:] = rin
+
+        skip = False
+        kLCL = 0                                          # 1-based
+        if saturated:
+            kLCL = K
+            Tp[ks] = T0 + (r0 - rs) / ((CP_AIR / (HLV + small)) + (HLV * rs) / RVGAS / T0 ** 2)
+            rp[ks] = self.mixing_ratio(self.es(Tp[ks]), pf[ks])
+        else:
+            theta0 = Tin[ks] * (self.PREF / pf[ks]) ** KAPPA
+            if r0 <= 0:
+                skip = True
+            else:
+                value = math.log(theta0 ** (-1 / KAPPA) * self.PREF * r0 / (RDGAS / RVGAS + r0))
+                TLCL = self.get_lcl_temp(value)
+                pLCL = self.PREF * (TLCL / theta0) ** (1.0 / KAPPA)
+                if pLCL < pf[0]:
+                    pLCL = pf[0]
+                    TLCL = theta0 * (pLCL / self.PREF) ** KAPPA
+                k = ks
+                st["CIN"] = 0.0
+                while pf[k] > pLCL:
+                    Tp[k] = theta0 * (pf[k] / self.PREF) ** KAPPA
+                    rp[k] = self.mixing_ratio(self.es(Tp[k]), pf[k])
+                    st["CIN"] = st["CIN"] + RDGAS * (Tv[k] - self.virtual_temp(Tp[k], r0)) * math.log(ph[k + 1] / ph[k])
+                    k -= 1
+                kLCL = k + 1
+                a = KAPPA * TLCL + (HLV / CP_AIR) * r0
+                b = (HLV ** 2) * r0 / (CP_AIR * RVGAS * TLCL ** 2)
+                dtdlnp = a / (1.0 + b)
+                Tp[k] = TLCL + dtdlnp * math.log(pf[k] / pLCL) / 2
+                if Tp[k] < self.Tmin and st["nocape"]:
+                    skip = True
+                    nocape_reset()
+                else:
+                    rp[k] = self.mixing_ratio(self.es(Tp[k]), (pf[k] + pLCL) / 2)
+                    a = KAPPA * Tp[k] + (HLV / CP_AIR) * rp[k]
+                    b = (HLV ** 2) * rp[k] / (CP_AIR * RVGAS * Tp[k] ** 2)
+                    dtdlnp = a / (1.0 + b)
+                    Tp[k] = TLCL + dtdlnp * math.log(pf[k] / pLCL)
+                    if Tp[k] < self.Tmin and st["nocape"]:
+                        skip = True
+                        nocape_reset()
+                    else:
+                        rp[k] = self.mixing_ratio(self.es(Tp[k]), pf[k])
+                        tvp = self.virtual_temp(Tp[k], rp[k])
+                        if tvp < Tv[k] and st["nocape"]:
+                            st["CIN"] = st["CIN"] + RDGAS * (Tv[k] - tvp) * math.log(ph[k + 1] / ph[k])
+                        else:
+                            st["CAPE"] = st["CAPE"] + RDGAS * (tvp - Tv[k]) * math.log(ph[k + 1] / ph[k])
+                            if st["nocape"]:
+                                st["nocape"] = False
+                                st["kLFC"] = k + 1
+        # CAPE_above_LCL
+        if skip:
+            if st["nocape"]:
+                nocape_reset()
+        else:
+            for k in range(kLCL - 2, -1, -1):
+                a = KAPPA * Tp[k + 1] + (HLV / CP_AIR) * rp[k + 1]
+                b = (HLV ** 2) * rp[k + 1] / (CP_AIR * RVGAS * Tp[k + 1] ** 2)
+                dtdlnp = a / (1.0 + b)
+                Tp[k] = Tp[k + 1] + dtdlnp * math.log(pf[k] / pf[k + 1]) / 2
+                if Tp[k] < self.Tmin and st["nocape"]:
+                    nocape_reset()
+                    break
+                rp[k] = self.mixing_ratio(self.es(Tp[k]), (pf[k] + pf[k + 1]) / 2)
+                a = KAPPA * Tp[k] + (HLV / CP_AIR) * rp[k]
+                b = (HLV ** 2) * rp[k] / (CP_AIR * RVGAS * Tp[k] ** 2)
+                dtdlnp = a / (1.0 + b)
+                Tp[k] = Tp[k + 1] + dtdlnp * math.log(pf[k] / pf[k + 1])
+                if Tp[k] < self.Tmin and st["nocape"]:
+                    nocape_reset()
+                    break
+                rp[k] = self.mixing_ratio(self.es(Tp[k]), pf[k])
+                tvp = self.virtual_temp(Tp[k], rp[k])
+                if tvp < Tv[k] and st["nocape"]:
+                    st["CIN"] = st["CIN"] + RDGAS * (Tv[k] - tvp) * math.log(ph[k + 1] / ph[k])
+                elif tvp < Tv[k] and not st["nocape"]:
+                    st["kLZB"] = k + 2
+                    break
+                else:
+                    st["CAPE"] = st["CAPE"] + RDGAS * (tvp - Tv[k]) * math.log(ph[k + 1] / ph[k])
+                    if st["nocape"]:
+                        st["nocape"] = False
+                        st["kLFC"] = k + 1
+        return st["kLZB"], kLCL, Tp, rp, st["CAPE"], st["CIN"]
+
+    def column(self, dt, Tin, qin, pf, ph):
+        """one column of SBM_convection_scheme :257-369"""
+        K = Tin.size
+        small = self.SMALL
+        rin = qin / (1.0 - qin)
+        kLZB, kLCL, Tp, rp, cape, cin = self.cape_calculation(pf, ph, Tin, rin)
+        deltaq, deltaT = np.zeros(K), np.zeros(K)
+        qref, Tref = np.zeros(K), np.zeros(K)
+        convflag, Pq, itq, itt = 0, 0.0, 0.0, 0.0
+
+        def full(k1, k2):                                   # set_profiles_to_full_model_values, 1-based inclusive
+            Tref[k1 - 1:k2] = Tin[k1 - 1:k2]; qref[k1 - 1:k2] = qin[k1 - 1:k2]
+            deltaT[k1 - 1:k2] = 0.0; deltaq[k1 - 1:k2] = 0.0
+
+        if cape > 0:
+            convflag = 1
+            lz = max(kLZB, 1)                               # kLZB = 0 (LZB above the model top) indexes out of bounds in the reference
+            Tref[:] = Tp                                    # set_reference_profiles :768-796
+            for k in range(lz - 1, K):
+                eref = self.rhbm * pf[k] * rp[k] / (rp[k] + (RDGAS / RVGAS))
+                rp[k] = self.mixing_ratio(eref, pf[k])
+                qref[k] = rp[k] / (1 + rp[k])
+            full(1, max(lz - 1, 1))
+            Pq = 0.0                                        # Pq_calculation :715-736
+            for k in range(lz - 1, K):
+                deltaq[k] = -(qin[k] - qref[k]) * dt / self.tau_bm
+                Pq = Pq + deltaq[k] * (ph[k] - ph[k + 1])
+            Pq = Pq / GRAV
+            Pt = 0.0                                        # Pt_calculation :739-764
+            for k in range(lz - 1, K):
+                deltaT[k] = -(Tin[k] - Tref[k]) * dt / self.tau_bm
+                Pt = Pt + (CP_AIR / (HLV + small)) * deltaT[k] * (ph[k + 1] - ph[k])
+            Pt = Pt / GRAV
+            if Pq > 0 and Pt > 0:
+                convflag = 2
+                if Pq > Pt:                                 # do_change_time_scale_deepconv :1001-1017
+                    itq = Pt / Pq / self.tau_bm
+                    deltaq[lz - 1:K] = self.tau_bm * itq * deltaq[lz - 1:K]
+                    Pq = Pt
+                    itt = 1.0 / self.tau_bm
+                else:                                       # do_change_Tref_deepconv :968-999
+                    deltak = 0.0
+                    for k in range(lz - 1, K):
+                        deltak = deltak - (deltaT[k] + (HLV / CP_AIR) * deltaq[k]) * (ph[k + 1] - ph[k])
+                    deltak = deltak / (ph[K] - ph[lz - 1])
+                    for k in range(lz - 1, K):
+                        Tref[k] = Tref[k] + deltak * self.tau_bm / dt
+                        deltaT[k] = deltaT[k] + deltak
+            elif Pt > 0:                                    # do_shallow_convection :800-929
+                k = lz
+                while Pq < 0.0 and k <= K:                  # level_of_zero_precip
+                    Pq = Pq - deltaq[k - 1] * (ph[k - 1] - ph[k]) / GRAV
+                    k += 1
+                k_top = k - 1
+                found = Pq > 0.0
+                if k_top > lz:
+                    full(lz, k_top - 1)
+                if found:                                   # change_Tref_LZB_shallowconv
+                    c = Pq * GRAV / (deltaq[k_top - 1] * (ph[k_top] - ph[k_top - 1]))
+                    deltaq[k_top - 1] = deltaq[k_top - 1] * c
+                    deltaT[k_top - 1] = deltaT[k_top - 1] * c
+                    deltak = 0.0
+                    for kk in range(k_top - 1, K):
+                        deltak = deltak + deltaT[kk] * (ph[kk] - ph[kk + 1])
+                    deltak = deltak / (ph[K] - ph[k_top - 1])
+                    if k_top != K:
+                        deltaT[k_top - 1:K] = deltaT[k_top - 1:K] + deltak
+                        Tref[k_top - 1:K] = Tref[k_top - 1:K] + deltak * self.tau_bm / dt
+                else:
+                    if k_top == lz:
+                        full(K, K)
+                    else:
+                        full(lz, k_top)
+                Pq = 0.0
+            else:
+                Pq = 0.0
+                full(1, K)
+        else:
+            Pq = 0.0
+            full(1, K)
+        return dict(rain=Pq, deltaT=deltaT, deltaq=deltaq, qref=qref, Tref=Tref, convflag=convflag, kLZB=kLZB, kLCL=kLCL,
+                    CAPE=cape, CIN=cin, invtau_q=itq, invtau_t=itt)
+
+    def __call__(self, dt, Tin, qin, p_full, p_half):
+        """qe_moist_convection :157-186 over [K, J, I] arrays."""
+        K, J, I = Tin.shape
+        out = dict(rain=np.zeros((J, I)), snow=np.zeros((J, I)), CAPE=np.zeros((J, I)), CIN=np.zeros((J, I)),
+                   deltaT=np.zeros_like(Tin), deltaq=np.zeros_like(Tin), qref=np.zeros_like(Tin), Tref=np.zeros_like(Tin),
+                   convflag=np.zeros((J, I), np.int32), kLZBs=np.zeros((J, I), np.int32), kLCLs=np.zeros((J, I), np.int32),
+                   invtau_q_relaxation=np.zeros((J, I)), invtau_t_relaxation=np.zeros((J, I)))
+        for j in range(J):
+            for i in range(I):
+                r = self.column(dt, Tin[:, j, i].copy(), qin[:, j, i].copy(), p_full[:, j, i], p_half[:, j, i])
+                out["rain"][j, i] = r["rain"]; out["CAPE"][j, i] = r["CAPE"]; out["CIN"][j, i] = r["CIN"]
+                for n in ("deltaT", "deltaq", "qref", "Tref"):
+                    out[n][:, j, i] = r[n]
+                out["convflag"][j, i] = r["convflag"]; out["kLZBs"][j, i] = r["kLZB"]; out["kLCLs"][j, i] = r["kLCL"]
+                # the reference zeroes the whole relaxation-rate arrays inside the column loop (:283-284): only the last
+                # column processed (i = I, j = J, the loop runs i outer / j inner) keeps its value
+                if i == I - 1 and j == J - 1:
+                    out["invtau_q_relaxation"][j, i] = r["invtau_q"]; out["invtau_t_relaxation"][j, i] = r["invtau_t"]
+        return out

@@ -290,3 +290,95 @@ def test_surface_flux(mods, nml):
     bad = dict(d); bad["t_surf"] = t_surf.copy(); bad["t_surf"][3, 3] = 20.0
     with pytest.raises(physics.IscaError):
         cp.surface_flux(land, q_surf, **bad)
+
+
+@pytest.mark.parametrize("nml", [dict(), dict(diffusivity_do_simple=1, diffusivity_do_entrain=0), dict(fixed_depth=1, depth_0=1500.0),
+                                 dict(background_m=0.5, background_t=0.25, rich_crit_pbl=0.5, frac_inner=0.2, parcel_buoy=1.0, entr_ratio=0.4)])
+def test_diffusivity(mods, nml):
+    physics, O = mods
+    K, J, I = 30, 16, 40
+    rng = np.random.default_rng(4)
+    ps = 1.0e5 + 1.0e3 * rng.standard_normal((J, I))
+    sig_h = np.linspace(0.0, 1.0, K + 1) ** 2.5
+    ph = sig_h[:, None, None] * ps[None]
+    pf = 0.5 * (ph[1:] + ph[:-1])
+    theta = 290.0 + rng.uniform(-1.0, 6.0, (J, I))[None] * (1.0 - pf / ps) * 20 + 0.3 * rng.standard_normal((K, J, I))
+    t = theta * (pf / 1.0e5) ** O.KAPPA
+    q = 8e-3 * (pf / 1e5) ** 3
+    dlnp = np.log(ph[1:] / np.maximum(ph[:-1], 0.3 * ph[1]))
+    zh = np.concatenate([np.cumsum((O.RDGAS * t * dlnp / O.GRAV)[::-1], 0)[::-1], np.zeros((1, J, I))]) + 50.0 * rng.uniform(size=(J, I))
+    zf = 0.5 * (zh[1:] + zh[:-1])
+    u, v = 8 + 3 * rng.standard_normal((K, J, I)), 2 * rng.standard_normal((K, J, I))
+    us, bs = rng.uniform(0.05, 0.6, (J, I)), rng.uniform(-0.01, 0.02, (J, I))
+    km_in, kt_in = rng.uniform(0, 1, t.shape), rng.uniform(0, 1, t.shape)
+    cp = physics.ColumnPhysics(I, J, K, **nml)
+    names = dict(diffusivity_do_simple="do_simple", diffusivity_do_entrain="do_entrain")
+    oc = O.DiffusivityConfig(**{names.get(k, k): (bool(v) if isinstance(v, int) else v) for k, v in nml.items()})
+    h_g, km_g, kt_g = cp.diffusivity(t, q, u, v, pf, ph, zf, zh, us, bs, km_in, kt_in)
+    h_o, km_o, kt_o = O.diffusivity(oc, O.MOConfig(), t, q, u, v, pf, ph, zf, zh, us, bs, km_in, kt_in)
+    assert rel(h_g, h_o) < 1e-12
+    assert rel(km_g, km_o) < 1e-11 and rel(kt_g, kt_o) < 1e-11
+    assert np.array_equal(km_g == km_in, km_o == km_in)                 # same levels inside / outside the boundary layer
+
+
+def test_diffusivity_unsupported_options_fail_loudly(mods):
+    physics, _ = mods
+    for bad in (dict(free_atm_diff=1), dict(pbl_mcm=1), dict(use_pog_bug_fix=0), dict(frac_inner=1.0), dict(znom=0.0)):
+        with pytest.raises(physics.IscaError):
+            physics.ColumnPhysics(4, 2, 3, **bad)
+
+
+def conv_case(O, K, J, I, seed):
+    svp = O.SatVaporPres()
+    rng = np.random.default_rng(seed)
+    ps = 1e5 + 1e3 * rng.standard_normal((J, I))
+    sig = np.linspace(0, 1, K + 1) ** 1.2
+    ph = sig[:, None, None] * ps
+    pf = 0.5 * (ph[1:] + ph[:-1]); pf[0] = ph[1] / np.e
+    Ts = rng.uniform(270, 305, (J, I))
+    lapse = (0.17 + 0.09 * rng.uniform(size=(J, I)))[None]
+    t = np.maximum(Ts[None] * (pf / ps) ** lapse, 200 + 5 * rng.uniform(size=(K, J, I)))
+    qs, _ = svp.compute_qs(t, pf)
+    rh = rng.uniform(0.1, 1.05, (J, I))[None] * rng.uniform(0.6, 1.0, (K, J, I))
+    q = np.minimum(qs * rh, 0.05)
+    q[:, 0, 0] = 0.0
+    q[-1, 0, 1] = 1.2 * qs[-1, 0, 1]
+    return svp, t, q, pf, ph
+
+
+@pytest.mark.parametrize("K,J,I,seed,nml", [(25, 16, 24, 1, dict(rhbm=0.7, Tmin=160.0, Tmax=350.0)), (40, 24, 32, 2, dict()),
+                                            (10, 8, 16, 3, dict(tau_bm=3600.0, rhbm=0.9, val_inc=0.02))])
+def test_qe_moist_convection(mods, K, J, I, seed, nml):
+    physics, O = mods
+    svp, t, q, pf, ph = conv_case(O, K, J, I, seed)
+    dt = 720.0
+    cp = physics.ColumnPhysics(I, J, K, **nml)
+    g = cp.qe_moist_convection(dt, t, q, pf, ph)
+    o = O.SBMConvection(svp, **nml)(dt, t, q, pf, ph)
+    flags = np.bincount(o["convflag"].ravel(), minlength=3)
+    assert flags[1] > 0 and flags[2] > 0                                 # the case exercises shallow and deep columns
+    for k in ("convflag", "kLZBs", "kLCLs"):
+        assert np.array_equal(g[k], o[k]), k                             # bit-exact integer outputs
+    for k in ("rain", "CAPE", "CIN", "deltaT", "deltaq", "qref", "Tref", "invtau_q_relaxation", "invtau_t_relaxation"):
+        assert rel(g[k], o[k]) < 1e-10, k
+    assert np.all(g["snow"] == 0)
+    dp = ph[1:] - ph[:-1]
+    assert np.abs(g["rain"] + (g["deltaq"] * dp).sum(0) / O.GRAV).max() < 1e-13
+
+
+def test_qe_moist_convection_errors(mods):
+    physics, O = mods
+    K, J, I = 12, 4, 8
+    svp, t, q, pf, ph = conv_case(O, K, J, I, 5)
+    cp = physics.ColumnPhysics(I, J, K)
+    bad = t.copy(); bad[-1, 2, 2] = 50.0
+    with pytest.raises(physics.IscaError):
+        cp.qe_moist_convection(600.0, bad, q, pf, ph)                    # es table overflow is FATAL
+    tiny = q.copy(); tiny[-1, 1, 1] = 1e-30
+    with pytest.raises(physics.IscaError) as e:
+        cp.qe_moist_convection(600.0, t, tiny, pf, ph)                   # get_lcl_temp: value too low is FATAL
+    assert "get_lcl_temp" in str(e.value)
+    with pytest.raises(physics.IscaError):
+        physics.ColumnPhysics(I, J, K, Tmin=50.0)                        # LCL table cannot be built outside the es table
+    g = cp.qe_moist_convection(600.0, t, q, pf, ph)                      # handle still usable
+    assert np.isfinite(g["deltaT"]).all()

@@ -229,3 +229,99 @@ def test_surface_flux_consistency():
     o2 = P.surface_flux(s, mo, P.SurfaceFluxConfig(), q_atm_in=d2["q_atm"], q_surf=q_surf, land=np.zeros_like(land),
                         **{k: v for k, v in d2.items() if k != "q_atm"})
     assert np.all(np.diff(o2["cd_t"].ravel()) <= 1e-15)
+
+
+def turb_case(K=20, J=5, I=7, seed=4):
+    rng = np.random.default_rng(seed)
+    ps = 1.0e5 + 1.0e3 * rng.standard_normal((J, I))
+    sig_h = np.linspace(0.0, 1.0, K + 1) ** 2.5                      # thin layers near the surface
+    ph = sig_h[:, None, None] * ps[None]
+    pf = 0.5 * (ph[1:] + ph[:-1])
+    theta = 290.0 + rng.uniform(-1.0, 6.0, (J, I))[None] * (1.0 - pf / ps) * 20 + 0.3 * rng.standard_normal((K, J, I))
+    t = theta * (pf / 1.0e5) ** P.KAPPA
+    q = 8e-3 * (pf / 1e5) ** 3
+    dlnp = np.log(ph[1:] / np.maximum(ph[:-1], 0.3 * ph[1]))
+    zh = np.concatenate([np.cumsum((P.RDGAS * t * dlnp / P.GRAV)[::-1], 0)[::-1], np.zeros((1, J, I))]) + 50.0 * rng.uniform(size=(J, I))
+    zf = 0.5 * (zh[1:] + zh[:-1])
+    u, v = 8 + 3 * rng.standard_normal((K, J, I)), 2 * rng.standard_normal((K, J, I))
+    u_star = rng.uniform(0.05, 0.6, (J, I))
+    b_star = rng.uniform(-0.01, 0.02, (J, I))
+    return t, q, u, v, pf, ph, zf, zh, u_star, b_star
+
+
+def test_diffusivity_profile_properties():
+    t, q, u, v, pf, ph, zf, zh, us, bs = turb_case()
+    K = t.shape[0]
+    mo = P.MOConfig()
+    for c in (P.DiffusivityConfig(), P.DiffusivityConfig(do_simple=True, do_entrain=False), P.DiffusivityConfig(fixed_depth=True, depth_0=1500.0)):
+        h, km, kt = P.diffusivity(c, mo, t, q, u, v, pf, ph, zf, zh, us, bs, np.zeros_like(t), np.zeros_like(t))
+        zag = zh - zh[K]
+        assert np.all(h >= zf[K - 1] - zh[K] - 1e-9)                         # at least the lowest full level
+        assert np.all(km >= 0) and np.all(kt >= 0) and np.all(km[0] == 0)
+        above = zag[:K] >= h[None]
+        if not (c.do_entrain and not c.fixed_depth):
+            assert np.all(km[above] == 0) and np.all(kt[above] == 0)          # use_pog_bug_fix: nothing above the PBL top
+        # surface layer: K = k u* z / phi(z/L)
+        inner = (zag[:K] < c.frac_inner * h[None]) & (np.arange(K)[:, None, None] > 0)
+        kref, _ = P.mo_diff(mo, zag[:K], us, bs)
+        assert np.allclose(km[inner], kref[inner], rtol=1e-14)
+        if c.fixed_depth:
+            assert np.all(h == 1500.0)
+    # the input diffusivities are added; the floors apply afterwards
+    c = P.DiffusivityConfig(do_entrain=False, background_m=0.5, background_t=0.25)
+    h0, km0, kt0 = P.diffusivity(P.DiffusivityConfig(do_entrain=False), mo, t, q, u, v, pf, ph, zf, zh, us, bs, np.ones_like(t), 2 * np.ones_like(t))
+    h1, km1, kt1 = P.diffusivity(P.DiffusivityConfig(do_entrain=False), mo, t, q, u, v, pf, ph, zf, zh, us, bs, np.zeros_like(t), np.zeros_like(t))
+    assert np.allclose(km0, km1 + 1) and np.allclose(kt0, kt1 + 2)
+    _, km2, kt2 = P.diffusivity(c, mo, t, q, u, v, pf, ph, zf, zh, us, bs, np.zeros_like(t), np.zeros_like(t))
+    assert np.array_equal(km2, np.maximum(km1, 0.5)) and np.array_equal(kt2, np.maximum(kt1, 0.25))
+
+
+def conv_case(K, J, I, seed):
+    svp = P.SatVaporPres()
+    rng = np.random.default_rng(seed)
+    ps = 1e5 + 1e3 * rng.standard_normal((J, I))
+    sig = np.linspace(0, 1, K + 1) ** 1.2
+    ph = sig[:, None, None] * ps
+    pf = 0.5 * (ph[1:] + ph[:-1]); pf[0] = ph[1] / np.e
+    Ts = rng.uniform(270, 305, (J, I))
+    lapse = (0.17 + 0.09 * rng.uniform(size=(J, I)))[None]
+    t = np.maximum(Ts[None] * (pf / ps) ** lapse, 200 + 5 * rng.uniform(size=(K, J, I)))
+    qs, _ = svp.compute_qs(t, pf)
+    rh = rng.uniform(0.1, 1.05, (J, I))[None] * rng.uniform(0.6, 1.0, (K, J, I))
+    q = np.minimum(qs * rh, 0.05)
+    q[:, 0, 0] = 0.0                                            # dry column: r0 <= 0 branch
+    q[-1, 0, 1] = 1.2 * qs[-1, 0, 1]                            # saturated lowest level
+    return svp, t, q, pf, ph
+
+
+def test_sbm_convection_conservation_and_branches():
+    svp, t, q, pf, ph = conv_case(25, 12, 20, 1)
+    sbm = P.SBMConvection(svp, rhbm=0.7, Tmin=160.0, Tmax=350.0)
+    assert sbm.lcl_temp_table.size == 1564 and abs(sbm.lcl_temp_table[0] - 160.0) < 1e-6
+    # the table inverts value(T) = log(es(T) T^(-1/kappa))
+    for T in (180.0, 250.0, 300.0, 340.0):
+        v = np.log(sbm.es(T) * T ** (-1 / P.KAPPA))
+        assert abs(sbm.get_lcl_temp(v) - T) < 2e-3
+    dt = 600.0
+    o = sbm(dt, t, q, pf, ph)
+    dp = ph[1:] - ph[:-1]
+    flags = np.bincount(o["convflag"].ravel(), minlength=3)
+    assert flags[0] > 0 and flags[1] > 0 and flags[2] > 0
+    assert np.all(o["snow"] == 0) and np.all(o["rain"] >= 0)
+    assert np.array_equal(o["rain"] > 0, o["convflag"] == 2)
+    # water: rain = -int dq dp/g ; enthalpy: int (cp dT + L dq) dp = 0 for every column
+    assert np.abs(o["rain"] + (o["deltaq"] * dp).sum(0) / P.GRAV).max() < 1e-14
+    ent = ((P.CP_AIR * o["deltaT"] + P.HLV * o["deltaq"]) * dp).sum(0) / P.GRAV
+    assert np.abs(ent).max() < 1e-9 * np.abs(P.CP_AIR * o["deltaT"] * dp).sum(0).max() / P.GRAV + 1e-12
+    # no convection: reference profiles are the model profiles, increments vanish
+    none = o["convflag"] == 0
+    assert np.all(o["deltaT"][:, none] == 0) and np.all(o["Tref"][:, none] == t[:, none]) and np.all(o["qref"][:, none] == q[:, none])
+    assert o["convflag"][0, 0] == 0 and o["kLCLs"][0, 0] == 0           # dry column
+    assert o["kLCLs"][0, 1] == 25                                        # saturated lowest level: LCL there
+    # increments relax towards the reference profiles on tau_bm where deep convection changed only the T reference
+    deep = o["convflag"] == 2
+    k = np.arange(25)[:, None, None] + 1 >= o["kLZBs"][None]
+    sel = deep[None] & k
+    assert np.allclose(o["deltaT"][sel], -(t - o["Tref"])[sel] * dt / sbm.tau_bm, rtol=1e-10, atol=1e-13)
+    # only the last column keeps its relaxation rates (array assignment inside the reference's column loop)
+    assert np.count_nonzero(o["invtau_q_relaxation"].ravel()[:-1]) == 0
