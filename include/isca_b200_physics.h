@@ -155,6 +155,44 @@ int isca_b200_qe_moist_convection(IscaPhysics p, double dt, const double* Tin, c
  * synthetic resident columns; returns average ms per launch (CUDA events) and the algorithmic bytes per launch. */
 int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, double* bytes);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * idealized_moist_model: atmosphere_mod boundary with idealized_moist_phys as the physics (atmosphere.F90:263-266, 300-302;
+ * idealized_moist_phys.F90:322-731, 819-1395) for the grey-radiation slab-ocean aquaplanet (Frierson test case):
+ * qe_moist_convection | none -> lscale_cond -> two_stream_gray_rad_down -> surface_flux -> two_stream_gray_rad_up ->
+ * [damping_driver rayleigh] -> vert_turb_driver (do_diffusivity) -> gcm_vert_diff_down -> mixed_layer -> gcm_vert_diff_up,
+ * then spectral_dynamics with the sphum grid tracer.  State, surface fields and all tendencies stay on the device.
+ * Not built: bucket hydrology, land, clouds, RRTMG/Socrates, the other convection schemes (create fails loudly). */
+#include "isca_b200.h"
+typedef struct IscaMoist_t* IscaMoist;
+typedef struct IscaMoistConfig {
+  int abi_version;                 /* 1 */
+  int convection_scheme;           /* 0 'NONE', 1 'SIMPLE_BETTS_MILLER' (idealized_moist_phys.F90:391-426) */
+  int do_damping;                  /* damping_driver rayleigh sponge */
+  double roughness_mom, roughness_heat, roughness_moist;      /* idealized_moist_phys_nml :136-138 */
+  double mixed_layer_depth, albedo_value, rho_cp;             /* mixed_layer_nml depth, albedo_value; constants RHO_CP */
+  double constant_gust;            /* vert_turb_driver_nml, gust_scheme = 'constant' */
+} IscaMoistConfig;
+
+int isca_b200_moist_default_config(IscaMoistConfig* cfg);
+/* dyn: the dynamical-core namelist (num_tracers must be 1 = sphum); phys: scheme namelists (its grid sizes are overwritten) */
+int isca_b200_moist_create(const IscaConfig* dyn, const IscaPhysicsConfig* phys, const IscaMoistConfig* mc, IscaMoist* out);
+int isca_b200_moist_destroy(IscaMoist m);
+const char* isca_b200_moist_last_error(IscaMoist m);            /* m may be NULL */
+/* the dynamical core inside (isca_b200_cold_start / set_grid_state / get_field ... operate on it) */
+IscaHandle isca_b200_moist_dycore(IscaMoist m);
+/* idealized_moist_phys_init after the atmospheric state is set: t_surf = tg(lowest level, current) + 1 (:643), q_surf = 0,
+ * gust = 1, heat capacity = depth * RHO_CP, albedo = albedo_value */
+int isca_b200_moist_init(IscaMoist m);
+/* n calls of atmosphere(Time) */
+int isca_b200_moist_step(IscaMoist m, int n_steps);
+/* 2-D fields [J][I] of the last step: 0 t_surf, 1 precip (kg/m2/s), 2 flux_t, 3 flux_q, 4 z_pbl, 5 net_surf_sw_down,
+ * 6 surf_lw_down, 7 convective rain, 8 cape, 9 convflag, 10 q_surf, 11 u_star, 12 b_star, 13 flux_u, 14 flux_v, 15 delta_t_surf;
+ * 3-D [K][J][I]: 32 dt_ug, 33 dt_vg, 34 dt_tg, 35 dt_tracers(sphum) (physics tendencies), 36 diff_m, 37 diff_t */
+int isca_b200_moist_get(IscaMoist m, int id, double* host);
+int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
+/* average ms per step of the last isca_b200_moist_step call (CUDA events), and of its physics part */
+int isca_b200_moist_timing(IscaMoist m, double* ms_step, double* ms_physics);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,10 +224,18 @@ def _in(a, shape=None, dtype=np.float64):
 class Atmosphere:
     """atmosphere_mod mirror.  State lives on the GPU; fields are fetched lazily."""
 
-    def __init__(self, config: IscaConfigStruct, rank: int = 0, nranks: int = 1, nccl_unique_id: bytes | None = None):
+    def __init__(self, config: IscaConfigStruct, rank: int = 0, nranks: int = 1, nccl_unique_id: bytes | None = None,
+                 _adopt_handle=None):
         self.lib = load_library()
         self.cfg = config
         self.h = C.c_void_p()
+        self._owns = _adopt_handle is None
+        if _adopt_handle is not None:              # a core owned by another object (the moist-model driver)
+            self.h = C.c_void_p(_adopt_handle)
+            self.I, self.J, self.K = config.lon_max, config.lat_max, config.num_levels
+            self.M, self.N = config.num_fourier, config.num_spherical
+            self.Jloc = self.J
+            return
         uid = None
         if nccl_unique_id is not None:
             self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
@@ -279,7 +287,8 @@ class Atmosphere:
 
     def atmosphere_end(self):
         if self.h is not None:
-            self.lib.isca_b200_destroy(self.h)
+            if self._owns:
+                self.lib.isca_b200_destroy(self.h)
             self.h = None
 
     def __del__(self):

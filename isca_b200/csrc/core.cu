@@ -7,6 +7,7 @@
 #include "grid.h"
 #include "nccl_dyn.h"
 #include "tracer.h"
+#include "core_internal.h"
 #include <cstring>
 #include <map>
 #include <algorithm>
@@ -414,7 +415,7 @@ static void dev_forward(H& h, const LevDesc* levs, int nlev, double2* spec, int 
 // ---------------------------------------------------------------------------------------------
 // one time step: atmosphere(Time) (atmosphere.F90:276-352)
 // ---------------------------------------------------------------------------------------------
-static void step_once(H& h, int physics_on, const double* dtu_in, const double* dtv_in, const double* dtt_in) {
+static void step_once(H& h, int physics_on, const double* dtu_in, const double* dtv_in, const double* dtt_in, const double* dtq_in = nullptr) {
   const Geometry& g = h.g; const int K = g.K;
   const int prev = h.previous, cur = h.current, fut = 1 - cur;
   const double delta_t = (prev == cur) ? h.cfg.dt_atmos : 2 * h.cfg.dt_atmos;     // atmosphere.F90:292-296
@@ -465,6 +466,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
     ta.trdamp = sink_s > 0. ? 1. / sink_s : 0.;
     ta.robert_coeff = c.tracer_robert_coeff < 0. ? c.robert_coeff : c.tracer_robert_coeff;
     ta.raw_filter_coeff = c.raw_filter_coeff; ta.water_limit = c.water_correction_limit; ta.physics_on = physics_on;
+    ta.dt_q_in = dtq_in;
     launch_tracer_source(h.dt, pr, ta, st);
     launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_W_PREV, h.red_tmp.p, st);
     allreduce_scalars(h, h.scal.p + SC_W_PREV, 1, NCCL_SUM);
@@ -945,6 +947,36 @@ int isca_b200_spectral_dynamics(IscaHandle h, const double* dt_psg, const double
     launch_press_heights(h->dt, h->pr, h->T[h->previous].p, h->ps[h->previous].p, h->phis.p, h->x_grid.p, nullptr, nullptr, nullptr, h->st);
     CK(cudaMemcpyAsync(p_full, h->x_grid.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   }
+  check_t_flag(*h);
+  API_END(h)
+}
+
+// ---- internal (C++) interface used by the moist-model driver (moist_model.cu); see core_internal.h
+int isca_core_view(IscaHandle h, IscaCoreView* v) {
+  API_BEGIN(h)
+  for (int s = 0; s < 2; ++s) {
+    launch_materialize_t(h->dt, h->T[s].p, h->scal.p, s, h->st);
+    v->u[s] = h->u[s].p; v->v[s] = h->v[s].p; v->T[s] = h->T[s].p; v->q[s] = h->q[s].p; v->ps[s] = h->ps[s].p;
+  }
+  v->phis = h->phis.p; v->wg_full = h->wg_full.p; v->rad_lat = h->d_rad_lat.p + h->g.j0;
+  v->I = h->g.I; v->Jloc = h->g.Jloc; v->K = h->g.K; v->j0 = h->g.j0; v->previous = h->previous; v->current = h->current;
+  v->st = h->st; v->dt_atmos = h->cfg.dt_atmos; v->grav = h->cfg.grav; v->num_tracers = h->cfg.num_tracers; v->nranks = h->g.P;
+  API_END(h)
+}
+int isca_core_press_heights(IscaHandle h, int slot, double* p_full, double* p_half, double* z_full, double* z_half) {
+  API_BEGIN(h)
+  launch_materialize_t(h->dt, h->T[slot].p, h->scal.p, slot, h->st);
+  launch_press_heights(h->dt, h->pr, h->T[slot].p, h->ps[slot].p, h->phis.p, p_full, p_half, z_full, z_half, h->st);
+  API_END(h)
+}
+int isca_core_step_ext(IscaHandle h, const double* dtu, const double* dtv, const double* dtt, const double* dtq) {
+  API_BEGIN(h)
+  if (dtq && h->cfg.num_tracers < 1) throw std::runtime_error("no tracer configured");
+  step_once(*h, 0, dtu, dtv, dtt, dtq);
+  API_END(h)
+}
+int isca_core_check(IscaHandle h) {
+  API_BEGIN(h)
   check_t_flag(*h);
   API_END(h)
 }

@@ -191,6 +191,10 @@ __global__ void rayleigh_kernel(PhysConst c, size_t ncol, int K, int nlev, doubl
   }
 }
 
+}  // namespace
+
+namespace isca_phys {
+
 void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd) {
   int nb = (int)((p->ncol + 127) / 128);
   lscale_cond_kernel<<<nb, 128, 0, p->st>>>(p->svp, p->pc, (int)p->ncol, p->K, t, q, pf, ph, rain, td, qd, p->d_err);
@@ -219,7 +223,7 @@ void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, con
                                               delt, p->cfg.do_conserve_energy, pf, u, v, udt, vdt, tdt);
 }
 
-}  // namespace
+}  // namespace isca_phys
 
 extern "C" {
 
@@ -307,7 +311,7 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
 int isca_b200_physics_destroy(IscaPhysics p) {
   if (!p) return 0;
   if (p->d_err) cudaFree(p->d_err);
-  if (p->st) cudaStreamDestroy(p->st);
+  if (p->st && p->owns_stream) cudaStreamDestroy(p->st);
   delete p;
   return 0;
 }

@@ -80,6 +80,7 @@ struct IscaPhysics_t {
   bool vert_diff_down_done = false;
   int* d_err = nullptr;
   cudaStream_t st = nullptr;
+  bool owns_stream = true;              // false when the moist-model driver runs the kernels on the dynamical core's stream
   std::string err;
   size_t ncol = 0; int K = 0;
 };
@@ -116,13 +117,21 @@ inline int finish(IscaPhysics p, const char* what) {
 }
 inline int col_blocks(IscaPhysics p, int threads) { return (int)((p->ncol + threads - 1) / threads); }
 
-// device-pointer launches shared between files (physics_diff.cu)
+// device-pointer launches shared between files
+void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd);
+void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* alb, double* sw, double* lw);
+void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* ts, const double* alb, double* tdt, double* olr);
+int rayleigh_nlev(const double* pref, int K, double pb);
+void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, const double* u, const double* v, double* udt, double* vdt, double* tdt);
 int prepare_vert_diff_state(IscaPhysics p);
 void launch_vert_diff_down(IscaPhysics p, double delt, const double* u, const double* v, const double* t, const double* q,
                            const double* diff_m, const double* diff_t, const double* p_half, const double* z_full, double* tau_u,
                            double* tau_v, const double* dtau_du, const double* dtau_dv, double* dt_u, double* dt_v, double* dt_t,
                            const double* dt_q, double* diss);
 void launch_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q);
+void launch_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double* flux_t, const double* flux_q, const double* flux_r,
+                        const double* net_surf_sw_down, const double* surf_lw_down, const double* dhdt_surf, const double* dedt_surf,
+                        const double* dedq_surf, const double* drdt_surf, const double* dhdt_atm, const double* dedq_atm, double* delta_t_surf);
 void launch_surface_flux(IscaPhysics p, const IscaSurfaceFluxArgs& dev);     // physics_surface.cu; device pointers
 int build_lcl_table(IscaPhysics p);                                             // physics_conv.cu
 void launch_sbm_convection(IscaPhysics p, double dt, const double* Tin, const double* qin, const double* p_full, const double* p_half,

@@ -236,6 +236,21 @@ void launch_vert_diff_up(IscaPhysics p, double delt, double* dt_t, double* dt_q)
 
 int prepare_vert_diff_state(IscaPhysics p) { return ensure_state(p); }
 
+void launch_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double* flux_t, const double* flux_q, const double* flux_r,
+                        const double* net_surf_sw_down, const double* surf_lw_down, const double* dhdt_surf, const double* dedt_surf,
+                        const double* dedq_surf, const double* drdt_surf, const double* dhdt_atm, const double* dedq_atm, double* delta_t_surf) {
+  const size_t nc = p->ncol;
+  MixedArgs a;
+  a.ncol = (int)nc; a.dt = dt; a.cp_air = p->cfg.cp_air; a.hlv = p->cfg.hlv; a.evaporation = p->cfg.evaporation;
+  a.t_surf = t_surf; a.flux_t = flux_t; a.flux_q = flux_q; a.flux_r = flux_r; a.sw = net_surf_sw_down; a.lw = surf_lw_down;
+  a.dhdt_surf = dhdt_surf; a.dedt_surf = dedt_surf; a.dedq_surf = dedq_surf; a.drdt_surf = drdt_surf; a.dhdt_atm = dhdt_atm;
+  a.dedq_atm = dedq_atm;
+  a.heat_cap = p->state[ST_ML_HEAT_CAP].p; a.qflux = p->state[ST_ML_QFLUX].p; a.dtmass = p->state[ST_TRI_DTMASS].p;
+  a.dflux_t = p->state[ST_TRI_DFLUX_T].p; a.dflux_q = p->state[ST_TRI_DFLUX_Q].p; a.delta_t = p->state[ST_TRI_DELTA_T].p;
+  a.delta_q = p->state[ST_TRI_DELTA_Q].p; a.delta_t_surf = delta_t_surf;
+  mixed_layer_kernel<<<(int)((nc + 255) / 256), 256, 0, p->st>>>(a, p->d_err);
+}
+
 }  // namespace isca_phys
 
 extern "C" {
@@ -298,14 +313,7 @@ int isca_b200_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double
                           dhdt_atm, dedq_atm};
   for (int i = 0; i < 12; ++i) if (up(p, b[i], in[i], nc)) return 1;
   if (!b[12].ensure(nc)) return fail(p, "cudaMalloc failed");
-  MixedArgs a;
-  a.ncol = (int)nc; a.dt = dt; a.cp_air = p->cfg.cp_air; a.hlv = p->cfg.hlv; a.evaporation = p->cfg.evaporation;
-  a.t_surf = b[0].p; a.flux_t = b[1].p; a.flux_q = b[2].p; a.flux_r = b[3].p; a.sw = b[4].p; a.lw = b[5].p; a.dhdt_surf = b[6].p;
-  a.dedt_surf = b[7].p; a.dedq_surf = b[8].p; a.drdt_surf = b[9].p; a.dhdt_atm = b[10].p; a.dedq_atm = b[11].p;
-  a.heat_cap = p->state[ST_ML_HEAT_CAP].p; a.qflux = p->state[ST_ML_QFLUX].p; a.dtmass = p->state[ST_TRI_DTMASS].p;
-  a.dflux_t = p->state[ST_TRI_DFLUX_T].p; a.dflux_q = p->state[ST_TRI_DFLUX_Q].p; a.delta_t = p->state[ST_TRI_DELTA_T].p;
-  a.delta_q = p->state[ST_TRI_DELTA_Q].p; a.delta_t_surf = b[12].p;
-  mixed_layer_kernel<<<(int)((nc + 255) / 256), 256, 0, p->st>>>(a, p->d_err);
+  launch_mixed_layer(p, dt, b[0].p, b[1].p, b[2].p, b[3].p, b[4].p, b[5].p, b[6].p, b[7].p, b[8].p, b[9].p, b[10].p, b[11].p, b[12].p);
   if (down(p, b[0], t_surf, nc)) return 1;
   if (delta_t_surf && down(p, b[12], delta_t_surf, nc)) return 1;
   int e = 0;

@@ -33,7 +33,7 @@ __global__ void tracer_source_kernel(DevTables t, Params pr, TracerArgs a) {
   for (int k = 0; k < K; ++k) {
     const size_t e = (size_t)k * plane + col;
     const double r = a.q_prev[e];
-    double rdt = 0.0;
+    double rdt = a.dt_q_in ? a.dt_q_in[e] : 0.0;
     if (a.physics_on && !pr.no_forcing) {
       // rst = rm + dt*rdt (rdt = 0 on entry); source = flux/pmass in the lowest layer; sink = rdamp*rst
       double source = 0.0;

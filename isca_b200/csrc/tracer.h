@@ -24,6 +24,7 @@ struct TracerArgs {
   double *part;                    // per-column partials [3][Jloc*I]
   double delta_t, trflux, trdamp, robert_coeff, raw_filter_coeff, water_limit;
   int physics_on;
+  const double* dt_q_in;           // externally computed tendency (moist physics), added to the source; may be null
 };
 
 void launch_tracer_source(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);

@@ -1,0 +1,128 @@
+"""idealized_moist_model mirror (include/isca_b200_physics.h, section idealized_moist_model): the atmosphere_mod boundary
+with idealized_moist_phys as physics (atmos_spectral/driver/solo/atmosphere.F90:263-266, 300-302 and
+idealized_moist_phys.F90).  The whole step -- column physics and spectral dynamics -- runs on the GPU."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from .api import load_library, IscaError, Atmosphere, IscaConfigStruct
+from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
+
+MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
+                 "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
+                 "isca_b200_moist_set_t_surf", "isca_b200_moist_timing"]
+
+FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
+                 q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15)
+FIELDS_3D = dict(dt_ug=32, dt_vg=33, dt_tg=34, dt_qg=35, diff_m=36, diff_t=37)
+CONVECTION = {"NONE": 0, "SIMPLE_BETTS_MILLER": 1}
+
+
+class IscaMoistConfigStruct(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("abi_version", "convection_scheme", "do_damping")] + \
+               [(n, C.c_double) for n in ("roughness_mom", "roughness_heat", "roughness_moist", "mixed_layer_depth", "albedo_value", "rho_cp",
+                                          "constant_gust")]
+
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = _physics_lib()
+    if not _bound:
+        vp, dp = C.c_void_p, C.POINTER(C.c_double)
+        lib.isca_b200_moist_default_config.argtypes = [C.POINTER(IscaMoistConfigStruct)]
+        lib.isca_b200_moist_create.argtypes = [C.POINTER(IscaConfigStruct), C.POINTER(IscaPhysicsConfigStruct), C.POINTER(IscaMoistConfigStruct),
+                                               C.POINTER(vp)]
+        lib.isca_b200_moist_destroy.argtypes = [vp]
+        lib.isca_b200_moist_last_error.argtypes = [vp]
+        lib.isca_b200_moist_last_error.restype = C.c_char_p
+        lib.isca_b200_moist_dycore.argtypes = [vp]
+        lib.isca_b200_moist_dycore.restype = vp
+        lib.isca_b200_moist_init.argtypes = [vp]
+        lib.isca_b200_moist_step.argtypes = [vp, C.c_int]
+        lib.isca_b200_moist_get.argtypes = [vp, C.c_int, dp]
+        lib.isca_b200_moist_set_t_surf.argtypes = [vp, dp]
+        lib.isca_b200_moist_timing.argtypes = [vp, dp, dp]
+        _bound = True
+    return lib
+
+
+class MoistAtmosphere:
+    """atmosphere_init / atmosphere / atmosphere_end of the idealized moist model.
+
+    dyn_config: IscaConfigStruct of the dynamical core (api.make_config / config_from_namelist_object, num_tracers = 1);
+    physics_nml: keyword namelist values of the column schemes (IscaPhysicsConfig field names);
+    convection_scheme, do_damping, roughness_*, mixed_layer_depth, albedo_value, constant_gust: idealized_moist_phys_nml /
+    mixed_layer_nml / vert_turb_driver_nml values."""
+
+    def __init__(self, dyn_config, physics_nml=None, convection_scheme="SIMPLE_BETTS_MILLER", **moist_nml):
+        lib = _lib()
+        self._lib = lib
+        pc = IscaPhysicsConfigStruct()
+        lib.isca_b200_physics_default_config(C.byref(pc))
+        names = {f[0] for f in IscaPhysicsConfigStruct._fields_}
+        for k, v in (physics_nml or {}).items():
+            if k not in names:
+                raise IscaError(f"unknown physics namelist variable {k}")
+            setattr(pc, k, v)
+        mc = IscaMoistConfigStruct()
+        lib.isca_b200_moist_default_config(C.byref(mc))
+        if convection_scheme.upper() not in CONVECTION:
+            raise IscaError(f"idealized_moist_phys: {convection_scheme} is not a valid convection scheme of this build")
+        mc.convection_scheme = CONVECTION[convection_scheme.upper()]
+        mnames = {f[0] for f in IscaMoistConfigStruct._fields_}
+        for k, v in moist_nml.items():
+            if k not in mnames:
+                raise IscaError(f"unknown namelist variable {k}")
+            setattr(mc, k, v)
+        self._h = C.c_void_p()
+        if lib.isca_b200_moist_create(C.byref(dyn_config), C.byref(pc), C.byref(mc), C.byref(self._h)) != 0:
+            raise IscaError("atmosphere_init: " + lib.isca_b200_moist_last_error(None).decode())
+        self.core = Atmosphere(dyn_config, _adopt_handle=lib.isca_b200_moist_dycore(self._h))
+        self.s2 = (dyn_config.lat_max, dyn_config.lon_max)
+        self.s3 = (dyn_config.num_levels,) + self.s2
+
+    def _ck(self, rc, where):
+        if rc != 0:
+            raise IscaError(f"{where}: " + self._lib.isca_b200_moist_last_error(self._h).decode())
+
+    def idealized_moist_phys_init(self):
+        """after the atmospheric state is in place (cold start or set_grid_state on .core)"""
+        self._ck(self._lib.isca_b200_moist_init(self._h), "idealized_moist_phys_init")
+
+    def atmosphere(self, n_steps=1):
+        self._ck(self._lib.isca_b200_moist_step(self._h, n_steps), "atmosphere")
+
+    def get(self, name):
+        if name in FIELDS_2D:
+            out, i = np.empty(self.s2), FIELDS_2D[name]
+        elif name in FIELDS_3D:
+            out, i = np.empty(self.s3), FIELDS_3D[name]
+        else:
+            raise IscaError(f"unknown field {name}")
+        self._ck(self._lib.isca_b200_moist_get(self._h, i, out.ctypes.data_as(C.POINTER(C.c_double))), "get")
+        return out
+
+    def set_t_surf(self, t_surf):
+        a = np.ascontiguousarray(t_surf, dtype=np.float64)
+        if a.shape != self.s2:
+            raise IscaError("t_surf has the wrong shape")
+        self._ck(self._lib.isca_b200_moist_set_t_surf(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_t_surf")
+
+    def timing(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self._lib.isca_b200_moist_timing(self._h, C.byref(a), C.byref(b)), "timing")
+        return a.value, b.value
+
+    def atmosphere_end(self):
+        if self._h:
+            self.core.h = None
+            self._lib.isca_b200_moist_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.atmosphere_end()
+        except Exception:
+            pass

@@ -147,6 +147,24 @@ def held_suarez_config(res: str, num_levels: int, dt_atmos: float, num_tracers: 
     return c
 
 
+def frierson_config(res: str, num_levels: int, dt_atmos: float) -> Config:
+    """exp/test_cases/frierson/frierson_test_case.py:153-165 spectral_dynamics_nml (uneven_sigma levels instead of the
+    'input' list, as SURVEY section 8d configures the benchmark cases): grey-radiation moist aquaplanet."""
+    c = Config(**RESOLUTIONS[res], num_levels=num_levels, dt_atmos=dt_atmos)
+    c.damping_order = 4
+    c.water_correction_limit = 200.0e2
+    c.reference_sea_level_press = 1.0e5
+    c.valid_range_t = (100.0, 800.0)
+    c.initial_sphum = 2.0e-6
+    c.vert_coord_option = "uneven_sigma"
+    c.scale_heights = 11.0
+    c.exponent = 7.0
+    c.surf_res = 0.5
+    c.robert_coeff = 0.03
+    c.num_tracers = 1
+    return c
+
+
 # --------------------------------------------------------------------------------------
 # Gaussian grid and Legendre tables
 # --------------------------------------------------------------------------------------
@@ -1072,7 +1090,9 @@ class SpectralCore:
         dt_tg = np.zeros_like(dt_ug)
         dt_psg = np.zeros_like(self.psg[0])
         dt_tracers = [np.zeros_like(dt_ug) for _ in range(cfg.num_tracers)]
-        if physics:
+        if physics and getattr(self, "moist_phys", None) is not None:      # idealized_moist_model (atmosphere.F90:300-302)
+            dt_ug, dt_vg, dt_tg, dt_tracers = self.moist_phys(self, delta_t)
+        elif physics:
             r = [self.grid_tracers[prev, n] for n in range(cfg.num_tracers)]
             dt_ug, dt_vg, dt_tg, dt_tracers = self.hs(delta_t, self.p_half[cur], self.p_full[cur],
                                                       self.ug[prev], self.vg[prev], self.tg[prev], r,

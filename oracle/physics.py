@@ -972,3 +972,113 @@ class SBMConvection:
                 if i == I - 1 and j == J - 1:
                     out["invtau_q_relaxation"][j, i] = r["invtau_q"]; out["invtau_t_relaxation"][j, i] = r["invtau_t"]
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# idealized_moist_phys dispatcher (atmos_spectral/driver/solo/idealized_moist_phys.F90:819-1395) for the grey-radiation /
+# slab-ocean aquaplanet configuration of the Frierson test case (exp/test_cases/frierson/frierson_test_case.py):
+# convection_scheme SIMPLE_BETTS_MILLER or NONE, lscale_cond, two_stream_gray, surface_flux, mixed_layer_bc, turb
+# (vert_turb_driver with do_diffusivity), gcm_vert_diff; optional rayleigh damping_driver.  No bucket, no land, no clouds.
+DENS_H2O = 1000.0
+RHO_CP = 1.035e3 * 3989.24495292815
+
+
+@dataclass
+class MoistPhysConfig:
+    convection_scheme: str = "SIMPLE_BETTS_MILLER"
+    do_damping: bool = False
+    roughness_mom: float = 0.05
+    roughness_heat: float = 0.05
+    roughness_moist: float = 0.05
+    do_virtual: bool = False
+    # mixed_layer_nml
+    depth: float = 40.0
+    albedo_value: float = 0.06
+    evaporation: bool = True
+    # lscale_cond_nml
+    hc: float = 1.0
+    do_evap: bool = False
+    # vert_turb_driver_nml
+    constant_gust: float = 1.0
+    # damping_driver_nml
+    trayfric: float = 0.0
+    sponge_pbottom: float = 50.0
+
+
+class IdealizedMoistPhys:
+    def __init__(self, cfg: MoistPhysConfig, dt_atmos, rad_lat, z_surf, t_surf_init, pref=None, svp=None, rad=None, mo=None,
+                 sflux=None, diff=None, sbm=None):
+        self.c, self.dt_real = cfg, float(dt_atmos)
+        self.svp = svp or SatVaporPres()
+        self.rad = GreyRadiation(rad or GreyRadConfig())
+        self.mo, self.sflux, self.diffc = mo or MOConfig(), sflux or SurfaceFluxConfig(), diff or DiffusivityConfig()
+        self.sbm = sbm or SBMConvection(self.svp)
+        self.rad_lat, self.z_surf, self.pref = rad_lat, z_surf, pref
+        shp = rad_lat.shape
+        self.t_surf = t_surf_init + 1.0                                   # idealized_moist_phys.F90:643
+        self.q_surf = np.zeros(shp); self.gust = np.ones(shp)
+        self.albedo = np.full(shp, cfg.albedo_value)
+        self.heat_capacity = np.full(shp, cfg.depth * RHO_CP)
+        self.ocean_qflux = np.zeros(shp)
+        self.diag = {}
+
+    def __call__(self, core, delta_t):
+        """core: the dynamical core state (ug, vg, tg, grid_tracers, p_half, p_full, z_half, z_full at two time levels)."""
+        c = self.c
+        prev, cur = core.previous, core.current
+        K = core.tg.shape[1]
+        tg_p, q_p, ug_p, vg_p = core.tg[prev], core.grid_tracers[prev, 0], core.ug[prev], core.vg[prev]
+        dt_ug, dt_vg, dt_tg, dt_q = (np.zeros_like(tg_p) for _ in range(4))
+        zero2 = np.zeros_like(self.t_surf)
+        if c.convection_scheme == "SIMPLE_BETTS_MILLER":
+            o = self.sbm(delta_t, tg_p, q_p, core.p_full[prev], core.p_half[prev])
+            conv_dt_tg, conv_dt_qg, rain = o["deltaT"], o["deltaq"], o["rain"]
+            tg_tmp, qg_tmp = conv_dt_tg + tg_p, conv_dt_qg + q_p
+            conv_dt_tg, conv_dt_qg = conv_dt_tg / delta_t, conv_dt_qg / delta_t
+            rain = rain / delta_t
+            precip = rain
+            self.diag.update(convflag=o["convflag"], cape=o["CAPE"])
+        elif c.convection_scheme == "NONE":
+            conv_dt_tg, conv_dt_qg = np.zeros_like(tg_p), np.zeros_like(tg_p)
+            tg_tmp, qg_tmp = tg_p, q_p
+            precip = zero2
+        else:
+            raise ValueError("convection scheme not restated")
+        dt_tg = dt_tg + conv_dt_tg
+        dt_q = dt_q + conv_dt_qg
+        rain, cond_dt_tg, cond_dt_qg = lscale_cond(self.svp, tg_tmp, qg_tmp, core.p_full[prev], core.p_half[prev], hc=c.hc, do_evap=c.do_evap)
+        cond_dt_tg, cond_dt_qg = cond_dt_tg / delta_t, cond_dt_qg / delta_t
+        rain = rain / delta_t
+        precip = precip + rain
+        dt_tg = dt_tg + cond_dt_tg
+        dt_q = dt_q + cond_dt_qg
+        d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p)
+        net_surf_sw_down = (1.0 - self.albedo) * d["sw_down_surf"]
+        surf_lw_down = d["surf_lw_down"]
+        sf = surface_flux(self.svp, self.mo, self.sflux, t_atm=tg_p[K - 1], q_atm_in=q_p[K - 1], u_atm=ug_p[K - 1], v_atm=vg_p[K - 1],
+                          p_atm=core.p_full[cur][K - 1], z_atm=core.z_full[cur][K - 1] - self.z_surf, p_surf=core.p_half[cur][K],
+                          t_surf=self.t_surf, t_ca=self.t_surf, q_surf=self.q_surf, u_surf=zero2, v_surf=zero2,
+                          rough_mom=np.full_like(zero2, c.roughness_mom), rough_heat=np.full_like(zero2, c.roughness_heat),
+                          rough_moist=np.full_like(zero2, c.roughness_moist), rough_scale=np.full_like(zero2, c.roughness_mom),
+                          gust=self.gust, land=np.zeros(zero2.shape, bool))
+        self.q_surf = sf["q_surf"]
+        dt_tg, _ = self.rad.up(self.t_surf, self.albedo, core.p_half[cur], dt_tg)
+        if c.do_damping:
+            udt, vdt, tdt, _ = rayleigh_sponge(delta_t, core.p_full[cur], ug_p, vg_p, self.pref, c.sponge_pbottom, c.trayfric, True)
+            dt_ug, dt_vg, dt_tg = dt_ug + udt, dt_vg + vdt, dt_tg + tdt
+        # vert_turb_driver (do_diffusivity) on the `current` fields (use_tau = .true.)
+        z_pbl, diff_m, diff_t = diffusivity(self.diffc, self.mo, core.tg[cur], core.grid_tracers[cur, 0], core.ug[cur], core.vg[cur],
+                                            core.p_full[cur], core.p_half[cur], core.z_full[cur], core.z_half[cur], sf["u_star"], sf["b_star"],
+                                            np.zeros_like(tg_p), np.zeros_like(tg_p))
+        self.gust = np.full_like(zero2, c.constant_gust)
+        r = gcm_vert_diff_down(delta_t, ug_p, vg_p, tg_p, q_p, diff_m, diff_t, core.p_half[cur], core.p_full[cur], core.z_full[cur],
+                               sf["flux_u"], sf["flux_v"], sf["dtaudu_atm"], sf["dtaudv_atm"], dt_ug, dt_vg, dt_tg, dt_q,
+                               do_conserve_energy=True, use_virtual_temp=c.do_virtual)
+        dt_ug, dt_vg = r["dt_u"], r["dt_v"]
+        self.t_surf, tri, dts = mixed_layer(r["tri"], self.dt_real, self.t_surf, sf["flux_t"], sf["flux_q"], sf["flux_r"], net_surf_sw_down,
+                                            surf_lw_down, sf["dhdt_surf"], sf["dedt_surf"], sf["dedq_surf"], sf["drdt_surf"], sf["dhdt_atm"],
+                                            sf["dedq_atm"], self.heat_capacity, self.ocean_qflux, evaporation=c.evaporation)
+        dt_tg, dt_q = gcm_vert_diff_up(delta_t, tri)
+        self.diag.update(precip=precip, z_pbl=z_pbl, flux_t=sf["flux_t"], flux_q=sf["flux_q"], delta_t_surf=dts, diff_m=diff_m, diff_t=diff_t,
+                         net_surf_sw_down=net_surf_sw_down, surf_lw_down=surf_lw_down)
+        return dt_ug, dt_vg, dt_tg, [dt_q]

@@ -359,8 +359,15 @@ def test_qe_moist_convection(mods, K, J, I, seed, nml):
     assert flags[1] > 0 and flags[2] > 0                                 # the case exercises shallow and deep columns
     for k in ("convflag", "kLZBs", "kLCLs"):
         assert np.array_equal(g[k], o[k]), k                             # bit-exact integer outputs
-    for k in ("rain", "CAPE", "CIN", "deltaT", "deltaq", "qref", "Tref", "invtau_q_relaxation", "invtau_t_relaxation"):
+    for k in ("rain", "CAPE", "CIN", "deltaT", "deltaq", "Tref", "invtau_q_relaxation", "invtau_t_relaxation"):
         assert rel(g[k], o[k]) < 1e-10, k
+    # Shallow convection that lowers its top all the way to the lowest level ends with a precipitation integral that is zero up
+    # to rounding; the reference then branches on its sign (level_of_zero_precip, qe_moist_convection.F90:868-872): either the
+    # lowest level keeps the reference humidity with an increment of O(1e-19), or it is reset to the model value with a zero
+    # increment.  Both are the same physical answer; the diagnostic qref of that one level is excluded there.
+    edge = (o["convflag"] == 1) & ((np.abs(o["deltaq"][-1]) < 1e-15) | (np.abs(g["deltaq"][-1]) < 1e-15))
+    m = np.ones(o["qref"].shape, bool); m[-1] = ~edge
+    assert float(np.abs(g["qref"] - o["qref"])[m].max() / np.abs(o["qref"]).max()) < 1e-10
     assert np.all(g["snow"] == 0)
     dp = ph[1:] - ph[:-1]
     assert np.abs(g["rain"] + (g["deltaq"] * dp).sum(0) / O.GRAV).max() < 1e-13
