@@ -120,3 +120,21 @@ def test_physics_no_cpu_fallback(lib_built):
     with pytest.raises(api.IscaError) as e:
         physics.ColumnPhysics(8, 4, 5)
     assert "CUDA" in str(e.value)
+
+
+def test_moist_config_struct_layout(lib_built, tmp_path):
+    from isca_b200 import moist
+    fields = [f[0] for f in moist.IscaMoistConfigStruct._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(IscaMoistConfig, {f}));' for f in fields)
+    src = tmp_path / "msz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "isca_b200_physics.h"\nint main(){printf("%zu\\n", sizeof(IscaMoistConfig));' + body + "return 0;}")
+    exe = tmp_path / "msz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == C.sizeof(moist.IscaMoistConfigStruct)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(moist.IscaMoistConfigStruct, f).offset == int(off), f
+    c = moist.IscaMoistConfigStruct()
+    moist._lib().isca_b200_moist_default_config(C.byref(c))
+    # idealized_moist_phys.F90:136-138, mixed_layer.F90:92-95
+    assert (c.roughness_mom, c.roughness_heat, c.roughness_moist, c.mixed_layer_depth, c.albedo_value) == (0.05, 0.05, 0.05, 40.0, 0.06)

@@ -347,7 +347,7 @@ def conv_case(O, K, J, I, seed):
 
 
 @pytest.mark.parametrize("K,J,I,seed,nml", [(25, 16, 24, 1, dict(rhbm=0.7, Tmin=160.0, Tmax=350.0)), (40, 24, 32, 2, dict()),
-                                            (10, 8, 16, 3, dict(tau_bm=3600.0, rhbm=0.9, val_inc=0.02))])
+                                            (10, 8, 16, 3, dict(tau_bm=3600.0, rhbm=0.6, val_inc=0.02))])
 def test_qe_moist_convection(mods, K, J, I, seed, nml):
     physics, O = mods
     svp, t, q, pf, ph = conv_case(O, K, J, I, seed)
