@@ -164,6 +164,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # The contract is ONE JSON line on stdout: keep a private handle on the real stdout for it and point fd 1 at stderr so that
+    # library chatter (e.g. NCCL's version banner, printed at communicator creation) cannot land in front of it.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     res, K = args.res, args.levels
@@ -188,7 +194,7 @@ def main():
             "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     # ------------------------------------------------------------------ this repo's CUDA arm
@@ -340,7 +346,7 @@ def main():
         "roofline": roofline, "legendre_gemm": legendre, "kernel_groups_ms": groups_out, "exchange_ms_per_step": exch_ms,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
     return 0
 
 

@@ -15,27 +15,31 @@ namespace {
 
 struct Surf { double mu_delt_n, nu_n, e_n1, f1_delt_n1, f2_delt_n1, delta1_n, delta2_n; };
 
-// vert_diff_down_2 (explicit_tend + compute_e + compute_f) for two fields sharing mu, nu.  xi*(k), dt*(k) load level k,
-// store(k, e, f1, f2) receives the factors of levels 0..K-2.
-template <class XI1, class XI2, class DT1, class DT2, class ST>
-__device__ __forceinline__ Surf down2(int K, double delt, const double* mu, const double* nu, XI1 xi1, XI2 xi2, DT1 dt1, DT2 dt2, ST store) {
+// vert_diff_down_2 (explicit_tend + compute_e + compute_f) for two fields sharing mu, nu.  mu_at(k), nu_at(k) evaluate
+// compute_mu / compute_nu for one level (nu_at only for k >= 1), xi*(k), dt*(k) load level k, store(k, e, f1, f2) receives
+// the factors of levels 0..K-2.  Nothing is kept in thread-local arrays.
+template <class MU, class NU, class XI1, class XI2, class DT1, class DT2, class ST>
+__device__ __forceinline__ Surf down2(int K, double delt, MU mu_at, NU nu_at, XI1 xi1, XI2 xi2, DT1 dt1, DT2 dt2, ST store) {
   Surf s;
   double x1 = xi1(0), x2 = xi2(0);
   double fl1 = 0.0, fl2 = 0.0;                    // fluxx(k)
   double e_prev = 0.0, f1_prev = 0.0, f2_prev = 0.0;
+  double nu_k = 0.0;                              // nu(1) is never referenced by the reference (c(1) = 0)
   for (int k = 0; k < K; ++k) {
+    const double mu_k = mu_at(k);
+    const double nu_k1 = (k < K - 1) ? nu_at(k + 1) : 0.0;
     double d1, d2, a = 0.0, x1p = 0.0, x2p = 0.0, fl1p = 0.0, fl2p = 0.0;
     if (k < K - 1) {
       x1p = xi1(k + 1); x2p = xi2(k + 1);
-      fl1p = nu[k + 1] * (x1p - x1); fl2p = nu[k + 1] * (x2p - x2);
-      d1 = dt1(k) + mu[k] * (fl1p - fl1);
-      d2 = dt2(k) + mu[k] * (fl2p - fl2);
-      a = -mu[k] * nu[k + 1] * delt;
+      fl1p = nu_k1 * (x1p - x1); fl2p = nu_k1 * (x2p - x2);
+      d1 = dt1(k) + mu_k * (fl1p - fl1);
+      d2 = dt2(k) + mu_k * (fl2p - fl2);
+      a = -mu_k * nu_k1 * delt;
     } else {
-      d1 = dt1(k) - mu[k] * fl1;
-      d2 = dt2(k) - mu[k] * fl2;
+      d1 = dt1(k) - mu_k * fl1;
+      d2 = dt2(k) - mu_k * fl2;
     }
-    double c = k > 0 ? -mu[k] * nu[k] * delt : 0.0;
+    double c = k > 0 ? -mu_k * nu_k * delt : 0.0;
     double b = 1.0 - a - c;
     if (k < K - 1) {
       double e, f1, f2;
@@ -47,11 +51,11 @@ __device__ __forceinline__ Surf down2(int K, double delt, const double* mu, cons
       store(k, e, f1, f2);
       e_prev = e; f1_prev = f1; f2_prev = f2;
     } else {
-      s.mu_delt_n = mu[k] * delt; s.nu_n = nu[k];
+      s.mu_delt_n = mu_k * delt; s.nu_n = nu_k;
       s.e_n1 = e_prev; s.f1_delt_n1 = f1_prev * delt; s.f2_delt_n1 = f2_prev * delt;
       s.delta1_n = d1 * delt; s.delta2_n = d2 * delt;
     }
-    x1 = x1p; x2 = x2p; fl1 = fl1p; fl2 = fl2p;
+    x1 = x1p; x2 = x2p; fl1 = fl1p; fl2 = fl2p; nu_k = nu_k1;
   }
   return s;
 }
@@ -79,25 +83,19 @@ __global__ void __launch_bounds__(128) vert_diff_down_kernel(DiffArgs a) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= a.ncol) return;
   const int K = a.K; const size_t nc = a.ncol;
-  double mu[ISCA_KMAX], nu[ISCA_KMAX], e[ISCA_KMAX], f1[ISCA_KMAX], f2[ISCA_KMAX];
   auto at = [&](const double* p, int k) { return p[(size_t)k * nc + col]; };
-  // compute_mu, compute_nu(diff_m)
-  {
-    double ph0 = at(a.p_half, 0), tv_prev = 0.0, z_prev = 0.0;
-    for (int k = 0; k < K; ++k) {
-      double ph1 = at(a.p_half, k + 1);
-      mu[k] = a.grav / (ph1 - ph0);
-      double tv = at(a.t, k); if (a.use_virtual) tv = tv * (1.0 + a.d608 * at(a.q, k));
-      double z = at(a.z_full, k);
-      if (k > 0) { double rho_half = 2.0 * ph0 / (a.rdgas * (tv + tv_prev)); nu[k] = rho_half * at(a.diff_m, k) / (z_prev - z); }
-      else nu[k] = 0.0;
-      ph0 = ph1; tv_prev = tv; z_prev = z;
-    }
-  }
+  // compute_mu / compute_nu for one level; the factors of the momentum system use e_global, f_t_global, f_q_global as scratch
+  // (they are rewritten by the temperature / humidity elimination below)
+  auto mu_at = [&](int k) { return a.grav / (at(a.p_half, k + 1) - at(a.p_half, k)); };
+  auto tv_at = [&](int k) { double tv = at(a.t, k); if (a.use_virtual) tv = tv * (1.0 + a.d608 * at(a.q, k)); return tv; };
+  auto nu_of = [&](const double* diff, int k) {
+    double rho_half = 2.0 * at(a.p_half, k) / (a.rdgas * (tv_at(k) + tv_at(k - 1)));
+    return rho_half * at(diff, k) / (at(a.z_full, k - 1) - at(a.z_full, k));
+  };
   // uv_vert_diff
-  Surf s = down2(K, a.delt, mu, nu, [&](int k) { return at(a.u, k); }, [&](int k) { return at(a.v, k); },
+  Surf s = down2(K, a.delt, mu_at, [&](int k) { return nu_of(a.diff_m, k); }, [&](int k) { return at(a.u, k); }, [&](int k) { return at(a.v, k); },
                  [&](int k) { return at(a.dt_u, k); }, [&](int k) { return at(a.dt_v, k); },
-                 [&](int k, double ee, double g1, double g2) { e[k] = ee; f1[k] = g1; f2[k] = g2; });
+                 [&](int k, double ee, double g1, double g2) { size_t o = (size_t)k * nc + col; a.e_g[o] = ee; a.ft_g[o] = g1; a.fq_g[o] = g2; });
   double tau_u = a.tau_u[col], tau_v = a.tau_v[col];
   double delta_u_n = s.delta1_n, delta_v_n = s.delta2_n;
   diff_surface(s.mu_delt_n, s.nu_n, s.e_n1, s.f1_delt_n1, a.dtau_du[col], tau_u, 1.0, delta_u_n);
@@ -108,7 +106,7 @@ __global__ void __launch_bounds__(128) vert_diff_down_kernel(DiffArgs a) {
     double nu_ = delta_u_n / a.delt, nv_ = delta_v_n / a.delt;
     for (int k = K - 1; k >= 0; --k) {
       size_t o = (size_t)k * nc + col;
-      if (k < K - 1) { nu_ = e[k] * nu_ + f1[k]; nv_ = e[k] * nv_ + f2[k]; }
+      if (k < K - 1) { double ee = a.e_g[o]; nu_ = ee * nu_ + a.ft_g[o]; nv_ = ee * nv_ + a.fq_g[o]; }
       double heat = 0.0;
       if (a.conserve) {
         double du = nu_ - a.dt_u[o], dv = nv_ - a.dt_v[o];
@@ -119,18 +117,9 @@ __global__ void __launch_bounds__(128) vert_diff_down_kernel(DiffArgs a) {
     }
   }
   // compute_nu(diff_t), vert_diff_down_2(tt, q)
-  {
-    double tv_prev = 0.0, z_prev = 0.0;
-    for (int k = 0; k < K; ++k) {
-      double tv = at(a.t, k); if (a.use_virtual) tv = tv * (1.0 + a.d608 * at(a.q, k));
-      double z = at(a.z_full, k);
-      if (k > 0) { double rho_half = 2.0 * at(a.p_half, k) / (a.rdgas * (tv + tv_prev)); nu[k] = rho_half * at(a.diff_t, k) / (z_prev - z); }
-      tv_prev = tv; z_prev = z;
-    }
-  }
   const double gcp = a.grav / a.cp_air;
-  s = down2(K, a.delt, mu, nu, [&](int k) { return at(a.t, k) + at(a.z_full, k) * gcp; }, [&](int k) { return at(a.q, k); },
-            [&](int k) { return at(a.dt_t, k); }, [&](int k) { return at(a.dt_q, k); },
+  s = down2(K, a.delt, mu_at, [&](int k) { return nu_of(a.diff_t, k); }, [&](int k) { return at(a.t, k) + at(a.z_full, k) * gcp; },
+            [&](int k) { return at(a.q, k); }, [&](int k) { return at(a.dt_t, k); }, [&](int k) { return at(a.dt_q, k); },
             [&](int k, double ee, double g1, double g2) { size_t o = (size_t)k * nc + col; a.e_g[o] = ee; a.ft_g[o] = g1; a.fq_g[o] = g2; });
   a.tri_delta_t[col] = s.delta1_n + s.mu_delt_n * s.nu_n * s.f1_delt_n1;
   a.tri_dflux_t[col] = -s.nu_n * (1.0 - s.e_n1);

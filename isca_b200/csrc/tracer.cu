@@ -197,115 +197,139 @@ void launch_tracer_flux(const DevTables& t, const FvTables& f, const TracerArgs&
 }
 
 // ---------------------------------------------------------------------------------------------
-// PPM vertical advection (one thread per column; per-thread arrays in local memory)
+// PPM vertical advection, one thread per column.  Nothing is kept in thread-local arrays: the limited parabola edge values
+// go through two scratch planes (q1, q2 of the horizontal step, free by now), slopes and interface values are produced by a
+// sliding window, layer thicknesses are recomputed from pk/bk, and the profile itself is re-read from tr1 (L1/L2 hits).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 tracer_ppm_kernel(DevTables t, Params pr, TracerArgs a) {
   const GeomDev& g = t.g;
   const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
   if (i >= g.I) return;
   const int K = g.K;
   const size_t col = (size_t)jl * g.I + i, plane = (size_t)g.Jloc * g.I;
-  double r[ISCA_KMAX], dz[ISCA_KMAX], rl[ISCA_KMAX], rr[ISCA_KMAX], slp[ISCA_KMAX], w[ISCA_KMAX + 1];
   const double ps_c = a.ps_cur[col];
   const double dt = a.delta_t;
-  for (int k = 0; k < K; ++k) {
-    r[k] = a.tr1[(size_t)k * plane + col];
-    dz[k] = (t.pk[k + 1] + t.bk[k + 1] * ps_c) - (t.pk[k] + t.bk[k] * ps_c);     // dp = p_half(k+1) - p_half(k)
-  }
-  for (int k = 0; k <= K; ++k) w[k] = a.wg[(size_t)k * plane + col];
-  // slope_z(linear=.false., limit=.true.) :504-563
-  for (int k = 1; k < K - 1; ++k) {
-    const double gk = (r[k] - r[k - 1]) / (dz[k] + dz[k - 1]), gk1 = (r[k + 1] - r[k]) / (dz[k + 1] + dz[k]);
-    double s = (gk1 * (2. * dz[k - 1] + dz[k]) + gk * (2. * dz[k + 1] + dz[k])) * dz[k] / (dz[k - 1] + dz[k] + dz[k + 1]);
-    const double rmin = min3(r[k - 1], r[k], r[k + 1]), rmax = max3(r[k - 1], r[k], r[k + 1]);
-    slp[k] = sign1(s) * min3(fabs(s), 2. * (r[k] - rmin), 2. * (rmax - r[k]));
-  }
-  slp[0] = 0.; slp[K - 1] = 0.;
-  // interface values :300-325 with compute_weights :567-629
-  for (int k = 2; k < K - 1; ++k) {
-    const double denom1 = 1.0 / (dz[k - 1] + dz[k]);
-    const double denom2 = 1.0 / (dz[k - 2] + dz[k - 1] + dz[k] + dz[k + 1]);
-    const double denom3 = 1.0 / (2 * dz[k - 1] + dz[k]);
-    const double denom4 = 1.0 / (dz[k - 1] + 2 * dz[k]);
-    const double num3 = dz[k - 2] + dz[k - 1], num4 = dz[k] + dz[k + 1];
+  const double* __restrict__ rp = a.tr1 + col;
+  double* __restrict__ rlp = a.q1 + col;
+  double* __restrict__ rrp = a.q2 + col;
+  auto R = [&](int k) { return __ldg(rp + (size_t)k * plane); };
+  auto DZ = [&](int k) { return (t.pk[k + 1] + t.bk[k + 1] * ps_c) - (t.pk[k] + t.bk[k] * ps_c); };     // dp = p_half(k+1) - p_half(k)
+  // slope_z(linear=.false., limit=.true.) :504-563 for an interior level
+  auto slope = [&](int k, double rm1, double r0, double rp1) {
+    const double dm = DZ(k - 1), d0 = DZ(k), dp = DZ(k + 1);
+    const double gk = (r0 - rm1) / (d0 + dm), gk1 = (rp1 - r0) / (dp + d0);
+    const double sl = (gk1 * (2. * dm + d0) + gk * (2. * dp + d0)) * d0 / (dm + d0 + dp);
+    const double rmin = min3(rm1, r0, rp1), rmax = max3(rm1, r0, rp1);
+    return sign1(sl) * min3(fabs(sl), 2. * (r0 - rmin), 2. * (rmax - r0));
+  };
+  // interface value between levels k-1 and k (:300-325 with compute_weights :567-629), 2 <= k <= K-2
+  auto iface = [&](int k, double rm1, double r0, double slp_k, double slp_km1) {
+    const double d2 = DZ(k - 2), d1 = DZ(k - 1), d0 = DZ(k), dp = DZ(k + 1);
+    const double denom1 = 1.0 / (d1 + d0);
+    const double denom2 = 1.0 / (d2 + d1 + d0 + dp);
+    const double denom3 = 1.0 / (2 * d1 + d0);
+    const double denom4 = 1.0 / (d1 + 2 * d0);
+    const double num3 = d2 + d1, num4 = d0 + dp;
     const double x = num3 * denom3 - num4 * denom4;
-    const double y = 2.0 * dz[k - 1] * dz[k];
-    const double z0 = dz[k - 1] * denom1;
+    const double y = 2.0 * d1 * d0;
+    const double z0 = d1 * denom1;
     const double z1 = z0 + x * y * denom1 * denom2;
-    const double z2 = dz[k - 1] * num3 * denom3 * denom2;
-    const double z3 = dz[k] * num4 * denom4 * denom2;
-    rl[k] = r[k - 1] + z1 * (r[k] - r[k - 1]) - z2 * slp[k] + z3 * slp[k - 1];
-    rr[k - 1] = rl[k];
+    const double z2 = d1 * num3 * denom3 * denom2;
+    const double z3 = d0 * num4 * denom4 * denom2;
+    return rm1 + z1 * (r0 - rm1) - z2 * slp_k + z3 * slp_km1;
+  };
+  // ---- pass 1: limited edge values of every level
+  {
+    double r_m1 = 0.0, r_0 = R(0), r_p1 = R(1);
+    double slp_k = 0.0;                                  // slp(0) = 0
+    double if_k = 0.0;                                   // interface value at the top of level k (valid for 2 <= k <= K-2)
+    for (int k = 0; k < K; ++k) {
+      const double r_p2 = (k + 2 < K) ? R(k + 2) : 0.0;
+      const double slp_k1 = (k + 1 >= 1 && k + 1 <= K - 2) ? slope(k + 1, r_0, r_p1, r_p2) : 0.0;
+      const double if_k1 = (k + 1 >= 2 && k + 1 <= K - 2) ? iface(k + 1, r_0, r_p1, slp_k1, slp_k) : 0.0;
+      double rl, rr;
+      if (k == 0 || k == K - 1) { rl = r_0 - 0.5 * slp_k; rr = r_0 + 0.5 * slp_k; }
+      else {
+        rl = (k == 1) ? r_0 - 0.5 * slp_k : if_k;
+        rr = (k == K - 2) ? r_0 + 0.5 * slp_k : if_k1;
+      }
+      // Colella-Woodward limiter :340-356
+      if ((rr - r_0) * (r_0 - rl) <= 0.0) { rl = r_0; rr = r_0; }
+      if (k != 0 && k != K - 1) {
+        const double rm = rr - rl;
+        const double aa = rm * (r_0 - 0.5 * (rr + rl));
+        const double bq = rm * rm / 6.;
+        if (aa > bq) rl = 3.0 * r_0 - 2.0 * rr;
+        if (aa < -bq) rr = 3.0 * r_0 - 2.0 * rl;
+      }
+      rlp[(size_t)k * plane] = rl; rrp[(size_t)k * plane] = rr;
+      r_m1 = r_0; r_0 = r_p1; r_p1 = r_p2; slp_k = slp_k1; if_k = if_k1;
+    }
+    (void)r_m1;
   }
-  rl[1] = r[1] - 0.5 * slp[1];
-  rr[K - 2] = r[K - 2] + 0.5 * slp[K - 2];
-  rl[0] = r[0] - 0.5 * slp[0]; rr[0] = r[0] + 0.5 * slp[0];
-  rl[K - 1] = r[K - 1] - 0.5 * slp[K - 1]; rr[K - 1] = r[K - 1] + 0.5 * slp[K - 1];
-  // Colella-Woodward limiter :340-356
-  for (int k = 0; k < K; ++k) {
-    if ((rr[k] - r[k]) * (r[k] - rl[k]) <= 0.0) { rl[k] = r[k]; rr[k] = r[k]; }
-    if (k == 0 || k == K - 1) continue;
-    const double rm = rr[k] - rl[k];
-    const double aa = rm * (r[k] - 0.5 * (rr[k] + rl[k]));
-    const double bq = rm * rm / 6.;
-    if (aa > bq) rl[k] = 3.0 * r[k] - 2.0 * rr[k];
-    if (aa < -bq) rr[k] = 3.0 * r[k] - 2.0 * rl[k];
-  }
-  // fluxes at interfaces :360-425 and advective-form tendency :466-476
+  auto RL = [&](int k) { return rlp[(size_t)k * plane]; };
+  auto RR = [&](int k) { return rrp[(size_t)k * plane]; };
+  auto W = [&](int k) { return __ldg(a.wg + (size_t)k * plane + col); };
+  // ---- pass 2: fluxes at interfaces :360-425 and advective-form tendency :466-476
   const double tt = 2. / 3.;
-  double flux_above = w[0] * r[0];                    // flux(ks) = w(ks)*r(ks)
+  double w_k = W(0), r_k = R(0);
+  double flux_above = w_k * r_k;                        // flux(ks) = w(ks)*r(ks)
   const double rc = a.robert_coeff, raw = a.raw_filter_coeff;
   for (int k = 0; k < K; ++k) {
+    const double w_k1 = W(k + 1);
+    const double r_k1 = (k + 1 < K) ? R(k + 1) : 0.0;
     double flux_below;
-    if (k == K - 1) flux_below = w[K] * r[K - 1];     // flux(ke+1) = w(ke+1)*r(ke)
+    if (k == K - 1) flux_below = w_k1 * r_k;            // flux(ke+1) = w(ke+1)*r(ke)
     else {
-      const int kf = k + 1;                           // interface index
-      const double wk = w[kf];
+      const int kf = k + 1;                             // interface index
+      const double wk = w_k1;
       double cn, xx, rst, rsum = 0.0;
       int kk;
       if (wk >= 0.) {
-        cn = dt * wk / dz[kf - 1];
+        cn = dt * wk / DZ(kf - 1);
         kk = kf - 1;
         if (cn > 1.) {
           double dzsum = 0.0; const double dtw = dt * wk;
-          while (dzsum + dz[kk] < dtw) { if (kk == 0) break; dzsum += dz[kk]; rsum += r[kk]; kk = kk - 1; }
-          xx = (dtw - dzsum) / dz[kk];
+          while (dzsum + DZ(kk) < dtw) { if (kk == 0) break; dzsum += DZ(kk); rsum += R(kk); kk = kk - 1; }
+          xx = (dtw - dzsum) / DZ(kk);
         } else xx = cn;
-        const double rm = rr[kk] - rl[kk];
-        double r6 = 6.0 * (r[kk] - 0.5 * (rr[kk] + rl[kk]));
+        const double rkk = (kk == k) ? r_k : R(kk), rrk = RR(kk), rlk = RL(kk);
+        const double rm = rrk - rlk;
+        double r6 = 6.0 * (rkk - 0.5 * (rrk + rlk));
         if (kk == 0) r6 = 0.;
-        rst = rr[kk] - 0.5 * xx * (rm - (1.0 - tt * xx) * r6);
+        rst = rrk - 0.5 * xx * (rm - (1.0 - tt * xx) * r6);
         if (cn > 1.) rst = (xx * rst + rsum) / cn;
       } else {
-        cn = -dt * wk / dz[kf];
+        cn = -dt * wk / DZ(kf);
         kk = kf;
         if (cn > 1.) {
           double dzsum = 0.0; const double dtw = -dt * wk;
-          while (dzsum + dz[kk] < dtw) { if (kk == 0) break; dzsum += dz[kk]; rsum += r[kk]; kk = kk + 1; if (kk >= K) { kk = K - 1; break; } }
-          xx = (dtw - dzsum) / dz[kk];
+          while (dzsum + DZ(kk) < dtw) { if (kk == 0) break; dzsum += DZ(kk); rsum += R(kk); kk = kk + 1; if (kk >= K) { kk = K - 1; break; } }
+          xx = (dtw - dzsum) / DZ(kk);
         } else xx = cn;
-        const double rm = rr[kk] - rl[kk];
-        double r6 = 6.0 * (r[kk] - 0.5 * (rr[kk] + rl[kk]));
+        const double rkk = (kk == k + 1) ? r_k1 : R(kk), rrk = RR(kk), rlk = RL(kk);
+        const double rm = rrk - rlk;
+        double r6 = 6.0 * (rkk - 0.5 * (rrk + rlk));
         if (kk == K - 1) r6 = 0.;
-        rst = rl[kk] + 0.5 * xx * (rm + (1.0 - tt * xx) * r6);
+        rst = rlk + 0.5 * xx * (rm + (1.0 - tt * xx) * r6);
         if (cn > 1.) rst = (xx * rst + rsum) / cn;
       }
       flux_below = wk * rst;
     }
-    const double rdt = -(flux_below - flux_above - r[k] * (w[k + 1] - w[k])) / dz[k];
+    const double rdt = -(flux_below - flux_above - r_k * (w_k1 - w_k)) / DZ(k);
     const size_t e = (size_t)k * plane + col;
     // leapfrog part A for the grid tracer (:1165-1169): current += rc*(previous - 2 current)*raw.
     // `future` shares its storage slot with `previous` (two time levels): read before the future value is written.
     const double qp = a.q_prev[e], qc = a.q_cur[e];
-    a.q_fut[e] = r[k] + dt * rdt;                     // tr_future + delta_t*dt_tmp
+    a.q_fut[e] = r_k + dt * rdt;                        // tr_future + delta_t*dt_tmp
     a.q_cur_w[e] = qc + rc * (qp - 2.0 * qc) * raw;
-    flux_above = flux_below;
+    flux_above = flux_below; w_k = w_k1; r_k = r_k1;
   }
 }
 void launch_tracer_ppm(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st) {
-  dim3 grid((t.g.I + 63) / 64, t.g.Jloc);
-  tracer_ppm_kernel<<<grid, 64, 0, st>>>(t, pr, a);
+  dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
+  tracer_ppm_kernel<<<grid, 128, 0, st>>>(t, pr, a);
 }
 
 // ---------------------------------------------------------------------------------------------
