@@ -964,8 +964,7 @@ int isca_core_view(IscaHandle h, IscaCoreView* v) {
   API_END(h)
 }
 int isca_core_press_heights(IscaHandle h, int slot, double* p_full, double* p_half, double* z_full, double* z_half) {
-  API_BEGIN(h)
-  launch_materialize_t(h->dt, h->T[slot].p, h->scal.p, slot, h->st);
+  API_BEGIN(h)                                             // T[slot] must be materialized (isca_core_view)
   launch_press_heights(h->dt, h->pr, h->T[slot].p, h->ps[slot].p, h->phis.p, p_full, p_half, z_full, z_half, h->st);
   API_END(h)
 }

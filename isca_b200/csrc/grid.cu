@@ -609,14 +609,14 @@ void launch_apply_energy(const DevTables& t, const Params& pr, int slot_fut, dou
 
 // T(slot) += pending shift; shift = 0   (host mirrors, restart, the spectral_dynamics host API)
 __global__ void materialize_t_kernel(double* __restrict__ T, size_t n, const double* __restrict__ scal, int slot) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const double sh = scal[SC_TSHIFT0 + slot];
-  if (sh != 0.0 && i < n) T[i] = T[i] + sh;
+  if (sh == 0.0) return;                                   // nothing pending: the launch costs a few microseconds
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) T[i] = T[i] + sh;
 }
 __global__ void clear_shift_kernel(double* scal, int slot) { scal[SC_TSHIFT0 + slot] = 0.0; }
 void launch_materialize_t(const DevTables& t, double* T, double* scal, int slot, cudaStream_t st) {
   const size_t n = (size_t)t.g.K * t.g.Jloc * t.g.I;
-  materialize_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, n, scal, slot);
+  materialize_t_kernel<<<148 * 8, 256, 0, st>>>(T, n, scal, slot);
   clear_shift_kernel<<<1, 1, 0, st>>>(scal, slot);
 }
 

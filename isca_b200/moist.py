@@ -126,3 +126,26 @@ class MoistAtmosphere:
             self.atmosphere_end()
         except Exception:
             pass
+
+
+RESOLUTIONS = {"T21": (64, 32, 21), "T42": (128, 64, 42), "T85": (256, 128, 85), "T170": (512, 256, 170), "T341": (1024, 512, 341)}
+
+# exp/test_cases/frierson/frierson_test_case.py: scheme namelists of the grey-radiation aquaplanet
+FRIERSON_PHYSICS_NML = dict(atm_abs=0.2,                                                 # two_stream_gray_rad_nml
+                            use_virtual_temp=0, surface_flux_do_simple=1, old_dtaudv=1,  # surface_flux_nml
+                            diffusivity_do_entrain=0, diffusivity_do_simple=1,           # diffusivity_nml
+                            rhbm=0.7, Tmin=160.0, Tmax=350.0)                            # qe_moist_convection_nml
+FRIERSON_MOIST_NML = dict(mixed_layer_depth=2.5, albedo_value=0.31)                      # mixed_layer_nml
+
+
+def frierson_test_case(res: str, num_levels: int, dt_atmos: float) -> MoistAtmosphere:
+    """The Frierson test case (frierson_test_case.py:60-170) at a given resolution: spectral_dynamics_nml with uneven sigma
+    levels (scale_heights 11, exponent 7, surf_res 0.5 -- the MiMA/Frierson level distribution of SURVEY section 8d), sphum as
+    the grid tracer, SIMPLE_BETTS_MILLER convection, slab ocean of 2.5 m."""
+    from .api import make_config
+    I, J, M = RESOLUTIONS[res]
+    cfg = make_config(lon_max=I, lat_max=J, num_fourier=M, num_spherical=M + 1, num_levels=num_levels, dt_atmos=dt_atmos,
+                      damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
+                      initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.5,
+                      robert_coeff=0.03, num_tracers=1)
+    return MoistAtmosphere(cfg, physics_nml=FRIERSON_PHYSICS_NML, convection_scheme="SIMPLE_BETTS_MILLER", **FRIERSON_MOIST_NML)
