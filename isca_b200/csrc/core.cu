@@ -117,7 +117,7 @@ struct IscaHandle_t {
   DBuf<LevDesc> levsA, levsB, levsC[2];
   DBuf<unsigned char> truncB;
   DBuf<double> part, scal, red_tmp;
-  DBuf<int> ops_sum2, ops_sum1, ops_en;
+  DBuf<int> ops_sum2, ops_sum1, ops_fix;
   int LpA = 0, LpB = 0, LpC = 0;
   int keep_tend = 0;
   bool grad_valid = false;   // gradA planes hold the gradients of the current level (computed by the previous step)
@@ -265,8 +265,8 @@ static void alloc_state(H& h) {
   h.ensure_four(Lmax);
   h.gradA.alloc((size_t)(2 * K + 2) * h.nplane());
   h.gridB.alloc((size_t)(4 * K + 1) * h.nplane());
-  h.part.alloc(3 * h.nplane()); h.scal.alloc(SC_COUNT); h.red_tmp.alloc(4 * 128);
-  h.ops_sum2.upload({0, 0}); h.ops_sum1.upload({0}); h.ops_en.upload({0, 1, 2});
+  h.part.alloc(5 * h.nplane()); h.scal.alloc(SC_COUNT); h.red_tmp.alloc(5 * 128);
+  h.ops_sum2.upload({0, 0}); h.ops_sum1.upload({0}); h.ops_fix.upload({0, 0, 0, 2, 2});
   const size_t pl = h.nplane();
   // level descriptors
   std::vector<LevDesc> la(2 * K + 2), lb(4 * K + 1);
@@ -451,7 +451,6 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   launch_grid_step(h.dt, pr, ga, st); h.launches++;
   h.mark("grid_step");
   launch_reduce(h.part.p, pl, 2, h.ops_sum2.p, h.scal.p + SC_SUM_PS_PREV, h.red_tmp.p, st); h.launches += 2;
-  allreduce_scalars(h, h.scal.p + SC_SUM_PS_PREV, 2, NCCL_SUM);
   h.mark("corr_reduce_prev");
 
   // ---- grid tracer: update_tracers (spectral_dynamics.F90:1116-1188); needs only the `current` winds and wg
@@ -498,21 +497,16 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   dev_inverse(h, h.specC.p, h.LpC, h.levsC[fut].p, 7 * K + 3, "_state");
   h.grad_valid = true;
 
-  // compute_corrections (spectral_dynamics.F90:1213-1302)
-  launch_colsum_ps(h.dt, h.ps[fut].p, h.part.p, st);
-  launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_SUM_PS_FUT, h.red_tmp.p, st);
-  allreduce_scalars(h, h.scal.p + SC_SUM_PS_FUT, 1, NCCL_SUM);
+  // compute_corrections (spectral_dynamics.F90:1213-1302): one column pass, one reduction, one SUM + one MAX all-reduce
+  // (the previous-level sums of initialize_corrections ride in the same SUM), one apply
+  launch_colsum_fixers(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.part.p, st);
+  launch_reduce(h.part.p, pl, 5, h.ops_fix.p, h.scal.p + SC_SUM_PS_FUT, h.red_tmp.p, st);
+  allreduce_scalars(h, h.scal.p + SC_SUM_PS_PREV, 5, NCCL_SUM);
+  allreduce_scalars(h, h.scal.p + SC_NTMIN, 2, NCCL_MAX);
   const double rc_raw = h.cfg.robert_coeff * h.cfg.raw_filter_coeff;
-  launch_apply_mass(h.dt, h.ps[fut].p, h.lnps[fut].p, h.lnps[cur].p, rc_raw, h.scal.p, h.denom(), h.owns_m0(),
-                    h.cfg.do_mass_correction, st);
-  launch_colsum_energy(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.part.p, st);
-  launch_reduce(h.part.p, pl, 3, h.ops_en.p, h.scal.p + SC_SUM_EN_FUT, h.red_tmp.p, st);
-  allreduce_scalars(h, h.scal.p + SC_SUM_EN_FUT, 1, NCCL_SUM);
-  allreduce_scalars(h, h.scal.p + SC_TMIN, 1, NCCL_MIN);
-  allreduce_scalars(h, h.scal.p + SC_TMAX, 1, NCCL_MAX);
-  launch_apply_energy(h.dt, pr, fut, h.ts[fut].p, h.ts[cur].p, rc_raw, h.scal.p, h.denom(), h.owns_m0(),
-                      h.cfg.do_energy_correction, st);
-  h.launches += 8;
+  launch_apply_fixers(h.dt, pr, fut, h.ps[fut].p, h.lnps[fut].p, h.lnps[cur].p, h.ts[fut].p, h.ts[cur].p, rc_raw, h.scal.p, h.denom(),
+                      h.owns_m0(), h.cfg.do_mass_correction, h.cfg.do_energy_correction, st);
+  h.launches += 4;
   h.mark("corr_mass_energy");
   if (h.cfg.num_tracers > 0) {
     launch_tracer_water_colsum(h.dt, pr, ta, st);
@@ -524,7 +518,7 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   }
 
   // time-level swap.  complete_robert_filter -> leapfrog_2level_B (a(previous) += rc*a(current)*raw) is fused into
-  // spec_update (all coefficients) and apply_mass / apply_energy (the fixers' (0,0) increments).
+  // spec_update (all coefficients) and apply_fixers (the fixers' (0,0) increments).
   h.previous = cur; h.current = fut;
   h.steps++;
 }

@@ -71,7 +71,7 @@ grid_step_kernel(DevTables t, Params pr, GridStepArgs a) {
 
   const double ps_c = a.ps_cur[col], ps_p = a.ps_prev[col];
   const double cosm = t.cosm_lat[j];
-  // the energy fixer's temperature increment is applied on read (see apply_energy_kernel)
+  // the energy fixer's temperature increment is applied on read (see apply_fixers_kernel)
   const double sh_c = a.scal[SC_TSHIFT0 + a.slot_cur], sh_p = a.scal[SC_TSHIFT0 + a.slot_prev];
   // compute_pressure_gradient: dx_psg = psg * S2G(dx ln ps), then divide_by_cos
   const double dx_psg = (ps_c * a.dx_lnps[col]) * cosm;
@@ -508,103 +508,88 @@ void launch_reduce(const double* part, size_t n, int nq, const int* ops, double*
 }
 
 // ---------------------------------------------------------------------------------------------
-// post-transform: mass fixer
+// post-transform: compute_corrections (spectral_dynamics.F90:1213-1302), mass + energy fixers in one pass.
+// The energy integral is taken with the mass-corrected surface pressure ps' = f*ps; as dp = dpk + dbk*ps' it is
+// A + f*B with A = sum e*dpk, B = sum e*dbk*ps, so both partial sums are formed before f is known and all global sums of the
+// step travel in one reduction (and one all-reduce).  part[0] = w*ps, part[1] = w*A, part[2] = w*B, part[3] = -min T, part[4] = max T
 // ---------------------------------------------------------------------------------------------
-__global__ void colsum_ps_kernel(DevTables t, const double* __restrict__ ps, double* __restrict__ part) {
-  const GeomDev& g = t.g;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
-  if (i >= g.I) return;
-  part[(size_t)jl * g.I + i] = t.wts_lat[g.j0 + jl] * ps[(size_t)jl * g.I + i];
-}
-void launch_colsum_ps(const DevTables& t, const double* ps, double* part, cudaStream_t st) {
-  dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
-  colsum_ps_kernel<<<grid, 128, 0, st>>>(t, ps, part);
-}
-
-// scal[SC_*]: see grid.h.  mass_correction_factor = mean_ps_prev / mean_ps_tmp
-__global__ void apply_mass_kernel(DevTables t, double* __restrict__ ps, double2* __restrict__ lnps_fut,
-                                  double2* __restrict__ lnps_cur, double rc_raw,
-                                  double* __restrict__ scal, double denom, int owns_m0, int do_mass) {
-  const GeomDev& g = t.g;
-  const size_t n = (size_t)g.Jloc * g.I;
-  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const double mean_prev = scal[SC_SUM_PS_PREV] / denom;
-  const double mean_tmp = scal[SC_SUM_PS_FUT] / denom;
-  const double f = do_mass ? (mean_prev / mean_tmp) : 1.0;
-  if (idx < n && do_mass) ps[idx] = f * ps[idx];
-  if (idx == 0) {
-    scal[SC_MEAN_PS_PREV] = mean_prev;
-    scal[SC_MASS_FACTOR] = f;
-    if (owns_m0 && do_mass) {
-      const double inc = sqrt(2.) * log(f);
-      lnps_fut[0].x = lnps_fut[0].x + inc;                                      // ln_ps(0,0,future) (:1231)
-      if (lnps_cur) lnps_cur[0].x = lnps_cur[0].x + rc_raw * inc;                // fused leapfrog_2level_B sees the fixed value
-    }
-  }
-}
-void launch_apply_mass(const DevTables& t, double* ps, double2* lnps_fut, double2* lnps_cur, double rc_raw, double* scal,
-                       double denom, int owns_m0, int do_mass, cudaStream_t st) {
-  size_t n = (size_t)t.g.Jloc * t.g.I;
-  apply_mass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, ps, lnps_fut, lnps_cur, rc_raw, scal, denom, owns_m0, do_mass);
-}
-
-// ---------------------------------------------------------------------------------------------
-// post-transform: energy fixer.  part[0] = w * sum_k (0.5(u^2+v^2)+cp T) dp ; part[1] = min T ; part[2] = max T
-// ---------------------------------------------------------------------------------------------
-__global__ void colsum_energy_kernel(DevTables t, Params pr, const double* __restrict__ u, const double* __restrict__ v,
+__global__ void colsum_fixers_kernel(DevTables t, Params pr, const double* __restrict__ u, const double* __restrict__ v,
                                      const double* __restrict__ T, const double* __restrict__ ps, double* __restrict__ part) {
   const GeomDev& g = t.g;
   const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
   if (i >= g.I) return;
   const size_t col = (size_t)jl * g.I + i, plane = (size_t)g.Jloc * g.I;
   const double p_s = ps[col];
-  double vi = 0.0, tmin = 1.0e300, tmax = -1.0e300;
+  double va = 0.0, vb = 0.0, tmin = 1.0e300, tmax = -1.0e300;
   for (int k = 0; k < g.K; ++k) {
     const size_t e = (size_t)k * plane + col;
     const double uu = u[e], vv = v[e], tt = T[e];
-    const double dp = (t.pk[k + 1] + t.bk[k + 1] * p_s) - (t.pk[k] + t.bk[k] * p_s);
-    vi = vi + (0.5 * (uu * uu + vv * vv) + pr.cp_air * tt) * dp;
+    const double en = 0.5 * (uu * uu + vv * vv) + pr.cp_air * tt;
+    va = va + en * (t.pk[k + 1] - t.pk[k]);
+    vb = vb + en * ((t.bk[k + 1] - t.bk[k]) * p_s);
     tmin = fmin(tmin, tt); tmax = fmax(tmax, tt);
   }
-  part[col] = t.wts_lat[g.j0 + jl] * vi;
-  part[plane + col] = tmin;
-  part[2 * plane + col] = tmax;
+  const double w = t.wts_lat[g.j0 + jl];
+  part[col] = w * p_s;
+  part[plane + col] = w * va;
+  part[2 * plane + col] = w * vb;
+  part[3 * plane + col] = -tmin;
+  part[4 * plane + col] = tmax;
 }
-void launch_colsum_energy(const DevTables& t, const Params& pr, const double* u, const double* v, const double* T,
+void launch_colsum_fixers(const DevTables& t, const Params& pr, const double* u, const double* v, const double* T,
                           const double* ps, double* part, cudaStream_t st) {
   dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
-  colsum_energy_kernel<<<grid, 128, 0, st>>>(t, pr, u, v, T, ps, part);
+  colsum_fixers_kernel<<<grid, 128, 0, st>>>(t, pr, u, v, T, ps, part);
 }
 
-// The temperature increment of the energy fixer (tg(future) = tg(future) + temperature_correction,
-// spectral_dynamics.F90:1239) is NOT applied with a pass over the 3-D field: it is stored as the pending shift
-// of the future slot and added by every reader (grid_step; materialize_t for host mirrors), which yields the
-// same rounded values fl(T + tc).  Only the spectral (0,0) coefficients are updated here.
-__global__ void apply_energy_kernel(DevTables t, Params pr, int slot_fut, double2* __restrict__ ts_fut,
-                                    double2* __restrict__ ts_cur, double rc_raw,
-                                    double* __restrict__ scal, double denom, int owns_m0, int do_energy) {
+// mass_correction_factor = mean_ps_prev / mean_ps_tmp (:1228-1231); temperature_correction (:1236-1241).
+// The temperature increment of the energy fixer (tg(future) = tg(future) + temperature_correction, :1239) is NOT applied with a
+// pass over the 3-D field: it is stored as the pending shift of the future slot and added by every reader (grid_step;
+// materialize_t for host mirrors), which yields the same rounded values fl(T + tc).  Only ps and the spectral (0,0)
+// coefficients are updated here.
+__global__ void apply_fixers_kernel(DevTables t, Params pr, int slot_fut, double* __restrict__ ps, double2* __restrict__ lnps_fut,
+                                    double2* __restrict__ lnps_cur, double2* __restrict__ ts_fut, double2* __restrict__ ts_cur,
+                                    double rc_raw, double* __restrict__ scal, double denom, int owns_m0, int do_mass, int do_energy) {
   const GeomDev& g = t.g;
-  const int idx = threadIdx.x;
+  const size_t n = (size_t)g.Jloc * g.I;
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const double mean_prev = scal[SC_SUM_PS_PREV] / denom;
+  const double mean_tmp = scal[SC_SUM_PS_FUT] / denom;
+  const double f = do_mass ? (mean_prev / mean_tmp) : 1.0;
   const double mean_e_prev = scal[SC_SUM_EN_PREV] / denom / pr.grav;
-  const double mean_e_tmp = scal[SC_SUM_EN_FUT] / denom / pr.grav;
-  const double tc = do_energy ? pr.grav * (mean_e_prev - mean_e_tmp) / (pr.cp_air * scal[SC_MEAN_PS_PREV]) : 0.0;
-  if (do_energy && owns_m0) {
-    for (int k = idx; k < g.K; k += blockDim.x) {
-      ts_fut[k].x = ts_fut[k].x + sqrt(2.) * tc;                                // ts(0,0,:,future) (:1241)
-      if (ts_cur) ts_cur[k].x = ts_cur[k].x + rc_raw * (sqrt(2.) * tc);          // fused leapfrog_2level_B
+  const double mean_e_tmp = (scal[SC_SUM_EN_FUT] + f * scal[SC_SUM_EN_FUTB]) / denom / pr.grav;
+  const double tc = do_energy ? pr.grav * (mean_e_prev - mean_e_tmp) / (pr.cp_air * mean_prev) : 0.0;
+  const double ntmin = scal[SC_NTMIN], tmax = scal[SC_TMAX];
+  if (idx < n && do_mass) ps[idx] = f * ps[idx];
+  if (blockIdx.x == 0) {
+    if (owns_m0 && do_energy) {
+      for (int k = threadIdx.x; k < g.K; k += blockDim.x) {
+        ts_fut[k].x = ts_fut[k].x + sqrt(2.) * tc;                               // ts(0,0,:,future) (:1241)
+        if (ts_cur) ts_cur[k].x = ts_cur[k].x + rc_raw * (sqrt(2.) * tc);         // fused leapfrog_2level_B
+      }
+    }
+    if (threadIdx.x == 0) {
+      if (owns_m0 && do_mass) {
+        const double inc = sqrt(2.) * log(f);
+        lnps_fut[0].x = lnps_fut[0].x + inc;                                     // ln_ps(0,0,future) (:1231)
+        if (lnps_cur) lnps_cur[0].x = lnps_cur[0].x + rc_raw * inc;               // fused leapfrog_2level_B sees the fixed value
+      }
+      scal[SC_MEAN_PS_PREV] = mean_prev;
+      scal[SC_MASS_FACTOR] = f;
+      scal[SC_TSHIFT0 + slot_fut] = tc;
+      scal[SC_MEAN_EN_PREV] = mean_e_prev;
+      scal[SC_T_CORR] = tc;
+      scal[SC_TMIN] = -ntmin;
+      if (-ntmin < pr.vr_tmin || tmax > pr.vr_tmax) scal[SC_T_FLAG] = 1.0;       // valid_range_t (:940)
     }
   }
-  __syncthreads();
-  if (idx == 0) {
-    scal[SC_TSHIFT0 + slot_fut] = tc;
-    scal[SC_MEAN_EN_PREV] = mean_e_prev;
-    scal[SC_T_CORR] = tc;
-    if (scal[SC_TMIN] < pr.vr_tmin || scal[SC_TMAX] > pr.vr_tmax) scal[SC_T_FLAG] = 1.0;   // valid_range_t (:940)
-  }
 }
-void launch_apply_energy(const DevTables& t, const Params& pr, int slot_fut, double2* ts_fut, double2* ts_cur, double rc_raw,
-                         double* scal, double denom, int owns_m0, int do_energy, cudaStream_t st) {
-  apply_energy_kernel<<<1, 128, 0, st>>>(t, pr, slot_fut, ts_fut, ts_cur, rc_raw, scal, denom, owns_m0, do_energy);
+void launch_apply_fixers(const DevTables& t, const Params& pr, int slot_fut, double* ps, double2* lnps_fut, double2* lnps_cur,
+                         double2* ts_fut, double2* ts_cur, double rc_raw, double* scal, double denom, int owns_m0, int do_mass,
+                         int do_energy, cudaStream_t st) {
+  size_t n = (size_t)t.g.Jloc * t.g.I;
+  apply_fixers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t, pr, slot_fut, ps, lnps_fut, lnps_cur, ts_fut, ts_cur, rc_raw, scal,
+                                                                  denom, owns_m0, do_mass, do_energy);
 }
 
 // T(slot) += pending shift; shift = 0   (host mirrors, restart, the spectral_dynamics host API)
