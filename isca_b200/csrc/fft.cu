@@ -239,10 +239,18 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
   double2* buf = reinterpret_cast<double2*>(fft_smem);              // [LT][LS]
+  int* s_row = reinterpret_cast<int*>(buf + FFT_LT * S::LS);        // [M+1] destination row of wavenumber m
+  int* s_own = s_row + (g.M + 1);                                   // [M+1] destination rank (peer-memory mode)
   const int lev0 = lev_begin + blockIdx.x * FFT_LT;
   const int jl = blockIdx.y;
   const int tid = threadIdx.x;
   constexpr int NT = FFT_LT * Q;
+  // the m -> destination tables go to shared memory (visible after the __syncthreads of the passes below): global lookups in the
+  // store loop put a second memory latency in front of every store
+  for (int q = tid; q <= g.M; q += NT) {
+    if (g.p2p) { const int r = g.owner[q]; s_own[q] = r; s_row[q] = g.rank * g.nm_rank[r] + g.lidx[q]; }
+    else { s_own[q] = 0; s_row[q] = g.pos[q]; }
+  }
   const int line = tid / Q, lt = tid - line * Q;
   const int lev = lev0 + line;
   double2* A = buf + line * S::LS;
@@ -297,11 +305,8 @@ fft_fwd_kernel(DevTables t, double* __restrict__ four, const LevDesc* __restrict
     const double2 e = cadd(zk, zc), o = csub(zk, zc);
     const double2 wo = cmul(o, tw<-1>(t.twiddle, k));
     const double2 x = make_double2(0.5 * (e.x + wo.y) * inv, 0.5 * (e.y - wo.x) * inv);
-    double* dst;
-    if (g.p2p) {        // store into the m-owner buffer of the rank that owns wavenumber k (peer memory over NVLink)
-      const int r = g.owner[k];
-      dst = g.peerA[r] + ((size_t)(g.rank * g.nm_rank[r] + g.lidx[k]) * g.Jloc + jl) * (size_t)C;
-    } else dst = four + fourB_index(g, k, jl, C);
+    // peer-memory mode: the row lives in the m-owner buffer of the rank that owns wavenumber k (store over NVLink)
+    double* dst = (g.p2p ? g.peerA[s_own[k]] : four) + ((size_t)s_row[k] * g.Jloc + jl) * (size_t)C;
     *reinterpret_cast<double2*>(dst + 2 * (lev0 + l)) = x;
   }
 }
@@ -318,9 +323,10 @@ static void launch_inv_shape(const DevTables& t, const double* four, const LevDe
 template <int H, int R1, int R2, int R3, int Q, int MINB>
 static void launch_fwd_shape(const DevTables& t, double* four, const LevDesc* levs, int nlev, int Lp, cudaStream_t st, int lev_begin) {
   typedef FftShape<H, R1> S;
-  const size_t smem = sizeof(double2) * FFT_LT * S::LS;
+  const size_t smem = sizeof(double2) * FFT_LT * S::LS + sizeof(int) * 2 * (t.g.M + 1);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(fft_fwd_kernel<H, R1, R2, R3, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(double2) * FFT_LT * S::LS + sizeof(int) * 2 * (H + 1))); attr = true; }
   dim3 grid((nlev - lev_begin + FFT_LT - 1) / FFT_LT, t.g.Jloc);
   fft_fwd_kernel<H, R1, R2, R3, Q, MINB><<<grid, FFT_LT * Q, smem, st>>>(t, four, levs, nlev, Lp, lev_begin);
 }
