@@ -30,13 +30,15 @@ RES = {  # lon, lat, M, dt (s) -- SURVEY.md section 8d (dt by CFL scaling from T
 }
 
 
-def hs_namelist(res: str, levels: int):
-    """exp/test_cases/held_suarez/held_suarez_test_case.py namelist (dry: no tracer, water fixer off)."""
+def hs_namelist(res: str, levels: int, tracer: bool = True):
+    """exp/test_cases/held_suarez/held_suarez_test_case.py namelist.  The reference's `dry` build carries the sphum grid tracer of
+    src/extra/model/dry/field_table (finite-volume horizontal + PPM vertical advection, Held-Suarez tracer source/sink,
+    do_water_correction at its default .true.): tracer=True reproduces that; tracer=False is the tracer-free dynamical core."""
     lon, lat, M, dt = RES[res]
     return dict(lon_max=lon, lat_max=lat, num_fourier=M, num_spherical=M + 1, num_levels=levels, dt_atmos=dt,
                 damping_order=4, water_correction_limit=200.e2, reference_sea_level_press=1.0e5,
                 valid_range_t=(100., 800.), initial_sphum=0.0, vert_coord_option="uneven_sigma",
-                scale_heights=6.0, exponent=7.5, surf_res=0.5, do_water_correction=False, num_tracers=0)
+                scale_heights=6.0, exponent=7.5, surf_res=0.5, do_water_correction=bool(tracer), num_tracers=1 if tracer else 0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -62,6 +64,8 @@ def work_model(res: str, K: int):
         "spectral": dict(bytes=spec_bytes * K * (4 + 6 + 6 + 8 + 5)),
         # corrections: colsum_energy reads 3 x 3-D, apply_energy r/w 1 x 3-D
         "corrections": dict(bytes=grid_bytes * K * 5),
+        # grid tracer (update_tracers + water fixer): ~14 3-D plane passes
+        "tracer": dict(bytes=grid_bytes * K * 14),
     }
     return w, dict(T=T, lev_inv=lev_inv, lev_fwd=lev_fwd)
 
@@ -128,9 +132,9 @@ FP64_TENSOR_PEAK_TFLOPS = 37.2   # measured on this pool: tools/probe_fp64.cu, p
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference algorithm), bounded sample
 # ---------------------------------------------------------------------------------------------
-def run_cpu(res, K, steps, warmup, spin=2):
+def run_cpu(res, K, steps, warmup, spin=2, tracer=True):
     from oracle.isca_oracle import SpectralCore, held_suarez_config
-    cfg = held_suarez_config(res, K, RES[res][3])
+    cfg = held_suarez_config(res, K, RES[res][3], num_tracers=1 if tracer else 0)
     t0 = time.time()
     core = SpectralCore(cfg)
     core.cold_start()
@@ -162,6 +166,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tracer", action="store_true", help="tracer-free dynamical core (the reference's dry build advects sphum)")
     ap.add_argument("--no-moist", action="store_true", help="skip the informational idealized-moist-model (BASELINE config 3) measurement")
     args = ap.parse_args()
 
@@ -175,7 +180,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     res, K = args.res, args.levels
     I, J, M, dt = RES[res]
-    workload = f"Held-Suarez dry core {res} L{K} (lon {I} x lat {J}, dt={dt:g}s), fp64, synthetic cold start + {args.spinup}-step spin-up"
+    tracer = not args.no_tracer
+    workload = (f"Held-Suarez dry core {res} L{K} (lon {I} x lat {J}, dt={dt:g}s), "
+                + ("sphum grid tracer of the reference's dry field_table advected (FV + PPM) with water fixer, " if tracer else "no tracer, ")
+                + f"fp64, synthetic cold start + {args.spinup}-step spin-up")
     metric, unit = "model_days_per_sec", "model-days/s"
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -183,7 +191,7 @@ def main():
         if rank != 0:
             return 0
         steps = max(1, min(args.steps, args.cpu_steps if args.steps > 20 else args.steps))
-        r = run_cpu(res, K, steps, min(args.warmup, 1))
+        r = run_cpu(res, K, steps, min(args.warmup, 1), tracer=tracer)
         line = {
             "impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["sec_per_step"] * 1e3,
@@ -229,12 +237,22 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    cfg = api.make_config(**hs_namelist(res, K))
+    def new_uid():
+        if dist is None:
+            return None
+        box = [api.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def map_peers(core):
+        if world > 1 and os.environ.get("ISCA_B200_NO_P2P") is None:
+            handles = [None] * world
+            dist.all_gather_object(handles, core.ipc_handles())
+            core.set_peer_handles(handles)           # Legendre/FFT epilogues now store straight into peer memory
+
+    cfg = api.make_config(**hs_namelist(res, K, tracer))
     atm = api.Atmosphere(cfg, rank=rank, nranks=world, nccl_unique_id=uid)
-    if world > 1 and os.environ.get("ISCA_B200_NO_P2P") is None:
-        handles = [None] * world
-        dist.all_gather_object(handles, atm.ipc_handles())
-        atm.set_peer_handles(handles)                # Legendre/FFT epilogues now store straight into peer memory
+    map_peers(atm)
     atm.cold_start()
     atm.atmosphere(args.spinup)                      # spin-up (untimed)
     atm.atmosphere(max(args.warmup, 3))              # warm-up (untimed; also captures the CUDA graphs)
@@ -266,7 +284,7 @@ def main():
         return sum(v for k, v in groups.items() if k.startswith(prefix))
     g_ms = {"legendre_inv": gsum("legendre_inv"), "legendre_fwd": gsum("legendre_fwd"), "fft_inv": gsum("fft_inv"),
             "fft_fwd": gsum("fft_fwd"), "grid_step": gsum("grid_step"), "spectral": gsum("spec"),
-            "corrections": gsum("corr")}
+            "corrections": gsum("corr"), "tracer": gsum("tracer")}
     exch_ms = gsum("exchange")
     tot = sum(groups.values())
     dom = max(g_ms, key=g_ms.get)
@@ -288,8 +306,10 @@ def main():
     # H2D of the tendencies and D2H of the new state inside the timed region.
     n3 = (K, J, I)
     pin = lambda shape: torch.zeros(shape, dtype=torch.float64).pin_memory().numpy()
-    tend = [pin(n3) for _ in range(3)]
+    tend = [pin(n3) for _ in range(4 if tracer else 3)]
     outs = {"psg": pin((J, I)), "ug": pin(n3), "vg": pin(n3), "tg": pin(n3)}
+    if tracer:
+        outs["grid_tracers"] = pin(n3)
     for _ in range(3):
         atm.spectral_dynamics_into(tend, outs)
     barrier()
@@ -298,8 +318,9 @@ def main():
         atm.spectral_dynamics_into(tend, outs)
     barrier()
     e2e_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
-    h2d = 3 * 8 * K * J_glob * I                     # whole job, all ranks
-    d2h = (3 * K + 1) * 8 * J_glob * I
+    nf = 4 if tracer else 3
+    h2d = nf * 8 * K * J_glob * I                    # whole job, all ranks
+    d2h = (nf * K + 1) * 8 * J_glob * I
     e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
            "api": "isca_b200_spectral_dynamics: host tendencies in, host state out, every step (reference spectral_dynamics argument list)"}
@@ -318,6 +339,51 @@ def main():
 
     tmin, tmax = atm.get_scalar(api.SC_T_MIN), atm.get_scalar(api.SC_T_MAX)
     atm.atmosphere_end()
+
+    # informational: the tracer-free dynamical core (transform + semi-implicit + Held-Suarez only), same timing method
+    no_tracer_core = None
+    if tracer:
+        a0 = api.Atmosphere(api.make_config(**hs_namelist(res, K, False)), rank=rank, nranks=world, nccl_unique_id=new_uid())
+        map_peers(a0)
+        a0.cold_start(); a0.atmosphere(args.spinup); a0.atmosphere(10)
+        barrier()
+        n0 = min(args.steps, 300)
+        a0.atmosphere(n0)
+        barrier()
+        ms0 = max_over_ranks(a0.get_scalar(api.SC_LAST_STEP_MS))
+        no_tracer_core = {"ms_per_step": ms0, "value": dt / 86400.0 / (ms0 * 1e-3), "unit": unit, "steps": n0}
+        a0.atmosphere_end()
+
+    # informational (not the headline metric): the Frierson grey-radiation moist aquaplanet (BASELINE config 3 at T85 L40 on one
+    # GPU; the grey-radiation stand-in for config 4 at T170 L40 on several), whole step (idealized_moist_phys + spectral_dynamics
+    # with the sphum tracer) device-resident after an on-device spin-up
+    moist_model = None
+    if not args.no_moist:
+        try:
+            from isca_b200 import moist
+            mres = "T85" if world == 1 else "T170"
+            mdt = 360.0 if world == 1 else 150.0
+            spin_days, msteps = (10.0, 300) if world == 1 else (3.0, 200)
+            mm = moist.frierson_test_case(mres, 40, mdt, rank=rank, nranks=world, nccl_unique_id=new_uid())
+            map_peers(mm.core)
+            mm.core.cold_start()
+            mm.idealized_moist_phys_init()
+            mm.atmosphere(int(spin_days * 86400 / mdt))
+            barrier()
+            mm.atmosphere(msteps)
+            barrier()
+            ms_m, ms_phys = mm.timing()
+            ms_m, ms_phys = max_over_ranks(ms_m), max_over_ranks(ms_phys)
+            flags = np.bincount(mm.get("convflag").astype(int).ravel(), minlength=3).tolist()
+            moist_model = {"workload": f"Frierson grey-radiation aquaplanet {mres} L40 (dt={mdt:g}s, SIMPLE_BETTS_MILLER, slab 2.5 m), "
+                                       f"{spin_days:g}-day on-device spin-up", "n_gpus": world, "ms_per_step": ms_m,
+                           "ms_physics_last_step": ms_phys,
+                           "value": mdt / 86400.0 / (ms_m * 1e-3), "unit": unit, "steps": msteps,
+                           "precip_mean_mm_per_day_rank0": float(mm.get("precip").mean() * 86400.0), "convflag_counts_rank0": flags}
+            mm.atmosphere_end()
+        except Exception as e:                         # never let the informational arm take the headline line down
+            moist_model = {"error": str(e)[:200]}
+
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -327,32 +393,10 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        r = run_cpu(res, K, args.cpu_steps, 1)
+        r = run_cpu(res, K, args.cpu_steps, 1, tracer=tracer)
         cpu_baseline = {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port",
                         "ms_per_step": r["sec_per_step"] * 1e3,
                         "sample": f"{args.cpu_steps} model steps of {res} L{K} (NumPy oracle, cold start + 2 steps)"}
-
-    # informational (not the headline metric): BASELINE config 3, the Frierson grey-radiation moist aquaplanet T85 L40, whole step
-    # (idealized_moist_phys + spectral_dynamics with the sphum tracer) device-resident after a 10-model-day spin-up
-    moist_model = None
-    if world == 1 and not args.no_moist:
-        try:
-            from isca_b200 import moist
-            mdt, spin_days, msteps = 360.0, 10.0, 300
-            mm = moist.frierson_test_case("T85", 40, mdt)
-            mm.core.cold_start()
-            mm.idealized_moist_phys_init()
-            mm.atmosphere(int(spin_days * 86400 / mdt))
-            mm.atmosphere(msteps)
-            ms_m, ms_phys = mm.timing()
-            flags = np.bincount(mm.get("convflag").astype(int).ravel(), minlength=3).tolist()
-            moist_model = {"workload": "Frierson grey-radiation aquaplanet T85 L40 (dt=360s, SIMPLE_BETTS_MILLER, slab 2.5 m), "
-                                       f"{spin_days:g}-day on-device spin-up", "ms_per_step": ms_m, "ms_physics_last_step": ms_phys,
-                           "value": mdt / 86400.0 / (ms_m * 1e-3), "unit": unit, "steps": msteps,
-                           "precip_mean_mm_per_day": float(mm.get("precip").mean() * 86400.0), "convflag_counts": flags}
-            mm.atmosphere_end()
-        except Exception as e:                         # never let the informational arm take the headline line down
-            moist_model = {"error": str(e)[:200]}
 
     working_set_mb = (8.0 * I * J * K * 25 + 16.0 * (M + 1) * J * (5 * K + 1)) / 1e6
     line = {
@@ -368,6 +412,7 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline, "legendre_gemm": legendre, "kernel_groups_ms": groups_out, "exchange_ms_per_step": exch_ms,
         "cpu_baseline": cpu_baseline,
+        "no_tracer_core": no_tracer_core,
         "moist_model": moist_model,
     }
     print(json.dumps(line), file=json_out, flush=True)

@@ -155,6 +155,14 @@ int isca_b200_spectral_dynamics(IscaHandle h, const double* dt_psg, const double
                                 double* psg_final, double* ug_final, double* vg_final,
                                 double* tg_final, double* wg_full, double* p_full);
 
+/* The same with the reference's tracer arguments (spectral_dynamics.F90:780-783: dt_tracers in, grid_tracers_final out;
+ * one grid tracer, sphum): dt_tracers / grid_tracers_final are (lon,lat,lev), either may be NULL. */
+int isca_b200_spectral_dynamics_tracers(IscaHandle h, const double* dt_psg, const double* dt_ug,
+                                        const double* dt_vg, const double* dt_tg, const double* dt_tracers,
+                                        double* psg_final, double* ug_final, double* vg_final,
+                                        double* tg_final, double* grid_tracers_final, double* wg_full,
+                                        double* p_full);
+
 /* lazy host mirrors for diag_manager send_data / restart writes
  * (spectral_dynamics.F90:1502-1531,1709-1867).  level: ISCA_LEVEL_CURRENT / _PREVIOUS or slot */
 int isca_b200_get_field(IscaHandle h, int field_id, int level, double* host);

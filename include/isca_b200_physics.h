@@ -176,6 +176,11 @@ typedef struct IscaMoistConfig {
 int isca_b200_moist_default_config(IscaMoistConfig* cfg);
 /* dyn: the dynamical-core namelist (num_tracers must be 1 = sphum); phys: scheme namelists (its grid sizes are overwritten) */
 int isca_b200_moist_create(const IscaConfig* dyn, const IscaPhysicsConfig* phys, const IscaMoistConfig* mc, IscaMoist* out);
+/* One process per GPU: this rank's latitude block of the same model (columns are independent; the dynamical core and the
+ * sphum tracer exchange over NCCL / peer memory as isca_b200_create describes).  Host arrays of the get/set calls are
+ * (lon, lat_local). */
+int isca_b200_moist_create_ranked(const IscaConfig* dyn, const IscaPhysicsConfig* phys, const IscaMoistConfig* mc, int rank, int nranks,
+                                  const void* nccl_unique_id, IscaMoist* out);
 int isca_b200_moist_destroy(IscaMoist m);
 const char* isca_b200_moist_last_error(IscaMoist m);            /* m may be NULL */
 /* the dynamical core inside (isca_b200_cold_start / set_grid_state / get_field ... operate on it) */

@@ -62,7 +62,7 @@ EXPORTS = [
     "isca_b200_nccl_unique_id", "isca_b200_cold_start", "isca_b200_set_grid_state",
     "isca_b200_set_spectral_state", "isca_b200_set_vor_div_grid", "isca_b200_set_surf_geopotential",
     "isca_b200_set_time_pointers", "isca_b200_step", "isca_b200_step_dynamics_only",
-    "isca_b200_spectral_dynamics", "isca_b200_get_field", "isca_b200_get_spectral", "isca_b200_get_scalar",
+    "isca_b200_spectral_dynamics", "isca_b200_spectral_dynamics_tracers", "isca_b200_get_field", "isca_b200_get_spectral", "isca_b200_get_scalar",
     "isca_b200_get_table", "isca_b200_get_time_pointers", "isca_b200_spherical_to_grid",
     "isca_b200_grid_to_spherical", "isca_b200_uv_grid_from_vor_div", "isca_b200_vor_div_from_uv_grid",
     "isca_b200_time_transforms", "isca_b200_profile_step", "isca_b200_decomposition",
@@ -112,6 +112,7 @@ def load_library() -> C.CDLL:
     lib.isca_b200_step.argtypes = [vp, C.c_int]
     lib.isca_b200_step_dynamics_only.argtypes = [vp, C.c_int]
     lib.isca_b200_spectral_dynamics.argtypes = [vp] + [vp] * 10
+    lib.isca_b200_spectral_dynamics_tracers.argtypes = [vp] + [vp] * 12
     lib.isca_b200_get_field.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.isca_b200_get_spectral.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.isca_b200_get_scalar.argtypes = [vp, C.c_int, dp]
@@ -298,17 +299,18 @@ class Atmosphere:
             pass
 
     # ---- spectral_dynamics_mod -------------------------------------------------------------
-    def spectral_dynamics(self, dt_ug=None, dt_vg=None, dt_tg=None, want=("psg", "ug", "vg", "tg")):
-        """spectral_dynamics(Time, psg_final, ug_final, ..., dt_psg, dt_ug, dt_vg, dt_tg, ...)
-        with host arrays in and out."""
+    def spectral_dynamics(self, dt_ug=None, dt_vg=None, dt_tg=None, dt_tracers=None, want=("psg", "ug", "vg", "tg")):
+        """spectral_dynamics(Time, psg_final, ug_final, vg_final, tg_final, tracer_attributes, grid_tracers_final, ..., dt_psg,
+        dt_ug, dt_vg, dt_tg, dt_tracers, wg_full, p_full, ...) with host arrays in and out."""
         s3 = (self.K, self.Jloc, self.I)
-        a = [_in(x, s3) for x in (dt_ug, dt_vg, dt_tg)]
+        a = [_in(x, s3) for x in (dt_ug, dt_vg, dt_tg, dt_tracers)]
         out = {}
-        for name, shape in (("psg", (self.Jloc, self.I)), ("ug", s3), ("vg", s3), ("tg", s3), ("wg_full", s3), ("p_full", s3)):
+        for name, shape in (("psg", (self.Jloc, self.I)), ("ug", s3), ("vg", s3), ("tg", s3), ("grid_tracers", s3), ("wg_full", s3),
+                            ("p_full", s3)):
             out[name] = np.empty(shape) if name in want else None
-        self._ck(self.lib.isca_b200_spectral_dynamics(self.h, None, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]),
-                                                      _ptr(out["psg"]), _ptr(out["ug"]), _ptr(out["vg"]),
-                                                      _ptr(out["tg"]), _ptr(out["wg_full"]), _ptr(out["p_full"])),
+        self._ck(self.lib.isca_b200_spectral_dynamics_tracers(self.h, None, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]),
+                                                              _ptr(out["psg"]), _ptr(out["ug"]), _ptr(out["vg"]), _ptr(out["tg"]),
+                                                              _ptr(out["grid_tracers"]), _ptr(out["wg_full"]), _ptr(out["p_full"])),
                  "spectral_dynamics")
         return {k: v for k, v in out.items() if v is not None}
 
@@ -429,11 +431,13 @@ class Atmosphere:
         return vors, divs
 
     def spectral_dynamics_into(self, tend, outs):
-        """spectral_dynamics with caller-owned (e.g. pinned) host arrays: tend = [dt_ug, dt_vg, dt_tg],
-        outs = dict(psg=, ug=, vg=, tg=); no allocation."""
-        self._ck(self.lib.isca_b200_spectral_dynamics(self.h, None, _ptr(tend[0]), _ptr(tend[1]), _ptr(tend[2]),
-                                                      _ptr(outs.get("psg")), _ptr(outs.get("ug")), _ptr(outs.get("vg")),
-                                                      _ptr(outs.get("tg")), _ptr(outs.get("wg_full")), _ptr(outs.get("p_full"))),
+        """spectral_dynamics with caller-owned (e.g. pinned) host arrays: tend = [dt_ug, dt_vg, dt_tg(, dt_tracers)],
+        outs = dict(psg=, ug=, vg=, tg=(, grid_tracers=)); no allocation."""
+        self._ck(self.lib.isca_b200_spectral_dynamics_tracers(self.h, None, _ptr(tend[0]), _ptr(tend[1]), _ptr(tend[2]),
+                                                              _ptr(tend[3]) if len(tend) > 3 else None,
+                                                              _ptr(outs.get("psg")), _ptr(outs.get("ug")), _ptr(outs.get("vg")),
+                                                              _ptr(outs.get("tg")), _ptr(outs.get("grid_tracers")),
+                                                              _ptr(outs.get("wg_full")), _ptr(outs.get("p_full"))),
                  "spectral_dynamics")
 
     def profile_step(self, n_steps=10):

@@ -94,6 +94,7 @@ struct IscaHandle_t {
   DBuf<double> vorg, divg, phis, wg_full;
   // ---- grid tracer (sphum)
   DBuf<double> q[2], tr0, trq1, trq2, tr1, wg;
+  DBuf<double> tr_halo;      // nranks > 1: [halo_s | halo_n | send_s | send_n] x [3][K][2][I], then q1_halo_s, q1_halo_n [K][2][I]
   DBuf<double> d_fv_c, d_fv_cc, d_fv_dy, d_fv_dyy, d_fv_dyp, d_fv_dym;
   FvTables fv;
   DBuf<int> ops_sum3;
@@ -250,6 +251,7 @@ static void alloc_state(H& h) {
     for (int s = 0; s < 2; ++s) h.q[s].alloc(h.n3());
     h.tr0.alloc(h.n3()); h.trq1.alloc(h.n3()); h.trq2.alloc(h.n3()); h.tr1.alloc(h.n3());
     h.wg.alloc(h.n3() + h.nplane());
+    if (g.P > 1) { h.tr_halo.alloc((size_t)14 * K * 2 * g.I); CK(cudaMemset(h.tr_halo.p, 0, (size_t)14 * K * 2 * g.I * sizeof(double))); }
     const HostTables& t = h.ht;
     h.d_fv_c.upload(t.fv_c); h.d_fv_cc.upload(t.fv_cc); h.d_fv_dy.upload(t.fv_dy); h.d_fv_dyy.upload(t.fv_dyy);
     h.d_fv_dyp.upload(t.fv_dy_plus); h.d_fv_dym.upload(t.fv_dy_minus);
@@ -343,6 +345,26 @@ static void exchange_fourier(H& h, int direction, int Lp) {
   }
   n.ck(n.GroupEnd(), "ncclGroupEnd");
   h.mark(direction == 0 ? "exchange_inv" : "exchange_fwd");
+}
+// latitude halo of the grid tracer step (fv_advection.F90:161-162): the two edge rows of (tr0, u, v), packed by
+// tracer_halo_pack_kernel, go to the southern / northern neighbour in one grouped send/recv
+static void exchange_tracer_halo(H& h, const TracerArgs& ta) {
+  const Geometry& g = h.g;
+  if (g.P == 1) return;
+  launch_tracer_halo_pack(h.dt, ta, h.st); h.launches++;
+  const size_t n = (size_t)3 * g.K * 2 * g.I;
+  const NcclApi& nc = h.nccl;
+  nc.ck(nc.GroupStart(), "ncclGroupStart");
+  if (g.rank > 0) {
+    nc.ck(nc.Send(ta.send_s, n, NCCL_FLOAT64, g.rank - 1, h.comm, h.st), "ncclSend(halo)");
+    nc.ck(nc.Recv(ta.halo_s, n, NCCL_FLOAT64, g.rank - 1, h.comm, h.st), "ncclRecv(halo)");
+  }
+  if (g.rank < g.P - 1) {
+    nc.ck(nc.Send(ta.send_n, n, NCCL_FLOAT64, g.rank + 1, h.comm, h.st), "ncclSend(halo)");
+    nc.ck(nc.Recv(ta.halo_n, n, NCCL_FLOAT64, g.rank + 1, h.comm, h.st), "ncclRecv(halo)");
+  }
+  nc.ck(nc.GroupEnd(), "ncclGroupEnd");
+  h.mark("tracer_halo");
 }
 // global reductions across ranks of `count` device scalars (area_weighted_global_mean's mpp_global_field +
 // sum, tools/transforms.F90:1059-1077, becomes a local fixed-order reduction + one small all-reduce)
@@ -466,9 +488,17 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
     ta.robert_coeff = c.tracer_robert_coeff < 0. ? c.robert_coeff : c.tracer_robert_coeff;
     ta.raw_filter_coeff = c.raw_filter_coeff; ta.water_limit = c.water_correction_limit; ta.physics_on = physics_on;
     ta.dt_q_in = dtq_in;
+    ta.halo_s = ta.halo_n = ta.send_s = ta.send_n = ta.q1_halo_s = ta.q1_halo_n = nullptr;
+    if (g.P > 1) {
+      const size_t hb = (size_t)3 * K * 2 * g.I, qb = (size_t)K * 2 * g.I;
+      double* p = h.tr_halo.p;
+      ta.halo_s = p; ta.halo_n = p + hb; ta.send_s = p + 2 * hb; ta.send_n = p + 3 * hb;
+      ta.q1_halo_s = p + 4 * hb; ta.q1_halo_n = p + 4 * hb + qb;
+    }
     launch_tracer_source(h.dt, pr, ta, st);
     launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_W_PREV, h.red_tmp.p, st);
     allreduce_scalars(h, h.scal.p + SC_W_PREV, 1, NCCL_SUM);
+    exchange_tracer_halo(h, ta);
     launch_tracer_semi(h.dt, h.fv, ta, st);
     launch_tracer_flux(h.dt, h.fv, ta, st);
     launch_tracer_ppm(h.dt, pr, ta, st);
@@ -753,7 +783,7 @@ int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* nc
     if (cfg->vert_advect_uv != 0 || cfg->vert_advect_t != 0) throw std::runtime_error("only second_centered vertical advection of u,v,T is supported");
     if (cfg->use_virtual_temperature) throw std::runtime_error("use_virtual_temperature is not supported");
     if (cfg->num_tracers < 0 || cfg->num_tracers > 1) throw std::runtime_error("only 0 or 1 (grid, finite_volume_parabolic sphum) tracers are supported");
-    if (cfg->num_tracers == 1 && nranks > 1) throw std::runtime_error("the grid tracer is single-rank only in this build (latitude halo exchange not built)");
+    if (cfg->num_tracers == 1 && nranks > 1 && cfg->lat_max / nranks < 4) throw std::runtime_error("the grid tracer needs at least 4 latitude rows per rank (2-row halos)");
     if (cfg->num_tracers == 1 && cfg->num_levels < 4) throw std::runtime_error("the PPM tracer advection needs num_levels >= 4");
     if (cfg->do_water_correction && cfg->num_tracers == 0) throw std::runtime_error("do_water_correction must be .false. in a dry model (spectral_dynamics.F90:1264)");
     if ((cfg->do_energy_correction || cfg->do_water_correction) && !cfg->do_mass_correction) throw std::runtime_error("energy/water correction requires mass correction (spectral_dynamics.F90:409-415)");
@@ -916,16 +946,26 @@ int isca_b200_step_dynamics_only(IscaHandle h, int n_steps) { return run_steps(h
 int isca_b200_spectral_dynamics(IscaHandle h, const double* dt_psg, const double* dt_ug, const double* dt_vg,
                                 const double* dt_tg, double* psg_final, double* ug_final, double* vg_final,
                                 double* tg_final, double* wg_full, double* p_full) {
+  return isca_b200_spectral_dynamics_tracers(h, dt_psg, dt_ug, dt_vg, dt_tg, nullptr, psg_final, ug_final, vg_final, tg_final, nullptr,
+                                             wg_full, p_full);
+}
+
+int isca_b200_spectral_dynamics_tracers(IscaHandle h, const double* dt_psg, const double* dt_ug, const double* dt_vg,
+                                        const double* dt_tg, const double* dt_tracers, double* psg_final, double* ug_final,
+                                        double* vg_final, double* tg_final, double* grid_tracers_final, double* wg_full,
+                                        double* p_full) {
   API_BEGIN(h)
   if (dt_psg) throw std::runtime_error("non-zero dt_psg is not supported (the solo driver always passes zero, atmosphere.F90:289)");
+  if ((dt_tracers || grid_tracers_final) && h->cfg.num_tracers < 1) throw std::runtime_error("no tracer configured");
   const size_t n3 = h->n3();
-  h->ext_tend.ensure(3 * n3);
-  const double* src[3] = {dt_ug, dt_vg, dt_tg};
-  for (int f = 0; f < 3; ++f) {
+  const int nf = dt_tracers ? 4 : 3;
+  h->ext_tend.ensure(nf * n3);
+  const double* src[4] = {dt_ug, dt_vg, dt_tg, dt_tracers};
+  for (int f = 0; f < nf; ++f) {
     if (src[f]) CK(cudaMemcpyAsync(h->ext_tend.p + f * n3, src[f], n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
     else CK(cudaMemsetAsync(h->ext_tend.p + f * n3, 0, n3 * sizeof(double), h->st));
   }
-  step_once(*h, 0, h->ext_tend.p, h->ext_tend.p + n3, h->ext_tend.p + 2 * n3);
+  step_once(*h, 0, h->ext_tend.p, h->ext_tend.p + n3, h->ext_tend.p + 2 * n3, dt_tracers ? h->ext_tend.p + 3 * n3 : nullptr);
   const int c = h->current;
   if (psg_final) CK(cudaMemcpyAsync(psg_final, h->ps[c].p, h->nplane() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   if (ug_final) CK(cudaMemcpyAsync(ug_final, h->u[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
@@ -934,6 +974,7 @@ int isca_b200_spectral_dynamics(IscaHandle h, const double* dt_psg, const double
     launch_materialize_t(h->dt, h->T[c].p, h->scal.p, c, h->st);
     CK(cudaMemcpyAsync(tg_final, h->T[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   }
+  if (grid_tracers_final) CK(cudaMemcpyAsync(grid_tracers_final, h->q[c].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   if (wg_full) CK(cudaMemcpyAsync(wg_full, h->wg_full.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   if (p_full) {
     h->x_grid.ensure(n3);

@@ -175,6 +175,11 @@ int isca_b200_moist_destroy(IscaMoist m) {
 }
 
 int isca_b200_moist_create(const IscaConfig* dyn, const IscaPhysicsConfig* phys, const IscaMoistConfig* mc, IscaMoist* out) {
+  return isca_b200_moist_create_ranked(dyn, phys, mc, 0, 1, nullptr, out);
+}
+
+int isca_b200_moist_create_ranked(const IscaConfig* dyn, const IscaPhysicsConfig* phys, const IscaMoistConfig* mc, int rank, int nranks,
+                                  const void* nccl_unique_id, IscaMoist* out) {
   IscaMoist m = nullptr;
   if (!dyn || !phys || !mc || !out) return mfail(nullptr, "null argument");
   if (mc->abi_version != 1) return mfail(nullptr, "IscaMoistConfig abi_version mismatch");
@@ -183,7 +188,7 @@ int isca_b200_moist_create(const IscaConfig* dyn, const IscaPhysicsConfig* phys,
   if (dyn->num_tracers != 1) return mfail(nullptr, "idealized_moist_model needs the sphum grid tracer (num_tracers = 1)");
   m = new IscaMoist_t();
   m->mc = *mc;
-  if (isca_b200_create(dyn, 0, 1, nullptr, &m->dyn)) { std::string e = isca_b200_last_error(nullptr); delete m; return mfail(nullptr, "dynamical core: " + e); }
+  if (isca_b200_create(dyn, rank, nranks, nccl_unique_id, &m->dyn)) { std::string e = isca_b200_last_error(nullptr); delete m; return mfail(nullptr, "dynamical core: " + e); }
   IscaCoreView v;
   if (isca_core_view(m->dyn, &v)) { std::string e = isca_b200_last_error(m->dyn); isca_b200_moist_destroy(m); return mfail(nullptr, e); }
   m->I = v.I; m->J = v.Jloc; m->K = v.K; m->nc = (size_t)v.I * v.Jloc; m->n3 = m->nc * v.K;

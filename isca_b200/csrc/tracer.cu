@@ -11,7 +11,8 @@
 //                          (atmos_shared/vert_advection/vert_advection.F90:297-478, slope_z :504-563, compute_weights :567-629)
 //                          + leapfrog part A for the grid tracer (spectral_dynamics.F90:1165-1169)
 //   tracer_water_*         water fixer of compute_corrections (spectral_dynamics.F90:1245-1278) + leapfrog_2level_B
-// Single rank only (the 2-row latitude halo of fv_advection.F90:161-162 is the polar mirror here).
+// nranks > 1: one exchange of the 2 edge rows of (tr0, u, v) with each latitude neighbour (tracer_halo_pack + grouped
+// ncclSend/ncclRecv in core.cu) replaces the reference's three mpp_update_domains calls (fv_advection.F90:161-162,189,196).
 #include "tracer.h"
 #include "grid.h"
 
@@ -52,52 +53,94 @@ void launch_tracer_source(const DevTables& t, const Params& pr, const TracerArgs
   tracer_source_kernel<<<grid, 128, 0, st>>>(t, pr, a);
 }
 
-// value of a [J][I] plane at Fortran latitude index jf in [-1, J+2] (1-based), longitude i (0-based), with the
-// polar mirror rows (fv_advection.F90:164-178): row 0 <- row 1 at i+nx/2, row -1 <- row 2, row J+1 <- row J, ...
-__device__ __forceinline__ double at_lat(const double* __restrict__ p, int jf, int i, int I, int J, double pole_sign) {
-  if (jf >= 1 && jf <= J) return p[(size_t)(jf - 1) * I + i];
+// A [K][Jloc][I] field together with its 2-row latitude halos [K][2][I] (null on a single rank)
+struct HaloField { const double* main; const double* s; const double* n; };
+
+// row jl (local, -2 <= jl < Jloc+2) of level k
+__device__ __forceinline__ const double* halo_row(const HaloField& F, int k, int jl, int I, int Jloc) {
+  if (jl >= 0 && jl < Jloc) return F.main + ((size_t)k * Jloc + jl) * I;
+  if (jl < 0) return F.s + ((size_t)k * 2 + (jl + 2)) * I;
+  return F.n + ((size_t)k * 2 + (jl - Jloc)) * I;
+}
+
+// value at Fortran latitude index jf in [-1, J+2] (1-based, global), longitude i (0-based), with the polar mirror
+// rows (fv_advection.F90:164-178): row 0 <- row 1 at i+nx/2, row -1 <- row 2, row J+1 <- row J, ...; rows owned by a
+// neighbouring rank come from the halo (mpp_update_domains of fv_advection.F90:161-162)
+__device__ __forceinline__ double at_lat(const HaloField& F, int k, int jf, int i, const GeomDev& g, double pole_sign) {
+  const int I = g.I, J = g.J;
+  if (jf >= 1 && jf <= J) return halo_row(F, k, jf - 1 - g.j0, I, g.Jloc)[i];
   int ii = i + I / 2; if (ii >= I) ii -= I;
   const int jm = (jf < 1) ? (1 - jf) : (2 * J + 1 - jf);       // 0 -> 1, -1 -> 2, J+1 -> J, J+2 -> J-1
-  return pole_sign * p[(size_t)(jm - 1) * I + ii];
+  return pole_sign * halo_row(F, k, jm - 1 - g.j0, I, g.Jloc)[ii];
 }
 
 // ---------------------------------------------------------------------------------------------
-// q1 = q + semi_x(q, dt/2), q2 = q + semi_y(q, dt/2)
+// edge rows of tr0, u, v packed for the two latitude neighbours: send_s = local rows 0,1 ; send_n = rows Jloc-2, Jloc-1
 // ---------------------------------------------------------------------------------------------
-__global__ void tracer_semi_kernel(DevTables t, FvTables f, TracerArgs a) {
+__global__ void tracer_halo_pack_kernel(DevTables t, TracerArgs a) {
   const GeomDev& g = t.g;
-  const int I = g.I, J = g.J;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;   // j 0-based
+  const int I = g.I, Jloc = g.Jloc, K = g.K;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, fk = blockIdx.z;     // r: 0,1 south rows; 2,3 north rows
   if (i >= I) return;
-  const size_t plane = (size_t)J * I;
-  const double* q = a.tr0 + (size_t)k * plane;
-  const size_t e = (size_t)k * plane + (size_t)j * I + i;
+  const int f = fk / K, k = fk - f * K;
+  const double* src = (f == 0) ? a.tr0 : (f == 1 ? a.u_cur : a.v_cur);
+  const int jl = (r < 2) ? r : (Jloc - 4 + r);
+  const double v = src[((size_t)k * Jloc + jl) * I + i];
+  double* dst = (r < 2) ? a.send_s : a.send_n;
+  dst[((size_t)fk * 2 + (r & 1)) * I + i] = v;
+}
+void launch_tracer_halo_pack(const DevTables& t, const TracerArgs& a, cudaStream_t st) {
+  dim3 grid((t.g.I + 127) / 128, 4, 3 * t.g.K);
+  tracer_halo_pack_kernel<<<grid, 128, 0, st>>>(t, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// q1 = q + semi_x(q, dt/2), q2 = q + semi_y(q, dt/2).  With latitude halos q1 is also evaluated on the two halo rows on
+// either side (semi_x only needs the row itself), which replaces the reference's second halo exchange of q1.
+// ---------------------------------------------------------------------------------------------
+__global__ void tracer_semi_kernel(DevTables t, FvTables f, TracerArgs a, int ext) {
+  const GeomDev& g = t.g;
+  const int I = g.I, Jloc = g.Jloc, K = g.K;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.z;
+  const int jl = (int)blockIdx.y - ext;                    // local row, -2 .. Jloc+1 when ext == 2
+  const int j = g.j0 + jl;                                 // global row, 0-based
+  if (i >= I || j < 0 || j >= g.J) return;                 // beyond a pole: the mirror rows are read from the interior
+  const HaloField Q{a.tr0, a.halo_s, a.halo_n};
+  const HaloField U{a.u_cur, a.halo_s ? a.halo_s + (size_t)K * 2 * I : nullptr, a.halo_n ? a.halo_n + (size_t)K * 2 * I : nullptr};
+  const double* qrow = halo_row(Q, k, jl, I, Jloc);
   const double dt = 0.5 * a.delta_t;
-  const double qc = q[(size_t)j * I + i];
+  const double qc = qrow[i];
+  const bool interior = (jl >= 0 && jl < Jloc);
   // semi_x: b = ua*dt/(dx*c); cell ii = i-1-floor(b) (1-based, wrapped)
   {
-    const double b = a.u_cur[e] * dt / (f.dx * f.c[j]);
+    const double b = halo_row(U, k, jl, I, Jloc)[i] * dt / (f.dx * f.c[j]);
     const double fl = floor(b);
     int il = (i + 1) - 1 - (int)fl;                    // 1-based i_left
     while (il > I) il -= I;
     while (il < 1) il += I;
     int ir = il + 1; if (ir > I) ir = 1;
     const double bb = b - fl;
-    a.q1[e] = qc + (bb * q[(size_t)j * I + il - 1] + (1.0 - bb) * q[(size_t)j * I + ir - 1] - qc);
+    const double q1v = qc + (bb * qrow[il - 1] + (1.0 - bb) * qrow[ir - 1] - qc);
+    if (interior) a.q1[((size_t)k * Jloc + jl) * I + i] = q1v;
+    else if (jl < 0) a.q1_halo_s[((size_t)k * 2 + (jl + 2)) * I + i] = q1v;
+    else a.q1_halo_n[((size_t)k * 2 + (jl - Jloc)) * I + i] = q1v;
   }
+  if (!interior) return;
   // semi_y
   {
+    const size_t e = ((size_t)k * Jloc + jl) * I + i;
     const double v = a.v_cur[e];
     const int jf = j + 1;
     double dq;
-    if (v >= 0.0) dq = v * dt * (at_lat(q, jf - 1, i, I, J, 1.0) - qc) / f.dyy[jf - 1];
-    else dq = v * dt * (qc - at_lat(q, jf + 1, i, I, J, 1.0)) / f.dyy[jf];
+    if (v >= 0.0) dq = v * dt * (at_lat(Q, k, jf - 1, i, g, 1.0) - qc) / f.dyy[jf - 1];
+    else dq = v * dt * (qc - at_lat(Q, k, jf + 1, i, g, 1.0)) / f.dyy[jf];
     a.q2[e] = qc + dq;
   }
 }
 void launch_tracer_semi(const DevTables& t, const FvTables& f, const TracerArgs& a, cudaStream_t st) {
-  dim3 grid((t.g.I + 127) / 128, t.g.J, t.g.K);
-  tracer_semi_kernel<<<grid, 128, 0, st>>>(t, f, a);
+  const int ext = (t.g.P > 1) ? 2 : 0;
+  dim3 grid((t.g.I + 127) / 128, t.g.Jloc + 2 * ext, t.g.K);
+  tracer_semi_kernel<<<grid, 128, 0, st>>>(t, f, a, ext);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -110,8 +153,8 @@ __device__ __forceinline__ double slope_x_at(const double* __restrict__ row, int
   return sign1(slope) * min3(fabs(slope), 2.0 * (q - min3(qm, q, qp)), 2.0 * (max3(qm, q, qp) - q));
 }
 
-__device__ __forceinline__ double slope_sphere_at(const double* __restrict__ q1, const FvTables& f, int jf, int i, int I, int J) {
-  const double qm = at_lat(q1, jf - 1, i, I, J, 1.0), q = at_lat(q1, jf, i, I, J, 1.0), qp = at_lat(q1, jf + 1, i, I, J, 1.0);
+__device__ __forceinline__ double slope_sphere_at(const HaloField& Q1, int k, const FvTables& f, int jf, int i, const GeomDev& g) {
+  const double qm = at_lat(Q1, k, jf - 1, i, g, 1.0), q = at_lat(Q1, k, jf, i, g, 1.0), qp = at_lat(Q1, k, jf + 1, i, g, 1.0);
   const double slope = (qp - q) * f.dy_plus[jf] + (q - qm) * f.dy_minus[jf];
   return sign1(slope) * min3(fabs(slope), 2.0 * (q - min3(qm, q, qp)), 2.0 * (max3(qm, q, qp) - q));
 }
@@ -119,13 +162,13 @@ __device__ __forceinline__ double slope_sphere_at(const double* __restrict__ q1,
 __global__ void tracer_flux_kernel(DevTables t, FvTables f, TracerArgs a) {
   extern __shared__ double sm[];
   const GeomDev& g = t.g;
-  const int I = g.I, J = g.J;
-  const int j = blockIdx.x, k = blockIdx.y;          // j 0-based
+  const int I = g.I, J = g.J, Jloc = g.Jloc, K = g.K;
+  const int jl = blockIdx.x, k = blockIdx.y;          // local row, 0-based
+  const int j = g.j0 + jl;                            // global row, 0-based
   const int jf = j + 1;
   double* row = sm;                                   // q2 row [I]
   double* flx = sm + I;                               // x flux at the west face of cell i [I]
-  const size_t plane = (size_t)J * I;
-  const size_t base = (size_t)k * plane + (size_t)j * I;
+  const size_t base = ((size_t)k * Jloc + jl) * I;
   const double dt = a.delta_t;
   const double cj = f.c[j];
   for (int i = threadIdx.x; i < I; i += blockDim.x) row[i] = a.q2[base + i];
@@ -159,18 +202,19 @@ __global__ void tracer_flux_kernel(DevTables t, FvTables f, TracerArgs a) {
     flx[i] = flux + bb * (qq + 0.5 * ss * (sign1(bb) - bb));
   }
   __syncthreads();
-  const double* q = a.tr0 + (size_t)k * plane;
-  const double* q1 = a.q1 + (size_t)k * plane;
-  const double* va = a.v_cur + (size_t)k * plane;
+  const double* q = a.tr0 + base;
+  const HaloField Q1{a.q1, a.q1_halo_s, a.q1_halo_n};
+  const HaloField V{a.v_cur, a.halo_s ? a.halo_s + (size_t)2 * K * 2 * I : nullptr, a.halo_n ? a.halo_n + (size_t)2 * K * 2 * I : nullptr};
+  const double* va = a.v_cur + base;
   for (int i = threadIdx.x; i < I; i += blockDim.x) {
     const int ip = (i == I - 1) ? 0 : i + 1, im = (i == 0) ? I - 1 : i - 1;
     // divergence term: dq_dt = q*div
-    const double vc_s = 0.5 * (at_lat(va, jf - 1, i, I, J, -1.0) + va[(size_t)j * I + i]);         // vc(j)
-    const double vc_n = 0.5 * (va[(size_t)j * I + i] + at_lat(va, jf + 1, i, I, J, -1.0));         // vc(j+1)
+    const double vc_s = 0.5 * (at_lat(V, k, jf - 1, i, g, -1.0) + va[i]);         // vc(j)
+    const double vc_n = 0.5 * (va[i] + at_lat(V, k, jf + 1, i, g, -1.0));         // vc(j+1)
     const double uc_w = 0.5 * (ua[im] + ua[i]), uc_e = 0.5 * (ua[i] + ua[ip]);
     double div = (vc_n * f.cc[jf] - vc_s * f.cc[jf - 1]) / (cj * f.dy[jf + 1]);
     div = div + (uc_e - uc_w) / (cj * f.dx);
-    const double qc = q[(size_t)j * I + i];
+    const double qc = q[i];
     double dq = 0.0 + qc * div;
     // vanleer_x
     dq = dq - (flx[ip] - flx[i]) / dt;
@@ -178,20 +222,20 @@ __global__ void tracer_flux_kernel(DevTables t, FvTables f, TracerArgs a) {
     double fl_s = 0.0, fl_n = 0.0;
     if (jf > 1) {
       const double v = vc_s;
-      if (v >= 0.0) fl_s = v * f.cc[jf - 1] * (at_lat(q1, jf - 1, i, I, J, 1.0) + 0.5 * slope_sphere_at(q1, f, jf - 1, i, I, J) * (1.0 - (dt / f.dy[jf]) * v));
-      else fl_s = v * f.cc[jf - 1] * (at_lat(q1, jf, i, I, J, 1.0) - 0.5 * slope_sphere_at(q1, f, jf, i, I, J) * (1.0 + (dt / f.dy[jf + 1]) * v));
+      if (v >= 0.0) fl_s = v * f.cc[jf - 1] * (at_lat(Q1, k, jf - 1, i, g, 1.0) + 0.5 * slope_sphere_at(Q1, k, f, jf - 1, i, g) * (1.0 - (dt / f.dy[jf]) * v));
+      else fl_s = v * f.cc[jf - 1] * (at_lat(Q1, k, jf, i, g, 1.0) - 0.5 * slope_sphere_at(Q1, k, f, jf, i, g) * (1.0 + (dt / f.dy[jf + 1]) * v));
     }
     if (jf < J) {
       const double v = vc_n;
-      if (v >= 0.0) fl_n = v * f.cc[jf] * (at_lat(q1, jf, i, I, J, 1.0) + 0.5 * slope_sphere_at(q1, f, jf, i, I, J) * (1.0 - (dt / f.dy[jf + 1]) * v));
-      else fl_n = v * f.cc[jf] * (at_lat(q1, jf + 1, i, I, J, 1.0) - 0.5 * slope_sphere_at(q1, f, jf + 1, i, I, J) * (1.0 + (dt / f.dy[jf + 2]) * v));
+      if (v >= 0.0) fl_n = v * f.cc[jf] * (at_lat(Q1, k, jf, i, g, 1.0) + 0.5 * slope_sphere_at(Q1, k, f, jf, i, g) * (1.0 - (dt / f.dy[jf + 1]) * v));
+      else fl_n = v * f.cc[jf] * (at_lat(Q1, k, jf + 1, i, g, 1.0) - 0.5 * slope_sphere_at(Q1, k, f, jf + 1, i, g) * (1.0 + (dt / f.dy[jf + 2]) * v));
     }
     dq = dq - (1.0 / (f.dy[jf + 1] * cj)) * (fl_n - fl_s);
     a.tr1[base + i] = qc + dt * dq;                   // tr_future = tr_future + delta_t*dt_tr
   }
 }
 void launch_tracer_flux(const DevTables& t, const FvTables& f, const TracerArgs& a, cudaStream_t st) {
-  dim3 grid(t.g.J, t.g.K);
+  dim3 grid(t.g.Jloc, t.g.K);
   const int threads = t.g.I < 256 ? t.g.I : 256;
   tracer_flux_kernel<<<grid, threads, sizeof(double) * 2 * t.g.I, st>>>(t, f, a);
 }

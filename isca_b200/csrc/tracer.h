@@ -22,12 +22,17 @@ struct TracerArgs {
   // work planes [K]
   double *tr0, *q1, *q2, *tr1;
   double *part;                    // per-column partials [3][Jloc*I]
+  // latitude halos (nranks > 1; fv_advection.F90:161-162 exchanges 2 rows N and S): [3][K][2][I] = tr0, u_cur, v_cur rows
+  // of the southern neighbour (global rows j0-2, j0-1) / northern neighbour (j0+Jloc, j0+Jloc+1); send_* are the packed
+  // edge rows of this rank; q1_halo_* [K][2][I] is q1 = q + semi_x(q) recomputed on the halo rows
+  double *halo_s, *halo_n, *send_s, *send_n, *q1_halo_s, *q1_halo_n;
   double delta_t, trflux, trdamp, robert_coeff, raw_filter_coeff, water_limit;
   int physics_on;
   const double* dt_q_in;           // externally computed tendency (moist physics), added to the source; may be null
 };
 
 void launch_tracer_source(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);
+void launch_tracer_halo_pack(const DevTables& t, const TracerArgs& a, cudaStream_t st);
 void launch_tracer_semi(const DevTables& t, const FvTables& f, const TracerArgs& a, cudaStream_t st);
 void launch_tracer_flux(const DevTables& t, const FvTables& f, const TracerArgs& a, cudaStream_t st);
 void launch_tracer_ppm(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);

@@ -7,7 +7,7 @@ import numpy as np
 from .api import load_library, IscaError, Atmosphere, IscaConfigStruct
 from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 
-MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
+MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
                  "isca_b200_moist_set_t_surf", "isca_b200_moist_timing"]
 
@@ -34,6 +34,8 @@ def _lib():
         lib.isca_b200_moist_default_config.argtypes = [C.POINTER(IscaMoistConfigStruct)]
         lib.isca_b200_moist_create.argtypes = [C.POINTER(IscaConfigStruct), C.POINTER(IscaPhysicsConfigStruct), C.POINTER(IscaMoistConfigStruct),
                                                C.POINTER(vp)]
+        lib.isca_b200_moist_create_ranked.argtypes = [C.POINTER(IscaConfigStruct), C.POINTER(IscaPhysicsConfigStruct),
+                                                      C.POINTER(IscaMoistConfigStruct), C.c_int, C.c_int, vp, C.POINTER(vp)]
         lib.isca_b200_moist_destroy.argtypes = [vp]
         lib.isca_b200_moist_last_error.argtypes = [vp]
         lib.isca_b200_moist_last_error.restype = C.c_char_p
@@ -56,7 +58,8 @@ class MoistAtmosphere:
     convection_scheme, do_damping, roughness_*, mixed_layer_depth, albedo_value, constant_gust: idealized_moist_phys_nml /
     mixed_layer_nml / vert_turb_driver_nml values."""
 
-    def __init__(self, dyn_config, physics_nml=None, convection_scheme="SIMPLE_BETTS_MILLER", **moist_nml):
+    def __init__(self, dyn_config, physics_nml=None, convection_scheme="SIMPLE_BETTS_MILLER", rank=0, nranks=1, nccl_unique_id=None,
+                 **moist_nml):
         lib = _lib()
         self._lib = lib
         pc = IscaPhysicsConfigStruct()
@@ -77,10 +80,15 @@ class MoistAtmosphere:
                 raise IscaError(f"unknown namelist variable {k}")
             setattr(mc, k, v)
         self._h = C.c_void_p()
-        if lib.isca_b200_moist_create(C.byref(dyn_config), C.byref(pc), C.byref(mc), C.byref(self._h)) != 0:
+        uid = None
+        if nccl_unique_id is not None:
+            self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            uid = C.cast(self._uid_buf, C.c_void_p)
+        if lib.isca_b200_moist_create_ranked(C.byref(dyn_config), C.byref(pc), C.byref(mc), rank, nranks, uid, C.byref(self._h)) != 0:
             raise IscaError("atmosphere_init: " + lib.isca_b200_moist_last_error(None).decode())
         self.core = Atmosphere(dyn_config, _adopt_handle=lib.isca_b200_moist_dycore(self._h))
-        self.s2 = (dyn_config.lat_max, dyn_config.lon_max)
+        self.core.Jloc = dyn_config.lat_max // nranks
+        self.s2 = (dyn_config.lat_max // nranks, dyn_config.lon_max)
         self.s3 = (dyn_config.num_levels,) + self.s2
 
     def _ck(self, rc, where):
@@ -138,7 +146,7 @@ FRIERSON_PHYSICS_NML = dict(atm_abs=0.2,                                        
 FRIERSON_MOIST_NML = dict(mixed_layer_depth=2.5, albedo_value=0.31)                      # mixed_layer_nml
 
 
-def frierson_test_case(res: str, num_levels: int, dt_atmos: float) -> MoistAtmosphere:
+def frierson_test_case(res: str, num_levels: int, dt_atmos: float, **ranks) -> MoistAtmosphere:
     """The Frierson test case (frierson_test_case.py:60-170) at a given resolution: spectral_dynamics_nml with uneven sigma
     levels (scale_heights 11, exponent 7, surf_res 0.5 -- the MiMA/Frierson level distribution of SURVEY section 8d), sphum as
     the grid tracer, SIMPLE_BETTS_MILLER convection, slab ocean of 2.5 m."""
@@ -148,4 +156,4 @@ def frierson_test_case(res: str, num_levels: int, dt_atmos: float) -> MoistAtmos
                       damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
                       initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.5,
                       robert_coeff=0.03, num_tracers=1)
-    return MoistAtmosphere(cfg, physics_nml=FRIERSON_PHYSICS_NML, convection_scheme="SIMPLE_BETTS_MILLER", **FRIERSON_MOIST_NML)
+    return MoistAtmosphere(cfg, physics_nml=FRIERSON_PHYSICS_NML, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **FRIERSON_MOIST_NML)

@@ -115,3 +115,62 @@ def test_gloo_world2_fourier_transpose(lib_built, tmp_path):
     for r in range(2):
         e = np.load(tmp_path / f"err_{r}.npy")
         assert e[0] < 1e-12 and e[1] < 1e-12, (r, e)
+
+
+# ---------------------------------------------------------------------------------------------
+# latitude halo of the grid tracer step (tracer.cu: tracer_halo_pack_kernel, core.cu: exchange_tracer_halo)
+# ---------------------------------------------------------------------------------------------
+def _halo_worker(rank, world, port, out_dir):
+    """Each rank owns a latitude block of (tr0, u, v), packs its 2 edge rows per neighbour in the library's [3][K][2][I] layout,
+    exchanges them (gloo isend/irecv in place of the grouped ncclSend/ncclRecv) and advects with ONLY its block + halos known
+    (everything else zeroed); its rows must equal the single-process oracle result: one 2-row exchange of (tr0, u, v) is
+    enough, q1 = q + semi_x(q) being recomputed on the halo rows (the reference exchanges three times, fv_advection.F90:161-196)."""
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from isca_b200 import api
+    from oracle.isca_oracle import Tables, held_suarez_config
+    from oracle.fv_advection import FVGrid, a_grid_horiz_advection
+    cfg = held_suarez_config("T21", 3, 1200.0, num_tracers=1)
+    tb = Tables(cfg)
+    g = FVGrid(cfg, tb)
+    I, J, K = cfg.lon_max, cfg.lat_max, cfg.num_levels
+    dec = api.decomposition(api.config_from_namelist_object(cfg), rank, world)
+    Jloc, j0 = dec["lat_count"], dec["lat_start"]
+    rng = np.random.default_rng(11)                           # the same global fields on every rank
+    q = rng.random((K, J, I))
+    u = 40.0 * rng.standard_normal((K, J, I))                 # Courant numbers above 1 near the poles: integer fluxes too
+    v = 10.0 * rng.standard_normal((K, J, I))
+    dt = 1200.0
+    ref = a_grid_horiz_advection(g, u, v, q, dt, np.zeros_like(q))
+    mine = [f[:, j0:j0 + Jloc, :] for f in (q, u, v)]
+    send_s = np.stack([f[:, 0:2, :] for f in mine])           # [3][K][2][I]: local rows 0, 1
+    send_n = np.stack([f[:, Jloc - 2:Jloc, :] for f in mine])  # local rows Jloc-2, Jloc-1
+    halo_s, halo_n = torch.zeros(3, K, 2, I, dtype=torch.float64), torch.zeros(3, K, 2, I, dtype=torch.float64)
+    reqs = []
+    if rank > 0:
+        reqs += [dist.isend(torch.from_numpy(np.ascontiguousarray(send_s)), rank - 1), dist.irecv(halo_s, rank - 1)]
+    if rank < world - 1:
+        reqs += [dist.isend(torch.from_numpy(np.ascontiguousarray(send_n)), rank + 1), dist.irecv(halo_n, rank + 1)]
+    for r in reqs:
+        r.wait()
+    known = [np.zeros((K, J, I)) for _ in range(3)]
+    for f in range(3):
+        known[f][:, j0:j0 + Jloc, :] = mine[f]
+        if rank > 0:
+            known[f][:, j0 - 2:j0, :] = halo_s[f].numpy()
+        if rank < world - 1:
+            known[f][:, j0 + Jloc:j0 + Jloc + 2, :] = halo_n[f].numpy()
+    got = a_grid_horiz_advection(g, known[1], known[2], known[0], dt, np.zeros_like(q))
+    err = np.abs(got[:, j0:j0 + Jloc, :] - ref[:, j0:j0 + Jloc, :]).max()
+    np.save(os.path.join(out_dir, f"halo_err_{rank}.npy"), np.array([err]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_tracer_halo(lib_built, tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_halo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / f"halo_err_{r}.npy")[0] == 0.0, r
