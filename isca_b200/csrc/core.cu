@@ -82,7 +82,7 @@ struct IscaHandle_t {
   bool p2p = false;
   DBuf<double> d_sin_lat, d_cos_lat, d_cosm_lat, d_wts_lat, d_coriolis, d_rad_lat, d_pk, d_bk, d_dpk, d_dbk;
   DBuf<double> d_leg, d_legw, d_ln_bk;
-  DBuf<double> d_sg[9];
+  DBuf<double> d_sg[14];
   DBuf<double> d_eigen, d_uvm, d_uvc, d_uvp, d_alpm, d_alpp, d_dym, d_dx, d_dyp, d_mask, d_damp, d_dampv, d_dampd, d_eddy, d_zmu, d_zmv;
   DBuf<double> d_rlh, d_rlf, d_rt, d_h;
   DBuf<double> d_twiddle;
@@ -93,9 +93,9 @@ struct IscaHandle_t {
   DBuf<double> u[2], v[2], T[2], ps[2];
   DBuf<double> vorg, divg, phis, wg_full;
   // ---- grid tracer (sphum)
-  DBuf<double> q[2], tr0, trq1, trq2, tr1, wg;
-  DBuf<double> tr_halo;      // nranks > 1: [halo_s | halo_n | send_s | send_n] x [3][K][2][I], then q1_halo_s, q1_halo_n [K][2][I]
-  DBuf<double> d_fv_c, d_fv_cc, d_fv_dy, d_fv_dyy, d_fv_dyp, d_fv_dym;
+  DBuf<double> q[2], tr1, wg, tr_wpart;
+  DBuf<double> tr_halo;      // nranks > 1: [halo_s | halo_n | send_s | send_n] x [3][K][2][I]
+  DBuf<double> d_fv_c, d_fv_cc, d_fv_dy, d_fv_dyy, d_fv_dyp, d_fv_dym, d_fv_rdxc, d_fv_rdyy, d_fv_rcdy, d_fv_rdy;
   FvTables fv;
   DBuf<int> ops_sum3;
   // ---- work
@@ -232,11 +232,28 @@ static void set_params(H& h) {
       pfk[k] = std::exp(p.kappa * lf[k]);
       x1c[k] = (bk[k + 1] * al[k] + bk[k] * d2) / db[k];
     }
-    const std::vector<double>* src[9] = {&bk, &db, &rdb, &al, &d3, &lf, &pf, &pfk, &x1c};
-    for (int q = 0; q < 9; ++q) h.d_sg[q].upload(*src[q]);
+    // PPM weights with dz = db (vert_advection.F90:504-563 slope_z, :567-629 compute_weights)
+    std::vector<double> c1(K, 0.0), c2(K, 0.0), z1(K, 0.0), z2(K, 0.0), z3(K, 0.0);
+    for (int k = 1; k <= K - 2; ++k) {
+      const double dm = db[k - 1], d0 = db[k], dp = db[k + 1];
+      c1[k] = (2. * dm + d0) / (dp + d0) * d0 / (dm + d0 + dp);
+      c2[k] = (2. * dp + d0) / (d0 + dm) * d0 / (dm + d0 + dp);
+    }
+    for (int k = 2; k <= K - 2; ++k) {
+      const double e2 = db[k - 2], e1 = db[k - 1], e0 = db[k], ep = db[k + 1];
+      const double denom1 = 1.0 / (e1 + e0), denom2 = 1.0 / (e2 + e1 + e0 + ep), denom3 = 1.0 / (2 * e1 + e0), denom4 = 1.0 / (e1 + 2 * e0);
+      const double num3 = e2 + e1, num4 = e0 + ep;
+      const double x = num3 * denom3 - num4 * denom4, y = 2.0 * e1 * e0, z0 = e1 * denom1;
+      z1[k] = z0 + x * y * denom1 * denom2;
+      z2[k] = e1 * num3 * denom3 * denom2;
+      z3[k] = e0 * num4 * denom4 * denom2;
+    }
+    const std::vector<double>* src[14] = {&bk, &db, &rdb, &al, &d3, &lf, &pf, &pfk, &x1c, &c1, &c2, &z1, &z2, &z3};
+    for (int q = 0; q < 14; ++q) h.d_sg[q].upload(*src[q]);
     SigmaTables& sg = h.dt.sig;
     sg.b = h.d_sg[0].p; sg.db = h.d_sg[1].p; sg.rdb = h.d_sg[2].p; sg.al = h.d_sg[3].p; sg.d3 = h.d_sg[4].p;
     sg.lf = h.d_sg[5].p; sg.pf = h.d_sg[6].p; sg.pfk = h.d_sg[7].p; sg.x1c = h.d_sg[8].p;
+    sg.ppm_c1 = h.d_sg[9].p; sg.ppm_c2 = h.d_sg[10].p; sg.ppm_z1 = h.d_sg[11].p; sg.ppm_z2 = h.d_sg[12].p; sg.ppm_z3 = h.d_sg[13].p;
   }
 }
 
@@ -249,14 +266,23 @@ static void alloc_state(H& h) {
   h.vorg.alloc(h.n3()); h.divg.alloc(h.n3()); h.phis.alloc(h.nplane()); h.wg_full.alloc(h.n3());
   if (h.cfg.num_tracers > 0) {
     for (int s = 0; s < 2; ++s) h.q[s].alloc(h.n3());
-    h.tr0.alloc(h.n3()); h.trq1.alloc(h.n3()); h.trq2.alloc(h.n3()); h.tr1.alloc(h.n3());
+    h.tr1.alloc(h.n3()); h.tr_wpart.alloc(4 * h.nplane());
     h.wg.alloc(h.n3() + h.nplane());
-    if (g.P > 1) { h.tr_halo.alloc((size_t)14 * K * 2 * g.I); CK(cudaMemset(h.tr_halo.p, 0, (size_t)14 * K * 2 * g.I * sizeof(double))); }
+    if (g.P > 1) { h.tr_halo.alloc((size_t)12 * K * 2 * g.I); CK(cudaMemset(h.tr_halo.p, 0, (size_t)12 * K * 2 * g.I * sizeof(double))); }
     const HostTables& t = h.ht;
     h.d_fv_c.upload(t.fv_c); h.d_fv_cc.upload(t.fv_cc); h.d_fv_dy.upload(t.fv_dy); h.d_fv_dyy.upload(t.fv_dyy);
     h.d_fv_dyp.upload(t.fv_dy_plus); h.d_fv_dym.upload(t.fv_dy_minus);
     h.fv.c = h.d_fv_c.p; h.fv.cc = h.d_fv_cc.p; h.fv.dy = h.d_fv_dy.p; h.fv.dyy = h.d_fv_dyy.p;
     h.fv.dy_plus = h.d_fv_dyp.p; h.fv.dy_minus = h.d_fv_dym.p; h.fv.dx = t.fv_dx;
+    {
+      const int J = g.J;
+      std::vector<double> rdxc(J), rdyy(J + 1), rcdy(J), rdy(J + 4);
+      for (int j = 0; j < J; ++j) { rdxc[j] = 1.0 / (t.fv_dx * t.fv_c[j]); rcdy[j] = 1.0 / (t.fv_c[j] * t.fv_dy[j + 2]); }
+      for (int j = 0; j <= J; ++j) rdyy[j] = 1.0 / t.fv_dyy[j];
+      for (int j = 0; j < J + 4; ++j) rdy[j] = 1.0 / t.fv_dy[j];
+      h.d_fv_rdxc.upload(rdxc); h.d_fv_rdyy.upload(rdyy); h.d_fv_rcdy.upload(rcdy); h.d_fv_rdy.upload(rdy);
+      h.fv.rdxc = h.d_fv_rdxc.p; h.fv.rdyy = h.d_fv_rdyy.p; h.fv.rcdy = h.d_fv_rcdy.p; h.fv.rdy = h.d_fv_rdy.p;
+    }
     h.ops_sum3.upload({0, 0, 0});
   }
   h.dt_vors.alloc(h.nspec3()); h.w_div.alloc(h.nspec3()); h.w_T.alloc(h.nspec3()); h.w_lnps.alloc(g.T);
@@ -351,7 +377,7 @@ static void exchange_fourier(H& h, int direction, int Lp) {
 static void exchange_tracer_halo(H& h, const TracerArgs& ta) {
   const Geometry& g = h.g;
   if (g.P == 1) return;
-  launch_tracer_halo_pack(h.dt, ta, h.st); h.launches++;
+  launch_tracer_halo_pack(h.dt, h.pr, ta, h.st); h.launches++;
   const size_t n = (size_t)3 * g.K * 2 * g.I;
   const NcclApi& nc = h.nccl;
   nc.ck(nc.GroupStart(), "ncclGroupStart");
@@ -481,28 +507,25 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
     const IscaConfig& c = h.cfg;
     ta.q_prev = h.q[prev].p; ta.q_cur = h.q[cur].p; ta.q_cur_w = h.q[cur].p; ta.q_fut = h.q[fut].p;
     ta.u_cur = h.u[cur].p; ta.v_cur = h.v[cur].p; ta.ps_cur = h.ps[cur].p; ta.ps_prev = h.ps[prev].p; ta.ps_fut = h.ps[fut].p;
-    ta.wg = h.wg.p; ta.tr0 = h.tr0.p; ta.q1 = h.trq1.p; ta.q2 = h.trq2.p; ta.tr1 = h.tr1.p; ta.part = h.part.p;
+    ta.wg = h.wg.p; ta.tr1 = h.tr1.p; ta.part = h.part.p; ta.wpart = h.tr_wpart.p;
     ta.delta_t = delta_t; ta.trflux = c.trflux;
     const double sink_s = c.trsink < 0. ? -86400. * c.trsink : c.trsink;       // hs_forcing.F90:408-409, 697-699
     ta.trdamp = sink_s > 0. ? 1. / sink_s : 0.;
     ta.robert_coeff = c.tracer_robert_coeff < 0. ? c.robert_coeff : c.tracer_robert_coeff;
     ta.raw_filter_coeff = c.raw_filter_coeff; ta.water_limit = c.water_correction_limit; ta.physics_on = physics_on;
     ta.dt_q_in = dtq_in;
-    ta.halo_s = ta.halo_n = ta.send_s = ta.send_n = ta.q1_halo_s = ta.q1_halo_n = nullptr;
+    ta.halo_s = ta.halo_n = ta.send_s = ta.send_n = nullptr;
     if (g.P > 1) {
-      const size_t hb = (size_t)3 * K * 2 * g.I, qb = (size_t)K * 2 * g.I;
+      const size_t hb = (size_t)3 * K * 2 * g.I;
       double* p = h.tr_halo.p;
       ta.halo_s = p; ta.halo_n = p + hb; ta.send_s = p + 2 * hb; ta.send_n = p + 3 * hb;
-      ta.q1_halo_s = p + 4 * hb; ta.q1_halo_n = p + 4 * hb + qb;
     }
-    launch_tracer_source(h.dt, pr, ta, st);
+    exchange_tracer_halo(h, ta);
+    launch_tracer_horiz(h.dt, h.fv, pr, ta, st);
+    launch_tracer_ppm(h.dt, pr, ta, st);
     launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_W_PREV, h.red_tmp.p, st);
     allreduce_scalars(h, h.scal.p + SC_W_PREV, 1, NCCL_SUM);
-    exchange_tracer_halo(h, ta);
-    launch_tracer_semi(h.dt, h.fv, ta, st);
-    launch_tracer_flux(h.dt, h.fv, ta, st);
-    launch_tracer_ppm(h.dt, pr, ta, st);
-    h.launches += 6;
+    h.launches += 4;
     h.mark("tracer_advection");
   }
 

@@ -16,6 +16,9 @@ struct SigmaTables {
   const double *pf;     // p_full/ps
   const double *pfk;    // (p_full/ps)^kappa
   const double *x1c;    // (bk(k+1)*dlog_1 + bk(k)*dlog_2) / db                 (x1 * ps)
+  // PPM vertical advection (tracer.cu): slope_z weights (levels 1..K-2) and compute_weights z1..z3 (levels 2..K-2) of
+  // atmos_shared/vert_advection/vert_advection.F90:504-629 with dz = db (the surface pressure cancels)
+  const double *ppm_c1, *ppm_c2, *ppm_z1, *ppm_z2, *ppm_z3;
 };
 
 // All device-resident constant tables.  Pointers are device pointers.
