@@ -451,13 +451,18 @@ tracer_ppm_kernel(DevTables t, Params pr, TracerArgs a) {
   double w_k = W(0);
   double flux_above = w_k * r_0;                        // flux(ks) = w(ks)*r(ks)
   double vi = 0.0, a_c = 0.0, b_c = 0.0, a_n = 0.0, b_n = 0.0;
+  // loads run one level ahead of the arithmetic (software pipeline: two levels of loads in flight per thread)
+  double n_r3 = (3 < K) ? c.R(3) : 0.0, n_w1 = W(1), n_qp = a.q_prev[col], n_qc = a.q_cur[col];
+  double n_dtq = a.dt_q_in ? a.dt_q_in[col] : 0.0;
   for (int k = 0; k < K; ++k) {
     const size_t e = (size_t)k * plane + col;
-    // loads of this level (issued ahead of the arithmetic)
-    const double r_p3 = (k + 3 < K) ? c.R(k + 3) : 0.0;
-    const double w_k1 = W(k + 1);
-    const double qp = a.q_prev[e], qc = a.q_cur[e];
-    const double dtq = a.dt_q_in ? a.dt_q_in[e] : 0.0;
+    const double r_p3 = n_r3, w_k1 = n_w1, qp = n_qp, qc = n_qc, dtq = n_dtq;
+    if (k + 1 < K) {
+      n_r3 = (k + 4 < K) ? c.R(k + 4) : 0.0;
+      n_w1 = W(k + 2);
+      n_qp = a.q_prev[e + plane]; n_qc = a.q_cur[e + plane];
+      if (a.dt_q_in) n_dtq = a.dt_q_in[e + plane];
+    }
     // ---- stage A: edges of level k+1 (needs r(k+3))
     if (k + 1 < K) {
       const int ka = k + 1;
