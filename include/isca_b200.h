@@ -182,6 +182,31 @@ int isca_b200_uv_grid_from_vor_div(IscaHandle h, const double* vors, const doubl
 int isca_b200_vor_div_from_uv_grid(IscaHandle h, const double* ug, const double* vg,
                                    double* vors, double* divs, int nlev);
 
+/* Stage-level entry points (unit tests / init-time callers; single rank -- with nranks > 1 the Fourier transpose sits between
+ * the two stages).  Fourier arrays are the reference's (0:num_fourier, lat, lev) complex arrays:
+ *   isca_b200_fft_r2c      trans_grid_to_fourier    (tools/grid_fourier.F90:129-150 -> fft_grid_to_fourier, shared/fft/fft.F90:483-591)
+ *   isca_b200_fft_c2r      trans_fourier_to_grid    (tools/grid_fourier.F90:154-179 -> fft_fourier_to_grid, fft.F90:600-718)
+ *   isca_b200_legendre_inv trans_spherical_to_fourier (tools/spherical_fourier.F90:177-261)
+ *   isca_b200_legendre_fwd trans_fourier_to_spherical (tools/spherical_fourier.F90:264-339), + triangular_truncation if asked */
+int isca_b200_fft_r2c(IscaHandle h, const double* grid, double* fourier, int nlev);
+int isca_b200_fft_c2r(IscaHandle h, const double* fourier, double* grid, int nlev);
+int isca_b200_legendre_inv(IscaHandle h, const double* spec, double* fourier, int nlev);
+int isca_b200_legendre_fwd(IscaHandle h, const double* fourier, double* spec, int nlev,
+                           int do_truncation);
+/* implicit_correction(dt_divs, dt_ts, dt_ln_ps, divs, ts, ln_ps, delta_t, previous, current)
+ * (atmos_spectral/model/implicit.F90:241-325): the three tendencies are updated in place; the two time levels of divs, ts,
+ * ln_ps are passed as separate (m,n,lev) / (m,n) complex arrays; wave matrices are (re)built for delta_t as :260-264 does. */
+int isca_b200_implicit_correction(IscaHandle h, double* dt_divs, double* dt_ts, double* dt_ln_ps,
+                                  const double* divs_prev, const double* divs_cur,
+                                  const double* ts_prev, const double* ts_cur,
+                                  const double* ln_ps_prev, const double* ln_ps_cur, double delta_t);
+
+/* Device-side time averaging for diag_manager (send_data with time_avg, diag_manager; spectral_diagnostics
+ * spectral_dynamics.F90:1709-1867): accumulate adds the current level's field (ISCA_F_* ids) to a device accumulator; fetch
+ * returns the mean over the accumulated samples (and their number), optionally resetting the accumulator. */
+int isca_b200_diag_accumulate(IscaHandle h, int field_id);
+int isca_b200_diag_fetch(IscaHandle h, int field_id, double* host, int reset, int* count_out);
+
 /* kernel-level entry points used by bench.py / tests for device-resident timing:
  * run `reps` batched inverse+forward transform pairs of `nlev` levels on resident synthetic
  * data and return the average milliseconds of each stage measured with CUDA events on the

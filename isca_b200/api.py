@@ -67,6 +67,8 @@ EXPORTS = [
     "isca_b200_grid_to_spherical", "isca_b200_uv_grid_from_vor_div", "isca_b200_vor_div_from_uv_grid",
     "isca_b200_time_transforms", "isca_b200_profile_step", "isca_b200_decomposition",
     "isca_b200_ipc_handles", "isca_b200_set_peer_handles",
+    "isca_b200_fft_r2c", "isca_b200_fft_c2r", "isca_b200_legendre_inv", "isca_b200_legendre_fwd",
+    "isca_b200_implicit_correction", "isca_b200_diag_accumulate", "isca_b200_diag_fetch",
 ]
 
 # field / scalar ids (include/isca_b200.h)
@@ -113,6 +115,12 @@ def load_library() -> C.CDLL:
     lib.isca_b200_step_dynamics_only.argtypes = [vp, C.c_int]
     lib.isca_b200_spectral_dynamics.argtypes = [vp] + [vp] * 10
     lib.isca_b200_spectral_dynamics_tracers.argtypes = [vp] + [vp] * 12
+    for f in (lib.isca_b200_fft_r2c, lib.isca_b200_fft_c2r, lib.isca_b200_legendre_inv):
+        f.argtypes = [vp, vp, vp, C.c_int]
+    lib.isca_b200_legendre_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    lib.isca_b200_implicit_correction.argtypes = [vp] + [vp] * 9 + [C.c_double]
+    lib.isca_b200_diag_accumulate.argtypes = [vp, C.c_int]
+    lib.isca_b200_diag_fetch.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
     lib.isca_b200_get_field.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.isca_b200_get_spectral.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.isca_b200_get_scalar.argtypes = [vp, C.c_int, dp]
@@ -313,6 +321,52 @@ class Atmosphere:
                                                               _ptr(out["grid_tracers"]), _ptr(out["wg_full"]), _ptr(out["p_full"])),
                  "spectral_dynamics")
         return {k: v for k, v in out.items() if v is not None}
+
+    # ---- stage-level transforms, implicit_correction, device-side diagnostics ------------------
+    def trans_grid_to_fourier(self, grid):
+        g = _in(grid); nlev = g.shape[0]
+        out = np.empty((nlev, self.J, self.M + 1), dtype=np.complex128)
+        self._ck(self.lib.isca_b200_fft_r2c(self.h, _ptr(g), _ptr(out), nlev), "trans_grid_to_fourier")
+        return out
+
+    def trans_fourier_to_grid(self, fourier):
+        f = _in(fourier, None, np.complex128); nlev = f.shape[0]
+        out = np.empty((nlev, self.J, self.I))
+        self._ck(self.lib.isca_b200_fft_c2r(self.h, _ptr(f), _ptr(out), nlev), "trans_fourier_to_grid")
+        return out
+
+    def trans_spherical_to_fourier(self, spec):
+        sp = _in(spec, None, np.complex128); nlev = sp.shape[0]
+        out = np.empty((nlev, self.J, self.M + 1), dtype=np.complex128)
+        self._ck(self.lib.isca_b200_legendre_inv(self.h, _ptr(sp), _ptr(out), nlev), "trans_spherical_to_fourier")
+        return out
+
+    def trans_fourier_to_spherical(self, fourier, do_truncation=True):
+        f = _in(fourier, None, np.complex128); nlev = f.shape[0]
+        out = np.empty((nlev, self.N + 1, self.M + 1), dtype=np.complex128)
+        self._ck(self.lib.isca_b200_legendre_fwd(self.h, _ptr(f), _ptr(out), nlev, int(do_truncation)), "trans_fourier_to_spherical")
+        return out
+
+    def implicit_correction(self, dt_divs, dt_ts, dt_ln_ps, divs, ts, ln_ps, delta_t, previous=0, current=1):
+        """implicit_correction(dt_divs, dt_ts, dt_ln_ps, divs, ts, ln_ps, delta_t, previous, current): divs/ts [2, K, N+1, M+1],
+        ln_ps [2, N+1, M+1] hold the two time levels; returns the corrected (dt_divs, dt_ts, dt_ln_ps)."""
+        s3, s2 = (self.K, self.N + 1, self.M + 1), (self.N + 1, self.M + 1)
+        o = [np.array(_in(x, s, np.complex128), copy=True) for x, s in ((dt_divs, s3), (dt_ts, s3), (dt_ln_ps, s2))]
+        lv = [_in(x[i], s, np.complex128) for x, s in ((divs, s3), (ts, s3), (ln_ps, s2)) for i in (previous, current)]
+        self._ck(self.lib.isca_b200_implicit_correction(self.h, _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), *[_ptr(x) for x in lv],
+                                                        float(delta_t)), "implicit_correction")
+        return tuple(o)
+
+    def diag_accumulate(self, field_id):
+        self._ck(self.lib.isca_b200_diag_accumulate(self.h, field_id), "diag_accumulate")
+
+    def diag_fetch(self, field_id, reset=True):
+        """time mean of the accumulated samples of a grid field and their number"""
+        n2 = (self.Jloc, self.I)
+        shape = n2 if field_id == F_PS else ((self.K + 1,) + n2 if field_id in (F_P_HALF, F_Z_HALF) else (self.K,) + n2)
+        out = np.empty(shape); cnt = C.c_int(0)
+        self._ck(self.lib.isca_b200_diag_fetch(self.h, field_id, _ptr(out), int(reset), C.byref(cnt)), "diag_fetch")
+        return out, cnt.value
 
     # ---- state I/O (restart path / diag mirrors) ---------------------------------------------
     def set_grid_state(self, slot, ug=None, vg=None, tg=None, psg=None, tracers=None):

@@ -135,8 +135,10 @@ struct IscaHandle_t {
     marks.emplace_back(name, e);
   }
   // ---- scratch for the transforms_mod-level API
-  DBuf<double2> x_rect, x_spec;
-  DBuf<double> x_grid, x_four;
+  DBuf<double2> x_rect, x_spec, x_fr, x_imp[9];
+  struct DiagAcc { DBuf<double>* sum = nullptr; long long count = 0; size_t n = 0; };
+  std::map<int, DiagAcc> diag;          // device-side time averages (isca_b200_diag_accumulate / _fetch)
+  DBuf<double> x_grid, x_four, x_pz;
   DBuf<LevDesc> x_levs;
   DBuf<unsigned char> x_trunc;
 
@@ -706,6 +708,25 @@ static void cold_start(H& h) {
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// stage-level ABI helpers (single rank): reference Fourier layout (0:M, lat, lev) complex <-> the library's Fourier buffer
+// [(pos[m]*J + j)][2*Lp]
+// ---------------------------------------------------------------------------------------------
+__global__ void four_layout_kernel(GeomDev g, double2* ref, double* four, int nlev, int Lp, int to_internal) {
+  const size_t n = (size_t)nlev * g.J * (g.M + 1);
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int m = (int)(idx % (g.M + 1));
+  const int j = (int)((idx / (g.M + 1)) % g.J);
+  const int lev = (int)(idx / ((size_t)(g.M + 1) * g.J));
+  double2* f = reinterpret_cast<double2*>(four + ((size_t)g.pos[m] * g.J + j) * 2 * Lp) + lev;
+  if (to_internal) *f = ref[idx]; else ref[idx] = *f;
+}
+__global__ void diag_axpy_kernel(double* __restrict__ acc, const double* __restrict__ x, size_t n, double scale, int accumulate) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) acc[i] = accumulate ? acc[i] + x[i] : x[i] * scale;
+}
+
 #define API_BEGIN(h) if (!(h)) return 1; try {
 #define API_END(h) } catch (const std::exception& e) { (h)->err = e.what(); return 2; } return 0;
 
@@ -1045,40 +1066,43 @@ static int slot_of(H& h, int level) {
   throw std::runtime_error("invalid time level selector");
 }
 
-int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
-  API_BEGIN(h)
-  const int s = slot_of(*h, level);
-  const size_t n3 = h->n3(), pl = h->nplane();
-  CK(cudaStreamSynchronize(h->st));
+// device pointer and element count of a grid field (materialised on the library's stream where needed)
+static size_t field_on_device(H& h, int id, int level, const double** ptr) {
+  const int s = slot_of(h, level);
+  const size_t n3 = h.n3(), pl = h.nplane();
   switch (id) {
-    case ISCA_F_PS: d2h_on(h->st, host, h->ps[s].p, pl * sizeof(double)); break;
-    case ISCA_F_U: d2h_on(h->st, host, h->u[s].p, n3 * sizeof(double)); break;
-    case ISCA_F_V: d2h_on(h->st, host, h->v[s].p, n3 * sizeof(double)); break;
-    case ISCA_F_T:
-      launch_materialize_t(h->dt, h->T[s].p, h->scal.p, s, h->st);
-      d2h_on(h->st, host, h->T[s].p, n3 * sizeof(double)); break;
-    case ISCA_F_VOR: d2h_on(h->st, host, h->vorg.p, n3 * sizeof(double)); break;
-    case ISCA_F_DIV: d2h_on(h->st, host, h->divg.p, n3 * sizeof(double)); break;
-    case ISCA_F_WG_FULL: d2h_on(h->st, host, h->wg_full.p, n3 * sizeof(double)); break;
+    case ISCA_F_PS: *ptr = h.ps[s].p; return pl;
+    case ISCA_F_U: *ptr = h.u[s].p; return n3;
+    case ISCA_F_V: *ptr = h.v[s].p; return n3;
+    case ISCA_F_T: launch_materialize_t(h.dt, h.T[s].p, h.scal.p, s, h.st); *ptr = h.T[s].p; return n3;
+    case ISCA_F_VOR: *ptr = h.vorg.p; return n3;
+    case ISCA_F_DIV: *ptr = h.divg.p; return n3;
+    case ISCA_F_WG_FULL: *ptr = h.wg_full.p; return n3;
     case ISCA_F_TRACER0:
-      if (h->cfg.num_tracers < 1) throw std::runtime_error("no tracer configured");
-      d2h_on(h->st, host, h->q[s].p, n3 * sizeof(double)); break;
+      if (h.cfg.num_tracers < 1) throw std::runtime_error("no tracer configured");
+      *ptr = h.q[s].p; return n3;
     case ISCA_F_P_FULL: case ISCA_F_P_HALF: case ISCA_F_Z_FULL: case ISCA_F_Z_HALF: {
       const size_t nh = n3 + pl;
-      h->x_grid.ensure(nh);
-      double* pf = (id == ISCA_F_P_FULL) ? h->x_grid.p : nullptr;
-      double* ph = (id == ISCA_F_P_HALF) ? h->x_grid.p : nullptr;
-      double* zf = (id == ISCA_F_Z_FULL) ? h->x_grid.p : nullptr;
-      double* zh = (id == ISCA_F_Z_HALF) ? h->x_grid.p : nullptr;
-      launch_materialize_t(h->dt, h->T[s].p, h->scal.p, s, h->st);
-      launch_press_heights(h->dt, h->pr, h->T[s].p, h->ps[s].p, h->phis.p, pf, ph, zf, zh, h->st);
-      CK(cudaStreamSynchronize(h->st));
-      const size_t cnt = (id == ISCA_F_P_HALF || id == ISCA_F_Z_HALF) ? nh : n3;
-      d2h_on(h->st, host, h->x_grid.p, cnt * sizeof(double));
-      break;
+      h.x_pz.ensure(nh);
+      double* pf = (id == ISCA_F_P_FULL) ? h.x_pz.p : nullptr;
+      double* ph = (id == ISCA_F_P_HALF) ? h.x_pz.p : nullptr;
+      double* zf = (id == ISCA_F_Z_FULL) ? h.x_pz.p : nullptr;
+      double* zh = (id == ISCA_F_Z_HALF) ? h.x_pz.p : nullptr;
+      launch_materialize_t(h.dt, h.T[s].p, h.scal.p, s, h.st);
+      launch_press_heights(h.dt, h.pr, h.T[s].p, h.ps[s].p, h.phis.p, pf, ph, zf, zh, h.st);
+      *ptr = h.x_pz.p;
+      return (id == ISCA_F_P_HALF || id == ISCA_F_Z_HALF) ? nh : n3;
     }
     default: throw std::runtime_error("unknown field id");
   }
+}
+
+int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
+  API_BEGIN(h)
+  const double* src = nullptr;
+  const size_t n = field_on_device(*h, id, level, &src);
+  CK(cudaStreamSynchronize(h->st));
+  d2h_on(h->st, host, src, n * sizeof(double));
   API_END(h)
 }
 
@@ -1162,6 +1186,124 @@ int isca_b200_grid_to_spherical(IscaHandle h, const double* grid, double* spec, 
   x_set_levs(*h, nlev, 0, 0);
   dev_forward(*h, h->x_levs.p, nlev, h->x_spec.p, Lp, h->x_trunc.p);
   get_spec(*h, h->x_spec.p, Lp, 0, spec, nlev);
+  API_END(h)
+}
+
+// ---- stage-level entry points (secondary ABI of SURVEY section 8b; single rank) -----------------------------------------
+static void stage_prepare(H& h, int nlev) {
+  if (h.g.P != 1) throw std::runtime_error("the stage-level entry points (fft_*, legendre_*) are single-rank: with nranks > 1 the Fourier transpose sits between them");
+  if (nlev < 1) throw std::runtime_error("nlev must be positive");
+  x_prepare(h, nlev, 1);
+  h.x_fr.ensure((size_t)nlev * h.g.J * (h.g.M + 1));
+}
+static void four_convert(H& h, int nlev, int Lp, int to_internal) {
+  const size_t n = (size_t)nlev * h.g.J * (h.g.M + 1);
+  four_layout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h.st>>>(h.dt.g, h.x_fr.p, h.four.p, nlev, Lp, to_internal);
+}
+
+int isca_b200_fft_c2r(IscaHandle h, const double* fourier, double* grid, int nlev) {
+  API_BEGIN(h)
+  stage_prepare(*h, nlev);
+  const int Lp = round_up(nlev, 16);
+  const size_t nf = (size_t)nlev * h->g.J * (h->g.M + 1);
+  h2d_on(h->st, h->x_fr.p, fourier, nf * sizeof(double2));
+  CK(cudaMemsetAsync(h->four.p, 0, (size_t)(h->g.M + 1) * h->g.J * 2 * Lp * sizeof(double), h->st));
+  four_convert(*h, nlev, Lp, 1);
+  x_set_levs(*h, nlev, 0, 0);
+  launch_fft_inv(h->dt, h->four.p, h->x_levs.p, nlev, Lp, h->st);
+  CK(cudaStreamSynchronize(h->st));
+  d2h_on(h->st, grid, h->x_grid.p, (size_t)nlev * h->nplane() * sizeof(double));
+  API_END(h)
+}
+
+int isca_b200_fft_r2c(IscaHandle h, const double* grid, double* fourier, int nlev) {
+  API_BEGIN(h)
+  stage_prepare(*h, nlev);
+  const int Lp = round_up(nlev, 16);
+  const size_t nf = (size_t)nlev * h->g.J * (h->g.M + 1);
+  h2d_on(h->st, h->x_grid.p, grid, (size_t)nlev * h->nplane() * sizeof(double));
+  x_set_levs(*h, nlev, 0, 0);
+  launch_fft_fwd(h->dt, h->four.p, h->x_levs.p, nlev, Lp, h->st);
+  four_convert(*h, nlev, Lp, 0);
+  CK(cudaStreamSynchronize(h->st));
+  d2h_on(h->st, fourier, h->x_fr.p, nf * sizeof(double2));
+  API_END(h)
+}
+
+int isca_b200_legendre_inv(IscaHandle h, const double* spec, double* fourier, int nlev) {
+  API_BEGIN(h)
+  stage_prepare(*h, nlev);
+  const Geometry& g = h->g;
+  const int Lp = round_up(nlev, 16);
+  h2d_on(h->st, h->x_rect.p, spec, (size_t)nlev * (g.N + 1) * (g.M + 1) * sizeof(double2));
+  CK(cudaMemsetAsync(h->x_spec.p, 0, (size_t)g.T * Lp * sizeof(double2), h->st));
+  launch_pack_spec(h->dt, h->x_rect.p, h->x_spec.p, nlev, Lp, 0, h->st);
+  launch_legendre_inv(h->dt, h->x_spec.p, h->four.p, Lp, h->st);
+  four_convert(*h, nlev, Lp, 0);
+  CK(cudaStreamSynchronize(h->st));
+  d2h_on(h->st, fourier, h->x_fr.p, (size_t)nlev * g.J * (g.M + 1) * sizeof(double2));
+  API_END(h)
+}
+
+int isca_b200_legendre_fwd(IscaHandle h, const double* fourier, double* spec, int nlev, int do_truncation) {
+  API_BEGIN(h)
+  stage_prepare(*h, nlev);
+  const Geometry& g = h->g;
+  const int Lp = round_up(nlev, 16);
+  h2d_on(h->st, h->x_fr.p, fourier, (size_t)nlev * g.J * (g.M + 1) * sizeof(double2));
+  CK(cudaMemsetAsync(h->four.p, 0, (size_t)(g.M + 1) * g.J * 2 * Lp * sizeof(double), h->st));
+  four_convert(*h, nlev, Lp, 1);
+  CK(cudaMemsetAsync(h->x_trunc.p, do_truncation ? 1 : 0, Lp, h->st));
+  launch_legendre_fwd(h->dt, h->four.p, h->x_spec.p, Lp, h->x_trunc.p, h->st);
+  get_spec(*h, h->x_spec.p, Lp, 0, spec, nlev);
+  API_END(h)
+}
+
+int isca_b200_implicit_correction(IscaHandle h, double* dt_divs, double* dt_ts, double* dt_ln_ps, const double* divs_prev,
+                                  const double* divs_cur, const double* ts_prev, const double* ts_cur, const double* ln_ps_prev,
+                                  const double* ln_ps_cur, double delta_t) {
+  API_BEGIN(h)
+  if (!h->cfg.use_implicit) throw std::runtime_error("implicit_correction: use_implicit is .false.");
+  if (!dt_divs || !dt_ts || !dt_ln_ps || !divs_prev || !divs_cur || !ts_prev || !ts_cur || !ln_ps_prev || !ln_ps_cur)
+    throw std::runtime_error("implicit_correction: null array");
+  const Geometry& g = h->g; const int K = g.K;
+  const double* src[9] = {dt_divs, dt_ts, dt_ln_ps, divs_prev, divs_cur, ts_prev, ts_cur, ln_ps_prev, ln_ps_cur};
+  const int lev[9] = {K, K, 1, K, K, K, K, 1, 1};
+  for (int i = 0; i < 9; ++i) { h->x_imp[i].ensure((size_t)g.T * lev[i]); set_spec(*h, h->x_imp[i], src[i], lev[i]); }
+  Params pr = h->pr;
+  pr.xi = delta_t * h->cfg.alpha_implicit;                    // implicit.F90:260-264: matrices follow the step passed in
+  ensure_wave_matrix(*h, pr.xi);
+  launch_implicit_correction(h->dt, pr, h->x_imp[0].p, h->x_imp[1].p, h->x_imp[2].p, h->x_imp[3].p, h->x_imp[4].p, h->x_imp[5].p,
+                             h->x_imp[6].p, h->x_imp[7].p, h->x_imp[8].p, h->st);
+  get_spec(*h, h->x_imp[0].p, K, 0, dt_divs, K);
+  get_spec(*h, h->x_imp[1].p, K, 0, dt_ts, K);
+  get_spec(*h, h->x_imp[2].p, 1, 0, dt_ln_ps, 1);
+  API_END(h)
+}
+
+// ---- device-side time averages for diag_manager (boundary list of 8b) ----------------------------
+int isca_b200_diag_accumulate(IscaHandle h, int field_id) {
+  API_BEGIN(h)
+  const double* src = nullptr;
+  const size_t n = field_on_device(*h, field_id, ISCA_LEVEL_CURRENT, &src);
+  H::DiagAcc& a = h->diag[field_id];
+  if (!a.sum) { a.sum = new DBuf<double>(); a.sum->alloc(n); a.n = n; a.count = 0; CK(cudaMemsetAsync(a.sum->p, 0, n * sizeof(double), h->st)); }
+  diag_axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(a.sum->p, src, n, 1.0, 1);
+  a.count++;
+  API_END(h)
+}
+
+int isca_b200_diag_fetch(IscaHandle h, int field_id, double* host, int reset, int* count_out) {
+  API_BEGIN(h)
+  auto it = h->diag.find(field_id);
+  if (it == h->diag.end() || it->second.count == 0) throw std::runtime_error("diag_fetch: nothing accumulated for this field");
+  H::DiagAcc& a = it->second;
+  h->x_grid.ensure(a.n);
+  diag_axpy_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, h->st>>>(h->x_grid.p, a.sum->p, a.n, 1.0 / (double)a.count, 0);
+  CK(cudaStreamSynchronize(h->st));
+  d2h_on(h->st, host, h->x_grid.p, a.n * sizeof(double));
+  if (count_out) *count_out = (int)a.count;
+  if (reset) { CK(cudaMemsetAsync(a.sum->p, 0, a.n * sizeof(double), h->st)); a.count = 0; }
   API_END(h)
 }
 

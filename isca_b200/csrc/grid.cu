@@ -609,8 +609,8 @@ void launch_materialize_t(const DevTables& t, double* T, double* scal, int slot,
 // compute_pressures_and_heights (dry): p_half, p_full, z_half, z_full for diagnostics / physics API
 // ---------------------------------------------------------------------------------------------
 __global__ void press_heights_kernel(DevTables t, Params pr, const double* __restrict__ T, const double* __restrict__ ps,
-                                     const double* __restrict__ phis, double* p_full, double* p_half, double* z_full,
-                                     double* z_half) {
+                                     const double* __restrict__ phis, double* __restrict__ p_full, double* __restrict__ p_half,
+                                     double* __restrict__ z_full, double* __restrict__ z_half) {
   const GeomDev& g = t.g;
   const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
   if (i >= g.I) return;
@@ -622,19 +622,27 @@ __global__ void press_heights_kernel(DevTables t, Params pr, const double* __res
   double ln_half_below = ln_p_half(t, pr, K, t.pk[K] + t.bk[K] * p_s, ln_ps);
   if (p_half) p_half[(size_t)K * plane + col] = t.pk[K] + t.bk[K] * p_s;
   if (z_half) z_half[(size_t)K * plane + col] = gh_below / pr.grav;
-  for (int k = K - 1; k >= 0; --k) {
-    const size_t e = (size_t)k * plane + col;
-    PressLevel pl;
-    press_level(t, pr, k, p_s, ln_ps, ln_half_below, pl);
-    const double tt = T[e];
-    const double gfull = gh_below + pr.rdgas * tt * (pl.ln_half_k1 - pl.ln_full);
-    double gh = 0.0;
-    if (!(k == 0 && pr.pk0_zero)) gh = gh_below + pr.rdgas * tt * (pl.ln_half_k1 - pl.ln_half_k);
-    if (p_full) p_full[e] = pl.p_full;
-    if (p_half) p_half[e] = pl.p_half_k;
-    if (z_full) z_full[e] = gfull / pr.grav;
-    if (z_half) z_half[e] = gh / pr.grav;
-    gh_below = gh; ln_half_below = pl.ln_half_k;
+  for (int k0 = K - 1; k0 >= 0; k0 -= 4) {            // four levels of loads in flight, consumed serially
+    double t4[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) if (k0 - d >= 0) t4[d] = T[(size_t)(k0 - d) * plane + col];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int k = k0 - d;
+      if (k < 0) break;
+      const size_t e = (size_t)k * plane + col;
+      PressLevel pl;
+      press_level(t, pr, k, p_s, ln_ps, ln_half_below, pl);
+      const double tt = t4[d];
+      const double gfull = gh_below + pr.rdgas * tt * (pl.ln_half_k1 - pl.ln_full);
+      double gh = 0.0;
+      if (!(k == 0 && pr.pk0_zero)) gh = gh_below + pr.rdgas * tt * (pl.ln_half_k1 - pl.ln_half_k);
+      if (p_full) p_full[e] = pl.p_full;
+      if (p_half) p_half[e] = pl.p_half_k;
+      if (z_full) z_full[e] = gfull / pr.grav;
+      if (z_half) z_half[e] = gh / pr.grav;
+      gh_below = gh; ln_half_below = pl.ln_half_k;
+    }
   }
 }
 void launch_press_heights(const DevTables& t, const Params& pr, const double* T, const double* ps, const double* phis,

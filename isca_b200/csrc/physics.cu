@@ -46,29 +46,39 @@ __global__ void __launch_bounds__(128) lscale_cond_kernel(SvpDev s, PhysConst c,
   double exq = 0.0, precip = 0.0;
   double ph0 = phalf[col];
   bool bad = false;
-  for (int k = 0; k < K; ++k) {
-    size_t o = (size_t)k * ncol + col;
-    double t = tin[o], q = qin[o], p = pfull[o], ph1 = phalf[o + ncol];
-    double es, des, qsat, dqsat;
-    bad |= !svp_lookup(s, t, es, des);
-    qs_from_es(es, des, p, c.hc, eps, qsat, dqsat);
-    double qd = 0.0, td = 0.0;
-    if ((q - qsat) * qsat > 0.0) { qd = (qsat - q) / (1.0 + hlcp * dqsat); td = -hlcp * qd; }
-    double pmass = (ph1 - ph0) / c.grav;
-    if (c.do_evap) {
-      if (qd < 0.0) exq = exq - qd * pmass;
-      if (qd >= 0.0 && exq > 0.0) {
-        exq = exq / pmass;
-        double d = (qsat - q) / (1.0 + hlcp * dqsat);
-        d = fmin(fmax(d, 0.0), exq);
-        qd = qd + d;
-        td = td - d * hlcp;
-        exq = (exq - d) * pmass;
+  // loads of four levels are issued together (the sweep is latency-bound), then consumed serially
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    double t4[4], q4[4], p4[4], ph4[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (k0 + d < K) { size_t o = (size_t)(k0 + d) * ncol + col; t4[d] = tin[o]; q4[d] = qin[o]; p4[d] = pfull[o]; ph4[d] = phalf[o + ncol]; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int k = k0 + d;
+      if (k >= K) break;
+      size_t o = (size_t)k * ncol + col;
+      double t = t4[d], q = q4[d], p = p4[d], ph1 = ph4[d];
+      double es, des, qsat, dqsat;
+      bad |= !svp_lookup(s, t, es, des);
+      qs_from_es(es, des, p, c.hc, eps, qsat, dqsat);
+      double qd = 0.0, td = 0.0;
+      if ((q - qsat) * qsat > 0.0) { qd = (qsat - q) / (1.0 + hlcp * dqsat); td = -hlcp * qd; }
+      double pmass = (ph1 - ph0) / c.grav;
+      if (c.do_evap) {
+        if (qd < 0.0) exq = exq - qd * pmass;
+        if (qd >= 0.0 && exq > 0.0) {
+          exq = exq / pmass;
+          double d2 = (qsat - q) / (1.0 + hlcp * dqsat);
+          d2 = fmin(fmax(d2, 0.0), exq);
+          qd = qd + d2;
+          td = td - d2 * hlcp;
+          exq = (exq - d2) * pmass;
+        }
       }
+      precip = precip - pmass * qd;
+      tdel[o] = td; qdel[o] = qd;
+      ph0 = ph1;
     }
-    precip = precip - pmass * qd;
-    tdel[o] = td; qdel[o] = qd;
-    ph0 = ph1;
   }
   rain[col] = fmax(precip, 0.0);
   if (bad) atomicExch(err, 1);
@@ -108,14 +118,21 @@ __global__ void __launch_bounds__(128) gray_down_kernel(PhysConst c, int ncol, i
   double lw_tau_0 = (c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * sl * sl) * c.odp;
   double tau0 = lw_tau_at(c, lw_tau_0, p_half[col]);
   double lw_down = 0.0;
-  for (int k = 0; k < K; ++k) {
-    size_t o = (size_t)k * ncol + col;
-    double tau1 = lw_tau_at(c, lw_tau_0, p_half[o + ncol]);
-    double tr = exp(-(tau1 - tau0));
-    double tk = t[o];
-    double b = c.stefan * ((tk * tk) * (tk * tk));
-    lw_down = lw_down * tr + b * (1.0 - tr);
-    tau0 = tau1;
+  for (int k0 = 0; k0 < K; k0 += 4) {                 // four levels of loads in flight, consumed serially
+    double ph4[4], t4[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (k0 + d < K) { size_t o = (size_t)(k0 + d) * ncol + col; ph4[d] = p_half[o + ncol]; t4[d] = t[o]; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      if (k0 + d >= K) break;
+      double tau1 = lw_tau_at(c, lw_tau_0, ph4[d]);
+      double tr = exp(-(tau1 - tau0));
+      double tk = t4[d];
+      double b = c.stefan * ((tk * tk) * (tk * tk));
+      lw_down = lw_down * tr + b * (1.0 - tr);
+      tau0 = tau1;
+    }
   }
   double ps = p_half[(size_t)K * ncol + col];
   double sw_down_s = sw_down_at(c, insolation, sw_tau_0, ps);
@@ -139,15 +156,23 @@ __global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int
   double lw_tau_0 = (c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * sl * sl) * c.odp;
   double tau0 = lw_tau_at(c, lw_tau_0, p_half[col]);
   lwd[0] = 0.0;
-  for (int k = 0; k < K; ++k) {
-    size_t o = (size_t)k * ncol + col;
-    double tau1 = lw_tau_at(c, lw_tau_0, p_half[o + ncol]);
-    double tr = exp(-(tau1 - tau0));
-    double tk = t[o];
-    double b = c.stefan * ((tk * tk) * (tk * tk));
-    lwd[k + 1] = lwd[k] * tr + b * (1.0 - tr);
-    trs[k] = tr;
-    tau0 = tau1;
+  for (int k0 = 0; k0 < K; k0 += 4) {                 // four levels of loads in flight, consumed serially
+    double ph4[4], t4[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (k0 + d < K) { size_t o = (size_t)(k0 + d) * ncol + col; ph4[d] = p_half[o + ncol]; t4[d] = t[o]; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int k = k0 + d;
+      if (k >= K) break;
+      double tau1 = lw_tau_at(c, lw_tau_0, ph4[d]);
+      double tr = exp(-(tau1 - tau0));
+      double tk = t4[d];
+      double b = c.stefan * ((tk * tk) * (tk * tk));
+      lwd[k + 1] = lwd[k] * tr + b * (1.0 - tr);
+      trs[k] = tr;
+      tau0 = tau1;
+    }
   }
   double ph1 = p_half[(size_t)K * ncol + col];
   double sw_down1 = sw_down_at(c, insolation, sw_tau_0, ph1);
@@ -155,17 +180,26 @@ __global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int
   double ts = t_surf[col];
   double lw_up1 = c.stefan * ((ts * ts) * (ts * ts));
   double flux1 = (lw_up1 - lwd[K]) + (sw_up - sw_down1);
-  for (int k = K - 1; k >= 0; --k) {
-    size_t o = (size_t)k * ncol + col;
-    double tk = t[o];
-    double b = c.stefan * ((tk * tk) * (tk * tk));
-    double lw_up0 = lw_up1 * trs[k] + b * (1.0 - trs[k]);
-    double ph0 = p_half[o];
-    double sw_down0 = sw_down_at(c, insolation, sw_tau_0, ph0);
-    double flux0 = (lw_up0 - lwd[k]) + (sw_up - sw_down0);
-    double tdt_rad = c.diabatic_acce * (flux1 - flux0) * c.grav / (c.cp_air * (ph1 - ph0));
-    tdt[o] = tdt[o] + tdt_rad;
-    lw_up1 = lw_up0; flux1 = flux0; ph1 = ph0;
+  for (int k0 = K - 1; k0 >= 0; k0 -= 4) {
+    double ph4[4], t4[4], td4[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (k0 - d >= 0) { size_t o = (size_t)(k0 - d) * ncol + col; ph4[d] = p_half[o]; t4[d] = t[o]; td4[d] = tdt[o]; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int k = k0 - d;
+      if (k < 0) break;
+      size_t o = (size_t)k * ncol + col;
+      double tk = t4[d];
+      double b = c.stefan * ((tk * tk) * (tk * tk));
+      double lw_up0 = lw_up1 * trs[k] + b * (1.0 - trs[k]);
+      double ph0 = ph4[d];
+      double sw_down0 = sw_down_at(c, insolation, sw_tau_0, ph0);
+      double flux0 = (lw_up0 - lwd[k]) + (sw_up - sw_down0);
+      double tdt_rad = c.diabatic_acce * (flux1 - flux0) * c.grav / (c.cp_air * (ph1 - ph0));
+      tdt[o] = td4[d] + tdt_rad;
+      lw_up1 = lw_up0; flux1 = flux0; ph1 = ph0;
+    }
   }
   if (olr) olr[col] = lw_up1;
 }

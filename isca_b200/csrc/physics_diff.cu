@@ -4,7 +4,7 @@
 //                         atmos_param/vert_diff/vert_diff.F90:270-467, 556-617, 806-1087
 //   mixed_layer           atmos_spectral/driver/solo/mixed_layer.F90:568-745
 //
-// One thread per column.  The momentum system is eliminated, closed by the surface stress and back-substituted inside the
+// One thread per column, loads software-pipelined three levels ahead of the serial recurrences.  The momentum system is eliminated, closed by the surface stress and back-substituted inside the
 // kernel (its factors never leave thread-local storage); the temperature / humidity elimination stores e, f_t, f_q (the
 // reference's module state) for gcm_vert_diff_up, which runs after the surface has been updated.
 #include "physics_common.h"
@@ -14,51 +14,6 @@ using namespace isca_phys;
 namespace {
 
 struct Surf { double mu_delt_n, nu_n, e_n1, f1_delt_n1, f2_delt_n1, delta1_n, delta2_n; };
-
-// vert_diff_down_2 (explicit_tend + compute_e + compute_f) for two fields sharing mu, nu.  mu_at(k), nu_at(k) evaluate
-// compute_mu / compute_nu for one level (nu_at only for k >= 1), xi*(k), dt*(k) load level k, store(k, e, f1, f2) receives
-// the factors of levels 0..K-2.  Nothing is kept in thread-local arrays.
-template <class MU, class NU, class XI1, class XI2, class DT1, class DT2, class ST>
-__device__ __forceinline__ Surf down2(int K, double delt, MU mu_at, NU nu_at, XI1 xi1, XI2 xi2, DT1 dt1, DT2 dt2, ST store) {
-  Surf s;
-  double x1 = xi1(0), x2 = xi2(0);
-  double fl1 = 0.0, fl2 = 0.0;                    // fluxx(k)
-  double e_prev = 0.0, f1_prev = 0.0, f2_prev = 0.0;
-  double nu_k = 0.0;                              // nu(1) is never referenced by the reference (c(1) = 0)
-  for (int k = 0; k < K; ++k) {
-    const double mu_k = mu_at(k);
-    const double nu_k1 = (k < K - 1) ? nu_at(k + 1) : 0.0;
-    double d1, d2, a = 0.0, x1p = 0.0, x2p = 0.0, fl1p = 0.0, fl2p = 0.0;
-    if (k < K - 1) {
-      x1p = xi1(k + 1); x2p = xi2(k + 1);
-      fl1p = nu_k1 * (x1p - x1); fl2p = nu_k1 * (x2p - x2);
-      d1 = dt1(k) + mu_k * (fl1p - fl1);
-      d2 = dt2(k) + mu_k * (fl2p - fl2);
-      a = -mu_k * nu_k1 * delt;
-    } else {
-      d1 = dt1(k) - mu_k * fl1;
-      d2 = dt2(k) - mu_k * fl2;
-    }
-    double c = k > 0 ? -mu_k * nu_k * delt : 0.0;
-    double b = 1.0 - a - c;
-    if (k < K - 1) {
-      double e, f1, f2;
-      if (k == 0) { e = -a / b; f1 = d1 / b; f2 = d2 / b; }
-      else {
-        double g = 1.0 / (b + c * e_prev);
-        e = -a * g; f1 = (d1 - c * f1_prev) * g; f2 = (d2 - c * f2_prev) * g;
-      }
-      store(k, e, f1, f2);
-      e_prev = e; f1_prev = f1; f2_prev = f2;
-    } else {
-      s.mu_delt_n = mu_k * delt; s.nu_n = nu_k;
-      s.e_n1 = e_prev; s.f1_delt_n1 = f1_prev * delt; s.f2_delt_n1 = f2_prev * delt;
-      s.delta1_n = d1 * delt; s.delta2_n = d2 * delt;
-    }
-    x1 = x1p; x2 = x2p; fl1 = fl1p; fl2 = fl2p; nu_k = nu_k1;
-  }
-  return s;
-}
 
 // diff_surface (vert_diff.F90:866-888)
 __device__ __forceinline__ void diff_surface(double mu_delt, double nu, double e_n1, double f_delt_n1, double dflux_datmos,
@@ -77,50 +32,126 @@ struct DiffArgs {
   double *e_g, *ft_g, *fq_g, *tri_delta_t, *tri_dflux_t, *tri_delta_q, *tri_dflux_q, *tri_dtmass, *tri_delta_u, *tri_delta_v;
 };
 
+// Raw inputs of one level of a down sweep.  The sweeps are latency-bound (one thread per column, a serial recurrence over the
+// levels), so the loads of level k+3 are issued while level k is eliminated: three levels of raw values travel in registers.
+struct DiffRaw { double ph, t, q, df, z, x1, x2, d1, d2; };
+
+// vert_diff_down_2 (explicit_tend + compute_e + compute_f + compute_mu + compute_nu) for two fields sharing mu, nu, software
+// pipelined.  TEMP: the fields are (t + z*grav/cp, q) instead of (X1, X2).
+template <bool TEMP>
+__device__ __forceinline__ Surf down2_pipe(const DiffArgs& a, int col, const double* __restrict__ diff, const double* __restrict__ X1,
+                                           const double* __restrict__ X2, const double* __restrict__ D1, const double* __restrict__ D2) {
+  const int K = a.K; const size_t nc = a.ncol;
+  const double delt = a.delt, gcp = a.grav / a.cp_air;
+  auto load = [&](int kk) {
+    DiffRaw r; r.ph = r.t = r.q = r.df = r.z = r.x1 = r.x2 = r.d1 = r.d2 = 0.0;
+    if (kk <= K) {
+      const size_t o = (size_t)kk * nc + col;
+      r.ph = a.p_half[o];
+      if (kk < K) {
+        r.t = a.t[o]; r.df = diff[o]; r.z = a.z_full[o]; r.d1 = D1[o]; r.d2 = D2[o];
+        if (TEMP || a.use_virtual) r.q = a.q[o];
+        if (!TEMP) { r.x1 = X1[o]; r.x2 = X2[o]; }
+      }
+    }
+    return r;
+  };
+  auto tv_of = [&](const DiffRaw& r) { double tv = r.t; if (a.use_virtual) tv = tv * (1.0 + a.d608 * r.q); return tv; };
+  auto x1_of = [&](const DiffRaw& r) { return TEMP ? r.t + r.z * gcp : r.x1; };
+  auto x2_of = [&](const DiffRaw& r) { return TEMP ? r.q : r.x2; };
+  Surf s;
+  DiffRaw r0 = load(0), r1 = load(1), r2 = load(2);
+  double x1 = x1_of(r0), x2 = x2_of(r0);
+  double fl1 = 0.0, fl2 = 0.0;                    // fluxx(k)
+  double e_prev = 0.0, f1_prev = 0.0, f2_prev = 0.0;
+  double nu_k = 0.0;                              // nu(1) is never referenced by the reference (c(1) = 0)
+  for (int k = 0; k < K; ++k) {
+    const DiffRaw r3 = load(k + 3);
+    const double mu_k = a.grav / (r1.ph - r0.ph);
+    double nu_k1 = 0.0;
+    if (k < K - 1) {
+      const double rho_half = 2.0 * r1.ph / (a.rdgas * (tv_of(r1) + tv_of(r0)));
+      nu_k1 = rho_half * r1.df / (r0.z - r1.z);
+    }
+    double d1, d2, aa = 0.0, x1p = 0.0, x2p = 0.0, fl1p = 0.0, fl2p = 0.0;
+    if (k < K - 1) {
+      x1p = x1_of(r1); x2p = x2_of(r1);
+      fl1p = nu_k1 * (x1p - x1); fl2p = nu_k1 * (x2p - x2);
+      d1 = r0.d1 + mu_k * (fl1p - fl1);
+      d2 = r0.d2 + mu_k * (fl2p - fl2);
+      aa = -mu_k * nu_k1 * delt;
+    } else {
+      d1 = r0.d1 - mu_k * fl1;
+      d2 = r0.d2 - mu_k * fl2;
+    }
+    double c = k > 0 ? -mu_k * nu_k * delt : 0.0;
+    double b = 1.0 - aa - c;
+    if (k < K - 1) {
+      double e, f1, f2;
+      if (k == 0) { e = -aa / b; f1 = d1 / b; f2 = d2 / b; }
+      else {
+        double g = 1.0 / (b + c * e_prev);
+        e = -aa * g; f1 = (d1 - c * f1_prev) * g; f2 = (d2 - c * f2_prev) * g;
+      }
+      const size_t o = (size_t)k * nc + col;
+      a.e_g[o] = e; a.ft_g[o] = f1; a.fq_g[o] = f2;
+      e_prev = e; f1_prev = f1; f2_prev = f2;
+    } else {
+      s.mu_delt_n = mu_k * delt; s.nu_n = nu_k;
+      s.e_n1 = e_prev; s.f1_delt_n1 = f1_prev * delt; s.f2_delt_n1 = f2_prev * delt;
+      s.delta1_n = d1 * delt; s.delta2_n = d2 * delt;
+    }
+    x1 = x1p; x2 = x2p; fl1 = fl1p; fl2 = fl2p; nu_k = nu_k1;
+    r0 = r1; r1 = r2; r2 = r3;
+  }
+  return s;
+}
+
 // bytes/column: read u,v,t,q,diff_m,diff_t,z_full,dt_u,dt_v,dt_t,dt_q (11K) + p_half (K+1) + 4; write dt_u,dt_v,dt_t,diss,
 // e,f_t,f_q (7K) + 9  =  (19K + 14) * 8
 __global__ void __launch_bounds__(128) vert_diff_down_kernel(DiffArgs a) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= a.ncol) return;
   const int K = a.K; const size_t nc = a.ncol;
-  auto at = [&](const double* p, int k) { return p[(size_t)k * nc + col]; };
-  // compute_mu / compute_nu for one level; the factors of the momentum system use e_global, f_t_global, f_q_global as scratch
-  // (they are rewritten by the temperature / humidity elimination below)
-  auto mu_at = [&](int k) { return a.grav / (at(a.p_half, k + 1) - at(a.p_half, k)); };
-  auto tv_at = [&](int k) { double tv = at(a.t, k); if (a.use_virtual) tv = tv * (1.0 + a.d608 * at(a.q, k)); return tv; };
-  auto nu_of = [&](const double* diff, int k) {
-    double rho_half = 2.0 * at(a.p_half, k) / (a.rdgas * (tv_at(k) + tv_at(k - 1)));
-    return rho_half * at(diff, k) / (at(a.z_full, k - 1) - at(a.z_full, k));
-  };
-  // uv_vert_diff
-  Surf s = down2(K, a.delt, mu_at, [&](int k) { return nu_of(a.diff_m, k); }, [&](int k) { return at(a.u, k); }, [&](int k) { return at(a.v, k); },
-                 [&](int k) { return at(a.dt_u, k); }, [&](int k) { return at(a.dt_v, k); },
-                 [&](int k, double ee, double g1, double g2) { size_t o = (size_t)k * nc + col; a.e_g[o] = ee; a.ft_g[o] = g1; a.fq_g[o] = g2; });
+  // uv_vert_diff: the factors of the momentum system use e_global, f_t_global, f_q_global as scratch (they are rewritten by
+  // the temperature / humidity elimination below)
+  Surf s = down2_pipe<false>(a, col, a.diff_m, a.u, a.v, a.dt_u, a.dt_v);
   double tau_u = a.tau_u[col], tau_v = a.tau_v[col];
   double delta_u_n = s.delta1_n, delta_v_n = s.delta2_n;
   diff_surface(s.mu_delt_n, s.nu_n, s.e_n1, s.f1_delt_n1, a.dtau_du[col], tau_u, 1.0, delta_u_n);
   diff_surface(s.mu_delt_n, s.nu_n, s.e_n1, s.f2_delt_n1, a.dtau_dv[col], tau_v, 1.0, delta_v_n);
   a.tau_u[col] = tau_u; a.tau_v[col] = tau_v;
   {
+    // back substitution bottom-up, loads two levels ahead of the recurrence
+    struct Back { double e, f1, f2, du, dv, u, v, dtt; };
+    auto loadb = [&](int kk) {
+      Back r; r.e = r.f1 = r.f2 = r.du = r.dv = r.u = r.v = r.dtt = 0.0;
+      if (kk >= 0) {
+        const size_t o = (size_t)kk * nc + col;
+        if (kk < K - 1) { r.e = a.e_g[o]; r.f1 = a.ft_g[o]; r.f2 = a.fq_g[o]; }
+        if (a.conserve) { r.du = a.dt_u[o]; r.dv = a.dt_v[o]; r.u = a.u[o]; r.v = a.v[o]; r.dtt = a.dt_t[o]; }
+      }
+      return r;
+    };
     const double half_delt = 0.5 * a.delt, cp_inv = 1.0 / a.cp_air;
     double nu_ = delta_u_n / a.delt, nv_ = delta_v_n / a.delt;
+    Back b0 = loadb(K - 1), b1 = loadb(K - 2), b2 = loadb(K - 3);
     for (int k = K - 1; k >= 0; --k) {
+      const Back b3 = loadb(k - 3);
       size_t o = (size_t)k * nc + col;
-      if (k < K - 1) { double ee = a.e_g[o]; nu_ = ee * nu_ + a.ft_g[o]; nv_ = ee * nv_ + a.fq_g[o]; }
+      if (k < K - 1) { nu_ = b0.e * nu_ + b0.f1; nv_ = b0.e * nv_ + b0.f2; }
       double heat = 0.0;
       if (a.conserve) {
-        double du = nu_ - a.dt_u[o], dv = nv_ - a.dt_v[o];
-        heat = -cp_inv * ((a.u[o] + half_delt * du) * du + (a.v[o] + half_delt * dv) * dv);
-        a.dt_t[o] = a.dt_t[o] + heat;
+        double du = nu_ - b0.du, dv = nv_ - b0.dv;
+        heat = -cp_inv * ((b0.u + half_delt * du) * du + (b0.v + half_delt * dv) * dv);
+        a.dt_t[o] = b0.dtt + heat;
       }
       a.dt_u[o] = nu_; a.dt_v[o] = nv_; a.diss[o] = heat;
+      b0 = b1; b1 = b2; b2 = b3;
     }
   }
   // compute_nu(diff_t), vert_diff_down_2(tt, q)
-  const double gcp = a.grav / a.cp_air;
-  s = down2(K, a.delt, mu_at, [&](int k) { return nu_of(a.diff_t, k); }, [&](int k) { return at(a.t, k) + at(a.z_full, k) * gcp; },
-            [&](int k) { return at(a.q, k); }, [&](int k) { return at(a.dt_t, k); }, [&](int k) { return at(a.dt_q, k); },
-            [&](int k, double ee, double g1, double g2) { size_t o = (size_t)k * nc + col; a.e_g[o] = ee; a.ft_g[o] = g1; a.fq_g[o] = g2; });
+  s = down2_pipe<true>(a, col, a.diff_t, nullptr, nullptr, a.dt_t, a.dt_q);
   a.tri_delta_t[col] = s.delta1_n + s.mu_delt_n * s.nu_n * s.f1_delt_n1;
   a.tri_dflux_t[col] = -s.nu_n * (1.0 - s.e_n1);
   a.tri_delta_q[col] = s.delta2_n + s.mu_delt_n * s.nu_n * s.f2_delt_n1;
@@ -139,11 +170,19 @@ __global__ void __launch_bounds__(128) vert_diff_up_kernel(int ncol, int K, doub
   double xt = delta_t[col] / delt, xq = delta_q[col] / delt;
   size_t o = (size_t)(K - 1) * ncol + col;
   dt_t[o] = xt; dt_q[o] = xq;
-  for (int k = K - 2; k >= 0; --k) {
-    o -= ncol;
-    double ee = e[o];
-    xt = ee * xt + ft[o]; xq = ee * xq + fq[o];
-    dt_t[o] = xt; dt_q[o] = xq;
+  // factors of four levels are loaded before the (serial) back substitution consumes them
+  for (int k0 = K - 2; k0 >= 0; k0 -= 4) {
+    double ee[4], f1[4], f2[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (k0 - d >= 0) { const size_t oo = (size_t)(k0 - d) * ncol + col; ee[d] = e[oo]; f1[d] = ft[oo]; f2[d] = fq[oo]; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (k0 - d >= 0) {
+        const size_t oo = (size_t)(k0 - d) * ncol + col;
+        xt = ee[d] * xt + f1[d]; xq = ee[d] * xq + f2[d];
+        dt_t[oo] = xt; dt_q[oo] = xq;
+      }
   }
 }
 

@@ -504,4 +504,95 @@ void launch_spec_robert_b(double2* aprev, const double2* acur, size_t n, double 
   spec_robert_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(aprev, acur, n, rc, raw);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stand-alone implicit_correction (model/implicit.F90:241-325) on packed spectra [T][K], for the transforms_mod-level ABI
+// (isca_b200_implicit_correction).  The time step runs the fused kernels above; these two kernels restate the routine one
+// packed row per thread (real and imaginary parts are independent real-linear problems) and share spec_wave_matvec_kernel.
+// ---------------------------------------------------------------------------------------------
+struct ImplArgs {
+  double2 *dt_divs, *dt_ts, *dt_lnps;
+  const double2 *divs_prev, *divs_cur, *ts_prev, *ts_cur, *lnps_prev, *lnps_cur;
+};
+
+// dt_t(k) of linear_tp_tendency (implicit.F90:414-480) for one level: `before` = sum of dmean above level k, `total` = column sum
+__device__ __forceinline__ double impl_tp_level(const DevTables& t, const Params& pr, int k, int K, double before, double dmean, double total) {
+  const double dp = t.dpk[k] + t.dbk[k] * pr.ref_ps, dp_inv = 1 / dp;
+  const double dlog_1 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_full[k], dlog_3 = t.ref_ln_p_half[k + 1] - t.ref_ln_p_half[k];
+  double dtt = -pr.kappa * t.ref_t[k] * (before * dlog_3 + dmean * dlog_1) * dp_inv;
+  // vert_vel(k) = -before + total*bk(k) (1 <= k <= K-1), vert_vel(k+1) = -(before + dmean) + total*bk(k+1); temp = -vert_vel*(t(k)-t(k-1))
+  double temp_k = 0.0, temp_k1 = 0.0;
+  if (k >= 1) temp_k = -((-before) + total * t.bk[k]) * (t.ref_t[k] - t.ref_t[k - 1]);
+  if (k + 1 <= K - 1) temp_k1 = -((-(before + dmean)) + total * t.bk[k + 1]) * (t.ref_t[k + 1] - t.ref_t[k]);
+  return dtt + 0.5 * dp_inv * (temp_k1 + temp_k);
+}
+
+__global__ void impl_adjust_kernel(DevTables t, Params pr, ImplArgs a) {
+  const GeomDev& g = t.g;
+  const int K = g.K;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * g.T) return;
+  const int row = idx >> 1, ri = idx & 1;
+  auto C = [&](const double2* p, int k) { return reinterpret_cast<const double*>(p)[((size_t)row * K + k) * 2 + ri]; };
+  auto W = [&](double2* p, int k) -> double& { return reinterpret_cast<double*>(p)[((size_t)row * K + k) * 2 + ri]; };
+  auto C2 = [&](const double2* p) { return reinterpret_cast<const double*>(p)[(size_t)row * 2 + ri]; };
+  // adjust_dt_divs: linear_tp_tendency(divs(previous) - divs(current))
+  double total = 0.0;
+  for (int k = 0; k < K; ++k) total = total + (C(a.divs_prev, k) - C(a.divs_cur, k)) * (t.dpk[k] + t.dbk[k] * pr.ref_ps);
+  double before = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double dmean = (C(a.divs_prev, k) - C(a.divs_cur, k)) * (t.dpk[k] + t.dbk[k] * pr.ref_ps);
+    W(a.dt_ts, k) = W(a.dt_ts, k) + impl_tp_level(t, pr, k, K, before, dmean, total);
+    before = before + dmean;
+  }
+  double& dlp = reinterpret_cast<double*>(a.dt_lnps)[(size_t)row * 2 + ri];
+  dlp = dlp + (-total) / pr.ref_ps;
+  const double ps_temp = C2(a.lnps_prev) - C2(a.lnps_cur) + pr.xi * dlp;
+  // linear_geopotential(ts_temp, 0, 0) bottom-up (:329-359) and the divergence-tendency adjustment
+  const double eig = t.eigen[row];
+  double gh = 0.0;                                             // geopot_half(k+1)
+  for (int k = K - 1; k >= 0; --k) {
+    const double ts_temp = C(a.ts_prev, k) - C(a.ts_cur, k) + pr.xi * W(a.dt_ts, k);
+    const double lh1 = t.ref_ln_p_half[k + 1], lh0 = t.ref_ln_p_half[k], lf = t.ref_ln_p_full[k];
+    const double geo = gh + pr.rdgas * (ts_temp * (lh1 - lf));
+    W(a.dt_divs, k) = W(a.dt_divs, k) + eig * (geo + t.h_impl[k] * ps_temp * pr.ref_ps);
+    if (k >= 1) gh = gh + pr.rdgas * (ts_temp * (lh1 - lh0));
+  }
+}
+
+__global__ void impl_back_kernel(DevTables t, Params pr, ImplArgs a) {
+  const GeomDev& g = t.g;
+  const int K = g.K;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * g.T) return;
+  const int row = idx >> 1, ri = idx & 1;
+  auto W = [&](double2* p, int k) -> double& { return reinterpret_cast<double*>(p)[((size_t)row * K + k) * 2 + ri]; };
+  double total = 0.0;
+  for (int k = 0; k < K; ++k) total = total + W(a.dt_divs, k) * (t.dpk[k] + t.dbk[k] * pr.ref_ps);
+  double before = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double dmean = W(a.dt_divs, k) * (t.dpk[k] + t.dbk[k] * pr.ref_ps);
+    W(a.dt_ts, k) = W(a.dt_ts, k) + pr.xi * impl_tp_level(t, pr, k, K, before, dmean, total);
+    before = before + dmean;
+  }
+  double& dlp = reinterpret_cast<double*>(a.dt_lnps)[(size_t)row * 2 + ri];
+  dlp = dlp + pr.xi * (-total) / pr.ref_ps;
+}
+
+void launch_implicit_correction(const DevTables& t, const Params& pr, double2* dt_divs, double2* dt_ts, double2* dt_lnps,
+                                const double2* divs_prev, const double2* divs_cur, const double2* ts_prev, const double2* ts_cur,
+                                const double2* lnps_prev, const double2* lnps_cur, cudaStream_t st) {
+  const GeomDev& g = t.g;
+  const int K = g.K;
+  ImplArgs a{dt_divs, dt_ts, dt_lnps, divs_prev, divs_cur, ts_prev, ts_cur, lnps_prev, lnps_cur};
+  const int nb = (2 * g.T + 127) / 128;
+  impl_adjust_kernel<<<nb, 128, 0, st>>>(t, pr, a);
+  {
+    size_t smem = sizeof(double) * ((size_t)K * K + (size_t)K * WM_COLS);
+    cudaFuncSetAttribute(spec_wave_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(g.M + 1, (2 * g.nm + WM_COLS - 1) / WM_COLS);
+    spec_wave_matvec_kernel<<<grid, WM_COLS * WM_KG, smem, st>>>(t, dt_divs);
+  }
+  impl_back_kernel<<<nb, 128, 0, st>>>(t, pr, a);
+}
+
 }  // namespace isca

@@ -30,6 +30,10 @@ void launch_spec_ucos_vcos(const DevTables& t, double2* buf, int Lp, int nlev, i
 void launch_spec_vor_div(const DevTables& t, const double2* buf, int Lp, int nlev, int a_off, int b_off,
                          double2* out, int Lo, int vor_off, int div_off, cudaStream_t st);
 void launch_spec_step(const DevTables& t, const Params& pr, const SpecStepArgs& a, cudaStream_t st);
+// stand-alone implicit_correction (implicit.F90:241-325) on packed spectra [T][K] / [T]; in place on dt_divs, dt_ts, dt_lnps
+void launch_implicit_correction(const DevTables& t, const Params& pr, double2* dt_divs, double2* dt_ts, double2* dt_lnps,
+                                const double2* divs_prev, const double2* divs_cur, const double2* ts_prev, const double2* ts_cur,
+                                const double2* lnps_prev, const double2* lnps_cur, cudaStream_t st);
 void launch_spec_robert_b(double2* aprev, const double2* acur, size_t n, double rc, double raw, cudaStream_t st);
 
 }  // namespace isca

@@ -281,3 +281,76 @@ def test_temperature_range_check_is_fatal(api):
         atm.atmosphere(1)
     assert "temperatures out of valid range" in str(e.value)
     atm.atmosphere_end()
+
+
+@pytest.mark.parametrize("res,nlev", [("T21", 3), ("T42", 17)])
+def test_stage_level_entry_points_match_oracle(api, res, nlev):
+    """isca_b200_legendre_inv / fft_c2r / fft_r2c / legendre_fwd: each stage of trans_spherical_to_grid / trans_grid_to_spherical
+    alone (spherical_fourier.F90:177-339, grid_fourier.F90:129-179) against the oracle's stage functions."""
+    cfg, core, atm = make(api, res, 4, 600.0)
+    tb, tr = core.tb, core.tr
+    s = rand_spec(tb, nlev, 23)
+    f_ref = tr.spherical_to_fourier(s)                                  # [lev, lat, m]
+    f = atm.trans_spherical_to_fourier(s)
+    assert rel(f, f_ref) < TOL_TRANSFORM
+    g_ref = tr.fourier_to_grid(f_ref)
+    g = atm.trans_fourier_to_grid(f_ref)
+    assert rel(g, g_ref) < TOL_TRANSFORM
+    f2 = atm.trans_grid_to_fourier(g_ref)
+    assert rel(f2, tr.grid_to_fourier(g_ref)) < TOL_TRANSFORM
+    s2 = atm.trans_fourier_to_spherical(f_ref)
+    assert rel(s2, tr.fourier_to_spherical(f_ref) * tb.triangle_mask) < TOL_TRANSFORM
+    assert rel(s2, s) < TOL_TRANSFORM                                   # Legendre round trip
+    atm.atmosphere_end()
+
+
+def test_implicit_correction_entry_point_matches_oracle(api):
+    """isca_b200_implicit_correction against the oracle's implicit_correction (implicit.F90:241-325), for the first-step
+    (delta_t = dt) and the leapfrog (delta_t = 2 dt) wave matrices; alpha_implicit = 0.5 default."""
+    cfg, core, atm = make(api, "T21", 6, 1200.0)
+    tb = core.tb
+    K = cfg.num_levels
+    rng = np.random.default_rng(5)
+
+    def spec3(scale, seed):
+        return rand_spec(tb, K, seed) * scale
+
+    divs = np.stack([spec3(1e-6, 1), spec3(1e-6, 2)])
+    ts = np.stack([spec3(1.0, 3), spec3(1.0, 4)])
+    ln_ps = np.stack([rand_spec(tb, 1, 5)[0] * 1e-3, rand_spec(tb, 1, 6)[0] * 1e-3])
+    dt_divs, dt_ts, dt_lnps = spec3(1e-10, 7), spec3(1e-5, 8), rand_spec(tb, 1, 9)[0] * 1e-8
+    for delta_t in (cfg.dt_atmos, 2 * cfg.dt_atmos):
+        ref = core.impl.implicit_correction(dt_divs.copy(), dt_ts.copy(), dt_lnps.copy(), divs, ts, ln_ps, delta_t, 0, 1)
+        got = atm.implicit_correction(dt_divs, dt_ts, dt_lnps, divs, ts, ln_ps, delta_t, 0, 1)
+        tri1 = tb.spherical_wave <= cfg.num_fourier + 1                 # rows the packed layout carries
+        for a, b in zip(got, ref):
+            assert rel(a * tri1, b * tri1) < 1e-11
+    # identity 6 of SURVEY 8c: no change between the time levels and alpha-weighted terms only
+    same = atm.implicit_correction(dt_divs * 0, dt_ts * 0, dt_lnps * 0, np.stack([divs[0]] * 2), np.stack([ts[0]] * 2),
+                                   np.stack([ln_ps[0]] * 2), cfg.dt_atmos, 0, 1)
+    assert all(np.abs(x).max() == 0.0 for x in same)
+    atm.atmosphere_end()
+
+
+def test_device_side_time_average(api):
+    """isca_b200_diag_accumulate / _fetch: the device-side mean over steps equals the mean of per-step host mirrors."""
+    cfg, core, atm = make(api, "T21", 5, 1200.0)
+    atm.cold_start()
+    atm.atmosphere(3)
+    acc_t, acc_ps, acc_z = 0.0, 0.0, 0.0
+    for _ in range(4):
+        atm.atmosphere(1)
+        for fid in (api.F_T, api.F_PS, api.F_Z_HALF):
+            atm.diag_accumulate(fid)
+        acc_t = acc_t + atm.get_field(api.F_T); acc_ps = acc_ps + atm.get_field(api.F_PS); acc_z = acc_z + atm.get_field(api.F_Z_HALF)
+    mt, n = atm.diag_fetch(api.F_T)
+    assert n == 4 and rel(mt, acc_t / 4) < 1e-15
+    mps, n = atm.diag_fetch(api.F_PS, reset=False)
+    assert n == 4 and rel(mps, acc_ps / 4) < 1e-15
+    mz, _ = atm.diag_fetch(api.F_Z_HALF)
+    assert rel(mz, acc_z / 4) < 1e-15
+    mps2, n2 = atm.diag_fetch(api.F_PS)                                 # not reset by the previous fetch
+    assert n2 == 4 and np.array_equal(mps, mps2)
+    with pytest.raises(api.IscaError):
+        atm.diag_fetch(api.F_T)                                         # reset: nothing accumulated
+    atm.atmosphere_end()
