@@ -64,8 +64,12 @@ def work_model(res: str, K: int):
         "spectral": dict(bytes=spec_bytes * K * (4 + 6 + 6 + 8 + 5)),
         # corrections: colsum_energy reads 3 x 3-D, apply_energy r/w 1 x 3-D
         "corrections": dict(bytes=grid_bytes * K * 5),
-        # grid tracer (update_tracers + water fixer): ~14 3-D plane passes
-        "tracer": dict(bytes=grid_bytes * K * 14),
+        # grid tracer, horizontal step (tracer_horiz_kernel): reads q_prev, u, v; writes tr_future: 4 3-D planes
+        "tracer_horiz": dict(bytes=grid_bytes * K * 4),
+        # grid tracer, PPM sweep (tracer_ppm_kernel): reads tr_future, wg (K+1), q_prev, q_cur; writes q_fut, q_cur: 7 planes
+        "tracer_ppm": dict(bytes=grid_bytes * K * 7),
+        # water fixer: column sums (2-D) + apply (reads q_fut, q_cur; writes q_cur): 3 planes
+        "tracer_water": dict(bytes=grid_bytes * K * 3),
     }
     return w, dict(T=T, lev_inv=lev_inv, lev_fwd=lev_fwd)
 
@@ -284,14 +288,19 @@ def main():
         return sum(v for k, v in groups.items() if k.startswith(prefix))
     g_ms = {"legendre_inv": gsum("legendre_inv"), "legendre_fwd": gsum("legendre_fwd"), "fft_inv": gsum("fft_inv"),
             "fft_fwd": gsum("fft_fwd"), "grid_step": gsum("grid_step"), "spectral": gsum("spec"),
-            "corrections": gsum("corr"), "tracer": gsum("tracer")}
+            "corrections": gsum("corr"), "tracer_horiz": gsum("tracer_horiz") + gsum("tracer_halo"),
+            "tracer_ppm": gsum("tracer_ppm"), "tracer_water": gsum("tracer_water") + gsum("tracer_reduce")}
     exch_ms = gsum("exchange")
     tot = sum(groups.values())
     dom = max(g_ms, key=g_ms.get)
     dom_bytes = wm[dom]["bytes"]
     achieved = dom_bytes / (g_ms[dom] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (T170 L40, 1 GPU;
+    # profiles/r01d_ncu_summary.txt, profiles/r01h_ncu_summary.txt); null for kernels / configurations without a capture
+    NCU_TRAFFIC = {"fft_inv": 447.5e6, "fft_fwd": 245.6e6, "grid_step": 699.1e6, "tracer_horiz": 151.7e6, "tracer_ppm": 294.0e6}
+    traffic = NCU_TRAFFIC.get(dom) if (world == 1 and res == "T170" and K == 40) else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
                 "share_of_step": g_ms[dom] / tot, "algorithmic_bytes_per_step": dom_bytes, "ms_per_step": g_ms[dom]}
     leg_ms = g_ms["legendre_inv"] + g_ms["legendre_fwd"]
     leg_fl = wm["legendre_inv"]["flops"] + wm["legendre_fwd"]["flops"]

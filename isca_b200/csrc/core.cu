@@ -524,11 +524,13 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
     }
     exchange_tracer_halo(h, ta);
     launch_tracer_horiz(h.dt, h.fv, pr, ta, st);
+    h.mark("tracer_horiz");
     launch_tracer_ppm(h.dt, pr, ta, st);
+    h.mark("tracer_ppm");
     launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_W_PREV, h.red_tmp.p, st);
     allreduce_scalars(h, h.scal.p + SC_W_PREV, 1, NCCL_SUM);
     h.launches += 4;
-    h.mark("tracer_advection");
+    h.mark("tracer_reduce");
   }
 
   dev_forward(h, h.levsB.p, 4 * K + 1, h.specB.p, h.LpB, h.truncB.p, "_tend");
