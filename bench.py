@@ -296,8 +296,9 @@ def main():
     dom_bytes = wm[dom]["bytes"]
     achieved = dom_bytes / (g_ms[dom] * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (T170 L40, 1 GPU;
-    # profiles/r01d_ncu_summary.txt, profiles/r01h_ncu_summary.txt); null for kernels / configurations without a capture
-    NCU_TRAFFIC = {"fft_inv": 447.5e6, "fft_fwd": 245.6e6, "grid_step": 699.1e6, "tracer_horiz": 151.7e6, "tracer_ppm": 294.0e6}
+    # profiles/r01i_ncu_summary.txt); null for kernels / configurations without a capture
+    NCU_TRAFFIC = {"fft_inv": 448.0e6, "fft_fwd": 244.7e6, "grid_step": 698.4e6, "tracer_horiz": 151.1e6, "tracer_ppm": 290.6e6,
+                   "legendre_inv": 301.2e6, "legendre_fwd": 365.0e6}
     traffic = NCU_TRAFFIC.get(dom) if (world == 1 and res == "T170" and K == 40) else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
@@ -332,7 +333,7 @@ def main():
     d2h = (nf * K + 1) * 8 * J_glob * I
     e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
-           "api": "isca_b200_spectral_dynamics: host tendencies in, host state out, every step (reference spectral_dynamics argument list)"}
+           "api": "isca_b200_spectral_dynamics_tracers: host tendencies in, host state out, every step (reference spectral_dynamics argument list)"}
     # informational: the atmosphere_mod boundary (state resident) with a per-step D2H of the ps diagnostic
     ps_host = pin((J, I))
     barrier()
