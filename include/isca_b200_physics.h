@@ -15,7 +15,7 @@ typedef struct IscaPhysics_t* IscaPhysics;
 
 /* physical constants (shared/constants/constants.F90) and the scheme namelists */
 typedef struct IscaPhysicsConfig {
-  int abi_version;                /* 1 */
+  int abi_version;                /* 2 */
   int num_lon, num_lat, num_levels;
   double grav, rdgas, rvgas, cp_air, hlv, tfreeze, stefan, pstd_mks;
   /* sat_vapor_pres_nml: do_simple tables only (sat_vapor_pres_k.F90:161-266) */
@@ -42,6 +42,13 @@ typedef struct IscaPhysicsConfig {
   double depth_0, frac_inner, rich_crit_pbl, entr_ratio, parcel_buoy, znom, background_m, background_t;
   /* qe_moist_convection_nml (qe_moist_convection.F90:61-75) */
   double tau_bm, rhbm, Tmin, Tmax, val_inc;
+  /* two_stream_gray_rad_nml, the other values of rad_scheme (two_stream_gray_rad.F90:89-118, 214-238):
+   * 0 'frierson', 1 'byrne' (Byrne & O'Gorman 2013), 2 'geen' (Geen et al. 2016, window band + water-vapour shortwave),
+   * 3 'schneider' (Schneider & Liu 2009 giant planet).  do_seasonal, do_read_co2 are not built. */
+  int rad_scheme;
+  double ir_tau_co2_win, ir_tau_wv_win1, ir_tau_wv_win2, ir_tau_co2, ir_tau_wv1, ir_tau_wv2, window, carbon_conc;
+  double single_albedo, back_scatter, lw_tau_0_gp, sw_tau_0_gp, lw_tau_exponent_gp, sw_tau_exponent_gp;
+  double bog_a, bog_b, bog_mu;
 } IscaPhysicsConfig;
 
 int isca_b200_physics_default_config(IscaPhysicsConfig* cfg);
@@ -60,17 +67,18 @@ int isca_b200_compute_qs(IscaPhysics p, int n, const double* temp, const double*
 int isca_b200_lscale_cond(IscaPhysics p, const double* tin, const double* qin, const double* pfull,
                           const double* phalf, double* rain, double* tdel, double* qdel);
 
-/* two_stream_gray_rad_down (two_stream_gray_rad.F90:386-655, frierson, no seasonal cycle):
- * lat [J][I] radians, p_half [K+1][J][I], t [K][J][I], albedo [J][I];
- * out net_surf_sw_down, surf_lw_down [J][I]. */
+/* two_stream_gray_rad_down(is, js, Time, lat, lon, p_half, t, net_surf_sw_down, surf_lw_down, albedo, q)
+ * (two_stream_gray_rad.F90:386-655, no seasonal cycle):
+ * lat [J][I] radians, p_half [K+1][J][I], t [K][J][I], albedo [J][I], q [K][J][I] specific humidity (read by the byrne and
+ * geen schemes only; may be NULL otherwise); out net_surf_sw_down, surf_lw_down [J][I]. */
 int isca_b200_two_stream_gray_rad_down(IscaPhysics p, const double* lat, const double* p_half, const double* t,
-                                       const double* albedo, double* net_surf_sw_down, double* surf_lw_down);
+                                       const double* albedo, const double* q, double* net_surf_sw_down, double* surf_lw_down);
 
-/* two_stream_gray_rad_up (two_stream_gray_rad.F90:659-776): same lat/p_half/t as the down call (the down sweep is
- * recomputed in registers rather than stored), t_surf, albedo [J][I]; tdt [K][J][I] is incremented; olr [J][I]
+/* two_stream_gray_rad_up (two_stream_gray_rad.F90:659-776): same lat/p_half/t/q as the down call (the down sweep is
+ * recomputed in registers rather than stored in module arrays), t_surf, albedo [J][I]; tdt [K][J][I] is incremented; olr [J][I]
  * (may be NULL). */
 int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const double* p_half, const double* t,
-                                     const double* t_surf, const double* albedo, double* tdt, double* olr);
+                                     const double* t_surf, const double* albedo, const double* q, double* tdt, double* olr);
 
 /* damping_driver, rayleigh sponge (damping_driver.f90:404-420, 594-636): p_full, u, v [K][J][I],
  * pref [K+1] reference pressures; udt, vdt, tdt [K][J][I] are the damping tendencies (overwritten). */

@@ -114,7 +114,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   }
   launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
   cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
-  launch_gray_down(p, m->lat2d.p, ph_c, tg_p, m->albedo.p, m->net_sw.p, m->lw_down.p);
+  launch_gray_down(p, m->lat2d.p, ph_c, tg_p, q_p, m->albedo.p, m->net_sw.p, m->lw_down.p);   // q = grid_tracers(previous, nsphum), :1068
   // surface_flux on the lowest model level (:1076-1132)
   sub_kernel<<<nblk(nc), 256, 0, st>>>(nc, m->z_atm.p, zf_c + (size_t)(K - 1) * nc, m->z_surf.p);
   IscaSurfaceFluxArgs a;
@@ -128,7 +128,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
                        &a.dtaudv_atm, &a.ex_del_m, &a.ex_del_h, &a.ex_del_q, &a.temp_2m, &a.u_10m, &a.v_10m, &a.q_2m, &a.rh_2m};
   for (int i = 0; i < 28; ++i) *outs[i] = m->sf.p + (size_t)i * nc;
   launch_surface_flux(p, a);
-  launch_gray_up(p, m->lat2d.p, ph_c, tg_p, m->t_surf.p, m->albedo.p, m->dt_t.p, nullptr);
+  launch_gray_up(p, m->lat2d.p, ph_c, tg_p, q_p, m->t_surf.p, m->albedo.p, m->dt_t.p, nullptr);
   if (m->mc.do_damping) {
     int nlev = rayleigh_nlev(m->pref.data(), K, p->cfg.sponge_pbottom);
     launch_rayleigh(p, nlev, delta_t, pf_c, ug_p, vg_p, m->w1.p, m->w2.p, m->w3.p);

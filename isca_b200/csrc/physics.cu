@@ -204,6 +204,145 @@ __global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int
   if (olr) olr[col] = lw_up1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// rad_scheme = 'byrne' | 'geen' | 'schneider' (two_stream_gray_rad.F90:458-508 shortwave, :512-616 longwave, :676-700 upward
+// sweep).  One thread per column; the per-level transmissivities (and, for GEEN, the window band and the recursive shortwave
+// beam) of the down sweep stay in thread-local storage for the up sweep.  The 'frierson' scheme keeps its own kernels above.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct RadVarCol {
+  double lwd[ISCA_KMAX + 1];      // total downward longwave at the half levels
+  double tr[ISCA_KMAX];           // lw_dtrans
+  double trw[ISCA_KMAX];          // lw_dtrans_win (GEEN)
+  double swd[ISCA_KMAX + 1];      // downward shortwave at the half levels
+};
+
+// down sweep of one column; returns surface lw_down and sw_down
+__device__ __forceinline__ void rad_var_down(const PhysConst& c, int ncol, int K, int col, double lat, const double* __restrict__ p_half,
+                                             const double* __restrict__ t, const double* __restrict__ q, RadVarCol& r) {
+  const int sch = c.rad_scheme;
+  const double lcc = log(c.carbon_conc / 360.);
+  double insolation;
+  if (sch == 3) insolation = (c.solar_constant / 3.14159265358979323846) * cos(lat);
+  else {
+    const double sl = sin(lat);
+    const double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
+    insolation = 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * sl);
+  }
+  const double ps = p_half[(size_t)K * ncol + col];
+  // shortwave
+  if (sch == 2) {
+    double sw_tau_k = 0.0;
+    r.swd[0] = insolation;
+    double ph0 = p_half[col];
+    for (int k = 0; k < K; ++k) {
+      const size_t o = (size_t)k * ncol + col;
+      const double ph1 = p_half[o + ncol];
+      double sw_wv = sw_tau_k + 0.5194;
+      sw_wv = exp(0.01887 / (sw_tau_k + 0.009522) + 1.603 / (sw_wv * sw_wv));
+      const double del_sol_tau = (0.0596 + 0.0029 * lcc + sw_wv * q[o]) * (ph1 - ph0) / ps;
+      r.swd[k + 1] = r.swd[k] * exp(-del_sol_tau);
+      sw_tau_k = sw_tau_k + del_sol_tau;
+      ph0 = ph1;
+    }
+  } else if (sch == 1) {
+    const double sl = sin(lat);
+    const double sw_tau_0 = (1.0 - c.sw_diff * sl * sl) * c.atm_abs;
+    for (int k = 0; k <= K; ++k) r.swd[k] = insolation * exp(-(sw_tau_0 * pow(p_half[(size_t)k * ncol + col] / c.pstd, c.solar_exponent)));
+  } else {
+    for (int k = 0; k <= K; ++k) {
+      const double sw_tau = c.sw_tau_0_gp * pow(p_half[(size_t)k * ncol + col] / c.pstd, c.sw_tau_exponent_gp);
+      r.swd[k] = insolation * (1.0 - c.gp_albedo) * exp(-(c.Ga_asym * sw_tau));
+    }
+  }
+  // longwave
+  double lw = 0.0, lww = 0.0;
+  r.lwd[0] = 0.0;
+  double ph0 = p_half[col];
+  double tau0 = (sch == 3) ? c.lw_tau_0_gp * pow(ph0 / c.pstd, c.lw_tau_exponent_gp) : 0.0;
+  for (int k = 0; k < K; ++k) {
+    const size_t o = (size_t)k * ncol + col;
+    const double ph1 = p_half[o + ncol];
+    const double tk = t[o];
+    double b = c.stefan * ((tk * tk) * (tk * tk));
+    double tr;
+    if (sch == 1) {
+      const double del = (c.bog_a * c.bog_mu + 0.17 * lcc + c.bog_b * q[o]) * ((ph1 - ph0) / c.pstd_earth);
+      tr = exp(-del);
+    } else if (sch == 2) {
+      const double qq = q[o];
+      const double del = (c.ir_tau_co2 + 0.2023 * lcc + c.ir_tau_wv1 * log(c.ir_tau_wv2 * qq + 1)) * (ph1 - ph0) / c.pstd_earth;
+      tr = exp(-del);
+      const double delw = (c.ir_tau_co2_win + 0.0954 * lcc + c.ir_tau_wv_win1 * qq + c.ir_tau_wv_win2 * qq * qq) * (ph1 - ph0) / c.pstd_earth;
+      const double trw = exp(-delw);
+      const double bw = c.window * b;
+      b = (1.0 - c.window) * b;
+      lww = lww * trw + bw * (1.0 - trw);
+      r.trw[k] = trw;
+    } else {
+      const double tau1 = c.lw_tau_0_gp * pow(ph1 / c.pstd, c.lw_tau_exponent_gp);
+      tr = exp(-(tau1 - tau0));
+      tau0 = tau1;
+    }
+    lw = lw * tr + b * (1.0 - tr);
+    r.tr[k] = tr;
+    r.lwd[k + 1] = (sch == 2) ? lw + lww : lw;
+    ph0 = ph1;
+  }
+}
+
+__global__ void __launch_bounds__(128) gray_down_var_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
+    const double* __restrict__ p_half, const double* __restrict__ t, const double* __restrict__ q, const double* __restrict__ albedo,
+    double* __restrict__ net_surf_sw_down, double* __restrict__ surf_lw_down) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  RadVarCol r;
+  rad_var_down(c, ncol, K, col, lat[col], p_half, t, q, r);
+  surf_lw_down[col] = r.lwd[K];
+  net_surf_sw_down[col] = r.swd[K] * (1. - albedo[col]);
+}
+
+__global__ void __launch_bounds__(128) gray_up_var_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
+    const double* __restrict__ p_half, const double* __restrict__ t, const double* __restrict__ q, const double* __restrict__ t_surf,
+    const double* __restrict__ albedo, double* __restrict__ tdt, double* __restrict__ olr) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  RadVarCol r;
+  rad_var_down(c, ncol, K, col, lat[col], p_half, t, q, r);
+  const int sch = c.rad_scheme;
+  const double alb = albedo[col];
+  const double sw_up = alb * r.swd[K];
+  const double ts = t_surf[col];
+  const double b_surf = c.stefan * ((ts * ts) * (ts * ts));
+  double lw_up1, lw_upw1 = 0.0;
+  if (sch == 2) { lw_up1 = b_surf * (1 - c.window); lw_upw1 = b_surf * c.window; }
+  else if (sch == 3) lw_up1 = r.lwd[K] + r.swd[K] * (1. - alb);          // b_surf_gp = surf_lw_down + net_surf_sw_down (:626-628)
+  else lw_up1 = b_surf;
+  double ph1 = p_half[(size_t)K * ncol + col];
+  double flux1 = (((sch == 2) ? lw_up1 + lw_upw1 : lw_up1) - r.lwd[K]) + (sw_up - r.swd[K]);
+  for (int k = K - 1; k >= 0; --k) {
+    const size_t o = (size_t)k * ncol + col;
+    const double tk = t[o];
+    double b = c.stefan * ((tk * tk) * (tk * tk));
+    double lw_tot;
+    if (sch == 2) {
+      const double bw = c.window * b;
+      b = (1.0 - c.window) * b;
+      lw_up1 = lw_up1 * r.tr[k] + b * (1.0 - r.tr[k]);
+      lw_upw1 = lw_upw1 * r.trw[k] + bw * (1.0 - r.trw[k]);
+      lw_tot = lw_up1 + lw_upw1;
+    } else {
+      lw_up1 = lw_up1 * r.tr[k] + b * (1.0 - r.tr[k]);
+      lw_tot = lw_up1;
+    }
+    const double ph0 = p_half[o];
+    const double flux0 = (lw_tot - r.lwd[k]) + (sw_up - r.swd[k]);
+    const double tdt_rad = c.diabatic_acce * (flux1 - flux0) * c.grav / (c.cp_air * (ph1 - ph0));
+    tdt[o] = tdt[o] + tdt_rad;
+    flux1 = flux0; ph1 = ph0;
+    if (k == 0 && olr) olr[col] = lw_tot;
+  }
+}
+
 // rayleigh sponge.  bytes/element over the damped levels: read p_full, u, v (3), write udt, vdt, tdt (3)
 __global__ void rayleigh_kernel(PhysConst c, size_t ncol, int K, int nlev, double rfactr, double pb, double delt, int conserve,
     const double* __restrict__ p_full, const double* __restrict__ u, const double* __restrict__ v,
@@ -233,13 +372,15 @@ void launch_lscale(IscaPhysics p, const double* t, const double* q, const double
   int nb = (int)((p->ncol + 127) / 128);
   lscale_cond_kernel<<<nb, 128, 0, p->st>>>(p->svp, p->pc, (int)p->ncol, p->K, t, q, pf, ph, rain, td, qd, p->d_err);
 }
-void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* alb, double* sw, double* lw) {
+void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* alb, double* sw, double* lw) {
   int nb = (int)((p->ncol + 127) / 128);
-  gray_down_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, alb, sw, lw);
+  if (p->pc.rad_scheme == 0) gray_down_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, alb, sw, lw);
+  else gray_down_var_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, q, alb, sw, lw);
 }
-void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* ts, const double* alb, double* tdt, double* olr) {
+void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* ts, const double* alb, double* tdt, double* olr) {
   int nb = (int)((p->ncol + 127) / 128);
-  gray_up_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, ts, alb, tdt, olr);
+  if (p->pc.rad_scheme == 0) gray_up_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, ts, alb, tdt, olr);
+  else gray_up_var_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, q, ts, alb, tdt, olr);
 }
 int rayleigh_nlev(const double* pref, int K, double pb) {      // minloc(abs(pref - 2*sponge_pbottom)) over the K+1 entries
   int best = 0; double bv = fabs(pref[0] - 2.0 * pb);
@@ -264,13 +405,17 @@ extern "C" {
 int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
   if (!c) return 1;
   std::memset(c, 0, sizeof(*c));
-  c->abi_version = 1;
+  c->abi_version = 2;
   c->grav = 9.80; c->rdgas = 287.04; c->rvgas = 461.50; c->cp_air = 287.04 / (2.0 / 7.0); c->hlv = 2.500e6;
   c->tfreeze = 273.16; c->stefan = 5.6734e-8; c->pstd_mks = 101325.0;
   c->es0 = 1.0; c->hc = 1.0; c->do_evap = 0;
   c->solar_constant = 1360.0; c->del_sol = 1.4; c->del_sw = 0.0; c->ir_tau_eq = 6.0; c->ir_tau_pole = 1.5;
   c->atm_abs = 0.0; c->sw_diff = 0.0; c->linear_tau = 0.1; c->wv_exponent = 4.0; c->solar_exponent = 4.0;
   c->odp = 1.0; c->diabatic_acce = 1.0;
+  c->rad_scheme = 0; c->ir_tau_co2_win = 0.2150; c->ir_tau_wv_win1 = 147.11; c->ir_tau_wv_win2 = 1.0814e4; c->ir_tau_co2 = 0.1;
+  c->ir_tau_wv1 = 23.8; c->ir_tau_wv2 = 254.0; c->window = 0.3732; c->carbon_conc = 360.0;
+  c->single_albedo = 0.8; c->back_scatter = 0.398; c->lw_tau_0_gp = 80.0; c->sw_tau_0_gp = 3.0; c->lw_tau_exponent_gp = 2.0;
+  c->sw_tau_exponent_gp = 1.0; c->bog_a = 0.8678; c->bog_b = 1997.9; c->bog_mu = 1.0;
   c->trayfric = 0.0; c->sponge_pbottom = 50.0; c->do_conserve_energy = 1;
   c->vert_diff_do_conserve_energy = 1; c->use_virtual_temp_vert_diff = 0; c->evaporation = 1;
   c->rich_crit = 2.0; c->drag_min = 1.0e-05; c->zeta_trans = 0.5; c->vonkarm = 0.40; c->neutral = 0; c->stable_option = 1;
@@ -288,7 +433,8 @@ const char* isca_b200_physics_last_error(IscaPhysics p) { return p ? p->err.c_st
 int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   IscaPhysics p = nullptr;
   if (!cfg || !out) return fail(nullptr, "null argument");
-  if (cfg->abi_version != 1) return fail(nullptr, "IscaPhysicsConfig abi_version mismatch");
+  if (cfg->abi_version != 2) return fail(nullptr, "IscaPhysicsConfig abi_version mismatch");
+  if (cfg->rad_scheme < 0 || cfg->rad_scheme > 3) return fail(nullptr, "two_stream_gray_rad: not a valid radiation scheme.");   // two_stream_gray_rad.F90:228
   if (cfg->num_lon < 1 || cfg->num_lat < 1 || cfg->num_levels < 1 || cfg->num_levels > ISCA_KMAX)
     return fail(nullptr, "bad dimensions (num_levels must be 1.." + std::to_string(ISCA_KMAX) + ")");
   if (!(cfg->hc > 0.0 && cfg->hc <= 1.0)) return fail(nullptr, "lscale_cond: hc must be in (0, 1]");   // lscale_cond.F90:323
@@ -316,6 +462,18 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   c.solar_constant = cfg->solar_constant; c.del_sol = cfg->del_sol; c.del_sw = cfg->del_sw; c.ir_tau_eq = cfg->ir_tau_eq;
   c.ir_tau_pole = cfg->ir_tau_pole; c.atm_abs = cfg->atm_abs; c.sw_diff = cfg->sw_diff; c.linear_tau = cfg->linear_tau;
   c.wv_exponent = cfg->wv_exponent; c.solar_exponent = cfg->solar_exponent; c.odp = cfg->odp; c.diabatic_acce = cfg->diabatic_acce;
+  c.rad_scheme = cfg->rad_scheme;
+  c.ir_tau_co2_win = cfg->ir_tau_co2_win; c.ir_tau_wv_win1 = cfg->ir_tau_wv_win1; c.ir_tau_wv_win2 = cfg->ir_tau_wv_win2;
+  c.ir_tau_co2 = cfg->ir_tau_co2; c.ir_tau_wv1 = cfg->ir_tau_wv1; c.ir_tau_wv2 = cfg->ir_tau_wv2; c.window = cfg->window;
+  c.carbon_conc = cfg->carbon_conc; c.lw_tau_0_gp = cfg->lw_tau_0_gp; c.sw_tau_0_gp = cfg->sw_tau_0_gp;
+  c.lw_tau_exponent_gp = cfg->lw_tau_exponent_gp; c.sw_tau_exponent_gp = cfg->sw_tau_exponent_gp;
+  c.bog_a = cfg->bog_a; c.bog_b = cfg->bog_b; c.bog_mu = cfg->bog_mu; c.pstd_earth = 101325.0;      // PSTD_MKS_EARTH, constants.F90:252
+  {                                                            // two_stream_gray_rad_init :233-238
+    const double g_asym = 1 - 2. * cfg->back_scatter;
+    const double r1 = std::sqrt(1. - g_asym * cfg->single_albedo), r2 = std::sqrt(1. - cfg->single_albedo);
+    c.gp_albedo = (r1 - r2) / (r1 + r2);
+    c.Ga_asym = 2. * std::sqrt((1. - cfg->single_albedo) * (1. - g_asym * cfg->single_albedo));
+  }
   // do_simple saturation vapour pressure tables (sat_vapor_pres_k.F90:161-266): tcmin=-173, tcmax=350, esres=10
   const int tcmin = -173, tcmax = 350, esres = 10;
   const int n = (tcmax - tcmin) * esres + 1;
@@ -382,24 +540,30 @@ int isca_b200_lscale_cond(IscaPhysics p, const double* tin, const double* qin, c
 }
 
 int isca_b200_two_stream_gray_rad_down(IscaPhysics p, const double* lat, const double* p_half, const double* t,
-                                       const double* albedo, double* net_surf_sw_down, double* surf_lw_down) {
+                                       const double* albedo, const double* q, double* net_surf_sw_down, double* surf_lw_down) {
   if (!p) return fail(nullptr, "null handle");
   size_t nc = p->ncol, n3 = nc * p->K;
+  const bool need_q = (p->pc.rad_scheme == 1 || p->pc.rad_scheme == 2);
+  if (need_q && !q) return fail(p, "two_stream_gray_rad_down: the byrne and geen schemes need the specific humidity q");
   if (up(p, p->buf[0], lat, nc) || up(p, p->buf[1], p_half, n3 + nc) || up(p, p->buf[2], t, n3) || up(p, p->buf[3], albedo, nc)) return 1;
+  if (need_q && up(p, p->buf[7], q, n3)) return 1;
   if (!p->buf[4].ensure(nc) || !p->buf[5].ensure(nc)) return fail(p, "cudaMalloc failed");
-  launch_gray_down(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p);
+  launch_gray_down(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, need_q ? p->buf[7].p : nullptr, p->buf[3].p, p->buf[4].p, p->buf[5].p);
   if (down(p, p->buf[4], net_surf_sw_down, nc) || down(p, p->buf[5], surf_lw_down, nc)) return 1;
   return finish(p, "two_stream_gray_rad_down");
 }
 
 int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const double* p_half, const double* t,
-                                     const double* t_surf, const double* albedo, double* tdt, double* olr) {
+                                     const double* t_surf, const double* albedo, const double* q, double* tdt, double* olr) {
   if (!p) return fail(nullptr, "null handle");
   size_t nc = p->ncol, n3 = nc * p->K;
+  const bool need_q = (p->pc.rad_scheme == 1 || p->pc.rad_scheme == 2);
+  if (need_q && !q) return fail(p, "two_stream_gray_rad_up: the byrne and geen schemes need the specific humidity q of the down call");
   if (up(p, p->buf[0], lat, nc) || up(p, p->buf[1], p_half, n3 + nc) || up(p, p->buf[2], t, n3) || up(p, p->buf[3], t_surf, nc) ||
       up(p, p->buf[4], albedo, nc) || up(p, p->buf[5], tdt, n3)) return 1;
+  if (need_q && up(p, p->buf[7], q, n3)) return 1;
   if (!p->buf[6].ensure(nc)) return fail(p, "cudaMalloc failed");
-  launch_gray_up(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p);
+  launch_gray_up(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, need_q ? p->buf[7].p : nullptr, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p);
   if (down(p, p->buf[5], tdt, n3)) return 1;
   if (olr && down(p, p->buf[6], olr, nc)) return 1;
   return finish(p, "two_stream_gray_rad_up");
@@ -458,8 +622,8 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
   auto run = [&]() {
     switch (which) {
       case 0: launch_lscale(p, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p); break;
-      case 1: launch_gray_down(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[9].p, p->buf[4].p, p->buf[5].p); break;
-      case 2: launch_gray_up(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[9].p + 0, p->buf[9].p, p->buf[6].p, p->buf[4].p); break;
+      case 1: launch_gray_down(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[1].p, p->buf[9].p, p->buf[4].p, p->buf[5].p); break;
+      case 2: launch_gray_up(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[1].p, p->buf[9].p + 0, p->buf[9].p, p->buf[6].p, p->buf[4].p); break;
       case 3: launch_rayleigh(p, nlev, 600.0, p->buf[2].p, p->buf[8].p, p->buf[8].p, p->buf[4].p, p->buf[5].p, p->buf[6].p); break;
       case 4:   // diffusivities = the wind profile (10..14 m2/s); stresses and their derivatives zero
         launch_vert_diff_down(p, 600.0, p->buf[8].p, p->buf[8].p, p->buf[0].p, p->buf[1].p, p->buf[8].p, p->buf[8].p, p->buf[3].p,
@@ -474,7 +638,7 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
     if (up(p, p->buf[1], ts.data(), nc)) return 1;
   }
   auto run2 = [&]() {
-    if (which == 2) launch_gray_up(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[1].p, p->buf[9].p, p->buf[6].p, p->buf[4].p);
+    if (which == 2) launch_gray_up(p, p->buf[7].p, p->buf[3].p, p->buf[0].p, p->buf[1].p, p->buf[1].p, p->buf[9].p, p->buf[6].p, p->buf[4].p);
     else run();
   };
   for (int i = 0; i < 3; ++i) run2();

@@ -23,6 +23,11 @@ struct PhysConst {
   double hc; int do_evap;
   double solar_constant, del_sol, del_sw, ir_tau_eq, ir_tau_pole, atm_abs, sw_diff, linear_tau, wv_exponent,
          solar_exponent, odp, diabatic_acce;
+  // rad_scheme variants (two_stream_gray_rad.F90:89-118): 0 frierson, 1 byrne, 2 geen, 3 schneider
+  int rad_scheme;
+  double ir_tau_co2_win, ir_tau_wv_win1, ir_tau_wv_win2, ir_tau_co2, ir_tau_wv1, ir_tau_wv2, window, carbon_conc;
+  double lw_tau_0_gp, sw_tau_0_gp, lw_tau_exponent_gp, sw_tau_exponent_gp, gp_albedo, Ga_asym;
+  double bog_a, bog_b, bog_mu, pstd_earth;
 };
 
 // lookup_es_des (sat_vapor_pres_k.F90:1132-1158): table index + 2nd-order Taylor; false = outside the table
@@ -119,8 +124,8 @@ inline int col_blocks(IscaPhysics p, int threads) { return (int)((p->ncol + thre
 
 // device-pointer launches shared between files
 void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd);
-void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* alb, double* sw, double* lw);
-void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* ts, const double* alb, double* tdt, double* olr);
+void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* alb, double* sw, double* lw);
+void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* ts, const double* alb, double* tdt, double* olr);
 int rayleigh_nlev(const double* pref, int K, double pb);
 void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, const double* u, const double* v, double* udt, double* vdt, double* tdt);
 int prepare_vert_diff_state(IscaPhysics p);

@@ -68,6 +68,11 @@ class MoistAtmosphere:
         for k, v in (physics_nml or {}).items():
             if k not in names:
                 raise IscaError(f"unknown physics namelist variable {k}")
+            if k == "rad_scheme" and isinstance(v, str):
+                from .physics import RAD_SCHEMES
+                if v.upper() not in RAD_SCHEMES:
+                    raise IscaError(f'two_stream_gray_rad: "{v}" is not a valid radiation scheme.')
+                v = RAD_SCHEMES[v.upper()]
             setattr(pc, k, v)
         mc = IscaMoistConfigStruct()
         lib.isca_b200_moist_default_config(C.byref(mc))

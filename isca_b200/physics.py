@@ -48,7 +48,13 @@ class IscaPhysicsConfigStruct(C.Structure):
                [(n, C.c_int) for n in ("fixed_depth", "diffusivity_do_entrain", "diffusivity_do_simple", "free_atm_diff", "pbl_mcm",
                                        "use_pog_bug_fix")] + \
                [(n, C.c_double) for n in ("depth_0", "frac_inner", "rich_crit_pbl", "entr_ratio", "parcel_buoy", "znom", "background_m",
-                                          "background_t", "tau_bm", "rhbm", "Tmin", "Tmax", "val_inc")]
+                                          "background_t", "tau_bm", "rhbm", "Tmin", "Tmax", "val_inc")] + \
+               [("rad_scheme", C.c_int)] + \
+               [(n, C.c_double) for n in ("ir_tau_co2_win", "ir_tau_wv_win1", "ir_tau_wv_win2", "ir_tau_co2", "ir_tau_wv1", "ir_tau_wv2",
+                                          "window", "carbon_conc", "single_albedo", "back_scatter", "lw_tau_0_gp", "sw_tau_0_gp",
+                                          "lw_tau_exponent_gp", "sw_tau_exponent_gp", "bog_a", "bog_b", "bog_mu")]
+
+RAD_SCHEMES = {"FRIERSON": 0, "BYRNE": 1, "GEEN": 2, "SCHNEIDER": 3}      # two_stream_gray_rad.F90:214-230
 
 
 _bound = False
@@ -67,8 +73,8 @@ def _lib():
         lib.isca_b200_lookup_es_des.argtypes = [vp, C.c_int, dp, dp, dp]
         lib.isca_b200_compute_qs.argtypes = [vp, C.c_int, dp, dp, dp, dp]
         lib.isca_b200_lscale_cond.argtypes = [vp] + [dp] * 7
-        lib.isca_b200_two_stream_gray_rad_down.argtypes = [vp] + [dp] * 6
-        lib.isca_b200_two_stream_gray_rad_up.argtypes = [vp] + [dp] * 7
+        lib.isca_b200_two_stream_gray_rad_down.argtypes = [vp] + [dp] * 7
+        lib.isca_b200_two_stream_gray_rad_up.argtypes = [vp] + [dp] * 8
         lib.isca_b200_rayleigh_damping.argtypes = [vp, C.c_double] + [dp] * 7
         lib.isca_b200_physics_time.argtypes = [vp, C.c_int, C.c_int, dp, dp]
         lib.isca_b200_gcm_vert_diff_down.argtypes = [vp, C.c_double] + [dp] * 18
@@ -111,6 +117,10 @@ class ColumnPhysics:
         for k, v in nml.items():
             if k not in names:
                 raise IscaError(f"unknown namelist variable {k}")
+            if k == "rad_scheme" and isinstance(v, str):          # the namelist value is a string (two_stream_gray_rad.F90:89)
+                if v.upper() not in RAD_SCHEMES:
+                    raise IscaError(f'two_stream_gray_rad: "{v}" is not a valid radiation scheme.')
+                v = RAD_SCHEMES[v.upper()]
             setattr(c, k, v)
         self.config = c
         self._h = C.c_void_p()
@@ -158,23 +168,25 @@ class ColumnPhysics:
                  "lscale_cond")
         return rain, tdel, qdel
 
-    def two_stream_gray_rad_down(self, lat, p_half, t, albedo):
-        """-> net_surf_sw_down, surf_lw_down [lat, lon]"""
+    def two_stream_gray_rad_down(self, lat, p_half, t, albedo, q=None):
+        """-> net_surf_sw_down, surf_lw_down [lat, lon]; q (specific humidity) is read by the byrne and geen schemes"""
         lat, albedo = _in(lat, self.s2, "lat"), _in(albedo, self.s2, "albedo")
         p_half, t = _in(p_half, self.s3h, "p_half"), _in(t, self.s3, "t")
+        q = None if q is None else _in(q, self.s3, "q")
         sw, lw = np.empty(self.s2), np.empty(self.s2)
-        self._ck(self._lib.isca_b200_two_stream_gray_rad_down(self._h, _p(lat), _p(p_half), _p(t), _p(albedo), _p(sw), _p(lw)),
-                 "two_stream_gray_rad_down")
+        self._ck(self._lib.isca_b200_two_stream_gray_rad_down(self._h, _p(lat), _p(p_half), _p(t), _p(albedo), _p(q) if q is not None else None,
+                                                              _p(sw), _p(lw)), "two_stream_gray_rad_down")
         return sw, lw
 
-    def two_stream_gray_rad_up(self, lat, p_half, t, t_surf, albedo, tdt):
+    def two_stream_gray_rad_up(self, lat, p_half, t, t_surf, albedo, tdt, q=None):
         """-> tdt + radiative heating [lev, lat, lon], olr [lat, lon]"""
         lat, albedo, t_surf = _in(lat, self.s2, "lat"), _in(albedo, self.s2, "albedo"), _in(t_surf, self.s2, "t_surf")
         p_half, t = _in(p_half, self.s3h, "p_half"), _in(t, self.s3, "t")
+        q = None if q is None else _in(q, self.s3, "q")
         out = np.array(_in(tdt, self.s3, "tdt"), copy=True)
         olr = np.empty(self.s2)
-        self._ck(self._lib.isca_b200_two_stream_gray_rad_up(self._h, _p(lat), _p(p_half), _p(t), _p(t_surf), _p(albedo), _p(out), _p(olr)),
-                 "two_stream_gray_rad_up")
+        self._ck(self._lib.isca_b200_two_stream_gray_rad_up(self._h, _p(lat), _p(p_half), _p(t), _p(t_surf), _p(albedo),
+                                                            _p(q) if q is not None else None, _p(out), _p(olr)), "two_stream_gray_rad_up")
         return out, olr
 
     def rayleigh_damping(self, delt, p_full, u, v, pref):

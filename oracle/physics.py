@@ -93,9 +93,13 @@ def lscale_cond(svp: SatVaporPres, tin, qin, pfull, phalf, hc=1.0, do_evap=True)
     return rain, tdel, qdel
 
 
+PSTD_MKS_EARTH = 101325.0        # constants.F90:252
+
+
 @dataclass
 class GreyRadConfig:
-    """two_stream_gray_rad_nml defaults (two_stream_gray_rad.F90:72-113), rad_scheme='frierson', do_seasonal=.false."""
+    """two_stream_gray_rad_nml defaults (two_stream_gray_rad.F90:72-125), do_seasonal=.false.;
+    rad_scheme in {'frierson', 'byrne', 'geen', 'schneider'} (:214-230)."""
     solar_constant: float = 1360.0
     del_sol: float = 1.4
     del_sw: float = 0.0
@@ -108,40 +112,127 @@ class GreyRadConfig:
     solar_exponent: float = 4.0
     odp: float = 1.0
     diabatic_acce: float = 1.0
+    rad_scheme: str = "frierson"
+    # Geen et al. 2016 two-band scheme (:96-104)
+    ir_tau_co2_win: float = 0.2150
+    ir_tau_wv_win1: float = 147.11
+    ir_tau_wv_win2: float = 1.0814e4
+    ir_tau_co2: float = 0.1
+    ir_tau_wv1: float = 23.8
+    ir_tau_wv2: float = 254.0
+    window: float = 0.3732
+    carbon_conc: float = 360.0
+    # Schneider & Liu 2009 giant-planet scheme (:106-113)
+    single_albedo: float = 0.8
+    back_scatter: float = 0.398
+    lw_tau_0_gp: float = 80.0
+    sw_tau_0_gp: float = 3.0
+    lw_tau_exponent_gp: float = 2.0
+    sw_tau_exponent_gp: float = 1.0
+    # Byrne & O'Gorman 2013 (:116-118)
+    bog_a: float = 0.8678
+    bog_b: float = 1997.9
+    bog_mu: float = 1.0
 
 
 class GreyRadiation:
     def __init__(self, cfg: GreyRadConfig):
         self.c = cfg
+        self.scheme = cfg.rad_scheme.upper()
+        if self.scheme not in ("FRIERSON", "BYRNE", "GEEN", "SCHNEIDER"):
+            raise ValueError(f'"{cfg.rad_scheme}" is not a valid radiation scheme.')       # :228
+        if self.scheme == "SCHNEIDER":                                                     # :233-238
+            self.g_asym = 1 - 2.0 * cfg.back_scatter
+            r1, r2 = np.sqrt(1.0 - self.g_asym * cfg.single_albedo), np.sqrt(1.0 - cfg.single_albedo)
+            self.gp_albedo = (r1 - r2) / (r1 + r2)
+            self.Ga_asym = 2.0 * np.sqrt((1.0 - cfg.single_albedo) * (1.0 - self.g_asym * cfg.single_albedo))
 
-    def down(self, lat, p_half, t):
-        """two_stream_gray_rad_down: lat [lat, lon] (radians), p_half [K+1,..], t [K,..]."""
-        c = self.c
+    def down(self, lat, p_half, t, q=None, albedo=None):
+        """two_stream_gray_rad_down (:386-655): lat [lat, lon] (radians), p_half [K+1,..], t [K,..], q [K,..] (BYRNE, GEEN)."""
+        c, sch = self.c, self.scheme
         n = t.shape[0]
-        p2 = (1.0 - 3.0 * np.sin(lat) ** 2) / 4.0
-        insolation = 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * np.sin(lat))
-        sw_tau_0 = (1.0 - c.sw_diff * np.sin(lat) ** 2) * c.atm_abs
-        sw_tau = sw_tau_0[None] * (p_half / PSTD_MKS) ** c.solar_exponent
-        sw_down = insolation[None] * np.exp(-sw_tau)
+        if sch == "SCHNEIDER":
+            insolation = (c.solar_constant / np.pi) * np.cos(lat)                          # :450-451
+        else:
+            p2 = (1.0 - 3.0 * np.sin(lat) ** 2) / 4.0
+            insolation = 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * np.sin(lat))
+        # ---- shortwave (:458-508)
+        sw_down = np.zeros_like(p_half)
+        if sch == "GEEN":
+            sw_tau_k = np.zeros_like(lat)
+            sw_down[0] = insolation
+            for k in range(n):
+                sw_wv = sw_tau_k + 0.5194
+                sw_wv = np.exp(0.01887 / (sw_tau_k + 0.009522) + 1.603 / (sw_wv * sw_wv))
+                del_sol_tau = (0.0596 + 0.0029 * np.log(c.carbon_conc / 360.0) + sw_wv * q[k]) * (p_half[k + 1] - p_half[k]) / p_half[n]
+                sw_dtrans = np.exp(-del_sol_tau)
+                sw_tau_k = sw_tau_k + del_sol_tau
+                sw_down[k + 1] = sw_down[k] * sw_dtrans
+        elif sch in ("FRIERSON", "BYRNE"):
+            sw_tau_0 = (1.0 - c.sw_diff * np.sin(lat) ** 2) * c.atm_abs
+            sw_tau = sw_tau_0[None] * (p_half / PSTD_MKS) ** c.solar_exponent
+            sw_down = insolation[None] * np.exp(-sw_tau)
+        else:
+            sw_tau = c.sw_tau_0_gp * (p_half / PSTD_MKS) ** c.sw_tau_exponent_gp
+            sw_down = insolation[None] * (1.0 - self.gp_albedo) * np.exp(-self.Ga_asym * sw_tau)
+        # ---- longwave (:512-616)
         b = STEFAN * t ** 4
-        lw_tau_0 = c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * np.sin(lat) ** 2
-        lw_tau_0 = lw_tau_0 * c.odp
-        lw_tau = lw_tau_0[None] * (c.linear_tau * p_half / PSTD_MKS + (1.0 - c.linear_tau) * (p_half / PSTD_MKS) ** c.wv_exponent)
-        lw_dtrans = np.exp(-(lw_tau[1:] - lw_tau[:-1]))
-        lw_down = np.zeros_like(p_half)
-        for k in range(n):
-            lw_down[k + 1] = lw_down[k] * lw_dtrans[k] + b[k] * (1.0 - lw_dtrans[k])
-        self._st = dict(sw_down=sw_down, lw_down=lw_down, lw_dtrans=lw_dtrans, b=b)
+        st = {}
+        if sch == "GEEN":
+            dp = p_half[1:] - p_half[:-1]
+            lw_del_tau = (c.ir_tau_co2 + 0.2023 * np.log(c.carbon_conc / 360.0) + c.ir_tau_wv1 * np.log(c.ir_tau_wv2 * q + 1)) * dp / PSTD_MKS_EARTH
+            lw_dtrans = np.exp(-lw_del_tau)
+            lw_del_tau_win = (c.ir_tau_co2_win + 0.0954 * np.log(c.carbon_conc / 360.0) + c.ir_tau_wv_win1 * q
+                              + c.ir_tau_wv_win2 * q * q) * dp / PSTD_MKS_EARTH
+            lw_dtrans_win = np.exp(-lw_del_tau_win)
+            b_win = c.window * b
+            b = (1.0 - c.window) * b
+            lw_down = np.zeros_like(p_half); lw_down_win = np.zeros_like(p_half)
+            for k in range(n):
+                lw_down[k + 1] = lw_down[k] * lw_dtrans[k] + b[k] * (1.0 - lw_dtrans[k])
+                lw_down_win[k + 1] = lw_down_win[k] * lw_dtrans_win[k] + b_win[k] * (1.0 - lw_dtrans_win[k])
+            lw_down = lw_down + lw_down_win
+            st.update(b_win=b_win, lw_dtrans_win=lw_dtrans_win)
+        else:
+            if sch == "BYRNE":
+                lw_del_tau = (c.bog_a * c.bog_mu + 0.17 * np.log(c.carbon_conc / 360.0) + c.bog_b * q) * ((p_half[1:] - p_half[:-1]) / PSTD_MKS_EARTH)
+                lw_dtrans = np.exp(-lw_del_tau)
+            elif sch == "FRIERSON":
+                lw_tau_0 = c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * np.sin(lat) ** 2
+                lw_tau_0 = lw_tau_0 * c.odp
+                lw_tau = lw_tau_0[None] * (c.linear_tau * p_half / PSTD_MKS + (1.0 - c.linear_tau) * (p_half / PSTD_MKS) ** c.wv_exponent)
+                lw_dtrans = np.exp(-(lw_tau[1:] - lw_tau[:-1]))
+            else:
+                lw_tau = c.lw_tau_0_gp * (p_half / PSTD_MKS) ** c.lw_tau_exponent_gp
+                lw_dtrans = np.exp(-(lw_tau[1:] - lw_tau[:-1]))
+            lw_down = np.zeros_like(p_half)
+            for k in range(n):
+                lw_down[k + 1] = lw_down[k] * lw_dtrans[k] + b[k] * (1.0 - lw_dtrans[k])
+        st.update(sw_down=sw_down, lw_down=lw_down, lw_dtrans=lw_dtrans, b=b)
+        if sch == "SCHNEIDER":                                   # :626-628 (needs the albedo of the down call)
+            alb = albedo if albedo is not None else np.zeros_like(lat)
+            st["b_surf_gp"] = lw_down[n] + sw_down[n] * (1.0 - alb)
+        self._st = st
         return dict(surf_lw_down=lw_down[n], sw_down_surf=sw_down[n])
 
     def up(self, t_surf, albedo, p_half, tdt):
-        """two_stream_gray_rad_up; net_surf_sw_down = (1-albedo)*sw_down(surface) (:647)."""
-        c, st = self.c, self._st
+        """two_stream_gray_rad_up (:659-776); net_surf_sw_down = (1-albedo)*sw_down(surface) (:647)."""
+        c, st, sch = self.c, self._st, self.scheme
         n = st["b"].shape[0]
+        b_surf = STEFAN * t_surf ** 4
         lw_up = np.zeros_like(p_half)
-        lw_up[n] = STEFAN * t_surf ** 4
-        for k in range(n - 1, -1, -1):
-            lw_up[k] = lw_up[k + 1] * st["lw_dtrans"][k] + st["b"][k] * (1.0 - st["lw_dtrans"][k])
+        if sch == "GEEN":
+            lw_up_win = np.zeros_like(p_half)
+            lw_up[n] = b_surf * (1 - c.window)
+            lw_up_win[n] = b_surf * c.window
+            for k in range(n - 1, -1, -1):
+                lw_up[k] = lw_up[k + 1] * st["lw_dtrans"][k] + st["b"][k] * (1.0 - st["lw_dtrans"][k])
+                lw_up_win[k] = lw_up_win[k + 1] * st["lw_dtrans_win"][k] + st["b_win"][k] * (1.0 - st["lw_dtrans_win"][k])
+            lw_up = lw_up + lw_up_win
+        else:
+            lw_up[n] = st["b_surf_gp"] if sch == "SCHNEIDER" else b_surf
+            for k in range(n - 1, -1, -1):
+                lw_up[k] = lw_up[k + 1] * st["lw_dtrans"][k] + st["b"][k] * (1.0 - st["lw_dtrans"][k])
         sw_up = albedo[None] * st["sw_down"][n][None] + 0 * p_half
         lw_flux = lw_up - st["lw_down"]
         sw_flux = sw_up - st["sw_down"]
@@ -1052,7 +1143,7 @@ class IdealizedMoistPhys:
         precip = precip + rain
         dt_tg = dt_tg + cond_dt_tg
         dt_q = dt_q + cond_dt_qg
-        d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p)
+        d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo)
         net_surf_sw_down = (1.0 - self.albedo) * d["sw_down_surf"]
         surf_lw_down = d["surf_lw_down"]
         sf = surface_flux(self.svp, self.mo, self.sflux, t_atm=tg_p[K - 1], q_atm_in=q_p[K - 1], u_atm=ug_p[K - 1], v_atm=vg_p[K - 1],

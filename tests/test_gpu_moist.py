@@ -16,7 +16,7 @@ FRIERSON_PHYS = dict(atm_abs=0.2, use_virtual_temp=0, surface_flux_do_simple=1, 
                      diffusivity_do_simple=1, rhbm=0.7, Tmin=160.0, Tmax=350.0)
 
 
-def build(res, K, dt, convection, seed=0, damping=False):
+def build(res, K, dt, convection, seed=0, damping=False, rad_scheme="frierson"):
     """oracle core + moist physics with the Frierson test-case namelists, started from a moist, conditionally unstable state"""
     from oracle.isca_oracle import SpectralCore, frierson_config
     from oracle import physics as P
@@ -47,7 +47,7 @@ def build(res, K, dt, convection, seed=0, damping=False):
     mp = P.IdealizedMoistPhys(P.MoistPhysConfig(convection_scheme=convection, depth=2.5, albedo_value=0.31, do_damping=damping,
                                                 trayfric=-0.5, sponge_pbottom=5000.0),
                               cfg.dt_atmos, lat, core.surf_geopotential / cfg.grav, core.tg[core.current][Kk - 1],
-                              pref=None, svp=svp, rad=P.GreyRadConfig(atm_abs=0.2),
+                              pref=None, svp=svp, rad=P.GreyRadConfig(atm_abs=0.2, rad_scheme=rad_scheme),
                               sflux=P.SurfaceFluxConfig(use_virtual_temp=False, do_simple=True, old_dtaudv=True),
                               diff=P.DiffusivityConfig(do_entrain=False, do_simple=True),
                               sbm=P.SBMConvection(svp, rhbm=0.7, Tmin=160.0, Tmax=350.0))
@@ -58,9 +58,9 @@ def build(res, K, dt, convection, seed=0, damping=False):
     return cfg, core, mp
 
 
-def make_gpu(cfg, core, convection, damping=False):
+def make_gpu(cfg, core, convection, damping=False, rad_scheme="frierson"):
     from isca_b200 import api, moist
-    phys = dict(FRIERSON_PHYS)
+    phys = dict(FRIERSON_PHYS, rad_scheme=rad_scheme)
     if damping:
         phys.update(trayfric=-0.5, sponge_pbottom=5000.0)
     m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=phys, convection_scheme=convection,
@@ -75,12 +75,15 @@ def make_gpu(cfg, core, convection, damping=False):
     return m, atm
 
 
-@pytest.mark.parametrize("res,K,dt,convection,damping", [("T21", 12, 900.0, "SIMPLE_BETTS_MILLER", False), ("T21", 15, 900.0, "NONE", True),
-                                                         ("T42", 10, 600.0, "SIMPLE_BETTS_MILLER", False)])
-def test_moist_model_steps_match_oracle(lib_built, res, K, dt, convection, damping):
+@pytest.mark.parametrize("res,K,dt,convection,damping,rad", [("T21", 12, 900.0, "SIMPLE_BETTS_MILLER", False, "frierson"),
+                                                             ("T21", 15, 900.0, "NONE", True, "frierson"),
+                                                             ("T42", 10, 600.0, "SIMPLE_BETTS_MILLER", False, "frierson"),
+                                                             ("T21", 10, 900.0, "SIMPLE_BETTS_MILLER", False, "byrne"),
+                                                             ("T21", 10, 900.0, "NONE", False, "geen")])
+def test_moist_model_steps_match_oracle(lib_built, res, K, dt, convection, damping, rad):
     from isca_b200 import api
-    cfg, core, mp = build(res, K, dt, convection, damping=damping)
-    m, atm = make_gpu(cfg, core, convection, damping)
+    cfg, core, mp = build(res, K, dt, convection, damping=damping, rad_scheme=rad)
+    m, atm = make_gpu(cfg, core, convection, damping, rad_scheme=rad)
     assert rel(m.get("t_surf"), mp.t_surf) < 1e-15
     for i in range(3):
         core.step()

@@ -101,6 +101,34 @@ def test_two_stream_gray_rad(mods, K, J, I, nml):
     assert np.allclose(col, o["rad_flux"][-1] - o["rad_flux"][0], rtol=1e-9)
 
 
+@pytest.mark.parametrize("K,J,I", [(10, 8, 16), (40, 32, 64)])
+@pytest.mark.parametrize("scheme,nml", [("byrne", dict(atm_abs=0.2, sw_diff=0.1, bog_mu=1.2, carbon_conc=720.0)),
+                                        ("geen", dict(carbon_conc=500.0, window=0.3)),
+                                        ("schneider", dict(lw_tau_0_gp=40.0, single_albedo=0.7, diabatic_acce=2.0))])
+def test_two_stream_gray_rad_variants(mods, K, J, I, scheme, nml):
+    """rad_scheme = byrne | geen | schneider (two_stream_gray_rad.F90:458-700) through isca_b200_two_stream_gray_rad_down/_up."""
+    physics, O = mods
+    rng, ps, ph, pf, t, lat = columns(K, J, I, 11 + K)
+    q = 0.02 * (pf / ps[None]) ** 3 * rng.uniform(0.2, 1.0, t.shape)
+    alb = rng.uniform(0.1, 0.4, (J, I))
+    ts = t[-1] + rng.uniform(-3, 3, (J, I))
+    tdt0 = 1e-5 * rng.standard_normal(t.shape)
+    cp = physics.ColumnPhysics(I, J, K, rad_scheme=scheme, **nml)
+    g = O.GreyRadiation(O.GreyRadConfig(rad_scheme=scheme, **nml))
+    d = g.down(lat, ph, t, q=q, albedo=alb)
+    sw, lw = cp.two_stream_gray_rad_down(lat, ph, t, alb, q=q)
+    assert rel(lw, d["surf_lw_down"]) < TOL and rel(sw, (1 - alb) * d["sw_down_surf"]) < TOL
+    tdt, olr = cp.two_stream_gray_rad_up(lat, ph, t, ts, alb, tdt0, q=q)
+    to, o = g.up(ts, alb, ph, tdt0)
+    assert rel(olr, o["olr"]) < TOL
+    assert rel(tdt - tdt0, to - tdt0) < 1e-11
+    if scheme in ("byrne", "geen"):
+        with pytest.raises(Exception):
+            cp.two_stream_gray_rad_down(lat, ph, t, alb)               # these schemes read q
+    with pytest.raises(Exception):
+        physics.ColumnPhysics(I, J, K, rad_scheme="rrtm")              # 'is not a valid radiation scheme' (:228)
+
+
 @pytest.mark.parametrize("conserve", [1, 0])
 def test_rayleigh_damping(mods, conserve):
     physics, O = mods

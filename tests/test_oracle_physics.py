@@ -80,6 +80,45 @@ def test_grey_radiation_flux_divergence_and_limits():
     assert np.max(np.abs(tdt0)) < 1e-18
 
 
+@pytest.mark.parametrize("scheme", ["byrne", "geen", "schneider"])
+def test_grey_radiation_variants_flux_divergence_and_limits(scheme):
+    """rad_scheme = byrne | geen | schneider (two_stream_gray_rad.F90:458-700): flux-divergence form, limits, scheme features."""
+    rng, ps, ph, pf, t = columns()
+    J, I = ps.shape
+    lat = np.repeat(np.linspace(-1.4, 1.4, J)[:, None], I, 1)
+    q = 0.02 * (pf / ps[None]) ** 3 * rng.uniform(0.2, 1.0, t.shape)
+    alb = np.full((J, I), 0.3)
+    ts = t[-1] + 2.0
+    g = P.GreyRadiation(P.GreyRadConfig(rad_scheme=scheme, atm_abs=0.2))
+    d = g.down(lat, ph, t, q=q, albedo=alb)
+    tdt, o = g.up(ts, alb, ph, np.zeros_like(t))
+    col = (tdt * P.CP_AIR * (ph[1:] - ph[:-1]) / P.GRAV).sum(0)
+    assert np.allclose(col, o["rad_flux"][-1] - o["rad_flux"][0], rtol=1e-12)
+    assert np.all(d["surf_lw_down"] > 0) and np.all(o["olr"] > 0) and np.all(d["sw_down_surf"] > 0)
+    if scheme in ("byrne", "geen"):
+        # more water vapour -> more back radiation, less outgoing longwave (surface warmer than the air above)
+        g2 = P.GreyRadiation(P.GreyRadConfig(rad_scheme=scheme, atm_abs=0.2))
+        d2 = g2.down(lat, ph, t, q=2.0 * q, albedo=alb)
+        assert np.all(d2["surf_lw_down"] > d["surf_lw_down"])
+        # isothermal column + surface at the same temperature: blackbody emission whatever the optical depths
+        tiso = np.full_like(t, 250.0)
+        g.down(lat, ph, tiso, q=q, albedo=alb)
+        _, o2 = g.up(np.full((J, I), 250.0), alb, ph, np.zeros_like(t))
+        assert np.allclose(o2["olr"], P.STEFAN * 250.0 ** 4, rtol=1e-13)
+    if scheme == "geen":
+        # the shortwave beam is attenuated by water vapour level by level: monotone, and weaker with more vapour
+        assert np.all(np.diff(g2._st["sw_down"], axis=0) < 0) and np.all(d2["sw_down_surf"] < d["sw_down_surf"])
+    if scheme == "schneider":
+        # giant planet: the lower boundary returns exactly what it receives (no surface energy budget), insolation ~ cos(lat)
+        assert np.allclose(o["rad_flux"][-1], 0.0, atol=1e-9)
+        assert np.allclose(g._st["sw_down"][0], 1360.0 / np.pi * np.cos(lat) * (1 - g.gp_albedo), rtol=1e-13)
+
+
+def test_grey_radiation_rejects_unknown_scheme():
+    with pytest.raises(ValueError):
+        P.GreyRadiation(P.GreyRadConfig(rad_scheme="rrtm"))
+
+
 def test_rayleigh_sponge_levels_and_energy():
     K, J, I = 20, 4, 6
     rng = np.random.default_rng(3)
