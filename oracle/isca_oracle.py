@@ -846,6 +846,9 @@ def vert_advection(dt, w, dz, r, scheme):
                         dzsum[c] += dzf[kc, c]
                         rsum[c] += rf[kc, c]
                         kc += step
+                        if kc >= K:              # the reference tests kk == ks here too and would read past ke (undefined);
+                            kc = K - 1           # the CUDA kernel and this oracle stop at the lowest layer instead
+                            break
                     kk[c] = kc
             xx = np.where(big, (dtw - dzsum) / dzf[kk, cols], cn)
             rm = rr[kk, cols] - rl[kk, cols]

@@ -354,3 +354,72 @@ def test_device_side_time_average(api):
     with pytest.raises(api.IscaError):
         atm.diag_fetch(api.F_T)                                         # reset: nothing accumulated
     atm.atmosphere_end()
+
+
+def test_restart_round_trip_reproduces_uninterrupted_run(api):
+    """Restart parity (the variables of spectral_dynamics.F90:509-575, 1502-1531): dump both time levels
+    through the host mirrors after 40 steps, load them into a fresh handle, continue 12 steps: same result as the
+    uninterrupted run (the fresh handle recomputes the gradient batch the resident one carries over; 1e-13)."""
+    from oracle.isca_oracle import held_suarez_config
+    cfg = api.config_from_namelist_object(held_suarez_config("T21", 10, 1200.0, num_tracers=1))
+    a = api.Atmosphere(cfg)
+    a.cold_start()
+    a.atmosphere(40)
+    prev, cur = a.get_time_pointers()
+    dump = {}
+    for slot in (0, 1):
+        dump[slot] = dict(ug=a.get_field(api.F_U, slot), vg=a.get_field(api.F_V, slot), tg=a.get_field(api.F_T, slot),
+                          psg=a.get_field(api.F_PS, slot), q=a.get_field(api.F_TRACER0, slot),
+                          vors=a.get_spectral(api.S_VOR, slot), divs=a.get_spectral(api.S_DIV, slot), ts=a.get_spectral(api.S_T, slot),
+                          ln_ps=a.get_spectral(api.S_LNPS, slot))
+    vorg, divg = a.get_field(api.F_VOR), a.get_field(api.F_DIV)
+    a.atmosphere(12)
+    ref = a.state(); ref["q"] = a.get_field(api.F_TRACER0)
+    b = api.Atmosphere(cfg)
+    for slot in (0, 1):
+        d = dump[slot]
+        b.set_grid_state(slot, d["ug"], d["vg"], d["tg"], d["psg"], d["q"])
+        b.set_spectral_state(slot, d["vors"], d["divs"], d["ts"], d["ln_ps"])
+    b.set_vor_div_grid(vorg, divg)
+    b.set_time_pointers(prev, cur)
+    b.atmosphere(12)
+    got = b.state(); got["q"] = b.get_field(api.F_TRACER0)
+    for k in ref:
+        assert rel(got[k], ref[k]) < 1e-13, k
+    a.atmosphere_end(); b.atmosphere_end()
+
+
+def test_grid_tracer_courant_numbers_above_one(api):
+    """The rare branches of the tracer path: zonal Courant numbers up to 3 on the polar rows (integer_flux_x, fv_advection.F90:483-521)
+    and vertical Courant numbers up to 2 (the 'extension for Courant numbers > 1' of vert_advection.F90:383-421), forced with
+    synthetic strong winds / divergence on a developed state; one step against the oracle."""
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    cfg = held_suarez_config("T21", 12, 1200.0, num_tracers=1)
+    cfg.initial_sphum = 2.0e-3
+    core = SpectralCore(cfg)
+    core.cold_start()
+    for _ in range(60):
+        core.step()
+    rng = np.random.default_rng(1)
+    K, J, I = core.ug[0].shape
+    lat = core.tb.rad_lat
+    for s in (0, 1):
+        core.ug[s] = core.ug[s] + (45.0 * np.cos(lat)[None, :, None] + 12.0 * rng.standard_normal((K, J, I)))
+        core.vg[s] = core.vg[s] + 6.0 * rng.standard_normal((K, J, I)) * np.cos(lat)[None, :, None]
+        core.grid_tracers[s, 0] = core.grid_tracers[s, 0] * (1 + 0.3 * rng.standard_normal((K, J, I))).clip(0.1)
+    core.divg = 1.2e-4 * rng.standard_normal((K, J, I))
+    b = core.ug[core.current] * 2 * cfg.dt_atmos / (core.fv.dx * core.fv.c[None, :, None])
+    assert np.abs(b).max() > 2.0                                           # the case does cross whole cells
+    atm = api.Atmosphere(api.config_from_namelist_object(cfg))
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    core.step()
+    atm.atmosphere(1)
+    c, p = core.current, core.previous
+    assert rel(atm.get_field(api.F_TRACER0), core.grid_tracers[c, 0]) < TOL_STEP
+    assert rel(atm.get_field(api.F_TRACER0, api.LEVEL_PREVIOUS), core.grid_tracers[p, 0]) < TOL_STEP
+    assert rel(atm.get_field(api.F_T), core.tg[c]) < TOL_STEP
+    atm.atmosphere_end()
