@@ -57,7 +57,7 @@ typedef struct IscaConfig {
   int32_t do_mass_correction, do_energy_correction, do_water_correction;
   int32_t use_virtual_temperature, use_implicit;
   double  robert_coeff, raw_filter_coeff, alpha_implicit;
-  int32_t vert_coord_option;      /* 0 even_sigma, 1 uneven_sigma, 2 input (pk/bk below) */
+  int32_t vert_coord_option;      /* 0 even_sigma, 1 uneven_sigma, 2 input (pk/bk below), 3 hybrid (p_press, p_sigma) */
   double  scale_heights, surf_res, exponent, p_press, p_sigma;
   int32_t vert_advect_uv, vert_advect_t;  /* 0 second_centered (only value supported) */
   double  reference_sea_level_press, initial_sphum, water_correction_limit;

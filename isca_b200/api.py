@@ -80,7 +80,7 @@ LEVEL_CURRENT, LEVEL_PREVIOUS = -1, -2
 SC_MEAN_PS, SC_MEAN_ENERGY, SC_T_MIN, SC_T_MAX, SC_STEP_COUNT, SC_KERNEL_LAUNCHES, SC_LAST_STEP_MS = range(7)
 TB_SIN_LAT, TB_WTS_LAT, TB_DEG_LAT, TB_DEG_LON, TB_PK, TB_BK = range(6)
 
-_VERT_COORD = {"even_sigma": 0, "uneven_sigma": 1, "input": 2}
+_VERT_COORD = {"even_sigma": 0, "uneven_sigma": 1, "input": 2, "hybrid": 3}
 _VERT_ADV = {"second_centered": 0}
 
 _lib = None

@@ -215,6 +215,29 @@ void build_tables(const IscaConfig& c, const Geometry& g, HostTables& t) {
   } else if (c.vert_coord_option == 2) {
     if (!c.pk || !c.bk) throw std::runtime_error("vert_coord_option=input needs pk and bk");
     for (int k = 0; k <= K; ++k) { t.pk[k] = c.pk[k]; t.bk[k] = c.bk[k]; }
+  } else if (c.vert_coord_option == 3) {
+    // 'hybrid' (vert_coordinate.F90:141-147): sigma near the surface, pressure aloft, blended by transition() (:161-183);
+    // both profiles are compute_uneven_sigma with zero_top = .false. (:248-272)
+    if (c.scale_heights == 0. || c.exponent == 0. || c.surf_res <= 0. || c.surf_res > 1.0)
+      throw std::runtime_error("compute_vert_coord: invalid scale_heights/exponent/surf_res");
+    if (c.p_sigma < c.p_press) throw std::runtime_error("compute_vert_coord: p_sigma must be greater than p_press");
+    double s2 = 1.0 - c.surf_res;
+    std::vector<double> prof(K + 1);
+    for (int k = 1; k <= K; ++k) {
+      double zeta = (1. - ((double)(k - 1) / (double)K));
+      double z = c.surf_res * zeta + s2 * std::pow(zeta, c.exponent);
+      prof[k - 1] = std::exp(-z * c.scale_heights);
+    }
+    prof[K] = 1.0;
+    for (int k = 0; k <= K; ++k) {
+      double f;
+      if (prof[k] <= c.p_press) f = 0.0;
+      else if (prof[k] >= c.p_sigma) f = 1.0;
+      else { double x = prof[k] - c.p_press, xx = c.p_sigma - c.p_press; double sn = std::sin(0.5 * PI * x / xx); f = sn * sn; }
+      double a = 0.0 * f + prof[k] * (1.0 - f);            // a_sigma = 0, a_press = prof
+      t.bk[k] = prof[k] * f + 0.0 * (1.0 - f);             // b_sigma = prof, b_press = 0
+      t.pk[k] = c.reference_sea_level_press * a;
+    }
   } else throw std::runtime_error("unsupported vert_coord_option");
   t.dpk.resize(K); t.dbk.resize(K);
   for (int k = 0; k < K; ++k) { t.dpk[k] = t.pk[k + 1] - t.pk[k]; t.dbk[k] = t.bk[k + 1] - t.bk[k]; }

@@ -357,6 +357,18 @@ spec_wave_matvec_kernel(DevTables t, double2* __restrict__ w_div) {
   }
 }
 
+// The dynamic shared-memory limit of the kernel only ever grows (one process-wide high-water mark shared by every caller:
+// lowering it for a handle with few levels would make later launches of a larger handle fail).
+static void launch_wave_matvec(const DevTables& t, double2* w_div, cudaStream_t st) {
+  const GeomDev& g = t.g;
+  const int K = g.K;
+  const size_t smem = sizeof(double) * ((size_t)K * K + (size_t)K * WM_COLS);
+  static size_t attr = 0;
+  if (smem > attr) { cudaFuncSetAttribute(spec_wave_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  dim3 grid(g.M + 1, (2 * g.nm + WM_COLS - 1) / WM_COLS);
+  spec_wave_matvec_kernel<<<grid, WM_COLS * WM_KG, smem, st>>>(t, w_div);
+}
+
 // ---------------------------------------------------------------------------------------------
 // S3: finish implicit correction, damping, leapfrog part A, and emit the next inverse batch
 // ---------------------------------------------------------------------------------------------
@@ -472,13 +484,7 @@ void launch_spec_step(const DevTables& t, const Params& pr, const SpecStepArgs& 
     if (smem > attr) { cudaFuncSetAttribute(spec_tend_adjust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
     spec_tend_adjust_kernel<<<nb, 128, smem, st>>>(t, pr, a);
   }
-  if (a.use_implicit) {
-    size_t smem = sizeof(double) * ((size_t)K * K + (size_t)K * WM_COLS);
-    static size_t attr = 0;
-    if (smem > attr) { cudaFuncSetAttribute(spec_wave_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-    dim3 grid(g.M + 1, (2 * g.nm + WM_COLS - 1) / WM_COLS);
-    spec_wave_matvec_kernel<<<grid, WM_COLS * WM_KG, smem, st>>>(t, a.w_div);
-  }
+  if (a.use_implicit) launch_wave_matvec(t, a.w_div, st);
   {
     size_t smem = sizeof(double) * ((size_t)2 * K * NCP + NC + (size_t)NLC * K);
     static size_t attr = 0;
@@ -586,12 +592,7 @@ void launch_implicit_correction(const DevTables& t, const Params& pr, double2* d
   ImplArgs a{dt_divs, dt_ts, dt_lnps, divs_prev, divs_cur, ts_prev, ts_cur, lnps_prev, lnps_cur};
   const int nb = (2 * g.T + 127) / 128;
   impl_adjust_kernel<<<nb, 128, 0, st>>>(t, pr, a);
-  {
-    size_t smem = sizeof(double) * ((size_t)K * K + (size_t)K * WM_COLS);
-    cudaFuncSetAttribute(spec_wave_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(g.M + 1, (2 * g.nm + WM_COLS - 1) / WM_COLS);
-    spec_wave_matvec_kernel<<<grid, WM_COLS * WM_KG, smem, st>>>(t, dt_divs);
-  }
+  launch_wave_matvec(t, dt_divs, st);
   impl_back_kernel<<<nb, 128, 0, st>>>(t, pr, a);
 }
 

@@ -440,6 +440,33 @@ def compute_vert_coord(cfg: Config):
             b[k - 1] = np.exp(-z * cfg.scale_heights)
         b[K] = 1.0
         b[0] = 0.0
+    elif cfg.vert_coord_option == "hybrid":
+        # vert_coordinate.F90:141-147 with compute_uneven_sigma(..., zero_top=.false.) :248-272 and transition :161-183
+        if cfg.p_sigma < cfg.p_press:
+            raise ValueError("p_sigma must be greater than p_press")
+        s2 = 1.0 - cfg.surf_res
+        prof = np.zeros(K + 1)
+        for k in range(1, K + 1):
+            zeta = 1.0 - (float(k - 1) / float(K))
+            z = cfg.surf_res * zeta + s2 * (zeta ** cfg.exponent)
+            prof[k - 1] = np.exp(-z * cfg.scale_heights)
+        prof[K] = 1.0
+        b_sigma, a_press = prof, prof                      # a_sigma = b_press = 0
+        f = np.zeros(K + 1)
+        for k in range(K + 1):
+            if b_sigma[k] <= cfg.p_press:
+                f[k] = 0.0
+            elif b_sigma[k] >= cfg.p_sigma:
+                f[k] = 1.0
+            else:
+                x, xx = b_sigma[k] - cfg.p_press, cfg.p_sigma - cfg.p_press
+                f[k] = (np.sin(0.5 * PI * x / xx)) ** 2
+        a = 0.0 * f + a_press * (1.0 - f)
+        b = b_sigma * f + 0.0 * (1.0 - f)
+        a = cfg.reference_sea_level_press * a
+    elif cfg.vert_coord_option == "input":
+        a = np.asarray(cfg.pk, dtype=float).copy()
+        b = np.asarray(cfg.bk, dtype=float).copy()
     else:
         raise ValueError(f'"{cfg.vert_coord_option}" is not a supported vert_coord_option')
     return a, b
