@@ -1,0 +1,75 @@
+/* isca_b200_rrtm.h -- C ABI of the RRTMG clear-sky radiation.
+ *
+ * Replaces, for the configuration Isca runs (`icld = 0`, `iaer = 0`, `idrv = 0`: clear sky, no aerosol;
+ * atmos_param/rrtm_radiation/rrtm_radiation.F90:113-116):
+ *   rrtmg_lw   rrtmg_lw/gcm_model/src/rrtmg_lw_rad.nomcica.f90:81   (inatm, setcoef, taumol, rtrnmr)
+ *   rrtmg_sw   rrtmg_sw/gcm_model/src/rrtmg_sw_rad.nomcica.f90:73   (inatm_sw, setcoef_sw, spcvrt_sw: taumol_sw, reftra_sw, vrtqdr_sw)
+ *   interp_temp + the column part of run_rrtmg   rrtm_radiation.F90:502-544, 816-1000
+ * The g-point reduction of rrtmg_lw_ini / rrtmg_sw_ini is done when the coefficient file is built
+ * (tools/make_rrtmg_tables.py -> isca_b200/data/rrtmg_tables.bin); create() loads that file.
+ *
+ * Host arrays, double precision.  The rrtmg_lw / rrtmg_sw entry points take the reference's own layout: (ncol, nlay)
+ * Fortran order (column index fastest), layer 1 = lowest layer, pressures in hPa, gases as volume mixing ratios.
+ * All functions return 0 on success; isca_b200_rrtm_last_error() describes a failure.  There is no CPU fallback.
+ */
+#ifndef ISCA_B200_RRTM_H
+#define ISCA_B200_RRTM_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct IscaRrtm_t* IscaRrtm;
+
+typedef struct IscaRrtmConfig {
+  int abi_version;                  /* 1 */
+  int num_lon, num_lat, num_levels; /* grid of run_rrtmg (this rank's latitude block); rrtmg_lw/sw take ncol per call */
+  /* constants_mod: CP_AIR (rrtmg_*_ini(cp_air), idealized_moist_phys.F90:781-782), RDGAS, GAS_CONSTANT, WTMH2O, WTMOZONE */
+  double cp_air, rdgas, gas_constant, wtmh2o, wtmozone;
+  /* rrtm_radiation_nml (rrtm_radiation.F90:117-226) */
+  double co2ppmv, h2o_lower_limit, temp_lower_limit, temp_upper_limit, solrad, solr_cnst;
+  int include_secondary_gases;
+  double ch4_val, n2o_val, o2_val, cfc11_val, cfc12_val, cfc22_val, ccl4_val;
+  int convert_sphum_to_vmr, input_o3_file_is_mmr;
+  int lonstep;                      /* only 1 is built */
+} IscaRrtmConfig;
+
+int isca_b200_rrtm_default_config(IscaRrtmConfig* cfg);
+int isca_b200_rrtm_create(const IscaRrtmConfig* cfg, const char* table_path, IscaRrtm* out);
+int isca_b200_rrtm_destroy(IscaRrtm r);
+const char* isca_b200_rrtm_last_error(IscaRrtm r);          /* r may be NULL */
+
+/* rrtmg_lw(ncol, nlay, icld=0, idrv=0, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+ *          cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, ... -> uflx, dflx, hr):
+ * play, tlay and the gases (ncol, nlay); plev, tlev (ncol, nlay+1); tsfc (ncol); emis (ncol, 16);
+ * out uflx, dflx (ncol, nlay+1) W/m2; hr (ncol, nlay) K/day.  Clear-sky and total-sky outputs coincide. */
+int isca_b200_rrtmg_lw(IscaRrtm r, int ncol, int nlay, const double* play, const double* plev, const double* tlay,
+                       const double* tlev, const double* tsfc, const double* h2ovmr, const double* o3vmr,
+                       const double* co2vmr, const double* ch4vmr, const double* n2ovmr, const double* o2vmr,
+                       const double* cfc11vmr, const double* cfc12vmr, const double* cfc22vmr, const double* ccl4vmr,
+                       const double* emis, double* uflx, double* dflx, double* hr);
+
+/* rrtmg_sw(ncol, nlay, icld=0, iaer=0, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+ *          asdir=asdif=aldir=aldif=albedo, coszen, adjes, dyofyr=0, scon, ... -> swuflx, swdflx, swhr):
+ * albedo, coszen (ncol); columns with coszen < 1e-10 return zeros as in the reference. */
+int isca_b200_rrtmg_sw(IscaRrtm r, int ncol, int nlay, const double* play, const double* plev, const double* tlay,
+                       const double* h2ovmr, const double* o3vmr, const double* co2vmr, const double* ch4vmr,
+                       const double* n2ovmr, const double* o2vmr, const double* albedo, const double* coszen,
+                       double adjes, double scon, double* swuflx, double* swdflx, double* swhr);
+
+/* interp_temp + run_rrtmg on a radiation step, model layout: 3-D arrays [K][J][I] (level 1 = model top), p_half /
+ * z_half [K+1][J][I], 2-D [J][I]; pressures Pa.  q = specific humidity, o3 = ozone as read from the ozone file (NULL =
+ * no ozone; mass mixing ratio if input_o3_file_is_mmr), coszen = the zenith angle run_rrtmg computed (astronomy stays
+ * on the host side).  tdt [K][J][I] is incremented by the radiative heating (K/s); tdt_rad (may be NULL) receives it
+ * (the `store_intermediate_rad` copy); flux_sw = net surface SW down, flux_lw = surface LW down; olr, toa_sw may be NULL. */
+int isca_b200_run_rrtmg(IscaRrtm r, const double* p_full, const double* p_half, const double* z_full, const double* z_half,
+                        const double* t, const double* q, const double* o3, const double* t_surf, const double* albedo,
+                        const double* coszen, double* tdt, double* tdt_rad, double* flux_sw, double* flux_lw, double* olr,
+                        double* toa_sw);
+
+/* average ms per launch (CUDA events) of the LW (which = 0) / SW (1) kernel on the columns of the last call */
+int isca_b200_rrtm_time(IscaRrtm r, int which, int reps, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

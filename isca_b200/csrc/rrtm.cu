@@ -1,0 +1,494 @@
+// rrtm.cu -- RRTMG clear-sky longwave and shortwave on the GPU behind include/isca_b200_rrtm.h.
+//
+// Mapping: one CTA per column.  Phase A: one thread per layer runs inatm + setcoef (+ the Planck interpolation) into
+// shared memory; thread 0 forms the column sums (precipitable water -> diffusivity angle, laytrop -> solar source
+// layers).  Phase B: one thread per g-point (140 LW / 112 SW) evaluates the gaseous optical depths layer by layer with
+// the descriptor-driven generic band code of rrtm_column.h and runs the radiative-transfer sweeps (rtrnmr clear-sky /
+// reftra + vrtqdr); the radiances of a level are summed over the g-points with warp shuffles + a fixed-order
+// cross-warp sum (deterministic).  Phase C: one thread per level writes fluxes and heating rates.
+// The absorption tables (1.9 MB, g-point fastest) stay L2-resident; lanes of one band read consecutive doubles.
+// Bound: fp64 issue + L1/L2 gather latency (≈ 6k table reads and ≈ 40k fp64 operations per (column, g-point)), not HBM:
+// a radiation call reads ≈ 12 3-D fields.  It runs every dt_rad (48 steps in the MiMA configuration).
+#include "../../include/isca_b200_rrtm.h"
+#include "rrtm_tables.h"
+#include <cuda_runtime.h>
+#include <string>
+
+using namespace rrtm;
+
+namespace {
+
+std::string& rr_thread_error() { static thread_local std::string e; return e; }
+
+struct DevBuf {
+  double* p = nullptr; size_t n = 0;
+  bool ensure(size_t count) {
+    if (count <= n) return true;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (cudaMalloc(&p, count * sizeof(double)) != cudaSuccess) return false;
+    n = count; return true;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct ColIn {                       // device pointers, (ncol, nlay) column-fastest; NULL gas = the constant beside it
+  int ncol, nlay;
+  const double *play, *plev, *tlay, *tlev, *tsfc, *emis, *albedo, *coszen;
+  const double* gas[NSP]; double gas_c[NSP];
+  const double* xs[4]; double xs_c[4];
+  double *uflx, *dflx, *hr;
+  double heatfac, adjflux;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct DevRed {                      // per-level sum over the g-points: warp shuffle, lane 0 stores the warp's partial
+  double* part; int warp, lane;      // part[warp][2][KMAX+1]
+  __device__ __forceinline__ void up(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 0) * (KMAX + 1) + lev] = v; }
+  __device__ __forceinline__ void down(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 1) * (KMAX + 1) + lev] = v; }
+};
+
+constexpr int LW_THREADS = 160, SW_THREADS = 128;
+constexpr double FLUXFAC = 3.14159265358979323846 * 2.0e4;      // pi * 2.e4 with pi = 2*asin(1)
+
+__global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __restrict__ A, Tab tb, const LwBand* __restrict__ bands, ColIn in) {
+  __shared__ Layer lay[KMAX];
+  __shared__ double planklay[NB_LW * (KMAX + 1)], planklev[NB_LW * (KMAX + 1)];
+  __shared__ double part[(LW_THREADS / 32) * 2 * (KMAX + 1)];
+  __shared__ double plankbnd[NB_LW], secdiff[NB_LW], semiss[NB_LW], pz[KMAX + 1], fnet[KMAX + 1];
+  const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
+  const int PS = KMAX + 1;           // row stride of the Planck arrays (planklay uses the same stride for simplicity)
+  // ---- phase A: inatm + setcoef per layer
+  for (int l = tid; l < nl; l += LW_THREADS) {
+    double vmr[NSP], xs[4];
+    for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + (size_t)nc * l] : in.gas_c[i];
+    for (int i = 0; i < 4; ++i) xs[i] = in.xs[i] ? in.xs[i][col + (size_t)nc * l] : in.xs_c[i];
+    double pb = in.plev[col + (size_t)nc * l], pa = in.plev[col + (size_t)nc * (l + 1)];
+    double coldry = coldry_of(pb, pa, vmr[0]);
+    double tav = in.tlay[col + (size_t)nc * l];
+    lw_setcoef_layer(A, tb, in.play[col + (size_t)nc * l], tav, coldry, vmr, xs, lay[l]);
+    planck16(A, tb, tav, planklay + l, PS);
+    planck16(A, tb, in.tlev[col + (size_t)nc * (l + 1)], planklev + l + 1, PS);
+    pz[l + 1] = pa;
+    if (l == 0) pz[0] = pb;
+  }
+  if (tid < NB_LW) semiss[tid] = in.emis ? in.emis[col + (size_t)nc * tid] : 1.0;
+  __syncthreads();
+  if (tid == 0) {
+    planck16(A, tb, in.tlev[col], planklev, PS);
+    double pb[NB_LW];
+    planck16(A, tb, in.tsfc[col], pb, 1);
+    for (int ib = 0; ib < NB_LW; ++ib) plankbnd[ib] = semiss[ib] * pb[ib];
+    // inatm: precipitable water (rrtmg_lw_rad.nomcica.f90:846-856), sequential over the layers
+    double amttl = 0.0, wvttl = 0.0;
+    for (int l = 0; l < nl; ++l) {
+      double wv = lay[l].col[SP_H2O] * 1.0e20;
+      amttl += lay[l].coldry + wv;
+      wvttl += wv;
+    }
+    double wvsh = (AMW * wvttl) / (AMD * amttl);
+    double pwvcm = wvsh * (1.0e3 * pz[0]) / (1.0e2 * GRAV);
+    for (int ib = 0; ib < NB_LW; ++ib) secdiff[ib] = lw_secdiff(ib, pwvcm);
+  }
+  __syncthreads();
+  // ---- phase B: one g-point per thread
+  {
+    const int valid = tid < NG_LW;
+    const int g = valid ? tid : NG_LW - 1;
+    int ib = 0;
+    while (ib < NB_LW - 1 && g >= bands[ib + 1].g0) ++ib;
+    const double delwave[NB_LW] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
+    DevRed red{part, tid >> 5, tid & 31};
+    lw_gpoint(A, tb, bands[ib], ib, g - bands[ib].g0, nl, lay, planklay, planklev, PS, plankbnd[ib], semiss[ib], secdiff[ib],
+              valid ? 0.5 * delwave[ib] : 0.0, red);
+  }
+  __syncthreads();
+  // ---- phase C: fluxes and heating rates
+  for (int lev = tid; lev <= nl; lev += LW_THREADS) {
+    double u = 0.0, d = 0.0;
+    for (int w = 0; w < LW_THREADS / 32; ++w) { u += part[(w * 2 + 0) * (KMAX + 1) + lev]; d += part[(w * 2 + 1) * (KMAX + 1) + lev]; }
+    u *= FLUXFAC; d *= FLUXFAC;
+    in.uflx[col + (size_t)nc * lev] = u;
+    in.dflx[col + (size_t)nc * lev] = d;
+    fnet[lev] = u - d;
+  }
+  __syncthreads();
+  for (int l = tid; l < nl; l += LW_THREADS)
+    in.hr[col + (size_t)nc * l] = in.heatfac * (fnet[l] - fnet[l + 1]) / (pz[l] - pz[l + 1]);
+}
+
+__global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __restrict__ A, Tab tb, const SwBand* __restrict__ bands, ColIn in) {
+  __shared__ Layer lay[KMAX];
+  __shared__ double part[(SW_THREADS / 32) * 2 * (KMAX + 1)];
+  __shared__ double pz[KMAX + 1], fnet[KMAX + 1];
+  __shared__ int lsol[NB_SW];
+  __shared__ int laytrop_s;
+  const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
+  const double cosz = in.coszen[col];
+  if (cosz < 1.0e-10) {              // `if (coszen(iplon) < zepzen) ... cycle` (rrtmg_sw_rad.nomcica.f90)
+    for (int lev = tid; lev <= nl; lev += SW_THREADS) { in.uflx[col + (size_t)nc * lev] = 0.0; in.dflx[col + (size_t)nc * lev] = 0.0; }
+    for (int l = tid; l < nl; l += SW_THREADS) in.hr[col + (size_t)nc * l] = 0.0;
+    return;
+  }
+  for (int l = tid; l < nl; l += SW_THREADS) {
+    double vmr[NSP];
+    for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + (size_t)nc * l] : in.gas_c[i];
+    double pb = in.plev[col + (size_t)nc * l], pa = in.plev[col + (size_t)nc * (l + 1)];
+    sw_setcoef_layer(A, tb, in.play[col + (size_t)nc * l], in.tlay[col + (size_t)nc * l], coldry_of(pb, pa, vmr[0]), vmr, lay[l]);
+    pz[l + 1] = pa;
+    if (l == 0) pz[0] = pb;
+  }
+  __syncthreads();
+  if (tid == 0) { int n = 0; for (int l = 0; l < nl; ++l) n += lay[l].lower; laytrop_s = n; }
+  __syncthreads();
+  if (tid < NB_SW) lsol[tid] = sw_laysolfr(bands[tid], lay, nl, laytrop_s);
+  __syncthreads();
+  {
+    const int valid = tid < NG_SW;
+    const int g = valid ? tid : NG_SW - 1;
+    int ib = 0;
+    while (ib < NB_SW - 1 && g >= bands[ib + 1].g0) ++ib;
+    DevRed red{part, tid >> 5, tid & 31};
+    sw_gpoint(A, tb, bands[ib], g - bands[ib].g0, nl, lay, lsol[ib], cosz, in.albedo[col], in.adjflux, valid ? 1.0 : 0.0, red);
+  }
+  __syncthreads();
+  for (int lev = tid; lev <= nl; lev += SW_THREADS) {
+    double u = 0.0, d = 0.0;
+    for (int w = 0; w < SW_THREADS / 32; ++w) { u += part[(w * 2 + 0) * (KMAX + 1) + lev]; d += part[(w * 2 + 1) * (KMAX + 1) + lev]; }
+    in.uflx[col + (size_t)nc * lev] = u;
+    in.dflx[col + (size_t)nc * lev] = d;
+    fnet[lev] = d - u;
+  }
+  __syncthreads();
+  for (int l = tid; l < nl; l += SW_THREADS)    // swhr(nlayers) = 0 in the reference
+    in.hr[col + (size_t)nc * l] = l == nl - 1 ? 0.0 : (fnet[l + 1] - fnet[l]) * in.heatfac / (pz[l] - pz[l + 1]);
+}
+
+// ---- run_rrtmg glue: model layout [K][J][I] top-down (Pa) -> RRTMG layout (ncol, nlay) bottom-up (hPa) ----
+struct PrepArgs {
+  int ncol, K;
+  const double *p_full, *p_half, *z_full, *z_half, *t, *q, *o3;
+  double *play, *plev, *tlay, *tlev, *h2o, *o3v;
+  double h2o_fac, o3_fac, h2o_lower_limit, t_lo, t_hi; int convert;
+};
+
+// interp_temp (rrtm_radiation.F90:502-544) and the reshape / unit block of run_rrtmg (:816-870)
+__global__ void rrtm_prepare_kernel(PrepArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncol) return;
+  const int K = a.K; const size_t nc = a.ncol;
+  auto lim = [&](double x) { return fmin(fmax(x, a.t_lo), a.t_hi); };
+  for (int k = 0; k < K; ++k) {                 // model level k (0 = top) -> rrtm layer K-1-k
+    const int l = K - 1 - k;
+    double tk = a.t[c + nc * k];
+    a.play[c + nc * l] = a.p_full[c + nc * k] * 0.01;
+    a.tlay[c + nc * l] = lim(tk);
+    double q = a.q[c + nc * k];
+    double v = a.convert ? (q / (1.0 - q)) * a.h2o_fac : q;
+    a.h2o[c + nc * l] = fmax(v, a.h2o_lower_limit);
+    a.o3v[c + nc * l] = a.o3 ? a.o3[c + nc * k] * a.o3_fac : 0.0;
+    // half level k (interface above layer k) -> rrtm level K-k
+    double th;
+    if (k == 0) th = 0.5 * (3.0 * tk - a.t[c + nc * 1]);
+    else {
+      double zf0 = a.z_full[c + nc * (k - 1)], zf1 = a.z_full[c + nc * k], zh = a.z_half[c + nc * k];
+      double dzk2 = 1.0 / (zf0 - zf1), dzk = (zh - zf1) * dzk2, dzk1 = (zf0 - zh) * dzk2;
+      th = tk * dzk1 + a.t[c + nc * (k - 1)] * dzk;
+    }
+    a.tlev[c + nc * (K - k)] = lim(th);
+    a.plev[c + nc * (K - k)] = a.p_half[c + nc * k] * 0.01;
+  }
+  {
+    double zf0 = a.z_full[c + nc * (K - 2)], zf1 = a.z_full[c + nc * (K - 1)];
+    double th = a.t[c + nc * (K - 2)] + (a.z_half[c + nc * K] - zf0) * (a.t[c + nc * (K - 1)] - a.t[c + nc * (K - 2)]) / (zf1 - zf0);
+    a.tlev[c] = lim(th);
+    a.plev[c] = a.p_half[c + nc * K] * 0.01;
+  }
+}
+// `if(minval(phalf(:,sk+1)) .le. 0.) phalf(:,sk+1) = pfull(:,sk)*0.5` -- the top interface pressure pk(1) + bk(1)*ps is the
+// same in every column (bk(1) = 0), so the reference's all-or-nothing replacement equals this per-column test
+__global__ void rrtm_fix_top_kernel(int ncol, int K, const double* play, double* plev) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncol && plev[c + (size_t)ncol * K] <= 0.0) plev[c + (size_t)ncol * K] = play[c + (size_t)ncol * (K - 1)] * 0.5;
+}
+
+struct FinishArgs {
+  int ncol, K;
+  const double *swhr, *lwhr, *swu, *swd, *lwu, *lwd;
+  double *tdt, *tdt_rad, *flux_sw, *flux_lw, *olr, *toa_sw;
+};
+__global__ void rrtm_finish_kernel(FinishArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncol) return;
+  const int K = a.K; const size_t nc = a.ncol;
+  const double daypersec = 1.0 / 86400.0;
+  for (int k = 0; k < K; ++k) {
+    const int l = K - 1 - k;
+    double h = a.swhr[c + nc * l] * daypersec + a.lwhr[c + nc * l] * daypersec;
+    if (a.tdt) a.tdt[c + nc * k] += h;
+    if (a.tdt_rad) a.tdt_rad[c + nc * k] = h;
+  }
+  if (a.flux_sw) a.flux_sw[c] = a.swd[c] - a.swu[c];
+  if (a.flux_lw) a.flux_lw[c] = a.lwd[c];
+  if (a.olr) a.olr[c] = a.lwu[c + nc * K] - a.lwd[c + nc * K];
+  if (a.toa_sw) a.toa_sw[c] = a.swd[c + nc * K] - a.swu[c + nc * K];
+}
+
+}  // namespace
+
+struct IscaRrtm_t {
+  IscaRrtmConfig cfg;
+  double* d_arena = nullptr;
+  LwBand* d_lw = nullptr;
+  SwBand* d_sw = nullptr;
+  Tab tab;
+  cudaStream_t st = nullptr;
+  bool owns_stream = true;
+  std::string err;
+  DevBuf buf[32];
+  ColIn last_lw{}, last_sw{};
+  bool have_lw = false, have_sw = false;
+};
+
+namespace {
+int rfail(IscaRrtm r, const std::string& m) { if (r) r->err = m; rr_thread_error() = m; return 1; }
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return rfail(r, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+int up(IscaRrtm r, DevBuf& d, const double* h, size_t n, const double** out) {
+  if (!h) { *out = nullptr; return 0; }
+  if (!d.ensure(n)) return rfail(r, "cudaMalloc failed");
+  RCK(cudaMemcpyAsync(d.p, h, n * sizeof(double), cudaMemcpyHostToDevice, r->st));
+  *out = d.p;
+  return 0;
+}
+double heatfac_of(double cp_air) { return GRAV * SECDY / (cp_air * 1.0e2); }
+
+// kernel launches on device pointers
+int isca_rrtm_lw_device(IscaRrtm r, const ColIn& in) {
+  if (in.nlay > KMAX || in.nlay < 2) return rfail(r, "rrtmg_lw: num_levels must be 2..64");
+  rrtmg_lw_kernel<<<in.ncol, LW_THREADS, 0, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
+  RCK(cudaGetLastError());
+  r->last_lw = in; r->have_lw = true;
+  return 0;
+}
+int isca_rrtm_sw_device(IscaRrtm r, const ColIn& in) {
+  if (in.nlay > KMAX || in.nlay < 2) return rfail(r, "rrtmg_sw: num_levels must be 2..64");
+  rrtmg_sw_kernel<<<in.ncol, SW_THREADS, 0, r->st>>>(r->d_arena, r->tab, r->d_sw, in);
+  RCK(cudaGetLastError());
+  r->last_sw = in; r->have_sw = true;
+  return 0;
+}
+
+}  // namespace
+
+// run_rrtmg on device pointers: used by the moist-model driver (moist_model.cu) -- same stream, nothing crosses PCIe
+
+// (model layout; scratch in r->buf[16..])
+int isca_rrtm_run_device(IscaRrtm r, cudaStream_t st, const double* p_full, const double* p_half, const double* z_full, const double* z_half,
+                         const double* t, const double* q, const double* o3, const double* t_surf, const double* albedo, const double* coszen,
+                         double* tdt, double* tdt_rad, double* flux_sw, double* flux_lw, double* olr, double* toa_sw) {
+  const IscaRrtmConfig& c = r->cfg;
+  const int K = c.num_levels; const size_t nc = (size_t)c.num_lon * c.num_lat;
+  cudaStream_t keep = r->st; r->st = st;
+  DevBuf* B = r->buf + 16;
+  const size_t n3 = nc * K, n3h = nc * (K + 1);
+  const size_t sizes[12] = {n3, n3h, n3, n3h, n3, n3, n3h, n3h, n3, n3h, n3h, n3};
+  for (int i = 0; i < 12; ++i) if (!B[i].ensure(sizes[i])) { r->st = keep; return rfail(r, "cudaMalloc failed"); }
+  double *play = B[0].p, *plev = B[1].p, *tlay = B[2].p, *tlev = B[3].p, *h2o = B[4].p, *o3v = B[5].p;
+  double *swu = B[6].p, *swd = B[7].p, *swhr = B[8].p, *lwu = B[9].p, *lwd = B[10].p, *lwhr = B[11].p;
+  PrepArgs pa{(int)nc, K, p_full, p_half, z_full, z_half, t, q, o3, play, plev, tlay, tlev, h2o, o3v,
+              (1000.0 * c.gas_constant / c.rdgas) / c.wtmh2o,
+              c.input_o3_file_is_mmr ? (1000.0 * c.gas_constant / c.rdgas) / c.wtmozone : 1.0,
+              c.h2o_lower_limit, c.temp_lower_limit, c.temp_upper_limit, c.convert_sphum_to_vmr};
+  const int T = 128, G = (int)((nc + T - 1) / T);
+  rrtm_prepare_kernel<<<G, T, 0, st>>>(pa);
+  rrtm_fix_top_kernel<<<G, T, 0, st>>>((int)nc, K, play, plev);
+  ColIn in{};
+  in.ncol = (int)nc; in.nlay = K; in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.tsfc = t_surf; in.emis = nullptr;
+  in.albedo = albedo; in.coszen = coszen;
+  for (int i = 0; i < NSP; ++i) { in.gas[i] = nullptr; in.gas_c[i] = 0.0; }
+  for (int i = 0; i < 4; ++i) { in.xs[i] = nullptr; in.xs_c[i] = 0.0; }
+  in.gas[SP_H2O] = h2o; in.gas[SP_O3] = o3v; in.gas_c[SP_CO2] = c.co2ppmv * 1.0e-6;
+  if (c.include_secondary_gases) { in.gas_c[SP_CH4] = c.ch4_val; in.gas_c[SP_N2O] = c.n2o_val; in.gas_c[SP_O2] = c.o2_val; }
+  in.heatfac = heatfac_of(c.cp_air);
+  ColIn sw = in; sw.uflx = swu; sw.dflx = swd; sw.hr = swhr; sw.adjflux = c.solrad * (c.solr_cnst / 1.36822e+03);
+  int rc = isca_rrtm_sw_device(r, sw);
+  if (!rc) {
+    ColIn lw = in; lw.uflx = lwu; lw.dflx = lwd; lw.hr = lwhr;
+    if (c.include_secondary_gases) { lw.xs_c[0] = c.ccl4_val; lw.xs_c[1] = c.cfc11_val; lw.xs_c[2] = c.cfc12_val; lw.xs_c[3] = c.cfc22_val; }
+    rc = isca_rrtm_lw_device(r, lw);
+  }
+  if (!rc) {
+    FinishArgs fa{(int)nc, K, swhr, lwhr, swu, swd, lwu, lwd, tdt, tdt_rad, flux_sw, flux_lw, olr, toa_sw};
+    rrtm_finish_kernel<<<G, T, 0, st>>>(fa);
+    if (cudaGetLastError() != cudaSuccess) rc = rfail(r, "rrtm_finish_kernel launch failed");
+  }
+  r->st = keep;
+  return rc;
+}
+
+void isca_rrtm_set_stream(IscaRrtm r, cudaStream_t st) {
+  if (r->owns_stream && r->st) cudaStreamDestroy(r->st);
+  r->st = st; r->owns_stream = false;
+}
+
+extern "C" {
+
+int isca_b200_rrtm_default_config(IscaRrtmConfig* c) {
+  if (!c) return 1;
+  memset(c, 0, sizeof *c);
+  c->abi_version = 1;
+  c->num_lon = 128; c->num_lat = 64; c->num_levels = 40;
+  c->rdgas = 287.04; c->cp_air = 287.04 / (2.0 / 7.0); c->gas_constant = 8.314;
+  c->wtmh2o = 2.896440E+01 * (287.04 / 461.50); c->wtmozone = 47.99820;
+  c->co2ppmv = 300.0; c->h2o_lower_limit = 2.0e-7; c->temp_lower_limit = 100.0; c->temp_upper_limit = 370.0;
+  c->solrad = 1.0; c->solr_cnst = 1368.22;
+  c->include_secondary_gases = 0;
+  c->convert_sphum_to_vmr = 1; c->input_o3_file_is_mmr = 1; c->lonstep = 1;
+  return 0;
+}
+
+const char* isca_b200_rrtm_last_error(IscaRrtm r) { return r ? r->err.c_str() : rr_thread_error().c_str(); }
+
+int isca_b200_rrtm_create(const IscaRrtmConfig* cfg, const char* table_path, IscaRrtm* out) {
+  IscaRrtm r = nullptr;
+  if (!cfg || !out || !table_path) return rfail(nullptr, "rrtm_create: null argument");
+  if (cfg->abi_version != 1) return rfail(nullptr, "rrtm_create: abi_version mismatch");
+  if (cfg->lonstep != 1) return rfail(nullptr, "rrtm_create: lonstep /= 1 is not built");
+  if (cfg->num_levels < 2 || cfg->num_levels > KMAX) return rfail(nullptr, "rrtm_create: num_levels must be 2..64");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return rfail(nullptr, "rrtm_create: no CUDA device (there is no CPU fallback)");
+  HostTables ht;
+  if (!ht.build(table_path)) return rfail(nullptr, "rrtm_create: " + ht.err);
+  r = new IscaRrtm_t();
+  r->cfg = *cfg; r->tab = ht.tab;
+  if (cudaStreamCreateWithFlags(&r->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&r->d_arena, ht.arena.size() * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&r->d_lw, sizeof ht.lw) != cudaSuccess || cudaMalloc(&r->d_sw, sizeof ht.sw) != cudaSuccess ||
+      cudaMemcpy(r->d_arena, ht.arena.data(), ht.arena.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(r->d_lw, ht.lw, sizeof ht.lw, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(r->d_sw, ht.sw, sizeof ht.sw, cudaMemcpyHostToDevice) != cudaSuccess) {
+    std::string m = std::string("rrtm_create: ") + cudaGetErrorString(cudaGetLastError());
+    isca_b200_rrtm_destroy(r);
+    return rfail(nullptr, m);
+  }
+  *out = r;
+  return 0;
+}
+
+int isca_b200_rrtm_destroy(IscaRrtm r) {
+  if (!r) return 0;
+  if (r->st && r->owns_stream) { cudaStreamSynchronize(r->st); cudaStreamDestroy(r->st); }
+  if (r->d_arena) cudaFree(r->d_arena);
+  if (r->d_lw) cudaFree(r->d_lw);
+  if (r->d_sw) cudaFree(r->d_sw);
+  delete r;
+  return 0;
+}
+
+int isca_b200_rrtmg_lw(IscaRrtm r, int ncol, int nlay, const double* play, const double* plev, const double* tlay,
+                       const double* tlev, const double* tsfc, const double* h2ovmr, const double* o3vmr,
+                       const double* co2vmr, const double* ch4vmr, const double* n2ovmr, const double* o2vmr,
+                       const double* cfc11vmr, const double* cfc12vmr, const double* cfc22vmr, const double* ccl4vmr,
+                       const double* emis, double* uflx, double* dflx, double* hr) {
+  if (!r) return rfail(nullptr, "rrtmg_lw: null handle");
+  if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !uflx || !dflx || !hr) return rfail(r, "rrtmg_lw: null array");
+  if (ncol < 1 || nlay < 2 || nlay > KMAX) return rfail(r, "rrtmg_lw: bad ncol / nlay");
+  const size_t n3 = (size_t)ncol * nlay, n3h = (size_t)ncol * (nlay + 1);
+  ColIn in{};
+  in.ncol = ncol; in.nlay = nlay;
+  DevBuf* B = r->buf;
+  if (up(r, B[0], play, n3, &in.play) || up(r, B[1], plev, n3h, &in.plev) || up(r, B[2], tlay, n3, &in.tlay) || up(r, B[3], tlev, n3h, &in.tlev) ||
+      up(r, B[4], tsfc, ncol, &in.tsfc) || up(r, B[5], emis, (size_t)ncol * NB_LW, &in.emis)) return 1;
+  const double* g[NSP] = {h2ovmr, co2vmr, o3vmr, n2ovmr, nullptr, ch4vmr, o2vmr};
+  for (int i = 0; i < NSP; ++i) { in.gas_c[i] = 0.0; if (up(r, B[6 + i], g[i], n3, &in.gas[i])) return 1; }
+  const double* x[4] = {ccl4vmr, cfc11vmr, cfc12vmr, cfc22vmr};
+  for (int i = 0; i < 4; ++i) { in.xs_c[i] = 0.0; if (up(r, B[13 + i], x[i], n3, &in.xs[i])) return 1; }
+  if (!r->buf[17].ensure(n3h) || !r->buf[18].ensure(n3h) || !r->buf[19].ensure(n3)) return rfail(r, "cudaMalloc failed");
+  in.uflx = r->buf[17].p; in.dflx = r->buf[18].p; in.hr = r->buf[19].p;
+  in.heatfac = heatfac_of(r->cfg.cp_air);
+  if (isca_rrtm_lw_device(r, in)) return 1;
+  RCK(cudaMemcpyAsync(uflx, in.uflx, n3h * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaMemcpyAsync(dflx, in.dflx, n3h * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaMemcpyAsync(hr, in.hr, n3 * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaStreamSynchronize(r->st));
+  return 0;
+}
+
+int isca_b200_rrtmg_sw(IscaRrtm r, int ncol, int nlay, const double* play, const double* plev, const double* tlay,
+                       const double* h2ovmr, const double* o3vmr, const double* co2vmr, const double* ch4vmr,
+                       const double* n2ovmr, const double* o2vmr, const double* albedo, const double* coszen,
+                       double adjes, double scon, double* swuflx, double* swdflx, double* swhr) {
+  if (!r) return rfail(nullptr, "rrtmg_sw: null handle");
+  if (!play || !plev || !tlay || !h2ovmr || !albedo || !coszen || !swuflx || !swdflx || !swhr) return rfail(r, "rrtmg_sw: null array");
+  if (ncol < 1 || nlay < 2 || nlay > KMAX) return rfail(r, "rrtmg_sw: bad ncol / nlay");
+  const size_t n3 = (size_t)ncol * nlay, n3h = (size_t)ncol * (nlay + 1);
+  ColIn in{};
+  in.ncol = ncol; in.nlay = nlay;
+  DevBuf* B = r->buf;
+  if (up(r, B[0], play, n3, &in.play) || up(r, B[1], plev, n3h, &in.plev) || up(r, B[2], tlay, n3, &in.tlay) ||
+      up(r, B[4], albedo, ncol, &in.albedo) || up(r, B[5], coszen, ncol, &in.coszen)) return 1;
+  const double* g[NSP] = {h2ovmr, co2vmr, o3vmr, n2ovmr, nullptr, ch4vmr, o2vmr};
+  for (int i = 0; i < NSP; ++i) { in.gas_c[i] = 0.0; if (up(r, B[6 + i], g[i], n3, &in.gas[i])) return 1; }
+  if (!r->buf[17].ensure(n3h) || !r->buf[18].ensure(n3h) || !r->buf[19].ensure(n3)) return rfail(r, "cudaMalloc failed");
+  in.uflx = r->buf[17].p; in.dflx = r->buf[18].p; in.hr = r->buf[19].p;
+  in.heatfac = heatfac_of(r->cfg.cp_air);
+  in.adjflux = adjes * (scon / 1.36822e+03);       // adjflux = adjflx * scon / rrsw_scon (inatm_sw; dyofyr = 0)
+  if (isca_rrtm_sw_device(r, in)) return 1;
+  RCK(cudaMemcpyAsync(swuflx, in.uflx, n3h * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaMemcpyAsync(swdflx, in.dflx, n3h * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaMemcpyAsync(swhr, in.hr, n3 * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaStreamSynchronize(r->st));
+  return 0;
+}
+
+int isca_b200_run_rrtmg(IscaRrtm r, const double* p_full, const double* p_half, const double* z_full, const double* z_half,
+                        const double* t, const double* q, const double* o3, const double* t_surf, const double* albedo,
+                        const double* coszen, double* tdt, double* tdt_rad, double* flux_sw, double* flux_lw, double* olr,
+                        double* toa_sw) {
+  if (!r) return rfail(nullptr, "run_rrtmg: null handle");
+  if (!p_full || !p_half || !z_full || !z_half || !t || !q || !t_surf || !albedo || !coszen || !tdt || !flux_sw || !flux_lw)
+    return rfail(r, "run_rrtmg: null array");
+  const int K = r->cfg.num_levels; const size_t nc = (size_t)r->cfg.num_lon * r->cfg.num_lat;
+  const size_t n3 = nc * K, n3h = nc * (K + 1);
+  DevBuf* B = r->buf;
+  const double *d_pf, *d_ph, *d_zf, *d_zh, *d_t, *d_q, *d_o3, *d_ts, *d_alb, *d_cz, *d_tdt;
+  if (up(r, B[0], p_full, n3, &d_pf) || up(r, B[1], p_half, n3h, &d_ph) || up(r, B[2], z_full, n3, &d_zf) || up(r, B[3], z_half, n3h, &d_zh) ||
+      up(r, B[4], t, n3, &d_t) || up(r, B[5], q, n3, &d_q) || up(r, B[6], o3, n3, &d_o3) || up(r, B[7], t_surf, nc, &d_ts) ||
+      up(r, B[8], albedo, nc, &d_alb) || up(r, B[9], coszen, nc, &d_cz) || up(r, B[10], tdt, n3, &d_tdt)) return 1;
+  if (!B[11].ensure(n3) || !B[12].ensure(nc) || !B[13].ensure(nc) || !B[14].ensure(nc) || !B[15].ensure(nc)) return rfail(r, "cudaMalloc failed");
+  if (isca_rrtm_run_device(r, r->st, d_pf, d_ph, d_zf, d_zh, d_t, d_q, d_o3, d_ts, d_alb, d_cz, (double*)d_tdt, B[11].p, B[12].p, B[13].p,
+                           B[14].p, B[15].p)) return 1;
+  RCK(cudaMemcpyAsync(tdt, d_tdt, n3 * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  if (tdt_rad) RCK(cudaMemcpyAsync(tdt_rad, B[11].p, n3 * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaMemcpyAsync(flux_sw, B[12].p, nc * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaMemcpyAsync(flux_lw, B[13].p, nc * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  if (olr) RCK(cudaMemcpyAsync(olr, B[14].p, nc * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  if (toa_sw) RCK(cudaMemcpyAsync(toa_sw, B[15].p, nc * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaStreamSynchronize(r->st));
+  return 0;
+}
+
+int isca_b200_rrtm_time(IscaRrtm r, int which, int reps, double* ms) {
+  if (!r || !ms || reps < 1) return rfail(r, "rrtm_time: bad argument");
+  if ((which == 0 && !r->have_lw) || (which == 1 && !r->have_sw)) return rfail(r, "rrtm_time: no previous call of that kernel");
+  cudaEvent_t e0, e1;
+  RCK(cudaEventCreate(&e0)); RCK(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; ++i) { if (which == 0 ? isca_rrtm_lw_device(r, r->last_lw) : isca_rrtm_sw_device(r, r->last_sw)) return 1; }
+  RCK(cudaEventRecord(e0, r->st));
+  for (int i = 0; i < reps; ++i) { if (which == 0 ? isca_rrtm_lw_device(r, r->last_lw) : isca_rrtm_sw_device(r, r->last_sw)) return 1; }
+  RCK(cudaEventRecord(e1, r->st));
+  RCK(cudaEventSynchronize(e1));
+  float t = 0.f;
+  RCK(cudaEventElapsedTime(&t, e0, e1));
+  *ms = (double)t / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+}  // extern "C"
