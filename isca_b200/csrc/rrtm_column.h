@@ -2,7 +2,7 @@
 //
 // Every function is `__host__ __device__`: the kernels call them per (column, g-point) thread, and the test-only host
 // build (tests/host/rrtm_host.cpp, compiled by g++) calls the very same functions in a serial loop so that the device
-// arithmetic can be checked against the NumPy oracle on a machine without a GPU.  The product never runs the host build.
+// arithmetic can be checked against an independent NumPy restatement on a machine without a GPU.  The product never runs the host build.
 //
 // Replaces (paths relative to /root/reference/src/atmos_param/rrtm_radiation):
 //   rrtmg_lw/gcm_model/src/rrtmg_lw_setcoef.f90:setcoef, rrtmg_lw_taumol.f90:taugb1..16,

@@ -141,3 +141,42 @@ def test_moist_config_struct_layout(lib_built, tmp_path):
     moist._lib().isca_b200_moist_default_config(C.byref(c))
     # idealized_moist_phys.F90:136-138, mixed_layer.F90:92-95
     assert (c.roughness_mom, c.roughness_heat, c.roughness_moist, c.mixed_layer_depth, c.albedo_value) == (0.05, 0.05, 0.05, 40.0, 0.06)
+
+
+RRTM_HEADER = os.path.join(ROOT, "include", "isca_b200_rrtm.h")
+
+
+def test_rrtm_header_symbols_exported_and_struct_layout(lib_built, tmp_path):
+    from isca_b200 import api, rrtm
+    lib = api.load_library()
+    txt = re.sub(r"/\*.*?\*/", "", open(RRTM_HEADER).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(isca_b200_\w+)\s*\(", txt)))
+    assert set(syms) == set(rrtm.RRTM_EXPORTS)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/isca_b200_rrtm.h but not exported"
+    fields = [f[0] for f in rrtm.IscaRrtmConfigStruct._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(IscaRrtmConfig, {f}));' for f in fields)
+    src = tmp_path / "rsz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "isca_b200_rrtm.h"\nint main(){printf("%zu\\n", sizeof(IscaRrtmConfig));' + body + "return 0;}")
+    exe = tmp_path / "rsz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == C.sizeof(rrtm.IscaRrtmConfigStruct)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(rrtm.IscaRrtmConfigStruct, f).offset == int(off), f
+    # rrtm_radiation_nml defaults (rrtm_radiation.F90:117-226)
+    c = rrtm.default_config()
+    assert (c.co2ppmv, c.h2o_lower_limit, c.temp_lower_limit, c.temp_upper_limit, c.solrad, c.solr_cnst) == (300.0, 2.0e-7, 100.0, 370.0, 1.0, 1368.22)
+    assert (c.include_secondary_gases, c.convert_sphum_to_vmr, c.input_o3_file_is_mmr, c.lonstep) == (0, 1, 1, 1)
+    assert os.path.exists(rrtm.TABLE_FILE)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_rrtm_no_cpu_fallback(lib_built):
+    from isca_b200 import api, rrtm
+    with pytest.raises(api.IscaError) as e:
+        rrtm.Rrtm()
+    assert "CUDA" in str(e.value)
+    with pytest.raises(api.IscaError) as e:
+        rrtm.Rrtm(lonstep=4)
+    assert "lonstep" in str(e.value)

@@ -1,0 +1,124 @@
+"""The RRTMG device arithmetic without a GPU.
+
+isca_b200/csrc/rrtm_column.h holds every formula of the CUDA kernels as `__host__ __device__` functions and
+rrtm_tables.h the band descriptors; tests/host/rrtm_host.cpp (TEST INFRASTRUCTURE, built here with g++, never part of the
+product library) runs the same functions in serial loops.  Comparing it with the independent NumPy oracle checks the
+descriptor-driven band code, the table re-tiling and the radiative-transfer sweeps that the GPU executes; the
+`-m gpu` tests (tests/test_gpu_rrtm.py) then only have the launch geometry and the cross-thread reductions left to prove.
+Tolerances: optical depths 1e-13, fluxes 1e-12, heating rates 1e-10 relative to the field maximum."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+
+from oracle import rrtmg as R
+from rrtm_cases import columns, mls_column, zero_if_none as z
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host", "rrtm_host.cpp")
+OUT = os.path.join(HERE, "host", "_build", "librrtm_host.so")
+P = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def host():
+    deps = [SRC] + [os.path.join(HERE, "..", "isca_b200", "csrc", f) for f in ("rrtm_column.h", "rrtm_tables.h")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", OUT, SRC])
+    lib = C.CDLL(OUT)
+    lib.rrtm_host_error.restype = C.c_char_p
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(P)
+
+
+def _F(a):
+    return None if a is None else np.asfortranarray(a)
+
+
+def host_lw(lib, g, cp=287.04 / (2 / 7)):
+    nc, K = g["play"].shape
+    arr = {k: _F(v) for k, v in g.items()}
+    u = np.zeros((nc, K + 1), order="F")
+    d = np.zeros((nc, K + 1), order="F")
+    hr = np.zeros((nc, K), order="F")
+    tg = np.zeros((nc, K, 140))
+    fr = np.zeros((nc, K, 140))
+    rc = lib.rrtm_host_lw(R.TABLE_FILE.encode(), C.c_double(cp), nc, K, _ptr(arr["play"]), _ptr(arr["plev"]), _ptr(arr["tlay"]),
+                          _ptr(arr["tlev"]), _ptr(np.ascontiguousarray(g["tsfc"])), _ptr(arr["h2o"]), _ptr(arr["o3"]), _ptr(arr["co2"]),
+                          _ptr(arr["ch4"]), _ptr(arr["n2o"]), _ptr(arr["o2"]), _ptr(arr["cfc11"]), _ptr(arr["cfc12"]), _ptr(arr["cfc22"]),
+                          _ptr(arr["ccl4"]), None, _ptr(u), _ptr(d), _ptr(hr), _ptr(tg), _ptr(fr))
+    assert rc == 0, lib.rrtm_host_error()
+    return u, d, hr, tg, fr
+
+
+def host_sw(lib, g, alb, cz, adjes=1.0, scon=1368.22, cp=287.04 / (2 / 7)):
+    nc, K = g["play"].shape
+    arr = {k: _F(v) for k, v in g.items()}
+    u = np.zeros((nc, K + 1), order="F")
+    d = np.zeros((nc, K + 1), order="F")
+    hr = np.zeros((nc, K), order="F")
+    tg = np.zeros((nc, K, 112))
+    tr = np.zeros((nc, K, 112))
+    sf = np.zeros((nc, 112))
+    rc = lib.rrtm_host_sw(R.TABLE_FILE.encode(), C.c_double(cp), nc, K, _ptr(arr["play"]), _ptr(arr["plev"]), _ptr(arr["tlay"]),
+                          _ptr(arr["h2o"]), _ptr(arr["o3"]), _ptr(arr["co2"]), _ptr(arr["ch4"]), _ptr(arr["n2o"]), _ptr(arr["o2"]),
+                          _ptr(np.ascontiguousarray(alb)), _ptr(np.ascontiguousarray(cz)), C.c_double(adjes), C.c_double(scon),
+                          _ptr(u), _ptr(d), _ptr(hr), _ptr(tg), _ptr(tr), _ptr(sf))
+    assert rc == 0, lib.rrtm_host_error()
+    return u, d, hr, tg, tr, sf
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("secondary,K,seed", [(False, 40, 1), (True, 40, 2), (True, 25, 3), (False, 60, 4)])
+def test_lw_device_arithmetic_matches_oracle(host, secondary, K, seed):
+    g = columns(48, K, seed, secondary=secondary)
+    u, d, hr, tg, fr = host_lw(host, g)
+    ou, od, ohr, opt = R.rrtmg_lw(g["play"], g["plev"], g["tlay"], g["tlev"], g["tsfc"], g["h2o"], g["o3"], g["co2"], z(g["ch4"]),
+                                  z(g["n2o"]), z(g["o2"]), z(g["cfc11"]), z(g["cfc12"]), z(g["cfc22"]), z(g["ccl4"]), return_optics=True)
+    ngs = np.concatenate([[0], np.cumsum(R.LW_NGC)])
+    for b in range(16):                                  # per band: every descriptor is exercised
+        s = slice(ngs[b], ngs[b + 1])
+        assert rel(tg[:, :, s], opt["taug"][:, :, s]) < 1e-13, b + 1
+        assert np.abs(fr[:, :, s] - opt["fracs"][:, :, s]).max() < 1e-14, b + 1
+    # both branches of every band were visited
+    assert opt["sc"]["lower"].any() and (~opt["sc"]["lower"]).any()
+    assert rel(u, ou) < 1e-12 and rel(d, od) < 1e-12 and rel(hr, ohr) < 1e-10
+
+
+@pytest.mark.parametrize("secondary,K,seed", [(False, 40, 5), (True, 40, 6), (True, 30, 7)])
+def test_sw_device_arithmetic_matches_oracle(host, secondary, K, seed):
+    g = columns(48, K, seed, secondary=secondary)
+    rng = np.random.default_rng(seed)
+    alb = rng.uniform(0.0, 0.9, 48)
+    cz = rng.uniform(-0.2, 1.0, 48)
+    cz[:4] = [1e-11, 1e-9, 1.0, 0.01]
+    su, sd, shr, tg, tr, sf = host_sw(host, g, alb, cz, 1.03, 1360.0)
+    ou, od, ohr, opt = R.rrtmg_sw(g["play"], g["plev"], g["tlay"], g["h2o"], g["o3"], g["co2"], z(g["ch4"]), z(g["n2o"]), z(g["o2"]),
+                                  alb, cz, 1.03, 1360.0, return_optics=True)
+    day = cz >= 1e-10
+    ngs = np.concatenate([[0], np.cumsum(R.SW_NGC)])
+    for b in range(14):
+        s = slice(ngs[b], ngs[b + 1])
+        assert rel(tg[day][:, :, s], opt["taug"][day][:, :, s] + 1e-300) < 1e-13 or np.abs(tg[day][:, :, s] - opt["taug"][day][:, :, s]).max() < 1e-300, b + 16
+        assert rel(tr[day][:, :, s], opt["taur"][day][:, :, s]) < 1e-13, b + 16
+        assert rel(sf[day][:, s], opt["sflux"][day][:, s]) < 1e-14, b + 16
+    assert (su[~day] == 0).all() and (sd[~day] == 0).all() and (shr[~day] == 0).all()
+    assert rel(su, ou) < 1e-12 and rel(sd, od) < 1e-12 and rel(shr, ohr) < 1e-10
+
+
+def test_mls_column_host(host):
+    g = mls_column(nc=2)
+    gg = dict(g, ch4=None, n2o=None, o2=None, cfc11=None, cfc12=None, cfc22=None, ccl4=None)
+    u, d, hr, _, _ = host_lw(host, gg)
+    assert 278.0 < u[0, -1] < 287.0 and 340.0 < d[0, 0] < 355.0
+    su, sd, shr, _, _, sf = host_sw(host, gg, np.full(2, 0.2), np.array([0.5, 1.0]))
+    assert np.allclose(sd[:, -1], 1368.22 * np.array([0.5, 1.0]), rtol=2e-3)
+    assert np.allclose(sf.sum(axis=1), sd[:, -1] / np.array([0.5, 1.0]), rtol=1e-12)
