@@ -69,6 +69,36 @@ int isca_b200_run_rrtmg(IscaRrtm r, const double* p_full, const double* p_half, 
 /* average ms per launch (CUDA events) of the LW (which = 0) / SW (1) kernel on the columns of the last call */
 int isca_b200_rrtm_time(IscaRrtm r, int which, int reps, double* ms);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Radiation time stepping and zenith angle of run_rrtmg (rrtm_radiation.F90:640-745) + astronomy_nml
+ * (shared/astronomy/astronomy.f90:141-164), and RRTMG as the radiation of the idealized moist model
+ * (idealized_moist_phys.F90:1167-1177: `do_rrtm_radiation` replaces `two_stream_gray`). */
+typedef struct IscaRrtmDriverConfig {
+  int abi_version;                 /* 1 */
+  int dt_rad, dt_rad_avg;          /* seconds; dt_rad <= 0: every step; dt_rad_avg <= 0: dt_rad */
+  int do_rad_time_avg, store_intermediate_rad, solday, frierson_solar_rad;
+  double equinox_day, del_sol, del_sw;
+  double ecc, obliq, per;          /* astronomy_nml */
+  int num_angles;
+  double day_in_s, year_in_s;      /* length_of_day(), length_of_year() of the calendar (360-day year in the test cases) */
+} IscaRrtmDriverConfig;
+
+int isca_b200_rrtm_driver_default_config(IscaRrtmDriverConfig* dc);
+
+/* diurnal_solar(lat, lon, gmt, time_since_ae, cosz, fracday, rrsun [, dt]) (astronomy.f90:1123-1410), n points, host arrays;
+ * dt <= 0: no time averaging.  rrsun may be NULL. */
+int isca_b200_diurnal_solar(IscaRrtm r, const IscaRrtmDriverConfig* dc, int n, const double* lat, const double* lon, double gmt,
+                            double time_since_ae, double dt, double* cosz, double* fracday, double* rrsun);
+
+#include "isca_b200_physics.h"
+/* Switch the moist model's radiation from two_stream_gray_rad to RRTMG (rc->num_lon/num_lat/num_levels are overwritten with the
+ * model's).  Must be called before isca_b200_moist_init. */
+int isca_b200_moist_use_rrtm(IscaMoist m, const IscaRrtmConfig* rc, const IscaRrtmDriverConfig* dc, const char* table_path);
+/* ozone as read from the ozone file, [K][J][I] on this rank's latitude block (do_read_ozone; NULL = no ozone) */
+int isca_b200_moist_set_ozone(IscaMoist m, const double* o3);
+/* model time of the next isca_b200_moist_step (Time of atmosphere(Time)); advanced by dt_atmos every step */
+int isca_b200_moist_set_time(IscaMoist m, long long days, int seconds);
+
 #ifdef __cplusplus
 }
 #endif

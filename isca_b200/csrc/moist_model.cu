@@ -3,6 +3,7 @@
 // by spectral_dynamics with the physics tendencies (atmosphere.F90:276-352).  Every kernel runs on the core's stream.
 #include "physics_common.h"
 #include "core_internal.h"
+#include "rrtm_internal.h"
 
 using namespace isca_phys;
 
@@ -23,6 +24,15 @@ struct IscaMoist_t {
   Dev lat2d, z_surf, t_surf, q_surf, gust, albedo, zero2, rough_m, rough_h, rough_q, z_atm, precip, rain, conv_rain, cape, cin, itq, itt,
       net_sw, lw_down, z_pbl, dts, sf;                         // sf: 28 surface-flux output planes
   Dev iwork;                                                   // int planes: land | convflag | kLZB | kLCL
+  // do_rrtm_radiation (idealized_moist_phys.F90:1167-1177): RRTMG instead of two_stream_gray_rad
+  IscaRrtm rr = nullptr;
+  IscaRrtmDriverConfig rdc{};
+  std::vector<double> orb_angle;
+  Dev tdt_rad, coszen, lon2d, o3, olr, toa_sw;
+  bool have_o3 = false;
+  double time_s = 0.0;                                         // Time of atmosphere(Time), seconds since Time_init
+  double dt_last = 0.0;                                        // rrtm_vars dt_last (radiation alarm)
+  long n_rad_calls = 0;
 };
 
 namespace {
@@ -63,6 +73,13 @@ __global__ void add3_kernel(size_t n, double* a, const double* da, double* b, co
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     a[i] = a[i] + da[i]; b[i] = b[i] + db[i]; c[i] = c[i] + dc[i];
   }
+}
+__global__ void add1_kernel(size_t n, double* a, const double* da) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = a[i] + da[i];
+}
+__global__ void lon2d_kernel(double* lon2d, int I, int J) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i < I) lon2d[(size_t)j * I + i] = (i * 360.0 / I) * (3.14159265358979323846 / 180.0);      // rad_lon = deg_lon * pi/180
 }
 __global__ void sub_kernel(size_t n, double* out, const double* a, const double* b) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = a[i] - b[i];
@@ -114,7 +131,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   }
   launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
   cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
-  launch_gray_down(p, m->lat2d.p, ph_c, tg_p, q_p, m->albedo.p, m->net_sw.p, m->lw_down.p);   // q = grid_tracers(previous, nsphum), :1068
+  if (!m->rr) launch_gray_down(p, m->lat2d.p, ph_c, tg_p, q_p, m->albedo.p, m->net_sw.p, m->lw_down.p);   // q = grid_tracers(previous, nsphum), :1068
   // surface_flux on the lowest model level (:1076-1132)
   sub_kernel<<<nblk(nc), 256, 0, st>>>(nc, m->z_atm.p, zf_c + (size_t)(K - 1) * nc, m->z_surf.p);
   IscaSurfaceFluxArgs a;
@@ -128,7 +145,25 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
                        &a.dtaudv_atm, &a.ex_del_m, &a.ex_del_h, &a.ex_del_q, &a.temp_2m, &a.u_10m, &a.v_10m, &a.q_2m, &a.rh_2m};
   for (int i = 0; i < 28; ++i) *outs[i] = m->sf.p + (size_t)i * nc;
   launch_surface_flux(p, a);
-  launch_gray_up(p, m->lat2d.p, ph_c, tg_p, q_p, m->t_surf.p, m->albedo.p, m->dt_t.p, nullptr);
+  if (!m->rr) launch_gray_up(p, m->lat2d.p, ph_c, tg_p, q_p, m->t_surf.p, m->albedo.p, m->dt_t.p, nullptr);
+  else {
+    // run_rrtmg (rrtm_radiation.F90:640-660): radiation alarm; between radiation steps the stored heating and surface fluxes are reused
+    const double dt_rad = m->rdc.dt_rad > 0 ? (double)m->rdc.dt_rad : (double)(long)v.dt_atmos;
+    if (m->time_s - m->dt_last >= dt_rad) {
+      m->dt_last = m->time_s;
+      if (isca_rrtm_coszen_device(m->rdc, m->orb_angle, st, m->time_s, (int)nc, m->lat2d.p, m->lon2d.p, m->coszen.p, nullptr))
+        return mfail(m, "run_rrtmg: zenith-angle kernel launch failed");
+      if (isca_rrtm_run_device(m->rr, st, pf_c, ph_c, zf_c, zh_c, tg_p, q_p, m->have_o3 ? m->o3.p : nullptr, m->t_surf.p, m->albedo.p,
+                               m->coszen.p, m->dt_t.p, m->tdt_rad.p, m->net_sw.p, m->lw_down.p, m->olr.p, m->toa_sw.p))
+        return mfail(m, std::string("run_rrtmg: ") + isca_b200_rrtm_last_error(m->rr));
+      m->n_rad_calls++;
+    } else if (m->rdc.store_intermediate_rad) {
+      add1_kernel<<<nblk(n3), 256, 0, st>>>(n3, m->dt_t.p, m->tdt_rad.p);
+    } else {
+      MCK(cudaMemsetAsync(m->net_sw.p, 0, nc * sizeof(double), st));
+      MCK(cudaMemsetAsync(m->lw_down.p, 0, nc * sizeof(double), st));
+    }
+  }
   if (m->mc.do_damping) {
     int nlev = rayleigh_nlev(m->pref.data(), K, p->cfg.sponge_pbottom);
     launch_rayleigh(p, nlev, delta_t, pf_c, ug_p, vg_p, m->w1.p, m->w2.p, m->w3.p);
@@ -146,6 +181,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   launch_vert_diff_up(p, delta_t, m->dt_t.p, m->dt_q.p);
   if (ev_phys_end) MCK(cudaEventRecord(ev_phys_end, st));
   if (isca_core_step_ext(m->dyn, m->dt_u.p, m->dt_v.p, m->dt_t.p, m->dt_q.p)) return mfail(m, std::string("spectral_dynamics: ") + isca_b200_last_error(m->dyn));
+  m->time_s += v.dt_atmos;                                     // atmos_model.F90: Time_atmos = Time_atmos + Time_step_atmos
   return 0;
 }
 
@@ -168,6 +204,7 @@ IscaHandle isca_b200_moist_dycore(IscaMoist m) { return m ? m->dyn : nullptr; }
 
 int isca_b200_moist_destroy(IscaMoist m) {
   if (!m) return 0;
+  if (m->rr) isca_b200_rrtm_destroy(m->rr);
   if (m->phy) isca_b200_physics_destroy(m->phy);
   if (m->dyn) isca_b200_destroy(m->dyn);
   delete m;
@@ -265,6 +302,16 @@ int isca_b200_moist_init(IscaMoist m) {
   MCK(cudaMemsetAsync(m->sf.p, 0, 28 * nc * sizeof(double), st));
   MCK(cudaStreamSynchronize(st));
   p->vert_diff_down_done = false;
+  if (m->rr) {
+    lon2d_kernel<<<g2, 128, 0, st>>>(m->lon2d.p, m->I, m->J);
+    Dev* z2[] = {&m->coszen, &m->olr, &m->toa_sw};
+    for (Dev* d : z2) MCK(cudaMemsetAsync(d->p, 0, nc * sizeof(double), st));
+    MCK(cudaMemsetAsync(m->tdt_rad.p, 0, m->n3 * sizeof(double), st));
+    MCK(cudaStreamSynchronize(st));
+    const double dt_rad = m->rdc.dt_rad > 0 ? (double)m->rdc.dt_rad : (double)(long)v.dt_atmos;
+    m->dt_last = -dt_rad;                                      // rrtm_radiation_init: radiation at the first time step
+    m->n_rad_calls = 0;
+  }
   m->initialized = true;
   return 0;
 }
@@ -326,6 +373,10 @@ int isca_b200_moist_get(IscaMoist m, int id, double* host) {
     case 13: src = m->sf.p + SF_FLUX_U * nc; break;
     case 14: src = m->sf.p + SF_FLUX_V * nc; break;
     case 15: src = m->dts.p; break;
+    case 16: if (!m->rr) return mfail(m, "moist_get: coszen needs do_rrtm_radiation"); src = m->coszen.p; break;
+    case 17: if (!m->rr) return mfail(m, "moist_get: olr needs do_rrtm_radiation"); src = m->olr.p; break;
+    case 18: if (!m->rr) return mfail(m, "moist_get: toa_sw needs do_rrtm_radiation"); src = m->toa_sw.p; break;
+    case 38: if (!m->rr) return mfail(m, "moist_get: tdt_rad needs do_rrtm_radiation"); src = m->tdt_rad.p; n = n3; break;
     case 32: src = m->dt_u.p; n = n3; break;
     case 33: src = m->dt_v.p; n = n3; break;
     case 34: src = m->dt_t.p; n = n3; break;
@@ -360,6 +411,49 @@ int isca_b200_moist_timing(IscaMoist m, double* ms_step, double* ms_physics) {
   if (!m) return mfail(nullptr, "null handle");
   if (ms_step) *ms_step = m->ms_step;
   if (ms_physics) *ms_physics = m->ms_phys;
+  return 0;
+}
+
+int isca_b200_moist_use_rrtm(IscaMoist m, const IscaRrtmConfig* rc, const IscaRrtmDriverConfig* dc, const char* table_path) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!rc || !dc || !table_path) return mfail(m, "moist_use_rrtm: null argument");
+  if (dc->abi_version != 1) return mfail(m, "IscaRrtmDriverConfig abi_version mismatch");
+  if (m->initialized) return mfail(m, "moist_use_rrtm must be called before isca_b200_moist_init");
+  if (m->rr) return mfail(m, "moist_use_rrtm: RRTMG is already enabled");
+  IscaCoreView v;
+  if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
+  if (dc->num_angles < 1 || dc->day_in_s <= 0.0 || dc->year_in_s <= 0.0) return mfail(m, "moist_use_rrtm: bad astronomy / calendar values");
+  if (dc->dt_rad > 0) {                                        // rrtm_radiation_init (rrtm_radiation.F90:384-402)
+    const long step = (long)v.dt_atmos;
+    if (dc->dt_rad > step && dc->dt_rad % step != 0) return mfail(m, "rrtm_gases_init: dt_rad must be an integer multiple of dt_atmos");
+  }
+  IscaRrtmConfig c = *rc;
+  c.num_lon = m->I; c.num_lat = m->J; c.num_levels = m->K;
+  if (isca_b200_rrtm_create(&c, table_path, &m->rr)) { m->rr = nullptr; return mfail(m, std::string("rrtm: ") + isca_b200_rrtm_last_error(nullptr)); }
+  m->rdc = *dc;
+  m->orb_angle = isca_rrtm_orbit(*dc);
+  bool ok = m->tdt_rad.ensure(m->n3) && m->coszen.ensure(m->nc) && m->lon2d.ensure(m->nc) && m->olr.ensure(m->nc) && m->toa_sw.ensure(m->nc);
+  if (!ok) return mfail(m, "cudaMalloc failed");
+  return 0;
+}
+
+int isca_b200_moist_set_ozone(IscaMoist m, const double* o3) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!m->rr) return mfail(m, "moist_set_ozone: do_rrtm_radiation is not enabled");
+  if (!o3) { m->have_o3 = false; return 0; }
+  IscaCoreView v;
+  if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
+  if (!m->o3.ensure(m->n3)) return mfail(m, "cudaMalloc failed");
+  MCK(cudaMemcpyAsync(m->o3.p, o3, m->n3 * sizeof(double), cudaMemcpyHostToDevice, v.st));
+  MCK(cudaStreamSynchronize(v.st));
+  m->have_o3 = true;
+  return 0;
+}
+
+int isca_b200_moist_set_time(IscaMoist m, long long days, int seconds) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (days < 0 || seconds < 0) return mfail(m, "moist_set_time: negative time");
+  m->time_s = (double)days * 86400.0 + (double)seconds;
   return 0;
 }
 

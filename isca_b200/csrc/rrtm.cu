@@ -11,6 +11,7 @@
 // a radiation call reads ≈ 12 3-D fields.  It runs every dt_rad (48 steps in the MiMA configuration).
 #include "../../include/isca_b200_rrtm.h"
 #include "rrtm_tables.h"
+#include "rrtm_internal.h"
 #include <cuda_runtime.h>
 #include <string>
 
@@ -239,6 +240,58 @@ __global__ void rrtm_finish_kernel(FinishArgs a) {
   if (a.toa_sw) a.toa_sw[c] = a.swd[c + nc * K] - a.swu[c + nc * K];
 }
 
+// diurnal_solar_2d (astronomy.f90:1123-1410; allow_negative_cosz absent): the chain of `where` statements in order
+__global__ void coszen_kernel(int n, const double* __restrict__ lat, const double* __restrict__ lon, double gmt, double dec, double dt,
+                              int frierson, double del_sol, double del_sw, double* __restrict__ cosz_out, double* __restrict__ fracday_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double PI = 3.14159265358979323846, twopi = 2.0 * PI;
+  double la = lat[i];
+  if (frierson) {                         // rrtm_radiation.F90:686-689
+    double sl = sin(la);
+    double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
+    cosz_out[i] = 0.25 * (1.0 + del_sol * p2 + del_sw * sl);
+    if (fracday_out) fracday_out[i] = 1.0;
+    return;
+  }
+  double aa = sin(la) * sin(dec), bb = cos(la) * cos(dec);
+  double t = gmt + lon[i] - PI;
+  if (t >= PI) t -= twopi;
+  if (t < -PI) t += twopi;
+  // half_day
+  double l2 = la;
+  if (la == 0.5 * PI) l2 = la - 1.0e-05;
+  if (la == -0.5 * PI) l2 = la + 1.0e-05;
+  double chd = -tan(l2) * tan(dec);
+  double h = chd <= -1.0 ? PI : (chd >= 1.0 ? 0.0 : acos(chd));
+  double cosz, fracday;
+  if (dt > 0.0) {
+    double tt = t + dt, st = sin(t), stt = sin(tt), sh = sin(h);
+    cosz = 0.0;
+    if (t < -h && tt < -h) cosz = 0.0;
+    if (t < -h && fabs(tt) <= h) cosz = (aa * (tt + h) / (tt - t)) + bb * (stt + sh) / (tt - t);
+    if (t < -h && h != 0.0 && h < tt) cosz = aa * (2. * h) / (tt - t) + bb * (sh + sh) / (tt - t);
+    if (fabs(t) <= h && fabs(tt) <= h) cosz = aa + bb * (stt - st) / (tt - t);
+    if (fabs(t) <= h && h < tt) cosz = (aa * (h - t) / (tt - t)) + bb * (sh - st) / (tt - t);
+    if (twopi - h < tt && t <= h) cosz = aa * ((tt + (2. * h) - t - twopi) / (tt - t)) + bb * (((sh - st) / (tt - t)) + ((stt + sh) / (tt - t)));
+    if (h < t && twopi - h >= tt) cosz = 0.0;
+    if (h < t && twopi - h < tt && tt < twopi + h) cosz = aa * (tt + h - twopi) / (tt - t) + bb * (stt + sh) / (tt - t);
+    if (h < t && twopi - h < tt && tt > twopi + h) cosz = aa * (2. * h) / (tt - t) + bb * (sh + sh) / (tt - t);
+    fracday = 0.0;
+    if (t < -h && tt < -h) fracday = 0.0;
+    if (t < -h && fabs(tt) <= h) fracday = (tt + h) / dt;
+    if (t < -h && h < tt) fracday = (h + h) / dt;
+    if (fabs(t) <= h && fabs(tt) <= h) fracday = (tt - t) / dt;
+    if (fabs(t) <= h && h < tt) fracday = (h - t) / dt;
+    if (h < t) fracday = 0.0;
+    if (twopi - h < tt) fracday = fracday + (tt + h - twopi) / dt;
+  } else {
+    if (fabs(t) < h) { cosz = aa + bb * cos(t); fracday = 1.0; } else { cosz = 0.0; fracday = 0.0; }
+  }
+  cosz_out[i] = fmax(0.0, cosz);
+  if (fracday_out) fracday_out[i] = fracday;
+}
+
 }  // namespace
 
 struct IscaRrtm_t {
@@ -335,6 +388,63 @@ int isca_rrtm_run_device(IscaRrtm r, cudaStream_t st, const double* p_full, cons
 void isca_rrtm_set_stream(IscaRrtm r, cudaStream_t st) {
   if (r->owns_stream && r->st) cudaStreamDestroy(r->st);
   r->st = st; r->owns_stream = false;
+}
+
+// ---- astronomy_mod on the host: orbit table, angle, declination (astronomy.f90) ----
+namespace {
+double r_inv_squared(const IscaRrtmDriverConfig& dc, double ang) {
+  const double deg_to_rad = 3.14159265358979323846 / 180.0;
+  double r = (1.0 - dc.ecc * dc.ecc) / (1.0 + dc.ecc * cos(ang - dc.per * deg_to_rad));
+  return 1.0 / (r * r);
+}
+}  // namespace
+
+std::vector<double> isca_rrtm_orbit(const IscaRrtmDriverConfig& dc) {
+  const double twopi = 2.0 * 3.14159265358979323846;
+  std::vector<double> orb(dc.num_angles + 1, 0.0);
+  double dt = twopi / (double)dc.num_angles;
+  dt = dt * sqrt(1.0 - dc.ecc * dc.ecc);
+  for (int n = 1; n <= dc.num_angles; ++n) {
+    double d1 = dt * r_inv_squared(dc, orb[n - 1]);
+    double d2 = dt * r_inv_squared(dc, orb[n - 1] + 0.5 * d1);
+    double d3 = dt * r_inv_squared(dc, orb[n - 1] + 0.5 * d2);
+    double d4 = dt * r_inv_squared(dc, orb[n - 1] + d3);
+    orb[n] = orb[n - 1] + (d1 / 6.0 + d2 / 3.0 + d3 / 3.0 + d4 / 6.0);
+  }
+  return orb;
+}
+
+namespace {
+int launch_coszen(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb, cudaStream_t st, double gmt, double time_since_ae, double dt,
+                  int n, const double* lat, const double* lon, double* coszen, double* fracday, double* rrsun) {
+  const double twopi = 2.0 * 3.14159265358979323846, deg_to_rad = 3.14159265358979323846 / 180.0;
+  // angle(time_since_ae): linear interpolation in the orbit table
+  double norm_time = time_since_ae * (double)dc.num_angles / twopi;
+  long fl = (long)floor(norm_time);
+  int i0 = (int)(((fl % dc.num_angles) + dc.num_angles) % dc.num_angles);
+  double x = norm_time - floor(norm_time);
+  double ang = (1.0 - x) * orb[i0] + x * orb[i0 + 1];
+  ang = fmod(ang, twopi); if (ang < 0.0) ang += twopi;
+  double dec = asin(-sin(dc.obliq * deg_to_rad) * sin(ang));
+  if (rrsun) *rrsun = r_inv_squared(dc, ang);
+  coszen_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, lat, lon, gmt, dec, dt, dc.frierson_solar_rad, dc.del_sol, dc.del_sw, coszen, fracday);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+}  // namespace
+
+int isca_rrtm_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb, cudaStream_t st, double total_seconds, int n,
+                            const double* lat, const double* lon, double* coszen, double* fracday) {
+  const double twopi = 2.0 * 3.14159265358979323846;
+  double ts = total_seconds;
+  if (dc.solday > 0) ts = fmod(total_seconds, 86400.0) + (double)dc.solday * 86400.0;     // Time_loc = set_time(seconds, solday)
+  double frac_of_day = ts / dc.day_in_s;
+  double frac_of_year = dc.solday > 0 ? ((double)dc.solday * dc.day_in_s) / dc.year_in_s : ts / dc.year_in_s;
+  double gmt = fabs(fmod(frac_of_day, 1.0)) * twopi;
+  double y = fmod(frac_of_year - dc.equinox_day, 1.0); if (y < 0.0) y += 1.0;               // modulo()
+  double time_since_ae = y * twopi;
+  int dt_rad_avg = dc.dt_rad_avg > 0 ? dc.dt_rad_avg : dc.dt_rad;
+  double dt = dc.do_rad_time_avg ? ((double)dt_rad_avg / dc.day_in_s) * twopi : 0.0;
+  return launch_coszen(dc, orb, st, gmt, time_since_ae, dt, n, lat, lon, coszen, fracday, nullptr);
 }
 
 extern "C" {
@@ -488,6 +598,36 @@ int isca_b200_rrtm_time(IscaRrtm r, int which, int reps, double* ms) {
   RCK(cudaEventElapsedTime(&t, e0, e1));
   *ms = (double)t / reps;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int isca_b200_rrtm_driver_default_config(IscaRrtmDriverConfig* dc) {
+  if (!dc) return 1;
+  memset(dc, 0, sizeof *dc);
+  dc->abi_version = 1;
+  dc->dt_rad = 0; dc->dt_rad_avg = -1; dc->do_rad_time_avg = 1; dc->store_intermediate_rad = 1; dc->solday = 0; dc->frierson_solar_rad = 0;
+  dc->equinox_day = 0.75; dc->del_sol = 0.95; dc->del_sw = 0.0;
+  dc->ecc = 0.0; dc->obliq = 23.439; dc->per = 102.932; dc->num_angles = 3600;
+  dc->day_in_s = 86400.0; dc->year_in_s = 360.0 * 86400.0;
+  return 0;
+}
+
+int isca_b200_diurnal_solar(IscaRrtm r, const IscaRrtmDriverConfig* dc, int n, const double* lat, const double* lon, double gmt,
+                            double time_since_ae, double dt, double* cosz, double* fracday, double* rrsun) {
+  if (!r) return rfail(nullptr, "diurnal_solar: null handle");
+  if (!dc || !lat || !lon || !cosz || !fracday || n < 1) return rfail(r, "diurnal_solar: null argument");
+  const double twopi = 2.0 * 3.14159265358979323846;
+  if (time_since_ae < 0.0 || time_since_ae > twopi) return rfail(r, "astronomy_mod: time_since_ae not between 0 and 2pi");
+  if (gmt < 0.0 || gmt > twopi) return rfail(r, "astronomy_mod: gmt not between 0 and 2pi");
+  const double *d_lat, *d_lon;
+  if (up(r, r->buf[0], lat, n, &d_lat) || up(r, r->buf[1], lon, n, &d_lon)) return 1;
+  if (!r->buf[2].ensure(n) || !r->buf[3].ensure(n)) return rfail(r, "cudaMalloc failed");
+  IscaRrtmDriverConfig c = *dc; c.frierson_solar_rad = 0;
+  if (launch_coszen(c, isca_rrtm_orbit(c), r->st, gmt, time_since_ae, dt, n, d_lat, d_lon, r->buf[2].p, r->buf[3].p, rrsun))
+    return rfail(r, "coszen_kernel launch failed");
+  RCK(cudaMemcpyAsync(cosz, r->buf[2].p, n * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaMemcpyAsync(fracday, r->buf[3].p, n * sizeof(double), cudaMemcpyDeviceToHost, r->st));
+  RCK(cudaStreamSynchronize(r->st));
   return 0;
 }
 

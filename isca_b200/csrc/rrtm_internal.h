@@ -1,0 +1,15 @@
+// rrtm_internal.h -- what moist_model.cu needs from rrtm.cu (device-pointer entry points on a caller-owned stream)
+#pragma once
+#include "../../include/isca_b200_rrtm.h"
+#include <cuda_runtime.h>
+#include <vector>
+
+// run_rrtmg on device arrays in the model layout ([K][J][I], Pa); see isca_b200_run_rrtmg
+int isca_rrtm_run_device(IscaRrtm r, cudaStream_t st, const double* p_full, const double* p_half, const double* z_full, const double* z_half,
+                         const double* t, const double* q, const double* o3, const double* t_surf, const double* albedo, const double* coszen,
+                         double* tdt, double* tdt_rad, double* flux_sw, double* flux_lw, double* olr, double* toa_sw);
+// the zenith-angle block of run_rrtmg (rrtm_radiation.F90:700-745) for model time `total_seconds`, on device lat / lon [n]
+int isca_rrtm_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb_angle, cudaStream_t st, double total_seconds,
+                            int n, const double* lat, const double* lon, double* coszen, double* fracday);
+// astronomy_mod orbit table (astronomy.f90:orbit)
+std::vector<double> isca_rrtm_orbit(const IscaRrtmDriverConfig& dc);

@@ -12,8 +12,10 @@ MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "is
                  "isca_b200_moist_set_t_surf", "isca_b200_moist_timing"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
-                 q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15)
-FIELDS_3D = dict(dt_ug=32, dt_vg=33, dt_tg=34, dt_qg=35, diff_m=36, diff_t=37)
+                 q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
+FIELDS_3D = dict(dt_ug=32, dt_vg=33, dt_tg=34, dt_qg=35, diff_m=36, diff_t=37, tdt_rad=38)
+# declared in include/isca_b200_rrtm.h (RRTMG as the moist model's radiation)
+MOIST_RRTM_EXPORTS = ["isca_b200_moist_use_rrtm", "isca_b200_moist_set_ozone", "isca_b200_moist_set_time"]
 CONVECTION = {"NONE": 0, "SIMPLE_BETTS_MILLER": 1}
 
 
@@ -116,6 +118,33 @@ class MoistAtmosphere:
             raise IscaError(f"unknown field {name}")
         self._ck(self._lib.isca_b200_moist_get(self._h, i, out.ctypes.data_as(C.POINTER(C.c_double))), "get")
         return out
+
+    def use_rrtm(self, rrtm_nml=None, table_file=None, **driver_nml):
+        """do_rrtm_radiation = .true. (idealized_moist_phys.F90:1167-1177): RRTMG replaces two_stream_gray_rad.
+        rrtm_nml: rrtm_radiation_nml gas / limit values (IscaRrtmConfig fields); driver_nml: dt_rad, dt_rad_avg, do_rad_time_avg,
+        store_intermediate_rad, solday, equinox_day, frierson_solar_rad, del_sol, del_sw and the astronomy_nml / calendar values.
+        Call before idealized_moist_phys_init."""
+        from . import rrtm
+        rc = rrtm.default_config(**(rrtm_nml or {}))
+        dc = rrtm.driver_config(**driver_nml)
+        lib = rrtm._lib()
+        self._ck(lib.isca_b200_moist_use_rrtm(self._h, C.byref(rc), C.byref(dc), (table_file or rrtm.TABLE_FILE).encode()), "rrtm_radiation_init")
+
+    def set_ozone(self, o3):
+        """the field read from `ozone_file` (do_read_ozone), [lev, lat, lon]; None = no ozone"""
+        from . import rrtm
+        lib = rrtm._lib()
+        if o3 is None:
+            self._ck(lib.isca_b200_moist_set_ozone(self._h, None), "set_ozone")
+            return
+        a = np.ascontiguousarray(o3, dtype=np.float64)
+        if a.shape != self.s3:
+            raise IscaError("ozone has the wrong shape")
+        self._ck(lib.isca_b200_moist_set_ozone(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_ozone")
+
+    def set_time(self, days, seconds):
+        from . import rrtm
+        self._ck(rrtm._lib().isca_b200_moist_set_time(self._h, int(days), int(seconds)), "set_time")
 
     def set_t_surf(self, t_surf):
         a = np.ascontiguousarray(t_surf, dtype=np.float64)

@@ -14,7 +14,9 @@ import numpy as np
 from .api import load_library, IscaError
 
 RRTM_EXPORTS = ["isca_b200_rrtm_default_config", "isca_b200_rrtm_create", "isca_b200_rrtm_destroy", "isca_b200_rrtm_last_error",
-                "isca_b200_rrtmg_lw", "isca_b200_rrtmg_sw", "isca_b200_run_rrtmg", "isca_b200_rrtm_time"]
+                "isca_b200_rrtmg_lw", "isca_b200_rrtmg_sw", "isca_b200_run_rrtmg", "isca_b200_rrtm_time",
+                "isca_b200_rrtm_driver_default_config", "isca_b200_diurnal_solar",
+                "isca_b200_moist_use_rrtm", "isca_b200_moist_set_ozone", "isca_b200_moist_set_time"]
 
 TABLE_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "rrtmg_tables.bin")
 
@@ -26,6 +28,13 @@ class IscaRrtmConfigStruct(C.Structure):
                [("include_secondary_gases", C.c_int)] + \
                [(n, C.c_double) for n in ("ch4_val", "n2o_val", "o2_val", "cfc11_val", "cfc12_val", "cfc22_val", "ccl4_val")] + \
                [(n, C.c_int) for n in ("convert_sphum_to_vmr", "input_o3_file_is_mmr", "lonstep")]
+
+
+class IscaRrtmDriverConfigStruct(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("abi_version", "dt_rad", "dt_rad_avg", "do_rad_time_avg", "store_intermediate_rad", "solday",
+                                       "frierson_solar_rad")] + \
+               [(n, C.c_double) for n in ("equinox_day", "del_sol", "del_sw", "ecc", "obliq", "per")] + \
+               [("num_angles", C.c_int)] + [(n, C.c_double) for n in ("day_in_s", "year_in_s")]
 
 
 _bound = False
@@ -45,6 +54,12 @@ def _lib():
         lib.isca_b200_rrtmg_sw.argtypes = [vp, C.c_int, C.c_int] + [dp] * 11 + [C.c_double, C.c_double] + [dp] * 3
         lib.isca_b200_run_rrtmg.argtypes = [vp] + [dp] * 16
         lib.isca_b200_rrtm_time.argtypes = [vp, C.c_int, C.c_int, dp]
+        lib.isca_b200_rrtm_driver_default_config.argtypes = [C.POINTER(IscaRrtmDriverConfigStruct)]
+        lib.isca_b200_diurnal_solar.argtypes = [vp, C.POINTER(IscaRrtmDriverConfigStruct), C.c_int, dp, dp, C.c_double, C.c_double, C.c_double,
+                                                dp, dp, dp]
+        lib.isca_b200_moist_use_rrtm.argtypes = [vp, C.POINTER(IscaRrtmConfigStruct), C.POINTER(IscaRrtmDriverConfigStruct), C.c_char_p]
+        lib.isca_b200_moist_set_ozone.argtypes = [vp, dp]
+        lib.isca_b200_moist_set_time.argtypes = [vp, C.c_longlong, C.c_int]
         _bound = True
     return lib
 
@@ -58,6 +73,17 @@ def default_config(**kw) -> IscaRrtmConfigStruct:
             raise IscaError(f"unknown rrtm_radiation_nml / config key {k}")
         setattr(cfg, k, v)
     return cfg
+
+
+def driver_config(**kw) -> IscaRrtmDriverConfigStruct:
+    """radiation time stepping / zenith angle values of rrtm_radiation_nml and astronomy_nml; keyword arguments override"""
+    dc = IscaRrtmDriverConfigStruct()
+    _lib().isca_b200_rrtm_driver_default_config(C.byref(dc))
+    for k, v in kw.items():
+        if not hasattr(dc, k):
+            raise IscaError(f"unknown rrtm_radiation_nml / astronomy_nml key {k}")
+        setattr(dc, k, v)
+    return dc
 
 
 def _f(a):
@@ -136,6 +162,17 @@ class Rrtm:
         self._check(self._lib.isca_b200_run_rrtmg(self._h, *[_p(x) for x in a], _p(tdt), _p(out["tdt_rad"]), _p(out["flux_sw"]),
                                                   _p(out["flux_lw"]), _p(out["olr"]), _p(out["toa_sw"])))
         return out
+
+    def diurnal_solar(self, lat, lon, gmt, time_since_ae, dt=None, **astronomy_nml):
+        """astronomy_mod diurnal_solar (astronomy.f90:1123) -> cosz, fracday, rrsun"""
+        shape = np.shape(lat)
+        la = np.ascontiguousarray(np.broadcast_to(lat, shape), dtype=np.float64).ravel()
+        lo = np.ascontiguousarray(np.broadcast_to(lon, shape), dtype=np.float64).ravel()
+        cosz, frac, rr = np.zeros(la.size), np.zeros(la.size), C.c_double()
+        dc = driver_config(**astronomy_nml)
+        self._check(self._lib.isca_b200_diurnal_solar(self._h, C.byref(dc), la.size, _p(la), _p(lo), float(gmt), float(time_since_ae),
+                                                      -1.0 if dt is None else float(dt), _p(cosz), _p(frac), C.byref(rr)))
+        return cosz.reshape(shape), frac.reshape(shape), rr.value
 
     def time_kernel(self, which: int, reps: int = 10) -> float:
         ms = C.c_double()

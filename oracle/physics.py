@@ -1112,6 +1112,9 @@ class IdealizedMoistPhys:
         self.heat_capacity = np.full(shp, cfg.depth * RHO_CP)
         self.ocean_qflux = np.zeros(shp)
         self.diag = {}
+        # do_rrtm_radiation (idealized_moist_phys.F90:1167-1177): an oracle.rrtmg.RrtmRadiation instead of the grey scheme
+        self.rrtm = None
+        self.time_s = 0.0
 
     def __call__(self, core, delta_t):
         """core: the dynamical core state (ug, vg, tg, grid_tracers, p_half, p_full, z_half, z_full at two time levels)."""
@@ -1143,9 +1146,10 @@ class IdealizedMoistPhys:
         precip = precip + rain
         dt_tg = dt_tg + cond_dt_tg
         dt_q = dt_q + cond_dt_qg
-        d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo)
-        net_surf_sw_down = (1.0 - self.albedo) * d["sw_down_surf"]
-        surf_lw_down = d["surf_lw_down"]
+        if self.rrtm is None:
+            d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo)
+            net_surf_sw_down = (1.0 - self.albedo) * d["sw_down_surf"]
+            surf_lw_down = d["surf_lw_down"]
         sf = surface_flux(self.svp, self.mo, self.sflux, t_atm=tg_p[K - 1], q_atm_in=q_p[K - 1], u_atm=ug_p[K - 1], v_atm=vg_p[K - 1],
                           p_atm=core.p_full[cur][K - 1], z_atm=core.z_full[cur][K - 1] - self.z_surf, p_surf=core.p_half[cur][K],
                           t_surf=self.t_surf, t_ca=self.t_surf, q_surf=self.q_surf, u_surf=zero2, v_surf=zero2,
@@ -1153,7 +1157,12 @@ class IdealizedMoistPhys:
                           rough_moist=np.full_like(zero2, c.roughness_moist), rough_scale=np.full_like(zero2, c.roughness_mom),
                           gust=self.gust, land=np.zeros(zero2.shape, bool))
         self.q_surf = sf["q_surf"]
-        dt_tg, _ = self.rad.up(self.t_surf, self.albedo, core.p_half[cur], dt_tg)
+        if self.rrtm is None:
+            dt_tg, _ = self.rad.up(self.t_surf, self.albedo, core.p_half[cur], dt_tg)
+        else:
+            dt_tg, net_surf_sw_down, surf_lw_down = self.rrtm(self.time_s, core.p_full[cur], core.p_half[cur], core.z_full[cur],
+                                                              core.z_half[cur], tg_p, q_p, self.t_surf, self.albedo, dt_tg)
+        self.time_s += self.dt_real
         if c.do_damping:
             udt, vdt, tdt, _ = rayleigh_sponge(delta_t, core.p_full[cur], ug_p, vg_p, self.pref, c.sponge_pbottom, c.trayfric, True)
             dt_ug, dt_vg, dt_tg = dt_ug + udt, dt_vg + vdt, dt_tg + tdt

@@ -983,3 +983,149 @@ def run_rrtmg_columns(p_full, p_half, t, t_half, q, t_surf, albedo, coszen, o3vm
     return dict(tdt_rad=tdt, tdt_sw=rev(swhr) * daypersec, tdt_lw=rev(lwhr) * daypersec,
                 flux_sw=swd[:, 0] - swu[:, 0], flux_lw=lwd[:, 0], olr=lwu[:, K] - lwd[:, K],
                 toa_sw=swd[:, K] - swu[:, K], swu=swu, swd=swd, lwu=lwu, lwd=lwd)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# astronomy_mod (shared/astronomy/astronomy.f90) as run_rrtmg uses it, and the radiation time stepping of run_rrtmg
+# ----------------------------------------------------------------------------------------------------------------
+class Astronomy:
+    """astronomy_nml defaults of Isca (ecc = 0, obliq = 23.439, per = 102.932, num_angles = 3600) and the orbit table of
+    `orbit` (astronomy.f90: 4th-order Runge-Kutta of d(angle)/dt = r_inv_squared)"""
+
+    def __init__(self, ecc=0.0, obliq=23.439, per=102.932, num_angles=3600):
+        self.ecc, self.obliq, self.per, self.num_angles = ecc, obliq, per, num_angles
+        self.deg_to_rad = np.pi / 180.0
+        orb = np.zeros(num_angles + 1)
+        dt = 2 * np.pi / float(num_angles)
+        dt = dt * np.sqrt(1.0 - ecc ** 2)
+        for n in range(1, num_angles + 1):
+            d1 = dt * self.r_inv_squared(orb[n - 1])
+            d2 = dt * self.r_inv_squared(orb[n - 1] + 0.5 * d1)
+            d3 = dt * self.r_inv_squared(orb[n - 1] + 0.5 * d2)
+            d4 = dt * self.r_inv_squared(orb[n - 1] + d3)
+            orb[n] = orb[n - 1] + (d1 / 6.0 + d2 / 3.0 + d3 / 3.0 + d4 / 6.0)
+        self.orb_angle = orb
+
+    def r_inv_squared(self, ang):
+        r = (1.0 - self.ecc ** 2) / (1.0 + self.ecc * np.cos(ang - self.per * self.deg_to_rad))
+        return r ** (-2)
+
+    def angle(self, t):
+        norm_time = t * float(self.num_angles) / (2 * np.pi)
+        i = int(np.floor(norm_time)) % self.num_angles
+        x = norm_time - np.floor(norm_time)
+        return ((1.0 - x) * self.orb_angle[i] + x * self.orb_angle[i + 1]) % (2 * np.pi)
+
+    def declination(self, ang):
+        return np.arcsin(-np.sin(self.obliq * self.deg_to_rad) * np.sin(ang))
+
+    def half_day(self, lat, dec):
+        eps = 1.0e-05
+        lat = np.where(lat == 0.5 * np.pi, lat - eps, lat)
+        lat = np.where(lat == -0.5 * np.pi, lat + eps, lat)
+        c = -np.tan(lat) * np.tan(dec)
+        with np.errstate(invalid="ignore"):
+            return np.where(c <= -1.0, np.pi, np.where(c >= 1.0, 0.0, np.arccos(np.clip(c, -1.0, 1.0))))
+
+    def diurnal_solar(self, lat, lon, gmt, time_since_ae, dt=None):
+        """diurnal_solar_2d (astronomy.f90:1123-1410), allow_negative_cosz absent -> cosz, fracday, rrsun"""
+        twopi = 2 * np.pi
+        ang = self.angle(time_since_ae)
+        dec = self.declination(ang)
+        rrsun = self.r_inv_squared(ang)
+        aa = np.sin(lat) * np.sin(dec)
+        bb = np.cos(lat) * np.cos(dec)
+        t = gmt + lon - np.pi
+        t = np.where(t >= np.pi, t - twopi, t)
+        t = np.where(t < -np.pi, t + twopi, t)
+        h = self.half_day(lat, dec)
+        if dt is None:
+            day = np.abs(t) < h
+            cosz = np.where(day, aa + bb * np.cos(t), 0.0)
+            return np.maximum(0.0, cosz), day.astype(float), rrsun
+        tt = t + dt
+        st, stt, sh = np.sin(t), np.sin(tt), np.sin(h)
+        cosz = np.zeros_like(t)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w = lambda m, v: np.where(m, v, cosz)
+            cosz = w((t < -h) & (tt < -h), 0.0)
+            cosz = w((t < -h) & (np.abs(tt) <= h), (aa * (tt + h) / (tt - t)) + bb * (stt + sh) / (tt - t))
+            cosz = w((t < -h) & (h != 0.0) & (h < tt), aa * (2. * h) / (tt - t) + bb * (sh + sh) / (tt - t))
+            cosz = w((np.abs(t) <= h) & (np.abs(tt) <= h), aa + bb * (stt - st) / (tt - t))
+            cosz = w((np.abs(t) <= h) & (h < tt), (aa * (h - t) / (tt - t)) + bb * (sh - st) / (tt - t))
+            cosz = w((twopi - h < tt) & (t <= h), aa * ((tt + (2. * h) - t - twopi) / (tt - t)) + bb * (((sh - st) / (tt - t)) + ((stt + sh) / (tt - t))))
+            cosz = w((h < t) & (twopi - h >= tt), 0.0)
+            cosz = w((h < t) & (twopi - h < tt) & (tt < twopi + h), aa * (tt + h - twopi) / (tt - t) + bb * (stt + sh) / (tt - t))
+            cosz = w((h < t) & (twopi - h < tt) & (tt > twopi + h), aa * (2. * h) / (tt - t) + bb * (sh + sh) / (tt - t))
+        fracday = np.zeros_like(t)
+        f = lambda m, v: np.where(m, v, fracday)
+        fracday = f((t < -h) & (tt < -h), 0.0)
+        fracday = f((t < -h) & (np.abs(tt) <= h), (tt + h) / dt)
+        fracday = f((t < -h) & (h < tt), (h + h) / dt)
+        fracday = f((np.abs(t) <= h) & (np.abs(tt) <= h), (tt - t) / dt)
+        fracday = f((np.abs(t) <= h) & (h < tt), (h - t) / dt)
+        fracday = f(h < t, 0.0)
+        fracday = np.where(twopi - h < tt, fracday + (tt + h - twopi) / dt, fracday)
+        return np.maximum(0.0, cosz), fracday, rrsun
+
+
+class RrtmRadiation:
+    """run_rrtmg (rrtm_radiation.F90:547-1056) as idealized_moist_phys calls it every step: radiation alarm (`dt_rad`,
+    `store_intermediate_rad`), zenith angle (`do_rad_time_avg`, `solday`, `equinox_day`, `frierson_solar_rad`), the column
+    computation on a radiation step.  Arrays [K, J, I]; o3 as read from the ozone file (mmr when input_o3_file_is_mmr)."""
+
+    def __init__(self, lat2d, lon2d, dt_atmos, dt_rad=0, dt_rad_avg=-1, do_rad_time_avg=True, store_intermediate_rad=True, solday=0,
+                 equinox_day=0.75, frierson_solar_rad=False, del_sol=0.95, del_sw=0.0, o3=None, input_o3_file_is_mmr=True,
+                 day_in_s=86400.0, year_in_s=360 * 86400, astronomy=None, **column_kw):
+        self.lat, self.lon = lat2d, lon2d
+        self.dt_rad = int(dt_rad) if dt_rad > 0 else int(dt_atmos)
+        self.dt_rad_avg = self.dt_rad if dt_rad_avg <= 0 else dt_rad_avg
+        self.do_rad_time_avg, self.store = do_rad_time_avg, store_intermediate_rad
+        self.solday, self.equinox_day = solday, equinox_day
+        self.frierson, self.del_sol, self.del_sw = frierson_solar_rad, del_sol, del_sw
+        self.day_in_s, self.year_in_s = day_in_s, year_in_s
+        self.astro = astronomy or Astronomy()
+        self.o3, self.o3_mmr = o3, input_o3_file_is_mmr
+        self.kw = column_kw
+        self.dt_last = -float(self.dt_rad)
+        self.tdt_rad = self.sw_flux = self.lw_flux = None
+        self.coszen = None
+        self.n_rad_calls = 0
+
+    def zenith(self, total_seconds):
+        if self.frierson:
+            p2 = (1.0 - 3.0 * np.sin(self.lat) ** 2) / 4.0
+            return 0.25 * (1.0 + self.del_sol * p2 + self.del_sw * np.sin(self.lat))
+        if self.solday > 0:                           # Time_loc = set_time(seconds, solday)
+            total_seconds = (total_seconds % 86400.0) + self.solday * 86400.0
+        frac_of_day = total_seconds / self.day_in_s
+        frac_of_year = (self.solday * self.day_in_s) / self.year_in_s if self.solday > 0 else total_seconds / self.year_in_s
+        gmt = abs(np.fmod(frac_of_day, 1.0)) * 2.0 * np.pi
+        time_since_ae = ((frac_of_year - self.equinox_day) % 1.0) * 2.0 * np.pi
+        dt = (self.dt_rad_avg / self.day_in_s) * 2.0 * np.pi if self.do_rad_time_avg else None
+        return self.astro.diurnal_solar(self.lat, self.lon, gmt, time_since_ae, dt)[0]
+
+    def __call__(self, total_seconds, p_full, p_half, z_full, z_half, t, q, t_surf, albedo, tdt):
+        """-> tdt + radiative heating, flux_sw, flux_lw"""
+        if total_seconds - self.dt_last >= self.dt_rad:
+            self.dt_last = total_seconds
+        else:
+            if self.store:
+                return tdt + self.tdt_rad, self.sw_flux, self.lw_flux
+            z2 = np.zeros_like(t_surf)
+            return tdt, z2, z2
+        K, J, I = t.shape
+        self.coszen = self.zenith(total_seconds)
+        col = lambda a: a.reshape(a.shape[0], -1).T
+        th = interp_temp(col(z_full), col(z_half), col(t))
+        o3v = 0.0
+        if self.o3 is not None:
+            o3v = col(self.o3) * ((1000.0 * GAS_CONSTANT / RDGAS) / WTMOZONE if self.o3_mmr else 1.0)
+        o = run_rrtmg_columns(col(p_full), col(p_half), col(t), th, col(q), t_surf.ravel(), albedo.ravel(), self.coszen.ravel(),
+                              o3vmr=o3v, **self.kw)
+        self.n_rad_calls += 1
+        self.tdt_rad = o["tdt_rad"].T.reshape(K, J, I)
+        self.sw_flux = o["flux_sw"].reshape(J, I)
+        self.lw_flux = o["flux_lw"].reshape(J, I)
+        self.olr, self.toa_sw = o["olr"].reshape(J, I), o["toa_sw"].reshape(J, I)
+        return tdt + self.tdt_rad, self.sw_flux, self.lw_flux

@@ -164,6 +164,20 @@ def test_rrtm_header_symbols_exported_and_struct_layout(lib_built, tmp_path):
     assert int(out[0]) == C.sizeof(rrtm.IscaRrtmConfigStruct)
     for f, off in zip(fields, out[1:]):
         assert getattr(rrtm.IscaRrtmConfigStruct, f).offset == int(off), f
+    fields = [f[0] for f in rrtm.IscaRrtmDriverConfigStruct._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(IscaRrtmDriverConfig, {f}));' for f in fields)
+    src = tmp_path / "dsz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "isca_b200_rrtm.h"\nint main(){printf("%zu\\n", sizeof(IscaRrtmDriverConfig));' + body + "return 0;}")
+    exe = tmp_path / "dsz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == C.sizeof(rrtm.IscaRrtmDriverConfigStruct)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(rrtm.IscaRrtmDriverConfigStruct, f).offset == int(off), f
+    d = rrtm.driver_config()
+    # rrtm_radiation.F90:163-189 and astronomy.f90:141-164 defaults
+    assert (d.dt_rad, d.dt_rad_avg, d.do_rad_time_avg, d.store_intermediate_rad, d.solday, d.equinox_day) == (0, -1, 1, 1, 0, 0.75)
+    assert (d.ecc, d.obliq, d.per, d.num_angles) == (0.0, 23.439, 102.932, 3600)
     # rrtm_radiation_nml defaults (rrtm_radiation.F90:117-226)
     c = rrtm.default_config()
     assert (c.co2ppmv, c.h2o_lower_limit, c.temp_lower_limit, c.temp_upper_limit, c.solrad, c.solr_cnst) == (300.0, 2.0e-7, 100.0, 370.0, 1.0, 1368.22)

@@ -109,3 +109,17 @@ def test_full_size_properties(lib_built):
     ms_lw, ms_sw = r.time_kernel(0, 3), r.time_kernel(1, 3)
     assert ms_lw > 0 and ms_sw > 0
     r.close()
+
+
+@pytest.mark.parametrize("dt", [None, 7200.0 / 86400.0 * 2 * np.pi, 2 * np.pi])
+def test_diurnal_solar_parity(rr, dt):
+    """astronomy_mod diurnal_solar (instantaneous and time-averaged zenith angle) at several times of day / year"""
+    from oracle import rrtmg as R
+    lat = np.repeat(np.linspace(-np.pi / 2, np.pi / 2, 33)[:, None], 64, 1)
+    lon = np.repeat(np.linspace(0, 2 * np.pi, 64, endpoint=False)[None, :], 33, 0)
+    for ecc in (0.0, 0.0167):
+        a = R.Astronomy(ecc=ecc)
+        for gmt, tsae in ((0.0, 0.0), (1.0, 0.3), (4.5, 2.0), (6.2, 5.5)):
+            c, f, r = rr.diurnal_solar(lat, lon, gmt, tsae, dt, ecc=ecc)
+            oc, of, orr = a.diurnal_solar(lat, lon, gmt, tsae, dt)
+            assert np.abs(c - oc).max() < 1e-13 and np.abs(f - of).max() < 1e-12 and abs(r - orr) < 1e-14

@@ -165,3 +165,56 @@ def test_random_columns_are_finite_and_consistent():
                               z(g["n2o"]), z(g["o2"]), z(g["cfc11"]), z(g["cfc12"]), z(g["cfc22"]), z(g["ccl4"]))
         assert np.isfinite(u).all() and np.isfinite(d).all() and np.isfinite(hr).all()
         assert (u > 0).all() and (d >= 0).all() and (d[:, -1] == 0).all()
+
+
+def test_astronomy_time_average_is_the_mean_of_instantaneous_values():
+    a = R.Astronomy()
+    lat = np.repeat(np.linspace(-np.pi / 2, np.pi / 2, 17)[:, None], 16, 1)
+    lon = np.repeat(np.linspace(0, 2 * np.pi, 16, endpoint=False)[None, :], 17, 0)
+    dt = 7200.0 / 86400.0 * 2 * np.pi
+    avg = a.diurnal_solar(lat, lon, 2.0, 0.3, dt=dt)[0]
+    fine = np.mean([a.diurnal_solar(lat, lon, 2.0 + s, 0.3)[0] for s in np.linspace(0, dt, 801)], axis=0)
+    assert np.abs(avg - fine).max() < 1e-3
+    # equinox, daily mean: cos(lat)/pi
+    daily = a.diurnal_solar(lat, lon, 0.0, 0.0, dt=2 * np.pi)[0]
+    assert np.allclose(daily, np.cos(lat) / np.pi, atol=1e-9)
+    # perpetual-equinox insolation integrates to S0/4 over the sphere
+    w = np.cos(lat[:, 0]); w /= w.sum()
+    assert abs((daily[:, 0] * w).sum() - 0.25) < 2e-3
+    assert a.angle(0.0) == 0.0 and abs(a.orb_angle[-1] - 2 * np.pi) < 1e-9     # circular orbit: the table closes after one year
+
+
+def test_radiation_alarm_and_storage():
+    """run_rrtmg's alarm: radiation at the first call and then every dt_rad; stored heating / fluxes are returned in between"""
+    rng = np.random.default_rng(0)
+    from rrtm_cases import model_columns
+    I, J, K = 4, 2, 20
+    m = model_columns(I, J, K, 4)
+    lat = np.repeat(np.linspace(-1.0, 1.0, J)[:, None], I, 1)
+    lon = np.repeat(np.linspace(0, 2 * np.pi, I, endpoint=False)[None, :], J, 0)
+    r = R.RrtmRadiation(lat, lon, 600.0, dt_rad=1800, o3=m["o3"])
+    calls = []
+    for step in range(7):
+        tdt, fsw, flw = r(step * 600.0, m["p_full"], m["p_half"], m["z_full"], m["z_half"], m["t"], m["q"], m["t_surf"], m["albedo"],
+                          np.zeros((K, J, I)))
+        calls.append(r.n_rad_calls)
+        assert np.array_equal(tdt, r.tdt_rad) and np.array_equal(fsw, r.sw_flux)
+    assert calls == [1, 1, 1, 2, 2, 2, 3]
+
+
+def test_moist_oracle_with_rrtm_radiation_runs():
+    """the oracle's idealized_moist_phys dispatcher with do_rrtm_radiation (what tests/test_gpu_moist.py compares the GPU
+    model with): two steps at T21 L25 stay finite, radiation cools the troposphere, the slab receives the RRTMG surface fluxes"""
+    from test_gpu_moist import build, _rrtm_setup
+    cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=5)
+    _, _, pf, _ = core.pg.compute_pressures_and_heights(core.tg[1], core.psg[1], core.surf_geopotential, None)
+    o3 = np.where(pf < 1.0e4, 1.2e-5 * np.exp(-((np.log(pf) - np.log(1.0e3)) ** 2) / 2), 6e-8)
+    _rrtm_setup(core, mp, cfg, 1800, o3)
+    mp.time_s = 3 * 86400.0 + 43200.0
+    for _ in range(2):
+        core.step(physics=True)
+    assert mp.rrtm.n_rad_calls == 1
+    assert np.isfinite(core.tg[core.current]).all() and np.isfinite(mp.t_surf).all()
+    assert (mp.rrtm.coszen >= 0).all() and (mp.rrtm.coszen > 0).any() and (mp.rrtm.coszen == 0).any()
+    assert mp.rrtm.tdt_rad[12:].mean() < 0 and 150.0 < mp.rrtm.olr.mean() < 330.0
+    assert np.array_equal(mp.diag["surf_lw_down"], mp.rrtm.lw_flux)
