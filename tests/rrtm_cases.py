@@ -78,3 +78,12 @@ def model_columns(I, J, K, seed):
     coszen = np.clip(rng.uniform(-0.3, 1.0, (J, I)), 0.0, 1.0)
     return dict(p_full=p_full, p_half=p_half, z_full=z_full, z_half=z_half, t=t, q=q, o3=o3, t_surf=ts + rng.normal(0, 1, (J, I)),
                 albedo=albedo, coszen=coszen)
+
+
+def rrtm_setup(core, mp, cfg, dt_rad, o3, **kw):
+    """attach an oracle RrtmRadiation (do_rrtm_radiation) to the oracle moist physics of tests/test_gpu_moist.build"""
+    from oracle import rrtmg as R
+    Kk, J, I = core.tg[0].shape
+    lat = np.repeat(core.tb.rad_lat[:, None], I, 1)
+    lon = np.repeat((np.arange(I) * 360.0 / I * np.pi / 180.0)[None, :], J, 0)
+    mp.rrtm = R.RrtmRadiation(lat, lon, cfg.dt_atmos, dt_rad=dt_rad, o3=o3, co2ppmv=360.0, solr_cnst=1360.0, **kw)

@@ -148,70 +148,3 @@ def test_moist_model_loud_failures(lib_built):
         m.atmosphere(1)
     m.atmosphere_end()
 
-
-def _rrtm_setup(core, mp, cfg, dt_rad, o3, **kw):
-    from oracle import rrtmg as R
-    Kk, J, I = core.tg[0].shape
-    lat = np.repeat(core.tb.rad_lat[:, None], I, 1)
-    lon = np.repeat((np.arange(I) * 360.0 / I * np.pi / 180.0)[None, :], J, 0)
-    mp.rrtm = R.RrtmRadiation(lat, lon, cfg.dt_atmos, dt_rad=dt_rad, o3=o3, co2ppmv=360.0, solr_cnst=1360.0, **kw)
-
-
-@pytest.mark.parametrize("dt_rad_steps,kw", [(2, {}), (1, dict(frierson_solar_rad=True)), (2, dict(solday=90, do_rad_time_avg=False))])
-def test_moist_model_with_rrtm_radiation(lib_built, dt_rad_steps, kw):
-    """do_rrtm_radiation = .true. (the MiMA configuration, idealized_moist_phys.F90:1167-1177): RRTMG on a radiation step, the
-    stored heating rates / surface fluxes in between (dt_rad = 2 dt_atmos), diurnal-mean zenith angle from astronomy_mod; four
-    steps of the whole model against the oracle."""
-    cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=5)
-    Kk, J, I = core.tg[0].shape
-    _, _, pf, _ = core.pg.compute_pressures_and_heights(core.tg[1], core.psg[1], core.surf_geopotential, None)
-    o3 = np.where(pf < 1.0e4, 1.2e-5 * np.exp(-((np.log(pf) - np.log(1.0e3)) ** 2) / 2), 6e-8)      # mass mixing ratio
-    dt_rad = int(dt_rad_steps * cfg.dt_atmos)
-    _rrtm_setup(core, mp, cfg, dt_rad, o3, **kw)
-    from isca_b200 import api, moist
-    phys = dict(FRIERSON_PHYS)
-    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER",
-                              mixed_layer_depth=2.5, albedo_value=0.31)
-    m.use_rrtm(dict(co2ppmv=360.0, solr_cnst=1360.0), dt_rad=dt_rad, **{k: int(v) if isinstance(v, bool) else v for k, v in kw.items()})
-    m.set_ozone(o3)
-    atm = m.core
-    for slot in (0, 1):
-        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
-        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
-    atm.set_vor_div_grid(core.vorg, core.divg)
-    atm.set_time_pointers(core.previous, core.current)
-    m.idealized_moist_phys_init()
-    # start in the afternoon of day 3 so that the zenith angle has day and night columns
-    m.set_time(3, 43200)
-    mp.time_s = 3 * 86400.0 + 43200.0
-    for step in range(4):
-        core.step(physics=True)
-        m.atmosphere(1)
-        if step == 0:
-            assert rel(m.get("coszen"), mp.rrtm.coszen) < 1e-12
-            assert rel(m.get("tdt_rad"), mp.rrtm.tdt_rad) < 1e-9
-            assert rel(m.get("net_surf_sw_down"), mp.rrtm.sw_flux) < 1e-11 and rel(m.get("surf_lw_down"), mp.rrtm.lw_flux) < 1e-11
-            assert rel(m.get("olr"), mp.rrtm.olr) < 1e-11
-        s = atm.get_time_pointers()[1]
-        assert rel(atm.get_field("t", s), core.tg[core.current]) < TOL, step
-        assert rel(atm.get_field("ps", s), core.psg[core.current]) < TOL, step
-        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
-    assert mp.rrtm.n_rad_calls == (4 if dt_rad_steps == 1 else 2)
-    m.atmosphere_end()
-
-
-def test_rrtm_driver_loud_failures(lib_built):
-    from isca_b200 import api, moist
-    cfg, core, mp = build("T21", 25, 900.0, "NONE", seed=1)
-    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS), convection_scheme="NONE")
-    with pytest.raises(api.IscaError) as e:
-        m.use_rrtm(dt_rad=1000)                        # rrtm_gases_init: dt_rad must be an integer multiple of dt_atmos
-    assert "integer multiple" in str(e.value)
-    with pytest.raises(api.IscaError):
-        m.set_ozone(np.zeros(m.s3))                    # before use_rrtm
-    with pytest.raises(api.IscaError):
-        m.use_rrtm(dict(lonstep=4))
-    m.use_rrtm()
-    with pytest.raises(api.IscaError):
-        m.use_rrtm()                                   # twice
-    m.atmosphere_end()

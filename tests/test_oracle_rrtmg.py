@@ -205,11 +205,12 @@ def test_radiation_alarm_and_storage():
 def test_moist_oracle_with_rrtm_radiation_runs():
     """the oracle's idealized_moist_phys dispatcher with do_rrtm_radiation (what tests/test_gpu_moist.py compares the GPU
     model with): two steps at T21 L25 stay finite, radiation cools the troposphere, the slab receives the RRTMG surface fluxes"""
-    from test_gpu_moist import build, _rrtm_setup
+    from test_gpu_moist import build
+    from rrtm_cases import rrtm_setup
     cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=5)
     _, _, pf, _ = core.pg.compute_pressures_and_heights(core.tg[1], core.psg[1], core.surf_geopotential, None)
     o3 = np.where(pf < 1.0e4, 1.2e-5 * np.exp(-((np.log(pf) - np.log(1.0e3)) ** 2) / 2), 6e-8)
-    _rrtm_setup(core, mp, cfg, 1800, o3)
+    rrtm_setup(core, mp, cfg, 1800, o3)
     mp.time_s = 3 * 86400.0 + 43200.0
     for _ in range(2):
         core.step(physics=True)
