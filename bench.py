@@ -401,6 +401,19 @@ def main():
         return 0
     J = J_glob
 
+    # informational: the RRTMG radiation kernels on a T170-sized batch of columns, in a subprocess with a timeout
+    # (their first GPU run happens here: a fault or hang there must not cost the headline line)
+    rrtm_radiation = None
+    if not args.no_moist and world == 1:
+        try:
+            import subprocess
+            pr = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "rrtm_bench.py")],
+                                capture_output=True, text=True, timeout=300)
+            last = [l for l in pr.stdout.strip().splitlines() if l.startswith("{")]
+            rrtm_radiation = json.loads(last[-1]) if pr.returncode == 0 and last else {"error": (pr.stderr or pr.stdout)[-300:]}
+        except Exception as e:
+            rrtm_radiation = {"error": str(e)[:200]}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         r = run_cpu(res, K, args.cpu_steps, 1, tracer=tracer)
@@ -424,6 +437,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "no_tracer_core": no_tracer_core,
         "moist_model": moist_model,
+        "rrtm_radiation": rrtm_radiation,
     }
     print(json.dumps(line), file=json_out, flush=True)
     return 0
