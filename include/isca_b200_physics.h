@@ -173,12 +173,14 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
 #include "isca_b200.h"
 typedef struct IscaMoist_t* IscaMoist;
 typedef struct IscaMoistConfig {
-  int abi_version;                 /* 1 */
+  int abi_version;                 /* 2 */
   int convection_scheme;           /* 0 'NONE', 1 'SIMPLE_BETTS_MILLER' (idealized_moist_phys.F90:391-426) */
   int do_damping;                  /* damping_driver rayleigh sponge */
   double roughness_mom, roughness_heat, roughness_moist;      /* idealized_moist_phys_nml :136-138 */
   double mixed_layer_depth, albedo_value, rho_cp;             /* mixed_layer_nml depth, albedo_value; constants RHO_CP */
   double constant_gust;            /* vert_turb_driver_nml, gust_scheme = 'constant' */
+  int use_tau;                     /* vert_turb_driver_nml (vert_turb_driver.F90:109, 202-214): 1 (default) = diffusivity from the
+                                    * `current` fields; 0 = from previous + delta_t * tendencies, as every shipped test case sets */
 } IscaMoistConfig;
 
 int isca_b200_moist_default_config(IscaMoistConfig* cfg);
@@ -203,6 +205,9 @@ int isca_b200_moist_step(IscaMoist m, int n_steps);
  * 3-D [K][J][I]: 32 dt_ug, 33 dt_vg, 34 dt_tg, 35 dt_tracers(sphum) (physics tendencies), 36 diff_m, 37 diff_t */
 int isca_b200_moist_get(IscaMoist m, int id, double* host);
 int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
+/* mixed_layer_init: ocean_qflux [J][I] (W/m2; `do_qflux` / `do_warmpool` of mixed_layer_nml, atmos_param/qflux/qflux.f90, or a
+ * q-flux file), added to the slab's heat budget every step.  Call after isca_b200_moist_init (which zeroes it). */
+int isca_b200_moist_set_ocean_qflux(IscaMoist m, const double* host);
 /* average ms per step of the last isca_b200_moist_step call (CUDA events), and of its physics part */
 int isca_b200_moist_timing(IscaMoist m, double* ms_step, double* ms_physics);
 

@@ -74,6 +74,15 @@ __global__ void add3_kernel(size_t n, double* a, const double* da, double* b, co
     a[i] = a[i] + da[i]; b[i] = b[i] + db[i]; c[i] = c[i] + dc[i];
   }
 }
+// vert_turb_driver.F90:209-213 (use_tau = .false.): variables at time tau+1
+__global__ void tau_plus1_kernel(size_t n, double dt, const double* __restrict__ um, const double* __restrict__ vm, const double* __restrict__ tm,
+                                 const double* __restrict__ qm, const double* __restrict__ udt, const double* __restrict__ vdt,
+                                 const double* __restrict__ tdt, const double* __restrict__ qdt, double* __restrict__ uu, double* __restrict__ vv,
+                                 double* __restrict__ tt, double* __restrict__ qq) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uu[i] = um[i] + dt * udt[i]; vv[i] = vm[i] + dt * vdt[i]; tt[i] = tm[i] + dt * tdt[i]; qq[i] = qm[i] + dt * qdt[i];
+  }
+}
 __global__ void add1_kernel(size_t n, double* a, const double* da) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = a[i] + da[i];
 }
@@ -172,7 +181,13 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   // vert_turb_driver, do_diffusivity branch on the `current` fields (vert_turb_driver.F90:277-292; use_tau = .true.)
   MCK(cudaMemsetAsync(m->diff_m.p, 0, n3 * sizeof(double), st));
   MCK(cudaMemsetAsync(m->diff_t.p, 0, n3 * sizeof(double), st));
-  launch_diffusivity(p, v.T[cur], v.q[cur], v.u[cur], v.v[cur], zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p);
+  if (m->mc.use_tau) {
+    launch_diffusivity(p, v.T[cur], v.q[cur], v.u[cur], v.v[cur], zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p);
+  } else {                                                       // w1..w3, c_dT are free here (rayleigh / condensation work arrays)
+    tau_plus1_kernel<<<nblk(n3), 256, 0, st>>>(n3, delta_t, ug_p, vg_p, tg_p, q_p, m->dt_u.p, m->dt_v.p, m->dt_t.p, m->dt_q.p, m->w1.p, m->w2.p,
+                                               m->w3.p, m->c_dT.p);
+    launch_diffusivity(p, m->w3.p, m->c_dT.p, m->w1.p, m->w2.p, zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p);
+  }
   fill_kernel<<<nblk(nc), 256, 0, st>>>(m->gust.p, nc, m->mc.constant_gust);
   launch_vert_diff_down(p, delta_t, ug_p, vg_p, tg_p, q_p, m->diff_m.p, m->diff_t.p, ph_c, zf_c, a.flux_u, a.flux_v, a.dtaudu_atm, a.dtaudv_atm,
                         m->dt_u.p, m->dt_v.p, m->dt_t.p, m->dt_q.p, m->diss.p);
@@ -192,7 +207,7 @@ extern "C" {
 int isca_b200_moist_default_config(IscaMoistConfig* c) {
   if (!c) return 1;
   std::memset(c, 0, sizeof(*c));
-  c->abi_version = 1; c->convection_scheme = 1; c->do_damping = 0;
+  c->abi_version = 2; c->convection_scheme = 1; c->do_damping = 0; c->use_tau = 1;
   c->roughness_mom = 0.05; c->roughness_heat = 0.05; c->roughness_moist = 0.05;
   c->mixed_layer_depth = 40.0; c->albedo_value = 0.06; c->rho_cp = 1.035e3 * 3989.24495292815;
   c->constant_gust = 1.0;
@@ -219,7 +234,7 @@ int isca_b200_moist_create_ranked(const IscaConfig* dyn, const IscaPhysicsConfig
                                   const void* nccl_unique_id, IscaMoist* out) {
   IscaMoist m = nullptr;
   if (!dyn || !phys || !mc || !out) return mfail(nullptr, "null argument");
-  if (mc->abi_version != 1) return mfail(nullptr, "IscaMoistConfig abi_version mismatch");
+  if (mc->abi_version != 2) return mfail(nullptr, "IscaMoistConfig abi_version mismatch");
   if (mc->convection_scheme != 0 && mc->convection_scheme != 1)
     return mfail(nullptr, "idealized_moist_phys: Invalid convection scheme (only NONE and SIMPLE_BETTS_MILLER are built)");
   if (dyn->num_tracers != 1) return mfail(nullptr, "idealized_moist_model needs the sphum grid tracer (num_tracers = 1)");
@@ -403,6 +418,17 @@ int isca_b200_moist_set_t_surf(IscaMoist m, const double* host) {
   IscaCoreView v;
   if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
   MCK(cudaMemcpyAsync(m->t_surf.p, host, m->nc * sizeof(double), cudaMemcpyHostToDevice, v.st));
+  MCK(cudaStreamSynchronize(v.st));
+  return 0;
+}
+
+int isca_b200_moist_set_ocean_qflux(IscaMoist m, const double* host) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!host) return mfail(m, "null input array");
+  if (!m->initialized) return mfail(m, "moist_set_ocean_qflux: call isca_b200_moist_init first");
+  IscaCoreView v;
+  if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
+  MCK(cudaMemcpyAsync(m->phy->state[ST_ML_QFLUX].p, host, m->nc * sizeof(double), cudaMemcpyHostToDevice, v.st));
   MCK(cudaStreamSynchronize(v.st));
   return 0;
 }

@@ -9,7 +9,7 @@ from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 
 MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
-                 "isca_b200_moist_set_t_surf", "isca_b200_moist_timing"]
+                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
                  q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
@@ -22,7 +22,7 @@ CONVECTION = {"NONE": 0, "SIMPLE_BETTS_MILLER": 1}
 class IscaMoistConfigStruct(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("abi_version", "convection_scheme", "do_damping")] + \
                [(n, C.c_double) for n in ("roughness_mom", "roughness_heat", "roughness_moist", "mixed_layer_depth", "albedo_value", "rho_cp",
-                                          "constant_gust")]
+                                          "constant_gust")] + [("use_tau", C.c_int)]
 
 
 _bound = False
@@ -47,6 +47,7 @@ def _lib():
         lib.isca_b200_moist_step.argtypes = [vp, C.c_int]
         lib.isca_b200_moist_get.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_moist_set_t_surf.argtypes = [vp, dp]
+        lib.isca_b200_moist_set_ocean_qflux.argtypes = [vp, dp]
         lib.isca_b200_moist_timing.argtypes = [vp, dp, dp]
         _bound = True
     return lib
@@ -152,6 +153,13 @@ class MoistAtmosphere:
             raise IscaError("t_surf has the wrong shape")
         self._ck(self._lib.isca_b200_moist_set_t_surf(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_t_surf")
 
+    def set_ocean_qflux(self, qflux):
+        """mixed_layer_init: the ocean q-flux [lat, lon] in W/m2 (see `qflux`); after idealized_moist_phys_init"""
+        a = np.ascontiguousarray(qflux, dtype=np.float64)
+        if a.shape != self.s2:
+            raise IscaError("ocean_qflux has the wrong shape")
+        self._ck(self._lib.isca_b200_moist_set_ocean_qflux(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_ocean_qflux")
+
     def timing(self):
         a, b = C.c_double(), C.c_double()
         self._ck(self._lib.isca_b200_moist_timing(self._h, C.byref(a), C.byref(b)), "timing")
@@ -191,3 +199,69 @@ def frierson_test_case(res: str, num_levels: int, dt_atmos: float, **ranks) -> M
                       initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.5,
                       robert_coeff=0.03, num_tracers=1)
     return MoistAtmosphere(cfg, physics_nml=FRIERSON_PHYSICS_NML, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **FRIERSON_MOIST_NML)
+
+
+def lat_boundaries(lat_max: int) -> np.ndarray:
+    """transforms_mod lat_boundaries_global (transforms.F90:314-323): latb(j+1) = asin(sum of the Gaussian weights up to j - 1),
+    south to north, radians"""
+    _, w = np.polynomial.legendre.leggauss(lat_max)
+    latb = np.empty(lat_max + 1)
+    latb[0], latb[-1] = -0.5 * np.pi, 0.5 * np.pi
+    latb[1:-1] = np.arcsin(np.clip(np.cumsum(w)[:-1] - 1.0, -1.0, 1.0))
+    return latb
+
+
+def qflux(latb: np.ndarray, num_lon: int, qflux_amp=30.0, qflux_width=16.0) -> np.ndarray:
+    """qflux_mod qflux (atmos_param/qflux/qflux.f90:64-83) on an initially zero flux: the Merlis & Schneider tropical ocean heat
+    transport, [lat, lon] in W/m2"""
+    lat = 0.5 * (latb[1:] + latb[:-1])
+    coslat = np.cos(lat)
+    lat = lat * 180.0 / np.pi
+    f = -qflux_amp * (1 - 2. * lat ** 2 / qflux_width ** 2) * np.exp(-((lat) ** 2 / (qflux_width) ** 2)) / coslat
+    return np.repeat(f[:, None], num_lon, 1)
+
+
+# exp/test_cases/MiMA/MiMA_test_case.py: scheme namelists of the RRTMG aquaplanet (Jucker & Gerber 2017)
+MIMA_PHYSICS_NML = dict(use_virtual_temp=0, surface_flux_do_simple=1, old_dtaudv=1,      # surface_flux_nml
+                        diffusivity_do_entrain=0, diffusivity_do_simple=1,               # diffusivity_nml
+                        rhbm=0.7, Tmin=160.0, Tmax=350.0,                                # qe_moist_convection_nml
+                        do_evap=1,                                                       # lscale_cond_nml
+                        trayfric=-0.5, sponge_pbottom=50.0, do_conserve_energy=1)        # damping_driver_nml
+MIMA_MOIST_NML = dict(mixed_layer_depth=100.0, albedo_value=0.205, roughness_mom=3.21e-05, roughness_heat=3.21e-05,
+                      roughness_moist=3.21e-05, constant_gust=0.0, use_tau=0, do_damping=1)
+MIMA_RRTM_NML = dict(solr_cnst=1360.0)
+MIMA_RRTM_DRIVER_NML = dict(dt_rad=7200)
+
+
+def mima_test_case(res: str, num_levels: int, dt_atmos: float, ozone=None, **ranks) -> MoistAtmosphere:
+    """The MiMA test case (MiMA_test_case.py:50-175): as the Frierson case but RRTMG radiation every 7200 s, Rayleigh sponge,
+    use_tau = .false., a 100 m slab with the prescribed initial SST distribution (mixed_layer.F90:347: tconst = 285, delta_T = 40) and
+    the tropical q-flux (qflux_amp = 30).  `ozone`: the field of ozone_1990.nc on the model levels ([lev, lat, lon], mass mixing
+    ratio) or None.  Returns the model after cold start and idealized_moist_phys_init."""
+    from .api import make_config
+    I, J, M = RESOLUTIONS[res]
+    nranks, rank = ranks.get("nranks", 1), ranks.get("rank", 0)
+    cfg = make_config(lon_max=I, lat_max=J, num_fourier=M, num_spherical=M + 1, num_levels=num_levels, dt_atmos=dt_atmos,
+                      damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
+                      initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.5,
+                      robert_coeff=0.03, num_tracers=1)
+    m = MoistAtmosphere(cfg, physics_nml=MIMA_PHYSICS_NML, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **MIMA_MOIST_NML)
+    dt_rad = MIMA_RRTM_DRIVER_NML["dt_rad"]
+    if dt_rad % int(dt_atmos) != 0:
+        dt_rad = int(dt_atmos) * max(1, round(dt_rad / dt_atmos))
+    m.use_rrtm(MIMA_RRTM_NML, dt_rad=dt_rad)
+    if ozone is not None:
+        m.set_ozone(ozone)
+    m.core.cold_start()
+    m.idealized_moist_phys_init()
+    from .api import TB_SIN_LAT, TB_WTS_LAT
+    Jloc = J // nranks
+    sin_lat = m.core.get_table(TB_SIN_LAT)                      # global tables of the core (Gaussian latitudes, south to north)
+    wts = m.core.get_table(TB_WTS_LAT)
+    latb = np.empty(J + 1)
+    latb[0], latb[-1] = -0.5 * np.pi, 0.5 * np.pi
+    latb[1:-1] = np.arcsin(np.clip(np.cumsum(wts)[:-1] * (2.0 / wts.sum()) - 1.0, -1.0, 1.0))
+    sl = slice(rank * Jloc, (rank + 1) * Jloc)
+    m.set_t_surf(np.repeat((285.0 - 40.0 * ((3. * sin_lat[sl] ** 2.) - 1.) / 3.)[:, None], I, 1))
+    m.set_ocean_qflux(qflux(latb, I)[sl])
+    return m

@@ -1091,6 +1091,7 @@ class MoistPhysConfig:
     do_evap: bool = False
     # vert_turb_driver_nml
     constant_gust: float = 1.0
+    use_tau: bool = True
     # damping_driver_nml
     trayfric: float = 0.0
     sponge_pbottom: float = 50.0
@@ -1167,7 +1168,11 @@ class IdealizedMoistPhys:
             udt, vdt, tdt, _ = rayleigh_sponge(delta_t, core.p_full[cur], ug_p, vg_p, self.pref, c.sponge_pbottom, c.trayfric, True)
             dt_ug, dt_vg, dt_tg = dt_ug + udt, dt_vg + vdt, dt_tg + tdt
         # vert_turb_driver (do_diffusivity) on the `current` fields (use_tau = .true.)
-        z_pbl, diff_m, diff_t = diffusivity(self.diffc, self.mo, core.tg[cur], core.grid_tracers[cur, 0], core.ug[cur], core.vg[cur],
+        if c.use_tau:
+            tt, qq, uu, vv = core.tg[cur], core.grid_tracers[cur, 0], core.ug[cur], core.vg[cur]
+        else:                                   # vert_turb_driver.F90:209-213: variables at time tau+1
+            uu, vv, tt, qq = ug_p + delta_t * dt_ug, vg_p + delta_t * dt_vg, tg_p + delta_t * dt_tg, q_p + delta_t * dt_q
+        z_pbl, diff_m, diff_t = diffusivity(self.diffc, self.mo, tt, qq, uu, vv,
                                             core.p_full[cur], core.p_half[cur], core.z_full[cur], core.z_half[cur], sf["u_star"], sf["b_star"],
                                             np.zeros_like(tg_p), np.zeros_like(tg_p))
         self.gust = np.full_like(zero2, c.constant_gust)

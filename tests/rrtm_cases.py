@@ -87,3 +87,20 @@ def rrtm_setup(core, mp, cfg, dt_rad, o3, **kw):
     lat = np.repeat(core.tb.rad_lat[:, None], I, 1)
     lon = np.repeat((np.arange(I) * 360.0 / I * np.pi / 180.0)[None, :], J, 0)
     mp.rrtm = R.RrtmRadiation(lat, lon, cfg.dt_atmos, dt_rad=dt_rad, o3=o3, co2ppmv=360.0, solr_cnst=1360.0, **kw)
+
+
+def unstable_boundary_layer(core, mp, amp=8.0):
+    """warm the lowest 30 % of the oracle model state of tests/test_gpu_moist.build so that the boundary layer is convectively
+    unstable: the K-profile diffusivity is then non-zero above the lowest level (the unmodified state is stably stratified and has
+    diff_m = diff_t = 0 everywhere)"""
+    tr = core.tr
+    for lev in (0, 1):
+        ps = core.psg[lev]
+        zf, zh, pf, ph = core.pg.compute_pressures_and_heights(core.tg[lev], ps, core.surf_geopotential, None)
+        sig = pf / ps[None]
+        tg = core.tg[lev] + amp * np.maximum(sig - 0.7, 0.0) / 0.3
+        ts = tr.grid_to_spherical(tg)
+        core.ts[lev] = ts
+        core.tg[lev] = tr.spherical_to_grid(ts)
+    core.finish_init()
+    mp.t_surf = core.tg[core.current][-1] + 3.0

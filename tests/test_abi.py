@@ -141,6 +141,7 @@ def test_moist_config_struct_layout(lib_built, tmp_path):
     moist._lib().isca_b200_moist_default_config(C.byref(c))
     # idealized_moist_phys.F90:136-138, mixed_layer.F90:92-95
     assert (c.roughness_mom, c.roughness_heat, c.roughness_moist, c.mixed_layer_depth, c.albedo_value) == (0.05, 0.05, 0.05, 40.0, 0.06)
+    assert (c.abi_version, c.use_tau, c.constant_gust) == (2, 1, 1.0)            # vert_turb_driver.F90:109,116
 
 
 RRTM_HEADER = os.path.join(ROOT, "include", "isca_b200_rrtm.h")

@@ -6,7 +6,7 @@ sizes here and the dedicated statistics in the full-size test)."""
 import numpy as np
 import pytest
 
-from rrtm_cases import columns, mls_column, model_columns, rrtm_setup, zero_if_none as z
+from rrtm_cases import columns, mls_column, model_columns, rrtm_setup, unstable_boundary_layer, zero_if_none as z
 
 pytestmark = pytest.mark.gpu
 
@@ -184,4 +184,62 @@ def test_rrtm_driver_loud_failures(lib_built):
     m.use_rrtm()
     with pytest.raises(api.IscaError):
         m.use_rrtm()                                   # twice
+    m.atmosphere_end()
+
+
+@pytest.mark.parametrize("radiation", ["grey", "rrtm"])
+def test_moist_model_test_case_options(lib_built, radiation):
+    """what every shipped moist test case sets and the default does not: vert_turb_driver_nml use_tau = .false. (diffusivity from
+    previous + delta_t * tendencies), constant_gust = 0, the MiMA roughness lengths, the Rayleigh sponge, a tropical ocean q-flux
+    (qflux_mod) under the slab -- with grey and with RRTMG radiation, three steps against the oracle"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=9, damping=True)
+    unstable_boundary_layer(core, mp)                       # non-zero diffusivities above the lowest level
+    Kk, J, I = core.tg[0].shape
+    mp.c.use_tau, mp.c.constant_gust = False, 0.0
+    mp.c.roughness_mom = mp.c.roughness_heat = mp.c.roughness_moist = 3.21e-05
+    qf = moist.qflux(moist.lat_boundaries(J), I)
+    mp.ocean_qflux = qf.copy()
+    phys = dict(FRIERSON_PHYS, trayfric=-0.5, sponge_pbottom=5000.0)
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER",
+                              mixed_layer_depth=2.5, albedo_value=0.31, do_damping=1, use_tau=0, constant_gust=0.0,
+                              roughness_mom=3.21e-05, roughness_heat=3.21e-05, roughness_moist=3.21e-05)
+    if radiation == "rrtm":
+        rrtm_setup(core, mp, cfg, 1800, None)
+        m.use_rrtm(dict(co2ppmv=360.0, solr_cnst=1360.0), dt_rad=1800)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    m.set_ocean_qflux(qf)
+    for step in range(3):
+        core.step(physics=True)
+        m.atmosphere(1)
+        s = atm.get_time_pointers()[1]
+        if step == 0:
+            assert mp.diag["diff_t"].max() > 0.0
+            assert rel(m.get("diff_t"), mp.diag["diff_t"]) < 1e-9 and rel(m.get("z_pbl"), mp.diag["z_pbl"]) < 1e-9
+        assert rel(atm.get_field("t", s), core.tg[core.current]) < TOL, step
+        assert rel(atm.get_field("u", s), core.ug[core.current]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+    m.atmosphere_end()
+
+
+def test_mima_test_case_runs(lib_built):
+    """MiMA_test_case.py at T21 L40: RRTMG every 7200 s, sponge, q-flux, prescribed initial SST; 30 steps stay physical"""
+    from isca_b200 import moist
+    m = moist.mima_test_case("T21", 40, 900.0)
+    ts0 = m.get("t_surf")
+    assert abs(ts0.max() - (285.0 + 40.0 / 3.0)) < 0.2 and ts0.min() > 285.0 - 2 * 40.0 / 3.0 - 1e-9
+    m.atmosphere(30)
+    olr, cz, tsw = m.get("olr"), m.get("coszen"), m.get("toa_sw")
+    assert np.isfinite(olr).all() and 120.0 < olr.mean() < 330.0
+    assert (cz >= 0).all() and cz.max() <= 1.0 and (tsw[cz == 0] == 0).all() and tsw.max() > 100.0
+    t = m.core.get_field("t", m.core.get_time_pointers()[1])
+    assert np.isfinite(t).all() and 150.0 < t.min() and t.max() < 330.0
     m.atmosphere_end()

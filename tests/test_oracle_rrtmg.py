@@ -219,3 +219,34 @@ def test_moist_oracle_with_rrtm_radiation_runs():
     assert (mp.rrtm.coszen >= 0).all() and (mp.rrtm.coszen > 0).any() and (mp.rrtm.coszen == 0).any()
     assert mp.rrtm.tdt_rad[12:].mean() < 0 and 150.0 < mp.rrtm.olr.mean() < 330.0
     assert np.array_equal(mp.diag["surf_lw_down"], mp.rrtm.lw_flux)
+
+
+def test_qflux_and_lat_boundaries():
+    """python helpers of the MiMA test case: lat_boundaries_global (transforms.F90:314-323) and qflux_mod"""
+    from isca_b200 import moist            # pure NumPy helpers; no library call
+    J = 64
+    latb = moist.lat_boundaries(J)
+    x, w = np.polynomial.legendre.leggauss(J)
+    assert latb[0] == -np.pi / 2 and latb[-1] == np.pi / 2 and (np.diff(latb) > 0).all()
+    assert ((np.arcsin(x) > latb[:-1]) & (np.arcsin(x) < latb[1:])).all()          # each Gaussian latitude inside its box
+    assert np.allclose(np.sin(latb[1:]) - np.sin(latb[:-1]), w, atol=1e-13)         # box area = Gaussian weight
+    q = moist.qflux(latb, 4)
+    assert q.shape == (J, 4) and np.allclose(q, q[::-1], atol=1e-12)               # symmetric about the equator
+    assert q[J // 2, 0] < -25.0 and q[J // 8, 0] >= 0.0                             # heat taken up at the equator, released poleward
+    assert abs((q[:, 0] * w).sum()) < 0.5                                           # a transport: no net heating (W/m2, area mean)
+
+
+def test_moist_oracle_use_tau_false():
+    """vert_turb_driver_nml use_tau = .false. in the oracle dispatcher, on a state with an unstable boundary layer"""
+    from test_gpu_moist import build
+    from rrtm_cases import unstable_boundary_layer
+    out = []
+    for use_tau in (True, False):
+        cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=9, damping=True)
+        unstable_boundary_layer(core, mp)
+        mp.c.use_tau = use_tau
+        core.step(physics=True)
+        assert np.isfinite(core.tg[core.current]).all() and mp.diag["diff_t"].max() > 0.0
+        out.append(mp.diag["diff_t"].copy())
+    d = np.abs(out[0] - out[1]).max()
+    assert 0.0 < d <= max(out[0].max(), out[1].max())               # a different, comparable diffusivity
