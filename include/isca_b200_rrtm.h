@@ -30,7 +30,7 @@ typedef struct IscaRrtmConfig {
   int include_secondary_gases;
   double ch4_val, n2o_val, o2_val, cfc11_val, cfc12_val, cfc22_val, ccl4_val;
   int convert_sphum_to_vmr, input_o3_file_is_mmr;
-  int lonstep;                      /* only 1 is built */
+  int lonstep;                      /* run_rrtmg: radiation on every lonstep-th longitude, linear interpolation in between */
 } IscaRrtmConfig;
 
 int isca_b200_rrtm_default_config(IscaRrtmConfig* cfg);

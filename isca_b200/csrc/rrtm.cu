@@ -172,43 +172,52 @@ __global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __re
 
 // ---- run_rrtmg glue: model layout [K][J][I] top-down (Pa) -> RRTMG layout (ncol, nlay) bottom-up (hPa) ----
 struct PrepArgs {
-  int ncol, K;
+  int ncol, K;                          // ncol = rrtm columns (= model columns / lonstep)
   const double *p_full, *p_half, *z_full, *z_half, *t, *q, *o3;
   double *play, *plev, *tlay, *tlev, *h2o, *o3v;
   double h2o_fac, o3_fac, h2o_lower_limit, t_lo, t_hi; int convert;
+  // lonstep > 1 (`p_full(1:si:lonstep,:,:)`, rrtm_radiation.F90:831-846): every lonstep-th longitude; the 2-D inputs are gathered too
+  int lonstep, I; size_t ncol_model;
+  const double *t_surf, *albedo, *coszen; double *tsfc_s, *albedo_s, *coszen_s;
 };
 
 // interp_temp (rrtm_radiation.F90:502-544) and the reshape / unit block of run_rrtmg (:816-870)
 __global__ void rrtm_prepare_kernel(PrepArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;          // rrtm column
   if (c >= a.ncol) return;
-  const int K = a.K; const size_t nc = a.ncol;
+  const int K = a.K; const size_t nc = a.ncol, nm = a.ncol_model;
+  size_t s = c;                                                 // model column it is taken from
+  if (a.lonstep > 1) {
+    const int Is = a.I / a.lonstep, j = c / Is, i = c - j * Is;
+    s = (size_t)j * a.I + (size_t)i * a.lonstep;
+    a.tsfc_s[c] = a.t_surf[s]; a.albedo_s[c] = a.albedo[s]; a.coszen_s[c] = a.coszen[s];
+  }
   auto lim = [&](double x) { return fmin(fmax(x, a.t_lo), a.t_hi); };
   for (int k = 0; k < K; ++k) {                 // model level k (0 = top) -> rrtm layer K-1-k
     const int l = K - 1 - k;
-    double tk = a.t[c + nc * k];
-    a.play[c + nc * l] = a.p_full[c + nc * k] * 0.01;
+    double tk = a.t[s + nm * k];
+    a.play[c + nc * l] = a.p_full[s + nm * k] * 0.01;
     a.tlay[c + nc * l] = lim(tk);
-    double q = a.q[c + nc * k];
+    double q = a.q[s + nm * k];
     double v = a.convert ? (q / (1.0 - q)) * a.h2o_fac : q;
     a.h2o[c + nc * l] = fmax(v, a.h2o_lower_limit);
-    a.o3v[c + nc * l] = a.o3 ? a.o3[c + nc * k] * a.o3_fac : 0.0;
+    a.o3v[c + nc * l] = a.o3 ? a.o3[s + nm * k] * a.o3_fac : 0.0;
     // half level k (interface above layer k) -> rrtm level K-k
     double th;
-    if (k == 0) th = 0.5 * (3.0 * tk - a.t[c + nc * 1]);
+    if (k == 0) th = 0.5 * (3.0 * tk - a.t[s + nm * 1]);
     else {
-      double zf0 = a.z_full[c + nc * (k - 1)], zf1 = a.z_full[c + nc * k], zh = a.z_half[c + nc * k];
+      double zf0 = a.z_full[s + nm * (k - 1)], zf1 = a.z_full[s + nm * k], zh = a.z_half[s + nm * k];
       double dzk2 = 1.0 / (zf0 - zf1), dzk = (zh - zf1) * dzk2, dzk1 = (zf0 - zh) * dzk2;
-      th = tk * dzk1 + a.t[c + nc * (k - 1)] * dzk;
+      th = tk * dzk1 + a.t[s + nm * (k - 1)] * dzk;
     }
     a.tlev[c + nc * (K - k)] = lim(th);
-    a.plev[c + nc * (K - k)] = a.p_half[c + nc * k] * 0.01;
+    a.plev[c + nc * (K - k)] = a.p_half[s + nm * k] * 0.01;
   }
   {
-    double zf0 = a.z_full[c + nc * (K - 2)], zf1 = a.z_full[c + nc * (K - 1)];
-    double th = a.t[c + nc * (K - 2)] + (a.z_half[c + nc * K] - zf0) * (a.t[c + nc * (K - 1)] - a.t[c + nc * (K - 2)]) / (zf1 - zf0);
+    double zf0 = a.z_full[s + nm * (K - 2)], zf1 = a.z_full[s + nm * (K - 1)];
+    double th = a.t[s + nm * (K - 2)] + (a.z_half[s + nm * K] - zf0) * (a.t[s + nm * (K - 1)] - a.t[s + nm * (K - 2)]) / (zf1 - zf0);
     a.tlev[c] = lim(th);
-    a.plev[c] = a.p_half[c + nc * K] * 0.01;
+    a.plev[c] = a.p_half[s + nm * K] * 0.01;
   }
 }
 // `if(minval(phalf(:,sk+1)) .le. 0.) phalf(:,sk+1) = pfull(:,sk)*0.5` -- the top interface pressure pk(1) + bk(1)*ps is the
@@ -219,25 +228,45 @@ __global__ void rrtm_fix_top_kernel(int ncol, int K, const double* play, double*
 }
 
 struct FinishArgs {
-  int ncol, K;
+  int ncol, K;                          // ncol = model columns
   const double *swhr, *lwhr, *swu, *swd, *lwu, *lwd;
   double *tdt, *tdt_rad, *flux_sw, *flux_lw, *olr, *toa_sw;
+  int lonstep, I;                       // lonstep > 1: linear interpolation in longitude, closed toroidally (rrtm_radiation.F90:918-935)
 };
 __global__ void rrtm_finish_kernel(FinishArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;          // model column
   if (c >= a.ncol) return;
-  const int K = a.K; const size_t nc = a.ncol;
+  const int K = a.K; const size_t nm = a.ncol;
   const double daypersec = 1.0 / 86400.0;
+  if (a.lonstep <= 1) {
+    for (int k = 0; k < K; ++k) {
+      const int l = K - 1 - k;
+      double h = a.swhr[c + nm * l] * daypersec + a.lwhr[c + nm * l] * daypersec;
+      if (a.tdt) a.tdt[c + nm * k] += h;
+      if (a.tdt_rad) a.tdt_rad[c + nm * k] = h;
+    }
+    if (a.flux_sw) a.flux_sw[c] = a.swd[c] - a.swu[c];
+    if (a.flux_lw) a.flux_lw[c] = a.lwd[c];
+    if (a.olr) a.olr[c] = a.lwu[c + nm * K] - a.lwd[c + nm * K];
+    if (a.toa_sw) a.toa_sw[c] = a.swd[c + nm * K] - a.swu[c + nm * K];
+    return;
+  }
+  const int Is = a.I / a.lonstep, j = c / a.I, i = c - j * a.I;
+  const int ic = i / a.lonstep, ij = i - ic * a.lonstep, i1 = ic + 1 < Is ? ic + 1 : 0;
+  const double di = (double)ij * (1.0 / (double)a.lonstep);     // di = (ij-1)*dlon, dlon = 1./lonstep
+  const size_t nr = nm / a.lonstep, c0 = (size_t)j * Is + ic, c1 = (size_t)j * Is + i1;
   for (int k = 0; k < K; ++k) {
     const int l = K - 1 - k;
-    double h = a.swhr[c + nc * l] * daypersec + a.lwhr[c + nc * l] * daypersec;
-    if (a.tdt) a.tdt[c + nc * k] += h;
-    if (a.tdt_rad) a.tdt_rad[c + nc * k] = h;
+    double s0 = a.swhr[c0 + nr * l] * daypersec, l0 = a.lwhr[c0 + nr * l] * daypersec;
+    double s1 = a.swhr[c1 + nr * l] * daypersec, l1 = a.lwhr[c1 + nr * l] * daypersec;
+    double h = di * (s1 + l1) + (1.0 - di) * (s0 + l0);
+    if (a.tdt) a.tdt[c + nm * k] += h;
+    if (a.tdt_rad) a.tdt_rad[c + nm * k] = h;
   }
-  if (a.flux_sw) a.flux_sw[c] = a.swd[c] - a.swu[c];
-  if (a.flux_lw) a.flux_lw[c] = a.lwd[c];
-  if (a.olr) a.olr[c] = a.lwu[c + nc * K] - a.lwd[c + nc * K];
-  if (a.toa_sw) a.toa_sw[c] = a.swd[c + nc * K] - a.swu[c + nc * K];
+  if (a.flux_sw) a.flux_sw[c] = di * (a.swd[c1] - a.swu[c1]) + (1.0 - di) * (a.swd[c0] - a.swu[c0]);
+  if (a.flux_lw) a.flux_lw[c] = di * a.lwd[c1] + (1.0 - di) * a.lwd[c0];
+  if (a.olr) a.olr[c] = di * (a.lwu[c1 + nr * K] - a.lwd[c1 + nr * K]) + (1.0 - di) * (a.lwu[c0 + nr * K] - a.lwd[c0 + nr * K]);
+  if (a.toa_sw) a.toa_sw[c] = di * (a.swd[c1 + nr * K] - a.swu[c1 + nr * K]) + (1.0 - di) * (a.swd[c0 + nr * K] - a.swu[c0 + nr * K]);
 }
 
 // diurnal_solar_2d (astronomy.f90:1123-1410; allow_negative_cosz absent): the chain of `where` statements in order
@@ -346,24 +375,25 @@ int isca_rrtm_run_device(IscaRrtm r, cudaStream_t st, const double* p_full, cons
                          const double* t, const double* q, const double* o3, const double* t_surf, const double* albedo, const double* coszen,
                          double* tdt, double* tdt_rad, double* flux_sw, double* flux_lw, double* olr, double* toa_sw) {
   const IscaRrtmConfig& c = r->cfg;
-  const int K = c.num_levels; const size_t nc = (size_t)c.num_lon * c.num_lat;
+  const int K = c.num_levels, ls = c.lonstep; const size_t nm = (size_t)c.num_lon * c.num_lat, nc = nm / ls;   // model / rrtm columns
   cudaStream_t keep = r->st; r->st = st;
   DevBuf* B = r->buf + 16;
   const size_t n3 = nc * K, n3h = nc * (K + 1);
-  const size_t sizes[12] = {n3, n3h, n3, n3h, n3, n3, n3h, n3h, n3, n3h, n3h, n3};
-  for (int i = 0; i < 12; ++i) if (!B[i].ensure(sizes[i])) { r->st = keep; return rfail(r, "cudaMalloc failed"); }
+  const size_t sizes[15] = {n3, n3h, n3, n3h, n3, n3, n3h, n3h, n3, n3h, n3h, n3, nc, nc, nc};
+  for (int i = 0; i < 15; ++i) if (!B[i].ensure(sizes[i])) { r->st = keep; return rfail(r, "cudaMalloc failed"); }
   double *play = B[0].p, *plev = B[1].p, *tlay = B[2].p, *tlev = B[3].p, *h2o = B[4].p, *o3v = B[5].p;
   double *swu = B[6].p, *swd = B[7].p, *swhr = B[8].p, *lwu = B[9].p, *lwd = B[10].p, *lwhr = B[11].p;
   PrepArgs pa{(int)nc, K, p_full, p_half, z_full, z_half, t, q, o3, play, plev, tlay, tlev, h2o, o3v,
               (1000.0 * c.gas_constant / c.rdgas) / c.wtmh2o,
               c.input_o3_file_is_mmr ? (1000.0 * c.gas_constant / c.rdgas) / c.wtmozone : 1.0,
-              c.h2o_lower_limit, c.temp_lower_limit, c.temp_upper_limit, c.convert_sphum_to_vmr};
-  const int T = 128, G = (int)((nc + T - 1) / T);
+              c.h2o_lower_limit, c.temp_lower_limit, c.temp_upper_limit, c.convert_sphum_to_vmr,
+              ls, c.num_lon, nm, t_surf, albedo, coszen, B[12].p, B[13].p, B[14].p};
+  const int T = 128, G = (int)((nc + T - 1) / T), Gm = (int)((nm + T - 1) / T);
   rrtm_prepare_kernel<<<G, T, 0, st>>>(pa);
   rrtm_fix_top_kernel<<<G, T, 0, st>>>((int)nc, K, play, plev);
   ColIn in{};
-  in.ncol = (int)nc; in.nlay = K; in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.tsfc = t_surf; in.emis = nullptr;
-  in.albedo = albedo; in.coszen = coszen;
+  in.ncol = (int)nc; in.nlay = K; in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.emis = nullptr;
+  in.tsfc = ls > 1 ? B[12].p : t_surf; in.albedo = ls > 1 ? B[13].p : albedo; in.coszen = ls > 1 ? B[14].p : coszen;
   for (int i = 0; i < NSP; ++i) { in.gas[i] = nullptr; in.gas_c[i] = 0.0; }
   for (int i = 0; i < 4; ++i) { in.xs[i] = nullptr; in.xs_c[i] = 0.0; }
   in.gas[SP_H2O] = h2o; in.gas[SP_O3] = o3v; in.gas_c[SP_CO2] = c.co2ppmv * 1.0e-6;
@@ -377,8 +407,8 @@ int isca_rrtm_run_device(IscaRrtm r, cudaStream_t st, const double* p_full, cons
     rc = isca_rrtm_lw_device(r, lw);
   }
   if (!rc) {
-    FinishArgs fa{(int)nc, K, swhr, lwhr, swu, swd, lwu, lwd, tdt, tdt_rad, flux_sw, flux_lw, olr, toa_sw};
-    rrtm_finish_kernel<<<G, T, 0, st>>>(fa);
+    FinishArgs fa{(int)nm, K, swhr, lwhr, swu, swd, lwu, lwd, tdt, tdt_rad, flux_sw, flux_lw, olr, toa_sw, ls, c.num_lon};
+    rrtm_finish_kernel<<<Gm, T, 0, st>>>(fa);
     if (cudaGetLastError() != cudaSuccess) rc = rfail(r, "rrtm_finish_kernel launch failed");
   }
   r->st = keep;
@@ -469,7 +499,8 @@ int isca_b200_rrtm_create(const IscaRrtmConfig* cfg, const char* table_path, Isc
   IscaRrtm r = nullptr;
   if (!cfg || !out || !table_path) return rfail(nullptr, "rrtm_create: null argument");
   if (cfg->abi_version != 1) return rfail(nullptr, "rrtm_create: abi_version mismatch");
-  if (cfg->lonstep != 1) return rfail(nullptr, "rrtm_create: lonstep /= 1 is not built");
+  if (cfg->lonstep < 1 || (cfg->lonstep > 1 && cfg->num_lon % cfg->lonstep != 0))
+    return rfail(nullptr, "rrtm_create: lonstep must be >= 1 and divide the number of longitudes");
   if (cfg->num_levels < 2 || cfg->num_levels > KMAX) return rfail(nullptr, "rrtm_create: num_levels must be 2..64");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return rfail(nullptr, "rrtm_create: no CUDA device (there is no CPU fallback)");

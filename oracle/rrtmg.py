@@ -1076,7 +1076,7 @@ class RrtmRadiation:
 
     def __init__(self, lat2d, lon2d, dt_atmos, dt_rad=0, dt_rad_avg=-1, do_rad_time_avg=True, store_intermediate_rad=True, solday=0,
                  equinox_day=0.75, frierson_solar_rad=False, del_sol=0.95, del_sw=0.0, o3=None, input_o3_file_is_mmr=True,
-                 day_in_s=86400.0, year_in_s=360 * 86400, astronomy=None, **column_kw):
+                 day_in_s=86400.0, year_in_s=360 * 86400, astronomy=None, lonstep=1, **column_kw):
         self.lat, self.lon = lat2d, lon2d
         self.dt_rad = int(dt_rad) if dt_rad > 0 else int(dt_atmos)
         self.dt_rad_avg = self.dt_rad if dt_rad_avg <= 0 else dt_rad_avg
@@ -1087,6 +1087,7 @@ class RrtmRadiation:
         self.astro = astronomy or Astronomy()
         self.o3, self.o3_mmr = o3, input_o3_file_is_mmr
         self.kw = column_kw
+        self.lonstep = int(lonstep)
         self.dt_last = -float(self.dt_rad)
         self.tdt_rad = self.sw_flux = self.lw_flux = None
         self.coszen = None
@@ -1116,16 +1117,31 @@ class RrtmRadiation:
             return tdt, z2, z2
         K, J, I = t.shape
         self.coszen = self.zenith(total_seconds)
+        ls = self.lonstep
+        sub = lambda a: a[..., ::ls]                  # `p_full(1:si:lonstep,:,:)` (rrtm_radiation.F90:831-846)
         col = lambda a: a.reshape(a.shape[0], -1).T
-        th = interp_temp(col(z_full), col(z_half), col(t))
+        th = interp_temp(col(sub(z_full)), col(sub(z_half)), col(sub(t)))
         o3v = 0.0
         if self.o3 is not None:
-            o3v = col(self.o3) * ((1000.0 * GAS_CONSTANT / RDGAS) / WTMOZONE if self.o3_mmr else 1.0)
-        o = run_rrtmg_columns(col(p_full), col(p_half), col(t), th, col(q), t_surf.ravel(), albedo.ravel(), self.coszen.ravel(),
-                              o3vmr=o3v, **self.kw)
+            o3v = col(sub(self.o3)) * ((1000.0 * GAS_CONSTANT / RDGAS) / WTMOZONE if self.o3_mmr else 1.0)
+        o = run_rrtmg_columns(col(sub(p_full)), col(sub(p_half)), col(sub(t)), th, col(sub(q)), sub(t_surf).ravel(), sub(albedo).ravel(),
+                              sub(self.coszen).ravel(), o3vmr=o3v, **self.kw)
         self.n_rad_calls += 1
-        self.tdt_rad = o["tdt_rad"].T.reshape(K, J, I)
-        self.sw_flux = o["flux_sw"].reshape(J, I)
-        self.lw_flux = o["flux_lw"].reshape(J, I)
-        self.olr, self.toa_sw = o["olr"].reshape(J, I), o["toa_sw"].reshape(J, I)
+        Is = I // ls
+
+        def back(a2):
+            """[.., J, I/lonstep] -> [.., J, I]: `di*x(i1) + (1-di)*x(i)`, closed toroidally (rrtm_radiation.F90:918-935)"""
+            if ls == 1:
+                return a2
+            out = np.empty(a2.shape[:-1] + (I,))
+            nxt = np.roll(a2, -1, axis=-1)
+            for ij in range(ls):
+                di = ij * (1.0 / ls)
+                out[..., ij::ls] = di * nxt + (1.0 - di) * a2
+            return out
+        sw3 = (o["tdt_sw"].T.reshape(K, J, Is), o["tdt_lw"].T.reshape(K, J, Is))
+        self.tdt_rad = back(sw3[0] + sw3[1]) if ls > 1 else o["tdt_rad"].T.reshape(K, J, I)
+        self.sw_flux = back(o["flux_sw"].reshape(J, Is))
+        self.lw_flux = back(o["flux_lw"].reshape(J, Is))
+        self.olr, self.toa_sw = back(o["olr"].reshape(J, Is)), back(o["toa_sw"].reshape(J, Is))
         return tdt + self.tdt_rad, self.sw_flux, self.lw_flux

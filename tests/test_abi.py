@@ -193,5 +193,5 @@ def test_rrtm_no_cpu_fallback(lib_built):
         rrtm.Rrtm()
     assert "CUDA" in str(e.value)
     with pytest.raises(api.IscaError) as e:
-        rrtm.Rrtm(lonstep=4)
+        rrtm.Rrtm(num_lon=128, lonstep=3)
     assert "lonstep" in str(e.value)

@@ -180,7 +180,7 @@ def test_rrtm_driver_loud_failures(lib_built):
     with pytest.raises(api.IscaError):
         m.set_ozone(np.zeros(m.s3))                    # before use_rrtm
     with pytest.raises(api.IscaError):
-        m.use_rrtm(dict(lonstep=4))
+        m.use_rrtm(dict(lonstep=5))                    # does not divide 64 longitudes
     m.use_rrtm()
     with pytest.raises(api.IscaError):
         m.use_rrtm()                                   # twice
@@ -243,3 +243,27 @@ def test_mima_test_case_runs(lib_built):
     t = m.core.get_field("t", m.core.get_time_pointers()[1])
     assert np.isfinite(t).all() and 150.0 < t.min() and t.max() < 330.0
     m.atmosphere_end()
+
+
+@pytest.mark.parametrize("lonstep", [2, 4])
+def test_run_rrtmg_lonstep(lib_built, lonstep):
+    """rrtm_radiation_nml lonstep: radiation on every lonstep-th longitude, linear interpolation closed around the latitude circle"""
+    from isca_b200 import rrtm
+    from oracle import rrtmg as R
+    I, J, K = 16, 4, 30
+    m = model_columns(I, J, K, 33)
+    r = rrtm.Rrtm(num_lon=I, num_lat=J, num_levels=K, lonstep=lonstep)
+    tdt = np.zeros((K, J, I))
+    out = r.run_rrtmg(m["p_full"], m["p_half"], m["z_full"], m["z_half"], m["t"], m["q"], m["t_surf"], m["albedo"], m["coszen"], tdt, o3=m["o3"])
+    r.close()
+    lat = np.zeros((J, I))
+    o = R.RrtmRadiation(lat, lat, 600.0, o3=m["o3"], lonstep=lonstep)
+    o.zenith = lambda total_seconds: m["coszen"]
+    t2, fsw, flw = o(0.0, m["p_full"], m["p_half"], m["z_full"], m["z_half"], m["t"], m["q"], m["t_surf"], m["albedo"], np.zeros((K, J, I)))
+    assert rel(out["tdt_rad"], o.tdt_rad) < 1e-9 and np.array_equal(tdt, out["tdt_rad"])
+    assert rel(out["flux_sw"], fsw) < 1e-11 and rel(out["flux_lw"], flw) < 1e-11 and rel(out["olr"], o.olr) < 1e-11
+    # the computed longitudes carry their own columns unchanged
+    full = R.RrtmRadiation(lat, lat, 600.0, o3=m["o3"])
+    full.zenith = o.zenith
+    full(0.0, m["p_full"], m["p_half"], m["z_full"], m["z_half"], m["t"], m["q"], m["t_surf"], m["albedo"], np.zeros((K, J, I)))
+    assert rel(out["flux_lw"][:, ::lonstep], full.lw_flux[:, ::lonstep]) < 1e-11

@@ -250,3 +250,23 @@ def test_moist_oracle_use_tau_false():
         out.append(mp.diag["diff_t"].copy())
     d = np.abs(out[0] - out[1]).max()
     assert 0.0 < d <= max(out[0].max(), out[1].max())               # a different, comparable diffusivity
+
+
+def test_lonstep_interpolation():
+    """run_rrtmg with lonstep > 1: computed longitudes keep their own columns, the others are the linear interpolation between
+    the neighbouring computed ones, closed around the latitude circle"""
+    from rrtm_cases import model_columns
+    I, J, K = 8, 2, 20
+    m = model_columns(I, J, K, 8)
+    lat = np.zeros((J, I))
+    args = (0.0, m["p_full"], m["p_half"], m["z_full"], m["z_half"], m["t"], m["q"], m["t_surf"], m["albedo"], np.zeros((K, J, I)))
+    full = R.RrtmRadiation(lat, lat, 600.0, o3=m["o3"])
+    full.zenith = lambda s: m["coszen"]
+    full(*args)
+    sub = R.RrtmRadiation(lat, lat, 600.0, o3=m["o3"], lonstep=4)
+    sub.zenith = full.zenith
+    sub(*args)
+    assert np.allclose(sub.lw_flux[:, ::4], full.lw_flux[:, ::4], rtol=1e-14)
+    assert np.allclose(sub.tdt_rad[:, :, ::4], full.tdt_rad[:, :, ::4], rtol=1e-12, atol=1e-20)
+    assert np.allclose(sub.lw_flux[:, 1], 0.25 * full.lw_flux[:, 4] + 0.75 * full.lw_flux[:, 0], rtol=1e-14)
+    assert np.allclose(sub.lw_flux[:, 7], 0.75 * full.lw_flux[:, 0] + 0.25 * full.lw_flux[:, 4], rtol=1e-14)     # wraps around
