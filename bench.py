@@ -406,13 +406,22 @@ def main():
     rrtm_radiation = None
     if not args.no_moist and world == 1:
         try:
-            import subprocess
             pr = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "rrtm_bench.py")],
                                 capture_output=True, text=True, timeout=300)
             last = [l for l in pr.stdout.strip().splitlines() if l.startswith("{")]
             rrtm_radiation = json.loads(last[-1]) if pr.returncode == 0 and last else {"error": (pr.stderr or pr.stdout)[-300:]}
         except Exception as e:
             rrtm_radiation = {"error": str(e)[:200]}
+    # informational: the MiMA configuration (BASELINE config 4 physics: RRTMG radiation) at T85 L40 on one GPU, same isolation
+    mima_model = None
+    if not args.no_moist and world == 1:
+        try:
+            pr = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "mima_bench.py")],
+                                capture_output=True, text=True, timeout=420)
+            last = [l for l in pr.stdout.strip().splitlines() if l.startswith("{")]
+            mima_model = json.loads(last[-1]) if pr.returncode == 0 and last else {"error": (pr.stderr or pr.stdout)[-300:]}
+        except Exception as e:
+            mima_model = {"error": str(e)[:200]}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -438,6 +447,7 @@ def main():
         "no_tracer_core": no_tracer_core,
         "moist_model": moist_model,
         "rrtm_radiation": rrtm_radiation,
+        "mima_model": mima_model,
     }
     print(json.dumps(line), file=json_out, flush=True)
     return 0

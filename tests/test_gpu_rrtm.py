@@ -161,9 +161,8 @@ def test_moist_model_with_rrtm_radiation(lib_built, dt_rad_steps, kw):
             assert rel(m.get("tdt_rad"), mp.rrtm.tdt_rad) < 1e-9
             assert rel(m.get("net_surf_sw_down"), mp.rrtm.sw_flux) < 1e-11 and rel(m.get("surf_lw_down"), mp.rrtm.lw_flux) < 1e-11
             assert rel(m.get("olr"), mp.rrtm.olr) < 1e-11
-        s = atm.get_time_pointers()[1]
-        assert rel(atm.get_field("t", s), core.tg[core.current]) < TOL, step
-        assert rel(atm.get_field("ps", s), core.psg[core.current]) < TOL, step
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(atm.get_field(api.F_PS), core.psg[core.current]) < TOL, step
         assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
     assert mp.rrtm.n_rad_calls == (4 if dt_rad_steps == 1 else 2)
     m.atmosphere_end()
@@ -220,12 +219,11 @@ def test_moist_model_test_case_options(lib_built, radiation):
     for step in range(3):
         core.step(physics=True)
         m.atmosphere(1)
-        s = atm.get_time_pointers()[1]
         if step == 0:
             assert mp.diag["diff_t"].max() > 0.0
             assert rel(m.get("diff_t"), mp.diag["diff_t"]) < 1e-9 and rel(m.get("z_pbl"), mp.diag["z_pbl"]) < 1e-9
-        assert rel(atm.get_field("t", s), core.tg[core.current]) < TOL, step
-        assert rel(atm.get_field("u", s), core.ug[core.current]) < TOL, step
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(atm.get_field(api.F_U), core.ug[core.current]) < TOL, step
         assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
     m.atmosphere_end()
 
@@ -240,7 +238,8 @@ def test_mima_test_case_runs(lib_built):
     olr, cz, tsw = m.get("olr"), m.get("coszen"), m.get("toa_sw")
     assert np.isfinite(olr).all() and 120.0 < olr.mean() < 330.0
     assert (cz >= 0).all() and cz.max() <= 1.0 and (tsw[cz == 0] == 0).all() and tsw.max() > 100.0
-    t = m.core.get_field("t", m.core.get_time_pointers()[1])
+    from isca_b200 import api
+    t = m.core.get_field(api.F_T)
     assert np.isfinite(t).all() and 150.0 < t.min() and t.max() < 330.0
     m.atmosphere_end()
 
