@@ -195,3 +195,60 @@ def test_rrtm_no_cpu_fallback(lib_built):
     with pytest.raises(api.IscaError) as e:
         rrtm.Rrtm(num_lon=128, lonstep=3)
     assert "lonstep" in str(e.value)
+
+
+def _prototypes(header):
+    txt = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\*|IscaHandle)\s+(isca_b200_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if params == ["void"] or params == [""] else params
+    return protos
+
+
+def _expected_ctype(param):
+    """C parameter declaration -> the ctypes class family the binding must use"""
+    p = re.sub(r"\s+", " ", param)
+    if "double*" in p.replace(" *", "*"):
+        return "double*"
+    if "int*" in p.replace(" *", "*"):
+        return "int*"
+    if "char*" in p.replace(" *", "*"):
+        return "char*"
+    if "*" in p or re.match(r"(const )?Isca(Rrtm|Moist|Physics|Handle)\b", p) and not re.search(r"Config", p):
+        return "ptr"
+    if p.startswith("long long"):
+        return "longlong"
+    if p.startswith("double"):
+        return "double"
+    if p.startswith("int"):
+        return "int"
+    return "ptr"
+
+
+def test_rrtm_ctypes_bindings_match_the_header(lib_built):
+    """every binding of isca_b200/rrtm.py has the parameter count and the scalar / pointer classes of its C prototype (a wrong
+    count or an int passed where a double is expected would only show up on the GPU box otherwise)"""
+    from isca_b200 import rrtm
+    lib = rrtm._lib()
+    protos = _prototypes(RRTM_HEADER)
+    assert set(protos) == set(rrtm.RRTM_EXPORTS)
+    for name, params in protos.items():
+        fn = getattr(lib, name)
+        at = fn.argtypes
+        assert at is not None, f"{name} has no argtypes"
+        assert len(at) == len(params), f"{name}: {len(at)} argtypes for {len(params)} parameters"
+        for t, p in zip(at, params):
+            want = _expected_ctype(p)
+            if want == "double":
+                assert t is C.c_double, (name, p)
+            elif want == "int":
+                assert t is C.c_int, (name, p)
+            elif want == "longlong":
+                assert t is C.c_longlong, (name, p)
+            elif want == "char*":
+                assert t is C.c_char_p, (name, p)
+            elif want == "double*":
+                assert t in (C.POINTER(C.c_double), C.c_void_p), (name, p)
+            else:
+                assert t is C.c_void_p or issubclass(t, C._Pointer), (name, p)
