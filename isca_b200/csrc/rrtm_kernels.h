@@ -1,0 +1,308 @@
+// rrtm_kernels.h -- the CUDA kernels of the RRTMG row: rrtmg_lw_kernel, rrtmg_sw_kernel, the run_rrtmg glue kernels
+// (model layout <-> RRTMG layout, interp_temp, units, lonstep) and the zenith-angle kernel.  Included by rrtm.cu (nvcc, the product)
+// and by the test-only thread emulator tests/host/rrtm_emu.cpp, which runs the same kernel bodies on CPU threads -- one OS thread
+// per CUDA thread of a block, std::barrier for __syncthreads, a per-warp exchange buffer for __shfl_xor_sync -- so that the phase
+// structure, the shared-memory staging and the shuffle reductions can be checked without a GPU.  The product never runs it.
+//
+// Mapping: one CTA per column.  Phase A: one thread per layer runs inatm + setcoef (+ the Planck interpolation) into
+// shared memory; thread 0 forms the column sums (precipitable water -> diffusivity angle, laytrop -> solar source
+// layers).  Phase B: one thread per g-point (140 LW / 112 SW) evaluates the gaseous optical depths layer by layer with
+// the descriptor-driven generic band code of rrtm_column.h and runs the radiative-transfer sweeps (rtrnmr clear-sky /
+// reftra + vrtqdr); the radiances of a level are summed over the g-points with warp shuffles + a fixed-order
+// cross-warp sum (deterministic).  Phase C: one thread per level writes fluxes and heating rates.
+#pragma once
+#include "rrtm_column.h"
+
+namespace rrtm_k {
+using namespace rrtm;
+
+struct ColIn {                       // device pointers, (ncol, nlay) column-fastest; NULL gas = the constant beside it
+  int ncol, nlay;
+  const double *play, *plev, *tlay, *tlev, *tsfc, *emis, *albedo, *coszen;
+  const double* gas[NSP]; double gas_c[NSP];
+  const double* xs[4]; double xs_c[4];
+  double *uflx, *dflx, *hr;
+  double heatfac, adjflux;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct DevRed {                      // per-level sum over the g-points: warp shuffle, lane 0 stores the warp's partial
+  double* part; int warp, lane;      // part[warp][2][KMAX+1]
+  __device__ __forceinline__ void up(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 0) * (KMAX + 1) + lev] = v; }
+  __device__ __forceinline__ void down(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 1) * (KMAX + 1) + lev] = v; }
+};
+
+constexpr int LW_THREADS = 160, SW_THREADS = 128;
+constexpr double FLUXFAC = 3.14159265358979323846 * 2.0e4;      // pi * 2.e4 with pi = 2*asin(1)
+
+__global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __restrict__ A, Tab tb, const LwBand* __restrict__ bands, ColIn in) {
+  __shared__ Layer lay[KMAX];
+  __shared__ double planklay[NB_LW * (KMAX + 1)], planklev[NB_LW * (KMAX + 1)];
+  __shared__ double part[(LW_THREADS / 32) * 2 * (KMAX + 1)];
+  __shared__ double plankbnd[NB_LW], secdiff[NB_LW], semiss[NB_LW], pz[KMAX + 1], fnet[KMAX + 1];
+  const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
+  const int PS = KMAX + 1;           // row stride of the Planck arrays (planklay uses the same stride for simplicity)
+  // ---- phase A: inatm + setcoef per layer
+  for (int l = tid; l < nl; l += LW_THREADS) {
+    double vmr[NSP], xs[4];
+    for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + (size_t)nc * l] : in.gas_c[i];
+    for (int i = 0; i < 4; ++i) xs[i] = in.xs[i] ? in.xs[i][col + (size_t)nc * l] : in.xs_c[i];
+    double pb = in.plev[col + (size_t)nc * l], pa = in.plev[col + (size_t)nc * (l + 1)];
+    double coldry = coldry_of(pb, pa, vmr[0]);
+    double tav = in.tlay[col + (size_t)nc * l];
+    lw_setcoef_layer(A, tb, in.play[col + (size_t)nc * l], tav, coldry, vmr, xs, lay[l]);
+    planck16(A, tb, tav, planklay + l, PS);
+    planck16(A, tb, in.tlev[col + (size_t)nc * (l + 1)], planklev + l + 1, PS);
+    pz[l + 1] = pa;
+    if (l == 0) pz[0] = pb;
+  }
+  if (tid < NB_LW) semiss[tid] = in.emis ? in.emis[col + (size_t)nc * tid] : 1.0;
+  __syncthreads();
+  if (tid == 0) {
+    planck16(A, tb, in.tlev[col], planklev, PS);
+    double pb[NB_LW];
+    planck16(A, tb, in.tsfc[col], pb, 1);
+    for (int ib = 0; ib < NB_LW; ++ib) plankbnd[ib] = semiss[ib] * pb[ib];
+    // inatm: precipitable water (rrtmg_lw_rad.nomcica.f90:846-856), sequential over the layers
+    double amttl = 0.0, wvttl = 0.0;
+    for (int l = 0; l < nl; ++l) {
+      double wv = lay[l].col[SP_H2O] * 1.0e20;
+      amttl += lay[l].coldry + wv;
+      wvttl += wv;
+    }
+    double wvsh = (AMW * wvttl) / (AMD * amttl);
+    double pwvcm = wvsh * (1.0e3 * pz[0]) / (1.0e2 * GRAV);
+    for (int ib = 0; ib < NB_LW; ++ib) secdiff[ib] = lw_secdiff(ib, pwvcm);
+  }
+  __syncthreads();
+  // ---- phase B: one g-point per thread
+  {
+    const int valid = tid < NG_LW;
+    const int g = valid ? tid : NG_LW - 1;
+    int ib = 0;
+    while (ib < NB_LW - 1 && g >= bands[ib + 1].g0) ++ib;
+    const double delwave[NB_LW] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
+    DevRed red{part, tid >> 5, tid & 31};
+    lw_gpoint(A, tb, bands[ib], ib, g - bands[ib].g0, nl, lay, planklay, planklev, PS, plankbnd[ib], semiss[ib], secdiff[ib],
+              valid ? 0.5 * delwave[ib] : 0.0, red);
+  }
+  __syncthreads();
+  // ---- phase C: fluxes and heating rates
+  for (int lev = tid; lev <= nl; lev += LW_THREADS) {
+    double u = 0.0, d = 0.0;
+    for (int w = 0; w < LW_THREADS / 32; ++w) { u += part[(w * 2 + 0) * (KMAX + 1) + lev]; d += part[(w * 2 + 1) * (KMAX + 1) + lev]; }
+    u *= FLUXFAC; d *= FLUXFAC;
+    in.uflx[col + (size_t)nc * lev] = u;
+    in.dflx[col + (size_t)nc * lev] = d;
+    fnet[lev] = u - d;
+  }
+  __syncthreads();
+  for (int l = tid; l < nl; l += LW_THREADS)
+    in.hr[col + (size_t)nc * l] = in.heatfac * (fnet[l] - fnet[l + 1]) / (pz[l] - pz[l + 1]);
+}
+
+__global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __restrict__ A, Tab tb, const SwBand* __restrict__ bands, ColIn in) {
+  __shared__ Layer lay[KMAX];
+  __shared__ double part[(SW_THREADS / 32) * 2 * (KMAX + 1)];
+  __shared__ double pz[KMAX + 1], fnet[KMAX + 1];
+  __shared__ int lsol[NB_SW];
+  __shared__ int laytrop_s;
+  const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
+  const double cosz = in.coszen[col];
+  if (cosz < 1.0e-10) {              // `if (coszen(iplon) < zepzen) ... cycle` (rrtmg_sw_rad.nomcica.f90)
+    for (int lev = tid; lev <= nl; lev += SW_THREADS) { in.uflx[col + (size_t)nc * lev] = 0.0; in.dflx[col + (size_t)nc * lev] = 0.0; }
+    for (int l = tid; l < nl; l += SW_THREADS) in.hr[col + (size_t)nc * l] = 0.0;
+    return;
+  }
+  for (int l = tid; l < nl; l += SW_THREADS) {
+    double vmr[NSP];
+    for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + (size_t)nc * l] : in.gas_c[i];
+    double pb = in.plev[col + (size_t)nc * l], pa = in.plev[col + (size_t)nc * (l + 1)];
+    sw_setcoef_layer(A, tb, in.play[col + (size_t)nc * l], in.tlay[col + (size_t)nc * l], coldry_of(pb, pa, vmr[0]), vmr, lay[l]);
+    pz[l + 1] = pa;
+    if (l == 0) pz[0] = pb;
+  }
+  __syncthreads();
+  if (tid == 0) { int n = 0; for (int l = 0; l < nl; ++l) n += lay[l].lower; laytrop_s = n; }
+  __syncthreads();
+  if (tid < NB_SW) lsol[tid] = sw_laysolfr(bands[tid], lay, nl, laytrop_s);
+  __syncthreads();
+  {
+    const int valid = tid < NG_SW;
+    const int g = valid ? tid : NG_SW - 1;
+    int ib = 0;
+    while (ib < NB_SW - 1 && g >= bands[ib + 1].g0) ++ib;
+    DevRed red{part, tid >> 5, tid & 31};
+    sw_gpoint(A, tb, bands[ib], g - bands[ib].g0, nl, lay, lsol[ib], cosz, in.albedo[col], in.adjflux, valid ? 1.0 : 0.0, red);
+  }
+  __syncthreads();
+  for (int lev = tid; lev <= nl; lev += SW_THREADS) {
+    double u = 0.0, d = 0.0;
+    for (int w = 0; w < SW_THREADS / 32; ++w) { u += part[(w * 2 + 0) * (KMAX + 1) + lev]; d += part[(w * 2 + 1) * (KMAX + 1) + lev]; }
+    in.uflx[col + (size_t)nc * lev] = u;
+    in.dflx[col + (size_t)nc * lev] = d;
+    fnet[lev] = d - u;
+  }
+  __syncthreads();
+  for (int l = tid; l < nl; l += SW_THREADS)    // swhr(nlayers) = 0 in the reference
+    in.hr[col + (size_t)nc * l] = l == nl - 1 ? 0.0 : (fnet[l + 1] - fnet[l]) * in.heatfac / (pz[l] - pz[l + 1]);
+}
+
+// ---- run_rrtmg glue: model layout [K][J][I] top-down (Pa) -> RRTMG layout (ncol, nlay) bottom-up (hPa) ----
+struct PrepArgs {
+  int ncol, K;                          // ncol = rrtm columns (= model columns / lonstep)
+  const double *p_full, *p_half, *z_full, *z_half, *t, *q, *o3;
+  double *play, *plev, *tlay, *tlev, *h2o, *o3v;
+  double h2o_fac, o3_fac, h2o_lower_limit, t_lo, t_hi; int convert;
+  // lonstep > 1 (`p_full(1:si:lonstep,:,:)`, rrtm_radiation.F90:831-846): every lonstep-th longitude; the 2-D inputs are gathered too
+  int lonstep, I; size_t ncol_model;
+  const double *t_surf, *albedo, *coszen; double *tsfc_s, *albedo_s, *coszen_s;
+};
+
+// interp_temp (rrtm_radiation.F90:502-544) and the reshape / unit block of run_rrtmg (:816-870)
+__global__ void rrtm_prepare_kernel(PrepArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;          // rrtm column
+  if (c >= a.ncol) return;
+  const int K = a.K; const size_t nc = a.ncol, nm = a.ncol_model;
+  size_t s = c;                                                 // model column it is taken from
+  if (a.lonstep > 1) {
+    const int Is = a.I / a.lonstep, j = c / Is, i = c - j * Is;
+    s = (size_t)j * a.I + (size_t)i * a.lonstep;
+    a.tsfc_s[c] = a.t_surf[s]; a.albedo_s[c] = a.albedo[s]; a.coszen_s[c] = a.coszen[s];
+  }
+  auto lim = [&](double x) { return fmin(fmax(x, a.t_lo), a.t_hi); };
+  for (int k = 0; k < K; ++k) {                 // model level k (0 = top) -> rrtm layer K-1-k
+    const int l = K - 1 - k;
+    double tk = a.t[s + nm * k];
+    a.play[c + nc * l] = a.p_full[s + nm * k] * 0.01;
+    a.tlay[c + nc * l] = lim(tk);
+    double q = a.q[s + nm * k];
+    double v = a.convert ? (q / (1.0 - q)) * a.h2o_fac : q;
+    a.h2o[c + nc * l] = fmax(v, a.h2o_lower_limit);
+    a.o3v[c + nc * l] = a.o3 ? a.o3[s + nm * k] * a.o3_fac : 0.0;
+    // half level k (interface above layer k) -> rrtm level K-k
+    double th;
+    if (k == 0) th = 0.5 * (3.0 * tk - a.t[s + nm * 1]);
+    else {
+      double zf0 = a.z_full[s + nm * (k - 1)], zf1 = a.z_full[s + nm * k], zh = a.z_half[s + nm * k];
+      double dzk2 = 1.0 / (zf0 - zf1), dzk = (zh - zf1) * dzk2, dzk1 = (zf0 - zh) * dzk2;
+      th = tk * dzk1 + a.t[s + nm * (k - 1)] * dzk;
+    }
+    a.tlev[c + nc * (K - k)] = lim(th);
+    a.plev[c + nc * (K - k)] = a.p_half[s + nm * k] * 0.01;
+  }
+  {
+    double zf0 = a.z_full[s + nm * (K - 2)], zf1 = a.z_full[s + nm * (K - 1)];
+    double th = a.t[s + nm * (K - 2)] + (a.z_half[s + nm * K] - zf0) * (a.t[s + nm * (K - 1)] - a.t[s + nm * (K - 2)]) / (zf1 - zf0);
+    a.tlev[c] = lim(th);
+    a.plev[c] = a.p_half[s + nm * K] * 0.01;
+  }
+}
+// `if(minval(phalf(:,sk+1)) .le. 0.) phalf(:,sk+1) = pfull(:,sk)*0.5` -- the top interface pressure pk(1) + bk(1)*ps is the
+// same in every column (bk(1) = 0), so the reference's all-or-nothing replacement equals this per-column test
+__global__ void rrtm_fix_top_kernel(int ncol, int K, const double* play, double* plev) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncol && plev[c + (size_t)ncol * K] <= 0.0) plev[c + (size_t)ncol * K] = play[c + (size_t)ncol * (K - 1)] * 0.5;
+}
+
+struct FinishArgs {
+  int ncol, K;                          // ncol = model columns
+  const double *swhr, *lwhr, *swu, *swd, *lwu, *lwd;
+  double *tdt, *tdt_rad, *flux_sw, *flux_lw, *olr, *toa_sw;
+  int lonstep, I;                       // lonstep > 1: linear interpolation in longitude, closed toroidally (rrtm_radiation.F90:918-935)
+};
+__global__ void rrtm_finish_kernel(FinishArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;          // model column
+  if (c >= a.ncol) return;
+  const int K = a.K; const size_t nm = a.ncol;
+  const double daypersec = 1.0 / 86400.0;
+  if (a.lonstep <= 1) {
+    for (int k = 0; k < K; ++k) {
+      const int l = K - 1 - k;
+      double h = a.swhr[c + nm * l] * daypersec + a.lwhr[c + nm * l] * daypersec;
+      if (a.tdt) a.tdt[c + nm * k] += h;
+      if (a.tdt_rad) a.tdt_rad[c + nm * k] = h;
+    }
+    if (a.flux_sw) a.flux_sw[c] = a.swd[c] - a.swu[c];
+    if (a.flux_lw) a.flux_lw[c] = a.lwd[c];
+    if (a.olr) a.olr[c] = a.lwu[c + nm * K] - a.lwd[c + nm * K];
+    if (a.toa_sw) a.toa_sw[c] = a.swd[c + nm * K] - a.swu[c + nm * K];
+    return;
+  }
+  const int Is = a.I / a.lonstep, j = c / a.I, i = c - j * a.I;
+  const int ic = i / a.lonstep, ij = i - ic * a.lonstep, i1 = ic + 1 < Is ? ic + 1 : 0;
+  const double di = (double)ij * (1.0 / (double)a.lonstep);     // di = (ij-1)*dlon, dlon = 1./lonstep
+  const size_t nr = nm / a.lonstep, c0 = (size_t)j * Is + ic, c1 = (size_t)j * Is + i1;
+  for (int k = 0; k < K; ++k) {
+    const int l = K - 1 - k;
+    double s0 = a.swhr[c0 + nr * l] * daypersec, l0 = a.lwhr[c0 + nr * l] * daypersec;
+    double s1 = a.swhr[c1 + nr * l] * daypersec, l1 = a.lwhr[c1 + nr * l] * daypersec;
+    double h = di * (s1 + l1) + (1.0 - di) * (s0 + l0);
+    if (a.tdt) a.tdt[c + nm * k] += h;
+    if (a.tdt_rad) a.tdt_rad[c + nm * k] = h;
+  }
+  if (a.flux_sw) a.flux_sw[c] = di * (a.swd[c1] - a.swu[c1]) + (1.0 - di) * (a.swd[c0] - a.swu[c0]);
+  if (a.flux_lw) a.flux_lw[c] = di * a.lwd[c1] + (1.0 - di) * a.lwd[c0];
+  if (a.olr) a.olr[c] = di * (a.lwu[c1 + nr * K] - a.lwd[c1 + nr * K]) + (1.0 - di) * (a.lwu[c0 + nr * K] - a.lwd[c0 + nr * K]);
+  if (a.toa_sw) a.toa_sw[c] = di * (a.swd[c1 + nr * K] - a.swu[c1 + nr * K]) + (1.0 - di) * (a.swd[c0 + nr * K] - a.swu[c0 + nr * K]);
+}
+
+// diurnal_solar_2d (astronomy.f90:1123-1410; allow_negative_cosz absent): the chain of `where` statements in order
+__global__ void coszen_kernel(int n, const double* __restrict__ lat, const double* __restrict__ lon, double gmt, double dec, double dt,
+                              int frierson, double del_sol, double del_sw, double* __restrict__ cosz_out, double* __restrict__ fracday_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double PI = 3.14159265358979323846, twopi = 2.0 * PI;
+  double la = lat[i];
+  if (frierson) {                         // rrtm_radiation.F90:686-689
+    double sl = sin(la);
+    double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
+    cosz_out[i] = 0.25 * (1.0 + del_sol * p2 + del_sw * sl);
+    if (fracday_out) fracday_out[i] = 1.0;
+    return;
+  }
+  double aa = sin(la) * sin(dec), bb = cos(la) * cos(dec);
+  double t = gmt + lon[i] - PI;
+  if (t >= PI) t -= twopi;
+  if (t < -PI) t += twopi;
+  // half_day
+  double l2 = la;
+  if (la == 0.5 * PI) l2 = la - 1.0e-05;
+  if (la == -0.5 * PI) l2 = la + 1.0e-05;
+  double chd = -tan(l2) * tan(dec);
+  double h = chd <= -1.0 ? PI : (chd >= 1.0 ? 0.0 : acos(chd));
+  double cosz, fracday;
+  if (dt > 0.0) {
+    double tt = t + dt, st = sin(t), stt = sin(tt), sh = sin(h);
+    cosz = 0.0;
+    if (t < -h && tt < -h) cosz = 0.0;
+    if (t < -h && fabs(tt) <= h) cosz = (aa * (tt + h) / (tt - t)) + bb * (stt + sh) / (tt - t);
+    if (t < -h && h != 0.0 && h < tt) cosz = aa * (2. * h) / (tt - t) + bb * (sh + sh) / (tt - t);
+    if (fabs(t) <= h && fabs(tt) <= h) cosz = aa + bb * (stt - st) / (tt - t);
+    if (fabs(t) <= h && h < tt) cosz = (aa * (h - t) / (tt - t)) + bb * (sh - st) / (tt - t);
+    if (twopi - h < tt && t <= h) cosz = aa * ((tt + (2. * h) - t - twopi) / (tt - t)) + bb * (((sh - st) / (tt - t)) + ((stt + sh) / (tt - t)));
+    if (h < t && twopi - h >= tt) cosz = 0.0;
+    if (h < t && twopi - h < tt && tt < twopi + h) cosz = aa * (tt + h - twopi) / (tt - t) + bb * (stt + sh) / (tt - t);
+    if (h < t && twopi - h < tt && tt > twopi + h) cosz = aa * (2. * h) / (tt - t) + bb * (sh + sh) / (tt - t);
+    fracday = 0.0;
+    if (t < -h && tt < -h) fracday = 0.0;
+    if (t < -h && fabs(tt) <= h) fracday = (tt + h) / dt;
+    if (t < -h && h < tt) fracday = (h + h) / dt;
+    if (fabs(t) <= h && fabs(tt) <= h) fracday = (tt - t) / dt;
+    if (fabs(t) <= h && h < tt) fracday = (h - t) / dt;
+    if (h < t) fracday = 0.0;
+    if (twopi - h < tt) fracday = fracday + (tt + h - twopi) / dt;
+  } else {
+    if (fabs(t) < h) { cosz = aa + bb * cos(t); fracday = 1.0; } else { cosz = 0.0; fracday = 0.0; }
+  }
+  cosz_out[i] = fmax(0.0, cosz);
+  if (fracday_out) fracday_out[i] = fracday;
+}
+
+
+}  // namespace rrtm_k

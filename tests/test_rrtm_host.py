@@ -122,3 +122,103 @@ def test_mls_column_host(host):
     su, sd, shr, _, _, sf = host_sw(host, gg, np.full(2, 0.2), np.array([0.5, 1.0]))
     assert np.allclose(sd[:, -1], 1368.22 * np.array([0.5, 1.0]), rtol=2e-3)
     assert np.allclose(sf.sum(axis=1), sd[:, -1] / np.array([0.5, 1.0]), rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the CUDA kernels themselves under CPU thread emulation (tests/host/rrtm_emu.cpp): same kernel bodies (rrtm_kernels.h),
+# one OS thread per CUDA thread, std::barrier for __syncthreads, per-warp exchange buffers for the shuffles
+# ----------------------------------------------------------------------------------------------------------------
+EMU_SRC = os.path.join(HERE, "host", "rrtm_emu.cpp")
+EMU_OUT = os.path.join(HERE, "host", "_build", "librrtm_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [EMU_SRC] + [os.path.join(HERE, "..", "isca_b200", "csrc", f) for f in ("rrtm_column.h", "rrtm_tables.h", "rrtm_kernels.h")]
+    if not os.path.exists(EMU_OUT) or any(os.path.getmtime(d) > os.path.getmtime(EMU_OUT) for d in deps):
+        os.makedirs(os.path.dirname(EMU_OUT), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-o", EMU_OUT, EMU_SRC])
+    return C.CDLL(EMU_OUT)
+
+
+def _cp(a):
+    return None if a is None else np.ascontiguousarray(a).ctypes.data_as(P)
+
+
+@pytest.mark.parametrize("secondary,K,seed", [(False, 40, 3), (True, 25, 4)])
+def test_emulated_lw_sw_kernels_match_oracle(emu, secondary, K, seed):
+    """rrtmg_lw_kernel / rrtmg_sw_kernel: phase structure, shared-memory staging, shuffle reductions with padding lanes (140 of
+    160, 112 of 128 threads carry a g-point), night columns leaving the SW kernel early"""
+    nc = 6
+    g = columns(nc, K, seed, secondary=secondary)
+    arr = {k: _F(v) for k, v in g.items()}
+    cp = C.c_double(287.04 / (2 / 7))
+    u = np.zeros((nc, K + 1), order="F")
+    d = np.zeros((nc, K + 1), order="F")
+    hr = np.zeros((nc, K), order="F")
+    emis = np.asfortranarray(np.tile(np.linspace(0.9, 1.0, 16), (nc, 1)))
+    rc = emu.rrtm_emu_lw(R.TABLE_FILE.encode(), cp, nc, K, _ptr(arr["play"]), _ptr(arr["plev"]), _ptr(arr["tlay"]), _ptr(arr["tlev"]),
+                         _cp(g["tsfc"]), _ptr(arr["h2o"]), _ptr(arr["o3"]), _ptr(arr["co2"]), _ptr(arr["ch4"]), _ptr(arr["n2o"]), _ptr(arr["o2"]),
+                         _ptr(arr["cfc11"]), _ptr(arr["cfc12"]), _ptr(arr["cfc22"]), _ptr(arr["ccl4"]), _ptr(emis), _ptr(u), _ptr(d), _ptr(hr))
+    assert rc == 0
+    ou, od, ohr = R.rrtmg_lw(g["play"], g["plev"], g["tlay"], g["tlev"], g["tsfc"], g["h2o"], g["o3"], g["co2"], z(g["ch4"]), z(g["n2o"]),
+                             z(g["o2"]), z(g["cfc11"]), z(g["cfc12"]), z(g["cfc22"]), z(g["ccl4"]), emis=np.ascontiguousarray(emis))
+    assert rel(u, ou) < 1e-12 and rel(d, od) < 1e-12 and rel(hr, ohr) < 1e-10
+    alb = np.linspace(0.0, 0.8, nc)
+    cz = np.array([1e-11, 1.0, 0.3, -0.1, 0.01, 0.7])
+    su = np.zeros((nc, K + 1), order="F")
+    sd = np.zeros((nc, K + 1), order="F")
+    shr = np.zeros((nc, K), order="F")
+    rc = emu.rrtm_emu_sw(R.TABLE_FILE.encode(), cp, nc, K, _ptr(arr["play"]), _ptr(arr["plev"]), _ptr(arr["tlay"]), _ptr(arr["h2o"]),
+                         _ptr(arr["o3"]), _ptr(arr["co2"]), _ptr(arr["ch4"]), _ptr(arr["n2o"]), _ptr(arr["o2"]), _cp(alb), _cp(cz),
+                         C.c_double(1.03), C.c_double(1360.0), _ptr(su), _ptr(sd), _ptr(shr))
+    assert rc == 0
+    osu, osd, oshr = R.rrtmg_sw(g["play"], g["plev"], g["tlay"], g["h2o"], g["o3"], g["co2"], z(g["ch4"]), z(g["n2o"]), z(g["o2"]), alb, cz,
+                                1.03, 1360.0)
+    assert (su[cz < 1e-10] == 0).all() and (shr[cz < 1e-10] == 0).all()
+    assert rel(su, osu) < 1e-12 and rel(sd, osd) < 1e-12 and rel(shr, oshr) < 1e-10
+
+
+@pytest.mark.parametrize("lonstep", [1, 2])
+def test_emulated_run_rrtmg_kernels_match_oracle(emu, lonstep):
+    """the kernel sequence of run_rrtmg: rrtm_prepare_kernel (layout reversal, interp_temp, units, limits, lonstep gather),
+    rrtm_fix_top_kernel, SW, LW, rrtm_finish_kernel (K/day -> K/s, surface / TOA fluxes, lonstep interpolation)"""
+    from rrtm_cases import model_columns
+    I, J, K = 4, 2, 20
+    m = model_columns(I, J, K, 5)
+    keep = {k: np.ascontiguousarray(v) for k, v in m.items()}
+    tdt0 = np.random.default_rng(0).normal(0, 1e-5, (K, J, I))
+    tdt = tdt0.copy()
+    tr, fs, fl, olr, ts = np.zeros((K, J, I)), np.zeros((J, I)), np.zeros((J, I)), np.zeros((J, I)), np.zeros((J, I))
+    d = C.c_double
+    rc = emu.rrtm_emu_run_rrtmg(R.TABLE_FILE.encode(), I, J, K, lonstep, d(287.04 / (2 / 7)), d(R.RDGAS), d(R.GAS_CONSTANT), d(R.WTMH2O),
+                                d(R.WTMOZONE), d(300.0), d(2e-7), d(100.0), d(370.0), d(1.0), d(1368.22),
+                                *[_cp(keep[k]) for k in ("p_full", "p_half", "z_full", "z_half", "t", "q", "o3", "t_surf", "albedo", "coszen")],
+                                _cp(tdt), _cp(tr), _cp(fs), _cp(fl), _cp(olr), _cp(ts))
+    assert rc == 0
+    lat = np.zeros((J, I))
+    o = R.RrtmRadiation(lat, lat, 600.0, o3=m["o3"], lonstep=lonstep)
+    o.zenith = lambda s: m["coszen"]
+    t2, fsw, flw = o(0.0, m["p_full"], m["p_half"], m["z_full"], m["z_half"], m["t"], m["q"], m["t_surf"], m["albedo"], tdt0.copy())
+    assert rel(tr, o.tdt_rad) < 1e-10 and rel(tdt, t2) < 1e-10
+    assert rel(fs, fsw) < 1e-12 and rel(fl, flw) < 1e-12 and rel(olr, o.olr) < 1e-12 and rel(ts, o.toa_sw) < 1e-12
+
+
+def test_emulated_coszen_kernel_matches_oracle(emu):
+    a = R.Astronomy()
+    lat = np.repeat(np.linspace(-np.pi / 2, np.pi / 2, 17)[:, None], 16, 1)
+    lon = np.repeat(np.linspace(0, 2 * np.pi, 16, endpoint=False)[None, :], 17, 0)
+    d = C.c_double
+    for dt in (None, 7200 / 86400 * 2 * np.pi, 2 * np.pi):
+        for gmt, tsae in ((0.0, 0.0), (1.0, 0.3), (4.5, 2.0), (6.2, 5.5)):
+            dec = a.declination(a.angle(tsae))
+            cz, fr = np.zeros(lat.size), np.zeros(lat.size)
+            emu.rrtm_emu_coszen(lat.size, _cp(lat.ravel()), _cp(lon.ravel()), d(gmt), d(dec), d(-1.0 if dt is None else dt), 0, d(0.95), d(0.0),
+                                _cp(cz), _cp(fr))
+            oc, of, _ = a.diurnal_solar(lat, lon, gmt, tsae, dt)
+            assert np.abs(cz.reshape(lat.shape) - oc).max() < 1e-14 and np.abs(fr.reshape(lat.shape) - of).max() < 1e-13, (dt, gmt)
+    # frierson_solar_rad
+    cz = np.zeros(lat.size)
+    emu.rrtm_emu_coszen(lat.size, _cp(lat.ravel()), _cp(lon.ravel()), d(0.0), d(0.0), d(-1.0), 1, d(0.95), d(0.1), _cp(cz), None)
+    p2 = (1.0 - 3.0 * np.sin(lat) ** 2) / 4.0
+    assert np.abs(cz.reshape(lat.shape) - 0.25 * (1.0 + 0.95 * p2 + 0.1 * np.sin(lat))).max() < 1e-15
