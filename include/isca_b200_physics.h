@@ -158,6 +158,13 @@ int isca_b200_qe_moist_convection(IscaPhysics p, double dt, const double* Tin, c
                                   double* qref, int* convflag, int* kLZBs, double* cape, double* cin,
                                   double* invtau_q_relaxation, double* invtau_t_relaxation, double* Tref, int* kLCLs);
 
+/* dry_convection(Time, tg, p_full, p_half, dt_tg, cape, cin, lzb, lcl) (atmos_param/dry_convection/dry_convection.f90:105-186 with
+ * capecalc :190-299), the Schneider & Walker dry convective adjustment of convection_scheme = 'dry'.  tau, gamma: dry_convection_nml
+ * (no defaults in the reference).  tg, p_full [K][J][I], p_half [K+1][J][I]; out dt_tg [K][J][I] (K/s), cape, cin [J][I], int lzb, lcl
+ * [J][I] (1-based levels).  The reference's FATALs ("LCL defined, LZB not defined", "LCL above LZB") are returned as errors. */
+int isca_b200_dry_convection(IscaPhysics p, double tau, double gamma, const double* tg, const double* p_full, const double* p_half,
+                             double* dt_tg, double* cape, double* cin, int* lzb, int* lcl);
+
 /* device-resident timing of one kernel (which: 0 lscale_cond, 1 gray_rad_down, 2 gray_rad_up, 3 rayleigh,
  * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up, 6 surface_flux, 7 diffusivity, 8 qe_moist_convection) on
  * synthetic resident columns; returns average ms per launch (CUDA events) and the algorithmic bytes per launch. */
@@ -174,7 +181,8 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
 typedef struct IscaMoist_t* IscaMoist;
 typedef struct IscaMoistConfig {
   int abi_version;                 /* 2 */
-  int convection_scheme;           /* 0 'NONE', 1 'SIMPLE_BETTS_MILLER' (idealized_moist_phys.F90:391-426) */
+  int convection_scheme;           /* 0 'NONE', 1 'SIMPLE_BETTS_MILLER', 2 'DRY' (idealized_moist_phys.F90:391-426; 'DRY' needs
+                                    * isca_b200_moist_set_dry_convection; large-scale condensation is then skipped, :977) */
   int do_damping;                  /* damping_driver rayleigh sponge */
   double roughness_mom, roughness_heat, roughness_moist;      /* idealized_moist_phys_nml :136-138 */
   double mixed_layer_depth, albedo_value, rho_cp;             /* mixed_layer_nml depth, albedo_value; constants RHO_CP */
@@ -205,6 +213,8 @@ int isca_b200_moist_step(IscaMoist m, int n_steps);
  * 3-D [K][J][I]: 32 dt_ug, 33 dt_vg, 34 dt_tg, 35 dt_tracers(sphum) (physics tendencies), 36 diff_m, 37 diff_t */
 int isca_b200_moist_get(IscaMoist m, int id, double* host);
 int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
+/* dry_convection_nml: relaxation time scale tau [s] and lapse-rate factor gamma of convection_scheme = 'DRY' */
+int isca_b200_moist_set_dry_convection(IscaMoist m, double tau, double gamma);
 /* mixed_layer_init: ocean_qflux [J][I] (W/m2; `do_qflux` / `do_warmpool` of mixed_layer_nml, atmos_param/qflux/qflux.f90, or a
  * q-flux file), added to the slab's heat budget every step.  Call after isca_b200_moist_init (which zeroes it). */
 int isca_b200_moist_set_ocean_qflux(IscaMoist m, const double* host);

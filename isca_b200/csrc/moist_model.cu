@@ -33,6 +33,7 @@ struct IscaMoist_t {
   double time_s = 0.0;                                         // Time of atmosphere(Time), seconds since Time_init
   double dt_last = 0.0;                                        // rrtm_vars dt_last (radiation alarm)
   long n_rad_calls = 0;
+  double dry_tau = 0.0, dry_gamma = 0.0;                       // dry_convection_nml (convection_scheme = 'DRY')
 };
 
 namespace {
@@ -134,12 +135,19 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
     conv_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, tg_p, q_p, m->tg_tmp.p, m->qg_tmp.p, m->dt_t.p, m->dt_q.p,
                                                m->rain.p, m->conv_rain.p, m->precip.p);
     t_in = m->tg_tmp.p; q_in = m->qg_tmp.p;
+  } else if (m->mc.convection_scheme == 2) {                     // 'DRY' (:918-928): dt_tg += conv_dt_tg; no precipitation
+    launch_dry_convection(p, m->dry_tau, m->dry_gamma, tg_p, pf_p, ph_p, m->c_Tref.p, m->c_dT.p, m->cape.p, m->cin.p, klzb, klcl);
+    add1_kernel<<<nblk(n3), 256, 0, st>>>(n3, m->dt_t.p, m->c_dT.p);
+    MCK(cudaMemsetAsync(m->precip.p, 0, nc * sizeof(double), st));
+    MCK(cudaMemsetAsync(m->conv_rain.p, 0, nc * sizeof(double), st));
   } else {
     MCK(cudaMemsetAsync(m->precip.p, 0, nc * sizeof(double), st));
     MCK(cudaMemsetAsync(m->conv_rain.p, 0, nc * sizeof(double), st));
   }
-  launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
-  cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
+  if (m->mc.convection_scheme != 2) {                            // `if (r_conv_scheme .ne. DRY_CONV)` (:977): no large-scale condensation
+    launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
+    cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
+  }
   if (!m->rr) launch_gray_down(p, m->lat2d.p, ph_c, tg_p, q_p, m->albedo.p, m->net_sw.p, m->lw_down.p);   // q = grid_tracers(previous, nsphum), :1068
   // surface_flux on the lowest model level (:1076-1132)
   sub_kernel<<<nblk(nc), 256, 0, st>>>(nc, m->z_atm.p, zf_c + (size_t)(K - 1) * nc, m->z_surf.p);
@@ -235,8 +243,8 @@ int isca_b200_moist_create_ranked(const IscaConfig* dyn, const IscaPhysicsConfig
   IscaMoist m = nullptr;
   if (!dyn || !phys || !mc || !out) return mfail(nullptr, "null argument");
   if (mc->abi_version != 2) return mfail(nullptr, "IscaMoistConfig abi_version mismatch");
-  if (mc->convection_scheme != 0 && mc->convection_scheme != 1)
-    return mfail(nullptr, "idealized_moist_phys: Invalid convection scheme (only NONE and SIMPLE_BETTS_MILLER are built)");
+  if (mc->convection_scheme < 0 || mc->convection_scheme > 2)
+    return mfail(nullptr, "idealized_moist_phys: Invalid convection scheme (NONE, SIMPLE_BETTS_MILLER and DRY are built)");
   if (dyn->num_tracers != 1) return mfail(nullptr, "idealized_moist_model needs the sphum grid tracer (num_tracers = 1)");
   m = new IscaMoist_t();
   m->mc = *mc;
@@ -334,6 +342,8 @@ int isca_b200_moist_init(IscaMoist m) {
 int isca_b200_moist_step(IscaMoist m, int n_steps) {
   if (!m) return mfail(nullptr, "null handle");
   if (!m->initialized) return mfail(m, "idealized_moist_phys: module not initialized (isca_b200_moist_init has not been called)");
+  if (m->mc.convection_scheme == 2 && !(m->dry_tau > 0.0))
+    return mfail(m, "dry_convection: tau / gamma not set (isca_b200_moist_set_dry_convection; dry_convection_nml has no defaults)");
   IscaCoreView v;
   if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
   cudaEvent_t e0, e1, e2;
@@ -419,6 +429,13 @@ int isca_b200_moist_set_t_surf(IscaMoist m, const double* host) {
   if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
   MCK(cudaMemcpyAsync(m->t_surf.p, host, m->nc * sizeof(double), cudaMemcpyHostToDevice, v.st));
   MCK(cudaStreamSynchronize(v.st));
+  return 0;
+}
+
+int isca_b200_moist_set_dry_convection(IscaMoist m, double tau, double gamma) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!(tau > 0.0)) return mfail(m, "dry_convection: tau must be positive");
+  m->dry_tau = tau; m->dry_gamma = gamma;
   return 0;
 }
 

@@ -142,6 +142,8 @@ int build_lcl_table(IscaPhysics p);                                             
 void launch_sbm_convection(IscaPhysics p, double dt, const double* Tin, const double* qin, const double* p_full, const double* p_half,
                            double* rain, double* deltaT, double* deltaq, double* qref, double* Tref, int* convflag, int* kLZBs, int* kLCLs,
                            double* cape, double* cin, double* itq, double* itt);
+void launch_dry_convection(IscaPhysics p, double tau, double gamma, const double* tg, const double* p_full, const double* p_half, double* tp,
+                           double* dt_tg, double* cape, double* cin, int* lzb, int* lcl);                         // physics_dry.cu
 void launch_diffusivity(IscaPhysics p, const double* t, const double* q, const double* u, const double* v, const double* z_full,
                         const double* z_half, const double* u_star, const double* b_star, double* h, double* k_m, double* k_t);
 

@@ -18,7 +18,7 @@ PHYSICS_EXPORTS = [
     "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_rayleigh_damping",
     "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
     "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
-    "isca_b200_mo_diff", "isca_b200_surface_flux", "isca_b200_diffusivity", "isca_b200_qe_moist_convection",
+    "isca_b200_mo_diff", "isca_b200_surface_flux", "isca_b200_diffusivity", "isca_b200_qe_moist_convection", "isca_b200_dry_convection",
 ]
 
 SURFACE_FLUX_IN = ("t_atm", "q_atm", "u_atm", "v_atm", "p_atm", "z_atm", "p_surf", "t_surf", "t_ca", "u_surf", "v_surf",
@@ -90,6 +90,7 @@ def _lib():
         lib.isca_b200_diffusivity.argtypes = [vp] + [dp] * 13
         ip = C.POINTER(C.c_int)
         lib.isca_b200_qe_moist_convection.argtypes = [vp, C.c_double] + [dp] * 9 + [ip, ip] + [dp] * 5 + [ip]
+        lib.isca_b200_dry_convection.argtypes = [vp, C.c_double, C.c_double] + [dp] * 6 + [ip, ip]
         _bound = True
     return lib
 
@@ -319,6 +320,17 @@ class ColumnPhysics:
                                                          _p(o["deltaT"]), _p(o["deltaq"]), _p(o["qref"]), ip(o["convflag"]), ip(o["kLZBs"]),
                                                          _p(o["CAPE"]), _p(o["CIN"]), _p(o["invtau_q_relaxation"]),
                                                          _p(o["invtau_t_relaxation"]), _p(o["Tref"]), ip(o["kLCLs"])), "qe_moist_convection")
+        return o
+
+    def dry_convection(self, tau, gamma, tg, p_full, p_half):
+        """dry_convection (dry_convection.f90:105) -> dict(dt_tg, cape, cin, lzb, lcl)"""
+        tg, p_full = (_in(x, self.s3, n) for x, n in ((tg, "tg"), (p_full, "p_full")))
+        p_half = _in(p_half, self.s3h, "p_half")
+        o = dict(dt_tg=np.empty(self.s3), cape=np.empty(self.s2), cin=np.empty(self.s2), lzb=np.empty(self.s2, dtype=np.int32),
+                 lcl=np.empty(self.s2, dtype=np.int32))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self._ck(self._lib.isca_b200_dry_convection(self._h, float(tau), float(gamma), _p(tg), _p(p_full), _p(p_half), _p(o["dt_tg"]),
+                                                    _p(o["cape"]), _p(o["cin"]), ip(o["lzb"]), ip(o["lcl"])), "dry_convection")
         return o
 
     def time_kernel(self, which, reps=20):

@@ -1074,6 +1074,57 @@ DENS_H2O = 1000.0
 RHO_CP = 1.035e3 * 3989.24495292815
 
 
+def dry_convection(tg, p_full, p_half, tau, gamma, rdgas=RDGAS, cp_air=CP_AIR):
+    """dry_convection + capecalc (atmos_param/dry_convection/dry_convection.f90:105-299): arrays [K, ...] top-down.
+    -> dt_tg, cape, cin, lzb, lcl (1-based level indices, btm = K)"""
+    K = tg.shape[0]
+    shp = tg.shape[1:]
+    cons1 = rdgas / cp_air
+    btm = K
+    tp = tg.copy()
+    for k in range(btm - 1, 0, -1):                                  # 1-based k
+        zdpkpk = np.exp(cons1 * np.log(p_full[k - 1] / p_full[k]))
+        tp[k - 1] = tp[k] + gamma * (tp[k] * zdpkpk - tp[k])
+    cape, cin = np.zeros(shp), np.zeros(shp)
+    lzb = np.full(shp, btm, dtype=np.int64)
+    lcl = np.full(shp, btm, dtype=np.int64)
+    for k in range(btm - 1, 0, -1):
+        with np.errstate(divide="ignore", invalid="ignore"):         # p_half(1) = 0 in sigma coordinates: log(inf), as in the Fortran
+            lg = np.log(p_half[k] / p_half[k - 1])
+        unst = tp[k - 1] > tg[k - 1]
+        nocloud = lzb == btm
+        a = unst & nocloud
+        with np.errstate(invalid="ignore"):
+            cape = np.where(a, cape + rdgas * (tp[k - 1] - tg[k - 1]) * lg, cape)
+        lcl = np.where(a & (tp[k] < tg[k]), k, lcl)
+        above = (tp[k - 2] < tg[k - 2]) if k > 1 else np.ones(shp, bool)
+        lzb = np.where(a & above, k, lzb)
+        tp[k - 1] = np.where(unst & ~nocloud, tg[k - 1], tp[k - 1])
+        stab = tp[k - 1] <= tg[k - 1]                                # re-evaluated after the reset above, as the Fortran does
+        nocloud = lzb == btm
+        with np.errstate(invalid="ignore"):
+            cin = np.where(stab & nocloud & (lcl == btm), cin - rdgas * (tp[k - 1] - tg[k - 1]) * lg, cin)
+        tp[k - 1] = np.where(stab & ~nocloud, tg[k - 1], tp[k - 1])
+    tp = np.where((cin > cape)[None], tg, tp)
+    if ((lcl != btm) & (lzb == btm)).any():
+        raise FloatingPointError("dry_convection: LCL defined, LZB not defined")
+    if (lcl < lzb).any():
+        raise FloatingPointError("dry_convection: LCL above LZB")
+    none = (lcl == btm) & (lzb == btm)
+    cape, cin = np.where(none, 0.0, cape), np.where(none, 0.0, cin)
+    ener_int, dp = np.zeros(shp), np.zeros(shp)
+    for k in range(1, K + 1):
+        inside = (k >= lzb) & (k <= btm)
+        dph = p_half[k] - p_half[k - 1]
+        ener_int = np.where(inside, ener_int + dph * (tg[k - 1] - tp[k - 1]), ener_int)
+        dp = np.where(inside, dp + dph, dp)
+        tp[k - 1] = np.where(inside, tp[k - 1], tg[k - 1])
+    ener_int = ener_int / dp
+    for k in range(btm, 0, -1):
+        tp[k - 1] = np.where(k >= lzb, tp[k - 1] + ener_int, tp[k - 1])
+    return (tp - tg) / tau, cape, cin, lzb, lcl
+
+
 @dataclass
 class MoistPhysConfig:
     convection_scheme: str = "SIMPLE_BETTS_MILLER"
@@ -1092,6 +1143,9 @@ class MoistPhysConfig:
     # vert_turb_driver_nml
     constant_gust: float = 1.0
     use_tau: bool = True
+    # dry_convection_nml (convection_scheme = "DRY"; no defaults in the reference)
+    dry_tau: float = 0.0
+    dry_gamma: float = 0.0
     # damping_driver_nml
     trayfric: float = 0.0
     sponge_pbottom: float = 50.0
@@ -1133,6 +1187,12 @@ class IdealizedMoistPhys:
             rain = rain / delta_t
             precip = rain
             self.diag.update(convflag=o["convflag"], cape=o["CAPE"])
+        elif c.convection_scheme == "DRY":                               # idealized_moist_phys.F90:918-928
+            conv_dt_tg, cape, cin, lzb, lcl = dry_convection(tg_p, core.p_full[prev], core.p_half[prev], c.dry_tau, c.dry_gamma)
+            conv_dt_qg = np.zeros_like(tg_p)
+            tg_tmp, qg_tmp = conv_dt_tg * delta_t + tg_p, q_p
+            precip = zero2
+            self.diag.update(cape=cape, cin=cin, lzb=lzb)
         elif c.convection_scheme == "NONE":
             conv_dt_tg, conv_dt_qg = np.zeros_like(tg_p), np.zeros_like(tg_p)
             tg_tmp, qg_tmp = tg_p, q_p
@@ -1141,12 +1201,13 @@ class IdealizedMoistPhys:
             raise ValueError("convection scheme not restated")
         dt_tg = dt_tg + conv_dt_tg
         dt_q = dt_q + conv_dt_qg
-        rain, cond_dt_tg, cond_dt_qg = lscale_cond(self.svp, tg_tmp, qg_tmp, core.p_full[prev], core.p_half[prev], hc=c.hc, do_evap=c.do_evap)
-        cond_dt_tg, cond_dt_qg = cond_dt_tg / delta_t, cond_dt_qg / delta_t
-        rain = rain / delta_t
-        precip = precip + rain
-        dt_tg = dt_tg + cond_dt_tg
-        dt_q = dt_q + cond_dt_qg
+        if c.convection_scheme != "DRY":                                   # `if (r_conv_scheme .ne. DRY_CONV)` (:977)
+            rain, cond_dt_tg, cond_dt_qg = lscale_cond(self.svp, tg_tmp, qg_tmp, core.p_full[prev], core.p_half[prev], hc=c.hc, do_evap=c.do_evap)
+            cond_dt_tg, cond_dt_qg = cond_dt_tg / delta_t, cond_dt_qg / delta_t
+            rain = rain / delta_t
+            precip = precip + rain
+            dt_tg = dt_tg + cond_dt_tg
+            dt_q = dt_q + cond_dt_qg
         if self.rrtm is None:
             d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo)
             net_surf_sw_down = (1.0 - self.albedo) * d["sw_down_surf"]

@@ -39,8 +39,11 @@ static inline double __shfl_xor_sync(unsigned, double v, int o) {
   return r;
 }
 
+static inline int atomicExch(int* a, int v) { int o = __atomic_exchange_n(a, v, __ATOMIC_SEQ_CST); return o; }
+
 #include "../../isca_b200/csrc/rrtm_tables.h"
 #include "../../isca_b200/csrc/rrtm_kernels.h"
+#include "../../isca_b200/csrc/physics_dry_kernels.h"
 
 using namespace rrtm;
 using namespace rrtm_k;
@@ -162,6 +165,17 @@ int rrtm_emu_run_rrtmg(const char* table_path, int I, int J, int K, int lonstep,
   FinishArgs fa{(int)nm, K, swhr.data(), lwhr.data(), swu.data(), swd.data(), lwu.data(), lwd.data(), tdt, tdt_rad, flux_sw, flux_lw, olr, toa_sw,
                 ls, I};
   launch(Gm, T, [=]() { rrtm_finish_kernel(fa); });
+  return 0;
+}
+
+// dry_convection_kernel (physics_dry_kernels.h) on host planes [K][ncol]
+int emu_dry_convection(int ncol, int K, double tau, double gamma, double cons1, double rdgas, const double* tg, const double* p_full,
+                       const double* p_half, double* dt_tg, double* cape, double* cin, int* lzb, int* lcl, int* err) {
+  std::vector<double> tp((size_t)ncol * K);
+  double* tpp = tp.data();
+  launch((ncol + 127) / 128, 128, [=]() {
+    dryconv_k::dry_convection_kernel(ncol, K, tau, gamma, cons1, rdgas, tg, p_full, p_half, tpp, dt_tg, cape, cin, lzb, lcl, err);
+  });
   return 0;
 }
 

@@ -266,3 +266,55 @@ def test_run_rrtmg_lonstep(lib_built, lonstep):
     full.zenith = o.zenith
     full(0.0, m["p_full"], m["p_half"], m["z_full"], m["z_half"], m["t"], m["q"], m["t_surf"], m["albedo"], np.zeros((K, J, I)))
     assert rel(out["flux_lw"][:, ::lonstep], full.lw_flux[:, ::lonstep]) < 1e-11
+
+
+def test_dry_convection_parity(lib_built):
+    """dry_convection (Schneider & Walker adjustment) through the C ABI: indices bit-exact, tendencies 1e-12"""
+    from isca_b200 import api, physics
+    from oracle import physics as PH
+    from test_rrtm_host import dry_columns
+    J, I, K = 8, 32, 25
+    tg, pf, ph = dry_columns(J, I, K, 11)
+    cp = physics.ColumnPhysics(I, J, K)
+    o = cp.dry_convection(14400.0, 0.7, tg, pf, ph)
+    dt, cape, cin, lzb, lcl = PH.dry_convection(tg, pf, ph, 14400.0, 0.7)
+    assert np.array_equal(o["lzb"], lzb) and np.array_equal(o["lcl"], lcl)
+    assert rel(o["dt_tg"], dt) < 1e-12 and rel(o["cape"], cape) < 1e-12
+    with pytest.raises(api.IscaError):
+        cp.dry_convection(0.0, 0.7, tg, pf, ph)          # dry_convection_nml has no defaults: tau must be given
+    cp.close()
+
+
+def test_moist_model_dry_convection_scheme(lib_built):
+    """convection_scheme = 'DRY': dry adjustment, no large-scale condensation (idealized_moist_phys.F90:918-928, 977)"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    cfg, core, mp = build("T21", 25, 900.0, "NONE", seed=4)
+    unstable_boundary_layer(core, mp, amp=14.0)             # dry-adiabatically unstable lower troposphere
+    mp.c.convection_scheme, mp.c.dry_tau, mp.c.dry_gamma = "DRY", 7200.0, 0.7
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS), convection_scheme="DRY",
+                              mixed_layer_depth=2.5, albedo_value=0.31)
+    m.set_dry_convection(7200.0, 0.7)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    for step in range(3):
+        core.step(physics=True)
+        m.atmosphere(1)
+        if step == 0:
+            assert (mp.diag["lzb"] < 25).any() and rel(m.get("cape"), mp.diag["cape"]) < 1e-11
+            assert np.abs(m.get("precip")).max() == 0.0
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+    m.atmosphere_end()
+    m2 = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS), convection_scheme="DRY")
+    m2.core.cold_start()
+    m2.idealized_moist_phys_init()
+    with pytest.raises(api.IscaError):
+        m2.atmosphere(1)                                     # tau / gamma not set
+    m2.atmosphere_end()

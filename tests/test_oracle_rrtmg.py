@@ -270,3 +270,16 @@ def test_lonstep_interpolation():
     assert np.allclose(sub.tdt_rad[:, :, ::4], full.tdt_rad[:, :, ::4], rtol=1e-12, atol=1e-20)
     assert np.allclose(sub.lw_flux[:, 1], 0.25 * full.lw_flux[:, 4] + 0.75 * full.lw_flux[:, 0], rtol=1e-14)
     assert np.allclose(sub.lw_flux[:, 7], 0.75 * full.lw_flux[:, 0] + 0.25 * full.lw_flux[:, 4], rtol=1e-14)     # wraps around
+
+
+def test_moist_oracle_dry_convection_scheme():
+    """the oracle dispatcher with convection_scheme = 'DRY' (what tests/test_gpu_rrtm.py compares the GPU model with)"""
+    from test_gpu_moist import build
+    from rrtm_cases import unstable_boundary_layer
+    cfg, core, mp = build("T21", 25, 900.0, "NONE", seed=4)
+    unstable_boundary_layer(core, mp, amp=14.0)
+    mp.c.convection_scheme, mp.c.dry_tau, mp.c.dry_gamma = "DRY", 7200.0, 0.7
+    t0 = core.tg[core.previous].copy()
+    core.step(physics=True)
+    assert (mp.diag["lzb"] < 25).any() and (mp.diag["cape"] > 0).any()
+    assert np.abs(mp.diag["precip"]).max() == 0.0 and np.isfinite(core.tg[core.current]).all()

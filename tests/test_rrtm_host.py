@@ -222,3 +222,40 @@ def test_emulated_coszen_kernel_matches_oracle(emu):
     emu.rrtm_emu_coszen(lat.size, _cp(lat.ravel()), _cp(lon.ravel()), d(0.0), d(0.0), d(-1.0), 1, d(0.95), d(0.1), _cp(cz), None)
     p2 = (1.0 - 3.0 * np.sin(lat) ** 2) / 4.0
     assert np.abs(cz.reshape(lat.shape) - 0.25 * (1.0 + 0.95 * p2 + 0.1 * np.sin(lat))).max() < 1e-15
+
+
+def dry_columns(J, I, K, seed):
+    """columns with unstable layers near the surface, stable caps, elevated unstable layers above a cloud top, fully stable ones"""
+    rng = np.random.default_rng(seed)
+    ps = rng.uniform(9.0e4, 1.03e5, (J, I))
+    ph = (np.linspace(0.0, 1.0, K + 1) ** 1.3)[:, None, None] * ps[None]
+    ph[0] = 10.0
+    pf = 0.5 * (ph[1:] + ph[:-1])
+    theta = 300.0 + rng.uniform(-1.0, 1.0, (J, I))[None] + np.cumsum(rng.normal(0.6, 2.5, (K, J, I))[::-1], axis=0)[::-1]
+    tg = theta * (pf / 1.0e5) ** (2.0 / 7.0)
+    tg[:, 0, 0] = 250.0 * (pf[:, 0, 0] / 1.0e5) ** 0.1            # very stable column: no convection at all
+    return tg, pf, ph
+
+
+def test_emulated_dry_convection_kernel_matches_oracle(emu):
+    """dry_convection_kernel under thread emulation against the NumPy restatement of dry_convection / capecalc"""
+    from oracle import physics as PH
+    J, I, K = 6, 20, 18
+    tg, pf, ph = dry_columns(J, I, K, 3)
+    tau, gamma = 14400.0, 0.7
+    dt, cape, cin, lzb, lcl = PH.dry_convection(tg, pf, ph, tau, gamma)
+    assert (lzb < K).any() and (lzb == K).any() and (cape > 0).any()          # convecting and non-convecting columns
+    nc = J * I
+    o_dt, o_cape, o_cin = np.zeros((K, J, I)), np.zeros((J, I)), np.zeros((J, I))
+    o_lzb, o_lcl, err = np.zeros((J, I), dtype=np.int32), np.zeros((J, I), dtype=np.int32), np.zeros(1, dtype=np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    d = C.c_double
+    emu.emu_dry_convection(nc, K, d(tau), d(gamma), d(PH.RDGAS / PH.CP_AIR), d(PH.RDGAS), _cp(tg), _cp(pf), _cp(ph), _cp(o_dt), _cp(o_cape),
+                           _cp(o_cin), ip(o_lzb), ip(o_lcl), ip(err))
+    assert err[0] == 0
+    assert np.array_equal(o_lzb, lzb) and np.array_equal(o_lcl, lcl)
+    assert np.abs(o_dt - dt).max() <= 1e-13 * np.abs(dt).max()
+    assert np.abs(o_cape - cape).max() <= 1e-12 * cape.max() and np.abs(o_cin - cin).max() <= 1e-12 * max(cin.max(), 1e-30)
+    # energy conservation of the adjustment: the mass-weighted temperature change vanishes in every column
+    dp = ph[1:] - ph[:-1]
+    assert np.abs((dt * dp).sum(axis=0)).max() < 1e-12 * np.abs(dt * dp).sum(axis=0).max() + 1e-9
