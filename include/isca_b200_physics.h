@@ -213,6 +213,11 @@ int isca_b200_moist_step(IscaMoist m, int n_steps);
  * 3-D [K][J][I]: 32 dt_ug, 33 dt_vg, 34 dt_tg, 35 dt_tracers(sphum) (physics tendencies), 36 diff_m, 37 diff_t */
 int isca_b200_moist_get(IscaMoist m, int id, double* host);
 int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
+/* Surface properties [J][I] that idealized_moist_phys_init / mixed_layer_init derive from the land options (land mask file,
+ * land_h_capacity_prefactor, land_albedo_prefactor, land_roughness_prefactor; idealized_moist_phys.F90:565-616, mixed_layer.F90:380-470):
+ * id 20 albedo, 21 rough_mom, 22 rough_heat, 23 rough_moist, 24 surface heat capacity (J/m2/K), 25 land mask (0. / 1.; used by
+ * surface_flux for land_humidity_prefactor / land_evap_prefactor).  Call after isca_b200_moist_init (which fills the aquaplanet values). */
+int isca_b200_moist_set_surface(IscaMoist m, int id, const double* host);
 /* dry_convection_nml: relaxation time scale tau [s] and lapse-rate factor gamma of convection_scheme = 'DRY' */
 int isca_b200_moist_set_dry_convection(IscaMoist m, double tau, double gamma);
 /* mixed_layer_init: ocean_qflux [J][I] (W/m2; `do_qflux` / `do_warmpool` of mixed_layer_nml, atmos_param/qflux/qflux.f90, or a

@@ -84,6 +84,9 @@ __global__ void tau_plus1_kernel(size_t n, double dt, const double* __restrict__
     uu[i] = um[i] + dt * udt[i]; vv[i] = vm[i] + dt * vdt[i]; tt[i] = tm[i] + dt * tdt[i]; qq[i] = qm[i] + dt * qdt[i];
   }
 }
+__global__ void mask_to_int_kernel(size_t n, const double* __restrict__ a, int* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = a[i] != 0.0 ? 1 : 0;
+}
 __global__ void add1_kernel(size_t n, double* a, const double* da) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = a[i] + da[i];
 }
@@ -428,6 +431,31 @@ int isca_b200_moist_set_t_surf(IscaMoist m, const double* host) {
   IscaCoreView v;
   if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
   MCK(cudaMemcpyAsync(m->t_surf.p, host, m->nc * sizeof(double), cudaMemcpyHostToDevice, v.st));
+  MCK(cudaStreamSynchronize(v.st));
+  return 0;
+}
+
+int isca_b200_moist_set_surface(IscaMoist m, int id, const double* host) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!host) return mfail(m, "null input array");
+  if (!m->initialized) return mfail(m, "moist_set_surface: call isca_b200_moist_init first");
+  IscaCoreView v;
+  if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
+  double* dst = nullptr;
+  switch (id) {
+    case 20: dst = m->albedo.p; break;
+    case 21: dst = m->rough_m.p; break;
+    case 22: dst = m->rough_h.p; break;
+    case 23: dst = m->rough_q.p; break;
+    case 24: dst = m->phy->state[ST_ML_HEAT_CAP].p; break;
+    case 25: dst = m->dts.p; break;                              // staged, converted to the int mask below
+    default: return mfail(m, "moist_set_surface: unknown field id");
+  }
+  MCK(cudaMemcpyAsync(dst, host, m->nc * sizeof(double), cudaMemcpyHostToDevice, v.st));
+  if (id == 25) {
+    mask_to_int_kernel<<<nblk(m->nc), 256, 0, v.st>>>(m->nc, m->dts.p, reinterpret_cast<int*>(m->iwork.p));
+    MCK(cudaMemsetAsync(m->dts.p, 0, m->nc * sizeof(double), v.st));
+  }
   MCK(cudaStreamSynchronize(v.st));
   return 0;
 }

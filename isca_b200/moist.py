@@ -9,7 +9,7 @@ from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 
 MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
-                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
+                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
                  q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
@@ -48,6 +48,7 @@ def _lib():
         lib.isca_b200_moist_get.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_moist_set_t_surf.argtypes = [vp, dp]
         lib.isca_b200_moist_set_ocean_qflux.argtypes = [vp, dp]
+        lib.isca_b200_moist_set_surface.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_moist_set_dry_convection.argtypes = [vp, C.c_double, C.c_double]
         lib.isca_b200_moist_timing.argtypes = [vp, dp, dp]
         _bound = True
@@ -153,6 +154,17 @@ class MoistAtmosphere:
         if a.shape != self.s2:
             raise IscaError("t_surf has the wrong shape")
         self._ck(self._lib.isca_b200_moist_set_t_surf(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_t_surf")
+
+    SURFACE_FIELDS = dict(albedo=20, rough_mom=21, rough_heat=22, rough_moist=23, heat_capacity=24, land=25)
+
+    def set_surface(self, name, field):
+        """per-column surface properties of the land options ([lat, lon]; `land` is a 0/1 mask); after idealized_moist_phys_init"""
+        if name not in self.SURFACE_FIELDS:
+            raise IscaError(f"unknown surface field {name}")
+        a = np.ascontiguousarray(field, dtype=np.float64)
+        if a.shape != self.s2:
+            raise IscaError(f"{name} has the wrong shape")
+        self._ck(self._lib.isca_b200_moist_set_surface(self._h, self.SURFACE_FIELDS[name], a.ctypes.data_as(C.POINTER(C.c_double))), "set_surface")
 
     def set_dry_convection(self, tau, gamma):
         """dry_convection_nml (convection_scheme = 'DRY'): relaxation time tau [s], lapse-rate factor gamma"""

@@ -1166,6 +1166,8 @@ class IdealizedMoistPhys:
         self.albedo = np.full(shp, cfg.albedo_value)
         self.heat_capacity = np.full(shp, cfg.depth * RHO_CP)
         self.ocean_qflux = np.zeros(shp)
+        # land options (idealized_moist_phys_init / mixed_layer_init): per-column roughness, land mask (None = aquaplanet values)
+        self.rough_mom = self.rough_heat = self.rough_moist = self.land = None
         self.diag = {}
         # do_rrtm_radiation (idealized_moist_phys.F90:1167-1177): an oracle.rrtmg.RrtmRadiation instead of the grey scheme
         self.rrtm = None
@@ -1215,9 +1217,11 @@ class IdealizedMoistPhys:
         sf = surface_flux(self.svp, self.mo, self.sflux, t_atm=tg_p[K - 1], q_atm_in=q_p[K - 1], u_atm=ug_p[K - 1], v_atm=vg_p[K - 1],
                           p_atm=core.p_full[cur][K - 1], z_atm=core.z_full[cur][K - 1] - self.z_surf, p_surf=core.p_half[cur][K],
                           t_surf=self.t_surf, t_ca=self.t_surf, q_surf=self.q_surf, u_surf=zero2, v_surf=zero2,
-                          rough_mom=np.full_like(zero2, c.roughness_mom), rough_heat=np.full_like(zero2, c.roughness_heat),
-                          rough_moist=np.full_like(zero2, c.roughness_moist), rough_scale=np.full_like(zero2, c.roughness_mom),
-                          gust=self.gust, land=np.zeros(zero2.shape, bool))
+                          rough_mom=np.full_like(zero2, c.roughness_mom) if self.rough_mom is None else self.rough_mom,
+                          rough_heat=np.full_like(zero2, c.roughness_heat) if self.rough_heat is None else self.rough_heat,
+                          rough_moist=np.full_like(zero2, c.roughness_moist) if self.rough_moist is None else self.rough_moist,
+                          rough_scale=np.full_like(zero2, c.roughness_mom) if self.rough_mom is None else self.rough_mom,
+                          gust=self.gust, land=np.zeros(zero2.shape, bool) if self.land is None else self.land)
         self.q_surf = sf["q_surf"]
         if self.rrtm is None:
             dt_tg, _ = self.rad.up(self.t_surf, self.albedo, core.p_half[cur], dt_tg)

@@ -318,3 +318,48 @@ def test_moist_model_dry_convection_scheme(lib_built):
     with pytest.raises(api.IscaError):
         m2.atmosphere(1)                                     # tau / gamma not set
     m2.atmosphere_end()
+
+
+def test_moist_model_with_land_surface_properties(lib_built):
+    """the land options of idealized_moist_phys_init / mixed_layer_init as per-column fields: a land mask (surface_flux humidity and
+    evaporation prefactors), land heat capacity, albedo and roughness; three steps against the oracle"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=12)
+    unstable_boundary_layer(core, mp)
+    Kk, J, I = core.tg[0].shape
+    rng = np.random.default_rng(12)
+    land = np.zeros((J, I), bool)
+    land[J // 4: J // 2, I // 8: I // 2] = True
+    land[3 * J // 5: 4 * J // 5, 5 * I // 8:] = True
+    albedo = np.where(land, 0.31 * 1.3, 0.31)
+    heat_cap = np.where(land, 0.1, 1.0) * mp.heat_capacity
+    rough = np.where(land, 10.0, 1.0) * 3.21e-05
+    mp.albedo, mp.heat_capacity, mp.land = albedo.copy(), heat_cap.copy(), land.copy()
+    mp.rough_mom = mp.rough_heat = mp.rough_moist = rough.copy()
+    mp.sflux.land_humidity_prefactor, mp.sflux.land_evap_prefactor = 0.7, 0.6
+    phys = dict(FRIERSON_PHYS, land_humidity_prefactor=0.7, land_evap_prefactor=0.6)
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER",
+                              mixed_layer_depth=2.5, albedo_value=0.31)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    for name, f in (("albedo", albedo), ("heat_capacity", heat_cap), ("land", land.astype(float)), ("rough_mom", rough), ("rough_heat", rough),
+                    ("rough_moist", rough)):
+        m.set_surface(name, f)
+    for step in range(3):
+        core.step(physics=True)
+        m.atmosphere(1)
+        assert rel(m.get("flux_q"), mp.diag["flux_q"]) < TOL and rel(m.get("flux_t"), mp.diag["flux_t"]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+    # the land columns did behave differently: faster surface temperature response of the small heat capacity
+    assert np.abs(m.get("delta_t_surf")[land]).mean() > 2.0 * np.abs(m.get("delta_t_surf")[~land]).mean()
+    with pytest.raises(api.IscaError):
+        m.set_surface("albedo", np.zeros((J, I + 1)))
+    m.atmosphere_end()

@@ -283,3 +283,25 @@ def test_moist_oracle_dry_convection_scheme():
     core.step(physics=True)
     assert (mp.diag["lzb"] < 25).any() and (mp.diag["cape"] > 0).any()
     assert np.abs(mp.diag["precip"]).max() == 0.0 and np.isfinite(core.tg[core.current]).all()
+
+
+def test_moist_oracle_land_surface_properties():
+    """oracle dispatcher with per-column land properties (what the GPU land test compares with)"""
+    from test_gpu_moist import build
+    from rrtm_cases import unstable_boundary_layer
+    cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=12)
+    unstable_boundary_layer(core, mp)
+    Kk, J, I = core.tg[0].shape
+    land = np.zeros((J, I), bool)
+    land[J // 4: J // 2, I // 8: I // 2] = True
+    land[3 * J // 5: 4 * J // 5, 5 * I // 8:] = True
+    mp.albedo = np.where(land, 0.31 * 1.3, 0.31)
+    mp.heat_capacity = np.where(land, 0.1, 1.0) * mp.heat_capacity
+    mp.land = land
+    mp.rough_mom = mp.rough_heat = mp.rough_moist = np.where(land, 10.0, 1.0) * 3.21e-05
+    mp.sflux.land_humidity_prefactor, mp.sflux.land_evap_prefactor = 0.7, 0.6
+    for _ in range(3):
+        core.step(physics=True)
+    d = mp.diag["delta_t_surf"]
+    assert np.isfinite(core.tg[core.current]).all()
+    assert np.abs(d[land]).mean() > 2.0 * np.abs(d[~land]).mean()
