@@ -209,6 +209,8 @@ def _prototypes(header):
 def _expected_ctype(param):
     """C parameter declaration -> the ctypes class family the binding must use"""
     p = re.sub(r"\s+", " ", param)
+    if "[" in p:                                   # array parameter = pointer
+        return "ptr"
     if "double*" in p.replace(" *", "*"):
         return "double*"
     if "int*" in p.replace(" *", "*"):
@@ -252,3 +254,38 @@ def test_rrtm_ctypes_bindings_match_the_header(lib_built):
                 assert t in (C.POINTER(C.c_double), C.c_void_p), (name, p)
             else:
                 assert t is C.c_void_p or issubclass(t, C._Pointer), (name, p)
+
+
+def _check_bindings(lib, protos):
+    for name, params in protos.items():
+        at = getattr(lib, name).argtypes
+        assert at is not None, f"{name} has no argtypes"
+        assert len(at) == len(params), f"{name}: {len(at)} argtypes for {len(params)} parameters"
+        for t, p in zip(at, params):
+            want = _expected_ctype(p)
+            if want == "double":
+                assert t is C.c_double, (name, p)
+            elif want == "int":
+                assert t is C.c_int, (name, p)
+            elif want == "longlong":
+                assert t is C.c_longlong, (name, p)
+            elif want == "char*":
+                assert t is C.c_char_p, (name, p)
+            else:
+                assert t is C.c_void_p or issubclass(t, C._Pointer), (name, p)
+
+
+def test_physics_and_moist_ctypes_bindings_match_the_header(lib_built):
+    from isca_b200 import physics, moist
+    physics._lib()
+    lib = moist._lib()
+    _check_bindings(lib, _prototypes(PHYS_HEADER))
+
+
+def test_core_ctypes_bindings_match_the_header(lib_built):
+    from isca_b200 import api
+    lib = api.load_library()
+    protos = _prototypes(HEADER)
+    bound = {n: p for n, p in protos.items() if getattr(getattr(lib, n), "argtypes", None) is not None}
+    assert len(bound) >= 30
+    _check_bindings(lib, bound)
