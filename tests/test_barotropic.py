@@ -83,20 +83,3 @@ def test_restatement_conserves_energy_and_enstrophy_without_damping():
     s = BarotropicModel(BarotropicConfig(dt_atmos=900.0, damping_coeff=0.0, zeta_0=0.0, initial_zonal_wind="zero", spec_tracer=False, **T21))
     s.step()
     assert np.abs(s.u).max() < 1e-12
-
-
-@pytest.mark.gpu
-def test_barotropic_model_on_the_gpu_transforms(lib_built):
-    from isca_b200 import barotropic
-    m = barotropic.BarotropicAtmosphere(1800.0, **T21)
-    o = BarotropicModel(BarotropicConfig(dt_atmos=1800.0, **T21))
-    _compare(m, o, 1e-11)
-    for step in range(24):
-        m.atmosphere(1)
-        o.step()
-        _compare(m, o, 1e-9)
-    m.atmosphere_end()
-    big = barotropic.BarotropicAtmosphere(1200.0)                  # the reference's default T85 (256 x 128)
-    big.atmosphere(36)
-    assert np.isfinite(big.energy) and 100.0 < big.energy < 2000.0 and np.abs(big.v).max() < 100.0
-    big.atmosphere_end()

@@ -1,0 +1,174 @@
+"""GPU tests of the rows widened after the core path that use only kernels already verified on a B200 plus small
+new ones: the moist test-case options (use_tau = .false., q-flux, sponge), the dry convection scheme, the land surface properties,
+the barotropic model on the transform-level ABI.  Runs after the established suites and before the RRTMG tests."""
+import numpy as np
+import pytest
+
+from rrtm_cases import rrtm_setup, unstable_boundary_layer
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def run_test_case_options(radiation):
+    """what every shipped moist test case sets and the default does not: vert_turb_driver_nml use_tau = .false. (diffusivity from
+    previous + delta_t * tendencies), constant_gust = 0, the MiMA roughness lengths, the Rayleigh sponge, a tropical ocean q-flux
+    (qflux_mod) under the slab -- with grey and with RRTMG radiation, three steps against the oracle"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=9, damping=True)
+    unstable_boundary_layer(core, mp)                       # non-zero diffusivities above the lowest level
+    Kk, J, I = core.tg[0].shape
+    mp.c.use_tau, mp.c.constant_gust = False, 0.0
+    mp.c.roughness_mom = mp.c.roughness_heat = mp.c.roughness_moist = 3.21e-05
+    qf = moist.qflux(moist.lat_boundaries(J), I)
+    mp.ocean_qflux = qf.copy()
+    phys = dict(FRIERSON_PHYS, trayfric=-0.5, sponge_pbottom=5000.0)
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER",
+                              mixed_layer_depth=2.5, albedo_value=0.31, do_damping=1, use_tau=0, constant_gust=0.0,
+                              roughness_mom=3.21e-05, roughness_heat=3.21e-05, roughness_moist=3.21e-05)
+    if radiation == "rrtm":
+        rrtm_setup(core, mp, cfg, 1800, None)
+        m.use_rrtm(dict(co2ppmv=360.0, solr_cnst=1360.0), dt_rad=1800)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    m.set_ocean_qflux(qf)
+    for step in range(3):
+        core.step(physics=True)
+        m.atmosphere(1)
+        if step == 0:
+            assert mp.diag["diff_t"].max() > 0.0
+            assert rel(m.get("diff_t"), mp.diag["diff_t"]) < 1e-9 and rel(m.get("z_pbl"), mp.diag["z_pbl"]) < 1e-9
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(atm.get_field(api.F_U), core.ug[core.current]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+    m.atmosphere_end()
+
+
+def test_moist_model_test_case_options_grey(lib_built):
+    run_test_case_options("grey")
+
+
+def test_dry_convection_parity(lib_built):
+    """dry_convection (Schneider & Walker adjustment) through the C ABI: indices bit-exact, tendencies 1e-12"""
+    from isca_b200 import api, physics
+    from oracle import physics as PH
+    from test_rrtm_host import dry_columns
+    J, I, K = 8, 32, 25
+    tg, pf, ph = dry_columns(J, I, K, 11)
+    cp = physics.ColumnPhysics(I, J, K)
+    o = cp.dry_convection(14400.0, 0.7, tg, pf, ph)
+    dt, cape, cin, lzb, lcl = PH.dry_convection(tg, pf, ph, 14400.0, 0.7)
+    assert np.array_equal(o["lzb"], lzb) and np.array_equal(o["lcl"], lcl)
+    assert rel(o["dt_tg"], dt) < 1e-12 and rel(o["cape"], cape) < 1e-12
+    with pytest.raises(api.IscaError):
+        cp.dry_convection(0.0, 0.7, tg, pf, ph)          # dry_convection_nml has no defaults: tau must be given
+    cp.close()
+
+
+def test_moist_model_dry_convection_scheme(lib_built):
+    """convection_scheme = 'DRY': dry adjustment, no large-scale condensation (idealized_moist_phys.F90:918-928, 977)"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    cfg, core, mp = build("T21", 25, 900.0, "NONE", seed=4)
+    unstable_boundary_layer(core, mp, amp=14.0)             # dry-adiabatically unstable lower troposphere
+    mp.c.convection_scheme, mp.c.dry_tau, mp.c.dry_gamma = "DRY", 7200.0, 0.7
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS), convection_scheme="DRY",
+                              mixed_layer_depth=2.5, albedo_value=0.31)
+    m.set_dry_convection(7200.0, 0.7)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    for step in range(3):
+        core.step(physics=True)
+        m.atmosphere(1)
+        if step == 0:
+            assert (mp.diag["lzb"] < 25).any() and rel(m.get("cape"), mp.diag["cape"]) < 1e-11
+            assert np.abs(m.get("precip")).max() == 0.0
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+    m.atmosphere_end()
+    m2 = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS), convection_scheme="DRY")
+    m2.core.cold_start()
+    m2.idealized_moist_phys_init()
+    with pytest.raises(api.IscaError):
+        m2.atmosphere(1)                                     # tau / gamma not set
+    m2.atmosphere_end()
+
+
+def test_moist_model_with_land_surface_properties(lib_built):
+    """the land options of idealized_moist_phys_init / mixed_layer_init as per-column fields: a land mask (surface_flux humidity and
+    evaporation prefactors), land heat capacity, albedo and roughness; three steps against the oracle"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    cfg, core, mp = build("T21", 25, 900.0, "SIMPLE_BETTS_MILLER", seed=12)
+    unstable_boundary_layer(core, mp)
+    Kk, J, I = core.tg[0].shape
+    rng = np.random.default_rng(12)
+    land = np.zeros((J, I), bool)
+    land[J // 4: J // 2, I // 8: I // 2] = True
+    land[3 * J // 5: 4 * J // 5, 5 * I // 8:] = True
+    albedo = np.where(land, 0.31 * 1.3, 0.31)
+    heat_cap = np.where(land, 0.1, 1.0) * mp.heat_capacity
+    rough = np.where(land, 10.0, 1.0) * 3.21e-05
+    mp.albedo, mp.heat_capacity, mp.land = albedo.copy(), heat_cap.copy(), land.copy()
+    mp.rough_mom = mp.rough_heat = mp.rough_moist = rough.copy()
+    mp.sflux.land_humidity_prefactor, mp.sflux.land_evap_prefactor = 0.7, 0.6
+    phys = dict(FRIERSON_PHYS, land_humidity_prefactor=0.7, land_evap_prefactor=0.6)
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER",
+                              mixed_layer_depth=2.5, albedo_value=0.31)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    for name, f in (("albedo", albedo), ("heat_capacity", heat_cap), ("land", land.astype(float)), ("rough_mom", rough), ("rough_heat", rough),
+                    ("rough_moist", rough)):
+        m.set_surface(name, f)
+    for step in range(3):
+        core.step(physics=True)
+        m.atmosphere(1)
+        assert rel(m.get("flux_q"), mp.diag["flux_q"]) < TOL and rel(m.get("flux_t"), mp.diag["flux_t"]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+    # the land columns did behave differently: faster surface temperature response of the small heat capacity
+    assert np.abs(m.get("delta_t_surf")[land]).mean() > 2.0 * np.abs(m.get("delta_t_surf")[~land]).mean()
+    with pytest.raises(api.IscaError):
+        m.set_surface("albedo", np.zeros((J, I + 1)))
+    m.atmosphere_end()
+
+
+def test_barotropic_model_on_the_gpu_transforms(lib_built):
+    from isca_b200 import barotropic
+    from oracle.barotropic import BarotropicConfig, BarotropicModel
+    from test_barotropic import _compare, T21
+    m = barotropic.BarotropicAtmosphere(1800.0, **T21)
+    o = BarotropicModel(BarotropicConfig(dt_atmos=1800.0, **T21))
+    _compare(m, o, 1e-11)
+    for step in range(24):
+        m.atmosphere(1)
+        o.step()
+        _compare(m, o, 1e-9)
+    m.atmosphere_end()
+    big = barotropic.BarotropicAtmosphere(1200.0)                  # the reference's default T85 (256 x 128)
+    big.atmosphere(36)
+    assert np.isfinite(big.energy) and 100.0 < big.energy < 2000.0 and np.abs(big.v).max() < 100.0
+    big.atmosphere_end()
+
