@@ -172,3 +172,23 @@ def test_barotropic_model_on_the_gpu_transforms(lib_built):
     assert np.isfinite(big.energy) and 100.0 < big.energy < 2000.0 and np.abs(big.v).max() < 100.0
     big.atmosphere_end()
 
+
+
+def test_shallow_water_model_on_the_gpu_transforms(lib_built):
+    from isca_b200 import shallow
+    from oracle.shallow import ShallowConfig, ShallowModel
+    from test_barotropic import T21
+    from test_shallow import compare
+    m = shallow.ShallowAtmosphere(900.0, **T21)
+    o = ShallowModel(ShallowConfig(dt_atmos=900.0, **T21))
+    compare(m, o, 1e-11)
+    for step in range(24):
+        m.atmosphere(1)
+        o.step()
+        compare(m, o, 1e-8)
+    m.atmosphere_end()
+    big = shallow.ShallowAtmosphere(600.0)                         # the reference's default T85 (256 x 128)
+    big.atmosphere(48)
+    ens, div2, fr = big.global_diag()
+    assert np.isfinite(ens) and ens > 0 and fr < 1.0
+    big.atmosphere_end()
