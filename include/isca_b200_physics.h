@@ -44,7 +44,8 @@ typedef struct IscaPhysicsConfig {
   double tau_bm, rhbm, Tmin, Tmax, val_inc;
   /* two_stream_gray_rad_nml, the other values of rad_scheme (two_stream_gray_rad.F90:89-118, 214-238):
    * 0 'frierson', 1 'byrne' (Byrne & O'Gorman 2013), 2 'geen' (Geen et al. 2016, window band + water-vapour shortwave),
-   * 3 'schneider' (Schneider & Liu 2009 giant planet).  do_seasonal, do_read_co2 are not built. */
+   * 3 'schneider' (Schneider & Liu 2009 giant planet).  do_seasonal: isca_b200_two_stream_gray_rad_set_insolation /
+   * isca_b200_moist_set_seasonal; do_read_co2 is not built. */
   int rad_scheme;
   double ir_tau_co2_win, ir_tau_wv_win1, ir_tau_wv_win2, ir_tau_co2, ir_tau_wv1, ir_tau_wv2, window, carbon_conc;
   double single_albedo, back_scatter, lw_tau_0_gp, sw_tau_0_gp, lw_tau_exponent_gp, sw_tau_exponent_gp;
@@ -79,6 +80,11 @@ int isca_b200_two_stream_gray_rad_down(IscaPhysics p, const double* lat, const d
  * (may be NULL). */
 int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const double* p_half, const double* t,
                                      const double* t_surf, const double* albedo, const double* q, double* tdt, double* olr);
+
+/* do_seasonal (two_stream_gray_rad.F90:417-447): the insolation [J][I] (= solar_constant * coszen from astronomy_mod
+ * diurnal_solar, see isca_b200_diurnal_solar) that the following two_stream_gray_rad_down / _up calls use instead of the analytic
+ * annual-mean profile; NULL switches back.  It takes precedence over the scheme's own profile, as in the reference. */
+int isca_b200_two_stream_gray_rad_set_insolation(IscaPhysics p, const double* insolation);
 
 /* damping_driver, rayleigh sponge (damping_driver.f90:404-420, 594-636): p_full, u, v [K][J][I],
  * pref [K+1] reference pressures; udt, vdt, tdt [K][J][I] are the damping tendencies (overwritten). */

@@ -94,6 +94,12 @@ int isca_b200_diurnal_solar(IscaRrtm r, const IscaRrtmDriverConfig* dc, int n, c
 /* Switch the moist model's radiation from two_stream_gray_rad to RRTMG (rc->num_lon/num_lat/num_levels are overwritten with the
  * model's).  Must be called before isca_b200_moist_init. */
 int isca_b200_moist_use_rrtm(IscaMoist m, const IscaRrtmConfig* rc, const IscaRrtmDriverConfig* dc, const char* table_path);
+/* two_stream_gray_rad_nml do_seasonal = .true. (two_stream_gray_rad.F90:417-447) for the moist model's grey radiation: every step
+ * insolation = solar_constant * coszen(Time) from astronomy_mod diurnal_solar instead of the analytic annual-mean profile.
+ * dc: solday (>= 0: perpetual day of the year; < 0, the namelist default -10: follow the model clock), equinox_day,
+ * do_rad_time_avg (= use_time_average_coszen), dt_rad_avg (seconds; <= 0: dt_atmos), ecc / obliq / per / num_angles,
+ * day_in_s / year_in_s; the other fields are ignored.  Must be called before isca_b200_moist_init; excludes isca_b200_moist_use_rrtm. */
+int isca_b200_moist_set_seasonal(IscaMoist m, const IscaRrtmDriverConfig* dc);
 /* ozone as read from the ozone file, [K][J][I] on this rank's latitude block (do_read_ozone; NULL = no ozone) */
 int isca_b200_moist_set_ozone(IscaMoist m, const double* o3);
 /* model time of the next isca_b200_moist_step (Time of atmosphere(Time)); advanced by dt_atmos every step */

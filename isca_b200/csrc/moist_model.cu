@@ -33,6 +33,10 @@ struct IscaMoist_t {
   double time_s = 0.0;                                         // Time of atmosphere(Time), seconds since Time_init
   double dt_last = 0.0;                                        // rrtm_vars dt_last (radiation alarm)
   long n_rad_calls = 0;
+  // two_stream_gray_rad_nml do_seasonal (two_stream_gray_rad.F90:417-447): insolation = solar_constant * coszen(Time) every step
+  bool seasonal = false;
+  IscaRrtmDriverConfig sdc{};
+  std::vector<double> s_orb;
   double dry_tau = 0.0, dry_gamma = 0.0;                       // dry_convection_nml (convection_scheme = 'DRY')
 };
 
@@ -94,6 +98,9 @@ __global__ void lon2d_kernel(double* lon2d, int I, int J) {
   int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i < I) lon2d[(size_t)j * I + i] = (i * 360.0 / I) * (3.14159265358979323846 / 180.0);      // rad_lon = deg_lon * pi/180
 }
+__global__ void scale_kernel(size_t n, double* out, const double* a, double c) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = c * a[i];
+}
 __global__ void sub_kernel(size_t n, double* out, const double* a, const double* b) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = a[i] - b[i];
 }
@@ -150,6 +157,12 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   if (m->mc.convection_scheme != 2) {                            // `if (r_conv_scheme .ne. DRY_CONV)` (:977): no large-scale condensation
     launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
     cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
+  }
+  if (!m->rr && m->seasonal) {                                   // Time_diag = Time (:1054); days of 86400 s as get_time returns them
+    const double days = floor(m->time_s / 86400.0), seconds = m->time_s - 86400.0 * days;
+    if (isca_gray_coszen_device(m->sdc, m->s_orb, st, days, seconds, (int)nc, m->lat2d.p, m->lon2d.p, m->coszen.p))
+      return mfail(m, "two_stream_gray_rad: zenith-angle kernel launch failed");
+    scale_kernel<<<nblk(nc), 256, 0, st>>>(nc, p->insol.p, m->coszen.p, p->pc.solar_constant);
   }
   if (!m->rr) launch_gray_down(p, m->lat2d.p, ph_c, tg_p, q_p, m->albedo.p, m->net_sw.p, m->lw_down.p);   // q = grid_tracers(previous, nsphum), :1068
   // surface_flux on the lowest model level (:1076-1132)
@@ -328,6 +341,11 @@ int isca_b200_moist_init(IscaMoist m) {
   MCK(cudaMemsetAsync(m->sf.p, 0, 28 * nc * sizeof(double), st));
   MCK(cudaStreamSynchronize(st));
   p->vert_diff_down_done = false;
+  if (m->seasonal && !m->rr) {
+    lon2d_kernel<<<g2, 128, 0, st>>>(m->lon2d.p, m->I, m->J);
+    MCK(cudaMemsetAsync(m->coszen.p, 0, nc * sizeof(double), st));
+    MCK(cudaStreamSynchronize(st));
+  }
   if (m->rr) {
     lon2d_kernel<<<g2, 128, 0, st>>>(m->lon2d.p, m->I, m->J);
     Dev* z2[] = {&m->coszen, &m->olr, &m->toa_sw};
@@ -401,7 +419,7 @@ int isca_b200_moist_get(IscaMoist m, int id, double* host) {
     case 13: src = m->sf.p + SF_FLUX_U * nc; break;
     case 14: src = m->sf.p + SF_FLUX_V * nc; break;
     case 15: src = m->dts.p; break;
-    case 16: if (!m->rr) return mfail(m, "moist_get: coszen needs do_rrtm_radiation"); src = m->coszen.p; break;
+    case 16: if (!m->rr && !m->seasonal) return mfail(m, "moist_get: coszen needs do_rrtm_radiation or do_seasonal"); src = m->coszen.p; break;
     case 17: if (!m->rr) return mfail(m, "moist_get: olr needs do_rrtm_radiation"); src = m->olr.p; break;
     case 18: if (!m->rr) return mfail(m, "moist_get: toa_sw needs do_rrtm_radiation"); src = m->toa_sw.p; break;
     case 38: if (!m->rr) return mfail(m, "moist_get: tdt_rad needs do_rrtm_radiation"); src = m->tdt_rad.p; n = n3; break;
@@ -491,6 +509,7 @@ int isca_b200_moist_use_rrtm(IscaMoist m, const IscaRrtmConfig* rc, const IscaRr
   if (dc->abi_version != 1) return mfail(m, "IscaRrtmDriverConfig abi_version mismatch");
   if (m->initialized) return mfail(m, "moist_use_rrtm must be called before isca_b200_moist_init");
   if (m->rr) return mfail(m, "moist_use_rrtm: RRTMG is already enabled");
+  if (m->seasonal) return mfail(m, "moist_use_rrtm: do_seasonal of two_stream_gray_rad is enabled on this handle");
   IscaCoreView v;
   if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
   if (dc->num_angles < 1 || dc->day_in_s <= 0.0 || dc->year_in_s <= 0.0) return mfail(m, "moist_use_rrtm: bad astronomy / calendar values");
@@ -505,6 +524,24 @@ int isca_b200_moist_use_rrtm(IscaMoist m, const IscaRrtmConfig* rc, const IscaRr
   m->orb_angle = isca_rrtm_orbit(*dc);
   bool ok = m->tdt_rad.ensure(m->n3) && m->coszen.ensure(m->nc) && m->lon2d.ensure(m->nc) && m->olr.ensure(m->nc) && m->toa_sw.ensure(m->nc);
   if (!ok) return mfail(m, "cudaMalloc failed");
+  return 0;
+}
+
+int isca_b200_moist_set_seasonal(IscaMoist m, const IscaRrtmDriverConfig* dc) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!dc) return mfail(m, "moist_set_seasonal: null argument");
+  if (dc->abi_version != 1) return mfail(m, "IscaRrtmDriverConfig abi_version mismatch");
+  if (m->initialized) return mfail(m, "moist_set_seasonal must be called before isca_b200_moist_init");
+  if (m->rr) return mfail(m, "moist_set_seasonal: do_seasonal belongs to two_stream_gray_rad; RRTMG has its own zenith angle");
+  if (dc->num_angles < 1 || dc->day_in_s <= 0.0 || dc->year_in_s <= 0.0) return mfail(m, "moist_set_seasonal: bad astronomy / calendar values");
+  IscaCoreView v;
+  if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
+  m->sdc = *dc;
+  if (m->sdc.dt_rad_avg <= 0) m->sdc.dt_rad_avg = (int)(long)v.dt_atmos;      // two_stream_gray_rad_init :207
+  m->s_orb = isca_rrtm_orbit(*dc);
+  if (!m->coszen.ensure(m->nc) || !m->lon2d.ensure(m->nc) || !m->phy->insol.ensure(m->nc)) return mfail(m, "cudaMalloc failed");
+  m->phy->pc.insol_dev = m->phy->insol.p;
+  m->seasonal = true;
   return 0;
 }
 

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) gray_down_kernel(PhysConst c, int ncol, i
   if (col >= ncol) return;
   double sl = sin(lat[col]);
   double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
-  double insolation = 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * sl);
+  double insolation = c.insol_dev ? c.insol_dev[col] : 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * sl);
   double sw_tau_0 = (1.0 - c.sw_diff * sl * sl) * c.atm_abs;
   double lw_tau_0 = (c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * sl * sl) * c.odp;
   double tau0 = lw_tau_at(c, lw_tau_0, p_half[col]);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int
   double lwd[ISCA_KMAX + 1], trs[ISCA_KMAX];
   double sl = sin(lat[col]);
   double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
-  double insolation = 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * sl);
+  double insolation = c.insol_dev ? c.insol_dev[col] : 0.25 * c.solar_constant * (1.0 + c.del_sol * p2 + c.del_sw * sl);
   double sw_tau_0 = (1.0 - c.sw_diff * sl * sl) * c.atm_abs;
   double lw_tau_0 = (c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * sl * sl) * c.odp;
   double tau0 = lw_tau_at(c, lw_tau_0, p_half[col]);
@@ -222,7 +222,8 @@ __device__ __forceinline__ void rad_var_down(const PhysConst& c, int ncol, int K
   const int sch = c.rad_scheme;
   const double lcc = log(c.carbon_conc / 360.);
   double insolation;
-  if (sch == 3) insolation = (c.solar_constant / 3.14159265358979323846) * cos(lat);
+  if (c.insol_dev) insolation = c.insol_dev[col];                 // do_seasonal takes precedence over the scheme's profile (:417)
+  else if (sch == 3) insolation = (c.solar_constant / 3.14159265358979323846) * cos(lat);
   else {
     const double sl = sin(lat);
     const double p2 = (1.0 - 3.0 * sl * sl) / 4.0;
@@ -567,6 +568,15 @@ int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const dou
   if (down(p, p->buf[5], tdt, n3)) return 1;
   if (olr && down(p, p->buf[6], olr, nc)) return 1;
   return finish(p, "two_stream_gray_rad_up");
+}
+
+int isca_b200_two_stream_gray_rad_set_insolation(IscaPhysics p, const double* insolation) {
+  if (!p) return fail(nullptr, "null handle");
+  if (!insolation) { p->pc.insol_dev = nullptr; return 0; }
+  if (up(p, p->insol, insolation, p->ncol)) return 1;
+  PCK(cudaStreamSynchronize(p->st));
+  p->pc.insol_dev = p->insol.p;
+  return 0;
 }
 
 int isca_b200_rayleigh_damping(IscaPhysics p, double delt, const double* p_full, const double* u, const double* v,

@@ -28,6 +28,9 @@ struct PhysConst {
   double ir_tau_co2_win, ir_tau_wv_win1, ir_tau_wv_win2, ir_tau_co2, ir_tau_wv1, ir_tau_wv2, window, carbon_conc;
   double lw_tau_0_gp, sw_tau_0_gp, lw_tau_exponent_gp, sw_tau_exponent_gp, gp_albedo, Ga_asym;
   double bog_a, bog_b, bog_mu, pstd_earth;
+  // do_seasonal (two_stream_gray_rad.F90:417-447): per-column insolation = solar_constant * coszen computed by the driver;
+  // nullptr = the analytic annual-mean profiles
+  const double* insol_dev = nullptr;
 };
 
 // lookup_es_des (sat_vapor_pres_k.F90:1132-1158): table index + 2nd-order Taylor; false = outside the table
@@ -82,6 +85,7 @@ struct IscaPhysics_t {
   int lcl_n = 0; double lcl_val_min = 0.0, lcl_val_max = 0.0;
   isca_phys::Dev buf[24];               // staging of the host-array entry points
   isca_phys::Dev state[isca_phys::ST_COUNT];
+  isca_phys::Dev insol;                 // do_seasonal insolation [J][I] (pc.insol_dev points here while it is set)
   bool vert_diff_down_done = false;
   int* d_err = nullptr;
   cudaStream_t st = nullptr;

@@ -191,6 +191,21 @@ int isca_rrtm_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<do
   return launch_coszen(dc, orb, st, gmt, time_since_ae, dt, n, lat, lon, coszen, fracday, nullptr);
 }
 
+int isca_gray_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb, cudaStream_t st, double days, double seconds,
+                            int n, const double* lat, const double* lon, double* coszen) {
+  const double twopi = 2.0 * 3.14159265358979323846;
+  const double frac_of_day = seconds / dc.day_in_s;
+  const double frac_of_year = dc.solday >= 0 ? ((double)dc.solday * dc.day_in_s) / dc.year_in_s      // `if(solday .ge. 0)` (:425)
+                                             : (seconds + days * dc.day_in_s) / dc.year_in_s;
+  const double gmt = fabs(fmod(frac_of_day, 1.0)) * twopi;
+  double y = fmod(frac_of_year - dc.equinox_day, 1.0); if (y < 0.0) y += 1.0;                        // modulo()
+  const double time_since_ae = y * twopi;
+  const double dt = dc.do_rad_time_avg ? ((double)dc.dt_rad_avg / dc.day_in_s) * twopi : 0.0;
+  IscaRrtmDriverConfig c = dc;
+  c.frierson_solar_rad = 0;
+  return launch_coszen(c, orb, st, gmt, time_since_ae, dt, n, lat, lon, coszen, nullptr, nullptr);
+}
+
 extern "C" {
 
 int isca_b200_rrtm_default_config(IscaRrtmConfig* c) {

@@ -15,7 +15,7 @@ FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_do
                  q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
 FIELDS_3D = dict(dt_ug=32, dt_vg=33, dt_tg=34, dt_qg=35, diff_m=36, diff_t=37, tdt_rad=38)
 # declared in include/isca_b200_rrtm.h (RRTMG as the moist model's radiation)
-MOIST_RRTM_EXPORTS = ["isca_b200_moist_use_rrtm", "isca_b200_moist_set_ozone", "isca_b200_moist_set_time"]
+MOIST_RRTM_EXPORTS = ["isca_b200_moist_use_rrtm", "isca_b200_moist_set_ozone", "isca_b200_moist_set_time", "isca_b200_moist_set_seasonal"]
 CONVECTION = {"NONE": 0, "SIMPLE_BETTS_MILLER": 1, "DRY": 2}
 
 
@@ -132,6 +132,15 @@ class MoistAtmosphere:
         dc = rrtm.driver_config(**driver_nml)
         lib = rrtm._lib()
         self._ck(lib.isca_b200_moist_use_rrtm(self._h, C.byref(rc), C.byref(dc), (table_file or rrtm.TABLE_FILE).encode()), "rrtm_radiation_init")
+
+    def set_seasonal(self, solday=-10, equinox_day=0.75, use_time_average_coszen=False, dt_rad_avg=-1, **astronomy_nml):
+        """two_stream_gray_rad_nml do_seasonal = .true. (two_stream_gray_rad.F90:83-87, 417-447): insolation = solar_constant *
+        coszen(Time) from astronomy_mod every step.  astronomy_nml: ecc, obliq, per, num_angles, day_in_s, year_in_s.
+        Call before idealized_moist_phys_init."""
+        from . import rrtm
+        dc = rrtm.driver_config(solday=int(solday), equinox_day=float(equinox_day), do_rad_time_avg=int(bool(use_time_average_coszen)),
+                                dt_rad_avg=int(dt_rad_avg), **astronomy_nml)
+        self._ck(rrtm._lib().isca_b200_moist_set_seasonal(self._h, C.byref(dc)), "two_stream_gray_rad_init")
 
     def set_ozone(self, o3):
         """the field read from `ozone_file` (do_read_ozone), [lev, lat, lon]; None = no ozone"""

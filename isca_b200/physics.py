@@ -15,7 +15,8 @@ from .api import load_library, IscaError
 PHYSICS_EXPORTS = [
     "isca_b200_physics_default_config", "isca_b200_physics_create", "isca_b200_physics_destroy",
     "isca_b200_physics_last_error", "isca_b200_lookup_es_des", "isca_b200_compute_qs", "isca_b200_lscale_cond",
-    "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_rayleigh_damping",
+    "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_two_stream_gray_rad_set_insolation",
+    "isca_b200_rayleigh_damping",
     "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
     "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
     "isca_b200_mo_diff", "isca_b200_surface_flux", "isca_b200_diffusivity", "isca_b200_qe_moist_convection", "isca_b200_dry_convection",
@@ -75,6 +76,7 @@ def _lib():
         lib.isca_b200_lscale_cond.argtypes = [vp] + [dp] * 7
         lib.isca_b200_two_stream_gray_rad_down.argtypes = [vp] + [dp] * 7
         lib.isca_b200_two_stream_gray_rad_up.argtypes = [vp] + [dp] * 8
+        lib.isca_b200_two_stream_gray_rad_set_insolation.argtypes = [vp, dp]
         lib.isca_b200_rayleigh_damping.argtypes = [vp, C.c_double] + [dp] * 7
         lib.isca_b200_physics_time.argtypes = [vp, C.c_int, C.c_int, dp, dp]
         lib.isca_b200_gcm_vert_diff_down.argtypes = [vp, C.c_double] + [dp] * 18
@@ -178,6 +180,12 @@ class ColumnPhysics:
         self._ck(self._lib.isca_b200_two_stream_gray_rad_down(self._h, _p(lat), _p(p_half), _p(t), _p(albedo), _p(q) if q is not None else None,
                                                               _p(sw), _p(lw)), "two_stream_gray_rad_down")
         return sw, lw
+
+    def two_stream_gray_rad_set_insolation(self, insolation):
+        """do_seasonal (two_stream_gray_rad.F90:417-447): insolation [lat, lon] = solar_constant * coszen for the following down / up
+        calls; None = back to the analytic annual-mean profile"""
+        a = None if insolation is None else _in(insolation, self.s2, "insolation")
+        self._ck(self._lib.isca_b200_two_stream_gray_rad_set_insolation(self._h, _p(a) if a is not None else None), "two_stream_gray_rad_down")
 
     def two_stream_gray_rad_up(self, lat, p_half, t, t_surf, albedo, tdt, q=None):
         """-> tdt + radiative heating [lev, lat, lon], olr [lat, lon]"""

@@ -16,7 +16,7 @@ from .api import load_library, IscaError
 RRTM_EXPORTS = ["isca_b200_rrtm_default_config", "isca_b200_rrtm_create", "isca_b200_rrtm_destroy", "isca_b200_rrtm_last_error",
                 "isca_b200_rrtmg_lw", "isca_b200_rrtmg_sw", "isca_b200_run_rrtmg", "isca_b200_rrtm_time",
                 "isca_b200_rrtm_driver_default_config", "isca_b200_diurnal_solar",
-                "isca_b200_moist_use_rrtm", "isca_b200_moist_set_ozone", "isca_b200_moist_set_time"]
+                "isca_b200_moist_use_rrtm", "isca_b200_moist_set_ozone", "isca_b200_moist_set_time", "isca_b200_moist_set_seasonal"]
 
 TABLE_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "rrtmg_tables.bin")
 
@@ -60,6 +60,7 @@ def _lib():
         lib.isca_b200_moist_use_rrtm.argtypes = [vp, C.POINTER(IscaRrtmConfigStruct), C.POINTER(IscaRrtmDriverConfigStruct), C.c_char_p]
         lib.isca_b200_moist_set_ozone.argtypes = [vp, dp]
         lib.isca_b200_moist_set_time.argtypes = [vp, C.c_longlong, C.c_int]
+        lib.isca_b200_moist_set_seasonal.argtypes = [vp, C.POINTER(IscaRrtmDriverConfigStruct)]
         _bound = True
     return lib
 

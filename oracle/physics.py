@@ -147,11 +147,14 @@ class GreyRadiation:
             self.gp_albedo = (r1 - r2) / (r1 + r2)
             self.Ga_asym = 2.0 * np.sqrt((1.0 - cfg.single_albedo) * (1.0 - self.g_asym * cfg.single_albedo))
 
-    def down(self, lat, p_half, t, q=None, albedo=None):
-        """two_stream_gray_rad_down (:386-655): lat [lat, lon] (radians), p_half [K+1,..], t [K,..], q [K,..] (BYRNE, GEEN)."""
+    def down(self, lat, p_half, t, q=None, albedo=None, insolation=None):
+        """two_stream_gray_rad_down (:386-655): lat [lat, lon] (radians), p_half [K+1,..], t [K,..], q [K,..] (BYRNE, GEEN);
+        insolation [lat, lon]: the do_seasonal value `solar_constant * coszen` (:417-447, `seasonal_insolation` below)."""
         c, sch = self.c, self.scheme
         n = t.shape[0]
-        if sch == "SCHNEIDER":
+        if insolation is not None:                                                         # do_seasonal wins over the scheme (:417)
+            insolation = np.asarray(insolation, dtype=float)
+        elif sch == "SCHNEIDER":
             insolation = (c.solar_constant / np.pi) * np.cos(lat)                          # :450-451
         else:
             p2 = (1.0 - 3.0 * np.sin(lat) ** 2) / 4.0
@@ -239,6 +242,23 @@ class GreyRadiation:
         rad_flux = lw_flux + sw_flux
         tdt_rad = c.diabatic_acce * (rad_flux[1:] - rad_flux[:-1]) * GRAV / (CP_AIR * (p_half[1:] - p_half[:-1]))
         return tdt + tdt_rad, dict(olr=lw_up[0], net_lw_surf=lw_flux[n], rad_flux=rad_flux)
+
+
+def seasonal_insolation(cfg: GreyRadConfig, astro, days, seconds, lat, lon, solday=-10, equinox_day=0.75,
+                        use_time_average_coszen=False, dt_rad_avg=None, day_in_s=86400.0, year_in_s=360 * 86400.0):
+    """do_seasonal branch of two_stream_gray_rad_down (two_stream_gray_rad.F90:417-447): `days`, `seconds` = get_time(Time_diag);
+    astro: an astronomy_mod restatement with diurnal_solar(lat, lon, gmt, time_since_ae, dt) (oracle/rrtmg.py Astronomy);
+    dt_rad_avg: seconds (two_stream_gray_rad_init sets it to dt_atmos when the namelist value is <= 0, :207)."""
+    frac_of_day = float(seconds) / day_in_s
+    if solday >= 0:
+        frac_of_year = (float(solday) * day_in_s) / year_in_s
+    else:
+        frac_of_year = (float(seconds) + float(days) * day_in_s) / year_in_s
+    gmt = abs(np.fmod(frac_of_day, 1.0)) * 2.0 * np.pi
+    time_since_ae = ((frac_of_year - equinox_day) % 1.0) * 2.0 * np.pi
+    dt = (float(dt_rad_avg) / day_in_s) * 2.0 * np.pi if use_time_average_coszen else None
+    coszen = astro.diurnal_solar(lat, lon, gmt, time_since_ae, dt)[0]
+    return cfg.solar_constant * coszen
 
 
 def rayleigh_sponge(dt, p_full, u, v, pref, sponge_pbottom=5000.0, trayfric=-0.25, do_conserve_energy=True):
@@ -1172,6 +1192,9 @@ class IdealizedMoistPhys:
         # do_rrtm_radiation (idealized_moist_phys.F90:1167-1177): an oracle.rrtmg.RrtmRadiation instead of the grey scheme
         self.rrtm = None
         self.time_s = 0.0
+        # two_stream_gray_rad_nml do_seasonal: dict(astro=, lon=, solday=, equinox_day=, use_time_average_coszen=, dt_rad_avg=,
+        # day_in_s=, year_in_s=) -> seasonal_insolation at Time (idealized_moist_phys.F90:1054 passes Time, not Time + Time_step)
+        self.seasonal = None
 
     def __call__(self, core, delta_t):
         """core: the dynamical core state (ug, vg, tg, grid_tracers, p_half, p_full, z_half, z_full at two time levels)."""
@@ -1211,7 +1234,16 @@ class IdealizedMoistPhys:
             dt_tg = dt_tg + cond_dt_tg
             dt_q = dt_q + cond_dt_qg
         if self.rrtm is None:
-            d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo)
+            insol = None
+            if self.seasonal is not None:
+                kw = dict(self.seasonal)
+                astro, lon = kw.pop("astro"), kw.pop("lon")
+                if kw.get("dt_rad_avg") is None or kw["dt_rad_avg"] <= 0:
+                    kw["dt_rad_avg"] = self.dt_real                      # two_stream_gray_rad_init :207
+                days = int(self.time_s // 86400.0)
+                insol = seasonal_insolation(self.rad.c, astro, days, self.time_s - 86400.0 * days, self.rad_lat, lon, **kw)
+                self.diag["insolation"] = insol
+            d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo, insolation=insol)
             net_surf_sw_down = (1.0 - self.albedo) * d["sw_down_surf"]
             surf_lw_down = d["surf_lw_down"]
         sf = surface_flux(self.svp, self.mo, self.sflux, t_atm=tg_p[K - 1], q_atm_in=q_p[K - 1], u_atm=ug_p[K - 1], v_atm=vg_p[K - 1],

@@ -192,3 +192,71 @@ def test_shallow_water_model_on_the_gpu_transforms(lib_built):
     ens, div2, fr = big.global_diag()
     assert np.isfinite(ens) and ens > 0 and fr < 1.0
     big.atmosphere_end()
+
+
+@pytest.mark.parametrize("scheme", ["frierson", "geen", "schneider"])
+def test_two_stream_gray_rad_seasonal_insolation(lib_built, scheme):
+    """do_seasonal (two_stream_gray_rad.F90:417-447): insolation = solar_constant * coszen handed to the down / up kernels"""
+    from isca_b200 import physics
+    from oracle import physics as O
+    from oracle.rrtmg import Astronomy
+    from test_gpu_physics import columns, TOL
+    K, J, I = 20, 16, 32
+    rng, ps, ph, pf, t, lat = columns(K, J, I, 31)
+    lon = np.repeat((np.arange(I) * 2 * np.pi / I)[None], J, 0)
+    q = 0.02 * (pf / ps[None]) ** 3 * rng.uniform(0.2, 1.0, t.shape)
+    alb = rng.uniform(0.1, 0.4, (J, I))
+    ts = t[-1] + rng.uniform(-3, 3, (J, I))
+    tdt0 = 1e-5 * rng.standard_normal(t.shape)
+    cp = physics.ColumnPhysics(I, J, K, rad_scheme=scheme, atm_abs=0.2)
+    g = O.GreyRadiation(O.GreyRadConfig(rad_scheme=scheme, atm_abs=0.2))
+    ins = O.seasonal_insolation(g.c, Astronomy(), 100, 30000.0, lat, lon, use_time_average_coszen=True, dt_rad_avg=3600.0)
+    assert (ins == 0).any() and ins.max() > 800.0                       # a night side and a sub-solar region
+    cp.two_stream_gray_rad_set_insolation(ins)
+    d = g.down(lat, ph, t, q=q, albedo=alb, insolation=ins)
+    sw, lw = cp.two_stream_gray_rad_down(lat, ph, t, alb, q=q)
+    assert rel(lw, d["surf_lw_down"]) < TOL and rel(sw, (1 - alb) * d["sw_down_surf"]) < TOL
+    tdt, olr = cp.two_stream_gray_rad_up(lat, ph, t, ts, alb, tdt0, q=q)
+    to, o = g.up(ts, alb, ph, tdt0)
+    assert rel(olr, o["olr"]) < TOL and rel(tdt - tdt0, to - tdt0) < 1e-11
+    cp.two_stream_gray_rad_set_insolation(None)                        # back to the analytic profile
+    d0 = g.down(lat, ph, t, q=q, albedo=alb)
+    sw0, _ = cp.two_stream_gray_rad_down(lat, ph, t, alb, q=q)
+    assert rel(sw0, (1 - alb) * d0["sw_down_surf"]) < TOL and not np.allclose(sw0, sw)
+
+
+def test_moist_model_seasonal_grey_radiation(lib_built):
+    """the moist model with two_stream_gray_rad_nml do_seasonal = .true.: diurnal + seasonal insolation from the model clock"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    from oracle.rrtmg import Astronomy
+    cfg, core, mp = build("T21", 12, 900.0, "SIMPLE_BETTS_MILLER", seed=4)
+    Kk, J, I = core.tg[0].shape
+    lon = np.repeat((np.arange(I) * 2 * np.pi / I)[None], J, 0)
+    nml = dict(solday=-10, equinox_day=0.75, use_time_average_coszen=True, dt_rad_avg=-1)
+    mp.seasonal = dict(nml, astro=Astronomy(), lon=lon, day_in_s=86400.0, year_in_s=360 * 86400.0)
+    mp.time_s = 47 * 86400.0 + 20000.0
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS), convection_scheme="SIMPLE_BETTS_MILLER",
+                              mixed_layer_depth=2.5, albedo_value=0.31)
+    m.set_seasonal(**nml)
+    with pytest.raises(api.IscaError):
+        m.use_rrtm(dict(co2ppmv=360.0))                                # do_seasonal belongs to the grey scheme
+    m.set_time(47, 20000)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    for step in range(3):
+        core.step()
+        m.atmosphere(1)
+        cz = m.get("coszen")
+        assert rel(cz * 1360.0, mp.diag["insolation"]) < 1e-12, step
+        assert (cz == 0).any() and cz.max() > 0.8
+        assert rel(m.get("net_surf_sw_down"), mp.diag["net_surf_sw_down"]) < TOL, step
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+    m.atmosphere_end()

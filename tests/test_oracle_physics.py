@@ -364,3 +364,78 @@ def test_sbm_convection_conservation_and_branches():
     assert np.allclose(o["deltaT"][sel], -(t - o["Tref"])[sel] * dt / sbm.tau_bm, rtol=1e-10, atol=1e-13)
     # only the last column keeps its relaxation rates (array assignment inside the reference's column loop)
     assert np.count_nonzero(o["invtau_q_relaxation"].ravel()[:-1]) == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# two_stream_gray_rad_nml do_seasonal (two_stream_gray_rad.F90:417-447)
+# ------------------------------------------------------------------------------------------------------------------
+def _gauss_grid(J, I):
+    x, w = np.polynomial.legendre.leggauss(J)
+    lat = np.repeat(np.arcsin(x)[:, None], I, 1)
+    lon = np.repeat((np.arange(I) * 2 * np.pi / I)[None], J, 0)
+    return lat, lon, w
+
+
+def test_seasonal_insolation_global_mean_is_a_quarter_of_the_solar_constant():
+    """the sunlit disc: area mean of solar_constant*coszen = solar_constant/4 at any date and time of day (ecc = 0)"""
+    from oracle import physics as P
+    from oracle.rrtmg import Astronomy
+    lat, lon, w = _gauss_grid(96, 256)
+    c = P.GreyRadConfig()
+    for days, seconds in ((0, 0.0), (93, 21600.0), (181, 80000.0), (275, 43200.0)):
+        ins = P.seasonal_insolation(c, Astronomy(), days, seconds, lat, lon)
+        mean = (ins.mean(1) * w).sum() / w.sum()
+        assert abs(mean / c.solar_constant - 0.25) < 2e-4, (days, seconds)
+        assert ins.min() == 0.0 and ins.max() <= c.solar_constant
+
+
+def test_seasonal_insolation_equinox_solstice_and_perpetual_day():
+    from oracle import physics as P
+    from oracle.rrtmg import Astronomy
+    lat, lon, w = _gauss_grid(32, 64)
+    c, a = P.GreyRadConfig(solar_constant=1000.0), Astronomy()
+    # equinox_day = 0.75 of a 360-day year: day 270 is the autumn equinox, declination 0, noon at lon = pi - gmt
+    ins = P.seasonal_insolation(c, a, 270, 0.0, lat, lon)
+    t = lon - np.pi
+    expect = 1000.0 * np.maximum(np.cos(lat) * np.cos(t), 0.0)
+    assert np.allclose(ins, expect, atol=1e-9)
+    # a quarter year later: northern winter solstice, the daily mean vanishes poleward of 90 - obliq in the north
+    daily = np.mean([P.seasonal_insolation(c, a, 0, s, lat, lon) for s in np.arange(0, 86400, 3600.0)], 0)
+    north_polar = lat[:, 0] > np.deg2rad(90 - 23.439 + 1.0)
+    assert north_polar.any() and np.all(daily[north_polar] == 0.0) and np.all(daily[lat[:, 0] < -np.deg2rad(70)] > 300.0)
+    # solday >= 0: the date is frozen, the time of day still runs
+    p1 = P.seasonal_insolation(c, a, 5, 1000.0, lat, lon, solday=90)
+    p2 = P.seasonal_insolation(c, a, 200, 1000.0, lat, lon, solday=90)
+    p3 = P.seasonal_insolation(c, a, 200, 40000.0, lat, lon, solday=90)
+    assert np.array_equal(p1, p2) and not np.allclose(p2, p3)
+    # use_time_average_coszen over a whole day = the daily mean insolation (h sin(lat) sin(dec) + cos(lat) cos(dec) sin h) / pi
+    avg = P.seasonal_insolation(c, a, 45, 0.0, lat, lon, use_time_average_coszen=True, dt_rad_avg=86400.0)
+    ang = a.angle(((45 * 86400.0 / (360 * 86400.0) - 0.75) % 1.0) * 2 * np.pi)
+    dec = a.declination(ang)
+    h = a.half_day(lat, dec)
+    want = 1000.0 * (h * np.sin(lat) * np.sin(dec) + np.cos(lat) * np.cos(dec) * np.sin(h)) / np.pi
+    assert np.allclose(avg, np.maximum(want, 0.0), rtol=1e-9, atol=1e-9)
+
+
+def test_grey_radiation_with_insolation_override():
+    """the do_seasonal insolation replaces the scheme's profile, schneider included (`if (do_seasonal) ... else if (B_SCHNEIDER_LIU)`);
+    handing the analytic profile over reproduces the default result exactly"""
+    from oracle import physics as P
+    rng = np.random.default_rng(3)
+    K, J, I = 12, 8, 16
+    lat = np.repeat(np.linspace(-1.4, 1.4, J)[:, None], I, 1)
+    ph = np.linspace(0, 1e5, K + 1)[:, None, None] * np.ones((1, J, I))
+    t = 220 + 70 * (0.5 * (ph[1:] + ph[:-1]) / 1e5) ** 0.3 + rng.standard_normal((K, J, I))
+    for scheme in ("frierson", "schneider"):
+        g = P.GreyRadiation(P.GreyRadConfig(rad_scheme=scheme, atm_abs=0.2))
+        d0 = g.down(lat, ph, t, albedo=np.zeros((J, I)))
+        c = g.c
+        if scheme == "schneider":
+            prof = (c.solar_constant / np.pi) * np.cos(lat)
+        else:
+            prof = 0.25 * c.solar_constant * (1.0 + c.del_sol * (1.0 - 3.0 * np.sin(lat) ** 2) / 4.0 + c.del_sw * np.sin(lat))
+        d1 = g.down(lat, ph, t, albedo=np.zeros((J, I)), insolation=prof)
+        assert np.array_equal(d0["sw_down_surf"], d1["sw_down_surf"])
+        d2 = g.down(lat, ph, t, albedo=np.zeros((J, I)), insolation=0.5 * prof)
+        assert np.allclose(d2["sw_down_surf"], 0.5 * d0["sw_down_surf"], rtol=1e-14)
+        assert np.array_equal(d2["surf_lw_down"], d0["surf_lw_down"])

@@ -83,6 +83,7 @@ def test_moist_wrapper_methods(lib_built, monkeypatch):
     m.set_ozone(np.ones(m.s3))
     m.set_ozone(None)
     m.set_time(3, 43200)
+    m.set_seasonal(solday=-10, equinox_day=0.75, use_time_average_coszen=True, dt_rad_avg=1800, obliq=25.0)
     m.set_ocean_qflux(np.ones(m.s2))
     m.set_dry_convection(7200.0, 0.7)
     for name in moist.MoistAtmosphere.SURFACE_FIELDS:
@@ -97,7 +98,8 @@ def test_moist_wrapper_methods(lib_built, monkeypatch):
         m.use_rrtm(not_a_namelist_value=1)
     seen = dict(stub.calls)
     for fn, hdr in (("isca_b200_moist_use_rrtm", "isca_b200_rrtm.h"), ("isca_b200_moist_set_ozone", "isca_b200_rrtm.h"),
-                    ("isca_b200_moist_set_time", "isca_b200_rrtm.h"), ("isca_b200_moist_set_ocean_qflux", "isca_b200_physics.h"),
+                    ("isca_b200_moist_set_time", "isca_b200_rrtm.h"), ("isca_b200_moist_set_seasonal", "isca_b200_rrtm.h"),
+                    ("isca_b200_moist_set_ocean_qflux", "isca_b200_physics.h"),
                     ("isca_b200_moist_set_dry_convection", "isca_b200_physics.h"), ("isca_b200_moist_set_surface", "isca_b200_physics.h"),
                     ("isca_b200_moist_get", "isca_b200_physics.h")):
         assert seen[fn] == _nparams(hdr, fn), fn
@@ -113,4 +115,10 @@ def test_physics_dry_convection_wrapper(lib_built):
     o = cp.dry_convection(7200.0, 0.7, np.ones(cp.s3), np.ones(cp.s3), np.ones(cp.s3h))
     assert o["lzb"].dtype == np.int32 and o["dt_tg"].shape == cp.s3
     assert dict(stub.calls)["isca_b200_dry_convection"] == _nparams("isca_b200_physics.h", "isca_b200_dry_convection")
+    cp.two_stream_gray_rad_set_insolation(np.ones(cp.s2))
+    cp.two_stream_gray_rad_set_insolation(None)
+    assert dict(stub.calls)["isca_b200_two_stream_gray_rad_set_insolation"] == \
+        _nparams("isca_b200_physics.h", "isca_b200_two_stream_gray_rad_set_insolation")
+    with pytest.raises(physics.IscaError):
+        cp.two_stream_gray_rad_set_insolation(np.ones((4, 9)))
     cp._h = C.c_void_p()
