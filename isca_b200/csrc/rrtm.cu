@@ -191,6 +191,13 @@ int isca_rrtm_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<do
   return launch_coszen(dc, orb, st, gmt, time_since_ae, dt, n, lat, lon, coszen, fracday, nullptr);
 }
 
+int isca_diurnal_solar_device(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb, cudaStream_t st, double gmt, double time_since_ae,
+                              double dt, int n, const double* lat, const double* lon, double* coszen) {
+  IscaRrtmDriverConfig c = dc;
+  c.frierson_solar_rad = 0;
+  return launch_coszen(c, orb, st, gmt, time_since_ae, dt, n, lat, lon, coszen, nullptr, nullptr);
+}
+
 int isca_gray_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb, cudaStream_t st, double days, double seconds,
                             int n, const double* lat, const double* lon, double* coszen) {
   const double twopi = 2.0 * 3.14159265358979323846;

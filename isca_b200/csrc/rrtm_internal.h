@@ -16,5 +16,8 @@ int isca_rrtm_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<do
 // (seconds, > 0), the astronomy_nml values and the calendar lengths
 int isca_gray_coszen_device(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb_angle, cudaStream_t st, double days,
                             double seconds, int n, const double* lat, const double* lon, double* coszen);
+// diurnal_solar_2d (astronomy.f90:1123-1410) on device lat / lon [n]; dt <= 0: instantaneous.  dc: the astronomy_nml values
+int isca_diurnal_solar_device(const IscaRrtmDriverConfig& dc, const std::vector<double>& orb_angle, cudaStream_t st, double gmt,
+                              double time_since_ae, double dt, int n, const double* lat, const double* lon, double* coszen);
 // astronomy_mod orbit table (astronomy.f90:orbit)
 std::vector<double> isca_rrtm_orbit(const IscaRrtmDriverConfig& dc);

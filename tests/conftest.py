@@ -16,3 +16,13 @@ def lib_built():
     """Build (or reuse) the in-tree shared library; nvcc cross-compiles without a GPU."""
     from isca_b200 import build
     return build.build()
+
+
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that hangs (a kernel that never returns) must end the run instead of holding the box until the outer limit:
+    every gpu-marked test gets a pytest-timeout limit (thread method: works while the main thread sits inside a CUDA call)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900, method="thread"))

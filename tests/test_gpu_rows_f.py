@@ -260,3 +260,99 @@ def test_moist_model_seasonal_grey_radiation(lib_built):
         assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
         assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
     m.atmosphere_end()
+
+
+# ---- hs_forcing_mod beyond the Held-Suarez default (include/isca_b200_hs.h); the column arithmetic of these kernels is checked on the
+# ---- CPU in tests/test_hs_host.py, here the launch geometry, the zenith-angle / spin-up kernels and the model driver
+def _hs_cases():
+    from test_hs_host import CASES
+    return CASES
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_hs_forcing_options_parity(lib_built, idx):
+    from isca_b200 import hs as HS
+    from oracle import hs_forcing as H
+    from oracle.rrtmg import Astronomy
+    from test_hs_host import case, run_oracle
+    nml = _hs_cases()[idx]
+    cfg = H.HsConfig(**nml)
+    g = case(K=20, J=32, I=64, seed=idx)
+    o = H.HsForcing(cfg, g["lat"], 3, 100, astronomy=Astronomy(ecc=cfg.ecc, obliq=cfg.obliq))
+    f = HS.HsForcing(64, 32, 20, lat=g["lat"], time=(3, 100), **nml)
+    if cfg.equilibrium_t_option == "top_down":
+        assert rel(f.tg_prev, o.tg_prev) < 1e-13                       # the spin-up kernel
+    ts = 86400 * 12 + 4321
+    _, (udt, vdt, tdt, rdt) = run_oracle(cfg, g, 1800.0, ts, hs=o, ntr=2)
+    z = np.zeros_like(g["t"])
+    gu, gv, gt, gr, d = f.hs_forcing(1800.0, (12, 4321), g["lon"], g["lat"], g["p_half"], g["p_full"], g["u"], g["v"], g["t"], z + 1e-6, z - 1e-6,
+                                     z + 1e-5, um=g["u"] * 0.9, vm=g["v"] * 1.1, rm=np.stack([g["r"]] * 2), rdt=np.stack([1e-9 * g["r"]] * 2),
+                                     zfull=g["zfull"])
+    assert rel(gu, udt) < 1e-12 and rel(gv, vdt) < 1e-12 and rel(gt, tdt) < 1e-12
+    assert rel(d["teq"], o.diag["teq"]) < 1e-12
+    for n in range(2):
+        assert rel(gr[n], rdt[n]) < 1e-12
+    if cfg.equilibrium_t_option == "top_down":
+        assert rel(d["h_trop"], o.diag["h_trop"]) < 1e-13 and rel(f.tg_prev, o.tg_prev) < 1e-13
+        f.tg_prev = o.tg_prev + 1.0                                    # restart hand-over
+        assert rel(f.tg_prev, o.tg_prev + 1.0) < 1e-15
+    f.hs_forcing_end()
+
+
+@pytest.mark.parametrize("nml,ntr", [(dict(equilibrium_t_option="EXOPLANET", obliq=30.0), 0),
+                                     (dict(equilibrium_t_option="top_down", stratosphere_t_option="hs_like", spinup_time=40.0,
+                                           orbital_period=360.0, local_heating_option="Isidoro", local_heating_srfamp=2.0), 1),
+                                     (dict(), 1)])
+def test_dry_model_with_general_hs_forcing(lib_built, nml, ntr):
+    """atmosphere() of the dry model with the general forcing against the oracle core driven by oracle/hs_forcing.py, three steps
+    from a developed state; with the default options the result must also equal the fused Held-Suarez path of isca_b200_step"""
+    from isca_b200 import api, hs as HS
+    from oracle import hs_forcing as H
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    from oracle.rrtmg import Astronomy
+    cfg = held_suarez_config("T21", 15, 1200.0, num_tracers=ntr)
+    core = SpectralCore(cfg)
+    core.cold_start()
+    for _ in range(40):
+        core.step()
+    Kk, J, I = core.tg[0].shape
+    lat = np.repeat(core.tb.rad_lat[:, None], I, 1)
+    lon = np.repeat((np.arange(I) * 2 * np.pi / I)[None], J, 0)
+    hc = H.HsConfig(kappa=cfg.kappa, rdgas=cfg.rdgas, grav=cfg.grav, **nml)
+    t0 = 5 * 86400 + 600
+    o = H.HsForcing(hc, lat, 5, 600, astronomy=Astronomy(ecc=hc.ecc, obliq=hc.obliq))
+    default = not nml
+    fused = None
+    if default:                                                          # the fused path, same start
+        fused = api.Atmosphere(api.config_from_namelist_object(cfg))
+    core.hs = H.CoreHsForcing(o, core, lon, lat, time_s=t0)
+    m = HS.HsAtmosphere(api.config_from_namelist_object(cfg), **nml)
+    for a in ([m.core, fused] if fused else [m.core]):
+        for slot in (0, 1):
+            tr = (core.grid_tracers[slot, 0],) if ntr else ()
+            a.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], *tr)
+            a.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+        a.set_vor_div_grid(core.vorg, core.divg)
+        a.set_time_pointers(core.previous, core.current)
+    m.set_time(5, 600)
+    m.hs_forcing_init()
+    if hc.equilibrium_t_option == "top_down":
+        assert rel(m.get("tg_prev"), o.tg_prev) < 1e-13
+    for step in range(3):
+        core.step()
+        m.atmosphere(1)
+        assert rel(m.get("teq"), o.diag["teq"]) < 1e-11, step
+        for name, fid in (("ug", api.F_U), ("vg", api.F_V), ("tg", api.F_T)):
+            assert rel(m.core.get_field(fid), getattr(core, name)[core.current]) < 1e-10, (step, name)
+        assert rel(m.core.get_field(api.F_PS), core.psg[core.current]) < 1e-10, step
+        if ntr:
+            assert rel(m.core.get_field(api.F_TRACER0), core.grid_tracers[core.current, 0]) < 1e-10, step
+        if fused:
+            fused.atmosphere(1)
+            assert rel(m.core.get_field(api.F_T), fused.get_field(api.F_T)) < 1e-12, step
+            assert rel(m.core.get_field(api.F_U), fused.get_field(api.F_U)) < 1e-12, step
+    if hc.equilibrium_t_option == "top_down":
+        assert rel(m.get("tg_prev"), o.tg_prev) < 1e-13 and rel(m.get("h_trop"), o.diag["h_trop"]) < 1e-13
+    m.atmosphere_end()
+    if fused:
+        fused.atmosphere_end()

@@ -1,0 +1,341 @@
+"""hs_forcing_mod beyond the Held-Suarez default without a GPU.
+
+(1) oracle/hs_forcing.py against the independent restatement of the default option in oracle/isca_oracle.py and against analytic
+    properties of the other options;
+(2) the `__host__ __device__` column functions of isca_b200/csrc/hs_forcing_column.h -- the very code the CUDA kernels of
+    hs_forcing.cu execute per column -- built for the host (tests/host/hs_host.cpp, test infrastructure) against the oracle:
+    tendencies 1e-13 relative to the field maximum;
+(3) the C ABI of include/isca_b200_hs.h: exported symbols, struct layout of the ctypes mirror, wrapper argument counts."""
+import ctypes as C
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+
+from oracle import hs_forcing as H
+from oracle.rrtmg import Astronomy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "host", "hs_host.cpp")
+OUT = os.path.join(HERE, "host", "_build", "libhs_host.so")
+P = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def host():
+    deps = [SRC, os.path.join(ROOT, "isca_b200", "csrc", "hs_forcing_column.h")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", OUT, SRC])
+    lib = C.CDLL(OUT)
+    assert lib.hs_host_nparams() == 29
+    return lib
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def case(K=14, J=12, I=16, seed=0, mountains=False):
+    """a plausible atmosphere on a small grid: sigma levels, surface pressure with some structure"""
+    rng = np.random.default_rng(seed)
+    x, _ = np.polynomial.legendre.leggauss(J)
+    lat = np.repeat(np.arcsin(x)[:, None], I, 1)
+    lon = np.repeat((np.arange(I) * 2 * np.pi / I)[None], J, 0)
+    ps = 1.0e5 + 2500.0 * rng.standard_normal((J, I))
+    sig_h = np.linspace(0.0, 1.0, K + 1) ** 1.5
+    p_half = sig_h[:, None, None] * ps[None]
+    p_full = 0.5 * (p_half[1:] + p_half[:-1])
+    t = 210.0 + 80.0 * (p_full / 1e5) ** 0.6 * np.cos(lat)[None] ** 0.5 + rng.standard_normal(p_full.shape)
+    u = 25.0 * rng.standard_normal(p_full.shape)
+    v = 10.0 * rng.standard_normal(p_full.shape)
+    zfull = 7500.0 * np.log(ps[None] / p_full) * (1 + 0.02 * rng.standard_normal(p_full.shape))
+    r = 1e-3 * rng.uniform(0, 1, p_full.shape)
+    return dict(lat=lat, lon=lon, ps=ps, p_half=p_half, p_full=p_full, t=t, u=u, v=v, zfull=zfull, r=r, rng=rng)
+
+
+def run_oracle(cfg, g, dt, total_seconds, hs=None, ntr=1):
+    hs = hs or H.HsForcing(cfg, g["lat"], 0, 0, astronomy=Astronomy(ecc=cfg.ecc, obliq=cfg.obliq))
+    z = np.zeros_like(g["t"])
+    rdt0 = [1e-9 * g["r"]] * ntr
+    out = hs(dt, total_seconds, g["lon"], g["lat"], g["p_half"], g["p_full"], g["u"], g["v"], g["t"], [g["r"]] * ntr, g["u"] * 0.9, g["v"] * 1.1,
+             g["t"], [g["r"]] * ntr, z + 1e-6, z - 1e-6, z + 1e-5, rdt0, zfull=g["zfull"])
+    return hs, out
+
+
+EQ = {"Held_Suarez": 0, "EXOPLANET": 1, "EXOPLANET2": 2, "top_down": 3}
+ST = {"extend_tp": 0, "c_above_tp": 1, "hs_like": 2}
+
+
+def pack(cfg, hs):
+    """HsParams as isca_b200_hs_forcing_create fills it (hs_forcing.cu)"""
+    ip = np.array([int(cfg.do_conserve_energy), EQ[cfg.equilibrium_t_option], ST.get(cfg.stratosphere_t_option, 3),
+                   int(cfg.local_heating_option == "Isidoro")], dtype=np.int32)
+    rd = cfg.trsink
+    if rd < 0:
+        rd = -86400.0 * rd
+    if rd > 0:
+        rd = 1.0 / rd
+    dp = np.array([hs.tka, hs.tks, hs.vkf, cfg.sigma_b, cfg.t_zero, cfg.t_strat, cfg.delh, cfg.delv, cfg.eps, cfg.P00, cfg.p_trop, cfg.alpha,
+                   cfg.kappa, cfg.cp_air, hs.xwidth, hs.ywidth, hs.xcenter, hs.ycenter, hs.srfamp, cfg.local_heating_vert_decay,
+                   cfg.lapse, cfg.h_a, cfg.tau_s, cfg.stefan, cfg.solar_const, cfg.albedo, cfg.ml_depth * cfg.heat_capacity, cfg.trflux, rd])
+    return ip, dp
+
+
+def run_host(lib, cfg, hs, g, dt, total_seconds, tg_prev=None, ntr=1):
+    K, J, I = g["t"].shape
+    ip, dp = pack(cfg, hs)
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(P)
+    z = np.zeros_like(g["t"])
+    udt, vdt, tdt = c(z + 1e-6), c(z - 1e-6), c(z + 1e-5)
+    rm = c(np.stack([g["r"]] * ntr)) if ntr else None
+    rdt = c(np.stack([1e-9 * g["r"]] * ntr)) if ntr else None
+    teq, h_trop = np.zeros_like(z), np.zeros((J, I))
+    coszen = None
+    dec = 0.0
+    if cfg.equilibrium_t_option == "EXOPLANET":
+        coszen = c(hs.diurnal_exoplanet(g["lat"], g["lon"], total_seconds))
+    if cfg.equilibrium_t_option == "top_down":
+        dec = float(hs.update_orbit(int(total_seconds)))
+    arrs = [c(g[k]) for k in ("lat", "lon")]
+    a3 = [c(g[k]) for k in ("p_half", "p_full", "u", "v", "t")]
+    um, vm, zf = c(g["u"] * 0.9), c(g["v"] * 1.1), c(g["zfull"])
+    tg = None if tg_prev is None else c(tg_prev.copy())
+    rc = lib.hs_host_forcing(K, C.c_long(J * I), ip.ctypes.data_as(C.POINTER(C.c_int)), ptr(dp), C.c_double(dt), C.c_double(dec), ptr(arrs[0]),
+                             ptr(arrs[1]), ptr(coszen), *[ptr(a) for a in a3], ptr(um), ptr(vm), ptr(zf), ptr(udt), ptr(vdt), ptr(tdt),
+                             ptr(teq), ptr(tg), ptr(h_trop), ntr, ptr(rm), ptr(rdt))
+    assert rc == 0
+    return udt, vdt, tdt, rdt, teq, h_trop, tg
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# (1) the oracle
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_default_option_matches_the_core_oracle():
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    cfg = held_suarez_config("T21", 10, 1200.0, num_tracers=1)
+    core = SpectralCore(cfg)
+    core.cold_start()
+    for _ in range(2):
+        core.step(physics=True)
+    K, J, I = core.tg[0].shape
+    lat = np.repeat(core.tb.rad_lat[:, None], I, 1)
+    lon = np.repeat((np.arange(I) * 2 * np.pi / I)[None], J, 0)
+    c = cfg
+    hc = H.HsConfig(t_zero=c.t_zero, t_strat=c.t_strat, delh=c.delh, delv=c.delv, eps=c.eps, sigma_b=c.sigma_b, P00=c.P00, ka=c.ka, ks=c.ks,
+                    kf=c.kf, do_conserve_energy=c.do_conserve_energy, trflux=c.trflux, trsink=c.trsink, kappa=c.kappa, rdgas=c.rdgas)
+    hs = H.HsForcing(hc)
+    cur = core.current
+    z = np.zeros_like(core.tg[0])
+    r = [core.grid_tracers[cur, n] for n in range(c.num_tracers)]
+    a = core.hs(2400.0, core.p_half[cur], core.p_full[cur], core.ug[cur], core.vg[cur], core.tg[cur], r, z, z, z, [z] * len(r))
+    b = hs(2400.0, 0, lon, lat, core.p_half[cur], core.p_full[cur], core.ug[cur], core.vg[cur], core.tg[cur], r, core.ug[cur], core.vg[cur],
+           core.tg[cur], r, z, z, z, [z] * len(r))
+    for x, y in zip(a[:3], b[:3]):
+        assert rel(x, y) < 1e-14                     # two independent restatements (cp_air = rdgas/kappa vs the configured value)
+    for x, y in zip(a[3], b[3]):
+        assert rel(x, y) < 1e-14
+    assert np.abs(a[2]).max() > 0
+
+
+def test_exoplanet_options():
+    g = case()
+    # EXOPLANET2: teq = max(t_strat cos(lat) (p/p_trop)^alpha, t_strat), independent of longitude and time
+    cfg = H.HsConfig(equilibrium_t_option="EXOPLANET2", t_strat=180.0)
+    hs, _ = run_oracle(cfg, g, 1200.0, 5000)
+    teq = hs.diag["teq"]
+    assert teq.min() == 180.0 and np.allclose(teq[-1], np.maximum(180.0 * np.cos(g["lat"]) * (g["p_full"][-1] / 1e4) ** (2 / 7), 180.0))
+    # EXOPLANET: on the night side coszen = 0 -> t_star = t_zero - delh, no vertical gradient term; tidally locked planet
+    # (omega = orbital_rate): the substellar longitude does not move
+    om = 2 * np.pi / (10 * 86400.0)
+    cfg = H.HsConfig(equilibrium_t_option="exoplanet", omega=om, orbital_period=10 * 86400.0, obliq=0.0)
+    hs, _ = run_oracle(cfg, g, 1200.0, 3000)
+    cz1 = hs.diag["coszen"].copy()
+    night = cz1 == 0
+    assert night.any() and (~night).any()
+    p_norm = g["p_full"] / cfg.P00
+    expect = np.maximum((cfg.t_zero - cfg.delh) * p_norm ** cfg.kappa, cfg.t_strat)
+    assert np.allclose(hs.diag["teq"][:, night], expect[:, night], rtol=1e-14)
+    day = cz1 > 0.5
+    assert (hs.diag["teq"][-1][day] > hs.diag["teq"][-1][night].max()).all()
+    # gmt is fixed for the locked planet; the declination stays 0 with obliq = 0: same coszen at a later time
+    hs2, _ = run_oracle(cfg, g, 1200.0, 3000 + 86400 * 3 + 777)
+    assert np.allclose(hs2.diag["coszen"], cz1, atol=1e-9)
+    # a rotating planet: the pattern moves
+    cfg3 = H.HsConfig(equilibrium_t_option="EXOPLANET")
+    a, _ = run_oracle(cfg3, g, 1200.0, 3000)
+    b, _ = run_oracle(cfg3, g, 1200.0, 3000 + 6 * 3600)
+    assert not np.allclose(a.diag["coszen"], b.diag["coszen"])
+    with pytest.raises(ValueError):
+        H.HsForcing(H.HsConfig(equilibrium_t_option="from_file"))
+
+
+def test_top_down_spinup_and_stratosphere_options():
+    g = case(J=16)
+    cfg = H.HsConfig(equilibrium_t_option="top_down", spinup_time=400.0, orbital_period=360.0, ml_depth=0.25)
+    hs = H.HsForcing(cfg, g["lat"], 0, 0)
+    tg0 = hs.tg_prev.copy()
+    assert tg0.shape == g["lat"].shape and 80.0 < tg0.min() and tg0.max() < 330.0     # the winter pole cools radiatively in the polar night
+    assert tg0[g["lat"].shape[0] // 2].mean() > tg0[0].mean()                          # equator warmer than the pole
+    # the slab relaxes towards the radiative surface temperature: a 10x longer spin-up moves it closer, and a second year returns
+    # to (almost) the same state
+    long_ = H.HsForcing(H.HsConfig(equilibrium_t_option="top_down", spinup_time=760.0, orbital_period=360.0, ml_depth=0.25), g["lat"], 0, 0)
+    again = H.HsForcing(H.HsConfig(equilibrium_t_option="top_down", spinup_time=1120.0, orbital_period=360.0, ml_depth=0.25), g["lat"], 0, 0)
+    assert np.abs(again.tg_prev - long_.tg_prev).max() < 0.5 * np.abs(long_.tg_prev - tg0).max() + 1e-6
+    outs = {}
+    for so in ("extend_tp", "c_above_tp", "hs_like", "none"):
+        c = H.HsConfig(equilibrium_t_option="top_down", stratosphere_t_option=so, spinup_time=50.0, orbital_period=360.0)
+        h, o = run_oracle(c, g, 1200.0, 86400 * 20, hs=H.HsForcing(c, g["lat"], 0, 0))
+        outs[so] = h.diag["teq"]
+        assert h.diag["h_trop"].min() >= 0 and h.diag["h_trop"].max() < 30.0
+    above = g["zfull"] / 1000 >= h.diag["h_trop"][None]
+    assert above.any() and (~above).any()
+    assert np.array_equal(outs["extend_tp"][~above], outs["c_above_tp"][~above])
+    assert np.all(outs["c_above_tp"][above] == 200.0)
+    assert np.all(outs["hs_like"] >= 200.0) and np.all(outs["none"] >= 0.0)
+    # tg_prev advances with every call
+    c = H.HsConfig(equilibrium_t_option="top_down", spinup_time=50.0, orbital_period=360.0)
+    h = H.HsForcing(c, g["lat"], 0, 0)
+    t0 = h.tg_prev.copy()
+    run_oracle(c, g, 1200.0, 86400 * 20, hs=h)
+    assert not np.array_equal(h.tg_prev, t0)
+
+
+def test_local_heating_and_tracer():
+    g = case(J=24, I=48)
+    cfg = H.HsConfig(local_heating_option="Isidoro", local_heating_srfamp=5.0, local_heating_xcenter=540.0 + 90.0, local_heating_ycenter=30.0,
+                     local_heating_xwidth=20.0, local_heating_ywidth=15.0)
+    hs, out = run_oracle(cfg, g, 1200.0, 0)
+    lh = hs.diag["local_heating"]
+    k, j, i = np.unravel_index(np.argmax(lh), lh.shape)
+    assert k == lh.shape[0] - 1
+    assert abs(np.rad2deg(g["lon"][j, i]) - 270.0) <= 7.5 and abs(np.rad2deg(g["lat"][j, i]) - 30.0) <= 7.5    # 630 deg = 270 deg
+    assert 0 < lh.max() <= 5.0 / 86400.0
+    no, out0 = run_oracle(H.HsConfig(), g, 1200.0, 0)
+    assert np.allclose(out[2] - out0[2], lh, rtol=0, atol=1e-18)
+    # tracer: a surface source in the lowest layer and a linear sink everywhere
+    rdt = out0[3][0]
+    rst = g["r"] + 1200.0 * 1e-9 * g["r"]
+    assert np.allclose(rdt[:-1], 1e-9 * g["r"][:-1] - rst[:-1] / (4 * 86400.0), rtol=1e-13)
+    src = rdt[-1] - (1e-9 * g["r"][-1] - rst[-1] / (4 * 86400.0))
+    assert np.allclose(src, 1.0e-5 / (g["p_half"][-1] - g["p_half"][-2]), rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# (2) the device column code, built for the host
+# ---------------------------------------------------------------------------------------------------------------------------
+CASES = [dict(), dict(do_conserve_energy=False, eps=10.0, sigma_b=0.6, ka=1e-6, ks=-3.0, kf=2e-5, delv=15.0, trsink=7200.0),
+         dict(equilibrium_t_option="EXOPLANET", obliq=40.0, ecc=0.1), dict(equilibrium_t_option="EXOPLANET2", p_trop=2e4, alpha=0.2),
+         dict(local_heating_option="Isidoro", local_heating_srfamp=3.0, local_heating_xcenter=-40.0),
+         dict(equilibrium_t_option="top_down", stratosphere_t_option="extend_tp", spinup_time=30.0, orbital_period=360.0),
+         dict(equilibrium_t_option="top_down", stratosphere_t_option="c_above_tp", spinup_time=30.0, orbital_period=360.0, eps=5.0),
+         dict(equilibrium_t_option="top_down", stratosphere_t_option="hs_like", spinup_time=30.0, orbital_period=360.0),
+         dict(equilibrium_t_option="top_down", stratosphere_t_option="something_else", spinup_time=30.0, orbital_period=360.0,
+              local_heating_option="Isidoro", local_heating_srfamp=1.0)]
+
+
+@pytest.mark.parametrize("nml", CASES)
+def test_device_column_code_matches_oracle(host, nml):
+    cfg = H.HsConfig(**nml)
+    g = case(seed=len(nml))
+    hs = H.HsForcing(cfg, g["lat"], 3, 100, astronomy=Astronomy(ecc=cfg.ecc, obliq=cfg.obliq))
+    tg0 = None if hs.tg_prev is None else hs.tg_prev.copy()
+    ts = 86400 * 12 + 4321
+    _, (udt, vdt, tdt, rdt) = run_oracle(cfg, g, 1800.0, ts, hs=hs, ntr=2)
+    hu, hv, ht, hr, teq, h_trop, tg = run_host(host, cfg, hs, g, 1800.0, ts, tg_prev=tg0, ntr=2)
+    assert rel(hu, udt) < 1e-13 and rel(hv, vdt) < 1e-13 and rel(ht, tdt) < 1e-13
+    assert rel(teq, hs.diag["teq"]) < 1e-14
+    for n in range(2):
+        assert rel(hr[n], rdt[n]) < 1e-13
+    if cfg.equilibrium_t_option == "top_down":
+        assert rel(h_trop, hs.diag["h_trop"]) < 1e-14 and rel(tg, hs.tg_prev) < 1e-14
+        above = g["zfull"] / 1000 >= hs.diag["h_trop"][None]
+        assert above.any() and (~above).any()
+
+
+def test_device_spinup_matches_oracle(host):
+    g = case(J=10, I=4)
+    cfg = H.HsConfig(equilibrium_t_option="top_down", spinup_time=200.0, orbital_period=360.0, ml_depth=0.5)
+    hs = H.HsForcing(cfg, g["lat"], 2, 500)
+    ip, dp = pack(cfg, hs)
+    n_iter = 200
+    t0 = 86400 * 2 + 500
+    dec = np.array([float(hs.update_orbit(t0 + 86400 * (i + 1))) for i in range(n_iter)])
+    lat = np.ascontiguousarray(g["lat"])
+    tg = np.zeros_like(lat)
+    host.hs_host_spinup(C.c_long(lat.size), ip.ctypes.data_as(C.POINTER(C.c_int)), dp.ctypes.data_as(P), n_iter, dec.ctypes.data_as(P),
+                        lat.ctypes.data_as(P), tg.ctypes.data_as(P))
+    assert rel(tg, hs.tg_prev) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# (3) the ABI
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_hs_header_symbols_and_struct_layout(lib_built, tmp_path):
+    from isca_b200 import hs
+    lib = hs.load_library()
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "isca_b200_hs.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(isca_b200_hs_\w+)\s*\(", txt))
+    assert declared == set(hs.HS_EXPORTS)
+    for s in declared:
+        assert hasattr(lib, s), f"{s} declared in include/isca_b200_hs.h but not exported"
+    body = "".join(f'printf("%zu\\n", offsetof(IscaHsForcingConfig, {n}));' for n, _ in hs.IscaHsForcingConfigStruct._fields_)
+    src = tmp_path / "l.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "isca_b200_hs.h"\nint main(){printf("%zu\\n", sizeof(IscaHsForcingConfig));'
+                   + body + "return 0;}")
+    exe = tmp_path / "l"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == C.sizeof(hs.IscaHsForcingConfigStruct)
+    for (n, _), off in zip(hs.IscaHsForcingConfigStruct._fields_, out[1:]):
+        assert getattr(hs.IscaHsForcingConfigStruct, n).offset == off, n
+    cfg = hs.hs_config(equilibrium_t_option="top_down", stratosphere_t_option="hs_like", local_heating_option="Isidoro", delh=50.0)
+    assert (cfg.abi_version, cfg.equilibrium_t_option, cfg.stratosphere_t_option, cfg.local_heating_option) == (1, 3, 2, 1)
+    assert cfg.delh == 50.0 and cfg.t_zero == 315.0 and cfg.spinup_time == 10800.0 and abs(cfg.kappa - 2 / 7) < 1e-16
+    d = H.HsConfig()
+    for n in ("t_strat", "delv", "eps", "sigma_b", "P00", "p_trop", "alpha", "ka", "ks", "kf", "trflux", "trsink", "albedo", "lapse", "h_a",
+              "tau_s", "heat_capacity", "ml_depth", "peri_time", "smaxis", "stefan", "solar_const", "omega", "orbital_period", "obliq"):
+        assert getattr(cfg, n) == getattr(d, n), n                                    # same defaults in the library and the oracle
+    with pytest.raises(hs.IscaError):
+        hs.hs_config(equilibrium_t_option="from_file")
+    with pytest.raises(hs.IscaError):
+        hs.hs_config(not_a_variable=1)
+    # no GPU here: creation must fail loudly, not fall back
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(hs.IscaError, match="no CUDA device"):
+            hs.HsForcing(8, 4, 5)
+
+
+def test_hs_wrapper_argument_counts(lib_built):
+    from isca_b200 import hs
+    from test_wrappers_stub import _StubLib, _nparams
+    stub = _StubLib()
+    f = hs.HsForcing.__new__(hs.HsForcing)
+    f._lib, f._h = stub, C.c_void_p(1)
+    f.s2, f.s3, f.s3h = (4, 8), (5, 4, 8), (6, 4, 8)
+    a2, a3, a3h = np.ones(f.s2), np.ones(f.s3), np.ones(f.s3h)
+    udt, vdt, tdt, rdt, d = f.hs_forcing(1200.0, (3, 100), a2, a2, a3h, a3, a3, a3, a3, a3, a3, a3, rm=np.ones((2,) + f.s3),
+                                         rdt=np.zeros((2,) + f.s3), zfull=a3)
+    assert udt.shape == f.s3 and rdt.shape == (2,) + f.s3 and d["teq"].shape == f.s3
+    f.hs_forcing(1200.0, (0, 0), a2, a2, a3h, a3, a3, a3, a3, a3, a3, a3)
+    with pytest.raises(hs.IscaError):
+        f.hs_forcing(1200.0, (0, 0), a2, a2, a3, a3, a3, a3, a3, a3, a3, a3)
+    _ = f.tg_prev
+    f.tg_prev = a2
+    m = hs.HsAtmosphere.__new__(hs.HsAtmosphere)
+    m._lib, m._h, m.s2, m.s3 = stub, C.c_void_p(1), f.s2, f.s3
+    m.set_time(2, 3)
+    m.hs_forcing_init()
+    m.atmosphere(3)
+    for n in hs.MODEL_FIELDS:
+        m.get(n)
+    seen = dict(stub.calls)
+    for fn in ("isca_b200_hs_forcing", "isca_b200_hs_forcing_get_tg_prev", "isca_b200_hs_forcing_set_tg_prev", "isca_b200_hs_model_set_time",
+               "isca_b200_hs_model_init", "isca_b200_hs_model_step", "isca_b200_hs_model_get"):
+        assert seen[fn] == _nparams("isca_b200_hs.h", fn), fn
+    f._h = C.c_void_p()
+    m._h = C.c_void_p()
