@@ -164,6 +164,26 @@ int isca_b200_qe_moist_convection(IscaPhysics p, double dt, const double* Tin, c
                                   double* qref, int* convflag, int* kLZBs, double* cape, double* cin,
                                   double* invtau_q_relaxation, double* invtau_t_relaxation, double* Tref, int* kLCLs);
 
+/* betts_miller_nml (atmos_param/betts_miller/betts_miller.f90:56-70), the full Betts-Miller scheme of convection_scheme =
+ * 'FULL_BETTS_MILLER'.  do_taucape is rejected (the reference rescales the module's tau_bm inside the grid loop, :237-240, so its
+ * result depends on the order of the columns); capetaubm / tau_min belong to it. */
+typedef struct IscaBettsMillerConfig {
+  int abi_version;                 /* 1 */
+  int do_simp, do_shallower, do_changeqref, do_envsat, do_taucape;
+  double tau_bm, rhbm, capetaubm, tau_min, buoyancy_kick;
+} IscaBettsMillerConfig;
+int isca_b200_betts_miller_default_config(IscaBettsMillerConfig* cfg);
+/* betts_miller_init: the namelist of the handle's betts_miller calls (defaults until called) */
+int isca_b200_betts_miller_init(IscaPhysics p, const IscaBettsMillerConfig* cfg);
+/* betts_miller(dt, tin, qin, pfull, phalf, coldT, rain, snow, tdel, qdel, q_ref, bmflag, klzbs, cape, cin, t_ref, invtau_bm_t,
+ * invtau_bm_q, capeflag, klcls) (betts_miller.f90:86-438 with capecalcnew :444-776 and lcltabl :779-845), without coldT / mask /
+ * conv.  tin, qin, pfull [K][J][I], phalf [K+1][J][I]; out rain, snow, cape, cin, invtau_bm_t, invtau_bm_q, capeflag [J][I] (snow = 0;
+ * capeflag = 0: the reference never assigns it; may be NULL), tdel, qdel, q_ref, t_ref [K][J][I] (increments over dt), int bmflag
+ * (0 no CAPE, 1 shallow, 2 deep), klzbs, klcls [J][I] (levels 1-based, 0 = none). */
+int isca_b200_betts_miller(IscaPhysics p, double dt, const double* tin, const double* qin, const double* pfull, const double* phalf,
+                           double* rain, double* snow, double* tdel, double* qdel, double* q_ref, int* bmflag, int* klzbs, double* cape,
+                           double* cin, double* t_ref, double* invtau_bm_t, double* invtau_bm_q, double* capeflag, int* klcls);
+
 /* dry_convection(Time, tg, p_full, p_half, dt_tg, cape, cin, lzb, lcl) (atmos_param/dry_convection/dry_convection.f90:105-186 with
  * capecalc :190-299), the Schneider & Walker dry convective adjustment of convection_scheme = 'dry'.  tau, gamma: dry_convection_nml
  * (no defaults in the reference).  tg, p_full [K][J][I], p_half [K+1][J][I]; out dt_tg [K][J][I] (K/s), cape, cin [J][I], int lzb, lcl
@@ -187,7 +207,8 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
 typedef struct IscaMoist_t* IscaMoist;
 typedef struct IscaMoistConfig {
   int abi_version;                 /* 2 */
-  int convection_scheme;           /* 0 'NONE', 1 'SIMPLE_BETTS_MILLER', 2 'DRY' (idealized_moist_phys.F90:391-426; 'DRY' needs
+  int convection_scheme;           /* 0 'NONE', 1 'SIMPLE_BETTS_MILLER', 2 'DRY', 3 'FULL_BETTS_MILLER' (idealized_moist_phys.F90:391-426;
+                                    * betts_miller_nml: isca_b200_moist_set_betts_miller; 'DRY' needs
                                     * isca_b200_moist_set_dry_convection; large-scale condensation is then skipped, :977) */
   int do_damping;                  /* damping_driver rayleigh sponge */
   double roughness_mom, roughness_heat, roughness_moist;      /* idealized_moist_phys_nml :136-138 */
@@ -224,6 +245,8 @@ int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
  * id 20 albedo, 21 rough_mom, 22 rough_heat, 23 rough_moist, 24 surface heat capacity (J/m2/K), 25 land mask (0. / 1.; used by
  * surface_flux for land_humidity_prefactor / land_evap_prefactor).  Call after isca_b200_moist_init (which fills the aquaplanet values). */
 int isca_b200_moist_set_surface(IscaMoist m, int id, const double* host);
+/* betts_miller_nml of convection_scheme = 'FULL_BETTS_MILLER' (defaults until called) */
+int isca_b200_moist_set_betts_miller(IscaMoist m, const IscaBettsMillerConfig* cfg);
 /* dry_convection_nml: relaxation time scale tau [s] and lapse-rate factor gamma of convection_scheme = 'DRY' */
 int isca_b200_moist_set_dry_convection(IscaMoist m, double tau, double gamma);
 /* mixed_layer_init: ocean_qflux [J][I] (W/m2; `do_qflux` / `do_warmpool` of mixed_layer_nml, atmos_param/qflux/qflux.f90, or a

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libisca_b200.so")
-SOURCES = ["host_tables.cpp", "legendre.cu", "fft.cu", "spectral.cu", "grid.cu", "tracer.cu", "physics.cu", "physics_diff.cu", "physics_surface.cu", "physics_turb.cu", "physics_conv.cu", "physics_dry.cu", "rrtm.cu", "moist_model.cu", "hs_forcing.cu", "core.cu"]
+SOURCES = ["host_tables.cpp", "legendre.cu", "fft.cu", "spectral.cu", "grid.cu", "tracer.cu", "physics.cu", "physics_diff.cu", "physics_surface.cu", "physics_turb.cu", "physics_conv.cu", "physics_dry.cu", "physics_bm.cu", "rrtm.cu", "moist_model.cu", "hs_forcing.cu", "core.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-diag-suppress", "550"]

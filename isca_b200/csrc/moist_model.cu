@@ -139,9 +139,13 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   int* land = reinterpret_cast<int*>(m->iwork.p);
   int* convflag = land + nc; int* klzb = convflag + nc; int* klcl = klzb + nc;
   const double *t_in = tg_p, *q_in = q_p;
-  if (m->mc.convection_scheme == 1) {
-    launch_sbm_convection(p, delta_t, tg_p, q_p, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p, m->c_qref.p, m->c_Tref.p, convflag, klzb, klcl,
-                          m->cape.p, m->cin.p, m->itq.p, m->itt.p);
+  if (m->mc.convection_scheme == 1 || m->mc.convection_scheme == 3) {
+    if (m->mc.convection_scheme == 1)
+      launch_sbm_convection(p, delta_t, tg_p, q_p, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p, m->c_qref.p, m->c_Tref.p, convflag, klzb, klcl,
+                            m->cape.p, m->cin.p, m->itq.p, m->itt.p);
+    else                                                          // 'FULL_BETTS_MILLER' (:889-916): same post-processing
+      launch_betts_miller(p, delta_t, tg_p, q_p, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p, m->c_qref.p, m->c_Tref.p, convflag, klzb, klcl,
+                          m->cape.p, m->cin.p, m->itt.p, m->itq.p);
     conv_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, tg_p, q_p, m->tg_tmp.p, m->qg_tmp.p, m->dt_t.p, m->dt_q.p,
                                                m->rain.p, m->conv_rain.p, m->precip.p);
     t_in = m->tg_tmp.p; q_in = m->qg_tmp.p;
@@ -259,8 +263,8 @@ int isca_b200_moist_create_ranked(const IscaConfig* dyn, const IscaPhysicsConfig
   IscaMoist m = nullptr;
   if (!dyn || !phys || !mc || !out) return mfail(nullptr, "null argument");
   if (mc->abi_version != 2) return mfail(nullptr, "IscaMoistConfig abi_version mismatch");
-  if (mc->convection_scheme < 0 || mc->convection_scheme > 2)
-    return mfail(nullptr, "idealized_moist_phys: Invalid convection scheme (NONE, SIMPLE_BETTS_MILLER and DRY are built)");
+  if (mc->convection_scheme < 0 || mc->convection_scheme > 3)
+    return mfail(nullptr, "idealized_moist_phys: Invalid convection scheme (NONE, SIMPLE_BETTS_MILLER, FULL_BETTS_MILLER and DRY are built)");
   if (dyn->num_tracers != 1) return mfail(nullptr, "idealized_moist_model needs the sphum grid tracer (num_tracers = 1)");
   m = new IscaMoist_t();
   m->mc = *mc;
@@ -482,6 +486,13 @@ int isca_b200_moist_set_dry_convection(IscaMoist m, double tau, double gamma) {
   if (!m) return mfail(nullptr, "null handle");
   if (!(tau > 0.0)) return mfail(m, "dry_convection: tau must be positive");
   m->dry_tau = tau; m->dry_gamma = gamma;
+  return 0;
+}
+
+int isca_b200_moist_set_betts_miller(IscaMoist m, const IscaBettsMillerConfig* cfg) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (m->mc.convection_scheme != 3) return mfail(m, "moist_set_betts_miller: convection_scheme is not 'FULL_BETTS_MILLER'");
+  if (isca_b200_betts_miller_init(m->phy, cfg)) return mfail(m, isca_b200_physics_last_error(m->phy));
   return 0;
 }
 

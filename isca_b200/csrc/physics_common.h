@@ -85,6 +85,7 @@ struct IscaPhysics_t {
   int lcl_n = 0; double lcl_val_min = 0.0, lcl_val_max = 0.0;
   isca_phys::Dev buf[24];               // staging of the host-array entry points
   isca_phys::Dev state[isca_phys::ST_COUNT];
+  IscaBettsMillerConfig bm{1, 1, 0, 0, 0, 0, 7200., .8, 900., 2400., 0.};      // betts_miller_nml defaults (betts_miller.f90:56-66)
   isca_phys::Dev insol;                 // do_seasonal insolation [J][I] (pc.insol_dev points here while it is set)
   bool vert_diff_down_done = false;
   int* d_err = nullptr;
@@ -146,6 +147,9 @@ int build_lcl_table(IscaPhysics p);                                             
 void launch_sbm_convection(IscaPhysics p, double dt, const double* Tin, const double* qin, const double* p_full, const double* p_half,
                            double* rain, double* deltaT, double* deltaq, double* qref, double* Tref, int* convflag, int* kLZBs, int* kLCLs,
                            double* cape, double* cin, double* itq, double* itt);
+void launch_betts_miller(IscaPhysics p, double dt, const double* tin, const double* qin, const double* p_full, const double* p_half,
+                         double* rain, double* tdel, double* qdel, double* q_ref, double* t_ref, int* bmflag, int* klzbs, int* klcls,
+                         double* cape, double* cin, double* invtau_t, double* invtau_q);                         // physics_bm.cu
 void launch_dry_convection(IscaPhysics p, double tau, double gamma, const double* tg, const double* p_full, const double* p_half, double* tp,
                            double* dt_tg, double* cape, double* cin, int* lzb, int* lcl);                         // physics_dry.cu
 void launch_diffusivity(IscaPhysics p, const double* t, const double* q, const double* u, const double* v, const double* z_full,

@@ -9,14 +9,14 @@ from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 
 MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
-                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
+                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
                  q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
 FIELDS_3D = dict(dt_ug=32, dt_vg=33, dt_tg=34, dt_qg=35, diff_m=36, diff_t=37, tdt_rad=38)
 # declared in include/isca_b200_rrtm.h (RRTMG as the moist model's radiation)
 MOIST_RRTM_EXPORTS = ["isca_b200_moist_use_rrtm", "isca_b200_moist_set_ozone", "isca_b200_moist_set_time", "isca_b200_moist_set_seasonal"]
-CONVECTION = {"NONE": 0, "SIMPLE_BETTS_MILLER": 1, "DRY": 2}
+CONVECTION = {"NONE": 0, "SIMPLE_BETTS_MILLER": 1, "DRY": 2, "FULL_BETTS_MILLER": 3}
 
 
 class IscaMoistConfigStruct(C.Structure):
@@ -50,6 +50,8 @@ def _lib():
         lib.isca_b200_moist_set_ocean_qflux.argtypes = [vp, dp]
         lib.isca_b200_moist_set_surface.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_moist_set_dry_convection.argtypes = [vp, C.c_double, C.c_double]
+        from .physics import IscaBettsMillerConfigStruct
+        lib.isca_b200_moist_set_betts_miller.argtypes = [vp, C.POINTER(IscaBettsMillerConfigStruct)]
         lib.isca_b200_moist_timing.argtypes = [vp, dp, dp]
         _bound = True
     return lib
@@ -174,6 +176,13 @@ class MoistAtmosphere:
         if a.shape != self.s2:
             raise IscaError(f"{name} has the wrong shape")
         self._ck(self._lib.isca_b200_moist_set_surface(self._h, self.SURFACE_FIELDS[name], a.ctypes.data_as(C.POINTER(C.c_double))), "set_surface")
+
+    def set_betts_miller(self, **nml):
+        """betts_miller_nml of convection_scheme = 'FULL_BETTS_MILLER' (tau_bm, rhbm, do_simp, do_shallower, do_changeqref, do_envsat,
+        buoyancy_kick)"""
+        from .physics import betts_miller_config
+        cfg = betts_miller_config(**nml)
+        self._ck(self._lib.isca_b200_moist_set_betts_miller(self._h, C.byref(cfg)), "betts_miller_init")
 
     def set_dry_convection(self, tau, gamma):
         """dry_convection_nml (convection_scheme = 'DRY'): relaxation time tau [s], lapse-rate factor gamma"""

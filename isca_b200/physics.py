@@ -20,7 +20,25 @@ PHYSICS_EXPORTS = [
     "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
     "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
     "isca_b200_mo_diff", "isca_b200_surface_flux", "isca_b200_diffusivity", "isca_b200_qe_moist_convection", "isca_b200_dry_convection",
+    "isca_b200_betts_miller_default_config", "isca_b200_betts_miller_init", "isca_b200_betts_miller",
 ]
+
+class IscaBettsMillerConfigStruct(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("abi_version", "do_simp", "do_shallower", "do_changeqref", "do_envsat", "do_taucape")] + \
+               [(n, C.c_double) for n in ("tau_bm", "rhbm", "capetaubm", "tau_min", "buoyancy_kick")]
+
+
+def betts_miller_config(**nml) -> "IscaBettsMillerConfigStruct":
+    """betts_miller_nml defaults (betts_miller.f90:56-66); keyword arguments override"""
+    cfg = IscaBettsMillerConfigStruct()
+    _lib().isca_b200_betts_miller_default_config(C.byref(cfg))
+    names = {f[0] for f in IscaBettsMillerConfigStruct._fields_}
+    for k, v in nml.items():
+        if k not in names:
+            raise IscaError(f"unknown betts_miller_nml variable {k}")
+        setattr(cfg, k, int(v) if k.startswith("do_") else v)
+    return cfg
+
 
 SURFACE_FLUX_IN = ("t_atm", "q_atm", "u_atm", "v_atm", "p_atm", "z_atm", "p_surf", "t_surf", "t_ca", "u_surf", "v_surf",
                    "rough_mom", "rough_heat", "rough_moist", "rough_scale", "gust")
@@ -93,6 +111,9 @@ def _lib():
         ip = C.POINTER(C.c_int)
         lib.isca_b200_qe_moist_convection.argtypes = [vp, C.c_double] + [dp] * 9 + [ip, ip] + [dp] * 5 + [ip]
         lib.isca_b200_dry_convection.argtypes = [vp, C.c_double, C.c_double] + [dp] * 6 + [ip, ip]
+        lib.isca_b200_betts_miller_default_config.argtypes = [C.POINTER(IscaBettsMillerConfigStruct)]
+        lib.isca_b200_betts_miller_init.argtypes = [vp, C.POINTER(IscaBettsMillerConfigStruct)]
+        lib.isca_b200_betts_miller.argtypes = [vp, C.c_double] + [dp] * 9 + [ip, ip] + [dp] * 6 + [ip]
         _bound = True
     return lib
 
@@ -328,6 +349,26 @@ class ColumnPhysics:
                                                          _p(o["deltaT"]), _p(o["deltaq"]), _p(o["qref"]), ip(o["convflag"]), ip(o["kLZBs"]),
                                                          _p(o["CAPE"]), _p(o["CIN"]), _p(o["invtau_q_relaxation"]),
                                                          _p(o["invtau_t_relaxation"]), _p(o["Tref"]), ip(o["kLCLs"])), "qe_moist_convection")
+        return o
+
+    def betts_miller_init(self, **nml):
+        """betts_miller_nml (tau_bm, rhbm, do_simp, do_shallower, do_changeqref, do_envsat, buoyancy_kick)"""
+        cfg = betts_miller_config(**nml)
+        self._ck(self._lib.isca_b200_betts_miller_init(self._h, C.byref(cfg)), "betts_miller_init")
+
+    def betts_miller(self, dt, tin, qin, pfull, phalf):
+        """betts_miller (betts_miller.f90:86) -> dict with the names of qe_moist_convection: rain, snow, deltaT (tdel), deltaq (qdel),
+        qref, Tref, convflag (bmflag), kLZBs, kLCLs, CAPE, CIN, invtau_t_relaxation, invtau_q_relaxation, capeflag"""
+        tin, qin, pfull = (_in(x, self.s3, n) for x, n in ((tin, "tin"), (qin, "qin"), (pfull, "pfull")))
+        phalf = _in(phalf, self.s3h, "phalf")
+        o = {n: np.empty(self.s2) for n in ("rain", "snow", "CAPE", "CIN", "invtau_q_relaxation", "invtau_t_relaxation", "capeflag")}
+        o.update({n: np.empty(self.s3) for n in ("deltaT", "deltaq", "qref", "Tref")})
+        o.update({n: np.empty(self.s2, dtype=np.int32) for n in ("convflag", "kLZBs", "kLCLs")})
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self._ck(self._lib.isca_b200_betts_miller(self._h, float(dt), _p(tin), _p(qin), _p(pfull), _p(phalf), _p(o["rain"]), _p(o["snow"]),
+                                                  _p(o["deltaT"]), _p(o["deltaq"]), _p(o["qref"]), ip(o["convflag"]), ip(o["kLZBs"]),
+                                                  _p(o["CAPE"]), _p(o["CIN"]), _p(o["Tref"]), _p(o["invtau_t_relaxation"]),
+                                                  _p(o["invtau_q_relaxation"]), _p(o["capeflag"]), ip(o["kLCLs"])), "betts_miller")
         return o
 
     def dry_convection(self, tau, gamma, tg, p_full, p_half):

@@ -1191,6 +1191,7 @@ class IdealizedMoistPhys:
         self.diag = {}
         # do_rrtm_radiation (idealized_moist_phys.F90:1167-1177): an oracle.rrtmg.RrtmRadiation instead of the grey scheme
         self.rrtm = None
+        self.bm = None                                                    # convection_scheme = "FULL_BETTS_MILLER": an oracle.betts_miller.BettsMiller
         self.time_s = 0.0
         # two_stream_gray_rad_nml do_seasonal: dict(astro=, lon=, solday=, equinox_day=, use_time_average_coszen=, dt_rad_avg=,
         # day_in_s=, year_in_s=) -> seasonal_insolation at Time (idealized_moist_phys.F90:1054 passes Time, not Time + Time_step)
@@ -1206,6 +1207,14 @@ class IdealizedMoistPhys:
         zero2 = np.zeros_like(self.t_surf)
         if c.convection_scheme == "SIMPLE_BETTS_MILLER":
             o = self.sbm(delta_t, tg_p, q_p, core.p_full[prev], core.p_half[prev])
+            conv_dt_tg, conv_dt_qg, rain = o["deltaT"], o["deltaq"], o["rain"]
+            tg_tmp, qg_tmp = conv_dt_tg + tg_p, conv_dt_qg + q_p
+            conv_dt_tg, conv_dt_qg = conv_dt_tg / delta_t, conv_dt_qg / delta_t
+            rain = rain / delta_t
+            precip = rain
+            self.diag.update(convflag=o["convflag"], cape=o["CAPE"])
+        elif c.convection_scheme == "FULL_BETTS_MILLER":                 # idealized_moist_phys.F90:889-916 (self.bm: oracle.betts_miller)
+            o = self.bm(delta_t, tg_p, q_p, core.p_full[prev], core.p_half[prev])
             conv_dt_tg, conv_dt_qg, rain = o["deltaT"], o["deltaq"], o["rain"]
             tg_tmp, qg_tmp = conv_dt_tg + tg_p, conv_dt_qg + q_p
             conv_dt_tg, conv_dt_qg = conv_dt_tg / delta_t, conv_dt_qg / delta_t

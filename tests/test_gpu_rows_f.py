@@ -356,3 +356,63 @@ def test_dry_model_with_general_hs_forcing(lib_built, nml, ntr):
     m.atmosphere_end()
     if fused:
         fused.atmosphere_end()
+
+
+# ---- betts_miller_mod, the full Betts-Miller scheme (physics_bm.cu); column code checked on the CPU in tests/test_betts_miller.py
+@pytest.mark.parametrize("idx", range(6))
+def test_betts_miller_parity(lib_built, idx):
+    from isca_b200 import physics
+    from oracle.betts_miller import BettsMiller, BettsMillerConfig
+    from test_betts_miller import OPTION_SETS, columns
+    nml = OPTION_SETS[idx]
+    svp, t, q, pf, ph = columns(768, K=24, seed=20 + idx)
+    K, J, I = 24, 12, 64
+    r = lambda a: np.ascontiguousarray(a.reshape(a.shape[0], J, I))
+    t, q, pf, ph = r(t), r(q), r(pf), r(ph)
+    o = BettsMiller(svp, BettsMillerConfig(**nml))(1200.0, t, q, pf, ph)
+    cp = physics.ColumnPhysics(I, J, K)
+    cp.betts_miller_init(**nml)
+    g = cp.betts_miller(1200.0, t, q, pf, ph)
+    assert np.array_equal(g["convflag"], o["convflag"]) and np.array_equal(g["kLZBs"], o["kLZB"]) and np.array_equal(g["kLCLs"], o["kLCL"])
+    for a, b in (("rain", "rain"), ("deltaT", "deltaT"), ("deltaq", "deltaq"), ("qref", "qref"), ("Tref", "Tref"), ("CAPE", "CAPE"), ("CIN", "CIN"),
+                 ("invtau_t_relaxation", "invtau_t"), ("invtau_q_relaxation", "invtau_q")):
+        assert rel(g[a], o[b]) < 1e-11, a
+    assert np.all(g["snow"] == 0) and np.all(g["capeflag"] == 0)
+    assert np.bincount(o["convflag"].ravel(), minlength=3).min() > 5
+    with pytest.raises(physics.IscaError):
+        cp.betts_miller_init(do_taucape=True)                          # order-dependent in the reference: rejected
+    with pytest.raises(physics.IscaError):
+        bad = t.copy(); bad[-1, 0, 0] = 900.0
+        cp.betts_miller(1200.0, bad, q, pf, ph)                        # saturation vapour pressure table overflow
+
+
+@pytest.mark.parametrize("nml", [dict(), dict(do_simp=False, do_shallower=True)])
+def test_moist_model_full_betts_miller(lib_built, nml):
+    """convection_scheme = 'FULL_BETTS_MILLER' in the moist model, three steps against the oracle"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    from oracle.betts_miller import BettsMiller, BettsMillerConfig
+    cfg, core, mp = build("T21", 12, 900.0, "FULL_BETTS_MILLER", seed=6)
+    mp.bm = BettsMiller(mp.svp, BettsMillerConfig(rhbm=0.7, **nml))
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS), convection_scheme="FULL_BETTS_MILLER",
+                              mixed_layer_depth=2.5, albedo_value=0.31)
+    m.set_betts_miller(rhbm=0.7, **nml)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    for step in range(3):
+        core.step()
+        m.atmosphere(1)
+        assert np.array_equal(m.get("convflag").astype(int), mp.diag["convflag"]), step
+        assert rel(m.get("precip"), mp.diag["precip"]) < 1e-9 or np.abs(mp.diag["precip"]).max() < 1e-12, step
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(atm.get_field(api.F_TRACER0), core.grid_tracers[core.current, 0]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+    flags = np.bincount(mp.diag["convflag"].ravel(), minlength=3)
+    assert flags[1] + flags[2] > 0
+    m.atmosphere_end()
