@@ -15,7 +15,7 @@ typedef struct IscaPhysics_t* IscaPhysics;
 
 /* physical constants (shared/constants/constants.F90) and the scheme namelists */
 typedef struct IscaPhysicsConfig {
-  int abi_version;                /* 2 */
+  int abi_version;                /* 3 */
   int num_lon, num_lat, num_levels;
   double grav, rdgas, rvgas, cp_air, hlv, tfreeze, stefan, pstd_mks;
   /* sat_vapor_pres_nml: do_simple tables only (sat_vapor_pres_k.F90:161-266) */
@@ -50,12 +50,20 @@ typedef struct IscaPhysicsConfig {
   double ir_tau_co2_win, ir_tau_wv_win1, ir_tau_wv_win2, ir_tau_co2, ir_tau_wv1, ir_tau_wv2, window, carbon_conc;
   double single_albedo, back_scatter, lw_tau_0_gp, sw_tau_0_gp, lw_tau_exponent_gp, sw_tau_exponent_gp;
   double bog_a, bog_b, bog_mu;
+  /* sat_vapor_pres_nml do_simple (sat_vapor_pres.F90; 1 in every Frierson / MiMA test case): 1 = the Clausius-Clapeyron form
+   * es0*610.78*exp(-hlv/rvgas*(1/T - 1/tfreeze)), 0 = compute_es_k (Goff-Gratch / Smithsonian tables, ice below freezing,
+   * sat_vapor_pres_k.F90:331-381) with finite-difference derivative tables */
+  int sat_vapor_pres_do_simple;
 } IscaPhysicsConfig;
 
 int isca_b200_physics_default_config(IscaPhysicsConfig* cfg);
 int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out);
 int isca_b200_physics_destroy(IscaPhysics p);
 const char* isca_b200_physics_last_error(IscaPhysics p);   /* p may be NULL */
+
+/* sat_vapor_pres_init_k (sat_vapor_pres_k.F90:161-266): the handle's TABLE | DTABLE | D2TABLE (n = 5231 values each: -173 C ... 350 C in
+ * 0.1 K steps) for cfg's tfreeze / hlv / rvgas / es0 / sat_vapor_pres_do_simple.  Host computation: needs no GPU and no handle. */
+int isca_b200_sat_vapor_pres_tables(const IscaPhysicsConfig* cfg, int n, double* tables);
 
 /* lookup_es_des (sat_vapor_pres_k.F90:1132-1158): n temperatures -> es, des.  Out-of-table temperatures fail. */
 int isca_b200_lookup_es_des(IscaPhysics p, int n, const double* temp, double* es, double* des);

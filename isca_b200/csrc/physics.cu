@@ -403,10 +403,65 @@ void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, con
 
 extern "C" {
 
+namespace {
+const int SVP_TCMIN = -173, SVP_TCMAX = 350, SVP_ESRES = 10;
+const int SVP_TABLE_SIZE = (SVP_TCMAX - SVP_TCMIN) * SVP_ESRES + 1;
+
+// compute_es_k (sat_vapor_pres_k.F90:331-381): Goff-Gratch over ice below freezing, over water above -20 C, blended in between
+double compute_es(double tem, double tfreeze) {
+  const double ESBASW = 101324.60, ESBASI = 610.71;
+  const double TBASW = tfreeze + 100., TBASI = tfreeze;
+  double esice = 0., esh2o = 0.;
+  if (tem < TBASI) {
+    const double x = -9.09718 * (TBASI / tem - 1.0) - 3.56654 * std::log10(TBASI / tem) + 0.876793 * (1.0 - tem / TBASI) + std::log10(ESBASI);
+    esice = std::pow(10., x);
+  }
+  if (tem > -20. + TBASI) {
+    const double x = -7.90298 * (TBASW / tem - 1) + 5.02808 * std::log10(TBASW / tem)
+                     - 1.3816e-07 * (std::pow(10., (1 - tem / TBASW) * 11.344) - 1)
+                     + 8.1328e-03 * (std::pow(10., (TBASW / tem - 1) * (-3.49149)) - 1) + std::log10(ESBASW);
+    esh2o = std::pow(10., x);
+  }
+  if (tem <= -20. + TBASI) return esice;
+  if (tem >= TBASI) return esh2o;
+  return 0.05 * ((TBASI - tem) * esice + (tem - TBASI + 20.) * esh2o);
+}
+
+// sat_vapor_pres_init_k (sat_vapor_pres_k.F90:161-266): TABLE | DTABLE | D2TABLE, n = SVP_TABLE_SIZE values each
+void build_svp_tables(const IscaPhysicsConfig& cfg, double* tb, double& dtres, double& tminl, double& dtinvl) {
+  const int n = SVP_TABLE_SIZE;
+  dtres = (double)(SVP_TCMAX - SVP_TCMIN) / (double)(n - 1);
+  tminl = (double)SVP_TCMIN + cfg.tfreeze; dtinvl = 1.0 / dtres;
+  const double tinrc = .1 * dtres, tfact = 5 * dtinvl;
+  for (int i = 0; i < n; ++i) {
+    const double tem = tminl + dtres * (double)i;
+    if (cfg.sat_vapor_pres_do_simple) {
+      tb[i] = cfg.es0 * 610.78 * std::exp(-cfg.hlv / cfg.rvgas * (1.0 / tem - 1.0 / cfg.tfreeze));
+      tb[n + i] = cfg.hlv * tb[i] / cfg.rvgas / (tem * tem);
+    } else {
+      tb[i] = compute_es(tem, cfg.tfreeze);
+      tb[n + i] = (compute_es(tem + tinrc, cfg.tfreeze) - compute_es(tem - tinrc, cfg.tfreeze)) * tfact;
+    }
+  }
+  for (int i = 1; i < n - 1; ++i) tb[2 * n + i] = 0.25 * dtinvl * (tb[n + i + 1] - tb[n + i - 1]);
+  tb[2 * n] = 0.50 * dtinvl * (tb[n + 1] - tb[n]);
+  tb[2 * n + n - 1] = 0.50 * dtinvl * (tb[n + n - 1] - tb[n + n - 2]);
+}
+}  // namespace
+
+int isca_b200_sat_vapor_pres_tables(const IscaPhysicsConfig* cfg, int n, double* tables) {
+  if (!cfg || !tables) return fail(nullptr, "null argument");
+  if (n != SVP_TABLE_SIZE) return fail(nullptr, "sat_vapor_pres: the tables hold " + std::to_string(SVP_TABLE_SIZE) + " values each");
+  double a, b, c;
+  build_svp_tables(*cfg, tables, a, b, c);
+  return 0;
+}
+
 int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
   if (!c) return 1;
   std::memset(c, 0, sizeof(*c));
-  c->abi_version = 2;
+  c->abi_version = 3;
+  c->sat_vapor_pres_do_simple = 1;
   c->grav = 9.80; c->rdgas = 287.04; c->rvgas = 461.50; c->cp_air = 287.04 / (2.0 / 7.0); c->hlv = 2.500e6;
   c->tfreeze = 273.16; c->stefan = 5.6734e-8; c->pstd_mks = 101325.0;
   c->es0 = 1.0; c->hc = 1.0; c->do_evap = 0;
@@ -434,7 +489,7 @@ const char* isca_b200_physics_last_error(IscaPhysics p) { return p ? p->err.c_st
 int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   IscaPhysics p = nullptr;
   if (!cfg || !out) return fail(nullptr, "null argument");
-  if (cfg->abi_version != 2) return fail(nullptr, "IscaPhysicsConfig abi_version mismatch");
+  if (cfg->abi_version != 3) return fail(nullptr, "IscaPhysicsConfig abi_version mismatch");
   if (cfg->rad_scheme < 0 || cfg->rad_scheme > 3) return fail(nullptr, "two_stream_gray_rad: not a valid radiation scheme.");   // two_stream_gray_rad.F90:228
   if (cfg->num_lon < 1 || cfg->num_lat < 1 || cfg->num_levels < 1 || cfg->num_levels > ISCA_KMAX)
     return fail(nullptr, "bad dimensions (num_levels must be 1.." + std::to_string(ISCA_KMAX) + ")");
@@ -475,20 +530,11 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
     c.gp_albedo = (r1 - r2) / (r1 + r2);
     c.Ga_asym = 2. * std::sqrt((1. - cfg->single_albedo) * (1. - g_asym * cfg->single_albedo));
   }
-  // do_simple saturation vapour pressure tables (sat_vapor_pres_k.F90:161-266): tcmin=-173, tcmax=350, esres=10
-  const int tcmin = -173, tcmax = 350, esres = 10;
-  const int n = (tcmax - tcmin) * esres + 1;
+  // saturation vapour pressure tables (sat_vapor_pres_k.F90:161-266): tcmin=-173, tcmax=350, esres=10
+  const int n = SVP_TABLE_SIZE;
   std::vector<double> tb(3 * (size_t)n);
-  double dtres = (double)(tcmax - tcmin) / (double)(n - 1);
-  double tminl = (double)tcmin + cfg->tfreeze, dtinvl = 1.0 / dtres;
-  for (int i = 0; i < n; ++i) {
-    double tem = tminl + dtres * (double)i;
-    tb[i] = cfg->es0 * 610.78 * std::exp(-cfg->hlv / cfg->rvgas * (1.0 / tem - 1.0 / cfg->tfreeze));
-    tb[n + i] = cfg->hlv * tb[i] / cfg->rvgas / (tem * tem);
-  }
-  for (int i = 1; i < n - 1; ++i) tb[2 * n + i] = 0.25 * dtinvl * (tb[n + i + 1] - tb[n + i - 1]);
-  tb[2 * n] = 0.50 * dtinvl * (tb[n + 1] - tb[n]);
-  tb[2 * n + n - 1] = 0.50 * dtinvl * (tb[n + n - 1] - tb[n + n - 2]);
+  double dtres, tminl, dtinvl;
+  build_svp_tables(*cfg, tb.data(), dtres, tminl, dtinvl);
   if (cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking) != cudaSuccess || !p->tab.ensure(tb.size()) ||
       cudaMalloc(&p->d_err, sizeof(int)) != cudaSuccess) { delete p; return fail(nullptr, "CUDA allocation failed"); }
   cudaMemcpyAsync(p->tab.p, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice, p->st);

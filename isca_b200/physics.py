@@ -20,12 +20,31 @@ PHYSICS_EXPORTS = [
     "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
     "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
     "isca_b200_mo_diff", "isca_b200_surface_flux", "isca_b200_diffusivity", "isca_b200_qe_moist_convection", "isca_b200_dry_convection",
-    "isca_b200_betts_miller_default_config", "isca_b200_betts_miller_init", "isca_b200_betts_miller",
+    "isca_b200_sat_vapor_pres_tables", "isca_b200_betts_miller_default_config", "isca_b200_betts_miller_init", "isca_b200_betts_miller",
 ]
 
 class IscaBettsMillerConfigStruct(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("abi_version", "do_simp", "do_shallower", "do_changeqref", "do_envsat", "do_taucape")] + \
                [(n, C.c_double) for n in ("tau_bm", "rhbm", "capetaubm", "tau_min", "buoyancy_kick")]
+
+
+SVP_TABLE_SIZE = 5231
+
+
+def sat_vapor_pres_tables(**nml):
+    """sat_vapor_pres_init_k (sat_vapor_pres_k.F90:161-266) -> TABLE, DTABLE, D2TABLE as the handle builds them for the namelist values
+    (tfreeze, hlv, rvgas, es0, sat_vapor_pres_do_simple).  Computed on the host: works without a GPU."""
+    lib = _lib()
+    cfg = IscaPhysicsConfigStruct()
+    lib.isca_b200_physics_default_config(C.byref(cfg))
+    for k, v in nml.items():
+        if not hasattr(cfg, k):
+            raise IscaError(f"unknown physics namelist variable {k}")
+        setattr(cfg, k, v)
+    out = np.empty(3 * SVP_TABLE_SIZE)
+    if lib.isca_b200_sat_vapor_pres_tables(C.byref(cfg), SVP_TABLE_SIZE, out.ctypes.data_as(C.POINTER(C.c_double))) != 0:
+        raise IscaError("sat_vapor_pres_init: " + lib.isca_b200_physics_last_error(None).decode())
+    return out[:SVP_TABLE_SIZE], out[SVP_TABLE_SIZE:2 * SVP_TABLE_SIZE], out[2 * SVP_TABLE_SIZE:]
 
 
 def betts_miller_config(**nml) -> "IscaBettsMillerConfigStruct":
@@ -71,7 +90,8 @@ class IscaPhysicsConfigStruct(C.Structure):
                [("rad_scheme", C.c_int)] + \
                [(n, C.c_double) for n in ("ir_tau_co2_win", "ir_tau_wv_win1", "ir_tau_wv_win2", "ir_tau_co2", "ir_tau_wv1", "ir_tau_wv2",
                                           "window", "carbon_conc", "single_albedo", "back_scatter", "lw_tau_0_gp", "sw_tau_0_gp",
-                                          "lw_tau_exponent_gp", "sw_tau_exponent_gp", "bog_a", "bog_b", "bog_mu")]
+                                          "lw_tau_exponent_gp", "sw_tau_exponent_gp", "bog_a", "bog_b", "bog_mu")] + \
+               [("sat_vapor_pres_do_simple", C.c_int)]
 
 RAD_SCHEMES = {"FRIERSON": 0, "BYRNE": 1, "GEEN": 2, "SCHNEIDER": 3}      # two_stream_gray_rad.F90:214-230
 
@@ -111,6 +131,7 @@ def _lib():
         ip = C.POINTER(C.c_int)
         lib.isca_b200_qe_moist_convection.argtypes = [vp, C.c_double] + [dp] * 9 + [ip, ip] + [dp] * 5 + [ip]
         lib.isca_b200_dry_convection.argtypes = [vp, C.c_double, C.c_double] + [dp] * 6 + [ip, ip]
+        lib.isca_b200_sat_vapor_pres_tables.argtypes = [C.POINTER(IscaPhysicsConfigStruct), C.c_int, dp]
         lib.isca_b200_betts_miller_default_config.argtypes = [C.POINTER(IscaBettsMillerConfigStruct)]
         lib.isca_b200_betts_miller_init.argtypes = [vp, C.POINTER(IscaBettsMillerConfigStruct)]
         lib.isca_b200_betts_miller.argtypes = [vp, C.c_double] + [dp] * 9 + [ip, ip] + [dp] * 6 + [ip]

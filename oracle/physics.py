@@ -23,11 +23,27 @@ PSTD_MKS = 101325.0
 PI = 3.14159265358979323846
 
 
+def compute_es(tem, tfreeze=None):
+    """compute_es_k (sat_vapor_pres_k.F90:331-381): Goff-Gratch saturation vapour pressure over ice below freezing, over water above
+    -20 C, linearly blended in between (Smithsonian Meteorological Tables p. 350)"""
+    tfreeze = TFREEZE if tfreeze is None else tfreeze
+    tem = np.asarray(tem, dtype=np.float64)
+    ESBASW, ESBASI = 101324.60, 610.71
+    TBASW, TBASI = tfreeze + 100., tfreeze
+    x = -9.09718 * (TBASI / tem - 1.0) - 3.56654 * np.log10(TBASI / tem) + 0.876793 * (1.0 - tem / TBASI) + np.log10(ESBASI)
+    esice = np.where(tem < TBASI, 10. ** x, 0.)
+    x = -7.90298 * (TBASW / tem - 1) + 5.02808 * np.log10(TBASW / tem) - 1.3816e-07 * (10 ** ((1 - tem / TBASW) * 11.344) - 1) \
+        + 8.1328e-03 * (10 ** ((TBASW / tem - 1) * (-3.49149)) - 1) + np.log10(ESBASW)
+    esh2o = np.where(tem > -20. + TBASI, 10. ** x, 0.)
+    blend = 0.05 * ((TBASI - tem) * esice + (tem - TBASI + 20.) * esh2o)
+    return np.where(tem <= -20. + TBASI, esice, np.where(tem >= TBASI, esh2o, blend))
+
+
 class SatVaporPres:
-    """sat_vapor_pres_init_k with do_simple=.true. (tcmin=-173, tcmax=350, esres=10) and the lookup
+    """sat_vapor_pres_init_k (tcmin=-173, tcmax=350, esres=10; do_simple=.true. unless told otherwise) and the lookup
     (2nd-order Taylor within a 0.1 K bin)."""
 
-    def __init__(self, es0: float = 1.0):
+    def __init__(self, es0: float = 1.0, do_simple: bool = True):
         tcmin, tcmax, esres = -173, 350, 10
         n = (tcmax - tcmin) * esres + 1
         self.table_siz = n
@@ -36,8 +52,13 @@ class SatVaporPres:
         self.dtinvl = 1.0 / self.dtres
         self.tepsl = 0.5 * self.dtres
         tem = self.tminl + self.dtres * np.arange(n, dtype=np.float64)
-        self.TABLE = es0 * 610.78 * np.exp(-HLV / RVGAS * (1.0 / tem - 1.0 / TFREEZE))
-        self.DTABLE = HLV * self.TABLE / RVGAS / tem ** 2.0
+        if do_simple:
+            self.TABLE = es0 * 610.78 * np.exp(-HLV / RVGAS * (1.0 / tem - 1.0 / TFREEZE))
+            self.DTABLE = HLV * self.TABLE / RVGAS / tem ** 2.0
+        else:                                                    # :238-246: centred difference over +-0.1*dtres, tfact = 5*dtinvl
+            tinrc, tfact = .1 * self.dtres, 5 * self.dtinvl
+            self.TABLE = compute_es(tem)
+            self.DTABLE = (compute_es(tem + tinrc) - compute_es(tem - tinrc)) * tfact
         d2 = np.zeros(n)
         d2[1:-1] = 0.25 * self.dtinvl * (self.DTABLE[2:] - self.DTABLE[:-2])
         d2[0] = 0.50 * self.dtinvl * (self.DTABLE[1] - self.DTABLE[0])

@@ -114,7 +114,8 @@ def test_physics_header_symbols_exported_and_struct_layout(lib_built, tmp_path):
     assert (c.hc, c.do_evap, c.trayfric, c.sponge_pbottom) == (1.0, 0, 0.0, 50.0)
     # the other rad_scheme values (two_stream_gray_rad.F90:96-118)
     assert (c.abi_version, c.rad_scheme, c.window, c.carbon_conc, c.bog_a, c.bog_b, c.lw_tau_0_gp, c.single_albedo) == \
-        (2, 0, 0.3732, 360.0, 0.8678, 1997.9, 80.0, 0.8)
+        (3, 0, 0.3732, 360.0, 0.8678, 1997.9, 80.0, 0.8)
+    assert c.sat_vapor_pres_do_simple == 1
 
 
 @pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")

@@ -416,3 +416,27 @@ def test_moist_model_full_betts_miller(lib_built, nml):
     flags = np.bincount(mp.diag["convflag"].ravel(), minlength=3)
     assert flags[1] + flags[2] > 0
     m.atmosphere_end()
+
+
+def test_full_saturation_vapour_pressure_tables(lib_built):
+    """sat_vapor_pres_nml do_simple = .false.: compute_es_k tables behind lookup_es_des / compute_qs / lscale_cond"""
+    from isca_b200 import physics
+    from oracle import physics as O
+    from test_gpu_physics import columns, TOL
+    K, J, I = 16, 8, 32
+    rng, ps, ph, pf, t, lat = columns(K, J, I, 5)
+    s = O.SatVaporPres(do_simple=False)
+    cp = physics.ColumnPhysics(I, J, K, sat_vapor_pres_do_simple=0, do_evap=1)
+    T = np.linspace(180.0, 330.0, 997)
+    es, des = cp.lookup_es_des(T)
+    eo, do_ = s.lookup_es_des(T)
+    assert rel(es, eo) < 1e-13 and rel(des, do_) < 1e-8
+    qs, _ = s.compute_qs(t, pf)
+    q = qs * rng.uniform(0.3, 1.4, size=t.shape)
+    rain, tdel, qdel = cp.lscale_cond(t, q, pf, ph)
+    ro, to, qo = O.lscale_cond(s, t, q, pf, ph, hc=1.0, do_evap=True)
+    assert rel(tdel, to) < 1e-9 and rel(qdel, qo) < 1e-9 and rel(rain, ro) < 1e-9
+    assert np.array_equal(qdel == 0.0, qo == 0.0)
+    simple = physics.ColumnPhysics(I, J, K, do_evap=1)
+    r2, _, _ = simple.lscale_cond(t, q, pf, ph)
+    assert not np.allclose(r2, rain)

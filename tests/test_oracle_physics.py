@@ -439,3 +439,45 @@ def test_grey_radiation_with_insolation_override():
         d2 = g.down(lat, ph, t, albedo=np.zeros((J, I)), insolation=0.5 * prof)
         assert np.allclose(d2["sw_down_surf"], 0.5 * d0["sw_down_surf"], rtol=1e-14)
         assert np.array_equal(d2["surf_lw_down"], d0["surf_lw_down"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sat_vapor_pres tables: the product's host table builder (no GPU needed) against the oracle, do_simple and compute_es_k
+# ------------------------------------------------------------------------------------------------------------------
+def test_sat_vapor_pres_tables_of_the_library_match_the_oracle(lib_built):
+    from isca_b200 import physics
+    from oracle import physics as P
+    for simple in (True, False):
+        t, d, d2 = physics.sat_vapor_pres_tables(sat_vapor_pres_do_simple=int(simple))
+        o = P.SatVaporPres(do_simple=simple)
+        assert t.size == o.table_siz == physics.SVP_TABLE_SIZE
+        assert np.abs(t / o.TABLE - 1).max() < 1e-13, simple
+        assert np.abs(d / o.DTABLE - 1).max() < (1e-13 if simple else 1e-8), simple      # centred difference of nearly equal numbers
+        assert np.abs(d2 - o.D2TABLE).max() < 1e-7 * np.abs(o.D2TABLE).max(), simple
+    t2, _, _ = physics.sat_vapor_pres_tables(es0=1.5)
+    assert np.allclose(t2, 1.5 * P.SatVaporPres().TABLE, rtol=1e-14)
+    with pytest.raises(physics.IscaError):
+        physics.sat_vapor_pres_tables(nonsense=1)
+
+
+def test_compute_es_known_values():
+    """compute_es_k: its anchor points by construction and the Smithsonian / Goff-Gratch table values it encodes"""
+    from oracle import physics as P
+    tf = P.TFREEZE
+    assert abs(P.compute_es(tf + 100.) / 101324.60 - 1) < 1e-13              # ESBASW at the steam point
+    assert abs(P.compute_es(tf - 1e-9) / 610.71 - 1) < 1e-3                  # ESBASI just below the ice point (blend weight ~0)
+    assert abs(P.compute_es(tf - 20.) - P.compute_es(tf - 20. - 1e-9)) < 1e-6          # continuous at the ends of the blend
+    assert abs(P.compute_es(tf) - P.compute_es(tf - 1e-9)) < 1e-3
+    # Goff-Gratch values (WMO / Smithsonian tables): 20 C over water 2338 Pa, -10 C over ice 259.9 Pa, -40 C over ice 12.84 Pa
+    assert abs(P.compute_es(293.15) / 2338.0 - 1) < 3e-3
+    assert abs(P.compute_es(233.15) / 12.84 - 1) < 5e-3
+    es = P.compute_es(np.linspace(150.0, 400.0, 2000))
+    assert np.all(np.diff(es) > 0)
+    # the simple Clausius-Clapeyron form agrees with it within a few per cent in the troposphere's warm range
+    s, f = P.SatVaporPres(do_simple=True), P.SatVaporPres(do_simple=False)
+    i0, i1 = int((273.16 - s.tminl) / s.dtres), int((303.16 - s.tminl) / s.dtres)
+    assert np.abs(s.TABLE[i0:i1] / f.TABLE[i0:i1] - 1).max() < 0.03
+    # lookup with the full tables: 2nd-order Taylor reproduces compute_es between the nodes
+    T = np.array([215.37, 262.91, 288.04, 301.55])
+    es_l, des_l = f.lookup_es_des(T)
+    assert np.abs(es_l / P.compute_es(T) - 1).max() < 1e-6
