@@ -90,7 +90,16 @@ enum { ISCA_SC_MEAN_PS = 0, ISCA_SC_MEAN_ENERGY = 1, ISCA_SC_T_MIN = 2, ISCA_SC_
        ISCA_SC_STEP_COUNT = 4, ISCA_SC_KERNEL_LAUNCHES = 5, ISCA_SC_LAST_STEP_MS = 6 };
 /* 1-D tables */
 enum { ISCA_TB_SIN_LAT = 0, ISCA_TB_WTS_LAT = 1, ISCA_TB_DEG_LAT = 2, ISCA_TB_DEG_LON = 3,
-       ISCA_TB_PK = 4, ISCA_TB_BK = 5 };
+       ISCA_TB_PK = 4, ISCA_TB_BK = 5,
+       /* isca_b200_host_table only.  Packed spectral rows: row r = (m, n) in the order ROW_M / ROW_N give (T rows) */
+       ISCA_TB_ROW_M = 16, ISCA_TB_ROW_N = 17,          /* [T] as doubles */
+       ISCA_TB_LEGENDRE = 18,                           /* [T][lat_max/2]: associated Legendre functions on the Gaussian latitudes of
+                                                           one hemisphere (tools/spherical.F90 compute_legendre) */
+       ISCA_TB_EIGEN_LAPLACIAN = 19,                    /* [T] n(n+1)/a^2 */
+       ISCA_TB_DAMPING = 20,                            /* [T] spectral_damping coefficients (spectral_damping.F90) */
+       ISCA_TB_REF_T = 21, ISCA_TB_IMPLICIT_H = 22,     /* [K] implicit.F90 reference temperature and h */
+       ISCA_TB_DIV_MAT = 23,                            /* [K][K] implicit.F90 div_mat, row-major */
+       ISCA_TB_WAVE_MATRIX = 24 };                      /* [M+1][K][K] implicit.F90 wave_matrix, see isca_b200_host_table */
 
 /* Fill cfg with the reference's namelist defaults (T42 L18 dt=600, Held-Suarez). */
 void isca_b200_default_config(IscaConfig* cfg);
@@ -122,6 +131,12 @@ int isca_b200_set_peer_handles(IscaHandle h, const void* all_handles);
  * Fourier buffer).  Needs no GPU. */
 int isca_b200_decomposition(const IscaConfig* cfg, int rank, int nranks, int* lat_start, int* lat_count,
                             int* num_m, int* m_list, int* owner, int* pos);
+
+/* The host-side tables the library builds at create time (Gaussian grid, vertical coordinate, Legendre functions, spectral
+ * coefficient tables, semi-implicit matrices; host_tables.cpp), without creating a handle: needs no GPU, so the table code can be
+ * checked against the oracle on any machine.  count must equal the table's size (queried with host == NULL: returns the size in
+ * *count_out).  ISCA_TB_WAVE_MATRIX is built for xi = 2 * dt_atmos * alpha_implicit (the leapfrog step). */
+int isca_b200_host_table(const IscaConfig* cfg, int table_id, double* host, int count, int* count_out);
 
 /* cold start: spectral_init_cond 'quiescent' -> spectral_initialize_fields
  * (atmos_spectral/init/spectral_initialize_fields.F90:45-135), previous = current. */

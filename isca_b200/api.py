@@ -79,6 +79,21 @@ S_DT_VOR, S_DT_DIV, S_DT_T, S_DT_LNPS = 8, 9, 10, 11
 LEVEL_CURRENT, LEVEL_PREVIOUS = -1, -2
 SC_MEAN_PS, SC_MEAN_ENERGY, SC_T_MIN, SC_T_MAX, SC_STEP_COUNT, SC_KERNEL_LAUNCHES, SC_LAST_STEP_MS = range(7)
 TB_SIN_LAT, TB_WTS_LAT, TB_DEG_LAT, TB_DEG_LON, TB_PK, TB_BK = range(6)
+# isca_b200_host_table only (packed spectral rows, see include/isca_b200.h)
+TB_ROW_M, TB_ROW_N, TB_LEGENDRE, TB_EIGEN_LAPLACIAN, TB_DAMPING, TB_REF_T, TB_IMPLICIT_H, TB_DIV_MAT, TB_WAVE_MATRIX = range(16, 25)
+
+
+def host_table(config, table_id) -> np.ndarray:
+    """The host-side table the library builds at create time for this configuration (host_tables.cpp), flat.  Needs no GPU."""
+    lib = load_library()
+    lib.isca_b200_host_table.argtypes = [C.POINTER(IscaConfigStruct), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+    n = C.c_int(0)
+    if lib.isca_b200_host_table(C.byref(config), table_id, None, 0, C.byref(n)) != 0:
+        raise IscaError("host_table: " + lib.isca_b200_last_error(None).decode())
+    out = np.empty(n.value)
+    if lib.isca_b200_host_table(C.byref(config), table_id, out.ctypes.data_as(C.POINTER(C.c_double)), n.value, None) != 0:
+        raise IscaError("host_table: " + lib.isca_b200_last_error(None).decode())
+    return out
 
 _VERT_COORD = {"even_sigma": 0, "uneven_sigma": 1, "input": 2, "hybrid": 3}
 _VERT_ADV = {"second_centered": 0}

@@ -813,6 +813,43 @@ int isca_b200_decomposition(const IscaConfig* cfg, int rank, int nranks, int* la
   return 0;
 }
 
+int isca_b200_host_table(const IscaConfig* cfg, int id, double* host, int count, int* count_out) {
+  try {
+    if (!cfg) throw std::runtime_error("null argument");
+    if (cfg->abi_version != ISCA_B200_ABI_VERSION) throw std::runtime_error("IscaConfig.abi_version mismatch");
+    Geometry g;
+    HostTables t;
+    build_geometry(*cfg, 0, 1, g);
+    build_tables(*cfg, g, t);
+    std::vector<double> tmp;
+    const std::vector<double>* v = nullptr;
+    switch (id) {
+      case ISCA_TB_SIN_LAT: v = &t.sin_lat; break;
+      case ISCA_TB_WTS_LAT: v = &t.wts_lat; break;
+      case ISCA_TB_DEG_LAT: v = &t.deg_lat; break;
+      case ISCA_TB_DEG_LON: v = &t.deg_lon; break;
+      case ISCA_TB_PK: v = &t.pk; break;
+      case ISCA_TB_BK: v = &t.bk; break;
+      case ISCA_TB_ROW_M: for (int r : t.row_m) tmp.push_back((double)g.m_of[r]); v = &tmp; break;     // zonal wavenumber of the row
+      case ISCA_TB_ROW_N: tmp.assign(t.row_n.begin(), t.row_n.end()); v = &tmp; break;
+      case ISCA_TB_LEGENDRE: v = &t.leg; break;
+      case ISCA_TB_EIGEN_LAPLACIAN: v = &t.eigen; break;
+      case ISCA_TB_DAMPING: v = &t.damping; break;
+      case ISCA_TB_REF_T: v = &t.ref_t; break;
+      case ISCA_TB_IMPLICIT_H: v = &t.h; break;
+      case ISCA_TB_DIV_MAT: v = &t.div_mat; break;
+      case ISCA_TB_WAVE_MATRIX: build_wave_matrices(*cfg, g, t, 2 * cfg->dt_atmos * cfg->alpha_implicit, tmp); v = &tmp; break;
+      default: throw std::runtime_error("unknown table id");
+    }
+    if (count_out) *count_out = (int)v->size();
+    if (host) {
+      if ((size_t)count != v->size()) throw std::runtime_error("table size mismatch");
+      std::memcpy(host, v->data(), v->size() * sizeof(double));
+    }
+  } catch (const std::exception& e) { g_create_error = e.what(); return 2; }
+  return 0;
+}
+
 int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* nccl_unique_id, IscaHandle* out) {
   if (!cfg || !out) { g_create_error = "null argument"; return 1; }
   *out = nullptr;
