@@ -58,7 +58,7 @@ class IscaConfigStruct(C.Structure):
 
 
 EXPORTS = [
-    "isca_b200_default_config", "isca_b200_create", "isca_b200_destroy", "isca_b200_last_error",
+    "isca_b200_default_config", "isca_b200_create", "isca_b200_destroy", "isca_b200_last_error", "isca_b200_host_table",
     "isca_b200_nccl_unique_id", "isca_b200_cold_start", "isca_b200_set_grid_state",
     "isca_b200_set_spectral_state", "isca_b200_set_vor_div_grid", "isca_b200_set_surf_geopotential",
     "isca_b200_set_time_pointers", "isca_b200_step", "isca_b200_step_dynamics_only",
