@@ -89,6 +89,11 @@ int isca_b200_two_stream_gray_rad_down(IscaPhysics p, const double* lat, const d
 int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const double* p_half, const double* t,
                                      const double* t_surf, const double* albedo, const double* q, double* tdt, double* olr);
 
+/* do_read_co2 (two_stream_gray_rad.F90:209-212, 519-521): the CO2 concentration (ppmv) the host read from `co2_file` for Time_diag
+ * (`carbon_conc = maxval(co2f)`), used by the longwave of the following two_stream_gray_rad_down / _up calls; as in the reference
+ * the shortwave of the geen scheme (:466, evaluated before the file is read) still sees the value of the previous down call. */
+int isca_b200_two_stream_gray_rad_set_co2(IscaPhysics p, double carbon_conc);
+
 /* do_seasonal (two_stream_gray_rad.F90:417-447): the insolation [J][I] (= solar_constant * coszen from astronomy_mod
  * diurnal_solar, see isca_b200_diurnal_solar) that the following two_stream_gray_rad_down / _up calls use instead of the analytic
  * annual-mean profile; NULL switches back.  It takes precedence over the scheme's own profile, as in the reference. */
@@ -253,6 +258,9 @@ int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
  * id 20 albedo, 21 rough_mom, 22 rough_heat, 23 rough_moist, 24 surface heat capacity (J/m2/K), 25 land mask (0. / 1.; used by
  * surface_flux for land_humidity_prefactor / land_evap_prefactor).  Call after isca_b200_moist_init (which fills the aquaplanet values). */
 int isca_b200_moist_set_surface(IscaMoist m, int id, const double* host);
+/* do_read_co2 for the resident moist model (see isca_b200_two_stream_gray_rad_set_co2): call before the isca_b200_moist_step whose
+ * Time the value belongs to */
+int isca_b200_moist_set_co2(IscaMoist m, double carbon_conc);
 /* betts_miller_nml of convection_scheme = 'FULL_BETTS_MILLER' (defaults until called) */
 int isca_b200_moist_set_betts_miller(IscaMoist m, const IscaBettsMillerConfig* cfg);
 /* dry_convection_nml: relaxation time scale tau [s] and lapse-rate factor gamma of convection_scheme = 'DRY' */

@@ -489,6 +489,13 @@ int isca_b200_moist_set_dry_convection(IscaMoist m, double tau, double gamma) {
   return 0;
 }
 
+int isca_b200_moist_set_co2(IscaMoist m, double carbon_conc) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (m->rr) return mfail(m, "moist_set_co2: do_read_co2 belongs to two_stream_gray_rad (RRTMG: co2ppmv of rrtm_radiation_nml)");
+  if (isca_b200_two_stream_gray_rad_set_co2(m->phy, carbon_conc)) return mfail(m, isca_b200_physics_last_error(m->phy));
+  return 0;
+}
+
 int isca_b200_moist_set_betts_miller(IscaMoist m, const IscaBettsMillerConfig* cfg) {
   if (!m) return mfail(nullptr, "null handle");
   if (m->mc.convection_scheme != 3) return mfail(m, "moist_set_betts_miller: convection_scheme is not 'FULL_BETTS_MILLER'");

@@ -221,6 +221,7 @@ __device__ __forceinline__ void rad_var_down(const PhysConst& c, int ncol, int K
                                              const double* __restrict__ t, const double* __restrict__ q, RadVarCol& r) {
   const int sch = c.rad_scheme;
   const double lcc = log(c.carbon_conc / 360.);
+  const double lcc_sw = log(c.carbon_conc_sw / 360.);            // do_read_co2: the shortwave of a call still sees the previous value (:466, :519-521)
   double insolation;
   if (c.insol_dev) insolation = c.insol_dev[col];                 // do_seasonal takes precedence over the scheme's profile (:417)
   else if (sch == 3) insolation = (c.solar_constant / 3.14159265358979323846) * cos(lat);
@@ -240,7 +241,7 @@ __device__ __forceinline__ void rad_var_down(const PhysConst& c, int ncol, int K
       const double ph1 = p_half[o + ncol];
       double sw_wv = sw_tau_k + 0.5194;
       sw_wv = exp(0.01887 / (sw_tau_k + 0.009522) + 1.603 / (sw_wv * sw_wv));
-      const double del_sol_tau = (0.0596 + 0.0029 * lcc + sw_wv * q[o]) * (ph1 - ph0) / ps;
+      const double del_sol_tau = (0.0596 + 0.0029 * lcc_sw + sw_wv * q[o]) * (ph1 - ph0) / ps;
       r.swd[k + 1] = r.swd[k] * exp(-del_sol_tau);
       sw_tau_k = sw_tau_k + del_sol_tau;
       ph0 = ph1;
@@ -375,6 +376,8 @@ void launch_lscale(IscaPhysics p, const double* t, const double* q, const double
 }
 void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* alb, double* sw, double* lw) {
   int nb = (int)((p->ncol + 127) / 128);
+  p->pc.carbon_conc_sw = p->co2_next_sw;                       // the value the longwave of the previous down call used
+  p->co2_next_sw = p->pc.carbon_conc;
   if (p->pc.rad_scheme == 0) gray_down_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, alb, sw, lw);
   else gray_down_var_kernel<<<nb, 128, 0, p->st>>>(p->pc, (int)p->ncol, p->K, lat, ph, t, q, alb, sw, lw);
 }
@@ -521,7 +524,7 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   c.rad_scheme = cfg->rad_scheme;
   c.ir_tau_co2_win = cfg->ir_tau_co2_win; c.ir_tau_wv_win1 = cfg->ir_tau_wv_win1; c.ir_tau_wv_win2 = cfg->ir_tau_wv_win2;
   c.ir_tau_co2 = cfg->ir_tau_co2; c.ir_tau_wv1 = cfg->ir_tau_wv1; c.ir_tau_wv2 = cfg->ir_tau_wv2; c.window = cfg->window;
-  c.carbon_conc = cfg->carbon_conc; c.lw_tau_0_gp = cfg->lw_tau_0_gp; c.sw_tau_0_gp = cfg->sw_tau_0_gp;
+  c.carbon_conc = cfg->carbon_conc; c.carbon_conc_sw = cfg->carbon_conc; p->co2_next_sw = cfg->carbon_conc; c.lw_tau_0_gp = cfg->lw_tau_0_gp; c.sw_tau_0_gp = cfg->sw_tau_0_gp;
   c.lw_tau_exponent_gp = cfg->lw_tau_exponent_gp; c.sw_tau_exponent_gp = cfg->sw_tau_exponent_gp;
   c.bog_a = cfg->bog_a; c.bog_b = cfg->bog_b; c.bog_mu = cfg->bog_mu; c.pstd_earth = 101325.0;      // PSTD_MKS_EARTH, constants.F90:252
   {                                                            // two_stream_gray_rad_init :233-238
@@ -614,6 +617,13 @@ int isca_b200_two_stream_gray_rad_up(IscaPhysics p, const double* lat, const dou
   if (down(p, p->buf[5], tdt, n3)) return 1;
   if (olr && down(p, p->buf[6], olr, nc)) return 1;
   return finish(p, "two_stream_gray_rad_up");
+}
+
+int isca_b200_two_stream_gray_rad_set_co2(IscaPhysics p, double carbon_conc) {
+  if (!p) return fail(nullptr, "null handle");
+  if (!(carbon_conc > 0.0)) return fail(p, "two_stream_gray_rad: carbon_conc must be positive");
+  p->pc.carbon_conc = carbon_conc;
+  return 0;
 }
 
 int isca_b200_two_stream_gray_rad_set_insolation(IscaPhysics p, const double* insolation) {

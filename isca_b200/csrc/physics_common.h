@@ -26,6 +26,7 @@ struct PhysConst {
   // rad_scheme variants (two_stream_gray_rad.F90:89-118): 0 frierson, 1 byrne, 2 geen, 3 schneider
   int rad_scheme;
   double ir_tau_co2_win, ir_tau_wv_win1, ir_tau_wv_win2, ir_tau_co2, ir_tau_wv1, ir_tau_wv2, window, carbon_conc;
+  double carbon_conc_sw;                // do_read_co2: value seen by the geen shortwave (the longwave value of the previous call)
   double lw_tau_0_gp, sw_tau_0_gp, lw_tau_exponent_gp, sw_tau_exponent_gp, gp_albedo, Ga_asym;
   double bog_a, bog_b, bog_mu, pstd_earth;
   // do_seasonal (two_stream_gray_rad.F90:417-447): per-column insolation = solar_constant * coszen computed by the driver;
@@ -86,6 +87,7 @@ struct IscaPhysics_t {
   isca_phys::Dev buf[24];               // staging of the host-array entry points
   isca_phys::Dev state[isca_phys::ST_COUNT];
   IscaBettsMillerConfig bm{1, 1, 0, 0, 0, 0, 7200., .8, 900., 2400., 0.};      // betts_miller_nml defaults (betts_miller.f90:56-66)
+  double co2_next_sw = 360.0;           // do_read_co2 bookkeeping of launch_gray_down
   isca_phys::Dev insol;                 // do_seasonal insolation [J][I] (pc.insol_dev points here while it is set)
   bool vert_diff_down_done = false;
   int* d_err = nullptr;

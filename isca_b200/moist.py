@@ -9,7 +9,7 @@ from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 
 MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
-                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
+                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_co2", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
                  q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
@@ -50,6 +50,7 @@ def _lib():
         lib.isca_b200_moist_set_ocean_qflux.argtypes = [vp, dp]
         lib.isca_b200_moist_set_surface.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_moist_set_dry_convection.argtypes = [vp, C.c_double, C.c_double]
+        lib.isca_b200_moist_set_co2.argtypes = [vp, C.c_double]
         from .physics import IscaBettsMillerConfigStruct
         lib.isca_b200_moist_set_betts_miller.argtypes = [vp, C.POINTER(IscaBettsMillerConfigStruct)]
         lib.isca_b200_moist_timing.argtypes = [vp, dp, dp]
@@ -176,6 +177,10 @@ class MoistAtmosphere:
         if a.shape != self.s2:
             raise IscaError(f"{name} has the wrong shape")
         self._ck(self._lib.isca_b200_moist_set_surface(self._h, self.SURFACE_FIELDS[name], a.ctypes.data_as(C.POINTER(C.c_double))), "set_surface")
+
+    def set_co2(self, carbon_conc):
+        """two_stream_gray_rad_nml do_read_co2: the value of co2_file at the Time of the next atmosphere() call (ppmv)"""
+        self._ck(self._lib.isca_b200_moist_set_co2(self._h, float(carbon_conc)), "two_stream_gray_rad")
 
     def set_betts_miller(self, **nml):
         """betts_miller_nml of convection_scheme = 'FULL_BETTS_MILLER' (tau_bm, rhbm, do_simp, do_shallower, do_changeqref, do_envsat,

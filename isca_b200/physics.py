@@ -15,7 +15,7 @@ from .api import load_library, IscaError
 PHYSICS_EXPORTS = [
     "isca_b200_physics_default_config", "isca_b200_physics_create", "isca_b200_physics_destroy",
     "isca_b200_physics_last_error", "isca_b200_lookup_es_des", "isca_b200_compute_qs", "isca_b200_lscale_cond",
-    "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_two_stream_gray_rad_set_insolation",
+    "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_two_stream_gray_rad_set_insolation", "isca_b200_two_stream_gray_rad_set_co2",
     "isca_b200_rayleigh_damping",
     "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
     "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
@@ -115,6 +115,7 @@ def _lib():
         lib.isca_b200_two_stream_gray_rad_down.argtypes = [vp] + [dp] * 7
         lib.isca_b200_two_stream_gray_rad_up.argtypes = [vp] + [dp] * 8
         lib.isca_b200_two_stream_gray_rad_set_insolation.argtypes = [vp, dp]
+        lib.isca_b200_two_stream_gray_rad_set_co2.argtypes = [vp, C.c_double]
         lib.isca_b200_rayleigh_damping.argtypes = [vp, C.c_double] + [dp] * 7
         lib.isca_b200_physics_time.argtypes = [vp, C.c_int, C.c_int, dp, dp]
         lib.isca_b200_gcm_vert_diff_down.argtypes = [vp, C.c_double] + [dp] * 18
@@ -222,6 +223,10 @@ class ColumnPhysics:
         self._ck(self._lib.isca_b200_two_stream_gray_rad_down(self._h, _p(lat), _p(p_half), _p(t), _p(albedo), _p(q) if q is not None else None,
                                                               _p(sw), _p(lw)), "two_stream_gray_rad_down")
         return sw, lw
+
+    def two_stream_gray_rad_set_co2(self, carbon_conc):
+        """do_read_co2 (two_stream_gray_rad.F90:519-521): carbon_conc (ppmv) read from co2_file for the following calls"""
+        self._ck(self._lib.isca_b200_two_stream_gray_rad_set_co2(self._h, float(carbon_conc)), "two_stream_gray_rad_down")
 
     def two_stream_gray_rad_set_insolation(self, insolation):
         """do_seasonal (two_stream_gray_rad.F90:417-447): insolation [lat, lon] = solar_constant * coszen for the following down / up

@@ -168,11 +168,14 @@ class GreyRadiation:
             self.gp_albedo = (r1 - r2) / (r1 + r2)
             self.Ga_asym = 2.0 * np.sqrt((1.0 - cfg.single_albedo) * (1.0 - self.g_asym * cfg.single_albedo))
 
-    def down(self, lat, p_half, t, q=None, albedo=None, insolation=None):
+    def down(self, lat, p_half, t, q=None, albedo=None, insolation=None, carbon_conc=None):
         """two_stream_gray_rad_down (:386-655): lat [lat, lon] (radians), p_half [K+1,..], t [K,..], q [K,..] (BYRNE, GEEN);
         insolation [lat, lon]: the do_seasonal value `solar_constant * coszen` (:417-447, `seasonal_insolation` below)."""
         c, sch = self.c, self.scheme
         n = t.shape[0]
+        cc_sw = getattr(self, "_cc_prev", c.carbon_conc)         # do_read_co2: the shortwave (:466) runs before the file is read (:519)
+        cc_lw = c.carbon_conc if carbon_conc is None else carbon_conc
+        self._cc_prev = cc_lw
         if insolation is not None:                                                         # do_seasonal wins over the scheme (:417)
             insolation = np.asarray(insolation, dtype=float)
         elif sch == "SCHNEIDER":
@@ -188,7 +191,7 @@ class GreyRadiation:
             for k in range(n):
                 sw_wv = sw_tau_k + 0.5194
                 sw_wv = np.exp(0.01887 / (sw_tau_k + 0.009522) + 1.603 / (sw_wv * sw_wv))
-                del_sol_tau = (0.0596 + 0.0029 * np.log(c.carbon_conc / 360.0) + sw_wv * q[k]) * (p_half[k + 1] - p_half[k]) / p_half[n]
+                del_sol_tau = (0.0596 + 0.0029 * np.log(cc_sw / 360.0) + sw_wv * q[k]) * (p_half[k + 1] - p_half[k]) / p_half[n]
                 sw_dtrans = np.exp(-del_sol_tau)
                 sw_tau_k = sw_tau_k + del_sol_tau
                 sw_down[k + 1] = sw_down[k] * sw_dtrans
@@ -204,9 +207,9 @@ class GreyRadiation:
         st = {}
         if sch == "GEEN":
             dp = p_half[1:] - p_half[:-1]
-            lw_del_tau = (c.ir_tau_co2 + 0.2023 * np.log(c.carbon_conc / 360.0) + c.ir_tau_wv1 * np.log(c.ir_tau_wv2 * q + 1)) * dp / PSTD_MKS_EARTH
+            lw_del_tau = (c.ir_tau_co2 + 0.2023 * np.log(cc_lw / 360.0) + c.ir_tau_wv1 * np.log(c.ir_tau_wv2 * q + 1)) * dp / PSTD_MKS_EARTH
             lw_dtrans = np.exp(-lw_del_tau)
-            lw_del_tau_win = (c.ir_tau_co2_win + 0.0954 * np.log(c.carbon_conc / 360.0) + c.ir_tau_wv_win1 * q
+            lw_del_tau_win = (c.ir_tau_co2_win + 0.0954 * np.log(cc_lw / 360.0) + c.ir_tau_wv_win1 * q
                               + c.ir_tau_wv_win2 * q * q) * dp / PSTD_MKS_EARTH
             lw_dtrans_win = np.exp(-lw_del_tau_win)
             b_win = c.window * b
@@ -219,7 +222,7 @@ class GreyRadiation:
             st.update(b_win=b_win, lw_dtrans_win=lw_dtrans_win)
         else:
             if sch == "BYRNE":
-                lw_del_tau = (c.bog_a * c.bog_mu + 0.17 * np.log(c.carbon_conc / 360.0) + c.bog_b * q) * ((p_half[1:] - p_half[:-1]) / PSTD_MKS_EARTH)
+                lw_del_tau = (c.bog_a * c.bog_mu + 0.17 * np.log(cc_lw / 360.0) + c.bog_b * q) * ((p_half[1:] - p_half[:-1]) / PSTD_MKS_EARTH)
                 lw_dtrans = np.exp(-lw_del_tau)
             elif sch == "FRIERSON":
                 lw_tau_0 = c.ir_tau_eq + (c.ir_tau_pole - c.ir_tau_eq) * np.sin(lat) ** 2
@@ -1217,6 +1220,7 @@ class IdealizedMoistPhys:
         # two_stream_gray_rad_nml do_seasonal: dict(astro=, lon=, solday=, equinox_day=, use_time_average_coszen=, dt_rad_avg=,
         # day_in_s=, year_in_s=) -> seasonal_insolation at Time (idealized_moist_phys.F90:1054 passes Time, not Time + Time_step)
         self.seasonal = None
+        self.co2 = None                                                   # do_read_co2: carbon_conc (ppmv) of co2_file at Time, set per step
 
     def __call__(self, core, delta_t):
         """core: the dynamical core state (ug, vg, tg, grid_tracers, p_half, p_full, z_half, z_full at two time levels)."""
@@ -1273,7 +1277,7 @@ class IdealizedMoistPhys:
                 days = int(self.time_s // 86400.0)
                 insol = seasonal_insolation(self.rad.c, astro, days, self.time_s - 86400.0 * days, self.rad_lat, lon, **kw)
                 self.diag["insolation"] = insol
-            d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo, insolation=insol)
+            d = self.rad.down(self.rad_lat, core.p_half[cur], tg_p, q=q_p, albedo=self.albedo, insolation=insol, carbon_conc=self.co2)
             net_surf_sw_down = (1.0 - self.albedo) * d["sw_down_surf"]
             surf_lw_down = d["surf_lw_down"]
         sf = surface_flux(self.svp, self.mo, self.sflux, t_atm=tg_p[K - 1], q_atm_in=q_p[K - 1], u_atm=ug_p[K - 1], v_atm=vg_p[K - 1],

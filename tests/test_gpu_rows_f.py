@@ -440,3 +440,68 @@ def test_full_saturation_vapour_pressure_tables(lib_built):
     simple = physics.ColumnPhysics(I, J, K, do_evap=1)
     r2, _, _ = simple.lscale_cond(t, q, pf, ph)
     assert not np.allclose(r2, rain)
+
+
+@pytest.mark.parametrize("scheme", ["geen", "byrne"])
+def test_two_stream_gray_rad_do_read_co2(lib_built, scheme):
+    """do_read_co2: a CO2 value that changes from call to call (the variable_co2_concentration test case), incl. the one-call lag
+    of the geen shortwave"""
+    from isca_b200 import physics
+    from oracle import physics as O
+    from test_gpu_physics import columns, TOL
+    K, J, I = 18, 8, 32
+    rng, ps, ph, pf, t, lat = columns(K, J, I, 41)
+    q = 0.02 * (pf / ps[None]) ** 3 * rng.uniform(0.2, 1.0, t.shape)
+    alb = rng.uniform(0.1, 0.4, (J, I))
+    ts = t[-1] + rng.uniform(-3, 3, (J, I))
+    tdt0 = np.zeros_like(t)
+    cp = physics.ColumnPhysics(I, J, K, rad_scheme=scheme, atm_abs=0.2)
+    g = O.GreyRadiation(O.GreyRadConfig(rad_scheme=scheme, atm_abs=0.2))
+    prev = None
+    for co2 in (360.0, 500.0, 500.0, 800.0):
+        cp.two_stream_gray_rad_set_co2(co2)
+        d = g.down(lat, ph, t, q=q, albedo=alb, carbon_conc=co2)
+        sw, lw = cp.two_stream_gray_rad_down(lat, ph, t, alb, q=q)
+        assert rel(lw, d["surf_lw_down"]) < TOL and rel(sw, (1 - alb) * d["sw_down_surf"]) < TOL, co2
+        tdt, olr = cp.two_stream_gray_rad_up(lat, ph, t, ts, alb, tdt0, q=q)
+        to, o = g.up(ts, alb, ph, tdt0)
+        assert rel(olr, o["olr"]) < TOL and rel(tdt, to) < 1e-11, co2
+        if prev is not None and co2 != prev[0]:
+            assert not np.allclose(lw, prev[1])
+        prev = (co2, lw)
+    with pytest.raises(physics.IscaError):
+        cp.two_stream_gray_rad_set_co2(0.0)
+
+
+def test_moist_model_variable_co2_test_case(lib_built):
+    """the options of exp/test_cases/variable_co2_concentration: rad_scheme = 'byrne', do_seasonal, do_read_co2"""
+    from test_gpu_moist import build, FRIERSON_PHYS, TOL
+    from isca_b200 import api, moist
+    from oracle.rrtmg import Astronomy
+    cfg, core, mp = build("T21", 12, 900.0, "SIMPLE_BETTS_MILLER", seed=11, rad_scheme="byrne")
+    Kk, J, I = core.tg[0].shape
+    lon = np.repeat((np.arange(I) * 2 * np.pi / I)[None], J, 0)
+    mp.seasonal = dict(solday=-10, equinox_day=0.75, use_time_average_coszen=True, dt_rad_avg=86400.0, astro=Astronomy(), lon=lon,
+                       day_in_s=86400.0, year_in_s=360 * 86400.0)
+    mp.time_s = 200 * 86400.0
+    m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=dict(FRIERSON_PHYS, rad_scheme="byrne"),
+                              convection_scheme="SIMPLE_BETTS_MILLER", mixed_layer_depth=2.5, albedo_value=0.31)
+    m.set_seasonal(solday=-10, equinox_day=0.75, use_time_average_coszen=True, dt_rad_avg=86400)
+    m.set_time(200, 0)
+    atm = m.core
+    for slot in (0, 1):
+        atm.set_grid_state(slot, core.ug[slot], core.vg[slot], core.tg[slot], core.psg[slot], core.grid_tracers[slot, 0])
+        atm.set_spectral_state(slot, core.vors[slot], core.divs[slot], core.ts[slot], core.ln_ps[slot])
+    atm.set_vor_div_grid(core.vorg, core.divg)
+    atm.set_time_pointers(core.previous, core.current)
+    m.idealized_moist_phys_init()
+    m.set_t_surf(mp.t_surf)
+    for step, co2 in enumerate((360.0, 540.0, 720.0)):
+        mp.co2 = co2
+        m.set_co2(co2)
+        core.step()
+        m.atmosphere(1)
+        assert rel(m.get("surf_lw_down"), mp.diag["surf_lw_down"]) < TOL, step
+        assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
+    m.atmosphere_end()

@@ -481,3 +481,25 @@ def test_compute_es_known_values():
     T = np.array([215.37, 262.91, 288.04, 301.55])
     es_l, des_l = f.lookup_es_des(T)
     assert np.abs(es_l / P.compute_es(T) - 1).max() < 1e-6
+
+
+def test_grey_radiation_do_read_co2_semantics():
+    """do_read_co2: carbon_conc is replaced by the file value between the shortwave and the longwave part of
+    two_stream_gray_rad_down (:466 vs :519-521): the geen shortwave lags by one call, the longwave does not"""
+    from oracle import physics as P
+    rng = np.random.default_rng(8)
+    K, J, I = 10, 4, 8
+    lat = np.repeat(np.linspace(-1.2, 1.2, J)[:, None], I, 1)
+    ph = np.linspace(0, 1e5, K + 1)[:, None, None] * np.ones((1, J, I))
+    pf = 0.5 * (ph[1:] + ph[:-1])
+    t = 220 + 70 * (pf / 1e5) ** 0.3 + rng.standard_normal((K, J, I))
+    q = 0.015 * (pf / 1e5) ** 3
+    ref = {c: P.GreyRadiation(P.GreyRadConfig(rad_scheme="geen", carbon_conc=c)).down(lat, ph, t, q=q) for c in (360.0, 720.0)}
+    g = P.GreyRadiation(P.GreyRadConfig(rad_scheme="geen", carbon_conc=360.0))
+    d1 = g.down(lat, ph, t, q=q, carbon_conc=720.0)                      # first call with the new value: SW old, LW new
+    assert np.array_equal(d1["sw_down_surf"], ref[360.0]["sw_down_surf"]) and np.array_equal(d1["surf_lw_down"], ref[720.0]["surf_lw_down"])
+    d2 = g.down(lat, ph, t, q=q, carbon_conc=720.0)                      # second call: both new
+    assert np.array_equal(d2["sw_down_surf"], ref[720.0]["sw_down_surf"]) and np.array_equal(d2["surf_lw_down"], ref[720.0]["surf_lw_down"])
+    assert ref[720.0]["surf_lw_down"].mean() > ref[360.0]["surf_lw_down"].mean()       # more CO2, more back radiation
+    b = P.GreyRadiation(P.GreyRadConfig(rad_scheme="byrne"))
+    assert b.down(lat, ph, t, q=q, carbon_conc=1440.0)["surf_lw_down"].mean() > b.down(lat, ph, t, q=q, carbon_conc=360.0)["surf_lw_down"].mean()

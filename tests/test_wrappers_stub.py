@@ -85,6 +85,7 @@ def test_moist_wrapper_methods(lib_built, monkeypatch):
     m.set_time(3, 43200)
     m.set_seasonal(solday=-10, equinox_day=0.75, use_time_average_coszen=True, dt_rad_avg=1800, obliq=25.0)
     m.set_ocean_qflux(np.ones(m.s2))
+    m.set_co2(420.0)
     m.set_dry_convection(7200.0, 0.7)
     for name in moist.MoistAtmosphere.SURFACE_FIELDS:
         m.set_surface(name, np.ones(m.s2))
@@ -98,7 +99,7 @@ def test_moist_wrapper_methods(lib_built, monkeypatch):
         m.use_rrtm(not_a_namelist_value=1)
     seen = dict(stub.calls)
     for fn, hdr in (("isca_b200_moist_use_rrtm", "isca_b200_rrtm.h"), ("isca_b200_moist_set_ozone", "isca_b200_rrtm.h"),
-                    ("isca_b200_moist_set_time", "isca_b200_rrtm.h"), ("isca_b200_moist_set_seasonal", "isca_b200_rrtm.h"),
+                    ("isca_b200_moist_set_time", "isca_b200_rrtm.h"), ("isca_b200_moist_set_seasonal", "isca_b200_rrtm.h"), ("isca_b200_moist_set_co2", "isca_b200_physics.h"),
                     ("isca_b200_moist_set_ocean_qflux", "isca_b200_physics.h"),
                     ("isca_b200_moist_set_dry_convection", "isca_b200_physics.h"), ("isca_b200_moist_set_surface", "isca_b200_physics.h"),
                     ("isca_b200_moist_get", "isca_b200_physics.h")):
@@ -117,6 +118,8 @@ def test_physics_dry_convection_wrapper(lib_built):
     assert dict(stub.calls)["isca_b200_dry_convection"] == _nparams("isca_b200_physics.h", "isca_b200_dry_convection")
     cp.two_stream_gray_rad_set_insolation(np.ones(cp.s2))
     cp.two_stream_gray_rad_set_insolation(None)
+    cp.two_stream_gray_rad_set_co2(400.0)
+    assert dict(stub.calls)["isca_b200_two_stream_gray_rad_set_co2"] == _nparams("isca_b200_physics.h", "isca_b200_two_stream_gray_rad_set_co2")
     assert dict(stub.calls)["isca_b200_two_stream_gray_rad_set_insolation"] == \
         _nparams("isca_b200_physics.h", "isca_b200_two_stream_gray_rad_set_insolation")
     with pytest.raises(physics.IscaError):
