@@ -205,7 +205,7 @@ int isca_b200_dry_convection(IscaPhysics p, double tau, double gamma, const doub
                              double* dt_tg, double* cape, double* cin, int* lzb, int* lcl);
 
 /* device-resident timing of one kernel (which: 0 lscale_cond, 1 gray_rad_down, 2 gray_rad_up, 3 rayleigh,
- * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up, 6 surface_flux, 7 diffusivity, 8 qe_moist_convection) on
+ * 4 gcm_vert_diff_down, 5 gcm_vert_diff_up, 9 betts_miller; any other value times gcm_vert_diff_up) on
  * synthetic resident columns; returns average ms per launch (CUDA events) and the algorithmic bytes per launch. */
 int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, double* bytes);
 

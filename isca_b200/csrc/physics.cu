@@ -696,6 +696,12 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
                               p->buf[10].p, p->buf[9].p, p->buf[9].p + nc, p->buf[9].p + 2 * nc, p->buf[9].p + 3 * nc, p->buf[11].p,
                               p->buf[12].p, p->buf[13].p, p->buf[4].p, p->buf[5].p);
         break;
+      case 9: {   // betts_miller on the synthetic columns (int planes in buf[12]; cape, cin, invtau_t, invtau_q in buf[13])
+        int* ip = reinterpret_cast<int*>(p->buf[12].p);
+        launch_betts_miller(p, 600.0, p->buf[0].p, p->buf[1].p, p->buf[2].p, p->buf[3].p, p->buf[4].p, p->buf[5].p, p->buf[6].p, p->buf[10].p,
+                            p->buf[11].p, ip, ip + nc, ip + 2 * nc, p->buf[13].p, p->buf[13].p + nc, p->buf[13].p + 2 * nc, p->buf[13].p + 3 * nc);
+        break;
+      }
       default: launch_vert_diff_up(p, 600.0, p->buf[5].p, p->buf[6].p); break;
     }
   };
@@ -723,6 +729,7 @@ int isca_b200_physics_time(IscaPhysics p, int which, int reps, double* ms, doubl
     case 2: per_col = 4.0 * K + 5.0; break;
     case 3: per_col = 6.0 * K; break;
     case 4: per_col = 19.0 * K + 14.0; break;
+    case 9: per_col = 8.0 * K + 9.0; break;
     default: per_col = 5.0 * K; break;
   }
   *bytes = per_col * 8.0 * (double)nc;

@@ -15,6 +15,7 @@ timeout 600 compute-sanitizer --tool memcheck python tools/rrtm_bench.py 32 16 4
 ( time timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_physics.py tests/test_gpu_moist.py -m gpu -q -x ) > gpurun_out/r02a_pytest_established.txt 2>&1
 timeout 600 python bench.py --steps 300 --warmup 10 > gpurun_out/r02a_bench.json 2> gpurun_out/r02a_bench.err
 # 4. RRTMG: first timings, launch list and full captures of the two kernels (tools/gpu_rrtm.sh without its pytest / sanitizer part)
+timeout 300 python tools/physbench.py > gpurun_out/r02a_physbench.json 2> gpurun_out/r02a_physbench.err
 timeout 300 python tools/rrtm_bench.py > gpurun_out/r02a_rrtm_bench.json 2> gpurun_out/r02a_rrtm_bench.err
 timeout 420 python tools/mima_bench.py > gpurun_out/r02a_mima_bench.json 2> gpurun_out/r02a_mima_bench.err
 SMALL="python tools/rrtm_bench.py 256 128 40 2"
