@@ -75,6 +75,9 @@ int isca_b200_hs_model_destroy(IscaHsModel m);
 IscaHandle isca_b200_hs_model_dycore(IscaHsModel m);
 /* model time of the next step (Time of atmosphere(Time)); call before isca_b200_hs_model_init */
 int isca_b200_hs_model_set_time(IscaHsModel m, long long days, int seconds);
+/* restart of the top_down option: tg_prev [J][I] read from INPUT/hs_forcing.res.nc (hs_forcing.F90:337); call before
+ * isca_b200_hs_model_init, which then skips the spin-up.  isca_b200_hs_model_get id 2 returns the value to write at the end. */
+int isca_b200_hs_model_set_tg_prev(IscaHsModel m, const double* tg_prev);
 /* hs_forcing_init on the model grid; call after the initial state is in place */
 int isca_b200_hs_model_init(IscaHsModel m);
 /* n_steps calls of atmosphere(Time): hs_forcing(Time + Time_step) on (previous) fields and p / z of (current), spectral_dynamics */

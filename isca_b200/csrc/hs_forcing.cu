@@ -339,6 +339,11 @@ int isca_b200_hs_model_set_time(IscaHsModel m, long long days, int seconds) {
   return 0;
 }
 
+int isca_b200_hs_model_set_tg_prev(IscaHsModel m, const double* tg_prev) {
+  if (!m) return hfail("null handle");
+  return isca_b200_hs_forcing_set_tg_prev(m->hs, tg_prev);
+}
+
 int isca_b200_hs_model_init(IscaHsModel m) {
   if (!m) return hfail("null handle");
   IscaCoreView v;

@@ -15,7 +15,7 @@ from .api import load_library, IscaError, IscaConfigStruct, Atmosphere
 
 HS_EXPORTS = ["isca_b200_hs_forcing_default_config", "isca_b200_hs_last_error", "isca_b200_hs_forcing_create", "isca_b200_hs_forcing_destroy",
               "isca_b200_hs_forcing", "isca_b200_hs_forcing_get_tg_prev", "isca_b200_hs_forcing_set_tg_prev", "isca_b200_hs_model_create",
-              "isca_b200_hs_model_destroy", "isca_b200_hs_model_dycore", "isca_b200_hs_model_set_time", "isca_b200_hs_model_init",
+              "isca_b200_hs_model_destroy", "isca_b200_hs_model_dycore", "isca_b200_hs_model_set_time", "isca_b200_hs_model_set_tg_prev", "isca_b200_hs_model_init",
               "isca_b200_hs_model_step", "isca_b200_hs_model_get"]
 
 EQUILIBRIUM_T = {"HELD_SUAREZ": 0, "EXOPLANET": 1, "EXOPLANET2": 2, "TOP_DOWN": 3}
@@ -56,6 +56,7 @@ def _lib():
         lib.isca_b200_hs_model_dycore.argtypes = [vp]
         lib.isca_b200_hs_model_dycore.restype = vp
         lib.isca_b200_hs_model_set_time.argtypes = [vp, C.c_longlong, C.c_int]
+        lib.isca_b200_hs_model_set_tg_prev.argtypes = [vp, dp]
         lib.isca_b200_hs_model_init.argtypes = [vp]
         lib.isca_b200_hs_model_step.argtypes = [vp, C.c_int]
         lib.isca_b200_hs_model_get.argtypes = [vp, C.c_int, dp]
@@ -177,6 +178,10 @@ class HsAtmosphere:
 
     def set_time(self, days, seconds):
         self._ck(self._lib.isca_b200_hs_model_set_time(self._h, int(days), int(seconds)), "set_time")
+
+    def set_tg_prev(self, tg_prev):
+        """restart of the top_down option (INPUT/hs_forcing.res.nc); before hs_forcing_init, which then skips the spin-up"""
+        self._ck(self._lib.isca_b200_hs_model_set_tg_prev(self._h, _p(_in(tg_prev, self.s2, "tg_prev"))), "hs_forcing_init")
 
     def hs_forcing_init(self):
         """after the atmospheric state is in place and the clock is set"""

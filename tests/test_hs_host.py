@@ -329,13 +329,14 @@ def test_hs_wrapper_argument_counts(lib_built):
     m = hs.HsAtmosphere.__new__(hs.HsAtmosphere)
     m._lib, m._h, m.s2, m.s3 = stub, C.c_void_p(1), f.s2, f.s3
     m.set_time(2, 3)
+    m.set_tg_prev(a2)
     m.hs_forcing_init()
     m.atmosphere(3)
     for n in hs.MODEL_FIELDS:
         m.get(n)
     seen = dict(stub.calls)
     for fn in ("isca_b200_hs_forcing", "isca_b200_hs_forcing_get_tg_prev", "isca_b200_hs_forcing_set_tg_prev", "isca_b200_hs_model_set_time",
-               "isca_b200_hs_model_init", "isca_b200_hs_model_step", "isca_b200_hs_model_get"):
+               "isca_b200_hs_model_set_tg_prev", "isca_b200_hs_model_init", "isca_b200_hs_model_step", "isca_b200_hs_model_get"):
         assert seen[fn] == _nparams("isca_b200_hs.h", fn), fn
     f._h = C.c_void_p()
     m._h = C.c_void_p()
