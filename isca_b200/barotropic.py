@@ -24,7 +24,7 @@ def _make_engine(nml):
     """the transform engine: a dynamical-core handle of the same horizontal resolution (its transforms_mod-level entry points)"""
     from . import api
     cfg = api.make_config(lon_max=nml["num_lon"], lat_max=nml["num_lat"], num_fourier=nml["num_fourier"], num_spherical=nml["num_spherical"],
-                          num_levels=10)
+                          num_levels=10, do_water_correction=False)   # no tracer in the engine (spectral_dynamics.F90:1264)
     return api.Atmosphere(cfg), cfg.radius, cfg.omega
 
 

@@ -539,6 +539,8 @@ int isca_b200_moist_use_rrtm(IscaMoist m, const IscaRrtmConfig* rc, const IscaRr
   c.num_lon = m->I; c.num_lat = m->J; c.num_levels = m->K;
   if (isca_b200_rrtm_create(&c, table_path, &m->rr)) { m->rr = nullptr; return mfail(m, std::string("rrtm: ") + isca_b200_rrtm_last_error(nullptr)); }
   m->rdc = *dc;
+  if (m->rdc.dt_rad <= 0) m->rdc.dt_rad = (int)(long)v.dt_atmos;               // rrtm_radiation_init (rrtm_radiation.F90:378-380)
+  if (m->rdc.dt_rad_avg <= 0) m->rdc.dt_rad_avg = m->rdc.dt_rad;              // :405
   m->orb_angle = isca_rrtm_orbit(*dc);
   bool ok = m->tdt_rad.ensure(m->n3) && m->coszen.ensure(m->nc) && m->lon2d.ensure(m->nc) && m->olr.ensure(m->nc) && m->toa_sw.ensure(m->nc);
   if (!ok) return mfail(m, "cudaMalloc failed");

@@ -125,7 +125,8 @@ def test_diurnal_solar_parity(rr, dt):
             assert np.abs(c - oc).max() < 1e-13 and np.abs(f - of).max() < 1e-12 and abs(r - orr) < 1e-14
 
 
-@pytest.mark.parametrize("dt_rad_steps,kw", [(2, {}), (1, dict(frierson_solar_rad=True)), (2, dict(solday=90, do_rad_time_avg=False))])
+@pytest.mark.parametrize("dt_rad_steps,kw", [(2, {}), (1, dict(frierson_solar_rad=True)), (2, dict(solday=90, do_rad_time_avg=False)),
+                                             (0, {})])    # dt_rad = 0: the namelist default, dt_rad = dt_rad_avg = dt_atmos (rrtm_radiation.F90:378-405)
 def test_moist_model_with_rrtm_radiation(lib_built, dt_rad_steps, kw):
     """do_rrtm_radiation = .true. (the MiMA configuration, idealized_moist_phys.F90:1167-1177): RRTMG on a radiation step, the
     stored heating rates / surface fluxes in between (dt_rad = 2 dt_atmos), diurnal-mean zenith angle from astronomy_mod; four
@@ -164,7 +165,7 @@ def test_moist_model_with_rrtm_radiation(lib_built, dt_rad_steps, kw):
         assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
         assert rel(atm.get_field(api.F_PS), core.psg[core.current]) < TOL, step
         assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
-    assert mp.rrtm.n_rad_calls == (4 if dt_rad_steps == 1 else 2)
+    assert mp.rrtm.n_rad_calls == (4 if dt_rad_steps <= 1 else 2)
     m.atmosphere_end()
 
 
