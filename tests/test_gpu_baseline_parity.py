@@ -1,0 +1,86 @@
+"""Step parity at the BASELINE.json configurations themselves (not only at T21 / T42): the state is spun up ON THE GPU (the oracle
+needs seconds per step at these sizes), both time levels are downloaded through the restart mirrors and loaded into the CPU
+oracle, and the next steps are compared field by field.
+
+* config 2: Held-Suarez T85 L40 with the sphum grid tracer, 3 steps
+* config 3: Frierson grey-radiation aquaplanet T85 L40 (SIMPLE_BETTS_MILLER), 3 steps (test_gpu_moist.build state)
+* configs 4/5 grid: Held-Suarez T170 L40 with the tracer, 2 steps (the oracle takes ~5 s per step there)
+
+Tolerance 1e-10 = max|a-b| / max|b| over the field (relative to the field maximum, not per coefficient), as everywhere else in
+the GPU suite; the per-step spectral tendencies are compared as well (north-star: 1e-10 relative)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_STEP = 1e-10
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def gpu_state_into_oracle(api, atm, core):
+    """both time levels of the device state -> oracle.SpectralCore (the restart variables of spectral_dynamics.F90:509-575)"""
+    prev, cur = atm.get_time_pointers()
+    for slot in (0, 1):
+        core.ug[slot], core.vg[slot] = atm.get_field(api.F_U, slot), atm.get_field(api.F_V, slot)
+        core.tg[slot], core.psg[slot] = atm.get_field(api.F_T, slot), atm.get_field(api.F_PS, slot)
+        core.vors[slot], core.divs[slot] = atm.get_spectral(api.S_VOR, slot), atm.get_spectral(api.S_DIV, slot)
+        core.ts[slot], core.ln_ps[slot] = atm.get_spectral(api.S_T, slot), atm.get_spectral(api.S_LNPS, slot)
+        if core.cfg.num_tracers:
+            core.grid_tracers[slot, 0] = atm.get_field(api.F_TRACER0, slot)
+    core.vorg, core.divg = atm.get_field(api.F_VOR), atm.get_field(api.F_DIV)
+    core.previous, core.current = prev, cur
+    core.finish_init()
+
+
+@pytest.mark.parametrize("res,K,dt,spin,nsteps", [("T85", 40, 300.0, 150, 3), ("T170", 40, 150.0, 200, 2)])
+def test_held_suarez_steps_at_baseline_sizes(lib_built, res, K, dt, spin, nsteps):
+    from isca_b200 import api
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    cfg = held_suarez_config(res, K, dt, num_tracers=1)
+    cfg.initial_sphum = 2.0e-3
+    core = SpectralCore(cfg)
+    atm = api.Atmosphere(api.config_from_namelist_object(cfg))
+    atm.cold_start()
+    atm.atmosphere(spin)                                   # device spin-up: leapfrog steps with 2 dt
+    gpu_state_into_oracle(api, atm, core)
+    assert np.abs(core.ug[core.current]).max() > 0.01      # the flow has started to develop (Held-Suarez forcing on a resting start)
+    atm.enable_tendency_capture()
+    for i in range(nsteps):
+        core.step(keep=True)
+        atm.atmosphere(1)
+        got, ref = atm.state(), core.state()
+        for k, sid in (("dt_vors", api.S_DT_VOR), ("dt_divs", api.S_DT_DIV), ("dt_ts", api.S_DT_T), ("dt_ln_ps", api.S_DT_LNPS)):
+            assert rel(atm.get_spectral(sid), core.last[k]) < TOL_STEP, (i, k)
+        for k in ("vors", "divs", "ts", "ln_ps", "vors_prev", "divs_prev", "ts_prev", "ln_ps_prev",
+                  "ug", "vg", "tg", "psg", "vorg", "divg", "wg_full", "p_full", "z_full"):
+            assert rel(got[k], ref[k]) < TOL_STEP, (i, k)
+        c, p = core.current, core.previous
+        assert rel(atm.get_field(api.F_TRACER0), core.grid_tracers[c, 0]) < TOL_STEP, i
+        assert rel(atm.get_field(api.F_TRACER0, api.LEVEL_PREVIOUS), core.grid_tracers[p, 0]) < TOL_STEP, i
+    atm.atmosphere_end()
+
+
+def test_frierson_steps_at_t85l40(lib_built):
+    """BASELINE config 3 at its own size: three steps of the whole moist model (physics + dynamics) against the oracle"""
+    from isca_b200 import api
+    from test_gpu_moist import build, make_gpu
+    cfg, core, mp = build("T85", 40, 360.0, "SIMPLE_BETTS_MILLER", seed=3)
+    m, atm = make_gpu(cfg, core, "SIMPLE_BETTS_MILLER")
+    for i in range(3):
+        core.step()
+        m.atmosphere(1)
+        c, p = core.current, core.previous
+        assert rel(m.get("t_surf"), mp.t_surf) < TOL_STEP, i
+        assert rel(m.get("precip"), mp.diag["precip"]) < 1e-9, i
+        assert np.array_equal(m.get("convflag").astype(int), mp.diag["convflag"]), i
+        for name, fid in (("ug", api.F_U), ("vg", api.F_V), ("tg", api.F_T)):
+            assert rel(atm.get_field(fid), getattr(core, name)[c]) < TOL_STEP, (i, name)
+        assert rel(atm.get_field(api.F_PS), core.psg[c]) < TOL_STEP, i
+        assert rel(atm.get_field(api.F_TRACER0), core.grid_tracers[c, 0]) < TOL_STEP, i
+        for k, sid in (("vors", api.S_VOR), ("divs", api.S_DIV), ("ts", api.S_T), ("ln_ps", api.S_LNPS)):
+            assert rel(atm.get_spectral(sid), getattr(core, k)[c]) < TOL_STEP, (i, k)
+    flags = np.bincount(mp.diag["convflag"].ravel(), minlength=3)
+    assert flags[2] > 0 and mp.diag["precip"].max() > 0
+    m.atmosphere_end()

@@ -30,6 +30,8 @@ def main():
             dist.all_gather_object(handles, core.ipc_handles())
             core.set_peer_handles(handles)
 
+    import json
+    report = {}
     nml = bench.hs_namelist(res, K, True)
     nml["initial_sphum"] = 1.0e-3                      # a non-trivial tracer field from the start
     cfg = api.make_config(**nml)
@@ -39,9 +41,12 @@ def main():
     atm.atmosphere(nsteps)
 
     def snap(a):
-        return dict(u=a.get_field(api.F_U), T=a.get_field(api.F_T), ps=a.get_field(api.F_PS), vor=a.get_field(api.F_VOR),
-                    q=a.get_field(api.F_TRACER0), ts=a.get_spectral(api.S_T), lnps=a.get_spectral(api.S_LNPS),
-                    divs=a.get_spectral(api.S_DIV))
+        return dict(u=a.get_field(api.F_U), v=a.get_field(api.F_V), T=a.get_field(api.F_T), ps=a.get_field(api.F_PS),
+                    vor=a.get_field(api.F_VOR), div=a.get_field(api.F_DIV), q=a.get_field(api.F_TRACER0),
+                    vors=a.get_spectral(api.S_VOR), divs=a.get_spectral(api.S_DIV), ts=a.get_spectral(api.S_T),
+                    lnps=a.get_spectral(api.S_LNPS), vors_prev=a.get_spectral(api.S_VOR, api.LEVEL_PREVIOUS),
+                    divs_prev=a.get_spectral(api.S_DIV, api.LEVEL_PREVIOUS), ts_prev=a.get_spectral(api.S_T, api.LEVEL_PREVIOUS),
+                    lnps_prev=a.get_spectral(api.S_LNPS, api.LEVEL_PREVIOUS))
     loc = snap(atm)
     torch.cuda.synchronize()
     t0 = time.time(); atm.atmosphere(50); torch.cuda.synchronize(); dt_ms = (time.time() - t0) / 50 * 1e3
@@ -72,12 +77,14 @@ def main():
         ms1 = one.get_scalar(api.SC_LAST_STEP_MS)
         one.atmosphere_end()
         out = {}
-        for k in ("u", "T", "ps", "vor", "q"):
+        for k in ("u", "v", "T", "ps", "vor", "div", "q"):
             full = np.concatenate([g[k] for g in gathered], axis=-2)
             out[k] = float(np.abs(full - ref[k]).max() / np.abs(ref[k]).max())
-        for k in ("ts", "lnps", "divs"):
+        for k in ("vors", "divs", "ts", "lnps", "vors_prev", "divs_prev", "ts_prev", "lnps_prev"):
             full = sum(g[k] for g in gathered)               # every rank returns zeros for the m it does not own
             out[k] = float(np.abs(full - ref[k]).max() / np.abs(ref[k]).max())
+        report["dry"] = out
+        report["max_abs"] = {k: float(np.abs(ref[k]).max()) for k in ("vors", "divs", "u", "v")}
         print(f"MULTIGPU {res} L{K} P={world} (HS + sphum tracer): rel diff vs 1 rank after {nsteps} steps: {out}")
         print(f"MULTIGPU ms/step P={world}: {ms:.3f} (events) {dt_ms:.3f} (wall); 1 rank: {ms1:.3f}")
         print("MULTIGPU groups:", {k: round(v, 4) for k, v in prof.items()})
@@ -93,8 +100,11 @@ def main():
             for k in mref:
                 full = np.concatenate([g[k] for g in mg], axis=-2)
                 mo[k] = float(np.abs(full - mref[k]).max() / max(np.abs(mref[k]).max(), 1e-300))
+            report["moist"] = mo
             print(f"MULTIGPU moist {res} L{K} P={world}: rel diff vs 1 rank after {moist_steps} steps: {mo}")
             print(f"MULTIGPU moist ms/step P={world}: {mms[0]:.3f} (physics {mms[1]:.3f}); 1 rank: {mms1[0]:.3f} (physics {mms1[1]:.3f})")
+    if rank == 0:
+        print("MULTIGPU_JSON " + json.dumps(dict(res=res, K=K, ranks=world, steps=nsteps, moist_steps=moist_steps, **report)))
     dist.barrier()
     dist.destroy_process_group()
 
