@@ -67,14 +67,18 @@ double heatfac_of(double cp_air) { return GRAV * SECDY / (cp_air * 1.0e2); }
 // kernel launches on device pointers
 int isca_rrtm_lw_device(IscaRrtm r, const ColIn& in) {
   if (in.nlay > KMAX || in.nlay < 2) return rfail(r, "rrtmg_lw: num_levels must be 2..64");
-  rrtmg_lw_kernel<<<in.ncol, LW_THREADS, 0, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
+  const size_t smem = lw_smem_doubles(in.nlay) * sizeof(double);
+  RCK(cudaFuncSetAttribute(rrtmg_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lw_smem_doubles(KMAX) * sizeof(double))));
+  rrtmg_lw_kernel<<<in.ncol, LW_THREADS, smem, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
   RCK(cudaGetLastError());
   r->last_lw = in; r->have_lw = true;
   return 0;
 }
 int isca_rrtm_sw_device(IscaRrtm r, const ColIn& in) {
   if (in.nlay > KMAX || in.nlay < 2) return rfail(r, "rrtmg_sw: num_levels must be 2..64");
-  rrtmg_sw_kernel<<<in.ncol, SW_THREADS, 0, r->st>>>(r->d_arena, r->tab, r->d_sw, in);
+  const size_t smem = sw_smem_doubles(in.nlay) * sizeof(double);
+  RCK(cudaFuncSetAttribute(rrtmg_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sw_smem_doubles(KMAX) * sizeof(double))));
+  rrtmg_sw_kernel<<<in.ncol, SW_THREADS, smem, r->st>>>(r->d_arena, r->tab, r->d_sw, in);
   RCK(cudaGetLastError());
   r->last_sw = in; r->have_sw = true;
   return 0;

@@ -59,7 +59,7 @@ struct SwRegion {
 struct SwBand { int ng, g0; SwRegion r[2]; int sflux_off, sflux2d, sflux_upper, layreffr; double sflux_scale; };
 
 struct Tab {                     // offsets (in doubles) into the arena
-  int preflog, tref, chi, totplnk, exp_tbl, tfn_tbl, sw_preflog, sw_tref;
+  int preflog, tref, chi, totplnk, exp_tbl, tfn_tbl, sw_preflog, sw_tref, exptfn;     // exptfn: (exp, tfn) pairs interleaved
 };
 
 struct Layer {                   // setcoef / setcoef_sw output of one layer
@@ -195,80 +195,80 @@ RR_HD Spec specparm_of(double ca, double cb, double rat, double mult) {
   return s;
 }
 
-// three-branch species-ratio interpolation of the lower-atmosphere binary bands (e.g. taugb3 :370-470); row = 0-based
-// row of absa(ind0, :)
-RR_HD double major3(const double* K, int ng, int g, int row, const Spec& s, double fa, double fb) {
-  double r;
+// ---------------------------------------------------------------------------------------------------------------
+// Term lists (round 2).  Everything lw_tau / sw_tau do that does not depend on the g-point -- species ratios and their
+// divisions, the three-branch interpolation weights, `pow` of the adjusted minor-gas amounts, continuum and minor-gas
+// interpolation weights, the band's pressure correction -- is evaluated ONCE per (layer, band) into a list of
+// (table row, weight) pairs; a g-point thread then only forms  tau = sum_i w_i * A[off_i + g]  (consecutive doubles across
+// the lanes of a band).  Same formulas as lw_tau / sw_tau with the products re-associated (differences at the 1e-16 level).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NT_LW = 24, NT_SW = 14;
+struct LwRec { double w[NT_LW]; int off[NT_LW]; int n, gs_off, f0, f1; double ffs; };
+struct SwRec { double w[NT_SW]; int off[NT_SW]; int n, r0, r1, rg, js, pad; double rc0, rc1, tconst, fs; };
+
+template <class Rec>
+RR_HD void rec_add(Rec& r, int off, double w) { r.off[r.n] = off; r.w[r.n] = w; ++r.n; }
+
+template <class Rec>
+RR_HD void major3_terms(Rec& r, int K, int ng, int row, const Spec& s, double fa, double fb) {
+  const double sc = s.speccomb;
   if (s.specparm < 0.125) {
     double p = s.fs - 1.0, p4 = p * p * p * p, fk0 = p4, fk1 = 1.0 - p - 2.0 * p4, fk2 = p + p4;
-    r = fk0 * fa * K[row * ng + g] + fk1 * fa * K[(row + 1) * ng + g] + fk2 * fa * K[(row + 2) * ng + g]
-      + fk0 * fb * K[(row + 9) * ng + g] + fk1 * fb * K[(row + 10) * ng + g] + fk2 * fb * K[(row + 11) * ng + g];
+    rec_add(r, K + row * ng, sc * (fk0 * fa)); rec_add(r, K + (row + 1) * ng, sc * (fk1 * fa)); rec_add(r, K + (row + 2) * ng, sc * (fk2 * fa));
+    rec_add(r, K + (row + 9) * ng, sc * (fk0 * fb)); rec_add(r, K + (row + 10) * ng, sc * (fk1 * fb)); rec_add(r, K + (row + 11) * ng, sc * (fk2 * fb));
   } else if (s.specparm > 0.875) {
     double p = -s.fs, p4 = p * p * p * p, fk0 = p4, fk1 = 1.0 - p - 2.0 * p4, fk2 = p + p4;
-    r = fk2 * fa * K[(row - 1) * ng + g] + fk1 * fa * K[row * ng + g] + fk0 * fa * K[(row + 1) * ng + g]
-      + fk2 * fb * K[(row + 8) * ng + g] + fk1 * fb * K[(row + 9) * ng + g] + fk0 * fb * K[(row + 10) * ng + g];
+    rec_add(r, K + (row - 1) * ng, sc * (fk2 * fa)); rec_add(r, K + row * ng, sc * (fk1 * fa)); rec_add(r, K + (row + 1) * ng, sc * (fk0 * fa));
+    rec_add(r, K + (row + 8) * ng, sc * (fk2 * fb)); rec_add(r, K + (row + 9) * ng, sc * (fk1 * fb)); rec_add(r, K + (row + 10) * ng, sc * (fk0 * fb));
   } else {
-    r = (1.0 - s.fs) * fa * K[row * ng + g] + s.fs * fa * K[(row + 1) * ng + g]
-      + (1.0 - s.fs) * fb * K[(row + 9) * ng + g] + s.fs * fb * K[(row + 10) * ng + g];
+    rec_add(r, K + row * ng, sc * ((1.0 - s.fs) * fa)); rec_add(r, K + (row + 1) * ng, sc * (s.fs * fa));
+    rec_add(r, K + (row + 9) * ng, sc * ((1.0 - s.fs) * fb)); rec_add(r, K + (row + 10) * ng, sc * (s.fs * fb));
   }
-  return s.speccomb * r;
 }
-RR_HD double major2(const double* K, int ng, int g, int row, double fs, double fa, double fb, int stride) {
-  return (1.0 - fs) * fa * K[row * ng + g] + fs * fa * K[(row + 1) * ng + g]
-       + (1.0 - fs) * fb * K[(row + stride) * ng + g] + fs * fb * K[(row + stride + 1) * ng + g];
+template <class Rec>
+RR_HD void major2_terms(Rec& r, int K, int ng, int row, double sc, double fs, double fa, double fb, int stride) {
+  rec_add(r, K + row * ng, sc * ((1.0 - fs) * fa)); rec_add(r, K + (row + 1) * ng, sc * (fs * fa));
+  rec_add(r, K + (row + stride) * ng, sc * ((1.0 - fs) * fb)); rec_add(r, K + (row + stride + 1) * ng, sc * (fs * fb));
 }
-RR_HD double itab(const double* T, int ng, int g, int ind1, double frac) {     // T(ind,g) + frac*(T(ind+1,g) - T(ind,g))
-  double a = T[(ind1 - 1) * ng + g];
-  return a + frac * (T[ind1 * ng + g] - a);
+template <class Rec>
+RR_HD void itab_terms(Rec& r, int T, int ng, int ind1, double frac, double amount) {   // amount * (T(ind) + frac*(T(ind+1)-T(ind)))
+  rec_add(r, T + (ind1 - 1) * ng, amount * (1.0 - frac)); rec_add(r, T + ind1 * ng, amount * frac);
 }
 
-// gaseous optical depth and Planck fraction of one (layer, g-point): taugbNN of rrtmg_lw_taumol.f90
-RR_HD void lw_tau(const double* A, const Tab& tb, const LwBand& B, const Layer& L, int g, double& tau, double& frac) {
+// the g-independent part of taugbNN for one (layer, band)
+RR_HD void lw_terms(const double* A, const Tab& tb, const LwBand& B, const Layer& L, LwRec& rec) {
   const LwRegion& R = B.r[L.lower ? 0 : 1];
   const int ng = B.ng, low = L.lower;
   const double mult = low ? 8.0 : 4.0;
-  double t = 0.0;
+  rec.n = 0;
   double ca = 0.0, cb = 0.0;
   if (R.major == 1) {
-    const double* K = A + R.k_off;
     int i0 = low ? (L.jp - 1) * 5 + (L.jt - 1) : (L.jp - 13) * 5 + (L.jt - 1);
     int i1 = low ? L.jp * 5 + (L.jt1 - 1) : (L.jp - 12) * 5 + (L.jt1 - 1);
-    t = L.col[R.spA] * (L.fac00 * K[i0 * ng + g] + L.fac10 * K[(i0 + 1) * ng + g]
-                        + L.fac01 * K[i1 * ng + g] + L.fac11 * K[(i1 + 1) * ng + g]);
+    const double c = L.col[R.spA];
+    rec_add(rec, R.k_off + i0 * ng, c * L.fac00); rec_add(rec, R.k_off + (i0 + 1) * ng, c * L.fac10);
+    rec_add(rec, R.k_off + i1 * ng, c * L.fac01); rec_add(rec, R.k_off + (i1 + 1) * ng, c * L.fac11);
   }
   if (R.spB >= 0) { ca = L.col[R.spA]; cb = L.col[R.spB]; }
   if (R.major == 2) {
-    const double* K = A + R.k_off;
     Spec s0 = specparm_of(ca, cb, chi_mls(A, tb, R.spA, L.jp) / chi_mls(A, tb, R.spB, L.jp), mult);
     Spec s1 = specparm_of(ca, cb, chi_mls(A, tb, R.spA, L.jp + 1) / chi_mls(A, tb, R.spB, L.jp + 1), mult);
     if (low) {
       int i0 = ((L.jp - 1) * 5 + (L.jt - 1)) * 9 + s0.js - 1;
       int i1 = (L.jp * 5 + (L.jt1 - 1)) * 9 + s1.js - 1;
-      t = major3(K, ng, g, i0, s0, L.fac00, L.fac10) + major3(K, ng, g, i1, s1, L.fac01, L.fac11);
+      major3_terms(rec, R.k_off, ng, i0, s0, L.fac00, L.fac10);
+      major3_terms(rec, R.k_off, ng, i1, s1, L.fac01, L.fac11);
     } else {
       int i0 = ((L.jp - 13) * 5 + (L.jt - 1)) * 5 + s0.js - 1;
       int i1 = ((L.jp - 12) * 5 + (L.jt1 - 1)) * 5 + s1.js - 1;
-      t = s0.speccomb * major2(K, ng, g, i0, s0.fs, L.fac00, L.fac10, 5)
-        + s1.speccomb * major2(K, ng, g, i1, s1.fs, L.fac01, L.fac11, 5);
+      major2_terms(rec, R.k_off, ng, i0, s0.speccomb, s0.fs, L.fac00, L.fac10, 5);
+      major2_terms(rec, R.k_off, ng, i1, s1.speccomb, s1.fs, L.fac01, L.fac11, 5);
     }
   }
-  if (R.self_off >= 0) t += L.selffac * itab(A + R.self_off, ng, g, L.indself, L.selffrac);
-  if (R.for_off >= 0) t += L.forfac * itab(A + R.for_off, ng, g, L.indfor, L.forfrac);
+  if (R.self_off >= 0) itab_terms(rec, R.self_off, ng, L.indself, L.selffrac, L.selffac);
+  if (R.for_off >= 0) itab_terms(rec, R.for_off, ng, L.indfor, L.forfrac, L.forfac);
   for (int m = 0; m < R.nminor; ++m) {
     const Minor& M = R.minor[m];
-    const double* K = A + M.k_off;
-    double ab;
-    if (M.binary) {
-      Spec s = specparm_of(ca, cb, M.refrat, mult);
-      int nsp = low ? 9 : 5;
-      // k(js, indm, g): row = (indm-1)*nsp + js-1
-      int r0 = (L.indminor - 1) * nsp + s.js - 1, r1 = L.indminor * nsp + s.js - 1;
-      double m1 = K[r0 * ng + g] + s.fs * (K[(r0 + 1) * ng + g] - K[r0 * ng + g]);
-      double m2 = K[r1 * ng + g] + s.fs * (K[(r1 + 1) * ng + g] - K[r1 * ng + g]);
-      ab = m1 + L.minorfrac * (m2 - m1);
-    } else {
-      ab = itab(K, ng, g, L.indminor, L.minorfrac);
-    }
     double amount;
     if (M.scale == SC_COL) amount = L.col[M.sp];
     else if (M.scale == SC_ADJ) {
@@ -278,57 +278,89 @@ RR_HD void lw_tau(const double* A, const Tab& tb, const LwBand& B, const Layer& 
     } else if (M.scale == SC_BRD_N2) amount = L.colbrd * L.scaleminorn2;
     else if (M.scale == SC_BRD) amount = L.colbrd * L.scaleminor;
     else amount = L.col[SP_O2] * L.scaleminor;
-    t += amount * ab;
+    if (M.binary) {
+      Spec s = specparm_of(ca, cb, M.refrat, mult);
+      int nsp = low ? 9 : 5;
+      int r0 = (L.indminor - 1) * nsp + s.js - 1, r1 = L.indminor * nsp + s.js - 1;
+      const double a0 = amount * (1.0 - L.minorfrac), a1 = amount * L.minorfrac;
+      rec_add(rec, M.k_off + r0 * ng, a0 * (1.0 - s.fs)); rec_add(rec, M.k_off + (r0 + 1) * ng, a0 * s.fs);
+      rec_add(rec, M.k_off + r1 * ng, a1 * (1.0 - s.fs)); rec_add(rec, M.k_off + (r1 + 1) * ng, a1 * s.fs);
+    } else {
+      itab_terms(rec, M.k_off, ng, L.indminor, L.minorfrac, amount);
+    }
   }
-  for (int c = 0; c < R.ncfc; ++c) t += L.wx[R.cfc_wx[c]] * A[R.cfc_off[c] + g];
-  if (R.corr == 1) t *= (L.pavel < 250.0 ? 1.0 - 0.15 * (250.0 - L.pavel) / 154.4 : 1.0);
-  else if (R.corr == 2) t *= 1.0 - 0.15 * (L.pavel / 95.6);
-  else if (R.corr == 3) t *= 1.0 - 0.05 * (L.pavel - 100.0) / 900.0;
-  if (R.gscale_off >= 0) t *= A[R.gscale_off + g];
+  for (int c = 0; c < R.ncfc; ++c) rec_add(rec, R.cfc_off[c], L.wx[R.cfc_wx[c]]);
+  double corr = 1.0;
+  if (R.corr == 1) corr = (L.pavel < 250.0 ? 1.0 - 0.15 * (250.0 - L.pavel) / 154.4 : 1.0);
+  else if (R.corr == 2) corr = 1.0 - 0.15 * (L.pavel / 95.6);
+  else if (R.corr == 3) corr = 1.0 - 0.05 * (L.pavel - 100.0) / 900.0;
+  if (corr != 1.0) for (int i = 0; i < rec.n; ++i) rec.w[i] *= corr;
+  rec.gs_off = R.gscale_off;
+  rec.f0 = rec.f1 = -1; rec.ffs = 0.0;
+  if (R.frac_off >= 0) {
+    if (R.frac2d) {
+      Spec s = specparm_of(ca, cb, R.refrat_planck, mult);
+      rec.f0 = R.frac_off + (s.js - 1) * ng; rec.f1 = R.frac_off + s.js * ng; rec.ffs = s.fs;
+    } else rec.f0 = R.frac_off;
+  }
+}
+// the g-dependent part: a dot product over the term list
+RR_HD void lw_tau_rec(const double* A, const LwRec& r, int g, double& tau, double& frac) {
+  double t = 0.0;
+  for (int i = 0; i < r.n; ++i) t += r.w[i] * A[r.off[i] + g];
+  if (r.gs_off >= 0) t *= A[r.gs_off + g];
   tau = t;
-  if (R.frac_off < 0) frac = 0.0;
-  else if (R.frac2d) {
-    Spec s = specparm_of(ca, cb, R.refrat_planck, mult);
-    const double* F = A + R.frac_off;
-    frac = F[(s.js - 1) * ng + g] + s.fs * (F[s.js * ng + g] - F[(s.js - 1) * ng + g]);
-  } else frac = A[R.frac_off + g];
+  if (r.f0 < 0) frac = 0.0;
+  else {
+    double a = A[r.f0 + g];
+    frac = r.f1 >= 0 ? a + r.ffs * (A[r.f1 + g] - a) : a;
+  }
 }
 
-// One g-point through rtrnmr's clear-sky sweeps (rrtmg_lw_rtrnmr.f90:390-480 down, :560-640 up).  lay[] = the column's
-// setcoef output, planklay/planklev [16][stride], w = wtdiff*delwave(band) (0 for padding lanes).  red.down(lev, v) /
-// red.up(lev, v) receive the weighted radiances of level lev = 0..nl (0 = surface).
+// one layer of rtrnmr's clear-sky downward sweep for one g-point (rrtmg_lw_rtrnmr.f90:390-480): transmittance from the Pade
+// table (exptfn = interleaved exp / tfn tables), layer emission towards both sides, update of the downward radiance
+RR_HD void lw_layer(const double* exptfn, double secdiff, double tau, double plfrac, double blay, double plev_up, double plev_dn,
+                    double& radld, double& atrans, double& bbugas) {
+  double dplankup = plev_up - blay;
+  double dplankdn = plev_dn - blay;
+  double odepth = secdiff * tau;
+  if (odepth < 0.0) odepth = 0.0;
+  double at, tfac;
+  if (odepth <= 0.06) {
+    at = odepth - 0.5 * odepth * odepth;
+    tfac = 0.166667 * odepth;
+  } else {
+    double tblind = odepth / (BPADE + odepth);
+    int itr = (int)(TBLINT * tblind + 0.5);
+    at = 1.0 - exptfn[2 * itr];
+    tfac = exptfn[2 * itr + 1];
+  }
+  double bbd = plfrac * (blay + tfac * dplankdn);
+  bbugas = plfrac * (blay + tfac * dplankup);
+  atrans = at;
+  radld = radld + (bbd - radld) * at;
+}
+
+// One g-point through rtrnmr's clear-sky sweeps, serially (rrtmg_lw_rtrnmr.f90:390-480 down, :560-640 up): the order of
+// operations of rrtmg_lw_kernel's phase B written as one loop nest.  Used by the test-only host build (tests/host/rrtm_host.cpp).
+// lay[] = the column's setcoef output, planklay/planklev [16][stride], w = wtdiff*delwave(band).  red.down(lev, v) / red.up(lev, v)
+// receive the weighted radiances of level lev = 0..nl (0 = surface).
 template <class Red>
 RR_HD void lw_gpoint(const double* A, const Tab& tb, const LwBand& B, int ib, int g, int nl, const Layer* lay,
                      const double* planklay, const double* planklev, int pstride, double plankbnd, double semiss,
                      double secdiff, double w, Red& red) {
   double atrans[KMAX], bbugas[KMAX];
-  const double* exp_tbl = A + tb.exp_tbl;
-  const double* tfn_tbl = A + tb.tfn_tbl;
+  const double* exptfn = A + tb.exptfn;
   double radld = 0.0, frac1 = 0.0;
   red.down(nl, 0.0);
   for (int lev = nl; lev >= 1; --lev) {
     double tau, plfrac;
-    lw_tau(A, tb, B, lay[lev - 1], g, tau, plfrac);
+    LwRec rec;
+    lw_terms(A, tb, B, lay[lev - 1], rec);
+    lw_tau_rec(A, rec, g, tau, plfrac);
     if (lev == 1) frac1 = plfrac;
-    double blay = planklay[ib * pstride + lev - 1];
-    double dplankup = planklev[ib * pstride + lev] - blay;
-    double dplankdn = planklev[ib * pstride + lev - 1] - blay;
-    double odepth = secdiff * tau;
-    if (odepth < 0.0) odepth = 0.0;
-    double at, tfac;
-    if (odepth <= 0.06) {
-      at = odepth - 0.5 * odepth * odepth;
-      tfac = 0.166667 * odepth;
-    } else {
-      double tblind = odepth / (BPADE + odepth);
-      int itr = (int)(TBLINT * tblind + 0.5);
-      at = 1.0 - exp_tbl[itr];
-      tfac = tfn_tbl[itr];
-    }
-    double bbd = plfrac * (blay + tfac * dplankdn);
-    bbugas[lev - 1] = plfrac * (blay + tfac * dplankup);
-    atrans[lev - 1] = at;
-    radld = radld + (bbd - radld) * at;
+    lw_layer(exptfn, secdiff, tau, plfrac, planklay[ib * pstride + lev - 1], planklev[ib * pstride + lev], planklev[ib * pstride + lev - 1],
+             radld, atrans[lev - 1], bbugas[lev - 1]);
     red.down(lev - 1, radld * w);
   }
   double rad0 = frac1 * plankbnd;
@@ -353,45 +385,48 @@ RR_HD double lw_secdiff(int ib, double pwvcm) {
 // ---------------------------------------------------------------------------------------------------------------
 // shortwave
 // ---------------------------------------------------------------------------------------------------------------
-struct SwOptics { double taug, taur, src; };
-
-// taumolNN of rrtmg_sw_taumol.f90 for one (layer, g-point); src = solar source if this layer is the band's laysolfr
-RR_HD void sw_tau(const double* A, const SwBand& B, const Layer& L, int g, double& taug, double& taur, double& src) {
+// the g-independent part of taumolNN for one (layer, band) (see the term lists above)
+RR_HD void sw_terms(const double* A, const SwBand& B, const Layer& L, SwRec& rec) {
   const SwRegion& R = B.r[L.lower ? 0 : 1];
   const int ng = B.ng, low = L.lower;
-  double t = 0.0;
-  Spec s; s.js = 1; s.fs = 0.0; s.speccomb = 0.0; s.specparm = 0.0;
+  rec.n = 0; rec.js = 1; rec.fs = 0.0; rec.pad = 0;
   if (R.major == 1) {
-    const double* K = A + R.k_off;
     int i0 = low ? (L.jp - 1) * 5 + (L.jt - 1) : (L.jp - 13) * 5 + (L.jt - 1);
     int i1 = low ? L.jp * 5 + (L.jt1 - 1) : (L.jp - 12) * 5 + (L.jt1 - 1);
-    t = L.col[R.spA] * R.kscale * (L.fac00 * K[i0 * ng + g] + L.fac10 * K[(i0 + 1) * ng + g]
-                                   + L.fac01 * K[i1 * ng + g] + L.fac11 * K[(i1 + 1) * ng + g]);
+    const double c = L.col[R.spA] * R.kscale;
+    rec_add(rec, R.k_off + i0 * ng, c * L.fac00); rec_add(rec, R.k_off + (i0 + 1) * ng, c * L.fac10);
+    rec_add(rec, R.k_off + i1 * ng, c * L.fac01); rec_add(rec, R.k_off + (i1 + 1) * ng, c * L.fac11);
   } else if (R.major == 2) {
-    const double* K = A + R.k_off;
     const int nsp = low ? 9 : 5;
-    s = specparm_of(L.col[R.spA], L.col[R.spB], R.strrat, low ? 8.0 : 4.0);
+    Spec s = specparm_of(L.col[R.spA], L.col[R.spB], R.strrat, low ? 8.0 : 4.0);
+    rec.js = s.js; rec.fs = s.fs;
     int i0 = low ? ((L.jp - 1) * 5 + (L.jt - 1)) * nsp + s.js - 1 : ((L.jp - 13) * 5 + (L.jt - 1)) * nsp + s.js - 1;
     int i1 = low ? (L.jp * 5 + (L.jt1 - 1)) * nsp + s.js - 1 : ((L.jp - 12) * 5 + (L.jt1 - 1)) * nsp + s.js - 1;
-    t = s.speccomb * (major2(K, ng, g, i0, s.fs, L.fac00, L.fac10, nsp) + major2(K, ng, g, i1, s.fs, L.fac01, L.fac11, nsp));
+    major2_terms(rec, R.k_off, ng, i0, s.speccomb, s.fs, L.fac00, L.fac10, nsp);
+    major2_terms(rec, R.k_off, ng, i1, s.speccomb, s.fs, L.fac01, L.fac11, nsp);
   }
-  double cont = 0.0;
-  if (R.self_off >= 0) cont += L.selffac * itab(A + R.self_off, ng, g, L.indself, L.selffrac);
-  if (R.for_off >= 0) cont += L.forfac * itab(A + R.for_off, ng, g, L.indfor, L.forfrac);
-  t += L.col[SP_H2O] * cont;
-  for (int e = 0; e < R.nextra; ++e) t += L.col[R.extra_sp[e]] * A[R.extra_off[e] + g];
-  if (R.o2cont) t += 4.35e-4 * L.col[SP_O2] / (350.0 * 2.0);
-  taug = t;
-  if (R.rayl_mode == 0) taur = L.colmol * A[R.rayl_off];
-  else if (R.rayl_mode == 1) taur = L.colmol * A[R.rayl_off + g];
-  else {
-    const double* Ra = A + R.rayl_off;
-    taur = L.colmol * (Ra[(s.js - 1) * ng + g] + s.fs * (Ra[s.js * ng + g] - Ra[(s.js - 1) * ng + g]));
-  }
+  if (R.self_off >= 0) itab_terms(rec, R.self_off, ng, L.indself, L.selffrac, L.col[SP_H2O] * L.selffac);
+  if (R.for_off >= 0) itab_terms(rec, R.for_off, ng, L.indfor, L.forfrac, L.col[SP_H2O] * L.forfac);
+  for (int e = 0; e < R.nextra; ++e) rec_add(rec, R.extra_off[e], L.col[R.extra_sp[e]]);
+  rec.tconst = R.o2cont ? 4.35e-4 * L.col[SP_O2] / (350.0 * 2.0) : 0.0;
+  rec.r1 = -1; rec.rc1 = 0.0;
+  if (R.rayl_mode == 0) { rec.r0 = R.rayl_off; rec.rg = 0; rec.rc0 = L.colmol; }
+  else if (R.rayl_mode == 1) { rec.r0 = R.rayl_off; rec.rg = 1; rec.rc0 = L.colmol; }
+  else { rec.r0 = R.rayl_off + (rec.js - 1) * ng; rec.r1 = R.rayl_off + rec.js * ng; rec.rg = 1; rec.rc0 = L.colmol; rec.rc1 = rec.fs; }
+}
+RR_HD void sw_tau_rec(const double* A, const SwRec& r, int g, double& taug, double& taur) {
+  double t = 0.0;
+  for (int i = 0; i < r.n; ++i) t += r.w[i] * A[r.off[i] + g];
+  taug = t + r.tconst;
+  double a = A[r.r0 + r.rg * g];
+  taur = r.rc0 * (r.r1 >= 0 ? a + r.rc1 * (A[r.r1 + g] - a) : a);
+}
+RR_HD double sw_src_rec(const double* A, const SwBand& B, const SwRec& r, int g) {       // solar source term of the band's laysolfr layer
   if (B.sflux2d) {
     const double* F = A + B.sflux_off;
-    src = F[(s.js - 1) * ng + g] + s.fs * (F[s.js * ng + g] - F[(s.js - 1) * ng + g]);
-  } else src = B.sflux_scale * A[B.sflux_off + g];
+    return F[(r.js - 1) * B.ng + g] + r.fs * (F[r.js * B.ng + g] - F[(r.js - 1) * B.ng + g]);
+  }
+  return B.sflux_scale * A[B.sflux_off + g];
 }
 
 // the layer (1-based) whose species ratio defines the band's solar source: the `laysolfr` logic of taumol16..29
@@ -465,56 +500,61 @@ RR_HD void sw_reftra(const double* exp_tbl, double zg, double prmuz, double zto1
   }
 }
 
-// One g-point through spcvrt_sw (clear sky, no aerosol) + vrtqdr_sw.  lsol[ib] = laysolfr of the band; incoming flux
-// zincflx = adjflux * sfluxzen * prmu0.  red.up(lev, v) / red.down(lev, v): lev = 0 surface .. nl top of atmosphere.
+// one layer of spcvrt_sw for one g-point (clear sky, no aerosol: asymmetry 0): two-stream reflectance / transmittance (reftra_sw),
+// direct-beam transmittance, and vrtqdr_sw's upward combination with everything below (rup_below, rupd_below)
+RR_HD void sw_layer(const double* exp_tbl, double prmu0, double taug, double taur, double rup_below, double rupd_below,
+                    double& zref, double& zrefd, double& ztra, double& ztrad, double& zdbt, double& zrup, double& zrupd) {
+  double ztauc = taur + taug;               // + aerosol (none)
+  double zomcc = taur / ztauc;              // single-scattering albedo
+  sw_reftra(exp_tbl, 0.0, prmu0, ztauc, zomcc, zref, zrefd, ztra, ztrad);
+  zdbt = sw_exp(exp_tbl, ztauc / prmu0);
+  double zreflect = 1.0 / (1.0 - rupd_below * zrefd);
+  zrup = zref + (ztrad * ((ztra - zdbt) * rupd_below + zdbt * rup_below)) * zreflect;
+  zrupd = zrefd + ztrad * ztrad * rupd_below * zreflect;
+}
+// one level of vrtqdr_sw's downward combination + the fluxes of spcvrt_sw at that level (jk = 0 top .. nl surface); tdbt = ztdbt(jk),
+// tdbt_prev = ztdbt(jk-1); layer values are those of layer j = jk-1
+RR_HD void sw_level(int jk, double tdbt, double tdbt_prev, double zref_j, double zrefd_j, double ztra_j, double ztrad_j, double zrup, double zrupd,
+                    double& ztdn, double& zrdnd, double& fu, double& fd) {
+  if (jk == 1) { ztdn = ztra_j; zrdnd = zrefd_j; }
+  else if (jk >= 2) {
+    double zr = 1.0 / (1.0 - zrefd_j * zrdnd);
+    double tdn_new = tdbt_prev * ztra_j + (ztrad_j * ((ztdn - tdbt_prev) + tdbt_prev * zref_j * zrdnd)) * zr;
+    double rdnd_new = zrefd_j + ztrad_j * ztrad_j * zrdnd * zr;
+    ztdn = tdn_new; zrdnd = rdnd_new;
+  }
+  double zreflect = 1.0 / (1.0 - zrdnd * zrupd);
+  fu = (tdbt * zrup + (ztdn - tdbt) * zrupd) * zreflect;
+  fd = tdbt + (ztdn - tdbt + tdbt * zrup * zrdnd) * zreflect;
+}
+
+// One g-point through spcvrt_sw + vrtqdr_sw, serially: the order of operations of rrtmg_sw_kernel written as one loop nest.  Used by
+// the test-only host build.  lsol = laysolfr of the band; incoming flux zincflx = adjflux * sfluxzen * prmu0.
+// red.up(lev, v) / red.down(lev, v): lev = 0 surface .. nl top of atmosphere.
 template <class Red>
 RR_HD void sw_gpoint(const double* A, const Tab& tb, const SwBand& B, int g, int nl, const Layer* lay, int lsol,
                      double prmu0, double albedo, double adjflux, double w, Red& red) {
   const double* exp_tbl = A + tb.exp_tbl;
   // layer arrays ordered top (0) to bottom (nl-1), as jk = 1..klev of spcvrt_sw
-  double zref[KMAX + 1], zrefd[KMAX + 1], ztra[KMAX], ztrad[KMAX], zdbt[KMAX], ztdbt[KMAX + 1], zrup[KMAX + 1], zrupd[KMAX + 1];
+  double zref[KMAX], zrefd[KMAX], ztra[KMAX], ztrad[KMAX], zdbt[KMAX], zrup[KMAX + 1], zrupd[KMAX + 1];
   double sflux = 0.0;
-  ztdbt[0] = 1.0;
-  for (int jk = 0; jk < nl; ++jk) {
-    int ikl = nl - 1 - jk;
-    double taug, taur, src;
-    sw_tau(A, B, lay[ikl], g, taug, taur, src);
-    if (ikl + 1 == lsol) sflux = src;
-    double ztauc = taur + taug;               // + aerosol (none)
-    double zomcc = taur / ztauc;              // single-scattering albedo; asymmetry 0 (Rayleigh only)
-    sw_reftra(exp_tbl, 0.0, prmu0, ztauc, zomcc, zref[jk], zrefd[jk], ztra[jk], ztrad[jk]);
-    zdbt[jk] = sw_exp(exp_tbl, ztauc / prmu0);
-    ztdbt[jk + 1] = zdbt[jk] * ztdbt[jk];
+  zrup[nl] = albedo; zrupd[nl] = albedo;
+  for (int l1 = 1; l1 <= nl; ++l1) {          // bottom-up: layer optics + upward combination
+    const int jk = nl - l1;
+    SwRec rec;
+    sw_terms(A, B, lay[l1 - 1], rec);
+    double taug, taur;
+    sw_tau_rec(A, rec, g, taug, taur);
+    if (l1 == lsol) sflux = sw_src_rec(A, B, rec, g);
+    sw_layer(exp_tbl, prmu0, taug, taur, zrup[jk + 1], zrupd[jk + 1], zref[jk], zrefd[jk], ztra[jk], ztrad[jk], zdbt[jk], zrup[jk], zrupd[jk]);
   }
-  zref[nl] = albedo; zrefd[nl] = albedo; zrup[nl] = albedo; zrupd[nl] = albedo;
-  // vrtqdr_sw: bottom-up combined reflectances
-  {
-    int k = nl - 1;
-    double zreflect = 1.0 / (1.0 - zrefd[nl] * zrefd[k]);
-    zrup[k] = zref[k] + (ztrad[k] * ((ztra[k] - zdbt[k]) * zrefd[nl] + zdbt[k] * zref[nl])) * zreflect;
-    zrupd[k] = zrefd[k] + ztrad[k] * ztrad[k] * zrefd[nl] * zreflect;
-    for (int ikx = nl - 2; ikx >= 0; --ikx) {
-      int ikp = ikx + 1;
-      zreflect = 1.0 / (1.0 - zrupd[ikp] * zrefd[ikx]);
-      zrup[ikx] = zref[ikx] + (ztrad[ikx] * ((ztra[ikx] - zdbt[ikx]) * zrupd[ikp] + zdbt[ikx] * zrup[ikp])) * zreflect;
-      zrupd[ikx] = zrefd[ikx] + ztrad[ikx] * ztrad[ikx] * zrupd[ikp] * zreflect;
-    }
-  }
-  // top-down transmittances and the fluxes at every level
-  double zinc = adjflux * sflux * prmu0 * w;
-  double ztdn = 1.0, zrdnd = 0.0;
-  for (int jk = 0; jk <= nl; ++jk) {
-    if (jk == 1) { ztdn = ztra[0]; zrdnd = zrefd[0]; }
-    else if (jk >= 2) {
-      int j = jk - 1;
-      double zr = 1.0 / (1.0 - zrefd[j] * zrdnd);
-      double tdn_new = ztdbt[j] * ztra[j] + (ztrad[j] * ((ztdn - ztdbt[j]) + ztdbt[j] * zref[j] * zrdnd)) * zr;
-      double rdnd_new = zrefd[j] + ztrad[j] * ztrad[j] * zrdnd * zr;
-      ztdn = tdn_new; zrdnd = rdnd_new;
-    }
-    double zreflect = 1.0 / (1.0 - zrdnd * zrupd[jk]);
-    double fu = (ztdbt[jk] * zrup[jk] + (ztdn - ztdbt[jk]) * zrupd[jk]) * zreflect;
-    double fd = ztdbt[jk] + (ztdn - ztdbt[jk] + ztdbt[jk] * zrup[jk] * zrdnd) * zreflect;
+  const double zinc = adjflux * sflux * prmu0 * w;
+  double ztdn = 1.0, zrdnd = 0.0, tdbt = 1.0, tdbt_prev = 1.0;
+  for (int jk = 0; jk <= nl; ++jk) {          // top-down: downward combination + fluxes
+    if (jk >= 1) { tdbt_prev = tdbt; tdbt = zdbt[jk - 1] * tdbt_prev; }
+    const int j = jk >= 1 ? jk - 1 : 0;
+    double fu, fd;
+    sw_level(jk, tdbt, tdbt_prev, zref[j], zrefd[j], ztra[j], ztrad[j], zrup[jk], zrupd[jk], ztdn, zrdnd, fu, fd);
     red.up(nl - jk, zinc * fu);
     red.down(nl - jk, zinc * fd);
   }

@@ -32,21 +32,50 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 struct DevRed {                      // per-level sum over the g-points: warp shuffle, lane 0 stores the warp's partial
-  double* part; int warp, lane;      // part[warp][2][KMAX+1]
-  __device__ __forceinline__ void up(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 0) * (KMAX + 1) + lev] = v; }
-  __device__ __forceinline__ void down(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 1) * (KMAX + 1) + lev] = v; }
+  double* part; int ps, warp, lane;  // part[warp][2][ps], ps = nlay + 1
+  __device__ __forceinline__ void up(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 0) * ps + lev] = v; }
+  __device__ __forceinline__ void down(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 1) * ps + lev] = v; }
 };
 
 constexpr int LW_THREADS = 160, SW_THREADS = 128;
+constexpr int LW_TILE = 10, SW_TILE = 8;      // layers whose (layer, band) term lists are resident in shared memory at a time
 constexpr double FLUXFAC = 3.14159265358979323846 * 2.0e4;      // pi * 2.e4 with pi = 2*asin(1)
 
+// dynamic shared memory (sized by the number of layers, so that more CTAs fit per SM); the CPU thread emulator of
+// tests/host/rrtm_emu.cpp defines ISCA_RRTM_EMU and gets a static buffer instead
+#ifdef ISCA_RRTM_EMU
+#define ISCA_DYN_SMEM(name) static double name[40000]
+#else
+#define ISCA_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+#endif
+__host__ __device__ inline size_t lw_smem_doubles(int nl) {
+  return (sizeof(Layer) * (size_t)nl + sizeof(LwRec) * (size_t)(LW_TILE * NB_LW)) / 8 + 2 * (size_t)NB_LW * (nl + 1)
+       + (size_t)(LW_THREADS / 32) * 2 * (nl + 1) + 3 * NB_LW + 2 * (size_t)(nl + 1) + 8;
+}
+__host__ __device__ inline size_t sw_smem_doubles(int nl) {
+  return (sizeof(Layer) * (size_t)nl + sizeof(SwRec) * (size_t)(SW_TILE * NB_SW)) / 8 + (size_t)(SW_THREADS / 32) * 2 * (nl + 1)
+       + 2 * (size_t)(nl + 1) + NB_SW + 8;
+}
+
+// Longwave.  Phase A: one thread per layer, inatm + setcoef + Planck functions.  Phase B, tile by tile (LW_TILE layers, top-down):
+// (i) one thread per (layer, band) builds the term list of that layer and band (everything of taugbNN that does not depend on the
+// g-point: species ratios, interpolation weights, `pow` of the adjusted minor-gas amounts); (ii) one thread per g-point forms
+// tau = sum_i w_i A[off_i + g] and advances rtrnmr's downward sweep.  The upward sweep needs no optical depths again
+// (atrans / bbugas of the column stay in thread-local memory).  Phase C: fluxes and heating rates.
 __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __restrict__ A, Tab tb, const LwBand* __restrict__ bands, ColIn in) {
-  __shared__ Layer lay[KMAX];
-  __shared__ double planklay[NB_LW * (KMAX + 1)], planklev[NB_LW * (KMAX + 1)];
-  __shared__ double part[(LW_THREADS / 32) * 2 * (KMAX + 1)];
-  __shared__ double plankbnd[NB_LW], secdiff[NB_LW], semiss[NB_LW], pz[KMAX + 1], fnet[KMAX + 1];
+  ISCA_DYN_SMEM(smem);
   const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
-  const int PS = KMAX + 1;           // row stride of the Planck arrays (planklay uses the same stride for simplicity)
+  const int PS = nl + 1;             // row stride of the Planck arrays
+  Layer* lay = reinterpret_cast<Layer*>(smem);
+  LwRec* recs = reinterpret_cast<LwRec*>(smem + (sizeof(Layer) * (size_t)nl + 7) / 8);
+  double* planklay = reinterpret_cast<double*>(recs + LW_TILE * NB_LW);
+  double* planklev = planklay + NB_LW * PS;
+  double* part = planklev + NB_LW * PS;                   // [warp][2][PS]
+  double* plankbnd = part + (LW_THREADS / 32) * 2 * PS;
+  double* secdiff = plankbnd + NB_LW;
+  double* semiss = secdiff + NB_LW;
+  double* pz = semiss + NB_LW;
+  double* fnet = pz + PS;
   // ---- phase A: inatm + setcoef per layer
   for (int l = tid; l < nl; l += LW_THREADS) {
     double vmr[NSP], xs[4];
@@ -79,23 +108,51 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
     double pwvcm = wvsh * (1.0e3 * pz[0]) / (1.0e2 * GRAV);
     for (int ib = 0; ib < NB_LW; ++ib) secdiff[ib] = lw_secdiff(ib, pwvcm);
   }
-  __syncthreads();
-  // ---- phase B: one g-point per thread
+  // ---- phase B: one g-point per thread, rtrnmr clear sky (rrtmg_lw_rtrnmr.f90:390-480 down, :560-640 up)
+  const int valid = tid < NG_LW;
+  const int g = valid ? tid : NG_LW - 1;
+  int ib = 0;
+  while (ib < NB_LW - 1 && g >= bands[ib + 1].g0) ++ib;
+  const int gb = g - bands[ib].g0;
+  const double delwave[NB_LW] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
+  const double w = valid ? 0.5 * delwave[ib] : 0.0;
+  DevRed red{part, PS, tid >> 5, tid & 31};
+  const double* exptfn = A + tb.exptfn;
+  double atrans[KMAX], bbugas[KMAX];
+  double radld = 0.0, frac1 = 0.0;
+  red.down(nl, 0.0);
+  for (int hi = nl; hi >= 1; hi -= LW_TILE) {          // layers lev = hi .. lo (1-based), top-down
+    const int lo = hi - LW_TILE + 1 > 1 ? hi - LW_TILE + 1 : 1, cnt = hi - lo + 1;
+    __syncthreads();                                    // phase A (first tile) / the previous tile's term lists are consumed
+    for (int task = tid; task < cnt * NB_LW; task += LW_THREADS) {
+      const int li = task / NB_LW, b = task - li * NB_LW;
+      lw_terms(A, tb, bands[b], lay[lo - 1 + li], recs[task]);
+    }
+    __syncthreads();
+    const double sd = secdiff[ib];
+    for (int lev = hi; lev >= lo; --lev) {
+      double tau, plfrac;
+      lw_tau_rec(A, recs[(lev - lo) * NB_LW + ib], gb, tau, plfrac);
+      if (lev == 1) frac1 = plfrac;
+      lw_layer(exptfn, sd, tau, plfrac, planklay[ib * PS + lev - 1], planklev[ib * PS + lev], planklev[ib * PS + lev - 1],
+               radld, atrans[lev - 1], bbugas[lev - 1]);
+      red.down(lev - 1, radld * w);
+    }
+  }
   {
-    const int valid = tid < NG_LW;
-    const int g = valid ? tid : NG_LW - 1;
-    int ib = 0;
-    while (ib < NB_LW - 1 && g >= bands[ib + 1].g0) ++ib;
-    const double delwave[NB_LW] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
-    DevRed red{part, tid >> 5, tid & 31};
-    lw_gpoint(A, tb, bands[ib], ib, g - bands[ib].g0, nl, lay, planklay, planklev, PS, plankbnd[ib], semiss[ib], secdiff[ib],
-              valid ? 0.5 * delwave[ib] : 0.0, red);
+    double rad0 = frac1 * plankbnd[ib];
+    double radlu = rad0 + (1.0 - semiss[ib]) * radld;
+    red.up(0, radlu * w);
+    for (int lev = 1; lev <= nl; ++lev) {
+      radlu = radlu + (bbugas[lev - 1] - radlu) * atrans[lev - 1];
+      red.up(lev, radlu * w);
+    }
   }
   __syncthreads();
   // ---- phase C: fluxes and heating rates
   for (int lev = tid; lev <= nl; lev += LW_THREADS) {
     double u = 0.0, d = 0.0;
-    for (int w = 0; w < LW_THREADS / 32; ++w) { u += part[(w * 2 + 0) * (KMAX + 1) + lev]; d += part[(w * 2 + 1) * (KMAX + 1) + lev]; }
+    for (int wp = 0; wp < LW_THREADS / 32; ++wp) { u += part[(wp * 2 + 0) * PS + lev]; d += part[(wp * 2 + 1) * PS + lev]; }
     u *= FLUXFAC; d *= FLUXFAC;
     in.uflx[col + (size_t)nc * lev] = u;
     in.dflx[col + (size_t)nc * lev] = d;
@@ -106,19 +163,27 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
     in.hr[col + (size_t)nc * l] = in.heatfac * (fnet[l] - fnet[l + 1]) / (pz[l] - pz[l + 1]);
 }
 
+// Shortwave (spcvrt_sw clear sky + reftra_sw + vrtqdr_sw).  Same structure as the longwave kernel; the sweeps are re-ordered so that
+// the optical depths are needed only once: pass 1 runs bottom-up (layer optics, two-stream reflectance / transmittance of the layer
+// and, in the same step, vrtqdr's upward combination zrup / zrupd, which is a bottom-up recurrence), pass 2 top-down (direct-beam
+// transmittance, downward combination, fluxes).  Values and their order of evaluation are those of the reference.
 __global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __restrict__ A, Tab tb, const SwBand* __restrict__ bands, ColIn in) {
-  __shared__ Layer lay[KMAX];
-  __shared__ double part[(SW_THREADS / 32) * 2 * (KMAX + 1)];
-  __shared__ double pz[KMAX + 1], fnet[KMAX + 1];
-  __shared__ int lsol[NB_SW];
-  __shared__ int laytrop_s;
+  ISCA_DYN_SMEM(smem);
   const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
+  const int PS = nl + 1;
   const double cosz = in.coszen[col];
   if (cosz < 1.0e-10) {              // `if (coszen(iplon) < zepzen) ... cycle` (rrtmg_sw_rad.nomcica.f90)
     for (int lev = tid; lev <= nl; lev += SW_THREADS) { in.uflx[col + (size_t)nc * lev] = 0.0; in.dflx[col + (size_t)nc * lev] = 0.0; }
     for (int l = tid; l < nl; l += SW_THREADS) in.hr[col + (size_t)nc * l] = 0.0;
     return;
   }
+  Layer* lay = reinterpret_cast<Layer*>(smem);
+  SwRec* recs = reinterpret_cast<SwRec*>(smem + (sizeof(Layer) * (size_t)nl + 7) / 8);
+  double* part = reinterpret_cast<double*>(recs + SW_TILE * NB_SW);      // [warp][2][PS]
+  double* pz = part + (SW_THREADS / 32) * 2 * PS;
+  double* fnet = pz + PS;
+  int* lsol = reinterpret_cast<int*>(fnet + PS);                           // [NB_SW] + laytrop
+  int* laytrop_s = lsol + NB_SW;
   for (int l = tid; l < nl; l += SW_THREADS) {
     double vmr[NSP];
     for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + (size_t)nc * l] : in.gas_c[i];
@@ -128,22 +193,56 @@ __global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __re
     if (l == 0) pz[0] = pb;
   }
   __syncthreads();
-  if (tid == 0) { int n = 0; for (int l = 0; l < nl; ++l) n += lay[l].lower; laytrop_s = n; }
+  if (tid == 0) { int n = 0; for (int l = 0; l < nl; ++l) n += lay[l].lower; *laytrop_s = n; }
   __syncthreads();
-  if (tid < NB_SW) lsol[tid] = sw_laysolfr(bands[tid], lay, nl, laytrop_s);
-  __syncthreads();
+  if (tid < NB_SW) lsol[tid] = sw_laysolfr(bands[tid], lay, nl, *laytrop_s);
+  const int valid = tid < NG_SW;
+  const int g = valid ? tid : NG_SW - 1;
+  int ib = 0;
+  while (ib < NB_SW - 1 && g >= bands[ib + 1].g0) ++ib;
+  const int gb = g - bands[ib].g0;
+  const double* exp_tbl = A + tb.exp_tbl;
+  const double albedo = in.albedo[col], prmu0 = cosz;
+  DevRed red{part, PS, tid >> 5, tid & 31};
+  // per-thread column arrays, index jk = 0 (top layer) .. nl-1 (bottom layer), levels 0 (top) .. nl (surface)
+  double zref[KMAX], zrefd[KMAX], ztra[KMAX], ztrad[KMAX], zdbt[KMAX], zrup[KMAX + 1], zrupd[KMAX + 1];
+  double sflux = 0.0;
+  zrup[nl] = albedo; zrupd[nl] = albedo;
+  for (int lo = 1; lo <= nl; lo += SW_TILE) {          // layers (1-based, bottom-up) lo .. hi
+    const int hi = lo + SW_TILE - 1 < nl ? lo + SW_TILE - 1 : nl, cnt = hi - lo + 1;
+    __syncthreads();
+    for (int task = tid; task < cnt * NB_SW; task += SW_THREADS) {
+      const int li = task / NB_SW, b = task - li * NB_SW;
+      sw_terms(A, bands[b], lay[lo - 1 + li], recs[task]);
+    }
+    __syncthreads();
+    const int ls = lsol[ib];
+    for (int l1 = lo; l1 <= hi; ++l1) {
+      const SwRec& rc = recs[(l1 - lo) * NB_SW + ib];
+      const int jk = nl - l1;                            // ikl = l1 - 1 = nl - 1 - jk
+      double taug, taur;
+      sw_tau_rec(A, rc, gb, taug, taur);
+      if (l1 == ls) sflux = sw_src_rec(A, bands[ib], rc, gb);
+      sw_layer(exp_tbl, prmu0, taug, taur, zrup[jk + 1], zrupd[jk + 1], zref[jk], zrefd[jk], ztra[jk], ztrad[jk], zdbt[jk], zrup[jk], zrupd[jk]);
+    }
+  }
   {
-    const int valid = tid < NG_SW;
-    const int g = valid ? tid : NG_SW - 1;
-    int ib = 0;
-    while (ib < NB_SW - 1 && g >= bands[ib + 1].g0) ++ib;
-    DevRed red{part, tid >> 5, tid & 31};
-    sw_gpoint(A, tb, bands[ib], g - bands[ib].g0, nl, lay, lsol[ib], cosz, in.albedo[col], in.adjflux, valid ? 1.0 : 0.0, red);
+    // top-down transmittances and the fluxes at every level
+    const double zinc = in.adjflux * sflux * prmu0 * (valid ? 1.0 : 0.0);
+    double ztdn = 1.0, zrdnd = 0.0, tdbt = 1.0, tdbt_prev = 1.0;     // tdbt = ztdbt(jk), tdbt_prev = ztdbt(jk-1)
+    for (int jk = 0; jk <= nl; ++jk) {
+      if (jk >= 1) { tdbt_prev = tdbt; tdbt = zdbt[jk - 1] * tdbt_prev; }
+      const int j = jk >= 1 ? jk - 1 : 0;
+      double fu, fd;
+      sw_level(jk, tdbt, tdbt_prev, zref[j], zrefd[j], ztra[j], ztrad[j], zrup[jk], zrupd[jk], ztdn, zrdnd, fu, fd);
+      red.up(nl - jk, zinc * fu);
+      red.down(nl - jk, zinc * fd);
+    }
   }
   __syncthreads();
   for (int lev = tid; lev <= nl; lev += SW_THREADS) {
     double u = 0.0, d = 0.0;
-    for (int w = 0; w < SW_THREADS / 32; ++w) { u += part[(w * 2 + 0) * (KMAX + 1) + lev]; d += part[(w * 2 + 1) * (KMAX + 1) + lev]; }
+    for (int wp = 0; wp < SW_THREADS / 32; ++wp) { u += part[(wp * 2 + 0) * PS + lev]; d += part[(wp * 2 + 1) * PS + lev]; }
     in.uflx[col + (size_t)nc * lev] = u;
     in.dflx[col + (size_t)nc * lev] = d;
     fnet[lev] = d - u;

@@ -124,6 +124,10 @@ struct HostTables {
         tfn[itr] = tau < 0.06 ? tau / 6.0 : 1.0 - 2.0 * ((1.0 / tau) - (e / (1.0 - e)));
       }
       tab.exp_tbl = add_vec(ex); tab.tfn_tbl = add_vec(tfn);
+      std::vector<double> both(2 * (NTBL + 1));
+      for (int itr = 0; itr <= NTBL; ++itr) { both[2 * itr] = ex[itr]; both[2 * itr + 1] = tfn[itr]; }
+      if (arena.size() & 1) arena.push_back(0.0);            // 16-byte alignment of the pairs
+      tab.exptfn = add_vec(both);
     }
     const int lw_ngc[NB_LW] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
     const int sw_ngc[NB_SW] = {6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12};

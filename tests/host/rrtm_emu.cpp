@@ -41,6 +41,7 @@ static inline double __shfl_xor_sync(unsigned, double v, int o) {
 
 static inline int atomicExch(int* a, int v) { int o = __atomic_exchange_n(a, v, __ATOMIC_SEQ_CST); return o; }
 
+#define ISCA_RRTM_EMU 1
 #include "../../isca_b200/csrc/rrtm_tables.h"
 #include "../../isca_b200/csrc/rrtm_kernels.h"
 #include "../../isca_b200/csrc/physics_dry_kernels.h"

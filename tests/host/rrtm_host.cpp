@@ -87,7 +87,9 @@ int rrtm_host_lw(const char* table_path, double cp_air, int ncol, int nlay, cons
         if (taug_out)
           for (int l = 0; l < nlay; ++l) {
             double tau, fr;
-            lw_tau(A, H.tab, H.lw[ib], lay[l], g, tau, fr);
+            LwRec rec;
+            lw_terms(A, H.tab, H.lw[ib], lay[l], rec);          // the term lists the kernels build per (layer, band) ...
+            lw_tau_rec(A, rec, g, tau, fr);                       // ... and the per-g-point dot product
             taug_out[((size_t)col * nlay + l) * NG_LW + H.lw[ib].g0 + g] = tau;
             fracs_out[((size_t)col * nlay + l) * NG_LW + H.lw[ib].g0 + g] = fr;
           }
@@ -142,7 +144,10 @@ int rrtm_host_sw(const char* table_path, double cp_air, int ncol, int nlay, cons
         if (taug_out)
           for (int l = 0; l < nlay; ++l) {
             double tg, tr, src;
-            sw_tau(A, H.sw[ib], lay[l], g, tg, tr, src);
+            SwRec rec;
+            sw_terms(A, H.sw[ib], lay[l], rec);
+            sw_tau_rec(A, rec, g, tg, tr);
+            src = sw_src_rec(A, H.sw[ib], rec, g);
             taug_out[((size_t)col * nlay + l) * NG_SW + H.sw[ib].g0 + g] = tg;
             taur_out[((size_t)col * nlay + l) * NG_SW + H.sw[ib].g0 + g] = tr;
             if (l + 1 == lsol) sflux_out[(size_t)col * NG_SW + H.sw[ib].g0 + g] = src;

@@ -19,5 +19,12 @@ done
 MOIST="python tools/moistbench.py T170 40 150 1 --ncu-steps 3"
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02a_moist_launches.csv $MOIST > gpurun_out/ncu_moist_launch.log 2>&1
 MOIST1="python tools/moistbench.py T170 40 150 1 --ncu-steps 1"
-timeout 900 ncu --profile-from-start off --set full --clock-control none -f -o gpurun_out/r02a_prof_moist_step $MOIST1 > gpurun_out/ncu_moist_full.log 2>&1
-ls -la gpurun_out
+timeout 900 ncu --profile-from-start off --section SpeedOfLight --section MemoryWorkloadAnalysis --section Occupancy --section LaunchStats --section WarpStateStats \
+  --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none -f -o gpurun_out/r02a_prof_moist_step $MOIST1 > gpurun_out/ncu_moist_full.log 2>&1
+# gpurun_out/ must stay below 64 MiB or nothing is copied back: turn any large report into its raw csv page and drop it
+for f in gpurun_out/*.ncu-rep; do
+  if [ $(stat -c %s "$f") -gt 25000000 ]; then ncu -i "$f" --page raw --csv > "${f%.ncu-rep}_raw.csv" 2>/dev/null; rm -f "$f"; fi
+done
+du -sh gpurun_out
+tail -25 gpurun_out/r02a_pytest_gpu.txt
+cat gpurun_out/r02a_box.txt gpurun_out/r02a_rrtm_bench.json gpurun_out/r02a_mima_bench.json
