@@ -275,6 +275,9 @@ int isca_b200_moist_create_ranked(const IscaConfig* dyn, const IscaPhysicsConfig
   IscaPhysicsConfig pc = *phys;
   pc.num_lon = v.I; pc.num_lat = v.Jloc; pc.num_levels = v.K; pc.grav = dyn->grav; pc.rdgas = dyn->rdgas; pc.cp_air = dyn->rdgas / dyn->kappa;
   if (isca_b200_physics_create(&pc, &m->phy)) { std::string e = isca_b200_physics_last_error(nullptr); isca_b200_moist_destroy(m); return mfail(nullptr, "physics: " + e); }
+  if (mc->convection_scheme == 1 && !m->phy->lcl_err.empty()) {      // qe_moist_convection_init (idealized_moist_phys.F90:505)
+    std::string e = m->phy->lcl_err; isca_b200_moist_destroy(m); return mfail(nullptr, "physics: " + e);
+  }
   cudaStreamDestroy(m->phy->st);
   m->phy->st = v.st; m->phy->owns_stream = false;
   const size_t nc = m->nc, n3 = m->n3;

@@ -545,7 +545,7 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   if (cudaStreamSynchronize(p->st) != cudaSuccess) { delete p; return fail(nullptr, "table upload failed"); }
   p->svp = SvpDev{p->tab.p, p->tab.p + n, p->tab.p + 2 * n, tminl, dtinvl, 0.5 * dtres, dtres, n};
   p->svp_host = tb;
-  if (build_lcl_table(p)) { std::string m = p->err; isca_b200_physics_destroy(p); return fail(nullptr, m); }
+  if (build_lcl_table(p)) { p->lcl_err = p->err; p->err.clear(); p->lcl_n = 0; }     // deferred: only qe_moist_convection needs the table
   *out = p;
   return 0;
 }

@@ -84,6 +84,7 @@ struct IscaPhysics_t {
   std::vector<double> svp_host;         // host copy of the same tables (LCL table construction)
   isca_phys::Dev lcl_tab;               // qe_moist_convection lcl_temp_table
   int lcl_n = 0; double lcl_val_min = 0.0, lcl_val_max = 0.0;
+  std::string lcl_err;                  // qe_moist_convection_init failure, raised when the scheme is used (the reference calls that init only for SIMPLE_BETTS_MILLER)
   isca_phys::Dev buf[24];               // staging of the host-array entry points
   isca_phys::Dev state[isca_phys::ST_COUNT];
   IscaBettsMillerConfig bm{1, 1, 0, 0, 0, 0, 7200., .8, 900., 2400., 0.};      // betts_miller_nml defaults (betts_miller.f90:56-66)

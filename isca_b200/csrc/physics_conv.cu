@@ -266,6 +266,7 @@ extern "C" int isca_b200_qe_moist_convection(IscaPhysics p, double dt, const dou
                                              double* invtau_q_relaxation, double* invtau_t_relaxation, double* Tref, int* kLCLs) {
   if (!p) return fail(nullptr, "null handle");
   if (!snow || !convflag || !kLZBs || !kLCLs) return fail(p, "null output array");
+  if (!p->lcl_err.empty()) return fail(p, p->lcl_err);
   size_t nc = p->ncol, n3 = nc * p->K;
   Dev* b = p->buf;
   if (up(p, b[0], Tin, n3) || up(p, b[1], qin, n3) || up(p, b[2], p_full, n3) || up(p, b[3], p_half, n3 + nc)) return 1;
