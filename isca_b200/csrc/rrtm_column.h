@@ -191,7 +191,7 @@ RR_HD Spec specparm_of(double ca, double cb, double rat, double mult) {
   if (s.specparm >= ONEMINUS) s.specparm = ONEMINUS;
   double specmult = mult * s.specparm;
   s.js = 1 + (int)specmult;
-  s.fs = fmod(specmult, 1.0);
+  s.fs = specmult - floor(specmult);         // = mod(specmult, 1.) exactly (specmult >= 0)
   return s;
 }
 
@@ -202,7 +202,7 @@ RR_HD Spec specparm_of(double ca, double cb, double rat, double mult) {
 // (table row, weight) pairs; a g-point thread then only forms  tau = sum_i w_i * A[off_i + g]  (consecutive doubles across
 // the lanes of a band).  Same formulas as lw_tau / sw_tau with the products re-associated (differences at the 1e-16 level).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NT_LW = 24, NT_SW = 14;
+constexpr int NT_LW = 24, NT_SW = 16;      // multiples of 4: the lists are padded with zero-weight terms to whole groups of four
 struct LwRec { double w[NT_LW]; int off[NT_LW]; int n, gs_off, f0, f1; double ffs; };
 struct SwRec { double w[NT_SW]; int off[NT_SW]; int n, r0, r1, rg, js, pad; double rc0, rc1, tconst, fs; };
 
@@ -295,6 +295,7 @@ RR_HD void lw_terms(const double* A, const Tab& tb, const LwBand& B, const Layer
   else if (R.corr == 2) corr = 1.0 - 0.15 * (L.pavel / 95.6);
   else if (R.corr == 3) corr = 1.0 - 0.05 * (L.pavel - 100.0) / 900.0;
   if (corr != 1.0) for (int i = 0; i < rec.n; ++i) rec.w[i] *= corr;
+  while (rec.n & 3) rec_add(rec, 0, 0.0);
   rec.gs_off = R.gscale_off;
   rec.f0 = rec.f1 = -1; rec.ffs = 0.0;
   if (R.frac_off >= 0) {
@@ -305,9 +306,18 @@ RR_HD void lw_terms(const double* A, const Tab& tb, const LwBand& B, const Layer
   }
 }
 // the g-dependent part: a dot product over the term list
+template <class Rec>
+RR_HD double rec_dot(const double* A, const Rec& r, int g) {     // four independent table reads in flight per step
+  const double* Ag = A + g;
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  for (int i = 0; i < r.n; i += 4) {
+    const double a0 = Ag[r.off[i]], a1 = Ag[r.off[i + 1]], a2 = Ag[r.off[i + 2]], a3 = Ag[r.off[i + 3]];
+    t0 += r.w[i] * a0; t1 += r.w[i + 1] * a1; t2 += r.w[i + 2] * a2; t3 += r.w[i + 3] * a3;
+  }
+  return (t0 + t1) + (t2 + t3);
+}
 RR_HD void lw_tau_rec(const double* A, const LwRec& r, int g, double& tau, double& frac) {
-  double t = 0.0;
-  for (int i = 0; i < r.n; ++i) t += r.w[i] * A[r.off[i] + g];
+  double t = rec_dot(A, r, g);
   if (r.gs_off >= 0) t *= A[r.gs_off + g];
   tau = t;
   if (r.f0 < 0) frac = 0.0;
@@ -408,6 +418,7 @@ RR_HD void sw_terms(const double* A, const SwBand& B, const Layer& L, SwRec& rec
   if (R.self_off >= 0) itab_terms(rec, R.self_off, ng, L.indself, L.selffrac, L.col[SP_H2O] * L.selffac);
   if (R.for_off >= 0) itab_terms(rec, R.for_off, ng, L.indfor, L.forfrac, L.col[SP_H2O] * L.forfac);
   for (int e = 0; e < R.nextra; ++e) rec_add(rec, R.extra_off[e], L.col[R.extra_sp[e]]);
+  while (rec.n & 3) rec_add(rec, 0, 0.0);
   rec.tconst = R.o2cont ? 4.35e-4 * L.col[SP_O2] / (350.0 * 2.0) : 0.0;
   rec.r1 = -1; rec.rc1 = 0.0;
   if (R.rayl_mode == 0) { rec.r0 = R.rayl_off; rec.rg = 0; rec.rc0 = L.colmol; }
@@ -415,9 +426,7 @@ RR_HD void sw_terms(const double* A, const SwBand& B, const Layer& L, SwRec& rec
   else { rec.r0 = R.rayl_off + (rec.js - 1) * ng; rec.r1 = R.rayl_off + rec.js * ng; rec.rg = 1; rec.rc0 = L.colmol; rec.rc1 = rec.fs; }
 }
 RR_HD void sw_tau_rec(const double* A, const SwRec& r, int g, double& taug, double& taur) {
-  double t = 0.0;
-  for (int i = 0; i < r.n; ++i) t += r.w[i] * A[r.off[i] + g];
-  taug = t + r.tconst;
+  taug = rec_dot(A, r, g) + r.tconst;
   double a = A[r.r0 + r.rg * g];
   taur = r.rc0 * (r.r1 >= 0 ? a + r.rc1 * (A[r.r1 + g] - a) : a);
 }
@@ -452,20 +461,19 @@ RR_HD double sw_exp(const double* exp_tbl, double ze) {            // exp(-ze) o
   return exp_tbl[itind];
 }
 
-// reftra_sw for one layer (kmodts = 2)
-RR_HD void sw_reftra(const double* exp_tbl, double zg, double prmuz, double zto1, double zw, double& pref, double& prefd,
+// reftra_sw for one layer (kmodts = 2) with asymmetry factor g = 0 (clear sky without aerosols: Rayleigh scattering only).  These are
+// the reference's expressions with zg = 0 substituted -- zg3 = 0, zgamma3 = zgamma4 = 1/2, zwo = zw / (1 - (1 - zw) * 0) = zw -- which
+// leaves every retained operation and its operands unchanged (bit-identical results), but spares a division and the dead products.
+// ze_dir = zto1 / prmuz (the caller needs it for the direct beam as well).
+RR_HD void sw_reftra(const double* exp_tbl, double prmuz, double ze_dir, double zto1, double zw, double& pref, double& prefd,
                      double& ptra, double& ptrad) {
   const double zwcrit = 0.9999995, eps = 1.0e-08;
-  double zg3 = 3.0 * zg;
-  double zgamma1 = (8.0 - zw * (5.0 + zg3)) * 0.25;
-  double zgamma2 = 3.0 * (zw * (1.0 - zg)) * 0.25;
-  double zgamma3 = (2.0 - zg3 * prmuz) * 0.25;
-  double zgamma4 = 1.0 - zgamma3;
-  double q = zg / (1.0 - zg);
-  double zwo = zw / (1.0 - (1.0 - zw) * q * q);
-  if (zwo >= zwcrit) {
+  const double zgamma1 = (8.0 - zw * 5.0) * 0.25;
+  const double zgamma2 = 3.0 * zw * 0.25;
+  const double zgamma3 = 0.5, zgamma4 = 0.5;
+  if (zw >= zwcrit) {
     double za = zgamma1 * prmuz, za1 = za - zgamma3, zgt = zgamma1 * zto1;
-    double ze1 = zto1 / prmuz; if (ze1 > 500.0) ze1 = 500.0;
+    double ze1 = ze_dir; if (ze1 > 500.0) ze1 = 500.0;
     double ze2 = sw_exp(exp_tbl, ze1);
     pref = (zgt - za1 * (1.0 - ze2)) / (1.0 + zgt);
     ptra = 1.0 - pref;
@@ -484,7 +492,7 @@ RR_HD void sw_reftra(const double* exp_tbl, double zg, double prmuz, double zto1
     double zt4 = zr4, zt5 = zr5;
     double zbeta = (zgamma1 - zrk) / zrkg;
     double ze1 = zrk * zto1; if (ze1 > 500.0) ze1 = 500.0;
-    double ze2 = zto1 / prmuz; if (ze2 > 500.0) ze2 = 500.0;
+    double ze2 = ze_dir; if (ze2 > 500.0) ze2 = 500.0;
     double zem1 = sw_exp(exp_tbl, ze1), zep1 = 1.0 / zem1;
     double zem2 = sw_exp(exp_tbl, ze2), zep2 = 1.0 / zem2;
     double zdenr = zr4 * zep1 + zr5 * zem1, zdent = zt4 * zep1 + zt5 * zem1;
@@ -506,8 +514,9 @@ RR_HD void sw_layer(const double* exp_tbl, double prmu0, double taug, double tau
                     double& zref, double& zrefd, double& ztra, double& ztrad, double& zdbt, double& zrup, double& zrupd) {
   double ztauc = taur + taug;               // + aerosol (none)
   double zomcc = taur / ztauc;              // single-scattering albedo
-  sw_reftra(exp_tbl, 0.0, prmu0, ztauc, zomcc, zref, zrefd, ztra, ztrad);
-  zdbt = sw_exp(exp_tbl, ztauc / prmu0);
+  const double ze_dir = ztauc / prmu0;      // optical path of the direct beam: reftra's ze1 / ze2 (clamped there) and the argument of zdbt
+  sw_reftra(exp_tbl, prmu0, ze_dir, ztauc, zomcc, zref, zrefd, ztra, ztrad);
+  zdbt = sw_exp(exp_tbl, ze_dir);
   double zreflect = 1.0 / (1.0 - rupd_below * zrefd);
   zrup = zref + (ztrad * ((ztra - zdbt) * rupd_below + zdbt * rup_below)) * zreflect;
   zrupd = zrefd + ztrad * ztrad * rupd_below * zreflect;

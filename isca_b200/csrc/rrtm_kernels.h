@@ -31,6 +31,31 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Sum eight per-lane values over the 32 lanes of a warp with 9 shuffles instead of 8 x 5: each exchange step halves the number of
+// values a lane is responsible for (lane bit 4 picks the half v[0..3] / v[4..7], bit 3 the next half, bit 2 the last one), the two last
+// steps are a plain butterfly.  Afterwards v[0] of lane L holds the total of value number ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 +
+// ((L >> 2) & 1); the order of the additions is fixed, so the result is reproducible.
+__device__ __forceinline__ void warp_sum8(double (&v)[8], int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = h3 ? v[i] : v[i + 2], keep = h3 ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const double send = h2 ? v[0] : v[1], keep = h2 ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int warp_sum8_slot(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
 struct DevRed {                      // per-level sum over the g-points: warp shuffle, lane 0 stores the warp's partial
   double* part; int ps, warp, lane;  // part[warp][2][ps], ps = nlay + 1
   __device__ __forceinline__ void up(int lev, double v) { v = warp_sum(v); if (lane == 0) part[(warp * 2 + 0) * ps + lev] = v; }
@@ -38,7 +63,7 @@ struct DevRed {                      // per-level sum over the g-points: warp sh
 };
 
 constexpr int LW_THREADS = 160, SW_THREADS = 128;
-constexpr int LW_TILE = 10, SW_TILE = 8;      // layers whose (layer, band) term lists are resident in shared memory at a time
+constexpr int LW_TILE = 8, SW_TILE = 8;       // = the batch of warp_sum8      // layers whose (layer, band) term lists are resident in shared memory at a time
 constexpr double FLUXFAC = 3.14159265358979323846 * 2.0e4;      // pi * 2.e4 with pi = 2*asin(1)
 
 // dynamic shared memory (sized by the number of layers, so that more CTAs fit per SM); the CPU thread emulator of
@@ -116,7 +141,8 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
   const int gb = g - bands[ib].g0;
   const double delwave[NB_LW] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
   const double w = valid ? 0.5 * delwave[ib] : 0.0;
-  DevRed red{part, PS, tid >> 5, tid & 31};
+  const int warp = tid >> 5, lane = tid & 31, slot = warp_sum8_slot(lane);
+  DevRed red{part, PS, warp, lane};
   const double* exptfn = A + tb.exptfn;
   double atrans[KMAX], bbugas[KMAX];
   double radld = 0.0, frac1 = 0.0;
@@ -124,28 +150,46 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
   for (int hi = nl; hi >= 1; hi -= LW_TILE) {          // layers lev = hi .. lo (1-based), top-down
     const int lo = hi - LW_TILE + 1 > 1 ? hi - LW_TILE + 1 : 1, cnt = hi - lo + 1;
     __syncthreads();                                    // phase A (first tile) / the previous tile's term lists are consumed
-    for (int task = tid; task < cnt * NB_LW; task += LW_THREADS) {
-      const int li = task / NB_LW, b = task - li * NB_LW;
-      lw_terms(A, tb, bands[b], lay[lo - 1 + li], recs[task]);
+    for (int task = tid; task < cnt * NB_LW; task += LW_THREADS) {     // band-major: the lanes of a warp share 3-4 bands (code paths), not 16
+      const int b = task / cnt, li = task - b * cnt;
+      lw_terms(A, tb, bands[b], lay[lo - 1 + li], recs[li * NB_LW + b]);
     }
     __syncthreads();
     const double sd = secdiff[ib];
-    for (int lev = hi; lev >= lo; --lev) {
-      double tau, plfrac;
-      lw_tau_rec(A, recs[(lev - lo) * NB_LW + ib], gb, tau, plfrac);
-      if (lev == 1) frac1 = plfrac;
-      lw_layer(exptfn, sd, tau, plfrac, planklay[ib * PS + lev - 1], planklev[ib * PS + lev], planklev[ib * PS + lev - 1],
-               radld, atrans[lev - 1], bbugas[lev - 1]);
-      red.down(lev - 1, radld * w);
+    double v8[8];
+#pragma unroll
+    for (int j = 0; j < LW_TILE; ++j) {
+      const int lev = hi - j;
+      v8[j] = 0.0;
+      if (lev >= lo) {
+        double tau, plfrac;
+        lw_tau_rec(A, recs[(lev - lo) * NB_LW + ib], gb, tau, plfrac);
+        if (lev == 1) frac1 = plfrac;
+        lw_layer(exptfn, sd, tau, plfrac, planklay[ib * PS + lev - 1], planklev[ib * PS + lev], planklev[ib * PS + lev - 1],
+                 radld, atrans[lev - 1], bbugas[lev - 1]);
+        v8[j] = radld * w;
+      }
     }
+    warp_sum8(v8, lane);                                 // the tile's eight downward radiances at once
+    if ((lane & 3) == 0 && slot < cnt) part[(warp * 2 + 1) * PS + hi - 1 - slot] = v8[0];
   }
   {
     double rad0 = frac1 * plankbnd[ib];
     double radlu = rad0 + (1.0 - semiss[ib]) * radld;
     red.up(0, radlu * w);
-    for (int lev = 1; lev <= nl; ++lev) {
-      radlu = radlu + (bbugas[lev - 1] - radlu) * atrans[lev - 1];
-      red.up(lev, radlu * w);
+    for (int l0 = 1; l0 <= nl; l0 += 8) {
+      double v8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int lev = l0 + j;
+        v8[j] = 0.0;
+        if (lev <= nl) {
+          radlu = radlu + (bbugas[lev - 1] - radlu) * atrans[lev - 1];
+          v8[j] = radlu * w;
+        }
+      }
+      warp_sum8(v8, lane);
+      if ((lane & 3) == 0 && l0 + slot <= nl) part[(warp * 2 + 0) * PS + l0 + slot] = v8[0];
     }
   }
   __syncthreads();
@@ -203,7 +247,7 @@ __global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __re
   const int gb = g - bands[ib].g0;
   const double* exp_tbl = A + tb.exp_tbl;
   const double albedo = in.albedo[col], prmu0 = cosz;
-  DevRed red{part, PS, tid >> 5, tid & 31};
+  const int warp = tid >> 5, lane = tid & 31, slot = warp_sum8_slot(lane);
   // per-thread column arrays, index jk = 0 (top layer) .. nl-1 (bottom layer), levels 0 (top) .. nl (surface)
   double zref[KMAX], zrefd[KMAX], ztra[KMAX], ztrad[KMAX], zdbt[KMAX], zrup[KMAX + 1], zrupd[KMAX + 1];
   double sflux = 0.0;
@@ -211,9 +255,9 @@ __global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __re
   for (int lo = 1; lo <= nl; lo += SW_TILE) {          // layers (1-based, bottom-up) lo .. hi
     const int hi = lo + SW_TILE - 1 < nl ? lo + SW_TILE - 1 : nl, cnt = hi - lo + 1;
     __syncthreads();
-    for (int task = tid; task < cnt * NB_SW; task += SW_THREADS) {
-      const int li = task / NB_SW, b = task - li * NB_SW;
-      sw_terms(A, bands[b], lay[lo - 1 + li], recs[task]);
+    for (int task = tid; task < cnt * NB_SW; task += SW_THREADS) {     // band-major (see the longwave kernel)
+      const int b = task / cnt, li = task - b * cnt;
+      sw_terms(A, bands[b], lay[lo - 1 + li], recs[li * NB_SW + b]);
     }
     __syncthreads();
     const int ls = lsol[ib];
@@ -230,13 +274,23 @@ __global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __re
     // top-down transmittances and the fluxes at every level
     const double zinc = in.adjflux * sflux * prmu0 * (valid ? 1.0 : 0.0);
     double ztdn = 1.0, zrdnd = 0.0, tdbt = 1.0, tdbt_prev = 1.0;     // tdbt = ztdbt(jk), tdbt_prev = ztdbt(jk-1)
-    for (int jk = 0; jk <= nl; ++jk) {
-      if (jk >= 1) { tdbt_prev = tdbt; tdbt = zdbt[jk - 1] * tdbt_prev; }
-      const int j = jk >= 1 ? jk - 1 : 0;
-      double fu, fd;
-      sw_level(jk, tdbt, tdbt_prev, zref[j], zrefd[j], ztra[j], ztrad[j], zrup[jk], zrupd[jk], ztdn, zrdnd, fu, fd);
-      red.up(nl - jk, zinc * fu);
-      red.down(nl - jk, zinc * fd);
+    for (int j0 = 0; j0 <= nl; j0 += 4) {                // four levels = eight values (up, down) per warp_sum8
+      double v8[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jk = j0 + j;
+        v8[2 * j] = 0.0; v8[2 * j + 1] = 0.0;
+        if (jk <= nl) {
+          if (jk >= 1) { tdbt_prev = tdbt; tdbt = zdbt[jk - 1] * tdbt_prev; }
+          const int jl = jk >= 1 ? jk - 1 : 0;
+          double fu, fd;
+          sw_level(jk, tdbt, tdbt_prev, zref[jl], zrefd[jl], ztra[jl], ztrad[jl], zrup[jk], zrupd[jk], ztdn, zrdnd, fu, fd);
+          v8[2 * j] = zinc * fu; v8[2 * j + 1] = zinc * fd;
+        }
+      }
+      warp_sum8(v8, lane);
+      const int jk = j0 + (slot >> 1);
+      if ((lane & 3) == 0 && jk <= nl) part[(warp * 2 + (slot & 1)) * PS + nl - jk] = v8[0];
     }
   }
   __syncthreads();
