@@ -252,6 +252,11 @@ int isca_b200_moist_step(IscaMoist m, int n_steps);
  * 6 surf_lw_down, 7 convective rain, 8 cape, 9 convflag, 10 q_surf, 11 u_star, 12 b_star, 13 flux_u, 14 flux_v, 15 delta_t_surf;
  * 3-D [K][J][I]: 32 dt_ug, 33 dt_vg, 34 dt_tg, 35 dt_tracers(sphum) (physics tendencies), 36 diff_m, 37 diff_t */
 int isca_b200_moist_get(IscaMoist m, int id, double* host);
+/* Measurement aid: n_steps eager steps with a CUDA event after every kernel group; writes the average milliseconds per group to
+   ms_out and the ';'-separated group names to `names` ("phys_*" = the column-physics kernels in call order, "phys_rrtmg_call" = a
+   whole radiation call on the steps where the alarm fires, the rest = the dynamical core's groups of isca_b200_profile_step).
+   Returns the number of groups, -1 on error. */
+int isca_b200_moist_profile_step(IscaMoist m, int n_steps, double* ms_out, int max_groups, char* names, int capacity);
 int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
 /* Surface properties [J][I] that idealized_moist_phys_init / mixed_layer_init derive from the land options (land mask file,
  * land_h_capacity_prefactor, land_albedo_prefactor, land_roughness_prefactor; idealized_moist_phys.F90:565-616, mixed_layer.F90:380-470):

@@ -1097,6 +1097,28 @@ int isca_core_check(IscaHandle h) {
   check_t_flag(*h);
   API_END(h)
 }
+void isca_core_profile_begin(IscaHandle h) {
+  if (!h) return;
+  for (auto& m : h->marks) cudaEventDestroy(m.second);
+  h->marks.clear();
+  h->profiling = true;
+  h->mark("start");
+}
+void isca_core_mark(IscaHandle h, const char* name) { if (h) h->mark(name); }
+int isca_core_profile_end(IscaHandle h, std::vector<std::string>& order, std::map<std::string, double>& acc) {
+  if (!h) return 1;
+  h->profiling = false;
+  int rc = cudaStreamSynchronize(h->st) == cudaSuccess ? 0 : 1;
+  for (size_t q = 1; q < h->marks.size() && !rc; ++q) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->marks[q - 1].second, h->marks[q].second) != cudaSuccess) { rc = 1; break; }
+    if (!acc.count(h->marks[q].first)) order.push_back(h->marks[q].first);
+    acc[h->marks[q].first] += ms;
+  }
+  for (auto& m : h->marks) cudaEventDestroy(m.second);
+  h->marks.clear();
+  return rc;
+}
 
 static int slot_of(H& h, int level) {
   if (level == ISCA_LEVEL_CURRENT) return h.current;

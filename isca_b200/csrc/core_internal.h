@@ -3,6 +3,9 @@
 #pragma once
 #include "../../include/isca_b200.h"
 #include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
 
 struct IscaCoreView {
   int I, Jloc, K, j0, previous, current, num_tracers, nranks;
@@ -22,4 +25,10 @@ int isca_core_press_heights(IscaHandle h, int slot, double* p_full, double* p_ha
 int isca_core_step_ext(IscaHandle h, const double* dtu, const double* dtv, const double* dtt, const double* dtq);
 // valid-temperature-range check of the last steps (spectral_dynamics.F90 FATAL); 0 = ok
 int isca_core_check(IscaHandle h);
+// per-kernel-group CUDA-event marks shared with the moist-model driver (isca_b200_moist_profile_step): begin clears the marks and
+// records "start"; mark() records an event named `name` on the core's stream (no-op unless profiling); end synchronises, adds the
+// elapsed ms between consecutive marks to acc (keyed by the later mark's name, first-seen order kept in `order`) and frees the events
+void isca_core_profile_begin(IscaHandle h);
+void isca_core_mark(IscaHandle h, const char* name);
+int isca_core_profile_end(IscaHandle h, std::vector<std::string>& order, std::map<std::string, double>& acc);
 }

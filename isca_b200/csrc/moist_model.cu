@@ -129,6 +129,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   if (isca_core_press_heights(m->dyn, prev, m->p_full[0].p, m->p_half[0].p, m->z_full[0].p, m->z_half[0].p) ||
       isca_core_press_heights(m->dyn, cur, m->p_full[1].p, m->p_half[1].p, m->z_full[1].p, m->z_half[1].p))
     return mfail(m, std::string("dynamical core: ") + isca_b200_last_error(m->dyn));
+  isca_core_mark(m->dyn, "phys_press_heights");
   const double *tg_p = v.T[prev], *q_p = v.q[prev], *ug_p = v.u[prev], *vg_p = v.v[prev];
   const double *pf_p = m->p_full[0].p, *ph_p = m->p_half[0].p, *pf_c = m->p_full[1].p, *ph_c = m->p_half[1].p;
   const double *zf_c = m->z_full[1].p, *zh_c = m->z_half[1].p;
@@ -148,6 +149,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
                           m->cape.p, m->cin.p, m->itt.p, m->itq.p);
     conv_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, tg_p, q_p, m->tg_tmp.p, m->qg_tmp.p, m->dt_t.p, m->dt_q.p,
                                                m->rain.p, m->conv_rain.p, m->precip.p);
+    isca_core_mark(m->dyn, "phys_convection");
     t_in = m->tg_tmp.p; q_in = m->qg_tmp.p;
   } else if (m->mc.convection_scheme == 2) {                     // 'DRY' (:918-928): dt_tg += conv_dt_tg; no precipitation
     launch_dry_convection(p, m->dry_tau, m->dry_gamma, tg_p, pf_p, ph_p, m->c_Tref.p, m->c_dT.p, m->cape.p, m->cin.p, klzb, klcl);
@@ -161,6 +163,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   if (m->mc.convection_scheme != 2) {                            // `if (r_conv_scheme .ne. DRY_CONV)` (:977): no large-scale condensation
     launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
     cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
+    isca_core_mark(m->dyn, "phys_lscale_cond");
   }
   if (!m->rr && m->seasonal) {                                   // Time_diag = Time (:1054); days of 86400 s as get_time returns them
     const double days = floor(m->time_s / 86400.0), seconds = m->time_s - 86400.0 * days;
@@ -169,6 +172,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
     scale_kernel<<<nblk(nc), 256, 0, st>>>(nc, p->insol.p, m->coszen.p, p->pc.solar_constant);
   }
   if (!m->rr) launch_gray_down(p, m->lat2d.p, ph_c, tg_p, q_p, m->albedo.p, m->net_sw.p, m->lw_down.p);   // q = grid_tracers(previous, nsphum), :1068
+  isca_core_mark(m->dyn, "phys_gray_down");
   // surface_flux on the lowest model level (:1076-1132)
   sub_kernel<<<nblk(nc), 256, 0, st>>>(nc, m->z_atm.p, zf_c + (size_t)(K - 1) * nc, m->z_surf.p);
   IscaSurfaceFluxArgs a;
@@ -182,6 +186,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
                        &a.dtaudv_atm, &a.ex_del_m, &a.ex_del_h, &a.ex_del_q, &a.temp_2m, &a.u_10m, &a.v_10m, &a.q_2m, &a.rh_2m};
   for (int i = 0; i < 28; ++i) *outs[i] = m->sf.p + (size_t)i * nc;
   launch_surface_flux(p, a);
+  isca_core_mark(m->dyn, "phys_surface_flux");
   if (!m->rr) launch_gray_up(p, m->lat2d.p, ph_c, tg_p, q_p, m->t_surf.p, m->albedo.p, m->dt_t.p, nullptr);
   else {
     // run_rrtmg (rrtm_radiation.F90:640-660): radiation alarm; between radiation steps the stored heating and surface fluxes are reused
@@ -194,6 +199,7 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
                                m->coszen.p, m->dt_t.p, m->tdt_rad.p, m->net_sw.p, m->lw_down.p, m->olr.p, m->toa_sw.p))
         return mfail(m, std::string("run_rrtmg: ") + isca_b200_rrtm_last_error(m->rr));
       m->n_rad_calls++;
+      isca_core_mark(m->dyn, "phys_rrtmg_call");                   // the whole radiation call (only on radiation steps)
     } else if (m->rdc.store_intermediate_rad) {
       add1_kernel<<<nblk(n3), 256, 0, st>>>(n3, m->dt_t.p, m->tdt_rad.p);
     } else {
@@ -201,11 +207,13 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
       MCK(cudaMemsetAsync(m->lw_down.p, 0, nc * sizeof(double), st));
     }
   }
+  isca_core_mark(m->dyn, "phys_radiation");
   if (m->mc.do_damping) {
     int nlev = rayleigh_nlev(m->pref.data(), K, p->cfg.sponge_pbottom);
     launch_rayleigh(p, nlev, delta_t, pf_c, ug_p, vg_p, m->w1.p, m->w2.p, m->w3.p);
     add3_kernel<<<nblk(n3), 256, 0, st>>>(n3, m->dt_u.p, m->w1.p, m->dt_v.p, m->w2.p, m->dt_t.p, m->w3.p);
   }
+  isca_core_mark(m->dyn, "phys_damping");
   // vert_turb_driver, do_diffusivity branch on the `current` fields (vert_turb_driver.F90:277-292; use_tau = .true.)
   MCK(cudaMemsetAsync(m->diff_m.p, 0, n3 * sizeof(double), st));
   MCK(cudaMemsetAsync(m->diff_t.p, 0, n3 * sizeof(double), st));
@@ -216,12 +224,15 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
                                                m->w3.p, m->c_dT.p);
     launch_diffusivity(p, m->w3.p, m->c_dT.p, m->w1.p, m->w2.p, zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p);
   }
+  isca_core_mark(m->dyn, "phys_diffusivity");
   fill_kernel<<<nblk(nc), 256, 0, st>>>(m->gust.p, nc, m->mc.constant_gust);
   launch_vert_diff_down(p, delta_t, ug_p, vg_p, tg_p, q_p, m->diff_m.p, m->diff_t.p, ph_c, zf_c, a.flux_u, a.flux_v, a.dtaudu_atm, a.dtaudv_atm,
                         m->dt_u.p, m->dt_v.p, m->dt_t.p, m->dt_q.p, m->diss.p);
+  isca_core_mark(m->dyn, "phys_vert_diff_down");
   launch_mixed_layer(p, v.dt_atmos, m->t_surf.p, a.flux_t, a.flux_q, a.flux_r, m->net_sw.p, m->lw_down.p, a.dhdt_surf, a.dedt_surf, a.dedq_surf,
                      a.drdt_surf, a.dhdt_atm, a.dedq_atm, m->dts.p);
   launch_vert_diff_up(p, delta_t, m->dt_t.p, m->dt_q.p);
+  isca_core_mark(m->dyn, "phys_mixed_layer_vert_diff_up");
   if (ev_phys_end) MCK(cudaEventRecord(ev_phys_end, st));
   if (isca_core_step_ext(m->dyn, m->dt_u.p, m->dt_v.p, m->dt_t.p, m->dt_q.p)) return mfail(m, std::string("spectral_dynamics: ") + isca_b200_last_error(m->dyn));
   m->time_s += v.dt_atmos;                                     // atmos_model.F90: Time_atmos = Time_atmos + Time_step_atmos
@@ -401,6 +412,29 @@ int isca_b200_moist_step(IscaMoist m, int n_steps) {
   }
   if (isca_core_check(m->dyn)) return mfail(m, isca_b200_last_error(m->dyn));
   return 0;
+}
+
+// average milliseconds per kernel group (physics kernels "phys_*" + the dynamical core's groups) over n eager steps
+int isca_b200_moist_profile_step(IscaMoist m, int n_steps, double* ms_out, int max_groups, char* names, int capacity) {
+  if (!m || !ms_out || !names) return -1;
+  if (!m->initialized) { mfail(m, "moist_profile_step: module not initialized"); return -1; }
+  std::vector<std::string> order;
+  std::map<std::string, double> acc;
+  for (int i = 0; i < n_steps; ++i) {
+    isca_core_profile_begin(m->dyn);
+    int rc = moist_step_once(m, nullptr);
+    if (isca_core_profile_end(m->dyn, order, acc) || rc) { if (!rc) mfail(m, "moist_profile_step: event timing failed"); return -1; }
+  }
+  std::string joined;
+  int n = 0;
+  for (auto& nm : order) {
+    if (n >= max_groups) break;
+    ms_out[n++] = acc[nm] / (n_steps > 0 ? n_steps : 1);
+    joined += (joined.empty() ? "" : ";") + nm;
+  }
+  if ((int)joined.size() + 1 > capacity) { mfail(m, "moist_profile_step: names buffer too small"); return -1; }
+  std::memcpy(names, joined.c_str(), joined.size() + 1);
+  return n;
 }
 
 int isca_b200_moist_get(IscaMoist m, int id, double* host) {

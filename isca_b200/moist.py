@@ -9,7 +9,8 @@ from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 
 MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
-                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_co2", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing"]
+                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_co2", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing",
+                 "isca_b200_moist_profile_step"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
                  q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
@@ -54,6 +55,7 @@ def _lib():
         from .physics import IscaBettsMillerConfigStruct
         lib.isca_b200_moist_set_betts_miller.argtypes = [vp, C.POINTER(IscaBettsMillerConfigStruct)]
         lib.isca_b200_moist_timing.argtypes = [vp, dp, dp]
+        lib.isca_b200_moist_profile_step.argtypes = [vp, C.c_int, dp, C.c_int, C.c_char_p, C.c_int]
         _bound = True
     return lib
 
@@ -204,6 +206,15 @@ class MoistAtmosphere:
         a, b = C.c_double(), C.c_double()
         self._ck(self._lib.isca_b200_moist_timing(self._h, C.byref(a), C.byref(b)), "timing")
         return a.value, b.value
+
+    def profile_step(self, n_steps=10):
+        """average milliseconds per kernel group over n eager steps: physics kernels ("phys_*") and the dynamical core's groups"""
+        ms = (C.c_double * 96)()
+        names = C.create_string_buffer(8192)
+        n = self._lib.isca_b200_moist_profile_step(self._h, int(n_steps), ms, 96, names, 8192)
+        if n < 0:
+            self._ck(1, "profile_step")
+        return dict(zip(names.value.decode().split(";"), [ms[i] for i in range(n)]))
 
     def atmosphere_end(self):
         if self._h:
