@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- model-days/sec of the Isca spectral-dynamical-core hot path on B200.
+"""bench.py -- model-days/sec of the Isca time step (column physics + spectral dynamical core) on B200.
 
-    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # CPU arm: the NumPy oracle (port of the reference algorithm)
+    python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W     # CPU arm (the reference's algorithm on the host cores)
 
-A "step" is one model time step (one `atmosphere(Time)` call: Held-Suarez forcing + spectral dynamics)
-on a synthetic Held-Suarez state (cold start + on-device spin-up).  Workload: Held-Suarez dry core
-T170 L40 (lon 512 x lat 256, dt = 150 s), the configuration BASELINE.json's metric is quoted on
-(MiMA physics of configs[3] is not built yet).  One JSON line is printed by rank 0.
-"""
+Headline workload (BASELINE.json: "model-days/sec T170L40", configs[3]): the MiMA test case (exp/test_cases/MiMA/MiMA_test_case.py)
+at T170 L40, dt = 150 s -- idealized_moist_phys with RRTMG radiation every 7200 s (48 steps), SIMPLE_BETTS_MILLER convection,
+large-scale condensation, Monin-Obukhov surface fluxes, K-profile diffusivity, implicit vertical diffusion, slab ocean, Rayleigh
+sponge -- followed by spectral_dynamics with the sphum grid tracer.  A "step" is one `atmosphere(Time)` call.  `--workload hs` selects
+the Held-Suarez dry core instead.  The other BASELINE configurations are measured as named extra keys of the same JSON line
+(`extra.hs_t85l40`, `extra.hs_t170l40`, `extra.hs_t341l60`, `extra.frierson_t85l40`).
+
+The timed region starts on a radiation step, so K steps contain ceil(K / 48) RRTMG calls (pessimistic for K < 48; `steady_state`
+gives the same measurement over whole radiation cycles).  One JSON line is printed by rank 0."""
 from __future__ import annotations
 
 import argparse
@@ -28,6 +32,8 @@ RES = {  # lon, lat, M, dt (s) -- SURVEY.md section 8d (dt by CFL scaling from T
     "T21": (64, 32, 21, 1200.0), "T42": (128, 64, 42, 600.0), "T85": (256, 128, 85, 300.0),
     "T170": (512, 256, 170, 150.0), "T341": (1024, 512, 341, 75.0),
 }
+MOIST_DT = {"T21": 900.0, "T42": 720.0, "T85": 360.0, "T170": 150.0, "T341": 75.0}
+DT_RAD = 7200
 
 
 def hs_namelist(res: str, levels: int, tracer: bool = True):
@@ -42,9 +48,9 @@ def hs_namelist(res: str, levels: int, tracer: bool = True):
 
 
 # ---------------------------------------------------------------------------------------------
-# algorithmic work per step (DESIGN.md section "Kernels and rooflines")
+# algorithmic work per step and rank-share
 # ---------------------------------------------------------------------------------------------
-def work_model(res: str, K: int):
+def work_model(res: str, K: int, moist: bool = False, nlev_sponge: int = 0):
     I, J, M, _ = RES[res]
     T = (M + 1) * (M + 4) // 2                      # retained (m,n) pairs incl. the extra row
     lev_inv = (2 * K + 2) + (5 * K + 1)             # gradient batch + future-state batch
@@ -53,17 +59,19 @@ def work_model(res: str, K: int):
     four_bytes = 16.0 * (M + 1) * J                 # Fourier intermediate per level
     grid_bytes = 8.0 * I * J
     spec_bytes = 16.0 * T
+    col = 8.0 * I * J                               # bytes of one double per column
     w = {
-        "legendre_inv": dict(flops=leg_flops * lev_inv, bytes=(spec_bytes + four_bytes) * lev_inv),
-        "legendre_fwd": dict(flops=leg_flops * lev_fwd, bytes=(spec_bytes + four_bytes) * lev_fwd),
+        "legendre_inv": dict(flops=leg_flops * lev_inv, bytes=(spec_bytes + four_bytes) * lev_inv, bound="tensor"),
+        "legendre_fwd": dict(flops=leg_flops * lev_fwd, bytes=(spec_bytes + four_bytes) * lev_fwd, bound="tensor"),
         "fft_inv": dict(bytes=(four_bytes + grid_bytes) * lev_inv),
         "fft_fwd": dict(bytes=(four_bytes + grid_bytes) * lev_fwd),
-        # grid column kernel: reads u,v,T (cur, prev), vor, div, dxT, dyT (10 x 3-D), writes A,B,dT,Phi,wg_full (5 x 3-D)
-        "grid_step": dict(bytes=grid_bytes * K * 15),
+        # grid column kernel: reads u,v,T (cur, prev), vor, div, dxT, dyT (10 x 3-D), writes A,B,dT,Phi,wg_full (5 x 3-D);
+        # with external physics tendencies (moist model) 3 more planes are read
+        "grid_step": dict(bytes=grid_bytes * K * (18 if moist else 15)),
         # spectral step: specB (4K+1 levels) in, 3x2 state levels in, 3 state out x2, work arrays, specC out (5K+1)
         "spectral": dict(bytes=spec_bytes * K * (4 + 6 + 6 + 8 + 5)),
         # corrections: colsum_energy reads 3 x 3-D, apply_energy r/w 1 x 3-D
-        "corrections": dict(bytes=grid_bytes * K * 5),
+        "corrections": dict(bytes=grid_bytes * K * 5, bound="latency"),
         # grid tracer, horizontal step (tracer_horiz_kernel): reads q_prev, u, v; writes tr_future: 4 3-D planes
         "tracer_horiz": dict(bytes=grid_bytes * K * 4),
         # grid tracer, PPM sweep (tracer_ppm_kernel): reads tr_future, wg (K+1), q_prev, q_cur; writes q_fut, q_cur: 7 planes
@@ -71,6 +79,18 @@ def work_model(res: str, K: int):
         # water fixer: column sums (2-D) + apply (reads q_fut, q_cur; writes q_cur): 3 planes
         "tracer_water": dict(bytes=grid_bytes * K * 3),
     }
+    if moist:                                        # column physics, bytes per column x columns (kernel headers of physics*.cu)
+        w.update({
+            "phys_press_heights": dict(bytes=col * 2 * (5 * K + 4)),
+            "phys_convection": dict(bytes=col * (8 * K + 9)),
+            "phys_lscale_cond": dict(bytes=col * (6 * K + 2)),
+            "phys_surface_flux": dict(bytes=col * 45, bound="latency"),
+            "phys_radiation": dict(bytes=col * 3 * K),
+            "phys_damping": dict(bytes=col * 15 * max(nlev_sponge, 1)),
+            "phys_diffusivity": dict(bytes=col * (20 * K + 4)),
+            "phys_vert_diff_down": dict(bytes=col * (19 * K + 14)),
+            "phys_mixed_layer_vert_diff_up": dict(bytes=col * (5 * K + 20)),
+        })
     return w, dict(T=T, lev_inv=lev_inv, lev_fwd=lev_fwd)
 
 
@@ -85,7 +105,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -126,52 +146,142 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json hbm_gbs)")
     return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
 FP64_TENSOR_PEAK_TFLOPS = 37.2   # measured on this pool: tools/probe_fp64.cu, profiles/r01_probe_fp64.txt (DMMA m8n8k4)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from committed `ncu` captures at T170 L40 on 1 GPU
+# (profiles/r01i_ncu_summary.txt, profiles/r02/r02a_moist_step_t170_ncu.txt); null for kernels / configurations without a capture
+NCU_TRAFFIC = {"fft_inv": 448.0e6, "fft_fwd": 244.7e6, "grid_step": 698.4e6, "tracer_horiz": 151.1e6, "tracer_ppm": 290.6e6,
+               "legendre_inv": 301.2e6, "legendre_fwd": 365.0e6}
+NCU_TRAFFIC_MOIST = {"grid_step": 840.6e6, "phys_vert_diff_down": 1253.1e6, "phys_convection": 864.4e6, "phys_lscale_cond": 435.3e6,
+                     "phys_press_heights": 309.4e6, "phys_diffusivity": 169.9e6, "tracer_horiz": 195.6e6, "tracer_ppm": 343.0e6,
+                     "fft_inv": 447.4e6, "fft_fwd": 245.1e6, "legendre_inv": 301.2e6, "legendre_fwd": 365.4e6}
+
+
+def group_ms(groups):
+    def gsum(prefix):
+        return sum(v for k, v in groups.items() if k.startswith(prefix))
+    g = {"legendre_inv": gsum("legendre_inv"), "legendre_fwd": gsum("legendre_fwd"), "fft_inv": gsum("fft_inv"),
+         "fft_fwd": gsum("fft_fwd"), "grid_step": gsum("grid_step"), "spectral": gsum("spec"),
+         "corrections": gsum("corr"), "tracer_horiz": gsum("tracer_horiz") + gsum("tracer_halo"),
+         "tracer_ppm": gsum("tracer_ppm"), "tracer_water": gsum("tracer_water") + gsum("tracer_reduce")}
+    for k, v in groups.items():
+        if k.startswith("phys_") and k != "phys_rrtmg_call":
+            g[k] = v
+    return g, gsum("exchange")
+
+
+def roofline_of(groups, wm, world, peaks, traffic_table):
+    g_ms, exch_ms = group_ms(groups)
+    tot = sum(v for k, v in groups.items() if k != "phys_rrtmg_call")
+    cand = {k: v for k, v in g_ms.items() if k in wm and wm[k].get("bound", "hbm") == "hbm" and v > 0}
+    dom = max(cand, key=cand.get)
+    dom_bytes = wm[dom]["bytes"] / world
+    achieved = dom_bytes / (g_ms[dom] * 1e-3) / 1e9
+    roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic_table.get(dom) if traffic_table else None,
+            "peak_source": peaks["source"], "share_of_step": g_ms[dom] / tot, "algorithmic_bytes_per_launch": dom_bytes,
+            "ms_per_launch": g_ms[dom]}
+    leg_ms = g_ms["legendre_inv"] + g_ms["legendre_fwd"]
+    leg_fl = (wm["legendre_inv"]["flops"] + wm["legendre_fwd"]["flops"]) / world
+    legendre = {"tflops": leg_fl / (leg_ms * 1e-3) / 1e12, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s (fp64 DMMA)",
+                "frac": leg_fl / (leg_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS, "ms_per_step": leg_ms,
+                "algorithmic_flops_per_step": leg_fl, "bound": "tensor (fp64 DMMA)",
+                "peak_source": "measured mma.sync m8n8k4 f64 peak on this pool (profiles/r01_probe_fp64.txt)"}
+    per_kernel = {}
+    for k, v in g_ms.items():
+        if k in wm and v > 0:
+            b = wm[k]["bytes"] / world
+            per_kernel[k] = {"ms": round(v, 5), "bound": wm[k].get("bound", "hbm"), "algorithmic_GBps": round(b / (v * 1e-3) / 1e9, 1),
+                             "frac_of_hbm_peak": round(b / (v * 1e-3) / 1e9 / peaks["hbm_gbs"], 3)}
+    return roof, legendre, per_kernel, exch_ms
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle (port of the reference algorithm), bounded sample
+# CPU arm: the C++/OpenMP restatement of the dynamical core + tracer (oracle/cstep, all host cores) and, for the moist workload,
+# the NumPy oracle's column physics on a column sample.  Bounded samples.
 # ---------------------------------------------------------------------------------------------
-def run_cpu(res, K, steps, warmup, spin=2, tracer=True):
-    from oracle.isca_oracle import SpectralCore, held_suarez_config
-    cfg = held_suarez_config(res, K, RES[res][3], num_tracers=1 if tracer else 0)
+def cpu_dynamics(res, K, dt, steps, moist=False, spin=2):
+    from oracle.isca_oracle import held_suarez_config, frierson_config
+    from oracle.cstep import CStep
+    cfg = frierson_config(res, K, dt) if moist else held_suarez_config(res, K, dt, num_tracers=1)
+    if moist:
+        cfg.no_forcing = True                        # the physics tendencies are timed separately (cpu_physics_sample)
     t0 = time.time()
-    core = SpectralCore(cfg)
-    core.cold_start()
+    cs = CStep(cfg)
+    cs.cold_start()
     t_init = time.time() - t0
-    for _ in range(max(warmup, spin)):
-        core.step()
+    cs.step(spin)
     t0 = time.time()
-    for _ in range(steps):
-        core.step()
-    sec = time.time() - t0
-    try:
-        import threadpoolctl
-        nthreads = max([p["num_threads"] for p in threadpoolctl.threadpool_info()] + [1])
-    except Exception:
-        nthreads = 1
-    return dict(sec_per_step=sec / steps, steps=steps, init_s=t_init, threads=nthreads,
-                value=steps * cfg.dt_atmos / 86400.0 / sec)
+    cs.step(steps)
+    sec = (time.time() - t0) / steps
+    th = cs.threads
+    cs.close()
+    return dict(sec_per_step=sec, threads=th, init_s=t_init)
 
 
+def cpu_physics_sample(K, with_rrtm=True):
+    """NumPy oracle of idealized_moist_phys (MiMA options) on the 8192 columns of a T42 grid with K levels: seconds per call of the
+    per-step physics and of one RRTMG radiation call.  The caller scales by (columns of the workload) / 8192."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_moist import build
+    from rrtm_cases import rrtm_setup
+    cfg, core, mp = build("T42", K, 720.0, "SIMPLE_BETTS_MILLER", seed=1, damping=True)
+    mp.c.use_tau, mp.c.constant_gust = False, 0.0
+    ncol = cfg.lon_max * cfg.lat_max
+    t_rrtm = 0.0
+    if with_rrtm:
+        rrtm_setup(core, mp, cfg, DT_RAD if DT_RAD % 720 == 0 else 7200, None)
+        t0 = time.time()
+        mp(core, 2 * cfg.dt_atmos)                    # first call: radiation step
+        t_first = time.time() - t0
+    t0 = time.time()
+    mp(core, 2 * cfg.dt_atmos)                        # stored heating rates: the per-step physics alone
+    t_phys = time.time() - t0
+    if with_rrtm:
+        t_rrtm = max(t_first - t_phys, 0.0)
+    return dict(ncol=ncol, sec_physics=t_phys, sec_rrtmg_call=t_rrtm)
+
+
+def run_cpu(workload, res, K, steps):
+    I, J, M, dt_hs = RES[res]
+    if workload == "hs":
+        d = cpu_dynamics(res, K, dt_hs, steps)
+        sec = d["sec_per_step"]
+        sample = (f"{steps} model steps of {res} L{K} after cold start + 2 steps: C++/OpenMP restatement of the step (oracle/cstep, "
+                  f"rectangular Legendre loops as the reference) on {d['threads']} host threads")
+        return dict(sec_per_step=sec, threads=d["threads"], value=dt_hs / 86400.0 / sec, sample=sample, parts={"dynamics_s": sec})
+    dt = MOIST_DT[res]
+    d = cpu_dynamics(res, K, dt, steps, moist=True)
+    ph = cpu_physics_sample(K)
+    scale = (I * J) / ph["ncol"]
+    per_rad = DT_RAD / dt
+    sec = d["sec_per_step"] + scale * ph["sec_physics"] + scale * ph["sec_rrtmg_call"] / per_rad
+    sample = (f"dynamics + tracer: {steps} steps of {res} L{K} with the C++/OpenMP restatement (oracle/cstep) on {d['threads']} host threads; "
+              f"column physics and one RRTMG call: NumPy oracle on {ph['ncol']} columns (T42 grid, {K} levels), scaled x{scale:g} to the "
+              f"{I * J} columns, RRTMG amortised over {per_rad:g} steps")
+    return dict(sec_per_step=sec, threads=d["threads"], value=dt / 86400.0 / sec, sample=sample,
+                parts={"dynamics_s": d["sec_per_step"], "physics_numpy_scaled_s": scale * ph["sec_physics"],
+                       "rrtmg_numpy_scaled_per_call_s": scale * ph["sec_rrtmg_call"]})
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=480)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mima", choices=["mima", "hs"])
     ap.add_argument("--res", default="T170")
     ap.add_argument("--levels", type=int, default=40)
-    ap.add_argument("--spinup", type=int, default=200, help="on-device spin-up steps before warm-up (non-trivial fields)")
-    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--spinup", type=int, default=-1, help="on-device spin-up steps before warm-up (default: 2 model days moist, 200 steps hs)")
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-tracer", action="store_true", help="tracer-free dynamical core (the reference's dry build advects sphum)")
-    ap.add_argument("--no-moist", action="store_true", help="skip the informational idealized-moist-model (BASELINE config 3) measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (hs T85/T170/T341, Frierson T85)")
     args = ap.parse_args()
 
     # The contract is ONE JSON line on stdout: keep a private handle on the real stdout for it and point fd 1 at stderr so that
@@ -183,11 +293,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     res, K = args.res, args.levels
-    I, J, M, dt = RES[res]
-    tracer = not args.no_tracer
-    workload = (f"Held-Suarez dry core {res} L{K} (lon {I} x lat {J}, dt={dt:g}s), "
-                + ("sphum grid tracer of the reference's dry field_table advected (FV + PPM) with water fixer, " if tracer else "no tracer, ")
-                + f"fp64, synthetic cold start + {args.spinup}-step spin-up")
+    I, J, M, dt_hs = RES[res]
+    moistw = args.workload == "mima"
+    dt = MOIST_DT[res] if moistw else dt_hs
+    spin = args.spinup if args.spinup >= 0 else (int(2 * 86400 / dt) if moistw else 200)
+    if moistw:
+        workload = (f"MiMA {res} L{K} (lon {I} x lat {J}, dt={dt:g}s; exp/test_cases/MiMA: RRTMG every {DT_RAD}s with an analytic ozone layer, "
+                    f"SIMPLE_BETTS_MILLER, lscale_cond, Monin-Obukhov surface flux, diffusivity, vert_diff, 100 m slab with q-flux, Rayleigh sponge; "
+                    f"sphum grid tracer), fp64, synthetic cold start + {spin}-step on-device spin-up")
+    else:
+        workload = (f"Held-Suarez dry core {res} L{K} (lon {I} x lat {J}, dt={dt:g}s), sphum grid tracer of the reference's dry field_table "
+                    f"advected (FV + PPM) with water fixer, fp64, synthetic cold start + {spin}-step spin-up")
     metric, unit = "model_days_per_sec", "model-days/s"
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -195,15 +311,16 @@ def main():
         if rank != 0:
             return 0
         steps = max(1, min(args.steps, args.cpu_steps if args.steps > 20 else args.steps))
-        r = run_cpu(res, K, steps, min(args.warmup, 1), tracer=tracer)
+        r = run_cpu(args.workload, res, K, steps)
         line = {
             "impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["sec_per_step"] * 1e3,
+            "steps": steps, "warmup": 2, "ms_per_step": r["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU arm = NumPy restatement (oracle port) of the reference algorithm; "
-                       "the Fortran/MPI reference cannot be built here (no Fortran compiler)"},
-            "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port",
-                             "sample": f"{steps} model steps of {res} L{K} after cold start + 2 steps"},
+            "config": {"workload": workload},
+            "note": "CPU arm = restatement (port) of the reference algorithm: the Fortran/MPI reference cannot be built here (no Fortran "
+                    "compiler in the image or on the GPU box). Dynamics + tracer: C++/OpenMP with the reference's rectangular loops on all "
+                    "host cores; moist column physics: NumPy oracle on a column sample (slower than compiled Fortran would be)",
+            "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port", "sample": r["sample"], "parts_s": r["parts"]},
             "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -212,21 +329,17 @@ def main():
 
     # ------------------------------------------------------------------ this repo's CUDA arm
     import torch
-    from isca_b200 import api
+    from isca_b200 import api, moist
     if args.gpus != world and world == 1 and args.gpus > 1:
         raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dist = None
-    uid = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        box = [api.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        uid = box[0]
     J_glob = J
-    J = J // world                                   # this rank's latitude block
+    Jloc = J // world                                # this rank's latitude block
 
     def barrier():
         torch.cuda.synchronize()
@@ -254,183 +367,214 @@ def main():
             dist.all_gather_object(handles, core.ipc_handles())
             core.set_peer_handles(handles)           # Legendre/FFT epilogues now store straight into peer memory
 
-    cfg = api.make_config(**hs_namelist(res, K, tracer))
-    atm = api.Atmosphere(cfg, rank=rank, nranks=world, nccl_unique_id=uid)
-    map_peers(atm)
-    atm.cold_start()
-    atm.atmosphere(args.spinup)                      # spin-up (untimed)
-    atm.atmosphere(max(args.warmup, 3))              # warm-up (untimed; also captures the CUDA graphs)
-
-    # ---- device-resident timed region: EXACTLY `steps` steps, CUDA events on the launching stream
-    l0 = atm.get_scalar(api.SC_KERNEL_LAUNCHES)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t0 = time.time()
-    atm.atmosphere(args.steps)
-    barrier()
-    wall = max_over_ranks(time.time() - t0)
-    clocks = sampler.stop()
-    ms_per_step = max_over_ranks(atm.get_scalar(api.SC_LAST_STEP_MS))      # CUDA events on the launching stream, max over ranks
-    launches = int(atm.get_scalar(api.SC_KERNEL_LAUNCHES) - l0) * world
-    value = dt / 86400.0 / (ms_per_step * 1e-3)
-
-    # ---- per-kernel-group timings (CUDA events inside the library, eager launches)
-    groups = atm.profile_step(20)
-    wm, sizes = work_model(res, K)
-    if world > 1:                                    # per-rank share of the algorithmic work
-        for v in wm.values():
-            for kk in v:
-                v[kk] = v[kk] / world
+    use_graph = world == 1 or os.environ.get("ISCA_B200_GRAPH_MULTI") == "1"
     peaks = measured_peaks()
-
-    def gsum(prefix):
-        return sum(v for k, v in groups.items() if k.startswith(prefix))
-    g_ms = {"legendre_inv": gsum("legendre_inv"), "legendre_fwd": gsum("legendre_fwd"), "fft_inv": gsum("fft_inv"),
-            "fft_fwd": gsum("fft_fwd"), "grid_step": gsum("grid_step"), "spectral": gsum("spec"),
-            "corrections": gsum("corr"), "tracer_horiz": gsum("tracer_horiz") + gsum("tracer_halo"),
-            "tracer_ppm": gsum("tracer_ppm"), "tracer_water": gsum("tracer_water") + gsum("tracer_reduce")}
-    exch_ms = gsum("exchange")
-    tot = sum(groups.values())
-    dom = max(g_ms, key=g_ms.get)
-    dom_bytes = wm[dom]["bytes"]
-    achieved = dom_bytes / (g_ms[dom] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (T170 L40, 1 GPU;
-    # profiles/r01i_ncu_summary.txt); null for kernels / configurations without a capture
-    NCU_TRAFFIC = {"fft_inv": 448.0e6, "fft_fwd": 244.7e6, "grid_step": 698.4e6, "tracer_horiz": 151.1e6, "tracer_ppm": 290.6e6,
-                   "legendre_inv": 301.2e6, "legendre_fwd": 365.0e6}
-    traffic = NCU_TRAFFIC.get(dom) if (world == 1 and res == "T170" and K == 40) else None
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
-                "share_of_step": g_ms[dom] / tot, "algorithmic_bytes_per_step": dom_bytes, "ms_per_step": g_ms[dom]}
-    leg_ms = g_ms["legendre_inv"] + g_ms["legendre_fwd"]
-    leg_fl = wm["legendre_inv"]["flops"] + wm["legendre_fwd"]["flops"]
-    legendre = {"tflops": leg_fl / (leg_ms * 1e-3) / 1e12, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s (fp64 DMMA)",
-                "frac": leg_fl / (leg_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS, "ms_per_step": leg_ms,
-                "algorithmic_flops_per_step": leg_fl,
-                "peak_source": "measured mma.sync m8n8k4 f64 peak on this pool (profiles/r01_probe_fp64.txt)"}
-    groups_out = {k: round(v, 5) for k, v in groups.items()}
-
-    # ---- end to end through the reference's operator API with HOST buffers:
-    # spectral_dynamics(dt_ug, dt_vg, dt_tg -> psg, ug, vg, tg) every step, pinned host memory,
-    # H2D of the tendencies and D2H of the new state inside the timed region.
-    n3 = (K, J, I)
     pin = lambda shape: torch.zeros(shape, dtype=torch.float64).pin_memory().numpy()
-    tend = [pin(n3) for _ in range(4 if tracer else 3)]
-    outs = {"psg": pin((J, I)), "ug": pin(n3), "vg": pin(n3), "tg": pin(n3)}
-    if tracer:
-        outs["grid_tracers"] = pin(n3)
-    for _ in range(3):
-        atm.spectral_dynamics_into(tend, outs)
-    barrier()
-    t0 = time.time()
-    for _ in range(args.e2e_steps):
-        atm.spectral_dynamics_into(tend, outs)
-    barrier()
-    e2e_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
-    nf = 4 if tracer else 3
-    h2d = nf * 8 * K * J_glob * I                    # whole job, all ranks
-    d2h = (nf * K + 1) * 8 * J_glob * I
-    e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
-           "api": "isca_b200_spectral_dynamics_tracers: host tendencies in, host state out, every step (reference spectral_dynamics argument list)"}
-    # informational: the atmosphere_mod boundary (state resident) with a per-step D2H of the ps diagnostic
-    ps_host = pin((J, I))
-    barrier()
-    t0 = time.time()
-    for _ in range(args.e2e_steps):
-        atm.atmosphere(1)
-        atm.get_field(api.F_PS, out=ps_host)
-    barrier()
-    res_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
-    e2e_atm = {"value": dt / 86400.0 / res_sec, "unit": unit, "ms_per_step": res_sec * 1e3,
-               "api": "isca_b200_step(1) + isca_b200_get_field(ps) every step (atmosphere_mod boundary, state resident)",
-               "d2h_bytes_per_step": 8 * J_glob * I, "h2d_bytes_per_step": 0}
 
-    tmin, tmax = atm.get_scalar(api.SC_T_MIN), atm.get_scalar(api.SC_T_MAX)
-    atm.atmosphere_end()
+    def analytic_ozone(Kk, Jl, Il, sigma_full):
+        """stand-in for ozone_1990.nc (no netCDF input in the benchmark): a stratospheric layer peaking near 10 hPa, mass mixing ratio"""
+        p = sigma_full * 1.0e5
+        prof = np.where(p < 1.0e4, 1.2e-5 * np.exp(-((np.log(p) - np.log(1.0e3)) ** 2) / 2), 6e-8)
+        return np.repeat(np.repeat(prof[:, None, None], Jl, 1), Il, 2)
 
-    # informational: the tracer-free dynamical core (transform + semi-implicit + Held-Suarez only), same timing method
-    no_tracer_core = None
-    if tracer:
-        a0 = api.Atmosphere(api.make_config(**hs_namelist(res, K, False)), rank=rank, nranks=world, nccl_unique_id=new_uid())
-        map_peers(a0)
-        a0.cold_start(); a0.atmosphere(args.spinup); a0.atmosphere(10)
+    def hs_run(r_res, r_K, steps, spinup, profile=True):
+        """device-resident Held-Suarez run: ms/step from CUDA events on the library stream, max over ranks"""
+        rI, rJ, rM, rdt = RES[r_res]
+        atm = api.Atmosphere(api.make_config(**hs_namelist(r_res, r_K, True)), rank=rank, nranks=world, nccl_unique_id=new_uid())
+        map_peers(atm)
+        atm.cold_start()
+        atm.atmosphere(spinup)
+        atm.atmosphere(max(args.warmup, 3))
+        l0 = atm.get_scalar(api.SC_KERNEL_LAUNCHES)
         barrier()
-        n0 = min(args.steps, 300)
-        a0.atmosphere(n0)
+        t0 = time.time()
+        atm.atmosphere(steps)
         barrier()
-        ms0 = max_over_ranks(a0.get_scalar(api.SC_LAST_STEP_MS))
-        no_tracer_core = {"ms_per_step": ms0, "value": dt / 86400.0 / (ms0 * 1e-3), "unit": unit, "steps": n0}
-        a0.atmosphere_end()
+        wall = max_over_ranks(time.time() - t0)
+        ms = max_over_ranks(atm.get_scalar(api.SC_LAST_STEP_MS))
+        launches = int(atm.get_scalar(api.SC_KERNEL_LAUNCHES) - l0) * world
+        out = {"ms_per_step": ms, "value": rdt / 86400.0 / (ms * 1e-3), "unit": unit, "steps": steps, "steps_per_sec": 1e3 / ms,
+               "wall_ms_per_step": wall / steps * 1e3, "n_gpus": world, "dt": rdt,
+               "workload": f"Held-Suarez {r_res} L{r_K} with the sphum grid tracer, {spinup}-step spin-up"}
+        groups = None
+        if profile:
+            groups = atm.profile_step(10)
+            wm, _ = work_model(r_res, r_K)
+            roof, leg, per_kernel, exch = roofline_of(groups, wm, world, peaks,
+                                                      NCU_TRAFFIC if (world == 1 and r_res == "T170" and r_K == 40) else None)
+            out.update(roofline=roof, legendre_gemm=leg, kernels=per_kernel, exchange_ms_per_step=exch)
+        out["T_range_K"] = [atm.get_scalar(api.SC_T_MIN), atm.get_scalar(api.SC_T_MAX)]
+        return out, atm, launches, groups
 
-    # informational (not the headline metric): the Frierson grey-radiation moist aquaplanet (BASELINE config 3 at T85 L40 on one
-    # GPU; the grey-radiation stand-in for config 4 at T170 L40 on several), whole step (idealized_moist_phys + spectral_dynamics
-    # with the sphum tracer) device-resident after an on-device spin-up
-    moist_model = None
-    if not args.no_moist:
-        try:
-            from isca_b200 import moist
-            mres = "T85" if world == 1 else "T170"
-            mdt = 360.0 if world == 1 else 150.0
-            spin_days, msteps = (10.0, 300) if world == 1 else (3.0, 200)
-            mm = moist.frierson_test_case(mres, 40, mdt, rank=rank, nranks=world, nccl_unique_id=new_uid())
-            map_peers(mm.core)
-            mm.core.cold_start()
-            mm.idealized_moist_phys_init()
-            mm.atmosphere(int(spin_days * 86400 / mdt))
-            barrier()
-            mm.atmosphere(msteps)
-            barrier()
-            ms_m, ms_phys = mm.timing()
-            ms_m, ms_phys = max_over_ranks(ms_m), max_over_ranks(ms_phys)
-            flags = np.bincount(mm.get("convflag").astype(int).ravel(), minlength=3).tolist()
-            moist_model = {"workload": f"Frierson grey-radiation aquaplanet {mres} L40 (dt={mdt:g}s, SIMPLE_BETTS_MILLER, slab 2.5 m), "
-                                       f"{spin_days:g}-day on-device spin-up", "n_gpus": world, "ms_per_step": ms_m,
-                           "ms_physics_last_step": ms_phys,
-                           "value": mdt / 86400.0 / (ms_m * 1e-3), "unit": unit, "steps": msteps,
-                           "precip_mean_mm_per_day_rank0": float(mm.get("precip").mean() * 86400.0), "convflag_counts_rank0": flags}
-            mm.atmosphere_end()
-        except Exception as e:                         # never let the informational arm take the headline line down
-            moist_model = {"error": str(e)[:200]}
+    line = {}
+    if moistw:
+        m = moist.mima_test_case(res, K, dt, rank=rank, nranks=world, nccl_unique_id=new_uid())
+        map_peers(m.core)
+        pk, bk = m.core.get_table(api.TB_PK), m.core.get_table(api.TB_BK)
+        sig = np.maximum(0.5 * (bk[:-1] + bk[1:]) + 0.5 * (pk[:-1] + pk[1:]) / 1.0e5, 1e-5)
+        o3_host = pin((K, Jloc, I))
+        o3_host[...] = analytic_ozone(K, Jloc, I, sig)
+        m.set_ozone(o3_host)
+        per_rad = int(round(DT_RAD / dt))
+        warm = max(args.warmup, 3)
+        warm += (-(spin + warm)) % per_rad           # the first timed step is a radiation step (the alarm fires at steps 0, 48, 96, ...)
+        m.atmosphere(spin)
+        m.atmosphere(warm)
+        l0 = m.core.get_scalar(api.SC_KERNEL_LAUNCHES)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        barrier()
+        t0 = time.time()
+        m.atmosphere(args.steps)
+        barrier()
+        wall = max_over_ranks(time.time() - t0)
+        clocks = sampler.stop()
+        ms_step, _ = m.timing()
+        ms_per_step = max_over_ranks(ms_step)
+        core_launches = int(m.core.get_scalar(api.SC_KERNEL_LAUNCHES) - l0)
+        rad_calls = -(-args.steps // per_rad)
+        # launches of this repo's kernels in the timed region: the dynamical core counts its own; the physics sequence issues 24 per step
+        # (moist_model.cu: 2 press_heights, 2 convection, 2 condensation, 2 surface, radiation add, 2 sponge, 2+2 diffusivity, gust fill,
+        # vert_diff_down, mixed_layer, vert_diff_up, 4 memsets) and a radiation call 6 (coszen, prepare, fix_top, sw, lw, finish)
+        launches = (core_launches + 24 * args.steps + 6 * rad_calls) * world
+        value = dt / 86400.0 / (ms_per_step * 1e-3)
+        # steady state over whole radiation cycles (informational; same timing method)
+        n_ss = per_rad * max(1, min(10, 480 // per_rad))
+        m.atmosphere((-(spin + warm + args.steps)) % per_rad)
+        barrier()
+        m.atmosphere(n_ss)
+        barrier()
+        ms_ss = max_over_ranks(m.timing()[0])
+        steady = {"ms_per_step": ms_ss, "value": dt / 86400.0 / (ms_ss * 1e-3), "unit": unit, "steps": n_ss,
+                  "radiation_calls": n_ss // per_rad}
+        # per-kernel-group timings: eager steps with CUDA events on the library stream; the alarm is kept off these steps except one
+        m.atmosphere((-(spin + warm + args.steps + n_ss)) % per_rad + 1)
+        groups = m.profile_step(per_rad)              # one whole radiation cycle: 47 plain steps + 1 radiation step
+        nlev_sp = 0
+        wm, _ = work_model(res, K, moist=True, nlev_sponge=max(1, int(np.sum(sig * 1.0e5 < 50.0))))
+        roofline, legendre, per_kernel, exch_ms = roofline_of(groups, wm, world, peaks,
+                                                              NCU_TRAFFIC_MOIST if (world == 1 and res == "T170" and K == 40) else None)
+        rr_ms = groups.get("phys_rrtmg_call", 0.0) * per_rad       # profile_step averages over the cycle's steps
+        # ---- end to end: the call a host model makes every step with HOST buffers: the ozone field of the radiation (H2D, what
+        # interpolator_mod hands over) in, one atmosphere(Time), and the fields of the MiMA diag_table (ps, precipitation, t_surf, sphum,
+        # ucomp, vcomp, temp, vor, div: what send_data passes to diag_manager) out, pinned host memory, copies inside the timed region
+        outs3 = {fid: pin((K, Jloc, I)) for fid in (api.F_TRACER0, api.F_U, api.F_V, api.F_T, api.F_VOR, api.F_DIV)}
+        ps_host, pr_host, ts_host = pin((Jloc, I)), pin((Jloc, I)), pin((Jloc, I))
+
+        def e2e_step():
+            m.set_ozone(o3_host)
+            m.atmosphere(1)
+            for fid, buf in outs3.items():
+                m.core.get_field(fid, out=buf)
+            m.core.get_field(api.F_PS, out=ps_host)
+            m.get("precip", out=pr_host)
+            m.get("t_surf", out=ts_host)
+        m.atmosphere((-(spin + warm + args.steps + n_ss + 1 + per_rad)) % per_rad)
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.time()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
+        h2d = 8 * K * J_glob * I
+        d2h = (6 * K + 3) * 8 * J_glob * I
+        e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
+               "api": "per step: isca_b200_moist_set_ozone (host ozone field in), isca_b200_moist_step(1), isca_b200_get_field x 7 + "
+                      "isca_b200_moist_get x 2 (the MiMA diag_table fields out to pinned host buffers)",
+               "note": f"{args.e2e_steps} steps after 2 untimed ones, none of them a radiation step" if args.e2e_steps + 2 < per_rad else ""}
+        tr = m.core.get_field(api.F_T)
+        extra_info = {"radiation_calls_in_timed_region": rad_calls, "steps_per_radiation_call": per_rad,
+                      "rrtmg_call_ms": rr_ms, "olr_mean_rank0": float(m.get("olr").mean()),
+                      "precip_mean_mm_per_day_rank0": float(m.get("precip").mean() * 86400.0),
+                      "T_range_K_rank0": [float(tr.min()), float(tr.max())]}
+        m.atmosphere_end()
+        working_set_mb = 8.0 * I * J * K * 60 / 1e6
+    else:
+        out, atm, launches, groups = hs_run(res, K, args.steps, spin)
+        sampler = ClockSampler(local_rank)           # clocks of a second pass of the same timed region
+        sampler.start()
+        barrier()
+        atm.atmosphere(args.steps)
+        barrier()
+        clocks = sampler.stop()
+        ms_per_step = max_over_ranks(atm.get_scalar(api.SC_LAST_STEP_MS))
+        value = dt / 86400.0 / (ms_per_step * 1e-3)
+        wall = out["wall_ms_per_step"] * args.steps / 1e3
+        roofline, legendre, per_kernel, exch_ms = out["roofline"], out["legendre_gemm"], out["kernels"], out["exchange_ms_per_step"]
+        steady = None
+        # end to end through spectral_dynamics with HOST tendencies in and HOST state out every step
+        n3 = (K, Jloc, I)
+        tend = [pin(n3) for _ in range(4)]
+        outs = {"psg": pin((Jloc, I)), "ug": pin(n3), "vg": pin(n3), "tg": pin(n3), "grid_tracers": pin(n3)}
+        for _ in range(3):
+            atm.spectral_dynamics_into(tend, outs)
+        barrier()
+        t0 = time.time()
+        for _ in range(args.e2e_steps):
+            atm.spectral_dynamics_into(tend, outs)
+        barrier()
+        e2e_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
+        e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": 4 * 8 * K * J_glob * I,
+               "d2h_bytes_per_step": (4 * K + 1) * 8 * J_glob * I, "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
+               "api": "isca_b200_spectral_dynamics_tracers: host tendencies in, host state out, every step (reference spectral_dynamics argument list)"}
+        extra_info = {"T_range_K": out["T_range_K"]}
+        atm.atmosphere_end()
+        working_set_mb = (8.0 * I * J * K * 25 + 16.0 * (M + 1) * J * (5 * K + 1)) / 1e6
+
+    # ------------------------------------------------------------------ the other BASELINE configurations (named extra keys)
+    extra = {}
+    if not args.no_extra:
+        for key, (xr, xk, xsteps, xspin) in (("hs_t85l40", ("T85", 40, 400, 200)), ("hs_t170l40", ("T170", 40, 300, 200)),
+                                            ("hs_t341l60", ("T341", 60, 60, 60))):
+            if (not moistw) and xr == res and xk == K:
+                continue
+            try:
+                o, a, _, _ = hs_run(xr, xk, xsteps, xspin)
+                a.atmosphere_end()
+                o["cuda_graph"] = use_graph
+                extra[key] = o
+            except Exception as e:                     # an extra configuration never takes the headline line down
+                extra[key] = {"error": str(e)[:300]}
+        if world == 1:
+            try:                                       # BASELINE config 3: Frierson grey-radiation aquaplanet T85 L40 on one GPU
+                mm = moist.frierson_test_case("T85", 40, 360.0)
+                mm.core.cold_start(); mm.idealized_moist_phys_init()
+                mm.atmosphere(int(10 * 86400 / 360.0))
+                barrier()
+                mm.atmosphere(300)
+                barrier()
+                ms_m, ms_phys = mm.timing()
+                extra["frierson_t85l40"] = {"workload": "Frierson grey-radiation aquaplanet T85 L40 (dt=360s, SIMPLE_BETTS_MILLER, slab 2.5 m), "
+                                                        "10-day on-device spin-up", "n_gpus": 1, "ms_per_step": ms_m,
+                                            "ms_physics_last_step": ms_phys, "value": 360.0 / 86400.0 / (ms_m * 1e-3), "unit": unit, "steps": 300,
+                                            "precip_mean_mm_per_day": float(mm.get("precip").mean() * 86400.0)}
+                mm.atmosphere_end()
+            except Exception as e:
+                extra["frierson_t85l40"] = {"error": str(e)[:300]}
 
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
-    J = J_glob
-
-    # informational: the RRTMG radiation kernels on a T170-sized batch of columns, in a subprocess with a timeout
-    # (their first GPU run happens here: a fault or hang there must not cost the headline line)
-    rrtm_radiation = None
-    if not args.no_moist and world == 1:
-        try:
-            pr = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "rrtm_bench.py")],
-                                capture_output=True, text=True, timeout=300)
-            last = [l for l in pr.stdout.strip().splitlines() if l.startswith("{")]
-            rrtm_radiation = json.loads(last[-1]) if pr.returncode == 0 and last else {"error": (pr.stderr or pr.stdout)[-300:]}
-        except Exception as e:
-            rrtm_radiation = {"error": str(e)[:200]}
-    # informational: the MiMA configuration (BASELINE config 4 physics: RRTMG radiation) at T85 L40 on one GPU, same isolation
-    mima_model = None
-    if not args.no_moist and world == 1:
-        try:
-            pr = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "mima_bench.py")],
-                                capture_output=True, text=True, timeout=420)
-            last = [l for l in pr.stdout.strip().splitlines() if l.startswith("{")]
-            mima_model = json.loads(last[-1]) if pr.returncode == 0 and last else {"error": (pr.stderr or pr.stdout)[-300:]}
-        except Exception as e:
-            mima_model = {"error": str(e)[:200]}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        r = run_cpu(res, K, args.cpu_steps, 1, tracer=tracer)
-        cpu_baseline = {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port",
-                        "ms_per_step": r["sec_per_step"] * 1e3,
-                        "sample": f"{args.cpu_steps} model steps of {res} L{K} (NumPy oracle, cold start + 2 steps)"}
+        try:
+            r = run_cpu(args.workload, res, K, args.cpu_steps)
+            cpu_baseline = {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port", "ms_per_step": r["sec_per_step"] * 1e3,
+                            "sample": r["sample"], "parts_s": r["parts"]}
+            if moistw and not args.no_extra:         # the all-compiled part of the CPU arm on its own: the dry core of the same grid
+                rh = run_cpu("hs", res, K, args.cpu_steps)
+                extra.setdefault("hs_t170l40" if res == "T170" else f"hs_{res.lower()}l{K}", {})["cpu_baseline"] = {
+                    "value": rh["value"], "unit": unit, "cores": rh["threads"], "kind": "port", "ms_per_step": rh["sec_per_step"] * 1e3,
+                    "sample": rh["sample"]}
+        except Exception as e:
+            cpu_baseline = {"error": str(e)[:300]}
 
-    working_set_mb = (8.0 * I * J * K * 25 + 16.0 * (M + 1) * J * (5 * K + 1)) / 1e6
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -438,16 +582,16 @@ def main():
         "config": {"workload": workload, "parallelism": f"dp{world} (latitudes x zonal wavenumbers)",
                    "steps_per_sec": 1e3 / ms_per_step, "wall_ms_per_step": wall / args.steps * 1e3,
                    "l2": f"per-step working set ~{working_set_mb:.0f} MB > 126 MB L2: inputs larger than L2, no flush",
-                   "cuda_graph": True, "T_range_K": [tmin, tmax]},
+                   "cuda_graph": bool(use_graph) if not moistw else "dynamics: " + ("graph replay" if use_graph else "eager") + "; physics: eager launches",
+                   **extra_info},
         "clocks": clocks,
-        "e2e": e2e, "e2e_atmosphere_mod": e2e_atm,
+        "e2e": e2e,
         "gpu_launches": launches,
-        "roofline": roofline, "legendre_gemm": legendre, "kernel_groups_ms": groups_out, "exchange_ms_per_step": exch_ms,
+        "roofline": roofline, "legendre_gemm": legendre, "kernels": per_kernel,
+        "kernel_groups_ms": {k: round(v, 5) for k, v in groups.items()}, "exchange_ms_per_step": exch_ms,
+        "steady_state": steady,
         "cpu_baseline": cpu_baseline,
-        "no_tracer_core": no_tracer_core,
-        "moist_model": moist_model,
-        "rrtm_radiation": rrtm_radiation,
-        "mima_model": mima_model,
+        "extra": extra,
     }
     print(json.dumps(line), file=json_out, flush=True)
     return 0

@@ -545,7 +545,14 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   if (cudaStreamSynchronize(p->st) != cudaSuccess) { delete p; return fail(nullptr, "table upload failed"); }
   p->svp = SvpDev{p->tab.p, p->tab.p + n, p->tab.p + 2 * n, tminl, dtinvl, 0.5 * dtres, dtres, n};
   p->svp_host = tb;
-  if (build_lcl_table(p)) { p->lcl_err = p->err; p->err.clear(); p->lcl_n = 0; }     // deferred: only qe_moist_convection needs the table
+  {
+    // Tmin / Tmax outside the saturation table is a namelist error (fails here); a Newton iteration that stalls on the piecewise
+    // table of sat_vapor_pres_nml do_simple = .false. only matters to qe_moist_convection, whose init the reference calls for
+    // SIMPLE_BETTS_MILLER alone: that failure is raised when the scheme is used
+    const int rc = build_lcl_table(p);
+    if (rc == 2) { p->lcl_err = p->err; p->err.clear(); p->lcl_n = 0; }
+    else if (rc) { std::string m = p->err; isca_b200_physics_destroy(p); return fail(nullptr, m); }
+  }
   *out = p;
   return 0;
 }

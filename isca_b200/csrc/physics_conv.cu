@@ -236,7 +236,7 @@ int build_lcl_table(IscaPhysics p) {
       double df = 1.0 / kappa * std::pow(T, -1.0) - g.hlv / g.rvgas * std::pow(T, -2.0);
       dT = f / df; T = T - dT; ++iter;
     }
-    if (!(dT < 1.0e-7) || bad) return fail(p, "qe_moist_convection: LCL calculation did not converge. Precision not achieved.");
+    if (!(dT < 1.0e-7) || bad) { fail(p, "qe_moist_convection: LCL calculation did not converge. Precision not achieved."); return 2; }
     tab[k] = T; guess = T;
   }
   if (!p->lcl_tab.ensure(size)) return fail(p, "cudaMalloc failed");

@@ -172,6 +172,16 @@ RR_HD void sw_setcoef_layer(const double* A, const Tab& tb, double pavel, double
   for (int i = 0; i < 4; ++i) L.wx[i] = 0.0;
 }
 
+// index and fraction of the totplnk interpolation of setcoef (:154-250) for one temperature; planck_at = the band's value
+RR_HD void planck_index(double t, int& ind, double& frac) {
+  ind = (int)(t - 159.0);
+  ind = ind < 1 ? 1 : (ind > 180 ? 180 : ind);
+  frac = t - 159.0 - (double)ind;
+}
+RR_HD double planck_at(const double* A, const Tab& tb, int ib, int ind, double frac) {
+  const double* p = A + tb.totplnk + ib * 181;
+  return p[ind - 1] + frac * (p[ind] - p[ind - 1]);
+}
 // Planck function of one temperature for all 16 bands: the totplnk interpolation of setcoef (:154-250)
 RR_HD void planck16(const double* A, const Tab& tb, double t, double* out, int stride) {
   int ind = (int)(t - 159.0);
@@ -202,9 +212,9 @@ RR_HD Spec specparm_of(double ca, double cb, double rat, double mult) {
 // (table row, weight) pairs; a g-point thread then only forms  tau = sum_i w_i * A[off_i + g]  (consecutive doubles across
 // the lanes of a band).  Same formulas as lw_tau / sw_tau with the products re-associated (differences at the 1e-16 level).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NT_LW = 24, NT_SW = 16;      // multiples of 4: the lists are padded with zero-weight terms to whole groups of four
-struct LwRec { double w[NT_LW]; int off[NT_LW]; int n, gs_off, f0, f1; double ffs; };
-struct SwRec { double w[NT_SW]; int off[NT_SW]; int n, r0, r1, rg, js, pad; double rc0, rc1, tconst, fs; };
+constexpr int NT_LW = 24, NT_SW = 16;      // multiples of 8: the lists are padded with zero-weight terms to whole groups of eight
+struct alignas(16) LwRec { double w[NT_LW]; int off[NT_LW]; int n, gs_off, f0, f1; double ffs, pad_; };     // 320 bytes
+struct alignas(16) SwRec { double w[NT_SW]; int off[NT_SW]; int n, r0, r1, rg, js, pad; double rc0, rc1, tconst, fs; };   // 248 -> 256 bytes
 
 template <class Rec>
 RR_HD void rec_add(Rec& r, int off, double w) { r.off[r.n] = off; r.w[r.n] = w; ++r.n; }
@@ -295,7 +305,7 @@ RR_HD void lw_terms(const double* A, const Tab& tb, const LwBand& B, const Layer
   else if (R.corr == 2) corr = 1.0 - 0.15 * (L.pavel / 95.6);
   else if (R.corr == 3) corr = 1.0 - 0.05 * (L.pavel - 100.0) / 900.0;
   if (corr != 1.0) for (int i = 0; i < rec.n; ++i) rec.w[i] *= corr;
-  while (rec.n & 3) rec_add(rec, 0, 0.0);
+  while (rec.n & 7) rec_add(rec, 0, 0.0);
   rec.gs_off = R.gscale_off;
   rec.f0 = rec.f1 = -1; rec.ffs = 0.0;
   if (R.frac_off >= 0) {
@@ -307,12 +317,15 @@ RR_HD void lw_terms(const double* A, const Tab& tb, const LwBand& B, const Layer
 }
 // the g-dependent part: a dot product over the term list
 template <class Rec>
-RR_HD double rec_dot(const double* A, const Rec& r, int g) {     // four independent table reads in flight per step
-  const double* Ag = A + g;
+RR_HD double rec_dot(const double* A, const Rec& r, int g) {     // eight independent table reads in flight per step (the reads mostly
+  const double* Ag = A + g;                                      // hit in L2: their latency, not their number, bounds the kernels)
   double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-  for (int i = 0; i < r.n; i += 4) {
-    const double a0 = Ag[r.off[i]], a1 = Ag[r.off[i + 1]], a2 = Ag[r.off[i + 2]], a3 = Ag[r.off[i + 3]];
-    t0 += r.w[i] * a0; t1 += r.w[i + 1] * a1; t2 += r.w[i + 2] * a2; t3 += r.w[i + 3] * a3;
+  for (int i = 0; i < r.n; i += 8) {
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = Ag[r.off[i + j]];
+    t0 += r.w[i] * a[0]; t1 += r.w[i + 1] * a[1]; t2 += r.w[i + 2] * a[2]; t3 += r.w[i + 3] * a[3];
+    t0 += r.w[i + 4] * a[4]; t1 += r.w[i + 5] * a[5]; t2 += r.w[i + 6] * a[6]; t3 += r.w[i + 7] * a[7];
   }
   return (t0 + t1) + (t2 + t3);
 }
@@ -418,7 +431,7 @@ RR_HD void sw_terms(const double* A, const SwBand& B, const Layer& L, SwRec& rec
   if (R.self_off >= 0) itab_terms(rec, R.self_off, ng, L.indself, L.selffrac, L.col[SP_H2O] * L.selffac);
   if (R.for_off >= 0) itab_terms(rec, R.for_off, ng, L.indfor, L.forfrac, L.col[SP_H2O] * L.forfac);
   for (int e = 0; e < R.nextra; ++e) rec_add(rec, R.extra_off[e], L.col[R.extra_sp[e]]);
-  while (rec.n & 3) rec_add(rec, 0, 0.0);
+  while (rec.n & 7) rec_add(rec, 0, 0.0);
   rec.tconst = R.o2cont ? 4.35e-4 * L.col[SP_O2] / (350.0 * 2.0) : 0.0;
   rec.r1 = -1; rec.rc1 = 0.0;
   if (R.rayl_mode == 0) { rec.r0 = R.rayl_off; rec.rg = 0; rec.rc0 = L.colmol; }

@@ -69,13 +69,13 @@ constexpr double FLUXFAC = 3.14159265358979323846 * 2.0e4;      // pi * 2.e4 wit
 // dynamic shared memory (sized by the number of layers, so that more CTAs fit per SM); the CPU thread emulator of
 // tests/host/rrtm_emu.cpp defines ISCA_RRTM_EMU and gets a static buffer instead
 #ifdef ISCA_RRTM_EMU
-#define ISCA_DYN_SMEM(name) static double name[40000]
+#define ISCA_DYN_SMEM(name) alignas(16) static double name[40000]
 #else
 #define ISCA_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
 #endif
 __host__ __device__ inline size_t lw_smem_doubles(int nl) {
-  return (sizeof(Layer) * (size_t)nl + sizeof(LwRec) * (size_t)(LW_TILE * NB_LW)) / 8 + 2 * (size_t)NB_LW * (nl + 1)
-       + (size_t)(LW_THREADS / 32) * 2 * (nl + 1) + 3 * NB_LW + 2 * (size_t)(nl + 1) + 8;
+  return (sizeof(Layer) * (size_t)nl + 15) / 16 * 2 + sizeof(LwRec) * (size_t)(LW_TILE * NB_LW) / 8 + (size_t)(LW_THREADS / 32) * 2 * (nl + 1)
+       + 3 * NB_LW + 2 * (size_t)(nl + 1) + (size_t)(2 * nl + 1) + (size_t)(2 * nl + 2) / 2 + 8;
 }
 __host__ __device__ inline size_t sw_smem_doubles(int nl) {
   return (sizeof(Layer) * (size_t)nl + sizeof(SwRec) * (size_t)(SW_TILE * NB_SW)) / 8 + (size_t)(SW_THREADS / 32) * 2 * (nl + 1)
@@ -92,15 +92,17 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
   const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
   const int PS = nl + 1;             // row stride of the Planck arrays
   Layer* lay = reinterpret_cast<Layer*>(smem);
-  LwRec* recs = reinterpret_cast<LwRec*>(smem + (sizeof(Layer) * (size_t)nl + 7) / 8);
-  double* planklay = reinterpret_cast<double*>(recs + LW_TILE * NB_LW);
-  double* planklev = planklay + NB_LW * PS;
-  double* part = planklev + NB_LW * PS;                   // [warp][2][PS]
+  LwRec* recs = reinterpret_cast<LwRec*>(smem + (sizeof(Layer) * (size_t)nl + 15) / 16 * 2);
+  double* part = reinterpret_cast<double*>(recs + LW_TILE * NB_LW);      // [warp][2][PS]
   double* plankbnd = part + (LW_THREADS / 32) * 2 * PS;
   double* secdiff = plankbnd + NB_LW;
   double* semiss = secdiff + NB_LW;
   double* pz = semiss + NB_LW;
   double* fnet = pz + PS;
+  // the Planck functions of the layers and levels are interpolated by the g-point threads themselves (two table reads each, L1-resident)
+  // from the index / fraction pairs below instead of being staged for all 16 bands: 10 KB less shared memory = one more CTA per SM
+  double* pl_frac = fnet + PS;                           // [nl] layers, then [nl + 1] levels
+  int* pl_ind = reinterpret_cast<int*>(pl_frac + 2 * nl + 1);
   // ---- phase A: inatm + setcoef per layer
   for (int l = tid; l < nl; l += LW_THREADS) {
     double vmr[NSP], xs[4];
@@ -110,15 +112,15 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
     double coldry = coldry_of(pb, pa, vmr[0]);
     double tav = in.tlay[col + (size_t)nc * l];
     lw_setcoef_layer(A, tb, in.play[col + (size_t)nc * l], tav, coldry, vmr, xs, lay[l]);
-    planck16(A, tb, tav, planklay + l, PS);
-    planck16(A, tb, in.tlev[col + (size_t)nc * (l + 1)], planklev + l + 1, PS);
+    planck_index(tav, pl_ind[l], pl_frac[l]);
+    planck_index(in.tlev[col + (size_t)nc * (l + 1)], pl_ind[nl + l + 1], pl_frac[nl + l + 1]);
     pz[l + 1] = pa;
     if (l == 0) pz[0] = pb;
   }
   if (tid < NB_LW) semiss[tid] = in.emis ? in.emis[col + (size_t)nc * tid] : 1.0;
+  if (tid == LW_THREADS - 1) planck_index(in.tlev[col], pl_ind[nl], pl_frac[nl]);
   __syncthreads();
   if (tid == 0) {
-    planck16(A, tb, in.tlev[col], planklev, PS);
     double pb[NB_LW];
     planck16(A, tb, in.tsfc[col], pb, 1);
     for (int ib = 0; ib < NB_LW; ++ib) plankbnd[ib] = semiss[ib] * pb[ib];
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
     __syncthreads();
     const double sd = secdiff[ib];
     double v8[8];
+    double pl_up = planck_at(A, tb, ib, pl_ind[nl + hi], pl_frac[nl + hi]);       // Planck function of level hi (top of the tile)
 #pragma unroll
     for (int j = 0; j < LW_TILE; ++j) {
       const int lev = hi - j;
@@ -165,8 +168,10 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
         double tau, plfrac;
         lw_tau_rec(A, recs[(lev - lo) * NB_LW + ib], gb, tau, plfrac);
         if (lev == 1) frac1 = plfrac;
-        lw_layer(exptfn, sd, tau, plfrac, planklay[ib * PS + lev - 1], planklev[ib * PS + lev], planklev[ib * PS + lev - 1],
+        const double pl_dn = planck_at(A, tb, ib, pl_ind[nl + lev - 1], pl_frac[nl + lev - 1]);
+        lw_layer(exptfn, sd, tau, plfrac, planck_at(A, tb, ib, pl_ind[lev - 1], pl_frac[lev - 1]), pl_up, pl_dn,
                  radld, atrans[lev - 1], bbugas[lev - 1]);
+        pl_up = pl_dn;
         v8[j] = radld * w;
       }
     }

@@ -47,7 +47,10 @@ def run_test_case_options(radiation):
         m.atmosphere(1)
         if step == 0:
             assert mp.diag["diff_t"].max() > 0.0
-            assert rel(m.get("diff_t"), mp.diag["diff_t"]) < 1e-9 and rel(m.get("z_pbl"), mp.diag["z_pbl"]) < 1e-9
+            # with RRTMG the K-profile sees T + dt * tdt (use_tau = .false.) with heating rates that are differences of fluxes
+            # (1e-10 relative between the two implementations): the Richardson-number dependence amplifies that
+            tol_d = 1e-8 if radiation == "rrtm" else 1e-9
+            assert rel(m.get("diff_t"), mp.diag["diff_t"]) < tol_d and rel(m.get("z_pbl"), mp.diag["z_pbl"]) < tol_d
         assert rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL, step
         assert rel(atm.get_field(api.F_U), core.ug[core.current]) < TOL, step
         assert rel(m.get("t_surf"), mp.t_surf) < TOL, step
