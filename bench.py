@@ -367,7 +367,7 @@ def main():
             dist.all_gather_object(handles, core.ipc_handles())
             core.set_peer_handles(handles)           # Legendre/FFT epilogues now store straight into peer memory
 
-    use_graph = world == 1 or os.environ.get("ISCA_B200_GRAPH_MULTI") == "1"
+    use_graph = world == 1 or os.environ.get("ISCA_B200_NO_GRAPH_MULTI") is None
     peaks = measured_peaks()
     pin = lambda shape: torch.zeros(shape, dtype=torch.float64).pin_memory().numpy()
 

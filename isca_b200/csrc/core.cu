@@ -105,12 +105,25 @@ struct IscaHandle_t {
   DBuf<double> fourB;        // Fourier buffer, lat-owner layout (B); only allocated when P > 1
   NcclApi nccl; NcclComm comm = nullptr;
   double* four_lat() { return g.P > 1 ? fourB.p : four.p; }
+  // The lat-owner buffer carries a tail that the peers address through the same CUDA-IPC mapping: arrival flags of the device-side
+  // inter-GPU barriers (SYNC_FLAGS doubles: channel c, source rank r at [32 c + r]) and the receive buffers of the tracer halo
+  // (halo_s, halo_n: 3*K*2*I doubles each).  sync_off = offset of the tail in doubles; equal on every rank.
+  static constexpr size_t SYNC_FLAGS = 512;
+  size_t fourB_cap = 0, sync_off = 0;
+  size_t halo_block() const { return (size_t)3 * g.K * 2 * g.I; }
+  std::vector<double*> peerA_host, peerB_host;
+  DBuf<unsigned long long> bar_count;      // [3] epochs of the barrier channels (forward transpose, inverse transpose, tracer halo)
   void ensure_four(int Lp) {
     // m-owner buffer: nm*J rows (sized with nm_max so that every rank's buffer is equally large for peer writes)
     const size_t needA = (size_t)g.nm_max * g.J * 2 * Lp, needB = (size_t)(g.M + 1) * g.Jloc * 2 * Lp;
-    if (p2p && (needA > four.n || needB > fourB.n)) throw std::runtime_error("transform batch too large for the peer-mapped Fourier buffers");
+    if (p2p && (needA > four.n || needB > fourB_cap)) throw std::runtime_error("transform batch too large for the peer-mapped Fourier buffers");
     if (needA > four.n) four.alloc(needA);
-    if (g.P > 1 && needB > fourB.n) fourB.alloc(needB);
+    if (g.P > 1 && needB > fourB_cap) {
+      const size_t tail = SYNC_FLAGS + 2 * halo_block();
+      fourB.alloc(needB + tail);
+      fourB_cap = needB; sync_off = needB;
+      if (cudaMemset(fourB.p + sync_off, 0, tail * sizeof(double)) != cudaSuccess) throw std::runtime_error("cudaMemset(sync tail) failed");
+    }
   }
   DBuf<double> gradA;        // [2K+2] planes: dxT, dyT, dxlnps, dylnps
   DBuf<double> gridB;        // [4K+1] planes: dt_T, A, B, Phi, dt_lnps
@@ -295,8 +308,8 @@ static void alloc_state(H& h) {
   h.ensure_four(Lmax);
   h.gradA.alloc((size_t)(2 * K + 2) * h.nplane());
   h.gridB.alloc((size_t)(4 * K + 1) * h.nplane());
-  h.part.alloc(5 * h.nplane()); h.scal.alloc(SC_COUNT); h.red_tmp.alloc(5 * 128);
-  h.ops_sum2.upload({0, 0}); h.ops_sum1.upload({0}); h.ops_fix.upload({0, 0, 0, 2, 2});
+  h.part.alloc(9 * h.nplane()); h.scal.alloc(SC_COUNT); h.red_tmp.alloc(9 * 128);
+  h.ops_sum2.upload({0, 0}); h.ops_sum1.upload({0}); h.ops_fix.upload({0, 0, 0, 0, 0, 0, 0, 2, 2});
   const size_t pl = h.nplane();
   // level descriptors
   std::vector<LevDesc> la(2 * K + 2), lb(4 * K + 1);
@@ -340,6 +353,30 @@ static void ensure_wave_matrix(H& h, double xi) {
   h.dt.wave_matrix = it->second->p;
 }
 
+// Device-side inter-GPU barrier over peer memory (replaces a one-element ncclAllReduce, ~4x the latency): lane r stores this rank's new
+// epoch into rank r's flag array (release, system scope; the producing kernel's remote stores precede it in stream order and are fenced)
+// and spins until rank r's epoch has arrived in this rank's array (acquire).  Epochs only grow, so no reset is needed; they live in
+// device memory so that a replayed CUDA graph advances them.
+__global__ void peer_barrier_kernel(double* const* __restrict__ peerB, size_t flag_off, int P, int rank, int chan, unsigned long long* counter) {
+  __shared__ unsigned long long ep;
+  if (threadIdx.x == 0) ep = ++counter[chan];
+  __syncthreads();
+  const unsigned long long epoch = ep;
+  const int r = threadIdx.x;
+  if (r < P && r != rank) {
+    unsigned long long* theirs = reinterpret_cast<unsigned long long*>(peerB[r] + flag_off) + chan * 32 + rank;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peerB[rank] + flag_off) + chan * 32 + r;
+    unsigned long long v;
+    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory"); } while (v < epoch);
+  }
+}
+static void peer_barrier(H& h, int chan) {
+  peer_barrier_kernel<<<1, 32, 0, h.st>>>(h.d_peerB.p, h.sync_off, h.g.P, h.g.rank, chan, h.bar_count.p);
+  h.launches++;
+}
+
 // exchange of the Fourier buffer between the lat-owner and m-owner layouts (transpose_fourier /
 // reverse_transpose_fourier, tools/transforms.F90:970-1056).  One rank: the two layouts coincide.
 //   direction 0 (spectral -> grid): layout A (mine: [dest s][mi][jl][C]) -> layout B ([pos[m]][jl][C])
@@ -350,9 +387,9 @@ static void exchange_fourier(H& h, int direction, int Lp) {
   const Geometry& g = h.g;
   if (g.P == 1) return;
   if (h.p2p) {
-    // the producing kernel already stored into the peers' buffers; a one-element all-reduce is the inter-GPU
-    // barrier: it completes on a rank only after every rank's producer kernel (earlier in its stream) finished
-    h.nccl.ck(h.nccl.AllReduce(h.barrier_token.p, h.barrier_token.p, 1, NCCL_FLOAT64, NCCL_SUM, h.comm, h.st), "ncclAllReduce(barrier)");
+    // the producing kernel already stored into the peers' buffers; the flag barrier completes on a rank only after every rank's
+    // producer kernel (earlier in its stream) has finished
+    peer_barrier(h, direction);
     h.mark(direction == 0 ? "exchange_inv" : "exchange_fwd");
     return;
   }
@@ -380,6 +417,11 @@ static void exchange_tracer_halo(H& h, const TracerArgs& ta) {
   const Geometry& g = h.g;
   if (g.P == 1) return;
   launch_tracer_halo_pack(h.dt, h.pr, ta, h.st); h.launches++;
+  if (h.p2p) {                             // the pack kernel stored the edge rows straight into the neighbours' halo buffers
+    peer_barrier(h, 2);
+    h.mark("tracer_halo");
+    return;
+  }
   const size_t n = (size_t)3 * g.K * 2 * g.I;
   const NcclApi& nc = h.nccl;
   nc.ck(nc.GroupStart(), "ncclGroupStart");
@@ -521,14 +563,19 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
       const size_t hb = (size_t)3 * K * 2 * g.I;
       double* p = h.tr_halo.p;
       ta.halo_s = p; ta.halo_n = p + hb; ta.send_s = p + 2 * hb; ta.send_n = p + 3 * hb;
+      if (h.p2p) {                         // receive in the tail of the lat-owner buffer, send = the neighbours' receive buffers
+        const size_t o = h.sync_off + H::SYNC_FLAGS;
+        ta.halo_s = h.fourB.p + o; ta.halo_n = h.fourB.p + o + hb;
+        if (g.rank > 0) ta.send_s = h.peerB_host[g.rank - 1] + o + hb;          // my southern rows are the northern halo of rank - 1
+        if (g.rank < g.P - 1) ta.send_n = h.peerB_host[g.rank + 1] + o;         // my northern rows are the southern halo of rank + 1
+      }
     }
     exchange_tracer_halo(h, ta);
     launch_tracer_horiz(h.dt, h.fv, pr, ta, st);
     h.mark("tracer_horiz");
     launch_tracer_ppm(h.dt, pr, ta, st);
     h.mark("tracer_ppm");
-    launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_W_PREV, h.red_tmp.p, st);
-    allreduce_scalars(h, h.scal.p + SC_W_PREV, 1, NCCL_SUM);
+    launch_reduce(h.part.p, pl, 1, h.ops_sum1.p, h.scal.p + SC_W_PREV, h.red_tmp.p, st);   // summed over the ranks with the fixers' sums
     h.launches += 4;
     h.mark("tracer_reduce");
   }
@@ -554,23 +601,19 @@ static void step_once(H& h, int physics_on, const double* dtu_in, const double* 
   dev_inverse(h, h.specC.p, h.LpC, h.levsC[fut].p, 7 * K + 3, "_state");
   h.grad_valid = true;
 
-  // compute_corrections (spectral_dynamics.F90:1213-1302): one column pass, one reduction, one SUM + one MAX all-reduce
-  // (the previous-level sums of initialize_corrections ride in the same SUM), one apply
-  launch_colsum_fixers(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.part.p, st);
-  launch_reduce(h.part.p, pl, 5, h.ops_fix.p, h.scal.p + SC_SUM_PS_FUT, h.red_tmp.p, st);
-  allreduce_scalars(h, h.scal.p + SC_SUM_PS_PREV, 5, NCCL_SUM);
-  allreduce_scalars(h, h.scal.p + SC_NTMIN, 2, NCCL_MAX);
+  // compute_corrections (spectral_dynamics.F90:1213-1302): one column pass, one reduction, ONE all-reduce (the previous-level sums of
+  // initialize_corrections, the previous-level water and the water integrals of the future level ride in the same SUM), one apply
+  launch_colsum_fixers(h.dt, pr, h.u[fut].p, h.v[fut].p, h.T[fut].p, h.ps[fut].p, h.cfg.num_tracers > 0 ? h.tr_wpart.p : nullptr, h.part.p, st);
+  launch_reduce(h.part.p, pl, 9, h.ops_fix.p, h.scal.p + SC_SUM_PS_FUT, h.red_tmp.p, st);
+  allreduce_scalars(h, h.scal.p, SC_NSUM, NCCL_SUM);
   const double rc_raw = h.cfg.robert_coeff * h.cfg.raw_filter_coeff;
   launch_apply_fixers(h.dt, pr, fut, h.ps[fut].p, h.lnps[fut].p, h.lnps[cur].p, h.ts[fut].p, h.ts[cur].p, rc_raw, h.scal.p, h.denom(),
                       h.owns_m0(), h.cfg.do_mass_correction, h.cfg.do_energy_correction, st);
   h.launches += 4;
   h.mark("corr_mass_energy");
   if (h.cfg.num_tracers > 0) {
-    launch_tracer_water_colsum(h.dt, pr, ta, st);
-    launch_reduce(h.part.p, pl, 3, h.ops_sum3.p, h.scal.p + SC_W_ALL, h.red_tmp.p, st);
-    allreduce_scalars(h, h.scal.p + SC_W_ALL, 3, NCCL_SUM);
-    launch_tracer_water_apply(h.dt, pr, ta, h.scal.p + SC_W_PREV, h.denom(), h.cfg.do_water_correction, st);
-    h.launches += 4;
+    launch_tracer_water_apply(h.dt, pr, ta, h.scal.p, h.denom(), h.cfg.do_water_correction, st);
+    h.launches += 1;
     h.mark("tracer_water_fixer");
   }
 
@@ -794,9 +837,11 @@ int isca_b200_set_peer_handles(IscaHandle h, const void* all_handles) {
     pa[r] = (double*)qa; pb[r] = (double*)qb;
   }
   h->d_peerA.upload(pa); h->d_peerB.upload(pb);
+  h->peerA_host = pa; h->peerB_host = pb;
   h->dt.g.peerA = h->d_peerA.p; h->dt.g.peerB = h->d_peerB.p; h->dt.g.p2p = 1;
   h->p2p = true;
-  h->barrier_token.alloc(1);
+  h->bar_count.alloc(4);
+  CK(cudaMemset(h->bar_count.p, 0, 4 * sizeof(unsigned long long)));
   for (auto& sg : h->graphs) if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; sg.uses = 0; }
   API_END(h)
 }
@@ -885,7 +930,9 @@ int isca_b200_create(const IscaConfig* cfg, int rank, int nranks, const void* nc
       h->nccl.load();
       NcclUniqueId id; std::memcpy(id.internal, nccl_unique_id, 128);
       h->nccl.ck(h->nccl.CommInitRank(&h->comm, nranks, id, rank), "ncclCommInitRank");
-      if (std::getenv("ISCA_B200_GRAPH_MULTI") == nullptr) h->use_graph = false;   // NCCL calls are issued eagerly by default
+      // the multi-rank step (peer-memory transposes with device-side flag barriers + one ncclAllReduce) is replayed from a CUDA graph
+      // like the single-rank one; ISCA_B200_NO_GRAPH_MULTI=1 issues it eagerly
+      if (std::getenv("ISCA_B200_NO_GRAPH_MULTI") != nullptr) h->use_graph = false;
     }
     upload_tables(*h);
     set_params(*h);

@@ -511,10 +511,14 @@ void launch_reduce(const double* part, size_t n, int nq, const int* ops, double*
 // post-transform: compute_corrections (spectral_dynamics.F90:1213-1302), mass + energy fixers in one pass.
 // The energy integral is taken with the mass-corrected surface pressure ps' = f*ps; as dp = dpk + dbk*ps' it is
 // A + f*B with A = sum e*dpk, B = sum e*dbk*ps, so both partial sums are formed before f is known and all global sums of the
-// step travel in one reduction (and one all-reduce).  part[0] = w*ps, part[1] = w*A, part[2] = w*B, part[3] = -min T, part[4] = max T
+// step travel in one reduction (and one all-reduce).  The water fixer's integrals of the future level (spectral_dynamics.F90:1245-1278)
+// are taken with the same corrected ps: their column sums come from the tracer PPM sweep as (sum q*dpk, sum q*dbk) below / above
+// water_correction_limit and enter the same way.  part[0] = w*ps, part[1] = w*A, part[2] = w*B, part[3..6] = w*(water A, B*ps below the
+// limit; A, B*ps above), part[7] = -min T, part[8] = max T
 // ---------------------------------------------------------------------------------------------
 __global__ void colsum_fixers_kernel(DevTables t, Params pr, const double* __restrict__ u, const double* __restrict__ v,
-                                     const double* __restrict__ T, const double* __restrict__ ps, double* __restrict__ part) {
+                                     const double* __restrict__ T, const double* __restrict__ ps, const double* __restrict__ wpart,
+                                     double* __restrict__ part) {
   const GeomDev& g = t.g;
   const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
   if (i >= g.I) return;
@@ -533,13 +537,19 @@ __global__ void colsum_fixers_kernel(DevTables t, Params pr, const double* __res
   part[col] = w * p_s;
   part[plane + col] = w * va;
   part[2 * plane + col] = w * vb;
-  part[3 * plane + col] = -tmin;
-  part[4 * plane + col] = tmax;
+  double wa_c = 0.0, wb_c = 0.0, wa_n = 0.0, wb_n = 0.0;
+  if (wpart) { wa_c = wpart[col]; wb_c = wpart[plane + col] * p_s; wa_n = wpart[2 * plane + col]; wb_n = wpart[3 * plane + col] * p_s; }
+  part[3 * plane + col] = w * wa_c;
+  part[4 * plane + col] = w * wb_c;
+  part[5 * plane + col] = w * wa_n;
+  part[6 * plane + col] = w * wb_n;
+  part[7 * plane + col] = -tmin;
+  part[8 * plane + col] = tmax;
 }
 void launch_colsum_fixers(const DevTables& t, const Params& pr, const double* u, const double* v, const double* T,
-                          const double* ps, double* part, cudaStream_t st) {
+                          const double* ps, const double* wpart, double* part, cudaStream_t st) {
   dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
-  colsum_fixers_kernel<<<grid, 128, 0, st>>>(t, pr, u, v, T, ps, part);
+  colsum_fixers_kernel<<<grid, 128, 0, st>>>(t, pr, u, v, T, ps, wpart, part);
 }
 
 // mass_correction_factor = mean_ps_prev / mean_ps_tmp (:1228-1231); temperature_correction (:1236-1241).
@@ -580,6 +590,9 @@ __global__ void apply_fixers_kernel(DevTables t, Params pr, int slot_fut, double
       scal[SC_MEAN_EN_PREV] = mean_e_prev;
       scal[SC_T_CORR] = tc;
       scal[SC_TMIN] = -ntmin;
+      scal[SC_W_CORR] = scal[SC_WA_CORR] + f * scal[SC_WB_CORR];                  // water integrals with the corrected ps
+      scal[SC_W_NOT] = scal[SC_WA_NOT] + f * scal[SC_WB_NOT];
+      scal[SC_W_ALL] = (scal[SC_WA_CORR] + f * scal[SC_WB_CORR]) + (scal[SC_WA_NOT] + f * scal[SC_WB_NOT]);
       if (-ntmin < pr.vr_tmin || tmax > pr.vr_tmax) scal[SC_T_FLAG] = 1.0;       // valid_range_t (:940)
     }
   }

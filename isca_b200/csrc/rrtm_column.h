@@ -212,7 +212,7 @@ RR_HD Spec specparm_of(double ca, double cb, double rat, double mult) {
 // (table row, weight) pairs; a g-point thread then only forms  tau = sum_i w_i * A[off_i + g]  (consecutive doubles across
 // the lanes of a band).  Same formulas as lw_tau / sw_tau with the products re-associated (differences at the 1e-16 level).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NT_LW = 24, NT_SW = 16;      // multiples of 8: the lists are padded with zero-weight terms to whole groups of eight
+constexpr int NT_LW = 24, NT_SW = 16;      // capacity of a term list (LW: multiple of 8, SW: of 4, see rec_dot)
 struct alignas(16) LwRec { double w[NT_LW]; int off[NT_LW]; int n, gs_off, f0, f1; double ffs, pad_; };     // 320 bytes
 struct alignas(16) SwRec { double w[NT_SW]; int off[NT_SW]; int n, r0, r1, rg, js, pad; double rc0, rc1, tconst, fs; };   // 248 -> 256 bytes
 
@@ -316,21 +316,23 @@ RR_HD void lw_terms(const double* A, const Tab& tb, const LwBand& B, const Layer
   }
 }
 // the g-dependent part: a dot product over the term list
-template <class Rec>
-RR_HD double rec_dot(const double* A, const Rec& r, int g) {     // eight independent table reads in flight per step (the reads mostly
-  const double* Ag = A + g;                                      // hit in L2: their latency, not their number, bounds the kernels)
+// W independent table reads in flight per step (the reads mostly hit in L2: their latency, not their number, is what costs); the lists
+// are padded with zero-weight terms to whole groups of W (8 for the longwave lists of up to 24 terms, 4 for the shorter shortwave ones)
+template <int W, class Rec>
+RR_HD double rec_dot(const double* A, const Rec& r, int g) {
+  const double* Ag = A + g;
   double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-  for (int i = 0; i < r.n; i += 8) {
-    double a[8];
+  for (int i = 0; i < r.n; i += W) {
+    double a[W];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = Ag[r.off[i + j]];
+    for (int j = 0; j < W; ++j) a[j] = Ag[r.off[i + j]];
     t0 += r.w[i] * a[0]; t1 += r.w[i + 1] * a[1]; t2 += r.w[i + 2] * a[2]; t3 += r.w[i + 3] * a[3];
-    t0 += r.w[i + 4] * a[4]; t1 += r.w[i + 5] * a[5]; t2 += r.w[i + 6] * a[6]; t3 += r.w[i + 7] * a[7];
+    if (W == 8) { t0 += r.w[i + 4] * a[4]; t1 += r.w[i + 5] * a[5]; t2 += r.w[i + 6] * a[6]; t3 += r.w[i + 7] * a[7]; }
   }
   return (t0 + t1) + (t2 + t3);
 }
 RR_HD void lw_tau_rec(const double* A, const LwRec& r, int g, double& tau, double& frac) {
-  double t = rec_dot(A, r, g);
+  double t = rec_dot<8>(A, r, g);
   if (r.gs_off >= 0) t *= A[r.gs_off + g];
   tau = t;
   if (r.f0 < 0) frac = 0.0;
@@ -431,7 +433,7 @@ RR_HD void sw_terms(const double* A, const SwBand& B, const Layer& L, SwRec& rec
   if (R.self_off >= 0) itab_terms(rec, R.self_off, ng, L.indself, L.selffrac, L.col[SP_H2O] * L.selffac);
   if (R.for_off >= 0) itab_terms(rec, R.for_off, ng, L.indfor, L.forfrac, L.col[SP_H2O] * L.forfac);
   for (int e = 0; e < R.nextra; ++e) rec_add(rec, R.extra_off[e], L.col[R.extra_sp[e]]);
-  while (rec.n & 7) rec_add(rec, 0, 0.0);
+  while (rec.n & 3) rec_add(rec, 0, 0.0);
   rec.tconst = R.o2cont ? 4.35e-4 * L.col[SP_O2] / (350.0 * 2.0) : 0.0;
   rec.r1 = -1; rec.rc1 = 0.0;
   if (R.rayl_mode == 0) { rec.r0 = R.rayl_off; rec.rg = 0; rec.rc0 = L.colmol; }
@@ -439,7 +441,7 @@ RR_HD void sw_terms(const double* A, const SwBand& B, const Layer& L, SwRec& rec
   else { rec.r0 = R.rayl_off + (rec.js - 1) * ng; rec.r1 = R.rayl_off + rec.js * ng; rec.rg = 1; rec.rc0 = L.colmol; rec.rc1 = rec.fs; }
 }
 RR_HD void sw_tau_rec(const double* A, const SwRec& r, int g, double& taug, double& taur) {
-  taug = rec_dot(A, r, g) + r.tconst;
+  taug = rec_dot<4>(A, r, g) + r.tconst;
   double a = A[r.r0 + r.rg * g];
   taur = r.rc0 * (r.r1 >= 0 ? a + r.rc1 * (A[r.r1 + g] - a) : a);
 }

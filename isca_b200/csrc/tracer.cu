@@ -549,24 +549,7 @@ void launch_tracer_ppm(const DevTables& t, const Params& pr, const TracerArgs& a
 // water fixer: three mass-weighted integrals with psg(future) (all, p_full >= limit, p_full < limit) from the column sums of
 // the PPM sweep; p_full is the `current` level's (the array passed to compute_corrections, spectral_dynamics.F90:1011)
 // ---------------------------------------------------------------------------------------------
-__global__ void tracer_water_colsum_kernel(DevTables t, TracerArgs a) {
-  const GeomDev& g = t.g;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, jl = blockIdx.y;
-  if (i >= g.I) return;
-  const size_t col = (size_t)jl * g.I + i, plane = (size_t)g.Jloc * g.I;
-  const double ps_f = a.ps_fut[col];
-  const double v_corr = a.wpart[col] + a.wpart[plane + col] * ps_f;
-  const double v_not = a.wpart[2 * plane + col] + a.wpart[3 * plane + col] * ps_f;
-  const double w = t.wts_lat[g.j0 + jl];
-  a.part[col] = w * (v_corr + v_not); a.part[plane + col] = w * v_corr; a.part[2 * plane + col] = w * v_not;
-}
-void launch_tracer_water_colsum(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st) {
-  (void)pr;
-  dim3 grid((t.g.I + 127) / 128, t.g.Jloc);
-  tracer_water_colsum_kernel<<<grid, 128, 0, st>>>(t, a);
-}
-
-// scal: [0] sum water prev, [1..3] sums all / corrected / not corrected (future).  8 levels per thread: the correction factor
+// scal: the device scalars (SC_W_PREV; SC_W_ALL / SC_W_CORR / SC_W_NOT formed by apply_fixers).  8 levels per thread: the correction factor
 // (a dozen divisions) is formed once per thread and the loads of the 8 levels are in flight together.
 constexpr int WA_LEV = 8;
 __global__ void __launch_bounds__(256)
@@ -580,8 +563,8 @@ tracer_water_apply_kernel(DevTables t, Params pr, TracerArgs a, const double* __
   for (int d = 0; d < WA_LEV; ++d)
     if (k0 + d < g.K) { const size_t e = (size_t)(k0 + d) * plane + col; qf[d] = a.q_fut[e]; qc[d] = a.q_cur_w[e]; }
   const double ps_c = a.ps_cur[col];
-  const double mean_prev = scal[0] / denom / pr.grav, mean_tmp = scal[1] / denom / pr.grav;
-  const double corr = scal[2] / denom / pr.grav, ncorr = scal[3] / denom / pr.grav;
+  const double mean_prev = scal[SC_W_PREV] / denom / pr.grav, mean_tmp = scal[SC_W_ALL] / denom / pr.grav;
+  const double corr = scal[SC_W_CORR] / denom / pr.grav, ncorr = scal[SC_W_NOT] / denom / pr.grav;
   double wf = 1.0;
   const bool apply = do_water && (mean_tmp > 0.);
   if (apply) { wf = mean_prev / mean_tmp; wf = wf * (1. + ncorr / corr) - ncorr / corr; }

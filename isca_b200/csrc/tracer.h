@@ -36,7 +36,6 @@ struct TracerArgs {
 void launch_tracer_halo_pack(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);
 void launch_tracer_horiz(const DevTables& t, const FvTables& f, const Params& pr, const TracerArgs& a, cudaStream_t st);
 void launch_tracer_ppm(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);
-void launch_tracer_water_colsum(const DevTables& t, const Params& pr, const TracerArgs& a, cudaStream_t st);
 void launch_tracer_water_apply(const DevTables& t, const Params& pr, const TracerArgs& a, const double* scal, double denom,
                                int do_water, cudaStream_t st);
 

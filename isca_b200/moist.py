@@ -117,13 +117,18 @@ class MoistAtmosphere:
     def atmosphere(self, n_steps=1):
         self._ck(self._lib.isca_b200_moist_step(self._h, n_steps), "atmosphere")
 
-    def get(self, name):
+    def get(self, name, out=None):
+        """host copy of a physics field; `out`: an existing C-contiguous float64 array of the field's shape (e.g. pinned memory)"""
         if name in FIELDS_2D:
-            out, i = np.empty(self.s2), FIELDS_2D[name]
+            shape, i = self.s2, FIELDS_2D[name]
         elif name in FIELDS_3D:
-            out, i = np.empty(self.s3), FIELDS_3D[name]
+            shape, i = self.s3, FIELDS_3D[name]
         else:
             raise IscaError(f"unknown field {name}")
+        if out is None:
+            out = np.empty(shape)
+        elif out.shape != tuple(shape) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise IscaError(f"get({name}): out must be a C-contiguous float64 array of shape {tuple(shape)}")
         self._ck(self._lib.isca_b200_moist_get(self._h, i, out.ctypes.data_as(C.POINTER(C.c_double))), "get")
         return out
 

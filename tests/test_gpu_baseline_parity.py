@@ -46,39 +46,50 @@ def test_held_suarez_steps_at_baseline_sizes(lib_built, res, K, dt, spin, nsteps
     atm.atmosphere(spin)                                   # device spin-up: leapfrog steps with 2 dt
     gpu_state_into_oracle(api, atm, core)
     assert np.abs(core.ug[core.current]).max() > 0.01      # the flow has started to develop (Held-Suarez forcing on a resting start)
+    # a second, independent CPU implementation of the same algorithm (oracle/cstep, C++) stepped from the same state: what two fp64 CPU
+    # implementations differ by among themselves is the conditioning of each field, and sets the scale of its tolerance
+    from oracle.cstep import CStep
+    cs = CStep(cfg)
+    cs.load_from(core)
     atm.enable_tendency_capture()
-    report = {}
+    report, cpu_cpu = {}, {}
     for i in range(nsteps):
         delta_t = 2 * cfg.dt_atmos
         prev_state = {"dt_vors": core.vors[core.previous], "dt_divs": core.divs[core.previous], "dt_ts": core.ts[core.previous],
                       "dt_ln_ps": core.ln_ps[core.previous]}
         scale = {k: np.abs(v).max() / delta_t for k, v in prev_state.items()}
         core.step(keep=True)
+        cs.step(1)
         atm.atmosphere(1)
-        got, ref = atm.state(), core.state()
+        got, ref, alt = atm.state(), core.state(), cs.state()
+        c, p = core.current, core.previous
+        ref["q"], ref["q_prev"] = core.grid_tracers[c, 0], core.grid_tracers[p, 0]
+        got["q"], got["q_prev"] = atm.get_field(api.F_TRACER0), atm.get_field(api.F_TRACER0, api.LEVEL_PREVIOUS)
         for k, sid in (("dt_vors", api.S_DT_VOR), ("dt_divs", api.S_DT_DIV), ("dt_ts", api.S_DT_T), ("dt_ln_ps", api.S_DT_LNPS)):
             d = np.abs(atm.get_spectral(sid) - core.last[k]).max()
             report[(i, k)] = (d / np.abs(core.last[k]).max(), d / max(np.abs(core.last[k]).max(), scale[k]))
         for k in ("vors", "divs", "ts", "ln_ps", "vors_prev", "divs_prev", "ts_prev", "ln_ps_prev",
-                  "ug", "vg", "tg", "psg", "vorg", "divg", "wg_full", "p_full", "z_full"):
+                  "ug", "vg", "tg", "psg", "vorg", "divg", "wg_full", "p_full", "z_full", "q", "q_prev"):
             report[(i, k)] = (rel(got[k], ref[k]),) * 2
-        c, p = core.current, core.previous
-        report[(i, "q")] = (rel(atm.get_field(api.F_TRACER0), core.grid_tracers[c, 0]),) * 2
-        report[(i, "q_prev")] = (rel(atm.get_field(api.F_TRACER0, api.LEVEL_PREVIOUS), core.grid_tracers[p, 0]),) * 2
-    print(f"\n{res} L{K}: (step, field): max|a-b|/max|b|  [tendencies also: on the scale max(|dt_X|, |X_prev|/delta_t)]")
+            if k in alt:
+                cpu_cpu[(i, k)] = rel(alt[k], ref[k])
+    print(f"\n{res} L{K}: (step, field): GPU vs NumPy oracle max|a-b|/max|b|   [tendencies: also on the scale max(|dt_X|, |X_prev|/delta_t)]"
+          "   C++ oracle vs NumPy oracle")
     for k, v in report.items():
-        print(f"  {k}: {v[0]:.2e}  {v[1]:.2e}")
-    # State, grid fields and the tendencies of vorticity, temperature and surface pressure: 1e-10 of the field maximum.  The divergence
-    # tendency of this weakly forced, nearly balanced flow is the small residual of large terms (laplacian of geopotential + kinetic energy
-    # against the Coriolis and pressure-gradient terms; max|dt_divs| * delta_t is < 0.1 max|divs|): two CPU implementations of the same
-    # algorithm (the NumPy oracle and the C++ restatement oracle/cstep) already differ by 1.2e-10 of max|dt_divs| at T85 L40
-    # (DESIGN.md section 7), so it is held to 1e-10 on the scale that matters for the step, max(|dt_divs|, |divs_prev| / delta_t), and to
-    # 2e-9 of its own maximum.
+        print(f"  {k}: {v[0]:.2e}  {v[1]:.2e}   {cpu_cpu.get(k, float('nan')):.2e}")
+    # Tolerances.  1e-10 of the field maximum for everything that is well conditioned.  The divergence of this weakly forced, nearly
+    # balanced flow is not: its tendency is the small residual of large terms (laplacian of geopotential + kinetic energy against the
+    # Coriolis and pressure-gradient terms; max|dt_divs| * delta_t < 0.1 max|divs|) and its round-off sits at the highest wavenumbers,
+    # where the grid-point divergence has no signal to hide it.  Two CPU implementations of the same algorithm (the NumPy oracle and the
+    # C++ restatement) differ by the amounts in the last column; a field is held to max(1e-10, 4 x that).  dt_divs (not exposed by the
+    # C++ oracle) is held to 1e-10 on the scale that matters for the step, max(|dt_divs|, |divs_prev| / delta_t), and to 2e-9 of its own
+    # maximum.
     for (i, k), v in report.items():
         if k == "dt_divs":
             assert v[1] < TOL_STEP and v[0] < 2e-9, (i, k, v)
         else:
-            assert v[0] < TOL_STEP, (i, k, v)
+            assert v[0] < max(TOL_STEP, 4.0 * cpu_cpu.get((i, k), 0.0)), (i, k, v, cpu_cpu.get((i, k)))
+    cs.close()
     atm.atmosphere_end()
 
 
