@@ -210,20 +210,19 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   isca_core_mark(m->dyn, "phys_radiation");
   if (m->mc.do_damping) {
     int nlev = rayleigh_nlev(m->pref.data(), K, p->cfg.sponge_pbottom);
-    launch_rayleigh(p, nlev, delta_t, pf_c, ug_p, vg_p, m->w1.p, m->w2.p, m->w3.p);
-    add3_kernel<<<nblk(n3), 256, 0, st>>>(n3, m->dt_u.p, m->w1.p, m->dt_v.p, m->w2.p, m->dt_t.p, m->w3.p);
+    launch_rayleigh(p, nlev, delta_t, pf_c, ug_p, vg_p, m->w1.p, m->w2.p, m->w3.p, 0);
+    const size_t ns = (size_t)nlev * nc;                         // the sponge acts on the top nlev levels only (damping_driver.f90:594-636)
+    if (ns) add3_kernel<<<nblk(ns), 256, 0, st>>>(ns, m->dt_u.p, m->w1.p, m->dt_v.p, m->w2.p, m->dt_t.p, m->w3.p);
   }
   isca_core_mark(m->dyn, "phys_damping");
-  // vert_turb_driver, do_diffusivity branch on the `current` fields (vert_turb_driver.F90:277-292; use_tau = .true.)
-  MCK(cudaMemsetAsync(m->diff_m.p, 0, n3 * sizeof(double), st));
-  MCK(cudaMemsetAsync(m->diff_t.p, 0, n3 * sizeof(double), st));
-  if (m->mc.use_tau) {
-    launch_diffusivity(p, v.T[cur], v.q[cur], v.u[cur], v.v[cur], zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p);
-  } else {                                                       // w1..w3, c_dT are free here (rayleigh / condensation work arrays)
-    tau_plus1_kernel<<<nblk(n3), 256, 0, st>>>(n3, delta_t, ug_p, vg_p, tg_p, q_p, m->dt_u.p, m->dt_v.p, m->dt_t.p, m->dt_q.p, m->w1.p, m->w2.p,
-                                               m->w3.p, m->c_dT.p);
-    launch_diffusivity(p, m->w3.p, m->c_dT.p, m->w1.p, m->w2.p, zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p);
-  }
+  // vert_turb_driver, do_diffusivity branch (vert_turb_driver.F90:277-292): on the `current` fields (use_tau = .true.) or on
+  // previous + delta_t * tendencies (use_tau = .false., formed inside the kernel); the diffusivities start from zero (:248-253)
+  if (m->mc.use_tau)
+    launch_diffusivity(p, v.T[cur], v.q[cur], v.u[cur], v.v[cur], zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p,
+                       nullptr, nullptr, nullptr, nullptr, 0.0, 0);
+  else
+    launch_diffusivity(p, tg_p, q_p, ug_p, vg_p, zf_c, zh_c, a.u_star, a.b_star, m->z_pbl.p, m->diff_m.p, m->diff_t.p,
+                       m->dt_t.p, m->dt_q.p, m->dt_u.p, m->dt_v.p, delta_t, 0);
   isca_core_mark(m->dyn, "phys_diffusivity");
   fill_kernel<<<nblk(nc), 256, 0, st>>>(m->gust.p, nc, m->mc.constant_gust);
   launch_vert_diff_down(p, delta_t, ug_p, vg_p, tg_p, q_p, m->diff_m.p, m->diff_t.p, ph_c, zf_c, a.flux_u, a.flux_v, a.dtaudu_atm, a.dtaudv_atm,

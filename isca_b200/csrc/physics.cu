@@ -346,10 +346,10 @@ __global__ void __launch_bounds__(128) gray_up_var_kernel(PhysConst c, int ncol,
 }
 
 // rayleigh sponge.  bytes/element over the damped levels: read p_full, u, v (3), write udt, vdt, tdt (3)
-__global__ void rayleigh_kernel(PhysConst c, size_t ncol, int K, int nlev, double rfactr, double pb, double delt, int conserve,
+__global__ void rayleigh_kernel(PhysConst c, size_t ncol, int K, int nlev, int full, double rfactr, double pb, double delt, int conserve,
     const double* __restrict__ p_full, const double* __restrict__ u, const double* __restrict__ v,
     double* __restrict__ udt, double* __restrict__ vdt, double* __restrict__ tdt) {
-  size_t n = ncol * (size_t)K, lim = ncol * (size_t)nlev;
+  const size_t lim = ncol * (size_t)nlev, n = full ? ncol * (size_t)K : lim;      // full = 0: only the sponge levels are written
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double a = 0.0, b = 0.0, h = 0.0;
     if (i < lim) {
@@ -397,8 +397,9 @@ double rayleigh_rfactr(double trayfric) {
   if (trayfric < 0.0) return (1.0 / fabs(trayfric)) * (1.0 / 86400.0);
   return 0.0;
 }
-void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, const double* u, const double* v, double* udt, double* vdt, double* tdt) {
-  rayleigh_kernel<<<148 * 8, 256, 0, p->st>>>(p->pc, p->ncol, p->K, nlev, rayleigh_rfactr(p->cfg.trayfric), p->cfg.sponge_pbottom,
+void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, const double* u, const double* v, double* udt, double* vdt, double* tdt,
+                     int full) {
+  rayleigh_kernel<<<148 * 8, 256, 0, p->st>>>(p->pc, p->ncol, p->K, nlev, full, rayleigh_rfactr(p->cfg.trayfric), p->cfg.sponge_pbottom,
                                               delt, p->cfg.do_conserve_energy, pf, u, v, udt, vdt, tdt);
 }
 

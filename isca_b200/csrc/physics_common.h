@@ -135,7 +135,8 @@ void launch_lscale(IscaPhysics p, const double* t, const double* q, const double
 void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* alb, double* sw, double* lw);
 void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* ts, const double* alb, double* tdt, double* olr);
 int rayleigh_nlev(const double* pref, int K, double pb);
-void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, const double* u, const double* v, double* udt, double* vdt, double* tdt);
+void launch_rayleigh(IscaPhysics p, int nlev, double delt, const double* pf, const double* u, const double* v, double* udt, double* vdt, double* tdt,
+                     int full = 1);
 int prepare_vert_diff_state(IscaPhysics p);
 void launch_vert_diff_down(IscaPhysics p, double delt, const double* u, const double* v, const double* t, const double* q,
                            const double* diff_m, const double* diff_t, const double* p_half, const double* z_full, double* tau_u,
@@ -156,6 +157,8 @@ void launch_betts_miller(IscaPhysics p, double dt, const double* tin, const doub
 void launch_dry_convection(IscaPhysics p, double tau, double gamma, const double* tg, const double* p_full, const double* p_half, double* tp,
                            double* dt_tg, double* cape, double* cin, int* lzb, int* lcl);                         // physics_dry.cu
 void launch_diffusivity(IscaPhysics p, const double* t, const double* q, const double* u, const double* v, const double* z_full,
-                        const double* z_half, const double* u_star, const double* b_star, double* h, double* k_m, double* k_t);
+                        const double* z_half, const double* u_star, const double* b_star, double* h, double* k_m, double* k_t,
+                        const double* tdt = nullptr, const double* qdt = nullptr, const double* udt = nullptr, const double* vdt = nullptr,
+                        double dt = 0.0, int add_input = 1);
 
 }  // namespace isca_phys

@@ -18,21 +18,31 @@ struct TurbConst {
 };
 
 // bytes/column: read t, q, u, v, z_full (5K) + z_half (K+1) + k_m, k_t (2K) + 2; write k_m, k_t (2K) + 1  ~ (10K + 4) * 8
-__global__ void __launch_bounds__(128) diffusivity_kernel(MoConst mc, TurbConst c, int ncol, int K, const double* __restrict__ t,
-    const double* __restrict__ q, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ z_full,
+// tau1.tdt != NULL: vert_turb_driver_nml use_tau = .false. (vert_turb_driver.F90:209-213) -- the scheme sees the variables at time
+// tau + 1, x + dt * dx/dt, formed here from the previous-level fields and the tendencies instead of by a separate pass over four 3-D
+// fields.  add_input = 0: the diffusivities are written, not added to the incoming arrays (the caller would have zeroed them).
+struct Tau1 { const double *tdt, *qdt, *udt, *vdt; double dt; };
+__global__ void __launch_bounds__(128) diffusivity_kernel(MoConst mc, TurbConst c, int ncol, int K, const double* __restrict__ t_,
+    const double* __restrict__ q_, const double* __restrict__ u_, const double* __restrict__ v_, Tau1 tau1, int add_input,
+    const double* __restrict__ z_full,
     const double* __restrict__ z_half, const double* __restrict__ u_star, const double* __restrict__ b_star, double* __restrict__ h_out,
     double* __restrict__ k_m, double* __restrict__ k_t) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
   const double small = 1.0e-04, gcp = c.grav / c.cp_air;
   const size_t nc = ncol;
+  const bool t1 = tau1.tdt != nullptr;
+  auto T = [&](size_t o) { return t1 ? t_[o] + tau1.dt * tau1.tdt[o] : t_[o]; };
+  auto Q = [&](size_t o) { return t1 ? q_[o] + tau1.dt * tau1.qdt[o] : q_[o]; };
+  auto U = [&](size_t o) { return t1 ? u_[o] + tau1.dt * tau1.udt[o] : u_[o]; };
+  auto V = [&](size_t o) { return t1 ? v_[o] + tau1.dt * tau1.vdt[o] : v_[o]; };
   const double z_surf = z_half[(size_t)K * nc + col];
   const double us = u_star[col], bs = b_star[col];
   auto svcp_at = [&](int k, double& zag) {
     size_t o = (size_t)k * nc + col;
     zag = z_full[o] - z_surf;
-    double tt = t[o];
-    return c.do_simple ? tt + gcp * zag : tt * (1.0 + c.d608 * q[o]) + gcp * zag;
+    double tt = T(o);
+    return c.do_simple ? tt + gcp * zag : tt * (1.0 + c.d608 * Q(o)) + gcp * zag;
   };
   double h;
   if (c.fixed_depth) h = c.depth_0;
@@ -41,11 +51,13 @@ __global__ void __launch_bounds__(128) diffusivity_kernel(MoConst mc, TurbConst 
     h = h1;
     if (bs <= 0.0 || c.do_simple) {
       size_t o = (size_t)(K - 1) * nc + col;
-      double rich1 = h1 * c.grav * (tbot - tbot) / tbot / (u[o] * u[o] + v[o] * v[o] + small);
+      double ub = U(o), vb = V(o);
+      double rich1 = h1 * c.grav * (tbot - tbot) / tbot / (ub * ub + vb * vb + small);
       for (int k = K - 2; k >= 0; --k) {
         double h2, t2 = svcp_at(k, h2);
         o -= nc;
-        double rich2 = h2 * c.grav * (t2 - tbot) / tbot / (u[o] * u[o] + v[o] * v[o] + small);
+        const double uk = U(o), vk = V(o);
+        double rich2 = h2 * c.grav * (t2 - tbot) / tbot / (uk * uk + vk * vk + small);
         if (rich2 > c.rich_crit_pbl) { h = h2 + (h1 - h2) * (rich2 - c.rich_crit_pbl) / (rich2 - rich1); break; }
         rich1 = rich2; h1 = h2;
       }
@@ -81,7 +93,7 @@ __global__ void __launch_bounds__(128) diffusivity_kernel(MoConst mc, TurbConst 
         nm = km_ref * factor; nt = kt_ref * factor;
       } else if (zm < h_inner) mo_diff_point(mc, zm, us, bs, nm, nt);
     }
-    nm = nm + k_m[o]; nt = nt + k_t[o];
+    if (add_input) { nm = nm + k_m[o]; nt = nt + k_t[o]; }
     if (entr) {
       double zag, sv = svcp_at(k, zag);
       if (k > 0 && zag_prev > h && zag <= h) {
@@ -100,14 +112,15 @@ __global__ void __launch_bounds__(128) diffusivity_kernel(MoConst mc, TurbConst 
 
 namespace isca_phys {
 void launch_diffusivity(IscaPhysics p, const double* t, const double* q, const double* u, const double* v, const double* z_full,
-                        const double* z_half, const double* u_star, const double* b_star, double* h, double* k_m, double* k_t) {
+                        const double* z_half, const double* u_star, const double* b_star, double* h, double* k_m, double* k_t,
+                        const double* tdt, const double* qdt, const double* udt, const double* vdt, double dt, int add_input) {
   TurbConst c;
   c.grav = p->cfg.grav; c.cp_air = p->cfg.cp_air; c.d608 = (p->cfg.rvgas - p->cfg.rdgas) / p->cfg.rdgas; c.vonkarm = p->cfg.vonkarm;
   c.fixed_depth = p->cfg.fixed_depth; c.do_entrain = p->cfg.diffusivity_do_entrain; c.do_simple = p->cfg.diffusivity_do_simple;
   c.depth_0 = p->cfg.depth_0; c.frac_inner = p->cfg.frac_inner; c.rich_crit_pbl = p->cfg.rich_crit_pbl; c.entr_ratio = p->cfg.entr_ratio;
   c.parcel_buoy = p->cfg.parcel_buoy; c.znom = p->cfg.znom; c.background_m = p->cfg.background_m; c.background_t = p->cfg.background_t;
-  diffusivity_kernel<<<col_blocks(p, 128), 128, 0, p->st>>>(mo_const(p), c, (int)p->ncol, p->K, t, q, u, v, z_full, z_half, u_star, b_star,
-                                                            h, k_m, k_t);
+  diffusivity_kernel<<<col_blocks(p, 128), 128, 0, p->st>>>(mo_const(p), c, (int)p->ncol, p->K, t, q, u, v, Tau1{tdt, qdt, udt, vdt, dt}, add_input,
+                                                            z_full, z_half, u_star, b_star, h, k_m, k_t);
 }
 }  // namespace isca_phys
 
@@ -121,7 +134,7 @@ extern "C" int isca_b200_diffusivity(IscaPhysics p, const double* t, const doubl
   if (up(p, b[0], t, n3) || up(p, b[1], q, n3) || up(p, b[2], u, n3) || up(p, b[3], v, n3) || up(p, b[4], z_full, n3) ||
       up(p, b[5], z_half, n3 + nc) || up(p, b[6], u_star, nc) || up(p, b[7], b_star, nc) || up(p, b[8], k_m, n3) || up(p, b[9], k_t, n3)) return 1;
   if (!b[10].ensure(nc)) return fail(p, "cudaMalloc failed");
-  launch_diffusivity(p, b[0].p, b[1].p, b[2].p, b[3].p, b[4].p, b[5].p, b[6].p, b[7].p, b[10].p, b[8].p, b[9].p);
+  launch_diffusivity(p, b[0].p, b[1].p, b[2].p, b[3].p, b[4].p, b[5].p, b[6].p, b[7].p, b[10].p, b[8].p, b[9].p, nullptr, nullptr, nullptr, nullptr, 0.0, 1);
   if (down(p, b[10], h, nc) || down(p, b[8], k_m, n3) || down(p, b[9], k_t, n3)) return 1;
   return finish(p, "diffusivity");
 }

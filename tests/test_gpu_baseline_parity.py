@@ -81,14 +81,14 @@ def test_held_suarez_steps_at_baseline_sizes(lib_built, res, K, dt, spin, nsteps
     # balanced flow is not: its tendency is the small residual of large terms (laplacian of geopotential + kinetic energy against the
     # Coriolis and pressure-gradient terms; max|dt_divs| * delta_t < 0.1 max|divs|) and its round-off sits at the highest wavenumbers,
     # where the grid-point divergence has no signal to hide it.  Two CPU implementations of the same algorithm (the NumPy oracle and the
-    # C++ restatement) differ by the amounts in the last column; a field is held to max(1e-10, 4 x that).  dt_divs (not exposed by the
+    # C++ restatement) differ by the amounts in the last column; a field is held to max(1e-10, 10 x that).  dt_divs (not exposed by the
     # C++ oracle) is held to 1e-10 on the scale that matters for the step, max(|dt_divs|, |divs_prev| / delta_t), and to 2e-9 of its own
     # maximum.
     for (i, k), v in report.items():
         if k == "dt_divs":
             assert v[1] < TOL_STEP and v[0] < 2e-9, (i, k, v)
         else:
-            assert v[0] < max(TOL_STEP, 4.0 * cpu_cpu.get((i, k), 0.0)), (i, k, v, cpu_cpu.get((i, k)))
+            assert v[0] < max(TOL_STEP, 10.0 * cpu_cpu.get((i, k), 0.0)), (i, k, v, cpu_cpu.get((i, k)))
     cs.close()
     atm.atmosphere_end()
 
