@@ -1,0 +1,619 @@
+!> atmosphere_mod on libisca_b200.so -- drop-in replacement of src/atmos_spectral/driver/solo/atmosphere.F90 of the reference.
+!!
+!! Same public interface (atmosphere_init, atmosphere, atmosphere_end, atmosphere_domain), same namelists read under the same names
+!! from input.nml (atmosphere_nml, spectral_dynamics_nml, hs_forcing_nml, spectral_init_cond_nml; constants through constants_mod),
+!! same restart files (INPUT/atmosphere.res.nc, INPUT/spectral_dynamics.res.nc -> RESTART/...), same diag_manager fields of module
+!! 'dynamics'.  src/atmos_solo/atmos_model.F90, FMS (mpp, fms_io, diag_manager, time_manager), field_table / diag_table and the isca
+!! Python experiment scripts stay unchanged.  The model state lives on the GPU; this module keeps host mirrors only for restarts
+!! and for the diagnostics that are due.
+!!
+!! Put this file and isca_b200_c.F90 in the executable's path_names instead of atmosphere.F90, drop atmos_spectral/model,
+!! atmos_spectral/tools (except spec_mpp.F90, which owns the FMS domains) and shared/fft from the GPU executable, and add
+!! `-L<repo>/isca_b200/lib -lisca_b200 -lcudart` to LDFLAGS of the mkmf template.
+!!
+!! This build image has no Fortran compiler, so this file has not been compiled here; tests/host/shim_driver.c performs the same call
+!! sequence through the C ABI with arrays in Fortran order (tests/test_fortran_shim.py), and tools/gen_fortran_interface.py keeps the
+!! bind(C) types in step with the headers.  Namelist values the library does not implement are rejected by isca_b200_create with the
+!! reference's wording and reach error_mesg(..., FATAL) here.
+module atmosphere_mod
+
+#ifdef INTERNAL_FILE_NML
+  use mpp_mod, only: input_nml_file
+#else
+  use fms_mod, only: open_namelist_file, close_file
+#endif
+  use iso_c_binding
+  use isca_b200_c
+  use fms_mod,            only: write_version_number, file_exist, field_size, stdlog, mpp_pe, mpp_root_pe, mpp_npes, error_mesg, FATAL, &
+                                read_data, write_data, set_domain, nullify_domain
+  use mpp_mod,            only: mpp_broadcast, mpp_gather
+  use constants_mod,      only: grav, rdgas, kappa, radius, omega, pi
+  use time_manager_mod,   only: time_type, get_time, operator(+)
+  use spec_mpp_mod,       only: spec_mpp_init, grid_domain, spectral_domain, get_grid_domain, get_spec_domain, atmosphere_domain
+  use diag_manager_mod,   only: diag_axis_init, register_diag_field, register_static_field, send_data, need_data
+  use field_manager_mod,  only: MODEL_ATMOS
+  use tracer_manager_mod, only: get_number_tracers, get_tracer_index, NO_TRACER
+
+  implicit none
+  private
+  public :: atmosphere_init, atmosphere, atmosphere_end, atmosphere_domain
+
+  character(len=128), parameter :: version = 'isca_b200 atmosphere_mod shim'
+  character(len=128), parameter :: tagname = 'libisca_b200'
+  character(len=8),   parameter :: mod_name = 'dynamics'
+
+  !------------------------------------------------------------------ atmosphere_nml (atmosphere.F90:84-86)
+  logical :: idealized_moist_model = .false.
+  namelist /atmosphere_nml/ idealized_moist_model
+
+  !------------------------------------------------------------------ spectral_dynamics_nml (spectral_dynamics.F90:152-224), same defaults
+  logical :: do_mass_correction = .true., do_water_correction = .true., do_energy_correction = .true., &
+             use_virtual_temperature = .false., use_implicit = .true., triang_trunc = .true., graceful_shutdown = .false., &
+             make_symmetric = .false., json_logging = .false.
+  integer :: damping_order = 2, damping_order_vor = -1, damping_order_div = -1, cutoff_wn = 15, lon_max = 128, lat_max = 64, &
+             num_fourier = 42, num_spherical = 43, fourier_inc = 1, num_levels = 18, num_steps = 1
+  integer, dimension(2) :: print_interval = (/1, 0/)
+  character(len=64) :: vert_coord_option = 'even_sigma', damping_option = 'resolution_dependent', vert_advect_uv = 'second_centered', &
+                       vert_advect_t = 'second_centered', vert_difference_option = 'simmons_and_burridge', &
+                       initial_state_option = 'quiescent'
+  real :: damping_coeff = 1.15740741e-4, damping_coeff_vor = -1., damping_coeff_div = -1., eddy_sponge_coeff = 0., &
+          zmu_sponge_coeff = 0., zmv_sponge_coeff = 0., robert_coeff = .04, alpha_implicit = .5, longitude_origin = 0., &
+          scale_heights = 4., surf_res = .1, p_press = .1, p_sigma = .3, exponent = 2.5, ocean_topog_smoothing = .93, &
+          initial_sphum = 0.0, reference_sea_level_press = 101325., water_correction_limit = 0.0, raw_filter_coeff = 1.0
+  real, dimension(2) :: valid_range_t = (/100., 500./)
+  namelist /spectral_dynamics_nml/ use_virtual_temperature, damping_option, cutoff_wn, damping_order, damping_coeff, damping_order_vor, &
+                                   damping_coeff_vor, damping_order_div, damping_coeff_div, do_mass_correction, do_water_correction, &
+                                   do_energy_correction, vert_advect_uv, vert_advect_t, use_implicit, longitude_origin, robert_coeff, &
+                                   alpha_implicit, vert_difference_option, reference_sea_level_press, lon_max, lat_max, num_levels, &
+                                   num_fourier, num_spherical, fourier_inc, triang_trunc, vert_coord_option, scale_heights, surf_res, &
+                                   p_press, p_sigma, exponent, ocean_topog_smoothing, initial_sphum, valid_range_t, eddy_sponge_coeff, &
+                                   zmu_sponge_coeff, zmv_sponge_coeff, print_interval, num_steps, initial_state_option, &
+                                   water_correction_limit, raw_filter_coeff, graceful_shutdown, json_logging, make_symmetric
+
+  !------------------------------------------------------------------ hs_forcing_nml (hs_forcing.F90:74-122): the Held-Suarez option
+  logical :: no_forcing = .false., do_conserve_energy = .true., relax_to_specified_wind = .false.
+  real :: t_zero = 315., t_strat = 200., delh = 60., delv = 10., eps = 0., sigma_b = 0.7, P00 = 1.e5, ka = -40., ks = -4., kf = -1., &
+          trflux = 1.e-5, trsink = -4.
+  character(len=256) :: local_heating_option = '', equilibrium_t_option = 'Held_Suarez'
+  namelist /hs_forcing_nml/ no_forcing, t_zero, t_strat, delh, delv, eps, sigma_b, ka, ks, kf, do_conserve_energy, trflux, trsink, &
+                            local_heating_option, relax_to_specified_wind, equilibrium_t_option, P00
+
+  !------------------------------------------------------------------ spectral_init_cond_nml (spectral_init_cond.F90:68-74)
+  real :: initial_temperature = 264.
+  character(len=64) :: topography_option = 'flat'
+  namelist /spectral_init_cond_nml/ initial_temperature, topography_option
+
+  !------------------------------------------------------------------ module state
+  type(c_ptr) :: h = c_null_ptr              ! dynamical-core handle (owned by hm when the moist model runs)
+  type(c_ptr) :: hm = c_null_ptr             ! idealized moist model handle
+  integer, parameter :: num_time_levels = 2
+  integer :: is, ie, js, je, ms, me, ns, ne, num_tracers, nsphum
+  integer :: previous, current
+  logical :: module_is_initialized = .false.
+  integer :: dt_integer
+  type(time_type) :: Time_step
+  ! host mirrors, filled on demand (diagnostics that are due, restart)
+  real(c_double), allocatable, target :: buf3(:,:,:), buf2(:,:)
+  complex(c_double_complex), allocatable :: sbuf3(:,:,:), sbuf2(:,:)
+  ! diag_manager ids of module 'dynamics' (spectral_dynamics.F90:1541-1700)
+  integer :: id_ps, id_u, id_v, id_t, id_vor, id_div, id_omega, id_sphum, id_pres_full, id_pres_half, id_zfull, id_zhalf, id_pk, id_bk
+
+contains
+
+  !=================================================================================================================================
+  subroutine atmosphere_init(Time_init, Time, Time_step_in)
+    type(time_type), intent(in) :: Time_init, Time, Time_step_in
+    type(isca_config) :: cfg
+    type(isca_physics_config) :: pcfg
+    type(isca_moist_config) :: mcfg
+    character(kind=c_char), target :: nccl_id(128)
+    character(kind=c_char), allocatable :: ipc_mine(:), ipc_all(:)
+    integer :: seconds, days, nml_unit, io, rc, nt, slot
+    real, dimension(2) :: time_pointers
+    integer, dimension(4) :: siz
+    character(len=64) :: file
+    character(len=256) :: message
+
+    if (module_is_initialized) return
+    call write_version_number(version, tagname)
+
+#ifdef INTERNAL_FILE_NML
+    read (input_nml_file, nml=atmosphere_nml, iostat=io)
+    read (input_nml_file, nml=spectral_dynamics_nml, iostat=io)
+    read (input_nml_file, nml=hs_forcing_nml, iostat=io)
+    read (input_nml_file, nml=spectral_init_cond_nml, iostat=io)
+#else
+    if (file_exist('input.nml')) then
+      nml_unit = open_namelist_file()
+      read (nml_unit, atmosphere_nml, iostat=io);          rewind(nml_unit)
+      read (nml_unit, spectral_dynamics_nml, iostat=io);   rewind(nml_unit)
+      read (nml_unit, hs_forcing_nml, iostat=io);          rewind(nml_unit)
+      read (nml_unit, spectral_init_cond_nml, iostat=io)
+      call close_file(nml_unit)
+    end if
+#endif
+    write (stdlog(), atmosphere_nml)
+    write (stdlog(), spectral_dynamics_nml)
+
+    Time_step = Time_step_in
+    call get_time(Time_step, seconds, days)
+    dt_integer = 86400*days + seconds
+
+    call get_number_tracers(MODEL_ATMOS, num_prog=num_tracers)
+    nsphum = get_tracer_index(MODEL_ATMOS, 'sphum')
+
+    ! options of the reference the library does not carry are FATAL here, with the library's own checks behind them
+    if (.not. triang_trunc)   call error_mesg('atmosphere_init', 'isca_b200: rhomboidal truncation (triang_trunc = .false.) is not built', FATAL)
+    if (fourier_inc /= 1)     call error_mesg('atmosphere_init', 'isca_b200: fourier_inc must be 1', FATAL)
+    if (num_steps /= 1)       call error_mesg('atmosphere_init', 'isca_b200: num_steps must be 1', FATAL)
+    if (make_symmetric)       call error_mesg('atmosphere_init', 'isca_b200: make_symmetric is not built', FATAL)
+    if (trim(damping_option) /= 'resolution_dependent') &
+      call error_mesg('atmosphere_init', 'isca_b200: damping_option must be resolution_dependent', FATAL)
+    if (trim(vert_difference_option) /= 'simmons_and_burridge') &
+      call error_mesg('atmosphere_init', 'isca_b200: vert_difference_option must be simmons_and_burridge', FATAL)
+    if (trim(initial_state_option) /= 'quiescent') &
+      call error_mesg('atmosphere_init', 'isca_b200: initial_state_option must be quiescent (or a restart)', FATAL)
+    if (trim(topography_option) /= 'flat') &
+      call error_mesg('atmosphere_init', 'isca_b200: topography is handed over with isca_b200_set_surf_geopotential by a site-specific reader', FATAL)
+    if (num_tracers > 1 .or. (num_tracers == 1 .and. nsphum == NO_TRACER)) &
+      call error_mesg('atmosphere_init', 'isca_b200: the field_table may hold the sphum grid tracer only', FATAL)
+    if (.not. idealized_moist_model) then
+      if (trim(equilibrium_t_option) /= 'Held_Suarez' .or. len_trim(local_heating_option) > 0 .or. relax_to_specified_wind) &
+        call error_mesg('atmosphere_init', 'isca_b200: this shim forwards the Held_Suarez option of hs_forcing_nml; the other options '// &
+                        'are reached through include/isca_b200_hs.h', FATAL)
+    end if
+
+    ! FMS domains: latitudes in contiguous blocks, zonal wavenumbers as spec_mpp_mod distributes them for I/O (spec_mpp.F90:61-110)
+    call spec_mpp_init(num_fourier, num_spherical, lon_max, lat_max)
+    call get_grid_domain(is, ie, js, je)
+    call get_spec_domain(ms, me, ns, ne)
+
+    !---------------------------------------------------------------- IscaConfig <- namelists (every field)
+    call isca_b200_default_config(cfg)
+    cfg%lon_max = lon_max;  cfg%lat_max = lat_max;  cfg%num_fourier = num_fourier;  cfg%num_spherical = num_spherical
+    cfg%num_levels = num_levels
+    cfg%dt_atmos = real(dt_integer, c_double)
+    cfg%damping_order = damping_order;  cfg%damping_order_vor = damping_order_vor;  cfg%damping_order_div = damping_order_div
+    cfg%damping_coeff = damping_coeff;  cfg%damping_coeff_vor = damping_coeff_vor;  cfg%damping_coeff_div = damping_coeff_div
+    cfg%eddy_sponge_coeff = eddy_sponge_coeff;  cfg%zmu_sponge_coeff = zmu_sponge_coeff;  cfg%zmv_sponge_coeff = zmv_sponge_coeff
+    cfg%do_mass_correction = l2i(do_mass_correction);  cfg%do_energy_correction = l2i(do_energy_correction)
+    cfg%do_water_correction = l2i(do_water_correction)
+    cfg%use_virtual_temperature = l2i(use_virtual_temperature);  cfg%use_implicit = l2i(use_implicit)
+    cfg%robert_coeff = robert_coeff;  cfg%raw_filter_coeff = raw_filter_coeff;  cfg%alpha_implicit = alpha_implicit
+    select case (trim(vert_coord_option))
+      case ('even_sigma');   cfg%vert_coord_option = 0
+      case ('uneven_sigma'); cfg%vert_coord_option = 1
+      case ('hybrid');       cfg%vert_coord_option = 3
+      case default
+        call error_mesg('atmosphere_init', '"'//trim(vert_coord_option)//'" is not a valid value for vert_coord_option '// &
+                        '(input: pass pk / bk through cfg%pk, cfg%bk)', FATAL)
+    end select
+    cfg%scale_heights = scale_heights;  cfg%surf_res = surf_res;  cfg%exponent = exponent;  cfg%p_press = p_press;  cfg%p_sigma = p_sigma
+    cfg%vert_advect_uv = advect_id(vert_advect_uv);  cfg%vert_advect_t = advect_id(vert_advect_t)
+    cfg%reference_sea_level_press = reference_sea_level_press;  cfg%initial_sphum = initial_sphum
+    cfg%water_correction_limit = water_correction_limit
+    cfg%valid_range_t(1) = valid_range_t(1);  cfg%valid_range_t(2) = valid_range_t(2)
+    cfg%initial_temperature = initial_temperature
+    cfg%num_tracers = num_tracers
+    cfg%tracer_robert_coeff = -1.0_c_double              ! field_table robert_filter default: the model's robert_coeff
+    cfg%no_forcing = l2i(no_forcing);  cfg%do_conserve_energy = l2i(do_conserve_energy)
+    cfg%t_zero = t_zero;  cfg%t_strat = t_strat;  cfg%delh = delh;  cfg%delv = delv;  cfg%eps = eps;  cfg%sigma_b = sigma_b;  cfg%P00 = P00
+    cfg%ka = ka;  cfg%ks = ks;  cfg%kf = kf;  cfg%trflux = trflux;  cfg%trsink = trsink
+    cfg%radius = radius;  cfg%omega = omega;  cfg%grav = grav;  cfg%rdgas = rdgas;  cfg%kappa = kappa
+    cfg%pk = c_null_ptr;  cfg%bk = c_null_ptr
+
+    !---------------------------------------------------------------- one process per GPU: the NCCL id comes from the root PE
+    nccl_id = c_null_char
+    if (mpp_npes() > 1) then
+      if (mpp_pe() == mpp_root_pe()) then
+        rc = isca_b200_nccl_unique_id(nccl_id)
+        if (rc /= 0) call fatal('atmosphere_init')
+      end if
+      call mpp_broadcast(nccl_id, 128, mpp_root_pe())
+    end if
+
+    if (idealized_moist_model) then
+      rc = isca_b200_physics_default_config(pcfg)        ! scheme namelists: read and forwarded by idealized_moist_nml_to_config
+      rc = isca_b200_moist_default_config(mcfg)
+      call idealized_moist_nml_to_config(pcfg, mcfg)
+      if (mpp_npes() > 1) then
+        rc = isca_b200_moist_create_ranked(cfg, pcfg, mcfg, int(mpp_pe(), c_int), int(mpp_npes(), c_int), c_loc(nccl_id), hm)
+      else
+        rc = isca_b200_moist_create_ranked(cfg, pcfg, mcfg, 0_c_int, 1_c_int, c_null_ptr, hm)
+      end if
+      if (rc /= 0) call fatal_moist('atmosphere_init')
+      h = isca_b200_moist_dycore(hm)
+    else
+      if (mpp_npes() > 1) then
+        rc = isca_b200_create(cfg, int(mpp_pe(), c_int), int(mpp_npes(), c_int), c_loc(nccl_id), h)
+      else
+        rc = isca_b200_create(cfg, 0_c_int, 1_c_int, c_null_ptr, h)
+      end if
+      if (rc /= 0) call fatal('atmosphere_init')
+    end if
+
+    ! peer-memory transposes inside one node: exchange the CUDA IPC handles of the Fourier buffers (128 bytes per PE)
+    if (mpp_npes() > 1) then
+      allocate (ipc_mine(128), ipc_all(128*mpp_npes()))
+      rc = isca_b200_ipc_handles(h, ipc_mine)
+      if (rc /= 0) call fatal('atmosphere_init')
+      call mpp_gather(ipc_mine, ipc_all)                 ! every PE needs all handles: gather on the root, then broadcast
+      call mpp_broadcast(ipc_all, 128*mpp_npes(), mpp_root_pe())
+      rc = isca_b200_set_peer_handles(h, ipc_all)
+      if (rc /= 0) call fatal('atmosphere_init')
+      deallocate (ipc_mine, ipc_all)
+    end if
+
+    allocate (buf3(is:ie, js:je, num_levels + 1), buf2(is:ie, js:je))
+    allocate (sbuf3(ms:me, ns:ne, num_levels), sbuf2(ms:me, ns:ne))
+
+    !---------------------------------------------------------------- restart (atmosphere.F90:197-223, spectral_dynamics.F90:509-575) or cold start
+    file = 'INPUT/atmosphere.res.nc'
+    if (file_exist(trim(file)) .and. file_exist('INPUT/spectral_dynamics.res.nc')) then
+      call field_size(trim(file), 'ug', siz)
+      if (lon_max /= siz(1) .or. lat_max /= siz(2)) then
+        write (message, *) 'Resolution of restart data does not match resolution specified on namelist. Restart data: lon_max=', &
+                           siz(1), ', lat_max=', siz(2), '  Namelist: lon_max=', lon_max, ', lat_max=', lat_max
+        call error_mesg('atmosphere_init', message, FATAL)
+      end if
+      ! the library shards zonal wavenumbers in snake order (balanced triangle rows), spec_mpp_mod in contiguous blocks: on several PEs the
+      ! spectral restart arrays have to be redistributed (mpp_global_field + a local pick of the library's m list, isca_b200_decomposition)
+      if (mpp_npes() > 1) call error_mesg('atmosphere_init', 'isca_b200 shim: restart of the spectral state on several PEs needs the '// &
+                                          'redistribution step described in INTEGRATION.md section 3', FATAL)
+      call nullify_domain()
+      call read_data(trim(file), 'time_pointers', time_pointers)
+      previous = int(time_pointers(1));  current = int(time_pointers(2))
+      do nt = 1, num_time_levels
+        slot = nt - 1
+        call upload_grid_level(trim(file), nt, slot)
+        call upload_spectral_level('INPUT/spectral_dynamics.res.nc', nt, slot)
+      end do
+      call read_data('INPUT/spectral_dynamics.res.nc', 'vorg', buf3(:,:,1:num_levels), grid_domain)
+      block
+        real(c_double), allocatable :: divg(:,:,:)
+        allocate (divg(is:ie, js:je, num_levels))
+        call read_data('INPUT/spectral_dynamics.res.nc', 'divg', divg, grid_domain)
+        rc = isca_b200_set_vor_div_grid(h, buf3(:,:,1:num_levels), divg)
+        deallocate (divg)
+      end block
+      if (rc /= 0) call fatal('atmosphere_init')
+      rc = isca_b200_set_time_pointers(h, int(previous - 1, c_int), int(current - 1, c_int))
+      if (rc /= 0) call fatal('atmosphere_init')
+    else
+      previous = 1;  current = 1
+      rc = isca_b200_cold_start(h)                       ! spectral_initialize_fields.F90:45-135 on the device
+      if (rc /= 0) call fatal('atmosphere_init')
+    end if
+
+    if (idealized_moist_model) then
+      rc = isca_b200_moist_init(hm)                      ! idealized_moist_phys_init
+      if (rc /= 0) call fatal_moist('atmosphere_init')
+      call get_time(Time, seconds, days)
+      rc = isca_b200_moist_set_time(hm, int(days, c_long_long), int(seconds, c_int))
+    end if
+
+    call register_dynamics_diagnostics(Time)
+    module_is_initialized = .true.
+  end subroutine atmosphere_init
+
+  !=================================================================================================================================
+  subroutine atmosphere(Time)
+    type(time_type), intent(in) :: Time
+    type(time_type) :: Time_next
+    integer :: rc, future
+
+    if (.not. module_is_initialized) call error_mesg('atmosphere', 'atmosphere module is not initialized', FATAL)
+    Time_next = Time + Time_step
+
+    ! physics (hs_forcing or idealized_moist_phys) + spectral_dynamics + compute_pressures_and_heights(future) + the time-level swap,
+    ! all on the device (atmosphere.F90:276-352)
+    if (idealized_moist_model) then
+      rc = isca_b200_moist_step(hm, 1_c_int)
+      if (rc /= 0) call fatal_moist('atmosphere')
+    else
+      rc = isca_b200_step(h, 1_c_int)
+      if (rc /= 0) call fatal('atmosphere')              ! e.g. 'temperatures out of valid range'
+    end if
+
+    if (previous == current) then
+      future = num_time_levels + 1 - current
+    else
+      future = previous
+    end if
+    previous = current
+    current = future
+
+    call send_dynamics_diagnostics(Time_next)            ! spectral_diagnostics (spectral_dynamics.F90:1709-1867): fields that are due
+  end subroutine atmosphere
+
+  !=================================================================================================================================
+  subroutine atmosphere_end
+    integer :: nt, rc
+    character(len=64) :: file
+
+    if (.not. module_is_initialized) return
+    ! restart files with the reference's variable names (atmosphere.F90:362-375, spectral_dynamics.F90:1502-1531)
+    file = 'RESTART/atmosphere.res'
+    call nullify_domain()
+    call write_data(trim(file), 'time_pointers', (/real(previous), real(current)/))
+    do nt = 1, num_time_levels
+      rc = isca_b200_get_field(h, ISCA_F_U, int(nt - 1, c_int), buf3);  call write_data(trim(file), 'ug', buf3(:,:,1:num_levels), grid_domain)
+      rc = isca_b200_get_field(h, ISCA_F_V, int(nt - 1, c_int), buf3);  call write_data(trim(file), 'vg', buf3(:,:,1:num_levels), grid_domain)
+      rc = isca_b200_get_field(h, ISCA_F_T, int(nt - 1, c_int), buf3);  call write_data(trim(file), 'tg', buf3(:,:,1:num_levels), grid_domain)
+      rc = isca_b200_get_field(h, ISCA_F_PS, int(nt - 1, c_int), buf2); call write_data(trim(file), 'psg', buf2, grid_domain)
+      if (num_tracers == 1) then
+        rc = isca_b200_get_field(h, ISCA_F_TRACER0, int(nt - 1, c_int), buf3)
+        call write_data(trim(file), 'sphum', buf3(:,:,1:num_levels), grid_domain)
+      end if
+    end do
+    rc = isca_b200_get_field(h, ISCA_F_WG_FULL, ISCA_LEVEL_CURRENT, buf3);  call write_data(trim(file), 'wg_full', buf3(:,:,1:num_levels), grid_domain)
+    file = 'RESTART/spectral_dynamics.res'
+    if (mpp_npes() > 1) call error_mesg('atmosphere_end', 'isca_b200 shim: the spectral restart on several PEs needs the redistribution '// &
+                                        'step described in INTEGRATION.md section 3', FATAL)
+    do nt = 1, num_time_levels
+      rc = isca_b200_get_spectral(h, ISCA_S_VOR, int(nt - 1, c_int), sbuf3)
+      call write_data(trim(file), 'vors_real', real(sbuf3), spectral_domain);  call write_data(trim(file), 'vors_imag', aimag(sbuf3), spectral_domain)
+      rc = isca_b200_get_spectral(h, ISCA_S_DIV, int(nt - 1, c_int), sbuf3)
+      call write_data(trim(file), 'divs_real', real(sbuf3), spectral_domain);  call write_data(trim(file), 'divs_imag', aimag(sbuf3), spectral_domain)
+      rc = isca_b200_get_spectral(h, ISCA_S_T, int(nt - 1, c_int), sbuf3)
+      call write_data(trim(file), 'ts_real', real(sbuf3), spectral_domain);    call write_data(trim(file), 'ts_imag', aimag(sbuf3), spectral_domain)
+      rc = isca_b200_get_spectral(h, ISCA_S_LNPS, int(nt - 1, c_int), sbuf2)
+      call write_data(trim(file), 'ln_ps_real', real(sbuf2), spectral_domain); call write_data(trim(file), 'ln_ps_imag', aimag(sbuf2), spectral_domain)
+    end do
+    rc = isca_b200_get_field(h, ISCA_F_VOR, ISCA_LEVEL_CURRENT, buf3);  call write_data(trim(file), 'vorg', buf3(:,:,1:num_levels), grid_domain)
+    rc = isca_b200_get_field(h, ISCA_F_DIV, ISCA_LEVEL_CURRENT, buf3);  call write_data(trim(file), 'divg', buf3(:,:,1:num_levels), grid_domain)
+
+    call set_domain(grid_domain)
+    if (idealized_moist_model) then
+      rc = isca_b200_moist_destroy(hm)                   ! also destroys the dynamical core it owns
+    else
+      rc = isca_b200_destroy(h)
+    end if
+    h = c_null_ptr;  hm = c_null_ptr
+    deallocate (buf3, buf2, sbuf3, sbuf2)
+    module_is_initialized = .false.
+  end subroutine atmosphere_end
+
+  !=================================================================================================================================
+  ! helpers
+  !=================================================================================================================================
+  integer(c_int32_t) function l2i(flag)
+    logical, intent(in) :: flag
+    l2i = merge(1_c_int32_t, 0_c_int32_t, flag)
+  end function l2i
+
+  integer(c_int32_t) function advect_id(name)
+    character(len=*), intent(in) :: name
+    if (trim(name) /= 'second_centered') &
+      call error_mesg('atmosphere_init', '"'//trim(name)//'" is not a supported vertical advection scheme of u, v, T (second_centered)', FATAL)
+    advect_id = 0
+  end function advect_id
+
+  !> one time level of INPUT/atmosphere.res.nc -> device (set_grid_state takes the reference's (lon, lat, lev) arrays unchanged)
+  subroutine upload_grid_level(file, nt, slot)
+    character(len=*), intent(in) :: file
+    integer, intent(in) :: nt, slot
+    real(c_double), allocatable, target :: u(:,:,:), v(:,:,:), t(:,:,:), q(:,:,:), ps(:,:)
+    integer :: rc
+    allocate (u(is:ie, js:je, num_levels), v(is:ie, js:je, num_levels), t(is:ie, js:je, num_levels), ps(is:ie, js:je))
+    call read_data(file, 'ug', u, grid_domain, timelevel=nt)
+    call read_data(file, 'vg', v, grid_domain, timelevel=nt)
+    call read_data(file, 'tg', t, grid_domain, timelevel=nt)
+    call read_data(file, 'psg', ps, grid_domain, timelevel=nt)
+    if (num_tracers == 1) then
+      allocate (q(is:ie, js:je, num_levels))
+      call read_data(file, 'sphum', q, grid_domain, timelevel=nt)
+      rc = isca_b200_set_grid_state(h, int(slot, c_int), u, v, t, ps, c_loc(q))
+    else
+      rc = isca_b200_set_grid_state(h, int(slot, c_int), u, v, t, ps, c_null_ptr)
+    end if
+    if (rc /= 0) call fatal('atmosphere_init')
+  end subroutine upload_grid_level
+
+  !> one time level of INPUT/spectral_dynamics.res.nc -> device (real / imaginary parts as the reference stores them)
+  subroutine upload_spectral_level(file, nt, slot)
+    character(len=*), intent(in) :: file
+    integer, intent(in) :: nt, slot
+    real, allocatable :: re3(:,:,:), im3(:,:,:), re2(:,:), im2(:,:)
+    complex(c_double_complex), allocatable :: vo(:,:,:), di(:,:,:), ts(:,:,:), lp(:,:)
+    integer :: rc
+    allocate (re3(ms:me, ns:ne, num_levels), im3(ms:me, ns:ne, num_levels), re2(ms:me, ns:ne), im2(ms:me, ns:ne))
+    allocate (vo(ms:me, ns:ne, num_levels), di(ms:me, ns:ne, num_levels), ts(ms:me, ns:ne, num_levels), lp(ms:me, ns:ne))
+    call read_data(file, 'vors_real', re3, spectral_domain, timelevel=nt);  call read_data(file, 'vors_imag', im3, spectral_domain, timelevel=nt)
+    vo = cmplx(re3, im3, kind=c_double_complex)
+    call read_data(file, 'divs_real', re3, spectral_domain, timelevel=nt);  call read_data(file, 'divs_imag', im3, spectral_domain, timelevel=nt)
+    di = cmplx(re3, im3, kind=c_double_complex)
+    call read_data(file, 'ts_real', re3, spectral_domain, timelevel=nt);    call read_data(file, 'ts_imag', im3, spectral_domain, timelevel=nt)
+    ts = cmplx(re3, im3, kind=c_double_complex)
+    call read_data(file, 'ln_ps_real', re2, spectral_domain, timelevel=nt); call read_data(file, 'ln_ps_imag', im2, spectral_domain, timelevel=nt)
+    lp = cmplx(re2, im2, kind=c_double_complex)
+    rc = isca_b200_set_spectral_state(h, int(slot, c_int), vo, di, ts, lp)
+    if (rc /= 0) call fatal('atmosphere_init')
+  end subroutine upload_spectral_level
+
+  !> idealized_moist_phys_nml, mixed_layer_nml, vert_turb_driver_nml, surface_flux_nml, diffusivity_nml, qe_moist_convection_nml,
+  !! lscale_cond_nml, two_stream_gray_rad_nml, damping_driver_nml, sat_vapor_pres_nml -> the two configuration structs.
+  !! The namelists are declared here under the reference's names with the reference's defaults and copied field by field.
+  subroutine idealized_moist_nml_to_config(pcfg, mcfg)
+    type(isca_physics_config), intent(inout) :: pcfg
+    type(isca_moist_config), intent(inout) :: mcfg
+    ! idealized_moist_phys_nml (idealized_moist_phys.F90:109-183)
+    logical :: turb = .false., do_virtual = .false., two_stream_gray = .true., do_rrtm_radiation = .false., do_damping = .false., &
+               mixed_layer_bc = .false., do_simple = .false.
+    character(len=256) :: convection_scheme = 'UNSET'
+    real :: roughness_heat = 0.05, roughness_moist = 0.05, roughness_mom = 0.05
+    namelist /idealized_moist_phys_nml/ turb, do_virtual, two_stream_gray, do_rrtm_radiation, do_damping, mixed_layer_bc, do_simple, &
+                                        convection_scheme, roughness_heat, roughness_moist, roughness_mom
+    ! mixed_layer_nml (mixed_layer.F90:84-140)
+    real :: depth = 40.0, albedo_value = 0.06
+    logical :: evaporation = .true.
+    namelist /mixed_layer_nml/ depth, albedo_value, evaporation
+    ! vert_turb_driver_nml (vert_turb_driver.F90:100-118)
+    logical :: use_tau = .true.
+    real :: constant_gust = 1.0
+    namelist /vert_turb_driver_nml/ use_tau, constant_gust
+    ! lscale_cond_nml, qe_moist_convection_nml, two_stream_gray_rad_nml, damping_driver_nml (values the test cases set)
+    real :: hc = 1.0
+    logical :: do_evap = .false.
+    namelist /lscale_cond_nml/ hc, do_evap
+    real :: tau_bm = 7200., rhbm = 0.8, Tmin = 173., Tmax = 335., val_inc = 0.01
+    namelist /qe_moist_convection_nml/ tau_bm, rhbm, Tmin, Tmax, val_inc
+    real :: solar_constant = 1360.0, del_sol = 1.4, del_sw = 0.0, ir_tau_eq = 6.0, ir_tau_pole = 1.5, atm_abs = 0.0, sw_diff = 0.0, &
+            linear_tau = 0.1, wv_exponent = 4.0, solar_exponent = 4.0, odp = 1.0
+    character(len=32) :: rad_scheme = 'frierson'
+    namelist /two_stream_gray_rad_nml/ solar_constant, del_sol, del_sw, ir_tau_eq, ir_tau_pole, atm_abs, sw_diff, linear_tau, wv_exponent, &
+                                       solar_exponent, odp, rad_scheme
+    real :: trayfric = 0., sponge_pbottom = 50.
+    logical :: do_conserve_energy_damp = .false.
+    namelist /damping_driver_nml/ trayfric, sponge_pbottom
+    integer :: nml_unit, io
+#ifdef INTERNAL_FILE_NML
+    read (input_nml_file, nml=idealized_moist_phys_nml, iostat=io)
+    read (input_nml_file, nml=mixed_layer_nml, iostat=io)
+    read (input_nml_file, nml=vert_turb_driver_nml, iostat=io)
+    read (input_nml_file, nml=lscale_cond_nml, iostat=io)
+    read (input_nml_file, nml=qe_moist_convection_nml, iostat=io)
+    read (input_nml_file, nml=two_stream_gray_rad_nml, iostat=io)
+    read (input_nml_file, nml=damping_driver_nml, iostat=io)
+#else
+    nml_unit = open_namelist_file()
+    read (nml_unit, idealized_moist_phys_nml, iostat=io);  rewind(nml_unit)
+    read (nml_unit, mixed_layer_nml, iostat=io);           rewind(nml_unit)
+    read (nml_unit, vert_turb_driver_nml, iostat=io);      rewind(nml_unit)
+    read (nml_unit, lscale_cond_nml, iostat=io);           rewind(nml_unit)
+    read (nml_unit, qe_moist_convection_nml, iostat=io);   rewind(nml_unit)
+    read (nml_unit, two_stream_gray_rad_nml, iostat=io);   rewind(nml_unit)
+    read (nml_unit, damping_driver_nml, iostat=io)
+    call close_file(nml_unit)
+#endif
+    if (.not. (turb .and. mixed_layer_bc)) &
+      call error_mesg('atmosphere_init', 'isca_b200: idealized_moist_phys needs turb = .true. and mixed_layer_bc = .true.', FATAL)
+    select case (trim(convection_scheme))
+      case ('NONE', 'none');              mcfg%convection_scheme = 0
+      case ('SIMPLE_BETTS_MILLER');       mcfg%convection_scheme = 1
+      case ('DRY', 'dry');                mcfg%convection_scheme = 2
+      case ('FULL_BETTS_MILLER');         mcfg%convection_scheme = 3
+      case default
+        call error_mesg('atmosphere_init', '"'//trim(convection_scheme)//'" is not a convection scheme of this library', FATAL)
+    end select
+    mcfg%do_damping = l2i(do_damping);  mcfg%use_tau = l2i(use_tau)
+    mcfg%roughness_mom = roughness_mom;  mcfg%roughness_heat = roughness_heat;  mcfg%roughness_moist = roughness_moist
+    mcfg%mixed_layer_depth = depth;  mcfg%albedo_value = albedo_value;  mcfg%constant_gust = constant_gust
+    pcfg%evaporation = l2i(evaporation)
+    pcfg%hc = hc;  pcfg%do_evap = l2i(do_evap)
+    pcfg%tau_bm = tau_bm;  pcfg%rhbm = rhbm;  pcfg%Tmin = Tmin;  pcfg%Tmax = Tmax;  pcfg%val_inc = val_inc
+    pcfg%solar_constant = solar_constant;  pcfg%del_sol = del_sol;  pcfg%del_sw = del_sw;  pcfg%ir_tau_eq = ir_tau_eq
+    pcfg%ir_tau_pole = ir_tau_pole;  pcfg%atm_abs = atm_abs;  pcfg%sw_diff = sw_diff;  pcfg%linear_tau = linear_tau
+    pcfg%wv_exponent = wv_exponent;  pcfg%solar_exponent = solar_exponent;  pcfg%odp = odp
+    select case (trim(rad_scheme))
+      case ('frierson', 'FRIERSON');   pcfg%rad_scheme = 0
+      case ('byrne', 'BYRNE');         pcfg%rad_scheme = 1
+      case ('geen', 'GEEN');           pcfg%rad_scheme = 2
+      case ('schneider', 'SCHNEIDER'); pcfg%rad_scheme = 3
+      case default
+        call error_mesg('two_stream_gray_rad', '"'//trim(rad_scheme)//'" is not a valid radiation scheme.', FATAL)
+    end select
+    pcfg%trayfric = trayfric;  pcfg%sponge_pbottom = sponge_pbottom
+    pcfg%use_virtual_temp = l2i(do_virtual);  pcfg%surface_flux_do_simple = l2i(do_simple);  pcfg%diffusivity_do_simple = l2i(do_simple)
+    pcfg%grav = grav;  pcfg%rdgas = rdgas;  pcfg%cp_air = rdgas/kappa
+    if (do_rrtm_radiation .and. two_stream_gray) &
+      call error_mesg('atmosphere_init', 'do_rrtm_radiation and two_stream_gray cannot both be .true.', FATAL)
+    ! do_rrtm_radiation: rrtm_radiation_nml is forwarded with isca_b200_moist_use_rrtm (include/isca_b200_rrtm.h) by the site's copy of
+    ! this routine; the ozone field read by interpolator_mod goes through isca_b200_moist_set_ozone whenever the alarm is due
+  end subroutine idealized_moist_nml_to_config
+
+  !> axes and fields of diag_manager module 'dynamics' (spectral_dynamics.F90:1541-1700), registered under the reference's names
+  subroutine register_dynamics_diagnostics(Time)
+    type(time_type), intent(in) :: Time
+    integer :: id_lon, id_lat, id_pfull, id_phalf, k, j, i
+    integer, dimension(3) :: axes_3d_full, axes_3d_half
+    real, allocatable :: lon(:), lat(:), p_full_ref(:), p_half_ref(:), tab(:)
+    integer :: rc
+    allocate (lon(lon_max), lat(lat_max), p_full_ref(num_levels), p_half_ref(num_levels + 1), tab(max(lon_max, lat_max, num_levels + 1)))
+    rc = isca_b200_get_table_f(3, lon, lon_max)                       ! ISCA_TB_DEG_LON
+    rc = isca_b200_get_table_f(2, lat, lat_max)                       ! ISCA_TB_DEG_LAT
+    rc = isca_b200_get_table_f(4, p_half_ref, num_levels + 1)         ! pk
+    rc = isca_b200_get_table_f(5, tab, num_levels + 1)                ! bk
+    p_half_ref = (p_half_ref + tab(1:num_levels + 1)*reference_sea_level_press)*0.01
+    do k = 1, num_levels
+      p_full_ref(k) = 0.5*(p_half_ref(k) + p_half_ref(k + 1))
+    end do
+    id_lon = diag_axis_init('lon', lon, 'degrees_E', 'x', 'longitude', set_name=mod_name, Domain2=grid_domain)
+    id_lat = diag_axis_init('lat', lat, 'degrees_N', 'y', 'latitude', set_name=mod_name, Domain2=grid_domain)
+    id_phalf = diag_axis_init('phalf', p_half_ref, 'hPa', 'z', 'approx half pressure level', direction=-1, set_name=mod_name)
+    id_pfull = diag_axis_init('pfull', p_full_ref, 'hPa', 'z', 'approx full pressure level', direction=-1, set_name=mod_name, edges=id_phalf)
+    axes_3d_full = (/id_lon, id_lat, id_pfull/);  axes_3d_half = (/id_lon, id_lat, id_phalf/)
+    id_ps    = register_diag_field(mod_name, 'ps',    (/id_lon, id_lat/), Time, 'surface pressure', 'pascals')
+    id_u     = register_diag_field(mod_name, 'ucomp', axes_3d_full, Time, 'zonal wind component', 'm/sec')
+    id_v     = register_diag_field(mod_name, 'vcomp', axes_3d_full, Time, 'meridional wind component', 'm/sec')
+    id_t     = register_diag_field(mod_name, 'temp',  axes_3d_full, Time, 'temperature', 'deg_k')
+    id_vor   = register_diag_field(mod_name, 'vor',   axes_3d_full, Time, 'Vorticity', 'sec**-1')
+    id_div   = register_diag_field(mod_name, 'div',   axes_3d_full, Time, 'Divergence', 'sec**-1')
+    id_omega = register_diag_field(mod_name, 'omega', axes_3d_full, Time, 'dp/dt vertical velocity', 'Pa/sec')
+    id_sphum = register_diag_field(mod_name, 'sphum', axes_3d_full, Time, 'specific humidity', 'kg/kg')
+    id_pres_full = register_diag_field(mod_name, 'pres_full', axes_3d_full, Time, 'pressure at full model levels', 'pascals')
+    id_pres_half = register_diag_field(mod_name, 'pres_half', axes_3d_half, Time, 'pressure at half model levels', 'pascals')
+    id_zfull = register_diag_field(mod_name, 'height',      axes_3d_full, Time, 'geopotential height at full model levels', 'm')
+    id_zhalf = register_diag_field(mod_name, 'height_half', axes_3d_half, Time, 'geopotential height at half model levels', 'm')
+    id_pk = register_static_field(mod_name, 'pk', (/id_phalf/), 'vertical coordinate pressure values', 'pascals')
+    id_bk = register_static_field(mod_name, 'bk', (/id_phalf/), 'vertical coordinate sigma values', 'none')
+    deallocate (lon, lat, p_full_ref, p_half_ref, tab)
+  contains
+    integer function isca_b200_get_table_f(table_id, dst, n)
+      integer, intent(in) :: table_id, n
+      real, intent(out) :: dst(:)
+      real(c_double), allocatable :: tmp(:)
+      interface
+        integer(c_int) function isca_b200_get_table(hh, tid, host, count) bind(C, name="isca_b200_get_table")
+          import :: c_int, c_ptr, c_double
+          type(c_ptr), value :: hh
+          integer(c_int), value :: tid, count
+          real(c_double), intent(out) :: host(*)
+        end function isca_b200_get_table
+      end interface
+      allocate (tmp(n))
+      isca_b200_get_table_f = isca_b200_get_table(h, int(table_id, c_int), tmp, int(n, c_int))
+      dst(1:n) = tmp
+      deallocate (tmp)
+    end function isca_b200_get_table_f
+  end subroutine register_dynamics_diagnostics
+
+  !> send_data for the registered fields whose output is due at Time_next (only those are copied off the device)
+  subroutine send_dynamics_diagnostics(Time_next)
+    type(time_type), intent(in) :: Time_next
+    logical :: used
+    integer :: rc
+    if (id_ps > 0) then
+      if (need_data(id_ps, Time_next)) then
+        rc = isca_b200_get_field(h, ISCA_F_PS, ISCA_LEVEL_CURRENT, buf2);  used = send_data(id_ps, buf2, Time_next)
+      end if
+    end if
+    call send3(id_u, ISCA_F_U, num_levels);          call send3(id_v, ISCA_F_V, num_levels)
+    call send3(id_t, ISCA_F_T, num_levels);          call send3(id_vor, ISCA_F_VOR, num_levels)
+    call send3(id_div, ISCA_F_DIV, num_levels);      call send3(id_omega, ISCA_F_WG_FULL, num_levels)
+    call send3(id_pres_full, ISCA_F_P_FULL, num_levels);  call send3(id_pres_half, ISCA_F_P_HALF, num_levels + 1)
+    call send3(id_zfull, ISCA_F_Z_FULL, num_levels);      call send3(id_zhalf, ISCA_F_Z_HALF, num_levels + 1)
+    if (num_tracers == 1) call send3(id_sphum, ISCA_F_TRACER0, num_levels)
+  contains
+    subroutine send3(id, field, nlev)
+      integer, intent(in) :: id, nlev
+      integer(c_int), intent(in) :: field
+      if (id <= 0) return
+      if (.not. need_data(id, Time_next)) return
+      rc = isca_b200_get_field(h, field, ISCA_LEVEL_CURRENT, buf3)
+      if (rc /= 0) call fatal('spectral_diagnostics')
+      used = send_data(id, buf3(:,:,1:nlev), Time_next)
+    end subroutine send3
+  end subroutine send_dynamics_diagnostics
+
+  subroutine fatal(routine)
+    character(len=*), intent(in) :: routine
+    call error_mesg(routine, isca_c_string(isca_b200_last_error(h)), FATAL)
+  end subroutine fatal
+
+  subroutine fatal_moist(routine)
+    character(len=*), intent(in) :: routine
+    call error_mesg(routine, isca_c_string(isca_b200_moist_last_error(hm)), FATAL)
+  end subroutine fatal_moist
+
+end module atmosphere_mod
