@@ -106,10 +106,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m isca_b200.build` "
+    path = os.environ.get("ISCA_B200_LIB", LIB_PATH)     # development only: a differently tuned build of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python -m isca_b200.build` "
                            "(isca_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     dp = C.POINTER(C.c_double)
     vp = C.c_void_p
     lib.isca_b200_default_config.argtypes = [C.POINTER(IscaConfigStruct)]

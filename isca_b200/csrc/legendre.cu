@@ -124,29 +124,40 @@ legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __res
     }
   }
 
-  // epilogue: south = even - odd, north = even + odd
+  // epilogue: south = even - odd, north = even + odd.  The CTA's two JT x 32 output tiles are staged in shared memory (the pipeline
+  // buffers are free now) so that every row leaves as ONE 256-byte run written by a whole warp -- full lines for HBM and, on several
+  // GPUs, full NVLink packets for the stores into the lat-owner buffer of the rank that owns the latitude (the fragment layout itself
+  // would give 64-byte pieces per row).  Row stride 40 doubles: the 16-byte fragment stores of a quarter warp fall into distinct banks.
+  constexpr int OS = LEG_CT + 8;
+  __syncthreads();
+  double* outS = reinterpret_cast<double*>(leg_smem_raw);
+  double* outN = outS + JT * OS;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    const int jh = jt0 + wj * WTJ + mt * 8 + (lane >> 2);
-    const int js = jh, jn = g.J - 1 - jh;
-    double *rowS, *rowN;
-    if (g.p2p) {        // store into the lat-owner buffer of the rank that owns the latitude (peer memory over NVLink)
-      const int ss = js / g.Jloc, sn = jn / g.Jloc;
-      const size_t prow = (size_t)(g.roff[g.rank] + mi) * g.Jloc;
-      rowS = g.peerB[ss] + (prow + (js - ss * g.Jloc)) * (size_t)C;
-      rowN = g.peerB[sn] + (prow + (jn - sn * g.Jloc)) * (size_t)C;
-    } else {
-      rowS = four + fourA_index(g, mi, js, C);
-      rowN = four + fourA_index(g, mi, jn, C);
-    }
+    const int r = wj * WTJ + mt * 8 + (lane >> 2);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      const int c = c0 + wc * WTC + nt * 8 + (lane & 3) * 2;
+      const int c = wc * WTC + nt * 8 + (lane & 3) * 2;
       double e0 = acc[0][mt][nt][0], e1 = acc[0][mt][nt][1];
       double o0 = acc[1][mt][nt][0], o1 = acc[1][mt][nt][1];
-      *reinterpret_cast<double2*>(rowS + c) = make_double2(e0 - o0, e1 - o1);
-      *reinterpret_cast<double2*>(rowN + c) = make_double2(e0 + o0, e1 + o1);
+      *reinterpret_cast<double2*>(outS + r * OS + c) = make_double2(e0 - o0, e1 - o1);
+      *reinterpret_cast<double2*>(outN + r * OS + c) = make_double2(e0 + o0, e1 + o1);
     }
+  }
+  __syncthreads();
+  for (int rr = warp; rr < 2 * JT; rr += 4) {
+    const int north = rr >= JT, r = north ? rr - JT : rr;
+    const int jh = jt0 + r;
+    const int j = north ? g.J - 1 - jh : jh;
+    double* row;
+    if (g.p2p) {        // peer memory over NVLink
+      const int sj = j / g.Jloc;
+      const size_t prow = (size_t)(g.roff[g.rank] + mi) * g.Jloc;
+      row = g.peerB[sj] + (prow + (j - sj * g.Jloc)) * (size_t)C;
+    } else {
+      row = four + fourA_index(g, mi, j, C);
+    }
+    row[c0 + lane] = (north ? outN : outS)[r * OS + lane];
   }
 }
 
@@ -192,11 +203,13 @@ legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __res
 
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  const int c0 = (ct_begin + blockIdx.x) * LEG_CT;
-  const int mi = blockIdx.y;
+  // grid: x = n tile (fastest), y = column tile, z = m.  The n tiles of one (m, column tile) read the same Fourier rows X; launched
+  // next to each other they share them through L2 instead of fetching them from HBM once per tile (ncu round 1: 2.4x the algorithmic bytes)
+  const int c0 = (ct_begin + blockIdx.y) * LEG_CT;
+  const int mi = blockIdx.z;
   const int m = g.m_of[mi];
   const int Nm = g.M - m + 2;
-  const int nt0 = blockIdx.z * FWD_NT;
+  const int nt0 = blockIdx.x * FWD_NT;
   if (nt0 >= Nm) return;
   const int row0 = g.off[mi];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -279,7 +292,7 @@ void launch_legendre_fwd(const DevTables& t, const double* four, double2* spec, 
                          const unsigned char* lev_trunc, cudaStream_t st, int ct_begin, int ct_count) {
   const GeomDev& g = t.g;
   const int C = 2 * Lp;
-  dim3 grid(ct_count < 0 ? C / LEG_CT - ct_begin : ct_count, g.nm, (g.M + 2 + FWD_NT - 1) / FWD_NT);
+  dim3 grid((g.M + 2 + FWD_NT - 1) / FWD_NT, ct_count < 0 ? C / LEG_CT - ct_begin : ct_count, g.nm);
   if (false) {                     // KC = 32 measured slower (fewer resident CTAs): profiles/r01_experiments.md
     constexpr int KC = 32;
     const size_t smem = sizeof(double) * (2 * 2 * KC * (LEG_CT + 4) + 2 * 2 * (FWD_NT / 2) * (KC + 4));

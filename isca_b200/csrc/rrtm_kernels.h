@@ -63,7 +63,21 @@ struct DevRed {                      // per-level sum over the g-points: warp sh
 };
 
 constexpr int LW_THREADS = 160, SW_THREADS = 128;
-constexpr int LW_TILE = 8, SW_TILE = 8;       // = the batch of warp_sum8      // layers whose (layer, band) term lists are resident in shared memory at a time
+// tile = layers whose term lists are resident at a time (<= 8 = the batch of warp_sum8); MINB = CTAs per SM the register allocation
+// is held to.  Tunable at compile time for the occupancy experiments of tools/rrtm_variants.sh (profiles/r02/r02_experiments.md).
+#ifndef ISCA_LW_TILE
+#define ISCA_LW_TILE 8
+#endif
+#ifndef ISCA_SW_TILE
+#define ISCA_SW_TILE 8
+#endif
+#ifndef ISCA_LW_MINB
+#define ISCA_LW_MINB 1
+#endif
+#ifndef ISCA_SW_MINB
+#define ISCA_SW_MINB 1
+#endif
+constexpr int LW_TILE = ISCA_LW_TILE, SW_TILE = ISCA_SW_TILE;      // layers whose (layer, band) term lists are resident in shared memory at a time
 constexpr double FLUXFAC = 3.14159265358979323846 * 2.0e4;      // pi * 2.e4 with pi = 2*asin(1)
 
 // dynamic shared memory (sized by the number of layers, so that more CTAs fit per SM); the CPU thread emulator of
@@ -87,7 +101,7 @@ __host__ __device__ inline size_t sw_smem_doubles(int nl) {
 // g-point: species ratios, interpolation weights, `pow` of the adjusted minor-gas amounts); (ii) one thread per g-point forms
 // tau = sum_i w_i A[off_i + g] and advances rtrnmr's downward sweep.  The upward sweep needs no optical depths again
 // (atrans / bbugas of the column stay in thread-local memory).  Phase C: fluxes and heating rates.
-__global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __restrict__ A, Tab tb, const LwBand* __restrict__ bands, ColIn in) {
+__global__ void __launch_bounds__(LW_THREADS, ISCA_LW_MINB) rrtmg_lw_kernel(const double* __restrict__ A, Tab tb, const LwBand* __restrict__ bands, ColIn in) {
   ISCA_DYN_SMEM(smem);
   const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
   const int PS = nl + 1;             // row stride of the Planck arrays
@@ -216,7 +230,7 @@ __global__ void __launch_bounds__(LW_THREADS) rrtmg_lw_kernel(const double* __re
 // the optical depths are needed only once: pass 1 runs bottom-up (layer optics, two-stream reflectance / transmittance of the layer
 // and, in the same step, vrtqdr's upward combination zrup / zrupd, which is a bottom-up recurrence), pass 2 top-down (direct-beam
 // transmittance, downward combination, fluxes).  Values and their order of evaluation are those of the reference.
-__global__ void __launch_bounds__(SW_THREADS) rrtmg_sw_kernel(const double* __restrict__ A, Tab tb, const SwBand* __restrict__ bands, ColIn in) {
+__global__ void __launch_bounds__(SW_THREADS, ISCA_SW_MINB) rrtmg_sw_kernel(const double* __restrict__ A, Tab tb, const SwBand* __restrict__ bands, ColIn in) {
   ISCA_DYN_SMEM(smem);
   const int col = blockIdx.x, tid = threadIdx.x, nl = in.nlay, nc = in.ncol;
   const int PS = nl + 1;
