@@ -124,10 +124,28 @@ legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __res
     }
   }
 
-  // epilogue: south = even - odd, north = even + odd.  The CTA's two JT x 32 output tiles are staged in shared memory (the pipeline
-  // buffers are free now) so that every row leaves as ONE 256-byte run written by a whole warp -- full lines for HBM and, on several
-  // GPUs, full NVLink packets for the stores into the lat-owner buffer of the rank that owns the latitude (the fragment layout itself
-  // would give 64-byte pieces per row).  Row stride 40 doubles: the 16-byte fragment stores of a quarter warp fall into distinct banks.
+  // epilogue: south = even - odd, north = even + odd.  On several GPUs the CTA's two JT x 32 output tiles are staged in shared memory
+  // (the pipeline buffers are free now) so that every row leaves as ONE 256-byte run written by a whole warp: full NVLink packets for the
+  // stores into the lat-owner buffer of the rank that owns the latitude (the fragment layout itself gives 64-byte pieces per row; measured
+  // on one GPU the staging costs 0.02 ms, so it is only used for peer stores).  Row stride 40 doubles: the 16-byte fragment stores of a
+  // quarter warp fall into distinct banks.
+  if (!g.p2p) {         // one GPU: the fragment layout stores 64-byte pieces per row, which HBM takes at full sector efficiency
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int jh = jt0 + wj * WTJ + mt * 8 + (lane >> 2);
+      double* rowS = four + fourA_index(g, mi, jh, C);
+      double* rowN = four + fourA_index(g, mi, g.J - 1 - jh, C);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = c0 + wc * WTC + nt * 8 + (lane & 3) * 2;
+        double e0 = acc[0][mt][nt][0], e1 = acc[0][mt][nt][1];
+        double o0 = acc[1][mt][nt][0], o1 = acc[1][mt][nt][1];
+        *reinterpret_cast<double2*>(rowS + c) = make_double2(e0 - o0, e1 - o1);
+        *reinterpret_cast<double2*>(rowN + c) = make_double2(e0 + o0, e1 + o1);
+      }
+    }
+    return;
+  }
   constexpr int OS = LEG_CT + 8;
   __syncthreads();
   double* outS = reinterpret_cast<double*>(leg_smem_raw);
@@ -149,14 +167,9 @@ legendre_inv_kernel(DevTables t, const double2* __restrict__ spec, double* __res
     const int north = rr >= JT, r = north ? rr - JT : rr;
     const int jh = jt0 + r;
     const int j = north ? g.J - 1 - jh : jh;
-    double* row;
-    if (g.p2p) {        // peer memory over NVLink
-      const int sj = j / g.Jloc;
-      const size_t prow = (size_t)(g.roff[g.rank] + mi) * g.Jloc;
-      row = g.peerB[sj] + (prow + (j - sj * g.Jloc)) * (size_t)C;
-    } else {
-      row = four + fourA_index(g, mi, j, C);
-    }
+    const int sj = j / g.Jloc;                          // peer memory over NVLink
+    const size_t prow = (size_t)(g.roff[g.rank] + mi) * g.Jloc;
+    double* row = g.peerB[sj] + (prow + (j - sj * g.Jloc)) * (size_t)C;
     row[c0 + lane] = (north ? outN : outS)[r * OS + lane];
   }
 }

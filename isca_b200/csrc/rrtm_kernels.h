@@ -64,18 +64,19 @@ struct DevRed {                      // per-level sum over the g-points: warp sh
 
 constexpr int LW_THREADS = 160, SW_THREADS = 128;
 // tile = layers whose term lists are resident at a time (<= 8 = the batch of warp_sum8); MINB = CTAs per SM the register allocation
-// is held to.  Tunable at compile time for the occupancy experiments of tools/rrtm_variants.sh (profiles/r02/r02_experiments.md).
+// is held to.  Tunable at compile time for the occupancy experiments of tools/rrtm_variants.sh; the defaults are the fastest measured
+// (profiles/r02/r02_experiments.md: LW tile 4 / 6 CTAs 32.3 ms, SW tile 4 / 8 CTAs 15.3 ms per T170 call).
 #ifndef ISCA_LW_TILE
-#define ISCA_LW_TILE 8
+#define ISCA_LW_TILE 4
 #endif
 #ifndef ISCA_SW_TILE
-#define ISCA_SW_TILE 8
+#define ISCA_SW_TILE 4
 #endif
 #ifndef ISCA_LW_MINB
-#define ISCA_LW_MINB 1
+#define ISCA_LW_MINB 6
 #endif
 #ifndef ISCA_SW_MINB
-#define ISCA_SW_MINB 1
+#define ISCA_SW_MINB 8
 #endif
 constexpr int LW_TILE = ISCA_LW_TILE, SW_TILE = ISCA_SW_TILE;      // layers whose (layer, band) term lists are resident in shared memory at a time
 constexpr double FLUXFAC = 3.14159265358979323846 * 2.0e4;      // pi * 2.e4 with pi = 2*asin(1)

@@ -27,7 +27,7 @@ static double g_shfl[64][32];
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __shared__ static
 static inline void __syncthreads() { g_block_barrier->arrive_and_wait(); }
 static inline double __shfl_xor_sync(unsigned, double v, int o) {
