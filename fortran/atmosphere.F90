@@ -146,7 +146,6 @@ contains
     if (.not. triang_trunc)   call error_mesg('atmosphere_init', 'isca_b200: rhomboidal truncation (triang_trunc = .false.) is not built', FATAL)
     if (fourier_inc /= 1)     call error_mesg('atmosphere_init', 'isca_b200: fourier_inc must be 1', FATAL)
     if (num_steps /= 1)       call error_mesg('atmosphere_init', 'isca_b200: num_steps must be 1', FATAL)
-    if (make_symmetric)       call error_mesg('atmosphere_init', 'isca_b200: make_symmetric is not built', FATAL)
     if (trim(damping_option) /= 'resolution_dependent') &
       call error_mesg('atmosphere_init', 'isca_b200: damping_option must be resolution_dependent', FATAL)
     if (trim(vert_difference_option) /= 'simmons_and_burridge') &
@@ -179,6 +178,7 @@ contains
     cfg%do_mass_correction = l2i(do_mass_correction);  cfg%do_energy_correction = l2i(do_energy_correction)
     cfg%do_water_correction = l2i(do_water_correction)
     cfg%use_virtual_temperature = l2i(use_virtual_temperature);  cfg%use_implicit = l2i(use_implicit)
+    cfg%make_symmetric = l2i(make_symmetric)
     cfg%robert_coeff = robert_coeff;  cfg%raw_filter_coeff = raw_filter_coeff;  cfg%alpha_implicit = alpha_implicit
     select case (trim(vert_coord_option))
       case ('even_sigma');   cfg%vert_coord_option = 0

@@ -45,6 +45,7 @@ module isca_b200_c
     integer(c_int32_t)   :: do_water_correction
     integer(c_int32_t)   :: use_virtual_temperature
     integer(c_int32_t)   :: use_implicit
+    integer(c_int32_t)   :: make_symmetric
     real(c_double)       :: robert_coeff
     real(c_double)       :: raw_filter_coeff
     real(c_double)       :: alpha_implicit

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ISCA_B200_ABI_VERSION 1
+#define ISCA_B200_ABI_VERSION 2
 
 typedef struct IscaHandle_t* IscaHandle;
 
@@ -56,6 +56,8 @@ typedef struct IscaConfig {
   double  eddy_sponge_coeff, zmu_sponge_coeff, zmv_sponge_coeff;
   int32_t do_mass_correction, do_energy_correction, do_water_correction;
   int32_t use_virtual_temperature, use_implicit;
+  int32_t make_symmetric;         /* zonally symmetric model: every coefficient with m > 0 is removed wherever the triangular truncation
+                                   * is applied (spherical.F90:185; the `axisymmetric` test case) */
   double  robert_coeff, raw_filter_coeff, alpha_implicit;
   int32_t vert_coord_option;      /* 0 even_sigma, 1 uneven_sigma, 2 input (pk/bk below), 3 hybrid (p_press, p_sigma) */
   double  scale_heights, surf_res, exponent, p_press, p_sigma;

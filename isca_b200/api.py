@@ -36,7 +36,7 @@ class IscaConfigStruct(C.Structure):
         ("damping_coeff", C.c_double), ("damping_coeff_vor", C.c_double), ("damping_coeff_div", C.c_double),
         ("eddy_sponge_coeff", C.c_double), ("zmu_sponge_coeff", C.c_double), ("zmv_sponge_coeff", C.c_double),
         ("do_mass_correction", C.c_int32), ("do_energy_correction", C.c_int32), ("do_water_correction", C.c_int32),
-        ("use_virtual_temperature", C.c_int32), ("use_implicit", C.c_int32),
+        ("use_virtual_temperature", C.c_int32), ("use_implicit", C.c_int32), ("make_symmetric", C.c_int32),
         ("robert_coeff", C.c_double), ("raw_filter_coeff", C.c_double), ("alpha_implicit", C.c_double),
         ("vert_coord_option", C.c_int32),
         ("scale_heights", C.c_double), ("surf_res", C.c_double), ("exponent", C.c_double),

@@ -49,6 +49,7 @@ struct GeomDev {
   // epilogue stores straight into the destination rank's lat-owner buffer and the FFT epilogue straight into the
   // destination rank's m-owner buffer, over NVLink; no send/recv, no staging copy.
   int p2p;
+  int symmetric;              // make_symmetric: the truncation also removes every m > 0
   const int* owner;           // [M+1] rank owning m
   const int* lidx;            // [M+1] local index of m on its owner
   const int* nm_rank;         // [P]

@@ -193,7 +193,7 @@ static void upload_tables(H& h) {
   d.g.I = g.I; d.g.J = g.J; d.g.K = g.K; d.g.M = g.M; d.g.N = g.N; d.g.Jh = g.Jh; d.g.P = g.P; d.g.rank = g.rank;
   d.g.Jloc = g.Jloc; d.g.j0 = g.j0; d.g.nm = g.nm; d.g.T = g.T;
   d.g.m_of = h.d_m_of.p; d.g.off = h.d_off.p; d.g.pos = h.d_pos.p; d.g.row_m = h.d_row_m.p;
-  d.g.p2p = 0; d.g.owner = h.d_owner.p; d.g.lidx = h.d_lidx.p; d.g.nm_rank = h.d_nm_rank.p; d.g.roff = h.d_roff.p;
+  d.g.p2p = 0; d.g.symmetric = h.cfg.make_symmetric ? 1 : 0; d.g.owner = h.d_owner.p; d.g.lidx = h.d_lidx.p; d.g.nm_rank = h.d_nm_rank.p; d.g.roff = h.d_roff.p;
   d.g.peerA = nullptr; d.g.peerB = nullptr;
   d.row_n = h.d_row_n.p;
   d.sin_lat = h.d_sin_lat.p; d.cos_lat = h.d_cos_lat.p; d.cosm_lat = h.d_cosm_lat.p; d.wts_lat = h.d_wts_lat.p;
@@ -784,7 +784,7 @@ void isca_b200_default_config(IscaConfig* c) {
   c->damping_order = 2; c->damping_order_vor = -1; c->damping_order_div = -1;
   c->damping_coeff = 1.15740741e-4; c->damping_coeff_vor = -1.; c->damping_coeff_div = -1.;
   c->do_mass_correction = 1; c->do_energy_correction = 1; c->do_water_correction = 1;
-  c->use_virtual_temperature = 0; c->use_implicit = 1;
+  c->use_virtual_temperature = 0; c->use_implicit = 1; c->make_symmetric = 0;
   c->robert_coeff = .04; c->raw_filter_coeff = 1.0; c->alpha_implicit = .5;
   c->vert_coord_option = 0; c->scale_heights = 4.; c->surf_res = .1; c->exponent = 2.5; c->p_press = .1; c->p_sigma = .3;
   c->reference_sea_level_press = 101325.; c->initial_sphum = 0.; c->water_correction_limit = 0.;

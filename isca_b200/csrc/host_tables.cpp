@@ -295,7 +295,7 @@ void build_tables(const IscaConfig& c, const Geometry& g, HostTables& t) {
       double e = epsf(fm, L);
       if (L == 0) e = 0.0;   // (0-0)/(0-1) = -0 -> sqrt = 0
       t.row_m[p] = mi; t.row_n[p] = n;
-      t.trunc_mask[p] = (m + n > N - 1) ? 0.0 : 1.0;
+      t.trunc_mask[p] = (m + n > N - 1 || (c.make_symmetric && m > 0)) ? 0.0 : 1.0;     // spherical.F90:183-185
       t.eigen[p] = L * (L + 1.0) / (a * a);
       if (L > 0) { t.coef_uvm[p] = -a * e / L; t.coef_uvc[p] = -a * fm / (L * (L + 1.0)); }
       double e1 = epsf(fm, L + 1.0);              // epsilon(m, n+1)

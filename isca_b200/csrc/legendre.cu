@@ -290,7 +290,7 @@ legendre_fwd_kernel(DevTables t, const double* __restrict__ four, double2* __res
   for (int mt = 0; mt < 2; ++mt) {
     const int n = nt0 + 2 * (mt * 8 + (lane >> 2)) + par;
     if (n >= Nm) continue;
-    const bool beyond = (m + n > g.M);
+    const bool beyond = (m + n > g.M) || (g.symmetric && m > 0);      // triangle_mask = 0 (spherical.F90:183-185)
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       const int c = c0 + wc * 16 + nt * 8 + (lane & 3) * 2;

@@ -72,6 +72,7 @@ class Config:
     do_water_correction: bool = True
     use_virtual_temperature: bool = False
     use_implicit: bool = True
+    make_symmetric: bool = False       # zonally symmetric model (spectral_dynamics.F90:159, spherical.F90:185)
     robert_coeff: float = 0.04
     raw_filter_coeff: float = 1.0
     alpha_implicit: float = 0.5
@@ -261,6 +262,8 @@ class Tables:
         self.fourier_wave = m
         self.spherical_wave = L
         self.triangle_mask = np.where(L > N - 1, 0.0, 1.0)
+        if cfg.make_symmetric:                          # spherical.F90:185
+            self.triangle_mask = np.where(m > 0, 0.0, self.triangle_mask)
         with np.errstate(invalid="ignore", divide="ignore"):
             eps = np.sqrt((L ** 2 - m ** 2) / (4.0 * L ** 2 - 1.0))
         self.epsilon = eps

@@ -37,7 +37,7 @@ def test_every_namelist_variable_of_the_config_is_forwarded():
     mod = open(os.path.join(ROOT, "fortran", "isca_b200_c.F90")).read()
     body = mod[mod.index("type, bind(C) :: isca_config"):mod.index("end type isca_config")]
     fields = re.findall(r"::\s*(\w+)", body)[1:]          # [0] is the type name itself
-    assert len(fields) == 60
+    assert len(fields) == 61
     missing = [f for f in fields if f != "abi_version" and not re.search(r"cfg%" + f + r"\b", src)]
     assert not missing, missing
 

@@ -176,3 +176,25 @@ def test_hybrid_vertical_coordinate():
         assert np.all(np.diff(ph) > 0.0) and ph[-1] == ps
     mix = (bk > 0) & (pk > 0)
     assert mix.any()                                             # and a blended zone in between
+
+
+def test_make_symmetric_keeps_the_model_zonally_symmetric():
+    """spectral_dynamics_nml make_symmetric (spherical.F90:185: triangle_mask = 0 for m > 0; the `axisymmetric` test case): the
+    truncation removes every zonal wavenumber but 0, so the cold-start perturbation (m = 1, 5) disappears and the run stays zonally
+    symmetric; the m = 0 part evolves as in the full model started from a symmetric state."""
+    import numpy as np
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    cfg = held_suarez_config("T21", 8, 1200.0)
+    cfg.make_symmetric = True
+    core = SpectralCore(cfg)
+    assert core.tb.triangle_mask[:, 1:].max() == 0.0 and core.tb.triangle_mask[:21, 0].min() == 1.0
+    core.cold_start()
+    assert np.abs(core.vors).max() == 0.0                   # the perturbation sits at m = 1 and 5
+    for _ in range(5):
+        core.step()
+    st = core.state()
+    for k in ("vors", "divs", "ts", "ln_ps"):
+        assert np.abs(st[k][..., 1:]).max() == 0.0, k
+    for k in ("ug", "tg", "psg"):
+        assert np.abs(st[k] - st[k][..., :1]).max() < 1e-12 * np.abs(st[k]).max(), k
+    assert np.abs(st["tg"] - 264.0).max() > 1e-3            # the Held-Suarez forcing is acting
