@@ -281,6 +281,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`; numbers of such a run are not bench values)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (hs T85/T170/T341, Frierson T85)")
     args = ap.parse_args()
 
@@ -424,9 +426,13 @@ def main():
         sampler = ClockSampler(local_rank)
         sampler.start()
         barrier()
+        if args.profile_range:
+            torch.cuda.cudart().cudaProfilerStart()
         t0 = time.time()
         m.atmosphere(args.steps)
         barrier()
+        if args.profile_range:
+            torch.cuda.cudart().cudaProfilerStop()
         wall = max_over_ranks(time.time() - t0)
         clocks = sampler.stop()
         ms_step, _ = m.timing()
