@@ -376,8 +376,12 @@ int isca_b200_moist_step(IscaMoist m, int n_steps) {
     return mfail(m, "dry_convection: tau / gamma not set (isca_b200_moist_set_dry_convection; dry_convection_nml has no defaults)");
   IscaCoreView v;
   if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
-  cudaEvent_t e0, e1, e2;
-  MCK(cudaEventCreate(&e0)); MCK(cudaEventCreate(&e1)); MCK(cudaEventCreate(&e2));
+  struct Events {                             // destroyed on every exit path
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+  } ev;
+  for (auto& x : ev.e) MCK(cudaEventCreate(&x));
+  cudaEvent_t &e0 = ev.e[0], &e1 = ev.e[1], &e2 = ev.e[2], &e3 = ev.e[3];
   double phys_ms = 0.0;
   MCK(cudaEventRecord(e0, v.st));
   for (int i = 0; i < n_steps; ++i) {
@@ -385,7 +389,6 @@ int isca_b200_moist_step(IscaMoist m, int n_steps) {
     if (last) MCK(cudaEventRecord(e2, v.st));
     if (moist_step_once(m, last ? e1 : nullptr)) return 1;
   }
-  cudaEvent_t e3; MCK(cudaEventCreate(&e3));
   MCK(cudaEventRecord(e3, v.st));
   // device error flags: saturation-table / LCL-table overflow, zero effective heat capacity; temperature range of the core
   int e = 0;
@@ -396,7 +399,6 @@ int isca_b200_moist_step(IscaMoist m, int n_steps) {
     MCK(cudaEventElapsedTime(&a, e0, e3)); MCK(cudaEventElapsedTime(&b, e2, e1));
     m->ms_step = a / n_steps; phys_ms = b; m->ms_phys = phys_ms;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   if (e) {
     MCK(cudaMemsetAsync(m->phy->d_err, 0, sizeof(int), v.st));
     return mfail(m, "idealized_moist_phys: lookup_es / get_lcl_temp table overflow or zero effective heat capacity (device error flag " + std::to_string(e) + ")");
