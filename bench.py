@@ -464,33 +464,36 @@ def main():
         # ---- end to end: the call a host model makes every step with HOST buffers: the ozone field of the radiation (H2D, what
         # interpolator_mod hands over) in, one atmosphere(Time), and the fields of the MiMA diag_table (ps, precipitation, t_surf, sphum,
         # ucomp, vcomp, temp, vor, div: what send_data passes to diag_manager) out, pinned host memory, copies inside the timed region
-        outs3 = {fid: pin((K, Jloc, I)) for fid in (api.F_TRACER0, api.F_U, api.F_V, api.F_T, api.F_VOR, api.F_DIV)}
-        ps_host, pr_host, ts_host = pin((Jloc, I)), pin((Jloc, I)), pin((Jloc, I))
+        def out_set():
+            o = [(0, fid, api.LEVEL_CURRENT, pin((K, Jloc, I))) for fid in (api.F_TRACER0, api.F_U, api.F_V, api.F_T, api.F_VOR, api.F_DIV)]
+            o.append((0, api.F_PS, api.LEVEL_CURRENT, pin((Jloc, I))))
+            o += [(1, "precip", 0, pin((Jloc, I))), (1, "t_surf", 0, pin((Jloc, I)))]
+            return o
+        sets = [out_set(), out_set()]                  # two alternating sets of pinned host arrays: set n-1 is consumed while step n runs
+        consumed = []
 
-        def e2e_step():
-            m.set_ozone(o3_host)
-            m.atmosphere(1)
-            for fid, buf in outs3.items():
-                m.core.get_field(fid, out=buf)
-            m.core.get_field(api.F_PS, out=ps_host)
-            m.get("precip", out=pr_host)
-            m.get("t_surf", out=ts_host)
+        def e2e_loop(n):
+            for i in range(n):
+                m.step_io(o3_host, sets[i % 2])        # H2D ozone, atmosphere(Time), D2H of the diag_table fields: pipelined
+                if i > 0:
+                    m.io_wait(1)                       # the downloads of step i-1 are complete: hand them on (here: read one value each)
+                    consumed.append(float(sets[(i - 1) % 2][3][3][0, 0, 0]))
+            m.io_sync()
         m.atmosphere((-(spin + warm + args.steps + n_ss + 1 + per_rad)) % per_rad)
-        for _ in range(2):
-            e2e_step()
+        e2e_loop(3)
         barrier()
         t0 = time.time()
-        for _ in range(args.e2e_steps):
-            e2e_step()
+        e2e_loop(args.e2e_steps)
         barrier()
         e2e_sec = max_over_ranks(time.time() - t0) / args.e2e_steps
         h2d = 8 * K * J_glob * I
         d2h = (6 * K + 3) * 8 * J_glob * I
         e2e = {"value": dt / 86400.0 / e2e_sec, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_sec * 1e3, "steps": args.e2e_steps,
-               "api": "per step: isca_b200_moist_set_ozone (host ozone field in), isca_b200_moist_step(1), isca_b200_get_field x 7 + "
-                      "isca_b200_moist_get x 2 (the MiMA diag_table fields out to pinned host buffers)",
-               "note": f"{args.e2e_steps} steps after 2 untimed ones, none of them a radiation step" if args.e2e_steps + 2 < per_rad else ""}
+               "api": "per step: isca_b200_moist_step_io = host ozone field in (H2D), atmosphere(Time), the MiMA diag_table fields (sphum, ucomp, "
+                      "vcomp, temp, vor, div, ps, precipitation, t_surf) out to pinned host arrays (D2H); the copies of step n overlap step n+1 "
+                      "(two alternating host sets, isca_b200_moist_io_wait), everything inside the timed region incl. the final drain",
+               "note": f"{args.e2e_steps} steps after 3 untimed ones, none of them a radiation step" if args.e2e_steps + 3 < per_rad else ""}
         tr = m.core.get_field(api.F_T)
         extra_info = {"radiation_calls_in_timed_region": rad_calls, "steps_per_radiation_call": per_rad,
                       "rrtmg_call_ms": rr_ms, "olr_mean_rank0": float(m.get("olr").mean()),

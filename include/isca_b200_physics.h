@@ -252,6 +252,18 @@ int isca_b200_moist_step(IscaMoist m, int n_steps);
  * 6 surf_lw_down, 7 convective rain, 8 cape, 9 convflag, 10 q_surf, 11 u_star, 12 b_star, 13 flux_u, 14 flux_v, 15 delta_t_surf;
  * 3-D [K][J][I]: 32 dt_ug, 33 dt_vg, 34 dt_tg, 35 dt_tracers(sphum) (physics tendencies), 36 diff_m, 37 diff_t */
 int isca_b200_moist_get(IscaMoist m, int id, double* host);
+/* atmosphere(Time) together with the host traffic of the step, software-pipelined: o3_host (may be NULL) = the ozone field of
+ * isca_b200_moist_set_ozone, copied to the device before the step; then n_out fields are copied to host_out[i] (page-locked memory for
+ * the copies to overlap): kinds[i] = 0 a field of isca_b200_get_field (ids[i], levels[i]), 1 a 2-D / 3-D field of isca_b200_moist_get
+ * (ids[i] in 0-8, 17, 18, 34, 35; levels[i] ignored).  The call RETURNS BEFORE the downloads have finished: they overlap the next step
+ * (what send_data of the reference's diag_manager consumes one step later); host_out is complete after isca_b200_moist_io_sync, which
+ * also reports the FATAL conditions of the steps since the last sync.  isca_b200_moist_io_wait(m, age) waits only for the downloads of the
+ * last call (age 0) or of the call before it (age 1) and leaves the pipeline running: with two alternating sets of host arrays, the set
+ * of call n-1 is consumed after call n was issued. */
+int isca_b200_moist_step_io(IscaMoist m, const double* o3_host, int n_out, const int* kinds, const int* ids, const int* levels,
+                            double* const* host_out);
+int isca_b200_moist_io_sync(IscaMoist m);
+int isca_b200_moist_io_wait(IscaMoist m, int age);
 /* Measurement aid: n_steps eager steps with a CUDA event after every kernel group; writes the average milliseconds per group to
    ms_out and the ';'-separated group names to `names` ("phys_*" = the column-physics kernels in call order, "phys_rrtmg_call" = a
    whole radiation call on the steps where the alarm fires, the rest = the dynamical core's groups of isca_b200_profile_step).

@@ -1205,6 +1205,12 @@ static size_t field_on_device(H& h, int id, int level, const double** ptr) {
   }
 }
 
+int isca_core_field_device(IscaHandle h, int field_id, int level, const double** ptr, size_t* count) {
+  API_BEGIN(h)
+  *count = field_on_device(*h, field_id, level, ptr);
+  API_END(h)
+}
+
 int isca_b200_get_field(IscaHandle h, int id, int level, double* host) {
   API_BEGIN(h)
   const double* src = nullptr;

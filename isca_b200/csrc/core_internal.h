@@ -25,6 +25,8 @@ int isca_core_press_heights(IscaHandle h, int slot, double* p_full, double* p_ha
 int isca_core_step_ext(IscaHandle h, const double* dtu, const double* dtv, const double* dtt, const double* dtq);
 // valid-temperature-range check of the last steps (spectral_dynamics.F90 FATAL); 0 = ok
 int isca_core_check(IscaHandle h);
+// device pointer and element count of a grid field of isca_b200_get_field (materialised on the core's stream where needed); 0 = ok
+int isca_core_field_device(IscaHandle h, int field_id, int level, const double** ptr, size_t* count);
 // per-kernel-group CUDA-event marks shared with the moist-model driver (isca_b200_moist_profile_step): begin clears the marks and
 // records "start"; mark() records an event named `name` on the core's stream (no-op unless profiling); end synchronises, adds the
 // elapsed ms between consecutive marks to acc (keyed by the later mark's name, first-seen order kept in `order`) and frees the events

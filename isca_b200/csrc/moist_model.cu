@@ -38,6 +38,11 @@ struct IscaMoist_t {
   IscaRrtmDriverConfig sdc{};
   std::vector<double> s_orb;
   double dry_tau = 0.0, dry_gamma = 0.0;                       // dry_convection_nml (convection_scheme = 'DRY')
+  // isca_b200_moist_step_io: software-pipelined host I/O of a step (copy streams, staging buffer, events)
+  cudaStream_t io_h2d = nullptr, io_d2h = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_snap = nullptr, ev_d2h = nullptr, ev_d2h_prev = nullptr, ev_main = nullptr;
+  Dev io_stage;
+  bool io_ready = false, io_pending = false;
 };
 
 namespace {
@@ -249,6 +254,11 @@ IscaHandle isca_b200_moist_dycore(IscaMoist m) { return m ? m->dyn : nullptr; }
 
 int isca_b200_moist_destroy(IscaMoist m) {
   if (!m) return 0;
+  if (m->io_ready) {
+    cudaStreamSynchronize(m->io_h2d); cudaStreamSynchronize(m->io_d2h);
+    for (cudaEvent_t e : {m->ev_h2d, m->ev_snap, m->ev_d2h, m->ev_d2h_prev, m->ev_main}) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(m->io_h2d); cudaStreamDestroy(m->io_d2h);
+  }
   if (m->rr) isca_b200_rrtm_destroy(m->rr);
   if (m->phy) isca_b200_physics_destroy(m->phy);
   if (m->dyn) isca_b200_destroy(m->dyn);
@@ -428,6 +438,120 @@ int isca_b200_moist_profile_step(IscaMoist m, int n_steps, double* ms_out, int m
   if ((int)joined.size() + 1 > capacity) { mfail(m, "moist_profile_step: names buffer too small"); return -1; }
   std::memcpy(names, joined.c_str(), joined.size() + 1);
   return n;
+}
+
+// device pointer / element count of a double-valued field of isca_b200_moist_get (id 9, convflag, is an int plane: not here)
+static int moist_field_device(IscaMoist m, int id, const double** out, size_t* count) {
+  const size_t nc = m->nc, n3 = m->n3;
+  const double* src = nullptr; size_t n = nc;
+  switch (id) {
+    case 0: src = m->t_surf.p; break;
+    case 1: src = m->precip.p; break;
+    case 2: src = m->sf.p + SF_FLUX_T * nc; break;
+    case 3: src = m->sf.p + SF_FLUX_Q * nc; break;
+    case 4: src = m->z_pbl.p; break;
+    case 5: src = m->net_sw.p; break;
+    case 6: src = m->lw_down.p; break;
+    case 7: src = m->conv_rain.p; break;
+    case 8: src = m->cape.p; break;
+    case 17: if (!m->rr) return mfail(m, "moist field: olr needs do_rrtm_radiation"); src = m->olr.p; break;
+    case 18: if (!m->rr) return mfail(m, "moist field: toa_sw needs do_rrtm_radiation"); src = m->toa_sw.p; break;
+    case 34: src = m->dt_t.p; n = n3; break;
+    case 35: src = m->dt_q.p; n = n3; break;
+    default: return mfail(m, "moist field: this id is not available to isca_b200_moist_step_io");
+  }
+  *out = src; *count = n;
+  return 0;
+}
+
+// atmosphere(Time) with the host I/O of a step, software-pipelined (include/isca_b200_physics.h).  Streams: the core's (compute), one
+// host->device and one device->host copy stream.  Per call: [h2d] ozone upload after the previous step has finished with the old field
+// -> [compute] the step, then device-to-device snapshots of the requested fields into a staging buffer (after the previous call's
+// downloads have drained it) -> [d2h] downloads of the snapshots into the caller's (pinned) arrays.  The call returns without waiting:
+// the downloads of step n overlap the compute of step n+1 and the upload of its input (PCIe is full duplex).
+int isca_b200_moist_step_io(IscaMoist m, const double* o3_host, int n_out, const int* kinds, const int* ids, const int* levels,
+                            double* const* host_out) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!m->initialized) return mfail(m, "idealized_moist_phys: module not initialized (isca_b200_moist_init has not been called)");
+  if (n_out < 0 || (n_out > 0 && (!kinds || !ids || !levels || !host_out))) return mfail(m, "moist_step_io: null output description");
+  IscaCoreView v;
+  if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
+  if (!m->io_ready) {
+    MCK(cudaStreamCreateWithFlags(&m->io_h2d, cudaStreamNonBlocking)); MCK(cudaStreamCreateWithFlags(&m->io_d2h, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&m->ev_h2d, &m->ev_snap, &m->ev_d2h, &m->ev_d2h_prev, &m->ev_main}) MCK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    MCK(cudaEventRecord(m->ev_d2h, m->io_d2h)); MCK(cudaEventRecord(m->ev_d2h_prev, m->io_d2h)); MCK(cudaEventRecord(m->ev_main, v.st));
+    m->io_ready = true;
+  }
+  if (o3_host) {
+    if (!m->rr) return mfail(m, "moist_step_io: the ozone field needs do_rrtm_radiation");
+    if (!m->o3.ensure(m->n3)) return mfail(m, "cudaMalloc failed");
+    MCK(cudaStreamWaitEvent(m->io_h2d, m->ev_main, 0));          // the previous step no longer reads the old field
+    MCK(cudaMemcpyAsync(m->o3.p, o3_host, m->n3 * sizeof(double), cudaMemcpyHostToDevice, m->io_h2d));
+    MCK(cudaEventRecord(m->ev_h2d, m->io_h2d));
+    MCK(cudaStreamWaitEvent(v.st, m->ev_h2d, 0));
+    m->have_o3 = true;
+  }
+  if (moist_step_once(m, nullptr)) return 1;
+  // resolve the fields (may launch materialising kernels on the compute stream), then snapshot them
+  std::vector<const double*> src(n_out, nullptr);
+  std::vector<size_t> cnt(n_out, 0);
+  size_t total = 0;
+  for (int i = 0; i < n_out; ++i) {
+    if (!host_out[i]) return mfail(m, "moist_step_io: null output array");
+    if (kinds[i] == 0) { if (isca_core_field_device(m->dyn, ids[i], levels[i], &src[i], &cnt[i])) return mfail(m, isca_b200_last_error(m->dyn)); }
+    else if (moist_field_device(m, ids[i], &src[i], &cnt[i])) return 1;
+    total += cnt[i];
+  }
+  if (total > m->io_stage.n) {                                  // first call (or a larger request): nothing is in flight that uses it
+    MCK(cudaStreamSynchronize(m->io_d2h));
+    if (!m->io_stage.ensure(total)) return mfail(m, "cudaMalloc failed");
+  }
+  MCK(cudaStreamWaitEvent(v.st, m->ev_d2h, 0));                 // the previous downloads have drained the staging buffer
+  size_t off = 0;
+  for (int i = 0; i < n_out; ++i) {
+    MCK(cudaMemcpyAsync(m->io_stage.p + off, src[i], cnt[i] * sizeof(double), cudaMemcpyDeviceToDevice, v.st));
+    off += cnt[i];
+  }
+  MCK(cudaEventRecord(m->ev_snap, v.st));
+  MCK(cudaEventRecord(m->ev_main, v.st));
+  MCK(cudaStreamWaitEvent(m->io_d2h, m->ev_snap, 0));
+  off = 0;
+  for (int i = 0; i < n_out; ++i) {
+    MCK(cudaMemcpyAsync(host_out[i], m->io_stage.p + off, cnt[i] * sizeof(double), cudaMemcpyDeviceToHost, m->io_d2h));
+    off += cnt[i];
+  }
+  std::swap(m->ev_d2h, m->ev_d2h_prev);                         // ev_d2h_prev = the call before this one (isca_b200_moist_io_wait)
+  MCK(cudaEventRecord(m->ev_d2h, m->io_d2h));
+  m->io_pending = true;
+  return 0;
+}
+
+// wait for the downloads of the last call (age = 0) or of the call before it (age = 1), without draining the pipeline
+int isca_b200_moist_io_wait(IscaMoist m, int age) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!m->io_ready) return 0;
+  if (age != 0 && age != 1) return mfail(m, "moist_io_wait: age must be 0 or 1");
+  MCK(cudaEventSynchronize(age == 0 ? m->ev_d2h : m->ev_d2h_prev));
+  return 0;
+}
+
+// wait until the host arrays of the last isca_b200_moist_step_io call are complete; reports the device error flags of the steps since
+int isca_b200_moist_io_sync(IscaMoist m) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (!m->io_ready) return 0;
+  IscaCoreView v;
+  if (isca_core_view(m->dyn, &v)) return mfail(m, isca_b200_last_error(m->dyn));
+  MCK(cudaEventSynchronize(m->ev_d2h));
+  int e = 0;
+  MCK(cudaMemcpyAsync(&e, m->phy->d_err, sizeof(int), cudaMemcpyDeviceToHost, v.st));
+  MCK(cudaStreamSynchronize(v.st));
+  m->io_pending = false;
+  if (e) {
+    MCK(cudaMemsetAsync(m->phy->d_err, 0, sizeof(int), v.st));
+    return mfail(m, "idealized_moist_phys: lookup_es / get_lcl_temp table overflow or zero effective heat capacity (device error flag " + std::to_string(e) + ")");
+  }
+  if (isca_core_check(m->dyn)) return mfail(m, isca_b200_last_error(m->dyn));
+  return 0;
 }
 
 int isca_b200_moist_get(IscaMoist m, int id, double* host) {

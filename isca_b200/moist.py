@@ -10,7 +10,7 @@ from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
                  "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_co2", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing",
-                 "isca_b200_moist_profile_step"]
+                 "isca_b200_moist_profile_step", "isca_b200_moist_step_io", "isca_b200_moist_io_sync", "isca_b200_moist_io_wait"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
                  q_surf=10, u_star=11, b_star=12, flux_u=13, flux_v=14, delta_t_surf=15, coszen=16, olr=17, toa_sw=18)
@@ -56,6 +56,10 @@ def _lib():
         lib.isca_b200_moist_set_betts_miller.argtypes = [vp, C.POINTER(IscaBettsMillerConfigStruct)]
         lib.isca_b200_moist_timing.argtypes = [vp, dp, dp]
         lib.isca_b200_moist_profile_step.argtypes = [vp, C.c_int, dp, C.c_int, C.c_char_p, C.c_int]
+        ip = C.POINTER(C.c_int)
+        lib.isca_b200_moist_step_io.argtypes = [vp, vp, C.c_int, ip, ip, ip, C.POINTER(vp)]
+        lib.isca_b200_moist_io_sync.argtypes = [vp]
+        lib.isca_b200_moist_io_wait.argtypes = [vp, C.c_int]
         _bound = True
     return lib
 
@@ -211,6 +215,25 @@ class MoistAtmosphere:
         a, b = C.c_double(), C.c_double()
         self._ck(self._lib.isca_b200_moist_timing(self._h, C.byref(a), C.byref(b)), "timing")
         return a.value, b.value
+
+    def step_io(self, ozone, outputs):
+        """atmosphere(Time) with the host I/O of the step, software-pipelined (isca_b200_moist_step_io): `ozone` a C-contiguous host
+        array [lev, lat, lon] or None; `outputs` a list of (kind, id, level, array) with kind 0 = dynamical-core field id of api.F_*,
+        1 = physics field name / id of FIELDS_2D / FIELDS_3D.  Returns at once; the arrays are complete after io_sync()."""
+        n = len(outputs)
+        kinds = (C.c_int * n)(*[int(o[0]) for o in outputs])
+        ids = (C.c_int * n)(*[int(FIELDS_2D.get(o[1], FIELDS_3D.get(o[1], -1)) if isinstance(o[1], str) else o[1]) for o in outputs])
+        levels = (C.c_int * n)(*[int(o[2]) for o in outputs])
+        ptrs = (C.c_void_p * n)(*[o[3].ctypes.data for o in outputs])
+        o3 = None if ozone is None else ozone.ctypes.data_as(C.c_void_p)
+        self._ck(self._lib.isca_b200_moist_step_io(self._h, o3, n, kinds, ids, levels, ptrs), "step_io")
+
+    def io_sync(self):
+        self._ck(self._lib.isca_b200_moist_io_sync(self._h), "io_sync")
+
+    def io_wait(self, age=0):
+        """wait for the downloads of the last step_io call (age 0) or of the one before it (age 1); the pipeline keeps running"""
+        self._ck(self._lib.isca_b200_moist_io_wait(self._h, int(age)), "io_wait")
 
     def profile_step(self, n_steps=10):
         """average milliseconds per kernel group over n eager steps: physics kernels ("phys_*") and the dynamical core's groups"""

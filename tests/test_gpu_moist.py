@@ -148,3 +148,33 @@ def test_moist_model_loud_failures(lib_built):
         m.atmosphere(1)
     m.atmosphere_end()
 
+
+
+def test_step_io_pipeline_returns_the_same_fields(lib_built):
+    """isca_b200_moist_step_io (the step with its host traffic, software-pipelined): the fields it delivers one call later are bitwise
+    those of the plain step + isca_b200_get_field / isca_b200_moist_get, also while the next step is already running."""
+    from isca_b200 import api, moist
+    a = moist.frierson_test_case("T21", 10, 900.0)
+    b = moist.frierson_test_case("T21", 10, 900.0)
+    for m in (a, b):
+        m.core.cold_start(); m.idealized_moist_phys_init(); m.atmosphere(20)
+    K, J, I = a.s3
+
+    def out_set():
+        return [(0, api.F_T, api.LEVEL_CURRENT, np.zeros((K, J, I))), (0, api.F_U, api.LEVEL_CURRENT, np.zeros((K, J, I))),
+                (0, api.F_PS, api.LEVEL_CURRENT, np.zeros((J, I))), (1, "precip", 0, np.zeros((J, I))), (1, "t_surf", 0, np.zeros((J, I)))]
+    sets = [out_set(), out_set()]
+    ref = []
+    for i in range(4):
+        b.atmosphere(1)
+        ref.append([b.core.get_field(api.F_T), b.core.get_field(api.F_U), b.core.get_field(api.F_PS), b.get("precip"), b.get("t_surf")])
+    for i in range(4):
+        a.step_io(None, sets[i % 2])
+        if i > 0:
+            a.io_wait(1)
+            for got, want in zip(sets[(i - 1) % 2], ref[i - 1]):
+                assert np.array_equal(got[3], want), (i - 1, got[1])
+    a.io_sync()
+    for got, want in zip(sets[3 % 2], ref[3]):
+        assert np.array_equal(got[3], want), (3, got[1])
+    a.atmosphere_end(); b.atmosphere_end()
