@@ -70,6 +70,15 @@ __global__ void conv_post_kernel(size_t n3, size_t nc, double delta_t, const dou
     if (i < nc) { double r = rain[i] / delta_t; conv_rain[i] = r; precip[i] = r; }
   }
 }
+// :981-1000: condensation increments -> rates, precip += rain/delta_t
+__global__ void cond_post_kernel(size_t n3, size_t nc, double delta_t, const double* __restrict__ dT, const double* __restrict__ dq,
+                                 double* __restrict__ dt_t, double* __restrict__ dt_q, const double* __restrict__ rain,
+                                 double* __restrict__ precip) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n3; i += (size_t)gridDim.x * blockDim.x) {
+    dt_t[i] = dt_t[i] + dT[i] / delta_t; dt_q[i] = dt_q[i] + dq[i] / delta_t;
+    if (i < nc) precip[i] = precip[i] + rain[i] / delta_t;
+  }
+}
 __global__ void add3_kernel(size_t n, double* a, const double* da, double* b, const double* db, double* c, const double* dc) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     a[i] = a[i] + da[i]; b[i] = b[i] + db[i]; c[i] = c[i] + dc[i];
@@ -137,15 +146,16 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   int* convflag = land + nc; int* klzb = convflag + nc; int* klcl = klzb + nc;
   const double *t_in = tg_p, *q_in = q_p;
   if (m->mc.convection_scheme == 1 || m->mc.convection_scheme == 3) {
-    if (m->mc.convection_scheme == 1)                             // the post-processing of :873-880 is fused into the kernel
+    // (fusing this post-processing into the convection kernel was measured and dropped: the latency-bound column kernel runs the extra
+    // level loop at a fraction of the bandwidth the streaming kernel reaches -- +0.08 ms at T170, profiles/r02/r02_experiments.md)
+    if (m->mc.convection_scheme == 1)
       launch_sbm_convection(p, delta_t, tg_p, q_p, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p, m->c_qref.p, m->c_Tref.p, convflag, klzb, klcl,
-                            m->cape.p, m->cin.p, m->itq.p, m->itt.p, m->tg_tmp.p, m->qg_tmp.p, m->dt_t.p, m->dt_q.p, m->conv_rain.p, m->precip.p);
-    else {                                                        // 'FULL_BETTS_MILLER' (:889-916): same post-processing
+                            m->cape.p, m->cin.p, m->itq.p, m->itt.p);
+    else                                                          // 'FULL_BETTS_MILLER' (:889-916): same post-processing
       launch_betts_miller(p, delta_t, tg_p, q_p, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p, m->c_qref.p, m->c_Tref.p, convflag, klzb, klcl,
                           m->cape.p, m->cin.p, m->itt.p, m->itq.p);
-      conv_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, tg_p, q_p, m->tg_tmp.p, m->qg_tmp.p, m->dt_t.p, m->dt_q.p,
-                                                 m->rain.p, m->conv_rain.p, m->precip.p);
-    }
+    conv_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, tg_p, q_p, m->tg_tmp.p, m->qg_tmp.p, m->dt_t.p, m->dt_q.p,
+                                               m->rain.p, m->conv_rain.p, m->precip.p);
     isca_core_mark(m->dyn, "phys_convection");
     t_in = m->tg_tmp.p; q_in = m->qg_tmp.p;
   } else if (m->mc.convection_scheme == 2) {                     // 'DRY' (:918-928): dt_tg += conv_dt_tg; no precipitation
@@ -158,8 +168,8 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
     MCK(cudaMemsetAsync(m->conv_rain.p, 0, nc * sizeof(double), st));
   }
   if (m->mc.convection_scheme != 2) {                            // `if (r_conv_scheme .ne. DRY_CONV)` (:977): no large-scale condensation
-    // the conversion of the increments to rates and their addition to the tendencies / precipitation (:981-1000) happen in the kernel
-    launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, nullptr, nullptr, delta_t, m->dt_t.p, m->dt_q.p, m->precip.p);
+    launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
+    cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
     isca_core_mark(m->dyn, "phys_lscale_cond");
   }
   if (!m->rr && m->seasonal) {                                   // Time_diag = Time (:1054); days of 86400 s as get_time returns them

@@ -39,8 +39,7 @@ __global__ void compute_qs_kernel(SvpDev s, PhysConst c, int n, const double* __
 // bytes/column: read t, q, pfull (3K) + phalf (K+1), write tdel, qdel (2K) + rain (1)  = (6K + 2) * 8
 __global__ void __launch_bounds__(128) lscale_cond_kernel(SvpDev s, PhysConst c, int ncol, int K,
     const double* __restrict__ tin, const double* __restrict__ qin, const double* __restrict__ pfull,
-    const double* __restrict__ phalf, double* __restrict__ rain, double* __restrict__ tdel, double* __restrict__ qdel, int* err,
-    double delta_t, double* __restrict__ dt_t, double* __restrict__ dt_q, double* __restrict__ precip_acc) {
+    const double* __restrict__ phalf, double* __restrict__ rain, double* __restrict__ tdel, double* __restrict__ qdel, int* err) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
   const double hlcp = c.hlv / c.cp_air, eps = c.rdgas / c.rvgas;
@@ -77,14 +76,11 @@ __global__ void __launch_bounds__(128) lscale_cond_kernel(SvpDev s, PhysConst c,
         }
       }
       precip = precip - pmass * qd;
-      if (dt_t) {          // idealized_moist_phys.F90:981-1000 fused: the increments become rates and join the tendencies at once
-        dt_t[o] = dt_t[o] + td / delta_t; dt_q[o] = dt_q[o] + qd / delta_t;
-      } else { tdel[o] = td; qdel[o] = qd; }
+      tdel[o] = td; qdel[o] = qd;
       ph0 = ph1;
     }
   }
   rain[col] = fmax(precip, 0.0);
-  if (precip_acc) precip_acc[col] = precip_acc[col] + fmax(precip, 0.0) / delta_t;
   if (bad) atomicExch(err, 1);
 }
 
@@ -374,11 +370,9 @@ __global__ void rayleigh_kernel(PhysConst c, size_t ncol, int K, int nlev, int f
 
 namespace isca_phys {
 
-void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd,
-                   double delta_t, double* dt_t, double* dt_q, double* precip_acc) {
+void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd) {
   int nb = (int)((p->ncol + 127) / 128);
-  lscale_cond_kernel<<<nb, 128, 0, p->st>>>(p->svp, p->pc, (int)p->ncol, p->K, t, q, pf, ph, rain, td, qd, p->d_err,
-                                            delta_t, dt_t, dt_q, precip_acc);
+  lscale_cond_kernel<<<nb, 128, 0, p->st>>>(p->svp, p->pc, (int)p->ncol, p->K, t, q, pf, ph, rain, td, qd, p->d_err);
 }
 void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* alb, double* sw, double* lw) {
   int nb = (int)((p->ncol + 127) / 128);

@@ -131,8 +131,7 @@ inline int finish(IscaPhysics p, const char* what) {
 inline int col_blocks(IscaPhysics p, int threads) { return (int)((p->ncol + threads - 1) / threads); }
 
 // device-pointer launches shared between files
-void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd,
-                   double delta_t = 0.0, double* dt_t = nullptr, double* dt_q = nullptr, double* precip_acc = nullptr);
+void launch_lscale(IscaPhysics p, const double* t, const double* q, const double* pf, const double* ph, double* rain, double* td, double* qd);
 void launch_gray_down(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* alb, double* sw, double* lw);
 void launch_gray_up(IscaPhysics p, const double* lat, const double* ph, const double* t, const double* q, const double* ts, const double* alb, double* tdt, double* olr);
 int rayleigh_nlev(const double* pref, int K, double pb);
@@ -151,8 +150,7 @@ void launch_surface_flux(IscaPhysics p, const IscaSurfaceFluxArgs& dev);     // 
 int build_lcl_table(IscaPhysics p);                                             // physics_conv.cu
 void launch_sbm_convection(IscaPhysics p, double dt, const double* Tin, const double* qin, const double* p_full, const double* p_half,
                            double* rain, double* deltaT, double* deltaq, double* qref, double* Tref, int* convflag, int* kLZBs, int* kLCLs,
-                           double* cape, double* cin, double* itq, double* itt, double* tg_tmp = nullptr, double* qg_tmp = nullptr,
-                           double* dt_t = nullptr, double* dt_q = nullptr, double* conv_rain = nullptr, double* precip = nullptr);
+                           double* cape, double* cin, double* itq, double* itt);
 void launch_betts_miller(IscaPhysics p, double dt, const double* tin, const double* qin, const double* p_full, const double* p_half,
                          double* rain, double* tdel, double* qdel, double* q_ref, double* t_ref, int* bmflag, int* klzbs, int* klcls,
                          double* cape, double* cin, double* invtau_t, double* invtau_q);                         // physics_bm.cu

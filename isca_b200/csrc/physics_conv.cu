@@ -26,16 +26,12 @@ __device__ __forceinline__ double virtual_temp(const ConvConst& c, double T, dou
   return T * (1.0 + q * (c.rvgas / c.rdgas - 1.0));
 }
 
-// idealized_moist_phys.F90:873-880 fused into the convection kernel when the moist model drives it (tg_tmp != NULL): the adjusted
-// profiles tg_tmp = T + deltaT, qg_tmp = q + deltaq that large-scale condensation sees, the increments as rates added to the tendencies,
-// the convective rain as a rate.  The thread re-reads its own deltaT / deltaq (L1 / L2 hits) instead of a second kernel streaming six planes.
-struct ConvPost { double delta_t; double *tg_tmp, *qg_tmp, *dt_t, *dt_q, *conv_rain, *precip; };
 // bytes/column: read Tin, qin, p_full (3K) + p_half (K+1); write deltaT, deltaq, qref, Tref (4K) + 7  ~ (8K + 8) * 8
 __global__ void __launch_bounds__(128) sbm_convection_kernel(SvpDev s, ConvConst c, int ncol, int K, double dt,
     const double* __restrict__ Tin, const double* __restrict__ qin, const double* __restrict__ p_full, const double* __restrict__ p_half,
     double* __restrict__ rain, double* __restrict__ deltaT, double* __restrict__ deltaq, double* __restrict__ qref, double* __restrict__ Tref,
     int* __restrict__ convflag, int* __restrict__ kLZBs, int* __restrict__ kLCLs, double* __restrict__ CAPE_o, double* __restrict__ CIN_o,
-    double* __restrict__ itq_o, double* __restrict__ itt_o, int* err, ConvPost post) {
+    double* __restrict__ itq_o, double* __restrict__ itt_o, int* err) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
   const size_t nc = ncol;
@@ -201,16 +197,6 @@ __global__ void __launch_bounds__(128) sbm_convection_kernel(SvpDev s, ConvConst
   // levels above the reference profiles that the branches above did not touch hold the model values / zero increments
   // (deltaq, deltaT are zero-initialised, Tref = Tp = Tin there in the reference); with cape > 0 they were set by full(1, lz-1)
   rain[col] = Pq; convflag[col] = flag; kLZBs[col] = kLZB; kLCLs[col] = kLCL; CAPE_o[col] = cape; CIN_o[col] = cin;
-  if (post.tg_tmp) {
-    for (int k = 0; k < K; ++k) {
-      const size_t o = (size_t)k * nc + col;
-      const double a = deltaT[o], b = deltaq[o];
-      post.tg_tmp[o] = a + T_in(k); post.qg_tmp[o] = b + q_in(k);
-      post.dt_t[o] = post.dt_t[o] + a / post.delta_t; post.dt_q[o] = post.dt_q[o] + b / post.delta_t;
-    }
-    const double r = Pq / post.delta_t;
-    post.conv_rain[col] = r; post.precip[col] = r;
-  }
   // the reference zeroes the whole relaxation-rate arrays inside its column loop (:283-284): only the last column keeps a value
   itq_o[col] = col == ncol - 1 ? itq : 0.0;
   itt_o[col] = col == ncol - 1 ? itt : 0.0;
@@ -262,16 +248,14 @@ int build_lcl_table(IscaPhysics p) {
 
 void launch_sbm_convection(IscaPhysics p, double dt, const double* Tin, const double* qin, const double* p_full, const double* p_half,
                            double* rain, double* deltaT, double* deltaq, double* qref, double* Tref, int* convflag, int* kLZBs, int* kLCLs,
-                           double* cape, double* cin, double* itq, double* itt, double* tg_tmp, double* qg_tmp, double* dt_t, double* dt_q,
-                           double* conv_rain, double* precip) {
+                           double* cape, double* cin, double* itq, double* itt) {
   ConvConst c;
   c.tau_bm = p->cfg.tau_bm; c.rhbm = p->cfg.rhbm; c.Tmin = p->cfg.Tmin; c.val_min = p->lcl_val_min; c.val_max = p->lcl_val_max;
   c.val_inc = p->cfg.val_inc; c.lcl_table = p->lcl_tab.p; c.ntab = p->lcl_n;
   c.rdgas = p->cfg.rdgas; c.rvgas = p->cfg.rvgas; c.cp_air = p->cfg.cp_air; c.hlv = p->cfg.hlv; c.kappa = p->cfg.rdgas / p->cfg.cp_air;
   c.grav = p->cfg.grav;
   sbm_convection_kernel<<<col_blocks(p, 128), 128, 0, p->st>>>(p->svp, c, (int)p->ncol, p->K, dt, Tin, qin, p_full, p_half, rain, deltaT, deltaq,
-                                                               qref, Tref, convflag, kLZBs, kLCLs, cape, cin, itq, itt, p->d_err,
-                                                               ConvPost{dt, tg_tmp, qg_tmp, dt_t, dt_q, conv_rain, precip});
+                                                               qref, Tref, convflag, kLZBs, kLCLs, cape, cin, itq, itt, p->d_err);
 }
 
 }  // namespace isca_phys

@@ -14,6 +14,7 @@
 #include "rrtm_internal.h"
 #include "rrtm_kernels.h"
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <string>
 
 using namespace rrtm;
@@ -67,9 +68,14 @@ double heatfac_of(double cp_air) { return GRAV * SECDY / (cp_air * 1.0e2); }
 // kernel launches on device pointers
 int isca_rrtm_lw_device(IscaRrtm r, const ColIn& in) {
   if (in.nlay > KMAX || in.nlay < 2) return rfail(r, "rrtmg_lw: num_levels must be 2..64");
-  const size_t smem = lw_smem_doubles(in.nlay) * sizeof(double);
-  RCK(cudaFuncSetAttribute(rrtmg_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lw_smem_doubles(KMAX) * sizeof(double))));
-  rrtmg_lw_kernel<<<in.ncol, LW_THREADS, smem, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
+  static const bool gpoint = std::getenv("ISCA_B200_RRTM_LW_GPOINT") != nullptr;     // development: the g-point-per-thread kernel
+  if (gpoint) {
+    const size_t smem = lw_smem_doubles(in.nlay) * sizeof(double);
+    RCK(cudaFuncSetAttribute(rrtmg_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lw_smem_doubles(KMAX) * sizeof(double))));
+    rrtmg_lw_kernel<<<in.ncol, LW_THREADS, smem, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
+  } else {
+    rrtmg_lw_col_kernel<<<(in.ncol + 31) / 32, 32 * LWC_WARPS, 0, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
+  }
   RCK(cudaGetLastError());
   r->last_lw = in; r->have_lw = true;
   return 0;

@@ -227,6 +227,166 @@ __global__ void __launch_bounds__(LW_THREADS, ISCA_LW_MINB) rrtmg_lw_kernel(cons
     in.hr[col + (size_t)nc * l] = in.heatfac * (fnet[l] - fnet[l + 1]) / (pz[l] - pz[l + 1]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Longwave, column-per-lane mapping (round 2, the production kernel).
+//
+// The g-point-per-thread kernel above is bound by the L1TEX pipe (ncu, T170: 85 % of its peak; 11.6 G warp instructions per call): each
+// warp instruction serves the 32 g-points of ONE column, the term lists have to travel through shared memory, and their construction
+// diverges 16 ways.  Here a LANE is a COLUMN (32 consecutive longitudes of one latitude) and a WARP owns a group of bands:
+//   * the term list of a (layer, band) is built by every lane for its own column with the same code path in all lanes, kept in
+//     thread-local memory, and read once per term -- not once per (term, g-point);
+//   * the table rows of neighbouring columns coincide (same pressure / temperature bins), so a table read is a broadcast (one L1
+//     wavefront for 32 columns) instead of 256 bytes per column;
+//   * the Planck functions of a layer are interpolated once per (layer, band), not per g-point;
+//   * the sum over the g-points is a serial sum in registers: no shuffles, no barriers inside the sweeps.
+// A CTA = 32 columns x 4 warps; the four band groups are balanced by sum(ng x terms).  The per-layer transmittance / source pairs of
+// the upward sweep stay in thread-local memory as before.  setcoef of a layer is recomputed per band (its inputs are L2-resident).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LWC_WARPS = 4;
+__device__ __constant__ int LWC_GROUP_OF_BAND[NB_LW] = {3, 3, 1, 0, 0, 3, 1, 2, 2, 3, 3, 2, 3, 3, 2, 3};   // 0-based band -> warp
+
+// one band of one column: rtrnmr's clear-sky down and up sweeps for the band's NG (padded) g-points held in registers
+template <int NG>
+__device__ __forceinline__ void lw_band_column(const double* __restrict__ A, const Tab& tb, const LwBand& B, int ib, const ColIn& in, int col,
+                                               int nl, double pwvcm, double* __restrict__ fu, double* __restrict__ fd,
+                                               double* __restrict__ AT, double* __restrict__ BBU) {
+  const size_t nc = in.ncol;
+  const int ng = B.ng;
+  const double* exptfn = A + tb.exptfn;
+  const double delwave[NB_LW] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
+  const double wb = 0.5 * delwave[ib];
+  const double sd = lw_secdiff(ib, pwvcm);
+  const double semiss = in.emis ? in.emis[col + nc * ib] : 1.0;
+  double radld[NG], frac1[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { radld[g] = 0.0; frac1[g] = 0.0; }
+  int ind; double fr;
+  planck_index(in.tlev[col + nc * nl], ind, fr);
+  double pl_up = planck_at(A, tb, ib, ind, fr);                // Planck function of the level above the current layer
+  for (int lev = nl; lev >= 1; --lev) {
+    const int l = lev - 1;
+    // inatm + setcoef of the layer
+    Layer L;
+    {
+      double vmr[NSP], xs[4];
+#pragma unroll
+      for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + nc * l] : in.gas_c[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xs[i] = in.xs[i] ? in.xs[i][col + nc * l] : in.xs_c[i];
+      const double pb = in.plev[col + nc * l], pa = in.plev[col + nc * (l + 1)];
+      lw_setcoef_layer(A, tb, in.play[col + nc * l], in.tlay[col + nc * l], coldry_of(pb, pa, vmr[0]), vmr, xs, L);
+    }
+    LwRec rec;
+    lw_terms(A, tb, B, L, rec);
+    double tau[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) tau[g] = 0.0;
+    for (int i = 0; i < rec.n; ++i) {                            // one (weight, row) pair per term, NG table reads each
+      const double w = rec.w[i];
+      const double* row = A + rec.off[i];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) if (g < ng) tau[g] += w * row[g];
+    }
+    planck_index(in.tlay[col + nc * l], ind, fr);
+    const double blay = planck_at(A, tb, ib, ind, fr);
+    planck_index(in.tlev[col + nc * l], ind, fr);
+    const double pl_dn = planck_at(A, tb, ib, ind, fr);
+    double sum = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      if (g < ng) {
+        double t = tau[g];
+        if (rec.gs_off >= 0) t *= A[rec.gs_off + g];
+        double plfrac = 0.0;
+        if (rec.f0 >= 0) { const double a = A[rec.f0 + g]; plfrac = rec.f1 >= 0 ? a + rec.ffs * (A[rec.f1 + g] - a) : a; }
+        if (lev == 1) frac1[g] = plfrac;
+        double at, bbu;
+        lw_layer(exptfn, sd, t, plfrac, blay, pl_up, pl_dn, radld[g], at, bbu);
+        AT[l * NG + g] = at; BBU[l * NG + g] = bbu;
+        sum += radld[g];
+      }
+    }
+    fd[l] += sum * wb;
+    pl_up = pl_dn;
+  }
+  planck_index(in.tsfc[col], ind, fr);
+  const double plankbnd = semiss * planck_at(A, tb, ib, ind, fr);
+  double radlu[NG];
+  {
+    double sum = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      radlu[g] = 0.0;
+      if (g < ng) { radlu[g] = frac1[g] * plankbnd + (1.0 - semiss) * radld[g]; sum += radlu[g]; }
+    }
+    fu[0] += sum * wb;
+  }
+  for (int lev = 1; lev <= nl; ++lev) {
+    const int l = lev - 1;
+    double sum = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+      if (g < ng) { radlu[g] = radlu[g] + (BBU[l * NG + g] - radlu[g]) * AT[l * NG + g]; sum += radlu[g]; }
+    fu[lev] += sum * wb;
+  }
+}
+
+#ifndef ISCA_LWC_MINB
+#define ISCA_LWC_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * LWC_WARPS, ISCA_LWC_MINB) rrtmg_lw_col_kernel(const double* __restrict__ A, Tab tb, const LwBand* __restrict__ bands, ColIn in) {
+  __shared__ double sfu[(KMAX + 1) * 32], sfd[(KMAX + 1) * 32];        // [level][column of the CTA]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nl = in.nlay;
+  const size_t nc = in.ncol;
+  const int col_raw = blockIdx.x * 32 + lane;
+  const bool live = col_raw < in.ncol;
+  const int col = live ? col_raw : in.ncol - 1;                   // padding lanes repeat the last column (no divergence, no stores)
+  double fu[KMAX + 1], fd[KMAX + 1];
+  double AT[KMAX * 16], BBU[KMAX * 16];
+  for (int lev = 0; lev <= nl; ++lev) { fu[lev] = 0.0; fd[lev] = 0.0; }
+  // inatm: precipitable water of the column (rrtmg_lw_rad.nomcica.f90:846-856) -> diffusivity angle of the bands
+  double pwvcm;
+  {
+    double amttl = 0.0, wvttl = 0.0;
+    for (int l = 0; l < nl; ++l) {
+      const double h2o = in.gas[SP_H2O] ? in.gas[SP_H2O][col + nc * l] : in.gas_c[SP_H2O];
+      const double coldry = coldry_of(in.plev[col + nc * l], in.plev[col + nc * (l + 1)], h2o);
+      const double wv = (1.0e-20 * (coldry * h2o)) * 1.0e20;   // colh2o * 1.e20 as setcoef / inatm form it
+      amttl += coldry + wv;
+      wvttl += wv;
+    }
+    const double wvsh = (AMW * wvttl) / (AMD * amttl);
+    pwvcm = wvsh * (1.0e3 * in.plev[col]) / (1.0e2 * GRAV);
+  }
+  for (int ib = 0; ib < NB_LW; ++ib) {
+    if (LWC_GROUP_OF_BAND[ib] != warp) continue;
+    const LwBand& B = bands[ib];
+    if (B.ng > 8) lw_band_column<16>(A, tb, B, ib, in, col, nl, pwvcm, fu, fd, AT, BBU);
+    else if (B.ng > 4) lw_band_column<8>(A, tb, B, ib, in, col, nl, pwvcm, fu, fd, AT, BBU);
+    else if (B.ng > 2) lw_band_column<4>(A, tb, B, ib, in, col, nl, pwvcm, fu, fd, AT, BBU);
+    else lw_band_column<2>(A, tb, B, ib, in, col, nl, pwvcm, fu, fd, AT, BBU);
+  }
+  // sum of the four band groups in a fixed order (warp 0, 1, 2, 3): reproducible
+  for (int w = 0; w < LWC_WARPS; ++w) {
+    if (warp == w)
+      for (int lev = 0; lev <= nl; ++lev) {
+        if (w == 0) { sfu[lev * 32 + lane] = fu[lev]; sfd[lev * 32 + lane] = fd[lev]; }
+        else { sfu[lev * 32 + lane] += fu[lev]; sfd[lev * 32 + lane] += fd[lev]; }
+      }
+    __syncthreads();
+  }
+  if (!live) return;
+  for (int lev = warp; lev <= nl; lev += LWC_WARPS) {
+    in.uflx[col + nc * lev] = sfu[lev * 32 + lane] * FLUXFAC;
+    in.dflx[col + nc * lev] = sfd[lev * 32 + lane] * FLUXFAC;
+  }
+  for (int l = warp; l < nl; l += LWC_WARPS) {
+    const double f0 = sfu[l * 32 + lane] * FLUXFAC - sfd[l * 32 + lane] * FLUXFAC;
+    const double f1 = sfu[(l + 1) * 32 + lane] * FLUXFAC - sfd[(l + 1) * 32 + lane] * FLUXFAC;
+    in.hr[col + nc * l] = in.heatfac * (f0 - f1) / (in.plev[col + nc * l] - in.plev[col + nc * (l + 1)]);
+  }
+}
+
 // Shortwave (spcvrt_sw clear sky + reftra_sw + vrtqdr_sw).  Same structure as the longwave kernel; the sweeps are re-ordered so that
 // the optical depths are needed only once: pass 1 runs bottom-up (layer optics, two-stream reflectance / transmittance of the layer
 // and, in the same step, vrtqdr's upward combination zrup / zrupd, which is a bottom-up recurrence), pass 2 top-down (direct-beam

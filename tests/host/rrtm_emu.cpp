@@ -9,6 +9,7 @@
 // Built by tests/test_rrtm_host.py into tests/host/_build/; never linked into the product library.
 #include <barrier>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -25,6 +26,7 @@ static double g_shfl[64][32];
 
 #define __global__
 #define __device__
+#define __constant__
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
@@ -108,7 +110,8 @@ int rrtm_emu_lw(const char* table_path, double cp_air, int ncol, int nlay, const
   const double* A = H.arena.data();
   const LwBand* bands = H.lw;
   Tab tb = H.tab;
-  launch(ncol, LW_THREADS, [=]() { rrtmg_lw_kernel(A, tb, bands, in); });
+  if (std::getenv("RRTM_EMU_LW_GPOINT")) launch(ncol, LW_THREADS, [=]() { rrtmg_lw_kernel(A, tb, bands, in); });
+  else launch((ncol + 31) / 32, 32 * LWC_WARPS, [=]() { rrtmg_lw_col_kernel(A, tb, bands, in); });
   return 0;
 }
 
@@ -162,7 +165,7 @@ int rrtm_emu_run_rrtmg(const char* table_path, int I, int J, int K, int lonstep,
   launch((int)nc, SW_THREADS, [=]() { rrtmg_sw_kernel(A, tb, sb, sw); });
   ColIn lw = in; lw.uflx = lwu.data(); lw.dflx = lwd.data(); lw.hr = lwhr.data();
   const LwBand* lb = H.lw;
-  launch((int)nc, LW_THREADS, [=]() { rrtmg_lw_kernel(A, tb, lb, lw); });
+  launch(((int)nc + 31) / 32, 32 * LWC_WARPS, [=]() { rrtmg_lw_col_kernel(A, tb, lb, lw); });
   FinishArgs fa{(int)nm, K, swhr.data(), lwhr.data(), swu.data(), swd.data(), lwu.data(), lwd.data(), tdt, tdt_rad, flux_sw, flux_lw, olr, toa_sw,
                 ls, I};
   launch(Gm, T, [=]() { rrtm_finish_kernel(fa); });

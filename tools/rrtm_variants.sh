@@ -5,8 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 NVCC=/usr/local/cuda/bin/nvcc
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -diag-suppress 550"
-VARIANTS=("lw8_1:-DISCA_LW_TILE=8 -DISCA_LW_MINB=1" "lw4_5:-DISCA_LW_TILE=4 -DISCA_LW_MINB=5" "lw4_6:-DISCA_LW_TILE=4 -DISCA_LW_MINB=6"
-          "lw6_4:-DISCA_LW_TILE=6 -DISCA_LW_MINB=4" "sw4_8:-DISCA_SW_TILE=4 -DISCA_SW_MINB=8" "sw4_6:-DISCA_SW_TILE=4 -DISCA_SW_MINB=6")
+VARIANTS=("lwc_1:-DISCA_LWC_MINB=1" "lwc_3:-DISCA_LWC_MINB=3" "lwc_4:-DISCA_LWC_MINB=4" "lwc_5:-DISCA_LWC_MINB=5")
 if [ "$1" = "build" ]; then
   for v in "${VARIANTS[@]}"; do
     name=${v%%:*}; defs=${v#*:}
@@ -21,6 +20,10 @@ else
   for v in "${VARIANTS[@]}"; do
     name=${v%%:*}
     echo "== $name"
-    ISCA_B200_LIB=$PWD/isca_b200/lib/variants/$name/libisca_b200.so timeout 200 python tools/rrtm_bench.py 2>&1 | python -c "import sys,json; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('lw_ms', round(d['lw_kernel_ms'],2), 'sw_ms', round(d['sw_kernel_ms'],2), 'olr', d['olr_mean'])"
+    if [ "$name" = "lwc_1" ]; then
+      echo "-- g-point-per-thread kernel (ISCA_B200_RRTM_LW_GPOINT=1)"
+      ISCA_B200_RRTM_LW_GPOINT=1 ISCA_B200_LIB=$PWD/isca_b200/lib/variants/$name/libisca_b200.so timeout 200 python tools/rrtm_bench.py 2>&1 | python -c "import sys,json; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('lw_ms', round(d['lw_kernel_ms'],2), 'sw_ms', round(d['sw_kernel_ms'],2), 'olr', repr(d['olr_mean']), 'sfc', repr(d['surf_lw_down_mean']))"
+    fi
+    ISCA_B200_LIB=$PWD/isca_b200/lib/variants/$name/libisca_b200.so timeout 200 python tools/rrtm_bench.py 2>&1 | python -c "import sys,json; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('lw_ms', round(d['lw_kernel_ms'],2), 'sw_ms', round(d['sw_kernel_ms'],2), 'olr', repr(d['olr_mean']), 'sfc', repr(d['surf_lw_down_mean']))"
   done
 fi
