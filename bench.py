@@ -87,7 +87,9 @@ def work_model(res: str, K: int, moist: bool = False, nlev_sponge: int = 0):
             "phys_surface_flux": dict(bytes=col * 45, bound="latency"),
             "phys_radiation": dict(bytes=col * 3 * K),
             "phys_damping": dict(bytes=col * 15 * max(nlev_sponge, 1)),
-            "phys_diffusivity": dict(bytes=col * (20 * K + 4)),
+            # diffusivity: k_m, k_t written on every level (2K) + surface inputs; the reads of t, q, u, v, their tendencies (tau + 1
+            # variables are formed in the kernel) and z_full stop at the PBL top (data dependent) and are not counted
+            "phys_diffusivity": dict(bytes=col * (2 * K + 4), bound="latency"),
             "phys_vert_diff_down": dict(bytes=col * (19 * K + 14)),
             "phys_mixed_layer_vert_diff_up": dict(bytes=col * (5 * K + 20)),
         })

@@ -37,7 +37,7 @@ __global__ void compute_qs_kernel(SvpDev s, PhysConst c, int n, const double* __
 
 // lscale_cond: one top-down sweep fuses compute_qs, the adjustment, precip_evap and the rain integral.
 // bytes/column: read t, q, pfull (3K) + phalf (K+1), write tdel, qdel (2K) + rain (1)  = (6K + 2) * 8
-__global__ void __launch_bounds__(128) lscale_cond_kernel(SvpDev s, PhysConst c, int ncol, int K,
+__global__ void __launch_bounds__(128, ISCA_COL_MINB) lscale_cond_kernel(SvpDev s, PhysConst c, int ncol, int K,
     const double* __restrict__ tin, const double* __restrict__ qin, const double* __restrict__ pfull,
     const double* __restrict__ phalf, double* __restrict__ rain, double* __restrict__ tdel, double* __restrict__ qdel, int* err) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,7 +106,7 @@ __device__ __forceinline__ double sw_down_at(const PhysConst& c, double insolati
 
 // two_stream_gray_rad_down: only the two surface fluxes leave the kernel.
 // bytes/column: read t (K) + p_half (K+1) + lat, albedo (2), write 2   = (2K + 5) * 8
-__global__ void __launch_bounds__(128) gray_down_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
+__global__ void __launch_bounds__(128, ISCA_COL_MINB) gray_down_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
     const double* __restrict__ p_half, const double* __restrict__ t, const double* __restrict__ albedo,
     double* __restrict__ net_surf_sw_down, double* __restrict__ surf_lw_down) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) gray_down_kernel(PhysConst c, int ncol, i
 // two_stream_gray_rad_up: the down sweep is recomputed (its fluxes stay in thread-local storage) and the up sweep
 // accumulates the flux divergence into tdt.
 // bytes/column: read t (K) + p_half (K+1) + tdt (K) + lat, t_surf, albedo (3), write tdt (K) + olr (1)  = (4K + 5) * 8
-__global__ void __launch_bounds__(128) gray_up_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
+__global__ void __launch_bounds__(128, ISCA_COL_MINB) gray_up_kernel(PhysConst c, int ncol, int K, const double* __restrict__ lat,
     const double* __restrict__ p_half, const double* __restrict__ t, const double* __restrict__ t_surf,
     const double* __restrict__ albedo, double* __restrict__ tdt, double* __restrict__ olr) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;

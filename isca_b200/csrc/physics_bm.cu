@@ -13,7 +13,7 @@ namespace {
 
 __constant__ double d_lcltable[127] = {ISCA_BM_LCLTABLE_VALUES};
 
-__global__ void __launch_bounds__(128) betts_miller_kernel(isca_bm::BmSvp s, isca_bm::BmConst c, int ncol, int K, double dt,
+__global__ void __launch_bounds__(128, ISCA_COL_MINB) betts_miller_kernel(isca_bm::BmSvp s, isca_bm::BmConst c, int ncol, int K, double dt,
     const double* __restrict__ tin, const double* __restrict__ qin, const double* __restrict__ pfull, const double* __restrict__ phalf,
     double* __restrict__ rain, double* __restrict__ tdel, double* __restrict__ qdel, double* __restrict__ q_ref, double* __restrict__ t_ref,
     int* __restrict__ bmflag, int* __restrict__ klzbs, int* __restrict__ klcls, double* __restrict__ cape, double* __restrict__ cin,

@@ -10,6 +10,19 @@
 #include <string>
 #include <vector>
 
+// Resident CTAs per SM asked of the 128-thread column kernels.  At T170 (131 072 columns = 1024 CTAs = 6.9 per SM) a latency-bound
+// kernel that keeps fewer than 7 CTAs resident runs a second, mostly empty wave and pays for two: (128, 7) caps the registers at 72,
+// which costs these kernels at most a few spilled values (ptxas -v).  vert_diff_down and surface_flux need more registers than that.
+#ifndef ISCA_COL_MINB
+#define ISCA_COL_MINB 7
+#endif
+#ifndef ISCA_VDD_MINB
+#define ISCA_VDD_MINB 4
+#endif
+#ifndef ISCA_SF_MINB
+#define ISCA_SF_MINB 4
+#endif
+
 namespace isca_phys {
 
 struct SvpDev {

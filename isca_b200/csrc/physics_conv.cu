@@ -27,7 +27,7 @@ __device__ __forceinline__ double virtual_temp(const ConvConst& c, double T, dou
 }
 
 // bytes/column: read Tin, qin, p_full (3K) + p_half (K+1); write deltaT, deltaq, qref, Tref (4K) + 7  ~ (8K + 8) * 8
-__global__ void __launch_bounds__(128) sbm_convection_kernel(SvpDev s, ConvConst c, int ncol, int K, double dt,
+__global__ void __launch_bounds__(128, ISCA_COL_MINB) sbm_convection_kernel(SvpDev s, ConvConst c, int ncol, int K, double dt,
     const double* __restrict__ Tin, const double* __restrict__ qin, const double* __restrict__ p_full, const double* __restrict__ p_half,
     double* __restrict__ rain, double* __restrict__ deltaT, double* __restrict__ deltaq, double* __restrict__ qref, double* __restrict__ Tref,
     int* __restrict__ convflag, int* __restrict__ kLZBs, int* __restrict__ kLCLs, double* __restrict__ CAPE_o, double* __restrict__ CIN_o,

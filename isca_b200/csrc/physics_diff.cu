@@ -109,7 +109,7 @@ __device__ __forceinline__ Surf down2_pipe(const DiffArgs& a, int col, const dou
 
 // bytes/column: read u,v,t,q,diff_m,diff_t,z_full,dt_u,dt_v,dt_t,dt_q (11K) + p_half (K+1) + 4; write dt_u,dt_v,dt_t,diss,
 // e,f_t,f_q (7K) + 9  =  (19K + 14) * 8
-__global__ void __launch_bounds__(128) vert_diff_down_kernel(DiffArgs a) {
+__global__ void __launch_bounds__(128, ISCA_VDD_MINB) vert_diff_down_kernel(DiffArgs a) {
   int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= a.ncol) return;
   const int K = a.K; const size_t nc = a.ncol;

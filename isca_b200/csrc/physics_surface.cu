@@ -42,7 +42,7 @@ struct SfConst {
 };
 
 // bytes/point: 17 inputs + 29 outputs = 46 * 8 (one 2-D sweep; negligible next to the 3-D kernels)
-__global__ void __launch_bounds__(128) surface_flux_kernel(SvpDev s, MoConst mc, SfConst c, int n, IscaSurfaceFluxArgs a, int* err) {
+__global__ void __launch_bounds__(128, ISCA_SF_MINB) surface_flux_kernel(SvpDev s, MoConst mc, SfConst c, int n, IscaSurfaceFluxArgs a, int* err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double del_temp = 0.1, del_temp_inv = 1.0 / del_temp;

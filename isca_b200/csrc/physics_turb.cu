@@ -22,7 +22,7 @@ struct TurbConst {
 // tau + 1, x + dt * dx/dt, formed here from the previous-level fields and the tendencies instead of by a separate pass over four 3-D
 // fields.  add_input = 0: the diffusivities are written, not added to the incoming arrays (the caller would have zeroed them).
 struct Tau1 { const double *tdt, *qdt, *udt, *vdt; double dt; };
-__global__ void __launch_bounds__(128) diffusivity_kernel(MoConst mc, TurbConst c, int ncol, int K, const double* __restrict__ t_,
+__global__ void __launch_bounds__(128, ISCA_COL_MINB) diffusivity_kernel(MoConst mc, TurbConst c, int ncol, int K, const double* __restrict__ t_,
     const double* __restrict__ q_, const double* __restrict__ u_, const double* __restrict__ v_, Tau1 tau1, int add_input,
     const double* __restrict__ z_full,
     const double* __restrict__ z_half, const double* __restrict__ u_star, const double* __restrict__ b_star, double* __restrict__ h_out,

@@ -48,6 +48,7 @@ struct IscaRrtm_t {
   bool owns_stream = true;
   std::string err;
   DevBuf buf[32];
+  DevBuf lays;                       // longwave setcoef planes (scratch of isca_rrtm_lw_device)
   ColIn last_lw{}, last_sw{};
   bool have_lw = false, have_sw = false;
 };
@@ -66,7 +67,8 @@ int up(IscaRrtm r, DevBuf& d, const double* h, size_t n, const double** out) {
 double heatfac_of(double cp_air) { return GRAV * SECDY / (cp_air * 1.0e2); }
 
 // kernel launches on device pointers
-int isca_rrtm_lw_device(IscaRrtm r, const ColIn& in) {
+int isca_rrtm_lw_device(IscaRrtm r, const ColIn& in_) {
+  ColIn in = in_;
   if (in.nlay > KMAX || in.nlay < 2) return rfail(r, "rrtmg_lw: num_levels must be 2..64");
   static const bool gpoint = std::getenv("ISCA_B200_RRTM_LW_GPOINT") != nullptr;     // development: the g-point-per-thread kernel
   if (gpoint) {
@@ -74,6 +76,12 @@ int isca_rrtm_lw_device(IscaRrtm r, const ColIn& in) {
     RCK(cudaFuncSetAttribute(rrtmg_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lw_smem_doubles(KMAX) * sizeof(double))));
     rrtmg_lw_kernel<<<in.ncol, LW_THREADS, smem, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
   } else {
+#if ISCA_LWC_PREPASS
+    const size_t ps = (size_t)in.ncol * in.nlay;
+    if (!r->lays.ensure(ps * LAYP_N)) return rfail(r, "cudaMalloc failed (longwave setcoef planes)");
+    in.lays = r->lays.p;
+    rrtmg_lw_setcoef_kernel<<<(unsigned)((ps + 127) / 128), 128, 0, r->st>>>(r->d_arena, r->tab, in);
+#endif
     rrtmg_lw_col_kernel<<<(in.ncol + 31) / 32, 32 * LWC_WARPS, 0, r->st>>>(r->d_arena, r->tab, r->d_lw, in);
   }
   RCK(cudaGetLastError());
@@ -82,9 +90,14 @@ int isca_rrtm_lw_device(IscaRrtm r, const ColIn& in) {
 }
 int isca_rrtm_sw_device(IscaRrtm r, const ColIn& in) {
   if (in.nlay > KMAX || in.nlay < 2) return rfail(r, "rrtmg_sw: num_levels must be 2..64");
-  const size_t smem = sw_smem_doubles(in.nlay) * sizeof(double);
-  RCK(cudaFuncSetAttribute(rrtmg_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sw_smem_doubles(KMAX) * sizeof(double))));
-  rrtmg_sw_kernel<<<in.ncol, SW_THREADS, smem, r->st>>>(r->d_arena, r->tab, r->d_sw, in);
+  static const bool percol = std::getenv("ISCA_B200_RRTM_SW_COL") != nullptr;     // development: the column-per-lane kernel (measured slower)
+  if (!percol) {
+    const size_t smem = sw_smem_doubles(in.nlay) * sizeof(double);
+    RCK(cudaFuncSetAttribute(rrtmg_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sw_smem_doubles(KMAX) * sizeof(double))));
+    rrtmg_sw_kernel<<<in.ncol, SW_THREADS, smem, r->st>>>(r->d_arena, r->tab, r->d_sw, in);
+  } else {
+    rrtmg_sw_col_kernel<<<(in.ncol + 31) / 32, 32 * SWC_WARPS, 0, r->st>>>(r->d_arena, r->tab, r->d_sw, in);
+  }
   RCK(cudaGetLastError());
   r->last_sw = in; r->have_sw = true;
   return 0;

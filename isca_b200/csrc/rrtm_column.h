@@ -342,6 +342,22 @@ RR_HD void lw_tau_rec(const double* A, const LwRec& r, int g, double& tau, doubl
   }
 }
 
+// Two consecutive doubles of a table with one 128-bit read (every table of the arena starts on a 16-byte boundary and the g-point
+// counts are even).  ISCA_TAB2_MODE 2 marks the read evict-last in L1 -- measured harmful (the thread-local transmittance arrays of
+// the sweeps lose their L1 lines: DRAM write traffic doubles), kept for the record; 1 = plain 128-bit read; 0 = two scalar reads.
+#ifndef ISCA_TAB2_MODE
+#define ISCA_TAB2_MODE 0
+#endif
+RR_HD void tab2(const double* p, double& a, double& b) {
+#if defined(__CUDA_ARCH__) && ISCA_TAB2_MODE == 2
+  asm("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(__cvta_generic_to_global(p)));
+#elif defined(__CUDA_ARCH__) && ISCA_TAB2_MODE == 1
+  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(__cvta_generic_to_global(p)));
+#else
+  a = p[0]; b = p[1];
+#endif
+}
+
 // one layer of rtrnmr's clear-sky downward sweep for one g-point (rrtmg_lw_rtrnmr.f90:390-480): transmittance from the Pade
 // table (exptfn = interleaved exp / tfn tables), layer emission towards both sides, update of the downward radiance
 RR_HD void lw_layer(const double* exptfn, double secdiff, double tau, double plfrac, double blay, double plev_up, double plev_dn,
@@ -357,8 +373,9 @@ RR_HD void lw_layer(const double* exptfn, double secdiff, double tau, double plf
   } else {
     double tblind = odepth / (BPADE + odepth);
     int itr = (int)(TBLINT * tblind + 0.5);
-    at = 1.0 - exptfn[2 * itr];
-    tfac = exptfn[2 * itr + 1];
+    double e;
+    tab2(exptfn + 2 * itr, e, tfac);
+    at = 1.0 - e;
   }
   double bbd = plfrac * (blay + tfac * dplankdn);
   bbugas = plfrac * (blay + tfac * dplankup);
@@ -451,6 +468,22 @@ RR_HD double sw_src_rec(const double* A, const SwBand& B, const SwRec& r, int g)
     return F[(r.js - 1) * B.ng + g] + r.fs * (F[r.js * B.ng + g] - F[(r.js - 1) * B.ng + g]);
   }
   return B.sflux_scale * A[B.sflux_off + g];
+}
+
+// sw_laysolfr from the pressure indices alone (the column-per-lane kernel keeps jp of every layer, not the whole setcoef output)
+RR_HD int sw_laysolfr_jp(const SwBand& B, const int* jp, int nl, int laytrop) {
+  if (B.sflux_upper) {
+    int ls = nl;
+    for (int l = (laytrop + 1 > 2 ? laytrop + 1 : 2); l <= nl; ++l)
+      if (jp[l - 2] < B.layreffr && jp[l - 1] >= B.layreffr) ls = l;
+    return ls > laytrop ? ls : 0;
+  }
+  int ls = laytrop;
+  for (int l = 1; l <= laytrop; ++l) {
+    int jpn = l < nl ? jp[l] : 0;
+    if (jp[l - 1] < B.layreffr && jpn >= B.layreffr) ls = (l + 1 < laytrop ? l + 1 : laytrop);
+  }
+  return ls;
 }
 
 // the layer (1-based) whose species ratio defines the band's solar source: the `laysolfr` logic of taumol16..29

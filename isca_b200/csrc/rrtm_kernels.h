@@ -23,6 +23,7 @@ struct ColIn {                       // device pointers, (ncol, nlay) column-fas
   const double* xs[4]; double xs_c[4];
   double *uflx, *dflx, *hr;
   double heatfac, adjflux;
+  double* lays;                      // longwave: setcoef planes [LAYP_N][nlay][ncol] written by rrtmg_lw_setcoef_kernel (scratch)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -240,16 +241,96 @@ __global__ void __launch_bounds__(LW_THREADS, ISCA_LW_MINB) rrtmg_lw_kernel(cons
 //   * the Planck functions of a layer are interpolated once per (layer, band), not per g-point;
 //   * the sum over the g-points is a serial sum in registers: no shuffles, no barriers inside the sweeps.
 // A CTA = 32 columns x 4 warps; the four band groups are balanced by sum(ng x terms).  The per-layer transmittance / source pairs of
-// the upward sweep stay in thread-local memory as before.  setcoef of a layer is recomputed per band (its inputs are L2-resident).
+// the upward sweep stay in thread-local memory as before.  setcoef is evaluated once per (column, layer) by a pre-pass kernel (below).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LWC_WARPS = 4;
-__device__ __constant__ int LWC_GROUP_OF_BAND[NB_LW] = {3, 3, 1, 0, 0, 3, 1, 2, 2, 3, 3, 2, 3, 3, 2, 3};   // 0-based band -> warp
+// longest-processing-time assignment of cost(band) = 550 (setcoef + term list per layer) + ng * (1.6 terms + 60):
+// warp 0: bands 5, 8, 6, 14; warp 1: 3, 1, 10, 13; warp 2: 4, 2, 12, 15; warp 3: 7, 9, 11, 16 (1-based band numbers), ~5200 each
+__device__ __constant__ int LWC_GROUP_OF_BAND[NB_LW] = {1, 2, 1, 2, 0, 0, 3, 0, 3, 1, 3, 2, 1, 0, 2, 3};   // 0-based band -> warp
 
-// one band of one column: rtrnmr's clear-sky down and up sweeps for the band's NG (padded) g-points held in registers
+#ifndef ISCA_LWC_PREPASS
+#define ISCA_LWC_PREPASS 1
+#endif
+// 0: scalar table reads, unrolling left to the compiler (fastest measured: 24.7 ms per T170 L40 call); 2 / 4: that many terms in flight
+// with explicit 128-bit reads (tab2; measured slower with the evict-last hint, which pushes the thread-local arrays out of L1)
+#ifndef ISCA_LWC_UNROLL
+#define ISCA_LWC_UNROLL 0
+#endif
+// setcoef does not depend on the band: rrtmg_lw_setcoef_kernel evaluates inatm + setcoef once per (column, layer) into planes
+// [LAYP_N][layer][column] (1.1 GB at T170 L40), and the band sweeps read back only the planes their band descriptor uses.
+// Plane 0 holds the seven small integers packed into one exactly representable double.
+enum { LAYP_PK = 0, LAYP_FAC00, LAYP_FAC01, LAYP_FAC10, LAYP_FAC11, LAYP_SELFFAC, LAYP_SELFFRAC, LAYP_FORFAC, LAYP_FORFRAC,
+       LAYP_MINORFRAC, LAYP_SCALEMINOR, LAYP_SCALEMINORN2, LAYP_COLBRD, LAYP_COLDRY, LAYP_PAVEL, LAYP_COL, LAYP_WX = LAYP_COL + NSP,
+       LAYP_N = LAYP_WX + 4 };
+
+__device__ __forceinline__ void lw_layer_inputs(const ColIn& in, int col, int l, const double* __restrict__ A, const Tab& tb, Layer& L) {
+  const size_t nc = in.ncol;
+  double vmr[NSP], xs[4];
+#pragma unroll
+  for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + nc * l] : in.gas_c[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xs[i] = in.xs[i] ? in.xs[i][col + nc * l] : in.xs_c[i];
+  const double pb = in.plev[col + nc * l], pa = in.plev[col + nc * (l + 1)];
+  lw_setcoef_layer(A, tb, in.play[col + nc * l], in.tlay[col + nc * l], coldry_of(pb, pa, vmr[0]), vmr, xs, L);
+}
+
+__global__ void __launch_bounds__(128) rrtmg_lw_setcoef_kernel(const double* __restrict__ A, Tab tb, ColIn in) {
+  const size_t nc = in.ncol, ps = nc * (size_t)in.nlay;
+  const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= ps) return;
+  const int l = (int)(i / nc), col = (int)(i - (size_t)l * nc);
+  Layer L;
+  lw_layer_inputs(in, col, l, A, tb, L);
+  double* o = in.lays + i;
+  const int pk = L.jp | (L.jt << 6) | (L.jt1 << 9) | (L.indself << 12) | (L.indfor << 16) | (L.indminor << 18) | (L.lower << 23);
+  o[LAYP_PK * ps] = (double)pk;
+  o[LAYP_FAC00 * ps] = L.fac00; o[LAYP_FAC01 * ps] = L.fac01; o[LAYP_FAC10 * ps] = L.fac10; o[LAYP_FAC11 * ps] = L.fac11;
+  o[LAYP_SELFFAC * ps] = L.selffac; o[LAYP_SELFFRAC * ps] = L.selffrac; o[LAYP_FORFAC * ps] = L.forfac; o[LAYP_FORFRAC * ps] = L.forfrac;
+  o[LAYP_MINORFRAC * ps] = L.minorfrac; o[LAYP_SCALEMINOR * ps] = L.scaleminor; o[LAYP_SCALEMINORN2 * ps] = L.scaleminorn2;
+  o[LAYP_COLBRD * ps] = L.colbrd; o[LAYP_COLDRY * ps] = L.coldry; o[LAYP_PAVEL * ps] = L.pavel;
+#pragma unroll
+  for (int k = 0; k < NSP; ++k) o[(LAYP_COL + k) * ps] = L.col[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[(LAYP_WX + k) * ps] = L.wx[k];
+}
+
+// The term list of one (column, layer, band) from the setcoef planes: reads exactly the planes lw_terms uses for this band / region.
+// One copy of this code serves every band (not inlined into the four g-point-count instantiations of the sweep: instruction cache).
+__device__ __noinline__ void lw_record_from_planes(const double* __restrict__ A, const Tab& tb, const LwBand& B,
+                                                   const double* __restrict__ p, size_t ps, LwRec& rec) {
+  Layer L;
+  const int pk = (int)p[LAYP_PK * ps];
+  L.jp = pk & 63; L.jt = (pk >> 6) & 7; L.jt1 = (pk >> 9) & 7; L.indself = (pk >> 12) & 15; L.indfor = (pk >> 16) & 3;
+  L.indminor = (pk >> 18) & 31; L.lower = (pk >> 23) & 1;
+  const LwRegion& R = B.r[L.lower ? 0 : 1];
+  L.fac00 = p[LAYP_FAC00 * ps]; L.fac01 = p[LAYP_FAC01 * ps]; L.fac10 = p[LAYP_FAC10 * ps]; L.fac11 = p[LAYP_FAC11 * ps];
+  if (R.major >= 1) L.col[R.spA] = p[(LAYP_COL + R.spA) * ps];
+  if (R.spB >= 0) { L.col[R.spA] = p[(LAYP_COL + R.spA) * ps]; L.col[R.spB] = p[(LAYP_COL + R.spB) * ps]; }
+  if (R.self_off >= 0) { L.selffac = p[LAYP_SELFFAC * ps]; L.selffrac = p[LAYP_SELFFRAC * ps]; }
+  if (R.for_off >= 0) { L.forfac = p[LAYP_FORFAC * ps]; L.forfrac = p[LAYP_FORFRAC * ps]; }
+  if (R.nminor > 0) {
+    L.minorfrac = p[LAYP_MINORFRAC * ps];
+    for (int m = 0; m < R.nminor; ++m) {
+      const Minor& M = R.minor[m];
+      if (M.scale == SC_COL) L.col[M.sp] = p[(LAYP_COL + M.sp) * ps];
+      else if (M.scale == SC_ADJ) { L.col[M.sp] = p[(LAYP_COL + M.sp) * ps]; L.coldry = p[LAYP_COLDRY * ps]; }
+      else if (M.scale == SC_BRD_N2) { L.colbrd = p[LAYP_COLBRD * ps]; L.scaleminorn2 = p[LAYP_SCALEMINORN2 * ps]; }
+      else if (M.scale == SC_BRD) { L.colbrd = p[LAYP_COLBRD * ps]; L.scaleminor = p[LAYP_SCALEMINOR * ps]; }
+      else { L.col[SP_O2] = p[(LAYP_COL + SP_O2) * ps]; L.scaleminor = p[LAYP_SCALEMINOR * ps]; }
+    }
+  }
+  for (int c = 0; c < R.ncfc; ++c) L.wx[R.cfc_wx[c]] = p[(LAYP_WX + R.cfc_wx[c]) * ps];
+  if (R.corr != 0) L.pavel = p[LAYP_PAVEL * ps];
+  lw_terms(A, tb, B, L, rec);
+}
+
+// one band of one column: rtrnmr's clear-sky down and up sweeps.  The downward radiances of the band's NG (padded) g-points stay in
+// registers; optical depths are formed and consumed in groups of H = min(NG, 8) g-points to bound the live registers.
 template <int NG>
 __device__ __forceinline__ void lw_band_column(const double* __restrict__ A, const Tab& tb, const LwBand& B, int ib, const ColIn& in, int col,
                                                int nl, double pwvcm, double* __restrict__ fu, double* __restrict__ fd,
                                                double* __restrict__ AT, double* __restrict__ BBU) {
+  constexpr int H = NG < 8 ? NG : 8;
   const size_t nc = in.ncol;
   const int ng = B.ng;
   const double* exptfn = A + tb.exptfn;
@@ -257,55 +338,100 @@ __device__ __forceinline__ void lw_band_column(const double* __restrict__ A, con
   const double wb = 0.5 * delwave[ib];
   const double sd = lw_secdiff(ib, pwvcm);
   const double semiss = in.emis ? in.emis[col + nc * ib] : 1.0;
-  double radld[NG], frac1[NG];
+  double radld[NG];
+  double* FR1 = BBU + (size_t)nl * NG;                          // Planck fractions of layer 1 (needed again at the surface)
 #pragma unroll
-  for (int g = 0; g < NG; ++g) { radld[g] = 0.0; frac1[g] = 0.0; }
+  for (int g = 0; g < NG; ++g) radld[g] = 0.0;
   int ind; double fr;
   planck_index(in.tlev[col + nc * nl], ind, fr);
   double pl_up = planck_at(A, tb, ib, ind, fr);                // Planck function of the level above the current layer
   for (int lev = nl; lev >= 1; --lev) {
     const int l = lev - 1;
-    // inatm + setcoef of the layer
-    Layer L;
-    {
-      double vmr[NSP], xs[4];
-#pragma unroll
-      for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + nc * l] : in.gas_c[i];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xs[i] = in.xs[i] ? in.xs[i][col + nc * l] : in.xs_c[i];
-      const double pb = in.plev[col + nc * l], pa = in.plev[col + nc * (l + 1)];
-      lw_setcoef_layer(A, tb, in.play[col + nc * l], in.tlay[col + nc * l], coldry_of(pb, pa, vmr[0]), vmr, xs, L);
-    }
     LwRec rec;
-    lw_terms(A, tb, B, L, rec);
-    double tau[NG];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) tau[g] = 0.0;
-    for (int i = 0; i < rec.n; ++i) {                            // one (weight, row) pair per term, NG table reads each
-      const double w = rec.w[i];
-      const double* row = A + rec.off[i];
-#pragma unroll
-      for (int g = 0; g < NG; ++g) if (g < ng) tau[g] += w * row[g];
+#if ISCA_LWC_PREPASS
+    lw_record_from_planes(A, tb, B, in.lays + (col + nc * l), nc * (size_t)nl, rec);
+#else
+    {
+      Layer L;                                                   // inatm + setcoef of the layer
+      lw_layer_inputs(in, col, l, A, tb, L);
+      lw_terms(A, tb, B, L, rec);
     }
+#endif
     planck_index(in.tlay[col + nc * l], ind, fr);
     const double blay = planck_at(A, tb, ib, ind, fr);
     planck_index(in.tlev[col + nc * l], ind, fr);
     const double pl_dn = planck_at(A, tb, ib, ind, fr);
     double sum = 0.0;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      if (g < ng) {
-        double t = tau[g];
-        if (rec.gs_off >= 0) t *= A[rec.gs_off + g];
-        double plfrac = 0.0;
-        if (rec.f0 >= 0) { const double a = A[rec.f0 + g]; plfrac = rec.f1 >= 0 ? a + rec.ffs * (A[rec.f1 + g] - a) : a; }
-        if (lev == 1) frac1[g] = plfrac;
-        double at, bbu;
-        lw_layer(exptfn, sd, t, plfrac, blay, pl_up, pl_dn, radld[g], at, bbu);
-        AT[l * NG + g] = at; BBU[l * NG + g] = bbu;
-        sum += radld[g];
+    for (int h0 = 0; h0 < NG; h0 += H) {
+      double tau[H];
+#pragma unroll
+      for (int g = 0; g < H; ++g) tau[g] = 0.0;
+#if ISCA_LWC_UNROLL == 0
+      for (int i = 0; i < rec.n; ++i) {                          // one (weight, row) pair per term, H table reads each
+        const double w = rec.w[i];
+        const double* row = A + rec.off[i] + h0;
+#pragma unroll
+        for (int g = 0; g < H; ++g) if (h0 + g < ng) tau[g] += w * row[g];
+      }
+#pragma unroll
+      for (int g = 0; g < H; ++g) {
+        const int gg = h0 + g;
+        if (gg < ng) {
+          double t = tau[g];
+          if (rec.gs_off >= 0) t *= A[rec.gs_off + gg];
+          double plfrac = 0.0;
+          if (rec.f0 >= 0) { const double a = A[rec.f0 + gg]; plfrac = rec.f1 >= 0 ? a + rec.ffs * (A[rec.f1 + gg] - a) : a; }
+          if (lev == 1) FR1[gg] = plfrac;
+          double at, bbu;
+          lw_layer(exptfn, sd, t, plfrac, blay, pl_up, pl_dn, radld[gg], at, bbu);
+          AT[l * NG + gg] = at; BBU[l * NG + gg] = bbu;
+          sum += radld[gg];
+        }
       }
     }
+#else
+      // one (weight, row) pair per term; the lists are padded to multiples of 8 terms, ISCA_LWC_UNROLL terms (x H / 2 128-bit table
+      // reads) are in flight at a time; the additions stay in list order
+      for (int i = 0; i < rec.n; i += ISCA_LWC_UNROLL) {
+        double w[ISCA_LWC_UNROLL], v[ISCA_LWC_UNROLL][H];
+#pragma unroll
+        for (int u = 0; u < ISCA_LWC_UNROLL; ++u) {
+          w[u] = rec.w[i + u];
+          const double* row = A + rec.off[i + u] + h0;
+#pragma unroll
+          for (int g = 0; g < H; g += 2) if (h0 + g < ng) tab2(row + g, v[u][g], v[u][g + 1]);
+        }
+#pragma unroll
+        for (int u = 0; u < ISCA_LWC_UNROLL; ++u)
+#pragma unroll
+          for (int g = 0; g < H; ++g) if (h0 + g < ng) tau[g] += w[u] * v[u][g];
+      }
+      double gsc[H], fa[H], fb[H];                               // per-g-point scaling and Planck fractions of the band's table rows
+#pragma unroll
+      for (int g = 0; g < H; g += 2)
+        if (h0 + g < ng) {
+          if (rec.gs_off >= 0) tab2(A + rec.gs_off + h0 + g, gsc[g], gsc[g + 1]);
+          if (rec.f0 >= 0) tab2(A + rec.f0 + h0 + g, fa[g], fa[g + 1]);
+          if (rec.f1 >= 0) tab2(A + rec.f1 + h0 + g, fb[g], fb[g + 1]);
+        }
+#pragma unroll
+      for (int g = 0; g < H; ++g) {
+        const int gg = h0 + g;
+        if (gg < ng) {
+          double t = tau[g];
+          if (rec.gs_off >= 0) t *= gsc[g];
+          double plfrac = 0.0;
+          if (rec.f0 >= 0) plfrac = rec.f1 >= 0 ? fa[g] + rec.ffs * (fb[g] - fa[g]) : fa[g];
+          if (lev == 1) FR1[gg] = plfrac;
+          double at, bbu;
+          lw_layer(exptfn, sd, t, plfrac, blay, pl_up, pl_dn, radld[gg], at, bbu);
+          AT[l * NG + gg] = at; BBU[l * NG + gg] = bbu;
+          sum += radld[gg];
+        }
+      }
+    }
+#endif
     fd[l] += sum * wb;
     pl_up = pl_dn;
   }
@@ -317,7 +443,7 @@ __device__ __forceinline__ void lw_band_column(const double* __restrict__ A, con
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       radlu[g] = 0.0;
-      if (g < ng) { radlu[g] = frac1[g] * plankbnd + (1.0 - semiss) * radld[g]; sum += radlu[g]; }
+      if (g < ng) { radlu[g] = FR1[g] * plankbnd + (1.0 - semiss) * radld[g]; sum += radlu[g]; }
     }
     fu[0] += sum * wb;
   }
@@ -332,7 +458,7 @@ __device__ __forceinline__ void lw_band_column(const double* __restrict__ A, con
 }
 
 #ifndef ISCA_LWC_MINB
-#define ISCA_LWC_MINB 1
+#define ISCA_LWC_MINB 5
 #endif
 __global__ void __launch_bounds__(32 * LWC_WARPS, ISCA_LWC_MINB) rrtmg_lw_col_kernel(const double* __restrict__ A, Tab tb, const LwBand* __restrict__ bands, ColIn in) {
   __shared__ double sfu[(KMAX + 1) * 32], sfd[(KMAX + 1) * 32];        // [level][column of the CTA]
@@ -342,7 +468,7 @@ __global__ void __launch_bounds__(32 * LWC_WARPS, ISCA_LWC_MINB) rrtmg_lw_col_ke
   const bool live = col_raw < in.ncol;
   const int col = live ? col_raw : in.ncol - 1;                   // padding lanes repeat the last column (no divergence, no stores)
   double fu[KMAX + 1], fd[KMAX + 1];
-  double AT[KMAX * 16], BBU[KMAX * 16];
+  double AT[KMAX * 16], BBU[(KMAX + 1) * 16];
   for (int lev = 0; lev <= nl; ++lev) { fu[lev] = 0.0; fd[lev] = 0.0; }
   // inatm: precipitable water of the column (rrtmg_lw_rad.nomcica.f90:846-856) -> diffusivity angle of the bands
   double pwvcm;
@@ -484,6 +610,138 @@ __global__ void __launch_bounds__(SW_THREADS, ISCA_SW_MINB) rrtmg_sw_kernel(cons
   __syncthreads();
   for (int l = tid; l < nl; l += SW_THREADS)    // swhr(nlayers) = 0 in the reference
     in.hr[col + (size_t)nc * l] = l == nl - 1 ? 0.0 : (fnet[l + 1] - fnet[l]) * in.heatfac / (pz[l] - pz[l + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shortwave, column-per-lane mapping (see the longwave kernel above): a lane = a column, a warp = a band group; bands are processed in
+// chunks of at most 8 g-points whose recurrences run in registers.  Pass 1 bottom-up (layer optics, reftra, upward combination), pass 2
+// top-down (direct beam, downward combination, fluxes); the seven per-(layer, g-point) values pass 2 needs stay in thread-local memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SWC_WARPS = 4, SWC_NG = 8;
+__device__ __constant__ int SWC_GROUP_OF_BAND[NB_SW] = {0, 0, 2, 2, 0, 1, 2, 2, 3, 1, 3, 3, 3, 1};        // 0-based band -> warp
+
+__device__ __forceinline__ void sw_band_chunk(const double* __restrict__ A, const Tab& tb, const SwBand& B, int g0, int ngc, const ColIn& in,
+                                              int col, int nl, int lsol, double prmu0, double albedo, double* __restrict__ fu,
+                                              double* __restrict__ fd, double* __restrict__ W) {
+  constexpr int NG = SWC_NG;
+  const size_t nc = in.ncol;
+  const double* exp_tbl = A + tb.exp_tbl;
+  // W: seven arrays [level or layer][NG]
+  double* zref = W; double* zrefd = zref + KMAX * NG; double* ztra = zrefd + KMAX * NG; double* ztrad = ztra + KMAX * NG;
+  double* zdbt = ztrad + KMAX * NG; double* zrup = zdbt + KMAX * NG; double* zrupd = zrup + (KMAX + 1) * NG;
+  double rup[NG], rupd[NG], sflux[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { rup[g] = albedo; rupd[g] = albedo; sflux[g] = 0.0; zrup[nl * NG + g] = albedo; zrupd[nl * NG + g] = albedo; }
+  for (int l1 = 1; l1 <= nl; ++l1) {                   // bottom-up: layer optics + upward combination
+    const int l = l1 - 1, jk = nl - l1;
+    Layer L;
+    {
+      double vmr[NSP];
+#pragma unroll
+      for (int i = 0; i < NSP; ++i) vmr[i] = in.gas[i] ? in.gas[i][col + nc * l] : in.gas_c[i];
+      const double pb = in.plev[col + nc * l], pa = in.plev[col + nc * (l + 1)];
+      sw_setcoef_layer(A, tb, in.play[col + nc * l], in.tlay[col + nc * l], coldry_of(pb, pa, vmr[0]), vmr, L);
+    }
+    SwRec rec;
+    sw_terms(A, B, L, rec);
+    double taug[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) taug[g] = 0.0;
+    for (int i = 0; i < rec.n; ++i) {
+      const double w = rec.w[i];
+      const double* row = A + rec.off[i] + g0;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) if (g < ngc) taug[g] += w * row[g];
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      if (g < ngc) {
+        const int gg = g0 + g;
+        const double tg = taug[g] + rec.tconst;
+        const double a = A[rec.r0 + rec.rg * gg];
+        const double tr = rec.rc0 * (rec.r1 >= 0 ? a + rec.rc1 * (A[rec.r1 + gg] - a) : a);
+        if (l1 == lsol) sflux[g] = sw_src_rec(A, B, rec, gg);
+        double rf, rfd, tt, ttd, db, ru, rud;
+        sw_layer(exp_tbl, prmu0, tg, tr, rup[g], rupd[g], rf, rfd, tt, ttd, db, ru, rud);
+        zref[jk * NG + g] = rf; zrefd[jk * NG + g] = rfd; ztra[jk * NG + g] = tt; ztrad[jk * NG + g] = ttd; zdbt[jk * NG + g] = db;
+        zrup[jk * NG + g] = ru; zrupd[jk * NG + g] = rud;
+        rup[g] = ru; rupd[g] = rud;
+      }
+    }
+  }
+  double ztdn[NG], zrdnd[NG], tdbt[NG], tdbt_prev[NG], zinc[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { ztdn[g] = 1.0; zrdnd[g] = 0.0; tdbt[g] = 1.0; tdbt_prev[g] = 1.0; zinc[g] = in.adjflux * sflux[g] * prmu0; }
+  for (int jk = 0; jk <= nl; ++jk) {                   // top-down: downward combination + fluxes
+    const int j = jk >= 1 ? jk - 1 : 0;
+    double su = 0.0, sdn = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      if (g < ngc) {
+        if (jk >= 1) { tdbt_prev[g] = tdbt[g]; tdbt[g] = zdbt[(jk - 1) * NG + g] * tdbt_prev[g]; }
+        double u, d;
+        sw_level(jk, tdbt[g], tdbt_prev[g], zref[j * NG + g], zrefd[j * NG + g], ztra[j * NG + g], ztrad[j * NG + g], zrup[jk * NG + g],
+                 zrupd[jk * NG + g], ztdn[g], zrdnd[g], u, d);
+        su += zinc[g] * u; sdn += zinc[g] * d;
+      }
+    }
+    fu[nl - jk] += su; fd[nl - jk] += sdn;
+  }
+}
+
+#ifndef ISCA_SWC_MINB
+#define ISCA_SWC_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * SWC_WARPS, ISCA_SWC_MINB) rrtmg_sw_col_kernel(const double* __restrict__ A, Tab tb, const SwBand* __restrict__ bands, ColIn in) {
+  __shared__ double sfu[(KMAX + 1) * 32], sfd[(KMAX + 1) * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nl = in.nlay;
+  const size_t nc = in.ncol;
+  const int col_raw = blockIdx.x * 32 + lane;
+  const bool live = col_raw < in.ncol;
+  const int col = live ? col_raw : in.ncol - 1;
+  const double cosz = in.coszen[col];
+  const bool day = cosz >= 1.0e-10;                    // `if (coszen(iplon) < zepzen) ... cycle` (rrtmg_sw_rad.nomcica.f90)
+  double fu[KMAX + 1], fd[KMAX + 1];
+  double W[(5 * KMAX + 2 * (KMAX + 1)) * SWC_NG];
+  int jp[KMAX];
+  for (int lev = 0; lev <= nl; ++lev) { fu[lev] = 0.0; fd[lev] = 0.0; }
+  if (day) {
+    int laytrop = 0;
+    for (int l = 0; l < nl; ++l) {                     // pressure indices of every layer: laytrop and the solar source layers
+      const double plog = log(in.play[col + nc * l]);
+      int j = (int)(36.0 - 5.0 * (plog + 0.04));
+      jp[l] = j < 1 ? 1 : (j > 58 ? 58 : j);
+      laytrop += plog > 4.56;
+    }
+    const double albedo = in.albedo[col];
+    for (int ib = 0; ib < NB_SW; ++ib) {
+      if (SWC_GROUP_OF_BAND[ib] != warp) continue;
+      const SwBand& B = bands[ib];
+      const int lsol = sw_laysolfr_jp(B, jp, nl, laytrop);
+      const int nchunk = (B.ng + SWC_NG - 1) / SWC_NG, per = (B.ng + nchunk - 1) / nchunk;
+      for (int c = 0; c < nchunk; ++c) {
+        const int g0 = c * per, ngc = (g0 + per <= B.ng) ? per : B.ng - g0;
+        sw_band_chunk(A, tb, B, g0, ngc, in, col, nl, lsol, cosz, albedo, fu, fd, W);
+      }
+    }
+  }
+  for (int w = 0; w < SWC_WARPS; ++w) {
+    if (warp == w)
+      for (int lev = 0; lev <= nl; ++lev) {
+        if (w == 0) { sfu[lev * 32 + lane] = fu[lev]; sfd[lev * 32 + lane] = fd[lev]; }
+        else { sfu[lev * 32 + lane] += fu[lev]; sfd[lev * 32 + lane] += fd[lev]; }
+      }
+    __syncthreads();
+  }
+  if (!live) return;
+  for (int lev = warp; lev <= nl; lev += SWC_WARPS) {
+    in.uflx[col + nc * lev] = sfu[lev * 32 + lane];
+    in.dflx[col + nc * lev] = sfd[lev * 32 + lane];
+  }
+  for (int l = warp; l < nl; l += SWC_WARPS) {         // swhr(nlayers) = 0 in the reference
+    const double f0 = sfd[l * 32 + lane] - sfu[l * 32 + lane], f1 = sfd[(l + 1) * 32 + lane] - sfu[(l + 1) * 32 + lane];
+    in.hr[col + nc * l] = l == nl - 1 ? 0.0 : (f1 - f0) * in.heatfac / (in.plev[col + nc * l] - in.plev[col + nc * (l + 1)]);
+  }
 }
 
 // ---- run_rrtmg glue: model layout [K][J][I] top-down (Pa) -> RRTMG layout (ncol, nlay) bottom-up (hPa) ----

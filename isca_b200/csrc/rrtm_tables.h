@@ -65,6 +65,7 @@ struct HostTables {
     if (!t) return -1;
     int ng = t->dims[t->ndim - 1];
     size_t rows = t->v.size() / ng;
+    if (arena.size() & 1) arena.push_back(0.0);               // every table starts on a 16-byte boundary (128-bit row reads)
     int off = (int)arena.size();
     arena.resize(arena.size() + t->v.size());
     for (size_t r = 0; r < rows; ++r)
@@ -75,11 +76,15 @@ struct HostTables {
   int add_raw(const std::string& name) {
     const RawTable* t = get(name);
     if (!t) return -1;
+    if (arena.size() & 1) arena.push_back(0.0);
     int off = (int)arena.size();
     arena.insert(arena.end(), t->v.begin(), t->v.end());
     return off;
   }
-  int add_vec(const std::vector<double>& v) { int off = (int)arena.size(); arena.insert(arena.end(), v.begin(), v.end()); return off; }
+  int add_vec(const std::vector<double>& v) {
+    if (arena.size() & 1) arena.push_back(0.0);
+    int off = (int)arena.size(); arena.insert(arena.end(), v.begin(), v.end()); return off;
+  }
   double chi(int sp1, int lev1) { const RawTable* t = get("lw_chi_mls"); return t ? t->v[(sp1 - 1) + 7 * (lev1 - 1)] : 0.0; }
 
   static std::string nm(const char* fam, int band, const char* what) {

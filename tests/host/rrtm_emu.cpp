@@ -29,6 +29,7 @@ static double g_shfl[64][32];
 #define __constant__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 static inline void __syncthreads() { g_block_barrier->arrive_and_wait(); }
@@ -111,7 +112,12 @@ int rrtm_emu_lw(const char* table_path, double cp_air, int ncol, int nlay, const
   const LwBand* bands = H.lw;
   Tab tb = H.tab;
   if (std::getenv("RRTM_EMU_LW_GPOINT")) launch(ncol, LW_THREADS, [=]() { rrtmg_lw_kernel(A, tb, bands, in); });
-  else launch((ncol + 31) / 32, 32 * LWC_WARPS, [=]() { rrtmg_lw_col_kernel(A, tb, bands, in); });
+  else {
+    std::vector<double> lays((size_t)LAYP_N * ncol * nlay);
+    in.lays = lays.data();
+    launch((ncol * nlay + 127) / 128, 128, [=]() { rrtmg_lw_setcoef_kernel(A, tb, in); });
+    launch((ncol + 31) / 32, 32 * LWC_WARPS, [=]() { rrtmg_lw_col_kernel(A, tb, bands, in); });
+  }
   return 0;
 }
 
@@ -129,7 +135,8 @@ int rrtm_emu_sw(const char* table_path, double cp_air, int ncol, int nlay, const
   const double* A = H.arena.data();
   const SwBand* bands = H.sw;
   Tab tb = H.tab;
-  launch(ncol, SW_THREADS, [=]() { rrtmg_sw_kernel(A, tb, bands, in); });
+  if (!std::getenv("RRTM_EMU_SW_COL")) launch(ncol, SW_THREADS, [=]() { rrtmg_sw_kernel(A, tb, bands, in); });
+  else launch((ncol + 31) / 32, 32 * SWC_WARPS, [=]() { rrtmg_sw_col_kernel(A, tb, bands, in); });
   return 0;
 }
 
@@ -165,6 +172,9 @@ int rrtm_emu_run_rrtmg(const char* table_path, int I, int J, int K, int lonstep,
   launch((int)nc, SW_THREADS, [=]() { rrtmg_sw_kernel(A, tb, sb, sw); });
   ColIn lw = in; lw.uflx = lwu.data(); lw.dflx = lwd.data(); lw.hr = lwhr.data();
   const LwBand* lb = H.lw;
+  std::vector<double> lays((size_t)LAYP_N * nc * K);
+  lw.lays = lays.data();
+  launch(((int)nc * K + 127) / 128, 128, [=]() { rrtmg_lw_setcoef_kernel(A, tb, lw); });
   launch(((int)nc + 31) / 32, 32 * LWC_WARPS, [=]() { rrtmg_lw_col_kernel(A, tb, lb, lw); });
   FinishArgs fa{(int)nm, K, swhr.data(), lwhr.data(), swu.data(), swd.data(), lwu.data(), lwd.data(), tdt, tdt_rad, flux_sw, flux_lw, olr, toa_sw,
                 ls, I};

@@ -145,10 +145,14 @@ def _cp(a):
     return None if a is None else np.ascontiguousarray(a).ctypes.data_as(P)
 
 
-@pytest.mark.parametrize("secondary,K,seed", [(False, 40, 3), (True, 25, 4)])
-def test_emulated_lw_sw_kernels_match_oracle(emu, secondary, K, seed):
-    """rrtmg_lw_kernel / rrtmg_sw_kernel: phase structure, shared-memory staging, shuffle reductions with padding lanes (140 of
-    160, 112 of 128 threads carry a g-point), night columns leaving the SW kernel early"""
+@pytest.mark.parametrize("secondary,K,seed,alternate", [(False, 40, 3, False), (True, 25, 4, False), (False, 40, 5, True), (True, 31, 6, True)])
+def test_emulated_lw_sw_kernels_match_oracle(emu, secondary, K, seed, alternate, monkeypatch):
+    """the production kernels (rrtmg_lw_setcoef_kernel + rrtmg_lw_col_kernel: a lane = a column, a warp = a band group;
+    rrtmg_sw_kernel: a thread = a g-point, shared-memory staging, shuffle reductions with padding lanes, night columns leaving
+    early) and, with `alternate`, the other mapping of each (rrtmg_lw_kernel, rrtmg_sw_col_kernel: selectable at run time)"""
+    if alternate:
+        monkeypatch.setenv("RRTM_EMU_LW_GPOINT", "1")
+        monkeypatch.setenv("RRTM_EMU_SW_COL", "1")
     nc = 6
     g = columns(nc, K, seed, secondary=secondary)
     arr = {k: _F(v) for k, v in g.items()}

@@ -54,6 +54,7 @@ def main():
            "amortised_ms_per_step_dt_rad_7200_dt_150": (lw_ms + sw_ms) / 48.0,
            "c_abi_host_call_s": {"rrtmg_lw": t1 - t0, "rrtmg_sw": t2 - t1},
            "olr_mean": float(u[:, -1].mean()), "surf_lw_down_mean": float(d[:, 0].mean()),
+           "sfc_sw_down_mean": float(sd[:, 0].mean()), "toa_sw_up_mean": float(su[:, -1].mean()),
            "toa_sw_down_over_s0cosz": float((sd[cz > 0, -1] / (1368.22 * cz[cz > 0])).mean()),
            "finite": bool(np.isfinite(u).all() and np.isfinite(hr).all() and np.isfinite(su).all() and np.isfinite(shr).all())}
     r.close()
