@@ -101,35 +101,46 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, indices=(0,)):
+        self.ids, self.proc, self.lines, self.t_mark = ",".join(str(i) for i in indices), None, [], 0.0
 
     def start(self):
+        """one nvidia-smi process for all the GPUs of the job (rank 0 runs it), started BEFORE the timed region and waited for until
+        its first sample has arrived: NVML initialisation touches every GPU of the box and takes about a second, which would
+        otherwise fall into (and, at 8 ranks in lock step, double) a timed region of a few hundred milliseconds"""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.ids}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 8.0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
+    def mark(self):
+        self.t_mark = time.time()                    # samples from here on belong to the timed region
+
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for t, ln in self.lines if t >= self.t_mark]
+        lines = inside if inside else [ln for _, ln in self.lines[-len(self.ids.split(",")):]]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -226,7 +237,7 @@ def cpu_dynamics(res, K, dt, steps, moist=False, spin=2):
 
 def cpu_physics_sample(K, with_rrtm=True):
     """NumPy oracle of idealized_moist_phys (MiMA options) on the 8192 columns of a T42 grid with K levels: seconds per call of the
-    per-step physics and of one RRTMG radiation call.  The caller scales by (columns of the workload) / 8192."""
+    per-step physics (and, with_rrtm, of one NumPy RRTMG radiation call).  The caller scales by (columns of the workload) / 8192."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_gpu_moist import build
     from rrtm_cases import rrtm_setup
@@ -239,12 +250,71 @@ def cpu_physics_sample(K, with_rrtm=True):
         t0 = time.time()
         mp(core, 2 * cfg.dt_atmos)                    # first call: radiation step
         t_first = time.time() - t0
+    else:
+        mp(core, 2 * cfg.dt_atmos)                    # warm-up call (table construction, first-touch)
     t0 = time.time()
-    mp(core, 2 * cfg.dt_atmos)                        # stored heating rates: the per-step physics alone
+    mp(core, 2 * cfg.dt_atmos)                        # stored heating rates / grey radiation: the per-step physics alone
     t_phys = time.time() - t0
     if with_rrtm:
         t_rrtm = max(t_first - t_phys, 0.0)
     return dict(ncol=ncol, sec_physics=t_phys, sec_rrtmg_call=t_rrtm)
+
+
+def cpu_physics_parallel(K, workers):
+    """`workers` processes (`bench.py --cpu-physics-worker K`) run the NumPy physics sample at the same time -- the column physics is
+    embarrassingly parallel over columns, this is how a multi-core CPU run shares it; returns the column throughput of the set."""
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    ps = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-physics-worker", str(K)], stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, env=env, text=True) for _ in range(workers)]
+    rs = []
+    for p_ in ps:
+        out, _ = p_.communicate(timeout=1200)
+        rs.append(json.loads([l for l in out.splitlines() if l.startswith("{")][-1]))
+    sec = sum(r["sec_physics"] for r in rs) / len(rs)                 # every worker ran while all the others were running
+    return dict(ncol=rs[0]["ncol"] * workers, sec_physics=sec, workers=workers)
+
+
+def cpu_rrtmg_sample(K, ncol=8192):
+    """One RRTMG radiation call (LW + SW, half of the columns in daylight) on `ncol` synthetic columns with the C++/OpenMP host build of
+    the column arithmetic (tests/host/rrtm_host.cpp, the build `pytest -m "not gpu"` checks against the NumPy oracle), all host cores.
+    Returns seconds for the sample; the caller scales by the column count."""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from rrtm_bench import columns
+    out = os.path.join(ROOT, "oracle", "_build", "librrtm_host_omp.so")
+    src = os.path.join(ROOT, "tests", "host", "rrtm_host.cpp")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-shared", "-fPIC", "-o", out, src])
+    lib = C.CDLL(out)
+    table = os.path.join(ROOT, "isca_b200", "data", "rrtmg_tables.bin").encode()
+    g = columns(ncol, K)
+    F = lambda a: np.asfortranarray(a, dtype=np.float64)
+    P = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    a = {k: F(v) for k, v in g.items()}
+    co2 = F(np.full((ncol, K), 300e-6))
+    u, d, hr = F(np.zeros((ncol, K + 1))), F(np.zeros((ncol, K + 1))), F(np.zeros((ncol, K)))
+    cp = C.c_double(287.04 / (2 / 7))
+    tsfc = np.ascontiguousarray(g["tsfc"])
+    cz = np.ascontiguousarray(np.clip(np.cos(np.linspace(-np.pi, np.pi, ncol)), 0.0, 1.0))
+    alb = np.full(ncol, 0.3)
+    lib.rrtm_host_lw.restype = lib.rrtm_host_sw.restype = C.c_int
+
+    def lw():
+        return lib.rrtm_host_lw(table, cp, ncol, K, P(a["play"]), P(a["plev"]), P(a["tlay"]), P(a["tlev"]), P(tsfc), P(a["h2o"]), P(a["o3"]), P(co2),
+                                None, None, None, None, None, None, None, None, P(u), P(d), P(hr), None, None)
+
+    def sw():
+        return lib.rrtm_host_sw(table, cp, ncol, K, P(a["play"]), P(a["plev"]), P(a["tlay"]), P(a["h2o"]), P(a["o3"]), P(co2), None, None, None,
+                                P(alb), P(cz), C.c_double(1.0), C.c_double(1368.22), P(u), P(d), P(hr), None, None, None)
+    if lw() or sw():                                   # first call: table load, page faults
+        raise RuntimeError("rrtm_host failed")
+    t0 = time.time(); lw(); t_lw = time.time() - t0
+    t0 = time.time(); sw(); t_sw = time.time() - t0
+    return dict(ncol=ncol, sec_lw=t_lw, sec_sw=t_sw, olr_mean=float(u[:, -1].mean()))
 
 
 def run_cpu(workload, res, K, steps):
@@ -257,16 +327,19 @@ def run_cpu(workload, res, K, steps):
         return dict(sec_per_step=sec, threads=d["threads"], value=dt_hs / 86400.0 / sec, sample=sample, parts={"dynamics_s": sec})
     dt = MOIST_DT[res]
     d = cpu_dynamics(res, K, dt, steps, moist=True)
-    ph = cpu_physics_sample(K)
+    ph = cpu_physics_parallel(K, max(1, d["threads"]))
+    rr = cpu_rrtmg_sample(K)
     scale = (I * J) / ph["ncol"]
+    rr_call = (rr["sec_lw"] + rr["sec_sw"]) * (I * J) / rr["ncol"]
     per_rad = DT_RAD / dt
-    sec = d["sec_per_step"] + scale * ph["sec_physics"] + scale * ph["sec_rrtmg_call"] / per_rad
+    sec = d["sec_per_step"] + scale * ph["sec_physics"] + rr_call / per_rad
     sample = (f"dynamics + tracer: {steps} steps of {res} L{K} with the C++/OpenMP restatement (oracle/cstep) on {d['threads']} host threads; "
-              f"column physics and one RRTMG call: NumPy oracle on {ph['ncol']} columns (T42 grid, {K} levels), scaled x{scale:g} to the "
-              f"{I * J} columns, RRTMG amortised over {per_rad:g} steps")
+              f"one RRTMG call (LW + SW): C++/OpenMP host build of the column arithmetic on {rr['ncol']} columns, scaled to the {I * J} columns "
+              f"and amortised over {per_rad:g} steps; the other column physics: NumPy oracle, {ph['workers']} processes x 8192 columns (T42 grid, {K} "
+              f"levels) running at the same time, scaled x{scale:g} -- a slow stand-in, no compiled CPU port of those schemes exists here")
     return dict(sec_per_step=sec, threads=d["threads"], value=dt / 86400.0 / sec, sample=sample,
-                parts={"dynamics_s": d["sec_per_step"], "physics_numpy_scaled_s": scale * ph["sec_physics"],
-                       "rrtmg_numpy_scaled_per_call_s": scale * ph["sec_rrtmg_call"]})
+                parts={"dynamics_cpp_s": d["sec_per_step"], "physics_numpy_scaled_s": scale * ph["sec_physics"],
+                       "rrtmg_cpp_scaled_per_call_s": rr_call})
 
 
 # ---------------------------------------------------------------------------------------------
@@ -283,10 +356,14 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-physics-worker", type=int, default=0, help=argparse.SUPPRESS)   # internal: one worker of cpu_physics_parallel
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`; numbers of such a run are not bench values)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (hs T85/T170/T341, Frierson T85)")
     args = ap.parse_args()
+    if args.cpu_physics_worker:
+        print(json.dumps(cpu_physics_sample(args.cpu_physics_worker, with_rrtm=False)))
+        return
 
     # The contract is ONE JSON line on stdout: keep a private handle on the real stdout for it and point fd 1 at stderr so that
     # library chatter (e.g. NCCL's version banner, printed at communicator creation) cannot land in front of it.
@@ -425,9 +502,12 @@ def main():
         m.atmosphere(spin)
         m.atmosphere(warm)
         l0 = m.core.get_scalar(api.SC_KERNEL_LAUNCHES)
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler = ClockSampler(range(world)) if rank == 0 else None      # one nvidia-smi for all the GPUs of the job
+        if sampler:
+            sampler.start()
         barrier()
+        if sampler:
+            sampler.mark()
         if args.profile_range:
             torch.cuda.cudart().cudaProfilerStart()
         t0 = time.time()
@@ -436,15 +516,15 @@ def main():
         if args.profile_range:
             torch.cuda.cudart().cudaProfilerStop()
         wall = max_over_ranks(time.time() - t0)
-        clocks = sampler.stop()
+        clocks = sampler.stop() if sampler else None
         ms_step, _ = m.timing()
         ms_per_step = max_over_ranks(ms_step)
         core_launches = int(m.core.get_scalar(api.SC_KERNEL_LAUNCHES) - l0)
         rad_calls = -(-args.steps // per_rad)
         # launches of this repo's kernels in the timed region: the dynamical core counts its own; the physics sequence issues 24 per step
         # (moist_model.cu: 2 press_heights, 2 convection, 2 condensation, 2 surface, radiation add, 2 sponge, 2+2 diffusivity, gust fill,
-        # vert_diff_down, mixed_layer, vert_diff_up, 4 memsets) and a radiation call 6 (coszen, prepare, fix_top, sw, lw, finish)
-        launches = (core_launches + 24 * args.steps + 6 * rad_calls) * world
+        # vert_diff_down, mixed_layer, vert_diff_up, 4 memsets) and a radiation call 7 (coszen, prepare, fix_top, sw, lw setcoef, lw, finish)
+        launches = (core_launches + 24 * args.steps + 7 * rad_calls) * world
         value = dt / 86400.0 / (ms_per_step * 1e-3)
         # steady state over whole radiation cycles (informational; same timing method)
         n_ss = per_rad * max(1, min(10, 480 // per_rad))
@@ -505,12 +585,15 @@ def main():
         working_set_mb = 8.0 * I * J * K * 60 / 1e6
     else:
         out, atm, launches, groups = hs_run(res, K, args.steps, spin)
-        sampler = ClockSampler(local_rank)           # clocks of a second pass of the same timed region
-        sampler.start()
+        sampler = ClockSampler(range(world)) if rank == 0 else None      # clocks of a second pass of the same timed region
+        if sampler:
+            sampler.start()
         barrier()
+        if sampler:
+            sampler.mark()
         atm.atmosphere(args.steps)
         barrier()
-        clocks = sampler.stop()
+        clocks = sampler.stop() if sampler else None
         ms_per_step = max_over_ranks(atm.get_scalar(api.SC_LAST_STEP_MS))
         value = dt / 86400.0 / (ms_per_step * 1e-3)
         wall = out["wall_ms_per_step"] * args.steps / 1e3

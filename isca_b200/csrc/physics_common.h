@@ -12,7 +12,8 @@
 
 // Resident CTAs per SM asked of the 128-thread column kernels.  At T170 (131 072 columns = 1024 CTAs = 6.9 per SM) a latency-bound
 // kernel that keeps fewer than 7 CTAs resident runs a second, mostly empty wave and pays for two: (128, 7) caps the registers at 72,
-// which costs these kernels at most a few spilled values (ptxas -v).  vert_diff_down and surface_flux need more registers than that.
+// which costs these kernels a few spilled values (ptxas -v; surface_flux 276 bytes, still faster: 0.058 -> 0.046 ms).  vert_diff_down
+// (125 registers) is fastest at 4: 0.29 ms against 0.31 (5) and 0.42 (7).
 #ifndef ISCA_COL_MINB
 #define ISCA_COL_MINB 7
 #endif
@@ -20,7 +21,7 @@
 #define ISCA_VDD_MINB 4
 #endif
 #ifndef ISCA_SF_MINB
-#define ISCA_SF_MINB 4
+#define ISCA_SF_MINB 7
 #endif
 
 namespace isca_phys {

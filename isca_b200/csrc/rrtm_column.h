@@ -384,22 +384,21 @@ RR_HD void lw_layer(const double* exptfn, double secdiff, double tau, double plf
 }
 
 // One g-point through rtrnmr's clear-sky sweeps, serially (rrtmg_lw_rtrnmr.f90:390-480 down, :560-640 up): the order of
-// operations of rrtmg_lw_kernel's phase B written as one loop nest.  Used by the test-only host build (tests/host/rrtm_host.cpp).
+// operations of rrtmg_lw_kernel's phase B written as one loop nest, on the term lists `recs` of the band's layers.  Used by the
+// host build (tests/host/rrtm_host.cpp: CPU check of this arithmetic, and the C++/OpenMP CPU baseline of bench.py).
 // lay[] = the column's setcoef output, planklay/planklev [16][stride], w = wtdiff*delwave(band).  red.down(lev, v) / red.up(lev, v)
 // receive the weighted radiances of level lev = 0..nl (0 = surface).
 template <class Red>
-RR_HD void lw_gpoint(const double* A, const Tab& tb, const LwBand& B, int ib, int g, int nl, const Layer* lay,
-                     const double* planklay, const double* planklev, int pstride, double plankbnd, double semiss,
-                     double secdiff, double w, Red& red) {
+RR_HD void lw_gpoint_recs(const double* A, const Tab& tb, const LwRec* recs, int ib, int g, int nl,
+                          const double* planklay, const double* planklev, int pstride, double plankbnd, double semiss,
+                          double secdiff, double w, Red& red) {
   double atrans[KMAX], bbugas[KMAX];
   const double* exptfn = A + tb.exptfn;
   double radld = 0.0, frac1 = 0.0;
   red.down(nl, 0.0);
   for (int lev = nl; lev >= 1; --lev) {
     double tau, plfrac;
-    LwRec rec;
-    lw_terms(A, tb, B, lay[lev - 1], rec);
-    lw_tau_rec(A, rec, g, tau, plfrac);
+    lw_tau_rec(A, recs[lev - 1], g, tau, plfrac);
     if (lev == 1) frac1 = plfrac;
     lw_layer(exptfn, secdiff, tau, plfrac, planklay[ib * pstride + lev - 1], planklev[ib * pstride + lev], planklev[ib * pstride + lev - 1],
              radld, atrans[lev - 1], bbugas[lev - 1]);
@@ -412,6 +411,10 @@ RR_HD void lw_gpoint(const double* A, const Tab& tb, const LwBand& B, int ib, in
     radlu = radlu + (bbugas[lev - 1] - radlu) * atrans[lev - 1];
     red.up(lev, radlu * w);
   }
+}
+// the term lists of one band for all layers of a column (built once per band, shared by the band's g-points)
+RR_HD void lw_band_recs(const double* A, const Tab& tb, const LwBand& B, int nl, const Layer* lay, LwRec* recs) {
+  for (int l = 0; l < nl; ++l) lw_terms(A, tb, B, lay[l], recs[l]);
 }
 
 // secant of the diffusivity angle per band (rrtmg_lw_rtrnmr.f90:262-272)
@@ -589,8 +592,8 @@ RR_HD void sw_level(int jk, double tdbt, double tdbt_prev, double zref_j, double
 // the test-only host build.  lsol = laysolfr of the band; incoming flux zincflx = adjflux * sfluxzen * prmu0.
 // red.up(lev, v) / red.down(lev, v): lev = 0 surface .. nl top of atmosphere.
 template <class Red>
-RR_HD void sw_gpoint(const double* A, const Tab& tb, const SwBand& B, int g, int nl, const Layer* lay, int lsol,
-                     double prmu0, double albedo, double adjflux, double w, Red& red) {
+RR_HD void sw_gpoint_recs(const double* A, const Tab& tb, const SwBand& B, const SwRec* recs, int g, int nl, int lsol,
+                          double prmu0, double albedo, double adjflux, double w, Red& red) {
   const double* exp_tbl = A + tb.exp_tbl;
   // layer arrays ordered top (0) to bottom (nl-1), as jk = 1..klev of spcvrt_sw
   double zref[KMAX], zrefd[KMAX], ztra[KMAX], ztrad[KMAX], zdbt[KMAX], zrup[KMAX + 1], zrupd[KMAX + 1];
@@ -598,8 +601,7 @@ RR_HD void sw_gpoint(const double* A, const Tab& tb, const SwBand& B, int g, int
   zrup[nl] = albedo; zrupd[nl] = albedo;
   for (int l1 = 1; l1 <= nl; ++l1) {          // bottom-up: layer optics + upward combination
     const int jk = nl - l1;
-    SwRec rec;
-    sw_terms(A, B, lay[l1 - 1], rec);
+    const SwRec& rec = recs[l1 - 1];
     double taug, taur;
     sw_tau_rec(A, rec, g, taug, taur);
     if (l1 == lsol) sflux = sw_src_rec(A, B, rec, g);
@@ -615,6 +617,9 @@ RR_HD void sw_gpoint(const double* A, const Tab& tb, const SwBand& B, int g, int
     red.up(nl - jk, zinc * fu);
     red.down(nl - jk, zinc * fd);
   }
+}
+RR_HD void sw_band_recs(const double* A, const SwBand& B, int nl, const Layer* lay, SwRec* recs) {
+  for (int l = 0; l < nl; ++l) sw_terms(A, B, lay[l], recs[l]);
 }
 
 }  // namespace rrtm

@@ -4,7 +4,9 @@
 // this file calls the very same functions (and the same descriptor builder, rrtm_tables.h) in plain loops, so that
 // `pytest -m "not gpu"` can check the device arithmetic against the NumPy oracle on a machine without a GPU.
 // It is compiled by tests/test_rrtm_host.py with g++ into tests/host/_build/ and is never linked into the product library
-// (isca_b200/lib/libisca_b200.so fails at create time when no CUDA device exists).
+// (isca_b200/lib/libisca_b200.so fails at create time when no CUDA device exists).  Built with -fopenmp (oracle/_build/, by
+// __graft_entry__.build() and bench.py) the column loops run on all host cores: that build is bench.py's C++/OpenMP CPU baseline
+// of one RRTMG radiation call (`cpu_baseline`, `--impl reference`) -- the same arithmetic, term lists built once per (layer, band).
 #include "../../isca_b200/csrc/rrtm_tables.h"
 #include <memory>
 #include <string>
@@ -48,9 +50,11 @@ int rrtm_host_lw(const char* table_path, double cp_air, int ncol, int nlay, cons
   const double delwave[NB_LW] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
   const int PS = KMAX + 1;
   const size_t nc = ncol;
-  std::vector<Layer> lay(KMAX);
-  std::vector<double> planklay(NB_LW * PS), planklev(NB_LW * PS);
+#pragma omp parallel for schedule(dynamic, 32)
   for (int col = 0; col < ncol; ++col) {
+    std::vector<Layer> lay(KMAX);
+    std::vector<double> planklay(NB_LW * PS), planklev(NB_LW * PS);
+    std::vector<LwRec> recs(KMAX);
     double pz[KMAX + 1], semiss[NB_LW], plankbnd[NB_LW], secdiff[NB_LW];
     for (int l = 0; l < nlay; ++l) {
       double vmr[NSP], xs[4];
@@ -80,10 +84,11 @@ int rrtm_host_lw(const char* table_path, double cp_air, int ncol, int nlay, cons
     for (int ib = 0; ib < NB_LW; ++ib) secdiff[ib] = lw_secdiff(ib, pwvcm);
     double u[KMAX + 1] = {0}, d[KMAX + 1] = {0};
     HostRed red{u, d};
-    for (int ib = 0; ib < NB_LW; ++ib)
+    for (int ib = 0; ib < NB_LW; ++ib) {
+      lw_band_recs(A, H.tab, H.lw[ib], nlay, lay.data(), recs.data());
       for (int g = 0; g < H.lw[ib].ng; ++g) {
-        lw_gpoint(A, H.tab, H.lw[ib], ib, g, nlay, lay.data(), planklay.data(), planklev.data(), PS, plankbnd[ib], semiss[ib],
-                  secdiff[ib], 0.5 * delwave[ib], red);
+        lw_gpoint_recs(A, H.tab, recs.data(), ib, g, nlay, planklay.data(), planklev.data(), PS, plankbnd[ib], semiss[ib],
+                       secdiff[ib], 0.5 * delwave[ib], red);
         if (taug_out)
           for (int l = 0; l < nlay; ++l) {
             double tau, fr;
@@ -94,6 +99,7 @@ int rrtm_host_lw(const char* table_path, double cp_air, int ncol, int nlay, cons
             fracs_out[((size_t)col * nlay + l) * NG_LW + H.lw[ib].g0 + g] = fr;
           }
       }
+    }
     double fnet[KMAX + 1];
     for (int lev = 0; lev <= nlay; ++lev) {
       uflx[col + nc * lev] = u[lev] * FLUXFAC;
@@ -117,8 +123,10 @@ int rrtm_host_sw(const char* table_path, double cp_air, int ncol, int nlay, cons
   const double heatfac = GRAV * SECDY / (cp_air * 1.0e2);
   const double adjflux = adjes * (scon / 1.36822e+03);
   const size_t nc = ncol;
-  std::vector<Layer> lay(KMAX);
+#pragma omp parallel for schedule(dynamic, 32)
   for (int col = 0; col < ncol; ++col) {
+    std::vector<Layer> lay(KMAX);
+    std::vector<SwRec> recs(KMAX);
     if (coszen[col] < 1.0e-10) {
       for (int lev = 0; lev <= nlay; ++lev) { swuflx[col + nc * lev] = 0.0; swdflx[col + nc * lev] = 0.0; }
       for (int l = 0; l < nlay; ++l) swhr[col + nc * l] = 0.0;
@@ -139,8 +147,9 @@ int rrtm_host_sw(const char* table_path, double cp_air, int ncol, int nlay, cons
     HostRed red{u, d};
     for (int ib = 0; ib < NB_SW; ++ib) {
       int lsol = sw_laysolfr(H.sw[ib], lay.data(), nlay, laytrop);
+      sw_band_recs(A, H.sw[ib], nlay, lay.data(), recs.data());
       for (int g = 0; g < H.sw[ib].ng; ++g) {
-        sw_gpoint(A, H.tab, H.sw[ib], g, nlay, lay.data(), lsol, coszen[col], albedo[col], adjflux, 1.0, red);
+        sw_gpoint_recs(A, H.tab, H.sw[ib], recs.data(), g, nlay, lsol, coszen[col], albedo[col], adjflux, 1.0, red);
         if (taug_out)
           for (int l = 0; l < nlay; ++l) {
             double tg, tr, src;
