@@ -29,6 +29,7 @@ module atmosphere_mod
   use mpp_mod,            only: mpp_broadcast, mpp_gather
   use constants_mod,      only: grav, rdgas, kappa, radius, omega, pi
   use time_manager_mod,   only: time_type, get_time, operator(+)
+  use interpolator_mod,   only: interpolate_type, interpolator_init, interpolator, CONSTANT
   use spec_mpp_mod,       only: spec_mpp_init, grid_domain, spectral_domain, get_grid_domain, get_spec_domain, atmosphere_domain
   use diag_manager_mod,   only: diag_axis_init, register_diag_field, register_static_field, send_data, need_data
   use field_manager_mod,  only: MODEL_ATMOS
@@ -45,6 +46,13 @@ module atmosphere_mod
   !------------------------------------------------------------------ atmosphere_nml (atmosphere.F90:84-86)
   logical :: idealized_moist_model = .false.
   namelist /atmosphere_nml/ idealized_moist_model
+
+  !------------------------------------------------------------------ mixed_layer_nml do_sc_sst / sst_file (mixed_layer.F90:116,146): the
+  ! prescribed SST is read on the host (interpolator_init in atmosphere_init, as mixed_layer_init :318-320 does) and handed to the library
+  logical :: do_sc_sst = .false.
+  character(len=256) :: sst_file = ''
+  type(interpolate_type), save :: sst_interp
+  real, allocatable :: sst_new(:,:)
 
   !------------------------------------------------------------------ spectral_dynamics_nml (spectral_dynamics.F90:152-224), same defaults
   logical :: do_mass_correction = .true., do_water_correction = .true., do_energy_correction = .true., &
@@ -308,6 +316,13 @@ contains
     ! physics (hs_forcing or idealized_moist_phys) + spectral_dynamics + compute_pressures_and_heights(future) + the time-level swap,
     ! all on the device (atmosphere.F90:276-352)
     if (idealized_moist_model) then
+      ! mixed_layer_nml do_sc_sst (mixed_layer.F90:681-691): the SST of the time stepped to is read by interpolator_mod on the host
+      ! and handed over; the library's mixed_layer then moves t_surf to it instead of stepping the slab
+      if (do_sc_sst) then
+        call interpolator(sst_interp, Time_next, sst_new, trim(sst_file))
+        rc = isca_b200_moist_set_sst(hm, sst_new)
+        if (rc /= 0) call fatal_moist('atmosphere')
+      end if
       rc = isca_b200_moist_step(hm, 1_c_int)
       if (rc /= 0) call fatal_moist('atmosphere')
     else
@@ -447,7 +462,7 @@ contains
     ! mixed_layer_nml (mixed_layer.F90:84-140)
     real :: depth = 40.0, albedo_value = 0.06
     logical :: evaporation = .true.
-    namelist /mixed_layer_nml/ depth, albedo_value, evaporation
+    namelist /mixed_layer_nml/ depth, albedo_value, evaporation, do_sc_sst, sst_file      ! do_sc_sst, sst_file: module variables
     ! vert_turb_driver_nml (vert_turb_driver.F90:100-118)
     logical :: use_tau = .true.
     real :: constant_gust = 1.0
@@ -466,6 +481,14 @@ contains
     real :: trayfric = 0., sponge_pbottom = 50.
     logical :: do_conserve_energy_damp = .false.
     namelist /damping_driver_nml/ trayfric, sponge_pbottom
+    ! diffusivity_nml (diffusivity.F90:124-153); pbl_mcm = .true. and use_pog_bug_fix = .false. are rejected by the library
+    logical :: fixed_depth = .false., free_atm_diff = .false., free_atm_skyhi_diff = .false., pbl_mcm = .false., ampns = .false., &
+               do_entrain = .true., diff_do_simple = .false., use_pog_bug_fix = .true.
+    real :: depth_0 = 5000.0, frac_inner = 0.1, rich_crit_pbl = 1.0, entr_ratio = 0.2, parcel_buoy = 2.0, znom = 1000.0, &
+            rich_crit_diff = 0.25, mix_len = 30., rich_prandtl = 1.0, background_m = 0.0, background_t = 0.0, ampns_max = 1.0E20
+    namelist /diffusivity_nml/ fixed_depth, depth_0, frac_inner, rich_crit_pbl, entr_ratio, parcel_buoy, znom, free_atm_diff, &
+                               free_atm_skyhi_diff, pbl_mcm, rich_crit_diff, mix_len, rich_prandtl, background_m, background_t, &
+                               ampns, ampns_max, do_entrain, diff_do_simple, use_pog_bug_fix
     integer :: nml_unit, io
 #ifdef INTERNAL_FILE_NML
     read (input_nml_file, nml=idealized_moist_phys_nml, iostat=io)
@@ -475,6 +498,7 @@ contains
     read (input_nml_file, nml=qe_moist_convection_nml, iostat=io)
     read (input_nml_file, nml=two_stream_gray_rad_nml, iostat=io)
     read (input_nml_file, nml=damping_driver_nml, iostat=io)
+    read (input_nml_file, nml=diffusivity_nml, iostat=io)
 #else
     nml_unit = open_namelist_file()
     read (nml_unit, idealized_moist_phys_nml, iostat=io);  rewind(nml_unit)
@@ -483,7 +507,8 @@ contains
     read (nml_unit, lscale_cond_nml, iostat=io);           rewind(nml_unit)
     read (nml_unit, qe_moist_convection_nml, iostat=io);   rewind(nml_unit)
     read (nml_unit, two_stream_gray_rad_nml, iostat=io);   rewind(nml_unit)
-    read (nml_unit, damping_driver_nml, iostat=io)
+    read (nml_unit, damping_driver_nml, iostat=io);        rewind(nml_unit)
+    read (nml_unit, diffusivity_nml, iostat=io)
     call close_file(nml_unit)
 #endif
     if (.not. (turb .and. mixed_layer_bc)) &
@@ -514,13 +539,56 @@ contains
         call error_mesg('two_stream_gray_rad', '"'//trim(rad_scheme)//'" is not a valid radiation scheme.', FATAL)
     end select
     pcfg%trayfric = trayfric;  pcfg%sponge_pbottom = sponge_pbottom
-    pcfg%use_virtual_temp = l2i(do_virtual);  pcfg%surface_flux_do_simple = l2i(do_simple);  pcfg%diffusivity_do_simple = l2i(do_simple)
+    pcfg%use_virtual_temp = l2i(do_virtual);  pcfg%surface_flux_do_simple = l2i(do_simple)
+    ! diffusivity_nml: its own `do_simple` is spelled diff_do_simple in this routine (the name is taken by idealized_moist_phys_nml);
+    ! a site whose input.nml sets diffusivity_nml do_simple renames the local variable pair instead
+    pcfg%fixed_depth = l2i(fixed_depth);  pcfg%diffusivity_do_entrain = l2i(do_entrain);  pcfg%diffusivity_do_simple = l2i(diff_do_simple .or. do_simple)
+    pcfg%free_atm_diff = l2i(free_atm_diff);  pcfg%free_atm_skyhi_diff = l2i(free_atm_skyhi_diff);  pcfg%pbl_mcm = l2i(pbl_mcm)
+    pcfg%use_pog_bug_fix = l2i(use_pog_bug_fix);  pcfg%ampns = l2i(ampns);  pcfg%ampns_max = ampns_max
+    pcfg%depth_0 = depth_0;  pcfg%frac_inner = frac_inner;  pcfg%rich_crit_pbl = rich_crit_pbl;  pcfg%entr_ratio = entr_ratio
+    pcfg%parcel_buoy = parcel_buoy;  pcfg%znom = znom;  pcfg%rich_crit_diff = rich_crit_diff;  pcfg%mix_len = mix_len
+    pcfg%rich_prandtl = rich_prandtl;  pcfg%background_m = background_m;  pcfg%background_t = background_t
     pcfg%grav = grav;  pcfg%rdgas = rdgas;  pcfg%cp_air = rdgas/kappa
+    if (do_sc_sst) call init_prescribed_sst()
     if (do_rrtm_radiation .and. two_stream_gray) &
       call error_mesg('atmosphere_init', 'do_rrtm_radiation and two_stream_gray cannot both be .true.', FATAL)
     ! do_rrtm_radiation: rrtm_radiation_nml is forwarded with isca_b200_moist_use_rrtm (include/isca_b200_rrtm.h) by the site's copy of
     ! this routine; the ozone field read by interpolator_mod goes through isca_b200_moist_set_ozone whenever the alarm is due
   end subroutine idealized_moist_nml_to_config
+
+  !> mixed_layer_init :318-320 for do_sc_sst: interpolator_init on the cell boundaries of this PE's grid block.  The boundaries are those
+  !! of get_grid_boundaries (transforms.F90: longitudes half a cell either side of the points, sin(latitude) boundaries accumulated from
+  !! the Gaussian weights), built from the library's host tables.
+  subroutine init_prescribed_sst()
+    real, allocatable :: lonb2(:,:), latb2(:,:), wts(:), slb(:)
+    real(c_double), allocatable :: tab(:)
+    integer :: i, j, rc
+    interface
+      integer(c_int) function isca_b200_get_table(hh, tid, host, count) bind(C, name="isca_b200_get_table")
+        import :: c_int, c_ptr, c_double
+        type(c_ptr), value :: hh
+        integer(c_int), value :: tid, count
+        real(c_double), intent(out) :: host(*)
+      end function isca_b200_get_table
+    end interface
+    allocate (sst_new(is:ie, js:je), lonb2(is:ie + 1, js:je + 1), latb2(is:ie + 1, js:je + 1), wts(lat_max), slb(lat_max + 1), tab(lat_max))
+    rc = isca_b200_get_table(h, 1_c_int, tab, int(lat_max, c_int))                   ! ISCA_TB_WTS_LAT
+    if (rc /= 0) call fatal('atmosphere_init')
+    wts = tab
+    slb(1) = -1.0
+    do j = 1, lat_max
+      slb(j + 1) = slb(j) + wts(j)
+    end do
+    slb(lat_max + 1) = 1.0
+    do i = is, ie + 1
+      lonb2(i, :) = (real(i) - 1.5)*2.0*pi/real(lon_max) + longitude_origin
+    end do
+    do j = js, je + 1
+      latb2(:, j) = asin(slb(j))
+    end do
+    call interpolator_init(sst_interp, trim(sst_file)//'.nc', lonb2, latb2, data_out_of_bounds=(/CONSTANT/))
+    deallocate (lonb2, latb2, wts, slb, tab)
+  end subroutine init_prescribed_sst
 
   !> axes and fields of diag_manager module 'dynamics' (spectral_dynamics.F90:1541-1700), registered under the reference's names
   subroutine register_dynamics_diagnostics(Time)

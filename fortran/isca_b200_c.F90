@@ -176,6 +176,12 @@ module isca_b200_c
     real(c_double)       :: bog_b
     real(c_double)       :: bog_mu
     integer(c_int)       :: sat_vapor_pres_do_simple
+    integer(c_int)       :: free_atm_skyhi_diff
+    integer(c_int)       :: ampns
+    real(c_double)       :: rich_crit_diff
+    real(c_double)       :: mix_len
+    real(c_double)       :: rich_prandtl
+    real(c_double)       :: ampns_max
   end type isca_physics_config
 
   ! struct IscaMoistConfig: idealized_moist_phys_nml, mixed_layer_nml, vert_turb_driver_nml

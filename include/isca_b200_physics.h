@@ -15,7 +15,7 @@ typedef struct IscaPhysics_t* IscaPhysics;
 
 /* physical constants (shared/constants/constants.F90) and the scheme namelists */
 typedef struct IscaPhysicsConfig {
-  int abi_version;                /* 3 */
+  int abi_version;                /* 4 */
   int num_lon, num_lat, num_levels;
   double grav, rdgas, rvgas, cp_air, hlv, tfreeze, stefan, pstd_mks;
   /* sat_vapor_pres_nml: do_simple tables only (sat_vapor_pres_k.F90:161-266) */
@@ -37,7 +37,8 @@ typedef struct IscaPhysicsConfig {
   /* surface_flux_nml (surface_flux.F90:225-253); bucket hydrology, ncar_ocean_flux and raoult_sat_vap are not built */
   int no_neg_q, use_virtual_temp, alt_gustiness, old_dtaudv, use_mixing_ratio, surface_flux_do_simple;
   double gust_const, gust_min, land_humidity_prefactor, land_evap_prefactor;
-  /* diffusivity_nml (diffusivity.F90:97-122).  free_atm_diff, pbl_mcm and use_pog_bug_fix = .false. are rejected at create */
+  /* diffusivity_nml (diffusivity.F90:124-153).  pbl_mcm and use_pog_bug_fix = .false. are rejected at create; the parameters of
+   * free_atm_diff are at the end of the struct */
   int fixed_depth, diffusivity_do_entrain, diffusivity_do_simple, free_atm_diff, pbl_mcm, use_pog_bug_fix;
   double depth_0, frac_inner, rich_crit_pbl, entr_ratio, parcel_buoy, znom, background_m, background_t;
   /* qe_moist_convection_nml (qe_moist_convection.F90:61-75) */
@@ -54,6 +55,10 @@ typedef struct IscaPhysicsConfig {
    * es0*610.78*exp(-hlv/rvgas*(1/T - 1/tfreeze)), 0 = compute_es_k (Goff-Gratch / Smithsonian tables, ice below freezing,
    * sat_vapor_pres_k.F90:331-381) with finite-difference derivative tables */
   int sat_vapor_pres_do_simple;
+  /* diffusivity_nml free_atm_diff = .true. (diffusivity_free, diffusivity.F90:604-697; the axisymmetric test case): Richardson-number
+   * mixing-length diffusivities above the boundary layer */
+  int free_atm_skyhi_diff, ampns;
+  double rich_crit_diff, mix_len, rich_prandtl, ampns_max;
 } IscaPhysicsConfig;
 
 int isca_b200_physics_default_config(IscaPhysicsConfig* cfg);
@@ -124,6 +129,10 @@ int isca_b200_mixed_layer_init(IscaPhysics p, const double* heat_capacity, const
 /* mixed_layer (mixed_layer.F90:568-745; do_calc_eff_heat_cap path, no prescribed SST / ice / flux anomalies):
  * implicit slab update of t_surf [J][I] (in place) and of the handle's Tri_surf delta_t, delta_tr(sphum).
  * delta_t_surf (may be NULL) receives the increment. */
+/* mixed_layer_nml do_sc_sst = .true. (mixed_layer.F90:495-502, 681-691): sst [J][I] = the SST the host's interpolator_mod read from
+ * sst_file for the time stepped to (Time_next).  While set, mixed_layer moves t_surf to it (delta_t_surf = sst - t_surf) instead of
+ * stepping the slab; NULL switches back to the slab ocean.  specify_sst_over_ocean_only and do_ape_sst are not built. */
+int isca_b200_mixed_layer_set_sst(IscaPhysics p, const double* sst);
 int isca_b200_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double* flux_t, const double* flux_q,
                           const double* flux_r, const double* net_surf_sw_down, const double* surf_lw_down,
                           const double* dhdt_surf, const double* dedt_surf, const double* dedq_surf,
@@ -270,6 +279,9 @@ int isca_b200_moist_io_wait(IscaMoist m, int age);
    Returns the number of groups, -1 on error. */
 int isca_b200_moist_profile_step(IscaMoist m, int n_steps, double* ms_out, int max_groups, char* names, int capacity);
 int isca_b200_moist_set_t_surf(IscaMoist m, const double* host);
+/* do_sc_sst for the moist model: the prescribed SST [J][I] (this rank's latitude block) of the next isca_b200_moist_step calls
+ * (see isca_b200_mixed_layer_set_sst); NULL = slab ocean again.  The shim calls it whenever interpolator_mod delivers a new field. */
+int isca_b200_moist_set_sst(IscaMoist m, const double* host);
 /* Surface properties [J][I] that idealized_moist_phys_init / mixed_layer_init derive from the land options (land mask file,
  * land_h_capacity_prefactor, land_albedo_prefactor, land_roughness_prefactor; idealized_moist_phys.F90:565-616, mixed_layer.F90:380-470):
  * id 20 albedo, 21 rough_mom, 22 rough_heat, 23 rough_moist, 24 surface heat capacity (J/m2/K), 25 land mask (0. / 1.; used by

@@ -96,7 +96,9 @@ int isca_b200_diurnal_solar(IscaRrtm r, const IscaRrtmDriverConfig* dc, int n, c
 int isca_b200_moist_use_rrtm(IscaMoist m, const IscaRrtmConfig* rc, const IscaRrtmDriverConfig* dc, const char* table_path);
 /* two_stream_gray_rad_nml do_seasonal = .true. (two_stream_gray_rad.F90:417-447) for the moist model's grey radiation: every step
  * insolation = solar_constant * coszen(Time) from astronomy_mod diurnal_solar instead of the analytic annual-mean profile.
- * dc: solday (>= 0: perpetual day of the year; < 0, the namelist default -10: follow the model clock), equinox_day,
+ * dc: solday (>= 0: perpetual day of the year; < 0, the namelist default -10: follow the model clock -- NOTE that
+ * isca_b200_rrtm_driver_default_config sets the rrtm_radiation_nml default solday = 0, which on THIS path is a perpetual day 0:
+ * a caller who wants the seasonal cycle must set solday = -10 after taking the defaults), equinox_day,
  * do_rad_time_avg (= use_time_average_coszen), dt_rad_avg (seconds; <= 0: dt_atmos), ecc / obliq / per / num_angles,
  * day_in_s / year_in_s; the other fields are ignored.  Must be called before isca_b200_moist_init; excludes isca_b200_moist_use_rrtm. */
 int isca_b200_moist_set_seasonal(IscaMoist m, const IscaRrtmDriverConfig* dc);

@@ -621,6 +621,12 @@ int isca_b200_moist_set_t_surf(IscaMoist m, const double* host) {
   return 0;
 }
 
+int isca_b200_moist_set_sst(IscaMoist m, const double* host) {
+  if (!m) return mfail(nullptr, "null handle");
+  if (isca_b200_mixed_layer_set_sst(m->phy, host)) return mfail(m, isca_b200_physics_last_error(m->phy));
+  return 0;
+}
+
 int isca_b200_moist_set_surface(IscaMoist m, int id, const double* host) {
   if (!m) return mfail(nullptr, "null handle");
   if (!host) return mfail(m, "null input array");

@@ -464,7 +464,7 @@ int isca_b200_sat_vapor_pres_tables(const IscaPhysicsConfig* cfg, int n, double*
 int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
   if (!c) return 1;
   std::memset(c, 0, sizeof(*c));
-  c->abi_version = 3;
+  c->abi_version = 4;
   c->sat_vapor_pres_do_simple = 1;
   c->grav = 9.80; c->rdgas = 287.04; c->rvgas = 461.50; c->cp_air = 287.04 / (2.0 / 7.0); c->hlv = 2.500e6;
   c->tfreeze = 273.16; c->stefan = 5.6734e-8; c->pstd_mks = 101325.0;
@@ -484,6 +484,7 @@ int isca_b200_physics_default_config(IscaPhysicsConfig* c) {
   c->fixed_depth = 0; c->diffusivity_do_entrain = 1; c->diffusivity_do_simple = 0; c->free_atm_diff = 0; c->pbl_mcm = 0; c->use_pog_bug_fix = 1;
   c->depth_0 = 5000.0; c->frac_inner = 0.1; c->rich_crit_pbl = 1.0; c->entr_ratio = 0.2; c->parcel_buoy = 2.0; c->znom = 1000.0;
   c->background_m = 0.0; c->background_t = 0.0;
+  c->free_atm_skyhi_diff = 0; c->ampns = 0; c->rich_crit_diff = 0.25; c->mix_len = 30.0; c->rich_prandtl = 1.0; c->ampns_max = 1.0e20;
   c->tau_bm = 7200.0; c->rhbm = 0.8; c->Tmin = 173.0; c->Tmax = 335.0; c->val_inc = 0.01;
   return 0;
 }
@@ -493,7 +494,7 @@ const char* isca_b200_physics_last_error(IscaPhysics p) { return p ? p->err.c_st
 int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   IscaPhysics p = nullptr;
   if (!cfg || !out) return fail(nullptr, "null argument");
-  if (cfg->abi_version != 3) return fail(nullptr, "IscaPhysicsConfig abi_version mismatch");
+  if (cfg->abi_version != 4) return fail(nullptr, "IscaPhysicsConfig abi_version mismatch");
   if (cfg->rad_scheme < 0 || cfg->rad_scheme > 3) return fail(nullptr, "two_stream_gray_rad: not a valid radiation scheme.");   // two_stream_gray_rad.F90:228
   if (cfg->num_lon < 1 || cfg->num_lat < 1 || cfg->num_levels < 1 || cfg->num_levels > ISCA_KMAX)
     return fail(nullptr, "bad dimensions (num_levels must be 1.." + std::to_string(ISCA_KMAX) + ")");
@@ -509,8 +510,10 @@ int isca_b200_physics_create(const IscaPhysicsConfig* cfg, IscaPhysics* out) {
   if (cfg->entr_ratio < 0.0) return fail(nullptr, "diffusivity_init: entr_ratio must be greater than or equal to zero");
   if (cfg->znom <= 0.0) return fail(nullptr, "diffusivity_init: znom must be greater than zero");
   if (cfg->background_m < 0.0 || cfg->background_t < 0.0) return fail(nullptr, "diffusivity_init: background diffusivities must be >= 0");
-  if (cfg->free_atm_diff || cfg->pbl_mcm || !cfg->use_pog_bug_fix)
-    return fail(nullptr, "diffusivity: free_atm_diff, pbl_mcm and use_pog_bug_fix = .false. are not supported by isca_b200");
+  if (cfg->pbl_mcm || !cfg->use_pog_bug_fix)
+    return fail(nullptr, "diffusivity: pbl_mcm and use_pog_bug_fix = .false. are not supported by isca_b200");
+  if (!cfg->free_atm_diff && cfg->free_atm_skyhi_diff)           // diffusivity_init (diffusivity.F90:207-210)
+    return fail(nullptr, "diffusivity_init: free_atm_diff must be set to true if free_atm_skyhi_diff = .true.");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, "no CUDA device: the physics kernels have no CPU path");
   p = new IscaPhysics_t();

@@ -86,7 +86,7 @@ struct Dev {                 // owning device array
 // module state kept between calls, as the Fortran modules keep it (vert_diff_mod e_global/f_t_global/f_q_global and the
 // surf_diff_type Tri_surf of idealized_moist_phys; mixed_layer_mod arrays)
 enum StateId { ST_E_GLOBAL = 0, ST_F_T_GLOBAL, ST_F_Q_GLOBAL, ST_TRI_DELTA_T, ST_TRI_DFLUX_T, ST_TRI_DELTA_Q, ST_TRI_DFLUX_Q,
-               ST_TRI_DTMASS, ST_TRI_DELTA_U, ST_TRI_DELTA_V, ST_ML_HEAT_CAP, ST_ML_QFLUX, ST_COUNT };
+               ST_TRI_DTMASS, ST_TRI_DELTA_U, ST_TRI_DELTA_V, ST_ML_HEAT_CAP, ST_ML_QFLUX, ST_ML_SST, ST_COUNT };
 
 }  // namespace isca_phys
 
@@ -105,6 +105,7 @@ struct IscaPhysics_t {
   double co2_next_sw = 360.0;           // do_read_co2 bookkeeping of launch_gray_down
   isca_phys::Dev insol;                 // do_seasonal insolation [J][I] (pc.insol_dev points here while it is set)
   bool vert_diff_down_done = false;
+  bool sc_sst = false;                  // mixed_layer_nml do_sc_sst: t_surf follows state[ST_ML_SST] (isca_b200_mixed_layer_set_sst)
   int* d_err = nullptr;
   cudaStream_t st = nullptr;
   bool owns_stream = true;              // false when the moist-model driver runs the kernels on the dynamical core's stream

@@ -191,6 +191,7 @@ struct MixedArgs {
   const double *flux_t, *flux_q, *flux_r, *sw, *lw, *dhdt_surf, *dedt_surf, *dedq_surf, *drdt_surf, *dhdt_atm, *dedq_atm,
                *heat_cap, *qflux, *dtmass, *dflux_t, *dflux_q;
   double *t_surf, *delta_t, *delta_q, *delta_t_surf;
+  const double* sst_new;             // do_sc_sst: the prescribed SST of the time stepped to; nullptr = slab ocean
 };
 
 // mixed_layer.F90:629-745; returns a non-finite increment when eff_heat_capacity == 0 (the reference aborts)
@@ -218,9 +219,14 @@ __global__ void mixed_layer_kernel(MixedArgs a, int* err) {
     corrected_flux = corrected_flux + alpha_q * a.hlv;
     t_surf_dependence = t_surf_dependence + beta_q * a.hlv;
   }
-  double eff = a.heat_cap[i] + t_surf_dependence * a.dt;
-  if (eff == 0.0) atomicExch(err, 2);
-  double d = -corrected_flux * a.dt / eff;
+  double d;
+  if (a.sst_new) {                    // do_sc_sst (mixed_layer.F90:681-691; do_calc_eff_heat_cap = .false., :495-502): no slab update
+    d = a.sst_new[i] - a.t_surf[i];
+  } else {
+    double eff = a.heat_cap[i] + t_surf_dependence * a.dt;
+    if (eff == 0.0) atomicExch(err, 2);
+    d = -corrected_flux * a.dt / eff;
+  }
   a.t_surf[i] = a.t_surf[i] + d;
   a.delta_t[i] = fn_t + en_t * d;
   if (a.evaporation) a.delta_q[i] = fn_q + en_q * d;
@@ -276,6 +282,7 @@ void launch_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double* 
   a.heat_cap = p->state[ST_ML_HEAT_CAP].p; a.qflux = p->state[ST_ML_QFLUX].p; a.dtmass = p->state[ST_TRI_DTMASS].p;
   a.dflux_t = p->state[ST_TRI_DFLUX_T].p; a.dflux_q = p->state[ST_TRI_DFLUX_Q].p; a.delta_t = p->state[ST_TRI_DELTA_T].p;
   a.delta_q = p->state[ST_TRI_DELTA_Q].p; a.delta_t_surf = delta_t_surf;
+  a.sst_new = p->sc_sst ? p->state[ST_ML_SST].p : nullptr;
   mixed_layer_kernel<<<(int)((nc + 255) / 256), 256, 0, p->st>>>(a, p->d_err);
 }
 
@@ -326,6 +333,15 @@ int isca_b200_mixed_layer_init(IscaPhysics p, const double* heat_capacity, const
   if (!p) return fail(nullptr, "null handle");
   if (up(p, p->state[ST_ML_HEAT_CAP], heat_capacity, p->ncol) || up(p, p->state[ST_ML_QFLUX], ocean_qflux, p->ncol)) return 1;
   return finish(p, "mixed_layer_init");
+}
+
+int isca_b200_mixed_layer_set_sst(IscaPhysics p, const double* sst) {
+  if (!p) return fail(nullptr, "null handle");
+  if (!sst) { p->sc_sst = false; return 0; }
+  if (up(p, p->state[ST_ML_SST], sst, p->ncol)) return 1;
+  PCK(cudaStreamSynchronize(p->st));
+  p->sc_sst = true;
+  return 0;
 }
 
 int isca_b200_mixed_layer(IscaPhysics p, double dt, double* t_surf, const double* flux_t, const double* flux_q,

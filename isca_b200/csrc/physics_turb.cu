@@ -15,9 +15,12 @@ struct TurbConst {
   double grav, cp_air, d608, vonkarm;
   int fixed_depth, do_entrain, do_simple;
   double depth_0, frac_inner, rich_crit_pbl, entr_ratio, parcel_buoy, znom, background_m, background_t;
+  int free_atm_diff, free_atm_skyhi_diff, ampns;
+  double rich_crit_diff, mix_len, rich_prandtl, ampns_max;
 };
 
-// bytes/column: read t, q, u, v, z_full (5K) + z_half (K+1) + k_m, k_t (2K) + 2; write k_m, k_t (2K) + 1  ~ (10K + 4) * 8
+// bytes/column: read t, q, u, v, z_full (5K; with free_atm_diff = .false. only up to the boundary-layer top) + z_half (K+1)
+// + k_m, k_t (2K, add_input) + 2; write k_m, k_t (2K) + 1  ~ (10K + 4) * 8
 // tau1.tdt != NULL: vert_turb_driver_nml use_tau = .false. (vert_turb_driver.F90:209-213) -- the scheme sees the variables at time
 // tau + 1, x + dt * dx/dt, formed here from the previous-level fields and the tendencies instead of by a separate pass over four 3-D
 // fields.  add_input = 0: the diffusivities are written, not added to the incoming arrays (the caller would have zeroed them).
@@ -93,6 +96,31 @@ __global__ void __launch_bounds__(128, ISCA_COL_MINB) diffusivity_kernel(MoConst
         nm = km_ref * factor; nt = kt_ref * factor;
       } else if (zm < h_inner) mo_diff_point(mc, zm, us, bs, nm, nt);
     }
+    if (c.free_atm_diff && k > 0) {                          // diffusivity_free :604-697 (overwrites the boundary-layer values)
+      double zag_k, zag_km1;
+      const double sv_k = svcp_at(k, zag_k), sv_km1 = svcp_at(k - 1, zag_km1);
+      const double dz = zag_km1 - zag_k;
+      const double b = c.grav * (sv_km1 - sv_k) / sv_k;
+      const double du = U(o - nc) - U(o), dv = V(o - nc) - V(o);
+      const double speed2 = du * du + dv * dv;
+      double rich = b * dz / (speed2 + small);
+      rich = fmax(rich, 0.0);
+      double fri2 = 0.0;
+      if (c.free_atm_skyhi_diff && rich < c.rich_crit_diff) { const double a = 1.0 - rich / c.rich_crit_diff; fri2 = a * a; }
+      double dz15 = 0.0;
+      if (c.ampns) { dz15 = pow(dz, 1.5); rich = rich / fmin(1.0 + 1.0e-04 * dz15, c.ampns_max); }
+      const double af = 1.0 - rich / c.rich_crit_diff, fri = af * af;
+      if (rich < c.rich_crit_diff && (z_half[o] - z_surf) > h) {
+        if (c.free_atm_skyhi_diff) {
+          nm = c.ampns ? c.mix_len * c.mix_len * sqrt(speed2) * fri * (1.0 + 1.0e-04 * dz15) / dz
+                       : c.mix_len * c.mix_len * sqrt(speed2) * fri / dz;
+          nt = nm * (0.1 + 0.9 * fri2);
+        } else {
+          nt = c.mix_len * c.mix_len * sqrt(speed2) * fri / dz;
+          nm = nt * c.rich_prandtl;
+        }
+      }
+    }
     if (add_input) { nm = nm + k_m[o]; nt = nt + k_t[o]; }
     if (entr) {
       double zag, sv = svcp_at(k, zag);
@@ -119,6 +147,8 @@ void launch_diffusivity(IscaPhysics p, const double* t, const double* q, const d
   c.fixed_depth = p->cfg.fixed_depth; c.do_entrain = p->cfg.diffusivity_do_entrain; c.do_simple = p->cfg.diffusivity_do_simple;
   c.depth_0 = p->cfg.depth_0; c.frac_inner = p->cfg.frac_inner; c.rich_crit_pbl = p->cfg.rich_crit_pbl; c.entr_ratio = p->cfg.entr_ratio;
   c.parcel_buoy = p->cfg.parcel_buoy; c.znom = p->cfg.znom; c.background_m = p->cfg.background_m; c.background_t = p->cfg.background_t;
+  c.free_atm_diff = p->cfg.free_atm_diff; c.free_atm_skyhi_diff = p->cfg.free_atm_skyhi_diff; c.ampns = p->cfg.ampns;
+  c.rich_crit_diff = p->cfg.rich_crit_diff; c.mix_len = p->cfg.mix_len; c.rich_prandtl = p->cfg.rich_prandtl; c.ampns_max = p->cfg.ampns_max;
   diffusivity_kernel<<<col_blocks(p, 128), 128, 0, p->st>>>(mo_const(p), c, (int)p->ncol, p->K, t, q, u, v, Tau1{tdt, qdt, udt, vdt, dt}, add_input,
                                                             z_full, z_half, u_star, b_star, h, k_m, k_t);
 }

@@ -377,17 +377,19 @@ int isca_b200_run_rrtmg(IscaRrtm r, const double* p_full, const double* p_half, 
 int isca_b200_rrtm_time(IscaRrtm r, int which, int reps, double* ms) {
   if (!r || !ms || reps < 1) return rfail(r, "rrtm_time: bad argument");
   if ((which == 0 && !r->have_lw) || (which == 1 && !r->have_sw)) return rfail(r, "rrtm_time: no previous call of that kernel");
-  cudaEvent_t e0, e1;
-  RCK(cudaEventCreate(&e0)); RCK(cudaEventCreate(&e1));
+  struct Ev {                                        // destroyed on every exit path
+    cudaEvent_t e = nullptr;
+    ~Ev() { if (e) cudaEventDestroy(e); }
+  } e0, e1;
+  RCK(cudaEventCreate(&e0.e)); RCK(cudaEventCreate(&e1.e));
   for (int i = 0; i < 2; ++i) { if (which == 0 ? isca_rrtm_lw_device(r, r->last_lw) : isca_rrtm_sw_device(r, r->last_sw)) return 1; }
-  RCK(cudaEventRecord(e0, r->st));
+  RCK(cudaEventRecord(e0.e, r->st));
   for (int i = 0; i < reps; ++i) { if (which == 0 ? isca_rrtm_lw_device(r, r->last_lw) : isca_rrtm_sw_device(r, r->last_sw)) return 1; }
-  RCK(cudaEventRecord(e1, r->st));
-  RCK(cudaEventSynchronize(e1));
+  RCK(cudaEventRecord(e1.e, r->st));
+  RCK(cudaEventSynchronize(e1.e));
   float t = 0.f;
-  RCK(cudaEventElapsedTime(&t, e0, e1));
+  RCK(cudaEventElapsedTime(&t, e0.e, e1.e));
   *ms = (double)t / reps;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
 }
 

@@ -9,7 +9,7 @@ from .physics import IscaPhysicsConfigStruct, _lib as _physics_lib
 
 MOIST_EXPORTS = ["isca_b200_moist_default_config", "isca_b200_moist_create", "isca_b200_moist_create_ranked", "isca_b200_moist_destroy", "isca_b200_moist_last_error",
                  "isca_b200_moist_dycore", "isca_b200_moist_init", "isca_b200_moist_step", "isca_b200_moist_get",
-                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_co2", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing",
+                 "isca_b200_moist_set_t_surf", "isca_b200_moist_set_sst", "isca_b200_moist_set_surface", "isca_b200_moist_set_dry_convection", "isca_b200_moist_set_betts_miller", "isca_b200_moist_set_co2", "isca_b200_moist_set_ocean_qflux", "isca_b200_moist_timing",
                  "isca_b200_moist_profile_step", "isca_b200_moist_step_io", "isca_b200_moist_io_sync", "isca_b200_moist_io_wait"]
 
 FIELDS_2D = dict(t_surf=0, precip=1, flux_t=2, flux_q=3, z_pbl=4, net_surf_sw_down=5, surf_lw_down=6, conv_rain=7, cape=8, convflag=9,
@@ -48,6 +48,7 @@ def _lib():
         lib.isca_b200_moist_step.argtypes = [vp, C.c_int]
         lib.isca_b200_moist_get.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_moist_set_t_surf.argtypes = [vp, dp]
+        lib.isca_b200_moist_set_sst.argtypes = [vp, dp]
         lib.isca_b200_moist_set_ocean_qflux.argtypes = [vp, dp]
         lib.isca_b200_moist_set_surface.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_moist_set_dry_convection.argtypes = [vp, C.c_double, C.c_double]
@@ -177,6 +178,17 @@ class MoistAtmosphere:
         if a.shape != self.s2:
             raise IscaError("t_surf has the wrong shape")
         self._ck(self._lib.isca_b200_moist_set_t_surf(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_t_surf")
+
+    def set_sst(self, sst):
+        """mixed_layer_nml do_sc_sst: the prescribed SST [lat, lon] the following steps move t_surf to (the field interpolator_mod
+        reads from sst_file for Time_next); None = slab ocean again"""
+        if sst is None:
+            self._ck(self._lib.isca_b200_moist_set_sst(self._h, None), "set_sst")
+            return
+        a = np.ascontiguousarray(sst, dtype=np.float64)
+        if a.shape != self.s2:
+            raise IscaError("sst has the wrong shape")
+        self._ck(self._lib.isca_b200_moist_set_sst(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_sst")
 
     SURFACE_FIELDS = dict(albedo=20, rough_mom=21, rough_heat=22, rough_moist=23, heat_capacity=24, land=25)
 
@@ -343,4 +355,29 @@ def mima_test_case(res: str, num_levels: int, dt_atmos: float, ozone=None, **ran
     sl = slice(rank * Jloc, (rank + 1) * Jloc)
     m.set_t_surf(np.repeat((285.0 - 40.0 * ((3. * sin_lat[sl] ** 2.) - 1.) / 3.)[:, None], I, 1))
     m.set_ocean_qflux(qflux(latb, I)[sl])
+    return m
+
+
+def axisymmetric_test_case(res: str, num_levels: int, dt_atmos: float, ozone=None, **ranks) -> MoistAtmosphere:
+    """The axisymmetric test case (exp/test_cases/axisymmetric/axisymmetric_test_case.py:52-178): the MiMA options with a zonally
+    symmetric dynamical core (spectral_dynamics_nml make_symmetric), vertical diffusion in the free atmosphere (diffusivity_nml
+    free_atm_diff), RRTMG every 3600 s, a sponge below 150 Pa, surf_res = 0.2 and prescribed SSTs (mixed_layer_nml do_sc_sst): the
+    caller hands the SST of sst_file for the time stepped to with set_sst() before each step (or once, for a perpetual field)."""
+    from .api import make_config
+    I, J, M = RESOLUTIONS[res]
+    cfg = make_config(lon_max=I, lat_max=J, num_fourier=M, num_spherical=M + 1, num_levels=num_levels, dt_atmos=dt_atmos,
+                      damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
+                      initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.2,
+                      robert_coeff=0.03, num_tracers=1, make_symmetric=1)
+    phys = dict(MIMA_PHYSICS_NML, sponge_pbottom=150.0, free_atm_diff=1)
+    moist_nml = dict(MIMA_MOIST_NML, albedo_value=0.25)
+    m = MoistAtmosphere(cfg, physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **moist_nml)
+    dt_rad = 3600
+    if dt_rad % int(dt_atmos) != 0:
+        dt_rad = int(dt_atmos) * max(1, round(dt_rad / dt_atmos))
+    m.use_rrtm(MIMA_RRTM_NML, dt_rad=dt_rad)
+    if ozone is not None:
+        m.set_ozone(ozone)
+    m.core.cold_start()
+    m.idealized_moist_phys_init()
     return m

@@ -17,7 +17,7 @@ PHYSICS_EXPORTS = [
     "isca_b200_physics_last_error", "isca_b200_lookup_es_des", "isca_b200_compute_qs", "isca_b200_lscale_cond",
     "isca_b200_two_stream_gray_rad_down", "isca_b200_two_stream_gray_rad_up", "isca_b200_two_stream_gray_rad_set_insolation", "isca_b200_two_stream_gray_rad_set_co2",
     "isca_b200_rayleigh_damping",
-    "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init",
+    "isca_b200_physics_time", "isca_b200_gcm_vert_diff_down", "isca_b200_get_tri_surf", "isca_b200_mixed_layer_init", "isca_b200_mixed_layer_set_sst",
     "isca_b200_mixed_layer", "isca_b200_gcm_vert_diff_up", "isca_b200_mo_drag", "isca_b200_mo_profile", "isca_b200_stable_mix",
     "isca_b200_mo_diff", "isca_b200_surface_flux", "isca_b200_diffusivity", "isca_b200_qe_moist_convection", "isca_b200_dry_convection",
     "isca_b200_sat_vapor_pres_tables", "isca_b200_betts_miller_default_config", "isca_b200_betts_miller_init", "isca_b200_betts_miller",
@@ -91,7 +91,8 @@ class IscaPhysicsConfigStruct(C.Structure):
                [(n, C.c_double) for n in ("ir_tau_co2_win", "ir_tau_wv_win1", "ir_tau_wv_win2", "ir_tau_co2", "ir_tau_wv1", "ir_tau_wv2",
                                           "window", "carbon_conc", "single_albedo", "back_scatter", "lw_tau_0_gp", "sw_tau_0_gp",
                                           "lw_tau_exponent_gp", "sw_tau_exponent_gp", "bog_a", "bog_b", "bog_mu")] + \
-               [("sat_vapor_pres_do_simple", C.c_int)]
+               [("sat_vapor_pres_do_simple", C.c_int), ("free_atm_skyhi_diff", C.c_int), ("ampns", C.c_int)] + \
+               [(n, C.c_double) for n in ("rich_crit_diff", "mix_len", "rich_prandtl", "ampns_max")]
 
 RAD_SCHEMES = {"FRIERSON": 0, "BYRNE": 1, "GEEN": 2, "SCHNEIDER": 3}      # two_stream_gray_rad.F90:214-230
 
@@ -121,6 +122,7 @@ def _lib():
         lib.isca_b200_gcm_vert_diff_down.argtypes = [vp, C.c_double] + [dp] * 18
         lib.isca_b200_get_tri_surf.argtypes = [vp, C.c_int, dp]
         lib.isca_b200_mixed_layer_init.argtypes = [vp, dp, dp]
+        lib.isca_b200_mixed_layer_set_sst.argtypes = [vp, dp]
         lib.isca_b200_mixed_layer.argtypes = [vp, C.c_double] + [dp] * 13
         lib.isca_b200_gcm_vert_diff_up.argtypes = [vp, C.c_double, dp, dp]
         lib.isca_b200_mo_drag.argtypes = [vp, C.c_int] + [dp] * 12
@@ -281,6 +283,10 @@ class ColumnPhysics:
     def mixed_layer_init(self, heat_capacity, ocean_qflux):
         hc, qf = _in(heat_capacity, self.s2, "heat_capacity"), _in(ocean_qflux, self.s2, "ocean_qflux")
         self._ck(self._lib.isca_b200_mixed_layer_init(self._h, _p(hc), _p(qf)), "mixed_layer_init")
+
+    def mixed_layer_set_sst(self, sst):
+        """do_sc_sst: prescribed SST [lat, lon] of the time stepped to; None = slab ocean"""
+        self._ck(self._lib.isca_b200_mixed_layer_set_sst(self._h, None if sst is None else _p(_in(sst, self.s2, "sst"))), "mixed_layer_set_sst")
 
     def mixed_layer(self, dt, t_surf, flux_t, flux_q, flux_r, net_surf_sw_down, surf_lw_down, dhdt_surf, dedt_surf, dedq_surf,
                     drdt_surf, dhdt_atm, dedq_atm):

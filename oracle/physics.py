@@ -417,8 +417,9 @@ def gcm_vert_diff_down(delt, u, v, t, q, diff_m, diff_t, p_half, p_full, z_full,
 
 
 def mixed_layer(tri, dt, t_surf, flux_t, flux_q, flux_r, net_surf_sw_down, surf_lw_down, dhdt_surf, dedt_surf, dedq_surf,
-                drdt_surf, dhdt_atm, dedq_atm, heat_capacity, ocean_qflux, evaporation=True):
-    """mixed_layer.F90:568-745, do_calc_eff_heat_cap path (no prescribed SST, no ice, no flux anomalies).
+                drdt_surf, dhdt_atm, dedq_atm, heat_capacity, ocean_qflux, evaporation=True, sst_new=None):
+    """mixed_layer.F90:568-745: the slab update (do_calc_eff_heat_cap path; no ice, no flux anomalies) or, with sst_new, do_sc_sst
+    (:681-691 with do_calc_eff_heat_cap = .false., :495-502): t_surf moves to the prescribed SST of the time stepped to.
     Returns the new t_surf and the updated Tri_surf delta_t / delta_q."""
     inv_cp = 1.0 / CP_AIR
     gamma_t = 1.0 / (1.0 - tri["dtmass"] * (tri["dflux_t"] + dhdt_atm * inv_cp))
@@ -438,8 +439,11 @@ def mixed_layer(tri, dt, t_surf, flux_t, flux_q, flux_r, net_surf_sw_down, surf_
     if evaporation:
         corrected_flux = corrected_flux + alpha_q * HLV
         t_surf_dependence = t_surf_dependence + beta_q * HLV
-    eff = heat_capacity + t_surf_dependence * dt
-    delta_t_surf = -corrected_flux * dt / eff
+    if sst_new is not None:
+        delta_t_surf = sst_new - t_surf
+    else:
+        eff = heat_capacity + t_surf_dependence * dt
+        delta_t_surf = -corrected_flux * dt / eff
     out = dict(tri)
     out["delta_t"] = fn_t + en_t * delta_t_surf
     if evaporation:
@@ -749,7 +753,7 @@ def surface_flux(svp: SatVaporPres, mo: MOConfig, c: SurfaceFluxConfig, t_atm, q
 # vert_turb_driver with do_diffusivity = .true. (vert_turb_driver.F90:277-292)
 @dataclass
 class DiffusivityConfig:
-    """diffusivity_nml defaults (diffusivity.F90:97-118); free_atm_diff, pbl_mcm, use_pog_bug_fix=.false. not restated."""
+    """diffusivity_nml defaults (diffusivity.F90:124-147); pbl_mcm, use_pog_bug_fix=.false. not restated."""
     fixed_depth: bool = False
     depth_0: float = 5000.0
     frac_inner: float = 0.1
@@ -761,6 +765,45 @@ class DiffusivityConfig:
     background_t: float = 0.0
     do_entrain: bool = True
     do_simple: bool = False
+    free_atm_diff: bool = False
+    free_atm_skyhi_diff: bool = False
+    rich_crit_diff: float = 0.25
+    mix_len: float = 30.0
+    rich_prandtl: float = 1.0
+    ampns: bool = False
+    ampns_max: float = 1.0e20
+
+
+def diffusivity_free(c: DiffusivityConfig, t, u, v, z, zz, h, k_m, k_t, small=1e-4):
+    """diffusivity.F90:604-697: Richardson-number mixing-length diffusivities above the boundary layer (zz > h) overwrite the
+    boundary-layer values where the local Richardson number is sub-critical.  t = (virtual) dry static energy / cp."""
+    K = t.shape[0]
+    k_m, k_t = k_m.copy(), k_t.copy()
+    for k in range(1, K):
+        dz = z[k - 1] - z[k]
+        b = GRAV * (t[k - 1] - t[k]) / t[k]
+        speed2 = (u[k - 1] - u[k]) ** 2 + (v[k - 1] - v[k]) ** 2
+        rich = b * dz / (speed2 + small)
+        rich = np.maximum(rich, 0.0)
+        fri2 = None
+        if c.free_atm_skyhi_diff:
+            fri2 = np.where(rich >= c.rich_crit_diff, 0.0, (1.0 - rich / c.rich_crit_diff) ** 2)
+        if c.ampns:
+            alpz = np.minimum(1.0 + 1.0e-04 * (dz ** 1.5), c.ampns_max)
+            rich = rich / alpz
+        fri = (1.0 - rich / c.rich_crit_diff) ** 2
+        m = (rich < c.rich_crit_diff) & (zz[k] > h)
+        if c.free_atm_skyhi_diff:
+            if c.ampns:
+                km = c.mix_len * c.mix_len * np.sqrt(speed2) * fri * (1.0 + 1.0e-04 * (dz ** 1.5)) / dz
+            else:
+                km = c.mix_len * c.mix_len * np.sqrt(speed2) * fri / dz
+            kt = km * (0.1 + 0.9 * fri2)
+        else:
+            kt = c.mix_len * c.mix_len * np.sqrt(speed2) * fri / dz
+            km = kt * c.rich_prandtl
+        k_m[k] = np.where(m, km, k_m[k]); k_t[k] = np.where(m, kt, k_t[k])
+    return k_m, k_t
 
 
 def pbl_depth(c: DiffusivityConfig, mo: MOConfig, t, u, v, z, u_star, b_star, small=1e-4):
@@ -823,6 +866,8 @@ def diffusivity(c: DiffusivityConfig, mo: MOConfig, t, q, u, v, p_full, p_half, 
             factor = (zm[k] / h_inner) * (1.0 - (zm[k] - h_inner) / (h - h_inner)) ** 2
         new_m[k] = np.where(mid, km_ref * factor, np.where(inner, km_sl[k], 0.0))
         new_t[k] = np.where(mid, kt_ref * factor, np.where(inner, kt_sl[k], 0.0))
+    if c.free_atm_diff:
+        new_m, new_t = diffusivity_free(c, svcp, u, v, z_full_ag, z_half_ag, h, new_m, new_t, small)
     k_m, k_t = new_m + k_m, new_t + k_t
     if c.entr_ratio > 0.0 and not c.fixed_depth and c.do_entrain:                      # diffusivity_entr :732-750
         for k in range(1, K):
@@ -1313,7 +1358,8 @@ class IdealizedMoistPhys:
         dt_ug, dt_vg = r["dt_u"], r["dt_v"]
         self.t_surf, tri, dts = mixed_layer(r["tri"], self.dt_real, self.t_surf, sf["flux_t"], sf["flux_q"], sf["flux_r"], net_surf_sw_down,
                                             surf_lw_down, sf["dhdt_surf"], sf["dedt_surf"], sf["dedq_surf"], sf["drdt_surf"], sf["dhdt_atm"],
-                                            sf["dedq_atm"], self.heat_capacity, self.ocean_qflux, evaporation=c.evaporation)
+                                            sf["dedq_atm"], self.heat_capacity, self.ocean_qflux, evaporation=c.evaporation,
+                                            sst_new=getattr(self, "sst_new", None))
         dt_tg, dt_q = gcm_vert_diff_up(delta_t, tri)
         self.diag.update(precip=precip, z_pbl=z_pbl, flux_t=sf["flux_t"], flux_q=sf["flux_q"], delta_t_surf=dts, diff_m=diff_m, diff_t=diff_t,
                          net_surf_sw_down=net_surf_sw_down, surf_lw_down=surf_lw_down)

@@ -114,7 +114,9 @@ def test_physics_header_symbols_exported_and_struct_layout(lib_built, tmp_path):
     assert (c.hc, c.do_evap, c.trayfric, c.sponge_pbottom) == (1.0, 0, 0.0, 50.0)
     # the other rad_scheme values (two_stream_gray_rad.F90:96-118)
     assert (c.abi_version, c.rad_scheme, c.window, c.carbon_conc, c.bog_a, c.bog_b, c.lw_tau_0_gp, c.single_albedo) == \
-        (3, 0, 0.3732, 360.0, 0.8678, 1997.9, 80.0, 0.8)
+        (4, 0, 0.3732, 360.0, 0.8678, 1997.9, 80.0, 0.8)
+    # diffusivity_nml free_atm_diff parameters (diffusivity.F90:132-143)
+    assert (c.free_atm_diff, c.free_atm_skyhi_diff, c.ampns, c.rich_crit_diff, c.mix_len, c.rich_prandtl, c.ampns_max) == (0, 0, 0, 0.25, 30.0, 1.0, 1.0e20)
     assert c.sat_vapor_pres_do_simple == 1
 
 

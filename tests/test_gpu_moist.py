@@ -16,11 +16,12 @@ FRIERSON_PHYS = dict(atm_abs=0.2, use_virtual_temp=0, surface_flux_do_simple=1, 
                      diffusivity_do_simple=1, rhbm=0.7, Tmin=160.0, Tmax=350.0)
 
 
-def build(res, K, dt, convection, seed=0, damping=False, rad_scheme="frierson"):
+def build(res, K, dt, convection, seed=0, damping=False, rad_scheme="frierson", make_symmetric=False, diff_nml=None, jet=0.0):
     """oracle core + moist physics with the Frierson test-case namelists, started from a moist, conditionally unstable state"""
     from oracle.isca_oracle import SpectralCore, frierson_config
     from oracle import physics as P
     cfg = frierson_config(res, K, dt)
+    cfg.make_symmetric = bool(make_symmetric)
     core = SpectralCore(cfg)
     core.cold_start()
     for _ in range(3):
@@ -42,6 +43,12 @@ def build(res, K, dt, convection, seed=0, damping=False, rad_scheme="frierson"):
         core.tg[lev] = tr.spherical_to_grid(ts)
         qs, _ = svp.compute_qs(core.tg[lev], pf)
         core.grid_tracers[lev, 0] = np.minimum(0.85 * qs, 0.03) * (pf / ps[None]) ** 0.5
+        if jet:                                                               # a sheared zonal jet (free-atmosphere mixing needs shear)
+            shear = np.cos(np.linspace(0.0, 3.0 * np.pi, Kk))[:, None, None] * (1.0 - pf / ps[None]) + 0.3
+            core.vors[lev], core.divs[lev] = tr.vor_div_from_uv_grid(jet * shear * np.cos(lat)[None] ** 2 * np.ones_like(pf), np.zeros_like(pf))
+            core.ug[lev], core.vg[lev] = tr.uv_grid_from_vor_div(core.vors[lev], core.divs[lev])
+            if lev == 1:
+                core.vorg, core.divg = tr.spherical_to_grid(core.vors[lev]), tr.spherical_to_grid(core.divs[lev])
     core.previous, core.current = 0, 1
     core.finish_init()
     mp = P.IdealizedMoistPhys(P.MoistPhysConfig(convection_scheme=convection, depth=2.5, albedo_value=0.31, do_damping=damping,
@@ -49,7 +56,7 @@ def build(res, K, dt, convection, seed=0, damping=False, rad_scheme="frierson"):
                               cfg.dt_atmos, lat, core.surf_geopotential / cfg.grav, core.tg[core.current][Kk - 1],
                               pref=None, svp=svp, rad=P.GreyRadConfig(atm_abs=0.2, rad_scheme=rad_scheme),
                               sflux=P.SurfaceFluxConfig(use_virtual_temp=False, do_simple=True, old_dtaudv=True),
-                              diff=P.DiffusivityConfig(do_entrain=False, do_simple=True),
+                              diff=P.DiffusivityConfig(do_entrain=False, do_simple=True, **(diff_nml or {})),
                               sbm=P.SBMConvection(svp, rhbm=0.7, Tmin=160.0, Tmax=350.0))
     if damping:
         _, _, pfr, _ = core.pg.compute_pressures_and_heights(core.tg[0][:, :1, :1], np.full((1, 1), P.PSTD_MKS), np.zeros((1, 1)), None)
@@ -58,9 +65,9 @@ def build(res, K, dt, convection, seed=0, damping=False, rad_scheme="frierson"):
     return cfg, core, mp
 
 
-def make_gpu(cfg, core, convection, damping=False, rad_scheme="frierson"):
+def make_gpu(cfg, core, convection, damping=False, rad_scheme="frierson", extra_phys=None):
     from isca_b200 import api, moist
-    phys = dict(FRIERSON_PHYS, rad_scheme=rad_scheme)
+    phys = dict(FRIERSON_PHYS, rad_scheme=rad_scheme, **(extra_phys or {}))
     if damping:
         phys.update(trayfric=-0.5, sponge_pbottom=5000.0)
     m = moist.MoistAtmosphere(api.config_from_namelist_object(cfg), physics_nml=phys, convection_scheme=convection,
@@ -107,6 +114,42 @@ def test_moist_model_steps_match_oracle(lib_built, res, K, dt, convection, dampi
     if convection != "NONE":
         flags = np.bincount(mp.diag["convflag"].ravel(), minlength=3)
         assert flags[2] > 0 and mp.diag["precip"].max() > 0                   # the case did exercise deep convection
+    m.atmosphere_end()
+
+
+def test_axisymmetric_test_case_options(lib_built):
+    """exp/test_cases/axisymmetric beyond MiMA: spectral_dynamics_nml make_symmetric, diffusivity_nml free_atm_diff and
+    mixed_layer_nml do_sc_sst (the SST of the time stepped to is handed over by the host every step)"""
+    from isca_b200 import api
+    cfg, core, mp = build("T21", 14, 900.0, "SIMPLE_BETTS_MILLER", seed=3, damping=True, make_symmetric=True,
+                          diff_nml=dict(free_atm_diff=True, rich_crit_diff=300.0, mix_len=100.0), jet=35.0)
+    # (14 coarse levels: the Richardson numbers of the sheared jet are O(10-100), hence the large critical value)
+    m, atm = make_gpu(cfg, core, "SIMPLE_BETTS_MILLER", True, extra_phys=dict(free_atm_diff=1, rich_crit_diff=300.0, mix_len=100.0))
+    lat = np.repeat(core.tb.rad_lat[:, None], core.tg[0].shape[2], 1)
+    changed = 0
+    for i in range(3):
+        sst = 285.0 + 16.0 * np.cos(lat) ** 2 + 0.5 * i + 0.2 * np.sin(3 * lat)
+        mp.sst_new = sst
+        m.set_sst(sst)
+        core.step()
+        m.atmosphere(1)
+        c = core.current
+        assert np.array_equal(m.get("t_surf"), mp.t_surf) or rel(m.get("t_surf"), mp.t_surf) < 1e-15, i
+        assert rel(mp.t_surf, sst) < 1e-15                                     # t_surf + (sst - t_surf)
+        assert rel(m.get("diff_m"), mp.diag["diff_m"]) < 1e-9 and rel(m.get("diff_t"), mp.diag["diff_t"]) < 1e-9, i
+        assert rel(m.get("z_pbl"), mp.diag["z_pbl"]) < TOL and rel(m.get("flux_t"), mp.diag["flux_t"]) < TOL, i
+        zag = core.z_half[core.previous][:-1] - core.z_half[core.previous][-1][None]
+        changed += int(np.count_nonzero((mp.diag["diff_t"] > 0) & (zag > mp.diag["z_pbl"][None])))
+        for name, fid in (("ug", api.F_U), ("vg", api.F_V), ("tg", api.F_T)):
+            assert rel(atm.get_field(fid), getattr(core, name)[c]) < TOL, (i, name)
+        assert rel(atm.get_field(api.F_PS), core.psg[c]) < TOL and rel(atm.get_field(api.F_TRACER0), core.grid_tracers[c, 0]) < TOL, i
+        assert np.array_equal(m.get("convflag").astype(int), mp.diag["convflag"]), i
+    assert changed > 0                                                         # free-atmosphere diffusivities were present
+    u = atm.get_field(api.F_U)
+    m.set_sst(None)                                                            # back to the slab ocean
+    mp.sst_new = None
+    core.step(); m.atmosphere(1)
+    assert rel(m.get("t_surf"), mp.t_surf) < TOL and rel(atm.get_field(api.F_T), core.tg[core.current]) < TOL
     m.atmosphere_end()
 
 

@@ -208,6 +208,33 @@ def test_vert_diff_and_mixed_layer(mods, K, J, I, virt, conserve):
     assert rel(t_g, t_o) < 1e-11 and rel(q_g, q_o) < 1e-11
 
 
+def test_mixed_layer_prescribed_sst(mods):
+    """mixed_layer_nml do_sc_sst (mixed_layer.F90:495-502, 681-691): t_surf moves to the SST handed over by the host, the slab heat
+    capacity is not used (a zero capacity, fatal for the slab, is harmless here), Tri_surf takes delta_t_surf = sst - t_surf"""
+    physics, O = mods
+    K, J, I = 9, 4, 6
+    rng, ph, pf, t, q, z, u, v, dm, dh = diff_case(K, J, I, 5)
+    f2 = lambda lo, hi: rng.uniform(lo, hi, (J, I))
+    z2 = np.zeros((J, I))
+    dt3 = [1e-4 * rng.standard_normal(t.shape) for _ in range(3)] + [1e-8 * rng.standard_normal(t.shape)]
+    ts, sst = f2(275, 300), f2(270, 305)
+    args = dict(flux_t=f2(-20, 60), flux_q=f2(0, 1e-4), flux_r=f2(350, 450), net_surf_sw_down=f2(0, 300), surf_lw_down=f2(250, 400),
+                dhdt_surf=f2(5, 20), dedt_surf=f2(1e-6, 5e-6), dedq_surf=f2(0, 1e-2), drdt_surf=f2(4, 6), dhdt_atm=f2(-20, -5),
+                dedq_atm=f2(-1e-2, -1e-3))
+    cp = physics.ColumnPhysics(I, J, K)
+    cp.gcm_vert_diff_down(720.0, u, v, t, q, dm, dh, ph, pf, z, f2(-.2, .2), f2(-.2, .2), f2(-.05, -.005), f2(-.05, -.005), *dt3)
+    tri0 = {k: cp.tri_surf(k) for k in ("delta_t", "dflux_t", "delta_q", "dflux_q", "dtmass")}
+    cp.mixed_layer_init(z2, z2)
+    cp.mixed_layer_set_sst(sst)
+    ts_g, d_g = cp.mixed_layer(360.0, ts, **args)
+    ts_o, tri_o, d_o = O.mixed_layer(tri0, 360.0, ts, heat_capacity=z2, ocean_qflux=z2, sst_new=sst, **args)
+    assert np.array_equal(d_g, sst - ts) and np.array_equal(ts_g, ts + (sst - ts)) and np.array_equal(ts_g, ts_o)
+    assert rel(cp.tri_surf("delta_t"), tri_o["delta_t"]) < 1e-12 and rel(cp.tri_surf("delta_q"), tri_o["delta_q"]) < 1e-12
+    cp.mixed_layer_set_sst(None)                                      # slab again: the zero heat capacity is fatal as before
+    with pytest.raises(physics.IscaError):
+        cp.mixed_layer(360.0, ts, **{k: z2 for k in args})
+
+
 def test_mixed_layer_zero_effective_heat_capacity_is_fatal(mods):
     physics, O = mods
     K, J, I = 5, 2, 4
@@ -321,7 +348,11 @@ def test_surface_flux(mods, nml):
 
 
 @pytest.mark.parametrize("nml", [dict(), dict(diffusivity_do_simple=1, diffusivity_do_entrain=0), dict(fixed_depth=1, depth_0=1500.0),
-                                 dict(background_m=0.5, background_t=0.25, rich_crit_pbl=0.5, frac_inner=0.2, parcel_buoy=1.0, entr_ratio=0.4)])
+                                 dict(background_m=0.5, background_t=0.25, rich_crit_pbl=0.5, frac_inner=0.2, parcel_buoy=1.0, entr_ratio=0.4),
+                                 dict(free_atm_diff=1),                                       # the axisymmetric test case
+                                 dict(free_atm_diff=1, rich_crit_diff=1.0, mix_len=50.0, rich_prandtl=0.7, diffusivity_do_simple=1),
+                                 dict(free_atm_diff=1, free_atm_skyhi_diff=1, rich_crit_diff=2.0),
+                                 dict(free_atm_diff=1, free_atm_skyhi_diff=1, ampns=1, ampns_max=1.5, rich_crit_diff=2.0)])
 def test_diffusivity(mods, nml):
     physics, O = mods
     K, J, I = 30, 16, 40
@@ -351,7 +382,7 @@ def test_diffusivity(mods, nml):
 
 def test_diffusivity_unsupported_options_fail_loudly(mods):
     physics, _ = mods
-    for bad in (dict(free_atm_diff=1), dict(pbl_mcm=1), dict(use_pog_bug_fix=0), dict(frac_inner=1.0), dict(znom=0.0)):
+    for bad in (dict(free_atm_skyhi_diff=1), dict(pbl_mcm=1), dict(use_pog_bug_fix=0), dict(frac_inner=1.0), dict(znom=0.0)):
         with pytest.raises(physics.IscaError):
             physics.ColumnPhysics(4, 2, 3, **bad)
 

@@ -204,6 +204,26 @@ def test_mima_test_case_runs(lib_built):
     m.atmosphere_end()
 
 
+def test_axisymmetric_test_case_runs(lib_built):
+    """axisymmetric_test_case.py at T21 L40: MiMA physics + make_symmetric + free_atm_diff + prescribed, seasonally moving SSTs;
+    the flow stays zonally symmetric (every field equals its zonal mean to rounding) and physical"""
+    from isca_b200 import moist, api
+    m = moist.axisymmetric_test_case("T21", 40, 900.0)
+    lat = np.repeat(np.arcsin(m.core.get_table(api.TB_SIN_LAT))[:, None], 64, 1)
+    for i in range(24):
+        sst = 273.0 + 27.0 * np.cos(lat - 0.1 * np.sin(2 * np.pi * i / 480.0)) ** 2        # stand-in for sn_1.000_sst.nc
+        m.set_sst(sst)
+        m.atmosphere(1)
+    assert np.array_equal(m.get("t_surf"), sst)
+    for fid in (api.F_U, api.F_V, api.F_T, api.F_TRACER0):
+        f = m.core.get_field(fid)
+        assert np.isfinite(f).all()
+        assert np.abs(f - f.mean(axis=-1, keepdims=True)).max() <= 1e-9 * max(np.abs(f).max(), 1e-30), fid
+    t = m.core.get_field(api.F_T)
+    assert 150.0 < t.min() and t.max() < 330.0 and np.isfinite(m.get("olr")).all()
+    m.atmosphere_end()
+
+
 @pytest.mark.parametrize("lonstep", [2, 4])
 def test_run_rrtmg_lonstep(lib_built, lonstep):
     """rrtm_radiation_nml lonstep: radiation on every lonstep-th longitude, linear interpolation closed around the latitude circle"""

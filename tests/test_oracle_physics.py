@@ -315,6 +315,48 @@ def test_diffusivity_profile_properties():
     assert np.array_equal(km2, np.maximum(km1, 0.5)) and np.array_equal(kt2, np.maximum(kt1, 0.25))
 
 
+def test_diffusivity_free_atmosphere_properties():
+    """diffusivity_nml free_atm_diff (diffusivity_free, diffusivity.F90:604-697): above the boundary layer the diffusivity is the
+    mixing-length value mix_len^2 |dU/dz| (1 - Ri/Ri_c)^2 where Ri < Ri_c, and untouched elsewhere"""
+    t, q, u, v, pf, ph, zf, zh, us, bs = turb_case()
+    K = t.shape[0]
+    mo = P.MOConfig()
+    z0 = np.zeros_like(t)
+    base = P.DiffusivityConfig(do_entrain=False)
+    h0, km0, kt0 = P.diffusivity(base, mo, t, q, u, v, pf, ph, zf, zh, us, bs, z0, z0)
+    c = P.DiffusivityConfig(do_entrain=False, free_atm_diff=True, rich_crit_diff=0.5, mix_len=40.0, rich_prandtl=0.8)
+    h1, km1, kt1 = P.diffusivity(c, mo, t, q, u, v, pf, ph, zf, zh, us, bs, z0, z0)
+    assert np.array_equal(h0, h1)
+    zag_h, zag_f = zh - zh[K], zf - zh[K]
+    gcp = P.GRAV / P.CP_AIR
+    svcp = t * (1 + P.D608 * q) + gcp * zag_f
+    changed = (km1 != km0) | (kt1 != kt0)
+    assert changed.any() and not changed[0].any()
+    for k in range(1, K):
+        dz = zag_f[k - 1] - zag_f[k]
+        sp2 = (u[k - 1] - u[k]) ** 2 + (v[k - 1] - v[k]) ** 2
+        ri = np.maximum(P.GRAV * (svcp[k - 1] - svcp[k]) / svcp[k] * dz / (sp2 + 1e-4), 0.0)
+        on = (ri < 0.5) & (zag_h[k] > h1)
+        want = 40.0 * 40.0 * np.sqrt(sp2) * (1 - ri / 0.5) ** 2 / dz
+        assert np.allclose(kt1[k][on], want[on], rtol=1e-14) and np.allclose(km1[k][on], 0.8 * want[on], rtol=1e-14)
+        assert np.array_equal(km1[k][~on], km0[k][~on]) and np.array_equal(kt1[k][~on], kt0[k][~on])
+    # skyhi form: k_t / k_m = 0.1 + 0.9 (1 - Ri/Ri_c)^2 with the Richardson number before the ampns factor; ampns scales Ri down
+    cs = P.DiffusivityConfig(do_entrain=False, free_atm_diff=True, free_atm_skyhi_diff=True, rich_crit_diff=0.5)
+    _, kms, kts = P.diffusivity(cs, mo, t, q, u, v, pf, ph, zf, zh, us, bs, z0, z0)
+    ca = P.DiffusivityConfig(do_entrain=False, free_atm_diff=True, free_atm_skyhi_diff=True, rich_crit_diff=0.5, ampns=True, ampns_max=3.0)
+    _, kma, kta = P.diffusivity(ca, mo, t, q, u, v, pf, ph, zf, zh, us, bs, z0, z0)
+    on = kms != km0
+    assert on.any() and np.all(kts[on] <= kms[on] * (1 + 1e-14)) and np.all(kts[on] >= 0.1 * kms[on] * (1 - 1e-14))
+    assert np.count_nonzero(kma != km0) >= np.count_nonzero(on)          # a smaller Ri is sub-critical at least as often
+    # the boundary-layer entrainment value is written after the free-atmosphere values (diffusivity.F90:347-350)
+    ce = P.DiffusivityConfig(free_atm_diff=True)
+    _, kme, kte = P.diffusivity(ce, mo, t, q, u, v, pf, ph, zf, zh, us, bs, z0, z0)
+    _, kmb, ktb = P.diffusivity(P.DiffusivityConfig(), mo, t, q, u, v, pf, ph, zf, zh, us, bs, z0, z0)
+    for k in range(1, K):
+        ent = (bs > 0.0) & (zag_f[k - 1] > h1) & (zag_f[k] <= h1)
+        assert np.array_equal(kte[k][ent], ktb[k][ent])
+
+
 def conv_case(K, J, I, seed):
     svp = P.SatVaporPres()
     rng = np.random.default_rng(seed)
