@@ -83,7 +83,11 @@ def work_model(res: str, K: int, moist: bool = False, nlev_sponge: int = 0):
         w.update({
             "phys_press_heights": dict(bytes=col * 2 * (5 * K + 4)),
             "phys_convection": dict(bytes=col * (8 * K + 9)),
+            # conv_post_kernel: reads the increments, T, q and both tendencies (6K), writes T, q after convection and the tendencies (4K)
+            "phys_conv_post": dict(bytes=col * (10 * K + 3)),
             "phys_lscale_cond": dict(bytes=col * (6 * K + 2)),
+            # cond_post_kernel: reads the increments and both tendencies (4K), writes the tendencies (2K)
+            "phys_cond_post": dict(bytes=col * (6 * K + 2)),
             "phys_surface_flux": dict(bytes=col * 45, bound="latency"),
             "phys_radiation": dict(bytes=col * 3 * K),
             "phys_damping": dict(bytes=col * 15 * max(nlev_sponge, 1)),
@@ -165,10 +169,12 @@ def measured_peaks():
 
 FP64_TENSOR_PEAK_TFLOPS = 37.2   # measured on this pool: tools/probe_fp64.cu, profiles/r01_probe_fp64.txt (DMMA m8n8k4)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from committed `ncu` captures at T170 L40 on 1 GPU
-# (profiles/r01i_ncu_summary.txt, profiles/r02/r02a_moist_step_t170_ncu.txt); null for kernels / configurations without a capture
+# (profiles/r01i_ncu_summary.txt, profiles/r02/r02a_moist_step_t170_ncu.txt, profiles/r02/r02g_ncu_summary.txt,
+# profiles/r02/r02p_ncu_summary.txt); null for kernels / configurations without a capture
 NCU_TRAFFIC = {"fft_inv": 448.0e6, "fft_fwd": 244.7e6, "grid_step": 698.4e6, "tracer_horiz": 151.1e6, "tracer_ppm": 290.6e6,
                "legendre_inv": 301.2e6, "legendre_fwd": 365.0e6}
-NCU_TRAFFIC_MOIST = {"grid_step": 840.6e6, "phys_vert_diff_down": 1253.1e6, "phys_convection": 864.4e6, "phys_lscale_cond": 435.3e6,
+NCU_TRAFFIC_MOIST = {"grid_step": 842.9e6, "phys_vert_diff_down": 1251.3e6, "phys_convection": 578.5e6, "phys_conv_post": 379.1e6,
+                     "phys_lscale_cond": 222.5e6, "phys_cond_post": 212.8e6,
                      "phys_press_heights": 309.4e6, "phys_diffusivity": 169.9e6, "tracer_horiz": 195.6e6, "tracer_ppm": 343.0e6,
                      "fft_inv": 447.4e6, "fft_fwd": 245.1e6, "legendre_inv": 301.2e6, "legendre_fwd": 365.4e6}
 

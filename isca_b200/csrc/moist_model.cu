@@ -154,9 +154,10 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
     else                                                          // 'FULL_BETTS_MILLER' (:889-916): same post-processing
       launch_betts_miller(p, delta_t, tg_p, q_p, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p, m->c_qref.p, m->c_Tref.p, convflag, klzb, klcl,
                           m->cape.p, m->cin.p, m->itt.p, m->itq.p);
+    isca_core_mark(m->dyn, "phys_convection");
     conv_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, tg_p, q_p, m->tg_tmp.p, m->qg_tmp.p, m->dt_t.p, m->dt_q.p,
                                                m->rain.p, m->conv_rain.p, m->precip.p);
-    isca_core_mark(m->dyn, "phys_convection");
+    isca_core_mark(m->dyn, "phys_conv_post");
     t_in = m->tg_tmp.p; q_in = m->qg_tmp.p;
   } else if (m->mc.convection_scheme == 2) {                     // 'DRY' (:918-928): dt_tg += conv_dt_tg; no precipitation
     launch_dry_convection(p, m->dry_tau, m->dry_gamma, tg_p, pf_p, ph_p, m->c_Tref.p, m->c_dT.p, m->cape.p, m->cin.p, klzb, klcl);
@@ -169,8 +170,9 @@ int moist_step_once(IscaMoist m, cudaEvent_t ev_phys_end) {
   }
   if (m->mc.convection_scheme != 2) {                            // `if (r_conv_scheme .ne. DRY_CONV)` (:977): no large-scale condensation
     launch_lscale(p, t_in, q_in, pf_p, ph_p, m->rain.p, m->c_dT.p, m->c_dq.p);
-    cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
     isca_core_mark(m->dyn, "phys_lscale_cond");
+    cond_post_kernel<<<nblk(n3), 256, 0, st>>>(n3, nc, delta_t, m->c_dT.p, m->c_dq.p, m->dt_t.p, m->dt_q.p, m->rain.p, m->precip.p);
+    isca_core_mark(m->dyn, "phys_cond_post");
   }
   if (!m->rr && m->seasonal) {                                   // Time_diag = Time (:1054); days of 86400 s as get_time returns them
     const double days = floor(m->time_s / 86400.0), seconds = m->time_s - 86400.0 * days;
