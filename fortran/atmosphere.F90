@@ -105,6 +105,22 @@ module atmosphere_mod
   complex(c_double_complex), allocatable :: sbuf3(:,:,:), sbuf2(:,:)
   ! diag_manager ids of module 'dynamics' (spectral_dynamics.F90:1541-1700)
   integer :: id_ps, id_u, id_v, id_t, id_vor, id_div, id_omega, id_sphum, id_pres_full, id_pres_half, id_zfull, id_zhalf, id_pk, id_bk
+  ! derived fields of spectral_diagnostics (spectral_dynamics.F90:1613-1700, 1747-1835), formed on the device
+  integer, parameter :: n_derived = 18
+  character(len=16), parameter :: derived_name(n_derived) = (/ character(len=16) :: 'ucomp_sq', 'vcomp_sq', 'ucomp_vcomp', 'ucomp_omega', &
+      'vcomp_omega', 'ucomp_temp', 'vcomp_temp', 'vcomp_vor', 'omega_temp', 'wspd', 'temp_sq', 'omega_sq', 'ucomp_height', &
+      'vcomp_height', 'omega_height', 'sphum_u', 'sphum_v', 'sphum_w' /)
+  integer(c_int), parameter :: derived_field(n_derived) = (/ ISCA_F_UU, ISCA_F_VV, ISCA_F_UV, ISCA_F_UW, ISCA_F_VW, ISCA_F_UT, ISCA_F_VT, &
+      ISCA_F_V_VOR, ISCA_F_OMEGA_T, ISCA_F_WSPD, ISCA_F_TT, ISCA_F_OMEGA_OMEGA, ISCA_F_UZ, ISCA_F_VZ, ISCA_F_OMEGA_Z, ISCA_F_UTR0, &
+      ISCA_F_VTR0, ISCA_F_WTR0 /)
+  integer :: id_derived(n_derived) = -1, id_slp = -1
+  !------------------------------------------------------------------ isca_b200_nml: options of this shim
+  ! device_time_average = .true.: every registered field is accumulated on the device each step (isca_b200_diag_accumulate) and the
+  ! finished mean is handed to diag_manager when output is due -- diag_table then lists the fields WITHOUT time averaging at the
+  ! output interval.  .false. (default): instantaneous values when need_data() says output is due, as the reference's send_data calls
+  ! would deliver for snapshot fields; fields the diag_table averages every step go through isca_b200_moist_step_io instead.
+  logical :: device_time_average = .false.
+  namelist /isca_b200_nml/ device_time_average
 
 contains
 
@@ -130,13 +146,15 @@ contains
     read (input_nml_file, nml=spectral_dynamics_nml, iostat=io)
     read (input_nml_file, nml=hs_forcing_nml, iostat=io)
     read (input_nml_file, nml=spectral_init_cond_nml, iostat=io)
+    read (input_nml_file, nml=isca_b200_nml, iostat=io)
 #else
     if (file_exist('input.nml')) then
       nml_unit = open_namelist_file()
       read (nml_unit, atmosphere_nml, iostat=io);          rewind(nml_unit)
       read (nml_unit, spectral_dynamics_nml, iostat=io);   rewind(nml_unit)
       read (nml_unit, hs_forcing_nml, iostat=io);          rewind(nml_unit)
-      read (nml_unit, spectral_init_cond_nml, iostat=io)
+      read (nml_unit, spectral_init_cond_nml, iostat=io);  rewind(nml_unit)
+      read (nml_unit, isca_b200_nml, iostat=io)
       call close_file(nml_unit)
     end if
 #endif
@@ -623,6 +641,11 @@ contains
     id_pres_half = register_diag_field(mod_name, 'pres_half', axes_3d_half, Time, 'pressure at half model levels', 'pascals')
     id_zfull = register_diag_field(mod_name, 'height',      axes_3d_full, Time, 'geopotential height at full model levels', 'm')
     id_zhalf = register_diag_field(mod_name, 'height_half', axes_3d_half, Time, 'geopotential height at half model levels', 'm')
+    do k = 1, n_derived
+      if (k > 15 .and. num_tracers /= 1) cycle
+      id_derived(k) = register_diag_field(mod_name, trim(derived_name(k)), axes_3d_full, Time, trim(derived_name(k)), 'mks')
+    end do
+    id_slp = register_diag_field(mod_name, 'slp', (/id_lon, id_lat/), Time, 'sea level pressure', 'pascals')
     id_pk = register_static_field(mod_name, 'pk', (/id_phalf/), 'vertical coordinate pressure values', 'pascals')
     id_bk = register_static_field(mod_name, 'bk', (/id_phalf/), 'vertical coordinate sigma values', 'none')
     deallocate (lon, lat, p_full_ref, p_half_ref, tab)
@@ -650,28 +673,48 @@ contains
   subroutine send_dynamics_diagnostics(Time_next)
     type(time_type), intent(in) :: Time_next
     logical :: used
-    integer :: rc
-    if (id_ps > 0) then
-      if (need_data(id_ps, Time_next)) then
-        rc = isca_b200_get_field(h, ISCA_F_PS, ISCA_LEVEL_CURRENT, buf2);  used = send_data(id_ps, buf2, Time_next)
-      end if
-    end if
+    integer :: rc, k
+    integer(c_int) :: cnt
+    call send2(id_ps, ISCA_F_PS);                    call send2(id_slp, ISCA_F_SLP)
     call send3(id_u, ISCA_F_U, num_levels);          call send3(id_v, ISCA_F_V, num_levels)
     call send3(id_t, ISCA_F_T, num_levels);          call send3(id_vor, ISCA_F_VOR, num_levels)
     call send3(id_div, ISCA_F_DIV, num_levels);      call send3(id_omega, ISCA_F_WG_FULL, num_levels)
     call send3(id_pres_full, ISCA_F_P_FULL, num_levels);  call send3(id_pres_half, ISCA_F_P_HALF, num_levels + 1)
     call send3(id_zfull, ISCA_F_Z_FULL, num_levels);      call send3(id_zhalf, ISCA_F_Z_HALF, num_levels + 1)
     if (num_tracers == 1) call send3(id_sphum, ISCA_F_TRACER0, num_levels)
+    do k = 1, n_derived
+      call send3(id_derived(k), derived_field(k), num_levels)
+    end do
   contains
+    !> the field (instantaneous, or its device-side mean since the last output) into buf3 / buf2 when output is due
+    logical function due(id, field, host)
+      integer, intent(in) :: id
+      integer(c_int), intent(in) :: field
+      real(c_double), intent(out) :: host(*)
+      due = .false.
+      if (id <= 0) return
+      if (device_time_average) then
+        rc = isca_b200_diag_accumulate(h, field)
+        if (rc /= 0) call fatal('spectral_diagnostics')
+        if (.not. need_data(id, Time_next)) return
+        rc = isca_b200_diag_fetch(h, field, host, 1_c_int, cnt)
+      else
+        if (.not. need_data(id, Time_next)) return
+        rc = isca_b200_get_field(h, field, ISCA_LEVEL_CURRENT, host)
+      end if
+      if (rc /= 0) call fatal('spectral_diagnostics')
+      due = .true.
+    end function due
     subroutine send3(id, field, nlev)
       integer, intent(in) :: id, nlev
       integer(c_int), intent(in) :: field
-      if (id <= 0) return
-      if (.not. need_data(id, Time_next)) return
-      rc = isca_b200_get_field(h, field, ISCA_LEVEL_CURRENT, buf3)
-      if (rc /= 0) call fatal('spectral_diagnostics')
-      used = send_data(id, buf3(:,:,1:nlev), Time_next)
+      if (due(id, field, buf3)) used = send_data(id, buf3(:,:,1:nlev), Time_next)
     end subroutine send3
+    subroutine send2(id, field)
+      integer, intent(in) :: id
+      integer(c_int), intent(in) :: field
+      if (due(id, field, buf2)) used = send_data(id, buf2, Time_next)
+    end subroutine send2
   end subroutine send_dynamics_diagnostics
 
   subroutine fatal(routine)

@@ -10,11 +10,15 @@ module isca_b200_c
   implicit none
   public
 
-  integer(c_int32_t), parameter :: ISCA_B200_ABI_VERSION = 1
+  integer(c_int32_t), parameter :: ISCA_B200_ABI_VERSION = 2
   ! field ids of isca_b200_get_field / isca_b200_get_spectral, time-level selectors, scalar ids (include/isca_b200.h)
   integer(c_int), parameter :: ISCA_F_PS = 0, ISCA_F_U = 1, ISCA_F_V = 2, ISCA_F_T = 3, ISCA_F_VOR = 4, ISCA_F_DIV = 5, &
-                               ISCA_F_WG_FULL = 6, ISCA_F_P_FULL = 7, ISCA_F_P_HALF = 8, ISCA_F_Z_FULL = 9, ISCA_F_Z_HALF = 10, &
-                               ISCA_F_TRACER0 = 16
+                               ISCA_F_WG_FULL = 6, ISCA_F_P_FULL = 7, ISCA_F_P_HALF = 8, ISCA_F_Z_FULL = 9, &
+                               ISCA_F_Z_HALF = 10, ISCA_F_TRACER0 = 16, ISCA_F_WSPD = 32, ISCA_F_UU = 33, ISCA_F_VV = 34, &
+                               ISCA_F_UV = 35, ISCA_F_V_VOR = 36, ISCA_F_TT = 37, ISCA_F_OMEGA_OMEGA = 38, &
+                               ISCA_F_OMEGA_T = 39, ISCA_F_UW = 40, ISCA_F_VW = 41, ISCA_F_UT = 42, ISCA_F_VT = 43, &
+                               ISCA_F_UZ = 44, ISCA_F_VZ = 45, ISCA_F_OMEGA_Z = 46, ISCA_F_UTR0 = 48, ISCA_F_VTR0 = 49, &
+                               ISCA_F_WTR0 = 50, ISCA_F_SLP = 56
   integer(c_int), parameter :: ISCA_S_VOR = 0, ISCA_S_DIV = 1, ISCA_S_T = 2, ISCA_S_LNPS = 3
   integer(c_int), parameter :: ISCA_LEVEL_CURRENT = -1, ISCA_LEVEL_PREVIOUS = -2
   integer(c_int), parameter :: ISCA_SC_MEAN_PS = 0, ISCA_SC_MEAN_ENERGY = 1, ISCA_SC_T_MIN = 2, ISCA_SC_T_MAX = 3

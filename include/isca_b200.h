@@ -83,6 +83,13 @@ enum {
   ISCA_F_PS = 0, ISCA_F_U = 1, ISCA_F_V = 2, ISCA_F_T = 3, ISCA_F_VOR = 4, ISCA_F_DIV = 5,
   ISCA_F_WG_FULL = 6, ISCA_F_P_FULL = 7, ISCA_F_P_HALF = 8, ISCA_F_Z_FULL = 9, ISCA_F_Z_HALF = 10,
   ISCA_F_TRACER0 = 16,
+  /* derived fields of spectral_diagnostics (spectral_dynamics.F90:1747-1835), formed on the device from the current level so that
+   * products can be time-averaged there (isca_b200_diag_accumulate) instead of shipping their factors every step:
+   * wspd = sqrt(u^2+v^2); ucomp_sq, vcomp_sq, ucomp_vcomp, vcomp_vor, temp_sq, omega_sq, omega_temp, ucomp_omega, vcomp_omega,
+   * ucomp_temp, vcomp_temp, ucomp_height, vcomp_height, omega_height; sphum_u, sphum_v, sphum_w (tracer 0); slp [J][I] */
+  ISCA_F_WSPD = 32, ISCA_F_UU = 33, ISCA_F_VV = 34, ISCA_F_UV = 35, ISCA_F_V_VOR = 36, ISCA_F_TT = 37, ISCA_F_OMEGA_OMEGA = 38,
+  ISCA_F_OMEGA_T = 39, ISCA_F_UW = 40, ISCA_F_VW = 41, ISCA_F_UT = 42, ISCA_F_VT = 43, ISCA_F_UZ = 44, ISCA_F_VZ = 45,
+  ISCA_F_OMEGA_Z = 46, ISCA_F_UTR0 = 48, ISCA_F_VTR0 = 49, ISCA_F_WTR0 = 50, ISCA_F_SLP = 56,
   ISCA_S_VOR = 0, ISCA_S_DIV = 1, ISCA_S_T = 2, ISCA_S_LNPS = 3
 };
 /* time-level selectors */

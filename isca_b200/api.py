@@ -74,6 +74,9 @@ EXPORTS = [
 # field / scalar ids (include/isca_b200.h)
 F_PS, F_U, F_V, F_T, F_VOR, F_DIV, F_WG_FULL, F_P_FULL, F_P_HALF, F_Z_FULL, F_Z_HALF = range(11)
 F_TRACER0 = 16
+# derived fields of spectral_diagnostics (spectral_dynamics.F90:1747-1835), formed on the device (include/isca_b200.h)
+(F_WSPD, F_UU, F_VV, F_UV, F_V_VOR, F_TT, F_OMEGA_OMEGA, F_OMEGA_T, F_UW, F_VW, F_UT, F_VT, F_UZ, F_VZ, F_OMEGA_Z) = range(32, 47)
+F_UTR0, F_VTR0, F_WTR0, F_SLP = 48, 49, 50, 56
 S_VOR, S_DIV, S_T, S_LNPS = range(4)
 S_DT_VOR, S_DT_DIV, S_DT_T, S_DT_LNPS = 8, 9, 10, 11
 LEVEL_CURRENT, LEVEL_PREVIOUS = -1, -2
@@ -379,7 +382,7 @@ class Atmosphere:
     def diag_fetch(self, field_id, reset=True):
         """time mean of the accumulated samples of a grid field and their number"""
         n2 = (self.Jloc, self.I)
-        shape = n2 if field_id == F_PS else ((self.K + 1,) + n2 if field_id in (F_P_HALF, F_Z_HALF) else (self.K,) + n2)
+        shape = n2 if field_id in (F_PS, F_SLP) else ((self.K + 1,) + n2 if field_id in (F_P_HALF, F_Z_HALF) else (self.K,) + n2)
         out = np.empty(shape); cnt = C.c_int(0)
         self._ck(self.lib.isca_b200_diag_fetch(self.h, field_id, _ptr(out), int(reset), C.byref(cnt)), "diag_fetch")
         return out, cnt.value
@@ -415,7 +418,7 @@ class Atmosphere:
         return p.value, c.value
 
     def get_field(self, field_id, level=LEVEL_CURRENT, out=None):
-        if field_id == F_PS:
+        if field_id in (F_PS, F_SLP):
             shape = (self.Jloc, self.I)
         elif field_id in (F_P_HALF, F_Z_HALF):
             shape = (self.K + 1, self.Jloc, self.I)

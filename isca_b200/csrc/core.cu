@@ -151,7 +151,7 @@ struct IscaHandle_t {
   DBuf<double2> x_rect, x_spec, x_fr, x_imp[9];
   struct DiagAcc { DBuf<double>* sum = nullptr; long long count = 0; size_t n = 0; };
   std::map<int, DiagAcc> diag;          // device-side time averages (isca_b200_diag_accumulate / _fetch)
-  DBuf<double> x_grid, x_four, x_pz;
+  DBuf<double> x_grid, x_four, x_pz, x_der;          // x_der: derived diagnostic fields (field_on_device)
   DBuf<LevDesc> x_levs;
   DBuf<unsigned char> x_trunc;
 
@@ -767,6 +767,23 @@ __global__ void four_layout_kernel(GeomDev g, double2* ref, double* four, int nl
   double2* f = reinterpret_cast<double2*>(four + ((size_t)g.pos[m] * g.J + j) * 2 * Lp) + lev;
   if (to_internal) *f = ref[idx]; else ref[idx] = *f;
 }
+// derived fields of spectral_diagnostics (spectral_dynamics.F90:1747-1821): mode 0: a*b, 1: sqrt(a^2 + b^2)
+__global__ void derived_product_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, size_t n, int mode) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mode ? sqrt(a[i] * a[i] + b[i] * b[i]) : a[i] * b[i];
+}
+// sea-level pressure (spectral_dynamics.F90:1823-1835): first level with p_full/p_surf > 0.8; -1 flags a column without one
+__global__ void slp_kernel(double* __restrict__ slp, const double* __restrict__ t, const double* __restrict__ p_full, const double* __restrict__ ps,
+                           const double* __restrict__ phis, size_t nc, int K, double expf, double gamma, double grav, int* __restrict__ err) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  const double p0 = ps[i];
+  int k = 0;
+  while (k < K && !(p_full[(size_t)k * nc + i] / p0 > 0.8)) ++k;
+  if (k == K) { *err = 1; slp[i] = 0.0; return; }
+  const double t_low = t[(size_t)k * nc + i] * pow(p_full[(size_t)k * nc + i] / p0, -expf);
+  slp[i] = p0 * pow((t_low + gamma * phis[i] / grav) / t_low, 1.0 / expf);
+}
 __global__ void diag_axpy_kernel(double* __restrict__ acc, const double* __restrict__ x, size_t n, double scale, int accumulate) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) acc[i] = accumulate ? acc[i] + x[i] : x[i] * scale;
@@ -1201,8 +1218,53 @@ static size_t field_on_device(H& h, int id, int level, const double** ptr) {
       *ptr = h.x_pz.p;
       return (id == ISCA_F_P_HALF || id == ISCA_F_Z_HALF) ? nh : n3;
     }
+    default: break;
+  }
+  // ---- derived fields of spectral_diagnostics (spectral_dynamics.F90:1747-1835), current / requested level
+  auto base = [&](int fid) { const double* q = nullptr; field_on_device(h, fid, level, &q); return q; };
+  int fa = -1, fb = -1, mode = 0;
+  switch (id) {
+    case ISCA_F_WSPD: fa = ISCA_F_U; fb = ISCA_F_V; mode = 1; break;
+    case ISCA_F_UU: fa = fb = ISCA_F_U; break;
+    case ISCA_F_VV: fa = fb = ISCA_F_V; break;
+    case ISCA_F_UV: fa = ISCA_F_U; fb = ISCA_F_V; break;
+    case ISCA_F_V_VOR: fa = ISCA_F_V; fb = ISCA_F_VOR; break;
+    case ISCA_F_TT: fa = fb = ISCA_F_T; break;
+    case ISCA_F_OMEGA_OMEGA: fa = fb = ISCA_F_WG_FULL; break;
+    case ISCA_F_OMEGA_T: fa = ISCA_F_WG_FULL; fb = ISCA_F_T; break;
+    case ISCA_F_UW: fa = ISCA_F_U; fb = ISCA_F_WG_FULL; break;
+    case ISCA_F_VW: fa = ISCA_F_WG_FULL; fb = ISCA_F_V; break;
+    case ISCA_F_UT: fa = ISCA_F_U; fb = ISCA_F_T; break;
+    case ISCA_F_VT: fa = ISCA_F_T; fb = ISCA_F_V; break;
+    case ISCA_F_UZ: fa = ISCA_F_U; fb = ISCA_F_Z_FULL; break;
+    case ISCA_F_VZ: fa = ISCA_F_V; fb = ISCA_F_Z_FULL; break;
+    case ISCA_F_OMEGA_Z: fa = ISCA_F_WG_FULL; fb = ISCA_F_Z_FULL; break;
+    case ISCA_F_UTR0: fa = ISCA_F_TRACER0; fb = ISCA_F_U; break;
+    case ISCA_F_VTR0: fa = ISCA_F_TRACER0; fb = ISCA_F_V; break;
+    case ISCA_F_WTR0: fa = ISCA_F_TRACER0; fb = ISCA_F_WG_FULL; break;
+    case ISCA_F_SLP: {
+      const double* t = base(ISCA_F_T);
+      const double* pf = base(ISCA_F_P_FULL);                       // into x_pz
+      h.x_der.ensure(pl + 1);
+      int* flag = reinterpret_cast<int*>(h.x_der.p + pl);
+      CK(cudaMemsetAsync(flag, 0, sizeof(int), h.st));
+      const double gamma = 0.006, expf = h.cfg.rdgas * gamma / h.cfg.grav;          // spectral_dynamics.F90:1686-1688
+      slp_kernel<<<(unsigned)((pl + 127) / 128), 128, 0, h.st>>>(h.x_der.p, t, pf, h.ps[s].p, h.phis.p, pl, h.g.K, expf, gamma, h.cfg.grav, flag);
+      int e = 0;
+      CK(cudaMemcpyAsync(&e, flag, sizeof(int), cudaMemcpyDeviceToHost, h.st));
+      CK(cudaStreamSynchronize(h.st));
+      if (e) throw std::runtime_error("spectral_diagnostics: No sigma values .gt. 0.8  Cannot compute slp");
+      *ptr = h.x_der.p;
+      return pl;
+    }
     default: throw std::runtime_error("unknown field id");
   }
+  const double* a = base(fa);
+  const double* b = fb == fa ? a : base(fb);
+  h.x_der.ensure(n3);
+  derived_product_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, h.st>>>(h.x_der.p, a, b, n3, mode);
+  *ptr = h.x_der.p;
+  return n3;
 }
 
 int isca_core_field_device(IscaHandle h, int field_id, int level, const double** ptr, size_t* count) {

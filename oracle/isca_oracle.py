@@ -1308,6 +1308,32 @@ class SpectralCore:
             self._fv = FVGrid(self.cfg, self.tb)
         return self._fv
 
+    def spectral_diagnostics(self):
+        """the derived fields of spectral_diagnostics (spectral_dynamics.F90:1747-1835) from the current time level, under the
+        reference's diag_table names; z_full is recomputed from the current level as the reference does (:1735-1736)"""
+        c, cfg = self.current, self.cfg
+        u, v, t, w, vor = self.ug[c], self.vg[c], self.tg[c], self.wg_full, self.vorg
+        q = self.grid_tracers[c, 0] if self.grid_tracers.shape[1] > 0 else None
+        zf, zh, pf, ph = self.pg.compute_pressures_and_heights(t, self.psg[c], self.surf_geopotential, q if not self.dry_model else None)
+        d = dict(wspd=np.sqrt(u ** 2 + v ** 2), ucomp_sq=u ** 2, vcomp_sq=v ** 2, ucomp_vcomp=u * v, vcomp_vor=v * vor, temp_sq=t ** 2,
+                 omega_sq=w * w, omega_temp=w * t, ucomp_omega=u * w, vcomp_omega=w * v, ucomp_temp=u * t, vcomp_temp=t * v,
+                 ucomp_height=u * zf, vcomp_height=v * zf, omega_height=w * zf)
+        if q is not None:
+            d.update(sphum_u=q * u, sphum_v=q * v, sphum_w=q * w)
+        gamma = 0.006                                                        # :1686-1688
+        expf = cfg.rdgas * gamma / cfg.grav
+        ps = self.psg[c]
+        K = t.shape[0]
+        above = pf / ps[None] > 0.8
+        if not above.any(axis=0).all():
+            raise FloatingPointError("spectral_diagnostics: No sigma values .gt. 0.8  Cannot compute slp")
+        k = np.argmax(above, axis=0)                                         # first level (from the top) with p_full/p_surf > 0.8
+        tk = np.take_along_axis(t, k[None], 0)[0]
+        pk = np.take_along_axis(pf, k[None], 0)[0]
+        t_low = tk * (pk / ps) ** (-expf)
+        d["slp"] = ps * ((t_low + gamma * self.surf_geopotential / cfg.grav) / t_low) ** (1.0 / expf)
+        return d
+
     # ---- convenience for tests / bench
     def state(self):
         c, p = self.current, self.previous

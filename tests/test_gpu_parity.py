@@ -356,6 +356,44 @@ def test_device_side_time_average(api):
     atm.atmosphere_end()
 
 
+def test_derived_spectral_diagnostics_fields(api):
+    """the derived fields of spectral_diagnostics (spectral_dynamics.F90:1747-1835: wspd, the second-moment products, tracer
+    fluxes, slp) formed on the device from the current level against the oracle, and the time mean of a product accumulated on
+    the device (mean of u*v, not the product of the means)"""
+    from oracle.isca_oracle import SpectralCore, held_suarez_config
+    cfg = held_suarez_config("T21", 8, 1200.0, num_tracers=1)
+    core = SpectralCore(cfg)
+    core.cold_start()
+    atm = api.Atmosphere(api.config_from_namelist_object(cfg))
+    atm.cold_start()
+    for _ in range(6):
+        core.step(); atm.atmosphere(1)
+    d = core.spectral_diagnostics()
+    ids = dict(wspd=api.F_WSPD, ucomp_sq=api.F_UU, vcomp_sq=api.F_VV, ucomp_vcomp=api.F_UV, vcomp_vor=api.F_V_VOR, temp_sq=api.F_TT,
+               omega_sq=api.F_OMEGA_OMEGA, omega_temp=api.F_OMEGA_T, ucomp_omega=api.F_UW, vcomp_omega=api.F_VW, ucomp_temp=api.F_UT,
+               vcomp_temp=api.F_VT, ucomp_height=api.F_UZ, vcomp_height=api.F_VZ, omega_height=api.F_OMEGA_Z, sphum_u=api.F_UTR0,
+               sphum_v=api.F_VTR0, sphum_w=api.F_WTR0, slp=api.F_SLP)
+    for name, fid in ids.items():
+        g = atm.get_field(fid)
+        assert g.shape == d[name].shape, name
+        # second moments of quantities that are themselves only 1e-10 accurate after 6 steps: the same bound, relative to the maximum
+        assert rel(g, d[name]) < 1e-9, name
+    # exact consistency with the device's own base fields
+    u, v = atm.get_field(api.F_U), atm.get_field(api.F_V)
+    assert np.array_equal(atm.get_field(api.F_UV), u * v) and np.array_equal(atm.get_field(api.F_WSPD), np.sqrt(u * u + v * v))
+    assert 9.0e4 < atm.get_field(api.F_SLP).min() and atm.get_field(api.F_SLP).max() < 1.1e5
+    acc = 0.0
+    for _ in range(3):
+        atm.atmosphere(1)
+        atm.diag_accumulate(api.F_UV)
+        acc = acc + atm.get_field(api.F_U) * atm.get_field(api.F_V)
+    m, n = atm.diag_fetch(api.F_UV)
+    assert n == 3 and rel(m, acc / 3) < 1e-15
+    with pytest.raises(api.IscaError):
+        atm.get_field(57)                                                # unknown field id
+    atm.atmosphere_end()
+
+
 def test_restart_round_trip_reproduces_uninterrupted_run(api):
     """Restart parity (the variables of spectral_dynamics.F90:509-575, 1502-1531): dump both time levels
     through the host mirrors after 40 steps, load them into a fresh handle, continue 12 steps: same result as the

@@ -198,3 +198,25 @@ def test_make_symmetric_keeps_the_model_zonally_symmetric():
     for k in ("ug", "tg", "psg"):
         assert np.abs(st[k] - st[k][..., :1]).max() < 1e-12 * np.abs(st[k]).max(), k
     assert np.abs(st["tg"] - 264.0).max() > 1e-3            # the Held-Suarez forcing is acting
+
+
+def test_spectral_diagnostics_derived_fields():
+    """spectral_diagnostics (spectral_dynamics.F90:1747-1835): sea-level pressure equals the surface pressure over a flat surface and
+    exceeds it over raised ground by the hypsometric amount of the standard lapse rate; the second moments are plain products"""
+    cfg = held_suarez_config("T21", 12, 1200.0, num_tracers=1)
+    core = SpectralCore(cfg)
+    core.cold_start()
+    for _ in range(4):
+        core.step()
+    d = core.spectral_diagnostics()
+    c = core.current
+    assert np.allclose(d["slp"], core.psg[c], rtol=1e-14)                    # surf_geopotential = 0
+    assert np.array_equal(d["ucomp_vcomp"], core.ug[c] * core.vg[c]) and np.array_equal(d["sphum_w"], core.grid_tracers[c, 0] * core.wg_full)
+    assert np.allclose(d["wspd"] ** 2, d["ucomp_sq"] + d["vcomp_sq"], rtol=1e-13)
+    core.surf_geopotential = core.surf_geopotential + cfg.grav * 500.0     # a 500 m plateau everywhere
+    s2 = core.spectral_diagnostics()["slp"]
+    gamma, ps = 0.006, core.psg[c]
+    k = np.argmax(core.p_full[c] / ps[None] > 0.8, axis=0)
+    tl = np.take_along_axis(core.tg[c], k[None], 0)[0] * (np.take_along_axis(core.p_full[c], k[None], 0)[0] / ps) ** (-cfg.rdgas * gamma / cfg.grav)
+    assert np.allclose(s2, ps * (1.0 + gamma * 500.0 / tl) ** (cfg.grav / (cfg.rdgas * gamma)), rtol=1e-13)
+    assert np.all(s2 > ps * 1.05) and np.all(s2 < ps * 1.08)                 # ~ exp(500 m / 8 km)

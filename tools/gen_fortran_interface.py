@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Regenerate the three bind(C) derived types of fortran/isca_b200_c.F90 (isca_config, isca_physics_config, isca_moist_config) from
-the C structs of include/isca_b200.h and include/isca_b200_physics.h, in place.  `--check` only reports whether the file is in step
+"""Regenerate the three bind(C) derived types of fortran/isca_b200_c.F90 (isca_config, isca_physics_config, isca_moist_config), the ABI
+version and the ISCA_F_* field ids from include/isca_b200.h and include/isca_b200_physics.h, in place.  `--check` only reports whether the file is in step
 (exit code 1 if not); tests/test_fortran_shim.py runs the same comparison."""
 import os
 import re
@@ -41,7 +41,29 @@ def type_body(fields, tname):
     return '\n'.join(lines)
 
 
+def constants(src):
+    """ISCA_B200_ABI_VERSION and the ISCA_F_* field ids from include/isca_b200.h"""
+    text = open(os.path.join(ROOT, 'include', 'isca_b200.h')).read()
+    ver = re.search(r'#define ISCA_B200_ABI_VERSION (\d+)', text).group(1)
+    src = re.sub(r'(ISCA_B200_ABI_VERSION = )\d+', r'\g<1>' + ver, src)
+    nocom = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    ids = re.findall(r'\b(ISCA_F_\w+)\s*=\s*(\d+)', nocom)
+    items = [f'{n} = {v}' for n, v in ids]
+    lines, cur = [], '  integer(c_int), parameter :: '
+    for k, it in enumerate(items):
+        piece = it + (', ' if k + 1 < len(items) else '')
+        if len(cur) + len(piece) > 126:
+            lines.append(cur.rstrip() + ' &')
+            cur = ' ' * 31
+        cur += piece
+    lines.append(cur.rstrip())
+    a = src.index('  integer(c_int), parameter :: ISCA_F_PS')
+    b = src.index('  integer(c_int), parameter :: ISCA_S_VOR')
+    return src[:a] + '\n'.join(lines) + '\n' + src[b:]
+
+
 def regenerate(src):
+    src = constants(src)
     for header, cname, tname in STRUCTS:
         text = open(os.path.join(ROOT, 'include', header)).read()
         a = src.index('  type, bind(C) :: ' + tname)
