@@ -219,15 +219,16 @@ def roofline_of(groups, wm, world, peaks, traffic_table):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the C++/OpenMP restatement of the dynamical core + tracer (oracle/cstep, all host cores) and, for the moist workload,
-# the NumPy oracle's column physics on a column sample.  Bounded samples.
+# CPU arm, every part compiled C++/OpenMP on all host cores: the restatement of the dynamical core + tracer (oracle/cstep) and, for the
+# moist workload, the host build of the production column-physics sources and of the RRTMG column arithmetic.  Bounded samples
+# (DESIGN.md section 5).
 # ---------------------------------------------------------------------------------------------
 def cpu_dynamics(res, K, dt, steps, moist=False, spin=2):
     from oracle.isca_oracle import held_suarez_config, frierson_config
     from oracle.cstep import CStep
     cfg = frierson_config(res, K, dt) if moist else held_suarez_config(res, K, dt, num_tracers=1)
     if moist:
-        cfg.no_forcing = True                        # the physics tendencies are timed separately (cpu_physics_sample)
+        cfg.no_forcing = True                        # the physics tendencies are timed separately (cpu_physics_cpp)
     t0 = time.time()
     cs = CStep(cfg)
     cs.cold_start()
@@ -241,44 +242,82 @@ def cpu_dynamics(res, K, dt, steps, moist=False, spin=2):
     return dict(sec_per_step=sec, threads=th, init_s=t_init)
 
 
-def cpu_physics_sample(K, with_rrtm=True):
-    """NumPy oracle of idealized_moist_phys (MiMA options) on the 8192 columns of a T42 grid with K levels: seconds per call of the
-    per-step physics (and, with_rrtm, of one NumPy RRTMG radiation call).  The caller scales by (columns of the workload) / 8192."""
+def cpu_physics_cpp_worker(K, I, J):
+    """(subprocess of cpu_physics_cpp) the per-step column physics of the MiMA configuration on I x J columns with the HOST build of the
+    production column-physics sources (tests/host/build_phys_cpu.py: the same kernels, launches = OpenMP loops over the columns):
+    simplified Betts-Miller convection, lscale_cond, surface_flux, Rayleigh sponge, diffusivity (tau + 1 variables), gcm_vert_diff_down,
+    mixed_layer, gcm_vert_diff_up -- on a moist, convectively active state of the NumPy oracle (T42 grid) tiled to I x J.  Prints one
+    JSON line with the milliseconds spent inside the kernels (the staging copies of the host-array C ABI are not counted)."""
+    import ctypes as C
+    import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
+    import build_phys_cpu
+    lib_path = build_phys_cpu.build()
+    from isca_b200 import api
+    api._lib = C.CDLL(lib_path)                          # this process only: the ctypes mirrors are bound to the host build
+    from isca_b200 import physics, moist
     from test_gpu_moist import build
-    from rrtm_cases import rrtm_setup
     cfg, core, mp = build("T42", K, 720.0, "SIMPLE_BETTS_MILLER", seed=1, damping=True)
-    mp.c.use_tau, mp.c.constant_gust = False, 0.0
-    ncol = cfg.lon_max * cfg.lat_max
-    t_rrtm = 0.0
-    if with_rrtm:
-        rrtm_setup(core, mp, cfg, DT_RAD if DT_RAD % 720 == 0 else 7200, None)
-        t0 = time.time()
-        mp(core, 2 * cfg.dt_atmos)                    # first call: radiation step
-        t_first = time.time() - t0
-    else:
-        mp(core, 2 * cfg.dt_atmos)                    # warm-up call (table construction, first-touch)
-    t0 = time.time()
-    mp(core, 2 * cfg.dt_atmos)                        # stored heating rates / grey radiation: the per-step physics alone
-    t_phys = time.time() - t0
-    if with_rrtm:
-        t_rrtm = max(t_first - t_phys, 0.0)
-    return dict(ncol=ncol, sec_physics=t_phys, sec_rrtmg_call=t_rrtm)
+    cur, prev = core.current, core.previous
+    rj, ri = J // cfg.lat_max, I // cfg.lon_max
+    T3 = lambda a: np.ascontiguousarray(np.tile(a, (1, rj, ri)))
+    T2 = lambda a: np.ascontiguousarray(np.tile(a, (rj, ri)))
+    tg, q, u, v = T3(core.tg[prev]), T3(core.grid_tracers[prev, 0]), T3(core.ug[prev]), T3(core.vg[prev])
+    pf, ph, zf, zh = T3(core.p_full[cur]), T3(core.p_half[cur]), T3(core.z_full[cur]), T3(core.z_half[cur])
+    t_surf = T2(mp.t_surf)
+    Kk = tg.shape[0]
+    dt, delta_t = 150.0, 300.0
+    cp = physics.ColumnPhysics(I, J, Kk, **moist.MIMA_PHYSICS_NML)
+    ms = api._lib.isca_cpu_kernel_ms
+    ms.restype, ms.argtypes = C.c_double, [C.c_int]
+    z2, z3 = np.zeros((J, I)), np.zeros_like(tg)
+    parts = {}
+
+    def timed(name, f):
+        f()                                              # warm-up (first touch of the staging buffers)
+        best = None
+        for _ in range(3):                               # best of three: other processes' / libraries' spinning threads disturb single runs
+            ms(1)
+            out = f()
+            t = ms(1)
+            best = t if best is None else min(best, t)
+        parts[name] = best
+        return out
+    conv = timed("convection", lambda: cp.qe_moist_convection(delta_t, tg, q, pf, ph))
+    t2, q2 = tg + conv["deltaT"], q + conv["deltaq"]
+    rain, tdel, qdel = timed("lscale_cond", lambda: cp.lscale_cond(t2, q2, pf, ph))
+    dt_t, dt_q = (conv["deltaT"] + tdel) / delta_t, (conv["deltaq"] + qdel) / delta_t
+    rough = np.full((J, I), 3.21e-05)
+    sf = timed("surface_flux", lambda: cp.surface_flux(np.zeros((J, I), np.int32), np.zeros((J, I)), t_atm=tg[-1], q_atm=q[-1], u_atm=u[-1],
+                                                       v_atm=v[-1], p_atm=pf[-1], z_atm=zf[-1] - zh[-1], p_surf=ph[-1], t_surf=t_surf,
+                                                       t_ca=t_surf, u_surf=z2, v_surf=z2, rough_mom=rough, rough_heat=rough,
+                                                       rough_moist=rough, rough_scale=rough, gust=z2))
+    pref = np.append(0.5 * (ph[1:, 0, 0] + ph[:-1, 0, 0]), 1.0e5) * 1.0e5 / ph[-1, 0, 0]
+    udt, vdt, tdt = timed("damping", lambda: cp.rayleigh_damping(delta_t, pf, u, v, pref))
+    dt_u, dt_v, dt_t = udt, vdt, dt_t + tdt
+    h, km, kt = timed("diffusivity", lambda: cp.diffusivity(tg + delta_t * dt_t, q + delta_t * dt_q, u + delta_t * dt_u, v + delta_t * dt_v,
+                                                            pf, ph, zf, zh, sf["u_star"], sf["b_star"]))
+    timed("vert_diff_down", lambda: cp.gcm_vert_diff_down(delta_t, u, v, tg, q, km, kt, ph, pf, zf, sf["flux_u"], sf["flux_v"],
+                                                          sf["dtaudu_atm"], sf["dtaudv_atm"], dt_u, dt_v, dt_t, dt_q))
+    cp.mixed_layer_init(np.full((J, I), 100.0 * 1.035e3 * 3989.24495292815), z2)
+    timed("mixed_layer", lambda: cp.mixed_layer(dt, t_surf, sf["flux_t"], sf["flux_q"], sf["flux_r"], 200.0 + z2, 350.0 + z2, sf["dhdt_surf"],
+                                                sf["dedt_surf"], sf["dedq_surf"], sf["drdt_surf"], sf["dhdt_atm"], sf["dedq_atm"]))
+    timed("vert_diff_up", lambda: cp.gcm_vert_diff_up(delta_t))
+    flags = np.bincount(conv["convflag"].astype(int).ravel(), minlength=3).tolist()
+    print(json.dumps(dict(ncol=I * J, K=Kk, kernel_ms=parts, total_ms=sum(parts.values()), convflag_counts=flags,
+                          threads=int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)))))
 
 
-def cpu_physics_parallel(K, workers):
-    """`workers` processes (`bench.py --cpu-physics-worker K`) run the NumPy physics sample at the same time -- the column physics is
-    embarrassingly parallel over columns, this is how a multi-core CPU run shares it; returns the column throughput of the set."""
+def cpu_physics_cpp(K, I, J):
+    """C++/OpenMP per-step column physics on the host cores: see cpu_physics_cpp_worker (run in a subprocess so that this process's
+    ctypes bindings stay on the product library)."""
     import subprocess
-    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
-    ps = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-physics-worker", str(K)], stdout=subprocess.PIPE,
-                           stderr=subprocess.DEVNULL, env=env, text=True) for _ in range(workers)]
-    rs = []
-    for p_ in ps:
-        out, _ = p_.communicate(timeout=1200)
-        rs.append(json.loads([l for l in out.splitlines() if l.startswith("{")][-1]))
-    sec = sum(r["sec_physics"] for r in rs) / len(rs)                 # every worker ran while all the others were running
-    return dict(ncol=rs[0]["ncol"] * workers, sec_physics=sec, workers=workers)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-physics-cpp", f"{K},{I},{J}"], capture_output=True, text=True, timeout=1800)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("cpu_physics_cpp failed: " + (r.stderr or r.stdout)[-2000:])
+    return json.loads(lines[-1])
 
 
 def cpu_rrtmg_sample(K, ncol=8192):
@@ -333,18 +372,20 @@ def run_cpu(workload, res, K, steps):
         return dict(sec_per_step=sec, threads=d["threads"], value=dt_hs / 86400.0 / sec, sample=sample, parts={"dynamics_s": sec})
     dt = MOIST_DT[res]
     d = cpu_dynamics(res, K, dt, steps, moist=True)
-    ph = cpu_physics_parallel(K, max(1, d["threads"]))
+    ph = cpu_physics_cpp(K, I, J)
     rr = cpu_rrtmg_sample(K)
-    scale = (I * J) / ph["ncol"]
     rr_call = (rr["sec_lw"] + rr["sec_sw"]) * (I * J) / rr["ncol"]
     per_rad = DT_RAD / dt
-    sec = d["sec_per_step"] + scale * ph["sec_physics"] + rr_call / per_rad
-    sample = (f"dynamics + tracer: {steps} steps of {res} L{K} with the C++/OpenMP restatement (oracle/cstep) on {d['threads']} host threads; "
-              f"one RRTMG call (LW + SW): C++/OpenMP host build of the column arithmetic on {rr['ncol']} columns, scaled to the {I * J} columns "
-              f"and amortised over {per_rad:g} steps; the other column physics: NumPy oracle, {ph['workers']} processes x 8192 columns (T42 grid, {K} "
-              f"levels) running at the same time, scaled x{scale:g} -- a slow stand-in, no compiled CPU port of those schemes exists here")
+    phys_s = ph["total_ms"] * 1e-3
+    sec = d["sec_per_step"] + phys_s + rr_call / per_rad
+    sample = (f"all parts C++/OpenMP on {d['threads']} host threads. Dynamics + tracer: {steps} steps of {res} L{K} with the restatement of the "
+              f"step (oracle/cstep, rectangular Legendre loops as the reference); per-step column physics (convection, condensation, surface flux, "
+              f"sponge, diffusivity, vertical diffusion, mixed layer): the host build of the production kernels' sources (tests/host/build_phys_cpu.py, "
+              f"launches = OpenMP loops) on all {I * J} columns of a moist NumPy-oracle state tiled from T42, kernel time only; one RRTMG call "
+              f"(LW + SW): host build of the column arithmetic on {rr['ncol']} columns, scaled to {I * J} and amortised over {per_rad:g} steps. "
+              f"Not included: compute_pressures_and_heights, the radiation glue")
     return dict(sec_per_step=sec, threads=d["threads"], value=dt / 86400.0 / sec, sample=sample,
-                parts={"dynamics_cpp_s": d["sec_per_step"], "physics_numpy_scaled_s": scale * ph["sec_physics"],
+                parts={"dynamics_cpp_s": d["sec_per_step"], "physics_cpp_s": phys_s, "physics_cpp_kernels_ms": ph["kernel_ms"],
                        "rrtmg_cpp_scaled_per_call_s": rr_call})
 
 
@@ -362,13 +403,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-physics-worker", type=int, default=0, help=argparse.SUPPRESS)   # internal: one worker of cpu_physics_parallel
+    ap.add_argument("--cpu-physics-cpp", default="", help=argparse.SUPPRESS)               # internal: "K,I,J" -> cpu_physics_cpp_worker
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`; numbers of such a run are not bench values)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (hs T85/T170/T341, Frierson T85)")
     args = ap.parse_args()
-    if args.cpu_physics_worker:
-        print(json.dumps(cpu_physics_sample(args.cpu_physics_worker, with_rrtm=False)))
+    if args.cpu_physics_cpp:
+        cpu_physics_cpp_worker(*[int(x) for x in args.cpu_physics_cpp.split(",")])
         return
 
     # The contract is ONE JSON line on stdout: keep a private handle on the real stdout for it and point fd 1 at stderr so that
@@ -404,9 +445,8 @@ def main():
             "steps": steps, "warmup": 2, "ms_per_step": r["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload},
-            "note": "CPU arm = restatement (port) of the reference algorithm: the Fortran/MPI reference cannot be built here (no Fortran "
-                    "compiler in the image or on the GPU box). Dynamics + tracer: C++/OpenMP with the reference's rectangular loops on all "
-                    "host cores; moist column physics: NumPy oracle on a column sample (slower than compiled Fortran would be)",
+            "note": "CPU arm = restatement (port) of the reference algorithm, every part compiled C++/OpenMP on all host cores (cpu_baseline.sample): the Fortran/MPI reference cannot be built here (no Fortran "
+                    "compiler in the image or on the GPU box)",
             "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["threads"], "kind": "port", "sample": r["sample"], "parts_s": r["parts"]},
             "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,

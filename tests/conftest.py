@@ -7,8 +7,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# TEST INFRASTRUCTURE: tests/test_phys_cpu.py re-runs the column-physics GPU tests in a subprocess against the HOST build of the same
+# sources (tests/host/build_phys_cpu.py).  That subprocess sets this variable to the path of libisca_phys_cpu.so; the ctypes mirrors
+# of the test process are then bound to it and the gpu-marked tests are not skipped.  The isca_b200 package itself never looks at it.
+CPU_BUILD = os.environ.get("ISCA_B200_TESTS_ON_CPU_BUILD")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    if CPU_BUILD:
+        import ctypes
+        from isca_b200 import api
+        api._lib = ctypes.CDLL(CPU_BUILD)
 
 
 @pytest.fixture(scope="session")
@@ -19,6 +29,8 @@ def lib_built():
 
 
 def _cuda_device_present() -> bool:
+    if CPU_BUILD:
+        return True
     try:
         import torch
         return bool(torch.cuda.is_available())
