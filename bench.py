@@ -438,6 +438,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        if world > 1:                                    # torchrun pins OMP_NUM_THREADS=1 per rank; this arm is one process on all host cores
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         steps = max(1, min(args.steps, args.cpu_steps if args.steps > 20 else args.steps))
         r = run_cpu(args.workload, res, K, steps)
         line = {
