@@ -682,14 +682,14 @@ def main():
                 extra[key] = {"error": str(e)[:300]}
         if world == 1:
             try:                                       # BASELINE config 3: Frierson grey-radiation aquaplanet T85 L40 on one GPU
-                mm = moist.frierson_test_case("T85", 40, 360.0)
+                mm = moist.frierson_test_case("T85", 40, 360.0, reference_options=True)
                 mm.core.cold_start(); mm.idealized_moist_phys_init()
                 mm.atmosphere(int(10 * 86400 / 360.0))
                 barrier()
                 mm.atmosphere(300)
                 barrier()
                 ms_m, ms_phys = mm.timing()
-                extra["frierson_t85l40"] = {"workload": "Frierson grey-radiation aquaplanet T85 L40 (dt=360s, SIMPLE_BETTS_MILLER, slab 2.5 m), "
+                extra["frierson_t85l40"] = {"workload": "Frierson grey-radiation aquaplanet T85 L40 (dt=360s, the scheme namelists of exp/test_cases/frierson: SIMPLE_BETTS_MILLER, slab 2.5 m, sponge, use_tau = .false.), "
                                                         "10-day on-device spin-up", "n_gpus": 1, "ms_per_step": ms_m,
                                             "ms_physics_last_step": ms_phys, "value": 360.0 / 86400.0 / (ms_m * 1e-3), "unit": unit, "steps": 300,
                                             "precip_mean_mm_per_day": float(mm.get("precip").mean() * 86400.0)}

@@ -271,25 +271,38 @@ class MoistAtmosphere:
 
 RESOLUTIONS = {"T21": (64, 32, 21), "T42": (128, 64, 42), "T85": (256, 128, 85), "T170": (512, 256, 170), "T341": (1024, 512, 341)}
 
+# spectral_dynamics_nml of the moist test cases (frierson / MiMA / axisymmetric _test_case.py; the axisymmetric case: surf_res 0.2,
+# make_symmetric).  tests/test_reference_python_pins.py holds these dicts against the reference's scripts.
+TEST_CASE_DYNAMICS_NML = dict(damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
+                              initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.5,
+                              robert_coeff=0.03)
+
 # exp/test_cases/frierson/frierson_test_case.py: scheme namelists of the grey-radiation aquaplanet
 FRIERSON_PHYSICS_NML = dict(atm_abs=0.2,                                                 # two_stream_gray_rad_nml
                             use_virtual_temp=0, surface_flux_do_simple=1, old_dtaudv=1,  # surface_flux_nml
                             diffusivity_do_entrain=0, diffusivity_do_simple=1,           # diffusivity_nml
                             rhbm=0.7, Tmin=160.0, Tmax=350.0)                            # qe_moist_convection_nml
 FRIERSON_MOIST_NML = dict(mixed_layer_depth=2.5, albedo_value=0.31)                      # mixed_layer_nml
+# the remaining scheme options of frierson_test_case.py (reference_options=True): lscale_cond_nml do_evap, the Rayleigh sponge of
+# damping_driver_nml, idealized_moist_phys_nml roughness lengths and do_damping, vert_turb_driver_nml constant_gust / use_tau
+FRIERSON_REFERENCE_PHYSICS_NML = dict(FRIERSON_PHYSICS_NML, do_evap=1, trayfric=-0.25, sponge_pbottom=5000.0, do_conserve_energy=1)
+FRIERSON_REFERENCE_MOIST_NML = dict(FRIERSON_MOIST_NML, roughness_mom=3.21e-05, roughness_heat=3.21e-05, roughness_moist=3.21e-05,
+                                    constant_gust=0.0, use_tau=0, do_damping=1)
 
 
-def frierson_test_case(res: str, num_levels: int, dt_atmos: float, **ranks) -> MoistAtmosphere:
+def frierson_test_case(res: str, num_levels: int, dt_atmos: float, reference_options: bool = False, **ranks) -> MoistAtmosphere:
     """The Frierson test case (frierson_test_case.py:60-170) at a given resolution: spectral_dynamics_nml with uneven sigma
-    levels (scale_heights 11, exponent 7, surf_res 0.5 -- the MiMA/Frierson level distribution of SURVEY section 8d), sphum as
-    the grid tracer, SIMPLE_BETTS_MILLER convection, slab ocean of 2.5 m."""
+    levels (scale_heights 11, exponent 7, surf_res 0.5 -- the MiMA/Frierson level distribution of SURVEY section 8d; the shipped script
+    reads 25 levels from a file with vert_coord_option = 'input'), sphum as the grid tracer, SIMPLE_BETTS_MILLER convection, slab ocean
+    of 2.5 m.  reference_options = True adds the script's remaining scheme options (re-evaporation in lscale_cond, the Rayleigh sponge
+    above 50 hPa, roughness lengths 3.21e-5 m, constant_gust = 0, use_tau = .false.: FRIERSON_REFERENCE_*_NML); the default leaves them
+    at the schemes' namelist defaults."""
     from .api import make_config
     I, J, M = RESOLUTIONS[res]
     cfg = make_config(lon_max=I, lat_max=J, num_fourier=M, num_spherical=M + 1, num_levels=num_levels, dt_atmos=dt_atmos,
-                      damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
-                      initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.5,
-                      robert_coeff=0.03, num_tracers=1)
-    return MoistAtmosphere(cfg, physics_nml=FRIERSON_PHYSICS_NML, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **FRIERSON_MOIST_NML)
+                      num_tracers=1, **TEST_CASE_DYNAMICS_NML)
+    phys, mnml = (FRIERSON_REFERENCE_PHYSICS_NML, FRIERSON_REFERENCE_MOIST_NML) if reference_options else (FRIERSON_PHYSICS_NML, FRIERSON_MOIST_NML)
+    return MoistAtmosphere(cfg, physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **mnml)
 
 
 def lat_boundaries(lat_max: int) -> np.ndarray:
@@ -333,9 +346,7 @@ def mima_test_case(res: str, num_levels: int, dt_atmos: float, ozone=None, **ran
     I, J, M = RESOLUTIONS[res]
     nranks, rank = ranks.get("nranks", 1), ranks.get("rank", 0)
     cfg = make_config(lon_max=I, lat_max=J, num_fourier=M, num_spherical=M + 1, num_levels=num_levels, dt_atmos=dt_atmos,
-                      damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
-                      initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.5,
-                      robert_coeff=0.03, num_tracers=1)
+                      num_tracers=1, **TEST_CASE_DYNAMICS_NML)
     m = MoistAtmosphere(cfg, physics_nml=MIMA_PHYSICS_NML, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **MIMA_MOIST_NML)
     dt_rad = MIMA_RRTM_DRIVER_NML["dt_rad"]
     if dt_rad % int(dt_atmos) != 0:
@@ -362,20 +373,21 @@ def axisymmetric_test_case(res: str, num_levels: int, dt_atmos: float, ozone=Non
     """The axisymmetric test case (exp/test_cases/axisymmetric/axisymmetric_test_case.py:52-178): the MiMA options with a zonally
     symmetric dynamical core (spectral_dynamics_nml make_symmetric), vertical diffusion in the free atmosphere (diffusivity_nml
     free_atm_diff), RRTMG every 3600 s, a sponge below 150 Pa, surf_res = 0.2 and prescribed SSTs (mixed_layer_nml do_sc_sst): the
-    caller hands the SST of sst_file for the time stepped to with set_sst() before each step (or once, for a perpetual field)."""
+    caller hands the SST of sst_file for the time stepped to with set_sst() before each step (or once, for a perpetual field).
+    diffusivity_nml: the shipped script's dict literal repeats the key 'diffusivity_nml', so Python keeps only {free_atm_diff: True} and
+    do_entrain / do_simple run at their defaults there; this helper keeps the MiMA values (do_entrain = .false., do_simple = .true.)
+    that the script's first entry intends, plus free_atm_diff."""
     from .api import make_config
     I, J, M = RESOLUTIONS[res]
     cfg = make_config(lon_max=I, lat_max=J, num_fourier=M, num_spherical=M + 1, num_levels=num_levels, dt_atmos=dt_atmos,
-                      damping_order=4, water_correction_limit=200.0e2, reference_sea_level_press=1.0e5, valid_range_t=(100.0, 800.0),
-                      initial_sphum=2.0e-6, vert_coord_option="uneven_sigma", scale_heights=11.0, exponent=7.0, surf_res=0.2,
-                      robert_coeff=0.03, num_tracers=1, make_symmetric=1)
+                      num_tracers=1, **dict(TEST_CASE_DYNAMICS_NML, surf_res=0.2, make_symmetric=1))
     phys = dict(MIMA_PHYSICS_NML, sponge_pbottom=150.0, free_atm_diff=1)
     moist_nml = dict(MIMA_MOIST_NML, albedo_value=0.25)
     m = MoistAtmosphere(cfg, physics_nml=phys, convection_scheme="SIMPLE_BETTS_MILLER", **ranks, **moist_nml)
     dt_rad = 3600
     if dt_rad % int(dt_atmos) != 0:
         dt_rad = int(dt_atmos) * max(1, round(dt_rad / dt_atmos))
-    m.use_rrtm(MIMA_RRTM_NML, dt_rad=dt_rad)
+    m.use_rrtm(dict(), dt_rad=dt_rad)                  # rrtm_radiation_nml of the script: dt_rad only (solr_cnst at its default 1368.22)
     if ozone is not None:
         m.set_ozone(ozone)
     m.core.cold_start()
