@@ -314,6 +314,7 @@ contains
     if (idealized_moist_model) then
       rc = isca_b200_moist_init(hm)                      ! idealized_moist_phys_init
       if (rc /= 0) call fatal_moist('atmosphere_init')
+      if (do_sc_sst) call init_prescribed_sst()          ! mixed_layer_init :318-320 (needs the handle: Gaussian weights from its tables)
       call get_time(Time, seconds, days)
       rc = isca_b200_moist_set_time(hm, int(days, c_long_long), int(seconds, c_int))
     end if
@@ -567,7 +568,6 @@ contains
     pcfg%parcel_buoy = parcel_buoy;  pcfg%znom = znom;  pcfg%rich_crit_diff = rich_crit_diff;  pcfg%mix_len = mix_len
     pcfg%rich_prandtl = rich_prandtl;  pcfg%background_m = background_m;  pcfg%background_t = background_t
     pcfg%grav = grav;  pcfg%rdgas = rdgas;  pcfg%cp_air = rdgas/kappa
-    if (do_sc_sst) call init_prescribed_sst()
     if (do_rrtm_radiation .and. two_stream_gray) &
       call error_mesg('atmosphere_init', 'do_rrtm_radiation and two_stream_gray cannot both be .true.', FATAL)
     ! do_rrtm_radiation: rrtm_radiation_nml is forwarded with isca_b200_moist_use_rrtm (include/isca_b200_rrtm.h) by the site's copy of
