@@ -465,113 +465,258 @@ contains
     if (rc /= 0) call fatal('atmosphere_init')
   end subroutine upload_spectral_level
 
-  !> idealized_moist_phys_nml, mixed_layer_nml, vert_turb_driver_nml, surface_flux_nml, diffusivity_nml, qe_moist_convection_nml,
-  !! lscale_cond_nml, two_stream_gray_rad_nml, damping_driver_nml, sat_vapor_pres_nml -> the two configuration structs.
-  !! The namelists are declared here under the reference's names with the reference's defaults and copied field by field.
+  !> The scheme namelists of the moist model -> the two configuration structs.  Every group is read by its own contained routine (the
+  !! groups share variable names: do_simple appears in five of them), declared under the reference's variable names and defaults.  A
+  !! group lists the variables the library consumes AND every variable the shipped test cases (exp/test_cases) set in that group, so that
+  !! their input.nml files read unchanged; options the library does not carry end in FATAL.  A read error (a variable of the site's
+  !! input.nml that the group below does not list) is FATAL as well -- never a silent fall-back to defaults.
   subroutine idealized_moist_nml_to_config(pcfg, mcfg)
     type(isca_physics_config), intent(inout) :: pcfg
     type(isca_moist_config), intent(inout) :: mcfg
-    ! idealized_moist_phys_nml (idealized_moist_phys.F90:109-183)
-    logical :: turb = .false., do_virtual = .false., two_stream_gray = .true., do_rrtm_radiation = .false., do_damping = .false., &
-               mixed_layer_bc = .false., do_simple = .false.
-    character(len=256) :: convection_scheme = 'UNSET'
-    real :: roughness_heat = 0.05, roughness_moist = 0.05, roughness_mom = 0.05
-    namelist /idealized_moist_phys_nml/ turb, do_virtual, two_stream_gray, do_rrtm_radiation, do_damping, mixed_layer_bc, do_simple, &
-                                        convection_scheme, roughness_heat, roughness_moist, roughness_mom
-    ! mixed_layer_nml (mixed_layer.F90:84-140)
-    real :: depth = 40.0, albedo_value = 0.06
-    logical :: evaporation = .true.
-    namelist /mixed_layer_nml/ depth, albedo_value, evaporation, do_sc_sst, sst_file      ! do_sc_sst, sst_file: module variables
-    ! vert_turb_driver_nml (vert_turb_driver.F90:100-118)
-    logical :: use_tau = .true.
-    real :: constant_gust = 1.0
-    namelist /vert_turb_driver_nml/ use_tau, constant_gust
-    ! lscale_cond_nml, qe_moist_convection_nml, two_stream_gray_rad_nml, damping_driver_nml (values the test cases set)
-    real :: hc = 1.0
-    logical :: do_evap = .false.
-    namelist /lscale_cond_nml/ hc, do_evap
-    real :: tau_bm = 7200., rhbm = 0.8, Tmin = 173., Tmax = 335., val_inc = 0.01
-    namelist /qe_moist_convection_nml/ tau_bm, rhbm, Tmin, Tmax, val_inc
-    real :: solar_constant = 1360.0, del_sol = 1.4, del_sw = 0.0, ir_tau_eq = 6.0, ir_tau_pole = 1.5, atm_abs = 0.0, sw_diff = 0.0, &
-            linear_tau = 0.1, wv_exponent = 4.0, solar_exponent = 4.0, odp = 1.0
-    character(len=32) :: rad_scheme = 'frierson'
-    namelist /two_stream_gray_rad_nml/ solar_constant, del_sol, del_sw, ir_tau_eq, ir_tau_pole, atm_abs, sw_diff, linear_tau, wv_exponent, &
-                                       solar_exponent, odp, rad_scheme
-    real :: trayfric = 0., sponge_pbottom = 50.
-    logical :: do_conserve_energy_damp = .false.
-    namelist /damping_driver_nml/ trayfric, sponge_pbottom
-    ! diffusivity_nml (diffusivity.F90:124-153); pbl_mcm = .true. and use_pog_bug_fix = .false. are rejected by the library
-    logical :: fixed_depth = .false., free_atm_diff = .false., free_atm_skyhi_diff = .false., pbl_mcm = .false., ampns = .false., &
-               do_entrain = .true., diff_do_simple = .false., use_pog_bug_fix = .true.
-    real :: depth_0 = 5000.0, frac_inner = 0.1, rich_crit_pbl = 1.0, entr_ratio = 0.2, parcel_buoy = 2.0, znom = 1000.0, &
-            rich_crit_diff = 0.25, mix_len = 30., rich_prandtl = 1.0, background_m = 0.0, background_t = 0.0, ampns_max = 1.0E20
-    namelist /diffusivity_nml/ fixed_depth, depth_0, frac_inner, rich_crit_pbl, entr_ratio, parcel_buoy, znom, free_atm_diff, &
-                               free_atm_skyhi_diff, pbl_mcm, rich_crit_diff, mix_len, rich_prandtl, background_m, background_t, &
-                               ampns, ampns_max, do_entrain, diff_do_simple, use_pog_bug_fix
-    integer :: nml_unit, io
-#ifdef INTERNAL_FILE_NML
-    read (input_nml_file, nml=idealized_moist_phys_nml, iostat=io)
-    read (input_nml_file, nml=mixed_layer_nml, iostat=io)
-    read (input_nml_file, nml=vert_turb_driver_nml, iostat=io)
-    read (input_nml_file, nml=lscale_cond_nml, iostat=io)
-    read (input_nml_file, nml=qe_moist_convection_nml, iostat=io)
-    read (input_nml_file, nml=two_stream_gray_rad_nml, iostat=io)
-    read (input_nml_file, nml=damping_driver_nml, iostat=io)
-    read (input_nml_file, nml=diffusivity_nml, iostat=io)
-#else
-    nml_unit = open_namelist_file()
-    read (nml_unit, idealized_moist_phys_nml, iostat=io);  rewind(nml_unit)
-    read (nml_unit, mixed_layer_nml, iostat=io);           rewind(nml_unit)
-    read (nml_unit, vert_turb_driver_nml, iostat=io);      rewind(nml_unit)
-    read (nml_unit, lscale_cond_nml, iostat=io);           rewind(nml_unit)
-    read (nml_unit, qe_moist_convection_nml, iostat=io);   rewind(nml_unit)
-    read (nml_unit, two_stream_gray_rad_nml, iostat=io);   rewind(nml_unit)
-    read (nml_unit, damping_driver_nml, iostat=io);        rewind(nml_unit)
-    read (nml_unit, diffusivity_nml, iostat=io)
-    call close_file(nml_unit)
-#endif
-    if (.not. (turb .and. mixed_layer_bc)) &
-      call error_mesg('atmosphere_init', 'isca_b200: idealized_moist_phys needs turb = .true. and mixed_layer_bc = .true.', FATAL)
-    select case (trim(convection_scheme))
-      case ('NONE', 'none');              mcfg%convection_scheme = 0
-      case ('SIMPLE_BETTS_MILLER');       mcfg%convection_scheme = 1
-      case ('DRY', 'dry');                mcfg%convection_scheme = 2
-      case ('FULL_BETTS_MILLER');         mcfg%convection_scheme = 3
-      case default
-        call error_mesg('atmosphere_init', '"'//trim(convection_scheme)//'" is not a convection scheme of this library', FATAL)
-    end select
-    mcfg%do_damping = l2i(do_damping);  mcfg%use_tau = l2i(use_tau)
-    mcfg%roughness_mom = roughness_mom;  mcfg%roughness_heat = roughness_heat;  mcfg%roughness_moist = roughness_moist
-    mcfg%mixed_layer_depth = depth;  mcfg%albedo_value = albedo_value;  mcfg%constant_gust = constant_gust
-    pcfg%evaporation = l2i(evaporation)
-    pcfg%hc = hc;  pcfg%do_evap = l2i(do_evap)
-    pcfg%tau_bm = tau_bm;  pcfg%rhbm = rhbm;  pcfg%Tmin = Tmin;  pcfg%Tmax = Tmax;  pcfg%val_inc = val_inc
-    pcfg%solar_constant = solar_constant;  pcfg%del_sol = del_sol;  pcfg%del_sw = del_sw;  pcfg%ir_tau_eq = ir_tau_eq
-    pcfg%ir_tau_pole = ir_tau_pole;  pcfg%atm_abs = atm_abs;  pcfg%sw_diff = sw_diff;  pcfg%linear_tau = linear_tau
-    pcfg%wv_exponent = wv_exponent;  pcfg%solar_exponent = solar_exponent;  pcfg%odp = odp
-    select case (trim(rad_scheme))
-      case ('frierson', 'FRIERSON');   pcfg%rad_scheme = 0
-      case ('byrne', 'BYRNE');         pcfg%rad_scheme = 1
-      case ('geen', 'GEEN');           pcfg%rad_scheme = 2
-      case ('schneider', 'SCHNEIDER'); pcfg%rad_scheme = 3
-      case default
-        call error_mesg('two_stream_gray_rad', '"'//trim(rad_scheme)//'" is not a valid radiation scheme.', FATAL)
-    end select
-    pcfg%trayfric = trayfric;  pcfg%sponge_pbottom = sponge_pbottom
-    pcfg%use_virtual_temp = l2i(do_virtual);  pcfg%surface_flux_do_simple = l2i(do_simple)
-    ! diffusivity_nml: its own `do_simple` is spelled diff_do_simple in this routine (the name is taken by idealized_moist_phys_nml);
-    ! a site whose input.nml sets diffusivity_nml do_simple renames the local variable pair instead
-    pcfg%fixed_depth = l2i(fixed_depth);  pcfg%diffusivity_do_entrain = l2i(do_entrain);  pcfg%diffusivity_do_simple = l2i(diff_do_simple .or. do_simple)
-    pcfg%free_atm_diff = l2i(free_atm_diff);  pcfg%free_atm_skyhi_diff = l2i(free_atm_skyhi_diff);  pcfg%pbl_mcm = l2i(pbl_mcm)
-    pcfg%use_pog_bug_fix = l2i(use_pog_bug_fix);  pcfg%ampns = l2i(ampns);  pcfg%ampns_max = ampns_max
-    pcfg%depth_0 = depth_0;  pcfg%frac_inner = frac_inner;  pcfg%rich_crit_pbl = rich_crit_pbl;  pcfg%entr_ratio = entr_ratio
-    pcfg%parcel_buoy = parcel_buoy;  pcfg%znom = znom;  pcfg%rich_crit_diff = rich_crit_diff;  pcfg%mix_len = mix_len
-    pcfg%rich_prandtl = rich_prandtl;  pcfg%background_m = background_m;  pcfg%background_t = background_t
+    logical :: do_rrtm_radiation, two_stream_gray
+    call read_idealized_moist_phys_nml()
+    call read_mixed_layer_nml()
+    call read_vert_turb_driver_nml()
+    call read_diffusivity_nml()
+    call read_surface_flux_nml()
+    call read_lscale_cond_nml()
+    call read_qe_moist_convection_nml()
+    call read_two_stream_gray_rad_nml()
+    call read_damping_driver_nml()
+    call read_sat_vapor_pres_nml()
     pcfg%grav = grav;  pcfg%rdgas = rdgas;  pcfg%cp_air = rdgas/kappa
     if (do_rrtm_radiation .and. two_stream_gray) &
       call error_mesg('atmosphere_init', 'do_rrtm_radiation and two_stream_gray cannot both be .true.', FATAL)
     ! do_rrtm_radiation: rrtm_radiation_nml is forwarded with isca_b200_moist_use_rrtm (include/isca_b200_rrtm.h) by the site's copy of
     ! this routine; the ozone field read by interpolator_mod goes through isca_b200_moist_set_ozone whenever the alarm is due
+  contains
+    !> one namelist group from input.nml; `reader` does the READ so that the group stays local to its routine
+    subroutine check(io, group)
+      integer, intent(in) :: io
+      character(len=*), intent(in) :: group
+      ! io > 0: the group is present but holds a variable this shim does not declare (or a malformed value); io < 0: group absent (defaults)
+      if (io > 0) call error_mesg('atmosphere_init', 'isca_b200 shim: error reading '//group//' (a variable of input.nml that '// &
+                                  'fortran/atmosphere.F90 does not declare in this group?)', FATAL)
+    end subroutine check
+    integer function open_nml()
+#ifdef INTERNAL_FILE_NML
+      open_nml = -1
+#else
+      open_nml = open_namelist_file()
+#endif
+    end function open_nml
+
+    subroutine read_idealized_moist_phys_nml()      ! idealized_moist_phys.F90:109-183
+      logical :: turb = .false., do_virtual = .false., do_damping = .false., mixed_layer_bc = .false., do_simple = .false., bucket = .false., &
+                 do_lcl_diffusivity_depth = .false.
+      character(len=256) :: convection_scheme = 'UNSET', land_option = 'none', land_file_name = 'INPUT/land.nc'
+      real :: roughness_heat = 0.05, roughness_moist = 0.05, roughness_mom = 0.05, init_bucket_depth_land = 20., max_bucket_depth_land = 0.15
+      integer :: u, io
+      namelist /idealized_moist_phys_nml/ turb, do_virtual, two_stream_gray, do_rrtm_radiation, do_damping, mixed_layer_bc, do_simple, &
+                                          convection_scheme, roughness_heat, roughness_moist, roughness_mom, bucket, &
+                                          do_lcl_diffusivity_depth, land_option, land_file_name, init_bucket_depth_land, &
+                                          max_bucket_depth_land
+      two_stream_gray = .true.;  do_rrtm_radiation = .false.
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=idealized_moist_phys_nml, iostat=io)
+#else
+      u = open_nml();  read (u, idealized_moist_phys_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'idealized_moist_phys_nml')
+      if (.not. (turb .and. mixed_layer_bc)) &
+        call error_mesg('atmosphere_init', 'isca_b200: idealized_moist_phys needs turb = .true. and mixed_layer_bc = .true.', FATAL)
+      if (bucket) call error_mesg('atmosphere_init', 'isca_b200: bucket hydrology is not built', FATAL)
+      if (do_lcl_diffusivity_depth) call error_mesg('atmosphere_init', 'isca_b200: do_lcl_diffusivity_depth is not built', FATAL)
+      select case (trim(convection_scheme))
+        case ('NONE', 'none');              mcfg%convection_scheme = 0
+        case ('SIMPLE_BETTS_MILLER');       mcfg%convection_scheme = 1
+        case ('DRY', 'dry');                mcfg%convection_scheme = 2
+        case ('FULL_BETTS_MILLER');         mcfg%convection_scheme = 3
+        case default
+          call error_mesg('atmosphere_init', '"'//trim(convection_scheme)//'" is not a convection scheme of this library', FATAL)
+      end select
+      mcfg%do_damping = l2i(do_damping)
+      mcfg%roughness_mom = roughness_mom;  mcfg%roughness_heat = roughness_heat;  mcfg%roughness_moist = roughness_moist
+      pcfg%use_virtual_temp_vert_diff = l2i(do_virtual)
+      ! land_option / land_file_name: the maps derived from them are handed over with isca_b200_moist_set_surface by the site's land set-up
+    end subroutine read_idealized_moist_phys_nml
+
+    subroutine read_mixed_layer_nml()               ! mixed_layer.F90:84-156
+      real :: depth = 40.0, albedo_value = 0.06, tconst = 305.0, delta_T = 40.0, land_albedo_prefactor = 1.0, land_h_capacity_prefactor = 1.0
+      logical :: evaporation = .true., prescribe_initial_dist = .false., do_qflux = .false.
+      character(len=256) :: land_option = 'none'
+      integer :: u, io
+      namelist /mixed_layer_nml/ depth, albedo_value, evaporation, tconst, delta_T, prescribe_initial_dist, do_qflux, do_sc_sst, sst_file, &
+                                 land_option, land_albedo_prefactor, land_h_capacity_prefactor      ! do_sc_sst, sst_file: module variables
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=mixed_layer_nml, iostat=io)
+#else
+      u = open_nml();  read (u, mixed_layer_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'mixed_layer_nml')
+      mcfg%mixed_layer_depth = depth;  mcfg%albedo_value = albedo_value
+      pcfg%evaporation = l2i(evaporation)
+      ! prescribe_initial_dist / tconst / delta_T: the initial t_surf (mixed_layer.F90:347) is set with isca_b200_moist_set_t_surf after
+      ! isca_b200_moist_init; do_qflux: isca_b200_moist_set_ocean_qflux with the field of qflux_mod; land_*: isca_b200_moist_set_surface
+    end subroutine read_mixed_layer_nml
+
+    subroutine read_vert_turb_driver_nml()          ! vert_turb_driver.F90:100-118
+      logical :: use_tau = .true., do_mellor_yamada = .true., do_diffusivity = .false., do_simple = .false., do_shallow_conv = .false., &
+                 do_edt = .false., do_entrain = .false.
+      real :: constant_gust = 1.0, gust_factor = 1.0
+      character(len=16) :: gust_scheme = 'constant'
+      integer :: u, io
+      namelist /vert_turb_driver_nml/ use_tau, constant_gust, do_mellor_yamada, do_diffusivity, do_simple, do_shallow_conv, do_edt, &
+                                      do_entrain, gust_scheme, gust_factor
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=vert_turb_driver_nml, iostat=io)
+#else
+      u = open_nml();  read (u, vert_turb_driver_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'vert_turb_driver_nml')
+      if (do_mellor_yamada .or. .not. do_diffusivity .or. do_shallow_conv .or. do_edt .or. do_entrain .or. trim(gust_scheme) /= 'constant') &
+        call error_mesg('vert_turb_driver', 'isca_b200: only do_diffusivity = .true. with gust_scheme = constant is built', FATAL)
+      mcfg%use_tau = l2i(use_tau);  mcfg%constant_gust = constant_gust
+    end subroutine read_vert_turb_driver_nml
+
+    subroutine read_diffusivity_nml()               ! diffusivity.F90:124-153
+      logical :: fixed_depth = .false., free_atm_diff = .false., free_atm_skyhi_diff = .false., pbl_mcm = .false., ampns = .false., &
+                 do_entrain = .true., do_simple = .false., use_pog_bug_fix = .true.
+      real :: depth_0 = 5000.0, frac_inner = 0.1, rich_crit_pbl = 1.0, entr_ratio = 0.2, parcel_buoy = 2.0, znom = 1000.0, &
+              rich_crit_diff = 0.25, mix_len = 30., rich_prandtl = 1.0, background_m = 0.0, background_t = 0.0, ampns_max = 1.0E20
+      integer :: u, io
+      namelist /diffusivity_nml/ fixed_depth, depth_0, frac_inner, rich_crit_pbl, entr_ratio, parcel_buoy, znom, free_atm_diff, &
+                                 free_atm_skyhi_diff, pbl_mcm, rich_crit_diff, mix_len, rich_prandtl, background_m, background_t, &
+                                 ampns, ampns_max, do_entrain, do_simple, use_pog_bug_fix
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=diffusivity_nml, iostat=io)
+#else
+      u = open_nml();  read (u, diffusivity_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'diffusivity_nml')
+      pcfg%fixed_depth = l2i(fixed_depth);  pcfg%diffusivity_do_entrain = l2i(do_entrain);  pcfg%diffusivity_do_simple = l2i(do_simple)
+      pcfg%free_atm_diff = l2i(free_atm_diff);  pcfg%free_atm_skyhi_diff = l2i(free_atm_skyhi_diff);  pcfg%pbl_mcm = l2i(pbl_mcm)
+      pcfg%use_pog_bug_fix = l2i(use_pog_bug_fix);  pcfg%ampns = l2i(ampns);  pcfg%ampns_max = ampns_max
+      pcfg%depth_0 = depth_0;  pcfg%frac_inner = frac_inner;  pcfg%rich_crit_pbl = rich_crit_pbl;  pcfg%entr_ratio = entr_ratio
+      pcfg%parcel_buoy = parcel_buoy;  pcfg%znom = znom;  pcfg%rich_crit_diff = rich_crit_diff;  pcfg%mix_len = mix_len
+      pcfg%rich_prandtl = rich_prandtl;  pcfg%background_m = background_m;  pcfg%background_t = background_t
+    end subroutine read_diffusivity_nml
+
+    subroutine read_surface_flux_nml()              ! surface_flux.F90:225-253
+      logical :: no_neg_q = .false., use_virtual_temp = .true., alt_gustiness = .false., old_dtaudv = .false., use_mixing_ratio = .false., &
+                 do_simple = .false., ncar_ocean_flux = .false., ncar_ocean_flux_orig = .false., raoult_sat_vap = .false.
+      real :: gust_const = 1.0, gust_min = 0.0, land_humidity_prefactor = 1.0, land_evap_prefactor = 1.0
+      integer :: u, io
+      namelist /surface_flux_nml/ no_neg_q, use_virtual_temp, alt_gustiness, gust_const, gust_min, old_dtaudv, use_mixing_ratio, &
+                                  ncar_ocean_flux, ncar_ocean_flux_orig, raoult_sat_vap, do_simple, land_humidity_prefactor, &
+                                  land_evap_prefactor
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=surface_flux_nml, iostat=io)
+#else
+      u = open_nml();  read (u, surface_flux_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'surface_flux_nml')
+      if (ncar_ocean_flux .or. ncar_ocean_flux_orig .or. raoult_sat_vap) &
+        call error_mesg('surface_flux', 'isca_b200: ncar_ocean_flux and raoult_sat_vap are not built', FATAL)
+      pcfg%no_neg_q = l2i(no_neg_q);  pcfg%use_virtual_temp = l2i(use_virtual_temp);  pcfg%alt_gustiness = l2i(alt_gustiness)
+      pcfg%old_dtaudv = l2i(old_dtaudv);  pcfg%use_mixing_ratio = l2i(use_mixing_ratio);  pcfg%surface_flux_do_simple = l2i(do_simple)
+      pcfg%gust_const = gust_const;  pcfg%gust_min = gust_min
+      pcfg%land_humidity_prefactor = land_humidity_prefactor;  pcfg%land_evap_prefactor = land_evap_prefactor
+    end subroutine read_surface_flux_nml
+
+    subroutine read_lscale_cond_nml()               ! lscale_cond.F90:48-52
+      real :: hc = 1.0
+      logical :: do_evap = .false., do_simple = .false.
+      integer :: u, io
+      namelist /lscale_cond_nml/ hc, do_evap, do_simple
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=lscale_cond_nml, iostat=io)
+#else
+      u = open_nml();  read (u, lscale_cond_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'lscale_cond_nml')
+      if (.not. do_simple) call error_mesg('lscale_cond', 'isca_b200: lscale_cond_nml do_simple = .true. only (no ice phase; every '// &
+                                           'shipped test case sets it)', FATAL)
+      pcfg%hc = hc;  pcfg%do_evap = l2i(do_evap)
+    end subroutine read_lscale_cond_nml
+
+    subroutine read_qe_moist_convection_nml()       ! qe_moist_convection.F90:61-75
+      real :: tau_bm = 7200., rhbm = 0.8, Tmin = 173., Tmax = 335., val_inc = 0.01
+      integer :: u, io
+      namelist /qe_moist_convection_nml/ tau_bm, rhbm, Tmin, Tmax, val_inc
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=qe_moist_convection_nml, iostat=io)
+#else
+      u = open_nml();  read (u, qe_moist_convection_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'qe_moist_convection_nml')
+      pcfg%tau_bm = tau_bm;  pcfg%rhbm = rhbm;  pcfg%Tmin = Tmin;  pcfg%Tmax = Tmax;  pcfg%val_inc = val_inc
+    end subroutine read_qe_moist_convection_nml
+
+    subroutine read_two_stream_gray_rad_nml()       ! two_stream_gray_rad.F90:72-118
+      real :: solar_constant = 1360.0, del_sol = 1.4, del_sw = 0.0, ir_tau_eq = 6.0, ir_tau_pole = 1.5, atm_abs = 0.0, sw_diff = 0.0, &
+              linear_tau = 0.1, wv_exponent = 4.0, solar_exponent = 4.0, odp = 1.0, equinox_day = 0.75, carbon_conc = 360.0
+      logical :: do_seasonal = .false., do_read_co2 = .false., use_time_average_coszen = .false.
+      integer :: solday = -10
+      character(len=32) :: rad_scheme = 'frierson'
+      character(len=256) :: co2_file = 'co2', co2_variable_name = 'co2'
+      integer :: u, io
+      namelist /two_stream_gray_rad_nml/ solar_constant, del_sol, del_sw, ir_tau_eq, ir_tau_pole, atm_abs, sw_diff, linear_tau, wv_exponent, &
+                                         solar_exponent, odp, rad_scheme, do_seasonal, equinox_day, solday, use_time_average_coszen, &
+                                         do_read_co2, co2_file, co2_variable_name, carbon_conc
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=two_stream_gray_rad_nml, iostat=io)
+#else
+      u = open_nml();  read (u, two_stream_gray_rad_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'two_stream_gray_rad_nml')
+      pcfg%solar_constant = solar_constant;  pcfg%del_sol = del_sol;  pcfg%del_sw = del_sw;  pcfg%ir_tau_eq = ir_tau_eq
+      pcfg%ir_tau_pole = ir_tau_pole;  pcfg%atm_abs = atm_abs;  pcfg%sw_diff = sw_diff;  pcfg%linear_tau = linear_tau
+      pcfg%wv_exponent = wv_exponent;  pcfg%solar_exponent = solar_exponent;  pcfg%odp = odp;  pcfg%carbon_conc = carbon_conc
+      select case (trim(rad_scheme))
+        case ('frierson', 'FRIERSON');   pcfg%rad_scheme = 0
+        case ('byrne', 'BYRNE');         pcfg%rad_scheme = 1
+        case ('geen', 'GEEN');           pcfg%rad_scheme = 2
+        case ('schneider', 'SCHNEIDER'); pcfg%rad_scheme = 3
+        case default
+          call error_mesg('two_stream_gray_rad', '"'//trim(rad_scheme)//'" is not a valid radiation scheme.', FATAL)
+      end select
+      ! do_seasonal: isca_b200_moist_set_seasonal (solday, equinox_day, use_time_average_coszen) after create; do_read_co2: the value
+      ! interpolator_mod reads from co2_file goes through isca_b200_moist_set_co2 before each step (include/isca_b200_physics.h)
+      if (do_seasonal .or. do_read_co2) call error_mesg('two_stream_gray_rad', 'isca_b200 shim: forward do_seasonal / do_read_co2 with '// &
+          'isca_b200_moist_set_seasonal / isca_b200_moist_set_co2 in the site''s copy of this routine', FATAL)
+    end subroutine read_two_stream_gray_rad_nml
+
+    subroutine read_damping_driver_nml()            ! damping_driver.f90:60-78
+      real :: trayfric = 0., sponge_pbottom = 50.
+      logical :: do_rayleigh = .false., do_conserve_energy = .false., do_mg_drag = .false., do_cg_drag = .false., do_topo_drag = .false.
+      integer :: nlev_rayfric = 1
+      integer :: u, io
+      namelist /damping_driver_nml/ trayfric, sponge_pbottom, do_rayleigh, do_conserve_energy, nlev_rayfric, do_mg_drag, do_cg_drag, do_topo_drag
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=damping_driver_nml, iostat=io)
+#else
+      u = open_nml();  read (u, damping_driver_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'damping_driver_nml')
+      if (do_mg_drag .or. do_cg_drag .or. do_topo_drag) call error_mesg('damping_driver', 'isca_b200: only the Rayleigh sponge is built', FATAL)
+      pcfg%trayfric = merge(trayfric, 0.0, do_rayleigh);  pcfg%sponge_pbottom = sponge_pbottom
+      pcfg%do_conserve_energy = l2i(do_conserve_energy)
+    end subroutine read_damping_driver_nml
+
+    subroutine read_sat_vapor_pres_nml()            ! sat_vapor_pres.F90 (do_simple = .true. in every Frierson / MiMA test case)
+      logical :: do_simple = .false., show_bad_value_count_by_slice = .true., show_all_bad_values = .false., use_exact_qs = .false., &
+                 do_not_calculate = .false.
+      integer :: u, io
+      namelist /sat_vapor_pres_nml/ do_simple, show_bad_value_count_by_slice, show_all_bad_values, use_exact_qs, do_not_calculate
+#ifdef INTERNAL_FILE_NML
+      read (input_nml_file, nml=sat_vapor_pres_nml, iostat=io)
+#else
+      u = open_nml();  read (u, sat_vapor_pres_nml, iostat=io);  call close_file(u)
+#endif
+      call check(io, 'sat_vapor_pres_nml')
+      pcfg%sat_vapor_pres_do_simple = l2i(do_simple)
+    end subroutine read_sat_vapor_pres_nml
   end subroutine idealized_moist_nml_to_config
 
   !> mixed_layer_init :318-320 for do_sc_sst: interpolator_init on the cell boundaries of this PE's grid block.  The boundaries are those
