@@ -78,13 +78,24 @@ module atmosphere_mod
                                    zmu_sponge_coeff, zmv_sponge_coeff, print_interval, num_steps, initial_state_option, &
                                    water_correction_limit, raw_filter_coeff, graceful_shutdown, json_logging, make_symmetric
 
-  !------------------------------------------------------------------ hs_forcing_nml (hs_forcing.F90:74-122): the Held-Suarez option
+  !------------------------------------------------------------------ hs_forcing_nml (hs_forcing.F90:74-122).  The group lists every variable
+  ! of the reference's group so that any input.nml reads; this shim forwards the Held_Suarez option (the parameters in the first two
+  ! lines), the EXOPLANET / top_down / local-heating options are served by the model of include/isca_b200_hs.h and end in FATAL here.
   logical :: no_forcing = .false., do_conserve_energy = .true., relax_to_specified_wind = .false.
   real :: t_zero = 315., t_strat = 200., delh = 60., delv = 10., eps = 0., sigma_b = 0.7, P00 = 1.e5, ka = -40., ks = -4., kf = -1., &
           trflux = 1.e-5, trsink = -4.
-  character(len=256) :: local_heating_option = '', equilibrium_t_option = 'Held_Suarez'
+  real :: local_heating_srfamp = 0.0, local_heating_xwidth = 10., local_heating_ywidth = 10., local_heating_xcenter = 180., &
+          local_heating_ycenter = 45., local_heating_vert_decay = 1.e4, p_trop = 1.e4, alpha = 2./7., peri_time = 0.25, smaxis = 1.5e6, &
+          albedo = 0.3, lapse = 6.5, h_a = 2, tau_s = 5, orbital_period = 31557600., heat_capacity = 4.2e6, ml_depth = 1, &
+          spinup_time = 10800.
+  character(len=256) :: local_heating_option = '', equilibrium_t_option = 'Held_Suarez', local_heating_file = '', u_wind_file = 'u', &
+                        v_wind_file = 'v', equilibrium_t_file = 'temp', stratosphere_t_option = 'extend_tp'
   namelist /hs_forcing_nml/ no_forcing, t_zero, t_strat, delh, delv, eps, sigma_b, ka, ks, kf, do_conserve_energy, trflux, trsink, &
-                            local_heating_option, relax_to_specified_wind, equilibrium_t_option, P00
+                            local_heating_srfamp, local_heating_xwidth, local_heating_ywidth, local_heating_xcenter, &
+                            local_heating_ycenter, local_heating_vert_decay, local_heating_option, local_heating_file, &
+                            relax_to_specified_wind, u_wind_file, v_wind_file, equilibrium_t_option, equilibrium_t_file, p_trop, alpha, &
+                            peri_time, smaxis, albedo, lapse, h_a, tau_s, orbital_period, heat_capacity, ml_depth, spinup_time, &
+                            stratosphere_t_option, P00
 
   !------------------------------------------------------------------ spectral_init_cond_nml (spectral_init_cond.F90:68-74)
   real :: initial_temperature = 264.

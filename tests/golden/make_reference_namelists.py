@@ -33,5 +33,33 @@ for name, rel in CASES.items():
         out[name] = ast.literal_eval(src[i:j + 1])
     except (ValueError, SyntaxError):
         continue                                        # namelists built from expressions: not a literal
+# the union over ALL scripts under exp/test_cases (every dict literal handed to Namelist(...) or to an .update(...)) of the variables set
+# per namelist group: what an input.nml produced by the shipped test cases can contain
+import glob
+union = {}
+for path in sorted(glob.glob("/root/reference/exp/test_cases/*/*.py")):
+    src = open(path).read()
+    for marker in ("Namelist({", ".update({"):
+        start = 0
+        while True:
+            i = src.find(marker, start)
+            if i < 0:
+                break
+            k = src.index("{", i)
+            depth = 0
+            for j in range(k, len(src)):
+                depth += src[j] == "{"
+                depth -= src[j] == "}"
+                if depth == 0:
+                    break
+            start = j
+            try:
+                d = ast.literal_eval(src[k:j + 1])
+            except (ValueError, SyntaxError):
+                continue
+            for g, vals in d.items():
+                if isinstance(vals, dict):
+                    union.setdefault(g, set()).update(vals)
+out["__union_of_all_test_cases__"] = {g: sorted(v) for g, v in union.items()}
 json.dump(out, open(OUT, "w"), indent=1, sort_keys=True)
 print("wrote", OUT, sorted(out))

@@ -78,3 +78,24 @@ def test_shim_call_sequence_cold_start_and_restart(driver):
     w = 1.0 + (np.arange(t.size) % 7)
     assert abs(float((t.ravel() * w).sum()) - float(vals["T_uninterrupted"])) <= 1e-10 * abs(float(vals["T_uninterrupted"]))
     atm.atmosphere_end()
+
+
+def test_shim_namelist_groups_cover_the_shipped_test_cases():
+    """every variable that a script under exp/test_cases sets in a namelist group the shim reads is declared in the shim's group of
+    that name (a Fortran namelist read fails on an unknown variable; the shim turns that into FATAL)"""
+    import json
+    union = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_test_case_namelists.json")))["__union_of_all_test_cases__"]
+    src = open(os.path.join(ROOT, "fortran", "atmosphere.F90")).read()
+    src = re.sub(r"&\s*\n\s*", " ", src)                                          # join continuation lines
+    src = re.sub(r"!.*", "", src)
+    groups = {}
+    for m in re.finditer(r"namelist\s*/(\w+)/\s*([^\n]*)", src, flags=re.I):
+        groups.setdefault(m.group(1).lower(), set()).update(v.strip().lower() for v in m.group(2).split(",") if v.strip())
+    for g in ("atmosphere_nml", "spectral_dynamics_nml", "idealized_moist_phys_nml", "mixed_layer_nml", "vert_turb_driver_nml", "diffusivity_nml",
+              "surface_flux_nml", "lscale_cond_nml", "qe_moist_convection_nml", "two_stream_gray_rad_nml", "damping_driver_nml",
+              "sat_vapor_pres_nml", "hs_forcing_nml"):
+        assert g in groups, g
+        missing = sorted(v for v in union.get(g, []) if v.lower() not in groups[g])
+        if g == "atmosphere_nml":                    # print_interval: atmosphere_nml of the barotropic / shallow-water atmosphere_mod, another module
+            missing = [v for v in missing if v != "print_interval"]
+        assert not missing, (g, missing)
